@@ -1,0 +1,303 @@
+/*
+ * ogrecu.h — C ABI of libogrecu.so, the B200-native (sm_100a) back end for OGRE's
+ * software-rendering hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no OGRE, torch or C++ types.
+ * Every entry point names the reference interface it serves (paths relative to the
+ * OGRE 14.6 tree).  The C++ host plugin (ogre_b200/plugin: RenderSystem_CUDA.so +
+ * CudaOptimisedUtil) is a thin adapter from OGRE's virtual interfaces to these calls;
+ * INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *  - every function returns 0 on success, a non-zero ogrecu_status otherwise;
+ *    ogrecu_last_error_string() describes the last failure on the calling thread.
+ *  - there is NO CPU fallback: with no usable CUDA device ogrecu_init fails.
+ *  - one context per device; a context is used from one thread at a time
+ *    (OGRE's render thread, SURVEY §8b "Threading").
+ *  - "dev" pointers are CUDA device pointers valid on the context's device; "host"
+ *    pointers are ordinary process memory.  Functions suffixed _host take host pointers
+ *    and perform the H2D/D2H staging themselves (the path OGRE's lock()/unlock() API
+ *    forces); functions suffixed _dev work on resident data and are asynchronous on the
+ *    context's stream.
+ *  - all arithmetic is IEEE binary32 replaying the reference's operation order without
+ *    FMA contraction.
+ */
+#ifndef OGRECU_H
+#define OGRECU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define OGRECU_API __attribute__((visibility("default")))
+#else
+#define OGRECU_API
+#endif
+
+#define OGRECU_ABI_VERSION 1
+
+typedef enum ogrecu_status {
+    OGRECU_OK = 0,
+    OGRECU_ERR_NO_DEVICE = 1,     /* no CUDA device / driver: there is no CPU fallback   */
+    OGRECU_ERR_CUDA = 2,          /* a CUDA runtime call failed (see last_error_string)  */
+    OGRECU_ERR_INVALID = 3,       /* bad argument (NULL, out of range, unsupported mode) */
+    OGRECU_ERR_OOM = 4,           /* device or pinned-host allocation failed             */
+    OGRECU_ERR_UNSUPPORTED = 5    /* e.g. operation type other than triangle list/strip  */
+} ogrecu_status;
+
+typedef struct ogrecu_ctx ogrecu_ctx;   /* one CUDA device + stream + scratch arenas     */
+typedef struct ogrecu_buf ogrecu_buf;   /* HardwareBuffer: device storage + pinned shadow */
+typedef struct ogrecu_tex ogrecu_tex;   /* RGBA8 texture, 0 mips (TinyTexture)            */
+typedef struct ogrecu_rt  ogrecu_rt;    /* render target: RGB8 colour + f32 depth planes  */
+
+/* ------------------------------------------------------------------ context -------- */
+
+OGRECU_API int ogrecu_abi_version(void);
+OGRECU_API const char* ogrecu_last_error_string(void);
+OGRECU_API int ogrecu_device_count(int* count);
+
+/* Create a context on CUDA device `device`.  Fails with OGRECU_ERR_NO_DEVICE when the
+ * driver or device is missing.  (TinyRenderSystem ctor / _createRenderWindow first-time
+ * init, RenderSystems/Tiny/src/OgreTinyRenderSystem.cpp:27-46,146-194.) */
+OGRECU_API int ogrecu_init(int device, ogrecu_ctx** out_ctx);
+OGRECU_API int ogrecu_shutdown(ogrecu_ctx* ctx);
+OGRECU_API int ogrecu_device(const ogrecu_ctx* ctx, int* device);
+
+/* Launch on an externally owned cudaStream_t (e.g. the bench's timing stream).  Passing
+ * NULL restores the context's own stream. */
+OGRECU_API int ogrecu_set_stream(ogrecu_ctx* ctx, void* cuda_stream);
+OGRECU_API void* ogrecu_get_stream(ogrecu_ctx* ctx);
+OGRECU_API int ogrecu_sync(ogrecu_ctx* ctx);
+/* number of kernels this context has launched since creation (bench "gpu_launches") */
+OGRECU_API uint64_t ogrecu_launch_count(const ogrecu_ctx* ctx);
+
+/* raw device / pinned memory for callers that keep data resident */
+OGRECU_API int ogrecu_malloc(ogrecu_ctx* ctx, size_t bytes, void** dev_ptr);
+OGRECU_API int ogrecu_free(ogrecu_ctx* ctx, void* dev_ptr);
+OGRECU_API int ogrecu_host_alloc(size_t bytes, void** host_ptr);    /* pinned */
+OGRECU_API int ogrecu_host_free(void* host_ptr);
+OGRECU_API int ogrecu_memcpy_h2d(ogrecu_ctx* ctx, void* dev, const void* host, size_t bytes);
+OGRECU_API int ogrecu_memcpy_d2h(ogrecu_ctx* ctx, void* host, const void* dev, size_t bytes);
+OGRECU_API int ogrecu_memcpy_d2d(ogrecu_ctx* ctx, void* dst, const void* src, size_t bytes);
+
+/* ------------------------------------------------------------ hardware buffers ----- */
+/* HardwareBuffer delegate (OgreMain/include/OgreHardwareBuffer.h:181-186,279-330):
+ * lock() returns a pinned host shadow; unlock() after a write uploads the dirty range on
+ * the context stream; a lock with read intent first downloads device-side writes
+ * (skinning results).  The shadow address range is registered so OptimisedUtil calls that
+ * arrive with pointers obtained from lock() resolve to the device copy with no staging. */
+enum { OGRECU_MAP_READ = 1, OGRECU_MAP_WRITE = 2, OGRECU_MAP_DISCARD = 4 };
+
+OGRECU_API int ogrecu_buf_create(ogrecu_ctx* ctx, size_t bytes, ogrecu_buf** out);
+OGRECU_API int ogrecu_buf_destroy(ogrecu_buf* buf);
+OGRECU_API int ogrecu_buf_map(ogrecu_buf* buf, size_t offset, size_t length, int mode, void** host_ptr);
+OGRECU_API int ogrecu_buf_unmap(ogrecu_buf* buf);
+OGRECU_API int ogrecu_buf_device_ptr(ogrecu_buf* buf, void** dev_ptr);
+OGRECU_API size_t ogrecu_buf_size(const ogrecu_buf* buf);
+/* mark [offset, offset+length) as written on the device (shadow stale) */
+OGRECU_API int ogrecu_buf_mark_device_dirty(ogrecu_buf* buf, size_t offset, size_t length);
+/* host shadow pointer -> owning buffer + offset; *out_buf = NULL when not ours */
+OGRECU_API int ogrecu_buf_resolve(ogrecu_ctx* ctx, const void* host_ptr, ogrecu_buf** out_buf, size_t* out_offset);
+
+/* -------------------------------------------------------------- OptimisedUtil ------ */
+/* Ogre::OptimisedUtil, OgreMain/include/OgreOptimisedUtil.h:99-206; arithmetic replays
+ * OgreMain/src/OgreOptimisedUtilSSE.cpp (see DESIGN.md §kernels for the per-function
+ * operation order and where the exact General formulation is followed instead). */
+
+/* One skinning job = one softwareVertexSkinning call (OgreOptimisedUtil.h:99-108).
+ * All pointers are DEVICE pointers; strides are in bytes.  `palette` is a dense array of
+ * `num_matrices` Affine3 (16 floats each, row major, OgreMatrix4.h:80-84) already
+ * gathered through the reference's pointer palette (OgreMesh.cpp:1782-1790). */
+typedef struct ogrecu_skin_job {
+    const float*   src_pos;        /* 3 floats per vertex                                 */
+    float*         dst_pos;
+    const float*   src_norm;       /* NULL => positions only                              */
+    float*         dst_norm;
+    const float*   blend_weight;   /* num_weights floats per vertex                       */
+    const uint8_t* blend_index;    /* num_weights bytes per vertex                        */
+    const float*   palette;        /* Affine3 array, 16 floats each, 16-byte aligned      */
+    const uint16_t* bone_map;      /* optional: matrix b = palette[bone_map[b]] (the      */
+                                   /* blendIndexToBoneIndexMap, OgreMesh.cpp:1782-1790);  */
+                                   /* NULL = identity                                     */
+    uint32_t src_pos_stride, dst_pos_stride;
+    uint32_t src_norm_stride, dst_norm_stride;
+    uint32_t blend_weight_stride, blend_index_stride;
+    uint32_t num_weights;          /* 1..4                                                */
+    uint32_t num_matrices;         /* matrices addressable by blend_index, <= 256         */
+    uint32_t num_vertices;
+    uint32_t reserved;
+} ogrecu_skin_job;
+
+/* Batched, device-resident skinning: `jobs` is a HOST array of n descriptors (copied to
+ * the device by the call); one launch covers all jobs.  Asynchronous on the stream. */
+OGRECU_API int ogrecu_skin_dev(ogrecu_ctx* ctx, const ogrecu_skin_job* jobs, uint32_t n);
+
+/* Instanced form of the same job (config 2: 10 000 animated instances of one mesh):
+ * instance i reads the shared source/blend streams and palette
+ * `palettes + i*palette_stride_floats`, and writes dst + i*dst_instance_stride bytes. */
+OGRECU_API int ogrecu_skin_instanced_dev(ogrecu_ctx* ctx, const ogrecu_skin_job* job,
+                                         uint32_t num_instances,
+                                         size_t palette_stride_floats,
+                                         size_t dst_instance_stride_bytes);
+
+/* Exact-signature host form (what CudaOptimisedUtil::softwareVertexSkinning forwards to):
+ * host pointers, pointer palette of Affine3 (`blend_matrices[i]` -> 16 floats).  Pointers
+ * that lie inside a mapped ogrecu_buf shadow are resolved to the device copy; anything
+ * else is staged through pinned memory.  Synchronous. */
+OGRECU_API int ogrecu_software_vertex_skinning_host(
+    ogrecu_ctx* ctx,
+    const float* src_pos, float* dst_pos, const float* src_norm, float* dst_norm,
+    const float* blend_weight, const uint8_t* blend_index,
+    const float* const* blend_matrices,
+    size_t src_pos_stride, size_t dst_pos_stride, size_t src_norm_stride, size_t dst_norm_stride,
+    size_t blend_weight_stride, size_t blend_index_stride,
+    size_t num_weights_per_vertex, size_t num_vertices);
+
+/* softwareVertexMorph (OgreOptimisedUtil.h:125-131): dst = a + t*(b-a); with
+ * morph_normals the interleaved normal is lerped then normalised (General formulation,
+ * OgreOptimisedUtilGeneral.cpp:236-283; the SSE one mis-sums the length).
+ * Strides in bytes; General accepts any stride >= 12 (24 with normals). */
+OGRECU_API int ogrecu_morph_dev(ogrecu_ctx* ctx, float t, const float* src1, const float* src2, float* dst,
+                                size_t stride1, size_t stride2, size_t dst_stride,
+                                size_t num_vertices, int morph_normals);
+OGRECU_API int ogrecu_software_vertex_morph_host(ogrecu_ctx* ctx, float t, const float* src1, const float* src2,
+                                                 float* dst, size_t stride1, size_t stride2, size_t dst_stride,
+                                                 size_t num_vertices, int morph_normals);
+
+/* concatenateAffineMatrices (OgreOptimisedUtil.h:142-146): dst[i] = base * src[i];
+ * 16 floats per matrix.  `base` is always a HOST pointer (it is a by-reference argument
+ * in the reference). */
+OGRECU_API int ogrecu_concat_affine_dev(ogrecu_ctx* ctx, const float* base_host16, const float* src, float* dst,
+                                        size_t num_matrices);
+OGRECU_API int ogrecu_concatenate_affine_matrices_host(ogrecu_ctx* ctx, const float* base16, const float* src,
+                                                       float* dst, size_t num_matrices);
+
+/* calculateFaceNormals (OgreOptimisedUtil.h:159-163).  `triangles` has the layout of
+ * EdgeData::Triangle (OgreEdgeListBuilder.h:59-72): 32-byte records, vertIndex[3] are the
+ * uint32 at byte offsets 8,12,16.  positions are packed xyz (stride 12).  Output: one
+ * float4 (nx,ny,nz,-n.v0) per triangle, not normalised. */
+OGRECU_API int ogrecu_face_normals_dev(ogrecu_ctx* ctx, const float* positions, const void* triangles,
+                                       float* face_normals, size_t num_triangles);
+OGRECU_API int ogrecu_calculate_face_normals_host(ogrecu_ctx* ctx, const float* positions, size_t num_vertices,
+                                                  const void* triangles, float* face_normals,
+                                                  size_t num_triangles);
+
+/* calculateLightFacing (OgreOptimisedUtil.h:181-185): facing[i] = !(dot4(light, n[i]) <= 0)
+ * with the SSE summation order (x+z)+(y+w).  light4 is a HOST pointer to 4 floats. */
+OGRECU_API int ogrecu_light_facing_dev(ogrecu_ctx* ctx, const float* light4_host, const float* face_normals,
+                                       char* facings, size_t num_faces);
+/* n_lights lights over the same normals in one launch; facings[l*facing_stride + i] */
+OGRECU_API int ogrecu_light_facing_multi_dev(ogrecu_ctx* ctx, const float* lights_host, uint32_t n_lights,
+                                             const float* face_normals, char* facings, size_t facing_stride,
+                                             size_t num_faces);
+OGRECU_API int ogrecu_calculate_light_facing_host(ogrecu_ctx* ctx, const float* light4, const float* face_normals,
+                                                  char* facings, size_t num_faces);
+
+/* extrudeVertices (OgreOptimisedUtil.h:201-206): packed xyz in/out.  light4[3]==0 =>
+ * directional, else point.  Exact 1/sqrt (General formulation; the SSE rsqrt estimate is
+ * CPU-vendor dependent). */
+OGRECU_API int ogrecu_extrude_dev(ogrecu_ctx* ctx, const float* light4_host, float extrude_dist,
+                                  const float* src, float* dst, size_t num_vertices);
+OGRECU_API int ogrecu_extrude_vertices_host(ogrecu_ctx* ctx, const float* light4, float extrude_dist,
+                                            const float* src, float* dst, size_t num_vertices);
+
+/* ------------------------------------------------------------------ rasteriser ----- */
+/* TinyTexture / TinyHardwarePixelBuffer (RenderSystems/Tiny/src/OgreTinyTexture.cpp:30-57):
+ * always RGBA8, tightly packed, 0 mips. */
+OGRECU_API int ogrecu_tex_create(ogrecu_ctx* ctx, uint32_t width, uint32_t height, ogrecu_tex** out);
+OGRECU_API int ogrecu_tex_destroy(ogrecu_tex* tex);
+OGRECU_API int ogrecu_tex_upload(ogrecu_tex* tex, const uint8_t* rgba_host, size_t row_pitch_bytes);
+OGRECU_API int ogrecu_tex_download(ogrecu_tex* tex, uint8_t* rgba_host, size_t row_pitch_bytes);
+OGRECU_API int ogrecu_tex_device_ptr(ogrecu_tex* tex, void** dev_ptr);
+
+/* Render target = TinyWindow colour Image (PF_BYTE_RGB, tightly packed,
+ * OgreTinyWindow.cpp:38-42) + TinyDepthBuffer Image (PF_FLOAT32_R, OgreTinyDepthBuffer.h:20). */
+OGRECU_API int ogrecu_rt_create(ogrecu_ctx* ctx, uint32_t width, uint32_t height, ogrecu_rt** out);
+OGRECU_API int ogrecu_rt_destroy(ogrecu_rt* rt);
+OGRECU_API int ogrecu_rt_size(const ogrecu_rt* rt, uint32_t* width, uint32_t* height);
+
+enum { OGRECU_CLEAR_COLOUR = 1, OGRECU_CLEAR_DEPTH = 2 };
+/* clearFrameBuffer (OgreTinyRenderSystem.cpp:421-433): whole target, ignores viewport;
+ * colour packed as (uint)(v*256) clamped to 255 (PixelUtil::packColour / Bitwise::floatToFixed,
+ * OgreBitwise.h:237-242); depth plane filled with `depth`.  Ordered with draws. */
+OGRECU_API int ogrecu_rt_clear(ogrecu_rt* rt, unsigned buffers, const float colour_rgba[4], float depth);
+
+enum { OGRECU_PRIM_TRIANGLE_LIST = 4, OGRECU_PRIM_TRIANGLE_STRIP = 5 };  /* RenderOperation::OperationType values */
+enum { OGRECU_INDEX_NONE = 0, OGRECU_INDEX_U16 = 2, OGRECU_INDEX_U32 = 4 };
+enum {
+    OGRECU_DRAW_DEPTH_TEST  = 1,   /* _setDepthBufferParams depthTest  (.cpp:270-274) */
+    OGRECU_DRAW_DEPTH_WRITE = 2,   /* _setDepthBufferParams depthWrite               */
+    OGRECU_DRAW_BLEND_ADD   = 4,   /* setColourBlendState destFactor==SBF_ONE (.cpp:284-287) */
+    OGRECU_DRAW_LIGHTING    = 8    /* setLightingEnabled && mesh has normals (.cpp:369) */
+};
+
+/* One TinyRenderSystem::_render(RenderOperation) (OgreTinyRenderSystem.cpp:349-414) with
+ * the render state and DefaultShader uniforms (include/OgreTinyRenderSystem.h:57-75) that
+ * were current when it was issued.  Vertex/index pointers are DEVICE pointers already
+ * offset the way getData() does (`base + elemOffset + vertexStart*stride`, .cpp:335-347;
+ * indices + indexStart).  Matrices are row-major float[16] (Ogre::Matrix4). */
+typedef struct ogrecu_draw_desc {
+    const void* positions;  uint32_t pos_stride;     /* float3 per vertex                 */
+    const void* uvs;        uint32_t uv_stride;      /* float2 or NULL                    */
+    const void* normals;    uint32_t normal_stride;  /* float3 or NULL                    */
+    const void* indices;    uint32_t index_type;     /* OGRECU_INDEX_*                    */
+    uint32_t draw_count;        /* indexCount, or vertexCount when not indexed (.cpp:373,387) */
+    uint32_t prim_type;         /* OGRECU_PRIM_*; lists are culled (cross>0), strips not (.cpp:410) */
+    uint32_t flags;             /* OGRECU_DRAW_*                                          */
+    const ogrecu_tex* texture;  /* unit 0 or NULL (white)  (.cpp:208-220)                 */
+    float mvp[16];              /* uniform_MVP                                            */
+    float tex_matrix[16];       /* uniform_Tex                                            */
+    float mvit[16];             /* uniform_MVIT (upper-left 3x3 used)                     */
+    float viewport[16];         /* mVP from _setViewport (.cpp:230-262)                   */
+    float light_dir[3];         /* uniform_lightDir                                       */
+    float ambient[4];           /* uniform_ambientCol                                     */
+} ogrecu_draw_desc;
+
+/* Record a draw on `rt` (cheap; nothing runs yet).  Draws and clears keep submission order. */
+OGRECU_API int ogrecu_draw(ogrecu_rt* rt, const ogrecu_draw_desc* desc);
+/* Run everything recorded on `rt`: vertex transform + triangle setup, order-preserving
+ * tile binning, per-tile raster/shade/blend, coalesced flush to the colour/depth planes.
+ * Asynchronous on the stream (_endFrame / readback / buffer lock are the sync points). */
+OGRECU_API int ogrecu_flush(ogrecu_rt* rt);
+
+/* Batched offscreen views (config 4): the same draw list (everything but mvp/mvit/light)
+ * rendered into n_views targets of identical size in one pipeline pass.
+ * per_view_mvp / per_view_mvit: n_views*16 floats (HOST); per_view_light_dir: n_views*3. */
+OGRECU_API int ogrecu_draw_views(ogrecu_rt* const* rts, uint32_t n_views, const ogrecu_draw_desc* desc,
+                                 const float* per_view_mvp, const float* per_view_mvit,
+                                 const float* per_view_light_dir);
+
+/* Split-frame (config 5): restrict rasterisation on this context to screen tile rows
+ * [y0, y1) (multiples of the tile height); planes outside are left untouched.  The owner
+ * of a strip is the only writer, so the composite is a disjoint gather. */
+OGRECU_API int ogrecu_rt_set_strip(ogrecu_rt* rt, uint32_t y0, uint32_t y1);
+
+/* Readback (TinyWindow::copyContentsToMemory, OgreTinyWindow.cpp:68-80;
+ * HardwarePixelBuffer::blitToMemory).  Flushes pending work, copies the box
+ * [left,right) x [top,bottom) to host as tightly described by dst_pitch_bytes.
+ * Colour is RGB8 (3 bytes/pixel); depth is float32. */
+OGRECU_API int ogrecu_rt_read_colour(ogrecu_rt* rt, uint32_t left, uint32_t top, uint32_t right, uint32_t bottom,
+                                     uint8_t* dst_host, size_t dst_pitch_bytes);
+OGRECU_API int ogrecu_rt_read_depth(ogrecu_rt* rt, uint32_t left, uint32_t top, uint32_t right, uint32_t bottom,
+                                    float* dst_host, size_t dst_pitch_bytes);
+/* upload into the planes (render-to-texture sources, tests) */
+OGRECU_API int ogrecu_rt_write_colour(ogrecu_rt* rt, const uint8_t* src_host, size_t src_pitch_bytes);
+OGRECU_API int ogrecu_rt_write_depth(ogrecu_rt* rt, const float* src_host, size_t src_pitch_bytes);
+OGRECU_API int ogrecu_rt_colour_device_ptr(ogrecu_rt* rt, void** dev_ptr);
+OGRECU_API int ogrecu_rt_depth_device_ptr(ogrecu_rt* rt, void** dev_ptr);
+
+/* statistics of the last flush on this target (triangles submitted / surviving cull+clip,
+ * (triangle,tile) pairs binned, tiles rasterised) */
+typedef struct ogrecu_raster_stats {
+    uint64_t triangles_in, triangles_binned, tile_pairs, tiles_active;
+} ogrecu_raster_stats;
+OGRECU_API int ogrecu_rt_last_stats(ogrecu_rt* rt, ogrecu_raster_stats* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OGRECU_H */

@@ -1,0 +1,224 @@
+"""ogre_b200 — B200-native back end for OGRE's software-rendering hot path.
+
+The product is libogrecu.so (hand-written sm_100a kernels behind the C ABI of
+include/ogrecu.h) plus the C++ drop-in plugin in ogre_b200/plugin.  This Python package
+is only the thin host-side mirror used by the tests and bench.py: it forwards to the C
+ABI through ctypes and keeps the reference's names and argument meaning
+(Ogre::OptimisedUtil, OgreMain/include/OgreOptimisedUtil.h:99-206;
+TinyRenderSystem::_render, RenderSystems/Tiny/src/OgreTinyRenderSystem.cpp:349-414).
+It never computes results itself and never touches oracle/.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .capi import DrawDesc, OgrecuError, RasterStats, SkinJob, check, lib
+
+__all__ = ["Context", "DeviceBuffer", "OptimisedUtil", "Texture", "RenderTarget", "DrawDesc", "SkinJob",
+           "OgrecuError", "addr"]
+
+MAP_READ, MAP_WRITE, MAP_DISCARD = 1, 2, 4
+CLEAR_COLOUR, CLEAR_DEPTH = 1, 2
+PRIM_TRIANGLE_LIST, PRIM_TRIANGLE_STRIP = 4, 5
+INDEX_NONE, INDEX_U16, INDEX_U32 = 0, 2, 4
+DRAW_DEPTH_TEST, DRAW_DEPTH_WRITE, DRAW_BLEND_ADD, DRAW_LIGHTING = 1, 2, 4, 8
+
+
+def addr(arr, byte_offset=0):
+    """Address of a numpy array's first byte (+offset); None stays None (NULL)."""
+    if arr is None:
+        return None
+    return arr.ctypes.data + int(byte_offset)
+
+
+class DeviceBuffer:
+    """Raw device allocation owned by a Context."""
+
+    def __init__(self, ctx, nbytes):
+        self.ctx = ctx
+        self.nbytes = int(nbytes)
+        p = C.c_void_p()
+        check(lib().ogrecu_malloc(ctx.handle, self.nbytes, C.byref(p)))
+        self.ptr = p.value
+
+    def upload(self, arr, byte_offset=0):
+        a = np.ascontiguousarray(arr)
+        assert byte_offset + a.nbytes <= self.nbytes
+        check(lib().ogrecu_memcpy_h2d(self.ctx.handle, self.ptr + byte_offset, a.ctypes.data, a.nbytes))
+        self.ctx.sync()   # the source numpy array may be pageable and short-lived
+        return self
+
+    def download(self, dtype=np.uint8, count=None, byte_offset=0):
+        dt = np.dtype(dtype)
+        n = (self.nbytes - byte_offset) // dt.itemsize if count is None else int(count)
+        out = np.empty(n, dtype=dt)
+        check(lib().ogrecu_memcpy_d2h(self.ctx.handle, out.ctypes.data, self.ptr + byte_offset, out.nbytes))
+        return out
+
+    def free(self):
+        if self.ptr:
+            check(lib().ogrecu_free(self.ctx.handle, self.ptr))
+            self.ptr = None
+
+
+class Context:
+    """One CUDA device (ogrecu_ctx).  Raises OgrecuError when no device is usable."""
+
+    def __init__(self, device=0):
+        h = C.c_void_p()
+        check(lib().ogrecu_init(int(device), C.byref(h)))
+        self.handle = h.value
+        self.device = int(device)
+
+    def close(self):
+        if self.handle:
+            check(lib().ogrecu_shutdown(self.handle))
+            self.handle = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def sync(self):
+        check(lib().ogrecu_sync(self.handle))
+
+    def set_stream(self, cuda_stream):
+        check(lib().ogrecu_set_stream(self.handle, cuda_stream))
+
+    @property
+    def launch_count(self):
+        return int(lib().ogrecu_launch_count(self.handle))
+
+    def alloc(self, nbytes):
+        return DeviceBuffer(self, nbytes)
+
+    def to_device(self, arr):
+        a = np.ascontiguousarray(arr)
+        return DeviceBuffer(self, max(a.nbytes, 1)).upload(a)
+
+
+def _light4(light):
+    a = np.ascontiguousarray(light, dtype=np.float32).reshape(-1)
+    return a, a.ctypes.data_as(capi.c_float_p)
+
+
+class OptimisedUtil:
+    """Host-pointer mirror of Ogre::OptimisedUtil (same method names and argument order as
+    OgreMain/include/OgreOptimisedUtil.h:99-206).  Pointer arguments are integer addresses
+    (use addr()); the work runs on the GPU through the *_host C-ABI entry points."""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+
+    def softwareVertexSkinning(self, srcPosPtr, destPosPtr, srcNormPtr, destNormPtr, blendWeightPtr, blendIndexPtr,
+                               blendMatrices, srcPosStride, destPosStride, srcNormStride, destNormStride,
+                               blendWeightStride, blendIndexStride, numWeightsPerVertex, numVertices):
+        # blendMatrices: sequence of float32[16] arrays (the reference's `const Affine3* const*`)
+        mats = [np.ascontiguousarray(m, dtype=np.float32).reshape(16) for m in blendMatrices]
+        ptrs = (C.c_void_p * max(len(mats), 1))(*[m.ctypes.data for m in mats])
+        check(lib().ogrecu_software_vertex_skinning_host(
+            self.ctx.handle, srcPosPtr, destPosPtr, srcNormPtr, destNormPtr, blendWeightPtr, blendIndexPtr, ptrs,
+            srcPosStride, destPosStride, srcNormStride, destNormStride, blendWeightStride, blendIndexStride,
+            numWeightsPerVertex, numVertices))
+
+    def softwareVertexMorph(self, t, srcPos1, srcPos2, dstPos, pos1VSize, pos2VSize, dstVSize, numVertices,
+                            morphNormals):
+        check(lib().ogrecu_software_vertex_morph_host(self.ctx.handle, float(t), srcPos1, srcPos2, dstPos,
+                                                      pos1VSize, pos2VSize, dstVSize, numVertices,
+                                                      1 if morphNormals else 0))
+
+    def concatenateAffineMatrices(self, baseMatrix, srcMatrices, dstMatrices, numMatrices):
+        b = np.ascontiguousarray(baseMatrix, dtype=np.float32).reshape(16)
+        check(lib().ogrecu_concatenate_affine_matrices_host(self.ctx.handle, b.ctypes.data_as(capi.c_float_p),
+                                                            srcMatrices, dstMatrices, numMatrices))
+
+    def calculateFaceNormals(self, positions, triangles, faceNormals, numTriangles, numVertices=0):
+        check(lib().ogrecu_calculate_face_normals_host(self.ctx.handle, positions, numVertices, triangles,
+                                                       faceNormals, numTriangles))
+
+    def calculateLightFacing(self, lightPos, faceNormals, lightFacings, numFaces):
+        keep, lp = _light4(lightPos)
+        check(lib().ogrecu_calculate_light_facing_host(self.ctx.handle, lp, faceNormals, lightFacings, numFaces))
+
+    def extrudeVertices(self, lightPos, extrudeDist, srcPositions, destPositions, numVertices):
+        keep, lp = _light4(lightPos)
+        check(lib().ogrecu_extrude_vertices_host(self.ctx.handle, lp, float(extrudeDist), srcPositions,
+                                                 destPositions, numVertices))
+
+
+class Texture:
+    """RGBA8 texture (TinyTexture, RenderSystems/Tiny/src/OgreTinyTexture.cpp:30-57)."""
+
+    def __init__(self, ctx, rgba):
+        a = np.ascontiguousarray(rgba, dtype=np.uint8)
+        assert a.ndim == 3 and a.shape[2] == 4
+        self.ctx = ctx
+        self.height, self.width = a.shape[0], a.shape[1]
+        h = C.c_void_p()
+        check(lib().ogrecu_tex_create(ctx.handle, self.width, self.height, C.byref(h)))
+        self.handle = h.value
+        check(lib().ogrecu_tex_upload(self.handle, a.ctypes.data, self.width * 4))
+
+    def destroy(self):
+        if self.handle:
+            check(lib().ogrecu_tex_destroy(self.handle))
+            self.handle = None
+
+
+class RenderTarget:
+    """RGB8 colour + f32 depth planes (TinyWindow + TinyDepthBuffer)."""
+
+    def __init__(self, ctx, width, height):
+        self.ctx, self.width, self.height = ctx, int(width), int(height)
+        h = C.c_void_p()
+        check(lib().ogrecu_rt_create(ctx.handle, self.width, self.height, C.byref(h)))
+        self.handle = h.value
+
+    def destroy(self):
+        if self.handle:
+            check(lib().ogrecu_rt_destroy(self.handle))
+            self.handle = None
+
+    def clear(self, buffers=CLEAR_COLOUR | CLEAR_DEPTH, colour=(0, 0, 0, 0), depth=1.0):
+        c = (C.c_float * 4)(*[float(v) for v in colour])
+        check(lib().ogrecu_rt_clear(self.handle, buffers, c, float(depth)))
+
+    def draw(self, desc):
+        check(lib().ogrecu_draw(self.handle, C.byref(desc)))
+
+    def flush(self):
+        check(lib().ogrecu_flush(self.handle))
+
+    def set_strip(self, y0, y1):
+        check(lib().ogrecu_rt_set_strip(self.handle, int(y0), int(y1)))
+
+    def read_colour(self, box=None):
+        l, t, r, b = box if box else (0, 0, self.width, self.height)
+        out = np.empty((b - t, r - l, 3), dtype=np.uint8)
+        check(lib().ogrecu_rt_read_colour(self.handle, l, t, r, b, out.ctypes.data, (r - l) * 3))
+        return out
+
+    def read_depth(self, box=None):
+        l, t, r, b = box if box else (0, 0, self.width, self.height)
+        out = np.empty((b - t, r - l), dtype=np.float32)
+        check(lib().ogrecu_rt_read_depth(self.handle, l, t, r, b, out.ctypes.data, (r - l) * 4))
+        return out
+
+    def write_colour(self, rgb):
+        a = np.ascontiguousarray(rgb, dtype=np.uint8)
+        assert a.shape == (self.height, self.width, 3)
+        check(lib().ogrecu_rt_write_colour(self.handle, a.ctypes.data, self.width * 3))
+
+    def write_depth(self, depth):
+        a = np.ascontiguousarray(depth, dtype=np.float32)
+        assert a.shape == (self.height, self.width)
+        check(lib().ogrecu_rt_write_depth(self.handle, a.ctypes.data, self.width * 4))
+
+    def stats(self):
+        s = RasterStats()
+        check(lib().ogrecu_rt_last_stats(self.handle, C.byref(s)))
+        return {"triangles_in": s.triangles_in, "triangles_binned": s.triangles_binned,
+                "tile_pairs": s.tile_pairs, "tiles_active": s.tiles_active}

@@ -1,0 +1,148 @@
+"""ctypes view of the C ABI declared in include/ogrecu.h (libogrecu.so).
+
+Nothing here computes anything: it declares argument types and loads the in-tree shared
+library.  If the library is missing or no CUDA device is usable the calls FAIL — there is
+no CPU fallback anywhere in the product path.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libogrecu.so")
+
+c_void_pp = C.POINTER(C.c_void_p)
+c_float_p = C.POINTER(C.c_float)
+
+
+class OgrecuError(RuntimeError):
+    def __init__(self, status, message):
+        super().__init__("ogrecu status %d: %s" % (status, message))
+        self.status = status
+
+
+class SkinJob(C.Structure):
+    """ogrecu_skin_job (include/ogrecu.h)"""
+    _fields_ = [
+        ("src_pos", C.c_void_p), ("dst_pos", C.c_void_p),
+        ("src_norm", C.c_void_p), ("dst_norm", C.c_void_p),
+        ("blend_weight", C.c_void_p), ("blend_index", C.c_void_p),
+        ("palette", C.c_void_p), ("bone_map", C.c_void_p),
+        ("src_pos_stride", C.c_uint32), ("dst_pos_stride", C.c_uint32),
+        ("src_norm_stride", C.c_uint32), ("dst_norm_stride", C.c_uint32),
+        ("blend_weight_stride", C.c_uint32), ("blend_index_stride", C.c_uint32),
+        ("num_weights", C.c_uint32), ("num_matrices", C.c_uint32),
+        ("num_vertices", C.c_uint32), ("reserved", C.c_uint32),
+    ]
+
+
+class DrawDesc(C.Structure):
+    """ogrecu_draw_desc (include/ogrecu.h)"""
+    _fields_ = [
+        ("positions", C.c_void_p), ("pos_stride", C.c_uint32),
+        ("uvs", C.c_void_p), ("uv_stride", C.c_uint32),
+        ("normals", C.c_void_p), ("normal_stride", C.c_uint32),
+        ("indices", C.c_void_p), ("index_type", C.c_uint32),
+        ("draw_count", C.c_uint32), ("prim_type", C.c_uint32), ("flags", C.c_uint32),
+        ("texture", C.c_void_p),
+        ("mvp", C.c_float * 16), ("tex_matrix", C.c_float * 16), ("mvit", C.c_float * 16),
+        ("viewport", C.c_float * 16), ("light_dir", C.c_float * 3), ("ambient", C.c_float * 4),
+    ]
+
+
+class RasterStats(C.Structure):
+    _fields_ = [("triangles_in", C.c_uint64), ("triangles_binned", C.c_uint64),
+                ("tile_pairs", C.c_uint64), ("tiles_active", C.c_uint64)]
+
+
+# name -> (restype, argtypes); every symbol include/ogrecu.h declares
+SIGNATURES = {
+    "ogrecu_abi_version": (C.c_int, []),
+    "ogrecu_last_error_string": (C.c_char_p, []),
+    "ogrecu_device_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "ogrecu_init": (C.c_int, [C.c_int, c_void_pp]),
+    "ogrecu_shutdown": (C.c_int, [C.c_void_p]),
+    "ogrecu_device": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
+    "ogrecu_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ogrecu_get_stream": (C.c_void_p, [C.c_void_p]),
+    "ogrecu_sync": (C.c_int, [C.c_void_p]),
+    "ogrecu_launch_count": (C.c_uint64, [C.c_void_p]),
+    "ogrecu_malloc": (C.c_int, [C.c_void_p, C.c_size_t, c_void_pp]),
+    "ogrecu_free": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ogrecu_host_alloc": (C.c_int, [C.c_size_t, c_void_pp]),
+    "ogrecu_host_free": (C.c_int, [C.c_void_p]),
+    "ogrecu_memcpy_h2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "ogrecu_memcpy_d2h": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "ogrecu_memcpy_d2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "ogrecu_buf_create": (C.c_int, [C.c_void_p, C.c_size_t, c_void_pp]),
+    "ogrecu_buf_destroy": (C.c_int, [C.c_void_p]),
+    "ogrecu_buf_map": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, c_void_pp]),
+    "ogrecu_buf_unmap": (C.c_int, [C.c_void_p]),
+    "ogrecu_buf_device_ptr": (C.c_int, [C.c_void_p, c_void_pp]),
+    "ogrecu_buf_size": (C.c_size_t, [C.c_void_p]),
+    "ogrecu_buf_mark_device_dirty": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t]),
+    "ogrecu_buf_resolve": (C.c_int, [C.c_void_p, C.c_void_p, c_void_pp, C.POINTER(C.c_size_t)]),
+    "ogrecu_skin_dev": (C.c_int, [C.c_void_p, C.POINTER(SkinJob), C.c_uint32]),
+    "ogrecu_skin_instanced_dev": (C.c_int, [C.c_void_p, C.POINTER(SkinJob), C.c_uint32, C.c_size_t, C.c_size_t]),
+    "ogrecu_software_vertex_skinning_host": (C.c_int, [
+        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+        C.POINTER(C.c_void_p), C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t,
+        C.c_size_t, C.c_size_t]),
+    "ogrecu_morph_dev": (C.c_int, [C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                   C.c_size_t, C.c_size_t, C.c_size_t, C.c_int]),
+    "ogrecu_software_vertex_morph_host": (C.c_int, [C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                    C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int]),
+    "ogrecu_concat_affine_dev": (C.c_int, [C.c_void_p, c_float_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "ogrecu_concatenate_affine_matrices_host": (C.c_int, [C.c_void_p, c_float_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "ogrecu_face_normals_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "ogrecu_calculate_face_normals_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "ogrecu_light_facing_dev": (C.c_int, [C.c_void_p, c_float_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "ogrecu_light_facing_multi_dev": (C.c_int, [C.c_void_p, c_float_p, C.c_uint32, C.c_void_p, C.c_void_p,
+                                                C.c_size_t, C.c_size_t]),
+    "ogrecu_calculate_light_facing_host": (C.c_int, [C.c_void_p, c_float_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "ogrecu_extrude_dev": (C.c_int, [C.c_void_p, c_float_p, C.c_float, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "ogrecu_extrude_vertices_host": (C.c_int, [C.c_void_p, c_float_p, C.c_float, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "ogrecu_tex_create": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, c_void_pp]),
+    "ogrecu_tex_destroy": (C.c_int, [C.c_void_p]),
+    "ogrecu_tex_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "ogrecu_tex_download": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "ogrecu_tex_device_ptr": (C.c_int, [C.c_void_p, c_void_pp]),
+    "ogrecu_rt_create": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, c_void_pp]),
+    "ogrecu_rt_destroy": (C.c_int, [C.c_void_p]),
+    "ogrecu_rt_size": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    "ogrecu_rt_clear": (C.c_int, [C.c_void_p, C.c_uint, c_float_p, C.c_float]),
+    "ogrecu_draw": (C.c_int, [C.c_void_p, C.POINTER(DrawDesc)]),
+    "ogrecu_flush": (C.c_int, [C.c_void_p]),
+    "ogrecu_draw_views": (C.c_int, [C.POINTER(C.c_void_p), C.c_uint32, C.POINTER(DrawDesc), c_float_p, c_float_p, c_float_p]),
+    "ogrecu_rt_set_strip": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
+    "ogrecu_rt_read_colour": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t]),
+    "ogrecu_rt_read_depth": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t]),
+    "ogrecu_rt_write_colour": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "ogrecu_rt_write_depth": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "ogrecu_rt_colour_device_ptr": (C.c_int, [C.c_void_p, c_void_pp]),
+    "ogrecu_rt_depth_device_ptr": (C.c_int, [C.c_void_p, c_void_pp]),
+    "ogrecu_rt_last_stats": (C.c_int, [C.c_void_p, C.POINTER(RasterStats)]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load libogrecu.so (in-tree).  Raises if it has not been built: no fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise OgrecuError(-1, "libogrecu.so is not built (%s); run __graft_entry__.build()" % LIB_PATH)
+        l = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(l, name)   # AttributeError if the library lacks a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(status):
+    if status != 0:
+        msg = lib().ogrecu_last_error_string()
+        raise OgrecuError(status, msg.decode() if msg else "")
+    return status

@@ -1,0 +1,90 @@
+// common.cuh — shared internals of libogrecu.so (not part of the public C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <mutex>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/ogrecu.h"
+
+namespace ogrecu {
+
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+#define OGRECU_CUDA(expr)                                                            \
+    do {                                                                             \
+        cudaError_t e__ = (expr);                                                    \
+        if (e__ != cudaSuccess) return ::ogrecu::cuda_fail(e__, #expr, __FILE__, __LINE__); \
+    } while (0)
+
+#define OGRECU_REQUIRE(cond, msg)                                     \
+    do {                                                              \
+        if (!(cond)) { ::ogrecu::set_error("%s: %s", __func__, msg); return OGRECU_ERR_INVALID; } \
+    } while (0)
+
+#define OGRECU_CHECK(expr)             \
+    do {                               \
+        int rc__ = (expr);             \
+        if (rc__) return rc__;         \
+    } while (0)
+
+// Growable device scratch (never shrinks; freed at shutdown).
+struct Scratch {
+    void* ptr = nullptr;
+    size_t cap = 0;
+};
+
+}  // namespace ogrecu
+
+struct ogrecu_buf {
+    ogrecu_ctx* ctx;
+    size_t size;
+    void* dev;          // device storage
+    uint8_t* shadow;    // pinned host shadow (allocated lazily on first map)
+    bool mapped;
+    int map_mode;
+    size_t map_off, map_len;
+    // device-side writes not yet visible in the shadow
+    bool dev_dirty;
+    size_t dev_dirty_lo, dev_dirty_hi;
+    // last shadow->device upload still in flight on the stream (the shadow must not be
+    // rewritten by the host before it completes)
+    cudaEvent_t upload_ev;
+    bool upload_pending;
+};
+
+struct ogrecu_tex {
+    ogrecu_ctx* ctx;
+    uint32_t w, h;
+    uint8_t* dev;       // RGBA8, tightly packed
+    int has_zero_alpha; // any texel with alpha == 0 (enables the discard test)
+};
+
+struct ogrecu_ctx {
+    int device;
+    cudaStream_t own_stream;
+    cudaStream_t stream;        // current launch stream (own or external)
+    uint64_t launches;
+    int sm_count;
+    // scratch arenas
+    ogrecu::Scratch jobs;       // skin job descriptors
+    ogrecu::Scratch stage_in;   // host-path staging (device side)
+    ogrecu::Scratch stage_out;
+    void* pinned;               // pinned staging (host side)
+    size_t pinned_cap;
+    // shadow registry: shadow base address -> buffer
+    std::map<uintptr_t, ogrecu_buf*> shadows;
+    std::vector<ogrecu_rt*> targets;
+};
+
+namespace ogrecu {
+int scratch_reserve(ogrecu_ctx* ctx, Scratch& s, size_t bytes);
+int pinned_reserve(ogrecu_ctx* ctx, size_t bytes);
+inline void count_launch(ogrecu_ctx* ctx, unsigned n = 1) { ctx->launches += n; }
+inline unsigned div_up(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+int rt_release(ogrecu_rt* rt);
+}  // namespace ogrecu

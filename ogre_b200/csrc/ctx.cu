@@ -1,0 +1,330 @@
+// ctx.cu — context, memory and HardwareBuffer delegate of libogrecu.so.
+//
+// Reference roles served here (OGRE 14.6 tree):
+//   - first-window initialisation of TinyRenderSystem (RenderSystems/Tiny/src/OgreTinyRenderSystem.cpp:146-194)
+//   - the HardwareBuffer delegate contract (OgreMain/include/OgreHardwareBuffer.h:181-186,279-330):
+//     lock()/unlock() become map()/unmap() on a pinned host shadow mirrored in HBM.
+// There is no CPU fallback: without a CUDA device ogrecu_init fails.
+#include "common.cuh"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+namespace ogrecu {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line)
+{
+    set_error("CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
+    if (e == cudaErrorMemoryAllocation) return OGRECU_ERR_OOM;
+    if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) return OGRECU_ERR_NO_DEVICE;
+    return OGRECU_ERR_CUDA;
+}
+
+int scratch_reserve(ogrecu_ctx* ctx, Scratch& s, size_t bytes)
+{
+    if (bytes <= s.cap) return OGRECU_OK;
+    // growing: the old block may still be in use by queued kernels on the stream
+    OGRECU_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (s.ptr) OGRECU_CUDA(cudaFree(s.ptr));
+    s.ptr = nullptr; s.cap = 0;
+    size_t want = bytes + bytes / 4 + 4096;
+    OGRECU_CUDA(cudaMalloc(&s.ptr, want));
+    s.cap = want;
+    return OGRECU_OK;
+}
+
+int pinned_reserve(ogrecu_ctx* ctx, size_t bytes)
+{
+    if (bytes <= ctx->pinned_cap) return OGRECU_OK;
+    OGRECU_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->pinned) OGRECU_CUDA(cudaFreeHost(ctx->pinned));
+    ctx->pinned = nullptr; ctx->pinned_cap = 0;
+    size_t want = bytes + bytes / 4 + 4096;
+    OGRECU_CUDA(cudaHostAlloc(&ctx->pinned, want, cudaHostAllocDefault));
+    ctx->pinned_cap = want;
+    return OGRECU_OK;
+}
+
+}  // namespace ogrecu
+
+using namespace ogrecu;
+
+extern "C" {
+
+int ogrecu_abi_version(void) { return OGRECU_ABI_VERSION; }
+const char* ogrecu_last_error_string(void) { return g_err; }
+
+int ogrecu_device_count(int* count)
+{
+    OGRECU_REQUIRE(count, "count is NULL");
+    *count = 0;
+    cudaError_t e = cudaGetDeviceCount(count);
+    if (e != cudaSuccess) { *count = 0; return cuda_fail(e, "cudaGetDeviceCount", __FILE__, __LINE__); }
+    return OGRECU_OK;
+}
+
+int ogrecu_init(int device, ogrecu_ctx** out_ctx)
+{
+    OGRECU_REQUIRE(out_ctx, "out_ctx is NULL");
+    *out_ctx = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        set_error("ogrecu_init: no usable CUDA device (%s); libogrecu has no CPU fallback",
+                  e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+        return OGRECU_ERR_NO_DEVICE;
+    }
+    OGRECU_REQUIRE(device >= 0 && device < n, "device index out of range");
+    OGRECU_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    OGRECU_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        set_error("ogrecu_init: device %d is sm_%d%d; this library is built for sm_100a only", device,
+                  prop.major, prop.minor);
+        return OGRECU_ERR_NO_DEVICE;
+    }
+    ogrecu_ctx* ctx = new ogrecu_ctx();
+    ctx->device = device;
+    ctx->launches = 0;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->pinned = nullptr;
+    ctx->pinned_cap = 0;
+    e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete ctx; return cuda_fail(e, "cudaStreamCreate", __FILE__, __LINE__); }
+    ctx->stream = ctx->own_stream;
+    *out_ctx = ctx;
+    return OGRECU_OK;
+}
+
+int ogrecu_shutdown(ogrecu_ctx* ctx)
+{
+    if (!ctx) return OGRECU_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    while (!ctx->targets.empty()) rt_release(ctx->targets.back());
+    for (Scratch* s : {&ctx->jobs, &ctx->stage_in, &ctx->stage_out})
+        if (s->ptr) cudaFree(s->ptr);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+    return OGRECU_OK;
+}
+
+int ogrecu_device(const ogrecu_ctx* ctx, int* device)
+{
+    OGRECU_REQUIRE(ctx && device, "NULL argument");
+    *device = ctx->device;
+    return OGRECU_OK;
+}
+
+int ogrecu_set_stream(ogrecu_ctx* ctx, void* cuda_stream)
+{
+    OGRECU_REQUIRE(ctx, "ctx is NULL");
+    OGRECU_CUDA(cudaSetDevice(ctx->device));
+    OGRECU_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return OGRECU_OK;
+}
+
+void* ogrecu_get_stream(ogrecu_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int ogrecu_sync(ogrecu_ctx* ctx)
+{
+    OGRECU_REQUIRE(ctx, "ctx is NULL");
+    OGRECU_CUDA(cudaSetDevice(ctx->device));
+    OGRECU_CUDA(cudaStreamSynchronize(ctx->stream));
+    return OGRECU_OK;
+}
+
+uint64_t ogrecu_launch_count(const ogrecu_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int ogrecu_malloc(ogrecu_ctx* ctx, size_t bytes, void** dev_ptr)
+{
+    OGRECU_REQUIRE(ctx && dev_ptr, "NULL argument");
+    OGRECU_CUDA(cudaSetDevice(ctx->device));
+    *dev_ptr = nullptr;
+    OGRECU_CUDA(cudaMalloc(dev_ptr, bytes ? bytes : 1));
+    return OGRECU_OK;
+}
+
+int ogrecu_free(ogrecu_ctx* ctx, void* dev_ptr)
+{
+    OGRECU_REQUIRE(ctx, "ctx is NULL");
+    if (!dev_ptr) return OGRECU_OK;
+    OGRECU_CUDA(cudaSetDevice(ctx->device));
+    OGRECU_CUDA(cudaStreamSynchronize(ctx->stream));
+    OGRECU_CUDA(cudaFree(dev_ptr));
+    return OGRECU_OK;
+}
+
+int ogrecu_host_alloc(size_t bytes, void** host_ptr)
+{
+    OGRECU_REQUIRE(host_ptr, "host_ptr is NULL");
+    *host_ptr = nullptr;
+    OGRECU_CUDA(cudaHostAlloc(host_ptr, bytes ? bytes : 1, cudaHostAllocDefault));
+    return OGRECU_OK;
+}
+
+int ogrecu_host_free(void* host_ptr)
+{
+    if (host_ptr) OGRECU_CUDA(cudaFreeHost(host_ptr));
+    return OGRECU_OK;
+}
+
+int ogrecu_memcpy_h2d(ogrecu_ctx* ctx, void* dev, const void* host, size_t bytes)
+{
+    OGRECU_REQUIRE(ctx && (bytes == 0 || (dev && host)), "NULL argument");
+    if (!bytes) return OGRECU_OK;
+    OGRECU_CUDA(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return OGRECU_OK;
+}
+
+int ogrecu_memcpy_d2h(ogrecu_ctx* ctx, void* host, const void* dev, size_t bytes)
+{
+    OGRECU_REQUIRE(ctx && (bytes == 0 || (dev && host)), "NULL argument");
+    if (!bytes) return OGRECU_OK;
+    OGRECU_CUDA(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    OGRECU_CUDA(cudaStreamSynchronize(ctx->stream));
+    return OGRECU_OK;
+}
+
+int ogrecu_memcpy_d2d(ogrecu_ctx* ctx, void* dst, const void* src, size_t bytes)
+{
+    OGRECU_REQUIRE(ctx && (bytes == 0 || (dst && src)), "NULL argument");
+    if (!bytes) return OGRECU_OK;
+    OGRECU_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    return OGRECU_OK;
+}
+
+/* ------------------------------------------------------------ hardware buffers ----- */
+
+int ogrecu_buf_create(ogrecu_ctx* ctx, size_t bytes, ogrecu_buf** out)
+{
+    OGRECU_REQUIRE(ctx && out, "NULL argument");
+    *out = nullptr;
+    OGRECU_CUDA(cudaSetDevice(ctx->device));
+    ogrecu_buf* b = new ogrecu_buf();
+    memset(b, 0, sizeof *b);
+    b->ctx = ctx;
+    b->size = bytes;
+    cudaError_t e = cudaMalloc(&b->dev, bytes ? bytes : 1);
+    if (e != cudaSuccess) { delete b; return cuda_fail(e, "cudaMalloc(buffer)", __FILE__, __LINE__); }
+    // OGRE hands lock() pointers straight to OptimisedUtil and Tiny keeps them after
+    // unlock(), so the shadow lives as long as the buffer.
+    e = cudaHostAlloc((void**)&b->shadow, bytes ? bytes : 1, cudaHostAllocDefault);
+    if (e != cudaSuccess) { cudaFree(b->dev); delete b; return cuda_fail(e, "cudaHostAlloc(shadow)", __FILE__, __LINE__); }
+    e = cudaEventCreateWithFlags(&b->upload_ev, cudaEventDisableTiming);
+    if (e != cudaSuccess) { cudaFree(b->dev); cudaFreeHost(b->shadow); delete b; return cuda_fail(e, "cudaEventCreate", __FILE__, __LINE__); }
+    ctx->shadows[(uintptr_t)b->shadow] = b;
+    *out = b;
+    return OGRECU_OK;
+}
+
+int ogrecu_buf_destroy(ogrecu_buf* b)
+{
+    if (!b) return OGRECU_OK;
+    ogrecu_ctx* ctx = b->ctx;
+    OGRECU_CUDA(cudaSetDevice(ctx->device));
+    OGRECU_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->shadows.erase((uintptr_t)b->shadow);
+    cudaFree(b->dev);
+    cudaFreeHost(b->shadow);
+    cudaEventDestroy(b->upload_ev);
+    delete b;
+    return OGRECU_OK;
+}
+
+size_t ogrecu_buf_size(const ogrecu_buf* b) { return b ? b->size : 0; }
+
+int ogrecu_buf_device_ptr(ogrecu_buf* b, void** dev_ptr)
+{
+    OGRECU_REQUIRE(b && dev_ptr, "NULL argument");
+    *dev_ptr = b->dev;
+    return OGRECU_OK;
+}
+
+int ogrecu_buf_mark_device_dirty(ogrecu_buf* b, size_t offset, size_t length)
+{
+    OGRECU_REQUIRE(b && offset <= b->size && length <= b->size - offset, "range out of bounds");
+    if (!length) return OGRECU_OK;
+    if (!b->dev_dirty) { b->dev_dirty = true; b->dev_dirty_lo = offset; b->dev_dirty_hi = offset + length; }
+    else {
+        if (offset < b->dev_dirty_lo) b->dev_dirty_lo = offset;
+        if (offset + length > b->dev_dirty_hi) b->dev_dirty_hi = offset + length;
+    }
+    return OGRECU_OK;
+}
+
+int ogrecu_buf_map(ogrecu_buf* b, size_t offset, size_t length, int mode, void** host_ptr)
+{
+    OGRECU_REQUIRE(b && host_ptr, "NULL argument");
+    OGRECU_REQUIRE(!b->mapped, "buffer is already mapped");          // HardwareBuffer::lock asserts the same
+    OGRECU_REQUIRE(offset <= b->size && length <= b->size - offset, "range out of bounds");
+    ogrecu_ctx* ctx = b->ctx;
+    if (b->upload_pending) {   // a previous unmap's upload still reads the shadow
+        OGRECU_CUDA(cudaEventSynchronize(b->upload_ev));
+        b->upload_pending = false;
+    }
+    // Bring device-side writes (skinning output) back before the host looks at or
+    // partially overwrites the shadow.  A DISCARD map skips the download.
+    if (b->dev_dirty && !(mode & OGRECU_MAP_DISCARD)) {
+        OGRECU_CUDA(cudaMemcpyAsync(b->shadow + b->dev_dirty_lo, (uint8_t*)b->dev + b->dev_dirty_lo,
+                                    b->dev_dirty_hi - b->dev_dirty_lo, cudaMemcpyDeviceToHost, ctx->stream));
+        OGRECU_CUDA(cudaStreamSynchronize(ctx->stream));
+        b->dev_dirty = false;
+    } else if (b->dev_dirty && (mode & OGRECU_MAP_DISCARD) && offset == 0 && length == b->size) {
+        b->dev_dirty = false;
+    }
+    b->mapped = true;
+    b->map_mode = mode;
+    b->map_off = offset;
+    b->map_len = length;
+    *host_ptr = b->shadow + offset;
+    return OGRECU_OK;
+}
+
+int ogrecu_buf_unmap(ogrecu_buf* b)
+{
+    OGRECU_REQUIRE(b, "NULL argument");
+    OGRECU_REQUIRE(b->mapped, "buffer is not mapped");
+    ogrecu_ctx* ctx = b->ctx;
+    b->mapped = false;
+    if ((b->map_mode & (OGRECU_MAP_WRITE | OGRECU_MAP_DISCARD)) && b->map_len) {
+        // pinned -> device, ordered on the stream before any later kernel
+        OGRECU_CUDA(cudaMemcpyAsync((uint8_t*)b->dev + b->map_off, b->shadow + b->map_off, b->map_len,
+                                    cudaMemcpyHostToDevice, ctx->stream));
+        OGRECU_CUDA(cudaEventRecord(b->upload_ev, ctx->stream));
+        b->upload_pending = true;
+    }
+    return OGRECU_OK;
+}
+
+int ogrecu_buf_resolve(ogrecu_ctx* ctx, const void* host_ptr, ogrecu_buf** out_buf, size_t* out_offset)
+{
+    OGRECU_REQUIRE(ctx && out_buf && out_offset, "NULL argument");
+    *out_buf = nullptr;
+    *out_offset = 0;
+    uintptr_t p = (uintptr_t)host_ptr;
+    auto it = ctx->shadows.upper_bound(p);
+    if (it == ctx->shadows.begin()) return OGRECU_OK;
+    --it;
+    ogrecu_buf* b = it->second;
+    if (p >= it->first && p < it->first + (b->size ? b->size : 1)) {
+        *out_buf = b;
+        *out_offset = (size_t)(p - it->first);
+    }
+    return OGRECU_OK;
+}
+
+}  // extern "C"

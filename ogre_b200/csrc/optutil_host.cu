@@ -1,0 +1,285 @@
+// optutil_host.cu — exact-signature host entry points of the OptimisedUtil back end.
+//
+// OGRE calls OptimisedUtil with raw host pointers obtained from HardwareBuffer::lock()
+// (OgreMain/src/OgreMesh.cpp:1827-1896, OgreEdgeListBuilder.cpp:400-436, OgreShadowCaster.cpp:517-538).
+// Pointers that fall inside an ogrecu_buf shadow are resolved to the device copy (no
+// transfer; the destination is marked device-dirty).  Anything else is staged through
+// pinned memory: H2D, kernel, D2H.  There is no CPU compute path.
+#include "common.cuh"
+
+#include <algorithm>
+#include <cstring>
+
+using namespace ogrecu;
+
+namespace {
+
+struct InReq { const uint8_t* host; size_t len; size_t dev_off; void* dev; bool resolved; };
+struct OutReq {
+    uint8_t* host; size_t len; size_t dev_off; void* dev; bool resolved;
+    size_t piece, stride, count;   // copy-back pattern inside [host, host+len)
+    bool preload;                  // extent also uploaded first (in-place / gaps preserved)
+};
+
+constexpr size_t ALIGN = 256;
+inline size_t up(size_t v) { return (v + ALIGN - 1) & ~(ALIGN - 1); }
+
+// Plans all transfers of one host call, then performs them with one H2D and one D2H.
+class Stager {
+public:
+    explicit Stager(ogrecu_ctx* c) : ctx(c) {}
+    size_t add_in(const void* host, size_t len) { ins.push_back({(const uint8_t*)host, len, 0, nullptr, false}); return ins.size() - 1; }
+    size_t add_out(void* host, size_t len, size_t piece, size_t stride, size_t count, bool preload = false)
+    {
+        outs.push_back({(uint8_t*)host, len, 0, nullptr, false, piece, stride, count, preload});
+        return outs.size() - 1;
+    }
+    void* in_dev(size_t k) const { return ins[k].dev; }
+    void* out_dev(size_t k) const { return outs[k].dev; }
+
+    int commit()
+    {
+        size_t in_total = 0, out_total = 0;
+        for (auto& r : ins) {
+            ogrecu_buf* b = nullptr; size_t off = 0;
+            OGRECU_CHECK(ogrecu_buf_resolve(ctx, r.host, &b, &off));
+            if (b && off + r.len <= b->size) { r.resolved = true; r.dev = (uint8_t*)b->dev + off; }
+            else { r.dev_off = in_total; in_total += up(r.len); }
+        }
+        for (auto& r : outs) {
+            ogrecu_buf* b = nullptr; size_t off = 0;
+            OGRECU_CHECK(ogrecu_buf_resolve(ctx, r.host, &b, &off));
+            if (b && off + r.len <= b->size) {
+                r.resolved = true; r.dev = (uint8_t*)b->dev + off;
+                OGRECU_CHECK(ogrecu_buf_mark_device_dirty(b, off, r.len));
+            } else { r.dev_off = out_total; out_total += up(r.len); }
+        }
+        in_bytes = in_total; out_bytes = out_total;
+        OGRECU_CHECK(scratch_reserve(ctx, ctx->stage_in, in_total + out_total + ALIGN));
+        OGRECU_CHECK(pinned_reserve(ctx, in_total + out_total + ALIGN));
+        OGRECU_CUDA(cudaStreamSynchronize(ctx->stream));   // pinned block free for reuse
+        uint8_t* pin = (uint8_t*)ctx->pinned;
+        uint8_t* dev = (uint8_t*)ctx->stage_in.ptr;
+        for (auto& r : ins)
+            if (!r.resolved) { memcpy(pin + r.dev_off, r.host, r.len); r.dev = dev + r.dev_off; }
+        bool preload_any = false;
+        for (auto& r : outs)
+            if (!r.resolved) {
+                r.dev = dev + in_total + r.dev_off;
+                if (r.preload) { memcpy(pin + in_total + r.dev_off, r.host, r.len); preload_any = true; }
+            }
+        size_t h2d = in_total + (preload_any ? out_total : 0);
+        if (h2d) OGRECU_CUDA(cudaMemcpyAsync(dev, pin, h2d, cudaMemcpyHostToDevice, ctx->stream));
+        return OGRECU_OK;
+    }
+
+    int finish()
+    {
+        if (out_bytes) {
+            uint8_t* pin = (uint8_t*)ctx->pinned + in_bytes;
+            uint8_t* dev = (uint8_t*)ctx->stage_in.ptr + in_bytes;
+            OGRECU_CUDA(cudaMemcpyAsync(pin, dev, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+            OGRECU_CUDA(cudaStreamSynchronize(ctx->stream));
+            for (auto& r : outs) {
+                if (r.resolved) continue;
+                const uint8_t* s = pin + r.dev_off;
+                if (r.piece == r.stride || r.count <= 1) memcpy(r.host, s, r.count ? (r.count - 1) * r.stride + r.piece : 0);
+                else for (size_t i = 0; i < r.count; ++i) memcpy(r.host + i * r.stride, s + i * r.stride, r.piece);
+            }
+        } else {
+            // results live in resolved device buffers; OGRE semantics are synchronous
+            OGRECU_CUDA(cudaStreamSynchronize(ctx->stream));
+        }
+        return OGRECU_OK;
+    }
+
+private:
+    ogrecu_ctx* ctx;
+    std::vector<InReq> ins;
+    std::vector<OutReq> outs;
+    size_t in_bytes = 0, out_bytes = 0;
+};
+
+}  // namespace
+
+extern "C" {
+
+int ogrecu_software_vertex_skinning_host(ogrecu_ctx* ctx, const float* src_pos, float* dst_pos, const float* src_norm,
+                                         float* dst_norm, const float* blend_weight, const uint8_t* blend_index,
+                                         const float* const* blend_matrices, size_t src_pos_stride, size_t dst_pos_stride,
+                                         size_t src_norm_stride, size_t dst_norm_stride, size_t blend_weight_stride,
+                                         size_t blend_index_stride, size_t nw, size_t n)
+{
+    OGRECU_REQUIRE(ctx, "ctx is NULL");
+    if (n == 0) return OGRECU_OK;
+    OGRECU_REQUIRE(src_pos && dst_pos && blend_weight && blend_index && blend_matrices, "NULL pointer");
+    OGRECU_REQUIRE(nw >= 1 && nw <= 4, "num_weights_per_vertex must be 1..4");
+    OGRECU_REQUIRE(!src_norm || dst_norm, "src_norm without dst_norm");
+    OGRECU_REQUIRE(n <= 0xffffffffull, "too many vertices");
+    OGRECU_CUDA(cudaSetDevice(ctx->device));
+
+    // highest palette slot referenced (the reference takes a bare pointer palette)
+    unsigned max_idx = 0;
+    for (size_t v = 0; v < n; ++v) {
+        const uint8_t* bi = blend_index + v * blend_index_stride;
+        for (size_t b = 0; b < nw; ++b) max_idx = std::max<unsigned>(max_idx, bi[b]);
+    }
+    const unsigned nmat = max_idx + 1;
+    std::vector<float> palette((size_t)nmat * 16);
+    for (unsigned m = 0; m < nmat; ++m) memcpy(&palette[(size_t)m * 16], blend_matrices[m], 64);
+
+    Stager st(ctx);
+    // source vertex stream(s): positions and normals interleaved in one buffer are one range
+    const uint8_t* sp = (const uint8_t*)src_pos;
+    const uint8_t* sn = (const uint8_t*)src_norm;
+    size_t sp_len = (n - 1) * src_pos_stride + 12;
+    size_t sn_len = src_norm ? (n - 1) * src_norm_stride + 12 : 0;
+    size_t k_pos, k_norm = 0;
+    bool shared_src = src_norm && !(sn + sn_len <= sp || sp + sp_len <= sn);
+    const uint8_t* s_lo = sp; size_t s_len = sp_len;
+    if (shared_src) { s_lo = std::min(sp, sn); s_len = (size_t)(std::max(sp + sp_len, sn + sn_len) - s_lo); }
+    k_pos = st.add_in(s_lo, s_len);
+    if (src_norm && !shared_src) k_norm = st.add_in(sn, sn_len);
+    // blend stream(s)
+    const uint8_t* wp = (const uint8_t*)blend_weight;
+    size_t w_len = (n - 1) * blend_weight_stride + 4 * nw;
+    size_t i_len = (n - 1) * blend_index_stride + nw;
+    bool shared_blend = !(blend_index + i_len <= wp || wp + w_len <= blend_index);
+    const uint8_t* b_lo = wp; size_t b_len = w_len;
+    if (shared_blend) { b_lo = std::min(wp, blend_index); b_len = (size_t)(std::max(wp + w_len, blend_index + i_len) - b_lo); }
+    size_t k_w = st.add_in(b_lo, b_len), k_i = 0;
+    if (!shared_blend) k_i = st.add_in(blend_index, i_len);
+    size_t k_pal = st.add_in(palette.data(), palette.size() * 4);
+    // destination(s)
+    uint8_t* dp = (uint8_t*)dst_pos;
+    uint8_t* dn = (uint8_t*)dst_norm;
+    size_t dp_len = (n - 1) * dst_pos_stride + 12;
+    size_t dn_len = dst_norm && src_norm ? (n - 1) * dst_norm_stride + 12 : 0;
+    bool shared_dst = src_norm && !(dn + dn_len <= dp || dp + dp_len <= dn);
+    size_t k_dp, k_dn = 0;
+    if (shared_dst) {
+        uint8_t* d_lo = std::min(dp, dn);
+        size_t d_len = (size_t)(std::max(dp + dp_len, dn + dn_len) - d_lo);
+        bool packed = dst_pos_stride == 24 && dst_norm_stride == 24 && dn == dp + 12;
+        // packed pos+normal: every byte of the extent is produced; otherwise keep the gaps
+        k_dp = packed ? st.add_out(d_lo, d_len, 24, 24, n) : st.add_out(d_lo, d_len, d_len, d_len, 1, /*preload=*/true);
+    } else {
+        k_dp = st.add_out(dp, dp_len, 12, dst_pos_stride, n);
+        if (src_norm) k_dn = st.add_out(dn, dn_len, 12, dst_norm_stride, n);
+    }
+    OGRECU_CHECK(st.commit());
+
+    ogrecu_skin_job j;
+    memset(&j, 0, sizeof j);
+    const uint8_t* dsrc = (const uint8_t*)st.in_dev(k_pos);
+    j.src_pos = (const float*)(dsrc + (sp - s_lo));
+    if (src_norm) j.src_norm = shared_src ? (const float*)(dsrc + (sn - s_lo)) : (const float*)st.in_dev(k_norm);
+    const uint8_t* dbl = (const uint8_t*)st.in_dev(k_w);
+    j.blend_weight = (const float*)(dbl + (wp - b_lo));
+    j.blend_index = shared_blend ? dbl + (blend_index - b_lo) : (const uint8_t*)st.in_dev(k_i);
+    j.palette = (const float*)st.in_dev(k_pal);
+    uint8_t* ddst = (uint8_t*)st.out_dev(k_dp);
+    if (shared_dst) {
+        uint8_t* d_lo = std::min(dp, dn);
+        j.dst_pos = (float*)(ddst + (dp - d_lo));
+        j.dst_norm = (float*)(ddst + (dn - d_lo));
+    } else {
+        j.dst_pos = (float*)ddst;
+        if (src_norm) j.dst_norm = (float*)st.out_dev(k_dn);
+    }
+    j.src_pos_stride = (uint32_t)src_pos_stride; j.dst_pos_stride = (uint32_t)dst_pos_stride;
+    j.src_norm_stride = (uint32_t)src_norm_stride; j.dst_norm_stride = (uint32_t)dst_norm_stride;
+    j.blend_weight_stride = (uint32_t)blend_weight_stride; j.blend_index_stride = (uint32_t)blend_index_stride;
+    j.num_weights = (uint32_t)nw; j.num_matrices = nmat; j.num_vertices = (uint32_t)n;
+    OGRECU_CHECK(ogrecu_skin_instanced_dev(ctx, &j, 1, 0, 0));
+    return st.finish();
+}
+
+int ogrecu_software_vertex_morph_host(ogrecu_ctx* ctx, float t, const float* src1, const float* src2, float* dst,
+                                      size_t stride1, size_t stride2, size_t dst_stride, size_t n, int morph_normals)
+{
+    OGRECU_REQUIRE(ctx, "ctx is NULL");
+    if (n == 0) return OGRECU_OK;
+    OGRECU_REQUIRE(src1 && src2 && dst, "NULL pointer");
+    const size_t vs = morph_normals ? 24 : 12;
+    OGRECU_REQUIRE(stride1 >= vs && stride2 >= vs && dst_stride >= vs, "stride smaller than the vertex");
+    OGRECU_CUDA(cudaSetDevice(ctx->device));
+    Stager st(ctx);
+    size_t k1 = st.add_in(src1, (n - 1) * stride1 + vs);
+    size_t k2 = st.add_in(src2, (n - 1) * stride2 + vs);
+    size_t kd = st.add_out(dst, (n - 1) * dst_stride + vs, vs, dst_stride, n);
+    OGRECU_CHECK(st.commit());
+    OGRECU_CHECK(ogrecu_morph_dev(ctx, t, (const float*)st.in_dev(k1), (const float*)st.in_dev(k2), (float*)st.out_dev(kd),
+                                  stride1, stride2, dst_stride, n, morph_normals));
+    return st.finish();
+}
+
+int ogrecu_concatenate_affine_matrices_host(ogrecu_ctx* ctx, const float* base16, const float* src, float* dst, size_t n)
+{
+    OGRECU_REQUIRE(ctx && base16, "NULL argument");
+    if (n == 0) return OGRECU_OK;
+    OGRECU_REQUIRE(src && dst, "NULL pointer");
+    OGRECU_CUDA(cudaSetDevice(ctx->device));
+    Stager st(ctx);
+    size_t ks = st.add_in(src, n * 64);
+    size_t kd = st.add_out(dst, n * 64, 64, 64, n);
+    OGRECU_CHECK(st.commit());
+    OGRECU_CHECK(ogrecu_concat_affine_dev(ctx, base16, (const float*)st.in_dev(ks), (float*)st.out_dev(kd), n));
+    return st.finish();
+}
+
+int ogrecu_calculate_face_normals_host(ogrecu_ctx* ctx, const float* positions, size_t num_vertices, const void* triangles,
+                                       float* face_normals, size_t n)
+{
+    OGRECU_REQUIRE(ctx, "ctx is NULL");
+    if (n == 0) return OGRECU_OK;
+    OGRECU_REQUIRE(positions && triangles && face_normals, "NULL pointer");
+    OGRECU_CUDA(cudaSetDevice(ctx->device));
+    if (num_vertices == 0) {   // the reference signature carries no vertex count: derive it
+        const uint8_t* t = (const uint8_t*)triangles;
+        uint32_t mx = 0;
+        for (size_t i = 0; i < n; ++i) {
+            uint32_t vi[3];
+            memcpy(vi, t + i * 32 + 8, 12);
+            mx = std::max(mx, std::max(vi[0], std::max(vi[1], vi[2])));
+        }
+        num_vertices = (size_t)mx + 1;
+    }
+    Stager st(ctx);
+    size_t kp = st.add_in(positions, num_vertices * 12);
+    size_t kt = st.add_in(triangles, n * 32);
+    size_t kd = st.add_out(face_normals, n * 16, 16, 16, n);
+    OGRECU_CHECK(st.commit());
+    OGRECU_CHECK(ogrecu_face_normals_dev(ctx, (const float*)st.in_dev(kp), st.in_dev(kt), (float*)st.out_dev(kd), n));
+    return st.finish();
+}
+
+int ogrecu_calculate_light_facing_host(ogrecu_ctx* ctx, const float* light4, const float* face_normals, char* facings, size_t n)
+{
+    OGRECU_REQUIRE(ctx && light4, "NULL argument");
+    if (n == 0) return OGRECU_OK;
+    OGRECU_REQUIRE(face_normals && facings, "NULL pointer");
+    OGRECU_CUDA(cudaSetDevice(ctx->device));
+    Stager st(ctx);
+    size_t kn = st.add_in(face_normals, n * 16);
+    size_t kd = st.add_out(facings, n, 1, 1, n);
+    OGRECU_CHECK(st.commit());
+    OGRECU_CHECK(ogrecu_light_facing_dev(ctx, light4, (const float*)st.in_dev(kn), (char*)st.out_dev(kd), n));
+    return st.finish();
+}
+
+int ogrecu_extrude_vertices_host(ogrecu_ctx* ctx, const float* light4, float dist, const float* src, float* dst, size_t n)
+{
+    OGRECU_REQUIRE(ctx && light4, "NULL argument");
+    if (n == 0) return OGRECU_OK;
+    OGRECU_REQUIRE(src && dst, "NULL pointer");
+    OGRECU_CUDA(cudaSetDevice(ctx->device));
+    Stager st(ctx);
+    size_t ks = st.add_in(src, n * 12);
+    size_t kd = st.add_out(dst, n * 12, 12, 12, n);
+    OGRECU_CHECK(st.commit());
+    OGRECU_CHECK(ogrecu_extrude_dev(ctx, light4, dist, (const float*)st.in_dev(ks), (float*)st.out_dev(kd), n));
+    return st.finish();
+}
+
+}  // extern "C"

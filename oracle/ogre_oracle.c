@@ -1,0 +1,418 @@
+/*
+ * ogre_oracle.c — CPU restatement of the reference algorithms on the hot path.
+ * TEST INFRASTRUCTURE ONLY (see ogre_oracle.h for the rules and the pinning status).
+ *
+ * Build: gcc -O2 -ffp-contract=off -fno-fast-math -shared -fPIC (oracle/Makefile).
+ * Every float operator below is one IEEE binary32 rounding, written in the reference's
+ * association; do not "simplify".
+ */
+#include "ogre_oracle.h"
+
+#include <float.h>
+#include <limits.h>
+#include <math.h>
+#include <string.h>
+
+/* std::min / std::max exactly as libstdc++ defines them (NaN handling matters) */
+static inline float std_minf(float a, float b) { return (b < a) ? b : a; }
+static inline float std_maxf(float a, float b) { return (a < b) ? b : a; }
+
+/* x86 cvttss2si: NaN and out-of-range give the "integer indefinite" value INT_MIN */
+static inline int x86_f2i(float f)
+{
+    if (!(f < 2147483648.0f) || f < -2147483648.0f) return INT_MIN;
+    return (int)f;
+}
+
+static inline const float* fptr(const void* p, size_t byte_off) { return (const float*)((const uint8_t*)p + byte_off); }
+
+/* ======================================================================= OptimisedUtil */
+
+void oracle_skin_general(const float* pSrcPos, float* pDestPos, const float* pSrcNorm, float* pDestNorm,
+                         const float* pBlendWeight, const uint8_t* pBlendIndex,
+                         const float* const* blendMatrices,
+                         size_t srcPosStride, size_t destPosStride, size_t srcNormStride,
+                         size_t destNormStride, size_t blendWeightStride, size_t blendIndexStride,
+                         size_t numWeightsPerVertex, size_t numVertices)
+{
+    /* OgreOptimisedUtilGeneral.cpp:98-219: per bone transform, scale by weight, accumulate */
+    for (size_t v = 0; v < numVertices; ++v) {
+        float sx = pSrcPos[0], sy = pSrcPos[1], sz = pSrcPos[2];
+        float nx = 0, ny = 0, nz = 0;
+        if (pSrcNorm) { nx = pSrcNorm[0]; ny = pSrcNorm[1]; nz = pSrcNorm[2]; }
+        float ap[3] = {0, 0, 0}, an[3] = {0, 0, 0};
+        for (size_t b = 0; b < numWeightsPerVertex; ++b) {
+            float weight = pBlendWeight[b];
+            if (weight) {
+                const float* m = blendMatrices[pBlendIndex[b]];
+                for (int r = 0; r < 3; ++r) {
+                    float t = ((m[4 * r + 0] * sx + m[4 * r + 1] * sy) + m[4 * r + 2] * sz) + m[4 * r + 3];
+                    ap[r] += t * weight;
+                }
+                if (pSrcNorm) {
+                    for (int r = 0; r < 3; ++r) {
+                        float t = (m[4 * r + 0] * nx + m[4 * r + 1] * ny) + m[4 * r + 2] * nz;
+                        an[r] += t * weight;
+                    }
+                }
+            }
+        }
+        pDestPos[0] = ap[0]; pDestPos[1] = ap[1]; pDestPos[2] = ap[2];
+        if (pSrcNorm) {
+            /* Vector3::normalise, OgreVector.h:494-508 */
+            float len2 = 0; len2 += an[0] * an[0]; len2 += an[1] * an[1]; len2 += an[2] * an[2];
+            float len = sqrtf(len2);
+            if (len > 0.0f) { float inv = 1.0f / len; an[0] *= inv; an[1] *= inv; an[2] *= inv; }
+            pDestNorm[0] = an[0]; pDestNorm[1] = an[1]; pDestNorm[2] = an[2];
+            pSrcNorm = fptr(pSrcNorm, srcNormStride);
+            pDestNorm = (float*)fptr(pDestNorm, destNormStride);
+        }
+        pSrcPos = fptr(pSrcPos, srcPosStride);
+        pDestPos = (float*)fptr(pDestPos, destPosStride);
+        pBlendWeight = fptr(pBlendWeight, blendWeightStride);
+        pBlendIndex += blendIndexStride;
+    }
+}
+
+/* collapse one vertex' matrix, OgreOptimisedUtilSSE.cpp:278-368 (rows 0..2, 4 lanes each) */
+static void collapse_matrix(float M[12], const float* w, const uint8_t* idx, const float* const* pal, size_t nw)
+{
+    const float* m0 = pal[idx[0]];
+    switch (nw) {
+    default:
+    case 1: /* __COLLAPSE_MATRIX_W1 :315-319: weight ignored */
+        for (int i = 0; i < 12; ++i) M[i] = m0[i];
+        break;
+    case 2: { /* __COLLAPSE_MATRIX_W2 :325-332: lerp(M0, M1, w[1]) = (M1-M0)*w1 + M0 */
+        const float* m1 = pal[idx[1]];
+        float w1 = w[1];
+        for (int i = 0; i < 12; ++i) M[i] = (m1[i] - m0[i]) * w1 + m0[i];
+        break;
+    }
+    case 3:
+    case 4: { /* __COLLAPSE_MATRIX_W3/W4 :336-368: M0*w0, then += Mi*wi in order */
+        for (int i = 0; i < 12; ++i) M[i] = m0[i] * w[0];
+        for (size_t b = 1; b < nw; ++b) {
+            const float* mb = pal[idx[b]];
+            for (int i = 0; i < 12; ++i) M[i] = mb[i] * w[b] + M[i];
+        }
+        break;
+    }
+    }
+}
+
+void oracle_skin_sse(const float* pSrcPos, float* pDestPos, const float* pSrcNorm, float* pDestNorm,
+                     const float* pBlendWeight, const uint8_t* pBlendIndex,
+                     const float* const* blendMatrices,
+                     size_t srcPosStride, size_t destPosStride, size_t srcNormStride,
+                     size_t destNormStride, size_t blendWeightStride, size_t blendIndexStride,
+                     size_t numWeightsPerVertex, size_t numVertices)
+{
+    for (size_t v = 0; v < numVertices; ++v) {
+        float M[12];
+        collapse_matrix(M, pBlendWeight, pBlendIndex, blendMatrices, numWeightsPerVertex);
+        float x = pSrcPos[0], y = pSrcPos[1], z = pSrcPos[2];
+        /* __MM_DOT4x3_PS -> __MM_ACCUM4_PS: (r0*x + r1*y) + (r2*z + r3), OgreSIMDHelper.h:204-217 */
+        for (int r = 0; r < 3; ++r)
+            pDestPos[r] = (M[4 * r + 0] * x + M[4 * r + 1] * y) + (M[4 * r + 2] * z + M[4 * r + 3]);
+        if (pSrcNorm) {
+            float nx = pSrcNorm[0], ny = pSrcNorm[1], nz = pSrcNorm[2];
+            float n[3];
+            /* __MM_DOT3x3_PS: (r0*x + r1*y) + r2*z, OgreSIMDHelper.h:220-227 */
+            for (int r = 0; r < 3; ++r)
+                n[r] = (M[4 * r + 0] * nx + M[4 * r + 1] * ny) + M[4 * r + 2] * nz;
+            /* :692-696 length^2 = __MM_DOT3x3_PS(d3,d4,d5,d3,d4,d5); rsqrt -> exact here */
+            float len2 = (n[0] * n[0] + n[1] * n[1]) + n[2] * n[2];
+            float rs = 1.0f / sqrtf(len2);
+            pDestNorm[0] = n[0] * rs; pDestNorm[1] = n[1] * rs; pDestNorm[2] = n[2] * rs;
+            pSrcNorm = fptr(pSrcNorm, srcNormStride);
+            pDestNorm = (float*)fptr(pDestNorm, destNormStride);
+        }
+        pSrcPos = fptr(pSrcPos, srcPosStride);
+        pDestPos = (float*)fptr(pDestPos, destPosStride);
+        pBlendWeight = fptr(pBlendWeight, blendWeightStride);
+        pBlendIndex += blendIndexStride;
+    }
+}
+
+void oracle_morph(float t, const float* pSrc1, const float* pSrc2, float* pDst, size_t pos1VSize,
+                  size_t pos2VSize, size_t dstVSize, size_t numVertices, int morphNormals)
+{
+    /* OgreOptimisedUtilGeneral.cpp:236-283 */
+    for (size_t i = 0; i < numVertices; ++i) {
+        for (int k = 0; k < 3; ++k) pDst[k] = pSrc1[k] + t * (pSrc2[k] - pSrc1[k]);
+        if (morphNormals) {
+            float n[3];
+            for (int k = 0; k < 3; ++k) n[k] = pSrc1[3 + k] + t * (pSrc2[3 + k] - pSrc1[3 + k]);
+            float len2 = 0; len2 += n[0] * n[0]; len2 += n[1] * n[1]; len2 += n[2] * n[2];
+            float len = sqrtf(len2);
+            if (len > 0.0f) { float inv = 1.0f / len; n[0] *= inv; n[1] *= inv; n[2] *= inv; }
+            pDst[3] = n[0]; pDst[4] = n[1]; pDst[5] = n[2];
+        }
+        pSrc1 = fptr(pSrc1, pos1VSize); pSrc2 = fptr(pSrc2, pos2VSize); pDst = (float*)fptr(pDst, dstVSize);
+    }
+}
+
+void oracle_concat_affine_sse(const float* m, const float* src, float* dst, size_t n)
+{
+    /* OgreOptimisedUtilSSE.cpp:1529-1582; m3 is the literal fourth row of the base matrix */
+    for (size_t i = 0; i < n; ++i, src += 16, dst += 16) {
+        float out[16];
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 4; ++c) {
+                float t0 = m[4 * r + 0] * src[0 + c];
+                float t1 = m[4 * r + 1] * src[4 + c];
+                float t2 = m[4 * r + 2] * src[8 + c];
+                float t3 = m[4 * r + c] * m[12 + c];
+                out[4 * r + c] = (t0 + t1) + (t2 + t3);
+            }
+        out[12] = 0; out[13] = 0; out[14] = 0; out[15] = 1;
+        memcpy(dst, out, sizeof out);
+    }
+}
+
+void oracle_concat_affine_general(const float* m, const float* src, float* dst, size_t n)
+{
+    /* OgreMatrix4.h:522-539 */
+    for (size_t i = 0; i < n; ++i, src += 16, dst += 16) {
+        float out[16];
+        for (int r = 0; r < 3; ++r) {
+            for (int c = 0; c < 3; ++c)
+                out[4 * r + c] = (m[4 * r + 0] * src[0 + c] + m[4 * r + 1] * src[4 + c]) + m[4 * r + 2] * src[8 + c];
+            out[4 * r + 3] = ((m[4 * r + 0] * src[3] + m[4 * r + 1] * src[7]) + m[4 * r + 2] * src[11]) + m[4 * r + 3];
+        }
+        out[12] = 0; out[13] = 0; out[14] = 0; out[15] = 1;
+        memcpy(dst, out, sizeof out);
+    }
+}
+
+void oracle_face_normals(const float* positions, const void* triangles32, float* fn, size_t n)
+{
+    /* OgreOptimisedUtilGeneral.cpp:285-307, OgreVector.h:870-883; vertIndex[3] at byte 8 */
+    const uint8_t* t = (const uint8_t*)triangles32;
+    for (size_t i = 0; i < n; ++i, t += 32, fn += 4) {
+        uint32_t vi[3];
+        memcpy(vi, t + 8, 12);
+        const float* v1 = positions + (size_t)vi[0] * 3;
+        const float* v2 = positions + (size_t)vi[1] * 3;
+        const float* v3 = positions + (size_t)vi[2] * 3;
+        float ax = v2[0] - v1[0], ay = v2[1] - v1[1], az = v2[2] - v1[2];
+        float bx = v3[0] - v1[0], by = v3[1] - v1[1], bz = v3[2] - v1[2];
+        float nx = ay * bz - az * by;
+        float ny = az * bx - ax * bz;
+        float nz = ax * by - ay * bx;
+        float d = 0; d += nx * v1[0]; d += ny * v1[1]; d += nz * v1[2];
+        fn[0] = nx; fn[1] = ny; fn[2] = nz; fn[3] = -d;
+    }
+}
+
+void oracle_light_facing_sse(const float* l, const float* fn, char* facings, size_t n)
+{
+    for (size_t i = 0; i < n; ++i, fn += 4) {
+        float x = fn[0] * l[0], y = fn[1] * l[1], z = fn[2] * l[2], w = fn[3] * l[3];
+        float dp = (x + z) + (y + w);           /* OgreOptimisedUtilSSE.cpp:1776-1786 */
+        facings[i] = !(dp <= 0.0f);             /* _mm_cmpnle_ps :1793 */
+    }
+}
+
+void oracle_light_facing_general(const float* l, const float* fn, char* facings, size_t n)
+{
+    for (size_t i = 0; i < n; ++i, fn += 4) {
+        float dp = 0; dp += l[0] * fn[0]; dp += l[1] * fn[1]; dp += l[2] * fn[2]; dp += l[3] * fn[3];
+        facings[i] = dp > 0;
+    }
+}
+
+void oracle_extrude(const float* l, float dist, const float* src, float* dst, size_t n)
+{
+    /* OgreOptimisedUtilGeneral.cpp:321-365 */
+    if (l[3] == 0.0f) {
+        float d[3] = {-l[0], -l[1], -l[2]};
+        float len2 = 0; len2 += d[0] * d[0]; len2 += d[1] * d[1]; len2 += d[2] * d[2];
+        float len = sqrtf(len2);
+        if (len > 0.0f) { float inv = 1.0f / len; d[0] *= inv; d[1] *= inv; d[2] *= inv; }
+        d[0] *= dist; d[1] *= dist; d[2] *= dist;
+        for (size_t i = 0; i < n; ++i, src += 3, dst += 3) {
+            float a = src[0] + d[0], b = src[1] + d[1], c = src[2] + d[2];
+            dst[0] = a; dst[1] = b; dst[2] = c;
+        }
+    } else {
+        for (size_t i = 0; i < n; ++i, src += 3, dst += 3) {
+            float d[3] = {src[0] - l[0], src[1] - l[1], src[2] - l[2]};
+            float len2 = 0; len2 += d[0] * d[0]; len2 += d[1] * d[1]; len2 += d[2] * d[2];
+            float len = sqrtf(len2);
+            if (len > 0.0f) { float inv = 1.0f / len; d[0] *= inv; d[1] *= inv; d[2] *= inv; }
+            d[0] *= dist; d[1] *= dist; d[2] *= dist;
+            float a = src[0] + d[0], b = src[1] + d[1], c = src[2] + d[2];
+            dst[0] = a; dst[1] = b; dst[2] = c;
+        }
+    }
+}
+
+/* ======================================================================= Tiny rasteriser */
+
+void oracle_tiny_clear(uint8_t* colour, float* depth, uint32_t w, uint32_t h, unsigned buffers,
+                       const float c[4], float depth_value)
+{
+    size_t npx = (size_t)w * h;
+    if (buffers & 1u) {
+        if (c[0] == 0.0f && c[1] == 0.0f && c[2] == 0.0f && c[3] == 0.0f) {
+            memset(colour, 0, npx * 3);          /* Image::setTo ZERO shortcut, OgreImage.cpp:124-128 */
+        } else {
+            uint8_t px[3];
+            for (int k = 0; k < 3; ++k) {        /* Bitwise::floatToFixed(v, 8), OgreBitwise.h:237-242 */
+                float v = c[k];
+                unsigned q = (v <= 0.0f) ? 0u : (v >= 1.0f) ? 255u : (unsigned)(v * 256.0f);
+                px[k] = (uint8_t)q;
+            }
+            for (size_t p = 0; p < npx; ++p) { colour[3 * p] = px[0]; colour[3 * p + 1] = px[1]; colour[3 * p + 2] = px[2]; }
+        }
+    }
+    if (buffers & 2u) {
+        /* setTo(ColourValue(depth)) = (depth,1,1,1): never ZERO, PF_FLOAT32_R stores r */
+        for (size_t p = 0; p < npx; ++p) depth[p] = depth_value;
+    }
+}
+
+static inline void mat4_mul_vec4(const float* m, const float v[4], float out[4])
+{
+    /* OgreMatrix4.h:571-578 */
+    for (int r = 0; r < 4; ++r)
+        out[r] = ((m[4 * r + 0] * v[0] + m[4 * r + 1] * v[1]) + m[4 * r + 2] * v[2]) + m[4 * r + 3] * v[3];
+}
+
+typedef struct tri_setup {
+    float c[9];       /* adjugate or inverse of ABC */
+    float iw[3], z[3];
+    float uv[3][2];
+    float n[3][3];
+    int x0, x1, y0, y1;
+} tri_setup;
+
+static uint64_t raster_triangle(const oracle_draw* d, const tri_setup* t, uint8_t* colour, float* depth, uint32_t W)
+{
+    uint64_t written = 0;
+    const float inv255 = 1.0f / 255.0f;
+    for (int x = t->x0; x <= t->x1; ++x) {
+        for (int y = t->y0; y <= t->y1; ++y) {
+            float Px = (float)x, Py = (float)y;
+            /* barycentric(): inverse * (x,y,1), OgreMatrix3.h:321-327 */
+            float bs0 = (t->c[0] * Px + t->c[1] * Py) + t->c[2] * 1.0f;
+            float bs1 = (t->c[3] * Px + t->c[4] * Py) + t->c[5] * 1.0f;
+            float bs2 = (t->c[6] * Px + t->c[7] * Py) + t->c[8] * 1.0f;
+            float bc0 = bs0 * t->iw[0], bc1 = bs1 * t->iw[1], bc2 = bs2 * t->iw[2];
+            float s = (bc0 + bc1) + bc2;
+            float f = 1.0f / s;                                  /* OgreVector.h:659-664 */
+            bc0 = f * bc0; bc1 = f * bc1; bc2 = f * bc2;
+            float fd = 0.0f; fd += t->z[0] * bc0; fd += t->z[1] * bc1; fd += t->z[2] * bc2;
+            if (bs0 < 0 || bs1 < 0 || bs2 < 0) continue;         /* tinyrenderer.h:74 */
+            if (fd < 0.0) continue;                              /* :76 */
+            size_t p = (size_t)y * W + (size_t)x;
+            if (d->depth_test && fd > depth[p]) continue;        /* :79 */
+
+            float col[4] = {1.0f, 1.0f, 1.0f, 1.0f};             /* default ColourValue: white */
+            if (d->tex_rgba) {                                   /* DefaultShader::fragment .cpp:312-322 */
+                float u = (t->uv[0][0] * bc0 + t->uv[1][0] * bc1) + t->uv[2][0] * bc2;
+                float v = (t->uv[0][1] * bc0 + t->uv[1][1] * bc1) + t->uv[2][1] * bc2;
+                int ix = x86_f2i(u * (float)(d->tex_w - 1u));    /* sample2D, OgreTinyRenderSystem.h:34-42 */
+                int iy = x86_f2i(v * (float)(d->tex_h - 1u));
+                int tw = (int)d->tex_w, th = (int)d->tex_h;
+                ix = (tw + (ix % tw)) % tw;
+                iy = (th + (iy % th)) % th;
+                const uint8_t* tx = d->tex_rgba + ((size_t)iy * d->tex_w + (size_t)ix) * 4;
+                if (tx[3] < 1) continue;                         /* alpha discard .cpp:318 */
+                for (int k = 0; k < 4; ++k) col[k] = (float)tx[k] * inv255;
+            }
+            if (d->lighting) {                                   /* .cpp:324-330 */
+                float n[3];
+                for (int k = 0; k < 3; ++k) n[k] = (t->n[0][k] * bc0 + t->n[1][k] * bc1) + t->n[2][k] * bc2;
+                float dp = 0.0f; dp += n[0] * d->light_dir[0]; dp += n[1] * d->light_dir[1]; dp += n[2] * d->light_dir[2];
+                float diffuse = std_maxf(0.f, dp);
+                for (int k = 0; k < 4; ++k) { col[k] *= diffuse; col[k] += d->ambient[k]; }
+            }
+            uint8_t* dst = colour + 3 * p;
+            if (d->blend_add)                                    /* tinyrenderer.h:86-87 */
+                for (int k = 0; k < 3; ++k) col[k] += (float)dst[k] * inv255;
+            for (int k = 0; k < 3; ++k) {
+                float c = std_maxf(std_minf(col[k], 1.0f), 0.0f); /* Math::saturate -> Clamp, OgreMath.h:395,704-708 */
+                c *= 255;
+                dst[k] = (uint8_t)x86_f2i(c);                    /* truncating float->uchar, OgreVector.h:294-298 */
+            }
+            if (d->depth_write) depth[p] = fd;
+            ++written;
+        }
+    }
+    return written;
+}
+
+uint64_t oracle_tiny_draw(const oracle_draw* d, uint8_t* colour, float* depth, uint32_t W, uint32_t H)
+{
+    uint64_t written = 0;
+    const int do_cull = !d->is_strip;
+    /* OgreTinyRenderSystem.cpp:396-411 */
+    for (size_t i = 0; i < d->draw_count; i += 3) {
+        if (i && d->is_strip) i -= 2;
+        if (i + 3 > d->draw_count) break;   /* the reference reads past the end here (UB); we stop */
+        tri_setup t;
+        float X[3], Y[3];
+        int finite = 1;
+        for (int j = 0; j < 3; ++j) {
+            size_t k = i + j;
+            int64_t idx;
+            if (d->index_type == 2) idx = ((const uint16_t*)d->indices)[k];   /* read unsigned; the reference reads int16 (UB >= 32768) */
+            else if (d->index_type == 4) idx = ((const uint32_t*)d->indices)[k];
+            else idx = (int64_t)k;
+            const float* p = (const float*)(d->positions + (size_t)d->pos_stride * idx);
+            float v[4] = {p[0], p[1], p[2], 1.0f}, clip[4], q[4];
+            mat4_mul_vec4(d->mvp, v, clip);                       /* DefaultShader::vertex .cpp:302 */
+            if (d->uvs) {
+                const float* uv = (const float*)(d->uvs + (size_t)d->uv_stride * idx);
+                float tv[4] = {uv[0], uv[1], 0.0f, 1.0f}, to[4];
+                mat4_mul_vec4(d->tex_matrix, tv, to);
+                t.uv[j][0] = to[0]; t.uv[j][1] = to[1];
+            } else { t.uv[j][0] = t.uv[j][1] = 0; }
+            if (d->normals) {
+                const float* n = (const float*)(d->normals + (size_t)d->normal_stride * idx);
+                for (int r = 0; r < 3; ++r)                       /* Matrix3 * Vector3, OgreMatrix3.h:321-327 */
+                    t.n[j][r] = (d->mvit[4 * r + 0] * n[0] + d->mvit[4 * r + 1] * n[1]) + d->mvit[4 * r + 2] * n[2];
+            } else { t.n[j][0] = t.n[j][1] = t.n[j][2] = 0; }
+            mat4_mul_vec4(d->viewport, clip, q);                  /* tinyrenderer.h:45 */
+            float w = q[3];
+            float fi = 1.0f / w;                                  /* pts[i] /= w, OgreVector.h:563-570 */
+            X[j] = q[0] * fi; Y[j] = q[1] * fi; t.z[j] = q[2] * fi;
+            t.iw[j] = 1 / w;                                      /* tinyrenderer.h:50 */
+            if (!isfinite(X[j]) || !isfinite(Y[j]) || !isfinite(t.z[j]) || !isfinite(t.iw[j])) finite = 0;
+        }
+        if (!finite) continue;   /* reference behaviour undefined here (see header) */
+
+        if (do_cull) {                                            /* tinyrenderer.h:37-39,55 */
+            float ax = X[2] - X[0], ay = Y[2] - Y[0], bx = X[2] - X[1], by = Y[2] - Y[1];
+            if (ax * by - ay * bx > 0) continue;
+        }
+        float mnx = FLT_MAX, mny = FLT_MAX, mxx = -FLT_MAX, mxy = -FLT_MAX;
+        float cx = (float)(W - 1u), cy = (float)(H - 1u);
+        for (int j = 0; j < 3; ++j) {                             /* :58-65 */
+            mnx = std_maxf(0.f, std_minf(mnx, X[j]));
+            mxx = std_minf(cx, std_maxf(mxx, X[j]));
+            mny = std_maxf(0.f, std_minf(mny, Y[j]));
+            mxy = std_minf(cy, std_maxf(mxy, Y[j]));
+        }
+        /* (int) casts :68-69; beyond +-2^31 the reference loop bounds are undefined -> skip */
+        if (!(mnx < 2147483648.0f) || !(mny < 2147483648.0f) || !(mxx > -2147483648.0f) || !(mxy > -2147483648.0f))
+            continue;
+        t.x0 = (int)mnx; t.x1 = (int)mxx; t.y0 = (int)mny; t.y1 = (int)mxy;
+        if (t.x0 > t.x1 || t.y0 > t.y1) continue;
+
+        /* Matrix3::Inverse of ABC, OgreMatrix3.cpp:155-202 (products with the 1-row are exact) */
+        t.c[0] = Y[1] * 1.0f - Y[2] * 1.0f; t.c[1] = X[2] * 1.0f - X[1] * 1.0f; t.c[2] = X[1] * Y[2] - X[2] * Y[1];
+        t.c[3] = Y[2] * 1.0f - Y[0] * 1.0f; t.c[4] = X[0] * 1.0f - X[2] * 1.0f; t.c[5] = X[2] * Y[0] - X[0] * Y[2];
+        t.c[6] = Y[0] * 1.0f - Y[1] * 1.0f; t.c[7] = X[1] * 1.0f - X[0] * 1.0f; t.c[8] = X[0] * Y[1] - X[1] * Y[0];
+        float det = (X[0] * t.c[0] + X[1] * t.c[3]) + X[2] * t.c[6];
+        if (!(fabsf(det) <= 1e-06f)) {
+            float g = 1.0f / det;
+            for (int k = 0; k < 9; ++k) t.c[k] *= g;
+        }
+        written += raster_triangle(d, &t, colour, depth, W);
+    }
+    return written;
+}
