@@ -1,26 +1,1142 @@
-// raster.cu — TEMPORARY stubs (rasteriser under construction): every entry fails loudly.
+// raster.cu — binned, tile-based triangle rasteriser reproducing Tiny's semantics bit for bit.
+//
+// Reference path replaced (OGRE 14.6 tree):
+//   TinyRenderSystem::_render + DefaultShader::vertex/fragment  RenderSystems/Tiny/src/OgreTinyRenderSystem.cpp:299-333,349-414
+//   triangle() / barycentric()                                  RenderSystems/Tiny/src/tinyrenderer.h:29-95
+//   IShader::sample2D                                           RenderSystems/Tiny/include/OgreTinyRenderSystem.h:34-42
+//   clearFrameBuffer, readback                                  OgreTinyRenderSystem.cpp:421-433, OgreTinyWindow.cpp:68-80
+//
+// Pipeline per flush (all on the context stream):
+//   K1 setup_kernel    1 thread / triangle: vertex shader x3, viewport, 1/w, cull, bbox, adjugate
+//                      -> 80-byte "hot" + 64-byte "cold" record, tile count
+//      scan            exclusive scan of tile counts (order-preserving pair offsets)
+//   K2 bin_kernel      (tile, triangle) pairs written in submission order
+//      radix sort      stable LSD sort of the pairs by tile key -> per-tile lists in submission order
+//   K3 raster_kernel   1 CTA / 16x16 tile, 1 pixel / thread; pixel depth+colour live in registers
+//                      while the tile's triangle list is replayed IN ORDER (bit-exact blend,
+//                      equal-depth and NaN semantics); colour staged in shared memory and
+//                      flushed with 16-byte stores
+// Every float op is an explicit __f*_rn intrinsic in the reference's association (SURVEY
+// Appendix A): no FMA contraction, IEEE division.
 #include "common.cuh"
-namespace ogrecu { int rt_release(ogrecu_rt*) { return 0; } }
-#define STUB(name, ...) int name(__VA_ARGS__) { ogrecu::set_error(#name ": rasteriser not built yet"); return OGRECU_ERR_UNSUPPORTED; }
-extern "C" {
-STUB(ogrecu_tex_create, ogrecu_ctx*, uint32_t, uint32_t, ogrecu_tex**)
-STUB(ogrecu_tex_destroy, ogrecu_tex*)
-STUB(ogrecu_tex_upload, ogrecu_tex*, const uint8_t*, size_t)
-STUB(ogrecu_tex_download, ogrecu_tex*, uint8_t*, size_t)
-STUB(ogrecu_tex_device_ptr, ogrecu_tex*, void**)
-STUB(ogrecu_rt_create, ogrecu_ctx*, uint32_t, uint32_t, ogrecu_rt**)
-STUB(ogrecu_rt_destroy, ogrecu_rt*)
-STUB(ogrecu_rt_size, const ogrecu_rt*, uint32_t*, uint32_t*)
-STUB(ogrecu_rt_clear, ogrecu_rt*, unsigned, const float*, float)
-STUB(ogrecu_draw, ogrecu_rt*, const ogrecu_draw_desc*)
-STUB(ogrecu_flush, ogrecu_rt*)
-STUB(ogrecu_draw_views, ogrecu_rt* const*, uint32_t, const ogrecu_draw_desc*, const float*, const float*, const float*)
-STUB(ogrecu_rt_set_strip, ogrecu_rt*, uint32_t, uint32_t)
-STUB(ogrecu_rt_read_colour, ogrecu_rt*, uint32_t, uint32_t, uint32_t, uint32_t, uint8_t*, size_t)
-STUB(ogrecu_rt_read_depth, ogrecu_rt*, uint32_t, uint32_t, uint32_t, uint32_t, float*, size_t)
-STUB(ogrecu_rt_write_colour, ogrecu_rt*, const uint8_t*, size_t)
-STUB(ogrecu_rt_write_depth, ogrecu_rt*, const float*, size_t)
-STUB(ogrecu_rt_colour_device_ptr, ogrecu_rt*, void**)
-STUB(ogrecu_rt_depth_device_ptr, ogrecu_rt*, void**)
-STUB(ogrecu_rt_last_stats, ogrecu_rt*, ogrecu_raster_stats*)
+
+#include <algorithm>
+#include <cfloat>
+#include <climits>
+#include <cstring>
+
+using namespace ogrecu;
+
+namespace {
+
+constexpr int TILE = 16;            // tile edge in pixels
+constexpr int TILE_SHIFT = 4;
+constexpr int RT_THREADS = 256;     // raster CTA = one thread per tile pixel
+constexpr int CHUNK = 256;          // triangles staged in shared memory per round
+
+__device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+// libstdc++ std::min/std::max (NaN falls through to the first argument)
+__device__ __forceinline__ float std_min(float a, float b) { return (b < a) ? b : a; }
+__device__ __forceinline__ float std_max(float a, float b) { return (a < b) ? b : a; }
+// x86 cvttss2si: NaN / out of range -> INT_MIN ("integer indefinite")
+__device__ __forceinline__ int x86_f2i(float f)
+{
+    if (!(f < 2147483648.0f) || f < -2147483648.0f) return INT_MIN;
+    return (int)f;
 }
+
+// Per-draw state on the device (one TinyRenderSystem::_render call)
+struct DrawDev {
+    const uint8_t* pos; const uint8_t* uv; const uint8_t* nrm; const void* idx;
+    const uint8_t* tex;
+    uint32_t pos_stride, uv_stride, nrm_stride, index_type;
+    uint32_t is_strip, flags, target, tri_base;
+    uint32_t tri_count, tex_w, tex_h, tex_zero_alpha;
+    float mvp[16], texm[16], vp[16];
+    float mvit[9];
+    float light[3];
+    float ambient[4];
+};
+
+struct TargetDev {
+    uint8_t* colour;
+    float* depth;
+};
+
+// hot record: everything the coverage/depth test needs (5 x float4)
+struct __align__(16) HotRec {
+    float c[9];       // adjugate / inverse of ABC (OgreMatrix3.cpp:155-202)
+    float iw[3];      // 1/w per vertex
+    float z[3];       // screen z per vertex
+    uint32_t bx;      // x0 | x1 << 16   (inclusive pixel bbox)
+    uint32_t by;      // y0 | y1 << 16
+    uint32_t draw;    // index into the DrawDev table
+    uint32_t pad0, pad1;
+};
+static_assert(sizeof(HotRec) == 80, "HotRec must be 5 float4");
+
+// cold record: varyings, touched only by fragments that pass (4 x float4)
+struct __align__(16) ColdRec {
+    float uv[6];      // u0 v0 u1 v1 u2 v2
+    float n[9];       // n0xyz n1xyz n2xyz
+    float pad;
+};
+static_assert(sizeof(ColdRec) == 64, "ColdRec must be 4 float4");
+
+struct SegParams {
+    const DrawDev* draws;
+    uint32_t ndraws;
+    uint32_t ntris;
+    HotRec* hot;
+    ColdRec* cold;
+    uint32_t* cnt;            // tile count per triangle, then exclusive offsets (ntris+1)
+    uint32_t width, height;
+    uint32_t tiles_x, tiles_y;        // tiles per target
+    uint32_t strip_ty0, strip_ty1;    // tile rows rasterised on this context
+    uint32_t* tile_count;     // [ntargets*tiles_x*tiles_y + 1]
+};
+
+/* ------------------------------------------------------------------- K1: setup ------ */
+
+__device__ __forceinline__ void mat4_mul(const float* __restrict__ m, float x, float y, float z, float w, float out[4])
+{
+    // Matrix4 * Vector4, OgreMatrix4.h:571-578: ((m0*x + m1*y) + m2*z) + m3*w
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+        out[r] = fadd(fadd(fadd(fmul(m[4 * r + 0], x), fmul(m[4 * r + 1], y)), fmul(m[4 * r + 2], z)), fmul(m[4 * r + 3], w));
+}
+
+__global__ void __launch_bounds__(256) setup_kernel(SegParams P)
+{
+    uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= P.ntris) return;
+    // which draw: last d with tri_base <= g
+    uint32_t lo = 0, hi = P.ndraws;
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(&P.draws[mid].tri_base) <= g) lo = mid; else hi = mid;
+    }
+    const DrawDev& D = P.draws[lo];
+    const uint32_t t = g - D.tri_base;
+    const size_t i0 = D.is_strip ? (size_t)t : (size_t)t * 3;   // OgreTinyRenderSystem.cpp:396-399
+
+    float X[3], Y[3], Z[3], IW[3];
+    ColdRec cold;
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        size_t k = i0 + j;
+        size_t vi;
+        if (D.index_type == 2) vi = __ldg((const uint16_t*)D.idx + k);        // unsigned; the reference reads int16 (UB >= 32768)
+        else if (D.index_type == 4) vi = __ldg((const uint32_t*)D.idx + k);
+        else vi = k;
+        const float* p = (const float*)(D.pos + vi * D.pos_stride);
+        float px = __ldg(p), py = __ldg(p + 1), pz = __ldg(p + 2);
+        float clip[4], q[4];
+        mat4_mul(D.mvp, px, py, pz, 1.0f, clip);                               // DefaultShader::vertex .cpp:302
+        if (D.uv) {
+            const float* u = (const float*)(D.uv + vi * D.uv_stride);
+            float to[4];
+            mat4_mul(D.texm, __ldg(u), __ldg(u + 1), 0.0f, 1.0f, to);          // .cpp:304-305
+            cold.uv[2 * j] = to[0]; cold.uv[2 * j + 1] = to[1];
+        } else { cold.uv[2 * j] = 0.f; cold.uv[2 * j + 1] = 0.f; }
+        if (D.nrm) {
+            const float* n = (const float*)(D.nrm + vi * D.nrm_stride);
+            float nx = __ldg(n), ny = __ldg(n + 1), nz = __ldg(n + 2);
+#pragma unroll
+            for (int r = 0; r < 3; ++r)                                        // Matrix3 * Vector3, OgreMatrix3.h:321-327
+                cold.n[3 * j + r] = fadd(fadd(fmul(D.mvit[3 * r + 0], nx), fmul(D.mvit[3 * r + 1], ny)), fmul(D.mvit[3 * r + 2], nz));
+        } else { cold.n[3 * j] = cold.n[3 * j + 1] = cold.n[3 * j + 2] = 0.f; }
+        mat4_mul(D.vp, clip[0], clip[1], clip[2], clip[3], q);                 // tinyrenderer.h:45
+        float w = q[3];
+        float fi = fdiv(1.0f, w);                                              // pts[i] /= w  (OgreVector.h:563-570)
+        X[j] = fmul(q[0], fi); Y[j] = fmul(q[1], fi); Z[j] = fmul(q[2], fi);
+        IW[j] = fdiv(1.0f, w);                                                 // tinyrenderer.h:50
+        // non-finite screen coordinates: the reference writes out of bounds (undefined) -> drop
+        ok = ok && isfinite(X[j]) && isfinite(Y[j]) && isfinite(Z[j]) && isfinite(IW[j]);
+    }
+    cold.pad = 0.f;
+
+    if (ok && !D.is_strip) {                                                   // cull: tinyrenderer.h:37-39,55
+        float ax = fsub(X[2], X[0]), ay = fsub(Y[2], Y[0]), bx = fsub(X[2], X[1]), by = fsub(Y[2], Y[1]);
+        if (fsub(fmul(ax, by), fmul(ay, bx)) > 0.0f) ok = false;
+    }
+    int x0 = 0, x1 = -1, y0 = 0, y1 = -1;
+    if (ok) {
+        float mnx = FLT_MAX, mny = FLT_MAX, mxx = -FLT_MAX, mxy = -FLT_MAX;
+        const float cx = (float)(P.width - 1u), cy = (float)(P.height - 1u);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {                                          // tinyrenderer.h:58-65
+            mnx = std_max(0.f, std_min(mnx, X[j]));
+            mxx = std_min(cx, std_max(mxx, X[j]));
+            mny = std_max(0.f, std_min(mny, Y[j]));
+            mxy = std_min(cy, std_max(mxy, Y[j]));
+        }
+        // beyond +-2^31 the reference's (int) loop bounds are undefined -> drop
+        if (!(mnx < 2147483648.0f) || !(mny < 2147483648.0f) || !(mxx > -2147483648.0f) || !(mxy > -2147483648.0f)) ok = false;
+        else {
+            x0 = (int)mnx; x1 = (int)mxx; y0 = (int)mny; y1 = (int)mxy;        // :68-69 truncation toward zero
+            if (x0 > x1 || y0 > y1) ok = false;
+        }
+    }
+    uint32_t ntiles = 0;
+    if (ok) {
+        int tx0 = x0 >> TILE_SHIFT, tx1 = x1 >> TILE_SHIFT;
+        int ty0 = max(y0 >> TILE_SHIFT, (int)P.strip_ty0), ty1 = min(y1 >> TILE_SHIFT, (int)P.strip_ty1 - 1);
+        if (ty0 <= ty1) ntiles = (uint32_t)(tx1 - tx0 + 1) * (uint32_t)(ty1 - ty0 + 1);
+    }
+    P.cnt[g] = ntiles;
+    if (!ntiles) return;
+
+    HotRec h;
+    // Matrix3::Inverse of ABC = [[X0,X1,X2],[Y0,Y1,Y2],[1,1,1]], OgreMatrix3.cpp:160-192
+    h.c[0] = fsub(Y[1], Y[2]); h.c[1] = fsub(X[2], X[1]); h.c[2] = fsub(fmul(X[1], Y[2]), fmul(X[2], Y[1]));
+    h.c[3] = fsub(Y[2], Y[0]); h.c[4] = fsub(X[0], X[2]); h.c[5] = fsub(fmul(X[2], Y[0]), fmul(X[0], Y[2]));
+    h.c[6] = fsub(Y[0], Y[1]); h.c[7] = fsub(X[1], X[0]); h.c[8] = fsub(fmul(X[0], Y[1]), fmul(X[1], Y[0]));
+    float det = fadd(fadd(fmul(X[0], h.c[0]), fmul(X[1], h.c[3])), fmul(X[2], h.c[6]));
+    if (!(fabsf(det) <= 1e-06f)) {       // else: the UNSCALED cofactors are used (:184-185)
+        float gi = fdiv(1.0f, det);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) h.c[k] = fmul(h.c[k], gi);
+    }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { h.iw[j] = IW[j]; h.z[j] = Z[j]; }
+    h.bx = (uint32_t)x0 | ((uint32_t)x1 << 16);
+    h.by = (uint32_t)y0 | ((uint32_t)y1 << 16);
+    h.draw = lo; h.pad0 = 0; h.pad1 = 0;
+    const float4* hs = reinterpret_cast<const float4*>(&h);
+    float4* hd = reinterpret_cast<float4*>(P.hot + g);
+#pragma unroll
+    for (int k = 0; k < 5; ++k) hd[k] = hs[k];
+    const float4* cs = reinterpret_cast<const float4*>(&cold);
+    float4* cd = reinterpret_cast<float4*>(P.cold + g);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) cd[k] = cs[k];
+}
+
+/* ------------------------------------------------------------ exclusive scan -------- */
+// three-phase scan of uint32 (block = 2048 items); totals in 64 bits to detect overflow.
+
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_BLOCK = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* total)
+{
+    __shared__ uint32_t warp_sums[SCAN_THREADS / 32];
+    const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t n = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (unsigned)o) inc += n;
+    }
+    if (lane == 31) warp_sums[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t s = lane < SCAN_THREADS / 32 ? warp_sums[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < SCAN_THREADS / 32; o <<= 1) {
+            uint32_t n = __shfl_up_sync(0xffffffffu, s, o);
+            if (lane >= (unsigned)o) s += n;
+        }
+        if (lane < SCAN_THREADS / 32) warp_sums[lane] = s;
+    }
+    __syncthreads();
+    uint32_t base = wid ? warp_sums[wid - 1] : 0;
+    if (total) *total = warp_sums[SCAN_THREADS / 32 - 1];
+    __syncthreads();
+    return base + inc - v;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_reduce_kernel(const uint32_t* __restrict__ in, uint64_t* __restrict__ block_sums, size_t n)
+{
+    size_t base = (size_t)blockIdx.x * SCAN_BLOCK;
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        size_t i = base + (size_t)k * SCAN_THREADS + threadIdx.x;
+        if (i < n) s += in[i];
+    }
+    uint32_t tot;
+    block_exclusive_scan(s, &tot);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = tot;
+}
+
+// single block: exclusive scan of the block sums in place; grand total -> block_sums[nblocks]
+__global__ void __launch_bounds__(SCAN_THREADS) scan_sums_kernel(uint64_t* block_sums, size_t nblocks)
+{
+    __shared__ uint64_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (size_t b0 = 0; b0 < nblocks; b0 += SCAN_THREADS) {
+        size_t i = b0 + threadIdx.x;
+        uint64_t v = i < nblocks ? block_sums[i] : 0;
+        // 64-bit inclusive scan across the block via two 32-bit halves would lose carries; do it in smem
+        __shared__ uint64_t tmp[SCAN_THREADS];
+        tmp[threadIdx.x] = v;
+        __syncthreads();
+        for (int o = 1; o < SCAN_THREADS; o <<= 1) {
+            uint64_t add = threadIdx.x >= (unsigned)o ? tmp[threadIdx.x - o] : 0;
+            __syncthreads();
+            tmp[threadIdx.x] += add;
+            __syncthreads();
+        }
+        uint64_t incl = tmp[threadIdx.x];
+        if (i < nblocks) block_sums[i] = carry + incl - v;
+        __syncthreads();
+        if (threadIdx.x == SCAN_THREADS - 1) carry += incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) block_sums[nblocks] = carry;
+}
+
+// out may alias in.  out[n] is NOT written here (grand total lives in block_sums[nblocks]).
+__global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(const uint32_t* in, uint32_t* out, const uint64_t* __restrict__ block_sums, size_t n)
+{
+    size_t base = (size_t)blockIdx.x * SCAN_BLOCK + (size_t)threadIdx.x * SCAN_ITEMS;
+    uint32_t v[SCAN_ITEMS];
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) { v[k] = (base + k < n) ? in[base + k] : 0; s += v[k]; }
+    uint32_t ex = block_exclusive_scan(s, nullptr) + (uint32_t)block_sums[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) { if (base + k < n) out[base + k] = ex; ex += v[k]; }
+}
+
+/* --------------------------------------------------------------------- K2: bin ------ */
+
+// pair = tile key << 32 | triangle id.  Pairs of one triangle are contiguous at off[g];
+// the stable sort by key keeps, inside every tile, the submission order of triangles.
+__global__ void __launch_bounds__(256) bin_kernel(SegParams P, const uint32_t* __restrict__ off, uint64_t* __restrict__ pairs)
+{
+    uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= P.ntris) return;
+    uint32_t o = off[g], n = off[g + 1] - o;
+    if (!n) return;
+    const HotRec* h = P.hot + g;
+    uint32_t bx = h->bx, by = h->by, d = h->draw;
+    uint32_t target = __ldg(&P.draws[d].target);
+    int tx0 = (int)(bx & 0xffff) >> TILE_SHIFT, tx1 = (int)(bx >> 16) >> TILE_SHIFT;
+    int ty0 = max((int)(by & 0xffff) >> TILE_SHIFT, (int)P.strip_ty0), ty1 = min((int)(by >> 16) >> TILE_SHIFT, (int)P.strip_ty1 - 1);
+    uint32_t tbase = target * P.tiles_x * P.tiles_y;
+    for (int ty = ty0; ty <= ty1; ++ty)
+        for (int tx = tx0; tx <= tx1; ++tx) {
+            uint32_t key = tbase + (uint32_t)ty * P.tiles_x + (uint32_t)tx;
+            pairs[o++] = ((uint64_t)key << 32) | g;
+            atomicAdd(&P.tile_count[key], 1u);
+        }
+}
+
+/* ------------------------------------------------------ stable LSD radix sort ------- */
+
+constexpr int RS_THREADS = 256;
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_PER_WARP = 256;                 // items per warp (8 rounds of 32)
+constexpr int RS_BLOCK = RS_WARPS * RS_PER_WARP; // 2048 items per block
+constexpr int RS_BINS = 256;
+
+// block_hist[bin * nblocks + block]
+__global__ void __launch_bounds__(RS_THREADS) radix_hist_kernel(const uint64_t* __restrict__ in, uint32_t* __restrict__ block_hist,
+                                                                size_t n, int shift, uint32_t nblocks)
+{
+    __shared__ uint32_t h[RS_BINS];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    size_t base = (size_t)blockIdx.x * RS_BLOCK;
+    for (int k = 0; k < RS_BLOCK / RS_THREADS; ++k) {
+        size_t i = base + (size_t)k * RS_THREADS + threadIdx.x;
+        if (i < n) atomicAdd(&h[(uint32_t)(in[i] >> shift) & (RS_BINS - 1)], 1u);
+    }
+    __syncthreads();
+    block_hist[(size_t)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const uint64_t* __restrict__ in, uint64_t* __restrict__ out,
+                                                                   const uint32_t* __restrict__ block_off, size_t n, int shift,
+                                                                   uint32_t nblocks)
+{
+    __shared__ uint32_t wcount[RS_WARPS][RS_BINS];   // per-warp digit counts -> per-warp bases
+    const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < RS_WARPS * RS_BINS; i += RS_THREADS) (&wcount[0][0])[i] = 0;
+    __syncthreads();
+    const size_t wbase = (size_t)blockIdx.x * RS_BLOCK + (size_t)wid * RS_PER_WARP;
+    uint64_t items[RS_PER_WARP / 32];
+    // pass 1: count digits of this warp's contiguous segment
+#pragma unroll
+    for (int r = 0; r < RS_PER_WARP / 32; ++r) {
+        size_t i = wbase + (size_t)r * 32 + lane;
+        bool valid = i < n;
+        items[r] = valid ? in[i] : 0;
+        if (valid) atomicAdd(&wcount[wid][(uint32_t)(items[r] >> shift) & (RS_BINS - 1)], 1u);
+    }
+    __syncthreads();
+    // per bin: exclusive prefix over warps + global base of this (bin, block)
+    {
+        uint32_t bin = threadIdx.x;
+        uint32_t run = block_off[(size_t)bin * nblocks + blockIdx.x];
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; ++w) { uint32_t c = wcount[w][bin]; wcount[w][bin] = run; run += c; }
+    }
+    __syncthreads();
+    // pass 2: stable scatter; ranks inside a round come from match_any (lower lanes first)
+#pragma unroll
+    for (int r = 0; r < RS_PER_WARP / 32; ++r) {
+        size_t i = wbase + (size_t)r * 32 + lane;
+        bool valid = i < n;
+        unsigned active = __ballot_sync(0xffffffffu, valid);
+        if (valid) {
+            uint32_t d = (uint32_t)(items[r] >> shift) & (RS_BINS - 1);
+            unsigned peers = __match_any_sync(active, d);
+            unsigned rank = __popc(peers & ((1u << lane) - 1u));
+            uint32_t basepos = wcount[wid][d];
+            out[basepos + rank] = items[r];
+            __syncwarp(active);
+            if (rank == 0) wcount[wid][d] = basepos + __popc(peers);
+        }
+        __syncwarp();
+    }
+}
+
+/* ------------------------------------------------------------------ K3: raster ------ */
+
+struct RasterParams {
+    const DrawDev* draws;
+    const TargetDev* targets;
+    const HotRec* hot;
+    const ColdRec* cold;
+    const uint64_t* pairs;         // sorted by tile key
+    const uint32_t* tile_start;    // exclusive scan of tile counts
+    uint32_t width, height, tiles_x, tiles_y;
+    uint32_t strip_ty0, strip_rows;
+};
+
+__device__ __forceinline__ uint32_t shade_pack(float r, float g, float b)
+{
+    // saturate (Math::Clamp: max(min(v,1),0), OgreMath.h:395,704-708), *255, truncating cast (tinyrenderer.h:88-91)
+    float c[3] = {r, g, b};
+    uint32_t out = 0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        float v = std_max(std_min(c[k], 1.0f), 0.0f);
+        v = fmul(v, 255.0f);
+        out |= ((uint32_t)x86_f2i(v) & 0xffu) << (8 * k);
+    }
+    return out;
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(RT_THREADS) raster_kernel(RasterParams P)
+{
+    __shared__ float4 s_hot[CHUNK][5];
+    __shared__ uint32_t s_tri[CHUNK];
+    __shared__ __align__(16) uint8_t s_rgb[TILE][TILE * 3];
+
+    // tile of this CTA
+    const uint32_t per_target = P.tiles_x * P.strip_rows;
+    const uint32_t target = blockIdx.x / per_target;
+    const uint32_t rem = blockIdx.x - target * per_target;
+    const uint32_t ty = P.strip_ty0 + rem / P.tiles_x, tx = rem % P.tiles_x;
+    const uint32_t key = target * P.tiles_x * P.tiles_y + ty * P.tiles_x + tx;
+    const uint32_t start = P.tile_start[key], end = P.tile_start[key + 1];
+    if (start == end) return;   // nothing to draw here: the planes already hold the result
+
+    const TargetDev T = P.targets[target];
+    const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    // warp = 8x4 pixel block of the tile
+    const int wx0 = (wid & 1) * 8, wy0 = (wid >> 1) * 4;
+    const int lx = wx0 + (lane & 7), ly = wy0 + (lane >> 3);
+    const int tile_x0 = tx * TILE, tile_y0 = ty * TILE;
+    const int x = tile_x0 + lx, y = tile_y0 + ly;
+    const bool inside = x < (int)P.width && y < (int)P.height;
+    const int tw = min(TILE, (int)P.width - tile_x0), th = min(TILE, (int)P.height - tile_y0);
+    const size_t pix = (size_t)y * P.width + x;
+
+    // ---- load the tile: depth straight to registers, colour through shared memory
+    float zbuf = inside ? T.depth[pix] : 0.f;
+    if (VEC) {
+        // full-width tile rows are 48 bytes = three aligned 16-byte vectors
+        if (threadIdx.x < TILE * 3) {
+            int r = threadIdx.x / 3, v = threadIdx.x % 3;
+            if (r < th) {
+                const uint4* src = reinterpret_cast<const uint4*>(T.colour + ((size_t)(tile_y0 + r) * P.width + tile_x0) * 3) + v;
+                reinterpret_cast<uint4*>(&s_rgb[r][0])[v] = *src;
+            }
+        }
+    } else {
+        for (int i = threadIdx.x; i < th * tw * 3; i += RT_THREADS) {
+            int r = i / (tw * 3), b = i - r * (tw * 3);
+            s_rgb[r][b] = T.colour[((size_t)(tile_y0 + r) * P.width + tile_x0) * 3 + b];
+        }
+    }
+    __syncthreads();
+    uint32_t rgb = 0;
+    if (inside) rgb = (uint32_t)s_rgb[ly][lx * 3] | ((uint32_t)s_rgb[ly][lx * 3 + 1] << 8) | ((uint32_t)s_rgb[ly][lx * 3 + 2] << 16);
+
+    const float Px = (float)x, Py = (float)y;
+    // warp's pixel rectangle in screen space (for the per-warp triangle prefilter)
+    const int wrx0 = tile_x0 + wx0, wrx1 = wrx0 + 7, wry0 = tile_y0 + wy0, wry1 = wry0 + 3;
+    const float inv255 = 1.0f / 255.0f;
+
+    for (uint32_t c0 = start; c0 < end; c0 += CHUNK) {
+        const uint32_t nchunk = min((uint32_t)CHUNK, end - c0);
+        __syncthreads();   // previous chunk fully consumed
+        // ---- stage the chunk's hot records (coalesced over 16-byte pieces)
+        if (threadIdx.x < nchunk) s_tri[threadIdx.x] = (uint32_t)P.pairs[c0 + threadIdx.x];
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < nchunk * 5; i += RT_THREADS) {
+            uint32_t j = i / 5, k = i - j * 5;
+            s_hot[j][k] = __ldg(reinterpret_cast<const float4*>(P.hot + s_tri[j]) + k);
+        }
+        __syncthreads();
+
+        // ---- replay the chunk in submission order
+        for (uint32_t r0 = 0; r0 < nchunk; r0 += 32) {
+            // prefilter: lane L tests triangle r0+L against this warp's 8x4 pixels
+            bool hit = false;
+            if (r0 + lane < nchunk) {
+                const uint32_t* w = reinterpret_cast<const uint32_t*>(&s_hot[r0 + lane][0]);
+                uint32_t bx = w[15], by = w[16];
+                int bx0 = bx & 0xffff, bx1 = bx >> 16, by0 = by & 0xffff, by1 = by >> 16;
+                hit = bx0 <= wrx1 && bx1 >= wrx0 && by0 <= wry1 && by1 >= wry0;
+            }
+            unsigned mask = __ballot_sync(0xffffffffu, hit);
+            while (mask) {
+                const int b = __ffs(mask) - 1;
+                mask &= mask - 1;
+                const uint32_t j = r0 + b;
+                const float* hf = reinterpret_cast<const float*>(&s_hot[j][0]);
+                const uint32_t* hw = reinterpret_cast<const uint32_t*>(hf);
+                const uint32_t bx = hw[15], by = hw[16];
+                const bool in_box = inside && x >= (int)(bx & 0xffff) && x <= (int)(bx >> 16) && y >= (int)(by & 0xffff) && y <= (int)(by >> 16);
+                bool pass = false;
+                float bc0 = 0.f, bc1 = 0.f, bc2 = 0.f, fd = 0.f;
+                const DrawDev* D = P.draws + hw[17];
+                const uint32_t flags = __ldg(&D->flags);
+                if (in_box) {
+                    // barycentric(): inverse * (x, y, 1)   (tinyrenderer.h:29-35, OgreMatrix3.h:321-327)
+                    float bs0 = fadd(fadd(fmul(hf[0], Px), fmul(hf[1], Py)), hf[2]);
+                    float bs1 = fadd(fadd(fmul(hf[3], Px), fmul(hf[4], Py)), hf[5]);
+                    float bs2 = fadd(fadd(fmul(hf[6], Px), fmul(hf[7], Py)), hf[8]);
+                    bc0 = fmul(bs0, hf[9]); bc1 = fmul(bs1, hf[10]); bc2 = fmul(bs2, hf[11]);   // :71
+                    float s = fadd(fadd(bc0, bc1), bc2);
+                    float f = fdiv(1.0f, s);                                                   // :72, OgreVector.h:659-664
+                    bc0 = fmul(f, bc0); bc1 = fmul(f, bc1); bc2 = fmul(f, bc2);
+                    fd = fadd(fadd(fadd(0.0f, fmul(hf[12], bc0)), fmul(hf[13], bc1)), fmul(hf[14], bc2));   // :73
+                    pass = !(bs0 < 0.f || bs1 < 0.f || bs2 < 0.f) && !(fd < 0.0f);             // :74,:76
+                    if (pass && (flags & OGRECU_DRAW_DEPTH_TEST) && fd > zbuf) pass = false;   // :79
+                }
+                if (!__any_sync(0xffffffffu, pass)) continue;
+                if (pass) {
+                    // ---- fragment shader (DefaultShader::fragment, OgreTinyRenderSystem.cpp:310-333)
+                    const float4* cp = reinterpret_cast<const float4*>(P.cold + s_tri[j]);
+                    float cr = 1.0f, cg = 1.0f, cb = 1.0f;   // default ColourValue: white (tinyrenderer.h:82)
+                    const uint8_t* tex = D->tex;
+                    bool discard = false;
+                    float4 v0 = __ldg(cp), v1 = __ldg(cp + 1);
+                    if (tex) {
+                        const int tw_ = (int)D->tex_w, th_ = (int)D->tex_h;
+                        float u = fadd(fadd(fmul(v0.x, bc0), fmul(v0.z, bc1)), fmul(v1.x, bc2));
+                        float v = fadd(fadd(fmul(v0.y, bc0), fmul(v0.w, bc1)), fmul(v1.y, bc2));
+                        int ix = x86_f2i(fmul(u, (float)(uint32_t)(tw_ - 1)));                 // sample2D, OgreTinyRenderSystem.h:36-41
+                        int iy = x86_f2i(fmul(v, (float)(uint32_t)(th_ - 1)));
+                        ix = (tw_ + (ix % tw_)) % tw_;
+                        iy = (th_ + (iy % th_)) % th_;
+                        uchar4 t4 = __ldg(reinterpret_cast<const uchar4*>(tex) + (size_t)iy * tw_ + ix);
+                        if (t4.w < 1) discard = true;                                          // .cpp:318
+                        cr = fmul((float)t4.x, inv255); cg = fmul((float)t4.y, inv255); cb = fmul((float)t4.z, inv255);
+                    }
+                    if (!discard) {
+                        if (flags & OGRECU_DRAW_LIGHTING) {
+                            float4 v2 = __ldg(cp + 2), v3 = __ldg(cp + 3);
+                            // n[9] = v1.z v1.w v2.x | v2.y v2.z v2.w | v3.x v3.y v3.z
+                            float nx = fadd(fadd(fmul(v1.z, bc0), fmul(v2.y, bc1)), fmul(v3.x, bc2));
+                            float ny = fadd(fadd(fmul(v1.w, bc0), fmul(v2.z, bc1)), fmul(v3.y, bc2));
+                            float nz = fadd(fadd(fmul(v2.x, bc0), fmul(v2.w, bc1)), fmul(v3.z, bc2));
+                            float dp = fadd(fadd(fadd(0.0f, fmul(nx, D->light[0])), fmul(ny, D->light[1])), fmul(nz, D->light[2]));
+                            float diffuse = std_max(0.f, dp);
+                            cr = fadd(fmul(cr, diffuse), D->ambient[0]);
+                            cg = fadd(fmul(cg, diffuse), D->ambient[1]);
+                            cb = fadd(fmul(cb, diffuse), D->ambient[2]);
+                        }
+                        if (flags & OGRECU_DRAW_BLEND_ADD) {                                  // tinyrenderer.h:86-87
+                            cr = fadd(cr, fmul((float)(rgb & 0xff), inv255));
+                            cg = fadd(cg, fmul((float)((rgb >> 8) & 0xff), inv255));
+                            cb = fadd(cb, fmul((float)((rgb >> 16) & 0xff), inv255));
+                        }
+                        rgb = shade_pack(cr, cg, cb);
+                        if (flags & OGRECU_DRAW_DEPTH_WRITE) zbuf = fd;                       // :92-93
+                    }
+                }
+            }
+        }
+    }
+
+    // ---- flush: depth from registers, colour via shared memory as 16-byte vectors
+    __syncthreads();
+    if (inside) {
+        T.depth[pix] = zbuf;
+        s_rgb[ly][lx * 3] = (uint8_t)(rgb & 0xff);
+        s_rgb[ly][lx * 3 + 1] = (uint8_t)((rgb >> 8) & 0xff);
+        s_rgb[ly][lx * 3 + 2] = (uint8_t)((rgb >> 16) & 0xff);
+    }
+    __syncthreads();
+    if (VEC) {
+        if (threadIdx.x < TILE * 3) {
+            int r = threadIdx.x / 3, v = threadIdx.x % 3;
+            if (r < th) {
+                uint4* dst = reinterpret_cast<uint4*>(T.colour + ((size_t)(tile_y0 + r) * P.width + tile_x0) * 3) + v;
+                *dst = reinterpret_cast<const uint4*>(&s_rgb[r][0])[v];
+            }
+        }
+    } else {
+        for (int i = threadIdx.x; i < th * tw * 3; i += RT_THREADS) {
+            int r = i / (tw * 3), b = i - r * (tw * 3);
+            T.colour[((size_t)(tile_y0 + r) * P.width + tile_x0) * 3 + b] = s_rgb[r][b];
+        }
+    }
+}
+
+/* ------------------------------------------------------------------ K5: clear ------- */
+
+// colour plane filled with a 3-byte pattern using 16-byte stores; depth with float4 stores
+__global__ void clear_colour_kernel(uint8_t* __restrict__ colour, size_t nbytes, uint32_t r, uint32_t g, uint32_t b)
+{
+    size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    if (i >= nbytes) return;
+    const uint32_t px[3] = {r, g, b};
+    if (i + 16 <= nbytes) {
+        uint32_t w[4];
+        uint32_t ph = (uint32_t)(i % 3);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            uint32_t v = 0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { v |= px[ph] << (8 * q); ph = ph == 2 ? 0 : ph + 1; }
+            w[k] = v;
+        }
+        *reinterpret_cast<uint4*>(colour + i) = make_uint4(w[0], w[1], w[2], w[3]);
+    } else {
+        for (size_t k = i; k < nbytes; ++k) colour[k] = (uint8_t)px[k % 3];
+    }
+}
+
+__global__ void clear_depth_kernel(float* __restrict__ depth, size_t n, float v)
+{
+    size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i >= n) return;
+    if (i + 4 <= n) *reinterpret_cast<float4*>(depth + i) = make_float4(v, v, v, v);
+    else for (size_t k = i; k < n; ++k) depth[k] = v;
+}
+
+}  // namespace
+
+/* ======================================================================= host side === */
+
+struct Cmd {
+    int kind;                  // 0 = draw, 1 = clear
+    ogrecu_draw_desc draw;
+    unsigned clear_buffers;
+    float clear_colour[4];
+    float clear_depth;
+};
+
+struct ogrecu_rt {
+    ogrecu_ctx* ctx;
+    uint32_t w, h;
+    uint8_t* colour;
+    float* depth;
+    uint32_t strip_y0, strip_y1;     // pixel rows rasterised here (multiples of TILE, or h)
+    std::vector<Cmd> cmds;
+    ogrecu_raster_stats stats;
+};
+
+namespace {
+
+// per-context raster scratch (grown on demand, reused across flushes)
+struct RasterScratch {
+    Scratch draws, targets, hot, cold, cnt, sums, pairs_a, pairs_b, tile_count, hist;
+};
+std::map<ogrecu_ctx*, RasterScratch>& scratch_map()
+{
+    static std::map<ogrecu_ctx*, RasterScratch> m;
+    return m;
+}
+
+int exclusive_scan_u32(ogrecu_ctx* ctx, Scratch& sums, uint32_t* data, size_t n, uint64_t** total_dev)
+{
+    // in place; afterwards (*total_dev)[0] holds the grand total on the device
+    size_t nblocks = div_up(n, SCAN_BLOCK);
+    OGRECU_CHECK(scratch_reserve(ctx, sums, (nblocks + 1) * sizeof(uint64_t)));
+    uint64_t* bs = (uint64_t*)sums.ptr;
+    scan_reduce_kernel<<<(unsigned)nblocks, SCAN_THREADS, 0, ctx->stream>>>(data, bs, n);
+    scan_sums_kernel<<<1, SCAN_THREADS, 0, ctx->stream>>>(bs, nblocks);
+    scan_apply_kernel<<<(unsigned)nblocks, SCAN_THREADS, 0, ctx->stream>>>(data, data, bs, n);
+    OGRECU_CUDA(cudaGetLastError());
+    count_launch(ctx, 3);
+    *total_dev = bs + nblocks;
+    return OGRECU_OK;
+}
+
+uint32_t tri_count_of(const ogrecu_draw_desc& d)
+{
+    if (d.prim_type == OGRECU_PRIM_TRIANGLE_STRIP) return d.draw_count >= 3 ? d.draw_count - 2 : 0;
+    return d.draw_count / 3;   // the reference reads past the end when drawCount%3 != 0 (UB); we stop
+}
+
+struct Item { const ogrecu_draw_desc* desc; uint32_t target; const float* mvp; const float* mvit; const float* light; };
+
+// Run the pipeline for `items` (draws in submission order) over `targets` (same size).
+int run_segment(ogrecu_ctx* ctx, ogrecu_rt* const* targets, uint32_t ntargets, const std::vector<Item>& items)
+{
+    if (items.empty()) return OGRECU_OK;
+    RasterScratch& S = scratch_map()[ctx];
+    ogrecu_rt* rt0 = targets[0];
+    const uint32_t W = rt0->w, H = rt0->h;
+    const uint32_t tiles_x = div_up(W, TILE), tiles_y = div_up(H, TILE);
+    const uint32_t strip_ty0 = rt0->strip_y0 / TILE, strip_ty1 = div_up(std::min(rt0->strip_y1, H), TILE);
+    if (strip_ty0 >= strip_ty1) return OGRECU_OK;
+
+    // ---- per-draw device table
+    std::vector<DrawDev> dd(items.size());
+    uint64_t ntris64 = 0;
+    for (size_t k = 0; k < items.size(); ++k) {
+        const ogrecu_draw_desc& d = *items[k].desc;
+        DrawDev& o = dd[k];
+        memset(&o, 0, sizeof o);
+        o.pos = (const uint8_t*)d.positions; o.uv = (const uint8_t*)d.uvs; o.nrm = (const uint8_t*)d.normals; o.idx = d.indices;
+        o.pos_stride = d.pos_stride; o.uv_stride = d.uv_stride; o.nrm_stride = d.normal_stride; o.index_type = d.index_type;
+        o.is_strip = d.prim_type == OGRECU_PRIM_TRIANGLE_STRIP;
+        o.flags = d.flags;
+        if (!d.normals) o.flags &= ~(uint32_t)OGRECU_DRAW_LIGHTING;    // uniform_doLighting &= hasNormals (.cpp:369)
+        o.target = items[k].target;
+        o.tri_base = (uint32_t)ntris64;
+        o.tri_count = tri_count_of(d);
+        ntris64 += o.tri_count;
+        if (d.texture) { o.tex = d.texture->dev; o.tex_w = d.texture->w; o.tex_h = d.texture->h; o.tex_zero_alpha = d.texture->has_zero_alpha; }
+        memcpy(o.mvp, items[k].mvp ? items[k].mvp : d.mvp, 64);
+        memcpy(o.texm, d.tex_matrix, 64);
+        memcpy(o.vp, d.viewport, 64);
+        const float* mv = items[k].mvit ? items[k].mvit : d.mvit;
+        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) o.mvit[3 * r + c] = mv[4 * r + c];   // Matrix4::linear()
+        memcpy(o.light, items[k].light ? items[k].light : d.light_dir, 12);
+        memcpy(o.ambient, d.ambient, 16);
+    }
+    OGRECU_REQUIRE(ntris64 < 0x7fffff00ull, "too many triangles in one flush");
+    const uint32_t ntris = (uint32_t)ntris64;
+    for (uint32_t t = 0; t < ntargets; ++t) { targets[t]->stats.triangles_in += 0; }
+    if (ntris == 0) return OGRECU_OK;
+    const uint32_t nkeys = ntargets * tiles_x * tiles_y;
+
+    std::vector<TargetDev> td(ntargets);
+    for (uint32_t t = 0; t < ntargets; ++t) { td[t].colour = targets[t]->colour; td[t].depth = targets[t]->depth; }
+
+    OGRECU_CHECK(scratch_reserve(ctx, S.draws, dd.size() * sizeof(DrawDev)));
+    OGRECU_CHECK(scratch_reserve(ctx, S.targets, td.size() * sizeof(TargetDev)));
+    OGRECU_CHECK(scratch_reserve(ctx, S.hot, (size_t)ntris * sizeof(HotRec)));
+    OGRECU_CHECK(scratch_reserve(ctx, S.cold, (size_t)ntris * sizeof(ColdRec)));
+    OGRECU_CHECK(scratch_reserve(ctx, S.cnt, ((size_t)ntris + 1) * sizeof(uint32_t)));
+    OGRECU_CHECK(scratch_reserve(ctx, S.tile_count, ((size_t)nkeys + 1) * sizeof(uint32_t)));
+    // tables go through the pinned block (stream-ordered, no pageable-copy stall)
+    size_t tab_bytes = dd.size() * sizeof(DrawDev) + td.size() * sizeof(TargetDev);
+    OGRECU_CHECK(pinned_reserve(ctx, tab_bytes));
+    OGRECU_CUDA(cudaStreamSynchronize(ctx->stream));
+    memcpy(ctx->pinned, dd.data(), dd.size() * sizeof(DrawDev));
+    memcpy((uint8_t*)ctx->pinned + dd.size() * sizeof(DrawDev), td.data(), td.size() * sizeof(TargetDev));
+    OGRECU_CUDA(cudaMemcpyAsync(S.draws.ptr, ctx->pinned, dd.size() * sizeof(DrawDev), cudaMemcpyHostToDevice, ctx->stream));
+    OGRECU_CUDA(cudaMemcpyAsync(S.targets.ptr, (uint8_t*)ctx->pinned + dd.size() * sizeof(DrawDev), td.size() * sizeof(TargetDev),
+                                cudaMemcpyHostToDevice, ctx->stream));
+
+    SegParams P;
+    P.draws = (const DrawDev*)S.draws.ptr; P.ndraws = (uint32_t)dd.size(); P.ntris = ntris;
+    P.hot = (HotRec*)S.hot.ptr; P.cold = (ColdRec*)S.cold.ptr; P.cnt = (uint32_t*)S.cnt.ptr;
+    P.width = W; P.height = H; P.tiles_x = tiles_x; P.tiles_y = tiles_y;
+    P.strip_ty0 = strip_ty0; P.strip_ty1 = strip_ty1;
+    P.tile_count = (uint32_t*)S.tile_count.ptr;
+
+    // ---- K1 + scan
+    OGRECU_CUDA(cudaMemsetAsync(P.tile_count, 0, ((size_t)nkeys + 1) * sizeof(uint32_t), ctx->stream));
+    setup_kernel<<<div_up(ntris, 256), 256, 0, ctx->stream>>>(P);
+    OGRECU_CUDA(cudaGetLastError());
+    count_launch(ctx);
+    OGRECU_CUDA(cudaMemsetAsync(P.cnt + ntris, 0, sizeof(uint32_t), ctx->stream));
+    uint64_t* total_dev = nullptr;
+    OGRECU_CHECK(exclusive_scan_u32(ctx, S.sums, P.cnt, (size_t)ntris + 1, &total_dev));
+    uint64_t npairs = 0;
+    OGRECU_CUDA(cudaMemcpyAsync(&npairs, total_dev, sizeof npairs, cudaMemcpyDeviceToHost, ctx->stream));
+    OGRECU_CUDA(cudaStreamSynchronize(ctx->stream));
+    OGRECU_REQUIRE(npairs < 0xffffffffull, "too many (triangle, tile) pairs in one flush");
+    for (uint32_t t = 0; t < ntargets; ++t) {
+        targets[t]->stats.triangles_in = ntris / ntargets;
+        targets[t]->stats.tile_pairs = npairs / ntargets;
+    }
+    if (npairs == 0) return OGRECU_OK;
+
+    // ---- K2 + stable sort by tile key
+    OGRECU_CHECK(scratch_reserve(ctx, S.pairs_a, npairs * sizeof(uint64_t)));
+    OGRECU_CHECK(scratch_reserve(ctx, S.pairs_b, npairs * sizeof(uint64_t)));
+    uint64_t* pa = (uint64_t*)S.pairs_a.ptr;
+    uint64_t* pb = (uint64_t*)S.pairs_b.ptr;
+    bin_kernel<<<div_up(ntris, 256), 256, 0, ctx->stream>>>(P, P.cnt, pa);
+    OGRECU_CUDA(cudaGetLastError());
+    count_launch(ctx);
+    int key_bits = 1;
+    while ((1ull << key_bits) < nkeys) ++key_bits;
+    const uint32_t rs_blocks = div_up(npairs, RS_BLOCK);
+    OGRECU_CHECK(scratch_reserve(ctx, S.hist, ((size_t)RS_BINS * rs_blocks + 1) * sizeof(uint32_t)));
+    uint32_t* hist = (uint32_t*)S.hist.ptr;
+    for (int shift = 0; shift < key_bits; shift += 8) {
+        radix_hist_kernel<<<rs_blocks, RS_THREADS, 0, ctx->stream>>>(pa, hist, npairs, 32 + shift, rs_blocks);
+        OGRECU_CUDA(cudaGetLastError());
+        count_launch(ctx);
+        uint64_t* dummy;
+        OGRECU_CHECK(exclusive_scan_u32(ctx, S.sums, hist, (size_t)RS_BINS * rs_blocks, &dummy));
+        radix_scatter_kernel<<<rs_blocks, RS_THREADS, 0, ctx->stream>>>(pa, pb, hist, npairs, 32 + shift, rs_blocks);
+        OGRECU_CUDA(cudaGetLastError());
+        count_launch(ctx);
+        std::swap(pa, pb);
+    }
+    uint64_t* dummy;
+    OGRECU_CHECK(exclusive_scan_u32(ctx, S.sums, P.tile_count, (size_t)nkeys + 1, &dummy));
+
+    // ---- K3
+    RasterParams R;
+    R.draws = P.draws; R.targets = (const TargetDev*)S.targets.ptr; R.hot = P.hot; R.cold = P.cold;
+    R.pairs = pa; R.tile_start = P.tile_count;
+    R.width = W; R.height = H; R.tiles_x = tiles_x; R.tiles_y = tiles_y;
+    R.strip_ty0 = strip_ty0; R.strip_rows = strip_ty1 - strip_ty0;
+    const unsigned grid = ntargets * tiles_x * R.strip_rows;
+    if (W % 16 == 0) raster_kernel<true><<<grid, RT_THREADS, 0, ctx->stream>>>(R);
+    else raster_kernel<false><<<grid, RT_THREADS, 0, ctx->stream>>>(R);
+    OGRECU_CUDA(cudaGetLastError());
+    count_launch(ctx);
+    return OGRECU_OK;
+}
+
+int rt_flush_cmds(ogrecu_rt* rt)
+{
+    ogrecu_ctx* ctx = rt->ctx;
+    OGRECU_CUDA(cudaSetDevice(ctx->device));
+    std::vector<Item> seg;
+    ogrecu_rt* one[1] = {rt};
+    for (size_t i = 0; i < rt->cmds.size(); ++i) {
+        Cmd& c = rt->cmds[i];
+        if (c.kind == 0) { seg.push_back({&c.draw, 0, nullptr, nullptr, nullptr}); continue; }
+        OGRECU_CHECK(run_segment(ctx, one, 1, seg));
+        seg.clear();
+        const size_t npx = (size_t)rt->w * rt->h;
+        if (c.clear_buffers & OGRECU_CLEAR_COLOUR) {
+            const float* col = c.clear_colour;
+            if (col[0] == 0.f && col[1] == 0.f && col[2] == 0.f && col[3] == 0.f) {
+                OGRECU_CUDA(cudaMemsetAsync(rt->colour, 0, npx * 3, ctx->stream));     // Image::setTo ZERO shortcut (OgreImage.cpp:124-128)
+            } else {
+                uint32_t q[3];
+                for (int k = 0; k < 3; ++k) {   // Bitwise::floatToFixed(v, 8), OgreBitwise.h:237-242
+                    float v = col[k];
+                    q[k] = (v <= 0.0f) ? 0u : (v >= 1.0f) ? 255u : (uint32_t)(v * 256.0f);
+                    q[k] &= 0xffu;
+                }
+                clear_colour_kernel<<<div_up(div_up(npx * 3, 16), 256), 256, 0, ctx->stream>>>(rt->colour, npx * 3, q[0], q[1], q[2]);
+                OGRECU_CUDA(cudaGetLastError());
+                count_launch(ctx);
+            }
+        }
+        if (c.clear_buffers & OGRECU_CLEAR_DEPTH) {
+            clear_depth_kernel<<<div_up(div_up(npx, 4), 256), 256, 0, ctx->stream>>>(rt->depth, npx, c.clear_depth);
+            OGRECU_CUDA(cudaGetLastError());
+            count_launch(ctx);
+        }
+    }
+    int rc = run_segment(ctx, one, 1, seg);
+    rt->cmds.clear();
+    return rc;
+}
+
+}  // namespace
+
+namespace ogrecu {
+int rt_release(ogrecu_rt* rt)
+{
+    if (!rt) return OGRECU_OK;
+    ogrecu_ctx* ctx = rt->ctx;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(rt->colour);
+    cudaFree(rt->depth);
+    auto it = std::find(ctx->targets.begin(), ctx->targets.end(), rt);
+    if (it != ctx->targets.end()) ctx->targets.erase(it);
+    if (ctx->targets.empty()) {
+        auto sm = scratch_map().find(ctx);
+        if (sm != scratch_map().end()) {
+            RasterScratch& S = sm->second;
+            for (Scratch* s : {&S.draws, &S.targets, &S.hot, &S.cold, &S.cnt, &S.sums, &S.pairs_a, &S.pairs_b, &S.tile_count, &S.hist})
+                if (s->ptr) cudaFree(s->ptr);
+            scratch_map().erase(sm);
+        }
+    }
+    delete rt;
+    return OGRECU_OK;
+}
+}  // namespace ogrecu
+
+extern "C" {
+
+/* ---- textures ---- */
+
+int ogrecu_tex_create(ogrecu_ctx* ctx, uint32_t w, uint32_t h, ogrecu_tex** out)
+{
+    OGRECU_REQUIRE(ctx && out, "NULL argument");
+    OGRECU_REQUIRE(w >= 1 && h >= 1 && w <= 32768 && h <= 32768, "texture size out of range");
+    *out = nullptr;
+    OGRECU_CUDA(cudaSetDevice(ctx->device));
+    ogrecu_tex* t = new ogrecu_tex();
+    t->ctx = ctx; t->w = w; t->h = h; t->has_zero_alpha = 0; t->dev = nullptr;
+    cudaError_t e = cudaMalloc((void**)&t->dev, (size_t)w * h * 4);
+    if (e != cudaSuccess) { delete t; return cuda_fail(e, "cudaMalloc(texture)", __FILE__, __LINE__); }
+    e = cudaMemsetAsync(t->dev, 0xff, (size_t)w * h * 4, ctx->stream);
+    if (e != cudaSuccess) { cudaFree(t->dev); delete t; return cuda_fail(e, "cudaMemset(texture)", __FILE__, __LINE__); }
+    *out = t;
+    return OGRECU_OK;
+}
+
+int ogrecu_tex_destroy(ogrecu_tex* t)
+{
+    if (!t) return OGRECU_OK;
+    OGRECU_CUDA(cudaSetDevice(t->ctx->device));
+    OGRECU_CUDA(cudaStreamSynchronize(t->ctx->stream));
+    cudaFree(t->dev);
+    delete t;
+    return OGRECU_OK;
+}
+
+int ogrecu_tex_upload(ogrecu_tex* t, const uint8_t* rgba, size_t pitch)
+{
+    OGRECU_REQUIRE(t && rgba, "NULL argument");
+    OGRECU_REQUIRE(pitch >= (size_t)t->w * 4, "row pitch smaller than a row");
+    ogrecu_ctx* ctx = t->ctx;
+    OGRECU_CUDA(cudaSetDevice(ctx->device));
+    const size_t row = (size_t)t->w * 4, bytes = row * t->h;
+    OGRECU_CHECK(pinned_reserve(ctx, bytes));
+    OGRECU_CUDA(cudaStreamSynchronize(ctx->stream));
+    int zero_alpha = 0;
+    for (uint32_t y = 0; y < t->h; ++y) {
+        const uint8_t* s = rgba + y * pitch;
+        memcpy((uint8_t*)ctx->pinned + y * row, s, row);
+        if (!zero_alpha) for (uint32_t x = 0; x < t->w; ++x) if (s[4 * x + 3] == 0) { zero_alpha = 1; break; }
+    }
+    t->has_zero_alpha = zero_alpha;
+    OGRECU_CUDA(cudaMemcpyAsync(t->dev, ctx->pinned, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return OGRECU_OK;
+}
+
+int ogrecu_tex_download(ogrecu_tex* t, uint8_t* rgba, size_t pitch)
+{
+    OGRECU_REQUIRE(t && rgba, "NULL argument");
+    OGRECU_REQUIRE(pitch >= (size_t)t->w * 4, "row pitch smaller than a row");
+    ogrecu_ctx* ctx = t->ctx;
+    OGRECU_CUDA(cudaSetDevice(ctx->device));
+    const size_t row = (size_t)t->w * 4, bytes = row * t->h;
+    OGRECU_CHECK(pinned_reserve(ctx, bytes));
+    OGRECU_CUDA(cudaMemcpyAsync(ctx->pinned, t->dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    OGRECU_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (uint32_t y = 0; y < t->h; ++y) memcpy(rgba + y * pitch, (uint8_t*)ctx->pinned + y * row, row);
+    return OGRECU_OK;
+}
+
+int ogrecu_tex_device_ptr(ogrecu_tex* t, void** dev_ptr)
+{
+    OGRECU_REQUIRE(t && dev_ptr, "NULL argument");
+    *dev_ptr = t->dev;
+    return OGRECU_OK;
+}
+
+/* ---- render targets ---- */
+
+int ogrecu_rt_create(ogrecu_ctx* ctx, uint32_t w, uint32_t h, ogrecu_rt** out)
+{
+    OGRECU_REQUIRE(ctx && out, "NULL argument");
+    OGRECU_REQUIRE(w >= 1 && h >= 1 && w <= 32768 && h <= 32768, "render target size out of range");
+    *out = nullptr;
+    OGRECU_CUDA(cudaSetDevice(ctx->device));
+    ogrecu_rt* rt = new ogrecu_rt();
+    rt->ctx = ctx; rt->w = w; rt->h = h; rt->colour = nullptr; rt->depth = nullptr;
+    rt->strip_y0 = 0; rt->strip_y1 = h;
+    memset(&rt->stats, 0, sizeof rt->stats);
+    const size_t npx = (size_t)w * h;
+    cudaError_t e = cudaMalloc((void**)&rt->colour, npx * 3 + 16);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&rt->depth, npx * 4 + 16);
+    if (e == cudaSuccess) e = cudaMemsetAsync(rt->colour, 0, npx * 3 + 16, ctx->stream);    // Image::create zero-fills
+    if (e == cudaSuccess) e = cudaMemsetAsync(rt->depth, 0, npx * 4 + 16, ctx->stream);
+    if (e != cudaSuccess) { cudaFree(rt->colour); cudaFree(rt->depth); delete rt; return cuda_fail(e, "render target allocation", __FILE__, __LINE__); }
+    ctx->targets.push_back(rt);
+    *out = rt;
+    return OGRECU_OK;
+}
+
+int ogrecu_rt_destroy(ogrecu_rt* rt) { return rt_release(rt); }
+
+int ogrecu_rt_size(const ogrecu_rt* rt, uint32_t* w, uint32_t* h)
+{
+    OGRECU_REQUIRE(rt && w && h, "NULL argument");
+    *w = rt->w; *h = rt->h;
+    return OGRECU_OK;
+}
+
+int ogrecu_rt_clear(ogrecu_rt* rt, unsigned buffers, const float colour_rgba[4], float depth)
+{
+    OGRECU_REQUIRE(rt, "rt is NULL");
+    OGRECU_REQUIRE(!(buffers & OGRECU_CLEAR_COLOUR) || colour_rgba, "colour is NULL");
+    Cmd c;
+    memset(&c, 0, sizeof c);
+    c.kind = 1;
+    c.clear_buffers = buffers;
+    if (colour_rgba) memcpy(c.clear_colour, colour_rgba, 16);
+    c.clear_depth = depth;
+    // a clear of both planes makes everything recorded before it dead
+    if ((buffers & (OGRECU_CLEAR_COLOUR | OGRECU_CLEAR_DEPTH)) == (OGRECU_CLEAR_COLOUR | OGRECU_CLEAR_DEPTH)) rt->cmds.clear();
+    rt->cmds.push_back(c);
+    return OGRECU_OK;
+}
+
+int ogrecu_draw(ogrecu_rt* rt, const ogrecu_draw_desc* d)
+{
+    OGRECU_REQUIRE(rt && d, "NULL argument");
+    if (d->prim_type != OGRECU_PRIM_TRIANGLE_LIST && d->prim_type != OGRECU_PRIM_TRIANGLE_STRIP) {
+        // TinyRenderSystem::_render silently ignores other operation types (.cpp:354-357)
+        return OGRECU_OK;
+    }
+    OGRECU_REQUIRE(d->positions, "VES_POSITION required");   // OgreAssert in the reference (.cpp:361)
+    OGRECU_REQUIRE(d->index_type == OGRECU_INDEX_NONE || d->index_type == OGRECU_INDEX_U16 || d->index_type == OGRECU_INDEX_U32, "bad index type");
+    OGRECU_REQUIRE(d->index_type == OGRECU_INDEX_NONE || d->indices, "indices are NULL");
+    OGRECU_REQUIRE(((d->pos_stride | d->uv_stride | d->normal_stride | (uintptr_t)d->positions | (uintptr_t)d->uvs | (uintptr_t)d->normals) & 3) == 0,
+                   "vertex streams must be 4-byte aligned");
+    OGRECU_REQUIRE(!d->texture || d->texture->ctx == rt->ctx, "texture belongs to another context");
+    if (tri_count_of(*d) == 0) return OGRECU_OK;
+    Cmd c;
+    memset(&c, 0, sizeof c);
+    c.kind = 0;
+    c.draw = *d;
+    rt->cmds.push_back(c);
+    return OGRECU_OK;
+}
+
+int ogrecu_flush(ogrecu_rt* rt)
+{
+    OGRECU_REQUIRE(rt, "rt is NULL");
+    if (rt->cmds.empty()) return OGRECU_OK;
+    return rt_flush_cmds(rt);
+}
+
+int ogrecu_draw_views(ogrecu_rt* const* rts, uint32_t n_views, const ogrecu_draw_desc* desc, const float* per_view_mvp,
+                      const float* per_view_mvit, const float* per_view_light_dir)
+{
+    OGRECU_REQUIRE(rts && desc && per_view_mvp, "NULL argument");
+    if (n_views == 0) return OGRECU_OK;
+    ogrecu_ctx* ctx = rts[0]->ctx;
+    for (uint32_t v = 0; v < n_views; ++v) {
+        OGRECU_REQUIRE(rts[v] && rts[v]->ctx == ctx, "targets must share one context");
+        OGRECU_REQUIRE(rts[v]->w == rts[0]->w && rts[v]->h == rts[0]->h, "targets must have identical size");
+        OGRECU_REQUIRE(rts[v]->strip_y0 == rts[0]->strip_y0 && rts[v]->strip_y1 == rts[0]->strip_y1, "targets must share the strip");
+        OGRECU_CHECK(ogrecu_flush(rts[v]));   // earlier clears / draws on each target come first
+    }
+    OGRECU_CUDA(cudaSetDevice(ctx->device));
+    if (desc->prim_type != OGRECU_PRIM_TRIANGLE_LIST && desc->prim_type != OGRECU_PRIM_TRIANGLE_STRIP) return OGRECU_OK;
+    OGRECU_REQUIRE(desc->positions, "VES_POSITION required");
+    std::vector<Item> items(n_views);
+    for (uint32_t v = 0; v < n_views; ++v)
+        items[v] = {desc, v, per_view_mvp + 16 * v, per_view_mvit ? per_view_mvit + 16 * v : nullptr,
+                    per_view_light_dir ? per_view_light_dir + 3 * v : nullptr};
+    return run_segment(ctx, rts, n_views, items);
+}
+
+int ogrecu_rt_set_strip(ogrecu_rt* rt, uint32_t y0, uint32_t y1)
+{
+    OGRECU_REQUIRE(rt, "rt is NULL");
+    OGRECU_REQUIRE(y0 % TILE == 0 && (y1 % TILE == 0 || y1 >= rt->h) && y0 <= y1, "strip rows must be multiples of the tile height");
+    OGRECU_CHECK(ogrecu_flush(rt));
+    rt->strip_y0 = std::min(y0, rt->h);
+    rt->strip_y1 = std::min(y1, rt->h);
+    return OGRECU_OK;
+}
+
+static int read_plane(ogrecu_rt* rt, const uint8_t* plane, size_t px_bytes, uint32_t l, uint32_t t, uint32_t r, uint32_t b,
+                      uint8_t* dst, size_t pitch)
+{
+    // validation mirrors TinyWindow::copyContentsToMemory (OgreTinyWindow.cpp:73-77)
+    OGRECU_REQUIRE(r <= rt->w && b <= rt->h && l <= r && t <= b, "Invalid box");
+    ogrecu_ctx* ctx = rt->ctx;
+    OGRECU_CHECK(ogrecu_flush(rt));
+    const size_t row = (size_t)(r - l) * px_bytes, rows = b - t;
+    if (!row || !rows) return OGRECU_OK;
+    OGRECU_REQUIRE(dst && pitch >= row, "bad destination");
+    OGRECU_CHECK(pinned_reserve(ctx, row * rows));
+    OGRECU_CUDA(cudaMemcpy2DAsync(ctx->pinned, row, plane + ((size_t)t * rt->w + l) * px_bytes, (size_t)rt->w * px_bytes, row, rows,
+                                  cudaMemcpyDeviceToHost, ctx->stream));
+    OGRECU_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (pitch == row) memcpy(dst, ctx->pinned, row * rows);
+    else for (size_t y = 0; y < rows; ++y) memcpy(dst + y * pitch, (uint8_t*)ctx->pinned + y * row, row);
+    return OGRECU_OK;
+}
+
+int ogrecu_rt_read_colour(ogrecu_rt* rt, uint32_t l, uint32_t t, uint32_t r, uint32_t b, uint8_t* dst, size_t pitch)
+{
+    OGRECU_REQUIRE(rt, "rt is NULL");
+    return read_plane(rt, rt->colour, 3, l, t, r, b, dst, pitch);
+}
+
+int ogrecu_rt_read_depth(ogrecu_rt* rt, uint32_t l, uint32_t t, uint32_t r, uint32_t b, float* dst, size_t pitch)
+{
+    OGRECU_REQUIRE(rt, "rt is NULL");
+    return read_plane(rt, (const uint8_t*)rt->depth, 4, l, t, r, b, (uint8_t*)dst, pitch);
+}
+
+static int write_plane(ogrecu_rt* rt, uint8_t* plane, size_t px_bytes, const uint8_t* src, size_t pitch)
+{
+    ogrecu_ctx* ctx = rt->ctx;
+    OGRECU_CHECK(ogrecu_flush(rt));
+    const size_t row = (size_t)rt->w * px_bytes;
+    OGRECU_REQUIRE(src && pitch >= row, "bad source");
+    OGRECU_CHECK(pinned_reserve(ctx, row * rt->h));
+    OGRECU_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (size_t y = 0; y < rt->h; ++y) memcpy((uint8_t*)ctx->pinned + y * row, src + y * pitch, row);
+    OGRECU_CUDA(cudaMemcpyAsync(plane, ctx->pinned, row * rt->h, cudaMemcpyHostToDevice, ctx->stream));
+    return OGRECU_OK;
+}
+
+int ogrecu_rt_write_colour(ogrecu_rt* rt, const uint8_t* src, size_t pitch)
+{
+    OGRECU_REQUIRE(rt, "rt is NULL");
+    return write_plane(rt, rt->colour, 3, src, pitch);
+}
+
+int ogrecu_rt_write_depth(ogrecu_rt* rt, const float* src, size_t pitch)
+{
+    OGRECU_REQUIRE(rt, "rt is NULL");
+    return write_plane(rt, (uint8_t*)rt->depth, 4, (const uint8_t*)src, pitch);
+}
+
+int ogrecu_rt_colour_device_ptr(ogrecu_rt* rt, void** p)
+{
+    OGRECU_REQUIRE(rt && p, "NULL argument");
+    *p = rt->colour;
+    return OGRECU_OK;
+}
+
+int ogrecu_rt_depth_device_ptr(ogrecu_rt* rt, void** p)
+{
+    OGRECU_REQUIRE(rt && p, "NULL argument");
+    *p = rt->depth;
+    return OGRECU_OK;
+}
+
+int ogrecu_rt_last_stats(ogrecu_rt* rt, ogrecu_raster_stats* out)
+{
+    OGRECU_REQUIRE(rt && out, "NULL argument");
+    *out = rt->stats;
+    return OGRECU_OK;
+}
+
+}  // extern "C"

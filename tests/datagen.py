@@ -124,3 +124,193 @@ def bits(a):
     b = a.view(np.uint32).copy()
     b[b == 0x80000000] = 0
     return b
+
+
+# ------------------------------------------------------------------ raster scenes ------
+
+def perspective(fovy_deg, aspect, near, far):
+    """OpenGL-style projection, depth range [-1,1] (TinyRenderSystem keeps OGRE's GL convention,
+    include/OgreTinyRenderSystem.h:90-92)."""
+    f = 1.0 / np.tan(np.radians(fovy_deg) / 2)
+    m = np.zeros((4, 4), dtype=np.float64)
+    m[0, 0] = f / aspect; m[1, 1] = f
+    m[2, 2] = -(far + near) / (far - near); m[2, 3] = -2 * far * near / (far - near)
+    m[3, 2] = -1
+    return m
+
+
+def look_at(eye, target, up=(0, 1, 0)):
+    eye = np.asarray(eye, float); target = np.asarray(target, float); up = np.asarray(up, float)
+    f = target - eye; f /= np.linalg.norm(f)
+    s = np.cross(f, up); s /= np.linalg.norm(s)
+    u = np.cross(s, f)
+    m = np.eye(4)
+    m[0, :3], m[1, :3], m[2, :3] = s, u, -f
+    m[:3, 3] = -m[:3, :3] @ eye
+    return m
+
+
+def viewport_matrix(w, h, left=0, top=0):
+    """mVP of TinyRenderSystem::_setViewport for a flipping target (OgreTinyRenderSystem.cpp:257-258)."""
+    m = np.zeros((4, 4), dtype=np.float32)
+    m[0, 0] = np.float32(w) / np.float32(2); m[0, 3] = np.float32(left) + np.float32(w) / np.float32(2)
+    m[1, 1] = np.float32(h) / np.float32(2); m[1, 3] = np.float32(top) + np.float32(h) / np.float32(2)
+    m[2, 2] = 0.5; m[2, 3] = 0.5
+    m[3, 3] = 1
+    return m
+
+
+def random_texture(rng, w, h, zero_alpha=False):
+    t = rng.integers(0, 256, size=(h, w, 4), dtype=np.uint8)
+    t[..., 3] = 255
+    if zero_alpha:
+        hole = rng.random((h, w)) < 0.3
+        t[hole, 3] = 0
+    return t
+
+
+class DrawCase:
+    """One _render call: interleaved vertex buffer (pos f3 @0, normal f3 @12, uv f2 @24, stride 32 —
+    ogrehead's layout) + indices + state + uniforms."""
+
+    def __init__(self, verts, indices=None, index_type=4, strip=False, texture=None, lighting=True,
+                 depth_test=True, depth_write=True, blend_add=False, mvp=None, mvit=None, tex_matrix=None,
+                 viewport=None, light_dir=(0.3, 0.5, 0.8), ambient=(0.2, 0.25, 0.3, 1.0),
+                 has_uv=True, has_normals=True):
+        self.verts = np.ascontiguousarray(verts, dtype=np.float32)      # [n, 8]
+        if indices is None:
+            self.index_type, self.indices = 0, None
+            self.draw_count = len(self.verts)
+        else:
+            self.index_type = index_type
+            self.indices = np.ascontiguousarray(indices, dtype=np.uint16 if index_type == 2 else np.uint32)
+            self.draw_count = len(self.indices)
+        self.strip, self.texture = strip, texture
+        self.lighting, self.depth_test, self.depth_write, self.blend_add = lighting, depth_test, depth_write, blend_add
+        self.mvp = np.ascontiguousarray(mvp, dtype=np.float32)
+        self.mvit = np.ascontiguousarray(np.eye(4) if mvit is None else mvit, dtype=np.float32)
+        self.tex_matrix = np.ascontiguousarray(np.eye(4) if tex_matrix is None else tex_matrix, dtype=np.float32)
+        self.viewport = np.ascontiguousarray(viewport, dtype=np.float32)
+        l = np.asarray(light_dir, dtype=np.float64)
+        self.light_dir = (l / np.linalg.norm(l)).astype(np.float32)
+        self.ambient = np.asarray(ambient, dtype=np.float32)
+        self.has_uv, self.has_normals = has_uv, has_normals
+
+    def oracle_desc(self):
+        import oracle
+        d = oracle.OracleDraw()
+        base = self.verts.ctypes.data
+        d.positions, d.pos_stride = base, 32
+        d.normals, d.normal_stride = (base + 12, 32) if self.has_normals else (None, 0)
+        d.uvs, d.uv_stride = (base + 24, 32) if self.has_uv else (None, 0)
+        d.indices = self.indices.ctypes.data if self.indices is not None else None
+        d.index_type, d.draw_count, d.is_strip = self.index_type, self.draw_count, int(self.strip)
+        d.depth_test, d.depth_write, d.blend_add = int(self.depth_test), int(self.depth_write), int(self.blend_add)
+        d.lighting = int(self.lighting and self.has_normals)
+        if self.texture is not None:
+            d.tex_rgba, d.tex_w, d.tex_h = self.texture.ctypes.data, self.texture.shape[1], self.texture.shape[0]
+        d.mvp[:] = self.mvp.reshape(16); d.tex_matrix[:] = self.tex_matrix.reshape(16)
+        d.mvit[:] = self.mvit.reshape(16); d.viewport[:] = self.viewport.reshape(16)
+        d.light_dir[:] = self.light_dir; d.ambient[:] = self.ambient
+        return d
+
+
+def random_soup(rng, ntri, spread=3.0, size=1.0, strip=False, indexed=True):
+    """Random triangles around the origin; returns (verts[n,8], indices or None)."""
+    if strip:
+        nv = ntri + 2
+        p = np.cumsum(rng.normal(scale=size * 0.4, size=(nv, 3)), axis=0) + rng.uniform(-spread, spread, size=3)
+        idx = np.arange(nv)
+    else:
+        c = rng.uniform(-spread, spread, size=(ntri, 1, 3))
+        p = (c + rng.normal(scale=size, size=(ntri, 3, 3))).reshape(-1, 3)
+        nv = len(p)
+        idx = np.arange(nv)
+        if indexed:   # share some vertices between triangles
+            share = rng.random(nv) < 0.3
+            idx[share] = rng.integers(0, nv, size=share.sum())
+    n = rng.normal(size=(nv, 3)); n /= np.linalg.norm(n, axis=1, keepdims=True)
+    uv = rng.uniform(-1.5, 2.5, size=(nv, 2))
+    verts = np.concatenate([p, n, uv], axis=1).astype(np.float32)
+    return verts, (idx if indexed else None)
+
+
+def make_scene(seed, w, h, ndraws=4, ntri=200, **kw):
+    """A list of DrawCase with assorted state covering every Tiny code path."""
+    rng = np.random.default_rng(seed)
+    proj = perspective(50, w / h, 0.5, 100.0)
+    view = look_at(rng.uniform(-2, 2, 3) + np.array([0, 0, 9.0]), rng.uniform(-1, 1, 3))
+    vp = viewport_matrix(w, h)
+    texs = [random_texture(rng, 37, 19), random_texture(rng, 64, 64, zero_alpha=True), None]
+    cases = []
+    for k in range(ndraws):
+        strip = kw.get("strip", k % 4 == 3)
+        index_type = kw.get("index_type", 2 if k % 2 else 4)
+        verts, idx = random_soup(rng, ntri, size=kw.get("size", 1.0), strip=strip, indexed=kw.get("indexed", k % 3 != 2))
+        if idx is not None and index_type == 2 and len(verts) > 65535:
+            index_type = 4
+        model = np.eye(4); model[:3, 3] = rng.uniform(-1, 1, 3)
+        mv = view @ model
+        mvp = (proj @ mv).astype(np.float32)
+        mvit = np.linalg.inv(mv).T.astype(np.float32)
+        texm = np.eye(4, dtype=np.float32)
+        if k % 2:
+            texm[0, 0], texm[1, 1], texm[0, 3] = 5.0, 5.0, 0.25      # Ogre/Tusks-style "scale 0.2 0.2"
+        cases.append(DrawCase(
+            verts, idx, index_type=index_type, strip=strip,
+            texture=kw.get("texture", texs[k % 3]), lighting=kw.get("lighting", k % 3 != 1),
+            depth_test=kw.get("depth_test", k != 2 or ndraws < 3), depth_write=kw.get("depth_write", k % 5 != 4),
+            blend_add=kw.get("blend_add", k % 4 == 1), mvp=mvp, mvit=mvit, tex_matrix=texm, viewport=vp,
+            light_dir=rng.normal(size=3), ambient=np.append(rng.uniform(0, 0.5, 3), 1.0)))
+    return cases
+
+
+def degenerate_soup(rng, w, h):
+    """Clip-space triangles [n,3,4] hitting Tiny's corner cases: slivers with |det| <= 1e-6,
+    coincident vertices, shared edges, equal depth, w < 0, partly/fully off-screen, axis-aligned
+    zero-area lines through integer pixels, negative depth."""
+    tris = []
+
+    def ndc(x, y, z=0.0, wv=1.0):
+        return [(x / w * 2 - 1) * wv, (y / h * 2 - 1) * wv, z * wv, wv]
+    tris += [[ndc(10, 10, .2), ndc(60, 10, .2), ndc(10, 60, .2)], [ndc(60, 10, .2), ndc(60, 60, .2), ndc(10, 60, .2)]]
+    tris += [[ndc(10, 10, .2), ndc(10, 60, .2), ndc(60, 10, .2)]]
+    tris += [[ndc(30, 30), ndc(30, 30), ndc(30, 30)]]
+    tris += [[ndc(5, 40), ndc(50, 40), ndc(50, 40)], [ndc(70, 5), ndc(70, 5), ndc(70, 90)], [ndc(0, 0), ndc(20, 20), ndc(40, 40)]]
+    for k in range(40):
+        x, y = rng.uniform(0, w), rng.uniform(0, h)
+        d = rng.normal(size=2) * rng.uniform(1, 80)
+        e = rng.normal(size=2) * 1e-4
+        tris += [[ndc(x, y, .5), ndc(x + d[0], y + d[1], .5), ndc(x + d[0] / 2 + e[0], y + d[1] / 2 + e[1], .5)]]
+    tris += [[ndc(20, 20, .1, -1.0), ndc(90, 25, .1, -1.0), ndc(40, 80, .1, -1.0)],
+             [ndc(20, 20, .1, 1.0), ndc(90, 25, .1, -0.5), ndc(40, 80, .1, 2.0)]]
+    tris += [[ndc(-50, -50), ndc(-10, -50), ndc(-50, -10)], [ndc(-30, 20, .3), ndc(w + 40, 50, .3), ndc(40, h + 60, .3)],
+             [ndc(-0.5, 10), ndc(-0.2, 30), ndc(-0.9, 50)]]
+    tris += [[ndc(50, 50, -1.5), ndc(90, 50, -1.5), ndc(50, 90, -1.5)], [ndc(55, 55, 1.5), ndc(95, 55, 1.5), ndc(55, 95, 1.5)]]
+    return np.array(tris, dtype=np.float64)
+
+
+def clip_case(clip_tris, w, h, **kw):
+    """DrawCases from clip-space triangles [n,3,4].  A vertex is stored as (xc, yc, wc) and drawn with an
+    MVP that yields clip = (x, y, ratio*w, w); consecutive triangles with the same depth ratio zc/wc
+    share a draw, so submission order is kept."""
+    a = np.asarray(clip_tris, dtype=np.float64)
+    ratios = np.round(a[:, 0, 2] / a[:, 0, 3], 6)
+    spans, start = [], 0
+    for i in range(1, len(a) + 1):
+        if i == len(a) or ratios[i] != ratios[start]:
+            spans.append((start, i)); start = i
+    vp = viewport_matrix(w, h)
+    rng = np.random.default_rng(11)
+    cases = []
+    for (s, e) in spans:
+        t = a[s:e]
+        nv = (e - s) * 3
+        pos = np.stack([t[..., 0].reshape(-1), t[..., 1].reshape(-1), t[..., 3].reshape(-1)], axis=1)
+        n = rng.normal(size=(nv, 3)); n /= np.linalg.norm(n, axis=1, keepdims=True)
+        uv = rng.uniform(0, 1, size=(nv, 2))
+        verts = np.concatenate([pos, n, uv], axis=1).astype(np.float32)
+        mvp = np.zeros((4, 4), dtype=np.float32)
+        mvp[0, 0] = 1; mvp[1, 1] = 1; mvp[2, 2] = ratios[s]; mvp[3, 2] = 1
+        cases.append(DrawCase(verts, None, mvp=mvp, viewport=vp, **kw))
+    return cases
