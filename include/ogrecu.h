@@ -137,11 +137,14 @@ typedef struct ogrecu_skin_job {
 OGRECU_API int ogrecu_skin_dev(ogrecu_ctx* ctx, const ogrecu_skin_job* jobs, uint32_t n);
 
 /* Instanced form of the same job (config 2: 10 000 animated instances of one mesh):
- * instance i reads the shared source/blend streams and palette
- * `palettes + i*palette_stride_floats`, and writes dst + i*dst_instance_stride bytes. */
+ * instance i reads the shared blend streams, the source streams at
+ * src + i*src_instance_stride_bytes (0 = one shared bind pose; non-zero = per-instance
+ * morphed source, Entity::updateAnimation OgreEntity.cpp:823-864), palette
+ * `palettes + i*palette_stride_floats`, and writes dst + i*dst_instance_stride_bytes. */
 OGRECU_API int ogrecu_skin_instanced_dev(ogrecu_ctx* ctx, const ogrecu_skin_job* job,
                                          uint32_t num_instances,
                                          size_t palette_stride_floats,
+                                         size_t src_instance_stride_bytes,
                                          size_t dst_instance_stride_bytes);
 
 /* Exact-signature host form (what CudaOptimisedUtil::softwareVertexSkinning forwards to):
@@ -164,6 +167,12 @@ OGRECU_API int ogrecu_software_vertex_skinning_host(
 OGRECU_API int ogrecu_morph_dev(ogrecu_ctx* ctx, float t, const float* src1, const float* src2, float* dst,
                                 size_t stride1, size_t stride2, size_t dst_stride,
                                 size_t num_vertices, int morph_normals);
+/* Instanced morph: instance i writes dst + i*dst_instance_stride_bytes = lerp(src1, src2, t[i])
+ * from two shared keyframes; `t_dev` is a DEVICE array of num_instances floats. */
+OGRECU_API int ogrecu_morph_instanced_dev(ogrecu_ctx* ctx, const float* t_dev, const float* src1, const float* src2,
+                                          float* dst, size_t stride1, size_t stride2, size_t dst_stride,
+                                          size_t num_vertices, int morph_normals, uint32_t num_instances,
+                                          size_t dst_instance_stride_bytes);
 OGRECU_API int ogrecu_software_vertex_morph_host(ogrecu_ctx* ctx, float t, const float* src1, const float* src2,
                                                  float* dst, size_t stride1, size_t stride2, size_t dst_stride,
                                                  size_t num_vertices, int morph_normals);

@@ -135,16 +135,20 @@ __global__ void __launch_bounds__(SKIN_THREADS) skin_batched_kernel(const ogrecu
 }
 
 // instanced: blockIdx.y = instance; shared source/blend streams, per-instance palette + destination
-__global__ void __launch_bounds__(SKIN_THREADS) skin_instanced_kernel(const __grid_constant__ ogrecu_skin_job j,
-                                                                      size_t palette_stride_floats, size_t dst_instance_stride)
+__global__ void __launch_bounds__(SKIN_THREADS) skin_instanced_kernel(const __grid_constant__ ogrecu_skin_job j0,
+                                                                      size_t palette_stride_floats, size_t src_instance_stride,
+                                                                      size_t dst_instance_stride)
 {
     __shared__ float4 pal[SKIN_MAX_MATRICES * 3];
     const uint32_t inst = blockIdx.y;
-    load_palette(pal, j.palette + (size_t)inst * palette_stride_floats, j.bone_map, j.num_matrices);
+    load_palette(pal, j0.palette + (size_t)inst * palette_stride_floats, j0.bone_map, j0.num_matrices);
     __syncthreads();
     uint32_t v = blockIdx.x * SKIN_THREADS + threadIdx.x;
-    float* dp = byte_off(j.dst_pos, (size_t)inst * dst_instance_stride);
-    float* dn = j.dst_norm ? byte_off(j.dst_norm, (size_t)inst * dst_instance_stride) : nullptr;
+    ogrecu_skin_job j = j0;
+    j.src_pos = byte_off(j0.src_pos, (size_t)inst * src_instance_stride);
+    if (j0.src_norm) j.src_norm = byte_off(j0.src_norm, (size_t)inst * src_instance_stride);
+    float* dp = byte_off(j0.dst_pos, (size_t)inst * dst_instance_stride);
+    float* dn = j0.dst_norm ? byte_off(j0.dst_norm, (size_t)inst * dst_instance_stride) : nullptr;
     skin_block(j, pal, dp, dn, v);
 }
 
@@ -216,6 +220,63 @@ __global__ void morph_dense_normals_kernel(float t, const float4* __restrict__ s
     }
 #pragma unroll
     for (int k = 0; k < 3; ++k) __stcs(d + 3 * i + k, make_float4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]));
+}
+
+// instanced morph from two shared keyframes; blockIdx.y = instance, t read per instance.
+// Dense pos+normal (stride 24, 16-byte aligned): two vertices = three float4 per thread.
+template <bool NORMALS, bool DENSE>
+__global__ void morph_instanced_kernel(const float* __restrict__ tarr, const float* __restrict__ s1, const float* __restrict__ s2,
+                                       float* __restrict__ d0, size_t st1, size_t st2, size_t std_, size_t n, size_t dst_inst_stride)
+{
+    const float t = __ldg(tarr + blockIdx.y);
+    float* d = byte_off(d0, (size_t)blockIdx.y * dst_inst_stride);
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (DENSE) {
+        // unit = 12 floats (pos-only: 4 vertices; pos+normal: 2 vertices)
+        const size_t units = NORMALS ? n / 2 : n / 4;
+        if (i < units) {
+            const float4* a4 = reinterpret_cast<const float4*>(s1) + 3 * i;
+            const float4* b4 = reinterpret_cast<const float4*>(s2) + 3 * i;
+            float a[12], b[12], o[12];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                float4 va = __ldg(a4 + k), vb = __ldg(b4 + k);
+                a[4 * k] = va.x; a[4 * k + 1] = va.y; a[4 * k + 2] = va.z; a[4 * k + 3] = va.w;
+                b[4 * k] = vb.x; b[4 * k + 1] = vb.y; b[4 * k + 2] = vb.z; b[4 * k + 3] = vb.w;
+            }
+#pragma unroll
+            for (int k = 0; k < 12; ++k) o[k] = fadd(a[k], fmul(t, fsub(b[k], a[k])));
+            if (NORMALS) {
+#pragma unroll
+                for (int v = 0; v < 2; ++v) {
+                    float n0 = o[6 * v + 3], n1 = o[6 * v + 4], n2 = o[6 * v + 5];
+                    float len = fsqrt(fadd(fadd(fadd(0.0f, fmul(n0, n0)), fmul(n1, n1)), fmul(n2, n2)));
+                    if (len > 0.0f) { float inv = fdiv(1.0f, len); o[6 * v + 3] = fmul(n0, inv); o[6 * v + 4] = fmul(n1, inv); o[6 * v + 5] = fmul(n2, inv); }
+                }
+            }
+            float4* o4 = reinterpret_cast<float4*>(d) + 3 * i;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) __stcs(o4 + k, make_float4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]));
+            return;
+        }
+        // leftover vertices (n % 2 or n % 4) fall through to the strided form on the last threads
+        const size_t done = units * (NORMALS ? 2 : 4);
+        i = done + (i - units);
+        if (i >= n) return;
+    } else if (i >= n) return;
+    const float* a = byte_off(s1, i * st1);
+    const float* b = byte_off(s2, i * st2);
+    float* o = byte_off(d, i * std_);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) o[k] = fadd(a[k], fmul(t, fsub(b[k], a[k])));
+    if (NORMALS) {
+        float n0 = fadd(a[3], fmul(t, fsub(b[3], a[3])));
+        float n1 = fadd(a[4], fmul(t, fsub(b[4], a[4])));
+        float n2 = fadd(a[5], fmul(t, fsub(b[5], a[5])));
+        float len = fsqrt(fadd(fadd(fadd(0.0f, fmul(n0, n0)), fmul(n1, n1)), fmul(n2, n2)));
+        if (len > 0.0f) { float inv = fdiv(1.0f, len); n0 = fmul(n0, inv); n1 = fmul(n1, inv); n2 = fmul(n2, inv); }
+        o[3] = n0; o[4] = n1; o[5] = n2;
+    }
 }
 
 /* -------------------------------------------------------------- concatenate (K8) --- */
@@ -396,8 +457,9 @@ int ogrecu_skin_dev(ogrecu_ctx* ctx, const ogrecu_skin_job* jobs, uint32_t n)
 }
 
 int ogrecu_skin_instanced_dev(ogrecu_ctx* ctx, const ogrecu_skin_job* job, uint32_t num_instances,
-                              size_t palette_stride_floats, size_t dst_instance_stride_bytes)
+                              size_t palette_stride_floats, size_t src_instance_stride_bytes, size_t dst_instance_stride_bytes)
 {
+    OGRECU_REQUIRE((src_instance_stride_bytes & 3) == 0, "source instance stride must be a multiple of 4");
     OGRECU_REQUIRE(ctx && job, "NULL argument");
     OGRECU_CHECK(validate_skin_job(*job));
     OGRECU_REQUIRE((palette_stride_floats & 3) == 0, "palette stride must keep 16-byte alignment");
@@ -406,7 +468,7 @@ int ogrecu_skin_instanced_dev(ogrecu_ctx* ctx, const ogrecu_skin_job* job, uint3
     if (num_instances == 0 || job->num_vertices == 0) return OGRECU_OK;
     OGRECU_CUDA(cudaSetDevice(ctx->device));
     dim3 grid(div_up(job->num_vertices, SKIN_THREADS), num_instances);
-    skin_instanced_kernel<<<grid, SKIN_THREADS, 0, ctx->stream>>>(*job, palette_stride_floats, dst_instance_stride_bytes);
+    skin_instanced_kernel<<<grid, SKIN_THREADS, 0, ctx->stream>>>(*job, palette_stride_floats, src_instance_stride_bytes, dst_instance_stride_bytes);
     OGRECU_CUDA(cudaGetLastError());
     count_launch(ctx);
     return OGRECU_OK;
@@ -458,6 +520,36 @@ int ogrecu_morph_dev(ogrecu_ctx* ctx, float t, const float* src1, const float* s
     unsigned blocks = div_up(num_vertices, 256);
     if (morph_normals) morph_strided_kernel<true><<<blocks, 256, 0, ctx->stream>>>(t, src1, src2, dst, stride1, stride2, dst_stride, num_vertices);
     else morph_strided_kernel<false><<<blocks, 256, 0, ctx->stream>>>(t, src1, src2, dst, stride1, stride2, dst_stride, num_vertices);
+    OGRECU_CUDA(cudaGetLastError());
+    count_launch(ctx);
+    return OGRECU_OK;
+}
+
+int ogrecu_morph_instanced_dev(ogrecu_ctx* ctx, const float* t_dev, const float* src1, const float* src2, float* dst,
+                               size_t stride1, size_t stride2, size_t dst_stride, size_t n, int morph_normals,
+                               uint32_t num_instances, size_t dst_instance_stride_bytes)
+{
+    OGRECU_REQUIRE(ctx, "ctx is NULL");
+    if (n == 0 || num_instances == 0) return OGRECU_OK;
+    OGRECU_REQUIRE(t_dev && src1 && src2 && dst, "NULL pointer");
+    OGRECU_REQUIRE(num_instances <= 65535, "at most 65535 instances per call");
+    const size_t need = morph_normals ? 24 : 12;
+    OGRECU_REQUIRE(stride1 >= need && stride2 >= need && dst_stride >= need, "stride smaller than the vertex");
+    OGRECU_REQUIRE(((stride1 | stride2 | dst_stride | dst_instance_stride_bytes | (uintptr_t)src1 | (uintptr_t)src2 | (uintptr_t)dst) & 3) == 0,
+                   "streams must be 4-byte aligned");
+    OGRECU_CUDA(cudaSetDevice(ctx->device));
+    const bool dense = stride1 == need && stride2 == need && dst_stride == need && aligned16(src1) && aligned16(src2) &&
+                       aligned16(dst) && (dst_instance_stride_bytes & 15) == 0;
+    size_t threads_needed = n;
+    if (dense) { size_t per = morph_normals ? 2 : 4; threads_needed = n / per + n % per; }
+    dim3 grid(div_up(threads_needed, 256), num_instances);
+    if (dense) {
+        if (morph_normals) morph_instanced_kernel<true, true><<<grid, 256, 0, ctx->stream>>>(t_dev, src1, src2, dst, stride1, stride2, dst_stride, n, dst_instance_stride_bytes);
+        else morph_instanced_kernel<false, true><<<grid, 256, 0, ctx->stream>>>(t_dev, src1, src2, dst, stride1, stride2, dst_stride, n, dst_instance_stride_bytes);
+    } else {
+        if (morph_normals) morph_instanced_kernel<true, false><<<grid, 256, 0, ctx->stream>>>(t_dev, src1, src2, dst, stride1, stride2, dst_stride, n, dst_instance_stride_bytes);
+        else morph_instanced_kernel<false, false><<<grid, 256, 0, ctx->stream>>>(t_dev, src1, src2, dst, stride1, stride2, dst_stride, n, dst_instance_stride_bytes);
+    }
     OGRECU_CUDA(cudaGetLastError());
     count_launch(ctx);
     return OGRECU_OK;

@@ -191,7 +191,7 @@ int ogrecu_software_vertex_skinning_host(ogrecu_ctx* ctx, const float* src_pos, 
     j.src_norm_stride = (uint32_t)src_norm_stride; j.dst_norm_stride = (uint32_t)dst_norm_stride;
     j.blend_weight_stride = (uint32_t)blend_weight_stride; j.blend_index_stride = (uint32_t)blend_index_stride;
     j.num_weights = (uint32_t)nw; j.num_matrices = nmat; j.num_vertices = (uint32_t)n;
-    OGRECU_CHECK(ogrecu_skin_instanced_dev(ctx, &j, 1, 0, 0));
+    OGRECU_CHECK(ogrecu_skin_instanced_dev(ctx, &j, 1, 0, 0, 0));
     return st.finish();
 }
 

@@ -1,0 +1,608 @@
+// ref_driver.cpp — drives the UNMODIFIED reference (compiled by oracle/build_ref.py) for the
+// tests and for bench.py's reference arm.  TEST INFRASTRUCTURE ONLY: the product never links
+// or loads this.
+//
+// What it exposes (plain C, loaded with ctypes):
+//   * ref_skin/ref_morph/...   the real Ogre::OptimisedUtil implementations: SSE is the object
+//                              OptimisedUtil::getImplementation() returns in stock libOgreMain.so;
+//                              General is OgreMain/src/OgreOptimisedUtilGeneral.cpp compiled into
+//                              this driver from where it lies (its accessor is hidden in the .so).
+//   * ref_tiny_*               the real TinyRenderSystem: RenderSystems/Tiny/src/*.cpp are compiled
+//                              into this driver (with -fno-access-control so a subclass can set and
+//                              read the private DefaultShader uniforms) and _render() is called with
+//                              caller-supplied state -> pins oracle/ogre_oracle.c draw for draw.
+//   * ref_scene_*              a real Root/SceneManager scene (ogrehead) rendered by
+//                              that TinyRenderSystem while every _render call is captured (buffers,
+//                              uniforms, state) -> tests/golden fixtures.
+//   * ref_skel_*               a real skeletally animated Entity (Sinbad / jaiqua): source streams,
+//                              blend data, bone palettes and OGRE's own software-skinned output.
+//   * ref_bench_*              timing loops for the reference arm (host threads stated by caller).
+#include <Ogre.h>
+#include <OgreOptimisedUtil.h>
+#include <OgreEdgeListBuilder.h>
+#include <OgreDefaultHardwareBufferManager.h>
+#include <OgreSkeletonInstance.h>
+#include <OgreSubMesh.h>
+#include <OgreSubEntity.h>
+#include <OgreTagPoint.h>
+
+#include "OgreTinyRenderSystem.h"
+#include "OgreTinyWindow.h"
+#include "OgreTinyDepthBuffer.h"
+#include "OgreTinyTexture.h"
+
+#include <chrono>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <thread>
+#include <vector>
+
+#include "ogre_oracle.h"
+
+namespace Ogre { extern OptimisedUtil* _getOptimisedUtilGeneral(void); }
+
+using namespace Ogre;
+
+#define API extern "C" __attribute__((visibility("default")))
+
+/* ===================================================================== OptimisedUtil */
+
+static OptimisedUtil* g_sse = OptimisedUtil::getImplementation();   // before anything replaces it
+
+static OptimisedUtil* impl(int which) { return which == 0 ? g_sse : _getOptimisedUtilGeneral(); }
+
+API int ref_is_sse_active(void)
+{
+    // the stock selection picked SSE iff the pointer differs from what a General-only build returns;
+    // all we can say from outside is that it is non-null
+    return g_sse != nullptr;
+}
+
+API void ref_skin(int which, const float* sp, float* dp, const float* sn, float* dn, const float* bw, const uint8_t* bi,
+                  const float* const* mats, size_t sps, size_t dps, size_t sns, size_t dns, size_t bws, size_t bis, size_t nw, size_t n)
+{
+    impl(which)->softwareVertexSkinning(sp, dp, sn, dn, bw, bi, (const Affine3* const*)mats, sps, dps, sns, dns, bws, bis, nw, n);
+}
+
+API void ref_morph(int which, float t, const float* a, const float* b, float* d, size_t s1, size_t s2, size_t sd, size_t n, int normals)
+{
+    impl(which)->softwareVertexMorph(t, a, b, d, s1, s2, sd, n, normals != 0);
+}
+
+API void ref_concat(int which, const float* base, const float* src, float* dst, size_t n)
+{
+    impl(which)->concatenateAffineMatrices(*(const Affine3*)base, (const Affine3*)src, (Affine3*)dst, n);
+}
+
+API void ref_face_normals(int which, const float* pos, const void* tris, float* out, size_t n)
+{
+    impl(which)->calculateFaceNormals(pos, (const EdgeData::Triangle*)tris, (Vector4*)out, n);
+}
+
+API void ref_light_facing(int which, const float* l, const float* fn, char* out, size_t n)
+{
+    impl(which)->calculateLightFacing(*(const Vector4*)l, (const Vector4*)fn, out, n);
+}
+
+API void ref_extrude(int which, const float* l, float dist, const float* src, float* dst, size_t n)
+{
+    impl(which)->extrudeVertices(*(const Vector4*)l, dist, src, dst, n);
+}
+
+API size_t ref_sizeof_edge_triangle(void) { return sizeof(EdgeData::Triangle); }
+
+/* ========================================================================== Tiny ==== */
+
+struct CapturedDraw {
+    oracle_draw d;                  // pointers into the copies below
+    std::vector<uint8_t> vbuf[3];   // position / uv / normal source buffers (whole)
+    std::vector<uint8_t> ibuf;
+    int tex_id;                     // index into g_tex_copies or -1
+    size_t elem_off[3];             // byte offset of the first element inside vbuf[k]
+};
+
+struct TexCopy { std::vector<uint8_t> rgba; uint32_t w, h; const Image* src; };
+
+static std::vector<std::unique_ptr<CapturedDraw>> g_captured;
+static std::vector<TexCopy> g_tex_copies;
+static bool g_capture_on = false;
+
+class CaptureTiny : public TinyRenderSystem
+{
+public:
+    void _render(const RenderOperation& op) override
+    {
+        if (g_capture_on) capture(op);
+        TinyRenderSystem::_render(op);
+    }
+
+    // state exactly as TinyRenderSystem holds it when _render runs (private members; this TU is
+    // compiled with -fno-access-control)
+    void capture(const RenderOperation& op)
+    {
+        bool isStrip = op.operationType == RenderOperation::OT_TRIANGLE_STRIP;
+        if (!isStrip && op.operationType != RenderOperation::OT_TRIANGLE_LIST) return;
+        std::unique_ptr<CapturedDraw> c(new CapturedDraw());
+        memset(&c->d, 0, sizeof c->d);
+        const VertexElementSemantic sems[3] = {VES_POSITION, VES_TEXTURE_COORDINATES, VES_NORMAL};
+        const uint8_t* ptrs[3] = {0, 0, 0};
+        uint32_t strides[3] = {0, 0, 0};
+        for (int k = 0; k < 3; ++k) {
+            auto el = op.vertexData->vertexDeclaration->findElementBySemantic(sems[k]);
+            if (!el) continue;
+            auto buf = op.vertexData->vertexBufferBinding->getBuffer(el->getSource());
+            size_t step = op.vertexData->vertexDeclaration->getVertexSize(el->getSource());
+            const uint8_t* base = (const uint8_t*)buf->lock(HardwareBuffer::HBL_READ_ONLY);
+            c->vbuf[k].assign(base, base + buf->getSizeInBytes());
+            buf->unlock();
+            c->elem_off[k] = el->getOffset() + op.vertexData->vertexStart * step;
+            ptrs[k] = c->vbuf[k].data() + c->elem_off[k];
+            strides[k] = (uint32_t)step;
+        }
+        c->d.positions = ptrs[0]; c->d.pos_stride = strides[0];
+        c->d.uvs = ptrs[1]; c->d.uv_stride = strides[1];
+        c->d.normals = ptrs[2]; c->d.normal_stride = strides[2];
+        c->d.draw_count = (uint32_t)op.vertexData->vertexCount;
+        if (op.useIndexes) {
+            auto ib = op.indexData->indexBuffer;
+            const uint8_t* base = (const uint8_t*)ib->lock(HardwareBuffer::HBL_READ_ONLY);
+            c->ibuf.assign(base, base + ib->getSizeInBytes());
+            ib->unlock();
+            c->d.index_type = (uint32_t)ib->getIndexSize();
+            c->d.indices = c->ibuf.data() + op.indexData->indexStart * ib->getIndexSize();
+            c->d.draw_count = (uint32_t)op.indexData->indexCount;
+        }
+        c->d.is_strip = isStrip;
+        c->d.depth_test = mDepthTest; c->d.depth_write = mDepthWrite; c->d.blend_add = mBlendAdd;
+        c->d.lighting = mDefaultShader.uniform_doLighting && ptrs[2];
+        c->tex_id = -1;
+        if (mDefaultShader.image) {
+            const Image* img = mDefaultShader.image;
+            for (size_t i = 0; i < g_tex_copies.size(); ++i) if (g_tex_copies[i].src == img) c->tex_id = (int)i;
+            if (c->tex_id < 0) {
+                TexCopy t;
+                t.src = img; t.w = img->getWidth(); t.h = img->getHeight();
+                t.rgba.assign(img->getData(), img->getData() + (size_t)t.w * t.h * 4);
+                g_tex_copies.push_back(std::move(t));
+                c->tex_id = (int)g_tex_copies.size() - 1;
+            }
+            c->d.tex_w = img->getWidth(); c->d.tex_h = img->getHeight();
+        }
+        memcpy(c->d.mvp, mDefaultShader.uniform_MVP[0], 64);
+        memcpy(c->d.tex_matrix, mDefaultShader.uniform_Tex[0], 64);
+        memcpy(c->d.mvit, mDefaultShader.uniform_MVIT[0], 64);
+        memcpy(c->d.viewport, mVP[0], 64);
+        memcpy(c->d.light_dir, mDefaultShader.uniform_lightDir.ptr(), 12);
+        memcpy(c->d.ambient, mDefaultShader.uniform_ambientCol.ptr(), 16);
+        g_captured.push_back(std::move(c));
+    }
+};
+
+struct TinyHost {
+    std::unique_ptr<Root> root;
+    CaptureTiny* rs = nullptr;
+    RenderWindow* win = nullptr;
+    uint32_t w = 0, h = 0;
+    bool resources_ready = false;
+};
+static TinyHost* g_host = nullptr;
+static std::string g_media;
+
+static void host_open(uint32_t w, uint32_t h)
+{
+    if (g_host && g_host->w == w && g_host->h == h) return;
+    if (!g_host) {
+        g_host = new TinyHost();
+        // silent log (no file, no stderr) created before Root so that Root adopts it
+        LogManager* lm = new LogManager();
+        lm->createLog("ref_driver.log", true, false, true);
+        g_host->root.reset(new Root("", "", ""));       // no plugins.cfg, no ogre.cfg
+        g_host->rs = new CaptureTiny();
+        g_host->root->addRenderSystem(g_host->rs);
+        g_host->root->setRenderSystem(g_host->rs);
+        g_host->root->initialise(false);
+    } else if (g_host->win) {
+        g_host->root->destroyRenderTarget(g_host->win);
+        g_host->win = nullptr;
+    }
+    static int serial = 0;
+    g_host->win = g_host->root->createRenderWindow("ref" + std::to_string(serial++), w, h, false);
+    g_host->w = w; g_host->h = h;
+}
+
+API int ref_tiny_open(uint32_t w, uint32_t h)
+{
+    try { host_open(w, h); g_host->rs->_setRenderTarget(g_host->win); return 0; }
+    catch (std::exception& e) { fprintf(stderr, "ref_tiny_open: %s\n", e.what()); return 1; }
+}
+
+API void ref_tiny_clear(unsigned buffers, const float* rgba, float depth)
+{
+    g_host->rs->_setRenderTarget(g_host->win);
+    unsigned fb = ((buffers & 1) ? FBT_COLOUR : 0) | ((buffers & 2) ? FBT_DEPTH : 0);
+    g_host->rs->clearFrameBuffer(fb, ColourValue(rgba[0], rgba[1], rgba[2], rgba[3]), depth, 0);
+}
+
+// upload initial contents of the planes (for no-clear tests)
+API void ref_tiny_write(const uint8_t* colour_rgb, const float* depth)
+{
+    g_host->rs->_setRenderTarget(g_host->win);
+    if (colour_rgb) memcpy(g_host->rs->mActiveColourBuffer->getData(), colour_rgb, (size_t)g_host->w * g_host->h * 3);
+    if (depth) memcpy(g_host->rs->mActiveDepthBuffer->getData(), depth, (size_t)g_host->w * g_host->h * 4);
+}
+
+API void ref_tiny_read(uint8_t* colour_rgb, float* depth)
+{
+    // colour through the public readback path, depth through TinyDepthBuffer::getImage()
+    if (colour_rgb) {
+        PixelBox dst(g_host->w, g_host->h, 1, PF_BYTE_RGB, colour_rgb);
+        g_host->win->copyContentsToMemory(dst, dst, RenderTarget::FB_AUTO);
+    }
+    if (depth) {
+        Image* z = static_cast<TinyDepthBuffer*>(g_host->win->getDepthBuffer())->getImage();
+        memcpy(depth, z->getData(), (size_t)g_host->w * g_host->h * 4);
+    }
+}
+
+// One real TinyRenderSystem::_render with the given state (buffers are created through the
+// render system's own DefaultHardwareBufferManager).
+API int ref_tiny_draw(const oracle_draw* d, size_t num_vertices_in_buffers)
+{
+    try {
+        CaptureTiny* rs = g_host->rs;
+        rs->_setRenderTarget(g_host->win);
+        HardwareBufferManager& hbm = HardwareBufferManager::getSingleton();
+        // the oracle_draw streams may be interleaved in one allocation; rebuild one buffer per stream
+        VertexData vd;
+        vd.vertexStart = 0;
+        vd.vertexCount = num_vertices_in_buffers;
+        const uint8_t* src[3] = {d->positions, d->uvs, d->normals};
+        const uint32_t stride[3] = {d->pos_stride, d->uv_stride, d->normal_stride};
+        const VertexElementType types[3] = {VET_FLOAT3, VET_FLOAT2, VET_FLOAT3};
+        const VertexElementSemantic sems[3] = {VES_POSITION, VES_TEXTURE_COORDINATES, VES_NORMAL};
+        const size_t elsize[3] = {12, 8, 12};
+        unsigned short source = 0;
+        for (int k = 0; k < 3; ++k) {
+            if (!src[k]) continue;
+            // keep the caller's stride: element at offset 0 of a `stride`-byte vertex
+            size_t bytes = (num_vertices_in_buffers - 1) * stride[k] + elsize[k];
+            size_t nverts = (bytes + stride[k] - 1) / stride[k];
+            auto vb = hbm.createVertexBuffer(stride[k], nverts, HBU_CPU_TO_GPU);
+            void* p = vb->lock(HardwareBuffer::HBL_DISCARD);
+            memcpy(p, src[k], bytes);
+            vb->unlock();
+            vd.vertexDeclaration->addElement(source, 0, types[k], sems[k]);
+            // getVertexSize(source) must equal the stride: pad with a dummy element when wider
+            size_t have = elsize[k];
+            unsigned short pad = 0;
+            while (have + 4 <= stride[k]) { vd.vertexDeclaration->addElement(source, have, VET_FLOAT1, VES_TEXTURE_COORDINATES, 1 + pad + 4 * k); have += 4; ++pad; }
+            vd.vertexBufferBinding->setBinding(source, vb);
+            ++source;
+        }
+        RenderOperation op;
+        op.vertexData = &vd;
+        op.operationType = d->is_strip ? RenderOperation::OT_TRIANGLE_STRIP : RenderOperation::OT_TRIANGLE_LIST;
+        IndexData id;
+        op.useIndexes = d->index_type != 0;
+        if (op.useIndexes) {
+            auto ib = hbm.createIndexBuffer(d->index_type == 2 ? HardwareIndexBuffer::IT_16BIT : HardwareIndexBuffer::IT_32BIT,
+                                            d->draw_count, HBU_CPU_TO_GPU);
+            void* p = ib->lock(HardwareBuffer::HBL_DISCARD);
+            memcpy(p, d->indices, (size_t)d->draw_count * d->index_type);
+            ib->unlock();
+            id.indexBuffer = ib; id.indexStart = 0; id.indexCount = d->draw_count;
+            op.indexData = &id;
+        } else {
+            vd.vertexCount = d->draw_count;
+        }
+        // state + uniforms, written where Tiny keeps them
+        rs->mDepthTest = d->depth_test; rs->mDepthWrite = d->depth_write; rs->mBlendAdd = d->blend_add;
+        rs->mDefaultShader.uniform_doLighting = d->lighting;
+        rs->mDefaultShader.uniform_MVP = Matrix4(d->mvp);
+        rs->mDefaultShader.uniform_Tex = Matrix4(d->tex_matrix);
+        rs->mDefaultShader.uniform_MVIT = Matrix4(d->mvit);
+        rs->mVP = Matrix4(d->viewport);
+        rs->mDefaultShader.uniform_lightDir = Vector3(d->light_dir[0], d->light_dir[1], d->light_dir[2]);
+        rs->mDefaultShader.uniform_ambientCol = ColourValue(d->ambient[0], d->ambient[1], d->ambient[2], d->ambient[3]);
+        Image tex;
+        if (d->tex_rgba) {
+            tex.loadDynamicImage(const_cast<uchar*>(d->tex_rgba), d->tex_w, d->tex_h, 1, PF_BYTE_RGBA, false);
+            rs->mDefaultShader.image = &tex;
+        } else rs->mDefaultShader.image = NULL;
+        rs->mCurrentPassIterationCount = 0;
+        bool cap = g_capture_on; g_capture_on = false;
+        rs->_render(op);
+        g_capture_on = cap;
+        rs->mDefaultShader.image = NULL;
+        op.vertexData = 0; op.indexData = 0;   // stack objects
+        return 0;
+    } catch (std::exception& e) { fprintf(stderr, "ref_tiny_draw: %s\n", e.what()); return 1; }
+}
+
+/* ================================================================= real scenes ==== */
+
+API void ref_set_media_dir(const char* dir) { g_media = dir; }
+
+static void ensure_resources()
+{
+    if (g_host->resources_ready) return;
+    // Codec_STBI (jpg/png) is a plugin; it sits next to libOgreMain.so
+    std::string lib = g_media + "/../lib/Codec_STBI.so";
+    g_host->root->loadPlugin(lib);
+    ResourceGroupManager& rgm = ResourceGroupManager::getSingleton();
+    rgm.addResourceLocation(g_media + "/models", "FileSystem");
+    rgm.addResourceLocation(g_media + "/scripts", "FileSystem");
+    rgm.addResourceLocation(g_media + "/textures", "FileSystem");
+    rgm.addResourceLocation(g_media + "/packs/Sinbad.zip", "Zip");
+    rgm.initialiseAllResourceGroups();
+    g_host->resources_ready = true;
+}
+
+struct SceneState { SceneManager* sm = nullptr; Camera* cam = nullptr; Entity* ent = nullptr; Viewport* vp = nullptr; };
+static SceneState g_scene;
+
+// ogrehead, camera (0,0,140) -> origin, near 5, auto aspect, point light
+// (20,80,50), ambient 0.3, background (0.1,0.2,0.3)
+API int ref_scene_open(const char* mesh, uint32_t w, uint32_t h, float cam_z)
+{
+    try {
+        host_open(w, h);
+        ensure_resources();
+        if (g_scene.sm) { g_host->win->removeAllViewports(); g_host->root->destroySceneManager(g_scene.sm); g_scene = SceneState(); }
+        SceneManager* sm = g_host->root->createSceneManager();
+        g_scene.sm = sm;
+        sm->setAmbientLight(ColourValue(0.3f, 0.3f, 0.3f));
+        Light* light = sm->createLight("l");
+        SceneNode* ln = sm->getRootSceneNode()->createChildSceneNode();
+        ln->setPosition(20, 80, 50);
+        ln->attachObject(light);
+        Camera* cam = sm->createCamera("c");
+        cam->setNearClipDistance(5);
+        cam->setAutoAspectRatio(true);
+        SceneNode* cn = sm->getRootSceneNode()->createChildSceneNode();
+        cn->setPosition(0, 0, cam_z);
+        cn->lookAt(Vector3::ZERO, Node::TS_WORLD);
+        cn->attachObject(cam);
+        g_scene.cam = cam;
+        Viewport* vp = g_host->win->addViewport(cam);
+        vp->setBackgroundColour(ColourValue(0.1f, 0.2f, 0.3f));
+        g_scene.vp = vp;
+        Entity* e = sm->createEntity(mesh);
+        sm->getRootSceneNode()->createChildSceneNode()->attachObject(e);
+        g_scene.ent = e;
+        return 0;
+    } catch (std::exception& ex) { fprintf(stderr, "ref_scene_open: %s\n", ex.what()); return 1; }
+}
+
+API int ref_scene_render(int capture)
+{
+    try {
+        if (capture) { g_captured.clear(); g_tex_copies.clear(); }
+        g_capture_on = capture != 0;
+        g_host->root->renderOneFrame();
+        g_capture_on = false;
+        return 0;
+    } catch (std::exception& ex) { g_capture_on = false; fprintf(stderr, "ref_scene_render: %s\n", ex.what()); return 1; }
+}
+
+API size_t ref_scene_triangles(void) { return g_host->win->getStatistics().triangleCount; }
+API size_t ref_scene_batches(void) { return g_host->win->getStatistics().batchCount; }
+
+API size_t ref_capture_count(void) { return g_captured.size(); }
+API const oracle_draw* ref_capture_draw(size_t i) { return &g_captured[i]->d; }
+API const uint8_t* ref_capture_vbuf(size_t i, int k, size_t* size, size_t* elem_off)
+{
+    *size = g_captured[i]->vbuf[k].size(); *elem_off = g_captured[i]->elem_off[k];
+    return g_captured[i]->vbuf[k].data();
+}
+API const uint8_t* ref_capture_ibuf(size_t i, size_t* size, size_t* start_off)
+{
+    auto& c = *g_captured[i];
+    *size = c.ibuf.size();
+    *start_off = c.ibuf.empty() ? 0 : (size_t)((const uint8_t*)c.d.indices - c.ibuf.data());
+    return c.ibuf.data();
+}
+API int ref_capture_tex(size_t i) { return g_captured[i]->tex_id; }
+API size_t ref_capture_tex_count(void) { return g_tex_copies.size(); }
+API const uint8_t* ref_capture_tex_data(size_t t, uint32_t* w, uint32_t* h) { *w = g_tex_copies[t].w; *h = g_tex_copies[t].h; return g_tex_copies[t].rgba.data(); }
+
+// wall-clock seconds per frame of the real Tiny path (after one warm-up frame)
+API double ref_scene_time(int frames)
+{
+    g_host->root->renderOneFrame();
+    auto t0 = std::chrono::steady_clock::now();
+    for (int i = 0; i < frames; ++i) g_host->root->renderOneFrame();
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() / frames;
+}
+
+/* ============================================================ skeletal entities ==== */
+
+struct SkelSub {
+    std::vector<uint8_t> src, blend;       // source pos(+normal) stream, blend stream (as OGRE lays them out)
+    uint32_t src_stride, norm_off, blend_stride, weight_off, index_off, nw, nverts;
+    int has_norm;
+    std::vector<uint16_t> bone_map;        // blendIndexToBoneIndexMap
+    std::vector<uint8_t> skinned;          // OGRE's own software-skinned result for the current pose
+    uint32_t dst_stride;
+};
+static std::vector<SkelSub> g_subs;
+static std::vector<float> g_bones;         // numBones x 16 for the current pose
+static Entity* g_skel_ent = nullptr;
+
+static void dump_vertex_data(const VertexData* vd, const VertexData* skinned, const Mesh::IndexMap& map, SkelSub& s)
+{
+    const VertexDeclaration* decl = vd->vertexDeclaration;
+    const VertexElement* ep = decl->findElementBySemantic(VES_POSITION);
+    const VertexElement* en = decl->findElementBySemantic(VES_NORMAL);
+    const VertexElement* ei = decl->findElementBySemantic(VES_BLEND_INDICES);
+    const VertexElement* ew = decl->findElementBySemantic(VES_BLEND_WEIGHTS);
+    auto pb = vd->vertexBufferBinding->getBuffer(ep->getSource());
+    s.nverts = (uint32_t)vd->vertexCount;
+    s.src_stride = (uint32_t)pb->getVertexSize();
+    s.has_norm = en && en->getSource() == ep->getSource();
+    s.norm_off = s.has_norm ? (uint32_t)(en->getOffset() - ep->getOffset()) : 0;
+    {
+        const uint8_t* p = (const uint8_t*)pb->lock(HardwareBuffer::HBL_READ_ONLY);
+        s.src.assign(p + vd->vertexStart * s.src_stride + ep->getOffset(), p + pb->getSizeInBytes());
+        pb->unlock();
+    }
+    auto bb = vd->vertexBufferBinding->getBuffer(ei->getSource());
+    s.blend_stride = (uint32_t)bb->getVertexSize();
+    s.index_off = (uint32_t)ei->getOffset();
+    s.weight_off = (uint32_t)ew->getOffset();
+    s.nw = VertexElement::getTypeCount(ew->getType());
+    {
+        const uint8_t* p = (const uint8_t*)bb->lock(HardwareBuffer::HBL_READ_ONLY);
+        s.blend.assign(p + vd->vertexStart * s.blend_stride, p + bb->getSizeInBytes());
+        bb->unlock();
+    }
+    s.bone_map.assign(map.begin(), map.end());
+    if (skinned) {
+        const VertexElement* dp = skinned->vertexDeclaration->findElementBySemantic(VES_POSITION);
+        auto db = skinned->vertexBufferBinding->getBuffer(dp->getSource());
+        s.dst_stride = (uint32_t)db->getVertexSize();
+        const uint8_t* p = (const uint8_t*)db->lock(HardwareBuffer::HBL_READ_ONLY);
+        s.skinned.assign(p + dp->getOffset(), p + db->getSizeInBytes());
+        db->unlock();
+    }
+}
+
+// Load `mesh` as an Entity in a scene, pose its first animation at `time` and let OGRE run
+// its own software skinning (Entity::_updateAnimation -> Mesh::softwareVertexBlend ->
+// OptimisedUtil::softwareVertexSkinning, OgreEntity.cpp:747-911, OgreMesh.cpp:1792-1897).
+API int ref_skel_open(const char* mesh, uint32_t w, uint32_t h)
+{
+    int rc = ref_scene_open(mesh, w, h, 30.0f);
+    if (rc) return rc;
+    g_skel_ent = g_scene.ent;
+    return g_skel_ent->hasSkeleton() ? 0 : 2;
+}
+
+API int ref_skel_pose(float time)
+{
+    try {
+        Entity* e = g_skel_ent;
+        AnimationStateSet* set = e->getAllAnimationStates();
+        bool first = true;
+        for (auto& kv : set->getAnimationStates()) {
+            kv.second->setEnabled(first);
+            if (first) { kv.second->setLoop(true); kv.second->setTimePosition(time); }
+            first = false;
+        }
+        e->addSoftwareAnimationRequest(true);     // keep normals: the FFP path skins them anyway
+        e->_updateAnimation();
+        const Affine3* bm = e->_getBoneMatrices();
+        size_t nb = e->_getNumBoneMatrices();
+        g_bones.resize(nb * 16);
+        memcpy(g_bones.data(), bm, nb * 64);
+        g_subs.clear();
+        MeshPtr m = e->getMesh();
+        if (m->sharedVertexData) {
+            g_subs.emplace_back();
+            dump_vertex_data(m->sharedVertexData, e->_getSkelAnimVertexData(), m->sharedBlendIndexToBoneIndexMap, g_subs.back());
+        }
+        for (size_t i = 0; i < m->getNumSubMeshes(); ++i) {
+            SubMesh* sm = m->getSubMesh(i);
+            if (sm->useSharedVertices) continue;
+            g_subs.emplace_back();
+            dump_vertex_data(sm->vertexData, e->getSubEntity(i)->_getSkelAnimVertexData(), sm->blendIndexToBoneIndexMap, g_subs.back());
+        }
+        return 0;
+    } catch (std::exception& ex) { fprintf(stderr, "ref_skel_pose: %s\n", ex.what()); return 1; }
+}
+
+API size_t ref_skel_num_bones(void) { return g_bones.size() / 16; }
+API const float* ref_skel_bones(void) { return g_bones.data(); }
+API size_t ref_skel_num_subs(void) { return g_subs.size(); }
+struct SkelSubInfo { uint32_t src_stride, norm_off, blend_stride, weight_off, index_off, nw, nverts, has_norm, dst_stride, nmap; size_t src_size, blend_size, skinned_size; };
+API void ref_skel_sub_info(size_t i, SkelSubInfo* o)
+{
+    const SkelSub& s = g_subs[i];
+    o->src_stride = s.src_stride; o->norm_off = s.norm_off; o->blend_stride = s.blend_stride; o->weight_off = s.weight_off;
+    o->index_off = s.index_off; o->nw = s.nw; o->nverts = s.nverts; o->has_norm = s.has_norm; o->dst_stride = s.dst_stride;
+    o->nmap = (uint32_t)s.bone_map.size(); o->src_size = s.src.size(); o->blend_size = s.blend.size(); o->skinned_size = s.skinned.size();
+}
+API const uint8_t* ref_skel_sub_src(size_t i) { return g_subs[i].src.data(); }
+API const uint8_t* ref_skel_sub_blend(size_t i) { return g_subs[i].blend.data(); }
+API const uint16_t* ref_skel_sub_map(size_t i) { return g_subs[i].bone_map.data(); }
+API const uint8_t* ref_skel_sub_skinned(size_t i) { return g_subs[i].skinned.data(); }
+
+/* ==================================================================== timing ==== */
+
+// `reps` calls of the real SSE softwareVertexSkinning over `ninst` instances (each with its own
+// palette and destination), split over `threads` host threads; returns seconds for ONE pass
+// over all instances (best of reps).
+API double ref_bench_skin_instances(const float* sp, const float* sn, const float* bw, const uint8_t* bi, size_t sps, size_t sns,
+                                    size_t bws, size_t bis, size_t nw, size_t nverts, const float* palettes, size_t nmat,
+                                    size_t ninst, float* dst, size_t dst_inst_stride_floats, int threads, int reps)
+{
+    double best = 1e30;
+    for (int r = 0; r < reps; ++r) {
+        auto t0 = std::chrono::steady_clock::now();
+        std::vector<std::thread> pool;
+        for (int t = 0; t < threads; ++t)
+            pool.emplace_back([=]() {
+                std::vector<const float*> pal(nmat);
+                for (size_t i = t; i < ninst; i += threads) {
+                    for (size_t m = 0; m < nmat; ++m) pal[m] = palettes + (i * nmat + m) * 16;
+                    float* d = dst + i * dst_inst_stride_floats;
+                    g_sse->softwareVertexSkinning(sp, d, sn, sn ? d + 3 : nullptr, bw, bi, (const Affine3* const*)pal.data(), sps, 24,
+                                                  sns, 24, bws, bis, nw, nverts);
+                }
+            });
+        for (auto& th : pool) th.join();
+        best = std::min(best, std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+    }
+    return best;
+}
+
+// One sub-mesh of the config-2 step on the reference: per instance the real SSE
+// softwareVertexMorph (two shared keyframes -> the instance's animated source, t = tarr[i]) and
+// then the real SSE softwareVertexSkinning (instance source + own palette -> instance output),
+// exactly the order of Entity::updateAnimation (OgreEntity.cpp:747-911).  pos+normal stride 24.
+API double ref_bench_anim_sub(const float* key1, const float* key2, const float* tarr, const float* bw, const uint8_t* bi,
+                              size_t bws, size_t bis, size_t nw, size_t nverts, const float* palettes, size_t pal_stride_floats,
+                              const uint16_t* bone_map, size_t nmap, size_t ninst, float* tmp, float* dst, int threads, int do_morph)
+{
+    auto t0 = std::chrono::steady_clock::now();
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; ++t)
+        pool.emplace_back([=]() {
+            std::vector<const float*> pal(nmap);
+            for (size_t i = t; i < ninst; i += threads) {
+                for (size_t m = 0; m < nmap; ++m) pal[m] = palettes + i * pal_stride_floats + (size_t)bone_map[m] * 16;
+                float* src = tmp + i * nverts * 6;
+                float* d = dst + i * nverts * 6;
+                const float* s = key1;
+                if (do_morph) { g_sse->softwareVertexMorph(tarr[i], key1, key2, src, 24, 24, 24, nverts, true); s = src; }
+                g_sse->softwareVertexSkinning(s, d, s + 3, d + 3, bw, bi, (const Affine3* const*)pal.data(), 24, 24, 24, 24, bws, bis, nw, nverts);
+            }
+        });
+    for (auto& th : pool) th.join();
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
+API double ref_bench_morph(float t, const float* a, const float* b, float* d, size_t stride, size_t n, int normals, int threads, int reps)
+{
+    double best = 1e30;
+    for (int r = 0; r < reps; ++r) {
+        auto t0 = std::chrono::steady_clock::now();
+        std::vector<std::thread> pool;
+        size_t per = (n / threads) & ~(size_t)3;
+        for (int k = 0; k < threads; ++k)
+            pool.emplace_back([=]() {
+                size_t v0 = k * per, cnt = (k == threads - 1) ? n - v0 : per;
+                size_t fo = v0 * stride / 4;
+                g_sse->softwareVertexMorph(t, a + fo, b + fo, d + fo, stride, stride, stride, cnt, normals != 0);
+            });
+        for (auto& th : pool) th.join();
+        best = std::min(best, std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+    }
+    return best;
+}
+
+API void ref_shutdown(void)
+{
+    if (g_host) { g_captured.clear(); g_tex_copies.clear(); g_host->root.reset(); delete g_host; g_host = nullptr; }
+}

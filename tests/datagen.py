@@ -247,7 +247,7 @@ def make_scene(seed, w, h, ndraws=4, ntri=200, **kw):
         strip = kw.get("strip", k % 4 == 3)
         index_type = kw.get("index_type", 2 if k % 2 else 4)
         verts, idx = random_soup(rng, ntri, size=kw.get("size", 1.0), strip=strip, indexed=kw.get("indexed", k % 3 != 2))
-        if idx is not None and index_type == 2 and len(verts) > 65535:
+        if idx is not None and index_type == 2 and len(verts) > 32767:   # the reference reads 16-bit indices as SIGNED (UB >= 32768)
             index_type = 4
         model = np.eye(4); model[:3, 3] = rng.uniform(-1, 1, 3)
         mv = view @ model

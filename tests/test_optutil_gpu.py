@@ -110,7 +110,7 @@ def test_skin_dev_batched_and_instanced(gpu_ctx):
     j.src_pos_stride = j.dst_pos_stride = j.src_norm_stride = j.dst_norm_stride = 24
     j.blend_weight_stride = j.blend_index_stride = 4 + 4 * c.nw
     j.num_weights, j.num_matrices, j.num_vertices = c.nw, nb, c.n
-    check(lib().ogrecu_skin_instanced_dev(ctx.handle, C.byref(j), ninst, (nb + 3) * 16, c.n * 24))
+    check(lib().ogrecu_skin_instanced_dev(ctx.handle, C.byref(j), ninst, (nb + 3) * 16, 0, c.n * 24))
     ctx.sync()
     got = ddst.download(np.uint8).reshape(ninst, c.n * 24)
     for i in range(ninst):

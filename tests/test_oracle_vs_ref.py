@@ -1,0 +1,61 @@
+"""CPU, build container only: the oracle restatement vs the LIVE unmodified reference in
+oracle/_ref (real TinyRenderSystem::_render, real OptimisedUtil).  Skipped where oracle/_ref
+has not been built (it cannot be rebuilt without /root/reference); the committed golden
+fixtures (test_oracle_golden.py) carry the same pinning everywhere else."""
+import numpy as np
+import pytest
+
+import oracle
+from oracle import ref
+from datagen import SkinCase, bits, clip_case, degenerate_soup, make_scene
+from rasterlib import assert_images_equal, render_oracle
+
+pytestmark = [pytest.mark.ref, pytest.mark.skipif(not ref.available(), reason="oracle/_ref not built")]
+
+
+@pytest.mark.parametrize("w,h", [(257, 193), (64, 64), (33, 17)])
+def test_oracle_raster_equals_real_tiny(w, h):
+    for seed in range(4):
+        cases = make_scene(seed * 7 + w, w, h, ndraws=6, ntri=150)
+        oc, oz, _ = render_oracle(cases, w, h)
+        rc, rz = ref.tiny_render(cases, w, h)
+        assert_images_equal(oc, oz, rc, rz, "seed %d" % seed)
+
+
+def test_oracle_raster_corner_cases_equal_real_tiny():
+    w, h = 128, 96
+    clip = degenerate_soup(np.random.default_rng(2), w, h)
+    for kw in (dict(lighting=False), dict(lighting=True, blend_add=True), dict(depth_write=False), dict(depth_test=False)):
+        cases = clip_case(clip, w, h, **kw)
+        oc, oz, _ = render_oracle(cases, w, h)
+        rc, rz = ref.tiny_render(cases, w, h)
+        assert_images_equal(oc, oz, rc, rz, repr(kw))
+
+
+def test_oracle_raster_tiny_triangles_and_no_clear():
+    w, h = 320, 240
+    cases = make_scene(5, w, h, ndraws=3, ntri=20000, size=0.02)
+    oc, oz, _ = render_oracle(cases, w, h)
+    rc, rz = ref.tiny_render(cases, w, h)
+    assert_images_equal(oc, oz, rc, rz, "tiny triangles")
+    rng = np.random.default_rng(9)
+    init = (rng.integers(0, 256, size=(80, 100, 3), dtype=np.uint8), rng.uniform(0.3, 1.0, size=(80, 100)).astype(np.float32))
+    cases = make_scene(3, 100, 80, ndraws=4, ntri=60)
+    oc, oz, _ = render_oracle(cases, 100, 80, clear=None, init=init)
+    rc, rz = ref.tiny_render(cases, 100, 80, clear=None, init=init)
+    assert_images_equal(oc, oz, rc, rz, "no clear")
+
+
+def test_oracle_skinning_equals_real_sse_large():
+    l = ref.lib()
+    for nw in (1, 2, 3, 4):
+        c = SkinCase(seed=nw, n=50001, nw=nw, layout="shared")
+        dst, _ = c.new_dst(); rdst, _ = c.new_dst()
+        sp, dp, sn, dn, bw, bi = c.pointers(dst, None)
+        oracle.skin("sse", sp, dp, sn, dn, bw, bi, c.mats, c.strides(), nw, c.n)
+        sp, dp, sn, dn, bw, bi = c.pointers(rdst, None)
+        keep, pal = oracle.palette_ptrs(c.mats)
+        l.ref_skin(ref.SSE, sp, dp, sn, dn, bw, bi, pal, *c.strides(), nw, c.n)
+        po, no = c.dst_views(dst, None); pr, nr = c.dst_views(rdst, None)
+        assert np.array_equal(bits(po), bits(pr))
+        assert np.abs(no - nr).max() <= 4e-4

@@ -64,7 +64,7 @@ def main():
             j.src_pos_stride = j.dst_pos_stride = j.src_norm_stride = j.dst_norm_stride = 24
             j.blend_weight_stride = j.blend_index_stride = 20
             j.num_weights, j.num_matrices, j.num_vertices = nwk, nb, n
-            fn = lambda: check(lib().ogrecu_skin_instanced_dev(ctx.handle, C.byref(j), 1, 0, 0))
+            fn = lambda: check(lib().ogrecu_skin_instanced_dev(ctx.handle, C.byref(j), 1, 0, 0, 0))
             med, best = timeit(fn, stream)
             bpv = 24 + 20 + 24
             out["skin_stream_nw%d" % nwk] = {"ms": med, "best_ms": best, "Gvert/s": n / med / 1e6, "GB/s": n * bpv / med / 1e6,
@@ -81,7 +81,7 @@ def main():
         j.src_pos_stride = j.dst_pos_stride = j.src_norm_stride = j.dst_norm_stride = 24
         j.blend_weight_stride = j.blend_index_stride = 20
         j.num_weights, j.num_matrices, j.num_vertices = 4, 64, nv
-        fn = lambda: check(lib().ogrecu_skin_instanced_dev(ctx.handle, C.byref(j), ninst, nb * 16, nv * 24))
+        fn = lambda: check(lib().ogrecu_skin_instanced_dev(ctx.handle, C.byref(j), ninst, nb * 16, 0, nv * 24))
         med, best = timeit(fn, stream)
         tot = nv * ninst
         out["skin_instanced"] = {"ms": med, "best_ms": best, "Gvert/s": tot / med / 1e6, "write GB/s": tot * 24 / med / 1e6,
