@@ -18,7 +18,8 @@ Lines printed (rank 0, one JSON line):
   e2e        same step through the C ABI with HOST inputs: every step uploads all instance bone
              palettes + morph weights from pinned host memory and reads one instance's skinned
              vertices back (the skinned buffers themselves stay in HBM for _render)
-  roofline   dominant kernel (skin_instanced_kernel, 4-weight body sub-mesh) vs measured HBM peak
+  roofline   dominant kernel of the timed step (the 4-weight body sub-mesh launch) vs measured HBM peak;
+             extra.roofline_other_form carries the same for the other --form
   cpu_baseline  the unmodified reference (real OptimisedUtilSSE via oracle/_ref) on the host cores
 """
 import argparse
@@ -234,6 +235,8 @@ def run_ours(args):
     ctx = ogre_b200.Context(local)          # raises if the CUDA library / device is missing: no fallback
     stream = torch.cuda.Stream(device=dev)
     ctx.set_stream(stream.cuda_stream)
+    ctx.set_config_option("skin_mode", args.skin_mode)
+    ctx.set_config_option("skin_ipc", args.skin_ipc)
     L = lib()
 
     with torch.cuda.stream(stream):
@@ -254,6 +257,9 @@ def run_ours(args):
             j.blend_weight_stride = j.blend_index_stride = s["blend_stride"]
             j.num_weights, j.num_matrices, j.num_vertices = s["nw"], len(s["bone_map"]), n
             e["job"] = j
+            jf = SkinJob.from_buffer_copy(j)
+            jf.src_pos, jf.src_norm = e["key1"].data_ptr(), e["key1"].data_ptr() + 12
+            e["job_fused"] = jf
             dsub.append(e)
     stream.synchronize()
 
@@ -264,10 +270,22 @@ def run_ours(args):
     def skin(e, s):
         check(L.ogrecu_skin_instanced_dev(ctx.handle, C.byref(e["job"]), ninst, nb * 16, s["nverts"] * 24, s["nverts"] * 24))
 
-    def step():
+    def fused(e, s):
+        # one pass per sub-mesh: source_i = morph(key1, key2, t[i]) in registers -> skin -> dst_i; no intermediate in HBM
+        j = e["job_fused"]
+        check(L.ogrecu_anim_instanced_dev(ctx.handle, C.byref(j), e["key2"].data_ptr(), d_t.data_ptr(), None, 0, ninst, nb * 16,
+                                          s["nverts"] * 24))
+
+    def step_separate():
         for e, s in zip(dsub, subs):
             morph(e, s)
             skin(e, s)
+
+    def step_fused():
+        for e, s in zip(dsub, subs):
+            fused(e, s)
+
+    step = step_fused if args.form == "fused" else step_separate
 
     def barrier():
         if dist is not None:
@@ -299,7 +317,6 @@ def run_ours(args):
     launches0 = ctx.launch_count
     ms = timed(step, args.steps)
     launches = ctx.launch_count - launches0
-    clk = clocks.stop() if rank == 0 else None
     value = world * ninst * nverts * args.steps / (ms * 1e-3) / 1e6
 
     # ---- end to end: host palettes + weights in, one instance's skinned vertices out, every step
@@ -323,6 +340,7 @@ def run_ours(args):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
     e2e_value = world * ninst * nverts * args.steps / (ms_e2e * 1e-3) / 1e6
+    clk = clocks.stop() if rank == 0 else None      # sampled across both timed regions (device-resident and e2e)
 
     # ---- per-kernel durations (outside the timed regions) for the roofline line
     kern = {}
@@ -330,7 +348,7 @@ def run_ours(args):
         evs = []
         for rep in range(5):
             for k, (e, s) in enumerate(zip(dsub, subs)):
-                for name, f in (("morph", morph), ("skin", skin)):
+                for name, f in (("morph", morph), ("skin", skin), ("fused", fused)):
                     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     a.record(stream); f(e, s); b.record(stream)
                     evs.append((name, k, a, b))
@@ -343,27 +361,37 @@ def run_ours(args):
     if rank == 0:
         k = 1                                           # dominant launch: 4-weight body sub-mesh
         s = subs[k]
-        dur = float(np.mean(kern[("skin", k)][1:])) * 1e-3
-        # algorithmic (compulsory DRAM) bytes per launch: per-instance source 24 B/vertex read +
-        # 24 B/vertex written + the instance palette rows actually referenced (48 B x matrices);
-        # the shared blend stream (4+4n B/vertex) is L2-resident and counted once
         nv = s["nverts"]
-        alg = ninst * nv * 48 + ninst * len(s["bone_map"]) * 48 + nv * s["blend_stride"]
-        traffic = None
+        shared_once = nv * s["blend_stride"]            # blend stream: read by every instance, L2-resident, counted once
+        pal_bytes = ninst * len(s["bone_map"]) * 48     # palette rows actually referenced (3 of 4 rows, mapped bones)
+        # algorithmic (compulsory DRAM) bytes per launch
+        alg_sep = ninst * nv * 48 + pal_bytes + shared_once          # skin alone: 24 B/vertex source read + 24 B/vertex written
+        alg_fused = ninst * nv * 24 + pal_bytes + shared_once + nv * 48 + ninst * 4   # fused: only the result is written; keys once
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get("skin_instanced_kernel_sub1_bytes")
+            traf = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
         except Exception:
-            pass
-        roof = {"bound": "hbm", "kernel": "skin_instanced_kernel (sub-mesh 1: %d verts x %d instances, 4 weights)" % (nv, ninst),
-                "achieved": alg / dur / 1e9, "peak": peak, "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback",
-                "unit": "GB/s", "frac": alg / dur / 1e9 / peak, "traffic": traffic, "launch_ms": dur * 1e3,
-                "algorithmic_bytes_per_launch": alg}
-        tot_skin = sum(np.mean(kern[("skin", i)][1:]) for i in range(len(subs)))
-        tot_morph = sum(np.mean(kern[("morph", i)][1:]) for i in range(len(subs)))
-        extra["kernel_ms_per_step"] = {"skin": tot_skin, "morph": tot_morph}
-        extra["skin_only_Mvert_per_s"] = ninst * nverts / (tot_skin * 1e-3) / 1e6
-        extra["morph_only_Mvert_per_s"] = ninst * nverts / (tot_morph * 1e-3) / 1e6
-        bytes_step = ninst * nverts * 72 + ninst * sum(len(s["bone_map"]) for s in subs) * 48
+            traf = {}
+
+        def roofline(name, label, alg, key):
+            dur = float(np.mean(kern[(name, k)][1:])) * 1e-3
+            return {"bound": "hbm", "kernel": label % (nv, ninst), "achieved": alg / dur / 1e9, "peak": peak,
+                    "peak_source": (peak_kind + " (MEASURED_PEAKS.json hbm_gbs)") if peak_kind == "measured" else "fallback",
+                    "unit": "GB/s", "frac": alg / dur / 1e9 / peak, "traffic": traf.get(key), "launch_ms": dur * 1e3,
+                    "algorithmic_bytes_per_launch": alg}
+        roof_fused = roofline("fused", "skin_tile_kernel<4,normals,fused morph> (sub-mesh 1: %d verts x %d instances, 4 weights)",
+                              alg_fused, "skin_tile_fused_sub1_bytes")
+        roof_sep = roofline("skin", "skin_tile_kernel<4,normals> (sub-mesh 1: %d verts x %d instances, 4 weights)", alg_sep,
+                            "skin_tile_sub1_bytes")
+        roof = roof_fused if args.form == "fused" else roof_sep
+        extra["roofline_other_form"] = roof_sep if args.form == "fused" else roof_fused
+        tot = {n: sum(np.mean(kern[(n, i)][1:]) for i in range(len(subs))) for n in ("skin", "morph", "fused")}
+        extra["kernel_ms_per_step"] = tot
+        extra["fused_Mvert_per_s"] = ninst * nverts / (tot["fused"] * 1e-3) / 1e6
+        extra["separate_Mvert_per_s"] = ninst * nverts / ((tot["skin"] + tot["morph"]) * 1e-3) / 1e6
+        extra["skin_only_Mvert_per_s"] = ninst * nverts / (tot["skin"] * 1e-3) / 1e6
+        extra["morph_only_Mvert_per_s"] = ninst * nverts / (tot["morph"] * 1e-3) / 1e6
+        pal_step = ninst * sum(len(s["bone_map"]) for s in subs) * 48
+        bytes_step = ninst * nverts * (24 if args.form == "fused" else 72) + pal_step
         extra["step_compulsory_GBps"] = bytes_step / (ms / args.steps * 1e-3) / 1e9
         extra["step_frac_of_hbm_peak"] = extra["step_compulsory_GBps"] / peak
 
@@ -386,7 +414,7 @@ def run_ours(args):
             "metric": "skinned_Mvert_per_s", "value": value, "unit": "Mvert/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict(workload_config(ninst, nverts), parallelism="instances sharded per GPU, no collective (dp%d)" % world),
+            "config": dict(workload_config(ninst, nverts), form=args.form, parallelism="instances sharded per GPU, no collective (dp%d)" % world),
             "clocks": clk, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": "Mvert/s", "h2d_bytes_per_step": int(pal_h.nbytes + t_h.nbytes),
                     "d2h_bytes_per_step": int(out_bytes), "ms_per_step": ms_e2e / args.steps,
@@ -404,9 +432,13 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--form", default="fused", choices=["fused", "separate"],
+                    help="fused: one morph+skin pass per sub-mesh (default); separate: softwareVertexMorph then softwareVertexSkinning")
+    ap.add_argument("--skin-mode", type=int, default=0, help="kernel selection for A/B runs (ogrecu_set_config_option)")
+    ap.add_argument("--skin-ipc", type=int, default=0, help="instances per CTA of the tiled kernel, 0 = auto")
     ap.add_argument("--instances", type=int, default=10000)
     ap.add_argument("--ref-instances", type=int, default=1000, help="bounded CPU sample of the instances")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)

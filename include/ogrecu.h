@@ -75,6 +75,14 @@ OGRECU_API int ogrecu_sync(ogrecu_ctx* ctx);
 /* number of kernels this context has launched since creation (bench "gpu_launches") */
 OGRECU_API uint64_t ogrecu_launch_count(const ogrecu_ctx* ctx);
 
+/* RenderSystem::setConfigOption-style integer knobs (OgreMain/include/OgreRenderSystem.h:246).
+ * Kernel-selection switches for A/B measurement only — every value runs on the GPU:
+ *   "skin_mode"  0 = auto (tiled stream kernel with TMA where alignment allows), 1 = tiled kernel
+ *                with cooperative LDG/STG only, 2 = one-thread-per-vertex kernel
+ *   "skin_ipc"   instances per CTA of the tiled kernel, 0 = auto
+ * Unknown names return OGRECU_ERR_INVALID. */
+OGRECU_API int ogrecu_set_config_option(ogrecu_ctx* ctx, const char* name, int value);
+
 /* raw device / pinned memory for callers that keep data resident */
 OGRECU_API int ogrecu_malloc(ogrecu_ctx* ctx, size_t bytes, void** dev_ptr);
 OGRECU_API int ogrecu_free(ogrecu_ctx* ctx, void* dev_ptr);
@@ -145,6 +153,21 @@ OGRECU_API int ogrecu_skin_instanced_dev(ogrecu_ctx* ctx, const ogrecu_skin_job*
                                          uint32_t num_instances,
                                          size_t palette_stride_floats,
                                          size_t src_instance_stride_bytes,
+                                         size_t dst_instance_stride_bytes);
+
+/* Fused vertex animation of many instances of one mesh — the two steps Entity::updateAnimation
+ * runs per entity (OgreMain/src/OgreEntity.cpp:747-911) in ONE pass with no intermediate in HBM:
+ *   source_i = softwareVertexMorph(t[i], key1, key2)      (OgreMesh.cpp:1899-1946)
+ *   dst_i    = softwareVertexSkinning(source_i, palette_i) (OgreMesh.cpp:1792-1897)
+ * `job` describes the skinning exactly as for ogrecu_skin_instanced_dev, with src_pos/src_norm
+ * pointing at keyframe 1; `key2` is keyframe 2 in the same dense layout (stride 24 pos+normal or
+ * 12 positions only); `t_dev` is a DEVICE array of num_instances morph weights.  When
+ * `morph_out` is non-NULL the morphed intermediate of instance i is also written to
+ * morph_out + i*morph_instance_stride_bytes (what OGRE keeps in mSoftwareVertexAnimVertexData).
+ * Results are bit-identical to ogrecu_morph_instanced_dev followed by ogrecu_skin_instanced_dev. */
+OGRECU_API int ogrecu_anim_instanced_dev(ogrecu_ctx* ctx, const ogrecu_skin_job* job, const float* key2,
+                                         const float* t_dev, float* morph_out, size_t morph_instance_stride_bytes,
+                                         uint32_t num_instances, size_t palette_stride_floats,
                                          size_t dst_instance_stride_bytes);
 
 /* Exact-signature host form (what CudaOptimisedUtil::softwareVertexSkinning forwards to):
@@ -222,6 +245,10 @@ OGRECU_API int ogrecu_tex_destroy(ogrecu_tex* tex);
 OGRECU_API int ogrecu_tex_upload(ogrecu_tex* tex, const uint8_t* rgba_host, size_t row_pitch_bytes);
 OGRECU_API int ogrecu_tex_download(ogrecu_tex* tex, uint8_t* rgba_host, size_t row_pitch_bytes);
 OGRECU_API int ogrecu_tex_device_ptr(ogrecu_tex* tex, void** dev_ptr);
+/* Render-to-texture resolve: copy a target's RGB8 colour plane into a texture of the same size as
+ * RGBA8 with alpha 255, on the device (what sampling a TU_RENDERTARGET texture needs; Tiny has no
+ * render textures).  Flushes the target first.  Ordered on the stream. */
+OGRECU_API int ogrecu_tex_copy_from_rt(ogrecu_tex* tex, ogrecu_rt* rt);
 
 /* Render target = TinyWindow colour Image (PF_BYTE_RGB, tightly packed,
  * OgreTinyWindow.cpp:38-42) + TinyDepthBuffer Image (PF_FLOAT32_R, OgreTinyDepthBuffer.h:20). */

@@ -88,6 +88,9 @@ class Context:
     def set_stream(self, cuda_stream):
         check(lib().ogrecu_set_stream(self.handle, cuda_stream))
 
+    def set_config_option(self, name, value):
+        check(lib().ogrecu_set_config_option(self.handle, name.encode(), int(value)))
+
     @property
     def launch_count(self):
         return int(lib().ogrecu_launch_count(self.handle))

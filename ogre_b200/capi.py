@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libogrecu.so")
+# OGRECU_LIB: load another build of the same library (kernel tuning experiments); still no fallback
+LIB_PATH = os.environ.get("OGRECU_LIB") or os.path.join(_HERE, "libogrecu.so")
 
 c_void_pp = C.POINTER(C.c_void_p)
 c_float_p = C.POINTER(C.c_float)
@@ -83,6 +84,9 @@ SIGNATURES = {
     "ogrecu_buf_resolve": (C.c_int, [C.c_void_p, C.c_void_p, c_void_pp, C.POINTER(C.c_size_t)]),
     "ogrecu_skin_dev": (C.c_int, [C.c_void_p, C.POINTER(SkinJob), C.c_uint32]),
     "ogrecu_skin_instanced_dev": (C.c_int, [C.c_void_p, C.POINTER(SkinJob), C.c_uint32, C.c_size_t, C.c_size_t, C.c_size_t]),
+    "ogrecu_anim_instanced_dev": (C.c_int, [C.c_void_p, C.POINTER(SkinJob), C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                            C.c_uint32, C.c_size_t, C.c_size_t]),
+    "ogrecu_set_config_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "ogrecu_morph_instanced_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t,
                                              C.c_size_t, C.c_size_t, C.c_int, C.c_uint32, C.c_size_t]),
     "ogrecu_software_vertex_skinning_host": (C.c_int, [
@@ -107,6 +111,7 @@ SIGNATURES = {
     "ogrecu_tex_destroy": (C.c_int, [C.c_void_p]),
     "ogrecu_tex_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "ogrecu_tex_download": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "ogrecu_tex_copy_from_rt": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ogrecu_tex_device_ptr": (C.c_int, [C.c_void_p, c_void_pp]),
     "ogrecu_rt_create": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, c_void_pp]),
     "ogrecu_rt_destroy": (C.c_int, [C.c_void_p]),

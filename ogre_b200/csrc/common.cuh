@@ -79,6 +79,10 @@ struct ogrecu_ctx {
     // shadow registry: shadow base address -> buffer
     std::map<uintptr_t, ogrecu_buf*> shadows;
     std::vector<ogrecu_rt*> targets;
+    // development switches read once from the environment (A/B measurements, never a fallback):
+    //   OGRECU_SKIN_MODE  0 auto | 1 tile kernel without TMA (cooperative LDG/STG) | 2 one-thread-per-vertex kernel
+    //   OGRECU_SKIN_IPC   instances per CTA of the tile kernel (0 = auto)
+    int skin_mode, skin_ipc;
 };
 
 namespace ogrecu {

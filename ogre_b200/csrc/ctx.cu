@@ -7,8 +7,10 @@
 // There is no CPU fallback: without a CUDA device ogrecu_init fails.
 #include "common.cuh"
 
+#include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace ogrecu {
@@ -100,6 +102,10 @@ int ogrecu_init(int device, ogrecu_ctx** out_ctx)
     ctx->sm_count = prop.multiProcessorCount;
     ctx->pinned = nullptr;
     ctx->pinned_cap = 0;
+    const char* ev = getenv("OGRECU_SKIN_MODE");
+    ctx->skin_mode = ev ? atoi(ev) : 0;
+    ev = getenv("OGRECU_SKIN_IPC");
+    ctx->skin_ipc = ev ? atoi(ev) : 0;
     e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete ctx; return cuda_fail(e, "cudaStreamCreate", __FILE__, __LINE__); }
     ctx->stream = ctx->own_stream;
@@ -145,6 +151,15 @@ int ogrecu_sync(ogrecu_ctx* ctx)
     OGRECU_CUDA(cudaSetDevice(ctx->device));
     OGRECU_CUDA(cudaStreamSynchronize(ctx->stream));
     return OGRECU_OK;
+}
+
+int ogrecu_set_config_option(ogrecu_ctx* ctx, const char* name, int value)
+{
+    OGRECU_REQUIRE(ctx && name, "NULL argument");
+    if (!strcmp(name, "skin_mode")) { OGRECU_REQUIRE(value >= 0 && value <= 2, "skin_mode is 0..2"); ctx->skin_mode = value; return OGRECU_OK; }
+    if (!strcmp(name, "skin_ipc")) { OGRECU_REQUIRE(value >= 0 && value <= 4096, "skin_ipc is 0..4096"); ctx->skin_ipc = value; return OGRECU_OK; }
+    set_error("ogrecu_set_config_option: unknown option '%s'", name);
+    return OGRECU_ERR_INVALID;
 }
 
 uint64_t ogrecu_launch_count(const ogrecu_ctx* ctx) { return ctx ? ctx->launches : 0; }
@@ -276,14 +291,17 @@ int ogrecu_buf_map(ogrecu_buf* b, size_t offset, size_t length, int mode, void**
         OGRECU_CUDA(cudaEventSynchronize(b->upload_ev));
         b->upload_pending = false;
     }
-    // Bring device-side writes (skinning output) back before the host looks at or
-    // partially overwrites the shadow.  A DISCARD map skips the download.
-    if (b->dev_dirty && !(mode & OGRECU_MAP_DISCARD)) {
-        OGRECU_CUDA(cudaMemcpyAsync(b->shadow + b->dev_dirty_lo, (uint8_t*)b->dev + b->dev_dirty_lo,
-                                    b->dev_dirty_hi - b->dev_dirty_lo, cudaMemcpyDeviceToHost, ctx->stream));
-        OGRECU_CUDA(cudaStreamSynchronize(ctx->stream));
-        b->dev_dirty = false;
-    } else if (b->dev_dirty && (mode & OGRECU_MAP_DISCARD) && offset == 0 && length == b->size) {
+    // Bring device-side writes (skinning output) back before the host looks at or partially
+    // overwrites the shadow.  Only a DISCARD map of the whole buffer skips the download; after
+    // this block dev_dirty is always clear, so anything marked while the buffer is mapped is a
+    // device write made DURING the map (OptimisedUtil writing into a locked destination).
+    if (b->dev_dirty) {
+        const bool whole_discard = (mode & OGRECU_MAP_DISCARD) && offset == 0 && length == b->size;
+        if (!whole_discard) {
+            OGRECU_CUDA(cudaMemcpyAsync(b->shadow + b->dev_dirty_lo, (uint8_t*)b->dev + b->dev_dirty_lo,
+                                        b->dev_dirty_hi - b->dev_dirty_lo, cudaMemcpyDeviceToHost, ctx->stream));
+            OGRECU_CUDA(cudaStreamSynchronize(ctx->stream));
+        }
         b->dev_dirty = false;
     }
     b->mapped = true;
@@ -301,11 +319,26 @@ int ogrecu_buf_unmap(ogrecu_buf* b)
     ogrecu_ctx* ctx = b->ctx;
     b->mapped = false;
     if ((b->map_mode & (OGRECU_MAP_WRITE | OGRECU_MAP_DISCARD)) && b->map_len) {
-        // pinned -> device, ordered on the stream before any later kernel
-        OGRECU_CUDA(cudaMemcpyAsync((uint8_t*)b->dev + b->map_off, b->shadow + b->map_off, b->map_len,
-                                    cudaMemcpyHostToDevice, ctx->stream));
-        OGRECU_CUDA(cudaEventRecord(b->upload_ev, ctx->stream));
-        b->upload_pending = true;
+        // pinned -> device, ordered on the stream before any later kernel.  A range written on the
+        // device while the buffer was mapped (Mesh::softwareVertexBlend locks the destination, then
+        // calls OptimisedUtil with the locked pointer, OgreMesh.cpp:1827-1896) holds the newer data:
+        // it is left alone and stays device-dirty.
+        size_t lo = b->map_off, hi = b->map_off + b->map_len;
+        size_t piece[2][2] = {{lo, hi}, {0, 0}};
+        if (b->dev_dirty && b->dev_dirty_lo < hi && b->dev_dirty_hi > lo) {
+            piece[0][0] = lo; piece[0][1] = std::max(lo, std::min(hi, b->dev_dirty_lo));
+            piece[1][0] = std::min(hi, std::max(lo, b->dev_dirty_hi)); piece[1][1] = hi;
+        }
+        bool any = false;
+        for (auto& pc : piece)
+            if (pc[1] > pc[0]) {
+                OGRECU_CUDA(cudaMemcpyAsync((uint8_t*)b->dev + pc[0], b->shadow + pc[0], pc[1] - pc[0], cudaMemcpyHostToDevice, ctx->stream));
+                any = true;
+            }
+        if (any) {
+            OGRECU_CUDA(cudaEventRecord(b->upload_ev, ctx->stream));
+            b->upload_pending = true;
+        }
     }
     return OGRECU_OK;
 }

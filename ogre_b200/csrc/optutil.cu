@@ -6,29 +6,14 @@
 // extrusion) or is wrong (morph normals) the exact General formulation
 // (OgreMain/src/OgreOptimisedUtilGeneral.cpp) is followed — see DESIGN.md.
 #include "common.cuh"
+#include "skin_math.cuh"
+#include "skin_tile.cuh"
 
 #include <cstring>
 
 using namespace ogrecu;
 
 namespace {
-
-__device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
-__device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
-__device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
-__device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
-__device__ __forceinline__ float fsqrt(float a) { return __fsqrt_rn(a); }
-
-__device__ __forceinline__ float4 mul4(float4 a, float w) { return make_float4(fmul(a.x, w), fmul(a.y, w), fmul(a.z, w), fmul(a.w, w)); }
-__device__ __forceinline__ float4 madd4(float4 a, float w, float4 c)  // a*w + c, two roundings
-{
-    return make_float4(fadd(fmul(a.x, w), c.x), fadd(fmul(a.y, w), c.y), fadd(fmul(a.z, w), c.z), fadd(fmul(a.w, w), c.w));
-}
-__device__ __forceinline__ float4 lerp4(float4 a, float4 b, float t)  // (b-a)*t + a
-{
-    return make_float4(fadd(fmul(fsub(b.x, a.x), t), a.x), fadd(fmul(fsub(b.y, a.y), t), a.y),
-                       fadd(fmul(fsub(b.z, a.z), t), a.z), fadd(fmul(fsub(b.w, a.w), t), a.w));
-}
 
 template <typename T>
 __device__ __forceinline__ const T* byte_off(const T* p, size_t off) { return (const T*)((const uint8_t*)p + off); }
@@ -464,14 +449,67 @@ int ogrecu_skin_instanced_dev(ogrecu_ctx* ctx, const ogrecu_skin_job* job, uint3
     OGRECU_CHECK(validate_skin_job(*job));
     OGRECU_REQUIRE((palette_stride_floats & 3) == 0, "palette stride must keep 16-byte alignment");
     OGRECU_REQUIRE((dst_instance_stride_bytes & 3) == 0, "destination instance stride must be a multiple of 4");
-    OGRECU_REQUIRE(num_instances <= 65535, "at most 65535 instances per call");
+    OGRECU_REQUIRE(num_instances <= 0x7fffffffu, "too many instances");
     if (num_instances == 0 || job->num_vertices == 0) return OGRECU_OK;
     OGRECU_CUDA(cudaSetDevice(ctx->device));
+    const ogrecu_skin_job& j = *job;
+    // dense layouts take the tiled stream kernel (skin_tile.cu): pos+normal interleaved at stride 24
+    // in source and destination (the reference's "shared packed" case, OgreOptimisedUtilSSE.cpp:1100-1130)
+    // or positions only at stride 12
+    const bool packed24 = j.src_norm && (const uint8_t*)j.src_norm == (const uint8_t*)j.src_pos + 12 &&
+                          (uint8_t*)j.dst_norm == (uint8_t*)j.dst_pos + 12 && j.src_pos_stride == 24 && j.src_norm_stride == 24 &&
+                          j.dst_pos_stride == 24 && j.dst_norm_stride == 24;
+    const bool packed12 = !j.src_norm && j.src_pos_stride == 12 && j.dst_pos_stride == 12;
+    if ((packed24 || packed12) && ctx->skin_mode != 2) {
+        SkinTileParams P;
+        memset(&P, 0, sizeof P);
+        P.src = (const uint8_t*)j.src_pos; P.dst = (uint8_t*)j.dst_pos;
+        P.blend_weight = j.blend_weight; P.blend_index = j.blend_index;
+        P.palette = j.palette; P.bone_map = j.bone_map;
+        P.palette_stride_floats = palette_stride_floats;
+        P.src_inst_stride = src_instance_stride_bytes; P.dst_inst_stride = dst_instance_stride_bytes;
+        P.blend_weight_stride = j.blend_weight_stride; P.blend_index_stride = j.blend_index_stride;
+        P.num_matrices = j.num_matrices; P.num_vertices = j.num_vertices; P.num_instances = num_instances;
+        return launch_skin_tile(ctx, P, j.num_weights, packed24, false);
+    }
+    OGRECU_REQUIRE(num_instances <= 65535, "at most 65535 instances per call for strided layouts");
     dim3 grid(div_up(job->num_vertices, SKIN_THREADS), num_instances);
     skin_instanced_kernel<<<grid, SKIN_THREADS, 0, ctx->stream>>>(*job, palette_stride_floats, src_instance_stride_bytes, dst_instance_stride_bytes);
     OGRECU_CUDA(cudaGetLastError());
     count_launch(ctx);
     return OGRECU_OK;
+}
+
+int ogrecu_anim_instanced_dev(ogrecu_ctx* ctx, const ogrecu_skin_job* job, const float* key2, const float* t_dev,
+                              float* morph_out, size_t morph_instance_stride_bytes, uint32_t num_instances,
+                              size_t palette_stride_floats, size_t dst_instance_stride_bytes)
+{
+    OGRECU_REQUIRE(ctx && job && key2 && t_dev, "NULL argument");
+    OGRECU_CHECK(validate_skin_job(*job));
+    const ogrecu_skin_job& j = *job;
+    OGRECU_REQUIRE((palette_stride_floats & 3) == 0, "palette stride must keep 16-byte alignment");
+    OGRECU_REQUIRE(((dst_instance_stride_bytes | morph_instance_stride_bytes | (uintptr_t)key2 | (uintptr_t)morph_out) & 3) == 0,
+                   "streams must be 4-byte aligned");
+    const bool packed24 = j.src_norm && (const uint8_t*)j.src_norm == (const uint8_t*)j.src_pos + 12 &&
+                          (uint8_t*)j.dst_norm == (uint8_t*)j.dst_pos + 12 && j.src_pos_stride == 24 && j.src_norm_stride == 24 &&
+                          j.dst_pos_stride == 24 && j.dst_norm_stride == 24;
+    const bool packed12 = !j.src_norm && j.src_pos_stride == 12 && j.dst_pos_stride == 12;
+    OGRECU_REQUIRE(packed24 || packed12, "fused morph+skin needs dense keyframes and destination (stride 24 pos+normal, or 12 pos only)");
+    OGRECU_REQUIRE(num_instances <= 0x7fffffffu, "too many instances");
+    if (num_instances == 0 || j.num_vertices == 0) return OGRECU_OK;
+    OGRECU_CUDA(cudaSetDevice(ctx->device));
+    SkinTileParams P;
+    memset(&P, 0, sizeof P);
+    P.src = (const uint8_t*)j.src_pos; P.key2 = (const uint8_t*)key2; P.tarr = t_dev;
+    P.morph_out = (uint8_t*)morph_out; P.morph_inst_stride = morph_instance_stride_bytes;
+    P.dst = (uint8_t*)j.dst_pos;
+    P.blend_weight = j.blend_weight; P.blend_index = j.blend_index;
+    P.palette = j.palette; P.bone_map = j.bone_map;
+    P.palette_stride_floats = palette_stride_floats;
+    P.dst_inst_stride = dst_instance_stride_bytes;
+    P.blend_weight_stride = j.blend_weight_stride; P.blend_index_stride = j.blend_index_stride;
+    P.num_matrices = j.num_matrices; P.num_vertices = j.num_vertices; P.num_instances = num_instances;
+    return launch_skin_tile(ctx, P, j.num_weights, packed24, true);
 }
 
 int ogrecu_morph_dev(ogrecu_ctx* ctx, float t, const float* src1, const float* src2, float* dst, size_t stride1,

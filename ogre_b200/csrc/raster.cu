@@ -624,6 +624,28 @@ __global__ void clear_colour_kernel(uint8_t* __restrict__ colour, size_t nbytes,
     }
 }
 
+// RGB8 plane -> RGBA8 texture (alpha 255): one thread per 4 pixels = 12 bytes in, 16 bytes out
+__global__ void rgb_to_rgba_kernel(const uint8_t* __restrict__ rgb, uint8_t* __restrict__ rgba, size_t npx)
+{
+    size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t p0 = q * 4;
+    if (p0 >= npx) return;
+    if (p0 + 4 <= npx) {
+        const uint32_t* s = reinterpret_cast<const uint32_t*>(rgb + p0 * 3);   // plane base is 256-byte aligned, 12*q is 4-aligned
+        uint32_t a = s[0], b = s[1], c = s[2];
+        uint4 o;
+        o.x = (a & 0x00ffffffu) | 0xff000000u;
+        o.y = ((a >> 24) | (b << 8)) & 0x00ffffffu | 0xff000000u;
+        o.z = ((b >> 16) | (c << 16)) & 0x00ffffffu | 0xff000000u;
+        o.w = (c >> 8) | 0xff000000u;
+        *reinterpret_cast<uint4*>(rgba + p0 * 4) = o;
+    } else {
+        for (size_t p = p0; p < npx; ++p) {
+            rgba[p * 4] = rgb[p * 3]; rgba[p * 4 + 1] = rgb[p * 3 + 1]; rgba[p * 4 + 2] = rgb[p * 3 + 2]; rgba[p * 4 + 3] = 0xff;
+        }
+    }
+}
+
 __global__ void clear_depth_kernel(float* __restrict__ depth, size_t n, float v)
 {
     size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
@@ -943,6 +965,22 @@ int ogrecu_tex_download(ogrecu_tex* t, uint8_t* rgba, size_t pitch)
     OGRECU_CUDA(cudaMemcpyAsync(ctx->pinned, t->dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     OGRECU_CUDA(cudaStreamSynchronize(ctx->stream));
     for (uint32_t y = 0; y < t->h; ++y) memcpy(rgba + y * pitch, (uint8_t*)ctx->pinned + y * row, row);
+    return OGRECU_OK;
+}
+
+int ogrecu_tex_copy_from_rt(ogrecu_tex* t, ogrecu_rt* rt)
+{
+    OGRECU_REQUIRE(t && rt, "NULL argument");
+    OGRECU_REQUIRE(t->ctx == rt->ctx, "texture and target belong to different contexts");
+    OGRECU_REQUIRE(t->w == rt->w && t->h == rt->h, "texture and target sizes differ");
+    OGRECU_CHECK(ogrecu_flush(rt));
+    ogrecu_ctx* ctx = t->ctx;
+    OGRECU_CUDA(cudaSetDevice(ctx->device));
+    const size_t npx = (size_t)t->w * t->h;
+    rgb_to_rgba_kernel<<<div_up(div_up(npx, 4), 256), 256, 0, ctx->stream>>>(rt->colour, t->dev, npx);
+    OGRECU_CUDA(cudaGetLastError());
+    count_launch(ctx);
+    t->has_zero_alpha = 0;
     return OGRECU_OK;
 }
 

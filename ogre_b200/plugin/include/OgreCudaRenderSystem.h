@@ -1,0 +1,97 @@
+// CudaRenderSystem — mirrors RenderSystems/Tiny/include/OgreTinyRenderSystem.h: same fixed-function
+// contract (5 auto-constants, 1 texture unit, [-1,1] depth range, identity projection conversion,
+// texture flipping on), same state honoured / ignored.  The difference: _render
+// RECORDS a draw descriptor (state + uniform snapshot + device buffer addresses) on the target's
+// ogrecu_rt; the binned tile rasteriser in libogrecu.so runs at _endFrame / readback / buffer lock.
+#ifndef __CudaRenderSystem_H__
+#define __CudaRenderSystem_H__
+
+#include "OgreCudaPrerequisites.h"
+#include "OgreRenderSystem.h"
+#include "OgreRenderWindow.h"
+#include "OgreMatrix4.h"
+
+namespace Ogre
+{
+class HardwareBufferManager;
+
+class CudaRenderSystem : public RenderSystem
+{
+    ogrecu_ctx* mCtx;
+    int mDeviceIndex;
+    Matrix4 mVP;   // viewport transform (TinyRenderSystem::mVP)
+
+    ogrecu_rt* mActiveTarget;
+    CudaTexture* mActiveTargetTexture;   // non-null when rendering into a RenderTexture
+
+    // DefaultShader uniforms (RenderSystems/Tiny/include/OgreTinyRenderSystem.h:57-75)
+    Matrix4 mUniformMVP, mUniformTex, mUniformMVIT;
+    Vector3 mUniformLightDir;
+    ColourValue mUniformAmbient;
+    bool mDoLighting;
+    CudaTexture* mTexture;   // unit 0 or NULL
+
+    bool mDepthTest, mDepthWrite, mBlendAdd;
+
+    HardwareBufferManager* mHardwareBufferManager;
+    bool mInitialised;
+    std::vector<ogrecu_rt*> mDirtyTargets;   // targets with recorded, unflushed work
+
+    static CudaRenderSystem* msInstance;
+    void noteRecorded(ogrecu_rt* rt);
+
+public:
+    CudaRenderSystem();
+    ~CudaRenderSystem();
+
+    /// the device context; created on first use, throws when no CUDA device is usable (no fallback)
+    ogrecu_ctx* getContext();
+    static CudaRenderSystem* getInstance() { return msInstance; }
+    /// run everything recorded on any target (called before buffers/textures that draws may reference change)
+    static void flushPendingDraws();
+    /// flush + read a colour box into an arbitrary-format PixelBox (readback path of windows and RTTs)
+    static void readColour(ogrecu_rt* rt, const Box& src, const PixelBox& dst);
+
+    Real getMinimumDepthInputValue(void) override { return -1.0f; }   // Range [-1.0f, 1.0f], as Tiny
+    Real getMaximumDepthInputValue(void) override { return 1.0f; }
+    void _convertProjectionMatrix(const Matrix4& matrix, Matrix4& dest, bool) override { dest = matrix; }
+
+    void initConfigOptions() override;
+    void setConfigOption(const String& name, const String& value) override;
+
+    const String& getName(void) const override;
+    RenderSystemCapabilities* createRenderSystemCapabilities() const override;
+    void shutdown(void) override;
+
+    RenderWindow* _createRenderWindow(const String& name, unsigned int width, unsigned int height, bool fullScreen,
+                                      const NameValuePairList* miscParams = 0) override;
+    DepthBuffer* _createDepthBufferFor(RenderTarget* renderTarget) override;
+    MultiRenderTarget* createMultiRenderTarget(const String& name) override;
+
+    void _setTexture(size_t unit, bool enabled, const TexturePtr& tex) override;
+    void _setSampler(size_t unit, Sampler& sampler) override {}
+    void setLightingEnabled(bool enabled) override { mDoLighting = enabled; }
+    void _setViewport(Viewport* vp) override;
+    void _endFrame(void) override;
+    void _setCullingMode(CullingMode mode) override { mCullingMode = mode; }
+    void _setDepthBufferParams(bool depthTest = true, bool depthWrite = true,
+                               CompareFunction depthFunction = CMPF_LESS_EQUAL) override;
+    void _setDepthBias(float, float) override {}
+    void setColourBlendState(const ColourBlendState& state) override;
+    void _setPolygonMode(PolygonMode) override {}
+    void setStencilState(const StencilState&) override {}
+    void applyFixedFunctionParams(const GpuProgramParametersPtr& params, uint16 variabilityMask) override;
+    void _render(const RenderOperation& op) override;
+    void setScissorTest(bool, const Rect& = Rect()) override {}
+    void clearFrameBuffer(unsigned int buffers, const ColourValue& colour = ColourValue::Black, float depth = 1.0f,
+                          unsigned short stencil = 0) override;
+    HardwareOcclusionQuery* createHardwareOcclusionQuery(void) override { return NULL; }
+    void _setRenderTarget(RenderTarget* target) override;
+    void bindGpuProgramParameters(GpuProgramType, const GpuProgramParametersPtr&, uint16) override {}
+    void _setAlphaRejectSettings(CompareFunction, unsigned char, bool) override {}
+    void beginProfileEvent(const String&) override {}
+    void endProfileEvent(void) override {}
+    void markProfileEvent(const String&) override {}
+};
+} // namespace Ogre
+#endif

@@ -1,0 +1,372 @@
+#include "OgreCudaRenderSystem.h"
+
+#include "OgreCudaDepthBuffer.h"
+#include "OgreCudaHardwareBufferManager.h"
+#include "OgreCudaTexture.h"
+#include "OgreCudaWindow.h"
+#include "OgreGpuProgramManager.h"
+#include "OgreLogManager.h"
+#include "OgreRoot.h"
+#include "OgreStringConverter.h"
+#include "OgreViewport.h"
+
+namespace Ogre
+{
+CudaRenderSystem* CudaRenderSystem::msInstance = 0;
+
+CudaRenderSystem::CudaRenderSystem()
+    : mCtx(0), mDeviceIndex(0), mActiveTarget(0), mActiveTargetTexture(0), mDoLighting(false), mTexture(0), mDepthTest(true),
+      mDepthWrite(true), mBlendAdd(false), mHardwareBufferManager(0), mInitialised(false)
+{
+    LogManager::getSingleton().logMessage(getName() + " created.");
+    msInstance = this;
+    if (const char* dev = getenv("OGRECU_DEVICE")) mDeviceIndex = atoi(dev);
+    initConfigOptions();
+
+    // the same five auto-constants as TinyRenderSystem (OgreTinyRenderSystem.cpp:35-42): OgreMain
+    // then produces bit-identical uniform values for both back ends
+    GpuLogicalBufferStructPtr logicalBufferStruct(new GpuLogicalBufferStruct());
+    mFixedFunctionParams.reset(new GpuProgramParameters);
+    mFixedFunctionParams->_setLogicalIndexes(logicalBufferStruct);
+    mFixedFunctionParams->setAutoConstant(0, GpuProgramParameters::ACT_WORLDVIEWPROJ_MATRIX);
+    mFixedFunctionParams->setAutoConstant(4, GpuProgramParameters::ACT_TEXTURE_MATRIX);
+    mFixedFunctionParams->setAutoConstant(8, GpuProgramParameters::ACT_DERIVED_AMBIENT_LIGHT_COLOUR);
+    mFixedFunctionParams->setAutoConstant(9, GpuProgramParameters::ACT_LIGHT_POSITION);
+    mFixedFunctionParams->setAutoConstant(10, GpuProgramParameters::ACT_INVERSE_TRANSPOSE_WORLDVIEW_MATRIX);
+
+    mActiveRenderTarget = 0;
+}
+
+CudaRenderSystem::~CudaRenderSystem()
+{
+    shutdown();
+    if (mCtx)
+    {
+        ogrecu_shutdown(mCtx);
+        mCtx = 0;
+    }
+    if (msInstance == this) msInstance = 0;
+}
+
+ogrecu_ctx* CudaRenderSystem::getContext()
+{
+    if (!mCtx)
+    {
+        OGRECU_THROW_IF(ogrecu_init(mDeviceIndex, &mCtx));
+        LogManager::getSingleton().logMessage("CUDA RenderSystem: libogrecu context on device " +
+                                              StringConverter::toString(mDeviceIndex));
+    }
+    return mCtx;
+}
+
+void CudaRenderSystem::initConfigOptions()
+{
+    RenderSystem::initConfigOptions();
+    ConfigOption dev;
+    dev.name = "Device";
+    dev.currentValue = StringConverter::toString(mDeviceIndex);
+    dev.immutable = false;
+    int n = 0;
+    ogrecu_device_count(&n);
+    for (int i = 0; i < n; ++i) dev.possibleValues.push_back(StringConverter::toString(i));
+    mOptions[dev.name] = dev;
+}
+
+void CudaRenderSystem::setConfigOption(const String& name, const String& value)
+{
+    auto it = mOptions.find(name);
+    if (it != mOptions.end()) it->second.currentValue = value;
+    if (name == "Device")
+    {
+        OgreAssert(!mCtx, "the device cannot change once the context exists");
+        mDeviceIndex = StringConverter::parseInt(value);
+    }
+}
+
+const String& CudaRenderSystem::getName(void) const
+{
+    static String strName("CUDA Rendering Subsystem");
+    return strName;
+}
+
+RenderSystemCapabilities* CudaRenderSystem::createRenderSystemCapabilities() const
+{
+    // mirrors OgreTinyRenderSystem.cpp:94-131 so OgreMain takes the same code paths (FFP, no RTSS)
+    RenderSystemCapabilities* rsc = OGRE_NEW RenderSystemCapabilities();
+    rsc->setDriverVersion(mDriverVersion);
+    rsc->setRenderSystemName(getName());
+    rsc->setDeviceName("NVIDIA B200 (sm_100a) via libogrecu");
+    rsc->setNumTextureUnits(1);
+    rsc->setCapability(RSC_FIXED_FUNCTION);
+    rsc->setCapability(RSC_MAPBUFFER);
+    rsc->setCapability(RSC_NON_POWER_OF_2_TEXTURES);
+    rsc->setCapability(RSC_USER_CLIP_PLANES);
+    rsc->setCapability(RSC_TEXTURE_1D);
+    rsc->setCapability(RSC_TEXTURE_3D);
+    rsc->setCapability(RSC_TEXTURE_2D_ARRAY);
+    rsc->setCapability(RSC_32BIT_INDEX);
+    rsc->setCapability(RSC_DEPTH_CLAMP);
+    rsc->setCapability(RSC_VERTEX_BUFFER_INSTANCE_DATA);
+    rsc->setCapability(RSC_TEXTURE_FLOAT);
+    rsc->setCapability(RSC_VERTEX_TEXTURE_FETCH);
+    return rsc;
+}
+
+void CudaRenderSystem::shutdown(void)
+{
+    if (mCtx) flushPendingDraws();
+    RenderSystem::shutdown();   // destroys render targets (windows, render textures)
+    mDirtyTargets.clear();
+    mActiveTarget = 0;
+    mActiveTargetTexture = 0;
+    mTexture = 0;
+
+    OGRE_DELETE mHardwareBufferManager;
+    mHardwareBufferManager = 0;
+    OGRE_DELETE mTextureManager;
+    mTextureManager = 0;
+    mInitialised = false;
+}
+
+RenderWindow* CudaRenderSystem::_createRenderWindow(const String& name, unsigned int width, unsigned int height,
+                                                    bool fullScreen, const NameValuePairList* miscParams)
+{
+    RenderSystem::_createRenderWindow(name, width, height, fullScreen, miscParams);
+
+    RenderWindow* win = new CudaWindow(getContext());
+    win->create(name, width, height, fullScreen, miscParams);
+    attachRenderTarget(*win);
+
+    if (!mInitialised)
+    {
+        LogManager::getSingleton().logMessage("***  CUDA (B200) software RenderSystem started  ***");
+        mRealCapabilities = createRenderSystemCapabilities();
+        if (!mUseCustomCapabilities) mCurrentCapabilities = mRealCapabilities;
+        fireEvent("RenderSystemCapabilitiesCreated");
+        mHardwareBufferManager = new CudaHardwareBufferManager(getContext());
+        mTextureManager = new CudaTextureManager(getContext());
+        mInitialised = true;
+    }
+
+    if (win->getDepthBufferPool() != RBP_NONE)
+    {
+        auto* depthBuffer = new CudaDepthBuffer(win->getDepthBufferPool(), win->getWidth(), win->getHeight(), win->getFSAA(), true);
+        mDepthBufferPool[depthBuffer->getPoolId()].push_back(depthBuffer);
+        win->attachDepthBuffer(depthBuffer);
+    }
+    return win;
+}
+
+DepthBuffer* CudaRenderSystem::_createDepthBufferFor(RenderTarget* rt)
+{
+    return new CudaDepthBuffer(rt->getDepthBufferPool(), rt->getWidth(), rt->getHeight(), rt->getFSAA(), false);
+}
+
+MultiRenderTarget* CudaRenderSystem::createMultiRenderTarget(const String&) { return NULL; }
+
+void CudaRenderSystem::_setTexture(size_t stage, bool enabled, const TexturePtr& texPtr)
+{
+    if (stage > 0) return;   // one texture unit (OgreTinyRenderSystem.cpp:208-220)
+    mTexture = (!enabled || !texPtr) ? NULL : static_cast<CudaTexture*>(texPtr.get());
+}
+
+void CudaRenderSystem::_setViewport(Viewport* vp)
+{
+    if (!vp)
+    {
+        mActiveViewport = NULL;
+        _setRenderTarget(NULL);
+    }
+    else if (vp != mActiveViewport || vp->_isUpdated())
+    {
+        RenderTarget* target = vp->getTarget();
+        _setRenderTarget(target);
+        mActiveViewport = vp;
+
+        // identical arithmetic to TinyRenderSystem::_setViewport (OgreTinyRenderSystem.cpp:230-262)
+        Rect vpRect = vp->getActualDimensions();
+        if (!target->requiresTextureFlipping())
+        {
+            std::swap(vpRect.top, vpRect.bottom);
+            vpRect.top = target->getHeight() - vpRect.top;
+            vpRect.bottom = target->getHeight() - vpRect.bottom;
+        }
+        mVP.makeTransform({vpRect.left + vpRect.width() / 2.f, vpRect.top + vpRect.height() / 2.f, 0.5},
+                          {vpRect.width() / 2.f, vpRect.height() / 2.f, 0.5}, Ogre::Quaternion::IDENTITY);
+        vp->_clearUpdatedFlag();
+    }
+}
+
+void CudaRenderSystem::noteRecorded(ogrecu_rt* rt)
+{
+    if (std::find(mDirtyTargets.begin(), mDirtyTargets.end(), rt) == mDirtyTargets.end()) mDirtyTargets.push_back(rt);
+}
+
+void CudaRenderSystem::flushPendingDraws()
+{
+    CudaRenderSystem* rs = msInstance;
+    if (!rs || rs->mDirtyTargets.empty()) return;
+    std::vector<ogrecu_rt*> targets;
+    targets.swap(rs->mDirtyTargets);
+    for (ogrecu_rt* rt : targets) OGRECU_THROW_IF(ogrecu_flush(rt));
+}
+
+void CudaRenderSystem::_endFrame(void)
+{
+    // launch the frame's recorded work now; it runs asynchronously while OgreMain goes on
+    // (Root::_fireFrameRenderingQueued, OgreRoot.cpp:1156, is the designed overlap window)
+    flushPendingDraws();
+}
+
+void CudaRenderSystem::_setDepthBufferParams(bool depthTest, bool depthWrite, CompareFunction)
+{
+    mDepthTest = depthTest;
+    mDepthWrite = depthWrite;
+}
+
+void CudaRenderSystem::setColourBlendState(const ColourBlendState& state) { mBlendAdd = state.destFactor == SBF_ONE; }
+
+void CudaRenderSystem::applyFixedFunctionParams(const GpuProgramParametersPtr& params, uint16 mask)
+{
+    // same slots, same conversions as TinyRenderSystem::applyFixedFunctionParams (OgreTinyRenderSystem.cpp:49-82)
+    for (const auto& ac : params->getAutoConstants())
+    {
+        if (!(ac.variability & mask)) continue;
+        const float* ptr = params->getFloatPointer(ac.physicalIndex);
+        switch (ac.paramType)
+        {
+        case GpuProgramParameters::ACT_WORLDVIEWPROJ_MATRIX: mUniformMVP = Matrix4(ptr); break;
+        case GpuProgramParameters::ACT_TEXTURE_MATRIX: mUniformTex = Matrix4(ptr); break;
+        case GpuProgramParameters::ACT_DERIVED_AMBIENT_LIGHT_COLOUR: memcpy(mUniformAmbient.ptr(), ptr, sizeof(float) * 4); break;
+        case GpuProgramParameters::ACT_LIGHT_POSITION:
+            mUniformLightDir = ptr[3] ? Vector3(ptr).normalisedCopy() : -Vector3(ptr);
+            break;
+        case GpuProgramParameters::ACT_INVERSE_TRANSPOSE_WORLDVIEW_MATRIX: mUniformMVIT = Matrix4(ptr); break;
+        default: break;
+        }
+    }
+}
+
+namespace
+{
+struct Stream
+{
+    const void* ptr;
+    uint32 stride;
+};
+
+// device address of the first element of `sem`, the way TinyRenderSystem's getData() computes the
+// host address (OgreTinyRenderSystem.cpp:335-347): base + elemOffset + vertexStart*stride
+Stream deviceStream(const RenderOperation& op, VertexElementSemantic sem)
+{
+    Stream s = {0, 0};
+    auto element = op.vertexData->vertexDeclaration->findElementBySemantic(sem);
+    if (!element) return s;
+    s.stride = (uint32)op.vertexData->vertexDeclaration->getVertexSize(element->getSource());
+    auto buf = op.vertexData->vertexBufferBinding->getBuffer(element->getSource());
+    auto impl = dynamic_cast<CudaHardwareBuffer*>(buf->_getImpl<HardwareBuffer>());
+    OgreAssert(impl, "vertex buffer was not created by CudaHardwareBufferManager");
+    s.ptr = impl->getDevicePtr(element->getOffset() + op.vertexData->vertexStart * s.stride);
+    return s;
+}
+} // namespace
+
+void CudaRenderSystem::_render(const RenderOperation& op)
+{
+    RenderSystem::_render(op);   // face / batch / vertex statistics (OgreMain/src/OgreRenderSystem.cpp:622)
+
+    bool isStrip = op.operationType == RenderOperation::OT_TRIANGLE_STRIP;
+    if (!isStrip && op.operationType != RenderOperation::OT_TRIANGLE_LIST)   // only triangle list / strip supported
+        return;
+    if (!mActiveTarget) return;
+
+    Stream pos = deviceStream(op, VES_POSITION);
+    OgreAssert(pos.ptr, "VES_POSITION required");
+    Stream uv = deviceStream(op, VES_TEXTURE_COORDINATES);
+    Stream nrm = deviceStream(op, VES_NORMAL);
+
+    mDoLighting &= bool(nrm.ptr);   // sticky, as in Tiny (OgreTinyRenderSystem.cpp:369)
+
+    ogrecu_draw_desc d;
+    memset(&d, 0, sizeof d);
+    d.positions = pos.ptr; d.pos_stride = pos.stride;
+    d.uvs = uv.ptr; d.uv_stride = uv.stride;
+    d.normals = nrm.ptr; d.normal_stride = nrm.stride;
+    d.index_type = OGRECU_INDEX_NONE;
+    d.draw_count = (uint32_t)op.vertexData->vertexCount;
+    if (op.useIndexes)
+    {
+        auto& ib = op.indexData->indexBuffer;
+        auto impl = dynamic_cast<CudaHardwareBuffer*>(ib->_getImpl<HardwareBuffer>());
+        OgreAssert(impl, "index buffer was not created by CudaHardwareBufferManager");
+        d.index_type = ib->getIndexSize() == 2 ? OGRECU_INDEX_U16 : OGRECU_INDEX_U32;
+        d.indices = impl->getDevicePtr(op.indexData->indexStart * ib->getIndexSize());
+        d.draw_count = (uint32_t)op.indexData->indexCount;
+    }
+    d.prim_type = isStrip ? OGRECU_PRIM_TRIANGLE_STRIP : OGRECU_PRIM_TRIANGLE_LIST;
+    d.flags = (mDepthTest ? OGRECU_DRAW_DEPTH_TEST : 0) | (mDepthWrite ? OGRECU_DRAW_DEPTH_WRITE : 0) |
+              (mBlendAdd ? OGRECU_DRAW_BLEND_ADD : 0) | (mDoLighting ? OGRECU_DRAW_LIGHTING : 0);
+    d.texture = mTexture ? mTexture->getDeviceTexture() : NULL;
+    memcpy(d.mvp, mUniformMVP[0], 64);
+    memcpy(d.tex_matrix, mUniformTex[0], 64);
+    memcpy(d.mvit, mUniformMVIT[0], 64);
+    memcpy(d.viewport, mVP[0], 64);
+    memcpy(d.light_dir, mUniformLightDir.ptr(), 12);
+    memcpy(d.ambient, mUniformAmbient.ptr(), 16);
+
+    do
+    {
+        OGRECU_THROW_IF(ogrecu_draw(mActiveTarget, &d));
+    } while (updatePassIterationRenderState());
+    noteRecorded(mActiveTarget);
+    if (mActiveTargetTexture) mActiveTargetTexture->markTargetRendered();
+}
+
+void CudaRenderSystem::clearFrameBuffer(unsigned int buffers, const ColourValue& colour, float depth, unsigned short)
+{
+    if (!mActiveTarget) return;
+    // whole target, like Tiny (OgreTinyRenderSystem.cpp:421-433); ordered with the recorded draws
+    unsigned mask = ((buffers & FBT_COLOUR) ? OGRECU_CLEAR_COLOUR : 0) | ((buffers & FBT_DEPTH) ? OGRECU_CLEAR_DEPTH : 0);
+    if (!mask) return;
+    OGRECU_THROW_IF(ogrecu_rt_clear(mActiveTarget, mask, colour.ptr(), depth));
+    noteRecorded(mActiveTarget);
+    if (mActiveTargetTexture) mActiveTargetTexture->markTargetRendered();
+}
+
+void CudaRenderSystem::_setRenderTarget(RenderTarget* target)
+{
+    mActiveRenderTarget = target;
+    mActiveTarget = 0;
+    mActiveTargetTexture = 0;
+    if (!target) return;
+
+    if (auto win = dynamic_cast<CudaWindow*>(target))
+        mActiveTarget = win->getTarget();
+    else if (auto rtt = dynamic_cast<CudaRenderTexture*>(target))
+    {
+        mActiveTarget = rtt->getTarget();
+        mActiveTargetTexture = rtt->getTexture();
+    }
+
+    // depth buffer pool bookkeeping exactly as Tiny (OgreTinyRenderSystem.cpp:447-456)
+    auto* depthBuffer = target->getDepthBuffer();
+    if (target->getDepthBufferPool() != RBP_NONE && !depthBuffer)
+        setDepthBufferFor(target);
+}
+
+void CudaRenderSystem::readColour(ogrecu_rt* rt, const Box& src, const PixelBox& dst)
+{
+    flushPendingDraws();
+    const size_t w = src.getWidth(), h = src.getHeight();
+    if (!w || !h) return;
+    if (dst.format == PF_BYTE_RGB && dst.isConsecutive())
+    {
+        OGRECU_THROW_IF(ogrecu_rt_read_colour(rt, src.left, src.top, src.right, src.bottom, dst.data, w * 3));
+        return;
+    }
+    std::vector<uint8> tmp(w * h * 3);
+    OGRECU_THROW_IF(ogrecu_rt_read_colour(rt, src.left, src.top, src.right, src.bottom, tmp.data(), w * 3));
+    PixelBox box(w, h, 1, PF_BYTE_RGB, tmp.data());
+    PixelUtil::bulkPixelConversion(box, dst);   // format conversion as TinyWindow::copyContentsToMemory (OgreTinyWindow.cpp:79)
+}
+} // namespace Ogre

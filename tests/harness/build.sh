@@ -1,0 +1,13 @@
+#!/bin/sh
+# Builds tests/harness/libplugin_harness.so (test infrastructure) against the reference's headers and
+# the stock libOgreMain.so in oracle/_ref/lib.  Needs the reference tree; the .so travels to the GPU box.
+set -e
+HERE="$(cd "$(dirname "$0")" && pwd)"
+ROOT="$(cd "$HERE/../.." && pwd)"
+REF="${OGRE_REFERENCE:-/root/reference}"
+[ -d "$REF" ] || { echo "harness/build.sh: $REF absent; keeping prebuilt harness"; exit 0; }
+/usr/bin/g++ -O2 -DNDEBUG -msse -std=c++14 -fPIC -w -pthread -fvisibility=hidden \
+    -I"$ROOT/oracle/_ref/include" -I"$REF/OgreMain/include" -I"$REF/OgreMain/include/Threading" \
+    -shared -o "$HERE/libplugin_harness.so" "$HERE/plugin_harness.cpp" \
+    -L"$ROOT/oracle/_ref/lib" -lOgreMain -Wl,-rpath,'$ORIGIN/../../oracle/_ref/lib'
+echo "harness/build.sh: ok"

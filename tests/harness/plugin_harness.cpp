@@ -1,0 +1,257 @@
+// plugin_harness.cpp — drives stock OgreMain with a render-system PLUGIN chosen at run time
+// (RenderSystem_CUDA.so under test, or RenderSystem_Tiny.so as the oracle), exactly the way an OGRE
+// application does: Root::loadPlugin -> setRenderSystem -> createRenderWindow -> renderOneFrame.
+// TEST INFRASTRUCTURE (tests/ only).  Plain C entry points for ctypes; one Root per process.
+#include <Ogre.h>
+#include <OgreOptimisedUtil.h>
+#include <OgreSubEntity.h>
+#include <OgreSubMesh.h>
+#include <OgreSkeletonInstance.h>
+#include <OgreHardwarePixelBuffer.h>
+#include <OgreRenderTexture.h>
+
+#include <chrono>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+using namespace Ogre;
+#define API extern "C" __attribute__((visibility("default")))
+
+static OptimisedUtil* g_stock_util = OptimisedUtil::getImplementation();   // before any plugin is loaded
+
+struct Host {
+    std::unique_ptr<Root> root;
+    RenderWindow* win = nullptr;
+    SceneManager* sm = nullptr;
+    Camera* cam = nullptr;
+    Entity* ent = nullptr;
+    std::string media;
+    uint32_t w = 0, h = 0;
+    TexturePtr rtt;
+};
+static Host* g = nullptr;
+static std::string g_err;
+
+API const char* ph_error(void) { return g_err.c_str(); }
+
+#define TRY try {
+#define CATCH(rc) } catch (std::exception& e) { g_err = e.what(); fprintf(stderr, "plugin_harness: %s\n", e.what()); return rc; }
+
+API int ph_open(const char* plugin_so, const char* rs_name_part, const char* stbi_so, const char* media_dir, uint32_t w, uint32_t h)
+{
+    TRY
+    if (g) { g_err = "already open"; return 1; }
+    g = new Host();
+    LogManager* lm = new LogManager();
+    lm->createLog("plugin_harness.log", true, false, true);
+    g->root.reset(new Root("", "", ""));
+    g->root->loadPlugin(plugin_so);
+    g->root->loadPlugin(stbi_so);
+    RenderSystem* rs = nullptr;
+    for (auto* r : g->root->getAvailableRenderers())
+        if (r->getName().find(rs_name_part) != String::npos) rs = r;
+    if (!rs) { g_err = "render system not found"; return 2; }
+    g->root->setRenderSystem(rs);
+    g->root->initialise(false);
+    g->win = g->root->createRenderWindow("harness", w, h, false);
+    g->w = w; g->h = h;
+    g->media = media_dir;
+    ResourceGroupManager& rgm = ResourceGroupManager::getSingleton();
+    rgm.addResourceLocation(g->media + "/models", "FileSystem");
+    rgm.addResourceLocation(g->media + "/scripts", "FileSystem");
+    rgm.addResourceLocation(g->media + "/textures", "FileSystem");
+    rgm.addResourceLocation(g->media + "/packs/Sinbad.zip", "Zip");
+    rgm.initialiseAllResourceGroups();
+    return 0;
+    CATCH(3)
+}
+
+API const char* ph_render_system_name(void) { return g->root->getRenderSystem()->getName().c_str(); }
+API int ph_optimised_util_replaced(void) { return OptimisedUtil::getImplementation() != g_stock_util; }
+
+// the scene of SURVEY §8d C1 (same as oracle/ref_driver.cpp ref_scene_open)
+API int ph_scene_open(const char* mesh, float cam_z)
+{
+    TRY
+    if (g->sm) { g->win->removeAllViewports(); g->root->destroySceneManager(g->sm); g->sm = nullptr; g->ent = nullptr; }
+    SceneManager* sm = g->root->createSceneManager();
+    g->sm = sm;
+    sm->setAmbientLight(ColourValue(0.3f, 0.3f, 0.3f));
+    Light* light = sm->createLight("l");
+    SceneNode* ln = sm->getRootSceneNode()->createChildSceneNode();
+    ln->setPosition(20, 80, 50);
+    ln->attachObject(light);
+    Camera* cam = sm->createCamera("c");
+    cam->setNearClipDistance(5);
+    cam->setAutoAspectRatio(true);
+    SceneNode* cn = sm->getRootSceneNode()->createChildSceneNode();
+    cn->setPosition(0, 0, cam_z);
+    cn->lookAt(Vector3::ZERO, Node::TS_WORLD);
+    cn->attachObject(cam);
+    g->cam = cam;
+    Viewport* vp = g->win->addViewport(cam);
+    vp->setBackgroundColour(ColourValue(0.1f, 0.2f, 0.3f));
+    Entity* e = sm->createEntity(mesh);
+    sm->getRootSceneNode()->createChildSceneNode()->attachObject(e);
+    g->ent = e;
+    return 0;
+    CATCH(1)
+}
+
+API int ph_render(void)
+{
+    TRY
+    g->root->renderOneFrame();
+    return 0;
+    CATCH(1)
+}
+
+API size_t ph_triangles(void) { return g->win->getStatistics().triangleCount; }
+API size_t ph_batches(void) { return g->win->getStatistics().batchCount; }
+
+// public readback path: RenderTarget::copyContentsToMemory into PF_BYTE_RGB (fmt 0) or PF_BYTE_RGBA (fmt 1)
+API int ph_read_colour(uint8_t* dst, int fmt)
+{
+    TRY
+    PixelBox box(g->w, g->h, 1, fmt ? PF_BYTE_RGBA : PF_BYTE_RGB, dst);
+    g->win->copyContentsToMemory(box, box, RenderTarget::FB_AUTO);
+    return 0;
+    CATCH(1)
+}
+
+API int ph_read_colour_box(uint32_t l, uint32_t t, uint32_t r, uint32_t b, uint8_t* dst)
+{
+    TRY
+    PixelBox box(r - l, b - t, 1, PF_BYTE_RGB, dst);
+    g->win->copyContentsToMemory(Box(l, t, r, b), box, RenderTarget::FB_AUTO);
+    return 0;
+    CATCH(1)
+}
+
+// CUDA plugin only: the window's ogrecu_rt (depth is read through the C ABI by the test)
+API void* ph_window_native_target(void)
+{
+    void* rt = nullptr;
+    try { g->win->getCustomAttribute("OGRECU_RT", &rt); } catch (...) { rt = nullptr; }
+    return rt;
+}
+
+// Render the current scene into a TU_RENDERTARGET texture of the window's size through the same
+// camera and read it back with RenderTexture::copyContentsToMemory (-> HardwarePixelBuffer::blitToMemory).
+API int ph_render_to_texture(uint8_t* dst_rgb)
+{
+    TRY
+    if (!g->rtt) {
+        g->rtt = TextureManager::getSingleton().createManual("harness_rtt", ResourceGroupManager::DEFAULT_RESOURCE_GROUP_NAME,
+                                                             TEX_TYPE_2D, g->w, g->h, 0, PF_BYTE_RGBA, TU_RENDERTARGET);
+        RenderTexture* rt = g->rtt->getBuffer()->getRenderTarget();
+        rt->setAutoUpdated(false);
+        Viewport* vp = rt->addViewport(g->cam);
+        vp->setBackgroundColour(ColourValue(0.1f, 0.2f, 0.3f));
+        vp->setOverlaysEnabled(false);
+    }
+    RenderTexture* rt = g->rtt->getBuffer()->getRenderTarget();
+    rt->update();
+    PixelBox box(g->w, g->h, 1, PF_BYTE_RGB, dst_rgb);
+    rt->copyContentsToMemory(box, box, RenderTarget::FB_AUTO);
+    return 0;
+    CATCH(1)
+}
+
+// Show the render texture on a full-window quad (textured, unlit) and render the window: exercises
+// sampling a TU_RENDERTARGET texture.
+API int ph_show_rtt_on_quad(void)
+{
+    TRY
+    if (!g->rtt) { g_err = "no rtt"; return 2; }
+    MaterialPtr mat = MaterialManager::getSingleton().getByName("harness_rtt_mat");
+    if (!mat) {
+        mat = MaterialManager::getSingleton().create("harness_rtt_mat", ResourceGroupManager::DEFAULT_RESOURCE_GROUP_NAME);
+        Pass* p = mat->getTechnique(0)->getPass(0);
+        p->setLightingEnabled(false);
+        p->createTextureUnitState()->setTexture(g->rtt);
+    }
+    if (g->ent) g->ent->setVisible(false);
+    ManualObject* mo = g->sm->hasManualObject("quad") ? g->sm->getManualObject("quad") : nullptr;
+    if (!mo) {
+        mo = g->sm->createManualObject("quad");
+        mo->begin("harness_rtt_mat", RenderOperation::OT_TRIANGLE_LIST);
+        const float s = 40.0f;
+        mo->position(-s, -s, 0); mo->textureCoord(0, 1);
+        mo->position(s, -s, 0); mo->textureCoord(1, 1);
+        mo->position(s, s, 0); mo->textureCoord(1, 0);
+        mo->position(-s, s, 0); mo->textureCoord(0, 0);
+        mo->triangle(0, 2, 1); mo->triangle(0, 3, 2);    // Tiny culls cross>0: wind to survive
+        mo->triangle(0, 1, 2); mo->triangle(0, 2, 3);
+        mo->end();
+        g->sm->getRootSceneNode()->createChildSceneNode()->attachObject(mo);
+    }
+    g->root->renderOneFrame();
+    return 0;
+    CATCH(1)
+}
+
+/* -------- skeletal entity: pose, let OGRE software-skin it (OptimisedUtil), read the result ---- */
+
+static std::vector<std::vector<uint8_t>> g_skinned;
+
+static void grab(const VertexData* skinned)
+{
+    const VertexElement* dp = skinned->vertexDeclaration->findElementBySemantic(VES_POSITION);
+    auto db = skinned->vertexBufferBinding->getBuffer(dp->getSource());
+    const uint8_t* p = (const uint8_t*)db->lock(HardwareBuffer::HBL_READ_ONLY);
+    g_skinned.emplace_back(p + dp->getOffset(), p + db->getSizeInBytes());
+    db->unlock();
+}
+
+API int ph_skel_pose(float time)
+{
+    TRY
+    Entity* e = g->ent;
+    if (!e || !e->hasSkeleton()) { g_err = "no skeletal entity"; return 2; }
+    AnimationStateSet* set = e->getAllAnimationStates();
+    bool first = true;
+    for (auto& kv : set->getAnimationStates()) {
+        kv.second->setEnabled(first);
+        if (first) { kv.second->setLoop(true); kv.second->setTimePosition(time); }
+        first = false;
+    }
+    e->addSoftwareAnimationRequest(true);
+    e->_updateAnimation();
+    g_skinned.clear();
+    MeshPtr m = e->getMesh();
+    if (m->sharedVertexData) grab(e->_getSkelAnimVertexData());
+    for (size_t i = 0; i < m->getNumSubMeshes(); ++i) {
+        if (m->getSubMesh(i)->useSharedVertices) continue;
+        grab(e->getSubEntity(i)->_getSkelAnimVertexData());
+    }
+    return 0;
+    CATCH(1)
+}
+
+API size_t ph_skel_num_subs(void) { return g_skinned.size(); }
+API size_t ph_skel_sub_size(size_t i) { return g_skinned[i].size(); }
+API const uint8_t* ph_skel_sub_data(size_t i) { return g_skinned[i].data(); }
+
+API double ph_frame_time(int frames)
+{
+    g->root->renderOneFrame();
+    auto t0 = std::chrono::steady_clock::now();
+    for (int i = 0; i < frames; ++i) g->root->renderOneFrame();
+    // include the device work: a 1-pixel readback synchronises
+    uint8_t px[3];
+    PixelBox box(1, 1, 1, PF_BYTE_RGB, px);
+    g->win->copyContentsToMemory(Box(0, 0, 1, 1), box, RenderTarget::FB_AUTO);
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() / frames;
+}
+
+API void ph_close(void)
+{
+    if (!g) return;
+    g->rtt.reset();
+    g->root.reset();
+    delete g;
+    g = nullptr;
+}

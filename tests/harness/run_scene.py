@@ -1,0 +1,106 @@
+#!/usr/bin/env python3
+"""Run one OGRE scene through a render-system plugin in THIS process (one Ogre::Root per process)
+and save what came back.  TEST INFRASTRUCTURE: used by tests/test_plugin_*.py via subprocess.
+
+  python tests/harness/run_scene.py --plugin cuda|tiny --mesh ogrehead.mesh --size 320x180 --out x.npz
+         [--cam-z 140] [--rtt] [--quad] [--skel 0.3,1.7] [--time N]
+"""
+import argparse
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REFLIB = os.path.join(ROOT, "oracle", "_ref", "lib")
+MEDIA = os.path.join(ROOT, "oracle", "_ref", "media")
+PLUGINS = {
+    "cuda": (os.path.join(ROOT, "ogre_b200", "plugin", "RenderSystem_CUDA.so"), "CUDA"),
+    "tiny": (os.path.join(REFLIB, "RenderSystem_Tiny.so"), "Tiny"),
+}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--plugin", required=True, choices=sorted(PLUGINS))
+    ap.add_argument("--mesh", default="ogrehead.mesh")
+    ap.add_argument("--size", default="320x180")
+    ap.add_argument("--cam-z", type=float, default=140.0)
+    ap.add_argument("--out", required=True)
+    ap.add_argument("--rtt", action="store_true")
+    ap.add_argument("--quad", action="store_true")
+    ap.add_argument("--skel", default="")
+    ap.add_argument("--time", type=int, default=0)
+    a = ap.parse_args()
+    w, h = [int(v) for v in a.size.split("x")]
+    so, name = PLUGINS[a.plugin]
+    L = C.CDLL(os.path.join(HERE, "libplugin_harness.so"), mode=C.RTLD_GLOBAL)
+    L.ph_error.restype = C.c_char_p
+    L.ph_render_system_name.restype = C.c_char_p
+    L.ph_window_native_target.restype = C.c_void_p
+    L.ph_triangles.restype = C.c_size_t
+    L.ph_batches.restype = C.c_size_t
+    L.ph_skel_num_subs.restype = C.c_size_t
+    L.ph_skel_sub_size.restype = C.c_size_t
+    L.ph_skel_sub_size.argtypes = [C.c_size_t]
+    L.ph_skel_sub_data.restype = C.c_void_p
+    L.ph_skel_sub_data.argtypes = [C.c_size_t]
+    L.ph_frame_time.restype = C.c_double
+    L.ph_scene_open.argtypes = [C.c_char_p, C.c_float]
+    L.ph_skel_pose.argtypes = [C.c_float]
+    L.ph_read_colour.argtypes = [C.c_void_p, C.c_int]
+    L.ph_read_colour_box.argtypes = [C.c_uint32] * 4 + [C.c_void_p]
+    L.ph_render_to_texture.argtypes = [C.c_void_p]
+
+    def ok(rc, what):
+        if rc:
+            raise SystemExit("%s failed (%d): %s" % (what, rc, L.ph_error().decode()))
+
+    ok(L.ph_open(so.encode(), name.encode(), os.path.join(REFLIB, "Codec_STBI.so").encode(), MEDIA.encode(), w, h), "ph_open")
+    out = {"render_system": np.array(L.ph_render_system_name().decode()),
+           "optimised_util_replaced": np.array(L.ph_optimised_util_replaced())}
+    ok(L.ph_scene_open(a.mesh.encode(), a.cam_z), "ph_scene_open")
+    if a.skel:
+        for k, t in enumerate(float(v) for v in a.skel.split(",")):
+            ok(L.ph_skel_pose(t), "ph_skel_pose")
+            for i in range(L.ph_skel_num_subs()):
+                n = L.ph_skel_sub_size(i)
+                out["skinned_t%d_s%d" % (k, i)] = np.ctypeslib.as_array(C.cast(L.ph_skel_sub_data(i), C.POINTER(C.c_uint8)), shape=(n,)).copy()
+    ok(L.ph_render(), "ph_render")
+    colour = np.zeros((h, w, 3), np.uint8)
+    ok(L.ph_read_colour(colour.ctypes.data, 0), "ph_read_colour")
+    out["colour"] = colour
+    rgba = np.zeros((h, w, 4), np.uint8)
+    ok(L.ph_read_colour(rgba.ctypes.data, 1), "ph_read_colour rgba")
+    out["colour_rgba"] = rgba
+    box = np.zeros((h // 2 - 3, w // 2 - 5, 3), np.uint8)
+    ok(L.ph_read_colour_box(5, 3, w // 2, h // 2, box.ctypes.data), "ph_read_colour_box")
+    out["colour_box"] = box
+    out["stats"] = np.array([L.ph_triangles(), L.ph_batches()])
+    rt = L.ph_window_native_target()
+    if rt and a.plugin == "cuda":
+        sys.path.insert(0, ROOT)
+        from ogre_b200 import capi
+        depth = np.zeros((h, w), np.float32)
+        capi.check(capi.lib().ogrecu_rt_read_depth(rt, 0, 0, w, h, depth.ctypes.data, w * 4))
+        out["depth"] = depth
+    if a.rtt:
+        rtt = np.zeros((h, w, 3), np.uint8)
+        ok(L.ph_render_to_texture(rtt.ctypes.data), "ph_render_to_texture")
+        out["rtt"] = rtt
+        if a.quad:
+            ok(L.ph_show_rtt_on_quad(), "ph_show_rtt_on_quad")
+            q = np.zeros((h, w, 3), np.uint8)
+            ok(L.ph_read_colour(q.ctypes.data, 0), "ph_read_colour quad")
+            out["quad"] = q
+    if a.time:
+        out["frame_seconds"] = np.array(L.ph_frame_time(a.time))
+    np.savez_compressed(a.out, **out)
+    L.ph_close()
+    print("ok", a.plugin, str(out["render_system"]), "tris", out["stats"][0], "batches", out["stats"][1])
+
+
+if __name__ == "__main__":
+    main()

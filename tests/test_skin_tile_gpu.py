@@ -1,0 +1,150 @@
+"""GPU parity of the tiled instanced skinning kernel (ogre_b200/csrc/skin_tile.cu) in all its
+transfer modes, and of the fused morph+skin pass, against the CPU oracle — bit patterns.
+
+Covers: full / partial / odd-sized tiles (odd vertex counts break the 16-byte TMA rule and must
+take the cooperative path), 8- and 4-byte misaligned bases, shared bind pose vs per-instance
+source, positions only, bone_map gather, instances-per-CTA > 1 with ragged last group, and the
+three kernel selections of the "skin_mode" option.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle
+from datagen import bits, rigid_matrices
+
+pytestmark = pytest.mark.gpu
+
+
+def make_inputs(rng, n, nw, nb, ninst, norm, per_instance_src):
+    vs = 24 if norm else 12
+    nsrc = ninst if per_instance_src else 1
+    src = rng.uniform(-10, 10, size=(nsrc, n, vs // 4)).astype(np.float32)
+    if norm:
+        nn = rng.normal(size=(nsrc, n, 3))
+        src[:, :, 3:] = (nn / np.linalg.norm(nn, axis=2, keepdims=True)).astype(np.float32)
+    w = rng.uniform(0.05, 1, size=(n, nw))
+    w = (w / w.sum(axis=1, keepdims=True)).astype(np.float32)
+    idx = rng.integers(0, nb, size=(n, nw)).astype(np.uint8)
+    bs = 4 + 4 * nw
+    blend = np.zeros((n, bs), np.uint8)
+    blend[:, :nw] = idx
+    blend[:, 4:] = w.view(np.uint8).reshape(n, 4 * nw)
+    pals = np.stack([rigid_matrices(rng, nb + 2) for _ in range(ninst)])     # [ninst, nb+2, 16]
+    bone_map = rng.permutation(nb + 2)[:nb].astype(np.uint16)
+    return src, blend, pals, bone_map
+
+
+def oracle_skin(src_i, blend, mats, nw, n, norm):
+    vs = 24 if norm else 12
+    out = np.zeros((n, vs // 4), np.float32)
+    s = np.ascontiguousarray(src_i)
+    sp, dp = s.ctypes.data, out.ctypes.data
+    sn, dn = (sp + 12, dp + 12) if norm else (None, None)
+    strides = (vs, vs, vs if norm else 0, vs if norm else 0, blend.shape[1], blend.shape[1])
+    oracle.skin("sse", sp, dp, sn, dn, blend.ctypes.data + 4, blend.ctypes.data, mats, strides, nw, n)
+    return out
+
+
+def gpu_job(ctx, dsrc_ptr, ddst_ptr, dbl, dpal, dmap, n, nw, nb, norm):
+    from ogre_b200 import SkinJob
+    vs = 24 if norm else 12
+    j = SkinJob()
+    j.src_pos, j.dst_pos = dsrc_ptr, ddst_ptr
+    if norm:
+        j.src_norm, j.dst_norm = dsrc_ptr + 12, ddst_ptr + 12
+        j.src_norm_stride = j.dst_norm_stride = vs
+    j.src_pos_stride = j.dst_pos_stride = vs
+    j.blend_weight, j.blend_index = dbl.ptr + 4, dbl.ptr
+    j.blend_weight_stride = j.blend_index_stride = 4 + 4 * nw
+    j.palette, j.bone_map = dpal.ptr, dmap.ptr
+    j.num_weights, j.num_matrices, j.num_vertices = nw, nb, n
+    return j
+
+
+CASES = [
+    # n,   nw, nb, ninst, norm, per_inst_src, src_off, dst_off, ipc
+    (1888, 4, 55, 7, True, True, 0, 0, 3),      # TMA both ways, ragged last instance group
+    (1888, 4, 55, 5, True, False, 0, 0, 0),     # shared bind pose
+    (1001, 3, 20, 4, True, True, 0, 0, 2),      # odd n: instance bases alternate 8-byte misalignment -> cooperative 8
+    (1001, 2, 9, 3, True, True, 8, 8, 0),       # 8-byte misaligned bases
+    (513, 1, 3, 3, True, True, 4, 12, 2),       # 4-byte misaligned bases -> cooperative 4
+    (256, 4, 64, 2, True, True, 0, 0, 0),       # exactly one full tile
+    (255, 4, 200, 2, True, True, 0, 0, 0),      # partial tile, odd, big palette (> 48 KB smem path)
+    (1, 2, 2, 3, True, True, 0, 0, 3),
+    (777, 4, 30, 6, False, True, 0, 0, 4),      # positions only
+    (1024, 3, 30, 3, False, False, 4, 4, 0),    # positions only, misaligned, shared source
+    (300, 4, 256, 2, True, True, 0, 0, 0),      # maximum palette
+]
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "n%d_w%d_b%d_i%d_%s%s_o%d_%d_ipc%d" % (
+    c[0], c[1], c[2], c[3], "pn" if c[4] else "p", "I" if c[5] else "S", c[6], c[7], c[8]))
+def test_instanced_skinning_all_modes(gpu_ctx, case, mode):
+    from ogre_b200 import check, lib
+    n, nw, nb, ninst, norm, per_inst, so, do, ipc = case
+    ctx = gpu_ctx
+    vs = 24 if norm else 12
+    rng = np.random.default_rng(n * 31 + nw)
+    src, blend, pals, bone_map = make_inputs(rng, n, nw, nb, ninst, norm, per_inst)
+    dsrc = ctx.alloc(src.nbytes + 64); dsrc.upload(src.reshape(-1).view(np.uint8), so)
+    ddst = ctx.alloc(ninst * n * vs + 64)
+    guard = np.full(ninst * n * vs + 64, 0xCD, np.uint8)
+    ddst.upload(guard)
+    dbl, dpal, dmap = ctx.to_device(blend), ctx.to_device(pals), ctx.to_device(bone_map)
+    j = gpu_job(ctx, dsrc.ptr + so, ddst.ptr + do, dbl, dpal, dmap, n, nw, nb, norm)
+    ctx.set_config_option("skin_mode", mode)
+    ctx.set_config_option("skin_ipc", ipc)
+    try:
+        check(lib().ogrecu_skin_instanced_dev(ctx.handle, C.byref(j), ninst, (nb + 2) * 16, n * vs if per_inst else 0, n * vs))
+        ctx.sync()
+    finally:
+        ctx.set_config_option("skin_mode", 0)
+        ctx.set_config_option("skin_ipc", 0)
+    raw = ddst.download(np.uint8)
+    assert (raw[:do] == 0xCD).all() and (raw[do + ninst * n * vs:] == 0xCD).all(), "wrote outside the destination"
+    got = raw[do:do + ninst * n * vs].view(np.float32).reshape(ninst, n, vs // 4)
+    for i in range(ninst):
+        ref = oracle_skin(src[i if per_inst else 0], blend, np.ascontiguousarray(pals[i][bone_map]), nw, n, norm)
+        assert np.array_equal(bits(got[i]), bits(ref)), (case, mode, i)
+    for b in (dsrc, ddst, dbl, dpal, dmap):
+        b.free()
+
+
+@pytest.mark.parametrize("norm", [True, False])
+@pytest.mark.parametrize("n,nw,nb,ninst,ipc,want_morph", [(1888, 4, 55, 9, 4, True), (1001, 3, 18, 5, 0, False),
+                                                           (302, 1, 2, 33, 0, True), (77, 2, 7, 2, 1, False)])
+def test_fused_morph_skin_equals_morph_then_skin(gpu_ctx, norm, n, nw, nb, ninst, ipc, want_morph):
+    from ogre_b200 import check, lib
+    ctx = gpu_ctx
+    vs = 24 if norm else 12
+    rng = np.random.default_rng(n + 1000 * nw)
+    keys, blend, pals, bone_map = make_inputs(rng, n, nw, nb, ninst, norm, True)
+    key1, key2 = np.ascontiguousarray(keys[0]), np.ascontiguousarray(keys[1 % len(keys)] if ninst > 1 else keys[0] * 0.9)
+    t = rng.uniform(0, 1, size=ninst).astype(np.float32)
+    dk1, dk2, dt = ctx.to_device(key1), ctx.to_device(key2), ctx.to_device(t)
+    dbl, dpal, dmap = ctx.to_device(blend), ctx.to_device(pals), ctx.to_device(bone_map)
+    ddst = ctx.alloc(ninst * n * vs)
+    dmo = ctx.alloc(ninst * n * vs) if want_morph else None
+    j = gpu_job(ctx, dk1.ptr, ddst.ptr, dbl, dpal, dmap, n, nw, nb, norm)
+    ctx.set_config_option("skin_ipc", ipc)
+    try:
+        check(lib().ogrecu_anim_instanced_dev(ctx.handle, C.byref(j), dk2.ptr, dt.ptr, dmo.ptr if dmo else None, n * vs, ninst,
+                                              (nb + 2) * 16, n * vs))
+        ctx.sync()
+    finally:
+        ctx.set_config_option("skin_ipc", 0)
+    got = ddst.download(np.float32).reshape(ninst, n, vs // 4)
+    gmo = dmo.download(np.float32).reshape(ninst, n, vs // 4) if dmo else None
+    for i in range(ninst):
+        mo = np.zeros((n, vs // 4), np.float32)
+        oracle.lib().oracle_morph(float(t[i]), key1.ctypes.data, key2.ctypes.data, mo.ctypes.data, vs, vs, vs, n, int(norm))
+        ref = oracle_skin(mo, blend, np.ascontiguousarray(pals[i][bone_map]), nw, n, norm)
+        assert np.array_equal(bits(got[i]), bits(ref)), (n, nw, i)
+        if gmo is not None:
+            assert np.array_equal(bits(gmo[i]), bits(mo))
+    for b in (dk1, dk2, dt, dbl, dpal, dmap, ddst, dmo):
+        if b is not None:
+            b.free()
