@@ -483,6 +483,9 @@ API int ref_skel_pose(float time)
 {
     try {
         Entity* e = g_skel_ent;
+        // Entity::cacheBoneMatrices refreshes the palette once per frame number (OgreEntity.cpp:1307-1330):
+        // advance the frame counter so that every pose is really evaluated
+        g_host->root->renderOneFrame();
         AnimationStateSet* set = e->getAllAnimationStates();
         bool first = true;
         for (auto& kv : set->getAnimationStates()) {

@@ -211,6 +211,8 @@ API int ph_skel_pose(float time)
     TRY
     Entity* e = g->ent;
     if (!e || !e->hasSkeleton()) { g_err = "no skeletal entity"; return 2; }
+    // the bone palette is refreshed once per frame number (Entity::cacheBoneMatrices): advance it
+    g->root->renderOneFrame();
     AnimationStateSet* set = e->getAllAnimationStates();
     bool first = true;
     for (auto& kv : set->getAnimationStates()) {
