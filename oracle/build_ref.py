@@ -177,6 +177,13 @@ def main():
         p = os.path.join(sm, "materials/scripts", f)
         if os.path.exists(p):
             shutil.copy2(p, os.path.join(media, "scripts", f))
+    # jaiqua's material lives in the 1 700-line Examples.material (full of unrelated dependencies);
+    # the test scenes only need its one texture unit.  Without a material Tiny falls back to
+    # BaseWhite and then reads its never-initialised DefaultShader::image pointer
+    # (TinyRenderSystem ctor, OgreTinyRenderSystem.cpp:27-46) — undefined behaviour we do not test.
+    with open(os.path.join(media, "scripts", "jaiqua.material"), "w") as f:
+        f.write("material jaiqua\n{\n\ttechnique\n\t{\n\t\tpass\n\t\t{\n\t\t\ttexture_unit\n\t\t\t{\n"
+                "\t\t\t\ttexture blue_jaiqua.jpg\n\t\t\t\ttex_address_mode clamp\n\t\t\t}\n\t\t}\n\t}\n}\n")
     for f in ("GreenSkin.jpg", "spheremap.png", "tusk.jpg", "WeirdEye.png", "dirt01.jpg",
               "blue_jaiqua.jpg"):
         p = os.path.join(sm, "materials/textures", f)

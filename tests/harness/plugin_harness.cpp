@@ -11,6 +11,9 @@
 #include <OgreRenderTexture.h>
 
 #include <chrono>
+#include <csignal>
+#include <execinfo.h>
+#include <unistd.h>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -39,13 +42,26 @@ API const char* ph_error(void) { return g_err.c_str(); }
 #define TRY try {
 #define CATCH(rc) } catch (std::exception& e) { g_err = e.what(); fprintf(stderr, "plugin_harness: %s\n", e.what()); return rc; }
 
+static void crash_handler(int sig)
+{
+    // native backtrace of a crash inside the render system under test (the reference can crash too)
+    void* frames[64];
+    int n = backtrace(frames, 64);
+    const char msg[] = "plugin_harness: fatal signal, native backtrace:\n";
+    (void)!write(2, msg, sizeof msg - 1);
+    backtrace_symbols_fd(frames, n, 2);
+    _exit(128 + sig);
+}
+
 API int ph_open(const char* plugin_so, const char* rs_name_part, const char* stbi_so, const char* media_dir, uint32_t w, uint32_t h)
 {
     TRY
     if (g) { g_err = "already open"; return 1; }
+    signal(SIGFPE, crash_handler);
+    signal(SIGSEGV, crash_handler);
     g = new Host();
     LogManager* lm = new LogManager();
-    lm->createLog("plugin_harness.log", true, false, true);
+    lm->createLog("plugin_harness.log", true, getenv("PH_LOG") != nullptr, true);   // PH_LOG=1: OGRE log to stderr
     g->root.reset(new Root("", "", ""));
     g->root->loadPlugin(plugin_so);
     g->root->loadPlugin(stbi_so);

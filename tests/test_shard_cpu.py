@@ -1,0 +1,106 @@
+"""CPU, world_size 2 over gloo: the multi-process plumbing of SURVEY §8e — instance sharding (no
+collective) and the split-frame strip gather — checked against the single-process oracle result."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from ogre_b200 import shard
+
+
+def test_partitions_cover_everything_once():
+    for n in (0, 1, 7, 10000, 10001):
+        for world in (1, 2, 3, 8):
+            got = []
+            for r in range(world):
+                lo, hi = shard.instance_range(n, r, world)
+                got += list(range(lo, hi))
+            assert got == list(range(n))
+            views = sorted(v for r in range(world) for v in shard.view_indices(n, r, world))
+            assert views == list(range(n))
+    for h in (1, 15, 16, 17, 480, 720, 2160):
+        for world in (1, 2, 4, 8):
+            rows = []
+            for r in range(world):
+                y0, y1 = shard.strip_rows(h, r, world)
+                assert y0 % 16 == 0 and (y1 % 16 == 0 or y1 == h) and y0 <= y1
+                rows += list(range(y0, y1))
+            assert rows == list(range(h))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, w, h, out_dir):
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, here)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from datagen import make_scene
+        from rasterlib import render_oracle
+        import oracle
+        # ---- split frame: every rank renders (here: the CPU oracle) and keeps only its strip
+        cases = make_scene(21, w, h, ndraws=4, ntri=80)
+        full, _, _ = render_oracle(cases, w, h)
+        y0, y1 = shard.strip_rows(h, rank, world)
+        frame = shard.gather_strips(torch.from_numpy(full[y0:y1].copy()), y0, y1, h, dst=0)
+        if rank == 0:
+            assert frame is not None and np.array_equal(frame.numpy(), full)
+            np.save(os.path.join(out_dir, "frame.npy"), frame.numpy())
+        else:
+            assert frame is None
+        # ---- instance sharding: each rank skins its own instances; no collective, only the timing max
+        n, ninst = 300, 11
+        rng = np.random.default_rng(5)
+        from datagen import SkinCase, rigid_matrices
+        case = SkinCase(seed=3, n=n, nw=3, layout="shared", nbones=20)
+        pals = np.stack([rigid_matrices(rng, 20) for _ in range(ninst)])
+        lo, hi = shard.instance_range(ninst, rank, world)
+        mine = np.zeros((hi - lo, n * 24 + 16), np.uint8)
+        for k, i in enumerate(range(lo, hi)):
+            case.mats = pals[i]
+            dst, _ = case.new_dst()
+            sp, dp, sn, dn, bw, bi = case.pointers(dst, None)
+            oracle.skin("sse", sp, dp, sn, dn, bw, bi, case.mats, case.strides(), case.nw, case.n)
+            mine[k] = dst
+        np.save(os.path.join(out_dir, "skin_%d.npy" % rank), mine)
+        t = torch.tensor([float(rank + 1)], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)      # the bench's max-over-ranks time
+        assert t.item() == world
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_world_size_2_gloo(tmp_path):
+    w, h = 96, 80   # 5 tile rows -> strips of 3 and 2 tile rows
+    mp.spawn(_worker, args=(2, _free_port(), w, h, str(tmp_path)), nprocs=2, join=True)
+    assert os.path.exists(tmp_path / "frame.npy")
+    a, b = np.load(tmp_path / "skin_0.npy"), np.load(tmp_path / "skin_1.npy")
+    assert a.shape[0] + b.shape[0] == 11 and a.shape[0] == 6
+    # the same 11 instances in one process
+    import oracle
+    from datagen import SkinCase, rigid_matrices
+    rng = np.random.default_rng(5)
+    case = SkinCase(seed=3, n=300, nw=3, layout="shared", nbones=20)
+    pals = np.stack([rigid_matrices(rng, 20) for _ in range(11)])
+    both = np.concatenate([a, b])
+    for i in range(11):
+        case.mats = pals[i]
+        dst, _ = case.new_dst()
+        sp, dp, sn, dn, bw, bi = case.pointers(dst, None)
+        oracle.skin("sse", sp, dp, sn, dn, bw, bi, case.mats, case.strides(), case.nw, case.n)
+        assert np.array_equal(both[i], dst)
