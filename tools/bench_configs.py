@@ -1,0 +1,306 @@
+#!/usr/bin/env python3
+"""Throughput of the BASELINE.json configs that are not bench.py's headline (config 2): development /
+reporting tool, prints one JSON line per config and (optionally) writes them to a file for profiles/.
+
+  python tools/bench_configs.py --config c1,c3,c4,c5 [--views 1024] [--c5-tris 20000000] [--cpu] [--out file]
+
+  c1  ogrehead 1280x720: the captured _render calls of the golden fixture replayed through the C ABI
+  c3  stencil-shadow streams: calculateFaceNormals + 8x calculateLightFacing + 8x extrudeVertices, 2 M triangles
+  c4  batched offscreen views: N 640x480 textured, lit views of a 1 M-triangle scene (ogrecu_draw_views)
+  c5  one 3840x2160 frame of a 20 M-triangle textured scene (single GPU here; strips in bench of §8e)
+CPU numbers (--cpu) come from the unmodified reference (oracle/_ref) when present, else the oracle port,
+on a bounded sample; they are baselines, not targets.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import ogre_b200  # noqa: E402
+from ogre_b200 import DrawDesc, capi, check, lib  # noqa: E402
+from datagen import DrawCase, edge_triangles, look_at, perspective, viewport_matrix  # noqa: E402
+
+PEAK = 6548.2
+try:
+    PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+except Exception:
+    pass
+
+
+class Timer:
+    """CUDA-event timing on the context's stream through torch (the stream is torch's)."""
+
+    def __init__(self, ctx):
+        import torch
+        self.torch = torch
+        self.stream = torch.cuda.Stream()
+        ctx.set_stream(self.stream.cuda_stream)
+        self.ctx = ctx
+
+    def time(self, fn, iters=10, warm=3):
+        for _ in range(warm):
+            fn()
+        self.stream.synchronize()
+        a, b = self.torch.cuda.Event(enable_timing=True), self.torch.cuda.Event(enable_timing=True)
+        a.record(self.stream)
+        for _ in range(iters):
+            fn()
+        b.record(self.stream)
+        self.stream.synchronize()
+        return a.elapsed_time(b) / iters * 1e-3
+
+
+def terrain(n, height=0.6, seed=3):
+    """(n+1)^2-vertex height field over [-10,10]^2 (y up), 2*n*n triangles wound to face +y viewers;
+    vertex = pos f3, normal f3, uv f2 (stride 32, ogrehead's layout)."""
+    g = np.linspace(-10, 10, n + 1)
+    x, z = np.meshgrid(g, g, indexing="xy")
+    y = height * (np.sin(0.9 * x) * np.cos(0.7 * z) + 0.3 * np.sin(2.3 * x + 1.7 * z))
+    dydx = height * (0.9 * np.cos(0.9 * x) * np.cos(0.7 * z) + 0.69 * np.cos(2.3 * x + 1.7 * z))
+    dydz = height * (-0.7 * np.sin(0.9 * x) * np.sin(0.7 * z) + 0.51 * np.cos(2.3 * x + 1.7 * z))
+    nrm = np.stack([-dydx, np.ones_like(x), -dydz], axis=-1)
+    nrm /= np.linalg.norm(nrm, axis=-1, keepdims=True)
+    uv = np.stack([(x + 10) / 20 * 8, (z + 10) / 20 * 8], axis=-1)
+    verts = np.concatenate([np.stack([x, y, z], axis=-1), nrm, uv], axis=-1).reshape(-1, 8).astype(np.float32)
+    i = np.arange(n)[None, :] + (n + 1) * np.arange(n)[:, None]
+    a, b, c, d = i, i + 1, i + n + 1, i + n + 2
+    # Tiny culls cross(p2-p0, p2-p1) > 0 in flipped screen space: this winding survives when seen from above
+    tris = np.stack([np.stack([a, c, b], -1), np.stack([b, c, d], -1)], axis=2).reshape(-1, 3)
+    return verts, tris.astype(np.uint32).reshape(-1)
+
+
+def camera_ring(nviews, w, h, radius=22.0):
+    proj = perspective(45, w / h, 1.0, 100.0)
+    proj[1, :] *= -1          # OgreMain flips the projection for targets with requiresTextureFlipping (Tiny windows)
+    mvps, mvits, lights = [], [], []
+    for k in range(nviews):
+        th = 2 * np.pi * k / nviews
+        ph = np.radians(25 + 40 * ((k * 7) % nviews) / max(nviews, 1))
+        eye = radius * np.array([np.cos(th) * np.cos(ph), np.sin(ph), np.sin(th) * np.cos(ph)])
+        view = look_at(eye, (0, 0, 0))
+        mvps.append((proj @ view).astype(np.float32))
+        mvits.append(np.linalg.inv(view).T.astype(np.float32))
+        l = view[:3, :3] @ np.array([0.4, 0.8, 0.3]); lights.append((l / np.linalg.norm(l)).astype(np.float32))
+    return np.stack(mvps), np.stack(mvits), np.stack(lights)
+
+
+def checker_texture(size):
+    y, x = np.mgrid[0:size, 0:size]
+    t = np.zeros((size, size, 4), np.uint8)
+    t[..., 0] = 80 + 100 * ((x // 32 + y // 32) % 2); t[..., 1] = 60 + (x * 3) % 160; t[..., 2] = 50 + (y * 5) % 180; t[..., 3] = 255
+    return t
+
+
+def upload_scene(ctx, verts, idx, tex, w, h):
+    vb, ib = ctx.to_device(verts), ctx.to_device(idx)
+    texture = ogre_b200.Texture(ctx, tex)
+    d = DrawDesc()
+    d.positions, d.pos_stride = vb.ptr, 32
+    d.normals, d.normal_stride = vb.ptr + 12, 32
+    d.uvs, d.uv_stride = vb.ptr + 24, 32
+    d.indices, d.index_type, d.draw_count = ib.ptr, 4, len(idx)
+    d.prim_type = ogre_b200.PRIM_TRIANGLE_LIST
+    d.flags = ogre_b200.DRAW_DEPTH_TEST | ogre_b200.DRAW_DEPTH_WRITE | ogre_b200.DRAW_LIGHTING
+    d.texture = texture.handle
+    d.tex_matrix[:] = np.eye(4, dtype=np.float32).reshape(16)
+    d.viewport[:] = viewport_matrix(w, h).reshape(16)
+    d.ambient[:] = (0.2, 0.2, 0.25, 1.0)
+    return d, (vb, ib, texture)
+
+
+def c1(ctx, T, args):
+    from goldenlib import load_scene
+    from rasterlib import GpuScene
+    cases, colour, depth, (w, h) = load_scene("ogrehead_1280x720.npz")
+    scene = GpuScene(ctx, cases)
+    rt = ogre_b200.RenderTarget(ctx, w, h)
+
+    def frame():
+        scene.render(rt, (0.1, 0.2, 0.3, 1.0), 1.0)
+    dt = T.time(frame, iters=50)
+    assert np.array_equal(rt.read_colour(), colour)
+    t0 = time.perf_counter()
+    for _ in range(20):
+        frame(); rt.read_colour()
+    dt_rb = (time.perf_counter() - t0) / 20
+    out = {"config": "c1 ogrehead 1280x720 (4336 tris, 4 draws) replayed through the C ABI", "ms_per_frame_device": dt * 1e3,
+           "frames_per_s_device": 1 / dt, "ms_per_frame_with_readback": dt_rb * 1e3, "frames_per_s_with_readback": 1 / dt_rb,
+           "Mtri_per_s_device": 4336 / dt / 1e6, "image_identical_to_tiny": True}
+    if args.cpu:
+        from oracle import ref
+        if ref.available():
+            l = ref.lib()
+            assert l.ref_scene_open(b"ogrehead.mesh", w, h, 140.0) == 0
+            out["cpu_tiny_ms_per_frame"] = l.ref_scene_time(5) * 1e3
+            out["cpu"] = "real TinyRenderSystem through Root::renderOneFrame, 1 thread"
+    return out
+
+
+def c3(ctx, T, args):
+    nu = int(round((args.c3_tris / 2) ** 0.5))
+    nv, nt = nu * nu, 2 * nu * nu
+    # closed torus grid: V = nu*nu, T = 2*nu*nu
+    u, v = np.meshgrid(np.linspace(0, 2 * np.pi, nu, endpoint=False), np.linspace(0, 2 * np.pi, nu, endpoint=False), indexing="ij")
+    pos = np.stack([(3 + np.cos(v)) * np.cos(u), np.sin(v), (3 + np.cos(v)) * np.sin(u)], -1).reshape(-1, 3).astype(np.float32)
+    i, j = np.meshgrid(np.arange(nu), np.arange(nu), indexing="ij")
+    a = i * nu + j; b = ((i + 1) % nu) * nu + j; c = i * nu + (j + 1) % nu; d = ((i + 1) % nu) * nu + (j + 1) % nu
+    tri_idx = np.stack([np.stack([a, b, c], -1), np.stack([b, d, c], -1)], 2).reshape(-1, 3)
+    tris = np.zeros((nt, 8), np.uint32)
+    tris[:, 2:5] = tri_idx; tris[:, 5:8] = tri_idx
+    lights = np.array([[12 * np.cos(k * np.pi / 4), 6.0, 12 * np.sin(k * np.pi / 4), 1.0] for k in range(8)], np.float32)
+    dpos, dtri = ctx.to_device(pos), ctx.to_device(tris)
+    dfn = ctx.alloc(nt * 16); dfac = ctx.alloc(8 * nt); dext = ctx.alloc(8 * nv * 12)
+    L = lib()
+    lp = lights.ctypes.data_as(capi.c_float_p)
+
+    def fn():
+        check(L.ogrecu_face_normals_dev(ctx.handle, dpos.ptr, dtri.ptr, dfn.ptr, nt))
+
+    def facing():
+        check(L.ogrecu_light_facing_multi_dev(ctx.handle, lp, 8, dfn.ptr, dfac.ptr, nt, nt))
+
+    def extrude():
+        for k in range(8):
+            check(L.ogrecu_extrude_dev(ctx.handle, C.cast(lights[k].ctypes.data, capi.c_float_p), 40.0, dpos.ptr, dext.ptr + k * nv * 12, nv))
+
+    def frame():
+        fn(); facing(); extrude()
+    t_fn, t_fac, t_ext, t_all = T.time(fn), T.time(facing), T.time(extrude), T.time(frame)
+    b_fn = nt * 48 + nv * 12
+    b_fac = nt * 16 + 8 * nt           # normals read ONCE for the 8 lights (fused), 8 facing bytes written
+    b_ext = 8 * nv * 24
+    out = {"config": "c3 shadow-volume streams: %d triangles, %d vertices, 8 point lights" % (nt, nv),
+           "ms_per_frame": t_all * 1e3, "frames_per_s": 1 / t_all,
+           "face_normals": {"ms": t_fn * 1e3, "Mtri_per_s": nt / t_fn / 1e6, "GBps": b_fn / t_fn / 1e9, "frac_of_hbm_peak": b_fn / t_fn / 1e9 / PEAK},
+           "light_facing_8_fused": {"ms": t_fac * 1e3, "Mface_light_per_s": 8 * nt / t_fac / 1e6, "GBps": b_fac / t_fac / 1e9, "frac_of_hbm_peak": b_fac / t_fac / 1e9 / PEAK},
+           "extrude_8": {"ms": t_ext * 1e3, "Mvert_per_s": 8 * nv / t_ext / 1e6, "GBps": b_ext / t_ext / 1e9, "frac_of_hbm_peak": b_ext / t_ext / 1e9 / PEAK}}
+    if args.cpu:
+        from oracle import ref
+        if ref.available():
+            l = ref.lib()
+            fnh = np.zeros((nt, 4), np.float32); fac = np.zeros(nt, np.int8); ext = np.zeros((nv, 3), np.float32)
+            t0 = time.perf_counter(); l.ref_face_normals(0, pos.ctypes.data, tris.ctypes.data, fnh.ctypes.data, nt); c_fn = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            for k in range(8):
+                l.ref_light_facing(0, lights[k].ctypes.data, fnh.ctypes.data, fac.ctypes.data, nt)
+            c_fac = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            for k in range(8):
+                l.ref_extrude(0, lights[k].ctypes.data, 40.0, pos.ctypes.data, ext.ctypes.data, nv)
+            c_ext = time.perf_counter() - t0
+            out["cpu_sse_1_thread_ms"] = {"face_normals": c_fn * 1e3, "light_facing_8": c_fac * 1e3, "extrude_8": c_ext * 1e3,
+                                          "frame": (c_fn + c_fac + c_ext) * 1e3}
+    return out
+
+
+def raster_views(ctx, T, desc, rts, mvps, mvits, lights, chunk):
+    L = lib()
+    n = len(rts)
+    handles = (C.c_void_p * n)(*[r.handle for r in rts])
+
+    def run():
+        for r in rts:
+            r.clear(colour=(0.1, 0.2, 0.3, 1.0), depth=1.0)
+        for s in range(0, n, chunk):
+            e = min(n, s + chunk)
+            hs = (C.c_void_p * (e - s))(*handles[s:e])
+            check(L.ogrecu_draw_views(hs, e - s, C.byref(desc), mvps[s:e].ctypes.data_as(capi.c_float_p),
+                                      mvits[s:e].ctypes.data_as(capi.c_float_p), lights[s:e].ctypes.data_as(capi.c_float_p)))
+    return run
+
+
+def c4(ctx, T, args):
+    w, h = 640, 480
+    n = int(round((args.c4_tris / 2) ** 0.5))
+    verts, idx = terrain(n)
+    ntri = len(idx) // 3
+    desc, keep = upload_scene(ctx, verts, idx, checker_texture(1024), w, h)
+    nviews = args.views
+    mvps, mvits, lights = camera_ring(nviews, w, h)
+    rts = [ogre_b200.RenderTarget(ctx, w, h) for _ in range(nviews)]
+    run = raster_views(ctx, T, desc, rts, mvps, mvits, lights, args.chunk)
+    dt = T.time(run, iters=2, warm=1)
+    stats = rts[0].stats()
+    t0 = time.perf_counter()
+    run()
+    imgs = [r.read_colour() for r in rts]
+    dt_rb = time.perf_counter() - t0
+    covered = float(np.mean([(im != np.array([25, 51, 76], np.uint8)).any(axis=2).mean() for im in imgs[:8]]))
+    out = {"config": "c4 batched offscreen views: %d views 640x480, %d triangles, 1024^2 texture, lit" % (nviews, ntri),
+           "views_per_s_device": nviews / dt, "Mtri_per_s_device": nviews * ntri / dt / 1e6, "ms_per_view_device": dt / nviews * 1e3,
+           "views_per_s_with_readback": nviews / dt_rb, "covered_fraction": covered, "stats_view0": stats,
+           "compulsory_GBps": nviews * (len(idx) * 4 + len(verts) * 32 + w * h * 7) / dt / 1e9}
+    if args.cpu:
+        from rasterlib import render_oracle
+        case = DrawCase(verts, idx, index_type=4, texture=checker_texture(1024), mvp=mvps[0], mvit=mvits[0], viewport=viewport_matrix(w, h),
+                        light_dir=(1, 0, 0), ambient=(0.2, 0.2, 0.25, 1.0))
+        case.light_dir = lights[0]
+        t0 = time.perf_counter()
+        rc, rz, _ = render_oracle([case], w, h)
+        out["cpu_oracle_port_s_per_view_1_thread"] = time.perf_counter() - t0
+        out["view0_identical_to_cpu"] = bool(np.array_equal(rc, imgs[0]))
+    for r in rts:
+        r.destroy()
+    return out
+
+
+def c5(ctx, T, args):
+    w, h = 3840, 2160
+    n = int(round((args.c5_tris / 2) ** 0.5))
+    verts, idx = terrain(n)
+    ntri = len(idx) // 3
+    desc, keep = upload_scene(ctx, verts, idx, checker_texture(1024), w, h)
+    mvps, mvits, lights = camera_ring(1, w, h)
+    rt = ogre_b200.RenderTarget(ctx, w, h)
+    run = raster_views(ctx, T, desc, [rt], mvps, mvits, lights, 1)
+    dt = T.time(run, iters=3, warm=1)
+    stats = rt.stats()
+    t0 = time.perf_counter(); run(); img = rt.read_colour(); dt_rb = time.perf_counter() - t0
+    out = {"config": "c5 one 3840x2160 frame, %d triangles, textured, lit (1 GPU, whole frame)" % ntri,
+           "ms_per_frame_device": dt * 1e3, "frames_per_s_device": 1 / dt, "Mtri_per_s_device": ntri / dt / 1e6,
+           "ms_per_frame_with_readback": dt_rb * 1e3, "stats": stats,
+           "compulsory_GBps": (len(idx) * 4 + len(verts) * 32 + w * h * 7) / dt / 1e9,
+           "covered_fraction": float((img != np.array([25, 51, 76], np.uint8)).any(axis=2).mean())}
+    rt.destroy()
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config", default="c1,c3,c4,c5")
+    ap.add_argument("--views", type=int, default=1024)
+    ap.add_argument("--chunk", type=int, default=16, help="views per ogrecu_draw_views pass")
+    ap.add_argument("--c3-tris", type=int, default=2000000)
+    ap.add_argument("--c4-tris", type=int, default=1000000)
+    ap.add_argument("--c5-tris", type=int, default=20000000)
+    ap.add_argument("--cpu", action="store_true")
+    ap.add_argument("--out", default="")
+    args = ap.parse_args()
+    import torch
+    torch.cuda.set_device(0)
+    ctx = ogre_b200.Context(0)
+    T = Timer(ctx)
+    lines = []
+    for name in args.config.split(","):
+        t0 = time.time()
+        res = {"c1": c1, "c3": c3, "c4": c4, "c5": c5}[name](ctx, T, args)
+        res["wall_s"] = time.time() - t0
+        print(json.dumps(res), flush=True)
+        lines.append(res)
+    if args.out:
+        with open(args.out, "w") as f:
+            for r in lines:
+                f.write(json.dumps(r) + "\n")
+    ctx.set_stream(None)
+
+
+if __name__ == "__main__":
+    main()

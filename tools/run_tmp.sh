@@ -1,4 +1,4 @@
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -30
-for p in tiny cuda; do python tests/harness/run_scene.py --plugin $p --mesh ogrehead.mesh --size 1280x720 --time 20 --out gpurun_out/c1_$p.npz; python -c "
-import numpy as np; a=np.load('gpurun_out/c1_$p.npz'); print('$p frame_seconds', float(a['frame_seconds']))"; done
+python tools/bench_configs.py --config c1,c3 --cpu --out gpurun_out/configs_c1c3.jsonl 2>&1 | tail -4
+python tools/bench_configs.py --config c4 --views 64 --cpu --out gpurun_out/configs_c4_64.jsonl 2>&1 | tail -3
+python tools/bench_configs.py --config c5 --c5-tris 2000000 --out gpurun_out/configs_c5_2M.jsonl 2>&1 | tail -3
