@@ -80,6 +80,8 @@ OGRECU_API uint64_t ogrecu_launch_count(const ogrecu_ctx* ctx);
  *   "skin_mode"  0 = auto (tiled stream kernel with TMA where alignment allows), 1 = tiled kernel
  *                with cooperative LDG/STG only, 2 = one-thread-per-vertex kernel
  *   "skin_ipc"   instances per CTA of the tiled kernel, 0 = auto
+ *   "raster_mode" 0 = auto (per tile: order-independent visibility resolve where it is provably
+ *                equivalent to Tiny's in-order loop, else in-order), 1 = always in-order
  * Unknown names return OGRECU_ERR_INVALID. */
 OGRECU_API int ogrecu_set_config_option(ogrecu_ctx* ctx, const char* name, int value);
 
@@ -330,6 +332,8 @@ OGRECU_API int ogrecu_rt_depth_device_ptr(ogrecu_rt* rt, void** dev_ptr);
  * (triangle,tile) pairs binned, tiles rasterised) */
 typedef struct ogrecu_raster_stats {
     uint64_t triangles_in, triangles_binned, tile_pairs, tiles_active;
+    uint64_t tiles_visibility;   /* tiles resolved by the order-independent visibility path            */
+    uint64_t tiles_ordered;      /* tiles replayed in submission order (state or NaN/depth fallback)   */
 } ogrecu_raster_stats;
 OGRECU_API int ogrecu_rt_last_stats(ogrecu_rt* rt, ogrecu_raster_stats* out);
 

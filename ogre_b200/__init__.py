@@ -224,4 +224,5 @@ class RenderTarget:
         s = RasterStats()
         check(lib().ogrecu_rt_last_stats(self.handle, C.byref(s)))
         return {"triangles_in": s.triangles_in, "triangles_binned": s.triangles_binned,
-                "tile_pairs": s.tile_pairs, "tiles_active": s.tiles_active}
+                "tile_pairs": s.tile_pairs, "tiles_active": s.tiles_active,
+                "tiles_visibility": s.tiles_visibility, "tiles_ordered": s.tiles_ordered}

@@ -52,7 +52,8 @@ class DrawDesc(C.Structure):
 
 class RasterStats(C.Structure):
     _fields_ = [("triangles_in", C.c_uint64), ("triangles_binned", C.c_uint64),
-                ("tile_pairs", C.c_uint64), ("tiles_active", C.c_uint64)]
+                ("tile_pairs", C.c_uint64), ("tiles_active", C.c_uint64),
+                ("tiles_visibility", C.c_uint64), ("tiles_ordered", C.c_uint64)]
 
 
 # name -> (restype, argtypes); every symbol include/ogrecu.h declares

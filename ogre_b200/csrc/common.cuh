@@ -82,7 +82,8 @@ struct ogrecu_ctx {
     // development switches read once from the environment (A/B measurements, never a fallback):
     //   OGRECU_SKIN_MODE  0 auto | 1 tile kernel without TMA (cooperative LDG/STG) | 2 one-thread-per-vertex kernel
     //   OGRECU_SKIN_IPC   instances per CTA of the tile kernel (0 = auto)
-    int skin_mode, skin_ipc;
+    //   OGRECU_RASTER_MODE 0 auto (visibility path where it is equivalent) | 1 always the in-order path
+    int skin_mode, skin_ipc, raster_mode;
 };
 
 namespace ogrecu {

@@ -97,6 +97,7 @@ struct SegParams {
     uint32_t tiles_x, tiles_y;        // tiles per target
     uint32_t strip_ty0, strip_ty1;    // tile rows rasterised on this context
     uint32_t* tile_count;     // [ntargets*tiles_x*tiles_y + 1]
+    uint32_t* tile_flags;     // [ntargets*tiles_x*tiles_y]  bit 0: some triangle needs the in-order path
 };
 
 /* ------------------------------------------------------------------- K1: setup ------ */
@@ -320,6 +321,12 @@ __global__ void __launch_bounds__(256) bin_kernel(SegParams P, const uint32_t* _
     const HotRec* h = P.hot + g;
     uint32_t bx = h->bx, by = h->by, d = h->draw;
     uint32_t target = __ldg(&P.draws[d].target);
+    // Order-independent resolution (raster_kernel's visibility path) is only equivalent to Tiny's
+    // in-order loop for opaque, depth-tested, depth-writing fragments that cannot be discarded.
+    const uint32_t fl = __ldg(&P.draws[d].flags);
+    const bool ordered = (fl & (OGRECU_DRAW_DEPTH_TEST | OGRECU_DRAW_DEPTH_WRITE | OGRECU_DRAW_BLEND_ADD)) !=
+                             (OGRECU_DRAW_DEPTH_TEST | OGRECU_DRAW_DEPTH_WRITE) ||
+                         (P.draws[d].tex != nullptr && __ldg(&P.draws[d].tex_zero_alpha) != 0);
     int tx0 = (int)(bx & 0xffff) >> TILE_SHIFT, tx1 = (int)(bx >> 16) >> TILE_SHIFT;
     int ty0 = max((int)(by & 0xffff) >> TILE_SHIFT, (int)P.strip_ty0), ty1 = min((int)(by >> 16) >> TILE_SHIFT, (int)P.strip_ty1 - 1);
     uint32_t tbase = target * P.tiles_x * P.tiles_y;
@@ -328,6 +335,7 @@ __global__ void __launch_bounds__(256) bin_kernel(SegParams P, const uint32_t* _
             uint32_t key = tbase + (uint32_t)ty * P.tiles_x + (uint32_t)tx;
             pairs[o++] = ((uint64_t)key << 32) | g;
             atomicAdd(&P.tile_count[key], 1u);
+            if (ordered) atomicOr(&P.tile_flags[key], 1u);
         }
 }
 
@@ -410,6 +418,9 @@ struct RasterParams {
     const ColdRec* cold;
     const uint64_t* pairs;         // sorted by tile key
     const uint32_t* tile_start;    // exclusive scan of tile counts
+    const uint32_t* tile_flags;    // bit 0: in-order path required
+    uint32_t force_ordered;        // config option raster_mode = 1: always take the in-order path (A/B, tests)
+    uint32_t* counters;            // [ntargets][2]: tiles resolved by the visibility path / replayed in order
     uint32_t width, height, tiles_x, tiles_y;
     uint32_t strip_ty0, strip_rows;
 };
@@ -428,12 +439,83 @@ __device__ __forceinline__ uint32_t shade_pack(float r, float g, float b)
     return out;
 }
 
+// DefaultShader::fragment + the blend / pack tail of triangle() for one fragment
+// (OgreTinyRenderSystem.cpp:310-333, tinyrenderer.h:82-93).  Returns false when the fragment is discarded.
+__device__ __forceinline__ bool shade_fragment(const DrawDev* D, uint32_t flags, const ColdRec* cold, float bc0, float bc1,
+                                               float bc2, uint32_t& rgb)
+{
+    const float inv255 = 1.0f / 255.0f;
+    const float4* cp = reinterpret_cast<const float4*>(cold);
+    float cr = 1.0f, cg = 1.0f, cb = 1.0f;   // default ColourValue: white (tinyrenderer.h:82)
+    const uint8_t* tex = D->tex;
+    float4 v0 = __ldg(cp), v1 = __ldg(cp + 1);
+    if (tex) {
+        const int tw_ = (int)D->tex_w, th_ = (int)D->tex_h;
+        float u = fadd(fadd(fmul(v0.x, bc0), fmul(v0.z, bc1)), fmul(v1.x, bc2));
+        float v = fadd(fadd(fmul(v0.y, bc0), fmul(v0.w, bc1)), fmul(v1.y, bc2));
+        int ix = x86_f2i(fmul(u, (float)(uint32_t)(tw_ - 1)));                 // sample2D, OgreTinyRenderSystem.h:36-41
+        int iy = x86_f2i(fmul(v, (float)(uint32_t)(th_ - 1)));
+        ix = (tw_ + (ix % tw_)) % tw_;
+        iy = (th_ + (iy % th_)) % th_;
+        uchar4 t4 = __ldg(reinterpret_cast<const uchar4*>(tex) + (size_t)iy * tw_ + ix);
+        if (t4.w < 1) return false;                                            // .cpp:318
+        cr = fmul((float)t4.x, inv255); cg = fmul((float)t4.y, inv255); cb = fmul((float)t4.z, inv255);
+    }
+    if (flags & OGRECU_DRAW_LIGHTING) {
+        float4 v2 = __ldg(cp + 2), v3 = __ldg(cp + 3);
+        // n[9] = v1.z v1.w v2.x | v2.y v2.z v2.w | v3.x v3.y v3.z
+        float nx = fadd(fadd(fmul(v1.z, bc0), fmul(v2.y, bc1)), fmul(v3.x, bc2));
+        float ny = fadd(fadd(fmul(v1.w, bc0), fmul(v2.z, bc1)), fmul(v3.y, bc2));
+        float nz = fadd(fadd(fmul(v2.x, bc0), fmul(v2.w, bc1)), fmul(v3.z, bc2));
+        float dp = fadd(fadd(fadd(0.0f, fmul(nx, D->light[0])), fmul(ny, D->light[1])), fmul(nz, D->light[2]));
+        float diffuse = std_max(0.f, dp);
+        cr = fadd(fmul(cr, diffuse), D->ambient[0]);
+        cg = fadd(fmul(cg, diffuse), D->ambient[1]);
+        cb = fadd(fmul(cb, diffuse), D->ambient[2]);
+    }
+    if (flags & OGRECU_DRAW_BLEND_ADD) {                                      // tinyrenderer.h:86-87
+        cr = fadd(cr, fmul((float)(rgb & 0xff), inv255));
+        cg = fadd(cg, fmul((float)((rgb >> 8) & 0xff), inv255));
+        cb = fadd(cb, fmul((float)((rgb >> 16) & 0xff), inv255));
+    }
+    rgb = shade_pack(cr, cg, cb);
+    return true;
+}
+
+// barycentric() + perspective correction + depth of one pixel against one hot record
+// (tinyrenderer.h:29-35,70-76): same operations, same order, for both raster paths.
+__device__ __forceinline__ bool eval_fragment(const float* hf, float Px, float Py, float& bc0, float& bc1, float& bc2, float& fd)
+{
+    float bs0 = fadd(fadd(fmul(hf[0], Px), fmul(hf[1], Py)), hf[2]);
+    float bs1 = fadd(fadd(fmul(hf[3], Px), fmul(hf[4], Py)), hf[5]);
+    float bs2 = fadd(fadd(fmul(hf[6], Px), fmul(hf[7], Py)), hf[8]);
+    bc0 = fmul(bs0, hf[9]); bc1 = fmul(bs1, hf[10]); bc2 = fmul(bs2, hf[11]);   // :71
+    float s = fadd(fadd(bc0, bc1), bc2);
+    float f = fdiv(1.0f, s);                                                   // :72, OgreVector.h:659-664
+    bc0 = fmul(f, bc0); bc1 = fmul(f, bc1); bc2 = fmul(f, bc2);
+    fd = fadd(fadd(fadd(0.0f, fmul(hf[12], bc0)), fmul(hf[13], bc1)), fmul(hf[14], bc2));   // :73
+    return !(bs0 < 0.f || bs1 < 0.f || bs2 < 0.f) && !(fd < 0.0f);             // :74,:76
+}
+
+constexpr int VIS_SMALL_MAX = 12;   // bbox pixels a single thread walks; larger triangles go to a warp
+
+// One CTA per 16x16 tile.  Two ways to resolve the tile's triangle list, same result:
+//  * visibility path (tiles whose triangles are all opaque, depth-tested, depth-writing, never
+//    discarded): fragments of ALL triangles are generated in parallel (thread per small triangle,
+//    warp per large one) and resolved per pixel with a 64-bit shared-memory atomicMin on
+//    (depth bits, ~submission order) — Tiny's in-order loop ends with exactly that fragment: the
+//    LAST one in submission order among those of minimal depth not above the initial depth
+//    ("frag_depth > zbuf" rejects, equal depth passes, tinyrenderer.h:79).  Only the winner of each
+//    pixel is shaded.  A NaN depth (degenerate triangle) or an initial depth that is NaN/negative
+//    makes the outcome order dependent: the tile then falls back to
+//  * the in-order path: one pixel per thread, triangles replayed in submission order.
 template <bool VEC>
 __global__ void __launch_bounds__(RT_THREADS) raster_kernel(RasterParams P)
 {
     __shared__ float4 s_hot[CHUNK][5];
     __shared__ uint32_t s_tri[CHUNK];
     __shared__ __align__(16) uint8_t s_rgb[TILE][TILE * 3];
+    __shared__ uint32_t s_nbig[2];
 
     // tile of this CTA
     const uint32_t per_target = P.tiles_x * P.strip_rows;
@@ -477,103 +559,152 @@ __global__ void __launch_bounds__(RT_THREADS) raster_kernel(RasterParams P)
     if (inside) rgb = (uint32_t)s_rgb[ly][lx * 3] | ((uint32_t)s_rgb[ly][lx * 3 + 1] << 8) | ((uint32_t)s_rgb[ly][lx * 3 + 2] << 16);
 
     const float Px = (float)x, Py = (float)y;
-    // warp's pixel rectangle in screen space (for the per-warp triangle prefilter)
-    const int wrx0 = tile_x0 + wx0, wrx1 = wrx0 + 7, wry0 = tile_y0 + wy0, wry1 = wry0 + 3;
-    const float inv255 = 1.0f / 255.0f;
+    bool resolved = false;
 
-    for (uint32_t c0 = start; c0 < end; c0 += CHUNK) {
-        const uint32_t nchunk = min((uint32_t)CHUNK, end - c0);
-        __syncthreads();   // previous chunk fully consumed
-        // ---- stage the chunk's hot records (coalesced over 16-byte pieces)
-        if (threadIdx.x < nchunk) s_tri[threadIdx.x] = (uint32_t)P.pairs[c0 + threadIdx.x];
-        __syncthreads();
-        for (uint32_t i = threadIdx.x; i < nchunk * 5; i += RT_THREADS) {
-            uint32_t j = i / 5, k = i - j * 5;
-            s_hot[j][k] = __ldg(reinterpret_cast<const float4*>(P.hot + s_tri[j]) + k);
-        }
-        __syncthreads();
-
-        // ---- replay the chunk in submission order
-        for (uint32_t r0 = 0; r0 < nchunk; r0 += 32) {
-            // prefilter: lane L tests triangle r0+L against this warp's 8x4 pixels
-            bool hit = false;
-            if (r0 + lane < nchunk) {
-                const uint32_t* w = reinterpret_cast<const uint32_t*>(&s_hot[r0 + lane][0]);
-                uint32_t bx = w[15], by = w[16];
-                int bx0 = bx & 0xffff, bx1 = bx >> 16, by0 = by & 0xffff, by1 = by >> 16;
-                hit = bx0 <= wrx1 && bx1 >= wrx0 && by0 <= wry1 && by1 >= wry0;
-            }
-            unsigned mask = __ballot_sync(0xffffffffu, hit);
-            while (mask) {
-                const int b = __ffs(mask) - 1;
-                mask &= mask - 1;
-                const uint32_t j = r0 + b;
-                const float* hf = reinterpret_cast<const float*>(&s_hot[j][0]);
-                const uint32_t* hw = reinterpret_cast<const uint32_t*>(hf);
-                const uint32_t bx = hw[15], by = hw[16];
-                const bool in_box = inside && x >= (int)(bx & 0xffff) && x <= (int)(bx >> 16) && y >= (int)(by & 0xffff) && y <= (int)(by >> 16);
-                bool pass = false;
-                float bc0 = 0.f, bc1 = 0.f, bc2 = 0.f, fd = 0.f;
-                const DrawDev* D = P.draws + hw[17];
-                const uint32_t flags = __ldg(&D->flags);
-                if (in_box) {
-                    // barycentric(): inverse * (x, y, 1)   (tinyrenderer.h:29-35, OgreMatrix3.h:321-327)
-                    float bs0 = fadd(fadd(fmul(hf[0], Px), fmul(hf[1], Py)), hf[2]);
-                    float bs1 = fadd(fadd(fmul(hf[3], Px), fmul(hf[4], Py)), hf[5]);
-                    float bs2 = fadd(fadd(fmul(hf[6], Px), fmul(hf[7], Py)), hf[8]);
-                    bc0 = fmul(bs0, hf[9]); bc1 = fmul(bs1, hf[10]); bc2 = fmul(bs2, hf[11]);   // :71
-                    float s = fadd(fadd(bc0, bc1), bc2);
-                    float f = fdiv(1.0f, s);                                                   // :72, OgreVector.h:659-664
-                    bc0 = fmul(f, bc0); bc1 = fmul(f, bc1); bc2 = fmul(f, bc2);
-                    fd = fadd(fadd(fadd(0.0f, fmul(hf[12], bc0)), fmul(hf[13], bc1)), fmul(hf[14], bc2));   // :73
-                    pass = !(bs0 < 0.f || bs1 < 0.f || bs2 < 0.f) && !(fd < 0.0f);             // :74,:76
-                    if (pass && (flags & OGRECU_DRAW_DEPTH_TEST) && fd > zbuf) pass = false;   // :79
+    // =============================================================== visibility path
+    if (!P.force_ordered && !(__ldg(&P.tile_flags[key]) & 1u)) {
+        unsigned long long* s_key = reinterpret_cast<unsigned long long*>(&s_hot[0][0]);   // [256]
+        uint32_t* s_big = reinterpret_cast<uint32_t*>(s_key + RT_THREADS);                   // [256]
+        const uint32_t pidx = (uint32_t)(ly * TILE + lx);
+        // the initial depth takes part in the minimum: a fragment wins iff depth <= initial depth
+        const bool zbad = inside && !(zbuf >= 0.0f);          // NaN or negative: order dependent
+        s_key[pidx] = ((unsigned long long)__float_as_uint(zbuf == 0.0f ? 0.0f : zbuf) << 32) | 0xFFFFFFFFull;
+        if (threadIdx.x < 2) s_nbig[threadIdx.x] = 0;
+        int fallback = __syncthreads_or(zbad);
+        const int tx1 = tile_x0 + tw - 1, ty1 = tile_y0 + th - 1;
+        uint32_t par = 0;
+        for (uint32_t c0 = start; c0 < end && !fallback; c0 += RT_THREADS, par ^= 1u) {
+            const uint32_t i = c0 + threadIdx.x;
+            int nan_seen = 0;
+            if (i < end) {
+                const uint32_t g = (uint32_t)P.pairs[i];
+                const float4* hp = reinterpret_cast<const float4*>(P.hot + g);
+                float hf[20];
+#pragma unroll
+                for (int k = 0; k < 5; ++k) { float4 v = __ldg(hp + k); hf[4 * k] = v.x; hf[4 * k + 1] = v.y; hf[4 * k + 2] = v.z; hf[4 * k + 3] = v.w; }
+                const uint32_t bx = __float_as_uint(hf[15]), by = __float_as_uint(hf[16]);
+                const int x0 = max((int)(bx & 0xffff), tile_x0), x1 = min((int)(bx >> 16), tx1);
+                const int y0 = max((int)(by & 0xffff), tile_y0), y1 = min((int)(by >> 16), ty1);
+                const int bw = x1 - x0 + 1, bh = y1 - y0 + 1;
+                if (bw > 0 && bh > 0) {
+                    if (bw * bh > VIS_SMALL_MAX) {
+                        s_big[atomicAdd(&s_nbig[par], 1u)] = i - start;
+                    } else {
+                        const unsigned long long lo = 0xFFFFFFFFull - (unsigned long long)(i - start + 1);
+                        for (int py = y0; py <= y1; ++py)
+                            for (int px = x0; px <= x1; ++px) {
+                                float b0, b1, b2, fd;
+                                if (eval_fragment(hf, (float)px, (float)py, b0, b1, b2, fd)) {
+                                    if (fd != fd) nan_seen = 1;
+                                    else atomicMin(&s_key[(py - tile_y0) * TILE + (px - tile_x0)],
+                                                   ((unsigned long long)__float_as_uint(fd == 0.0f ? 0.0f : fd) << 32) | lo);
+                                }
+                            }
+                    }
                 }
-                if (!__any_sync(0xffffffffu, pass)) continue;
-                if (pass) {
-                    // ---- fragment shader (DefaultShader::fragment, OgreTinyRenderSystem.cpp:310-333)
-                    const float4* cp = reinterpret_cast<const float4*>(P.cold + s_tri[j]);
-                    float cr = 1.0f, cg = 1.0f, cb = 1.0f;   // default ColourValue: white (tinyrenderer.h:82)
-                    const uint8_t* tex = D->tex;
-                    bool discard = false;
-                    float4 v0 = __ldg(cp), v1 = __ldg(cp + 1);
-                    if (tex) {
-                        const int tw_ = (int)D->tex_w, th_ = (int)D->tex_h;
-                        float u = fadd(fadd(fmul(v0.x, bc0), fmul(v0.z, bc1)), fmul(v1.x, bc2));
-                        float v = fadd(fadd(fmul(v0.y, bc0), fmul(v0.w, bc1)), fmul(v1.y, bc2));
-                        int ix = x86_f2i(fmul(u, (float)(uint32_t)(tw_ - 1)));                 // sample2D, OgreTinyRenderSystem.h:36-41
-                        int iy = x86_f2i(fmul(v, (float)(uint32_t)(th_ - 1)));
-                        ix = (tw_ + (ix % tw_)) % tw_;
-                        iy = (th_ + (iy % th_)) % th_;
-                        uchar4 t4 = __ldg(reinterpret_cast<const uchar4*>(tex) + (size_t)iy * tw_ + ix);
-                        if (t4.w < 1) discard = true;                                          // .cpp:318
-                        cr = fmul((float)t4.x, inv255); cg = fmul((float)t4.y, inv255); cb = fmul((float)t4.z, inv255);
+            }
+            __syncthreads();
+            // large triangles of this chunk: one warp each, lanes over the bbox pixels inside the tile
+            const uint32_t nbig = s_nbig[par];
+            for (uint32_t b = wid; b < nbig; b += RT_THREADS / 32) {
+                const uint32_t ord = s_big[b];
+                const uint32_t g = (uint32_t)P.pairs[start + ord];
+                const float4* hp = reinterpret_cast<const float4*>(P.hot + g);
+                float hf[20];
+#pragma unroll
+                for (int k = 0; k < 5; ++k) { float4 v = __ldg(hp + k); hf[4 * k] = v.x; hf[4 * k + 1] = v.y; hf[4 * k + 2] = v.z; hf[4 * k + 3] = v.w; }
+                const uint32_t bx = __float_as_uint(hf[15]), by = __float_as_uint(hf[16]);
+                const int x0 = max((int)(bx & 0xffff), tile_x0), x1 = min((int)(bx >> 16), tx1);
+                const int y0 = max((int)(by & 0xffff), tile_y0), y1 = min((int)(by >> 16), ty1);
+                const int bw = x1 - x0 + 1, npx = bw * (y1 - y0 + 1);
+                const unsigned long long lo = 0xFFFFFFFFull - (unsigned long long)(ord + 1);
+                for (int q = lane; q < npx; q += 32) {
+                    const int py = y0 + q / bw, px = x0 + q % bw;
+                    float b0, b1, b2, fd;
+                    if (eval_fragment(hf, (float)px, (float)py, b0, b1, b2, fd)) {
+                        if (fd != fd) nan_seen = 1;
+                        else atomicMin(&s_key[(py - tile_y0) * TILE + (px - tile_x0)],
+                                       ((unsigned long long)__float_as_uint(fd == 0.0f ? 0.0f : fd) << 32) | lo);
                     }
-                    if (!discard) {
-                        if (flags & OGRECU_DRAW_LIGHTING) {
-                            float4 v2 = __ldg(cp + 2), v3 = __ldg(cp + 3);
-                            // n[9] = v1.z v1.w v2.x | v2.y v2.z v2.w | v3.x v3.y v3.z
-                            float nx = fadd(fadd(fmul(v1.z, bc0), fmul(v2.y, bc1)), fmul(v3.x, bc2));
-                            float ny = fadd(fadd(fmul(v1.w, bc0), fmul(v2.z, bc1)), fmul(v3.y, bc2));
-                            float nz = fadd(fadd(fmul(v2.x, bc0), fmul(v2.w, bc1)), fmul(v3.z, bc2));
-                            float dp = fadd(fadd(fadd(0.0f, fmul(nx, D->light[0])), fmul(ny, D->light[1])), fmul(nz, D->light[2]));
-                            float diffuse = std_max(0.f, dp);
-                            cr = fadd(fmul(cr, diffuse), D->ambient[0]);
-                            cg = fadd(fmul(cg, diffuse), D->ambient[1]);
-                            cb = fadd(fmul(cb, diffuse), D->ambient[2]);
-                        }
-                        if (flags & OGRECU_DRAW_BLEND_ADD) {                                  // tinyrenderer.h:86-87
-                            cr = fadd(cr, fmul((float)(rgb & 0xff), inv255));
-                            cg = fadd(cg, fmul((float)((rgb >> 8) & 0xff), inv255));
-                            cb = fadd(cb, fmul((float)((rgb >> 16) & 0xff), inv255));
-                        }
-                        rgb = shade_pack(cr, cg, cb);
-                        if (flags & OGRECU_DRAW_DEPTH_WRITE) zbuf = fd;                       // :92-93
+                }
+            }
+            if (threadIdx.x == 0) s_nbig[par ^ 1u] = 0;      // the other counter is idle during this chunk
+            fallback = __syncthreads_or(nan_seen);
+        }
+        if (!fallback) {
+            // ---- shade the winner of my pixel (deferred: one fragment per covered pixel)
+            const unsigned long long k = s_key[pidx];
+            const uint32_t field = (uint32_t)k;
+            if (inside && field != 0xFFFFFFFFu) {
+                const uint32_t ord = 0xFFFFFFFFu - field - 1u;
+                const uint32_t g = (uint32_t)P.pairs[start + ord];
+                const float4* hp = reinterpret_cast<const float4*>(P.hot + g);
+                float hf[20];
+#pragma unroll
+                for (int q = 0; q < 5; ++q) { float4 v = __ldg(hp + q); hf[4 * q] = v.x; hf[4 * q + 1] = v.y; hf[4 * q + 2] = v.z; hf[4 * q + 3] = v.w; }
+                float b0, b1, b2, fd;
+                eval_fragment(hf, Px, Py, b0, b1, b2, fd);      // same operations as in the resolve pass
+                const DrawDev* D = P.draws + __float_as_uint(hf[17]);
+                shade_fragment(D, __ldg(&D->flags), P.cold + g, b0, b1, b2, rgb);   // never discards here
+                zbuf = fd;
+            }
+            resolved = true;
+        }
+        __syncthreads();   // s_key (aliases s_hot) is dead from here on
+    }
+
+    // ================================================================== in-order path
+    if (!resolved) {
+        // warp's pixel rectangle in screen space (for the per-warp triangle prefilter)
+        const int wrx0 = tile_x0 + wx0, wrx1 = wrx0 + 7, wry0 = tile_y0 + wy0, wry1 = wry0 + 3;
+        for (uint32_t c0 = start; c0 < end; c0 += CHUNK) {
+            const uint32_t nchunk = min((uint32_t)CHUNK, end - c0);
+            __syncthreads();   // previous chunk fully consumed
+            // ---- stage the chunk's hot records (coalesced over 16-byte pieces)
+            if (threadIdx.x < nchunk) s_tri[threadIdx.x] = (uint32_t)P.pairs[c0 + threadIdx.x];
+            __syncthreads();
+            for (uint32_t i = threadIdx.x; i < nchunk * 5; i += RT_THREADS) {
+                uint32_t j = i / 5, k = i - j * 5;
+                s_hot[j][k] = __ldg(reinterpret_cast<const float4*>(P.hot + s_tri[j]) + k);
+            }
+            __syncthreads();
+
+            // ---- replay the chunk in submission order
+            for (uint32_t r0 = 0; r0 < nchunk; r0 += 32) {
+                // prefilter: lane L tests triangle r0+L against this warp's 8x4 pixels
+                bool hit = false;
+                if (r0 + lane < nchunk) {
+                    const uint32_t* w = reinterpret_cast<const uint32_t*>(&s_hot[r0 + lane][0]);
+                    uint32_t bx = w[15], by = w[16];
+                    int bx0 = bx & 0xffff, bx1 = bx >> 16, by0 = by & 0xffff, by1 = by >> 16;
+                    hit = bx0 <= wrx1 && bx1 >= wrx0 && by0 <= wry1 && by1 >= wry0;
+                }
+                unsigned mask = __ballot_sync(0xffffffffu, hit);
+                while (mask) {
+                    const int b = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const uint32_t j = r0 + b;
+                    const float* hf = reinterpret_cast<const float*>(&s_hot[j][0]);
+                    const uint32_t* hw = reinterpret_cast<const uint32_t*>(hf);
+                    const uint32_t bx = hw[15], by = hw[16];
+                    const bool in_box = inside && x >= (int)(bx & 0xffff) && x <= (int)(bx >> 16) && y >= (int)(by & 0xffff) && y <= (int)(by >> 16);
+                    bool pass = false;
+                    float bc0 = 0.f, bc1 = 0.f, bc2 = 0.f, fd = 0.f;
+                    const DrawDev* D = P.draws + hw[17];
+                    const uint32_t flags = __ldg(&D->flags);
+                    if (in_box) {
+                        pass = eval_fragment(hf, Px, Py, bc0, bc1, bc2, fd);
+                        if (pass && (flags & OGRECU_DRAW_DEPTH_TEST) && fd > zbuf) pass = false;   // :79
                     }
+                    if (!__any_sync(0xffffffffu, pass)) continue;
+                    if (pass && shade_fragment(D, flags, P.cold + s_tri[j], bc0, bc1, bc2, rgb))
+                        if (flags & OGRECU_DRAW_DEPTH_WRITE) zbuf = fd;                           // :92-93
                 }
             }
         }
     }
+
+    if (threadIdx.x == 0) atomicAdd(&P.counters[2 * target + (resolved ? 0 : 1)], 1u);
 
     // ---- flush: depth from registers, colour via shared memory as 16-byte vectors
     __syncthreads();
@@ -674,13 +805,15 @@ struct ogrecu_rt {
     uint32_t strip_y0, strip_y1;     // pixel rows rasterised here (multiples of TILE, or h)
     std::vector<Cmd> cmds;
     ogrecu_raster_stats stats;
+    int stats_slot;          // index of this target in the last segment's counter table
+    bool stats_pending;      // counters of the last segment not fetched yet
 };
 
 namespace {
 
 // per-context raster scratch (grown on demand, reused across flushes)
 struct RasterScratch {
-    Scratch draws, targets, hot, cold, cnt, sums, pairs_a, pairs_b, tile_count, hist;
+    Scratch draws, targets, hot, cold, cnt, sums, pairs_a, pairs_b, tile_count, hist, counters;
 };
 std::map<ogrecu_ctx*, RasterScratch>& scratch_map()
 {
@@ -761,7 +894,7 @@ int run_segment(ogrecu_ctx* ctx, ogrecu_rt* const* targets, uint32_t ntargets, c
     OGRECU_CHECK(scratch_reserve(ctx, S.hot, (size_t)ntris * sizeof(HotRec)));
     OGRECU_CHECK(scratch_reserve(ctx, S.cold, (size_t)ntris * sizeof(ColdRec)));
     OGRECU_CHECK(scratch_reserve(ctx, S.cnt, ((size_t)ntris + 1) * sizeof(uint32_t)));
-    OGRECU_CHECK(scratch_reserve(ctx, S.tile_count, ((size_t)nkeys + 1) * sizeof(uint32_t)));
+    OGRECU_CHECK(scratch_reserve(ctx, S.tile_count, (2 * (size_t)nkeys + 2) * sizeof(uint32_t)));   // counts[nkeys+1] + flags[nkeys]
     // tables go through the pinned block (stream-ordered, no pageable-copy stall)
     size_t tab_bytes = dd.size() * sizeof(DrawDev) + td.size() * sizeof(TargetDev);
     OGRECU_CHECK(pinned_reserve(ctx, tab_bytes));
@@ -778,9 +911,10 @@ int run_segment(ogrecu_ctx* ctx, ogrecu_rt* const* targets, uint32_t ntargets, c
     P.width = W; P.height = H; P.tiles_x = tiles_x; P.tiles_y = tiles_y;
     P.strip_ty0 = strip_ty0; P.strip_ty1 = strip_ty1;
     P.tile_count = (uint32_t*)S.tile_count.ptr;
+    P.tile_flags = P.tile_count + nkeys + 1;
 
     // ---- K1 + scan
-    OGRECU_CUDA(cudaMemsetAsync(P.tile_count, 0, ((size_t)nkeys + 1) * sizeof(uint32_t), ctx->stream));
+    OGRECU_CUDA(cudaMemsetAsync(P.tile_count, 0, (2 * (size_t)nkeys + 1) * sizeof(uint32_t), ctx->stream));
     setup_kernel<<<div_up(ntris, 256), 256, 0, ctx->stream>>>(P);
     OGRECU_CUDA(cudaGetLastError());
     count_launch(ctx);
@@ -794,6 +928,8 @@ int run_segment(ogrecu_ctx* ctx, ogrecu_rt* const* targets, uint32_t ntargets, c
     for (uint32_t t = 0; t < ntargets; ++t) {
         targets[t]->stats.triangles_in = ntris / ntargets;
         targets[t]->stats.tile_pairs = npairs / ntargets;
+        targets[t]->stats.tiles_visibility = targets[t]->stats.tiles_ordered = targets[t]->stats.tiles_active = 0;
+        targets[t]->stats_pending = false;
     }
     if (npairs == 0) return OGRECU_OK;
 
@@ -827,7 +963,12 @@ int run_segment(ogrecu_ctx* ctx, ogrecu_rt* const* targets, uint32_t ntargets, c
     // ---- K3
     RasterParams R;
     R.draws = P.draws; R.targets = (const TargetDev*)S.targets.ptr; R.hot = P.hot; R.cold = P.cold;
-    R.pairs = pa; R.tile_start = P.tile_count;
+    R.pairs = pa; R.tile_start = P.tile_count; R.tile_flags = P.tile_flags;
+    R.force_ordered = ctx->raster_mode == 1;
+    for (ogrecu_rt* other : ctx->targets) other->stats_pending = false;   // the counter table is per context: last flush wins
+    OGRECU_CHECK(scratch_reserve(ctx, S.counters, (size_t)ntargets * 2 * sizeof(uint32_t)));
+    OGRECU_CUDA(cudaMemsetAsync(S.counters.ptr, 0, (size_t)ntargets * 2 * sizeof(uint32_t), ctx->stream));
+    R.counters = (uint32_t*)S.counters.ptr;
     R.width = W; R.height = H; R.tiles_x = tiles_x; R.tiles_y = tiles_y;
     R.strip_ty0 = strip_ty0; R.strip_rows = strip_ty1 - strip_ty0;
     const unsigned grid = ntargets * tiles_x * R.strip_rows;
@@ -835,6 +976,8 @@ int run_segment(ogrecu_ctx* ctx, ogrecu_rt* const* targets, uint32_t ntargets, c
     else raster_kernel<false><<<grid, RT_THREADS, 0, ctx->stream>>>(R);
     OGRECU_CUDA(cudaGetLastError());
     count_launch(ctx);
+    // per-target path counters: fetched (synchronously) only if ogrecu_rt_last_stats asks
+    for (uint32_t t = 0; t < ntargets; ++t) { targets[t]->stats_slot = (int)t; targets[t]->stats_pending = true; }
     return OGRECU_OK;
 }
 
@@ -894,7 +1037,7 @@ int rt_release(ogrecu_rt* rt)
         auto sm = scratch_map().find(ctx);
         if (sm != scratch_map().end()) {
             RasterScratch& S = sm->second;
-            for (Scratch* s : {&S.draws, &S.targets, &S.hot, &S.cold, &S.cnt, &S.sums, &S.pairs_a, &S.pairs_b, &S.tile_count, &S.hist})
+            for (Scratch* s : {&S.draws, &S.targets, &S.hot, &S.cold, &S.cnt, &S.sums, &S.pairs_a, &S.pairs_b, &S.tile_count, &S.hist, &S.counters})
                 if (s->ptr) cudaFree(s->ptr);
             scratch_map().erase(sm);
         }
@@ -1003,6 +1146,7 @@ int ogrecu_rt_create(ogrecu_ctx* ctx, uint32_t w, uint32_t h, ogrecu_rt** out)
     rt->ctx = ctx; rt->w = w; rt->h = h; rt->colour = nullptr; rt->depth = nullptr;
     rt->strip_y0 = 0; rt->strip_y1 = h;
     memset(&rt->stats, 0, sizeof rt->stats);
+    rt->stats_slot = 0; rt->stats_pending = false;
     const size_t npx = (size_t)w * h;
     cudaError_t e = cudaMalloc((void**)&rt->colour, npx * 3 + 16);
     if (e == cudaSuccess) e = cudaMalloc((void**)&rt->depth, npx * 4 + 16);
@@ -1173,6 +1317,19 @@ int ogrecu_rt_depth_device_ptr(ogrecu_rt* rt, void** p)
 int ogrecu_rt_last_stats(ogrecu_rt* rt, ogrecu_raster_stats* out)
 {
     OGRECU_REQUIRE(rt && out, "NULL argument");
+    if (rt->stats_pending) {
+        auto sm = scratch_map().find(rt->ctx);
+        if (sm != scratch_map().end() && sm->second.counters.ptr) {
+            uint32_t c[2] = {0, 0};
+            OGRECU_CUDA(cudaSetDevice(rt->ctx->device));
+            OGRECU_CUDA(cudaMemcpyAsync(c, (uint32_t*)sm->second.counters.ptr + 2 * rt->stats_slot, sizeof c, cudaMemcpyDeviceToHost, rt->ctx->stream));
+            OGRECU_CUDA(cudaStreamSynchronize(rt->ctx->stream));
+            rt->stats.tiles_visibility = c[0];
+            rt->stats.tiles_ordered = c[1];
+            rt->stats.tiles_active = (uint64_t)c[0] + c[1];
+        }
+        rt->stats_pending = false;
+    }
     *out = rt->stats;
     return OGRECU_OK;
 }

@@ -82,3 +82,44 @@ def test_split_frame_strips_compose(gpu_ctx):
         rt.destroy()
     scene.free()
     assert_images_equal(full_c, full_z, rc, rz, "split frame")
+
+
+def test_draw_views_equals_one_draw_per_view(gpu_ctx):
+    # config 4 mechanics: one pipeline pass over n_views x triangles with per-view mvp / mvit / light
+    import ctypes as C
+    import ogre_b200
+    from ogre_b200 import capi, check, lib
+    from datagen import DrawCase, look_at, perspective, random_soup, random_texture, viewport_matrix
+    from rasterlib import GpuScene
+    ctx = gpu_ctx
+    w, h = 200, 152
+    rng = np.random.default_rng(77)
+    verts, idx = random_soup(rng, 3000, size=0.4)
+    tex = random_texture(rng, 64, 32, zero_alpha=True)
+    nviews = 5
+    proj = perspective(50, w / h, 0.5, 100.0)
+    mvps, mvits, lights, refs = [], [], [], []
+    for k in range(nviews):
+        view = look_at(rng.uniform(-2, 2, 3) + np.array([0, 0, 9.0]), rng.uniform(-1, 1, 3))
+        mvps.append((proj @ view).astype(np.float32))
+        mvits.append(np.ascontiguousarray(np.linalg.inv(view).T, dtype=np.float32))
+        l = rng.normal(size=3); lights.append((l / np.linalg.norm(l)).astype(np.float32))
+        c = DrawCase(verts, idx, index_type=4, texture=tex, mvp=mvps[k], mvit=mvits[k], viewport=viewport_matrix(w, h),
+                     ambient=(0.2, 0.2, 0.25, 1.0))
+        c.light_dir = lights[k]
+        refs.append(render_oracle([c], w, h))
+    mvps, mvits, lights = [np.ascontiguousarray(np.stack(a)) for a in (mvps, mvits, lights)]
+    base = DrawCase(verts, idx, index_type=4, texture=tex, mvp=mvps[0], mvit=mvits[0], viewport=viewport_matrix(w, h),
+                    ambient=(0.2, 0.2, 0.25, 1.0))
+    scene = GpuScene(ctx, [base])
+    rts = [ogre_b200.RenderTarget(ctx, w, h) for _ in range(nviews)]
+    for r in rts:
+        r.clear(colour=(0.1, 0.2, 0.3, 1.0), depth=1.0)
+    hs = (C.c_void_p * nviews)(*[r.handle for r in rts])
+    fp = capi.c_float_p
+    check(lib().ogrecu_draw_views(hs, nviews, C.byref(scene.descs[0]), mvps.ctypes.data_as(fp), mvits.ctypes.data_as(fp),
+                                  lights.ctypes.data_as(fp)))
+    for k, r in enumerate(rts):
+        assert_images_equal(r.read_colour(), r.read_depth(), refs[k][0], refs[k][1], "draw_views view %d" % k)
+        r.destroy()
+    scene.free()

@@ -89,7 +89,8 @@ def camera_ring(nviews, w, h, radius=22.0):
         mvps.append((proj @ view).astype(np.float32))
         mvits.append(np.linalg.inv(view).T.astype(np.float32))
         l = view[:3, :3] @ np.array([0.4, 0.8, 0.3]); lights.append((l / np.linalg.norm(l)).astype(np.float32))
-    return np.stack(mvps), np.stack(mvits), np.stack(lights)
+    # np.stack keeps the F-order of the transposed inverses: force C layout before handing out raw pointers
+    return (np.ascontiguousarray(np.stack(mvps)), np.ascontiguousarray(np.stack(mvits)), np.ascontiguousarray(np.stack(lights)))
 
 
 def checker_texture(size):

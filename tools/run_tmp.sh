@@ -1,4 +1,4 @@
 mkdir -p gpurun_out
-python tools/bench_configs.py --config c1,c3 --cpu --out gpurun_out/configs_c1c3.jsonl 2>&1 | tail -4
-python tools/bench_configs.py --config c4 --views 64 --cpu --out gpurun_out/configs_c4_64.jsonl 2>&1 | tail -3
-python tools/bench_configs.py --config c5 --c5-tris 2000000 --out gpurun_out/configs_c5_2M.jsonl 2>&1 | tail -3
+timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -15
+python tools/bench_configs.py --config c1,c4,c5 --views 256 --out gpurun_out/configs_vis.jsonl 2>&1 | cut -c1-700
+ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/launches_c5.csv python tools/bench_configs.py --config c5 > /dev/null 2>&1
