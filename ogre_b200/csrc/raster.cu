@@ -66,37 +66,35 @@ struct TargetDev {
     float* depth;
 };
 
-// hot record: everything the coverage/depth test needs (5 x float4)
-struct __align__(16) HotRec {
-    float c[9];       // adjugate / inverse of ABC (OgreMatrix3.cpp:155-202)
-    float iw[3];      // 1/w per vertex
-    float z[3];       // screen z per vertex
-    uint32_t bx;      // x0 | x1 << 16   (inclusive pixel bbox)
-    uint32_t by;      // y0 | y1 << 16
-    uint32_t draw;    // index into the DrawDev table
-    uint32_t pad0, pad1;
+// Per-triangle record written by setup (4 x float4 = 64 bytes), COMPACT: only triangles that
+// survive cull / clip and touch a tile of this strip get one, in submission order.
+struct __align__(16) TriRec {
+    float x[3], y[3];   // screen X, Y per vertex (after the divide)
+    float iw[3];        // 1/w per vertex
+    float z[3];         // screen z per vertex
+    uint32_t bx;        // x0 | x1 << 16   (inclusive pixel bbox)
+    uint32_t by;        // y0 | y1 << 16
+    uint32_t draw;      // index into the DrawDev table
+    uint32_t tri;       // triangle index inside its draw (varyings are fetched from the source streams at shade time)
 };
-static_assert(sizeof(HotRec) == 80, "HotRec must be 5 float4");
+static_assert(sizeof(TriRec) == 64, "TriRec must be 4 float4");
 
-// cold record: varyings, touched only by fragments that pass (4 x float4)
-struct __align__(16) ColdRec {
-    float uv[6];      // u0 v0 u1 v1 u2 v2
-    float n[9];       // n0xyz n1xyz n2xyz
-    float pad;
-};
-static_assert(sizeof(ColdRec) == 64, "ColdRec must be 4 float4");
+// decoupled look-back descriptors of the single-pass setup+bin kernel: status | pairs (31 bit) | triangles (31 bit)
+constexpr unsigned long long LB_AGG = 1ull << 62, LB_PREFIX = 2ull << 62, LB_STATUS = 3ull << 62;
+constexpr unsigned long long LB_FIELD = 0x7fffffffull;     // saturating: 2^31-1 = "too many"
 
 struct SegParams {
     const DrawDev* draws;
     uint32_t ndraws;
     uint32_t ntris;
-    HotRec* hot;
-    ColdRec* cold;
-    uint32_t* cnt;            // tile count per triangle, then exclusive offsets (ntris+1)
+    TriRec* rec;              // [survivors]
+    uint64_t* pairs;          // (tile key << 32 | compact triangle index), submission order
+    uint64_t pair_capacity;
+    unsigned long long* desc; // [nblocks] look-back descriptors (zeroed before launch)
+    uint32_t* ctl;            // [0] block ticket  [1] overflow flag  [2] total pairs  [3] total survivors
     uint32_t width, height;
     uint32_t tiles_x, tiles_y;        // tiles per target
     uint32_t strip_ty0, strip_ty1;    // tile rows rasterised on this context
-    uint32_t* tile_count;     // [ntargets*tiles_x*tiles_y + 1]
     uint32_t* tile_flags;     // [ntargets*tiles_x*tiles_y]  bit 0: some triangle needs the in-order path
 };
 
@@ -110,116 +108,197 @@ __device__ __forceinline__ void mat4_mul(const float* __restrict__ m, float x, f
         out[r] = fadd(fadd(fadd(fmul(m[4 * r + 0], x), fmul(m[4 * r + 1], y)), fmul(m[4 * r + 2], z)), fmul(m[4 * r + 3], w));
 }
 
-__global__ void __launch_bounds__(256) setup_kernel(SegParams P)
+// index of vertex j of triangle t (list: 3t+j, strip: t+j — sliding window without winding flip,
+// OgreTinyRenderSystem.cpp:396-403); 16-bit indices are read unsigned (the reference reads int16: UB >= 32768)
+__device__ __forceinline__ size_t vertex_index(const DrawDev& D, uint32_t t, int j)
 {
-    uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= P.ntris) return;
-    // which draw: last d with tri_base <= g
-    uint32_t lo = 0, hi = P.ndraws;
-    while (hi - lo > 1) {
-        uint32_t mid = (lo + hi) >> 1;
-        if (__ldg(&P.draws[mid].tri_base) <= g) lo = mid; else hi = mid;
-    }
-    const DrawDev& D = P.draws[lo];
-    const uint32_t t = g - D.tri_base;
-    const size_t i0 = D.is_strip ? (size_t)t : (size_t)t * 3;   // OgreTinyRenderSystem.cpp:396-399
+    const size_t k = (D.is_strip ? (size_t)t : (size_t)t * 3) + j;
+    if (D.index_type == 2) return __ldg((const uint16_t*)D.idx + k);
+    if (D.index_type == 4) return __ldg((const uint32_t*)D.idx + k);
+    return k;
+}
 
+__device__ __forceinline__ unsigned long long lb_load(const unsigned long long* p)
+{
+    return *reinterpret_cast<const volatile unsigned long long*>(p);
+}
+__device__ __forceinline__ unsigned long long lb_pack(unsigned long long pairs, unsigned long long tris)
+{
+    return (min(pairs, LB_FIELD) << 31) | min(tris, LB_FIELD);
+}
+
+// K1+K2 in ONE pass: vertex shader x3, viewport, 1/w, cull, bbox (exactly Tiny's operations), then an
+// order-preserving compaction of the surviving triangles and of their (tile, triangle) pairs through a
+// chained scan with decoupled look-back — no count array, no separate scan, no re-read of the records.
+__global__ void __launch_bounds__(256) setup_bin_kernel(SegParams P)
+{
+    __shared__ uint32_t s_vb;
+    __shared__ unsigned long long s_excl;
+    __shared__ uint32_t s_wp[8], s_wt[8];
+    __shared__ float4 s_rec[256][4];
+    const unsigned tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+
+    if (tid == 0) s_vb = atomicAdd(&P.ctl[0], 1u);   // blocks take tickets in dispatch order: look-back never waits on an unscheduled block
+    __syncthreads();
+    const uint32_t vb = s_vb;
+    const uint32_t g = vb * 256u + tid;
+
+    uint32_t ntiles = 0, lo = 0, t = 0;
     float X[3], Y[3], Z[3], IW[3];
-    ColdRec cold;
-    bool ok = true;
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-        size_t k = i0 + j;
-        size_t vi;
-        if (D.index_type == 2) vi = __ldg((const uint16_t*)D.idx + k);        // unsigned; the reference reads int16 (UB >= 32768)
-        else if (D.index_type == 4) vi = __ldg((const uint32_t*)D.idx + k);
-        else vi = k;
-        const float* p = (const float*)(D.pos + vi * D.pos_stride);
-        float px = __ldg(p), py = __ldg(p + 1), pz = __ldg(p + 2);
-        float clip[4], q[4];
-        mat4_mul(D.mvp, px, py, pz, 1.0f, clip);                               // DefaultShader::vertex .cpp:302
-        if (D.uv) {
-            const float* u = (const float*)(D.uv + vi * D.uv_stride);
-            float to[4];
-            mat4_mul(D.texm, __ldg(u), __ldg(u + 1), 0.0f, 1.0f, to);          // .cpp:304-305
-            cold.uv[2 * j] = to[0]; cold.uv[2 * j + 1] = to[1];
-        } else { cold.uv[2 * j] = 0.f; cold.uv[2 * j + 1] = 0.f; }
-        if (D.nrm) {
-            const float* n = (const float*)(D.nrm + vi * D.nrm_stride);
-            float nx = __ldg(n), ny = __ldg(n + 1), nz = __ldg(n + 2);
-#pragma unroll
-            for (int r = 0; r < 3; ++r)                                        // Matrix3 * Vector3, OgreMatrix3.h:321-327
-                cold.n[3 * j + r] = fadd(fadd(fmul(D.mvit[3 * r + 0], nx), fmul(D.mvit[3 * r + 1], ny)), fmul(D.mvit[3 * r + 2], nz));
-        } else { cold.n[3 * j] = cold.n[3 * j + 1] = cold.n[3 * j + 2] = 0.f; }
-        mat4_mul(D.vp, clip[0], clip[1], clip[2], clip[3], q);                 // tinyrenderer.h:45
-        float w = q[3];
-        float fi = fdiv(1.0f, w);                                              // pts[i] /= w  (OgreVector.h:563-570)
-        X[j] = fmul(q[0], fi); Y[j] = fmul(q[1], fi); Z[j] = fmul(q[2], fi);
-        IW[j] = fdiv(1.0f, w);                                                 // tinyrenderer.h:50
-        // non-finite screen coordinates: the reference writes out of bounds (undefined) -> drop
-        ok = ok && isfinite(X[j]) && isfinite(Y[j]) && isfinite(Z[j]) && isfinite(IW[j]);
-    }
-    cold.pad = 0.f;
-
-    if (ok && !D.is_strip) {                                                   // cull: tinyrenderer.h:37-39,55
-        float ax = fsub(X[2], X[0]), ay = fsub(Y[2], Y[0]), bx = fsub(X[2], X[1]), by = fsub(Y[2], Y[1]);
-        if (fsub(fmul(ax, by), fmul(ay, bx)) > 0.0f) ok = false;
-    }
     int x0 = 0, x1 = -1, y0 = 0, y1 = -1;
-    if (ok) {
-        float mnx = FLT_MAX, mny = FLT_MAX, mxx = -FLT_MAX, mxy = -FLT_MAX;
-        const float cx = (float)(P.width - 1u), cy = (float)(P.height - 1u);
+    bool ordered = false;
+    if (g < P.ntris) {
+        // which draw: last d with tri_base <= g
+        uint32_t hi = P.ndraws;
+        while (hi - lo > 1) {
+            uint32_t mid = (lo + hi) >> 1;
+            if (__ldg(&P.draws[mid].tri_base) <= g) lo = mid; else hi = mid;
+        }
+        const DrawDev& D = P.draws[lo];
+        t = g - D.tri_base;
+        bool ok = true;
 #pragma unroll
-        for (int j = 0; j < 3; ++j) {                                          // tinyrenderer.h:58-65
-            mnx = std_max(0.f, std_min(mnx, X[j]));
-            mxx = std_min(cx, std_max(mxx, X[j]));
-            mny = std_max(0.f, std_min(mny, Y[j]));
-            mxy = std_min(cy, std_max(mxy, Y[j]));
+        for (int j = 0; j < 3; ++j) {
+            const size_t vi = vertex_index(D, t, j);
+            const float* p = (const float*)(D.pos + vi * D.pos_stride);
+            float px = __ldg(p), py = __ldg(p + 1), pz = __ldg(p + 2);
+            float clip[4], q[4];
+            mat4_mul(D.mvp, px, py, pz, 1.0f, clip);                               // DefaultShader::vertex .cpp:302
+            mat4_mul(D.vp, clip[0], clip[1], clip[2], clip[3], q);                 // tinyrenderer.h:45
+            float w = q[3];
+            float fi = fdiv(1.0f, w);                                              // pts[i] /= w  (OgreVector.h:563-570)
+            X[j] = fmul(q[0], fi); Y[j] = fmul(q[1], fi); Z[j] = fmul(q[2], fi);
+            IW[j] = fdiv(1.0f, w);                                                 // tinyrenderer.h:50
+            // non-finite screen coordinates: the reference writes out of bounds (undefined) -> drop
+            ok = ok && isfinite(X[j]) && isfinite(Y[j]) && isfinite(Z[j]) && isfinite(IW[j]);
         }
-        // beyond +-2^31 the reference's (int) loop bounds are undefined -> drop
-        if (!(mnx < 2147483648.0f) || !(mny < 2147483648.0f) || !(mxx > -2147483648.0f) || !(mxy > -2147483648.0f)) ok = false;
-        else {
-            x0 = (int)mnx; x1 = (int)mxx; y0 = (int)mny; y1 = (int)mxy;        // :68-69 truncation toward zero
-            if (x0 > x1 || y0 > y1) ok = false;
+        if (ok && !D.is_strip) {                                                   // cull: tinyrenderer.h:37-39,55
+            float ax = fsub(X[2], X[0]), ay = fsub(Y[2], Y[0]), bx = fsub(X[2], X[1]), by = fsub(Y[2], Y[1]);
+            if (fsub(fmul(ax, by), fmul(ay, bx)) > 0.0f) ok = false;
         }
+        if (ok) {
+            float mnx = FLT_MAX, mny = FLT_MAX, mxx = -FLT_MAX, mxy = -FLT_MAX;
+            const float cx = (float)(P.width - 1u), cy = (float)(P.height - 1u);
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {                                          // tinyrenderer.h:58-65
+                mnx = std_max(0.f, std_min(mnx, X[j]));
+                mxx = std_min(cx, std_max(mxx, X[j]));
+                mny = std_max(0.f, std_min(mny, Y[j]));
+                mxy = std_min(cy, std_max(mxy, Y[j]));
+            }
+            // beyond +-2^31 the reference's (int) loop bounds are undefined -> drop
+            if (!(mnx < 2147483648.0f) || !(mny < 2147483648.0f) || !(mxx > -2147483648.0f) || !(mxy > -2147483648.0f)) ok = false;
+            else {
+                x0 = (int)mnx; x1 = (int)mxx; y0 = (int)mny; y1 = (int)mxy;        // :68-69 truncation toward zero
+                if (x0 > x1 || y0 > y1) ok = false;
+            }
+        }
+        if (ok) {
+            int tx0 = x0 >> TILE_SHIFT, tx1 = x1 >> TILE_SHIFT;
+            int ty0 = max(y0 >> TILE_SHIFT, (int)P.strip_ty0), ty1 = min(y1 >> TILE_SHIFT, (int)P.strip_ty1 - 1);
+            if (ty0 <= ty1) ntiles = (uint32_t)(tx1 - tx0 + 1) * (uint32_t)(ty1 - ty0 + 1);
+        }
+        // Order-independent resolution (raster_kernel's visibility path) is only equivalent to Tiny's
+        // in-order loop for opaque, depth-tested, depth-writing fragments that cannot be discarded.
+        const uint32_t fl = D.flags;
+        ordered = (fl & (OGRECU_DRAW_DEPTH_TEST | OGRECU_DRAW_DEPTH_WRITE | OGRECU_DRAW_BLEND_ADD)) !=
+                      (OGRECU_DRAW_DEPTH_TEST | OGRECU_DRAW_DEPTH_WRITE) ||
+                  (D.tex != nullptr && D.tex_zero_alpha != 0);
     }
-    uint32_t ntiles = 0;
-    if (ok) {
-        int tx0 = x0 >> TILE_SHIFT, tx1 = x1 >> TILE_SHIFT;
-        int ty0 = max(y0 >> TILE_SHIFT, (int)P.strip_ty0), ty1 = min(y1 >> TILE_SHIFT, (int)P.strip_ty1 - 1);
-        if (ty0 <= ty1) ntiles = (uint32_t)(tx1 - tx0 + 1) * (uint32_t)(ty1 - ty0 + 1);
-    }
-    P.cnt[g] = ntiles;
-    if (!ntiles) return;
 
-    HotRec h;
-    // Matrix3::Inverse of ABC = [[X0,X1,X2],[Y0,Y1,Y2],[1,1,1]], OgreMatrix3.cpp:160-192
-    h.c[0] = fsub(Y[1], Y[2]); h.c[1] = fsub(X[2], X[1]); h.c[2] = fsub(fmul(X[1], Y[2]), fmul(X[2], Y[1]));
-    h.c[3] = fsub(Y[2], Y[0]); h.c[4] = fsub(X[0], X[2]); h.c[5] = fsub(fmul(X[2], Y[0]), fmul(X[0], Y[2]));
-    h.c[6] = fsub(Y[0], Y[1]); h.c[7] = fsub(X[1], X[0]); h.c[8] = fsub(fmul(X[0], Y[1]), fmul(X[1], Y[0]));
-    float det = fadd(fadd(fmul(X[0], h.c[0]), fmul(X[1], h.c[3])), fmul(X[2], h.c[6]));
-    if (!(fabsf(det) <= 1e-06f)) {       // else: the UNSCALED cofactors are used (:184-185)
-        float gi = fdiv(1.0f, det);
+    // ---- block-level exclusive scans of (pairs, survivors)
+    const uint32_t surv = ntiles ? 1u : 0u;
+    uint32_t ip = ntiles, it = surv;
 #pragma unroll
-        for (int k = 0; k < 9; ++k) h.c[k] = fmul(h.c[k], gi);
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t np = __shfl_up_sync(0xffffffffu, ip, o), nt = __shfl_up_sync(0xffffffffu, it, o);
+        if (lane >= (unsigned)o) { ip += np; it += nt; }
     }
+    if (lane == 31) { s_wp[wid] = ip; s_wt[wid] = it; }
+    __syncthreads();
+    uint32_t wbase_p = 0, wbase_t = 0, bp = 0, bt = 0;
 #pragma unroll
-    for (int j = 0; j < 3; ++j) { h.iw[j] = IW[j]; h.z[j] = Z[j]; }
-    h.bx = (uint32_t)x0 | ((uint32_t)x1 << 16);
-    h.by = (uint32_t)y0 | ((uint32_t)y1 << 16);
-    h.draw = lo; h.pad0 = 0; h.pad1 = 0;
-    const float4* hs = reinterpret_cast<const float4*>(&h);
-    float4* hd = reinterpret_cast<float4*>(P.hot + g);
+    for (int k = 0; k < 8; ++k) {
+        if (k < (int)wid) { wbase_p += s_wp[k]; wbase_t += s_wt[k]; }
+        bp += s_wp[k]; bt += s_wt[k];
+    }
+    const uint32_t ep = wbase_p + ip - ntiles, et = wbase_t + it - surv;   // exclusive inside the block
+
+    // ---- chained scan across blocks (decoupled look-back, warp 0)
+    if (wid == 0) {
+        const unsigned long long agg = lb_pack(bp, bt);
+        if (lane == 0) {
+            *reinterpret_cast<volatile unsigned long long*>(&P.desc[vb]) = (vb == 0 ? LB_PREFIX : LB_AGG) | agg;
+        }
+        unsigned long long ex_p = 0, ex_t = 0;
+        int j = (int)vb - 1;
+        while (j >= 0) {
+            const int idx = j - (int)lane;
+            unsigned long long d = idx >= 0 ? lb_load(&P.desc[idx]) : LB_PREFIX;
+            while (__any_sync(0xffffffffu, (d & LB_STATUS) == 0)) {
+                if ((d & LB_STATUS) == 0) d = lb_load(&P.desc[idx]);
+            }
+            const unsigned pmask = __ballot_sync(0xffffffffu, (d & LB_STATUS) == LB_PREFIX);
+            const int first = pmask ? __ffs(pmask) - 1 : 32;
+            unsigned long long vp = ((int)lane <= first) ? ((d >> 31) & LB_FIELD) : 0ull;
+            unsigned long long vt = ((int)lane <= first) ? (d & LB_FIELD) : 0ull;
 #pragma unroll
-    for (int k = 0; k < 5; ++k) hd[k] = hs[k];
-    const float4* cs = reinterpret_cast<const float4*>(&cold);
-    float4* cd = reinterpret_cast<float4*>(P.cold + g);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) cd[k] = cs[k];
+            for (int o = 16; o > 0; o >>= 1) { vp += __shfl_xor_sync(0xffffffffu, vp, o); vt += __shfl_xor_sync(0xffffffffu, vt, o); }
+            ex_p = min(ex_p + vp, LB_FIELD); ex_t = min(ex_t + vt, LB_FIELD);
+            if (pmask) break;
+            j -= 32;
+        }
+        if (lane == 0) {
+            const unsigned long long incl = lb_pack(ex_p + bp, ex_t + bt);
+            if (vb != 0) *reinterpret_cast<volatile unsigned long long*>(&P.desc[vb]) = LB_PREFIX | incl;
+            s_excl = lb_pack(ex_p, ex_t);
+            if ((size_t)(vb + 1) * 256u >= P.ntris) {      // last block: grand totals
+                P.ctl[2] = (uint32_t)((incl >> 31) & LB_FIELD);
+                P.ctl[3] = (uint32_t)(incl & LB_FIELD);
+            }
+        }
+    }
+    __syncthreads();
+    const unsigned long long base_p = (s_excl >> 31) & LB_FIELD, base_t = s_excl & LB_FIELD;
+
+    // ---- records: staged in shared memory, written as one contiguous run of float4
+    if (surv) {
+        s_rec[et][0] = make_float4(X[0], X[1], X[2], Y[0]);
+        s_rec[et][1] = make_float4(Y[1], Y[2], IW[0], IW[1]);
+        s_rec[et][2] = make_float4(IW[2], Z[0], Z[1], Z[2]);
+        s_rec[et][3] = make_float4(__uint_as_float((uint32_t)x0 | ((uint32_t)x1 << 16)), __uint_as_float((uint32_t)y0 | ((uint32_t)y1 << 16)),
+                                   __uint_as_float(lo), __uint_as_float(t));
+    }
+    __syncthreads();
+    {
+        float4* dst = reinterpret_cast<float4*>(P.rec + base_t);
+        const float4* src = &s_rec[0][0];
+        for (uint32_t k = tid; k < bt * 4u; k += 256u) dst[k] = src[k];
+    }
+
+    // ---- pairs, contiguous per triangle in submission order; the stable sort by tile key keeps that order per tile
+    if (base_p + bp > P.pair_capacity || base_p + bp >= LB_FIELD) {
+        if (tid == 0 && bp) atomicExch(&P.ctl[1], 1u);   // host grows the pair buffers and runs the pass again
+        return;
+    }
+    if (ntiles) {
+        const uint32_t target = P.draws[lo].target;
+        const int tx0 = x0 >> TILE_SHIFT, tx1 = x1 >> TILE_SHIFT;
+        const int ty0 = max(y0 >> TILE_SHIFT, (int)P.strip_ty0), ty1 = min(y1 >> TILE_SHIFT, (int)P.strip_ty1 - 1);
+        const uint32_t tbase = target * P.tiles_x * P.tiles_y;
+        const uint32_t ci = (uint32_t)(base_t + et);
+        uint64_t* out = P.pairs + base_p + ep;
+        for (int ty = ty0; ty <= ty1; ++ty)
+            for (int tx = tx0; tx <= tx1; ++tx) {
+                const uint32_t key = tbase + (uint32_t)ty * P.tiles_x + (uint32_t)tx;
+                *out++ = ((uint64_t)key << 32) | ci;
+                if (ordered) atomicOr(&P.tile_flags[key], 1u);
+            }
+    }
 }
 
 /* ------------------------------------------------------------ exclusive scan -------- */
-// three-phase scan of uint32 (block = 2048 items); totals in 64 bits to detect overflow.
+// three-phase scan of uint32 (block = 2048 items), used on the radix-sort histograms.
 
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS = 8;
@@ -308,35 +387,18 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(const uint32_t
     for (int k = 0; k < SCAN_ITEMS; ++k) { if (base + k < n) out[base + k] = ex; ex += v[k]; }
 }
 
-/* --------------------------------------------------------------------- K2: bin ------ */
-
-// pair = tile key << 32 | triangle id.  Pairs of one triangle are contiguous at off[g];
-// the stable sort by key keeps, inside every tile, the submission order of triangles.
-__global__ void __launch_bounds__(256) bin_kernel(SegParams P, const uint32_t* __restrict__ off, uint64_t* __restrict__ pairs)
+/* ------------------------------------------------------------- tile boundaries ------ */
+// tile_start[k] = first position of key k in the SORTED pair array (== position of the next larger key
+// for empty tiles), tile_start[nkeys] = npairs.  Every entry is written exactly once: no memset, no atomics.
+__global__ void __launch_bounds__(256) tile_bounds_kernel(const uint64_t* __restrict__ pairs, uint32_t npairs, uint32_t nkeys,
+                                                          uint32_t* __restrict__ tile_start)
 {
-    uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= P.ntris) return;
-    uint32_t o = off[g], n = off[g + 1] - o;
-    if (!n) return;
-    const HotRec* h = P.hot + g;
-    uint32_t bx = h->bx, by = h->by, d = h->draw;
-    uint32_t target = __ldg(&P.draws[d].target);
-    // Order-independent resolution (raster_kernel's visibility path) is only equivalent to Tiny's
-    // in-order loop for opaque, depth-tested, depth-writing fragments that cannot be discarded.
-    const uint32_t fl = __ldg(&P.draws[d].flags);
-    const bool ordered = (fl & (OGRECU_DRAW_DEPTH_TEST | OGRECU_DRAW_DEPTH_WRITE | OGRECU_DRAW_BLEND_ADD)) !=
-                             (OGRECU_DRAW_DEPTH_TEST | OGRECU_DRAW_DEPTH_WRITE) ||
-                         (P.draws[d].tex != nullptr && __ldg(&P.draws[d].tex_zero_alpha) != 0);
-    int tx0 = (int)(bx & 0xffff) >> TILE_SHIFT, tx1 = (int)(bx >> 16) >> TILE_SHIFT;
-    int ty0 = max((int)(by & 0xffff) >> TILE_SHIFT, (int)P.strip_ty0), ty1 = min((int)(by >> 16) >> TILE_SHIFT, (int)P.strip_ty1 - 1);
-    uint32_t tbase = target * P.tiles_x * P.tiles_y;
-    for (int ty = ty0; ty <= ty1; ++ty)
-        for (int tx = tx0; tx <= tx1; ++tx) {
-            uint32_t key = tbase + (uint32_t)ty * P.tiles_x + (uint32_t)tx;
-            pairs[o++] = ((uint64_t)key << 32) | g;
-            atomicAdd(&P.tile_count[key], 1u);
-            if (ordered) atomicOr(&P.tile_flags[key], 1u);
-        }
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npairs) return;
+    const uint32_t key = (uint32_t)(pairs[i] >> 32);
+    const uint32_t first = i ? (uint32_t)(pairs[i - 1] >> 32) + 1u : 0u;
+    for (uint32_t k = first; k <= key; ++k) tile_start[k] = i;       // empty when key == previous key
+    if (i == npairs - 1) for (uint32_t k = key + 1; k <= nkeys; ++k) tile_start[k] = npairs;
 }
 
 /* ------------------------------------------------------ stable LSD radix sort ------- */
@@ -414,8 +476,7 @@ __global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const uint64_
 struct RasterParams {
     const DrawDev* draws;
     const TargetDev* targets;
-    const HotRec* hot;
-    const ColdRec* cold;
+    const TriRec* rec;             // compact per-triangle records (setup_bin_kernel)
     const uint64_t* pairs;         // sorted by tile key
     const uint32_t* tile_start;    // exclusive scan of tile counts
     const uint32_t* tile_flags;    // bit 0: in-order path required
@@ -441,18 +502,36 @@ __device__ __forceinline__ uint32_t shade_pack(float r, float g, float b)
 
 // DefaultShader::fragment + the blend / pack tail of triangle() for one fragment
 // (OgreTinyRenderSystem.cpp:310-333, tinyrenderer.h:82-93).  Returns false when the fragment is discarded.
-__device__ __forceinline__ bool shade_fragment(const DrawDev* D, uint32_t flags, const ColdRec* cold, float bc0, float bc1,
-                                               float bc2, uint32_t& rgb)
+// The varyings DefaultShader::vertex produced (var_uv = (Tex*(u,v,0,1)).xy, var_normal = MVIT.linear()*n,
+// .cpp:304-308) are recomputed here from the source streams with the same operations, only for fragments
+// that are actually shaded, instead of being stored per triangle.
+__device__ __forceinline__ bool shade_fragment(const DrawDev* D, uint32_t flags, uint32_t tri, float bc0, float bc1, float bc2,
+                                               uint32_t& rgb)
 {
     const float inv255 = 1.0f / 255.0f;
-    const float4* cp = reinterpret_cast<const float4*>(cold);
     float cr = 1.0f, cg = 1.0f, cb = 1.0f;   // default ColourValue: white (tinyrenderer.h:82)
     const uint8_t* tex = D->tex;
-    float4 v0 = __ldg(cp), v1 = __ldg(cp + 1);
+    const bool lit = (flags & OGRECU_DRAW_LIGHTING) != 0;
+    size_t vi[3];
+    if (tex || lit) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) vi[j] = vertex_index(*D, tri, j);
+    }
     if (tex) {
+        float uu[3], vv[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            if (D->uv) {
+                const float* p = (const float*)(D->uv + vi[j] * D->uv_stride);
+                const float a = __ldg(p), b = __ldg(p + 1);
+                const float* m = D->texm;   // rows 0 and 1 of Matrix4 * (u, v, 0, 1), OgreMatrix4.h:571-578
+                uu[j] = fadd(fadd(fadd(fmul(m[0], a), fmul(m[1], b)), fmul(m[2], 0.0f)), fmul(m[3], 1.0f));
+                vv[j] = fadd(fadd(fadd(fmul(m[4], a), fmul(m[5], b)), fmul(m[6], 0.0f)), fmul(m[7], 1.0f));
+            } else { uu[j] = 0.f; vv[j] = 0.f; }
+        }
         const int tw_ = (int)D->tex_w, th_ = (int)D->tex_h;
-        float u = fadd(fadd(fmul(v0.x, bc0), fmul(v0.z, bc1)), fmul(v1.x, bc2));
-        float v = fadd(fadd(fmul(v0.y, bc0), fmul(v0.w, bc1)), fmul(v1.y, bc2));
+        float u = fadd(fadd(fmul(uu[0], bc0), fmul(uu[1], bc1)), fmul(uu[2], bc2));
+        float v = fadd(fadd(fmul(vv[0], bc0), fmul(vv[1], bc1)), fmul(vv[2], bc2));
         int ix = x86_f2i(fmul(u, (float)(uint32_t)(tw_ - 1)));                 // sample2D, OgreTinyRenderSystem.h:36-41
         int iy = x86_f2i(fmul(v, (float)(uint32_t)(th_ - 1)));
         ix = (tw_ + (ix % tw_)) % tw_;
@@ -461,12 +540,19 @@ __device__ __forceinline__ bool shade_fragment(const DrawDev* D, uint32_t flags,
         if (t4.w < 1) return false;                                            // .cpp:318
         cr = fmul((float)t4.x, inv255); cg = fmul((float)t4.y, inv255); cb = fmul((float)t4.z, inv255);
     }
-    if (flags & OGRECU_DRAW_LIGHTING) {
-        float4 v2 = __ldg(cp + 2), v3 = __ldg(cp + 3);
-        // n[9] = v1.z v1.w v2.x | v2.y v2.z v2.w | v3.x v3.y v3.z
-        float nx = fadd(fadd(fmul(v1.z, bc0), fmul(v2.y, bc1)), fmul(v3.x, bc2));
-        float ny = fadd(fadd(fmul(v1.w, bc0), fmul(v2.z, bc1)), fmul(v3.y, bc2));
-        float nz = fadd(fadd(fmul(v2.x, bc0), fmul(v2.w, bc1)), fmul(v3.z, bc2));
+    if (lit) {
+        float nn[3][3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const float* p = (const float*)(D->nrm + vi[j] * D->nrm_stride);    // lighting implies normals (run_segment)
+            const float a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+#pragma unroll
+            for (int r = 0; r < 3; ++r)                                        // Matrix3 * Vector3, OgreMatrix3.h:321-327
+                nn[j][r] = fadd(fadd(fmul(D->mvit[3 * r + 0], a), fmul(D->mvit[3 * r + 1], b)), fmul(D->mvit[3 * r + 2], c));
+        }
+        float nx = fadd(fadd(fmul(nn[0][0], bc0), fmul(nn[1][0], bc1)), fmul(nn[2][0], bc2));
+        float ny = fadd(fadd(fmul(nn[0][1], bc0), fmul(nn[1][1], bc1)), fmul(nn[2][1], bc2));
+        float nz = fadd(fadd(fmul(nn[0][2], bc0), fmul(nn[1][2], bc1)), fmul(nn[2][2], bc2));
         float dp = fadd(fadd(fadd(0.0f, fmul(nx, D->light[0])), fmul(ny, D->light[1])), fmul(nz, D->light[2]));
         float diffuse = std_max(0.f, dp);
         cr = fadd(fmul(cr, diffuse), D->ambient[0]);
@@ -480,6 +566,29 @@ __device__ __forceinline__ bool shade_fragment(const DrawDev* D, uint32_t flags,
     }
     rgb = shade_pack(cr, cg, cb);
     return true;
+}
+
+// TriRec -> the 20-word form the pixel loops read: hf[0..8] = Matrix3::Inverse of
+// ABC = [[X0,X1,X2],[Y0,Y1,Y2],[1,1,1]] (OgreMatrix3.cpp:160-192, incl. the UNSCALED cofactors when
+// abs(det) <= 1e-6, :184-185), hf[9..11] = 1/w, hf[12..14] = z, words 15..18 = bx, by, draw, tri.
+// Pixel independent, so it is evaluated once per (triangle, tile) instead of once per pixel as Tiny does.
+__device__ __forceinline__ void expand_rec(const TriRec* r, float hf[20])
+{
+    const float4* rp = reinterpret_cast<const float4*>(r);
+    const float4 a = __ldg(rp), b = __ldg(rp + 1), c = __ldg(rp + 2), d = __ldg(rp + 3);
+    const float X0 = a.x, X1 = a.y, X2 = a.z, Y0 = a.w, Y1 = b.x, Y2 = b.y;
+    hf[0] = fsub(Y1, Y2); hf[1] = fsub(X2, X1); hf[2] = fsub(fmul(X1, Y2), fmul(X2, Y1));
+    hf[3] = fsub(Y2, Y0); hf[4] = fsub(X0, X2); hf[5] = fsub(fmul(X2, Y0), fmul(X0, Y2));
+    hf[6] = fsub(Y0, Y1); hf[7] = fsub(X1, X0); hf[8] = fsub(fmul(X0, Y1), fmul(X1, Y0));
+    const float det = fadd(fadd(fmul(X0, hf[0]), fmul(X1, hf[3])), fmul(X2, hf[6]));
+    if (!(fabsf(det) <= 1e-06f)) {
+        const float gi = fdiv(1.0f, det);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) hf[k] = fmul(hf[k], gi);
+    }
+    hf[9] = b.z; hf[10] = b.w; hf[11] = c.x;
+    hf[12] = c.y; hf[13] = c.z; hf[14] = c.w;
+    hf[15] = d.x; hf[16] = d.y; hf[17] = d.z; hf[18] = d.w; hf[19] = 0.f;
 }
 
 // barycentric() + perspective correction + depth of one pixel against one hot record
@@ -513,7 +622,6 @@ template <bool VEC>
 __global__ void __launch_bounds__(RT_THREADS) raster_kernel(RasterParams P)
 {
     __shared__ float4 s_hot[CHUNK][5];
-    __shared__ uint32_t s_tri[CHUNK];
     __shared__ __align__(16) uint8_t s_rgb[TILE][TILE * 3];
     __shared__ uint32_t s_nbig[2];
 
@@ -578,10 +686,8 @@ __global__ void __launch_bounds__(RT_THREADS) raster_kernel(RasterParams P)
             int nan_seen = 0;
             if (i < end) {
                 const uint32_t g = (uint32_t)P.pairs[i];
-                const float4* hp = reinterpret_cast<const float4*>(P.hot + g);
                 float hf[20];
-#pragma unroll
-                for (int k = 0; k < 5; ++k) { float4 v = __ldg(hp + k); hf[4 * k] = v.x; hf[4 * k + 1] = v.y; hf[4 * k + 2] = v.z; hf[4 * k + 3] = v.w; }
+                expand_rec(P.rec + g, hf);
                 const uint32_t bx = __float_as_uint(hf[15]), by = __float_as_uint(hf[16]);
                 const int x0 = max((int)(bx & 0xffff), tile_x0), x1 = min((int)(bx >> 16), tx1);
                 const int y0 = max((int)(by & 0xffff), tile_y0), y1 = min((int)(by >> 16), ty1);
@@ -609,10 +715,8 @@ __global__ void __launch_bounds__(RT_THREADS) raster_kernel(RasterParams P)
             for (uint32_t b = wid; b < nbig; b += RT_THREADS / 32) {
                 const uint32_t ord = s_big[b];
                 const uint32_t g = (uint32_t)P.pairs[start + ord];
-                const float4* hp = reinterpret_cast<const float4*>(P.hot + g);
                 float hf[20];
-#pragma unroll
-                for (int k = 0; k < 5; ++k) { float4 v = __ldg(hp + k); hf[4 * k] = v.x; hf[4 * k + 1] = v.y; hf[4 * k + 2] = v.z; hf[4 * k + 3] = v.w; }
+                expand_rec(P.rec + g, hf);
                 const uint32_t bx = __float_as_uint(hf[15]), by = __float_as_uint(hf[16]);
                 const int x0 = max((int)(bx & 0xffff), tile_x0), x1 = min((int)(bx >> 16), tx1);
                 const int y0 = max((int)(by & 0xffff), tile_y0), y1 = min((int)(by >> 16), ty1);
@@ -638,14 +742,12 @@ __global__ void __launch_bounds__(RT_THREADS) raster_kernel(RasterParams P)
             if (inside && field != 0xFFFFFFFFu) {
                 const uint32_t ord = 0xFFFFFFFFu - field - 1u;
                 const uint32_t g = (uint32_t)P.pairs[start + ord];
-                const float4* hp = reinterpret_cast<const float4*>(P.hot + g);
                 float hf[20];
-#pragma unroll
-                for (int q = 0; q < 5; ++q) { float4 v = __ldg(hp + q); hf[4 * q] = v.x; hf[4 * q + 1] = v.y; hf[4 * q + 2] = v.z; hf[4 * q + 3] = v.w; }
+                expand_rec(P.rec + g, hf);
                 float b0, b1, b2, fd;
                 eval_fragment(hf, Px, Py, b0, b1, b2, fd);      // same operations as in the resolve pass
                 const DrawDev* D = P.draws + __float_as_uint(hf[17]);
-                shade_fragment(D, __ldg(&D->flags), P.cold + g, b0, b1, b2, rgb);   // never discards here
+                shade_fragment(D, __ldg(&D->flags), __float_as_uint(hf[18]), b0, b1, b2, rgb);   // never discards here
                 zbuf = fd;
             }
             resolved = true;
@@ -660,12 +762,12 @@ __global__ void __launch_bounds__(RT_THREADS) raster_kernel(RasterParams P)
         for (uint32_t c0 = start; c0 < end; c0 += CHUNK) {
             const uint32_t nchunk = min((uint32_t)CHUNK, end - c0);
             __syncthreads();   // previous chunk fully consumed
-            // ---- stage the chunk's hot records (coalesced over 16-byte pieces)
-            if (threadIdx.x < nchunk) s_tri[threadIdx.x] = (uint32_t)P.pairs[c0 + threadIdx.x];
-            __syncthreads();
-            for (uint32_t i = threadIdx.x; i < nchunk * 5; i += RT_THREADS) {
-                uint32_t j = i / 5, k = i - j * 5;
-                s_hot[j][k] = __ldg(reinterpret_cast<const float4*>(P.hot + s_tri[j]) + k);
+            // ---- stage the chunk: one thread expands one record (inverse computed once per triangle and tile)
+            if (threadIdx.x < nchunk) {
+                float hf[20];
+                expand_rec(P.rec + (uint32_t)P.pairs[c0 + threadIdx.x], hf);
+#pragma unroll
+                for (int k = 0; k < 5; ++k) s_hot[threadIdx.x][k] = make_float4(hf[4 * k], hf[4 * k + 1], hf[4 * k + 2], hf[4 * k + 3]);
             }
             __syncthreads();
 
@@ -697,7 +799,7 @@ __global__ void __launch_bounds__(RT_THREADS) raster_kernel(RasterParams P)
                         if (pass && (flags & OGRECU_DRAW_DEPTH_TEST) && fd > zbuf) pass = false;   // :79
                     }
                     if (!__any_sync(0xffffffffu, pass)) continue;
-                    if (pass && shade_fragment(D, flags, P.cold + s_tri[j], bc0, bc1, bc2, rgb))
+                    if (pass && shade_fragment(D, flags, hw[18], bc0, bc1, bc2, rgb))
                         if (flags & OGRECU_DRAW_DEPTH_WRITE) zbuf = fd;                           // :92-93
                 }
             }
@@ -813,7 +915,7 @@ namespace {
 
 // per-context raster scratch (grown on demand, reused across flushes)
 struct RasterScratch {
-    Scratch draws, targets, hot, cold, cnt, sums, pairs_a, pairs_b, tile_count, hist, counters;
+    Scratch draws, targets, rec, cnt, sums, pairs_a, pairs_b, tile_count, hist, counters;
 };
 std::map<ogrecu_ctx*, RasterScratch>& scratch_map()
 {
@@ -891,12 +993,21 @@ int run_segment(ogrecu_ctx* ctx, ogrecu_rt* const* targets, uint32_t ntargets, c
 
     OGRECU_CHECK(scratch_reserve(ctx, S.draws, dd.size() * sizeof(DrawDev)));
     OGRECU_CHECK(scratch_reserve(ctx, S.targets, td.size() * sizeof(TargetDev)));
-    OGRECU_CHECK(scratch_reserve(ctx, S.hot, (size_t)ntris * sizeof(HotRec)));
-    OGRECU_CHECK(scratch_reserve(ctx, S.cold, (size_t)ntris * sizeof(ColdRec)));
-    OGRECU_CHECK(scratch_reserve(ctx, S.cnt, ((size_t)ntris + 1) * sizeof(uint32_t)));
-    OGRECU_CHECK(scratch_reserve(ctx, S.tile_count, (2 * (size_t)nkeys + 2) * sizeof(uint32_t)));   // counts[nkeys+1] + flags[nkeys]
+    const uint32_t nblocks = div_up(ntris, 256);
+    OGRECU_CHECK(scratch_reserve(ctx, S.rec, (size_t)ntris * sizeof(TriRec)));
+    // control block: look-back descriptors [nblocks] | ctl[4] | tile flags [nkeys]  (zeroed per pass)
+    const size_t ctl_bytes = (size_t)nblocks * 8 + 16 + (size_t)nkeys * 4;
+    OGRECU_CHECK(scratch_reserve(ctx, S.cnt, ctl_bytes));
+    OGRECU_CHECK(scratch_reserve(ctx, S.tile_count, ((size_t)nkeys + 1) * sizeof(uint32_t)));
+    // pair buffers: the count is only known after the pass; start from what earlier flushes needed
+    // (at least 1.25 pairs per triangle) and re-run the pass in the rare case it does not fit
+    {
+        const size_t want = std::max<size_t>(S.pairs_a.cap, ((size_t)ntris + ntris / 4 + 1024) * sizeof(uint64_t));
+        OGRECU_CHECK(scratch_reserve(ctx, S.pairs_a, want));
+        OGRECU_CHECK(scratch_reserve(ctx, S.pairs_b, want));
+    }
     // tables go through the pinned block (stream-ordered, no pageable-copy stall)
-    size_t tab_bytes = dd.size() * sizeof(DrawDev) + td.size() * sizeof(TargetDev);
+    size_t tab_bytes = dd.size() * sizeof(DrawDev) + td.size() * sizeof(TargetDev) + 16;
     OGRECU_CHECK(pinned_reserve(ctx, tab_bytes));
     OGRECU_CUDA(cudaStreamSynchronize(ctx->stream));
     memcpy(ctx->pinned, dd.data(), dd.size() * sizeof(DrawDev));
@@ -904,43 +1015,47 @@ int run_segment(ogrecu_ctx* ctx, ogrecu_rt* const* targets, uint32_t ntargets, c
     OGRECU_CUDA(cudaMemcpyAsync(S.draws.ptr, ctx->pinned, dd.size() * sizeof(DrawDev), cudaMemcpyHostToDevice, ctx->stream));
     OGRECU_CUDA(cudaMemcpyAsync(S.targets.ptr, (uint8_t*)ctx->pinned + dd.size() * sizeof(DrawDev), td.size() * sizeof(TargetDev),
                                 cudaMemcpyHostToDevice, ctx->stream));
+    uint32_t* ctl_host = (uint32_t*)((uint8_t*)ctx->pinned + dd.size() * sizeof(DrawDev) + td.size() * sizeof(TargetDev));
 
     SegParams P;
     P.draws = (const DrawDev*)S.draws.ptr; P.ndraws = (uint32_t)dd.size(); P.ntris = ntris;
-    P.hot = (HotRec*)S.hot.ptr; P.cold = (ColdRec*)S.cold.ptr; P.cnt = (uint32_t*)S.cnt.ptr;
+    P.rec = (TriRec*)S.rec.ptr;
+    P.desc = (unsigned long long*)S.cnt.ptr;
+    P.ctl = (uint32_t*)((uint8_t*)S.cnt.ptr + (size_t)nblocks * 8);
+    P.tile_flags = P.ctl + 4;
     P.width = W; P.height = H; P.tiles_x = tiles_x; P.tiles_y = tiles_y;
     P.strip_ty0 = strip_ty0; P.strip_ty1 = strip_ty1;
-    P.tile_count = (uint32_t*)S.tile_count.ptr;
-    P.tile_flags = P.tile_count + nkeys + 1;
 
-    // ---- K1 + scan
-    OGRECU_CUDA(cudaMemsetAsync(P.tile_count, 0, (2 * (size_t)nkeys + 1) * sizeof(uint32_t), ctx->stream));
-    setup_kernel<<<div_up(ntris, 256), 256, 0, ctx->stream>>>(P);
-    OGRECU_CUDA(cudaGetLastError());
-    count_launch(ctx);
-    OGRECU_CUDA(cudaMemsetAsync(P.cnt + ntris, 0, sizeof(uint32_t), ctx->stream));
-    uint64_t* total_dev = nullptr;
-    OGRECU_CHECK(exclusive_scan_u32(ctx, S.sums, P.cnt, (size_t)ntris + 1, &total_dev));
-    uint64_t npairs = 0;
-    OGRECU_CUDA(cudaMemcpyAsync(&npairs, total_dev, sizeof npairs, cudaMemcpyDeviceToHost, ctx->stream));
-    OGRECU_CUDA(cudaStreamSynchronize(ctx->stream));
-    OGRECU_REQUIRE(npairs < 0xffffffffull, "too many (triangle, tile) pairs in one flush");
+    // ---- K1+K2: setup, compaction and binning in one pass
+    uint64_t npairs = 0, nsurv = 0;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        P.pairs = (uint64_t*)S.pairs_a.ptr;
+        P.pair_capacity = S.pairs_a.cap / sizeof(uint64_t);
+        OGRECU_CUDA(cudaMemsetAsync(S.cnt.ptr, 0, ctl_bytes, ctx->stream));
+        setup_bin_kernel<<<nblocks, 256, 0, ctx->stream>>>(P);
+        OGRECU_CUDA(cudaGetLastError());
+        count_launch(ctx);
+        OGRECU_CUDA(cudaMemcpyAsync(ctl_host, P.ctl, 16, cudaMemcpyDeviceToHost, ctx->stream));
+        OGRECU_CUDA(cudaStreamSynchronize(ctx->stream));
+        npairs = ctl_host[2]; nsurv = ctl_host[3];
+        OGRECU_REQUIRE(npairs < 0x7fffffffull, "too many (triangle, tile) pairs in one flush");
+        if (!ctl_host[1]) break;
+        OGRECU_REQUIRE(attempt == 0, "pair buffer overflow after regrow");
+        OGRECU_CHECK(scratch_reserve(ctx, S.pairs_a, (npairs + 1024) * sizeof(uint64_t)));
+        OGRECU_CHECK(scratch_reserve(ctx, S.pairs_b, (npairs + 1024) * sizeof(uint64_t)));
+    }
     for (uint32_t t = 0; t < ntargets; ++t) {
         targets[t]->stats.triangles_in = ntris / ntargets;
+        targets[t]->stats.triangles_binned = nsurv / ntargets;
         targets[t]->stats.tile_pairs = npairs / ntargets;
         targets[t]->stats.tiles_visibility = targets[t]->stats.tiles_ordered = targets[t]->stats.tiles_active = 0;
         targets[t]->stats_pending = false;
     }
     if (npairs == 0) return OGRECU_OK;
 
-    // ---- K2 + stable sort by tile key
-    OGRECU_CHECK(scratch_reserve(ctx, S.pairs_a, npairs * sizeof(uint64_t)));
-    OGRECU_CHECK(scratch_reserve(ctx, S.pairs_b, npairs * sizeof(uint64_t)));
+    // ---- stable sort by tile key
     uint64_t* pa = (uint64_t*)S.pairs_a.ptr;
     uint64_t* pb = (uint64_t*)S.pairs_b.ptr;
-    bin_kernel<<<div_up(ntris, 256), 256, 0, ctx->stream>>>(P, P.cnt, pa);
-    OGRECU_CUDA(cudaGetLastError());
-    count_launch(ctx);
     int key_bits = 1;
     while ((1ull << key_bits) < nkeys) ++key_bits;
     const uint32_t rs_blocks = div_up(npairs, RS_BLOCK);
@@ -957,13 +1072,15 @@ int run_segment(ogrecu_ctx* ctx, ogrecu_rt* const* targets, uint32_t ntargets, c
         count_launch(ctx);
         std::swap(pa, pb);
     }
-    uint64_t* dummy;
-    OGRECU_CHECK(exclusive_scan_u32(ctx, S.sums, P.tile_count, (size_t)nkeys + 1, &dummy));
+    uint32_t* tile_start = (uint32_t*)S.tile_count.ptr;
+    tile_bounds_kernel<<<div_up(npairs, 256), 256, 0, ctx->stream>>>(pa, (uint32_t)npairs, nkeys, tile_start);
+    OGRECU_CUDA(cudaGetLastError());
+    count_launch(ctx);
 
     // ---- K3
     RasterParams R;
-    R.draws = P.draws; R.targets = (const TargetDev*)S.targets.ptr; R.hot = P.hot; R.cold = P.cold;
-    R.pairs = pa; R.tile_start = P.tile_count; R.tile_flags = P.tile_flags;
+    R.draws = P.draws; R.targets = (const TargetDev*)S.targets.ptr; R.rec = P.rec;
+    R.pairs = pa; R.tile_start = tile_start; R.tile_flags = P.tile_flags;
     R.force_ordered = ctx->raster_mode == 1;
     for (ogrecu_rt* other : ctx->targets) other->stats_pending = false;   // the counter table is per context: last flush wins
     OGRECU_CHECK(scratch_reserve(ctx, S.counters, (size_t)ntargets * 2 * sizeof(uint32_t)));
@@ -1037,7 +1154,7 @@ int rt_release(ogrecu_rt* rt)
         auto sm = scratch_map().find(ctx);
         if (sm != scratch_map().end()) {
             RasterScratch& S = sm->second;
-            for (Scratch* s : {&S.draws, &S.targets, &S.hot, &S.cold, &S.cnt, &S.sums, &S.pairs_a, &S.pairs_b, &S.tile_count, &S.hist, &S.counters})
+            for (Scratch* s : {&S.draws, &S.targets, &S.rec, &S.cnt, &S.sums, &S.pairs_a, &S.pairs_b, &S.tile_count, &S.hist, &S.counters})
                 if (s->ptr) cudaFree(s->ptr);
             scratch_map().erase(sm);
         }
