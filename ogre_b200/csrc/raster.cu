@@ -127,35 +127,46 @@ __device__ __forceinline__ unsigned long long lb_pack(unsigned long long pairs, 
     return (min(pairs, LB_FIELD) << 31) | min(tris, LB_FIELD);
 }
 
+constexpr int SB_THREADS = 256;
+constexpr int SB_ITEMS = 4;                          // triangles per thread (independent: memory-level parallelism)
+constexpr int SB_BLOCK = SB_THREADS * SB_ITEMS;      // triangles per CTA = per look-back descriptor
+constexpr int SB_SMEM = SB_BLOCK * 64 + 256;         // staged records + scan scratch
+
 // K1+K2 in ONE pass: vertex shader x3, viewport, 1/w, cull, bbox (exactly Tiny's operations), then an
 // order-preserving compaction of the surviving triangles and of their (tile, triangle) pairs through a
 // chained scan with decoupled look-back — no count array, no separate scan, no re-read of the records.
-__global__ void __launch_bounds__(256) setup_bin_kernel(SegParams P)
+// A CTA handles 1024 consecutive triangles (4 per thread, strided so that a warp reads consecutive
+// indices), stages their records in shared memory, and does ONE look-back for all of them.
+__global__ void __launch_bounds__(SB_THREADS) setup_bin_kernel(SegParams P)
 {
-    __shared__ uint32_t s_vb;
-    __shared__ unsigned long long s_excl;
-    __shared__ uint32_t s_wp[8], s_wt[8];
-    __shared__ float4 s_rec[256][4];
+    extern __shared__ __align__(16) uint8_t sb_smem[];
+    float4 (*s_rec)[SB_BLOCK] = reinterpret_cast<float4 (*)[SB_BLOCK]>(sb_smem);        // [4][1024]: piece q of slot i
+    uint32_t* s_wp = reinterpret_cast<uint32_t*>(sb_smem + SB_BLOCK * 64);              // [8]
+    uint32_t* s_wt = s_wp + 8;                                                          // [8]
+    unsigned long long* s_excl = reinterpret_cast<unsigned long long*>(s_wt + 8);       // [1]
+    uint32_t* s_vb = reinterpret_cast<uint32_t*>(s_excl + 1);                           // [1]
     const unsigned tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 
-    if (tid == 0) s_vb = atomicAdd(&P.ctl[0], 1u);   // blocks take tickets in dispatch order: look-back never waits on an unscheduled block
+    if (tid == 0) *s_vb = atomicAdd(&P.ctl[0], 1u);   // blocks take tickets in dispatch order: look-back never waits on an unscheduled block
     __syncthreads();
-    const uint32_t vb = s_vb;
-    const uint32_t g = vb * 256u + tid;
+    const uint32_t vb = *s_vb;
 
-    uint32_t ntiles = 0, lo = 0, t = 0;
-    float X[3], Y[3], Z[3], IW[3];
-    int x0 = 0, x1 = -1, y0 = 0, y1 = -1;
-    bool ordered = false;
-    if (g < P.ntris) {
+    uint32_t ntiles[SB_ITEMS], pk[SB_ITEMS];          // pk: draw | ordered << 31
+#pragma unroll
+    for (int k = 0; k < SB_ITEMS; ++k) {
+        const uint32_t slot = (uint32_t)k * SB_THREADS + tid;
+        const uint32_t g = vb * (uint32_t)SB_BLOCK + slot;
+        ntiles[k] = 0; pk[k] = 0;
+        if (g >= P.ntris) continue;
         // which draw: last d with tri_base <= g
-        uint32_t hi = P.ndraws;
+        uint32_t lo = 0, hi = P.ndraws;
         while (hi - lo > 1) {
             uint32_t mid = (lo + hi) >> 1;
             if (__ldg(&P.draws[mid].tri_base) <= g) lo = mid; else hi = mid;
         }
         const DrawDev& D = P.draws[lo];
-        t = g - D.tri_base;
+        const uint32_t t = g - D.tri_base;
+        float X[3], Y[3], Z[3], IW[3];
         bool ok = true;
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
@@ -165,10 +176,11 @@ __global__ void __launch_bounds__(256) setup_bin_kernel(SegParams P)
             float clip[4], q[4];
             mat4_mul(D.mvp, px, py, pz, 1.0f, clip);                               // DefaultShader::vertex .cpp:302
             mat4_mul(D.vp, clip[0], clip[1], clip[2], clip[3], q);                 // tinyrenderer.h:45
-            float w = q[3];
-            float fi = fdiv(1.0f, w);                                              // pts[i] /= w  (OgreVector.h:563-570)
+            // pts[i] /= w is "fInv = 1.0f / w; x *= fInv ..." (OgreVector.h:563-570) and pts[i][3] = 1/w
+            // (tinyrenderer.h:50) is the same correctly rounded quotient: one division serves both
+            const float fi = fdiv(1.0f, q[3]);
             X[j] = fmul(q[0], fi); Y[j] = fmul(q[1], fi); Z[j] = fmul(q[2], fi);
-            IW[j] = fdiv(1.0f, w);                                                 // tinyrenderer.h:50
+            IW[j] = fi;
             // non-finite screen coordinates: the reference writes out of bounds (undefined) -> drop
             ok = ok && isfinite(X[j]) && isfinite(Y[j]) && isfinite(Z[j]) && isfinite(IW[j]);
         }
@@ -176,6 +188,7 @@ __global__ void __launch_bounds__(256) setup_bin_kernel(SegParams P)
             float ax = fsub(X[2], X[0]), ay = fsub(Y[2], Y[0]), bx = fsub(X[2], X[1]), by = fsub(Y[2], Y[1]);
             if (fsub(fmul(ax, by), fmul(ay, bx)) > 0.0f) ok = false;
         }
+        int x0 = 0, x1 = -1, y0 = 0, y1 = -1;
         if (ok) {
             float mnx = FLT_MAX, mny = FLT_MAX, mxx = -FLT_MAX, mxy = -FLT_MAX;
             const float cx = (float)(P.width - 1u), cy = (float)(P.height - 1u);
@@ -196,40 +209,55 @@ __global__ void __launch_bounds__(256) setup_bin_kernel(SegParams P)
         if (ok) {
             int tx0 = x0 >> TILE_SHIFT, tx1 = x1 >> TILE_SHIFT;
             int ty0 = max(y0 >> TILE_SHIFT, (int)P.strip_ty0), ty1 = min(y1 >> TILE_SHIFT, (int)P.strip_ty1 - 1);
-            if (ty0 <= ty1) ntiles = (uint32_t)(tx1 - tx0 + 1) * (uint32_t)(ty1 - ty0 + 1);
+            if (ty0 <= ty1) ntiles[k] = (uint32_t)(tx1 - tx0 + 1) * (uint32_t)(ty1 - ty0 + 1);
         }
-        // Order-independent resolution (raster_kernel's visibility path) is only equivalent to Tiny's
-        // in-order loop for opaque, depth-tested, depth-writing fragments that cannot be discarded.
-        const uint32_t fl = D.flags;
-        ordered = (fl & (OGRECU_DRAW_DEPTH_TEST | OGRECU_DRAW_DEPTH_WRITE | OGRECU_DRAW_BLEND_ADD)) !=
-                      (OGRECU_DRAW_DEPTH_TEST | OGRECU_DRAW_DEPTH_WRITE) ||
-                  (D.tex != nullptr && D.tex_zero_alpha != 0);
+        if (ntiles[k]) {
+            // Order-independent resolution (raster_kernel's visibility path) is only equivalent to Tiny's
+            // in-order loop for opaque, depth-tested, depth-writing fragments that cannot be discarded.
+            const uint32_t fl = D.flags;
+            const bool ordered = (fl & (OGRECU_DRAW_DEPTH_TEST | OGRECU_DRAW_DEPTH_WRITE | OGRECU_DRAW_BLEND_ADD)) !=
+                                     (OGRECU_DRAW_DEPTH_TEST | OGRECU_DRAW_DEPTH_WRITE) ||
+                                 (D.tex != nullptr && D.tex_zero_alpha != 0);
+            pk[k] = lo | (ordered ? 0x80000000u : 0u);
+            s_rec[0][slot] = make_float4(X[0], X[1], X[2], Y[0]);
+            s_rec[1][slot] = make_float4(Y[1], Y[2], IW[0], IW[1]);
+            s_rec[2][slot] = make_float4(IW[2], Z[0], Z[1], Z[2]);
+            s_rec[3][slot] = make_float4(__uint_as_float((uint32_t)x0 | ((uint32_t)x1 << 16)), __uint_as_float((uint32_t)y0 | ((uint32_t)y1 << 16)),
+                                         __uint_as_float(lo), __uint_as_float(t));
+        }
     }
 
-    // ---- block-level exclusive scans of (pairs, survivors)
-    const uint32_t surv = ntiles ? 1u : 0u;
-    uint32_t ip = ntiles, it = surv;
+    // ---- block-level exclusive scans of (pairs, survivors) in triangle order: slot = k*256 + tid
+    uint32_t ep[SB_ITEMS], et[SB_ITEMS];
+    uint32_t run_p = 0, run_t = 0;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        uint32_t np = __shfl_up_sync(0xffffffffu, ip, o), nt = __shfl_up_sync(0xffffffffu, it, o);
-        if (lane >= (unsigned)o) { ip += np; it += nt; }
-    }
-    if (lane == 31) { s_wp[wid] = ip; s_wt[wid] = it; }
-    __syncthreads();
-    uint32_t wbase_p = 0, wbase_t = 0, bp = 0, bt = 0;
+    for (int k = 0; k < SB_ITEMS; ++k) {
+        const uint32_t surv = ntiles[k] ? 1u : 0u;
+        uint32_t ip = ntiles[k], it = surv;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        if (k < (int)wid) { wbase_p += s_wp[k]; wbase_t += s_wt[k]; }
-        bp += s_wp[k]; bt += s_wt[k];
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t np = __shfl_up_sync(0xffffffffu, ip, o), nt = __shfl_up_sync(0xffffffffu, it, o);
+            if (lane >= (unsigned)o) { ip += np; it += nt; }
+        }
+        __syncthreads();                    // previous round's s_wp / s_wt consumed
+        if (lane == 31) { s_wp[wid] = ip; s_wt[wid] = it; }
+        __syncthreads();
+        uint32_t wbp = 0, wbt = 0, tp = 0, tt = 0;
+#pragma unroll
+        for (int w = 0; w < SB_THREADS / 32; ++w) {
+            if (w < (int)wid) { wbp += s_wp[w]; wbt += s_wt[w]; }
+            tp += s_wp[w]; tt += s_wt[w];
+        }
+        ep[k] = run_p + wbp + ip - ntiles[k];
+        et[k] = run_t + wbt + it - surv;
+        run_p += tp; run_t += tt;
     }
-    const uint32_t ep = wbase_p + ip - ntiles, et = wbase_t + it - surv;   // exclusive inside the block
+    const uint32_t bp = run_p, bt = run_t;      // block totals
 
     // ---- chained scan across blocks (decoupled look-back, warp 0)
     if (wid == 0) {
         const unsigned long long agg = lb_pack(bp, bt);
-        if (lane == 0) {
-            *reinterpret_cast<volatile unsigned long long*>(&P.desc[vb]) = (vb == 0 ? LB_PREFIX : LB_AGG) | agg;
-        }
+        if (lane == 0) *reinterpret_cast<volatile unsigned long long*>(&P.desc[vb]) = (vb == 0 ? LB_PREFIX : LB_AGG) | agg;
         unsigned long long ex_p = 0, ex_t = 0;
         int j = (int)vb - 1;
         while (j >= 0) {
@@ -251,43 +279,37 @@ __global__ void __launch_bounds__(256) setup_bin_kernel(SegParams P)
         if (lane == 0) {
             const unsigned long long incl = lb_pack(ex_p + bp, ex_t + bt);
             if (vb != 0) *reinterpret_cast<volatile unsigned long long*>(&P.desc[vb]) = LB_PREFIX | incl;
-            s_excl = lb_pack(ex_p, ex_t);
-            if ((size_t)(vb + 1) * 256u >= P.ntris) {      // last block: grand totals
+            *s_excl = lb_pack(ex_p, ex_t);
+            if ((size_t)(vb + 1) * SB_BLOCK >= P.ntris) {      // last block: grand totals
                 P.ctl[2] = (uint32_t)((incl >> 31) & LB_FIELD);
                 P.ctl[3] = (uint32_t)(incl & LB_FIELD);
             }
         }
     }
     __syncthreads();
-    const unsigned long long base_p = (s_excl >> 31) & LB_FIELD, base_t = s_excl & LB_FIELD;
+    const unsigned long long base_p = (*s_excl >> 31) & LB_FIELD, base_t = *s_excl & LB_FIELD;
+    const bool fits = !(base_p + bp > P.pair_capacity || base_p + bp >= LB_FIELD);
+    if (!fits && tid == 0 && bp) atomicExch(&P.ctl[1], 1u);   // host grows the pair buffers and runs the pass again
 
-    // ---- records: staged in shared memory, written as one contiguous run of float4
-    if (surv) {
-        s_rec[et][0] = make_float4(X[0], X[1], X[2], Y[0]);
-        s_rec[et][1] = make_float4(Y[1], Y[2], IW[0], IW[1]);
-        s_rec[et][2] = make_float4(IW[2], Z[0], Z[1], Z[2]);
-        s_rec[et][3] = make_float4(__uint_as_float((uint32_t)x0 | ((uint32_t)x1 << 16)), __uint_as_float((uint32_t)y0 | ((uint32_t)y1 << 16)),
-                                   __uint_as_float(lo), __uint_as_float(t));
-    }
-    __syncthreads();
-    {
-        float4* dst = reinterpret_cast<float4*>(P.rec + base_t);
-        const float4* src = &s_rec[0][0];
-        for (uint32_t k = tid; k < bt * 4u; k += 256u) dst[k] = src[k];
-    }
-
-    // ---- pairs, contiguous per triangle in submission order; the stable sort by tile key keeps that order per tile
-    if (base_p + bp > P.pair_capacity || base_p + bp >= LB_FIELD) {
-        if (tid == 0 && bp) atomicExch(&P.ctl[1], 1u);   // host grows the pair buffers and runs the pass again
-        return;
-    }
-    if (ntiles) {
-        const uint32_t target = P.draws[lo].target;
-        const int tx0 = x0 >> TILE_SHIFT, tx1 = x1 >> TILE_SHIFT;
-        const int ty0 = max(y0 >> TILE_SHIFT, (int)P.strip_ty0), ty1 = min(y1 >> TILE_SHIFT, (int)P.strip_ty1 - 1);
+    // ---- write out: compact records (consecutive ranks from consecutive threads) and the pairs,
+    //      contiguous per triangle in submission order; the stable sort by tile key keeps that order per tile
+#pragma unroll
+    for (int k = 0; k < SB_ITEMS; ++k) {
+        if (!ntiles[k]) continue;
+        const uint32_t slot = (uint32_t)k * SB_THREADS + tid;
+        const uint32_t ci = (uint32_t)(base_t + et[k]);
+        float4* dst = reinterpret_cast<float4*>(P.rec + ci);
+        const float4 r3 = s_rec[3][slot];
+        dst[0] = s_rec[0][slot]; dst[1] = s_rec[1][slot]; dst[2] = s_rec[2][slot]; dst[3] = r3;
+        if (!fits) continue;
+        const uint32_t bx = __float_as_uint(r3.x), by = __float_as_uint(r3.y);
+        const uint32_t lo = pk[k] & 0x7fffffffu;
+        const bool ordered = (pk[k] >> 31) != 0;
+        const uint32_t target = __ldg(&P.draws[lo].target);
+        const int tx0 = (int)(bx & 0xffff) >> TILE_SHIFT, tx1 = (int)(bx >> 16) >> TILE_SHIFT;
+        const int ty0 = max((int)(by & 0xffff) >> TILE_SHIFT, (int)P.strip_ty0), ty1 = min((int)(by >> 16) >> TILE_SHIFT, (int)P.strip_ty1 - 1);
         const uint32_t tbase = target * P.tiles_x * P.tiles_y;
-        const uint32_t ci = (uint32_t)(base_t + et);
-        uint64_t* out = P.pairs + base_p + ep;
+        uint64_t* out = P.pairs + base_p + ep[k];
         for (int ty = ty0; ty <= ty1; ++ty)
             for (int tx = tx0; tx <= tx1; ++tx) {
                 const uint32_t key = tbase + (uint32_t)ty * P.tiles_x + (uint32_t)tx;
@@ -993,7 +1015,7 @@ int run_segment(ogrecu_ctx* ctx, ogrecu_rt* const* targets, uint32_t ntargets, c
 
     OGRECU_CHECK(scratch_reserve(ctx, S.draws, dd.size() * sizeof(DrawDev)));
     OGRECU_CHECK(scratch_reserve(ctx, S.targets, td.size() * sizeof(TargetDev)));
-    const uint32_t nblocks = div_up(ntris, 256);
+    const uint32_t nblocks = div_up(ntris, SB_BLOCK);
     OGRECU_CHECK(scratch_reserve(ctx, S.rec, (size_t)ntris * sizeof(TriRec)));
     // control block: look-back descriptors [nblocks] | ctl[4] | tile flags [nkeys]  (zeroed per pass)
     const size_t ctl_bytes = (size_t)nblocks * 8 + 16 + (size_t)nkeys * 4;
@@ -1027,12 +1049,13 @@ int run_segment(ogrecu_ctx* ctx, ogrecu_rt* const* targets, uint32_t ntargets, c
     P.strip_ty0 = strip_ty0; P.strip_ty1 = strip_ty1;
 
     // ---- K1+K2: setup, compaction and binning in one pass
+    OGRECU_CUDA(cudaFuncSetAttribute(setup_bin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SB_SMEM));
     uint64_t npairs = 0, nsurv = 0;
     for (int attempt = 0; attempt < 2; ++attempt) {
         P.pairs = (uint64_t*)S.pairs_a.ptr;
         P.pair_capacity = S.pairs_a.cap / sizeof(uint64_t);
         OGRECU_CUDA(cudaMemsetAsync(S.cnt.ptr, 0, ctl_bytes, ctx->stream));
-        setup_bin_kernel<<<nblocks, 256, 0, ctx->stream>>>(P);
+        setup_bin_kernel<<<nblocks, SB_THREADS, SB_SMEM, ctx->stream>>>(P);
         OGRECU_CUDA(cudaGetLastError());
         count_launch(ctx);
         OGRECU_CUDA(cudaMemcpyAsync(ctl_host, P.ctl, 16, cudaMemcpyDeviceToHost, ctx->stream));
