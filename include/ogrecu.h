@@ -38,7 +38,7 @@ extern "C" {
 #define OGRECU_API
 #endif
 
-#define OGRECU_ABI_VERSION 1
+#define OGRECU_ABI_VERSION 2
 
 typedef enum ogrecu_status {
     OGRECU_OK = 0,
@@ -82,6 +82,8 @@ OGRECU_API uint64_t ogrecu_launch_count(const ogrecu_ctx* ctx);
  *   "skin_ipc"   instances per CTA of the tiled kernel, 0 = auto
  *   "raster_mode" 0 = auto (per tile: order-independent visibility resolve where it is provably
  *                equivalent to Tiny's in-order loop, else in-order), 1 = always in-order
+ *   "raster_xf"  1 = transform every vertex once per flush when the draw gives vertex_count (default),
+ *                0 = once per index like Tiny; identical results
  * Unknown names return OGRECU_ERR_INVALID. */
 OGRECU_API int ogrecu_set_config_option(ogrecu_ctx* ctx, const char* name, int value);
 
@@ -286,6 +288,9 @@ typedef struct ogrecu_draw_desc {
     uint32_t draw_count;        /* indexCount, or vertexCount when not indexed (.cpp:373,387) */
     uint32_t prim_type;         /* OGRECU_PRIM_*; lists are culled (cross>0), strips not (.cpp:410) */
     uint32_t flags;             /* OGRECU_DRAW_*                                          */
+    uint32_t vertex_count;      /* vertexData->vertexCount: indices are < vertex_count.  Optional (0 = unknown):
+                                 * when given, every vertex is transformed ONCE per flush instead of once per
+                                 * index as Tiny does (.cpp:400-408) — same operations per vertex, same bits */
     const ogrecu_tex* texture;  /* unit 0 or NULL (white)  (.cpp:208-220)                 */
     float mvp[16];              /* uniform_MVP                                            */
     float tex_matrix[16];       /* uniform_Tex                                            */

@@ -43,7 +43,7 @@ class DrawDesc(C.Structure):
         ("uvs", C.c_void_p), ("uv_stride", C.c_uint32),
         ("normals", C.c_void_p), ("normal_stride", C.c_uint32),
         ("indices", C.c_void_p), ("index_type", C.c_uint32),
-        ("draw_count", C.c_uint32), ("prim_type", C.c_uint32), ("flags", C.c_uint32),
+        ("draw_count", C.c_uint32), ("prim_type", C.c_uint32), ("flags", C.c_uint32), ("vertex_count", C.c_uint32),
         ("texture", C.c_void_p),
         ("mvp", C.c_float * 16), ("tex_matrix", C.c_float * 16), ("mvit", C.c_float * 16),
         ("viewport", C.c_float * 16), ("light_dir", C.c_float * 3), ("ambient", C.c_float * 4),

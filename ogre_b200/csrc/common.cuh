@@ -83,7 +83,8 @@ struct ogrecu_ctx {
     //   OGRECU_SKIN_MODE  0 auto | 1 tile kernel without TMA (cooperative LDG/STG) | 2 one-thread-per-vertex kernel
     //   OGRECU_SKIN_IPC   instances per CTA of the tile kernel (0 = auto)
     //   OGRECU_RASTER_MODE 0 auto (visibility path where it is equivalent) | 1 always the in-order path
-    int skin_mode, skin_ipc, raster_mode;
+    //   OGRECU_RASTER_XF   1 (default) transform each vertex once per flush when the draw gives a vertex count | 0 per index
+    int skin_mode, skin_ipc, raster_mode, raster_xf;
 };
 
 namespace ogrecu {

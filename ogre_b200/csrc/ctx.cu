@@ -108,6 +108,8 @@ int ogrecu_init(int device, ogrecu_ctx** out_ctx)
     ctx->skin_ipc = ev ? atoi(ev) : 0;
     ev = getenv("OGRECU_RASTER_MODE");
     ctx->raster_mode = ev ? atoi(ev) : 0;
+    ev = getenv("OGRECU_RASTER_XF");
+    ctx->raster_xf = ev ? atoi(ev) : 1;
     e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete ctx; return cuda_fail(e, "cudaStreamCreate", __FILE__, __LINE__); }
     ctx->stream = ctx->own_stream;
@@ -159,6 +161,7 @@ int ogrecu_set_config_option(ogrecu_ctx* ctx, const char* name, int value)
 {
     OGRECU_REQUIRE(ctx && name, "NULL argument");
     if (!strcmp(name, "skin_mode")) { OGRECU_REQUIRE(value >= 0 && value <= 2, "skin_mode is 0..2"); ctx->skin_mode = value; return OGRECU_OK; }
+    if (!strcmp(name, "raster_xf")) { OGRECU_REQUIRE(value >= 0 && value <= 1, "raster_xf is 0..1"); ctx->raster_xf = value; return OGRECU_OK; }
     if (!strcmp(name, "raster_mode")) { OGRECU_REQUIRE(value >= 0 && value <= 1, "raster_mode is 0..1"); ctx->raster_mode = value; return OGRECU_OK; }
     if (!strcmp(name, "skin_ipc")) { OGRECU_REQUIRE(value >= 0 && value <= 4096, "skin_ipc is 0..4096"); ctx->skin_ipc = value; return OGRECU_OK; }
     set_error("ogrecu_set_config_option: unknown option '%s'", name);

@@ -55,6 +55,8 @@ struct DrawDev {
     uint32_t pos_stride, uv_stride, nrm_stride, index_type;
     uint32_t is_strip, flags, target, tri_base;
     uint32_t tri_count, tex_w, tex_h, tex_zero_alpha;
+    const float4* xf;         // optional: pre-transformed vertices (X, Y, Z, 1/w) of this draw, [vertex_count]
+    uint32_t vertex_count, vert_base, pad0, pad1;
     float mvp[16], texm[16], vp[16];
     float mvit[9];
     float light[3];
@@ -108,6 +110,38 @@ __device__ __forceinline__ void mat4_mul(const float* __restrict__ m, float x, f
         out[r] = fadd(fadd(fadd(fmul(m[4 * r + 0], x), fmul(m[4 * r + 1], y)), fmul(m[4 * r + 2], z)), fmul(m[4 * r + 3], w));
 }
 
+// DefaultShader::vertex position part + the head of triangle() for ONE vertex: clip = MVP*(p,1)
+// (OgreTinyRenderSystem.cpp:302), q = Viewport*clip (tinyrenderer.h:45), pts /= w as "fInv = 1.0f/w; x*fInv"
+// (OgreVector.h:563-570); pts[3] = 1/w (tinyrenderer.h:50) is the same correctly rounded quotient.
+// Pure function of the vertex and the draw's matrices: evaluating it once per vertex instead of once per
+// index (Tiny has no vertex cache) gives the same bits.
+__device__ __forceinline__ float4 transform_vertex(const float* __restrict__ mvp, const float* __restrict__ vp, float px, float py, float pz)
+{
+    float clip[4], q[4];
+    mat4_mul(mvp, px, py, pz, 1.0f, clip);
+    mat4_mul(vp, clip[0], clip[1], clip[2], clip[3], q);
+    const float fi = fdiv(1.0f, q[3]);
+    return make_float4(fmul(q[0], fi), fmul(q[1], fi), fmul(q[2], fi), fi);
+}
+
+struct XfParams { const DrawDev* draws; uint32_t ndraws; uint32_t nverts; float4* out; };
+
+// vertex pre-transform: one thread per (draw, vertex) over all draws of the flush that gave a vertex count
+__global__ void __launch_bounds__(256) vertex_xf_kernel(XfParams P)
+{
+    const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= P.nverts) return;
+    uint32_t lo = 0, hi = P.ndraws;                    // last draw with vert_base <= v (draws without xf have vertex_count 0)
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(&P.draws[mid].vert_base) <= v) lo = mid; else hi = mid;
+    }
+    const DrawDev& D = P.draws[lo];
+    const uint32_t vi = v - D.vert_base;
+    const float* p = (const float*)(D.pos + (size_t)vi * D.pos_stride);
+    P.out[v] = transform_vertex(D.mvp, D.vp, __ldg(p), __ldg(p + 1), __ldg(p + 2));
+}
+
 // index of vertex j of triangle t (list: 3t+j, strip: t+j — sliding window without winding flip,
 // OgreTinyRenderSystem.cpp:396-403); 16-bit indices are read unsigned (the reference reads int16: UB >= 32768)
 __device__ __forceinline__ size_t vertex_index(const DrawDev& D, uint32_t t, int j)
@@ -128,9 +162,12 @@ __device__ __forceinline__ unsigned long long lb_pack(unsigned long long pairs, 
 }
 
 constexpr int SB_THREADS = 256;
-constexpr int SB_ITEMS = 4;                          // triangles per thread (independent: memory-level parallelism)
+#ifndef SB_ITEMS_N
+#define SB_ITEMS_N 4
+#endif
+constexpr int SB_ITEMS = SB_ITEMS_N;                 // triangles per thread (independent: memory-level parallelism)
 constexpr int SB_BLOCK = SB_THREADS * SB_ITEMS;      // triangles per CTA = per look-back descriptor
-constexpr int SB_SMEM = SB_BLOCK * 64 + 256;         // staged records + scan scratch
+constexpr int SB_SMEM = SB_BLOCK * 64 + 512;         // staged records + scan scratch + cached matrices
 
 // K1+K2 in ONE pass: vertex shader x3, viewport, 1/w, cull, bbox (exactly Tiny's operations), then an
 // order-preserving compaction of the surviving triangles and of their (tile, triangle) pairs through a
@@ -144,43 +181,63 @@ __global__ void __launch_bounds__(SB_THREADS) setup_bin_kernel(SegParams P)
     uint32_t* s_wp = reinterpret_cast<uint32_t*>(sb_smem + SB_BLOCK * 64);              // [8]
     uint32_t* s_wt = s_wp + 8;                                                          // [8]
     unsigned long long* s_excl = reinterpret_cast<unsigned long long*>(s_wt + 8);       // [1]
-    uint32_t* s_vb = reinterpret_cast<uint32_t*>(s_excl + 1);                           // [1]
+    uint32_t* s_vb = reinterpret_cast<uint32_t*>(s_excl + 1);                           // [2]: ticket, draw of the CTA's first triangle
+    float* s_mat = reinterpret_cast<float*>(s_vb + 2);                                  // [32]: mvp, vp of that draw
     const unsigned tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 
-    if (tid == 0) *s_vb = atomicAdd(&P.ctl[0], 1u);   // blocks take tickets in dispatch order: look-back never waits on an unscheduled block
+    if (tid == 0) {
+        const uint32_t ticket = atomicAdd(&P.ctl[0], 1u);   // blocks take tickets in dispatch order: look-back never waits on an unscheduled block
+        s_vb[0] = ticket;
+        uint32_t lo = 0, hi = P.ndraws;
+        const uint32_t g0 = ticket * (uint32_t)SB_BLOCK;
+        while (hi - lo > 1) {
+            uint32_t mid = (lo + hi) >> 1;
+            if (__ldg(&P.draws[mid].tri_base) <= g0) lo = mid; else hi = mid;
+        }
+        s_vb[1] = lo;
+    }
     __syncthreads();
-    const uint32_t vb = *s_vb;
+    const uint32_t vb = s_vb[0], lo0 = s_vb[1];
+    if (tid < 32) s_mat[tid] = tid < 16 ? P.draws[lo0].mvp[tid] : P.draws[lo0].vp[tid - 16];
+    const uint32_t lo0_end = lo0 + 1 < P.ndraws ? __ldg(&P.draws[lo0 + 1].tri_base) : 0xffffffffu;   // triangles below this belong to draw lo0
+    __syncthreads();
 
     uint32_t ntiles[SB_ITEMS], pk[SB_ITEMS];          // pk: draw | ordered << 31
 #pragma unroll
     for (int k = 0; k < SB_ITEMS; ++k) {
-        const uint32_t slot = (uint32_t)k * SB_THREADS + tid;
+        // a warp owns 32*SB_ITEMS consecutive triangles, 32 per round: coalesced index reads, in-warp scan carry
+        const uint32_t slot = wid * (32u * SB_ITEMS) + (uint32_t)k * 32u + lane;
         const uint32_t g = vb * (uint32_t)SB_BLOCK + slot;
         ntiles[k] = 0; pk[k] = 0;
         if (g >= P.ntris) continue;
-        // which draw: last d with tri_base <= g
-        uint32_t lo = 0, hi = P.ndraws;
-        while (hi - lo > 1) {
-            uint32_t mid = (lo + hi) >> 1;
-            if (__ldg(&P.draws[mid].tri_base) <= g) lo = mid; else hi = mid;
+        // which draw: last d with tri_base <= g (almost always the CTA's first draw, whose matrices sit in shared memory)
+        uint32_t lo = lo0;
+        const bool same = g < lo0_end;
+        if (!same) {
+            uint32_t hi = P.ndraws;
+            while (hi - lo > 1) {
+                uint32_t mid = (lo + hi) >> 1;
+                if (__ldg(&P.draws[mid].tri_base) <= g) lo = mid; else hi = mid;
+            }
         }
         const DrawDev& D = P.draws[lo];
+        const float* Mmvp = same ? s_mat : D.mvp;
+        const float* Mvp = same ? s_mat + 16 : D.vp;
         const uint32_t t = g - D.tri_base;
         float X[3], Y[3], Z[3], IW[3];
         bool ok = true;
+        const float4* xf = D.xf;
+        const uint32_t nxf = D.vertex_count;
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
             const size_t vi = vertex_index(D, t, j);
-            const float* p = (const float*)(D.pos + vi * D.pos_stride);
-            float px = __ldg(p), py = __ldg(p + 1), pz = __ldg(p + 2);
-            float clip[4], q[4];
-            mat4_mul(D.mvp, px, py, pz, 1.0f, clip);                               // DefaultShader::vertex .cpp:302
-            mat4_mul(D.vp, clip[0], clip[1], clip[2], clip[3], q);                 // tinyrenderer.h:45
-            // pts[i] /= w is "fInv = 1.0f / w; x *= fInv ..." (OgreVector.h:563-570) and pts[i][3] = 1/w
-            // (tinyrenderer.h:50) is the same correctly rounded quotient: one division serves both
-            const float fi = fdiv(1.0f, q[3]);
-            X[j] = fmul(q[0], fi); Y[j] = fmul(q[1], fi); Z[j] = fmul(q[2], fi);
-            IW[j] = fi;
+            float4 sv;
+            if (xf && vi < nxf) sv = __ldg(xf + vi);                               // transformed once per vertex (vertex_xf_kernel)
+            else {
+                const float* p = (const float*)(D.pos + vi * D.pos_stride);
+                sv = transform_vertex(Mmvp, Mvp, __ldg(p), __ldg(p + 1), __ldg(p + 2));
+            }
+            X[j] = sv.x; Y[j] = sv.y; Z[j] = sv.z; IW[j] = sv.w;
             // non-finite screen coordinates: the reference writes out of bounds (undefined) -> drop
             ok = ok && isfinite(X[j]) && isfinite(Y[j]) && isfinite(Z[j]) && isfinite(IW[j]);
         }
@@ -227,9 +284,9 @@ __global__ void __launch_bounds__(SB_THREADS) setup_bin_kernel(SegParams P)
         }
     }
 
-    // ---- block-level exclusive scans of (pairs, survivors) in triangle order: slot = k*256 + tid
+    // ---- exclusive scans of (pairs, survivors) in triangle order: rounds chained inside the warp, warps combined once
     uint32_t ep[SB_ITEMS], et[SB_ITEMS];
-    uint32_t run_p = 0, run_t = 0;
+    uint32_t wrun_p = 0, wrun_t = 0;
 #pragma unroll
     for (int k = 0; k < SB_ITEMS; ++k) {
         const uint32_t surv = ntiles[k] ? 1u : 0u;
@@ -239,20 +296,21 @@ __global__ void __launch_bounds__(SB_THREADS) setup_bin_kernel(SegParams P)
             uint32_t np = __shfl_up_sync(0xffffffffu, ip, o), nt = __shfl_up_sync(0xffffffffu, it, o);
             if (lane >= (unsigned)o) { ip += np; it += nt; }
         }
-        __syncthreads();                    // previous round's s_wp / s_wt consumed
-        if (lane == 31) { s_wp[wid] = ip; s_wt[wid] = it; }
-        __syncthreads();
-        uint32_t wbp = 0, wbt = 0, tp = 0, tt = 0;
-#pragma unroll
-        for (int w = 0; w < SB_THREADS / 32; ++w) {
-            if (w < (int)wid) { wbp += s_wp[w]; wbt += s_wt[w]; }
-            tp += s_wp[w]; tt += s_wt[w];
-        }
-        ep[k] = run_p + wbp + ip - ntiles[k];
-        et[k] = run_t + wbt + it - surv;
-        run_p += tp; run_t += tt;
+        ep[k] = wrun_p + ip - ntiles[k];
+        et[k] = wrun_t + it - surv;
+        wrun_p += __shfl_sync(0xffffffffu, ip, 31);
+        wrun_t += __shfl_sync(0xffffffffu, it, 31);
     }
-    const uint32_t bp = run_p, bt = run_t;      // block totals
+    if (lane == 0) { s_wp[wid] = wrun_p; s_wt[wid] = wrun_t; }
+    __syncthreads();
+    uint32_t wbp = 0, wbt = 0, bp = 0, bt = 0;      // warp bases, block totals
+#pragma unroll
+    for (int w = 0; w < SB_THREADS / 32; ++w) {
+        if (w < (int)wid) { wbp += s_wp[w]; wbt += s_wt[w]; }
+        bp += s_wp[w]; bt += s_wt[w];
+    }
+#pragma unroll
+    for (int k = 0; k < SB_ITEMS; ++k) { ep[k] += wbp; et[k] += wbt; }
 
     // ---- chained scan across blocks (decoupled look-back, warp 0)
     if (wid == 0) {
@@ -296,7 +354,7 @@ __global__ void __launch_bounds__(SB_THREADS) setup_bin_kernel(SegParams P)
 #pragma unroll
     for (int k = 0; k < SB_ITEMS; ++k) {
         if (!ntiles[k]) continue;
-        const uint32_t slot = (uint32_t)k * SB_THREADS + tid;
+        const uint32_t slot = wid * (32u * SB_ITEMS) + (uint32_t)k * 32u + lane;
         const uint32_t ci = (uint32_t)(base_t + et[k]);
         float4* dst = reinterpret_cast<float4*>(P.rec + ci);
         const float4 r3 = s_rec[3][slot];
@@ -937,7 +995,7 @@ namespace {
 
 // per-context raster scratch (grown on demand, reused across flushes)
 struct RasterScratch {
-    Scratch draws, targets, rec, cnt, sums, pairs_a, pairs_b, tile_count, hist, counters;
+    Scratch draws, targets, rec, cnt, sums, pairs_a, pairs_b, tile_count, hist, counters, xf;
 };
 std::map<ogrecu_ctx*, RasterScratch>& scratch_map()
 {
@@ -981,7 +1039,7 @@ int run_segment(ogrecu_ctx* ctx, ogrecu_rt* const* targets, uint32_t ntargets, c
 
     // ---- per-draw device table
     std::vector<DrawDev> dd(items.size());
-    uint64_t ntris64 = 0;
+    uint64_t ntris64 = 0, nverts64 = 0;
     for (size_t k = 0; k < items.size(); ++k) {
         const ogrecu_draw_desc& d = *items[k].desc;
         DrawDev& o = dd[k];
@@ -995,6 +1053,12 @@ int run_segment(ogrecu_ctx* ctx, ogrecu_rt* const* targets, uint32_t ntargets, c
         o.tri_base = (uint32_t)ntris64;
         o.tri_count = tri_count_of(d);
         ntris64 += o.tri_count;
+        // vertex pre-transform when the caller bounded the vertex range and it is not mostly unused
+        o.vert_base = (uint32_t)nverts64;
+        if (d.vertex_count && (uint64_t)d.vertex_count <= 4ull * o.tri_count + 64 && ctx->raster_xf != 0) {
+            o.vertex_count = d.vertex_count;
+            nverts64 += d.vertex_count;
+        }
         if (d.texture) { o.tex = d.texture->dev; o.tex_w = d.texture->w; o.tex_h = d.texture->h; o.tex_zero_alpha = d.texture->has_zero_alpha; }
         memcpy(o.mvp, items[k].mvp ? items[k].mvp : d.mvp, 64);
         memcpy(o.texm, d.tex_matrix, 64);
@@ -1005,6 +1069,7 @@ int run_segment(ogrecu_ctx* ctx, ogrecu_rt* const* targets, uint32_t ntargets, c
         memcpy(o.ambient, d.ambient, 16);
     }
     OGRECU_REQUIRE(ntris64 < 0x7fffff00ull, "too many triangles in one flush");
+    OGRECU_REQUIRE(nverts64 < 0x7fffff00ull, "too many vertices in one flush");
     const uint32_t ntris = (uint32_t)ntris64;
     for (uint32_t t = 0; t < ntargets; ++t) { targets[t]->stats.triangles_in += 0; }
     if (ntris == 0) return OGRECU_OK;
@@ -1015,6 +1080,11 @@ int run_segment(ogrecu_ctx* ctx, ogrecu_rt* const* targets, uint32_t ntargets, c
 
     OGRECU_CHECK(scratch_reserve(ctx, S.draws, dd.size() * sizeof(DrawDev)));
     OGRECU_CHECK(scratch_reserve(ctx, S.targets, td.size() * sizeof(TargetDev)));
+    const uint32_t nverts = (uint32_t)nverts64;
+    if (nverts) {
+        OGRECU_CHECK(scratch_reserve(ctx, S.xf, (size_t)nverts * sizeof(float4)));
+        for (DrawDev& o : dd) if (o.vertex_count) o.xf = (const float4*)S.xf.ptr + o.vert_base;
+    }
     const uint32_t nblocks = div_up(ntris, SB_BLOCK);
     OGRECU_CHECK(scratch_reserve(ctx, S.rec, (size_t)ntris * sizeof(TriRec)));
     // control block: look-back descriptors [nblocks] | ctl[4] | tile flags [nkeys]  (zeroed per pass)
@@ -1048,6 +1118,14 @@ int run_segment(ogrecu_ctx* ctx, ogrecu_rt* const* targets, uint32_t ntargets, c
     P.width = W; P.height = H; P.tiles_x = tiles_x; P.tiles_y = tiles_y;
     P.strip_ty0 = strip_ty0; P.strip_ty1 = strip_ty1;
 
+    // ---- K0: every vertex of the flush transformed once
+    if (nverts) {
+        XfParams X;
+        X.draws = P.draws; X.ndraws = P.ndraws; X.nverts = nverts; X.out = (float4*)S.xf.ptr;
+        vertex_xf_kernel<<<div_up(nverts, 256), 256, 0, ctx->stream>>>(X);
+        OGRECU_CUDA(cudaGetLastError());
+        count_launch(ctx);
+    }
     // ---- K1+K2: setup, compaction and binning in one pass
     OGRECU_CUDA(cudaFuncSetAttribute(setup_bin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SB_SMEM));
     uint64_t npairs = 0, nsurv = 0;
@@ -1177,7 +1255,7 @@ int rt_release(ogrecu_rt* rt)
         auto sm = scratch_map().find(ctx);
         if (sm != scratch_map().end()) {
             RasterScratch& S = sm->second;
-            for (Scratch* s : {&S.draws, &S.targets, &S.rec, &S.cnt, &S.sums, &S.pairs_a, &S.pairs_b, &S.tile_count, &S.hist, &S.counters})
+            for (Scratch* s : {&S.draws, &S.targets, &S.rec, &S.cnt, &S.sums, &S.pairs_a, &S.pairs_b, &S.tile_count, &S.hist, &S.counters, &S.xf})
                 if (s->ptr) cudaFree(s->ptr);
             scratch_map().erase(sm);
         }

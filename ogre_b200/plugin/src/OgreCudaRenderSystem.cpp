@@ -294,6 +294,7 @@ void CudaRenderSystem::_render(const RenderOperation& op)
     d.normals = nrm.ptr; d.normal_stride = nrm.stride;
     d.index_type = OGRECU_INDEX_NONE;
     d.draw_count = (uint32_t)op.vertexData->vertexCount;
+    d.vertex_count = (uint32_t)op.vertexData->vertexCount;   // indices address [vertexStart, vertexStart + vertexCount)
     if (op.useIndexes)
     {
         auto& ib = op.indexData->indexBuffer;

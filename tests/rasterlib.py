@@ -38,6 +38,7 @@ class GpuScene:
             d.uvs, d.uv_stride = (vb.ptr + 24, 32) if case.has_uv else (None, 0)
             d.indices = ib.ptr if ib is not None else None
             d.index_type, d.draw_count = case.index_type, case.draw_count
+            d.vertex_count = len(case.verts) if getattr(case, "give_vertex_count", True) else 0
             d.prim_type = ogre_b200.PRIM_TRIANGLE_STRIP if case.strip else ogre_b200.PRIM_TRIANGLE_LIST
             d.flags = ((ogre_b200.DRAW_DEPTH_TEST if case.depth_test else 0) | (ogre_b200.DRAW_DEPTH_WRITE if case.depth_write else 0) |
                        (ogre_b200.DRAW_BLEND_ADD if case.blend_add else 0) | (ogre_b200.DRAW_LIGHTING if case.lighting else 0))

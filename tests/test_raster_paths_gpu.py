@@ -17,12 +17,15 @@ def both_modes(ctx, cases, w, h, what, expect_visibility=None, **kw):
     rc, rz, frags = render_oracle(cases, w, h, **kw)
     out = {}
     for mode in (0, 1):
-        ctx.set_config_option("raster_mode", mode)
-        try:
-            gc, gz, stats = render_gpu(ctx, cases, w, h, **kw)
-        finally:
-            ctx.set_config_option("raster_mode", 0)
-        assert_images_equal(gc, gz, rc, rz, "%s (raster_mode %d)" % (what, mode))
+        for xf in (1, 0):       # vertex pre-transform on / off: same bits either way
+            ctx.set_config_option("raster_mode", mode)
+            ctx.set_config_option("raster_xf", xf)
+            try:
+                gc, gz, stats = render_gpu(ctx, cases, w, h, **kw)
+            finally:
+                ctx.set_config_option("raster_mode", 0)
+                ctx.set_config_option("raster_xf", 1)
+            assert_images_equal(gc, gz, rc, rz, "%s (raster_mode %d, raster_xf %d)" % (what, mode, xf))
         out[mode] = stats
     assert out[1]["tiles_visibility"] == 0 and out[1]["tiles_ordered"] == out[1]["tiles_active"] > 0
     if expect_visibility is True:

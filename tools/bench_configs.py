@@ -108,6 +108,7 @@ def upload_scene(ctx, verts, idx, tex, w, h):
     d.normals, d.normal_stride = vb.ptr + 12, 32
     d.uvs, d.uv_stride = vb.ptr + 24, 32
     d.indices, d.index_type, d.draw_count = ib.ptr, 4, len(idx)
+    d.vertex_count = len(verts)
     d.prim_type = ogre_b200.PRIM_TRIANGLE_LIST
     d.flags = ogre_b200.DRAW_DEPTH_TEST | ogre_b200.DRAW_DEPTH_WRITE | ogre_b200.DRAW_LIGHTING
     d.texture = texture.handle
