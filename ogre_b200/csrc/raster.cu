@@ -81,10 +81,6 @@ struct __align__(16) TriRec {
 };
 static_assert(sizeof(TriRec) == 64, "TriRec must be 4 float4");
 
-// decoupled look-back descriptors of the single-pass setup+bin kernel: status | pairs (31 bit) | triangles (31 bit)
-constexpr unsigned long long LB_AGG = 1ull << 62, LB_PREFIX = 2ull << 62, LB_STATUS = 3ull << 62;
-constexpr unsigned long long LB_FIELD = 0x7fffffffull;     // saturating: 2^31-1 = "too many"
-
 struct SegParams {
     const DrawDev* draws;
     uint32_t ndraws;
@@ -92,8 +88,9 @@ struct SegParams {
     TriRec* rec;              // [survivors]
     uint64_t* pairs;          // (tile key << 32 | compact triangle index), submission order
     uint64_t pair_capacity;
-    unsigned long long* desc; // [nblocks] look-back descriptors (zeroed before launch)
-    uint32_t* ctl;            // [0] block ticket  [1] overflow flag  [2] total pairs  [3] total survivors
+    uint32_t* block_agg;      // [nblocks][2]: pairs, survivors of each 1024-triangle CTA
+    unsigned long long* bases;// [nblocks][2]: their exclusive scans
+    uint32_t* ctl;            // [2] total pairs  [3] total survivors
     uint32_t width, height;
     uint32_t tiles_x, tiles_y;        // tiles per target
     uint32_t strip_ty0, strip_ty1;    // tile rows rasterised on this context
@@ -152,228 +149,232 @@ __device__ __forceinline__ size_t vertex_index(const DrawDev& D, uint32_t t, int
     return k;
 }
 
-__device__ __forceinline__ unsigned long long lb_load(const unsigned long long* p)
-{
-    return *reinterpret_cast<const volatile unsigned long long*>(p);
-}
-__device__ __forceinline__ unsigned long long lb_pack(unsigned long long pairs, unsigned long long tris)
-{
-    return (min(pairs, LB_FIELD) << 31) | min(tris, LB_FIELD);
-}
-
 constexpr int SB_THREADS = 256;
-#ifndef SB_ITEMS_N
-#define SB_ITEMS_N 4
-#endif
-constexpr int SB_ITEMS = SB_ITEMS_N;                 // triangles per thread (independent: memory-level parallelism)
-constexpr int SB_BLOCK = SB_THREADS * SB_ITEMS;      // triangles per CTA = per look-back descriptor
-constexpr int SB_SMEM = SB_BLOCK * 64 + 512;         // staged records + scan scratch + cached matrices
+constexpr int SB_ROUNDS = 4;                         // 256-triangle rounds per CTA
+constexpr int SB_BLOCK = SB_THREADS * SB_ROUNDS;     // triangles per CTA = per entry of the block-aggregate table
 
-// K1+K2 in ONE pass: vertex shader x3, viewport, 1/w, cull, bbox (exactly Tiny's operations), then an
-// order-preserving compaction of the surviving triangles and of their (tile, triangle) pairs through a
-// chained scan with decoupled look-back — no count array, no separate scan, no re-read of the records.
-// A CTA handles 1024 consecutive triangles (4 per thread, strided so that a warp reads consecutive
-// indices), stages their records in shared memory, and does ONE look-back for all of them.
-__global__ void __launch_bounds__(SB_THREADS) setup_bin_kernel(SegParams P)
+struct TriSetup {
+    float X[3], Y[3], Z[3], IW[3];
+    int x0, x1, y0, y1;
+    uint32_t draw, tri, ntiles;
+    bool ordered;
+};
+
+// Everything Tiny does per triangle before its pixel loop (OgreTinyRenderSystem.cpp:396-410,
+// tinyrenderer.h:45-69): fetch / transform the three vertices, cull, bounding box, plus the number of
+// 16x16 tiles of this strip the box touches.  Pure function of (g, draw table): both passes below call it.
+__device__ __forceinline__ void setup_triangle(const SegParams& P, uint32_t g, uint32_t lo0, uint32_t lo0_end, const float* s_mat, TriSetup& T)
 {
-    extern __shared__ __align__(16) uint8_t sb_smem[];
-    float4 (*s_rec)[SB_BLOCK] = reinterpret_cast<float4 (*)[SB_BLOCK]>(sb_smem);        // [4][1024]: piece q of slot i
-    uint32_t* s_wp = reinterpret_cast<uint32_t*>(sb_smem + SB_BLOCK * 64);              // [8]
-    uint32_t* s_wt = s_wp + 8;                                                          // [8]
-    unsigned long long* s_excl = reinterpret_cast<unsigned long long*>(s_wt + 8);       // [1]
-    uint32_t* s_vb = reinterpret_cast<uint32_t*>(s_excl + 1);                           // [2]: ticket, draw of the CTA's first triangle
-    float* s_mat = reinterpret_cast<float*>(s_vb + 2);                                  // [32]: mvp, vp of that draw
-    const unsigned tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    T.ntiles = 0; T.ordered = false; T.x0 = 0; T.x1 = -1; T.y0 = 0; T.y1 = -1;
+    // which draw: last d with tri_base <= g (almost always the CTA's first draw, whose matrices sit in shared memory)
+    uint32_t lo = lo0;
+    const bool same = g < lo0_end;
+    if (!same) {
+        uint32_t hi = P.ndraws;
+        while (hi - lo > 1) {
+            uint32_t mid = (lo + hi) >> 1;
+            if (__ldg(&P.draws[mid].tri_base) <= g) lo = mid; else hi = mid;
+        }
+    }
+    const DrawDev& D = P.draws[lo];
+    const float* Mmvp = same ? s_mat : D.mvp;
+    const float* Mvp = same ? s_mat + 16 : D.vp;
+    const uint32_t t = g - D.tri_base;
+    T.draw = lo; T.tri = t;
+    bool ok = true;
+    const float4* xf = D.xf;
+    const uint32_t nxf = D.vertex_count;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const size_t vi = vertex_index(D, t, j);
+        float4 sv;
+        if (xf && vi < nxf) sv = __ldg(xf + vi);                               // transformed once per vertex (vertex_xf_kernel)
+        else {
+            const float* p = (const float*)(D.pos + vi * D.pos_stride);
+            sv = transform_vertex(Mmvp, Mvp, __ldg(p), __ldg(p + 1), __ldg(p + 2));
+        }
+        T.X[j] = sv.x; T.Y[j] = sv.y; T.Z[j] = sv.z; T.IW[j] = sv.w;
+        // non-finite screen coordinates: the reference writes out of bounds (undefined) -> drop
+        ok = ok && isfinite(sv.x) && isfinite(sv.y) && isfinite(sv.z) && isfinite(sv.w);
+    }
+    if (ok && !D.is_strip) {                                                   // cull: tinyrenderer.h:37-39,55
+        float ax = fsub(T.X[2], T.X[0]), ay = fsub(T.Y[2], T.Y[0]), bx = fsub(T.X[2], T.X[1]), by = fsub(T.Y[2], T.Y[1]);
+        if (fsub(fmul(ax, by), fmul(ay, bx)) > 0.0f) ok = false;
+    }
+    if (ok) {
+        float mnx = FLT_MAX, mny = FLT_MAX, mxx = -FLT_MAX, mxy = -FLT_MAX;
+        const float cx = (float)(P.width - 1u), cy = (float)(P.height - 1u);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {                                          // tinyrenderer.h:58-65
+            mnx = std_max(0.f, std_min(mnx, T.X[j]));
+            mxx = std_min(cx, std_max(mxx, T.X[j]));
+            mny = std_max(0.f, std_min(mny, T.Y[j]));
+            mxy = std_min(cy, std_max(mxy, T.Y[j]));
+        }
+        // beyond +-2^31 the reference's (int) loop bounds are undefined -> drop
+        if (!(mnx < 2147483648.0f) || !(mny < 2147483648.0f) || !(mxx > -2147483648.0f) || !(mxy > -2147483648.0f)) ok = false;
+        else {
+            T.x0 = (int)mnx; T.x1 = (int)mxx; T.y0 = (int)mny; T.y1 = (int)mxy;    // :68-69 truncation toward zero
+            if (T.x0 > T.x1 || T.y0 > T.y1) ok = false;
+        }
+    }
+    if (ok) {
+        int tx0 = T.x0 >> TILE_SHIFT, tx1 = T.x1 >> TILE_SHIFT;
+        int ty0 = max(T.y0 >> TILE_SHIFT, (int)P.strip_ty0), ty1 = min(T.y1 >> TILE_SHIFT, (int)P.strip_ty1 - 1);
+        if (ty0 <= ty1) T.ntiles = (uint32_t)(tx1 - tx0 + 1) * (uint32_t)(ty1 - ty0 + 1);
+    }
+    if (T.ntiles) {
+        // Order-independent resolution (raster_kernel's visibility path) is only equivalent to Tiny's
+        // in-order loop for opaque, depth-tested, depth-writing fragments that cannot be discarded.
+        const uint32_t fl = D.flags;
+        T.ordered = (fl & (OGRECU_DRAW_DEPTH_TEST | OGRECU_DRAW_DEPTH_WRITE | OGRECU_DRAW_BLEND_ADD)) !=
+                        (OGRECU_DRAW_DEPTH_TEST | OGRECU_DRAW_DEPTH_WRITE) ||
+                    (D.tex != nullptr && D.tex_zero_alpha != 0);
+    }
+}
 
-    if (tid == 0) {
-        const uint32_t ticket = atomicAdd(&P.ctl[0], 1u);   // blocks take tickets in dispatch order: look-back never waits on an unscheduled block
-        s_vb[0] = ticket;
+// the draw of the CTA's first triangle: its matrices are cached in shared memory
+__device__ __forceinline__ void cta_draw_cache(const SegParams& P, uint32_t g0, uint32_t* s_lo, float* s_mat, uint32_t& lo0, uint32_t& lo0_end)
+{
+    if (threadIdx.x == 0) {
         uint32_t lo = 0, hi = P.ndraws;
-        const uint32_t g0 = ticket * (uint32_t)SB_BLOCK;
         while (hi - lo > 1) {
             uint32_t mid = (lo + hi) >> 1;
             if (__ldg(&P.draws[mid].tri_base) <= g0) lo = mid; else hi = mid;
         }
-        s_vb[1] = lo;
+        *s_lo = lo;
     }
     __syncthreads();
-    const uint32_t vb = s_vb[0], lo0 = s_vb[1];
-    if (tid < 32) s_mat[tid] = tid < 16 ? P.draws[lo0].mvp[tid] : P.draws[lo0].vp[tid - 16];
-    const uint32_t lo0_end = lo0 + 1 < P.ndraws ? __ldg(&P.draws[lo0 + 1].tri_base) : 0xffffffffu;   // triangles below this belong to draw lo0
+    lo0 = *s_lo;
+    if (threadIdx.x < 32) s_mat[threadIdx.x] = threadIdx.x < 16 ? P.draws[lo0].mvp[threadIdx.x] : P.draws[lo0].vp[threadIdx.x - 16];
+    lo0_end = lo0 + 1 < P.ndraws ? __ldg(&P.draws[lo0 + 1].tri_base) : 0xffffffffu;   // triangles below this belong to draw lo0
     __syncthreads();
+}
 
-    uint32_t ntiles[SB_ITEMS], pk[SB_ITEMS];          // pk: draw | ordered << 31
-#pragma unroll
-    for (int k = 0; k < SB_ITEMS; ++k) {
-        // a warp owns 32*SB_ITEMS consecutive triangles, 32 per round: coalesced index reads, in-warp scan carry
-        const uint32_t slot = wid * (32u * SB_ITEMS) + (uint32_t)k * 32u + lane;
-        const uint32_t g = vb * (uint32_t)SB_BLOCK + slot;
-        ntiles[k] = 0; pk[k] = 0;
-        if (g >= P.ntris) continue;
-        // which draw: last d with tri_base <= g (almost always the CTA's first draw, whose matrices sit in shared memory)
-        uint32_t lo = lo0;
-        const bool same = g < lo0_end;
-        if (!same) {
-            uint32_t hi = P.ndraws;
-            while (hi - lo > 1) {
-                uint32_t mid = (lo + hi) >> 1;
-                if (__ldg(&P.draws[mid].tri_base) <= g) lo = mid; else hi = mid;
-            }
-        }
-        const DrawDev& D = P.draws[lo];
-        const float* Mmvp = same ? s_mat : D.mvp;
-        const float* Mvp = same ? s_mat + 16 : D.vp;
-        const uint32_t t = g - D.tri_base;
-        float X[3], Y[3], Z[3], IW[3];
-        bool ok = true;
-        const float4* xf = D.xf;
-        const uint32_t nxf = D.vertex_count;
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            const size_t vi = vertex_index(D, t, j);
-            float4 sv;
-            if (xf && vi < nxf) sv = __ldg(xf + vi);                               // transformed once per vertex (vertex_xf_kernel)
-            else {
-                const float* p = (const float*)(D.pos + vi * D.pos_stride);
-                sv = transform_vertex(Mmvp, Mvp, __ldg(p), __ldg(p + 1), __ldg(p + 2));
-            }
-            X[j] = sv.x; Y[j] = sv.y; Z[j] = sv.z; IW[j] = sv.w;
-            // non-finite screen coordinates: the reference writes out of bounds (undefined) -> drop
-            ok = ok && isfinite(X[j]) && isfinite(Y[j]) && isfinite(Z[j]) && isfinite(IW[j]);
-        }
-        if (ok && !D.is_strip) {                                                   // cull: tinyrenderer.h:37-39,55
-            float ax = fsub(X[2], X[0]), ay = fsub(Y[2], Y[0]), bx = fsub(X[2], X[1]), by = fsub(Y[2], Y[1]);
-            if (fsub(fmul(ax, by), fmul(ay, bx)) > 0.0f) ok = false;
-        }
-        int x0 = 0, x1 = -1, y0 = 0, y1 = -1;
-        if (ok) {
-            float mnx = FLT_MAX, mny = FLT_MAX, mxx = -FLT_MAX, mxy = -FLT_MAX;
-            const float cx = (float)(P.width - 1u), cy = (float)(P.height - 1u);
-#pragma unroll
-            for (int j = 0; j < 3; ++j) {                                          // tinyrenderer.h:58-65
-                mnx = std_max(0.f, std_min(mnx, X[j]));
-                mxx = std_min(cx, std_max(mxx, X[j]));
-                mny = std_max(0.f, std_min(mny, Y[j]));
-                mxy = std_min(cy, std_max(mxy, Y[j]));
-            }
-            // beyond +-2^31 the reference's (int) loop bounds are undefined -> drop
-            if (!(mnx < 2147483648.0f) || !(mny < 2147483648.0f) || !(mxx > -2147483648.0f) || !(mxy > -2147483648.0f)) ok = false;
-            else {
-                x0 = (int)mnx; x1 = (int)mxx; y0 = (int)mny; y1 = (int)mxy;        // :68-69 truncation toward zero
-                if (x0 > x1 || y0 > y1) ok = false;
-            }
-        }
-        if (ok) {
-            int tx0 = x0 >> TILE_SHIFT, tx1 = x1 >> TILE_SHIFT;
-            int ty0 = max(y0 >> TILE_SHIFT, (int)P.strip_ty0), ty1 = min(y1 >> TILE_SHIFT, (int)P.strip_ty1 - 1);
-            if (ty0 <= ty1) ntiles[k] = (uint32_t)(tx1 - tx0 + 1) * (uint32_t)(ty1 - ty0 + 1);
-        }
-        if (ntiles[k]) {
-            // Order-independent resolution (raster_kernel's visibility path) is only equivalent to Tiny's
-            // in-order loop for opaque, depth-tested, depth-writing fragments that cannot be discarded.
-            const uint32_t fl = D.flags;
-            const bool ordered = (fl & (OGRECU_DRAW_DEPTH_TEST | OGRECU_DRAW_DEPTH_WRITE | OGRECU_DRAW_BLEND_ADD)) !=
-                                     (OGRECU_DRAW_DEPTH_TEST | OGRECU_DRAW_DEPTH_WRITE) ||
-                                 (D.tex != nullptr && D.tex_zero_alpha != 0);
-            pk[k] = lo | (ordered ? 0x80000000u : 0u);
-            s_rec[0][slot] = make_float4(X[0], X[1], X[2], Y[0]);
-            s_rec[1][slot] = make_float4(Y[1], Y[2], IW[0], IW[1]);
-            s_rec[2][slot] = make_float4(IW[2], Z[0], Z[1], Z[2]);
-            s_rec[3][slot] = make_float4(__uint_as_float((uint32_t)x0 | ((uint32_t)x1 << 16)), __uint_as_float((uint32_t)y0 | ((uint32_t)y1 << 16)),
-                                         __uint_as_float(lo), __uint_as_float(t));
+// K1a: per CTA of 1024 triangles, how many survive and how many (tile, triangle) pairs they make.
+// (A spin-free "reduce, scan the block table, then write" compaction: the single-pass chained scan
+//  measured 30 % of its time waiting in the look-back, profiles/r01d notes.)
+__global__ void __launch_bounds__(SB_THREADS) setup_count_kernel(SegParams P)
+{
+    __shared__ uint32_t s_lo, s_wp[8], s_wt[8];
+    __shared__ float s_mat[32];
+    const unsigned tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t g0 = blockIdx.x * (uint32_t)SB_BLOCK;
+    uint32_t lo0, lo0_end;
+    cta_draw_cache(P, g0, &s_lo, s_mat, lo0, lo0_end);
+    uint32_t np = 0, nt = 0;
+#pragma unroll 2
+    for (int k = 0; k < SB_ROUNDS; ++k) {
+        const uint32_t g = g0 + (uint32_t)k * SB_THREADS + tid;
+        if (g < P.ntris) {
+            TriSetup T;
+            setup_triangle(P, g, lo0, lo0_end, s_mat, T);
+            np += T.ntiles; nt += T.ntiles ? 1u : 0u;
         }
     }
-
-    // ---- exclusive scans of (pairs, survivors) in triangle order: rounds chained inside the warp, warps combined once
-    uint32_t ep[SB_ITEMS], et[SB_ITEMS];
-    uint32_t wrun_p = 0, wrun_t = 0;
 #pragma unroll
-    for (int k = 0; k < SB_ITEMS; ++k) {
-        const uint32_t surv = ntiles[k] ? 1u : 0u;
-        uint32_t ip = ntiles[k], it = surv;
+    for (int o = 16; o > 0; o >>= 1) { np += __shfl_xor_sync(0xffffffffu, np, o); nt += __shfl_xor_sync(0xffffffffu, nt, o); }
+    if (lane == 0) { s_wp[wid] = np; s_wt[wid] = nt; }
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t a = 0, b = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { a += s_wp[w]; b += s_wt[w]; }
+        P.block_agg[2 * blockIdx.x] = a; P.block_agg[2 * blockIdx.x + 1] = b;
+    }
+}
+
+// K1b: exclusive scan of the block table in place (one CTA; 64-bit running sums), totals -> ctl[2..3]
+__global__ void __launch_bounds__(1024) setup_scan_kernel(uint32_t* block_agg, uint32_t nblocks, uint32_t* ctl, unsigned long long* bases)
+{
+    __shared__ unsigned long long s_wp[32], s_wt[32], s_carry[2];
+    const unsigned tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) { s_carry[0] = 0; s_carry[1] = 0; }
+    __syncthreads();
+    for (uint32_t b0 = 0; b0 < nblocks; b0 += 1024) {
+        const uint32_t b = b0 + tid;
+        unsigned long long vp = b < nblocks ? block_agg[2 * b] : 0, vt = b < nblocks ? block_agg[2 * b + 1] : 0;
+        unsigned long long ip = vp, it = vt;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            uint32_t np = __shfl_up_sync(0xffffffffu, ip, o), nt = __shfl_up_sync(0xffffffffu, it, o);
-            if (lane >= (unsigned)o) { ip += np; it += nt; }
+            unsigned long long a = __shfl_up_sync(0xffffffffu, ip, o), c = __shfl_up_sync(0xffffffffu, it, o);
+            if (lane >= (unsigned)o) { ip += a; it += c; }
         }
-        ep[k] = wrun_p + ip - ntiles[k];
-        et[k] = wrun_t + it - surv;
-        wrun_p += __shfl_sync(0xffffffffu, ip, 31);
-        wrun_t += __shfl_sync(0xffffffffu, it, 31);
+        if (lane == 31) { s_wp[wid] = ip; s_wt[wid] = it; }
+        __syncthreads();
+        unsigned long long wbp = 0, wbt = 0, tp = 0, tt = 0;
+        for (int w = 0; w < 32; ++w) { if (w < (int)wid) { wbp += s_wp[w]; wbt += s_wt[w]; } tp += s_wp[w]; tt += s_wt[w]; }
+        if (b < nblocks) { bases[2 * b] = s_carry[0] + wbp + ip - vp; bases[2 * b + 1] = s_carry[1] + wbt + it - vt; }
+        __syncthreads();
+        if (tid == 0) { s_carry[0] += tp; s_carry[1] += tt; }
+        __syncthreads();
     }
-    if (lane == 0) { s_wp[wid] = wrun_p; s_wt[wid] = wrun_t; }
-    __syncthreads();
-    uint32_t wbp = 0, wbt = 0, bp = 0, bt = 0;      // warp bases, block totals
-#pragma unroll
-    for (int w = 0; w < SB_THREADS / 32; ++w) {
-        if (w < (int)wid) { wbp += s_wp[w]; wbt += s_wt[w]; }
-        bp += s_wp[w]; bt += s_wt[w];
+    if (tid == 0) {
+        ctl[2] = (uint32_t)min(s_carry[0], 0xffffffffull);
+        ctl[3] = (uint32_t)min(s_carry[1], 0xffffffffull);
     }
-#pragma unroll
-    for (int k = 0; k < SB_ITEMS; ++k) { ep[k] += wbp; et[k] += wbt; }
+}
 
-    // ---- chained scan across blocks (decoupled look-back, warp 0)
-    if (wid == 0) {
-        const unsigned long long agg = lb_pack(bp, bt);
-        if (lane == 0) *reinterpret_cast<volatile unsigned long long*>(&P.desc[vb]) = (vb == 0 ? LB_PREFIX : LB_AGG) | agg;
-        unsigned long long ex_p = 0, ex_t = 0;
-        int j = (int)vb - 1;
-        while (j >= 0) {
-            const int idx = j - (int)lane;
-            unsigned long long d = idx >= 0 ? lb_load(&P.desc[idx]) : LB_PREFIX;
-            while (__any_sync(0xffffffffu, (d & LB_STATUS) == 0)) {
-                if ((d & LB_STATUS) == 0) d = lb_load(&P.desc[idx]);
-            }
-            const unsigned pmask = __ballot_sync(0xffffffffu, (d & LB_STATUS) == LB_PREFIX);
-            const int first = pmask ? __ffs(pmask) - 1 : 32;
-            unsigned long long vp = ((int)lane <= first) ? ((d >> 31) & LB_FIELD) : 0ull;
-            unsigned long long vt = ((int)lane <= first) ? (d & LB_FIELD) : 0ull;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) { vp += __shfl_xor_sync(0xffffffffu, vp, o); vt += __shfl_xor_sync(0xffffffffu, vt, o); }
-            ex_p = min(ex_p + vp, LB_FIELD); ex_t = min(ex_t + vt, LB_FIELD);
-            if (pmask) break;
-            j -= 32;
-        }
-        if (lane == 0) {
-            const unsigned long long incl = lb_pack(ex_p + bp, ex_t + bt);
-            if (vb != 0) *reinterpret_cast<volatile unsigned long long*>(&P.desc[vb]) = LB_PREFIX | incl;
-            *s_excl = lb_pack(ex_p, ex_t);
-            if ((size_t)(vb + 1) * SB_BLOCK >= P.ntris) {      // last block: grand totals
-                P.ctl[2] = (uint32_t)((incl >> 31) & LB_FIELD);
-                P.ctl[3] = (uint32_t)(incl & LB_FIELD);
-            }
-        }
-    }
-    __syncthreads();
-    const unsigned long long base_p = (*s_excl >> 31) & LB_FIELD, base_t = *s_excl & LB_FIELD;
-    const bool fits = !(base_p + bp > P.pair_capacity || base_p + bp >= LB_FIELD);
-    if (!fits && tid == 0 && bp) atomicExch(&P.ctl[1], 1u);   // host grows the pair buffers and runs the pass again
+// K1c: the same per-triangle work again, now with the CTA's global bases known: compact records and
+// pairs are written in submission order, records through shared memory as one contiguous run per round.
+__global__ void __launch_bounds__(SB_THREADS) setup_write_kernel(SegParams P)
+{
+    __shared__ uint32_t s_lo, s_wp[8], s_wt[8];
+    __shared__ float s_mat[32];
+    __shared__ float4 s_rec[SB_THREADS][4];
+    const unsigned tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t g0 = blockIdx.x * (uint32_t)SB_BLOCK;
+    uint32_t lo0, lo0_end;
+    cta_draw_cache(P, g0, &s_lo, s_mat, lo0, lo0_end);
+    unsigned long long base_p = P.bases[2 * blockIdx.x], base_t = P.bases[2 * blockIdx.x + 1];
 
-    // ---- write out: compact records (consecutive ranks from consecutive threads) and the pairs,
-    //      contiguous per triangle in submission order; the stable sort by tile key keeps that order per tile
+    for (int k = 0; k < SB_ROUNDS; ++k) {
+        const uint32_t g = g0 + (uint32_t)k * SB_THREADS + tid;
+        TriSetup T;
+        T.ntiles = 0;
+        if (g < P.ntris) setup_triangle(P, g, lo0, lo0_end, s_mat, T);
+        const uint32_t surv = T.ntiles ? 1u : 0u;
+        uint32_t ip = T.ntiles, it = surv;
 #pragma unroll
-    for (int k = 0; k < SB_ITEMS; ++k) {
-        if (!ntiles[k]) continue;
-        const uint32_t slot = wid * (32u * SB_ITEMS) + (uint32_t)k * 32u + lane;
-        const uint32_t ci = (uint32_t)(base_t + et[k]);
-        float4* dst = reinterpret_cast<float4*>(P.rec + ci);
-        const float4 r3 = s_rec[3][slot];
-        dst[0] = s_rec[0][slot]; dst[1] = s_rec[1][slot]; dst[2] = s_rec[2][slot]; dst[3] = r3;
-        if (!fits) continue;
-        const uint32_t bx = __float_as_uint(r3.x), by = __float_as_uint(r3.y);
-        const uint32_t lo = pk[k] & 0x7fffffffu;
-        const bool ordered = (pk[k] >> 31) != 0;
-        const uint32_t target = __ldg(&P.draws[lo].target);
-        const int tx0 = (int)(bx & 0xffff) >> TILE_SHIFT, tx1 = (int)(bx >> 16) >> TILE_SHIFT;
-        const int ty0 = max((int)(by & 0xffff) >> TILE_SHIFT, (int)P.strip_ty0), ty1 = min((int)(by >> 16) >> TILE_SHIFT, (int)P.strip_ty1 - 1);
-        const uint32_t tbase = target * P.tiles_x * P.tiles_y;
-        uint64_t* out = P.pairs + base_p + ep[k];
-        for (int ty = ty0; ty <= ty1; ++ty)
-            for (int tx = tx0; tx <= tx1; ++tx) {
-                const uint32_t key = tbase + (uint32_t)ty * P.tiles_x + (uint32_t)tx;
-                *out++ = ((uint64_t)key << 32) | ci;
-                if (ordered) atomicOr(&P.tile_flags[key], 1u);
-            }
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t a = __shfl_up_sync(0xffffffffu, ip, o), c = __shfl_up_sync(0xffffffffu, it, o);
+            if (lane >= (unsigned)o) { ip += a; it += c; }
+        }
+        __syncthreads();                       // previous round's s_rec / s_wp consumed
+        if (lane == 31) { s_wp[wid] = ip; s_wt[wid] = it; }
+        __syncthreads();
+        uint32_t wbp = 0, wbt = 0, tp = 0, tt = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { if (w < (int)wid) { wbp += s_wp[w]; wbt += s_wt[w]; } tp += s_wp[w]; tt += s_wt[w]; }
+        const uint32_t ep = wbp + ip - T.ntiles, et = wbt + it - surv;   // exclusive inside the round
+        if (surv) {
+            s_rec[et][0] = make_float4(T.X[0], T.X[1], T.X[2], T.Y[0]);
+            s_rec[et][1] = make_float4(T.Y[1], T.Y[2], T.IW[0], T.IW[1]);
+            s_rec[et][2] = make_float4(T.IW[2], T.Z[0], T.Z[1], T.Z[2]);
+            s_rec[et][3] = make_float4(__uint_as_float((uint32_t)T.x0 | ((uint32_t)T.x1 << 16)), __uint_as_float((uint32_t)T.y0 | ((uint32_t)T.y1 << 16)),
+                                       __uint_as_float(T.draw), __uint_as_float(T.tri));
+        }
+        __syncthreads();
+        {
+            float4* dst = reinterpret_cast<float4*>(P.rec + base_t);
+            const float4* src = &s_rec[0][0];
+            for (uint32_t q = tid; q < tt * 4u; q += SB_THREADS) dst[q] = src[q];
+        }
+        if (T.ntiles && base_p + tp <= P.pair_capacity) {
+            const uint32_t target = __ldg(&P.draws[T.draw].target);
+            const int tx0 = T.x0 >> TILE_SHIFT, tx1 = T.x1 >> TILE_SHIFT;
+            const int ty0 = max(T.y0 >> TILE_SHIFT, (int)P.strip_ty0), ty1 = min(T.y1 >> TILE_SHIFT, (int)P.strip_ty1 - 1);
+            const uint32_t tbase = target * P.tiles_x * P.tiles_y;
+            const uint32_t ci = (uint32_t)(base_t + et);
+            uint64_t* out = P.pairs + base_p + ep;
+            for (int ty = ty0; ty <= ty1; ++ty)
+                for (int tx = tx0; tx <= tx1; ++tx) {
+                    const uint32_t key = tbase + (uint32_t)ty * P.tiles_x + (uint32_t)tx;
+                    *out++ = ((uint64_t)key << 32) | ci;
+                    if (T.ordered) atomicOr(&P.tile_flags[key], 1u);
+                }
+        }
+        base_p += tp; base_t += tt;
     }
 }
 
@@ -1087,17 +1088,11 @@ int run_segment(ogrecu_ctx* ctx, ogrecu_rt* const* targets, uint32_t ntargets, c
     }
     const uint32_t nblocks = div_up(ntris, SB_BLOCK);
     OGRECU_CHECK(scratch_reserve(ctx, S.rec, (size_t)ntris * sizeof(TriRec)));
-    // control block: look-back descriptors [nblocks] | ctl[4] | tile flags [nkeys]  (zeroed per pass)
-    const size_t ctl_bytes = (size_t)nblocks * 8 + 16 + (size_t)nkeys * 4;
+    // control block: block aggregates [nblocks][2] u32 | bases [nblocks][2] u64 | ctl[4] | tile flags [nkeys] (flags zeroed per pass)
+    const size_t agg_bytes = ((size_t)nblocks * 8 + 15) & ~(size_t)15, base_bytes = (size_t)nblocks * 16;
+    const size_t ctl_bytes = agg_bytes + base_bytes + 16 + (size_t)nkeys * 4;
     OGRECU_CHECK(scratch_reserve(ctx, S.cnt, ctl_bytes));
     OGRECU_CHECK(scratch_reserve(ctx, S.tile_count, ((size_t)nkeys + 1) * sizeof(uint32_t)));
-    // pair buffers: the count is only known after the pass; start from what earlier flushes needed
-    // (at least 1.25 pairs per triangle) and re-run the pass in the rare case it does not fit
-    {
-        const size_t want = std::max<size_t>(S.pairs_a.cap, ((size_t)ntris + ntris / 4 + 1024) * sizeof(uint64_t));
-        OGRECU_CHECK(scratch_reserve(ctx, S.pairs_a, want));
-        OGRECU_CHECK(scratch_reserve(ctx, S.pairs_b, want));
-    }
     // tables go through the pinned block (stream-ordered, no pageable-copy stall)
     size_t tab_bytes = dd.size() * sizeof(DrawDev) + td.size() * sizeof(TargetDev) + 16;
     OGRECU_CHECK(pinned_reserve(ctx, tab_bytes));
@@ -1112,9 +1107,11 @@ int run_segment(ogrecu_ctx* ctx, ogrecu_rt* const* targets, uint32_t ntargets, c
     SegParams P;
     P.draws = (const DrawDev*)S.draws.ptr; P.ndraws = (uint32_t)dd.size(); P.ntris = ntris;
     P.rec = (TriRec*)S.rec.ptr;
-    P.desc = (unsigned long long*)S.cnt.ptr;
-    P.ctl = (uint32_t*)((uint8_t*)S.cnt.ptr + (size_t)nblocks * 8);
+    P.block_agg = (uint32_t*)S.cnt.ptr;
+    P.bases = (unsigned long long*)((uint8_t*)S.cnt.ptr + agg_bytes);
+    P.ctl = (uint32_t*)((uint8_t*)S.cnt.ptr + agg_bytes + base_bytes);
     P.tile_flags = P.ctl + 4;
+    P.pairs = nullptr; P.pair_capacity = 0;
     P.width = W; P.height = H; P.tiles_x = tiles_x; P.tiles_y = tiles_y;
     P.strip_ty0 = strip_ty0; P.strip_ty1 = strip_ty1;
 
@@ -1126,25 +1123,16 @@ int run_segment(ogrecu_ctx* ctx, ogrecu_rt* const* targets, uint32_t ntargets, c
         OGRECU_CUDA(cudaGetLastError());
         count_launch(ctx);
     }
-    // ---- K1+K2: setup, compaction and binning in one pass
-    OGRECU_CUDA(cudaFuncSetAttribute(setup_bin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SB_SMEM));
-    uint64_t npairs = 0, nsurv = 0;
-    for (int attempt = 0; attempt < 2; ++attempt) {
-        P.pairs = (uint64_t*)S.pairs_a.ptr;
-        P.pair_capacity = S.pairs_a.cap / sizeof(uint64_t);
-        OGRECU_CUDA(cudaMemsetAsync(S.cnt.ptr, 0, ctl_bytes, ctx->stream));
-        setup_bin_kernel<<<nblocks, SB_THREADS, SB_SMEM, ctx->stream>>>(P);
-        OGRECU_CUDA(cudaGetLastError());
-        count_launch(ctx);
-        OGRECU_CUDA(cudaMemcpyAsync(ctl_host, P.ctl, 16, cudaMemcpyDeviceToHost, ctx->stream));
-        OGRECU_CUDA(cudaStreamSynchronize(ctx->stream));
-        npairs = ctl_host[2]; nsurv = ctl_host[3];
-        OGRECU_REQUIRE(npairs < 0x7fffffffull, "too many (triangle, tile) pairs in one flush");
-        if (!ctl_host[1]) break;
-        OGRECU_REQUIRE(attempt == 0, "pair buffer overflow after regrow");
-        OGRECU_CHECK(scratch_reserve(ctx, S.pairs_a, (npairs + 1024) * sizeof(uint64_t)));
-        OGRECU_CHECK(scratch_reserve(ctx, S.pairs_b, (npairs + 1024) * sizeof(uint64_t)));
-    }
+    // ---- K1a/K1b: count survivors and pairs per CTA, scan the CTA table
+    OGRECU_CUDA(cudaMemsetAsync(P.ctl, 0, 16 + (size_t)nkeys * 4, ctx->stream));
+    setup_count_kernel<<<nblocks, SB_THREADS, 0, ctx->stream>>>(P);
+    setup_scan_kernel<<<1, 1024, 0, ctx->stream>>>(P.block_agg, nblocks, P.ctl, P.bases);
+    OGRECU_CUDA(cudaGetLastError());
+    count_launch(ctx, 2);
+    OGRECU_CUDA(cudaMemcpyAsync(ctl_host, P.ctl, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    OGRECU_CUDA(cudaStreamSynchronize(ctx->stream));
+    const uint64_t npairs = ctl_host[2], nsurv = ctl_host[3];
+    OGRECU_REQUIRE(npairs < 0xffffffffull, "too many (triangle, tile) pairs in one flush");
     for (uint32_t t = 0; t < ntargets; ++t) {
         targets[t]->stats.triangles_in = ntris / ntargets;
         targets[t]->stats.triangles_binned = nsurv / ntargets;
@@ -1153,6 +1141,15 @@ int run_segment(ogrecu_ctx* ctx, ogrecu_rt* const* targets, uint32_t ntargets, c
         targets[t]->stats_pending = false;
     }
     if (npairs == 0) return OGRECU_OK;
+
+    // ---- K1c: compact records + (tile, triangle) pairs in submission order
+    OGRECU_CHECK(scratch_reserve(ctx, S.pairs_a, npairs * sizeof(uint64_t)));
+    OGRECU_CHECK(scratch_reserve(ctx, S.pairs_b, npairs * sizeof(uint64_t)));
+    P.pairs = (uint64_t*)S.pairs_a.ptr;
+    P.pair_capacity = npairs;
+    setup_write_kernel<<<nblocks, SB_THREADS, 0, ctx->stream>>>(P);
+    OGRECU_CUDA(cudaGetLastError());
+    count_launch(ctx);
 
     // ---- stable sort by tile key
     uint64_t* pa = (uint64_t*)S.pairs_a.ptr;
