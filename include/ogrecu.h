@@ -93,7 +93,9 @@ OGRECU_API int ogrecu_free(ogrecu_ctx* ctx, void* dev_ptr);
 OGRECU_API int ogrecu_host_alloc(size_t bytes, void** host_ptr);    /* pinned */
 OGRECU_API int ogrecu_host_free(void* host_ptr);
 OGRECU_API int ogrecu_memcpy_h2d(ogrecu_ctx* ctx, void* dev, const void* host, size_t bytes);
-OGRECU_API int ogrecu_memcpy_d2h(ogrecu_ctx* ctx, void* host, const void* dev, size_t bytes);
+OGRECU_API int ogrecu_memcpy_d2h(ogrecu_ctx* ctx, void* host, const void* dev, size_t bytes);   /* waits for the copy */
+/* enqueue only (host must be pinned); the data is there after ogrecu_sync or an event the caller records on the stream */
+OGRECU_API int ogrecu_memcpy_d2h_async(ogrecu_ctx* ctx, void* host, const void* dev, size_t bytes);
 OGRECU_API int ogrecu_memcpy_d2d(ogrecu_ctx* ctx, void* dst, const void* src, size_t bytes);
 
 /* ------------------------------------------------------------ hardware buffers ----- */

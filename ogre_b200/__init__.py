@@ -16,13 +16,38 @@ from . import capi
 from .capi import DrawDesc, OgrecuError, RasterStats, SkinJob, check, lib
 
 __all__ = ["Context", "DeviceBuffer", "OptimisedUtil", "Texture", "RenderTarget", "DrawDesc", "SkinJob",
-           "OgrecuError", "addr"]
+           "OgrecuError", "addr", "pinned_empty"]
 
 MAP_READ, MAP_WRITE, MAP_DISCARD = 1, 2, 4
 CLEAR_COLOUR, CLEAR_DEPTH = 1, 2
 PRIM_TRIANGLE_LIST, PRIM_TRIANGLE_STRIP = 4, 5
 INDEX_NONE, INDEX_U16, INDEX_U32 = 0, 2, 4
 DRAW_DEPTH_TEST, DRAW_DEPTH_WRITE, DRAW_BLEND_ADD, DRAW_LIGHTING = 1, 2, 4, 8
+
+
+class _Pinned:
+    """Owner of one ogrecu_host_alloc block; freed when the last numpy view goes away."""
+
+    def __init__(self, nbytes):
+        p = C.c_void_p()
+        check(lib().ogrecu_host_alloc(int(nbytes), C.byref(p)))
+        self.ptr, self.nbytes = p.value, int(nbytes)
+
+    def __del__(self):
+        if getattr(self, "ptr", None):
+            lib().ogrecu_host_free(self.ptr)
+            self.ptr = None
+
+
+def pinned_empty(shape, dtype=np.uint8):
+    """numpy array over pinned host memory (ogrecu_host_alloc): read-backs into it are direct DMA."""
+    dt = np.dtype(dtype)
+    n = int(np.prod(shape)) * dt.itemsize
+    own = _Pinned(max(n, 1))
+    buf = (C.c_uint8 * max(n, 1)).from_address(own.ptr)
+    buf._owner = own
+    arr = np.frombuffer(buf, dtype=dt, count=int(np.prod(shape))).reshape(shape)
+    return arr
 
 
 def addr(arr, byte_offset=0):
@@ -198,15 +223,20 @@ class RenderTarget:
     def set_strip(self, y0, y1):
         check(lib().ogrecu_rt_set_strip(self.handle, int(y0), int(y1)))
 
-    def read_colour(self, box=None):
+    def read_colour(self, box=None, out=None):
+        """copyContentsToMemory: `out` may be a preallocated (ideally pinned, see pinned_empty) array."""
         l, t, r, b = box if box else (0, 0, self.width, self.height)
-        out = np.empty((b - t, r - l, 3), dtype=np.uint8)
+        if out is None:
+            out = np.empty((b - t, r - l, 3), dtype=np.uint8)
+        assert out.dtype == np.uint8 and out.shape == (b - t, r - l, 3) and out.flags.c_contiguous
         check(lib().ogrecu_rt_read_colour(self.handle, l, t, r, b, out.ctypes.data, (r - l) * 3))
         return out
 
-    def read_depth(self, box=None):
+    def read_depth(self, box=None, out=None):
         l, t, r, b = box if box else (0, 0, self.width, self.height)
-        out = np.empty((b - t, r - l), dtype=np.float32)
+        if out is None:
+            out = np.empty((b - t, r - l), dtype=np.float32)
+        assert out.dtype == np.float32 and out.shape == (b - t, r - l) and out.flags.c_contiguous
         check(lib().ogrecu_rt_read_depth(self.handle, l, t, r, b, out.ctypes.data, (r - l) * 4))
         return out
 

@@ -220,6 +220,14 @@ int ogrecu_memcpy_d2h(ogrecu_ctx* ctx, void* host, const void* dev, size_t bytes
     return OGRECU_OK;
 }
 
+int ogrecu_memcpy_d2h_async(ogrecu_ctx* ctx, void* host, const void* dev, size_t bytes)
+{
+    OGRECU_REQUIRE(ctx && (bytes == 0 || (dev && host)), "NULL argument");
+    if (!bytes) return OGRECU_OK;
+    OGRECU_CUDA(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return OGRECU_OK;
+}
+
 int ogrecu_memcpy_d2d(ogrecu_ctx* ctx, void* dst, const void* src, size_t bytes)
 {
     OGRECU_REQUIRE(ctx && (bytes == 0 || (dst && src)), "NULL argument");

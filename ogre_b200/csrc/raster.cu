@@ -1469,6 +1469,16 @@ static int read_plane(ogrecu_rt* rt, const uint8_t* plane, size_t px_bytes, uint
     const size_t row = (size_t)(r - l) * px_bytes, rows = b - t;
     if (!row || !rows) return OGRECU_OK;
     OGRECU_REQUIRE(dst && pitch >= row, "bad destination");
+    // a destination in pinned host memory (ogrecu_host_alloc, a buffer shadow, cudaHostRegister'ed application
+    // memory) takes the DMA directly; anything else is staged through the context's pinned block
+    cudaPointerAttributes pa;
+    if (cudaPointerGetAttributes(&pa, dst) == cudaSuccess && pa.type == cudaMemoryTypeHost) {
+        OGRECU_CUDA(cudaMemcpy2DAsync(dst, pitch, plane + ((size_t)t * rt->w + l) * px_bytes, (size_t)rt->w * px_bytes, row, rows,
+                                      cudaMemcpyDeviceToHost, ctx->stream));
+        OGRECU_CUDA(cudaStreamSynchronize(ctx->stream));
+        return OGRECU_OK;
+    }
+    (void)cudaGetLastError();
     OGRECU_CHECK(pinned_reserve(ctx, row * rows));
     OGRECU_CUDA(cudaMemcpy2DAsync(ctx->pinned, row, plane + ((size_t)t * rt->w + l) * px_bytes, (size_t)rt->w * px_bytes, row, rows,
                                   cudaMemcpyDeviceToHost, ctx->stream));
