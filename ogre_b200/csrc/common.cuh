@@ -80,7 +80,8 @@ struct ogrecu_ctx {
     std::map<uintptr_t, ogrecu_buf*> shadows;
     std::vector<ogrecu_rt*> targets;
     // development switches read once from the environment (A/B measurements, never a fallback):
-    //   OGRECU_SKIN_MODE  0 auto | 1 tile kernel without TMA (cooperative LDG/STG) | 2 one-thread-per-vertex kernel
+    //   OGRECU_SKIN_MODE  0 auto | 1 tile kernels without TMA (cooperative copies) | 2 one-thread-per-vertex kernel |
+    //                     3 single-instance tile kernel even for >= 2 instances (skin_tile.cu instead of skin_pair.cu)
     //   OGRECU_SKIN_IPC   instances per CTA of the tile kernel (0 = auto)
     //   OGRECU_RASTER_MODE 0 auto (visibility path where it is equivalent) | 1 always the in-order path
     //   OGRECU_RASTER_XF   1 (default) transform each vertex once per flush when the draw gives a vertex count | 0 per index

@@ -24,4 +24,7 @@ struct SkinTileParams {
 // Fills the derived fields (TMA eligibility, cooperative unit, instances per CTA) and launches.
 int launch_skin_tile(ogrecu_ctx* ctx, SkinTileParams P, uint32_t num_weights, bool with_normals, bool fused_morph);
 
+// skin_pair.cu: same parameters (alignment fields already derived), two instances per pass.
+int launch_skin_pair(ogrecu_ctx* ctx, SkinTileParams P, uint32_t num_weights, bool with_normals, bool fused_morph);
+
 }  // namespace ogrecu

@@ -1,10 +1,12 @@
-"""GPU parity of the tiled instanced skinning kernel (ogre_b200/csrc/skin_tile.cu) in all its
-transfer modes, and of the fused morph+skin pass, against the CPU oracle — bit patterns.
+"""GPU parity of the tiled instanced skinning kernels (ogre_b200/csrc/skin_pair.cu: two instances per pass,
+packed f32x2 arithmetic; ogre_b200/csrc/skin_tile.cu: one instance per pass) in all their transfer modes, and of
+the fused morph+skin pass, against the CPU oracle — bit patterns.
 
 Covers: full / partial / odd-sized tiles (odd vertex counts break the 16-byte TMA rule and must
 take the cooperative path), 8- and 4-byte misaligned bases, shared bind pose vs per-instance
 source, positions only, bone_map gather, instances-per-CTA > 1 with ragged last group, and the
-three kernel selections of the "skin_mode" option.
+four kernel selections of the "skin_mode" option (0 pair kernel, 1 without TMA, 2 one thread per vertex,
+3 single-instance tile kernel), and signed zeros / denormals / extreme magnitudes through the packed arithmetic.
 """
 import ctypes as C
 
@@ -76,10 +78,12 @@ CASES = [
     (777, 4, 30, 6, False, True, 0, 0, 4),      # positions only
     (1024, 3, 30, 3, False, False, 4, 4, 0),    # positions only, misaligned, shared source
     (300, 4, 256, 2, True, True, 0, 0, 0),      # maximum palette
+    (600, 4, 100, 9, True, True, 0, 0, 0),      # palette of more than 64 matrices, odd instance count
+    (1533, 4, 18, 11, True, True, 0, 0, 6),     # odd n and odd instances: half-empty last pass of every CTA
 ]
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
 @pytest.mark.parametrize("case", CASES, ids=lambda c: "n%d_w%d_b%d_i%d_%s%s_o%d_%d_ipc%d" % (
     c[0], c[1], c[2], c[3], "pn" if c[4] else "p", "I" if c[5] else "S", c[6], c[7], c[8]))
 def test_instanced_skinning_all_modes(gpu_ctx, case, mode):
@@ -113,10 +117,12 @@ def test_instanced_skinning_all_modes(gpu_ctx, case, mode):
         b.free()
 
 
+@pytest.mark.parametrize("mode", [0, 3])
 @pytest.mark.parametrize("norm", [True, False])
 @pytest.mark.parametrize("n,nw,nb,ninst,ipc,want_morph", [(1888, 4, 55, 9, 4, True), (1001, 3, 18, 5, 0, False),
-                                                           (302, 1, 2, 33, 0, True), (77, 2, 7, 2, 1, False)])
-def test_fused_morph_skin_equals_morph_then_skin(gpu_ctx, norm, n, nw, nb, ninst, ipc, want_morph):
+                                                           (302, 1, 2, 33, 0, True), (77, 2, 7, 2, 1, False),
+                                                           (583, 3, 6, 7, 0, True)])
+def test_fused_morph_skin_equals_morph_then_skin(gpu_ctx, norm, n, nw, nb, ninst, ipc, want_morph, mode):
     from ogre_b200 import check, lib
     ctx = gpu_ctx
     vs = 24 if norm else 12
@@ -130,12 +136,14 @@ def test_fused_morph_skin_equals_morph_then_skin(gpu_ctx, norm, n, nw, nb, ninst
     dmo = ctx.alloc(ninst * n * vs) if want_morph else None
     j = gpu_job(ctx, dk1.ptr, ddst.ptr, dbl, dpal, dmap, n, nw, nb, norm)
     ctx.set_config_option("skin_ipc", ipc)
+    ctx.set_config_option("skin_mode", mode)
     try:
         check(lib().ogrecu_anim_instanced_dev(ctx.handle, C.byref(j), dk2.ptr, dt.ptr, dmo.ptr if dmo else None, n * vs, ninst,
                                               (nb + 2) * 16, n * vs))
         ctx.sync()
     finally:
         ctx.set_config_option("skin_ipc", 0)
+        ctx.set_config_option("skin_mode", 0)
     got = ddst.download(np.float32).reshape(ninst, n, vs // 4)
     gmo = dmo.download(np.float32).reshape(ninst, n, vs // 4) if dmo else None
     for i in range(ninst):
@@ -148,3 +156,43 @@ def test_fused_morph_skin_equals_morph_then_skin(gpu_ctx, norm, n, nw, nb, ninst
     for b in (dk1, dk2, dt, dbl, dpal, dmap, ddst, dmo):
         if b is not None:
             b.free()
+
+
+@pytest.mark.parametrize("mode", [0, 3])
+@pytest.mark.parametrize("nw", [1, 2, 3, 4])
+def test_special_values_through_packed_arithmetic(gpu_ctx, nw, mode):
+    """Signed zeros, denormals, tiny and huge magnitudes (no overflow, so no NaN payload questions): the packed
+    multiply is fma(a, b, -0.0) and must round exactly like the scalar multiply the oracle does."""
+    from ogre_b200 import check, lib
+    ctx = gpu_ctx
+    n, nb, ninst, norm = 512, 16, 4, True
+    rng = np.random.default_rng(77 + nw)
+    src, blend, pals, bone_map = make_inputs(rng, n, nw, nb, ninst, norm, True)
+    special = np.array([0.0, -0.0, 1e-45, -1e-45, 1e-39, -3e-39, 1.1754944e-38, 1e-30, -1e-25, 1e15, -3e15, 1.0, -1.0],
+                       np.float32)
+    pick = lambda shape: special[rng.integers(0, len(special), size=shape)]
+    m = rng.random(src.shape) < 0.4
+    src[m] = pick(int(m.sum()))
+    pm = rng.random(pals.shape) < 0.3
+    pals[pm] = pick(int(pm.sum()))
+    w = blend[:, 4:].view(np.float32).reshape(n, nw).copy()
+    wm = rng.random(w.shape) < 0.3
+    w[wm] = pick(int(wm.sum()))
+    blend[:, 4:] = w.view(np.uint8).reshape(n, 4 * nw)
+    dsrc, ddst = ctx.to_device(src), ctx.alloc(ninst * n * 24)
+    dbl, dpal, dmap = ctx.to_device(blend), ctx.to_device(pals), ctx.to_device(bone_map)
+    j = gpu_job(ctx, dsrc.ptr, ddst.ptr, dbl, dpal, dmap, n, nw, nb, norm)
+    ctx.set_config_option("skin_mode", mode)
+    try:
+        check(lib().ogrecu_skin_instanced_dev(ctx.handle, C.byref(j), ninst, (nb + 2) * 16, n * 24, n * 24))
+        ctx.sync()
+    finally:
+        ctx.set_config_option("skin_mode", 0)
+    got = ddst.download(np.float32).reshape(ninst, n, 6)
+    for i in range(ninst):
+        ref = oracle_skin(src[i], blend, np.ascontiguousarray(pals[i][bone_map]), nw, n, norm)
+        ok = ~np.isnan(ref)                      # 0/0 normals: NaN on both sides, payload is not part of the contract
+        assert np.array_equal(np.isnan(got[i]), np.isnan(ref))
+        assert np.array_equal(bits(got[i])[ok], bits(ref)[ok]), (nw, mode, i)
+    for b in (dsrc, ddst, dbl, dpal, dmap):
+        b.free()

@@ -1,5 +1,8 @@
-mkdir -p gpurun_out
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
-timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -6
-python bench.py > gpurun_out/bench_r01e.json 2> gpurun_out/bench_r01e.err; echo "bench rc=$?"; cut -c1-1500 gpurun_out/bench_r01e.json
-python tools/bench_configs.py --config c1,c3,c4,c5 --views 256 --cpu --out gpurun_out/configs_r01e.jsonl 2>&1 | cut -c1-600
+timeout 900 python -m pytest tests/test_skin_tile_gpu.py -x -q 2>&1 | tail -3
+OGRECU_LIB=$PWD/ogre_b200/libogrecu_t128_c6.so timeout 900 python -m pytest tests/test_skin_tile_gpu.py -x -q 2>&1 | tail -3
+for lib in libogrecu.so libogrecu_t128_c6.so; do
+OGRECU_LIB=$PWD/ogre_b200/$lib python bench.py --no-cpu-baseline --steps 50 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); x=d['extra']
+print('$lib value=%.0f fused=%.0f separate=%.0f skin_only=%.0f roof=%.3f (%.3f ms) other=%.3f (%.3f ms)' % (d['value'], x['fused_Mvert_per_s'], x['separate_Mvert_per_s'], x['skin_only_Mvert_per_s'], d['roofline']['frac'], d['roofline']['launch_ms'], x['roofline_other_form']['frac'], x['roofline_other_form']['launch_ms']))"
+done
