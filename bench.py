@@ -363,11 +363,11 @@ def run_ours(args):
     def step_e2e():
         k = e2e_k[0]; e2e_k[0] += 1
         b = k & 1
-        ctx.set_stream(cstream.cuda_stream)              # set b was last read by step k-2, already waited for below
-        check(L.ogrecu_memcpy_h2d(ctx.handle, pal_sets[b].data_ptr(), hp.value, pal_h.nbytes))
-        check(L.ogrecu_memcpy_h2d(ctx.handle, t_sets[b].data_ptr(), ht.value, t_h.nbytes))
+        # copy stream; set b was last read by step k-2, already waited for below.  (ogrecu_set_stream would drain the
+        # launch stream — it is a synchronisation point — so the upload names its stream explicitly.)
+        check(L.ogrecu_memcpy_h2d_on(ctx.handle, cstream.cuda_stream, pal_sets[b].data_ptr(), hp.value, pal_h.nbytes))
+        check(L.ogrecu_memcpy_h2d_on(ctx.handle, cstream.cuda_stream, t_sets[b].data_ptr(), ht.value, t_h.nbytes))
         uploaded[b].record(cstream)
-        ctx.set_stream(stream.cuda_stream)
         stream.wait_event(uploaded[b])
         step_set(b)
         check(L.ogrecu_memcpy_d2h_async(ctx.handle, houts[b].value, last["dst"].data_ptr() + (ninst - 1) * out_bytes, out_bytes))
@@ -429,14 +429,16 @@ def run_ours(args):
                     "peak_source": (peak_kind + " (MEASURED_PEAKS.json hbm_gbs)") if peak_kind == "measured" else "fallback",
                     "unit": "GB/s", "frac": alg / dur / 1e9 / peak, "traffic": traf.get(key), "launch_ms": dur * 1e3,
                     "algorithmic_bytes_per_launch": alg}
-        roof_fused = roofline("fused", "skin_tile_kernel<4,normals,fused morph> (sub-mesh 1: %d verts x %d instances, 4 weights)",
-                              alg_fused, "skin_tile_fused_sub1_bytes")
-        roof_sep = roofline("skin", "skin_tile_kernel<4,normals> (sub-mesh 1: %d verts x %d instances, 4 weights)", alg_sep,
-                            "skin_tile_sub1_bytes")
+        roof_fused = roofline("fused", "skin_pair_kernel<4,normals,fused morph> (sub-mesh 1: %d verts x %d instances, 4 weights)",
+                              alg_fused, "skin_pair_fused_sub1_bytes")
+        roof_sep = roofline("skin", "skin_pair_kernel<4,normals> (sub-mesh 1: %d verts x %d instances, 4 weights)", alg_sep,
+                            "skin_pair_sub1_bytes")
         roof = roof_fused if args.form == "fused" else roof_sep
         extra["roofline_other_form"] = roof_sep if args.form == "fused" else roof_fused
         tot = {n: sum(np.mean(kern[(n, i)][1:]) for i in range(len(subs))) for n in ("skin", "morph", "fused")}
         extra["kernel_ms_per_step"] = tot
+        extra["fused_ms_per_submesh"] = [float(np.mean(kern[("fused", i)][1:])) for i in range(len(subs))]
+        extra["skin_ms_per_submesh"] = [float(np.mean(kern[("skin", i)][1:])) for i in range(len(subs))]
         extra["fused_Mvert_per_s"] = ninst * nverts / (tot["fused"] * 1e-3) / 1e6
         extra["separate_Mvert_per_s"] = ninst * nverts / ((tot["skin"] + tot["morph"]) * 1e-3) / 1e6
         extra["skin_only_Mvert_per_s"] = ninst * nverts / (tot["skin"] * 1e-3) / 1e6

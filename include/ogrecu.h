@@ -38,7 +38,7 @@ extern "C" {
 #define OGRECU_API
 #endif
 
-#define OGRECU_ABI_VERSION 2
+#define OGRECU_ABI_VERSION 3
 
 typedef enum ogrecu_status {
     OGRECU_OK = 0,
@@ -97,6 +97,10 @@ OGRECU_API int ogrecu_memcpy_d2h(ogrecu_ctx* ctx, void* host, const void* dev, s
 /* enqueue only (host must be pinned); the data is there after ogrecu_sync or an event the caller records on the stream */
 OGRECU_API int ogrecu_memcpy_d2h_async(ogrecu_ctx* ctx, void* host, const void* dev, size_t bytes);
 OGRECU_API int ogrecu_memcpy_d2d(ogrecu_ctx* ctx, void* dst, const void* src, size_t bytes);
+/* host -> device on a stream of the CALLER's (a copy stream), not the context's launch stream: lets a renderer upload
+ * frame k+1's inputs (bone palettes, weights) while frame k's kernels run.  Ordering against the launch stream is the
+ * caller's job (events).  host should be pinned for the copy to be asynchronous. */
+OGRECU_API int ogrecu_memcpy_h2d_on(ogrecu_ctx* ctx, void* cuda_stream, void* dev, const void* host, size_t bytes);
 
 /* ------------------------------------------------------------ hardware buffers ----- */
 /* HardwareBuffer delegate (OgreMain/include/OgreHardwareBuffer.h:181-186,279-330):

@@ -75,6 +75,7 @@ SIGNATURES = {
     "ogrecu_memcpy_h2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "ogrecu_memcpy_d2h": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "ogrecu_memcpy_d2h_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "ogrecu_memcpy_h2d_on": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "ogrecu_memcpy_d2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "ogrecu_buf_create": (C.c_int, [C.c_void_p, C.c_size_t, c_void_pp]),
     "ogrecu_buf_destroy": (C.c_int, [C.c_void_p]),

@@ -211,6 +211,14 @@ int ogrecu_memcpy_h2d(ogrecu_ctx* ctx, void* dev, const void* host, size_t bytes
     return OGRECU_OK;
 }
 
+int ogrecu_memcpy_h2d_on(ogrecu_ctx* ctx, void* cuda_stream, void* dev, const void* host, size_t bytes)
+{
+    OGRECU_REQUIRE(ctx && (bytes == 0 || (dev && host)), "NULL argument");
+    if (!bytes) return OGRECU_OK;
+    OGRECU_CUDA(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, (cudaStream_t)cuda_stream));
+    return OGRECU_OK;
+}
+
 int ogrecu_memcpy_d2h(ogrecu_ctx* ctx, void* host, const void* dev, size_t bytes)
 {
     OGRECU_REQUIRE(ctx && (bytes == 0 || (dev && host)), "NULL argument");

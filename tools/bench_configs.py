@@ -28,6 +28,9 @@ import ogre_b200  # noqa: E402
 from ogre_b200 import DrawDesc, capi, check, lib  # noqa: E402
 from datagen import DrawCase, edge_triangles, look_at, perspective, viewport_matrix  # noqa: E402
 
+RANK = int(os.environ.get("RANK", "0"))
+WORLD = int(os.environ.get("WORLD_SIZE", "1"))
+LOCAL = int(os.environ.get("LOCAL_RANK", "0"))
 PEAK = 6548.2
 try:
     PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
@@ -45,17 +48,30 @@ class Timer:
         ctx.set_stream(self.stream.cuda_stream)
         self.ctx = ctx
 
+    def barrier(self):
+        if WORLD > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        self.torch.cuda.synchronize()
+
     def time(self, fn, iters=10, warm=3):
+        """Seconds per call: CUDA events on the launch stream, barrier + synchronize on both sides, max over ranks."""
         for _ in range(warm):
             fn()
-        self.stream.synchronize()
+        self.barrier()
         a, b = self.torch.cuda.Event(enable_timing=True), self.torch.cuda.Event(enable_timing=True)
         a.record(self.stream)
         for _ in range(iters):
             fn()
         b.record(self.stream)
-        self.stream.synchronize()
-        return a.elapsed_time(b) / iters * 1e-3
+        self.barrier()
+        ms = a.elapsed_time(b)
+        if WORLD > 1:
+            import torch.distributed as dist
+            t = self.torch.tensor([ms], dtype=self.torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / iters * 1e-3
 
 
 def terrain(n, height=0.6, seed=3):
@@ -228,8 +244,13 @@ def c4(ctx, T, args):
     verts, idx = terrain(n)
     ntri = len(idx) // 3
     desc, keep = upload_scene(ctx, verts, idx, checker_texture(1024), w, h)
-    nviews = args.views
-    mvps, mvits, lights = camera_ring(nviews, w, h)
+    total_views = args.views
+    mvps, mvits, lights = camera_ring(total_views, w, h)
+    if WORLD > 1:                                        # view i -> rank i mod G, geometry replicated, no collective
+        from ogre_b200.shard import view_indices
+        mine = view_indices(total_views, RANK, WORLD)
+        mvps, mvits, lights = (np.ascontiguousarray(a[mine]) for a in (mvps, mvits, lights))
+    nviews = len(mvps)
     rts = [ogre_b200.RenderTarget(ctx, w, h) for _ in range(nviews)]
     run = raster_views(ctx, T, desc, rts, mvps, mvits, lights, args.chunk)
     dt = T.time(run, iters=2, warm=1)
@@ -243,10 +264,17 @@ def c4(ctx, T, args):
     dt_rb = time.perf_counter() - t0
     assert all(np.array_equal(host[k], imgs[k]) for k in range(0, nviews, max(1, nviews // 8)))
     covered = float(np.mean([(im != np.array([25, 51, 76], np.uint8)).any(axis=2).mean() for im in imgs[:8]]))
-    out = {"config": "c4 batched offscreen views: %d views 640x480, %d triangles, 1024^2 texture, lit" % (nviews, ntri),
-           "views_per_s_device": nviews / dt, "Mtri_per_s_device": nviews * ntri / dt / 1e6, "ms_per_view_device": dt / nviews * 1e3,
-           "views_per_s_with_readback": nviews / dt_rb, "covered_fraction": covered, "stats_view0": stats,
-           "compulsory_GBps": nviews * (len(idx) * 4 + len(verts) * 32 + w * h * 7) / dt / 1e9}
+    if WORLD > 1:
+        import torch
+        import torch.distributed as dist
+        t = torch.tensor([dt_rb], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt_rb = float(t.item())
+    out = {"config": "c4 batched offscreen views: %d views 640x480, %d triangles, 1024^2 texture, lit" % (total_views, ntri),
+           "n_gpus": WORLD, "views_per_gpu": nviews, "sharding": "view i -> GPU i mod G, geometry replicated, no collective",
+           "views_per_s_device": total_views / dt, "Mtri_per_s_device": total_views * ntri / dt / 1e6, "ms_per_view_device": dt / total_views * 1e3,
+           "views_per_s_with_readback": total_views / dt_rb, "covered_fraction": covered, "stats_view0": stats,
+           "compulsory_GBps_per_gpu": nviews * (len(idx) * 4 + len(verts) * 32 + w * h * 7) / dt / 1e9}
     if args.cpu:
         from rasterlib import render_oracle
         case = DrawCase(verts, idx, index_type=4, texture=checker_texture(1024), mvp=mvps[0], mvit=mvits[0], viewport=viewport_matrix(w, h),
@@ -270,6 +298,8 @@ def c5(ctx, T, args):
     mvps, mvits, lights = camera_ring(1, w, h)
     rt = ogre_b200.RenderTarget(ctx, w, h)
     run = raster_views(ctx, T, desc, [rt], mvps, mvits, lights, 1)
+    if WORLD > 1:
+        return c5_split(ctx, T, args, rt, run, ntri, len(idx), len(verts))
     dt = T.time(run, iters=3, warm=1)
     stats = rt.stats()
     host = ogre_b200.pinned_empty((h, w, 3))
@@ -288,6 +318,43 @@ def c5(ctx, T, args):
     return out
 
 
+def c5_split(ctx, T, args, rt, run, ntri, nidx, nverts):
+    """Split-frame form of c5: every rank holds the geometry, rasterises its strip of screen-tile rows
+    (ogrecu_rt_set_strip) and the disjoint strips are gathered to rank 0 over NVLink (NCCL gather) at readback only.
+    Checked on rank 0 against the same frame rendered whole on one GPU."""
+    import torch
+    import torch.distributed as dist
+    from ogre_b200.shard import DevicePlane, gather_strips, strip_rows
+    w, h = rt.width, rt.height
+    p = C.c_void_p()
+    check(lib().ogrecu_rt_colour_device_ptr(rt.handle, C.byref(p)))
+    plane = DevicePlane(p.value, (h, w, 3)).tensor(torch.device("cuda", LOCAL))
+    y0, y1 = strip_rows(h, RANK, WORLD)
+    rt.set_strip(y0, y1)
+    result = [None]
+
+    def render_and_composite():
+        run()
+        with torch.cuda.stream(T.stream):
+            result[0] = gather_strips(plane[y0:y1], y0, y1, h, dst=0)
+    dt_render = T.time(run, iters=3, warm=1)
+    strip_stats = rt.stats()
+    dt = T.time(render_and_composite, iters=3, warm=1)
+    ok = None
+    if RANK == 0:
+        frame = result[0].cpu().numpy()
+        rt.set_strip(0, h)
+        run()
+        whole = rt.read_colour()
+        ok = bool(np.array_equal(frame, whole))
+    T.barrier()
+    return {"config": "c5 one 3840x2160 frame, %d triangles, textured, lit: split-frame over %d GPUs (contiguous strips of tile rows), "
+                      "NCCL gather of the strips to rank 0 at readback" % (ntri, WORLD), "n_gpus": WORLD,
+            "ms_per_frame_render_only": dt_render * 1e3, "ms_per_frame_with_composite": dt * 1e3, "frames_per_s": 1 / dt,
+            "Mtri_per_s": ntri / dt / 1e6, "composite_bytes": int(w * h * 3 * (WORLD - 1) / WORLD),
+            "identical_to_single_gpu_frame": ok, "stats_rank0_strip": strip_stats}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", default="c1,c3,c4,c5")
@@ -300,21 +367,29 @@ def main():
     ap.add_argument("--out", default="")
     args = ap.parse_args()
     import torch
-    torch.cuda.set_device(0)
-    ctx = ogre_b200.Context(0)
+    torch.cuda.set_device(LOCAL)
+    if WORLD > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", LOCAL))
+    ctx = ogre_b200.Context(LOCAL)
     T = Timer(ctx)
     lines = []
     for name in args.config.split(","):
         t0 = time.time()
         res = {"c1": c1, "c3": c3, "c4": c4, "c5": c5}[name](ctx, T, args)
         res["wall_s"] = time.time() - t0
-        print(json.dumps(res), flush=True)
+        if RANK == 0:
+            print(json.dumps(res), flush=True)
         lines.append(res)
-    if args.out:
+    if args.out and RANK == 0:
         with open(args.out, "w") as f:
             for r in lines:
                 f.write(json.dumps(r) + "\n")
     ctx.set_stream(None)
+    if WORLD > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -9,7 +9,7 @@ python bench.py > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; echo 
 python bench.py --form separate --no-cpu-baseline > gpurun_out/bench_separate_$TAG.json 2>> gpurun_out/bench_$TAG.err; echo "bench separate rc=$?"; cat gpurun_out/bench_separate_$TAG.json
 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_ref_$TAG.json 2>/dev/null; cut -c1-300 gpurun_out/bench_ref_$TAG.json
 # A/B sweep of the kernel-selection knobs (short runs)
-for cfg in "0 0" "1 0" "2 0" "0 1" "0 4" "0 8" "0 16" "0 32"; do
+for cfg in "0 0" "3 0" "1 0"; do
   set -- $cfg
   python bench.py --no-cpu-baseline --steps 50 --skin-mode $1 --skin-ipc $2 2>/dev/null | python -c "
 import json,sys
@@ -20,8 +20,8 @@ done | tee gpurun_out/sweep_$TAG.txt
 ncu --metrics gpu__time_duration.sum --clock-control none -s 21 -c 42 --csv --log-file gpurun_out/launches_$TAG.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline > /dev/null 2>&1; echo "ncu list rc=$?"
 # full capture of the dominant kernel: 9th skin_tile launch = second step, sub-mesh 1 (1888 verts x 10000, 4 weights)
-ncu --set full --clock-control none --import-source on -k regex:skin_tile -s 8 -c 1 -o gpurun_out/prof_fused_$TAG -f \
+ncu --set full --clock-control none --import-source on -k regex:skin_ -s 8 -c 1 -o gpurun_out/prof_fused_$TAG -f \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline > /dev/null 2>&1; echo "ncu full fused rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:skin_tile -s 8 -c 1 -o gpurun_out/prof_skin_$TAG -f \
+ncu --set full --clock-control none --import-source on -k regex:skin_ -s 8 -c 1 -o gpurun_out/prof_skin_$TAG -f \
     python bench.py --form separate --steps 2 --warmup 1 --no-cpu-baseline > /dev/null 2>&1; echo "ncu full separate rc=$?"
 ls -la gpurun_out | tail -14
