@@ -35,6 +35,48 @@ class OracleDraw(C.Structure):
     ]
 
 
+class OracleSkeleton(C.Structure):
+    """oracle_skeleton (oracle/ogre_oracle.h)"""
+    _fields_ = [("num_bones", C.c_uint32), ("blend_mode", C.c_uint32), ("parent", vp), ("bind", vp), ("inherit", vp)]
+
+
+class OracleAnimation(C.Structure):
+    """oracle_animation (oracle/ogre_oracle.h)"""
+    _fields_ = [("length", c_f), ("interpolation", C.c_uint32), ("rotation_interpolation", C.c_uint32), ("num_tracks", C.c_uint32),
+                ("track_bone", vp), ("track_shortest", vp), ("key_offset", vp), ("keys", vp)]
+
+
+class Skeleton:
+    """Oracle-side skeleton built from the flat dict of oracle.ref.skeleton_def / tests.goldenlib.load_skeleton."""
+
+    def __init__(self, d):
+        self.d = d
+        self.keep = [np.ascontiguousarray(d["parent"], np.int32), np.ascontiguousarray(d["bind"], np.float32),
+                     np.ascontiguousarray(d["inherit"], np.uint8)]
+        self.sk = OracleSkeleton(d["num_bones"], d["blend_mode"], *[a.ctypes.data for a in self.keep])
+        self.anims = (OracleAnimation * max(1, len(d["anims"])))()
+        for i, a in enumerate(d["anims"]):
+            arrs = [np.ascontiguousarray(a["track_bone"], np.int32), np.ascontiguousarray(a["track_shortest"], np.uint8),
+                    np.ascontiguousarray(a["key_offset"], np.uint32), np.ascontiguousarray(a["keys"], np.float32)]
+            self.keep += arrs
+            self.anims[i] = OracleAnimation(a["length"], a["interpolation"], a["rotation_interpolation"], len(arrs[0]),
+                                            *[x.ctypes.data for x in arrs])
+        self.bind_inverse = np.zeros((d["num_bones"], 10), np.float32)
+        lib().oracle_skeleton_bind_inverse(C.byref(self.sk), self.bind_inverse.ctypes.data)
+
+    def palette(self, anim, time, weight, bind_inverse=None, blend_mode=None):
+        self.sk.blend_mode = self.d["blend_mode"] if blend_mode is None else int(blend_mode)
+        anim = np.ascontiguousarray(anim, np.int32); time = np.ascontiguousarray(time, np.float32)
+        weight = np.ascontiguousarray(weight, np.float32)
+        bi = self.bind_inverse if bind_inverse is None else np.ascontiguousarray(bind_inverse, np.float32)
+        out = np.zeros((self.d["num_bones"], 16), np.float32)
+        rc = lib().oracle_skeleton_palette(C.byref(self.sk), bi.ctypes.data, self.anims, len(anim), anim.ctypes.data,
+                                           time.ctypes.data, weight.ctypes.data, out.ctypes.data)
+        if rc:
+            raise ValueError("interpolation mode not restated by the oracle")
+        return out
+
+
 def build():
     subprocess.check_call(["make", "-s", "-C", _HERE])
 
@@ -58,6 +100,9 @@ def lib():
         l.oracle_tiny_clear.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_uint, vp, c_f]
         l.oracle_tiny_draw.argtypes = [C.POINTER(OracleDraw), vp, vp, C.c_uint32, C.c_uint32]
         l.oracle_tiny_draw.restype = C.c_uint64
+        l.oracle_skeleton_bind_inverse.argtypes = [C.POINTER(OracleSkeleton), vp]
+        l.oracle_skeleton_bind_inverse.restype = None
+        l.oracle_skeleton_palette.argtypes = [C.POINTER(OracleSkeleton), vp, C.POINTER(OracleAnimation), C.c_uint32, vp, vp, vp, vp]
         for n in ("oracle_skin_general", "oracle_skin_sse", "oracle_morph", "oracle_concat_affine_sse",
                   "oracle_concat_affine_general", "oracle_face_normals", "oracle_light_facing_sse",
                   "oracle_light_facing_general", "oracle_extrude", "oracle_tiny_clear"):

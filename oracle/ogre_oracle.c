@@ -11,6 +11,7 @@
 #include <float.h>
 #include <limits.h>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 /* std::min / std::max exactly as libstdc++ defines them (NaN handling matters) */
@@ -415,4 +416,220 @@ uint64_t oracle_tiny_draw(const oracle_draw* d, uint8_t* colour, float* depth, u
         written += raster_triangle(d, &t, colour, depth, W);
     }
     return written;
+}
+
+
+/* ============================================================ Skeleton bone palettes */
+
+typedef struct { float w, x, y, z; } quat;
+typedef struct { float x, y, z; } vec3;
+
+/* Quaternion::operator*(const Quaternion&), OgreQuaternion.cpp:260-272 */
+static quat q_mul(quat a, quat b)
+{
+    quat r;
+    r.w = a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z;
+    r.x = a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y;
+    r.y = a.w * b.y + a.y * b.w + a.z * b.x - a.x * b.z;
+    r.z = a.w * b.z + a.z * b.w + a.x * b.y - a.y * b.x;
+    return r;
+}
+
+/* Quaternion::normalise, OgreQuaternion.h:213-218: *this = 1.0f / len * *this */
+static quat q_normalise(quat q)
+{
+    float len = sqrtf(q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z);
+    float s = 1.0f / len;
+    quat r = {s * q.w, s * q.x, s * q.y, s * q.z};
+    return r;
+}
+
+/* Quaternion::nlerp, OgreQuaternion.cpp:534-549 */
+static quat q_nlerp(float t, quat p, quat q, int shortest)
+{
+    float c = p.w * q.w + p.x * q.x + p.y * q.y + p.z * q.z;
+    quat r;
+    if (c < 0.0f && shortest) {
+        r.w = p.w + t * ((-q.w) - p.w); r.x = p.x + t * ((-q.x) - p.x); r.y = p.y + t * ((-q.y) - p.y); r.z = p.z + t * ((-q.z) - p.z);
+    } else {
+        r.w = p.w + t * (q.w - p.w); r.x = p.x + t * (q.x - p.x); r.y = p.y + t * (q.y - p.y); r.z = p.z + t * (q.z - p.z);
+    }
+    return q_normalise(r);
+}
+
+/* Quaternion::operator*(const Vector3&), OgreQuaternion.cpp:359-371 */
+static vec3 q_rot(quat q, vec3 v)
+{
+    vec3 uv = {q.y * v.z - q.z * v.y, q.z * v.x - q.x * v.z, q.x * v.y - q.y * v.x};
+    vec3 uuv = {q.y * uv.z - q.z * uv.y, q.z * uv.x - q.x * uv.z, q.x * uv.y - q.y * uv.x};
+    float tw = 2.0f * q.w;
+    uv.x *= tw; uv.y *= tw; uv.z *= tw;
+    uuv.x *= 2.0f; uuv.y *= 2.0f; uuv.z *= 2.0f;
+    vec3 r = {(v.x + uv.x) + uuv.x, (v.y + uv.y) + uuv.y, (v.z + uv.z) + uuv.z};
+    return r;
+}
+
+typedef struct { vec3 p; quat q; vec3 s; } xform;
+
+static xform load10(const float* f)
+{
+    xform t = {{f[0], f[1], f[2]}, {f[3], f[4], f[5], f[6]}, {f[7], f[8], f[9]}};
+    return t;
+}
+
+/* Node::updateFromParentImpl, OgreNode.cpp:202-256, for every bone (parents first, whatever the handle order) */
+static void derive_all(const oracle_skeleton* sk, const xform* local, xform* derived)
+{
+    uint32_t n = sk->num_bones, done = 0;
+    uint8_t* ok = (uint8_t*)calloc(n ? n : 1, 1);
+    while (done < n) {
+        uint32_t before = done;
+        for (uint32_t b = 0; b < n; ++b) {
+            if (ok[b]) continue;
+            int32_t p = sk->parent[b];
+            if (p >= 0 && !ok[p]) continue;
+            if (p < 0) {
+                derived[b] = local[b];
+            } else {
+                const xform* P = &derived[p];
+                int io = sk->inherit ? sk->inherit[2 * b] : 1, is = sk->inherit ? sk->inherit[2 * b + 1] : 1;
+                derived[b].q = io ? q_mul(P->q, local[b].q) : local[b].q;
+                if (is) { derived[b].s.x = P->s.x * local[b].s.x; derived[b].s.y = P->s.y * local[b].s.y; derived[b].s.z = P->s.z * local[b].s.z; }
+                else derived[b].s = local[b].s;
+                vec3 sp = {P->s.x * local[b].p.x, P->s.y * local[b].p.y, P->s.z * local[b].p.z};
+                vec3 r = q_rot(P->q, sp);
+                derived[b].p.x = r.x + P->p.x; derived[b].p.y = r.y + P->p.y; derived[b].p.z = r.z + P->p.z;
+            }
+            ok[b] = 1; ++done;
+        }
+        if (done == before) break;      /* cycle in the parent table: leave the rest untouched */
+    }
+    free(ok);
+}
+
+void oracle_skeleton_bind_inverse(const oracle_skeleton* sk, float* out10)
+{
+    uint32_t n = sk->num_bones;
+    xform* local = (xform*)malloc(sizeof(xform) * (n ? n : 1));
+    xform* derived = (xform*)malloc(sizeof(xform) * (n ? n : 1));
+    for (uint32_t b = 0; b < n; ++b) local[b] = load10(sk->bind + 10 * b);
+    derive_all(sk, local, derived);
+    for (uint32_t b = 0; b < n; ++b) {
+        float* o = out10 + 10 * b;
+        const xform* d = &derived[b];
+        o[0] = -d->p.x; o[1] = -d->p.y; o[2] = -d->p.z;
+        /* Quaternion::Inverse, OgreQuaternion.cpp:274-287 */
+        float norm = d->q.w * d->q.w + d->q.x * d->q.x + d->q.y * d->q.y + d->q.z * d->q.z;
+        if (norm > 0.0f) { float inv = 1.0f / norm; o[3] = d->q.w * inv; o[4] = -d->q.x * inv; o[5] = -d->q.y * inv; o[6] = -d->q.z * inv; }
+        else { o[3] = o[4] = o[5] = o[6] = 0.0f; }
+        o[7] = 1.0f / d->s.x; o[8] = 1.0f / d->s.y; o[9] = 1.0f / d->s.z;
+    }
+    free(local); free(derived);
+}
+
+static int cmp_float(const void* a, const void* b)
+{
+    float x = *(const float*)a, y = *(const float*)b;
+    return (x > y) - (x < y);
+}
+
+int oracle_skeleton_palette(const oracle_skeleton* sk, const float* bind_inverse10, const oracle_animation* anims,
+                            uint32_t nstates, const int32_t* anim, const float* time, const float* weight, float* out16)
+{
+    uint32_t n = sk->num_bones;
+    xform* local = (xform*)malloc(sizeof(xform) * (n ? n : 1));
+    xform* derived = (xform*)malloc(sizeof(xform) * (n ? n : 1));
+    int rc = 0;
+    /* Skeleton::reset -> Node::resetToInitialState */
+    for (uint32_t b = 0; b < n; ++b) local[b] = load10(sk->bind + 10 * b);
+
+    /* ANIMBLEND_AVERAGE: rebalance when the enabled weights sum to more than 1 (OgreSkeleton.cpp:174-195) */
+    float weight_factor = 1.0f;
+    if (sk->blend_mode == 0) {
+        float total = 0.0f;
+        for (uint32_t s = 0; s < nstates; ++s) total += weight[s];
+        if (total > 1.0f) weight_factor = 1.0f / total;
+    }
+    for (uint32_t s = 0; s < nstates && !rc; ++s) {
+        const oracle_animation* A = &anims[anim[s]];
+        if (A->interpolation != 0 || A->rotation_interpolation != 0) { rc = 1; break; }
+        float w = weight[s] * weight_factor;
+        const float scl = 1.0f;                                  /* linked-skeleton scale: none */
+        uint32_t nkeys = A->key_offset[A->num_tracks];
+        /* Animation::buildKeyFrameTimeList: the sorted set of all key times */
+        float* times = (float*)malloc(sizeof(float) * (nkeys ? nkeys : 1));
+        for (uint32_t k = 0; k < nkeys; ++k) times[k] = A->keys[11 * k];
+        qsort(times, nkeys, sizeof(float), cmp_float);
+        uint32_t nt = 0;
+        for (uint32_t k = 0; k < nkeys; ++k) if (nt == 0 || times[k] != times[nt - 1]) times[nt++] = times[k];
+        /* Animation::_getTimeIndex */
+        float tp = time[s];
+        if (tp > A->length && A->length > 0.0f) tp = fmodf(tp, A->length);
+        uint32_t gi = 0;
+        if (nt) { while (gi + 1 < nt && times[gi] < tp) ++gi; }   /* lower_bound over [begin, end-1) */
+        for (uint32_t t = 0; t < A->num_tracks; ++t) {
+            uint32_t k0 = A->key_offset[t], nk = A->key_offset[t + 1] - k0;
+            if (nk == 0 || !w) continue;
+            const float* K = A->keys + 11 * (size_t)k0;
+            /* AnimationTrack::_buildKeyFrameIndexMap, entry gi only: the first local key whose time is >= times[gi]
+             * (clamped to the last key) */
+            uint32_t i = 0;
+            for (uint32_t j = 0; j < gi; ++j)
+                while (i + 1 < nk && K[11 * i] <= times[j]) ++i;
+            /* getKeyFramesAtTime */
+            const float* k2 = K + 11 * i;
+            float t2 = k2[0];
+            if (i != 0 && tp < K[11 * i]) --i;
+            const float* k1 = K + 11 * i;
+            float t1 = k1[0];
+            float f = (t1 == t2) ? 0.0f : (tp - t1) / (t2 - t1);
+            /* getInterpolatedKeyFrame (IM_LINEAR, RIM_LINEAR) */
+            vec3 tr, sc; quat ro;
+            if (f == 0.0f) {
+                tr.x = k1[1]; tr.y = k1[2]; tr.z = k1[3]; ro.w = k1[4]; ro.x = k1[5]; ro.y = k1[6]; ro.z = k1[7]; sc.x = k1[8]; sc.y = k1[9]; sc.z = k1[10];
+            } else {
+                quat a = {k1[4], k1[5], k1[6], k1[7]}, b = {k2[4], k2[5], k2[6], k2[7]};
+                ro = q_nlerp(f, a, b, A->track_shortest[t]);
+                tr.x = k1[1] + f * (k2[1] - k1[1]); tr.y = k1[2] + f * (k2[2] - k1[2]); tr.z = k1[3] + f * (k2[3] - k1[3]);
+                sc.x = k1[8] + f * (k2[8] - k1[8]); sc.y = k1[9] + f * (k2[9] - k1[9]); sc.z = k1[10] + f * (k2[10] - k1[10]);
+            }
+            /* applyToNode */
+            xform* B = &local[A->track_bone[t]];
+            B->p.x += tr.x * w * scl; B->p.y += tr.y * w * scl; B->p.z += tr.z * w * scl;
+            quat ident = {1.0f, 0.0f, 0.0f, 0.0f};
+            quat rot = q_nlerp(w, ident, ro, A->track_shortest[t]);
+            B->q = q_normalise(q_mul(B->q, rot));                 /* Node::rotate, TS_LOCAL */
+            if (sc.x != 1.0f || sc.y != 1.0f || sc.z != 1.0f) {
+                if (scl != 1.0f) { sc.x = 1.0f + scl * (sc.x - 1.0f); sc.y = 1.0f + scl * (sc.y - 1.0f); sc.z = 1.0f + scl * (sc.z - 1.0f); }
+                else if (w != 1.0f) { sc.x = 1.0f + w * (sc.x - 1.0f); sc.y = 1.0f + w * (sc.y - 1.0f); sc.z = 1.0f + w * (sc.z - 1.0f); }
+            }
+            B->s.x *= sc.x; B->s.y *= sc.y; B->s.z *= sc.z;
+        }
+        free(times);
+    }
+    if (!rc) {
+        derive_all(sk, local, derived);
+        for (uint32_t b = 0; b < n; ++b) {
+            /* Bone::_getOffsetTransform */
+            xform inv = load10(bind_inverse10 + 10 * b);
+            const xform* d = &derived[b];
+            vec3 ls = {d->s.x * inv.s.x, d->s.y * inv.s.y, d->s.z * inv.s.z};
+            quat lr = q_mul(d->q, inv.q);
+            vec3 sp = {ls.x * inv.p.x, ls.y * inv.p.y, ls.z * inv.p.z};
+            vec3 rp = q_rot(lr, sp);
+            vec3 lt = {d->p.x + rp.x, d->p.y + rp.y, d->p.z + rp.z};
+            /* Quaternion::ToRotationMatrix (OgreQuaternion.cpp:84-108) + makeTransform */
+            float tx = lr.x + lr.x, ty = lr.y + lr.y, tz = lr.z + lr.z;
+            float twx = tx * lr.w, twy = ty * lr.w, twz = tz * lr.w;
+            float txx = tx * lr.x, txy = ty * lr.x, txz = tz * lr.x;
+            float tyy = ty * lr.y, tyz = tz * lr.y, tzz = tz * lr.z;
+            float* m = out16 + 16 * b;
+            m[0] = ls.x * (1.0f - (tyy + tzz)); m[1] = ls.y * (txy - twz);          m[2] = ls.z * (txz + twy);           m[3] = lt.x;
+            m[4] = ls.x * (txy + twz);          m[5] = ls.y * (1.0f - (txx + tzz)); m[6] = ls.z * (tyz - twx);           m[7] = lt.y;
+            m[8] = ls.x * (txz - twy);          m[9] = ls.y * (tyz + twx);          m[10] = ls.z * (1.0f - (txx + tyy)); m[11] = lt.z;
+            m[12] = 0.0f; m[13] = 0.0f; m[14] = 0.0f; m[15] = 1.0f;
+        }
+    }
+    free(local); free(derived);
+    return rc;
 }

@@ -94,6 +94,50 @@ void oracle_tiny_clear(uint8_t* colour_rgb, float* depth, uint32_t w, uint32_t h
  * behaviour there is undefined: out-of-bounds writes).  Returns fragments written. */
 uint64_t oracle_tiny_draw(const oracle_draw* d, uint8_t* colour_rgb, float* depth, uint32_t w, uint32_t h);
 
+
+/* ---- Skeleton bone-palette production ---- */
+
+/* Flat description of a Skeleton: bones indexed by handle.  bind[b] = initial (binding-pose) position xyz,
+ * orientation wxyz, scale xyz (Node::setInitialState); inherit[b] = {inheritOrientation, inheritScale}. */
+typedef struct oracle_skeleton {
+    uint32_t num_bones;
+    uint32_t blend_mode;            /* 0 = ANIMBLEND_AVERAGE, 1 = ANIMBLEND_CUMULATIVE (OgreSkeleton.h:50-52) */
+    const int32_t* parent;          /* [num_bones], -1 = root */
+    const float* bind;              /* [num_bones][10] */
+    const uint8_t* inherit;         /* [num_bones][2], NULL = all inherit */
+} oracle_skeleton;
+
+/* One Animation's node tracks.  keys[k] = time, translate xyz, rotation wxyz, scale xyz (TransformKeyFrame);
+ * track t owns keys[key_offset[t] .. key_offset[t+1]) sorted by time. */
+typedef struct oracle_animation {
+    float length;
+    uint32_t interpolation;             /* 0 = IM_LINEAR (1 = IM_SPLINE: not restated, returns an error) */
+    uint32_t rotation_interpolation;    /* 0 = RIM_LINEAR (1 = RIM_SPHERICAL: not restated) */
+    uint32_t num_tracks;
+    const int32_t* track_bone;          /* [num_tracks] */
+    const uint8_t* track_shortest;      /* [num_tracks] NodeAnimationTrack::getUseShortestRotationPath */
+    const uint32_t* key_offset;         /* [num_tracks + 1] */
+    const float* keys;                  /* [key_offset[num_tracks]][11] */
+} oracle_animation;
+
+/* Bone::setBindingPose, OgreMain/src/OgreBone.cpp:66-74 (on the derived transforms of the binding pose,
+ * Node::updateFromParentImpl OgreNode.cpp:202-256): out[b] = inverse position xyz, inverse orientation wxyz,
+ * inverse scale xyz. */
+void oracle_skeleton_bind_inverse(const oracle_skeleton* sk, float* out10);
+
+/* Skeleton::setAnimationState + Skeleton::_getBoneMatrices for ONE skeleton instance:
+ * OgreSkeleton.cpp:162-217,402-424; Animation::apply/_getTimeIndex OgreAnimation.cpp:326-342,594-618,620-660;
+ * AnimationTrack::getKeyFramesAtTime/_collectKeyFrameTimes/_buildKeyFrameIndexMap OgreAnimationTrack.cpp:57-126,175-206;
+ * NodeAnimationTrack::getInterpolatedKeyFrame/applyToNode OgreAnimationTrack.cpp:373-512; Quaternion::nlerp
+ * OgreQuaternion.cpp:534-549; Node::translate/rotate/scale OgreNode.cpp:378-428,579-584; Bone::_getOffsetTransform
+ * OgreBone.cpp:88-105; TransformBaseReal::makeTransform OgreMatrix4.cpp:205-222.
+ * The enabled animation states are given in application order: anim[s] indexes `anims`, time[s] is
+ * AnimationState::getTimePosition(), weight[s] its weight.  bind_inverse = oracle_skeleton_bind_inverse's output
+ * (or the reference's own).  out = num_bones x 16 floats (Affine3).  Returns 0, or 1 for an interpolation mode
+ * that is not restated. */
+int oracle_skeleton_palette(const oracle_skeleton* sk, const float* bind_inverse10, const oracle_animation* anims,
+                            uint32_t nstates, const int32_t* anim, const float* time, const float* weight, float* out16);
+
 #ifdef __cplusplus
 }
 #endif

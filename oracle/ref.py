@@ -77,6 +77,17 @@ def lib():
         l.ref_bench_anim_sub.restype = C.c_double
         l.ref_bench_morph.argtypes = [c_f, vp, vp, vp, sz, sz, C.c_int, C.c_int, C.c_int]
         l.ref_bench_morph.restype = C.c_double
+        l.ref_skel_def_sizes.argtypes = [vp, vp, vp]
+        l.ref_skel_set_blend_mode.argtypes = [C.c_uint32]
+        l.ref_skel_set_blend_mode.restype = None
+        l.ref_skel_def_bones.argtypes = [vp, vp, vp, vp]
+        l.ref_skel_def_bones.restype = None
+        l.ref_skel_anim_info.argtypes = [C.c_uint32, vp, vp, vp, vp, vp, C.c_char_p]
+        l.ref_skel_anim_data.argtypes = [C.c_uint32, vp, vp, vp, vp]
+        l.ref_skel_anim_data.restype = None
+        l.ref_skel_pose_states.argtypes = [C.c_uint32, vp, vp, vp, vp]
+        l.ref_bench_palettes.argtypes = [C.c_uint32, vp, sz, vp]
+        l.ref_bench_palettes.restype = C.c_double
         l.ref_set_media_dir(MEDIA.encode())
         _lib = l
     return _lib
@@ -161,3 +172,40 @@ def skeleton_pose(mesh, time, w=64, h=64, reopen=True):
         s["bone_map"] = np.ctypeslib.as_array(C.cast(l.ref_skel_sub_map(i), C.POINTER(C.c_uint16)), shape=(info.nmap,)).copy()
         subs.append(s)
     return bones, subs
+
+
+def skeleton_def(mesh=None, w=64, h=64):
+    """The skeleton of `mesh` (or of the mesh already open) as flat arrays, straight from the real SkeletonInstance:
+    {num_bones, blend_mode, parent[n], bind[n,10], inherit[n,2], bind_inverse[n,10], anims: [{name, length,
+    interpolation, rotation_interpolation, track_bone, track_shortest, key_offset, keys[k,11]}]}."""
+    l = lib()
+    if mesh is not None:
+        rc = l.ref_skel_open(mesh.encode(), w, h)
+        assert rc == 0, rc
+    nb, na, bm = C.c_uint32(), C.c_uint32(), C.c_uint32()
+    assert l.ref_skel_def_sizes(C.addressof(nb), C.addressof(na), C.addressof(bm)) == 0
+    n = nb.value
+    d = {"num_bones": n, "blend_mode": bm.value, "parent": np.zeros(n, np.int32), "bind": np.zeros((n, 10), np.float32),
+         "inherit": np.zeros((n, 2), np.uint8), "bind_inverse": np.zeros((n, 10), np.float32), "anims": []}
+    l.ref_skel_def_bones(d["parent"].ctypes.data, d["bind"].ctypes.data, d["inherit"].ctypes.data, d["bind_inverse"].ctypes.data)
+    for a in range(na.value):
+        length = C.c_float(); im, rim, nt, nk = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint32()
+        name = C.create_string_buffer(64)
+        assert l.ref_skel_anim_info(a, C.addressof(length), C.addressof(im), C.addressof(rim), C.addressof(nt), C.addressof(nk), name) == 0
+        an = {"name": name.value.decode(), "length": length.value, "interpolation": im.value, "rotation_interpolation": rim.value,
+              "track_bone": np.zeros(nt.value, np.int32), "track_shortest": np.zeros(nt.value, np.uint8),
+              "key_offset": np.zeros(nt.value + 1, np.uint32), "keys": np.zeros((nk.value, 11), np.float32)}
+        l.ref_skel_anim_data(a, an["track_bone"].ctypes.data, an["track_shortest"].ctypes.data, an["key_offset"].ctypes.data,
+                             an["keys"].ctypes.data)
+        d["anims"].append(an)
+    return d
+
+
+def skeleton_pose_states(num_bones, anim, time, weight):
+    """Real SkeletonInstance::setAnimationState + _getBoneMatrices with exactly these states enabled, in this order."""
+    anim = np.ascontiguousarray(anim, np.uint32); time = np.ascontiguousarray(time, np.float32)
+    weight = np.ascontiguousarray(weight, np.float32)
+    out = np.zeros((num_bones, 16), np.float32)
+    rc = lib().ref_skel_pose_states(len(anim), anim.ctypes.data, time.ctypes.data, weight.ctypes.data, out.ctypes.data)
+    assert rc == 0, rc
+    return out

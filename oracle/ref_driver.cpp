@@ -531,6 +531,129 @@ API const uint8_t* ref_skel_sub_blend(size_t i) { return g_subs[i].blend.data();
 API const uint16_t* ref_skel_sub_map(size_t i) { return g_subs[i].bone_map.data(); }
 API const uint8_t* ref_skel_sub_skinned(size_t i) { return g_subs[i].skinned.data(); }
 
+/* ============================================ skeleton definition + palette evaluation ==== */
+// Exports what Skeleton::setAnimationState / _getBoneMatrices (OgreMain/src/OgreSkeleton.cpp:150-217,402-424) consume,
+// so that the oracle restatement and the device kernel can be checked against the real pipeline on the real data.
+
+static Animation* skel_anim(uint32_t a)
+{
+    SkeletonInstance* sk = g_skel_ent->getSkeleton();
+    return a < sk->getNumAnimations() ? sk->getAnimation((unsigned short)a) : nullptr;
+}
+
+API int ref_skel_def_sizes(uint32_t* nbones, uint32_t* nanims, uint32_t* blend_mode)
+{
+    if (!g_skel_ent || !g_skel_ent->hasSkeleton()) return 1;
+    SkeletonInstance* sk = g_skel_ent->getSkeleton();
+    *nbones = sk->getNumBones();
+    *nanims = sk->getNumAnimations();
+    *blend_mode = (uint32_t)sk->getBlendMode();
+    return 0;
+}
+
+API void ref_skel_set_blend_mode(uint32_t mode) { g_skel_ent->getSkeleton()->setBlendMode((SkeletonAnimationBlendMode)mode); }
+
+// parent[n] (-1 = root); bind[n][10] = initial position xyz, orientation wxyz, scale xyz; inherit[n][2] = orientation, scale;
+// bindinv[n][10] = the Bone::setBindingPose products (inverse position xyz, inverse orientation wxyz, inverse scale xyz)
+API void ref_skel_def_bones(int32_t* parent, float* bind, uint8_t* inherit, float* bindinv)
+{
+    SkeletonInstance* sk = g_skel_ent->getSkeleton();
+    for (unsigned short h = 0; h < sk->getNumBones(); ++h) {
+        Bone* b = sk->getBone(h);
+        Node* p = b->getParent();
+        parent[h] = p ? (int32_t) static_cast<Bone*>(p)->getHandle() : -1;
+        const Vector3& ip = b->getInitialPosition(); const Quaternion& iq = b->getInitialOrientation(); const Vector3& is = b->getInitialScale();
+        float* o = bind + 10 * h;
+        o[0] = ip.x; o[1] = ip.y; o[2] = ip.z; o[3] = iq.w; o[4] = iq.x; o[5] = iq.y; o[6] = iq.z; o[7] = is.x; o[8] = is.y; o[9] = is.z;
+        inherit[2 * h] = b->getInheritOrientation(); inherit[2 * h + 1] = b->getInheritScale();
+        const Vector3& bp = b->_getBindingPoseInversePosition(); const Quaternion& bq = b->_getBindingPoseInverseOrientation();
+        const Vector3& bs = b->_getBindingPoseInverseScale();
+        o = bindinv + 10 * h;
+        o[0] = bp.x; o[1] = bp.y; o[2] = bp.z; o[3] = bq.w; o[4] = bq.x; o[5] = bq.y; o[6] = bq.z; o[7] = bs.x; o[8] = bs.y; o[9] = bs.z;
+    }
+}
+
+API int ref_skel_anim_info(uint32_t a, float* length, uint32_t* interp, uint32_t* rot_interp, uint32_t* ntracks, uint32_t* nkeys, char* name64)
+{
+    Animation* an = skel_anim(a);
+    if (!an) return 1;
+    *length = an->getLength(); *interp = (uint32_t)an->getInterpolationMode(); *rot_interp = (uint32_t)an->getRotationInterpolationMode();
+    *ntracks = (uint32_t)an->_getNodeTrackList().size();
+    uint32_t k = 0;
+    for (auto& t : an->_getNodeTrackList()) k += t.second->getNumKeyFrames();
+    *nkeys = k;
+    snprintf(name64, 64, "%s", an->getName().c_str());
+    return 0;
+}
+
+// track_bone[ntracks], track_shortest[ntracks], key_offset[ntracks + 1], keys[nkeys][11] = time, translate xyz, rotation wxyz, scale xyz
+API void ref_skel_anim_data(uint32_t a, int32_t* track_bone, uint8_t* track_shortest, uint32_t* key_offset, float* keys)
+{
+    Animation* an = skel_anim(a);
+    uint32_t t = 0, k = 0;
+    for (auto& kv : an->_getNodeTrackList()) {
+        NodeAnimationTrack* tr = kv.second;
+        track_bone[t] = kv.first; track_shortest[t] = tr->getUseShortestRotationPath(); key_offset[t] = k;
+        for (unsigned short i = 0; i < tr->getNumKeyFrames(); ++i, ++k) {
+            TransformKeyFrame* kf = tr->getNodeKeyFrame(i);
+            float* o = keys + 11 * k;
+            const Vector3& tv = kf->getTranslate(); const Quaternion& q = kf->getRotation(); const Vector3& sc = kf->getScale();
+            o[0] = kf->getTime(); o[1] = tv.x; o[2] = tv.y; o[3] = tv.z; o[4] = q.w; o[5] = q.x; o[6] = q.y; o[7] = q.z; o[8] = sc.x; o[9] = sc.y; o[10] = sc.z;
+        }
+        ++t;
+    }
+    key_offset[t] = k;
+}
+
+// Enable exactly the given animation states (index into the skeleton's animation list, time position as
+// AnimationState::getTimePosition would return it, weight), run SkeletonInstance::setAnimationState and
+// _getBoneMatrices, copy the numBones x 16 palette out.
+API int ref_skel_pose_states(uint32_t n, const uint32_t* anim, const float* time, const float* weight, float* bones_out)
+{
+    try {
+        Entity* e = g_skel_ent;
+        SkeletonInstance* sk = e->getSkeleton();
+        AnimationStateSet* set = e->getAllAnimationStates();
+        for (auto& kv : set->getAnimationStates()) kv.second->setEnabled(false);
+        for (uint32_t i = 0; i < n; ++i) {
+            Animation* an = skel_anim(anim[i]);
+            if (!an) return 2;
+            AnimationState* st = set->getAnimationState(an->getName());
+            st->setLoop(false);                       // clamp, not wrap: the caller passes the final time position
+            st->setEnabled(true);
+            st->setTimePosition(time[i]);
+            st->setWeight(weight[i]);
+        }
+        sk->setAnimationState(*set);
+        std::vector<Affine3> m(sk->getNumBones());
+        sk->_getBoneMatrices(m.data());
+        memcpy(bones_out, m.data(), m.size() * 64);
+        return 0;
+    } catch (std::exception& ex) { fprintf(stderr, "ref_skel_pose_states: %s\n", ex.what()); return 1; }
+}
+
+// CPU timing of the same: `ninst` palette evaluations (one enabled state each, time[i]); seconds for one pass, 1 thread
+// (SkeletonInstance is not thread-safe and OGRE evaluates entities serially on the render thread).
+API double ref_bench_palettes(uint32_t anim, const float* time, size_t ninst, float* bones_out)
+{
+    Entity* e = g_skel_ent;
+    SkeletonInstance* sk = e->getSkeleton();
+    AnimationStateSet* set = e->getAllAnimationStates();
+    for (auto& kv : set->getAnimationStates()) kv.second->setEnabled(false);
+    AnimationState* st = set->getAnimationState(skel_anim(anim)->getName());
+    st->setLoop(false); st->setEnabled(true); st->setWeight(1.0f);
+    const size_t nb = sk->getNumBones();
+    std::vector<Affine3> m(nb);
+    auto t0 = std::chrono::steady_clock::now();
+    for (size_t i = 0; i < ninst; ++i) {
+        st->setTimePosition(time[i]);
+        sk->setAnimationState(*set);
+        sk->_getBoneMatrices(m.data());
+        if (bones_out) memcpy(bones_out + i * nb * 16, m.data(), nb * 64);
+    }
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
 /* ==================================================================== timing ==== */
 
 // `reps` calls of the real SSE softwareVertexSkinning over `ninst` instances (each with its own

@@ -11,6 +11,10 @@ container only; the GPU box and the CPU test suite just read the .npz files.
   jaiqua_skin.npz        maps, 32 bone palettes sampled from the first animation, and OGRE's
                          own software-skinned vertices (Entity::_updateAnimation with the SSE
                          OptimisedUtil) for two of the poses
+  sinbad_skeleton.npz    the skeletons themselves (bone table, binding pose, the engine's own binding-pose
+  jaiqua_skeleton.npz    inverses, every animation's node tracks and key frames) + 96 poses each: 1-3 enabled
+                         animation states (order, time position, weight, both blend modes) and the palette
+                         the real SkeletonInstance::setAnimationState + _getBoneMatrices produced
   optutil_golden.npz     outputs of the real OptimisedUtilSSE / OptimisedUtilGeneral on small
                          seeded inputs (all six functions, edge-case counts and alignments)
 """
@@ -64,6 +68,42 @@ def save_skeleton(name, mesh, ntimes=32, dt=0.1):
     out["times"] = np.arange(ntimes, dtype=np.float32) * dt
     np.savez_compressed(os.path.join(HERE, name), **out)
     print(name, out["palettes"].shape, [int(out["s%d_meta" % i][6]) for i in range(len(subs))])
+
+
+def save_skeleton_def(name, mesh, nposes=96, seed=7):
+    d = ref.skeleton_def(mesh)
+    out = {"num_bones": np.array(d["num_bones"]), "blend_mode": np.array(d["blend_mode"]), "parent": d["parent"], "bind": d["bind"],
+           "inherit": d["inherit"], "bind_inverse": d["bind_inverse"], "nanims": np.array(len(d["anims"]))}
+    for i, a in enumerate(d["anims"]):
+        out["a%d_name" % i] = np.array(a["name"])
+        out["a%d_meta" % i] = np.array([a["length"], a["interpolation"], a["rotation_interpolation"]], np.float32)
+        for k in ("track_bone", "track_shortest", "key_offset", "keys"):
+            out["a%d_%s" % (i, k)] = a[k]
+    rng = np.random.default_rng(seed)
+    S = 3
+    pa = -np.ones((nposes, S), np.int32); pt = np.zeros((nposes, S), np.float32); pw = np.zeros((nposes, S), np.float32)
+    pn = np.zeros(nposes, np.int32); pm = np.zeros(nposes, np.int32); pal = np.zeros((nposes, d["num_bones"], 16), np.float32)
+    for p in range(nposes):
+        ns = 1 if p < nposes // 3 else int(rng.integers(1, S + 1))
+        an = rng.choice(len(d["anims"]), ns, replace=False)
+        tm = np.array([rng.uniform(0, d["anims"][a]["length"]) for a in an], np.float32)
+        if p % 7 == 0:
+            tm[0] = d["anims"][an[0]]["length"]           # exactly the last key
+        if p % 11 == 0:
+            tm[0] = 0.0
+        if p % 13 == 0 and len(d["anims"][an[0]]["keys"]) > 3:
+            tm[0] = d["anims"][an[0]]["keys"][2, 0]        # exactly on a key time
+        w = np.ones(ns, np.float32) if p % 3 == 0 else rng.uniform(0.05, 1.0, ns).astype(np.float32)
+        if p % 17 == 5:
+            w[-1] = 0.0                                    # zero weight: the track is skipped
+        mode = int(p % 4 == 3)
+        ref.lib().ref_skel_set_blend_mode(mode)
+        pal[p] = ref.skeleton_pose_states(d["num_bones"], an, tm, w)
+        pa[p, :ns], pt[p, :ns], pw[p, :ns], pn[p], pm[p] = an, tm, w, ns, mode
+    ref.lib().ref_skel_set_blend_mode(d["blend_mode"])
+    out.update(pose_anim=pa, pose_time=pt, pose_weight=pw, pose_nstates=pn, pose_blend_mode=pm, pose_palette=pal)
+    np.savez_compressed(os.path.join(HERE, name), **out)
+    print(name, d["num_bones"], "bones", len(d["anims"]), "animations", nposes, "poses")
 
 
 def save_optutil(name):
@@ -135,3 +175,5 @@ if __name__ == "__main__":
     save_scene("ogrehead_1280x720.npz", "ogrehead.mesh", 1280, 720)
     save_skeleton("sinbad_skin.npz", "Sinbad.mesh")
     save_skeleton("jaiqua_skin.npz", "jaiqua.mesh")
+    save_skeleton_def("sinbad_skeleton.npz", "Sinbad.mesh")
+    save_skeleton_def("jaiqua_skeleton.npz", "jaiqua.mesh")

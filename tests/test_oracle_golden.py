@@ -120,3 +120,18 @@ def test_oracle_reproduces_ogres_own_skinned_entities(name):
             ref = s["skinned"][t].view(np.float32).reshape(n, 6)
             assert np.array_equal(bits(got[:, :3]), bits(ref[:, :3])), (name, t, nw)
             assert np.abs(got[:, 3:] - ref[:, 3:]).max() <= 4e-4
+
+
+@pytest.mark.parametrize("name", ["sinbad_skeleton.npz", "jaiqua_skeleton.npz"])
+def test_oracle_reproduces_ogres_own_bone_palettes(name):
+    """Skeleton::setAnimationState + _getBoneMatrices (SURVEY §8f rank 1): 96 poses per skeleton dumped from the real
+    SkeletonInstance — 1-3 enabled states, both blend modes, times on keys / at 0 / at the end, zero weights — bit for bit;
+    the binding-pose inverses the engine computed in Bone::setBindingPose as well."""
+    from goldenlib import load_skeleton
+    d, poses = load_skeleton(name)
+    sk = oracle.Skeleton(d)
+    assert np.array_equal(bits(sk.bind_inverse), bits(d["bind_inverse"]))
+    for p in range(len(poses["nstates"])):
+        n = int(poses["nstates"][p])
+        got = sk.palette(poses["anim"][p, :n], poses["time"][p, :n], poses["weight"][p, :n], blend_mode=poses["blend_mode"][p])
+        assert np.array_equal(bits(got), bits(poses["palette"][p])), (name, p)

@@ -59,3 +59,25 @@ def test_oracle_skinning_equals_real_sse_large():
         po, no = c.dst_views(dst, None); pr, nr = c.dst_views(rdst, None)
         assert np.array_equal(bits(po), bits(pr))
         assert np.abs(no - nr).max() <= 4e-4
+
+
+@pytest.mark.parametrize("mesh", ["Sinbad.mesh", "jaiqua.mesh"])
+def test_oracle_bone_palettes_equal_real_skeleton_instance(mesh):
+    """300 random poses (1-3 states, random order, times and weights, both blend modes) through the real
+    SkeletonInstance::setAnimationState + _getBoneMatrices vs the restatement: bit-identical."""
+    d = ref.skeleton_def(mesh)
+    sk = oracle.Skeleton(d)
+    assert np.array_equal(bits(sk.bind_inverse), bits(d["bind_inverse"]))
+    rng = np.random.default_rng(11)
+    for trial in range(300):
+        ns = int(rng.integers(1, 4))
+        an = rng.choice(len(d["anims"]), ns, replace=False)
+        tm = [rng.uniform(0, 1.2 * d["anims"][a]["length"]) for a in an]       # beyond the end: clamped by AnimationState
+        tm = [min(t, d["anims"][a]["length"]) for t, a in zip(tm, an)]
+        w = rng.uniform(0.0, 1.0, ns) if trial % 3 else np.ones(ns)
+        mode = trial % 2
+        ref.lib().ref_skel_set_blend_mode(mode)
+        r = ref.skeleton_pose_states(d["num_bones"], an, tm, w)
+        o = sk.palette(an, tm, w, bind_inverse=d["bind_inverse"], blend_mode=mode)
+        assert np.array_equal(bits(r), bits(o)), (mesh, trial)
+    ref.lib().ref_skel_set_blend_mode(d["blend_mode"])
