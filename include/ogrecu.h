@@ -121,6 +121,54 @@ OGRECU_API int ogrecu_buf_mark_device_dirty(ogrecu_buf* buf, size_t offset, size
 /* host shadow pointer -> owning buffer + offset; *out_buf = NULL when not ours */
 OGRECU_API int ogrecu_buf_resolve(ogrecu_ctx* ctx, const void* host_ptr, ogrecu_buf** out_buf, size_t* out_offset);
 
+/* ------------------------------------------------ skeleton bone palettes ------ */
+/* Bone-palette production for many instances of one skeleton, on the device: what
+ * SkeletonInstance::setAnimationState + Skeleton::_getBoneMatrices do per entity on the CPU
+ * (OgreMain/src/OgreSkeleton.cpp:162-217,402-424, called from Entity::cacheBoneMatrices OgreEntity.cpp:1307-1330;
+ * Animation::apply OgreAnimation.cpp:326-342, NodeAnimationTrack::applyToNode OgreAnimationTrack.cpp:473-512,
+ * Node::updateFromParentImpl OgreNode.cpp:202-256, Bone::_getOffsetTransform OgreBone.cpp:88-105).  With it a
+ * frame uploads the animation STATES of the instances (a few bytes each) instead of 64 B x bones palettes.
+ * Results are bit-identical to the engine's (tests/test_skeleton_gpu.py).  Not covered (the call fails with
+ * OGRECU_ERR_UNSUPPORTED): IM_SPLINE, RIM_SPHERICAL, blend masks, manually controlled bones. */
+typedef struct ogrecu_skel ogrecu_skel;
+
+typedef struct ogrecu_skeleton_desc {
+    uint32_t num_bones;             /* <= 256 (OGRE_MAX_NUM_BONES), indexed by bone handle                           */
+    uint32_t blend_mode;            /* 0 = ANIMBLEND_AVERAGE, 1 = ANIMBLEND_CUMULATIVE (OgreSkeleton.h:50-52)        */
+    const int32_t* parent;          /* [num_bones] parent handle, -1 = root bone                                     */
+    const float*   bind;            /* [num_bones][10] initial position xyz, orientation wxyz, scale xyz             */
+    const uint8_t* inherit;         /* [num_bones][2] inheritOrientation, inheritScale; NULL = all inherit           */
+    const float*   bind_inverse;    /* [num_bones][10] Bone::setBindingPose products (inverse position, orientation, */
+                                    /* scale); NULL = computed here the way Bone::setBindingPose does                */
+} ogrecu_skeleton_desc;
+
+typedef struct ogrecu_animation_desc {
+    float length;                       /* Animation::getLength                                                     */
+    uint32_t interpolation;             /* 0 = IM_LINEAR                                                            */
+    uint32_t rotation_interpolation;    /* 0 = RIM_LINEAR                                                           */
+    uint32_t num_tracks;                /* node tracks, at most one per bone                                        */
+    const int32_t*  track_bone;         /* [num_tracks] bone handle                                                 */
+    const uint8_t*  track_shortest;     /* [num_tracks] getUseShortestRotationPath                                  */
+    const uint32_t* key_offset;         /* [num_tracks + 1] key range of each track                                 */
+    const float*    keys;               /* [key_offset[num_tracks]][11] time, translate xyz, rotation wxyz, scale xyz */
+} ogrecu_animation_desc;
+
+/* All desc pointers are HOST pointers, copied by the call. */
+OGRECU_API int ogrecu_skel_create(ogrecu_ctx* ctx, const ogrecu_skeleton_desc* desc, ogrecu_skel** out);
+OGRECU_API int ogrecu_skel_destroy(ogrecu_skel* skel);
+OGRECU_API int ogrecu_skel_add_animation(ogrecu_skel* skel, const ogrecu_animation_desc* desc, uint32_t* out_index);
+OGRECU_API int ogrecu_skel_set_blend_mode(ogrecu_skel* skel, uint32_t blend_mode);
+/* the binding-pose inverses in use (computed or given), [num_bones][10], to a HOST array */
+OGRECU_API int ogrecu_skel_get_bind_inverse(ogrecu_skel* skel, float* out10_host);
+/* num_instances skeleton instances, each with `num_states` animation-state slots applied in slot order:
+ * anim_dev[i*num_states + s] = animation index (< 0: slot disabled), time_dev = AnimationState::getTimePosition,
+ * weight_dev = AnimationState::getWeight (all DEVICE arrays).  Writes num_bones Affine3 per instance to
+ * palettes_dev + i*palette_stride_floats (16-byte aligned, stride a multiple of 4 floats) — the layout
+ * ogrecu_skin_instanced_dev / ogrecu_anim_instanced_dev read.  One launch, asynchronous on the stream. */
+OGRECU_API int ogrecu_skel_palettes_dev(ogrecu_skel* skel, uint32_t num_instances, uint32_t num_states,
+                                        const int32_t* anim_dev, const float* time_dev, const float* weight_dev,
+                                        float* palettes_dev, size_t palette_stride_floats);
+
 /* -------------------------------------------------------------- OptimisedUtil ------ */
 /* Ogre::OptimisedUtil, OgreMain/include/OgreOptimisedUtil.h:99-206; arithmetic replays
  * OgreMain/src/OgreOptimisedUtilSSE.cpp (see DESIGN.md §kernels for the per-function

@@ -13,9 +13,9 @@ import ctypes as C
 import numpy as np
 
 from . import capi
-from .capi import DrawDesc, OgrecuError, RasterStats, SkinJob, check, lib
+from .capi import AnimationDesc, DrawDesc, OgrecuError, RasterStats, SkeletonDesc, SkinJob, check, lib
 
-__all__ = ["Context", "DeviceBuffer", "OptimisedUtil", "Texture", "RenderTarget", "DrawDesc", "SkinJob",
+__all__ = ["Context", "DeviceBuffer", "OptimisedUtil", "Skeleton", "Texture", "RenderTarget", "DrawDesc", "SkinJob",
            "OgrecuError", "addr", "pinned_empty"]
 
 MAP_READ, MAP_WRITE, MAP_DISCARD = 1, 2, 4
@@ -175,6 +175,66 @@ class OptimisedUtil:
         keep, lp = _light4(lightPos)
         check(lib().ogrecu_extrude_vertices_host(self.ctx.handle, lp, float(extrudeDist), srcPositions,
                                                  destPositions, numVertices))
+
+
+class Skeleton:
+    """Device-side skeleton (ogrecu_skel): bone-palette production for many instances, the work of
+    SkeletonInstance::setAnimationState + Skeleton::_getBoneMatrices (OgreMain/src/OgreSkeleton.cpp:162-217,402-424).
+    `d` is the flat description {num_bones, blend_mode, parent, bind, inherit, [bind_inverse], anims: [{length,
+    interpolation, rotation_interpolation, track_bone, track_shortest, key_offset, keys}]}."""
+
+    def __init__(self, ctx, d, use_given_bind_inverse=False):
+        self.ctx, self.num_bones = ctx, int(d["num_bones"])
+        keep = [np.ascontiguousarray(d["parent"], np.int32), np.ascontiguousarray(d["bind"], np.float32),
+                np.ascontiguousarray(d["inherit"], np.uint8)]
+        desc = SkeletonDesc(self.num_bones, int(d["blend_mode"]), *[a.ctypes.data for a in keep], None)
+        if use_given_bind_inverse:
+            bi = np.ascontiguousarray(d["bind_inverse"], np.float32)
+            desc.bind_inverse = bi.ctypes.data
+        h = C.c_void_p()
+        check(lib().ogrecu_skel_create(ctx.handle, C.byref(desc), C.byref(h)))
+        self.handle = h.value
+        for a in d["anims"]:
+            self.add_animation(a)
+
+    def add_animation(self, a):
+        arrs = [np.ascontiguousarray(a["track_bone"], np.int32), np.ascontiguousarray(a["track_shortest"], np.uint8),
+                np.ascontiguousarray(a["key_offset"], np.uint32), np.ascontiguousarray(a["keys"], np.float32)]
+        desc = AnimationDesc(float(a["length"]), int(a["interpolation"]), int(a["rotation_interpolation"]), len(arrs[0]),
+                             *[x.ctypes.data for x in arrs])
+        idx = C.c_uint32()
+        check(lib().ogrecu_skel_add_animation(self.handle, C.byref(desc), C.byref(idx)))
+        return idx.value
+
+    def set_blend_mode(self, mode):
+        check(lib().ogrecu_skel_set_blend_mode(self.handle, int(mode)))
+
+    def bind_inverse(self):
+        out = np.zeros((self.num_bones, 10), np.float32)
+        check(lib().ogrecu_skel_get_bind_inverse(self.handle, out.ctypes.data))
+        return out
+
+    def palettes_dev(self, num_instances, num_states, anim_ptr, time_ptr, weight_ptr, out_ptr, stride_floats=None):
+        check(lib().ogrecu_skel_palettes_dev(self.handle, int(num_instances), int(num_states), anim_ptr, time_ptr, weight_ptr,
+                                             out_ptr, int(stride_floats or self.num_bones * 16)))
+
+    def palettes(self, anim, time, weight):
+        """Host convenience (tests): anim/time/weight [num_instances, num_states] -> palettes [num_instances, num_bones, 16]."""
+        anim = np.ascontiguousarray(anim, np.int32); time = np.ascontiguousarray(time, np.float32)
+        weight = np.ascontiguousarray(weight, np.float32)
+        ni, ns = anim.shape
+        da, dt, dw = self.ctx.to_device(anim), self.ctx.to_device(time), self.ctx.to_device(weight)
+        out = self.ctx.alloc(ni * self.num_bones * 64)
+        self.palettes_dev(ni, ns, da.ptr, dt.ptr, dw.ptr, out.ptr)
+        res = out.download(np.float32).reshape(ni, self.num_bones, 16)
+        for b in (da, dt, dw, out):
+            b.free()
+        return res
+
+    def destroy(self):
+        if self.handle:
+            check(lib().ogrecu_skel_destroy(self.handle))
+            self.handle = None
 
 
 class Texture:

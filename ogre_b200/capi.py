@@ -50,6 +50,19 @@ class DrawDesc(C.Structure):
     ]
 
 
+class SkeletonDesc(C.Structure):
+    """ogrecu_skeleton_desc (include/ogrecu.h)"""
+    _fields_ = [("num_bones", C.c_uint32), ("blend_mode", C.c_uint32), ("parent", C.c_void_p), ("bind", C.c_void_p),
+                ("inherit", C.c_void_p), ("bind_inverse", C.c_void_p)]
+
+
+class AnimationDesc(C.Structure):
+    """ogrecu_animation_desc (include/ogrecu.h)"""
+    _fields_ = [("length", C.c_float), ("interpolation", C.c_uint32), ("rotation_interpolation", C.c_uint32),
+                ("num_tracks", C.c_uint32), ("track_bone", C.c_void_p), ("track_shortest", C.c_void_p),
+                ("key_offset", C.c_void_p), ("keys", C.c_void_p)]
+
+
 class RasterStats(C.Structure):
     _fields_ = [("triangles_in", C.c_uint64), ("triangles_binned", C.c_uint64),
                 ("tile_pairs", C.c_uint64), ("tiles_active", C.c_uint64),
@@ -86,6 +99,13 @@ SIGNATURES = {
     "ogrecu_buf_mark_device_dirty": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t]),
     "ogrecu_buf_resolve": (C.c_int, [C.c_void_p, C.c_void_p, c_void_pp, C.POINTER(C.c_size_t)]),
     "ogrecu_skin_dev": (C.c_int, [C.c_void_p, C.POINTER(SkinJob), C.c_uint32]),
+    "ogrecu_skel_create": (C.c_int, [C.c_void_p, C.POINTER(SkeletonDesc), c_void_pp]),
+    "ogrecu_skel_destroy": (C.c_int, [C.c_void_p]),
+    "ogrecu_skel_add_animation": (C.c_int, [C.c_void_p, C.POINTER(AnimationDesc), C.POINTER(C.c_uint32)]),
+    "ogrecu_skel_set_blend_mode": (C.c_int, [C.c_void_p, C.c_uint32]),
+    "ogrecu_skel_get_bind_inverse": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ogrecu_skel_palettes_dev": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                           C.c_size_t]),
     "ogrecu_skin_instanced_dev": (C.c_int, [C.c_void_p, C.POINTER(SkinJob), C.c_uint32, C.c_size_t, C.c_size_t, C.c_size_t]),
     "ogrecu_anim_instanced_dev": (C.c_int, [C.c_void_p, C.POINTER(SkinJob), C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
                                             C.c_uint32, C.c_size_t, C.c_size_t]),

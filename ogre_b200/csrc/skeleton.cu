@@ -1,0 +1,438 @@
+// skeleton.cu — bone-palette production for many instances of one skeleton, on the device.
+//
+// Reference work replaced (per entity, per frame, on the CPU render thread):
+//   Entity::cacheBoneMatrices                     OgreMain/src/OgreEntity.cpp:1307-1330
+//     SkeletonInstance::setAnimationState         OgreMain/src/OgreSkeleton.cpp:162-217
+//       Animation::apply / _getTimeIndex          OgreMain/src/OgreAnimation.cpp:326-342,594-618
+//       NodeAnimationTrack::applyToNode           OgreMain/src/OgreAnimationTrack.cpp:57-126,373-512
+//     Skeleton::_getBoneMatrices                  OgreMain/src/OgreSkeleton.cpp:402-424
+//       Node::updateFromParentImpl                OgreMain/src/OgreNode.cpp:202-256
+//       Bone::_getOffsetTransform                 OgreMain/src/OgreBone.cpp:88-105
+//       TransformBaseReal::makeTransform          OgreMain/src/OgreMatrix4.cpp:205-222
+//
+// Why on the device: at 10 000 instances the palettes are 44 MB per frame; uploading them costs more than skinning
+// the 55 M vertices.  The animation STATES (index, time, weight) are 12 bytes per slot.
+//
+// Layout: the key frames of every animation live in HBM once (shared by all instances, L2-resident: Sinbad's 13
+// animations are 440 KB).  One thread per (instance, bone):
+//   1. local transform = binding pose, then each enabled state's interpolated key frame applied in slot order;
+//   2. derived transforms level by level through shared memory (parents are one level up, __syncthreads between);
+//   3. offset transform -> Affine3, written as four 16-byte stores (consecutive bones are consecutive in memory).
+// Every float operation is written in the reference's association; the library is compiled with -fmad=false, so
+// each operator below is one IEEE binary32 rounding on the device exactly as it is on the host (x86-64, no FMA).
+#include "common.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+using namespace ogrecu;
+
+namespace ogrecu {
+
+struct Quat { float w, x, y, z; };
+struct Vec3 { float x, y, z; };
+struct Xform { Vec3 p; Quat q; Vec3 s; };
+
+#define HD __host__ __device__ __forceinline__
+
+HD Quat q_mul(const Quat& a, const Quat& b)
+{
+    return Quat{a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z, a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y,
+                a.w * b.y + a.y * b.w + a.z * b.x - a.x * b.z, a.w * b.z + a.z * b.w + a.x * b.y - a.y * b.x};
+}
+
+HD Quat q_unit(const Quat& q)       // Quaternion::normalise: (1.0f / len) * q
+{
+    const float len = sqrtf(q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z);
+    const float s = 1.0f / len;
+    return Quat{s * q.w, s * q.x, s * q.y, s * q.z};
+}
+
+HD Quat q_nlerp(float t, const Quat& p, const Quat& q, bool shortest)
+{
+    const float c = p.w * q.w + p.x * q.x + p.y * q.y + p.z * q.z;
+    Quat r;
+    if (c < 0.0f && shortest) r = Quat{p.w + t * ((-q.w) - p.w), p.x + t * ((-q.x) - p.x), p.y + t * ((-q.y) - p.y), p.z + t * ((-q.z) - p.z)};
+    else r = Quat{p.w + t * (q.w - p.w), p.x + t * (q.x - p.x), p.y + t * (q.y - p.y), p.z + t * (q.z - p.z)};
+    return q_unit(r);
+}
+
+HD Vec3 q_rotate(const Quat& q, const Vec3& v)      // Quaternion * Vector3 ("nVidia SDK implementation")
+{
+    Vec3 uv{q.y * v.z - q.z * v.y, q.z * v.x - q.x * v.z, q.x * v.y - q.y * v.x};
+    Vec3 uuv{q.y * uv.z - q.z * uv.y, q.z * uv.x - q.x * uv.z, q.x * uv.y - q.y * uv.x};
+    const float tw = 2.0f * q.w;
+    uv.x *= tw; uv.y *= tw; uv.z *= tw;
+    uuv.x *= 2.0f; uuv.y *= 2.0f; uuv.z *= 2.0f;
+    return Vec3{(v.x + uv.x) + uuv.x, (v.y + uv.y) + uuv.y, (v.z + uv.z) + uuv.z};
+}
+
+// Node::updateFromParentImpl with a parent
+HD Xform derive(const Xform& P, const Xform& L, bool inherit_orientation, bool inherit_scale)
+{
+    Xform d;
+    d.q = inherit_orientation ? q_mul(P.q, L.q) : L.q;
+    d.s = inherit_scale ? Vec3{P.s.x * L.s.x, P.s.y * L.s.y, P.s.z * L.s.z} : L.s;
+    const Vec3 r = q_rotate(P.q, Vec3{P.s.x * L.p.x, P.s.y * L.p.y, P.s.z * L.p.z});
+    d.p = Vec3{r.x + P.p.x, r.y + P.p.y, r.z + P.p.z};
+    return d;
+}
+
+HD Xform load_xform(const float* f) { return Xform{Vec3{f[0], f[1], f[2]}, Quat{f[3], f[4], f[5], f[6]}, Vec3{f[7], f[8], f[9]}}; }
+
+// per-animation device record
+struct AnimDev {
+    float length;
+    uint32_t num_times;             // entries of the global key-time list (Animation::buildKeyFrameTimeList)
+    const float* times;             // [num_times] sorted, unique
+    const int32_t* bone_track;      // [num_bones] track of the bone, -1 = none
+    const uint32_t* key_offset;     // [num_tracks + 1]
+    const uint8_t* shortest;        // [num_tracks]
+    const uint16_t* index_map;      // [num_tracks][num_times] AnimationTrack::_buildKeyFrameIndexMap
+    const float4* keys;             // [num_keys][3]: (time, tx, ty, tz) (rw, rx, ry, rz) (sx, sy, sz, -)
+};
+
+struct SkelDev {
+    uint32_t num_bones, blend_mode, num_levels, num_anims;
+    const int32_t* parent;          // [num_bones]
+    const uint8_t* level;           // [num_bones] depth below the root
+    const uint8_t* inherit;         // [num_bones][2]
+    const float* bind;              // [num_bones][10]
+    const float* bind_inverse;      // [num_bones][10]
+    const AnimDev* anims;           // [num_anims]
+};
+
+// blockDim = (bones rounded up to a warp, instances per CTA)
+__global__ void __launch_bounds__(512) skel_palette_kernel(const SkelDev S, uint32_t num_instances, uint32_t num_states,
+                                                           const int32_t* __restrict__ anim, const float* __restrict__ time,
+                                                           const float* __restrict__ weight, float* __restrict__ out,
+                                                           size_t stride_floats)
+{
+    extern __shared__ float s_derived[];                      // [instances per CTA][num_bones][10]
+    const uint32_t b = threadIdx.x;
+    const uint32_t inst = blockIdx.x * blockDim.y + threadIdx.y;
+    const bool live = b < S.num_bones && inst < num_instances;
+    float* mine = s_derived + ((size_t)threadIdx.y * S.num_bones + (live ? b : 0)) * 10;
+
+    Xform L{};
+    uint32_t lvl = 0xffffffffu;
+    int32_t par = -1;
+    if (live) {
+        L = load_xform(S.bind + 10 * b);                      // Skeleton::reset
+        lvl = S.level[b];
+        par = S.parent[b];
+        const int32_t* ia = anim + (size_t)inst * num_states;
+        const float* it = time + (size_t)inst * num_states;
+        const float* iw = weight + (size_t)inst * num_states;
+        float factor = 1.0f;
+        if (S.blend_mode == 0) {                              // ANIMBLEND_AVERAGE: rebalance when the weights sum above 1
+            float total = 0.0f;
+            for (uint32_t s = 0; s < num_states; ++s)
+                if (ia[s] >= 0) total += iw[s];
+            if (total > 1.0f) factor = 1.0f / total;
+        }
+        for (uint32_t s = 0; s < num_states; ++s) {
+            const int32_t a = ia[s];
+            if (a < 0 || (uint32_t)a >= S.num_anims) continue;
+            const AnimDev A = S.anims[a];
+            const float w = iw[s] * factor;
+            const int32_t trk = A.bone_track[b];
+            if (trk < 0 || !w) continue;
+            const uint32_t k0 = A.key_offset[trk], nk = A.key_offset[trk + 1] - k0;
+            if (nk == 0) continue;
+            // Animation::_getTimeIndex: wrap, then lower_bound over [begin, end - 1)
+            float tp = it[s];
+            if (tp > A.length && A.length > 0.0f) tp = fmodf(tp, A.length);
+            uint32_t lo = 0, hi = A.num_times - 1;
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (A.times[mid] < tp) lo = mid + 1; else hi = mid;
+            }
+            // AnimationTrack::getKeyFramesAtTime
+            uint32_t i = A.index_map[(size_t)trk * A.num_times + lo];
+            const float4* K = A.keys + 3 * (size_t)k0;
+            const uint32_t i2 = i;                            // k2: the key the index map names (k1 may step back from it)
+            const float4 k2a = K[3 * i2];
+            const float t2 = k2a.x;
+            if (i != 0 && tp < t2) --i;
+            const float4 k1a = K[3 * i], k1b = K[3 * i + 1], k1c = K[3 * i + 2];
+            const float t1 = k1a.x;
+            const float f = (t1 == t2) ? 0.0f : (tp - t1) / (t2 - t1);
+            const bool shortest = A.shortest[trk] != 0;
+            // NodeAnimationTrack::getInterpolatedKeyFrame (IM_LINEAR, RIM_LINEAR)
+            Vec3 tr{k1a.y, k1a.z, k1a.w}, sc{k1c.x, k1c.y, k1c.z};
+            Quat ro{k1b.x, k1b.y, k1b.z, k1b.w};
+            if (f != 0.0f) {
+                const float4 k2b = K[3 * i2 + 1], k2c = K[3 * i2 + 2];
+                ro = q_nlerp(f, ro, Quat{k2b.x, k2b.y, k2b.z, k2b.w}, shortest);
+                tr = Vec3{k1a.y + f * (k2a.y - k1a.y), k1a.z + f * (k2a.z - k1a.z), k1a.w + f * (k2a.w - k1a.w)};
+                sc = Vec3{k1c.x + f * (k2c.x - k1c.x), k1c.y + f * (k2c.y - k1c.y), k1c.z + f * (k2c.z - k1c.z)};
+            }
+            // NodeAnimationTrack::applyToNode (scale argument 1.0: no linked skeleton)
+            const float scl = 1.0f;
+            L.p.x += tr.x * w * scl; L.p.y += tr.y * w * scl; L.p.z += tr.z * w * scl;
+            const Quat rot = q_nlerp(w, Quat{1.0f, 0.0f, 0.0f, 0.0f}, ro, shortest);
+            L.q = q_unit(q_mul(L.q, rot));                    // Node::rotate, TS_LOCAL, then normalise
+            if ((sc.x != 1.0f || sc.y != 1.0f || sc.z != 1.0f) && w != 1.0f)
+                sc = Vec3{1.0f + w * (sc.x - 1.0f), 1.0f + w * (sc.y - 1.0f), 1.0f + w * (sc.z - 1.0f)};
+            L.s.x *= sc.x; L.s.y *= sc.y; L.s.z *= sc.z;
+        }
+    }
+
+    // derived transforms, one tree level per round
+    Xform D = L;
+    for (uint32_t l = 0; l < S.num_levels; ++l) {
+        if (live && lvl == l) {
+            if (par >= 0) {
+                const Xform P = load_xform(s_derived + ((size_t)threadIdx.y * S.num_bones + par) * 10);
+                D = derive(P, L, S.inherit[2 * b] != 0, S.inherit[2 * b + 1] != 0);
+            }
+            mine[0] = D.p.x; mine[1] = D.p.y; mine[2] = D.p.z; mine[3] = D.q.w; mine[4] = D.q.x; mine[5] = D.q.y; mine[6] = D.q.z;
+            mine[7] = D.s.x; mine[8] = D.s.y; mine[9] = D.s.z;
+        }
+        __syncthreads();
+    }
+    if (!live) return;
+
+    // Bone::_getOffsetTransform + makeTransform (Quaternion::ToRotationMatrix, OgreQuaternion.cpp:84-108)
+    const Xform I = load_xform(S.bind_inverse + 10 * b);
+    const Vec3 ls{D.s.x * I.s.x, D.s.y * I.s.y, D.s.z * I.s.z};
+    const Quat lr = q_mul(D.q, I.q);
+    const Vec3 rp = q_rotate(lr, Vec3{ls.x * I.p.x, ls.y * I.p.y, ls.z * I.p.z});
+    const Vec3 lt{D.p.x + rp.x, D.p.y + rp.y, D.p.z + rp.z};
+    const float tx = lr.x + lr.x, ty = lr.y + lr.y, tz = lr.z + lr.z;
+    const float twx = tx * lr.w, twy = ty * lr.w, twz = tz * lr.w;
+    const float txx = tx * lr.x, txy = ty * lr.x, txz = tz * lr.x;
+    const float tyy = ty * lr.y, tyz = tz * lr.y, tzz = tz * lr.z;
+    float4* o = reinterpret_cast<float4*>(out + (size_t)inst * stride_floats + 16 * (size_t)b);
+    o[0] = make_float4(ls.x * (1.0f - (tyy + tzz)), ls.y * (txy - twz), ls.z * (txz + twy), lt.x);
+    o[1] = make_float4(ls.x * (txy + twz), ls.y * (1.0f - (txx + tzz)), ls.z * (tyz - twx), lt.y);
+    o[2] = make_float4(ls.x * (txz - twy), ls.y * (tyz + twx), ls.z * (1.0f - (txx + tyy)), lt.z);
+    o[3] = make_float4(0.0f, 0.0f, 0.0f, 1.0f);
+}
+
+}  // namespace ogrecu
+
+// ---------------------------------------------------------------------------------------------- host side
+
+struct ogrecu_skel {
+    ogrecu_ctx* ctx;
+    uint32_t num_bones, blend_mode, num_levels;
+    std::vector<int32_t> parent;
+    std::vector<float> bind_inverse;
+    // device copies of the bone table
+    int32_t* d_parent; uint8_t* d_level; uint8_t* d_inherit; float* d_bind; float* d_bind_inverse;
+    // animations: host mirror of the device records + the device table
+    std::vector<AnimDev> anims;
+    std::vector<void*> owned;               // device blocks of the animations
+    AnimDev* d_anims; size_t d_anims_cap;
+};
+
+namespace {
+
+template <typename T>
+int upload(ogrecu_ctx* ctx, const T* host, size_t n, T** dev)
+{
+    *dev = nullptr;
+    OGRECU_CUDA(cudaMalloc((void**)dev, std::max<size_t>(n, 1) * sizeof(T)));
+    if (n) OGRECU_CUDA(cudaMemcpyAsync(*dev, host, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    OGRECU_CUDA(cudaStreamSynchronize(ctx->stream));      // the host source may be a temporary
+    return OGRECU_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ogrecu_skel_create(ogrecu_ctx* ctx, const ogrecu_skeleton_desc* d, ogrecu_skel** out)
+{
+    OGRECU_REQUIRE(ctx && d && out, "NULL argument");
+    *out = nullptr;
+    OGRECU_REQUIRE(d->num_bones >= 1 && d->num_bones <= 256, "num_bones must be 1..256");
+    OGRECU_REQUIRE(d->parent && d->bind, "parent and bind tables are required");
+    OGRECU_REQUIRE(d->blend_mode <= 1, "blend_mode is 0 (average) or 1 (cumulative)");
+    const uint32_t n = d->num_bones;
+    // tree levels (also rejects cycles and dangling parents)
+    std::vector<uint8_t> level(n, 0xff);
+    uint32_t done = 0, levels = 0;
+    for (uint32_t b = 0; b < n; ++b) OGRECU_REQUIRE(d->parent[b] < (int32_t)n && d->parent[b] != (int32_t)b, "bad parent handle");
+    for (uint32_t l = 0; done < n; ++l) {
+        OGRECU_REQUIRE(l < 255, "bone hierarchy deeper than 254 levels or cyclic");
+        uint32_t before = done;
+        std::vector<uint32_t> now;
+        for (uint32_t b = 0; b < n; ++b)
+            if (level[b] == 0xff && (d->parent[b] < 0 ? l == 0 : (level[d->parent[b]] != 0xff && level[d->parent[b]] < l))) now.push_back(b);
+        for (uint32_t b : now) { level[b] = (uint8_t)l; ++done; }
+        OGRECU_REQUIRE(done > before, "bone hierarchy is cyclic");
+        levels = l + 1;
+    }
+    std::vector<uint8_t> inherit(2 * n, 1);
+    if (d->inherit) memcpy(inherit.data(), d->inherit, 2 * n);
+    // binding-pose inverses (Bone::setBindingPose, OgreBone.cpp:66-74) unless the engine's own are given
+    std::vector<float> inv(10 * (size_t)n);
+    if (d->bind_inverse) {
+        memcpy(inv.data(), d->bind_inverse, inv.size() * sizeof(float));
+    } else {
+        std::vector<Xform> der(n);
+        for (uint32_t l = 0; l < levels; ++l)
+            for (uint32_t b = 0; b < n; ++b) {
+                if (level[b] != l) continue;
+                const Xform L = load_xform(d->bind + 10 * b);
+                der[b] = d->parent[b] < 0 ? L : derive(der[d->parent[b]], L, inherit[2 * b] != 0, inherit[2 * b + 1] != 0);
+            }
+        for (uint32_t b = 0; b < n; ++b) {
+            float* o = inv.data() + 10 * (size_t)b;
+            const Xform& D = der[b];
+            o[0] = -D.p.x; o[1] = -D.p.y; o[2] = -D.p.z;
+            const float norm = D.q.w * D.q.w + D.q.x * D.q.x + D.q.y * D.q.y + D.q.z * D.q.z;     // Quaternion::Inverse
+            if (norm > 0.0f) { const float r = 1.0f / norm; o[3] = D.q.w * r; o[4] = -D.q.x * r; o[5] = -D.q.y * r; o[6] = -D.q.z * r; }
+            else o[3] = o[4] = o[5] = o[6] = 0.0f;
+            o[7] = 1.0f / D.s.x; o[8] = 1.0f / D.s.y; o[9] = 1.0f / D.s.z;
+        }
+    }
+    OGRECU_CUDA(cudaSetDevice(ctx->device));
+    ogrecu_skel* s = new ogrecu_skel();
+    s->ctx = ctx; s->num_bones = n; s->blend_mode = d->blend_mode; s->num_levels = levels;
+    s->parent.assign(d->parent, d->parent + n);
+    s->bind_inverse = inv;
+    s->d_anims = nullptr; s->d_anims_cap = 0;
+    int rc = upload(ctx, d->parent, n, &s->d_parent);
+    if (!rc) rc = upload(ctx, level.data(), n, &s->d_level);
+    if (!rc) rc = upload(ctx, inherit.data(), 2 * (size_t)n, &s->d_inherit);
+    if (!rc) rc = upload(ctx, d->bind, 10 * (size_t)n, &s->d_bind);
+    if (!rc) rc = upload(ctx, inv.data(), inv.size(), &s->d_bind_inverse);
+    if (rc) { ogrecu_skel_destroy(s); return rc; }
+    *out = s;
+    return OGRECU_OK;
+}
+
+int ogrecu_skel_destroy(ogrecu_skel* s)
+{
+    if (!s) return OGRECU_OK;
+    cudaSetDevice(s->ctx->device);
+    cudaStreamSynchronize(s->ctx->stream);
+    for (void* p : {(void*)s->d_parent, (void*)s->d_level, (void*)s->d_inherit, (void*)s->d_bind, (void*)s->d_bind_inverse, (void*)s->d_anims})
+        if (p) cudaFree(p);
+    for (void* p : s->owned) cudaFree(p);
+    delete s;
+    return OGRECU_OK;
+}
+
+int ogrecu_skel_set_blend_mode(ogrecu_skel* s, uint32_t mode)
+{
+    OGRECU_REQUIRE(s && mode <= 1, "blend_mode is 0 (average) or 1 (cumulative)");
+    s->blend_mode = mode;
+    return OGRECU_OK;
+}
+
+int ogrecu_skel_get_bind_inverse(ogrecu_skel* s, float* out)
+{
+    OGRECU_REQUIRE(s && out, "NULL argument");
+    memcpy(out, s->bind_inverse.data(), s->bind_inverse.size() * sizeof(float));
+    return OGRECU_OK;
+}
+
+int ogrecu_skel_add_animation(ogrecu_skel* s, const ogrecu_animation_desc* d, uint32_t* out_index)
+{
+    OGRECU_REQUIRE(s && d, "NULL argument");
+    if (d->interpolation != 0 || d->rotation_interpolation != 0) {
+        set_error("ogrecu_skel_add_animation: only IM_LINEAR / RIM_LINEAR animations are supported (got %u / %u)", d->interpolation,
+                  d->rotation_interpolation);
+        return OGRECU_ERR_UNSUPPORTED;
+    }
+    OGRECU_REQUIRE(d->num_tracks == 0 || (d->track_bone && d->key_offset && d->keys), "track tables are required");
+    const uint32_t nt = d->num_tracks, nb = s->num_bones;
+    const uint32_t nkeys = nt ? d->key_offset[nt] : 0;
+    std::vector<int32_t> bone_track(nb, -1);
+    for (uint32_t t = 0; t < nt; ++t) {
+        OGRECU_REQUIRE(d->track_bone[t] >= 0 && (uint32_t)d->track_bone[t] < nb, "track names a bone outside the skeleton");
+        OGRECU_REQUIRE(bone_track[d->track_bone[t]] < 0, "two tracks for one bone");
+        OGRECU_REQUIRE(d->key_offset[t] <= d->key_offset[t + 1] && d->key_offset[t + 1] - d->key_offset[t] <= 65535, "bad key range");
+        bone_track[d->track_bone[t]] = (int32_t)t;
+        for (uint32_t k = d->key_offset[t] + 1; k < d->key_offset[t + 1]; ++k)
+            OGRECU_REQUIRE(d->keys[11 * (size_t)k] >= d->keys[11 * (size_t)(k - 1)], "key frames of a track must be sorted by time");
+    }
+    // Animation::buildKeyFrameTimeList (OgreAnimation.cpp:620-660): the sorted set of all key times ...
+    std::vector<float> times(nkeys);
+    for (uint32_t k = 0; k < nkeys; ++k) times[k] = d->keys[11 * (size_t)k];
+    std::sort(times.begin(), times.end());
+    times.erase(std::unique(times.begin(), times.end()), times.end());
+    if (times.empty()) times.push_back(0.0f);
+    const uint32_t ntimes = (uint32_t)times.size();
+    // ... and every track's global -> local key index map (AnimationTrack::_buildKeyFrameIndexMap, OgreAnimationTrack.cpp:190-206)
+    std::vector<uint16_t> index_map((size_t)std::max(nt, 1u) * ntimes, 0);
+    for (uint32_t t = 0; t < nt; ++t) {
+        const uint32_t k0 = d->key_offset[t], nk = d->key_offset[t + 1] - k0;
+        uint32_t i = 0;
+        for (uint32_t j = 0; j < ntimes; ++j) {
+            index_map[(size_t)t * ntimes + j] = (uint16_t)i;
+            while (nk && i + 1 < nk && d->keys[11 * (size_t)(k0 + i)] <= times[j]) ++i;
+        }
+    }
+    std::vector<float4> keys(3 * (size_t)std::max(nkeys, 1u));
+    for (uint32_t k = 0; k < nkeys; ++k) {
+        const float* f = d->keys + 11 * (size_t)k;
+        keys[3 * k] = make_float4(f[0], f[1], f[2], f[3]);
+        keys[3 * k + 1] = make_float4(f[4], f[5], f[6], f[7]);
+        keys[3 * k + 2] = make_float4(f[8], f[9], f[10], 0.0f);
+    }
+    std::vector<uint8_t> shortest(std::max(nt, 1u), 1);
+    if (d->track_shortest) memcpy(shortest.data(), d->track_shortest, nt);
+    std::vector<uint32_t> key_offset(nt + 1, 0);
+    if (nt) memcpy(key_offset.data(), d->key_offset, (nt + 1) * sizeof(uint32_t));
+
+    ogrecu_ctx* ctx = s->ctx;
+    OGRECU_CUDA(cudaSetDevice(ctx->device));
+    AnimDev A{};
+    A.length = d->length; A.num_times = ntimes;
+    float* d_times; int32_t* d_bt; uint32_t* d_ko; uint8_t* d_sh; uint16_t* d_im; float4* d_keys;
+    OGRECU_CHECK(upload(ctx, times.data(), times.size(), &d_times)); s->owned.push_back(d_times);
+    OGRECU_CHECK(upload(ctx, bone_track.data(), bone_track.size(), &d_bt)); s->owned.push_back(d_bt);
+    OGRECU_CHECK(upload(ctx, key_offset.data(), key_offset.size(), &d_ko)); s->owned.push_back(d_ko);
+    OGRECU_CHECK(upload(ctx, shortest.data(), shortest.size(), &d_sh)); s->owned.push_back(d_sh);
+    OGRECU_CHECK(upload(ctx, index_map.data(), index_map.size(), &d_im)); s->owned.push_back(d_im);
+    OGRECU_CHECK(upload(ctx, keys.data(), keys.size(), &d_keys)); s->owned.push_back(d_keys);
+    A.times = d_times; A.bone_track = d_bt; A.key_offset = d_ko; A.shortest = d_sh; A.index_map = d_im; A.keys = d_keys;
+    s->anims.push_back(A);
+    // the device table of records: regrown geometrically, rewritten whole (animations are added at load time)
+    if (s->anims.size() > s->d_anims_cap) {
+        OGRECU_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (s->d_anims) OGRECU_CUDA(cudaFree(s->d_anims));
+        s->d_anims = nullptr;
+        s->d_anims_cap = std::max<size_t>(16, 2 * s->anims.size());
+        OGRECU_CUDA(cudaMalloc((void**)&s->d_anims, s->d_anims_cap * sizeof(AnimDev)));
+    }
+    OGRECU_CUDA(cudaMemcpyAsync(s->d_anims, s->anims.data(), s->anims.size() * sizeof(AnimDev), cudaMemcpyHostToDevice, ctx->stream));
+    OGRECU_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (out_index) *out_index = (uint32_t)s->anims.size() - 1;
+    return OGRECU_OK;
+}
+
+int ogrecu_skel_palettes_dev(ogrecu_skel* s, uint32_t num_instances, uint32_t num_states, const int32_t* anim_dev,
+                             const float* time_dev, const float* weight_dev, float* palettes_dev, size_t stride_floats)
+{
+    OGRECU_REQUIRE(s && palettes_dev, "NULL argument");
+    if (!num_instances) return OGRECU_OK;
+    OGRECU_REQUIRE(num_states == 0 || (anim_dev && time_dev && weight_dev), "state arrays are required");
+    OGRECU_REQUIRE(num_states <= 64, "at most 64 animation-state slots per instance");
+    OGRECU_REQUIRE(stride_floats >= 16 * (size_t)s->num_bones && (stride_floats & 3) == 0, "palette stride too small or not a multiple of 4 floats");
+    OGRECU_REQUIRE(((uintptr_t)palettes_dev & 15) == 0, "palettes_dev must be 16-byte aligned");
+    ogrecu_ctx* ctx = s->ctx;
+    OGRECU_CUDA(cudaSetDevice(ctx->device));
+    SkelDev S{};
+    S.num_bones = s->num_bones; S.blend_mode = s->blend_mode; S.num_levels = s->num_levels; S.num_anims = (uint32_t)s->anims.size();
+    S.parent = s->d_parent; S.level = s->d_level; S.inherit = s->d_inherit; S.bind = s->d_bind; S.bind_inverse = s->d_bind_inverse;
+    S.anims = s->d_anims;
+    const uint32_t bx = (s->num_bones + 31) & ~31u;
+    const uint32_t by = std::max(1u, 256u / bx);
+    dim3 block(bx, by), grid(div_up(num_instances, by));
+    const size_t smem = (size_t)by * s->num_bones * 10 * sizeof(float);
+    skel_palette_kernel<<<grid, block, smem, ctx->stream>>>(S, num_instances, num_states, anim_dev, time_dev, weight_dev, palettes_dev,
+                                                           stride_floats);
+    OGRECU_CUDA(cudaGetLastError());
+    count_launch(ctx);
+    return OGRECU_OK;
+}
+
+}  // extern "C"
