@@ -382,9 +382,61 @@ def run_ours(args):
         # device -> pinned host, synchronous: the step's result is on the host when this returns
         check(L.ogrecu_memcpy_d2h(ctx.handle, houts[0].value, last["dst"].data_ptr() + (ninst - 1) * out_bytes, out_bytes))
 
+    # ---- end to end with the bone palettes PRODUCED ON THE DEVICE: the host supplies only each
+    # instance's animation state (animation index, time position, weight: 12 B) and morph weight; ogrecu_skel_palettes_dev
+    # does SkeletonInstance::setAnimationState + _getBoneMatrices for all instances, the skinning kernels read the result.
+    from ogre_b200 import Skeleton
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from goldenlib import load_skeleton
+    skel_def, _ = load_skeleton("sinbad_skeleton.npz")
+    assert skel_def["num_bones"] == nb
+    skel = Skeleton(ctx, skel_def)
+    st_n = 3 * ninst * 4
+    hs = C.c_void_p()
+    check(L.ogrecu_host_alloc(st_n, C.byref(hs)))
+    st_h = np.ctypeslib.as_array(C.cast(hs.value, C.POINTER(C.c_uint8)), shape=(st_n,))
+    dance_len = np.float32(skel_def["anims"][0]["length"])
+    st_h[:ninst * 4].view(np.int32)[:] = 0                                                   # animation 0 ("Dance")
+    st_h[ninst * 4:2 * ninst * 4].view(np.float32)[:] = np.mod((np.arange(ninst) * 0.01 + rank).astype(np.float32), dance_len)
+    st_h[2 * ninst * 4:].view(np.float32)[:] = 1.0
+    with torch.cuda.stream(stream):
+        st_sets = [torch.empty(st_n, dtype=torch.uint8, device=dev) for _ in range(2)]
+
+    def produce_palettes(b):
+        p = st_sets[b].data_ptr()
+        skel.palettes_dev(ninst, 1, p, p + ninst * 4, p + 2 * ninst * 4, pal_sets[b].data_ptr(), nb * 16)
+
+    st_k = [0]
+
+    def step_states():
+        k = st_k[0]; st_k[0] += 1
+        b = k & 1
+        check(L.ogrecu_memcpy_h2d_on(ctx.handle, cstream.cuda_stream, st_sets[b].data_ptr(), hs.value, st_n))
+        check(L.ogrecu_memcpy_h2d_on(ctx.handle, cstream.cuda_stream, t_sets[b].data_ptr(), ht.value, t_h.nbytes))
+        uploaded[b].record(cstream)
+        stream.wait_event(uploaded[b])
+        produce_palettes(b)
+        step_set(b)
+        check(L.ogrecu_memcpy_d2h_async(ctx.handle, houts[b].value, last["dst"].data_ptr() + (ninst - 1) * out_bytes, out_bytes))
+        done[b].record(stream)
+        if k > 0:
+            done[b ^ 1].synchronize()
+
     for _ in range(3):
         step_e2e_serial()
     ms_e2e_serial = timed(step_e2e_serial, args.steps)
+    for _ in range(4):
+        step_states()
+    torch.cuda.synchronize()
+    launches1 = ctx.launch_count
+    ms_states = timed(step_states, args.steps)
+    launches_states = ctx.launch_count - launches1
+    states_value = world * ninst * nverts * args.steps / (ms_states * 1e-3) / 1e6
+    ms_pal = timed(lambda: produce_palettes(0), 50) / 50
+    # restore the host-palette inputs in both sets for the timing below (the palette kernel overwrote them)
+    for b in (0, 1):
+        check(L.ogrecu_memcpy_h2d(ctx.handle, pal_sets[b].data_ptr(), hp.value, pal_h.nbytes))
+    ctx.sync()
     for _ in range(4):
         step_e2e()
     torch.cuda.synchronize()
@@ -472,6 +524,11 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": "Mvert/s", "h2d_bytes_per_step": int(pal_h.nbytes + t_h.nbytes),
                     "d2h_bytes_per_step": int(out_bytes), "ms_per_step": ms_e2e / args.steps,
                     "serial_value": e2e_serial_value, "serial_ms_per_step": ms_e2e_serial / args.steps,
+                    "states_value": states_value, "states_ms_per_step": ms_states / args.steps,
+                    "states_h2d_bytes_per_step": int(st_n + t_h.nbytes), "states_gpu_launches": int(launches_states),
+                    "states_note": "same step with the bone palettes produced on the device (ogrecu_skel_palettes_dev, %.1f us per "
+                                   "launch for %d instances x %d bones): the host uploads each instance's animation state (12 B) and "
+                                   "morph weight instead of its %d-byte palette" % (ms_pal * 1e3, ninst, nb, nb * 64),
                     "note": "two frames in flight (upload of step k+1 on a copy stream overlaps the kernels of step k); serial_value = "
                             "upload -> kernels -> read-back on one stream; skinned vertex buffers stay in HBM for _render, one instance "
                             "is read back per step as the result"},
@@ -479,7 +536,8 @@ def run_ours(args):
         }
         print(json.dumps(line))
     ctx.set_stream(None)
-    for h in [hp, ht] + houts:
+    skel.destroy()
+    for h in [hp, ht, hs] + houts:
         L.ogrecu_host_free(h)
     if dist is not None:
         dist.destroy_process_group()
