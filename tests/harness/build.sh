@@ -8,6 +8,8 @@ REF="${OGRE_REFERENCE:-/root/reference}"
 [ -d "$REF" ] || { echo "harness/build.sh: $REF absent; keeping prebuilt harness"; exit 0; }
 /usr/bin/g++ -O2 -DNDEBUG -msse -std=c++14 -fPIC -w -pthread -fvisibility=hidden \
     -I"$ROOT/oracle/_ref/include" -I"$REF/OgreMain/include" -I"$REF/OgreMain/include/Threading" \
+    -I"$ROOT/ogre_b200/plugin/include" -I"$ROOT/include" \
     -shared -o "$HERE/libplugin_harness.so" "$HERE/plugin_harness.cpp" \
-    -L"$ROOT/oracle/_ref/lib" -lOgreMain -Wl,-rpath,'$ORIGIN/../../oracle/_ref/lib'
+    -L"$ROOT/oracle/_ref/lib" -lOgreMain -L"$ROOT/ogre_b200/plugin" -l:RenderSystem_CUDA.so \
+    -Wl,-rpath,'$ORIGIN/../../oracle/_ref/lib' -Wl,-rpath,'$ORIGIN/../../ogre_b200/plugin'
 echo "harness/build.sh: ok"

@@ -9,6 +9,7 @@
 #include <OgreSkeletonInstance.h>
 #include <OgreHardwarePixelBuffer.h>
 #include <OgreRenderTexture.h>
+#include "OgreCudaSkeletonPalettes.h"
 
 #include <chrono>
 #include <csignal>
@@ -248,6 +249,36 @@ API int ph_skel_pose(float time)
     return 0;
     CATCH(1)
 }
+
+// Bone palettes of the entity's first animation at n time positions: `engine` from the real SkeletonInstance
+// (setAnimationState + _getBoneMatrices, one pose after the other), `device` from the plugin's CudaSkeletonPalettes
+// (all n AnimationStateSets in one launch).  Both n x numBones x 16 floats.  CUDA plugin only.
+API int ph_skel_palettes(uint32_t n, const float* times, float* engine, float* device)
+{
+    TRY
+    Entity* e = g->ent;
+    if (!e || !e->hasSkeleton()) { g_err = "no skeletal entity"; return 2; }
+    SkeletonInstance* sk = e->getSkeleton();
+    const size_t nb = sk->getNumBones();
+    AnimationStateSet* set = e->getAllAnimationStates();
+    AnimationState* first = nullptr;
+    for (auto& kv : set->getAnimationStates()) { kv.second->setEnabled(false); if (!first) first = kv.second; }
+    first->setLoop(true); first->setEnabled(true); first->setWeight(1.0f);
+    std::vector<std::unique_ptr<AnimationStateSet>> copies;
+    std::vector<const AnimationStateSet*> ptrs;
+    for (uint32_t i = 0; i < n; ++i) {
+        first->setTimePosition(times[i]);
+        sk->setAnimationState(*set);
+        sk->_getBoneMatrices(reinterpret_cast<Affine3*>(engine) + i * nb);
+        copies.emplace_back(new AnimationStateSet(*set));
+        ptrs.push_back(copies.back().get());
+    }
+    CudaSkeletonPalettes pal(sk);
+    pal.getBoneMatrices(ptrs.data(), n, reinterpret_cast<Affine3*>(device));
+    return 0;
+    CATCH(1)
+}
+API size_t ph_skel_num_bones(void) { return g->ent && g->ent->hasSkeleton() ? g->ent->getSkeleton()->getNumBones() : 0; }
 
 API size_t ph_skel_num_subs(void) { return g_skinned.size(); }
 API size_t ph_skel_sub_size(size_t i) { return g_skinned[i].size(); }

@@ -33,6 +33,7 @@ def main():
     ap.add_argument("--quad", action="store_true")
     ap.add_argument("--skel", default="")
     ap.add_argument("--time", type=int, default=0)
+    ap.add_argument("--palettes", type=int, default=0, help="bone palettes at N time positions: engine vs CudaSkeletonPalettes")
     a = ap.parse_args()
     w, h = [int(v) for v in a.size.split("x")]
     so, name = PLUGINS[a.plugin]
@@ -68,6 +69,14 @@ def main():
             for i in range(L.ph_skel_num_subs()):
                 n = L.ph_skel_sub_size(i)
                 out["skinned_t%d_s%d" % (k, i)] = np.ctypeslib.as_array(C.cast(L.ph_skel_sub_data(i), C.POINTER(C.c_uint8)), shape=(n,)).copy()
+    if a.palettes:
+        L.ph_skel_num_bones.restype = C.c_size_t
+        L.ph_skel_palettes.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+        nb = L.ph_skel_num_bones()
+        times = (np.arange(a.palettes, dtype=np.float32) * np.float32(0.0371)).astype(np.float32)
+        eng = np.zeros((a.palettes, nb, 16), np.float32); dev = np.zeros_like(eng)
+        ok(L.ph_skel_palettes(a.palettes, times.ctypes.data, eng.ctypes.data, dev.ctypes.data), "ph_skel_palettes")
+        out["palettes_engine"], out["palettes_device"], out["palette_times"] = eng, dev, times
     ok(L.ph_render(), "ph_render")
     colour = np.zeros((h, w, 3), np.uint8)
     ok(L.ph_read_colour(colour.ctypes.data, 0), "ph_read_colour")

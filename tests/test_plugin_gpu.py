@@ -100,3 +100,12 @@ def test_render_texture_can_be_sampled(tmp_path):
     texels = set(map(tuple, rtt.reshape(-1, 3)))
     sample = q[fg][::97]
     assert all(tuple(p) in texels for p in sample)
+
+
+@pytest.mark.parametrize("mesh", ["Sinbad.mesh", "jaiqua.mesh"])
+def test_bone_palettes_through_the_plugin_equal_the_engines(tmp_path, mesh):
+    """CudaSkeletonPalettes (plugin class over ogrecu_skel_*) built from the entity's real SkeletonInstance: 200 poses
+    of the first animation in one launch vs SkeletonInstance::setAnimationState + _getBoneMatrices pose by pose."""
+    z = run_scene(tmp_path, "cuda", "--mesh", mesh, "--size", "64x64", "--cam-z", "30", "--palettes", "200")
+    assert z["palettes_engine"].shape[0] == 200 and np.abs(z["palettes_engine"]).sum() > 0
+    assert np.array_equal(bits(z["palettes_device"]), bits(z["palettes_engine"]))
