@@ -292,6 +292,10 @@ OGRECU_API int ogrecu_calculate_light_facing_host(ogrecu_ctx* ctx, const float* 
  * CPU-vendor dependent). */
 OGRECU_API int ogrecu_extrude_dev(ogrecu_ctx* ctx, const float* light4_host, float extrude_dist,
                                   const float* src, float* dst, size_t num_vertices);
+/* the same for 1..8 lights in one launch (lights_host = n_lights x 4 floats): the positions are read once, light k
+ * writes dst + k*dst_light_stride_floats; per light bit-identical to ogrecu_extrude_dev */
+OGRECU_API int ogrecu_extrude_multi_dev(ogrecu_ctx* ctx, const float* lights_host, uint32_t n_lights, float extrude_dist,
+                                        const float* src, float* dst, size_t dst_light_stride_floats, size_t num_vertices);
 OGRECU_API int ogrecu_extrude_vertices_host(ogrecu_ctx* ctx, const float* light4, float extrude_dist,
                                             const float* src, float* dst, size_t num_vertices);
 

@@ -129,6 +129,7 @@ SIGNATURES = {
                                                 C.c_size_t, C.c_size_t]),
     "ogrecu_calculate_light_facing_host": (C.c_int, [C.c_void_p, c_float_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "ogrecu_extrude_dev": (C.c_int, [C.c_void_p, c_float_p, C.c_float, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "ogrecu_extrude_multi_dev": (C.c_int, [C.c_void_p, c_float_p, C.c_uint32, C.c_float, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]),
     "ogrecu_extrude_vertices_host": (C.c_int, [C.c_void_p, c_float_p, C.c_float, C.c_void_p, C.c_void_p, C.c_size_t]),
     "ogrecu_tex_create": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, c_void_pp]),
     "ogrecu_tex_destroy": (C.c_int, [C.c_void_p]),

@@ -386,6 +386,53 @@ __global__ void extrude_kernel(float lx, float ly, float lz, float dist, const f
     }
 }
 
+// 1..8 lights per launch: the positions are read once and extruded away from (or along) every light; light k
+// writes dst + k*dst_light_stride floats.  Per light the arithmetic is extrude_kernel's.  A shadow-casting frame
+// extrudes the same vertices for each light (ShadowCaster::extrudeVertices, OgreShadowCaster.cpp:535), so 8 lights move
+// 12 + 8*12 B per vertex in one launch instead of 8 x 24 B in eight 24 MB launches whose latency dominates.
+__global__ void extrude_multi_kernel(const __grid_constant__ Lights L, uint32_t nlights, float dist, const float* __restrict__ src,
+                                     float* __restrict__ dst, size_t dst_light_stride, size_t n, int aligned)
+{
+    size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t v0 = g * 4;
+    if (v0 >= n) return;
+    int cnt = (n - v0) >= 4 ? 4 : (int)(n - v0);
+    float s[12], o[12];
+    const bool vec = aligned && cnt == 4;
+    if (vec) {
+        const float4* p = reinterpret_cast<const float4*>(src + v0 * 3);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { float4 v = __ldg(p + k); s[4 * k] = v.x; s[4 * k + 1] = v.y; s[4 * k + 2] = v.z; s[4 * k + 3] = v.w; }
+    } else {
+        for (int k = 0; k < cnt * 3; ++k) s[k] = src[v0 * 3 + k];
+    }
+    {
+        // blockIdx.y = light: the eight passes over the positions run concurrently and re-read them from L2 (12 MB per
+        // million vertices), so DRAM still sees them once; one thread per light keeps 8x the threads in flight than a
+        // per-thread loop over the lights (measured: 34.8 us for 8 lights x 1 M vertices with the loop)
+        const uint32_t li = blockIdx.y;
+        const float lx = L.l[li][0], ly = L.l[li][1], lz = L.l[li][2];
+        const bool point = !(L.l[li][3] == 0.0f);
+        float ex = 0.f, ey = 0.f, ez = 0.f;
+        if (!point) extrude_dir(-lx, -ly, -lz, dist, ex, ey, ez);
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            if (v < cnt) {
+                if (point) extrude_dir(fsub(s[3 * v], lx), fsub(s[3 * v + 1], ly), fsub(s[3 * v + 2], lz), dist, ex, ey, ez);
+                o[3 * v] = fadd(s[3 * v], ex); o[3 * v + 1] = fadd(s[3 * v + 1], ey); o[3 * v + 2] = fadd(s[3 * v + 2], ez);
+            }
+        }
+        float* d = dst + li * dst_light_stride + v0 * 3;
+        if (vec) {
+            float4* q = reinterpret_cast<float4*>(d);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) __stcs(q + k, make_float4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]));
+        } else {
+            for (int k = 0; k < cnt * 3; ++k) d[k] = o[k];
+        }
+    }
+}
+
 inline bool aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
 
 int validate_skin_job(const ogrecu_skin_job& j)
@@ -641,6 +688,25 @@ int ogrecu_light_facing_multi_dev(ogrecu_ctx* ctx, const float* lights_host, uin
 int ogrecu_light_facing_dev(ogrecu_ctx* ctx, const float* light4_host, const float* face_normals, char* facings, size_t n)
 {
     return ogrecu_light_facing_multi_dev(ctx, light4_host, 1, face_normals, facings, 0, n);
+}
+
+int ogrecu_extrude_multi_dev(ogrecu_ctx* ctx, const float* lights_host, uint32_t n_lights, float dist, const float* src, float* dst,
+                             size_t dst_light_stride_floats, size_t n)
+{
+    OGRECU_REQUIRE(ctx && lights_host, "NULL argument");
+    OGRECU_REQUIRE(n_lights >= 1 && n_lights <= 8, "1..8 lights per launch");
+    if (n == 0) return OGRECU_OK;
+    OGRECU_REQUIRE(src && dst && ((((uintptr_t)src | (uintptr_t)dst) & 3) == 0), "streams must be non-NULL and 4-byte aligned");
+    OGRECU_REQUIRE(n_lights == 1 || dst_light_stride_floats >= 3 * n, "destinations of different lights overlap");
+    OGRECU_CUDA(cudaSetDevice(ctx->device));
+    Lights L;
+    memset(&L, 0, sizeof L);
+    memcpy(L.l, lights_host, (size_t)n_lights * 16);
+    const int al = aligned16(src) && aligned16(dst) && (n_lights == 1 || (dst_light_stride_floats & 3) == 0);
+    extrude_multi_kernel<<<dim3(div_up(div_up(n, 4), 256), n_lights), 256, 0, ctx->stream>>>(L, n_lights, dist, src, dst, dst_light_stride_floats, n, al);
+    OGRECU_CUDA(cudaGetLastError());
+    count_launch(ctx);
+    return OGRECU_OK;
 }
 
 int ogrecu_extrude_dev(ogrecu_ctx* ctx, const float* l, float dist, const float* src, float* dst, size_t n)

@@ -7,10 +7,10 @@
 //   clearFrameBuffer, readback                                  OgreTinyRenderSystem.cpp:421-433, OgreTinyWindow.cpp:68-80
 //
 // Pipeline per flush (all on the context stream):
-//   K1 setup_kernel    1 thread / triangle: vertex shader x3, viewport, 1/w, cull, bbox, adjugate
-//                      -> 80-byte "hot" + 64-byte "cold" record, tile count
-//      scan            exclusive scan of tile counts (order-preserving pair offsets)
-//   K2 bin_kernel      (tile, triangle) pairs written in submission order
+//   K0 vertex_xf       1 thread / vertex: vertex shader, viewport, 1/w -> float4 (once per flush, not per index)
+//   K1 setup_count / setup_scan / setup_write   1 thread / triangle, 1024 per CTA: cull, bbox, tile coverage;
+//                      survivors get a compact 64-byte record (varyings are fetched at shade time) and their
+//                      (tile, triangle) pairs, both in submission order (spin-free count -> scan -> write)
 //      radix sort      stable LSD sort of the pairs by tile key -> per-tile lists in submission order
 //   K3 raster_kernel   1 CTA / 16x16 tile, 1 pixel / thread; pixel depth+colour live in registers
 //                      while the tile's triangle list is replayed IN ORDER (bit-exact blend,
@@ -253,7 +253,9 @@ __device__ __forceinline__ void cta_draw_cache(const SegParams& P, uint32_t g0, 
 
 // K1a: per CTA of 1024 triangles, how many survive and how many (tile, triangle) pairs they make.
 // (A spin-free "reduce, scan the block table, then write" compaction: the single-pass chained scan
-//  measured 30 % of its time waiting in the look-back, profiles/r01d notes.)
+//  measured 30 % of its time waiting in the look-back, profiles/r01d notes.  Measured and rejected in r01k: issuing
+//  the index loads of all four rounds before the first vertex gather — setup_write goes from 64 to 80 registers,
+//  one CTA less per SM, C5 2.16 -> 2.25 ms.)
 __global__ void __launch_bounds__(SB_THREADS) setup_count_kernel(SegParams P)
 {
     __shared__ uint32_t s_lo, s_wp[8], s_wt[8];

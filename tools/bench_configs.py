@@ -192,9 +192,14 @@ def c3(ctx, T, args):
         for k in range(8):
             check(L.ogrecu_extrude_dev(ctx.handle, C.cast(lights[k].ctypes.data, capi.c_float_p), 40.0, dpos.ptr, dext.ptr + k * nv * 12, nv))
 
+    def extrude_fused():
+        check(L.ogrecu_extrude_multi_dev(ctx.handle, lp, 8, 40.0, dpos.ptr, dext.ptr, nv * 3, nv))
+
     def frame():
-        fn(); facing(); extrude()
+        fn(); facing(); extrude_fused()
     t_fn, t_fac, t_ext, t_all = T.time(fn), T.time(facing), T.time(extrude), T.time(frame)
+    t_extf = T.time(extrude_fused)
+    b_extf = nv * 12 + 8 * nv * 12
     b_fn = nt * 48 + nv * 12
     b_fac = nt * 16 + 8 * nt           # normals read ONCE for the 8 lights (fused), 8 facing bytes written
     b_ext = 8 * nv * 24
@@ -202,7 +207,9 @@ def c3(ctx, T, args):
            "ms_per_frame": t_all * 1e3, "frames_per_s": 1 / t_all,
            "face_normals": {"ms": t_fn * 1e3, "Mtri_per_s": nt / t_fn / 1e6, "GBps": b_fn / t_fn / 1e9, "frac_of_hbm_peak": b_fn / t_fn / 1e9 / PEAK},
            "light_facing_8_fused": {"ms": t_fac * 1e3, "Mface_light_per_s": 8 * nt / t_fac / 1e6, "GBps": b_fac / t_fac / 1e9, "frac_of_hbm_peak": b_fac / t_fac / 1e9 / PEAK},
-           "extrude_8": {"ms": t_ext * 1e3, "Mvert_per_s": 8 * nv / t_ext / 1e6, "GBps": b_ext / t_ext / 1e9, "frac_of_hbm_peak": b_ext / t_ext / 1e9 / PEAK}}
+           "extrude_8": {"ms": t_ext * 1e3, "Mvert_per_s": 8 * nv / t_ext / 1e6, "GBps": b_ext / t_ext / 1e9, "frac_of_hbm_peak": b_ext / t_ext / 1e9 / PEAK},
+           "extrude_8_fused": {"ms": t_extf * 1e3, "Mvert_per_s": 8 * nv / t_extf / 1e6, "GBps": b_extf / t_extf / 1e9,
+                               "frac_of_hbm_peak": b_extf / t_extf / 1e9 / PEAK, "note": "one launch, positions read once (frame uses this)"}}
     if args.cpu:
         from oracle import ref
         if ref.available():

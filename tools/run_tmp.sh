@@ -1,2 +1,2 @@
-ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_c5_r01k.csv python tools/bench_configs.py --config c5 > /dev/null 2>&1; echo rc=$?
-ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_c4_r01k.csv python tools/bench_configs.py --config c4 --views 32 > /dev/null 2>&1; echo rc=$?
+timeout 900 python -m pytest tests/test_raster_gpu.py tests/test_raster_paths_gpu.py tests/test_golden_gpu.py tests/test_optutil_gpu.py -x -q 2>&1 | tail -3
+python tools/bench_configs.py --config c3,c4,c5 --views 256 | cut -c1-1000
