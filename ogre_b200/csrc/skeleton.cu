@@ -17,6 +17,7 @@
 // animations are 440 KB).  One thread per (instance, bone):
 //   1. local transform = binding pose, then each enabled state's interpolated key frame applied in slot order;
 //   2. derived transforms level by level through shared memory (parents are one level up, __syncthreads between);
+//      threads take the bones in level order, so a warp runs the derivation step for one or two levels only;
 //   3. offset transform -> Affine3, written as four 16-byte stores (consecutive bones are consecutive in memory).
 // Every float operation is written in the reference's association; the library is compiled with -fmad=false, so
 // each operator below is one IEEE binary32 rounding on the device exactly as it is on the host (x86-64, no FMA).
@@ -97,6 +98,8 @@ struct SkelDev {
     uint32_t num_bones, blend_mode, num_levels, num_anims;
     const int32_t* parent;          // [num_bones]
     const uint8_t* level;           // [num_bones] depth below the root
+    const uint16_t* order;          // [num_bones] bone handled by thread x: bones sorted by level, so that a warp holds one or
+                                    // two adjacent levels and runs the derivation step once or twice, not once per level
     const uint8_t* inherit;         // [num_bones][2]
     const float* bind;              // [num_bones][10]
     const float* bind_inverse;      // [num_bones][10]
@@ -110,9 +113,9 @@ __global__ void __launch_bounds__(512) skel_palette_kernel(const SkelDev S, uint
                                                            size_t stride_floats)
 {
     extern __shared__ float s_derived[];                      // [instances per CTA][num_bones][10]
-    const uint32_t b = threadIdx.x;
     const uint32_t inst = blockIdx.x * blockDim.y + threadIdx.y;
-    const bool live = b < S.num_bones && inst < num_instances;
+    const bool live = threadIdx.x < S.num_bones && inst < num_instances;
+    const uint32_t b = live ? S.order[threadIdx.x] : 0u;
     float* mine = s_derived + ((size_t)threadIdx.y * S.num_bones + (live ? b : 0)) * 10;
 
     Xform L{};
@@ -222,7 +225,7 @@ struct ogrecu_skel {
     std::vector<int32_t> parent;
     std::vector<float> bind_inverse;
     // device copies of the bone table
-    int32_t* d_parent; uint8_t* d_level; uint8_t* d_inherit; float* d_bind; float* d_bind_inverse;
+    int32_t* d_parent; uint8_t* d_level; uint16_t* d_order; uint8_t* d_inherit; float* d_bind; float* d_bind_inverse;
     // animations: host mirror of the device records + the device table
     std::vector<AnimDev> anims;
     std::vector<void*> owned;               // device blocks of the animations
@@ -299,6 +302,10 @@ int ogrecu_skel_create(ogrecu_ctx* ctx, const ogrecu_skeleton_desc* d, ogrecu_sk
     s->d_anims = nullptr; s->d_anims_cap = 0;
     int rc = upload(ctx, d->parent, n, &s->d_parent);
     if (!rc) rc = upload(ctx, level.data(), n, &s->d_level);
+    std::vector<uint16_t> order(n);
+    for (uint32_t b = 0; b < n; ++b) order[b] = (uint16_t)b;
+    std::stable_sort(order.begin(), order.end(), [&](uint16_t x, uint16_t y) { return level[x] < level[y]; });
+    if (!rc) rc = upload(ctx, order.data(), n, &s->d_order);
     if (!rc) rc = upload(ctx, inherit.data(), 2 * (size_t)n, &s->d_inherit);
     if (!rc) rc = upload(ctx, d->bind, 10 * (size_t)n, &s->d_bind);
     if (!rc) rc = upload(ctx, inv.data(), inv.size(), &s->d_bind_inverse);
@@ -312,7 +319,7 @@ int ogrecu_skel_destroy(ogrecu_skel* s)
     if (!s) return OGRECU_OK;
     cudaSetDevice(s->ctx->device);
     cudaStreamSynchronize(s->ctx->stream);
-    for (void* p : {(void*)s->d_parent, (void*)s->d_level, (void*)s->d_inherit, (void*)s->d_bind, (void*)s->d_bind_inverse, (void*)s->d_anims})
+    for (void* p : {(void*)s->d_parent, (void*)s->d_level, (void*)s->d_order, (void*)s->d_inherit, (void*)s->d_bind, (void*)s->d_bind_inverse, (void*)s->d_anims})
         if (p) cudaFree(p);
     for (void* p : s->owned) cudaFree(p);
     delete s;
@@ -422,7 +429,7 @@ int ogrecu_skel_palettes_dev(ogrecu_skel* s, uint32_t num_instances, uint32_t nu
     OGRECU_CUDA(cudaSetDevice(ctx->device));
     SkelDev S{};
     S.num_bones = s->num_bones; S.blend_mode = s->blend_mode; S.num_levels = s->num_levels; S.num_anims = (uint32_t)s->anims.size();
-    S.parent = s->d_parent; S.level = s->d_level; S.inherit = s->d_inherit; S.bind = s->d_bind; S.bind_inverse = s->d_bind_inverse;
+    S.parent = s->d_parent; S.level = s->d_level; S.order = s->d_order; S.inherit = s->d_inherit; S.bind = s->d_bind; S.bind_inverse = s->d_bind_inverse;
     S.anims = s->d_anims;
     const uint32_t bx = (s->num_bones + 31) & ~31u;
     const uint32_t by = std::max(1u, 256u / bx);
