@@ -376,6 +376,10 @@ OGRECU_API int ogrecu_draw_views(ogrecu_rt* const* rts, uint32_t n_views, const 
  * [y0, y1) (multiples of the tile height); planes outside are left untouched.  The owner
  * of a strip is the only writer, so the composite is a disjoint gather. */
 OGRECU_API int ogrecu_rt_set_strip(ogrecu_rt* rt, uint32_t y0, uint32_t y1);
+/* The load-balanced form: the frame is cut into bands of `band_rows` pixel rows (a multiple of the tile height) and this
+ * context rasterises the bands b with b % period == phase (rank and world size of the split).  Dense and empty
+ * regions of the screen then spread over all GPUs.  ogrecu_rt_set_strip(rt, 0, height) returns to the whole frame. */
+OGRECU_API int ogrecu_rt_set_bands(ogrecu_rt* rt, uint32_t band_rows, uint32_t phase, uint32_t period);
 
 /* Readback (TinyWindow::copyContentsToMemory, OgreTinyWindow.cpp:68-80;
  * HardwarePixelBuffer::blitToMemory).  Flushes pending work, copies the box

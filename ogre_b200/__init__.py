@@ -283,6 +283,9 @@ class RenderTarget:
     def set_strip(self, y0, y1):
         check(lib().ogrecu_rt_set_strip(self.handle, int(y0), int(y1)))
 
+    def set_bands(self, band_rows, phase, period):
+        check(lib().ogrecu_rt_set_bands(self.handle, int(band_rows), int(phase), int(period)))
+
     def read_colour(self, box=None, out=None):
         """copyContentsToMemory: `out` may be a preallocated (ideally pinned, see pinned_empty) array."""
         l, t, r, b = box if box else (0, 0, self.width, self.height)

@@ -145,6 +145,7 @@ SIGNATURES = {
     "ogrecu_flush": (C.c_int, [C.c_void_p]),
     "ogrecu_draw_views": (C.c_int, [C.POINTER(C.c_void_p), C.c_uint32, C.POINTER(DrawDesc), c_float_p, c_float_p, c_float_p]),
     "ogrecu_rt_set_strip": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
+    "ogrecu_rt_set_bands": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]),
     "ogrecu_rt_read_colour": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t]),
     "ogrecu_rt_read_depth": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t]),
     "ogrecu_rt_write_colour": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),

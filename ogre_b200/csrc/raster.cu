@@ -94,6 +94,7 @@ struct SegParams {
     uint32_t width, height;
     uint32_t tiles_x, tiles_y;        // tiles per target
     uint32_t strip_ty0, strip_ty1;    // tile rows rasterised on this context
+    uint32_t band_tiles, band_phase, band_period;   // ... of which only bands with (ty / band_tiles) % period == phase (period 1: all)
     uint32_t* tile_flags;     // [ntargets*tiles_x*tiles_y]  bit 0: some triangle needs the in-order path
 };
 
@@ -152,6 +153,11 @@ __device__ __forceinline__ size_t vertex_index(const DrawDev& D, uint32_t t, int
 constexpr int SB_THREADS = 256;
 constexpr int SB_ROUNDS = 4;                         // 256-triangle rounds per CTA
 constexpr int SB_BLOCK = SB_THREADS * SB_ROUNDS;     // triangles per CTA = per entry of the block-aggregate table
+
+__device__ __forceinline__ bool owns_row(const SegParams& P, uint32_t ty)
+{
+    return P.band_period <= 1 || (ty / P.band_tiles) % P.band_period == P.band_phase;
+}
 
 struct TriSetup {
     float X[3], Y[3], Z[3], IW[3];
@@ -221,7 +227,14 @@ __device__ __forceinline__ void setup_triangle(const SegParams& P, uint32_t g, u
     if (ok) {
         int tx0 = T.x0 >> TILE_SHIFT, tx1 = T.x1 >> TILE_SHIFT;
         int ty0 = max(T.y0 >> TILE_SHIFT, (int)P.strip_ty0), ty1 = min(T.y1 >> TILE_SHIFT, (int)P.strip_ty1 - 1);
-        if (ty0 <= ty1) T.ntiles = (uint32_t)(tx1 - tx0 + 1) * (uint32_t)(ty1 - ty0 + 1);
+        if (ty0 <= ty1) {
+            uint32_t rows = (uint32_t)(ty1 - ty0 + 1);
+            if (P.band_period > 1) {                                           // interleaved bands: count the rows owned here
+                rows = 0;
+                for (int ty = ty0; ty <= ty1; ++ty) rows += owns_row(P, (uint32_t)ty) ? 1u : 0u;
+            }
+            T.ntiles = (uint32_t)(tx1 - tx0 + 1) * rows;
+        }
     }
     if (T.ntiles) {
         // Order-independent resolution (raster_kernel's visibility path) is only equivalent to Tiny's
@@ -369,12 +382,14 @@ __global__ void __launch_bounds__(SB_THREADS) setup_write_kernel(SegParams P)
             const uint32_t tbase = target * P.tiles_x * P.tiles_y;
             const uint32_t ci = (uint32_t)(base_t + et);
             uint64_t* out = P.pairs + base_p + ep;
-            for (int ty = ty0; ty <= ty1; ++ty)
+            for (int ty = ty0; ty <= ty1; ++ty) {
+                if (!owns_row(P, (uint32_t)ty)) continue;
                 for (int tx = tx0; tx <= tx1; ++tx) {
                     const uint32_t key = tbase + (uint32_t)ty * P.tiles_x + (uint32_t)tx;
                     *out++ = ((uint64_t)key << 32) | ci;
                     if (T.ordered) atomicOr(&P.tile_flags[key], 1u);
                 }
+            }
         }
         base_p += tp; base_t += tt;
     }
@@ -567,6 +582,7 @@ struct RasterParams {
     uint32_t* counters;            // [ntargets][2]: tiles resolved by the visibility path / replayed in order
     uint32_t width, height, tiles_x, tiles_y;
     uint32_t strip_ty0, strip_rows;
+    uint32_t band_tiles, band_phase, band_period;
 };
 
 __device__ __forceinline__ uint32_t shade_pack(float r, float g, float b)
@@ -712,7 +728,13 @@ __global__ void __launch_bounds__(RT_THREADS) raster_kernel(RasterParams P)
     const uint32_t per_target = P.tiles_x * P.strip_rows;
     const uint32_t target = blockIdx.x / per_target;
     const uint32_t rem = blockIdx.x - target * per_target;
-    const uint32_t ty = P.strip_ty0 + rem / P.tiles_x, tx = rem % P.tiles_x;
+    uint32_t ty = P.strip_ty0 + rem / P.tiles_x;
+    const uint32_t tx = rem % P.tiles_x;
+    if (P.band_period > 1) {                     // row r of this context's bands -> tile row of the frame
+        const uint32_t r = rem / P.tiles_x;
+        ty = (P.band_phase + (r / P.band_tiles) * P.band_period) * P.band_tiles + r % P.band_tiles;
+        if (ty >= P.tiles_y) return;
+    }
     const uint32_t key = target * P.tiles_x * P.tiles_y + ty * P.tiles_x + tx;
     const uint32_t start = P.tile_start[key], end = P.tile_start[key + 1];
     if (start == end) return;   // nothing to draw here: the planes already hold the result
@@ -988,6 +1010,7 @@ struct ogrecu_rt {
     uint8_t* colour;
     float* depth;
     uint32_t strip_y0, strip_y1;     // pixel rows rasterised here (multiples of TILE, or h)
+    uint32_t band_tiles = 1, band_phase = 0, band_period = 1;   // interleaved bands of tile rows (period 1 = every band)
     std::vector<Cmd> cmds;
     ogrecu_raster_stats stats;
     int stats_slot;          // index of this target in the last segment's counter table
@@ -1116,6 +1139,7 @@ int run_segment(ogrecu_ctx* ctx, ogrecu_rt* const* targets, uint32_t ntargets, c
     P.pairs = nullptr; P.pair_capacity = 0;
     P.width = W; P.height = H; P.tiles_x = tiles_x; P.tiles_y = tiles_y;
     P.strip_ty0 = strip_ty0; P.strip_ty1 = strip_ty1;
+    P.band_tiles = rt0->band_tiles; P.band_phase = rt0->band_phase; P.band_period = rt0->band_period;
 
     // ---- K0: every vertex of the flush transformed once
     if (nverts) {
@@ -1188,6 +1212,13 @@ int run_segment(ogrecu_ctx* ctx, ogrecu_rt* const* targets, uint32_t ntargets, c
     R.counters = (uint32_t*)S.counters.ptr;
     R.width = W; R.height = H; R.tiles_x = tiles_x; R.tiles_y = tiles_y;
     R.strip_ty0 = strip_ty0; R.strip_rows = strip_ty1 - strip_ty0;
+    R.band_tiles = rt0->band_tiles; R.band_phase = rt0->band_phase; R.band_period = rt0->band_period;
+    if (R.band_period > 1) {                     // rows of the bands owned here (the last band may be cut by the frame: those CTAs exit)
+        const uint32_t nbands = div_up(tiles_y, R.band_tiles);
+        const uint32_t mine = nbands > R.band_phase ? (nbands - R.band_phase + R.band_period - 1) / R.band_period : 0;
+        R.strip_rows = mine * R.band_tiles;
+        if (R.strip_rows == 0) return OGRECU_OK;
+    }
     const unsigned grid = ntargets * tiles_x * R.strip_rows;
     if (W % 16 == 0) raster_kernel<true><<<grid, RT_THREADS, 0, ctx->stream>>>(R);
     else raster_kernel<false><<<grid, RT_THREADS, 0, ctx->stream>>>(R);
@@ -1438,7 +1469,8 @@ int ogrecu_draw_views(ogrecu_rt* const* rts, uint32_t n_views, const ogrecu_draw
     for (uint32_t v = 0; v < n_views; ++v) {
         OGRECU_REQUIRE(rts[v] && rts[v]->ctx == ctx, "targets must share one context");
         OGRECU_REQUIRE(rts[v]->w == rts[0]->w && rts[v]->h == rts[0]->h, "targets must have identical size");
-        OGRECU_REQUIRE(rts[v]->strip_y0 == rts[0]->strip_y0 && rts[v]->strip_y1 == rts[0]->strip_y1, "targets must share the strip");
+        OGRECU_REQUIRE(rts[v]->strip_y0 == rts[0]->strip_y0 && rts[v]->strip_y1 == rts[0]->strip_y1 && rts[v]->band_period == rts[0]->band_period &&
+                       rts[v]->band_phase == rts[0]->band_phase && rts[v]->band_tiles == rts[0]->band_tiles, "targets must share the strip");
         OGRECU_CHECK(ogrecu_flush(rts[v]));   // earlier clears / draws on each target come first
     }
     OGRECU_CUDA(cudaSetDevice(ctx->device));
@@ -1458,6 +1490,18 @@ int ogrecu_rt_set_strip(ogrecu_rt* rt, uint32_t y0, uint32_t y1)
     OGRECU_CHECK(ogrecu_flush(rt));
     rt->strip_y0 = std::min(y0, rt->h);
     rt->strip_y1 = std::min(y1, rt->h);
+    rt->band_tiles = 1; rt->band_phase = 0; rt->band_period = 1;
+    return OGRECU_OK;
+}
+
+int ogrecu_rt_set_bands(ogrecu_rt* rt, uint32_t band_rows, uint32_t phase, uint32_t period)
+{
+    OGRECU_REQUIRE(rt, "rt is NULL");
+    OGRECU_REQUIRE(band_rows >= TILE && band_rows % TILE == 0, "band height must be a positive multiple of the tile height");
+    OGRECU_REQUIRE(period >= 1 && phase < period, "phase must be below period");
+    OGRECU_CHECK(ogrecu_flush(rt));
+    rt->strip_y0 = 0; rt->strip_y1 = rt->h;
+    rt->band_tiles = band_rows / TILE; rt->band_phase = phase; rt->band_period = period;
     return OGRECU_OK;
 }
 

@@ -3,9 +3,10 @@
 Three partitions, all without a data-path collective except the one exchange the path really has:
   * instances (skinning / morph / shadow streams): contiguous ranges, palettes travel with their instance;
   * offscreen views (config 4): view i -> rank i mod G, static geometry replicated once;
-  * one large frame (config 5): contiguous strips of screen-tile rows; every rank rasterises only its
-    strip (ogrecu_rt_set_strip) and the disjoint strips are GATHERED to one rank at readback — the only
-    collective, <= 24.9 MB for a 4K RGB8 frame, no blending.
+  * one large frame (config 5): contiguous strips of screen-tile rows (ogrecu_rt_set_strip) or, load-balanced,
+    interleaved bands of tile rows (ogrecu_rt_set_bands: band b -> rank b mod G); every rank rasterises only
+    its rows and the disjoint rows are GATHERED to one rank at readback — the only collective, <= 24.9 MB for a
+    4K RGB8 frame, no blending.
 torch.distributed is plumbing here (NCCL on GPUs, gloo in the CPU tests); nothing is computed.
 """
 import numpy as np
@@ -34,6 +35,37 @@ def strip_rows(height, rank, world, tile=TILE):
     if lo == hi:
         return 0, 0
     return lo * tile, min(hi * tile, height)
+
+
+def band_row_indices(height, rank, world, band_rows=TILE):
+    """Pixel rows owned by `rank` under the interleaved split (ogrecu_rt_set_bands): bands of `band_rows` rows,
+    band b -> rank b mod G.  Dense and empty screen regions spread over all ranks."""
+    rows = np.arange(int(height))
+    return rows[(rows // int(band_rows)) % int(world) == int(rank)]
+
+
+def gather_bands(plane, height, band_rows=TILE, dst=0, group=None):
+    """Composite of the interleaved split at readback: every rank passes its whole plane (torch tensor [height, width,
+    channels], only its own bands valid); its rows are packed, gathered to `dst` (padded to a common count) and scattered
+    back into place there.  Returns the full frame on `dst`, None elsewhere."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    idx = [band_row_indices(height, r, world, band_rows) for r in range(world)]
+    rows = max(len(i) for i in idx)
+    mine = torch.as_tensor(idx[rank], device=plane.device, dtype=torch.long)
+    send = torch.zeros((rows,) + tuple(plane.shape[1:]), dtype=plane.dtype, device=plane.device)
+    send[: len(mine)] = plane.index_select(0, mine)
+    recv = [torch.empty_like(send) for _ in range(world)] if rank == dst else None
+    dist.gather(send, recv, dst=dst, group=group)
+    if rank != dst:
+        return None
+    frame = torch.empty_like(plane)
+    for r in range(world):
+        ir = torch.as_tensor(idx[r], device=plane.device, dtype=torch.long)
+        frame.index_copy_(0, ir, recv[r][: len(ir)])
+    return frame
 
 
 def gather_strips(strip, y0, y1, height, dst=0, group=None):

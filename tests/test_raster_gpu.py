@@ -84,6 +84,34 @@ def test_split_frame_strips_compose(gpu_ctx):
     assert_images_equal(full_c, full_z, rc, rz, "split frame")
 
 
+@pytest.mark.parametrize("w,h,band,world", [(256, 160, 16, 3), (250, 150, 32, 4), (64, 33, 16, 8)])
+def test_split_frame_interleaved_bands_compose(gpu_ctx, w, h, band, world):
+    # load-balanced split (ogrecu_rt_set_bands): rank r owns the bands b with b % world == r; the owned rows of all
+    # ranks compose to the full frame, rows a rank does not own stay untouched (cleared value)
+    import ogre_b200
+    from ogre_b200.shard import band_row_indices
+    from rasterlib import GpuScene
+    cases = make_scene(21, w, h, ndraws=5, ntri=400)
+    rc, rz, _ = render_oracle(cases, w, h)
+    scene = GpuScene(gpu_ctx, cases)
+    full_c = np.zeros((h, w, 3), np.uint8); full_z = np.zeros((h, w), np.float32)
+    seen = np.zeros(h, int)
+    for r in range(world):
+        rt = ogre_b200.RenderTarget(gpu_ctx, w, h)
+        rt.set_bands(band, r, world)
+        scene.render(rt)
+        rows = band_row_indices(h, r, world, band)
+        seen[rows] += 1
+        c, z = rt.read_colour(), rt.read_depth()
+        full_c[rows] = c[rows]; full_z[rows] = z[rows]
+        others = np.setdiff1d(np.arange(h), rows)
+        assert (z[others] == 1.0).all(), "a rank wrote rows it does not own"
+        rt.destroy()
+    scene.free()
+    assert (seen == 1).all()
+    assert_images_equal(full_c, full_z, rc, rz, "interleaved split frame")
+
+
 def test_draw_views_equals_one_draw_per_view(gpu_ctx):
     # config 4 mechanics: one pipeline pass over n_views x triangles with per-view mvp / mvit / light
     import ctypes as C

@@ -12,6 +12,16 @@ import torch.multiprocessing as mp
 from ogre_b200 import shard
 
 
+def test_interleaved_bands_cover_every_row_once():
+    for h in (1, 15, 16, 17, 160, 2160):
+        for world in (1, 2, 3, 8):
+            for band in (16, 32, 64):
+                seen = np.zeros(h, int)
+                for r in range(world):
+                    seen[shard.band_row_indices(h, r, world, band)] += 1
+                assert (seen == 1).all(), (h, world, band)
+
+
 def test_partitions_cover_everything_once():
     for n in (0, 1, 7, 10000, 10001):
         for world in (1, 2, 3, 8):
@@ -59,6 +69,15 @@ def _worker(rank, world, port, w, h, out_dir):
         if rank == 0:
             assert frame is not None and np.array_equal(frame.numpy(), full)
             np.save(os.path.join(out_dir, "frame.npy"), frame.numpy())
+        else:
+            assert frame is None
+        # ---- the load-balanced split: interleaved bands; a rank's plane holds garbage outside its own rows
+        rows = shard.band_row_indices(h, rank, world, 16)
+        plane = np.full_like(full, 7 + rank)
+        plane[rows] = full[rows]
+        frame = shard.gather_bands(torch.from_numpy(plane), h, 16, dst=0)
+        if rank == 0:
+            assert np.array_equal(frame.numpy(), full)
         else:
             assert frame is None
         # ---- instance sharding: each rank skins its own instances; no collective, only the timing max

@@ -331,7 +331,7 @@ def c5_split(ctx, T, args, rt, run, ntri, nidx, nverts):
     Checked on rank 0 against the same frame rendered whole on one GPU."""
     import torch
     import torch.distributed as dist
-    from ogre_b200.shard import DevicePlane, gather_strips, strip_rows
+    from ogre_b200.shard import DevicePlane, gather_bands, gather_strips, strip_rows
     w, h = rt.width, rt.height
     p = C.c_void_p()
     check(lib().ogrecu_rt_colour_device_ptr(rt.handle, C.byref(p)))
@@ -354,12 +354,28 @@ def c5_split(ctx, T, args, rt, run, ntri, nidx, nverts):
         run()
         whole = rt.read_colour()
         ok = bool(np.array_equal(frame, whole))
+    # the load-balanced split: interleaved bands of one tile row each (band b -> rank b mod G)
+    rt.set_bands(16, RANK, WORLD)
+
+    def render_and_composite_bands():
+        run()
+        with torch.cuda.stream(T.stream):
+            result[0] = gather_bands(plane, h, 16, dst=0)
+    dt_render_b = T.time(run, iters=3, warm=1)
+    band_stats = rt.stats()
+    dt_b = T.time(render_and_composite_bands, iters=3, warm=1)
+    ok_b = None
+    if RANK == 0:
+        ok_b = bool(np.array_equal(result[0].cpu().numpy(), whole))
     T.barrier()
+    interleaved = {"ms_per_frame_render_only": dt_render_b * 1e3, "ms_per_frame_with_composite": dt_b * 1e3, "frames_per_s": 1 / dt_b,
+                   "Mtri_per_s": ntri / dt_b / 1e6, "identical_to_single_gpu_frame": ok_b, "stats_rank0": band_stats,
+                   "split": "interleaved bands of one tile row (ogrecu_rt_set_bands), band b -> GPU b mod G"}
     return {"config": "c5 one 3840x2160 frame, %d triangles, textured, lit: split-frame over %d GPUs (contiguous strips of tile rows), "
                       "NCCL gather of the strips to rank 0 at readback" % (ntri, WORLD), "n_gpus": WORLD,
             "ms_per_frame_render_only": dt_render * 1e3, "ms_per_frame_with_composite": dt * 1e3, "frames_per_s": 1 / dt,
             "Mtri_per_s": ntri / dt / 1e6, "composite_bytes": int(w * h * 3 * (WORLD - 1) / WORLD),
-            "identical_to_single_gpu_frame": ok, "stats_rank0_strip": strip_stats}
+            "identical_to_single_gpu_frame": ok, "stats_rank0_strip": strip_stats, "interleaved": interleaved}
 
 
 def main():
