@@ -103,6 +103,7 @@ __global__ void __launch_bounds__(SP_THREADS, SP_MIN_CTAS) skin_pair_kernel(cons
     uint8_t* s_src = s_dst + 4 * TILE_BYTES;                            // [2][2][TILE_BYTES]  (absent when FUSED)
     uint8_t* s_pal = s_src + (FUSED ? 0 : 4 * TILE_BYTES);              // [2][num_matrices][28 floats]
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_pal + 2 * pal_stage_bytes);   // [2]
+    float* s_t = reinterpret_cast<float*>(s_bar + 2);                   // [inst_per_cta] morph weights of this CTA's instances (FUSED)
 
     const uint32_t tid = threadIdx.x;
     const uint32_t v0 = blockIdx.x * SP_THREADS;
@@ -219,8 +220,11 @@ __global__ void __launch_bounds__(SP_THREADS, SP_MIN_CTAS) skin_pair_kernel(cons
 
     if (cnt == 0) return;
     issue_loads(0, i0, cnt > 1, true);
-    float tA_next = 0.f, tB_next = 0.f;
-    if (FUSED) { tA_next = __ldg(P.tarr + i0); tB_next = cnt > 1 ? __ldg(P.tarr + i0 + 1) : tA_next; }
+    // the morph weights of all this CTA's instances, staged once (a per-pass __ldg of the next pair's weights showed up
+    // as 7 % long-scoreboard stalls in ncu although it was issued a whole pass ahead)
+    if (FUSED) {
+        for (uint32_t k = tid; k < cnt; k += SP_THREADS) s_t[k] = __ldg(P.tarr + i0 + k);
+    }
 
     for (uint32_t j = 0; j < npairs; ++j) {
         const uint32_t s = j & 1u;
@@ -234,8 +238,7 @@ __global__ void __launch_bounds__(SP_THREADS, SP_MIN_CTAS) skin_pair_kernel(cons
         if (j + 1 < npairs) issue_loads(s ^ 1u, instA + 2, 2 * j + 3 < cnt, !src_shared);
         float tA = 0.f, tB = 0.f;
         if (FUSED) {
-            tA = tA_next; tB = tB_next;
-            if (j + 1 < npairs) { tA_next = __ldg(P.tarr + instA + 2); tB_next = (2 * j + 3 < cnt) ? __ldg(P.tarr + instA + 3) : tA_next; }
+            tA = s_t[2 * j]; tB = hasB ? s_t[2 * j + 1] : tA;           // visible since barrier (A) of pass 0
         }
 
         if (active) {
@@ -361,7 +364,7 @@ __global__ void __launch_bounds__(SP_THREADS, SP_MIN_CTAS) skin_pair_kernel(cons
 static size_t skin_pair_smem(bool norm, bool fused, uint32_t num_matrices)
 {
     const size_t tile = (size_t)SP_THREADS * (norm ? 24 : 12);
-    return 4 * tile + (fused ? 0 : 4 * tile) + 2 * (size_t)num_matrices * (SP_MSTRIDE * 4) + 16;
+    return 4 * tile + (fused ? 0 : 4 * tile) + 2 * (size_t)num_matrices * (SP_MSTRIDE * 4) + 16;   // + morph weights, see the launch
 }
 
 template <int NW, bool NORM, bool FUSED>
@@ -404,7 +407,7 @@ int launch_skin_pair(ogrecu_ctx* ctx, SkinTileParams P, uint32_t nw, bool norm, 
     P.inst_per_cta = (uint32_t)ipc;
     const uint32_t gy = div_up(P.num_instances, P.inst_per_cta);
     OGRECU_REQUIRE(gy <= 65535, "too many instance groups");
-    const size_t smem = skin_pair_smem(norm, fused, P.num_matrices);
+    const size_t smem = skin_pair_smem(norm, fused, P.num_matrices) + (fused ? (size_t)P.inst_per_cta * sizeof(float) : 0);
     dim3 grid(tiles, gy);
     if (norm) return fused ? launch_nw<true, true>(ctx, P, nw, grid, smem) : launch_nw<true, false>(ctx, P, nw, grid, smem);
     return fused ? launch_nw<false, true>(ctx, P, nw, grid, smem) : launch_nw<false, false>(ctx, P, nw, grid, smem);
