@@ -27,4 +27,8 @@ int launch_skin_tile(ogrecu_ctx* ctx, SkinTileParams P, uint32_t num_weights, bo
 // skin_pair.cu: same parameters (alignment fields already derived), two instances per pass.
 int launch_skin_pair(ogrecu_ctx* ctx, SkinTileParams P, uint32_t num_weights, bool with_normals, bool fused_morph);
 
+// skin_wide.cu: instances across the lanes (pos+normal, one source for all instances); alignment fields already derived.
+bool skin_wide_eligible(const SkinTileParams& P, bool with_normals, bool fused_morph);
+int launch_skin_wide(ogrecu_ctx* ctx, SkinTileParams P, uint32_t num_weights, bool fused_morph);
+
 }  // namespace ogrecu
