@@ -299,6 +299,32 @@ OGRECU_API int ogrecu_extrude_multi_dev(ogrecu_ctx* ctx, const float* lights_hos
 OGRECU_API int ogrecu_extrude_vertices_host(ogrecu_ctx* ctx, const float* light4, float extrude_dist,
                                             const float* src, float* dst, size_t num_vertices);
 
+/* ------------------------------------------ silhouette / shadow-volume indices ------ */
+/* ShadowCaster::generateShadowVolume (OgreMain/src/OgreShadowCaster.cpp:191-515) as an order-preserving stream
+ * compaction on the device.  The edge list of a mesh (EdgeData, OgreEdgeListBuilder.h:50-160) is uploaded once:
+ *   groups5[g] = {edge_start, edge_count, tri_start, tri_count, vertex_count}   (EdgeGroup; edge ranges consecutive)
+ *   edges5[e]  = {triIndex[0], triIndex[1], vertIndex[0], vertIndex[1], degenerate}
+ *   tris3[t]   = EdgeData::Triangle::vertIndex */
+typedef struct ogrecu_edges ogrecu_edges;
+#define OGRECU_SRF_INCLUDE_LIGHT_CAP 1u      /* ShadowRenderableFlags, OgreShadowCaster.h:110-120 */
+#define OGRECU_SRF_INCLUDE_DARK_CAP 2u
+#define OGRECU_SRF_EXTRUDE_TO_INFINITY 4u
+OGRECU_API int ogrecu_edges_create(ogrecu_ctx* ctx, uint32_t num_groups, const uint32_t* groups5, const uint32_t* edges5,
+                                   const uint32_t* tris3, uint32_t num_tris, ogrecu_edges** out);
+OGRECU_API int ogrecu_edges_destroy(ogrecu_edges* edges);
+/* the reference's useMcGuire decision (host arithmetic): bounds6 = light-cap bounds min xyz, max xyz; light4 = Light::getAs4DVector */
+OGRECU_API int ogrecu_shadow_use_mcguire(uint32_t num_groups, const float* bounds6, const float* light4);
+/* facings_dev = EdgeData::triangleLightFacings on the device (what ogrecu_light_facing_dev wrote).  Writes the indices
+ * (index_type 2 = 16-bit as the reference, 4 = 32-bit: lifts the 65 536-vertex limit of OgreShadowCaster.cpp:387) into
+ * indices_dev from *used_inout on — or from 0 when they would not fit behind it, as the reference wraps its shared
+ * buffer — and updates *used_inout.  ranges4_host[g] = {indexStart, indexCount, lightCapStart, lightCapCount} of the
+ * group's ShadowRenderable (the last two only with separate_light_cap and a light cap).  Synchronous, like the
+ * reference.  OGRECU_ERR_INVALID when the indices do not fit the buffer at all. */
+OGRECU_API int ogrecu_shadow_volume_dev(ogrecu_edges* edges, const char* facings_dev, int directional, int use_mcguire,
+                                        uint32_t flags, int separate_light_cap, uint32_t index_type, void* indices_dev,
+                                        uint32_t buffer_indices, uint32_t* used_inout, uint32_t* ranges4_host,
+                                        uint32_t* emitted);
+
 /* ------------------------------------------------------------------ rasteriser ----- */
 /* TinyTexture / TinyHardwarePixelBuffer (RenderSystems/Tiny/src/OgreTinyTexture.cpp:30-57):
  * always RGBA8, tightly packed, 0 mips. */

@@ -15,7 +15,7 @@ import numpy as np
 from . import capi
 from .capi import AnimationDesc, DrawDesc, OgrecuError, RasterStats, SkeletonDesc, SkinJob, check, lib
 
-__all__ = ["Context", "DeviceBuffer", "OptimisedUtil", "Skeleton", "Texture", "RenderTarget", "DrawDesc", "SkinJob",
+__all__ = ["Context", "DeviceBuffer", "OptimisedUtil", "Skeleton", "EdgeList", "Texture", "RenderTarget", "DrawDesc", "SkinJob",
            "OgrecuError", "addr", "pinned_empty"]
 
 MAP_READ, MAP_WRITE, MAP_DISCARD = 1, 2, 4
@@ -234,6 +234,39 @@ class Skeleton:
     def destroy(self):
         if self.handle:
             check(lib().ogrecu_skel_destroy(self.handle))
+            self.handle = None
+
+
+class EdgeList:
+    """Device-resident EdgeData (ogrecu_edges) + ShadowCaster::generateShadowVolume on it
+    (OgreMain/src/OgreShadowCaster.cpp:191-515).  `ed` = {groups[g,5], edges[e,5], tris[t,3]} (uint32)."""
+
+    def __init__(self, ctx, ed):
+        self.ctx = ctx
+        self.groups = np.ascontiguousarray(ed["groups"], np.uint32)
+        edges = np.ascontiguousarray(ed["edges"], np.uint32); tris = np.ascontiguousarray(ed["tris"], np.uint32)
+        self.num_tris = len(tris)
+        h = C.c_void_p()
+        check(lib().ogrecu_edges_create(ctx.handle, len(self.groups), self.groups.ctypes.data, edges.ctypes.data, tris.ctypes.data,
+                                        len(tris), C.byref(h)))
+        self.handle = h.value
+
+    def use_mcguire(self, bounds6, light4):
+        b = np.ascontiguousarray(bounds6, np.float32); l = np.ascontiguousarray(light4, np.float32)
+        return int(lib().ogrecu_shadow_use_mcguire(len(self.groups), b.ctypes.data, l.ctypes.data))
+
+    def shadow_volume(self, facings_ptr, directional, use_mcguire, flags, separate_light_cap, index_type, indices_ptr, buffer_indices,
+                      used_in):
+        used, emitted = C.c_uint32(int(used_in)), C.c_uint32()
+        ranges = np.zeros((len(self.groups), 4), np.uint32)
+        check(lib().ogrecu_shadow_volume_dev(self.handle, facings_ptr, int(directional), int(use_mcguire), int(flags), int(separate_light_cap),
+                                             int(index_type), indices_ptr, int(buffer_indices), C.byref(used), ranges.ctypes.data,
+                                             C.byref(emitted)))
+        return ranges, used.value, emitted.value
+
+    def destroy(self):
+        if self.handle:
+            check(lib().ogrecu_edges_destroy(self.handle))
             self.handle = None
 
 

@@ -100,6 +100,9 @@ def lib():
         l.oracle_tiny_clear.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_uint, vp, c_f]
         l.oracle_tiny_draw.argtypes = [C.POINTER(OracleDraw), vp, vp, C.c_uint32, C.c_uint32]
         l.oracle_tiny_draw.restype = C.c_uint64
+        l.oracle_shadow_use_mcguire.argtypes = [C.c_uint32, vp, vp]
+        l.oracle_shadow_volume.argtypes = [C.c_uint32, vp, vp, vp, vp, C.c_int, C.c_int, C.c_uint32, C.c_int, vp, C.c_uint32, vp, vp]
+        l.oracle_shadow_volume.restype = C.c_long
         l.oracle_skeleton_bind_inverse.argtypes = [C.POINTER(OracleSkeleton), vp]
         l.oracle_skeleton_bind_inverse.restype = None
         l.oracle_skeleton_palette.argtypes = [C.POINTER(OracleSkeleton), vp, C.POINTER(OracleAnimation), C.c_uint32, vp, vp, vp, vp]
@@ -129,3 +132,18 @@ def skin(kind, src_pos, dst_pos, src_norm, dst_norm, weight, index, mats, stride
     fn = lib().oracle_skin_sse if kind == "sse" else lib().oracle_skin_general
     fn(src_pos, dst_pos, src_norm, dst_norm, weight, index, pal, *strides, nw, n)
     return keep
+
+
+def shadow_volume(ed, facings, light4, bounds6, flags, separate_light_cap, buffer_indices, used_in, fill=0xCDCD):
+    """generateShadowVolume on the flat edge data `ed` = {groups[g,5], edges[e,5], tris[t,3]} -> (indices u16
+    [buffer_indices], ranges [g,4], used_out, emitted, use_mcguire)."""
+    light4 = np.ascontiguousarray(light4, np.float32); bounds6 = np.ascontiguousarray(bounds6, np.float32)
+    mc = lib().oracle_shadow_use_mcguire(len(ed["groups"]), bounds6.ctypes.data, light4.ctypes.data)
+    out = np.full(buffer_indices, fill, np.uint16)
+    ranges = np.zeros((len(ed["groups"]), 4), np.uint32)
+    used = C.c_uint32(used_in)
+    f = np.ascontiguousarray(facings, np.int8)
+    n = lib().oracle_shadow_volume(len(ed["groups"]), ed["groups"].ctypes.data, ed["edges"].ctypes.data, ed["tris"].ctypes.data, f.ctypes.data,
+                                   int(light4[3] == 0), mc, flags, int(separate_light_cap), out.ctypes.data, buffer_indices,
+                                   C.addressof(used), ranges.ctypes.data)
+    return out, ranges, used.value, n, mc

@@ -633,3 +633,121 @@ int oracle_skeleton_palette(const oracle_skeleton* sk, const float* bind_inverse
     free(local); free(derived);
     return rc;
 }
+
+
+/* ================================================== Silhouette / shadow-volume indices */
+
+int oracle_shadow_use_mcguire(uint32_t num_groups, const float* b, const float* light4)
+{
+    if (num_groups > 1) return 0;
+    if (light4[3] == 0.0f) return 1;                        /* LT_DIRECTIONAL */
+    const float lx = light4[0], ly = light4[1], lz = light4[2];
+    const float mnx = b[0], mny = b[1], mnz = b[2], mxx = b[3], mxy = b[4], mxz = b[5];
+    if (mnx <= lx && lx <= mxx && mny <= ly && ly <= mxy && mnz <= lz && lz <= mxz) return 0;      /* contains */
+    {
+        float hx = (mxx - mnx) * 0.5f, hy = (mxy - mny) * 0.5f, hz = (mxz - mnz) * 0.5f;
+        float cx = (mxx + mnx) * 0.5f - lx, cy = (mxy + mny) * 0.5f - ly, cz = (mxz + mnz) * 0.5f - lz;
+        float hl = sqrtf(((0.0f + hx * hx) + hy * hy) + hz * hz), cl = sqrtf(((0.0f + cx * cx) + cy * cy) + cz * cz);
+        if (!(hl / cl > 0.5f)) return 1;
+    }
+    enum { L = 1, R = 2, B = 4, T = 8, F = 16, N = 32 };
+    unsigned mask = (lx < mnx ? L : 0) | (lx > mxx ? R : 0) | (ly < mny ? B : 0) | (ly > mxy ? T : 0) | (lz < mnz ? F : 0) | (lz > mxz ? N : 0);
+    /* cornerMap order of the reference, corners as AxisAlignedBox::getCorner gives them */
+    const unsigned cm[8] = {F | L | B, F | R | B, F | L | T, F | R | T, N | L | B, N | R | B, N | L | T, N | R | T};
+    const float cx8[8] = {mnx, mxx, mnx, mxx, mnx, mxx, mnx, mxx};
+    const float cy8[8] = {mny, mny, mxy, mxy, mny, mny, mxy, mxy};
+    const float cz8[8] = {mnz, mnz, mnz, mnz, mxz, mxz, mxz, mxz};
+    float ex[8], ey[8], ez[8];
+    unsigned n = 0;
+    for (int k = 0; k < 8; ++k)
+        if ((mask & cm[k]) != 0 && (mask & cm[k]) != cm[k]) { ex[n] = cx8[k]; ey[n] = cy8[k]; ez[n] = cz8[k]; ++n; }
+    float cosAngle = 1.0f;
+    for (unsigned i0 = 0; i0 + 1 < n; ++i0)
+        for (unsigned i1 = i0 + 1; i1 < n; ++i1) {
+            float a[3] = {ex[i0] - lx, ey[i0] - ly, ez[i0] - lz}, c[3] = {ex[i1] - lx, ey[i1] - ly, ez[i1] - lz};
+            float la = sqrtf(((0.0f + a[0] * a[0]) + a[1] * a[1]) + a[2] * a[2]);
+            if (la > 0.0f) { float inv = 1.0f / la; a[0] *= inv; a[1] *= inv; a[2] *= inv; }
+            float lc = sqrtf(((0.0f + c[0] * c[0]) + c[1] * c[1]) + c[2] * c[2]);
+            if (lc > 0.0f) { float inv = 1.0f / lc; c[0] *= inv; c[1] *= inv; c[2] *= inv; }
+            float cosAB = ((0.0f + a[0] * c[0]) + a[1] * c[1]) + a[2] * c[2];
+            if (cosAngle > cosAB) cosAngle = cosAB;
+        }
+    return cosAngle < 0.5f ? 0 : 1;
+}
+
+static int silhouette_edge(const uint32_t* e, const int8_t* facings)
+{
+    int lf = facings[e[0]];
+    return (e[4] && lf) || (!e[4] && (lf != facings[e[1]]));
+}
+
+long oracle_shadow_volume(uint32_t num_groups, const uint32_t* groups, const uint32_t* edges, const uint32_t* tris, const int8_t* facings,
+                          int directional, int use_mcguire, uint32_t flags, int separate_light_cap, uint16_t* indices,
+                          uint32_t buffer_indices, uint32_t* used, uint32_t* ranges)
+{
+    const int two_tris = !(directional && (flags & ORACLE_SRF_EXTRUDE_TO_INFINITY));
+    /* pre-count */
+    uint32_t pre = 0;
+    for (uint32_t g = 0; g < num_groups; ++g) {
+        const uint32_t* G = groups + 5 * g;
+        int first = 1;
+        for (uint32_t k = 0; k < G[1]; ++k) {
+            const uint32_t* e = edges + 5 * (size_t)(G[0] + k);
+            if (silhouette_edge(e, facings)) {
+                pre += 3;
+                if (two_tris) pre += 3;
+                if (use_mcguire && (flags & ORACLE_SRF_INCLUDE_DARK_CAP)) { if (first) first = 0; else pre += 3; }
+            }
+        }
+        uint32_t lit = 0;
+        for (uint32_t t = 0; t < G[3]; ++t) lit += facings[G[2] + t] ? 1u : 0u;
+        if (use_mcguire) { if (flags & ORACLE_SRF_INCLUDE_LIGHT_CAP) pre += 3 * lit; }
+        else pre += lit * (((flags & ORACLE_SRF_INCLUDE_DARK_CAP) ? 3u : 0u) + ((flags & ORACLE_SRF_INCLUDE_LIGHT_CAP) ? 3u : 0u));
+    }
+    if (pre > buffer_indices) return -1;
+    if (*used + pre > buffer_indices) *used = 0;
+    uint16_t* p = indices + *used;
+    uint32_t num = *used;
+    for (uint32_t g = 0; g < num_groups; ++g) {
+        const uint32_t* G = groups + 5 * g;
+        uint32_t* R = ranges + 4 * g;
+        R[0] = num; R[2] = 0; R[3] = 0;
+        const uint32_t ovc = G[4];
+        int first = 1;
+        uint16_t dark_start = 0;
+        for (uint32_t k = 0; k < G[1]; ++k) {
+            const uint32_t* e = edges + 5 * (size_t)(G[0] + k);
+            if (!silhouette_edge(e, facings)) continue;
+            uint32_t v0 = e[2], v1 = e[3];
+            if (!facings[e[0]]) { uint32_t t = v0; v0 = v1; v1 = t; }
+            *p++ = (uint16_t)v1; *p++ = (uint16_t)v0; *p++ = (uint16_t)(v0 + ovc); num += 3;
+            if (two_tris) { *p++ = (uint16_t)(v0 + ovc); *p++ = (uint16_t)(v1 + ovc); *p++ = (uint16_t)v1; num += 3; }
+            if (use_mcguire && (flags & ORACLE_SRF_INCLUDE_DARK_CAP)) {
+                if (first) { dark_start = (uint16_t)(v0 + ovc); first = 0; }
+                else { *p++ = dark_start; *p++ = (uint16_t)(v1 + ovc); *p++ = (uint16_t)(v0 + ovc); num += 3; }
+            }
+        }
+        if (!use_mcguire && (flags & ORACLE_SRF_INCLUDE_DARK_CAP)) {
+            for (uint32_t t = 0; t < G[3]; ++t) {
+                if (!facings[G[2] + t]) continue;
+                const uint32_t* T = tris + 3 * (size_t)(G[2] + t);
+                *p++ = (uint16_t)(T[1] + ovc); *p++ = (uint16_t)(T[0] + ovc); *p++ = (uint16_t)(T[2] + ovc); num += 3;
+            }
+        }
+        if (flags & ORACLE_SRF_INCLUDE_LIGHT_CAP) {
+            uint32_t* cnt = &R[1];
+            if (separate_light_cap) { R[1] = num - R[0]; R[2] = num; cnt = &R[3]; }
+            uint32_t start = separate_light_cap ? R[2] : R[0];
+            for (uint32_t t = 0; t < G[3]; ++t) {
+                if (!facings[G[2] + t]) continue;
+                const uint32_t* T = tris + 3 * (size_t)(G[2] + t);
+                *p++ = (uint16_t)T[0]; *p++ = (uint16_t)T[1]; *p++ = (uint16_t)T[2]; num += 3;
+            }
+            *cnt = num - start;
+        } else {
+            R[1] = num - R[0];
+        }
+    }
+    *used = num;
+    return (long)pre;
+}

@@ -138,6 +138,27 @@ void oracle_skeleton_bind_inverse(const oracle_skeleton* sk, float* out10);
 int oracle_skeleton_palette(const oracle_skeleton* sk, const float* bind_inverse10, const oracle_animation* anims,
                             uint32_t nstates, const int32_t* anim, const float* time, const float* weight, float* out16);
 
+/* ---- Silhouette extraction / shadow-volume index generation ---- */
+
+/* static isBoundOkForMcGuire + the useMcGuire decision, OgreMain/src/OgreShadowCaster.cpp:134-189,203-204.
+ * bounds6 = light-cap bounds min xyz, max xyz; light4 = Light::getAs4DVector (w == 0: directional). */
+int oracle_shadow_use_mcguire(uint32_t num_groups, const float* bounds6, const float* light4);
+
+#define ORACLE_SRF_INCLUDE_LIGHT_CAP 1u
+#define ORACLE_SRF_INCLUDE_DARK_CAP 2u
+#define ORACLE_SRF_EXTRUDE_TO_INFINITY 4u
+
+/* ShadowCaster::generateShadowVolume, OgreShadowCaster.cpp:191-515: the pre-count (:209-296), the wrap of the shared
+ * index buffer (:321-324) and the emission (:339-506).
+ *   groups[g] = {edge_start, edge_count, tri_start, tri_count, vertex_count}, edges[e] = {tri0, tri1, v0, v1, degenerate},
+ *   tris[t] = vertIndex[3], facings[t] = EdgeData::triangleLightFacings.
+ * Writes 16-bit indices into `indices` (capacity `buffer_indices`) from *used on (from 0 after a wrap), fills
+ * ranges[g] = {indexStart, indexCount, lightCapStart, lightCapCount} and updates *used.  Returns the number of indices
+ * emitted, or -1 when they do not fit the buffer at all (the reference then asks the SceneManager for a bigger one). */
+long oracle_shadow_volume(uint32_t num_groups, const uint32_t* groups, const uint32_t* edges, const uint32_t* tris, const int8_t* facings,
+                          int directional, int use_mcguire, uint32_t flags, int separate_light_cap, uint16_t* indices,
+                          uint32_t buffer_indices, uint32_t* used, uint32_t* ranges);
+
 #ifdef __cplusplus
 }
 #endif

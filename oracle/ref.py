@@ -88,6 +88,13 @@ def lib():
         l.ref_skel_pose_states.argtypes = [C.c_uint32, vp, vp, vp, vp]
         l.ref_bench_palettes.argtypes = [C.c_uint32, vp, sz, vp]
         l.ref_bench_palettes.restype = C.c_double
+        l.ref_shadow_open.argtypes = [C.c_char_p, vp, vp, vp]
+        l.ref_shadow_edges.argtypes = [vp, vp, vp]
+        l.ref_shadow_edges.restype = None
+        l.ref_shadow_volume.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp]
+        l.ref_shadow_volume.restype = C.c_long
+        l.ref_shadow_indices.restype = vp
+        l.ref_shadow_ranges.restype = vp
         l.ref_set_media_dir(MEDIA.encode())
         _lib = l
     return _lib
@@ -209,3 +216,29 @@ def skeleton_pose_states(num_bones, anim, time, weight):
     rc = lib().ref_skel_pose_states(len(anim), anim.ctypes.data, time.ctypes.data, weight.ctypes.data, out.ctypes.data)
     assert rc == 0, rc
     return out
+
+
+def shadow_open(mesh):
+    """Edge list of `mesh` (Mesh::buildEdgeList) as flat arrays {groups[g,5], edges[e,5], tris[t,3]}."""
+    l = lib()
+    ng, ne, nt = C.c_uint32(), C.c_uint32(), C.c_uint32()
+    rc = l.ref_shadow_open(mesh.encode(), C.addressof(ng), C.addressof(ne), C.addressof(nt))
+    assert rc == 0, rc
+    ed = {"groups": np.zeros((ng.value, 5), np.uint32), "edges": np.zeros((ne.value, 5), np.uint32), "tris": np.zeros((nt.value, 3), np.uint32)}
+    l.ref_shadow_edges(ed["groups"].ctypes.data, ed["edges"].ctypes.data, ed["tris"].ctypes.data)
+    return ed
+
+
+def shadow_volume(ed, light4, bounds6, flags, separate_light_cap, buffer_indices, used_in):
+    """The real ShadowCaster::generateShadowVolume on the open mesh's EdgeData (light facings from the real
+    EdgeData::updateTriangleLightFacing) -> (indices u16 [buffer_indices], ranges [g,4], used_out, facings[t])."""
+    l = lib()
+    light4 = np.ascontiguousarray(light4, np.float32); bounds6 = np.ascontiguousarray(bounds6, np.float32)
+    facings = np.zeros(len(ed["tris"]), np.int8)
+    used = C.c_uint32()
+    n = l.ref_shadow_volume(light4.ctypes.data, bounds6.ctypes.data, flags, int(separate_light_cap), buffer_indices, used_in,
+                            facings.ctypes.data, C.addressof(used))
+    assert n == buffer_indices, n
+    idx = np.ctypeslib.as_array(C.cast(l.ref_shadow_indices(), C.POINTER(C.c_uint16)), shape=(buffer_indices,)).copy()
+    rng = np.ctypeslib.as_array(C.cast(l.ref_shadow_ranges(), C.POINTER(C.c_uint32)), shape=(len(ed["groups"]), 4)).copy()
+    return idx, rng, used.value, facings

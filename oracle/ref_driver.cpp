@@ -654,6 +654,126 @@ API double ref_bench_palettes(uint32_t anim, const float* time, size_t ninst, fl
     return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 
+/* ========================================= silhouette / shadow-volume index generation ==== */
+// ShadowCaster::generateShadowVolume (OgreMain/src/OgreShadowCaster.cpp:191-515) driven on the edge list of the open
+// mesh: the step after calculateLightFacing / extrudeVertices in the stencil-shadow chain.
+
+struct RefCaster : public ShadowCaster {
+    AxisAlignedBox box;
+    bool getCastShadows() const override { return true; }
+    const AxisAlignedBox& getWorldBoundingBox(bool) const override { return box; }
+    Real getPointExtrusionDistance(const Light*) const override { return 0; }
+    void run(EdgeData* ed, const HardwareIndexBufferSharedPtr& ib, size_t& used, const Light* l, ShadowRenderableList& list, unsigned long flags)
+    {
+        generateShadowVolume(ed, ib, used, l, list, flags);
+    }
+};
+
+struct ShadowState {
+    EdgeData* ed = nullptr;
+    Light* light = nullptr;
+    SceneNode* lnode = nullptr;
+    std::vector<uint16_t> out;
+    std::vector<uint32_t> ranges;          // per group: indexStart, indexCount, capStart, capCount
+};
+static ShadowState g_shadow;
+
+API int ref_shadow_open(const char* mesh, uint32_t* ngroups, uint32_t* nedges, uint32_t* ntris)
+{
+    try {
+        int rc = ref_scene_open(mesh, 64, 64, 100.0f);
+        if (rc) return rc;
+        MeshPtr m = g_scene.ent->getMesh();
+        m->freeEdgeList();
+        m->buildEdgeList();
+        g_shadow = ShadowState();
+        g_shadow.ed = m->getEdgeList(0);
+        if (!g_shadow.ed) return 2;
+        g_shadow.light = g_scene.sm->createLight("shadow_probe");
+        g_shadow.lnode = g_scene.sm->getRootSceneNode()->createChildSceneNode();
+        g_shadow.lnode->attachObject(g_shadow.light);
+        uint32_t ne = 0;
+        for (auto& eg : g_shadow.ed->edgeGroups) ne += (uint32_t)eg.edges.size();
+        *ngroups = (uint32_t)g_shadow.ed->edgeGroups.size(); *nedges = ne; *ntris = (uint32_t)g_shadow.ed->triangles.size();
+        return 0;
+    } catch (std::exception& ex) { fprintf(stderr, "ref_shadow_open: %s\n", ex.what()); return 1; }
+}
+
+// groups[g] = {edge_start, edge_count, tri_start, tri_count, vertex_count}; edges[e] = {tri0, tri1, v0, v1, degenerate};
+// tris[t] = vertIndex[3]
+API void ref_shadow_edges(uint32_t* groups, uint32_t* edges, uint32_t* tris)
+{
+    EdgeData* ed = g_shadow.ed;
+    uint32_t e = 0, g = 0;
+    for (auto& eg : ed->edgeGroups) {
+        uint32_t* o = groups + 5 * g++;
+        o[0] = e; o[1] = (uint32_t)eg.edges.size(); o[2] = eg.triStart; o[3] = eg.triCount; o[4] = (uint32_t)eg.vertexData->vertexCount;
+        for (auto& ed1 : eg.edges) {
+            uint32_t* q = edges + 5 * e++;
+            q[0] = ed1.triIndex[0]; q[1] = ed1.triIndex[1]; q[2] = ed1.vertIndex[0]; q[3] = ed1.vertIndex[1]; q[4] = ed1.degenerate ? 1u : 0u;
+        }
+    }
+    for (size_t t = 0; t < ed->triangles.size(); ++t)
+        for (int k = 0; k < 3; ++k) tris[3 * t + k] = ed->triangles[t].vertIndex[k];
+}
+
+// light4 = position (w=1, point light) or direction-to-light (w=0, directional) as Light::getAs4DVector gives it;
+// bounds6 = the caster's light-cap bounds (min xyz, max xyz) for the McGuire test; `used_in` = indices already in the
+// shared buffer.  Returns the number of indices written (from used_in on, or from 0 when the buffer wrapped), -1 on error;
+// facings_out gets the per-triangle light facings the real EdgeData computed.
+API long ref_shadow_volume(const float* light4, const float* bounds6, uint32_t flags, uint32_t separate_light_cap, uint32_t buffer_indices,
+                           uint32_t used_in, int8_t* facings_out, uint32_t* used_out)
+{
+    try {
+        EdgeData* ed = g_shadow.ed;
+        Light* l = g_shadow.light;
+        if (light4[3] == 0.0f) {
+            l->setType(Light::LT_DIRECTIONAL);
+            g_shadow.lnode->setPosition(0, 0, 0);
+            g_shadow.lnode->setDirection(Vector3(-light4[0], -light4[1], -light4[2]), Node::TS_WORLD);
+        } else {
+            l->setType(Light::LT_POINT);
+            g_shadow.lnode->resetOrientation();
+            g_shadow.lnode->setPosition(light4[0], light4[1], light4[2]);
+        }
+        g_shadow.lnode->_update(true, true);
+        const Vector4 lv = l->getAs4DVector();
+        ed->updateTriangleLightFacing(lv);
+        memcpy(facings_out, ed->triangleLightFacings.data(), ed->triangleLightFacings.size());
+        HardwareIndexBufferSharedPtr ib = HardwareBufferManager::getSingleton().createIndexBuffer(HardwareIndexBuffer::IT_16BIT, buffer_indices,
+                                                                                                  HBU_CPU_TO_GPU);
+        {   // recognisable background so that untouched ranges show
+            uint16_t* p = (uint16_t*)ib->lock(HardwareBuffer::HBL_DISCARD);
+            for (uint32_t i = 0; i < buffer_indices; ++i) p[i] = 0xCDCD;
+            ib->unlock();
+        }
+        RefCaster caster;
+        caster.box.setExtents(bounds6[0], bounds6[1], bounds6[2], bounds6[3], bounds6[4], bounds6[5]);
+        ShadowRenderableList list;
+        for (auto& eg : ed->edgeGroups) list.push_back(OGRE_NEW ShadowRenderable(nullptr, ib, eg.vertexData, separate_light_cap != 0));
+        size_t used = used_in;
+        caster.run(ed, ib, used, l, list, flags);
+        *used_out = (uint32_t)used;
+        g_shadow.out.resize(buffer_indices);
+        const uint16_t* p = (const uint16_t*)ib->lock(HardwareBuffer::HBL_READ_ONLY);
+        memcpy(g_shadow.out.data(), p, buffer_indices * 2);
+        ib->unlock();
+        g_shadow.ranges.clear();
+        for (auto* sr : list) {
+            IndexData* id = sr->getRenderOperationForUpdate()->indexData;
+            g_shadow.ranges.push_back((uint32_t)id->indexStart); g_shadow.ranges.push_back((uint32_t)id->indexCount);
+            if (sr->isLightCapSeparate()) {
+                IndexData* ic = sr->getLightCapRenderable()->getRenderOperationForUpdate()->indexData;
+                g_shadow.ranges.push_back((uint32_t)ic->indexStart); g_shadow.ranges.push_back((uint32_t)ic->indexCount);
+            } else { g_shadow.ranges.push_back(0); g_shadow.ranges.push_back(0); }
+        }
+        for (auto* sr : list) OGRE_DELETE sr;
+        return (long)buffer_indices;
+    } catch (std::exception& ex) { fprintf(stderr, "ref_shadow_volume: %s\n", ex.what()); return -1; }
+}
+API const uint16_t* ref_shadow_indices(void) { return g_shadow.out.data(); }
+API const uint32_t* ref_shadow_ranges(void) { return g_shadow.ranges.data(); }
+
 /* ==================================================================== timing ==== */
 
 // `reps` calls of the real SSE softwareVertexSkinning over `ninst` instances (each with its own

@@ -15,6 +15,9 @@ container only; the GPU box and the CPU test suite just read the .npz files.
   jaiqua_skeleton.npz    inverses, every animation's node tracks and key frames) + 96 poses each: 1-3 enabled
                          animation states (order, time position, weight, both blend modes) and the palette
                          the real SkeletonInstance::setAnimationState + _getBoneMatrices produced
+  jaiqua_shadow.npz      the meshes' edge lists (Mesh::buildEdgeList) + 14 shadow-volume cases each (lights, bounds,
+  sinbad_shadow.npz      flag combinations, shared-buffer offsets incl. a wrap): light facings from the real EdgeData and the
+                         index buffer contents / ShadowRenderable ranges the real ShadowCaster::generateShadowVolume wrote
   optutil_golden.npz     outputs of the real OptimisedUtilSSE / OptimisedUtilGeneral on small
                          seeded inputs (all six functions, edge-case counts and alignments)
 """
@@ -106,6 +109,34 @@ def save_skeleton_def(name, mesh, nposes=96, seed=7):
     print(name, d["num_bones"], "bones", len(d["anims"]), "animations", nposes, "poses")
 
 
+def save_shadow(name, mesh, ncases=14, seed=4):
+    """Edge list of `mesh` + shadow-volume cases: light, light-cap bounds, flags -> the light facings the real EdgeData
+    computed and the indices / ranges the real ShadowCaster::generateShadowVolume wrote."""
+    ed = ref.shadow_open(mesh)
+    out = {"groups": ed["groups"], "edges": ed["edges"], "tris": ed["tris"], "ncases": np.array(ncases)}
+    rng = np.random.default_rng(seed)
+    for c in range(ncases):
+        if c % 3 == 0:
+            v = rng.normal(size=3); light = np.array([*(v / np.linalg.norm(v)), 0], np.float32)
+        else:
+            light = np.array([*(rng.uniform(-1, 1, 3) * rng.choice([5, 40, 300])), 1], np.float32)
+        half = rng.uniform(3, 40, 3); ctr = rng.uniform(-5, 5, 3)
+        bounds = np.array([*(ctr - half), *(ctr + half)], np.float32)
+        flags = c % 8
+        sep = bool(c % 2)
+        cap = 120000
+        used = [0, 1000, cap - 500][c % 3]
+        idx, ranges, used_out, fac = ref.shadow_volume(ed, light, bounds, flags, sep, cap, used)
+        oi, orr, ou, n, mc = oracle.shadow_volume(ed, fac, light, bounds, flags, sep, cap, used)     # the emitted count comes from the restatement
+        assert np.array_equal(oi, idx) and ou == used_out, "oracle and reference disagree: fix that first"
+        start = used_out - n
+        out["c%d_meta" % c] = np.array([flags, int(sep), cap, used, used_out, n, mc], np.int64)
+        out["c%d_light" % c], out["c%d_bounds" % c], out["c%d_facings" % c] = light, bounds, fac
+        out["c%d_ranges" % c], out["c%d_indices" % c] = ranges, idx[start:start + n]
+    np.savez_compressed(os.path.join(HERE, name), **out)
+    print(name, len(ed["groups"]), "groups", len(ed["edges"]), "edges", ncases, "cases")
+
+
 def save_optutil(name):
     l = ref.lib()
     rng = np.random.default_rng(2024)
@@ -177,3 +208,5 @@ if __name__ == "__main__":
     save_skeleton("jaiqua_skin.npz", "jaiqua.mesh")
     save_skeleton_def("sinbad_skeleton.npz", "Sinbad.mesh")
     save_skeleton_def("jaiqua_skeleton.npz", "jaiqua.mesh")
+    save_shadow("jaiqua_shadow.npz", "jaiqua.mesh")
+    save_shadow("sinbad_shadow.npz", "Sinbad.mesh")

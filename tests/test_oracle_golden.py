@@ -135,3 +135,19 @@ def test_oracle_reproduces_ogres_own_bone_palettes(name):
         n = int(poses["nstates"][p])
         got = sk.palette(poses["anim"][p, :n], poses["time"][p, :n], poses["weight"][p, :n], blend_mode=poses["blend_mode"][p])
         assert np.array_equal(bits(got), bits(poses["palette"][p])), (name, p)
+
+
+@pytest.mark.parametrize("name", ["jaiqua_shadow.npz", "sinbad_shadow.npz"])
+def test_oracle_reproduces_ogres_own_shadow_volume_indices(name):
+    """ShadowCaster::generateShadowVolume (SURVEY §8f rank 2): 14 cases per mesh dumped from the real engine — every flag
+    combination, McGuire fan and full caps, separate light caps, offsets into the shared buffer including a wrap."""
+    from goldenlib import load_shadow
+    ed, cases = load_shadow(name)
+    for k, c in enumerate(cases):
+        idx, ranges, used, n, mc = oracle.shadow_volume(ed, c["facings"], c["light"], c["bounds"], c["flags"], c["separate"], c["capacity"],
+                                                        c["used_in"])
+        assert (n, used, mc) == (c["emitted"], c["used_out"], c["mcguire"]), (name, k)
+        assert np.array_equal(idx[used - n:used], c["indices"]), (name, k)
+        assert (idx[:used - n] == 0xCDCD).all() and (idx[used:] == 0xCDCD).all()
+        cols = 4 if (c["separate"] and c["flags"] & 1) else 2
+        assert np.array_equal(ranges[:, :cols], c["ranges"][:, :cols]), (name, k)

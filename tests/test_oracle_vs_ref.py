@@ -81,3 +81,24 @@ def test_oracle_bone_palettes_equal_real_skeleton_instance(mesh):
         o = sk.palette(an, tm, w, bind_inverse=d["bind_inverse"], blend_mode=mode)
         assert np.array_equal(bits(r), bits(o)), (mesh, trial)
     ref.lib().ref_skel_set_blend_mode(d["blend_mode"])
+
+
+@pytest.mark.parametrize("mesh", ["jaiqua.mesh", "ogrehead.mesh", "Sinbad.mesh"])
+def test_oracle_shadow_volume_equals_real_generate_shadow_volume(mesh):
+    """60 random (light, bounds, flags, offset) cases per mesh through the real ShadowCaster::generateShadowVolume on the
+    mesh's own EdgeData vs the restatement: identical index buffers, ranges and buffer positions."""
+    ed = ref.shadow_open(mesh)
+    rng = np.random.default_rng(2)
+    for trial in range(60):
+        if trial % 3 == 0:
+            v = rng.normal(size=3); light = np.array([*(v / np.linalg.norm(v)), 0], np.float32)
+        else:
+            light = np.array([*(rng.uniform(-1, 1, 3) * rng.choice([5, 40, 300])), 1], np.float32)
+        half = rng.uniform(3, 40, 3); c = rng.uniform(-5, 5, 3)
+        bounds = np.array([*(c - half), *(c + half)], np.float32)
+        flags = int(rng.integers(0, 8)); sep = bool(rng.integers(0, 2)); cap = 200000; used = int(rng.choice([0, 1000, 199000]))
+        ri, rr, ru, fac = ref.shadow_volume(ed, light, bounds, flags, sep, cap, used)
+        oi, orr, ou, n, mc = oracle.shadow_volume(ed, fac, light, bounds, flags, sep, cap, used)
+        assert np.array_equal(ri, oi) and ru == ou, (mesh, trial)
+        cols = 4 if (sep and flags & 1) else 2
+        assert np.array_equal(rr[:, :cols], orr[:, :cols]), (mesh, trial)

@@ -165,6 +165,25 @@ def c1(ctx, T, args):
     return out
 
 
+def manifold_edges(tri_idx, nv):
+    """EdgeData of a closed manifold triangle list (vectorised EdgeListBuilder stand-in for the synthetic mesh): every
+    directed half-edge (v0, v1) of triangle t pairs with the opposite half-edge (v1, v0) of its neighbour; the edge is
+    stored once, by the half-edge that comes first in triangle order, as {tri0, tri1, v0, v1, degenerate=0}."""
+    nt = len(tri_idx)
+    v0 = tri_idx.reshape(-1).astype(np.int64)
+    v1 = np.roll(tri_idx, -1, axis=1).reshape(-1).astype(np.int64)
+    t = np.repeat(np.arange(nt, dtype=np.int64), 3)
+    key, rkey = v0 * nv + v1, v1 * nv + v0
+    order = np.argsort(key)
+    pos = np.searchsorted(key[order], rkey)
+    mate = order[pos]                                   # half-edge index of the opposite direction
+    assert np.array_equal(key[mate], rkey), "mesh is not a closed manifold"
+    keep = np.arange(len(key)) < mate                   # the earlier half-edge owns the edge
+    e = np.stack([t[keep], t[mate[keep]], v0[keep], v1[keep], np.zeros(keep.sum(), np.int64)], 1).astype(np.uint32)
+    groups = np.array([[0, len(e), 0, nt, nv]], np.uint32)
+    return {"groups": groups, "edges": e, "tris": tri_idx.astype(np.uint32)}
+
+
 def c3(ctx, T, args):
     nu = int(round((args.c3_tris / 2) ** 0.5))
     nv, nt = nu * nu, 2 * nu * nu
@@ -200,6 +219,23 @@ def c3(ctx, T, args):
     t_fn, t_fac, t_ext, t_all = T.time(fn), T.time(facing), T.time(extrude), T.time(frame)
     t_extf = T.time(extrude_fused)
     b_extf = nv * 12 + 8 * nv * 12
+    # silhouette extraction (ShadowCaster::generateShadowVolume) for the 8 lights, 32-bit indices (V + V > 65 536)
+    el = ogre_b200.EdgeList(ctx, manifold_edges(tri_idx, nv))
+    didx = ctx.alloc(8 * 12 * nt * 4)
+    sil = {"emitted": 0}
+
+    def silhouettes():
+        used = 0
+        for k in range(8):
+            _, used, n = el.shadow_volume(dfac.ptr + k * nt, False, 0, 3, False, 4, didx.ptr, 8 * 12 * nt, used)
+        sil["emitted"] = used
+    t0 = time.perf_counter(); silhouettes(); ctx.sync()
+    reps = 5
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        silhouettes()
+    ctx.sync()
+    t_sil = (time.perf_counter() - t0) / reps           # synchronous API (counts come back to the host): wall clock
     b_fn = nt * 48 + nv * 12
     b_fac = nt * 16 + 8 * nt           # normals read ONCE for the 8 lights (fused), 8 facing bytes written
     b_ext = 8 * nv * 24
@@ -209,7 +245,10 @@ def c3(ctx, T, args):
            "light_facing_8_fused": {"ms": t_fac * 1e3, "Mface_light_per_s": 8 * nt / t_fac / 1e6, "GBps": b_fac / t_fac / 1e9, "frac_of_hbm_peak": b_fac / t_fac / 1e9 / PEAK},
            "extrude_8": {"ms": t_ext * 1e3, "Mvert_per_s": 8 * nv / t_ext / 1e6, "GBps": b_ext / t_ext / 1e9, "frac_of_hbm_peak": b_ext / t_ext / 1e9 / PEAK},
            "extrude_8_fused": {"ms": t_extf * 1e3, "Mvert_per_s": 8 * nv / t_extf / 1e6, "GBps": b_extf / t_extf / 1e9,
-                               "frac_of_hbm_peak": b_extf / t_extf / 1e9 / PEAK, "note": "one launch, positions read once (frame uses this)"}}
+                               "frac_of_hbm_peak": b_extf / t_extf / 1e9 / PEAK, "note": "one launch, positions read once (frame uses this)"},
+           "shadow_volume_indices_8": {"ms": t_sil * 1e3, "edges": int(len(el.groups) and el.groups[0][1]), "indices_emitted": int(sil["emitted"]),
+                                       "Medge_per_s": 8 * int(el.groups[0][1]) / t_sil / 1e6,
+                                       "note": "generateShadowVolume for 8 lights, dark + light caps, 32-bit indices; synchronous calls, wall clock"}}
     if args.cpu:
         from oracle import ref
         if ref.available():

@@ -1,1 +1,4 @@
-ncu --set full --clock-control none --import-source on -k regex:skin_wide -s 13 -c 1 -o gpurun_out/prof_wide_sub6 -f python bench.py --steps 2 --warmup 1 --no-cpu-baseline --skin-mode 4 > /dev/null 2>&1; echo rc=$?
+python tools/bench_configs.py --config c3 | python -c "
+import sys,json
+d=json.loads(sys.stdin.read())
+print(d['ms_per_frame'], json.dumps(d['shadow_volume_indices_8']))"
