@@ -9,7 +9,7 @@ python bench.py > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; echo 
 python bench.py --form separate --no-cpu-baseline > gpurun_out/bench_separate_$TAG.json 2>> gpurun_out/bench_$TAG.err; echo "bench separate rc=$?"; cat gpurun_out/bench_separate_$TAG.json
 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_ref_$TAG.json 2>/dev/null; cut -c1-300 gpurun_out/bench_ref_$TAG.json
 # A/B sweep of the kernel-selection knobs (short runs)
-for cfg in "0 0" "3 0" "1 0"; do
+for cfg in "0 0" "3 0" "4 0"; do
   set -- $cfg
   python bench.py --no-cpu-baseline --steps 50 --skin-mode $1 --skin-ipc $2 2>/dev/null | python -c "
 import json,sys
