@@ -10,6 +10,9 @@
 #include <OgreHardwarePixelBuffer.h>
 #include <OgreRenderTexture.h>
 #include "OgreCudaSkeletonPalettes.h"
+#include "OgreCudaShadowVolume.h"
+#include <OgreShadowCaster.h>
+#include <OgreEdgeListBuilder.h>
 
 #include <chrono>
 #include <csignal>
@@ -279,6 +282,88 @@ API int ph_skel_palettes(uint32_t n, const float* times, float* engine, float* d
     CATCH(1)
 }
 API size_t ph_skel_num_bones(void) { return g->ent && g->ent->hasSkeleton() ? g->ent->getSkeleton()->getNumBones() : 0; }
+
+// generateShadowVolume side by side on the entity's own edge list: the real ShadowCaster::generateShadowVolume (a
+// ShadowCaster subclass reaches the protected member) into one index buffer, CudaShadowVolume::generate into another,
+// both created by the render system under test.  Outputs: the two index buffers (n16 16-bit indices each) and the
+// ShadowRenderable ranges (per group indexStart, indexCount, cap start, cap count).  CUDA plugin only.
+struct HarnessCaster : public ShadowCaster {
+    AxisAlignedBox box;
+    bool getCastShadows() const override { return true; }
+    const AxisAlignedBox& getWorldBoundingBox(bool) const override { return box; }
+    Real getPointExtrusionDistance(const Light*) const override { return 0; }
+    void run(EdgeData* ed, const HardwareIndexBufferSharedPtr& ib, size_t& used, const Light* l, ShadowRenderableList& list, unsigned long flags)
+    {
+        updateEdgeListLightFacing(ed, l->getAs4DVector());
+        generateShadowVolume(ed, ib, used, l, list, flags);
+    }
+};
+
+API int ph_shadow_volume(const float* light4, const float* bounds6, uint32_t flags, uint32_t separate, uint32_t n16, uint32_t used_in,
+                         uint16_t* engine, uint16_t* device, uint32_t* ranges_engine, uint32_t* ranges_device, uint32_t* used_out2)
+{
+    TRY
+    Entity* e = g->ent;
+    MeshPtr m = e->getMesh();
+    if (!m->isEdgeListBuilt()) m->buildEdgeList();
+    EdgeData* ed = m->getEdgeList(0);
+    if (!ed) { g_err = "no edge list"; return 2; }
+    static Light* light = nullptr;
+    static SceneNode* ln = nullptr;
+    if (!light) { light = g->sm->createLight("shadow_probe"); ln = g->sm->getRootSceneNode()->createChildSceneNode(); ln->attachObject(light); }
+    if (light4[3] == 0.0f) {
+        light->setType(Light::LT_DIRECTIONAL);
+        ln->setPosition(0, 0, 0);
+        ln->setDirection(Vector3(-light4[0], -light4[1], -light4[2]), Node::TS_WORLD);
+    } else {
+        light->setType(Light::LT_POINT);
+        ln->resetOrientation();
+        ln->setPosition(light4[0], light4[1], light4[2]);
+    }
+    ln->_update(true, true);
+    HarnessCaster caster;
+    caster.box.setExtents(bounds6[0], bounds6[1], bounds6[2], bounds6[3], bounds6[4], bounds6[5]);
+    HardwareIndexBufferSharedPtr ib[2];
+    for (int k = 0; k < 2; ++k) {
+        ib[k] = HardwareBufferManager::getSingleton().createIndexBuffer(HardwareIndexBuffer::IT_16BIT, n16, HBU_CPU_TO_GPU);
+        uint16_t* p = (uint16_t*)ib[k]->lock(HardwareBuffer::HBL_DISCARD);
+        for (uint32_t i = 0; i < n16; ++i) p[i] = 0xCDCD;
+        ib[k]->unlock();
+    }
+    auto collect = [&](ShadowRenderableList& list, uint32_t* out) {
+        size_t q = 0;
+        for (auto* sr : list) {
+            IndexData* id = sr->getRenderOperationForUpdate()->indexData;
+            out[q++] = (uint32_t)id->indexStart; out[q++] = (uint32_t)id->indexCount;
+            if (sr->isLightCapSeparate()) {
+                IndexData* ic = sr->getLightCapRenderable()->getRenderOperationForUpdate()->indexData;
+                out[q++] = (uint32_t)ic->indexStart; out[q++] = (uint32_t)ic->indexCount;
+            } else { out[q++] = 0; out[q++] = 0; }
+        }
+    };
+    for (int k = 0; k < 2; ++k) {
+        ShadowRenderableList list;
+        for (auto& eg : ed->edgeGroups) list.push_back(OGRE_NEW ShadowRenderable(nullptr, ib[k], eg.vertexData, separate != 0));
+        size_t used = used_in;
+        if (k == 0) caster.run(ed, ib[0], used, light, list, flags);
+        else { CudaShadowVolume sv(ed); sv.generate(ib[1], used, light, caster.box, list, flags); }
+        used_out2[k] = (uint32_t)used;
+        collect(list, k == 0 ? ranges_engine : ranges_device);
+        const uint16_t* p = (const uint16_t*)ib[k]->lock(HardwareBuffer::HBL_READ_ONLY);
+        memcpy(k == 0 ? engine : device, p, (size_t)n16 * 2);
+        ib[k]->unlock();
+        for (auto* sr : list) OGRE_DELETE sr;
+    }
+    return 0;
+    CATCH(1)
+}
+API size_t ph_shadow_num_groups(void)
+{
+    MeshPtr m = g->ent->getMesh();
+    if (!m->isEdgeListBuilt()) m->buildEdgeList();
+    EdgeData* ed = m->getEdgeList(0);
+    return ed ? ed->edgeGroups.size() : 0;
+}
 
 API size_t ph_skel_num_subs(void) { return g_skinned.size(); }
 API size_t ph_skel_sub_size(size_t i) { return g_skinned[i].size(); }

@@ -33,6 +33,7 @@ def main():
     ap.add_argument("--quad", action="store_true")
     ap.add_argument("--skel", default="")
     ap.add_argument("--time", type=int, default=0)
+    ap.add_argument("--shadow", type=int, default=0, help="N shadow-volume cases: real generateShadowVolume vs CudaShadowVolume")
     ap.add_argument("--palettes", type=int, default=0, help="bone palettes at N time positions: engine vs CudaSkeletonPalettes")
     a = ap.parse_args()
     w, h = [int(v) for v in a.size.split("x")]
@@ -77,6 +78,32 @@ def main():
         eng = np.zeros((a.palettes, nb, 16), np.float32); dev = np.zeros_like(eng)
         ok(L.ph_skel_palettes(a.palettes, times.ctypes.data, eng.ctypes.data, dev.ctypes.data), "ph_skel_palettes")
         out["palettes_engine"], out["palettes_device"], out["palette_times"] = eng, dev, times
+    if a.shadow:
+        L.ph_shadow_num_groups.restype = C.c_size_t
+        L.ph_shadow_volume.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32] + [C.c_void_p] * 5
+        ng = L.ph_shadow_num_groups()
+        rng = np.random.default_rng(12)
+        cap = 150000
+        bad = []
+        for k in range(a.shadow):
+            if k % 3 == 0:
+                v = rng.normal(size=3); light = np.array([*(v / np.linalg.norm(v)), 0], np.float32)
+            else:
+                light = np.array([*(rng.uniform(-1, 1, 3) * rng.choice([5, 40, 300])), 1], np.float32)
+            half = rng.uniform(3, 40, 3); ctr = rng.uniform(-5, 5, 3)
+            bounds = np.array([*(ctr - half), *(ctr + half)], np.float32)
+            flags, sep, used = k % 8, (k // 2) % 2, [0, 1000, cap - 500][k % 3]
+            eng = np.zeros(cap, np.uint16); dev = np.zeros(cap, np.uint16)
+            re_, rd = np.zeros((ng, 4), np.uint32), np.zeros((ng, 4), np.uint32)
+            used2 = np.zeros(2, np.uint32)
+            ok(L.ph_shadow_volume(light.ctypes.data, bounds.ctypes.data, flags, sep, cap, used, eng.ctypes.data, dev.ctypes.data,
+                                  re_.ctypes.data, rd.ctypes.data, used2.ctypes.data), "ph_shadow_volume")
+            cols = 4 if (sep and flags & 1) else 2
+            if not (np.array_equal(eng, dev) and used2[0] == used2[1] and np.array_equal(re_[:, :cols], rd[:, :cols])):
+                bad.append(k)
+            if k == 0:
+                out["shadow_indices_emitted"] = np.array(int((eng != 0xCDCD).sum()))
+        out["shadow_cases"], out["shadow_mismatches"] = np.array(a.shadow), np.array(bad, np.int64)
     ok(L.ph_render(), "ph_render")
     colour = np.zeros((h, w, 3), np.uint8)
     ok(L.ph_read_colour(colour.ctypes.data, 0), "ph_read_colour")

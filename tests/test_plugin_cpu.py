@@ -45,8 +45,14 @@ def test_harness_with_the_real_tiny_plugin_reproduces_the_golden_image(tmp_path)
     # validates the harness itself: same scene, real Tiny plugin loaded by path -> the committed fixture
     import numpy as np
     out = str(tmp_path / "tiny.npz")
-    r = subprocess.run([sys.executable, os.path.join(HERE, "harness", "run_scene.py"), "--plugin", "tiny", "--size", "320x180",
-                        "--out", out], capture_output=True, text=True, timeout=300)
+    # The REFERENCE plugin is retried: TinyRenderSystem never initialises DefaultShader::image / mDepthTest / mBlendAdd
+    # (ctor, OgreTinyRenderSystem.cpp:27-46) and was seen to die in sample2D on some runs — the oracle's own undefined
+    # behaviour, not the harness under validation.
+    for attempt in range(4):
+        r = subprocess.run([sys.executable, os.path.join(HERE, "harness", "run_scene.py"), "--plugin", "tiny", "--size", "320x180",
+                            "--out", out], capture_output=True, text=True, timeout=300)
+        if r.returncode == 0:
+            break
     assert r.returncode == 0, r.stdout + r.stderr
     a = np.load(out)
     g = np.load(os.path.join(HERE, "golden", "ogrehead_320x180.npz"))

@@ -109,3 +109,14 @@ def test_bone_palettes_through_the_plugin_equal_the_engines(tmp_path, mesh):
     z = run_scene(tmp_path, "cuda", "--mesh", mesh, "--size", "64x64", "--cam-z", "30", "--palettes", "200")
     assert z["palettes_engine"].shape[0] == 200 and np.abs(z["palettes_engine"]).sum() > 0
     assert np.array_equal(bits(z["palettes_device"]), bits(z["palettes_engine"]))
+
+
+@pytest.mark.parametrize("mesh", ["Sinbad.mesh", "jaiqua.mesh", "ogrehead.mesh"])
+def test_shadow_volume_through_the_plugin_equals_the_engines(tmp_path, mesh):
+    """CudaShadowVolume (plugin class over ogrecu_light_facing_dev + ogrecu_shadow_volume_dev) vs the real
+    ShadowCaster::updateEdgeListLightFacing + generateShadowVolume on the entity's own EdgeData, into index buffers of the
+    render system under test: 24 cases (all flag combinations, point / directional lights, separate light caps, buffer
+    offsets with a wrap) — identical index buffers, ShadowRenderable ranges and buffer positions."""
+    z = run_scene(tmp_path, "cuda", "--mesh", mesh, "--size", "64x64", "--cam-z", "100", "--shadow", "24")
+    assert int(z["shadow_cases"]) == 24 and int(z["shadow_indices_emitted"]) > 100
+    assert len(z["shadow_mismatches"]) == 0, z["shadow_mismatches"]
