@@ -299,6 +299,20 @@ OGRECU_API int ogrecu_extrude_multi_dev(ogrecu_ctx* ctx, const float* lights_hos
 OGRECU_API int ogrecu_extrude_vertices_host(ogrecu_ctx* ctx, const float* light4, float extrude_dist,
                                             const float* src, float* dst, size_t num_vertices);
 
+/* ---------------------------------------------------------- pose blending ------ */
+/* Mesh::softwareVertexPoseBlend (OgreMain/src/OgreMesh.cpp:1948-2007, called per pose by VertexAnimationTrack::applyPoseToVertexData,
+ * OgreAnimationTrack.cpp:942) for ONE element — call it with the pose's vertex offsets and the position element, and again
+ * with the pose's normals and the normal element: dst[vertex_index[e]] += offsets[e] * weight as `d + (o * w)`, nothing
+ * at all when weight == 0.  vertex_index / offsets (3 floats per entry) are the pose's std::map flattened, on the device;
+ * dst_dev points at the element's first float of vertex 0.  The instanced form blends the pose into num_instances
+ * buffers with a weight per instance (device array). */
+OGRECU_API int ogrecu_pose_blend_dev(ogrecu_ctx* ctx, float weight, const uint32_t* vertex_index_dev, const float* offsets_dev,
+                                     uint32_t num_entries, float* dst_dev, uint32_t dst_stride_bytes);
+OGRECU_API int ogrecu_pose_blend_instanced_dev(ogrecu_ctx* ctx, const float* weights_dev, const uint32_t* vertex_index_dev,
+                                               const float* offsets_dev, uint32_t num_entries, float* dst_dev,
+                                               uint32_t dst_stride_bytes, uint32_t num_instances,
+                                               size_t dst_instance_stride_bytes);
+
 /* ------------------------------------------ silhouette / shadow-volume indices ------ */
 /* ShadowCaster::generateShadowVolume (OgreMain/src/OgreShadowCaster.cpp:191-515) as an order-preserving stream
  * compaction on the device.  The edge list of a mesh (EdgeData, OgreEdgeListBuilder.h:50-160) is uploaded once:

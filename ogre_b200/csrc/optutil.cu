@@ -433,6 +433,27 @@ __global__ void extrude_multi_kernel(const __grid_constant__ Lights L, uint32_t 
     }
 }
 
+/* ------------------------------------------------------------- pose blending ------- */
+
+// Mesh::softwareVertexPoseBlend (OgreMesh.cpp:1948-2007) for one element (positions or normals) of many instances:
+// thread (entry e, instance i): dst_i[idx[e]] = dst_i[idx[e]] + (offset[e] * weight_i), nothing when weight_i == 0 (the
+// reference returns before touching the buffer).  A pose names a vertex at most once (std::map keys), so the writes of
+// one launch never collide; successive poses are successive launches, as the reference applies them one after the other.
+__global__ void pose_blend_kernel(const float* __restrict__ weights, float weight0, const uint32_t* __restrict__ idx,
+                                  const float* __restrict__ off3, uint32_t n, uint8_t* __restrict__ dst, uint32_t stride_bytes,
+                                  size_t inst_stride_bytes)
+{
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const float w = weights ? __ldg(weights + blockIdx.y) : weight0;
+    if (w == 0.0f) return;
+    float* p = reinterpret_cast<float*>(dst + (size_t)blockIdx.y * inst_stride_bytes + (size_t)__ldg(idx + e) * stride_bytes);
+    const float ox = __ldg(off3 + 3 * (size_t)e), oy = __ldg(off3 + 3 * (size_t)e + 1), oz = __ldg(off3 + 3 * (size_t)e + 2);
+    p[0] = fadd(p[0], fmul(ox, w));
+    p[1] = fadd(p[1], fmul(oy, w));
+    p[2] = fadd(p[2], fmul(oz, w));
+}
+
 inline bool aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
 
 int validate_skin_job(const ogrecu_skin_job& j)
@@ -688,6 +709,38 @@ int ogrecu_light_facing_multi_dev(ogrecu_ctx* ctx, const float* lights_host, uin
 int ogrecu_light_facing_dev(ogrecu_ctx* ctx, const float* light4_host, const float* face_normals, char* facings, size_t n)
 {
     return ogrecu_light_facing_multi_dev(ctx, light4_host, 1, face_normals, facings, 0, n);
+}
+
+int ogrecu_pose_blend_instanced_dev(ogrecu_ctx* ctx, const float* weights_dev, const uint32_t* vertex_index_dev, const float* offsets_dev,
+                                    uint32_t num_entries, float* dst_dev, uint32_t dst_stride_bytes, uint32_t num_instances,
+                                    size_t dst_instance_stride_bytes)
+{
+    OGRECU_REQUIRE(ctx && weights_dev, "NULL argument");
+    if (num_entries == 0 || num_instances == 0) return OGRECU_OK;
+    OGRECU_REQUIRE(vertex_index_dev && offsets_dev && dst_dev, "NULL stream pointer");
+    OGRECU_REQUIRE((((uintptr_t)dst_dev | dst_stride_bytes | dst_instance_stride_bytes) & 3) == 0, "destination must be 4-byte aligned");
+    OGRECU_REQUIRE(num_instances <= 65535, "at most 65535 instances per call");
+    OGRECU_CUDA(cudaSetDevice(ctx->device));
+    pose_blend_kernel<<<dim3(div_up(num_entries, 256), num_instances), 256, 0, ctx->stream>>>(weights_dev, 0.f, vertex_index_dev, offsets_dev, num_entries,
+                                                                                             (uint8_t*)dst_dev, dst_stride_bytes, dst_instance_stride_bytes);
+    OGRECU_CUDA(cudaGetLastError());
+    count_launch(ctx);
+    return OGRECU_OK;
+}
+
+int ogrecu_pose_blend_dev(ogrecu_ctx* ctx, float weight, const uint32_t* vertex_index_dev, const float* offsets_dev, uint32_t num_entries,
+                          float* dst_dev, uint32_t dst_stride_bytes)
+{
+    OGRECU_REQUIRE(ctx, "ctx is NULL");
+    if (num_entries == 0 || weight == 0.0f) return OGRECU_OK;
+    OGRECU_REQUIRE(vertex_index_dev && offsets_dev && dst_dev, "NULL stream pointer");
+    OGRECU_REQUIRE((((uintptr_t)dst_dev | dst_stride_bytes) & 3) == 0, "destination must be 4-byte aligned");
+    OGRECU_CUDA(cudaSetDevice(ctx->device));
+    pose_blend_kernel<<<dim3(div_up(num_entries, 256), 1), 256, 0, ctx->stream>>>(nullptr, weight, vertex_index_dev, offsets_dev, num_entries,
+                                                                                 (uint8_t*)dst_dev, dst_stride_bytes, 0);
+    OGRECU_CUDA(cudaGetLastError());
+    count_launch(ctx);
+    return OGRECU_OK;
 }
 
 int ogrecu_extrude_multi_dev(ogrecu_ctx* ctx, const float* lights_host, uint32_t n_lights, float dist, const float* src, float* dst,

@@ -751,3 +751,17 @@ long oracle_shadow_volume(uint32_t num_groups, const uint32_t* groups, const uin
     *used = num;
     return (long)pre;
 }
+
+
+/* ======================================================================= Pose blending */
+
+void oracle_pose_blend(float weight, const uint32_t* idx, const float* off3, uint32_t n, float* dst, uint32_t stride_floats)
+{
+    if (weight == 0.0f) return;
+    for (uint32_t i = 0; i < n; ++i) {
+        float* p = dst + (size_t)idx[i] * stride_floats;
+        p[0] = p[0] + (off3[3 * i] * weight);
+        p[1] = p[1] + (off3[3 * i + 1] * weight);
+        p[2] = p[2] + (off3[3 * i + 2] * weight);
+    }
+}

@@ -159,6 +159,12 @@ long oracle_shadow_volume(uint32_t num_groups, const uint32_t* groups, const uin
                           int directional, int use_mcguire, uint32_t flags, int separate_light_cap, uint16_t* indices,
                           uint32_t buffer_indices, uint32_t* used, uint32_t* ranges);
 
+/* ---- Pose blending ---- */
+/* Mesh::softwareVertexPoseBlend, OgreMain/src/OgreMesh.cpp:1948-2007, one element (positions or normals): for every map
+ * entry dst[idx] += offset * weight, as `*pdst = *pdst + (off * weight)`; nothing at all when weight == 0.
+ * `dst` points at the element's first float of vertex 0, stride in floats. */
+void oracle_pose_blend(float weight, const uint32_t* idx, const float* off3, uint32_t n, float* dst, uint32_t stride_floats);
+
 #ifdef __cplusplus
 }
 #endif

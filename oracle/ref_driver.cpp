@@ -774,6 +774,30 @@ API long ref_shadow_volume(const float* light4, const float* bounds6, uint32_t f
 API const uint16_t* ref_shadow_indices(void) { return g_shadow.out.data(); }
 API const uint32_t* ref_shadow_ranges(void) { return g_shadow.ranges.data(); }
 
+/* ================================================================ pose blending ==== */
+// Mesh::softwareVertexPoseBlend (OgreMain/src/OgreMesh.cpp:1948-2007, public static) on a vertex buffer of `nverts`
+// vertices, `floats_per_vertex` floats each (position at 0, normal at 3 when with_normals).  SURVEY §8f rank 3.
+API int ref_pose_blend(float weight, uint32_t n_off, const uint32_t* off_idx, const float* off3, uint32_t n_nrm, const uint32_t* nrm_idx,
+                       const float* nrm3, float* buf, uint32_t nverts, uint32_t floats_per_vertex, int with_normals)
+{
+    try {
+        host_open(64, 64);
+        std::map<uint32, Vector3f> offsets, normals;
+        for (uint32_t i = 0; i < n_off; ++i) offsets[off_idx[i]] = Vector3f(off3[3 * i], off3[3 * i + 1], off3[3 * i + 2]);
+        for (uint32_t i = 0; i < n_nrm; ++i) normals[nrm_idx[i]] = Vector3f(nrm3[3 * i], nrm3[3 * i + 1], nrm3[3 * i + 2]);
+        VertexData vd;
+        vd.vertexCount = nverts;
+        vd.vertexDeclaration->addElement(0, 0, VET_FLOAT3, VES_POSITION);
+        if (with_normals) vd.vertexDeclaration->addElement(0, 12, VET_FLOAT3, VES_NORMAL);
+        auto vb = HardwareBufferManager::getSingleton().createVertexBuffer(floats_per_vertex * 4, nverts, HBU_CPU_TO_GPU);
+        vb->writeData(0, (size_t)nverts * floats_per_vertex * 4, buf, true);
+        vd.vertexBufferBinding->setBinding(0, vb);
+        Mesh::softwareVertexPoseBlend(weight, offsets, normals, &vd);
+        vb->readData(0, (size_t)nverts * floats_per_vertex * 4, buf);
+        return 0;
+    } catch (std::exception& ex) { fprintf(stderr, "ref_pose_blend: %s\n", ex.what()); return 1; }
+}
+
 /* ==================================================================== timing ==== */
 
 // `reps` calls of the real SSE softwareVertexSkinning over `ninst` instances (each with its own

@@ -314,3 +314,22 @@ def clip_case(clip_tris, w, h, **kw):
         mvp[0, 0] = 1; mvp[1, 1] = 1; mvp[2, 2] = ratios[s]; mvp[3, 2] = 1
         cases.append(DrawCase(verts, None, mvp=mvp, viewport=vp, **kw))
     return cases
+
+
+def pose_case(seed, nverts=4000, frac=0.3, with_normals=True):
+    """A pose (sparse vertex offsets, optionally normals: Pose::getVertexOffsets / getNormals, std::map order = ascending
+    vertex index) and a pos[+normal] vertex buffer to blend it into."""
+    rng = np.random.default_rng(seed)
+    fpv = 6 if with_normals else 3
+    buf = rng.uniform(-5, 5, size=(nverts, fpv)).astype(np.float32)
+    special = np.array([0.0, -0.0, 1e-39, -1e-45, 3e38], np.float32)
+    m = rng.random(buf.shape) < 0.02
+    buf[m] = special[rng.integers(0, len(special), size=int(m.sum()))]
+    k = max(1, int(nverts * frac))
+    off_idx = np.sort(rng.choice(nverts, k, replace=False)).astype(np.uint32)
+    off = rng.uniform(-1, 1, size=(k, 3)).astype(np.float32)
+    off[rng.random(off.shape) < 0.05] = np.float32(-0.0)
+    kn = max(1, k // 2) if with_normals else 0
+    nrm_idx = np.sort(rng.choice(nverts, kn, replace=False)).astype(np.uint32) if kn else np.zeros(0, np.uint32)
+    nrm = rng.uniform(-1, 1, size=(kn, 3)).astype(np.float32)
+    return buf, off_idx, off, nrm_idx, nrm

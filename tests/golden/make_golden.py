@@ -15,6 +15,7 @@ container only; the GPU box and the CPU test suite just read the .npz files.
   jaiqua_skeleton.npz    inverses, every animation's node tracks and key frames) + 96 poses each: 1-3 enabled
                          animation states (order, time position, weight, both blend modes) and the palette
                          the real SkeletonInstance::setAnimationState + _getBoneMatrices produced
+  pose_blend.npz         outputs of the real Mesh::softwareVertexPoseBlend on seeded poses (datagen.pose_case)
   jaiqua_shadow.npz      the meshes' edge lists (Mesh::buildEdgeList) + 14 shadow-volume cases each (lights, bounds,
   sinbad_shadow.npz      flag combinations, shared-buffer offsets incl. a wrap): light facings from the real EdgeData and the
                          index buffer contents / ShadowRenderable ranges the real ShadowCaster::generateShadowVolume wrote
@@ -137,6 +138,25 @@ def save_shadow(name, mesh, ncases=14, seed=4):
     print(name, len(ed["groups"]), "groups", len(ed["edges"]), "edges", ncases, "cases")
 
 
+def save_pose_blend(name):
+    """Mesh::softwareVertexPoseBlend (the real static method) on seeded poses: inputs are regenerated by
+    datagen.pose_case(seed, ...), the outputs are stored."""
+    from datagen import pose_case
+    l = ref.lib()
+    out = {}
+    cases = [(1, 4000, 0.3, 1), (2, 17, 1.0, 1), (3, 1000, 0.01, 0), (4, 1, 1.0, 1)]
+    out["cases"] = np.array(cases, np.float64)
+    for k, (seed, nv, frac, normals) in enumerate(cases):
+        buf, oi, off, ni, nrm = pose_case(seed, nv, frac, bool(normals))
+        for j, w in enumerate((0.0, 1.0, 0.37, -0.5)):
+            r = buf.copy()
+            assert l.ref_pose_blend(w, len(oi), oi.ctypes.data, off.ctypes.data, len(ni), ni.ctypes.data, nrm.ctypes.data, r.ctypes.data, nv,
+                                    buf.shape[1], normals) == 0
+            out["c%d_w%d" % (k, j)] = r
+    np.savez_compressed(os.path.join(HERE, name), **out)
+    print(name, len(cases), "cases")
+
+
 def save_optutil(name):
     l = ref.lib()
     rng = np.random.default_rng(2024)
@@ -208,5 +228,6 @@ if __name__ == "__main__":
     save_skeleton("jaiqua_skin.npz", "jaiqua.mesh")
     save_skeleton_def("sinbad_skeleton.npz", "Sinbad.mesh")
     save_skeleton_def("jaiqua_skeleton.npz", "jaiqua.mesh")
+    save_pose_blend("pose_blend.npz")
     save_shadow("jaiqua_shadow.npz", "jaiqua.mesh")
     save_shadow("sinbad_shadow.npz", "Sinbad.mesh")

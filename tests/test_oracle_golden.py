@@ -151,3 +151,17 @@ def test_oracle_reproduces_ogres_own_shadow_volume_indices(name):
         assert (idx[:used - n] == 0xCDCD).all() and (idx[used:] == 0xCDCD).all()
         cols = 4 if (c["separate"] and c["flags"] & 1) else 2
         assert np.array_equal(ranges[:, :cols], c["ranges"][:, :cols]), (name, k)
+
+
+def test_oracle_reproduces_ogres_own_pose_blend():
+    """Mesh::softwareVertexPoseBlend (SURVEY §8f rank 3): outputs of the real static method on seeded poses."""
+    from datagen import pose_case
+    z = np.load(os.path.join(GOLDEN, "pose_blend.npz"))
+    for k, (seed, nv, frac, normals) in enumerate(z["cases"]):
+        buf, oi, off, ni, nrm = pose_case(int(seed), int(nv), float(frac), bool(normals))
+        for j, w in enumerate((0.0, 1.0, 0.37, -0.5)):
+            o = buf.copy()
+            oracle.lib().oracle_pose_blend(w, oi.ctypes.data, off.ctypes.data, len(oi), o.ctypes.data, buf.shape[1])
+            if normals:
+                oracle.lib().oracle_pose_blend(w, ni.ctypes.data, nrm.ctypes.data, len(ni), o.ctypes.data + 12, buf.shape[1])
+            assert np.array_equal(bits(o), bits(z["c%d_w%d" % (k, j)])), (k, w)

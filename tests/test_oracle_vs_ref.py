@@ -102,3 +102,21 @@ def test_oracle_shadow_volume_equals_real_generate_shadow_volume(mesh):
         assert np.array_equal(ri, oi) and ru == ou, (mesh, trial)
         cols = 4 if (sep and flags & 1) else 2
         assert np.array_equal(rr[:, :cols], orr[:, :cols]), (mesh, trial)
+
+
+def test_oracle_pose_blend_equals_real_mesh_pose_blend():
+    """Mesh::softwareVertexPoseBlend (public static) on a real HardwareVertexBuffer vs the restatement: weights incl. 0
+    (early return), 1, negative; positions only and positions + normals; signed zeros and denormals in the buffer."""
+    from datagen import pose_case
+    l = ref.lib()
+    for seed, nv, frac, normals in [(1, 4000, 0.3, True), (2, 17, 1.0, True), (3, 1000, 0.01, False), (4, 1, 1.0, True)]:
+        buf, oi, off, ni, nrm = pose_case(seed, nv, frac, normals)
+        fpv = buf.shape[1]
+        for w in (0.0, 1.0, 0.37, -0.5, 1e-30):
+            r = buf.copy(); o = buf.copy()
+            assert l.ref_pose_blend(w, len(oi), oi.ctypes.data, off.ctypes.data, len(ni), ni.ctypes.data, nrm.ctypes.data, r.ctypes.data, nv, fpv,
+                                    int(normals)) == 0
+            oracle.lib().oracle_pose_blend(w, oi.ctypes.data, off.ctypes.data, len(oi), o.ctypes.data, fpv)
+            if normals:
+                oracle.lib().oracle_pose_blend(w, ni.ctypes.data, nrm.ctypes.data, len(ni), o.ctypes.data + 12, fpv)
+            assert np.array_equal(bits(r), bits(o)), (seed, w)
