@@ -421,6 +421,17 @@ OGRECU_API int ogrecu_rt_set_strip(ogrecu_rt* rt, uint32_t y0, uint32_t y1);
  * regions of the screen then spread over all GPUs.  ogrecu_rt_set_strip(rt, 0, height) returns to the whole frame. */
 OGRECU_API int ogrecu_rt_set_bands(ogrecu_rt* rt, uint32_t band_rows, uint32_t phase, uint32_t period);
 
+/* Sort-last split of one frame (config 5, the scalable form): rank r draws the r-th slice of the TRIANGLES (in submission
+ * order) into its own full-size target, and the targets are merged per pixel: smallest depth wins, the later rank on ties,
+ * pixels a rank did not touch (still the cleared colour AND depth) never win.  That is Tiny's result whenever every
+ * triangle is opaque, depth-tested and depth-writing (ogrecu_raster_stats.tiles_ordered == 0 on every rank); blended or
+ * depth-write-off content must use the screen-space split (ogrecu_rt_set_strip / _set_bands).  The call merges
+ * num_sources source planes (RGB8 + f32 depth, num_pixels each, source s at src + s*src_stride_pixels pixels), which must
+ * be those of the ranks AFTER the one `dst` holds, in rank order, into `dst`. */
+OGRECU_API int ogrecu_composite_depth_dev(ogrecu_ctx* ctx, uint8_t* dst_rgb, float* dst_depth, const uint8_t* src_rgb,
+                                          const float* src_depth, size_t num_pixels, uint32_t num_sources,
+                                          size_t src_stride_pixels, const float clear_rgba[4], float clear_depth);
+
 /* Readback (TinyWindow::copyContentsToMemory, OgreTinyWindow.cpp:68-80;
  * HardwarePixelBuffer::blitToMemory).  Flushes pending work, copies the box
  * [left,right) x [top,bottom) to host as tightly described by dst_pitch_bytes.

@@ -154,6 +154,8 @@ SIGNATURES = {
     "ogrecu_draw_views": (C.c_int, [C.POINTER(C.c_void_p), C.c_uint32, C.POINTER(DrawDesc), c_float_p, c_float_p, c_float_p]),
     "ogrecu_rt_set_strip": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
     "ogrecu_rt_set_bands": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]),
+    "ogrecu_composite_depth_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_size_t, c_float_p,
+                                             C.c_float]),
     "ogrecu_rt_read_colour": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t]),
     "ogrecu_rt_read_depth": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t]),
     "ogrecu_rt_write_colour": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),

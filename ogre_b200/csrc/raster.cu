@@ -1023,6 +1023,35 @@ __global__ void rgb_to_rgba_kernel(const uint8_t* __restrict__ rgb, uint8_t* __r
     }
 }
 
+// Sort-last composite of one frame (or band) rendered by a LATER rank into the accumulated frame of the earlier ranks:
+// Tiny's per-pixel outcome over a sequence of opaque, depth-tested, depth-writing triangles is the fragment with the
+// smallest depth, the later one on ties (`depth > zbuf` rejects, tinyrenderer.h:76) — the same minimum over
+// (depth, ~submission order) the visibility path of raster_kernel takes.  The minimum over all triangles is the minimum
+// of the per-rank minima when rank r holds triangles that come after those of rank r-1.  A source pixel that still
+// holds the cleared colour and depth was not touched and never wins.
+__global__ void composite_depth_kernel(uint8_t* __restrict__ dst_rgb, float* __restrict__ dst_z, const uint8_t* __restrict__ src_rgb,
+                                       const float* __restrict__ src_z, size_t npx, uint32_t nsrc, size_t src_stride_px, uint32_t clear_rgb,
+                                       float clear_z)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npx) return;
+    float dz = dst_z[i];
+    uint32_t dc = 0;
+    bool changed = false;
+    for (uint32_t s = 0; s < nsrc; ++s) {                             // sources in rank order: a later one wins ties
+        const size_t j = (size_t)s * src_stride_px + i;
+        const float sz = src_z[j];
+        if (!(sz <= dz)) continue;
+        const uint32_t c = (uint32_t)src_rgb[3 * j] | ((uint32_t)src_rgb[3 * j + 1] << 8) | ((uint32_t)src_rgb[3 * j + 2] << 16);
+        if (sz == clear_z && c == clear_rgb) continue;                // untouched
+        dz = sz; dc = c; changed = true;
+    }
+    if (changed) {
+        dst_z[i] = dz;
+        dst_rgb[3 * i] = (uint8_t)dc; dst_rgb[3 * i + 1] = (uint8_t)(dc >> 8); dst_rgb[3 * i + 2] = (uint8_t)(dc >> 16);
+    }
+}
+
 __global__ void clear_depth_kernel(float* __restrict__ depth, size_t n, float v)
 {
     size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
@@ -1530,6 +1559,26 @@ int ogrecu_rt_set_strip(ogrecu_rt* rt, uint32_t y0, uint32_t y1)
     rt->strip_y0 = std::min(y0, rt->h);
     rt->strip_y1 = std::min(y1, rt->h);
     rt->band_tiles = 1; rt->band_phase = 0; rt->band_period = 1;
+    return OGRECU_OK;
+}
+
+int ogrecu_composite_depth_dev(ogrecu_ctx* ctx, uint8_t* dst_rgb, float* dst_depth, const uint8_t* src_rgb, const float* src_depth,
+                               size_t num_pixels, uint32_t num_sources, size_t src_stride_pixels, const float clear_rgba[4], float clear_depth)
+{
+    OGRECU_REQUIRE(ctx && clear_rgba, "NULL argument");
+    if (!num_pixels || !num_sources) return OGRECU_OK;
+    OGRECU_REQUIRE(dst_rgb && dst_depth && src_rgb && src_depth, "NULL plane");
+    OGRECU_CUDA(cudaSetDevice(ctx->device));
+    uint32_t q = 0;
+    for (int k = 0; k < 3; ++k) {                                   // the bytes clearFrameBuffer writes (Bitwise::floatToFixed(v, 8))
+        const float v = clear_rgba[k];
+        const uint32_t b = (v <= 0.0f) ? 0u : (v >= 1.0f) ? 255u : ((uint32_t)(v * 256.0f) & 0xffu);
+        q |= b << (8 * k);
+    }
+    composite_depth_kernel<<<div_up(num_pixels, 256), 256, 0, ctx->stream>>>(dst_rgb, dst_depth, src_rgb, src_depth, num_pixels, num_sources,
+                                                                             src_stride_pixels, q, clear_depth);
+    OGRECU_CUDA(cudaGetLastError());
+    count_launch(ctx);
     return OGRECU_OK;
 }
 

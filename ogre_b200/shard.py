@@ -3,7 +3,10 @@
 Three partitions, all without a data-path collective except the one exchange the path really has:
   * instances (skinning / morph / shadow streams): contiguous ranges, palettes travel with their instance;
   * offscreen views (config 4): view i -> rank i mod G, static geometry replicated once;
-  * one large frame (config 5): contiguous strips of screen-tile rows (ogrecu_rt_set_strip) or, load-balanced,
+  * one large frame (config 5), sort-last: rank r draws the r-th slice of the triangles into a full-size target and the
+    targets are merged per pixel by depth (composite_sort_last: one all-to-all of strips + ogrecu_composite_depth_dev) —
+    nothing is replicated, so this is the form that scales; valid for opaque depth-tested content;
+  * one large frame (config 5), sort-first: contiguous strips of screen-tile rows (ogrecu_rt_set_strip) or, load-balanced,
     interleaved bands of tile rows (ogrecu_rt_set_bands: band b -> rank b mod G); every rank rasterises only
     its rows and the disjoint rows are GATHERED to one rank at readback — the only collective, <= 24.9 MB for a
     4K RGB8 frame, no blending.
@@ -66,6 +69,58 @@ def gather_bands(plane, height, band_rows=TILE, dst=0, group=None):
         ir = torch.as_tensor(idx[r], device=plane.device, dtype=torch.long)
         frame.index_copy_(0, ir, recv[r][: len(ir)])
     return frame
+
+
+def triangle_range(num_triangles, rank, world):
+    """Sort-last split: contiguous slice [lo, hi) of the triangle list (submission order) drawn by `rank`."""
+    return instance_range(num_triangles, rank, world)
+
+
+def composite_sort_last(ctx, colour, depth, height, clear_rgba, clear_depth, dst=0, group=None, want_depth=False):
+    """Sort-last composite (ogrecu_composite_depth_dev): every rank passes its full-size planes (torch CUDA tensors
+    colour [H, W, 3] uint8, depth [H, W] float32) holding ITS slice of the triangles.  One all-to-all per plane sends
+    rows [q R, (q+1) R) of every rank to rank q (R = ceil(H / G) pixel rows), which merges the G versions of its rows in
+    rank order with one kernel (smallest depth, later rank on ties); the merged rows are then gathered to `dst`.
+    Returns (colour, depth or None) of the whole frame on `dst`, None elsewhere.  The path's one real exchange step:
+    (G-1)/G of 7 bytes per pixel per rank over NVLink.  When G divides H the planes are sent in place (no packing)."""
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    from .capi import check, lib
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    w = colour.shape[1]
+    rows = (height + world - 1) // world
+    if rows * world == height:
+        send_c, send_z = colour.view(world, rows, w, 3), depth.view(world, rows, w)
+    else:                                                  # pad the last owner's rows; padding is never read back
+        send_c = torch.empty((world * rows, w, 3), dtype=torch.uint8, device=colour.device)
+        send_z = torch.empty((world * rows, w), dtype=torch.float32, device=colour.device)
+        send_c[:height] = colour; send_z[:height] = depth
+        send_c, send_z = send_c.view(world, rows, w, 3), send_z.view(world, rows, w)
+    recv_c, recv_z = torch.empty_like(send_c), torch.empty_like(send_z)
+    dist.all_to_all_single(recv_c, send_c, group=group)
+    dist.all_to_all_single(recv_z, send_z, group=group)
+    n = rows * w
+    clear = (C.c_float * 4)(*[float(v) for v in clear_rgba])
+    same_stream = int(lib().ogrecu_get_stream(ctx.handle) or 0) == int(torch.cuda.current_stream().cuda_stream)
+    if not same_stream:
+        torch.cuda.current_stream().synchronize()       # the merge runs on the context's stream
+    if world > 1:                                       # recv[0] (rank 0's version) accumulates ranks 1 .. G-1, in order, in one launch
+        check(lib().ogrecu_composite_depth_dev(ctx.handle, recv_c[0].data_ptr(), recv_z[0].data_ptr(), recv_c[1].data_ptr(),
+                                               recv_z[1].data_ptr(), n, world - 1, n, clear, float(clear_depth)))
+    if not same_stream:
+        ctx.sync()
+
+    def gather_rows(part, shape, dtype):
+        full = torch.empty((world * rows,) + shape, dtype=dtype, device=part.device) if rank == dst else None
+        dist.gather(part.contiguous(), [full[r * rows:(r + 1) * rows] for r in range(world)] if rank == dst else None, dst=dst, group=group)
+        return full[:height] if rank == dst else None
+    frame_c = gather_rows(recv_c[0], (w, 3), torch.uint8)
+    frame_z = gather_rows(recv_z[0], (w,), torch.float32) if want_depth else None
+    if rank != dst:
+        return None
+    return frame_c, frame_z
 
 
 def gather_strips(strip, y0, y1, height, dst=0, group=None):

@@ -151,3 +151,76 @@ def test_draw_views_equals_one_draw_per_view(gpu_ctx):
         assert_images_equal(r.read_colour(), r.read_depth(), refs[k][0], refs[k][1], "draw_views view %d" % k)
         r.destroy()
     scene.free()
+
+
+@pytest.mark.parametrize("world", [2, 5])
+def test_sort_last_composite_equals_whole_frame(gpu_ctx, world):
+    """Sort-last split of one frame: slice r of the TRIANGLES (submission order) rendered into its own full-size target,
+    targets merged per pixel with ogrecu_composite_depth_dev in rank order — equals the frame rendered at once, including
+    pixels where fragments of different slices tie in depth (the later slice must win) and untouched pixels."""
+    import ctypes as C
+    import os
+    import sys
+    import ogre_b200
+    from ogre_b200 import capi, check, lib
+    from ogre_b200.shard import triangle_range
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import bench_configs as bc
+    ctx = gpu_ctx
+    w, h = 640, 480
+    verts, idx = bc.terrain(200)
+    # coplanar duplicates with other texture coordinates, appended at the end: they tie in depth with the original
+    # triangles of the first slices and must win (later in submission order)
+    tri = idx.reshape(-1, 3)
+    dup = tri[1000:3000].copy()
+    extra = verts[dup.reshape(-1)].copy()
+    extra[:, 6:8] += 0.37
+    base = len(verts)
+    verts2 = np.concatenate([verts, extra]).astype(np.float32)
+    idx2 = np.concatenate([idx, base + np.arange(len(extra), dtype=np.uint32)]).astype(np.uint32)
+    ntri = len(idx2) // 3
+    desc, keep = bc.upload_scene(ctx, verts2, idx2, bc.checker_texture(256), w, h)
+    mvps, mvits, lights = bc.camera_ring(1, w, h)
+    clear = (0.1, 0.2, 0.3, 1.0)
+
+    def render(rt, lo, hi):
+        d = ogre_b200.DrawDesc.from_buffer_copy(desc)
+        d.indices = desc.indices + lo * 12
+        d.draw_count = (hi - lo) * 3
+        rt.clear(colour=clear, depth=1.0)
+        hs = (C.c_void_p * 1)(rt.handle)
+        check(lib().ogrecu_draw_views(hs, 1, C.byref(d), mvps.ctypes.data_as(capi.c_float_p), mvits.ctypes.data_as(capi.c_float_p),
+                                      lights.ctypes.data_as(capi.c_float_p)))
+        rt.flush()
+    whole = ogre_b200.RenderTarget(ctx, w, h)
+    render(whole, 0, ntri)
+    wc, wz = whole.read_colour(), whole.read_depth()
+    assert whole.stats()["tiles_ordered"] == 0
+    parts = []
+    for r in range(world):
+        rt = ogre_b200.RenderTarget(ctx, w, h)
+        render(rt, *triangle_range(ntri, r, world))
+        parts.append(rt)
+    ptr = lambda rt, f: (lambda p: (check(f(rt.handle, C.byref(p))), p.value)[1])(C.c_void_p())
+    c0, z0 = ptr(parts[0], lib().ogrecu_rt_colour_device_ptr), ptr(parts[0], lib().ogrecu_rt_depth_device_ptr)
+    cl = (C.c_float * 4)(*clear)
+    if world == 2:
+        check(lib().ogrecu_composite_depth_dev(ctx.handle, c0, z0, ptr(parts[1], lib().ogrecu_rt_colour_device_ptr),
+                                               ptr(parts[1], lib().ogrecu_rt_depth_device_ptr), w * h, 1, 0, cl, 1.0))
+    else:
+        # several sources in ONE call: stacked planes of ranks 1 .. G-1, in rank order
+        sc = ctx.alloc((world - 1) * w * h * 3); sz = ctx.alloc((world - 1) * w * h * 4)
+        for r in range(1, world):
+            check(lib().ogrecu_memcpy_d2d(ctx.handle, sc.ptr + (r - 1) * w * h * 3, ptr(parts[r], lib().ogrecu_rt_colour_device_ptr), w * h * 3))
+            check(lib().ogrecu_memcpy_d2d(ctx.handle, sz.ptr + (r - 1) * w * h * 4, ptr(parts[r], lib().ogrecu_rt_depth_device_ptr), w * h * 4))
+        check(lib().ogrecu_composite_depth_dev(ctx.handle, c0, z0, sc.ptr, sz.ptr, w * h, world - 1, w * h, cl, 1.0))
+    ctx.sync()
+    gc, gz = parts[0].read_colour(), parts[0].read_depth()
+    assert np.array_equal(gz.view(np.uint32), wz.view(np.uint32))
+    assert np.array_equal(gc, wc)
+    # the duplicates really decided some pixels (otherwise the tie rule was not exercised)
+    only_first = ogre_b200.RenderTarget(ctx, w, h)
+    render(only_first, 0, len(idx) // 3)
+    assert (only_first.read_colour() != wc).any()
+    for rt in parts + [whole, only_first]:
+        rt.destroy()

@@ -12,6 +12,17 @@ import torch.multiprocessing as mp
 from ogre_b200 import shard
 
 
+def test_triangle_slices_cover_the_list_in_order():
+    for n in (0, 1, 7, 19996488):
+        for world in (1, 2, 3, 8):
+            prev = 0
+            for r in range(world):
+                lo, hi = shard.triangle_range(n, r, world)
+                assert lo == prev and hi >= lo
+                prev = hi
+            assert prev == n
+
+
 def test_interleaved_bands_cover_every_row_once():
     for h in (1, 15, 16, 17, 160, 2160):
         for world in (1, 2, 3, 8):

@@ -345,6 +345,7 @@ def c5(ctx, T, args):
     rt = ogre_b200.RenderTarget(ctx, w, h)
     run = raster_views(ctx, T, desc, [rt], mvps, mvits, lights, 1)
     if WORLD > 1:
+        args._c5_desc, args._c5_cam = desc, (mvps, mvits, lights)
         return c5_split(ctx, T, args, rt, run, ntri, len(idx), len(verts))
     dt = T.time(run, iters=3, warm=1)
     stats = rt.stats()
@@ -370,7 +371,7 @@ def c5_split(ctx, T, args, rt, run, ntri, nidx, nverts):
     Checked on rank 0 against the same frame rendered whole on one GPU."""
     import torch
     import torch.distributed as dist
-    from ogre_b200.shard import DevicePlane, gather_bands, gather_strips, strip_rows
+    from ogre_b200.shard import DevicePlane, composite_sort_last, gather_bands, gather_strips, strip_rows, triangle_range
     w, h = rt.width, rt.height
     p = C.c_void_p()
     check(lib().ogrecu_rt_colour_device_ptr(rt.handle, C.byref(p)))
@@ -410,11 +411,59 @@ def c5_split(ctx, T, args, rt, run, ntri, nidx, nverts):
     interleaved = {"ms_per_frame_render_only": dt_render_b * 1e3, "ms_per_frame_with_composite": dt_b * 1e3, "frames_per_s": 1 / dt_b,
                    "Mtri_per_s": ntri / dt_b / 1e6, "identical_to_single_gpu_frame": ok_b, "stats_rank0": band_stats,
                    "split": "interleaved bands of one tile row (ogrecu_rt_set_bands), band b -> GPU b mod G"}
+    # sort-last: this rank draws only ITS slice of the triangles into the full-size target; planes merged by depth
+    rt.set_strip(0, h)
+    pz = C.c_void_p()
+    check(lib().ogrecu_rt_depth_device_ptr(rt.handle, C.byref(pz)))
+    zplane = DevicePlane(pz.value, (h, w), "<f4").tensor(torch.device("cuda", LOCAL))
+    lo, hi = triangle_range(ntri, RANK, WORLD)
+    dslice = DrawDesc.from_buffer_copy(args._c5_desc)
+    dslice.indices = args._c5_desc.indices + lo * 12
+    dslice.draw_count = (hi - lo) * 3
+    hs = (C.c_void_p * 1)(rt.handle)
+    mv, mi, li = args._c5_cam
+
+    def render_slice():
+        rt.clear(colour=(0.1, 0.2, 0.3, 1.0), depth=1.0)
+        check(lib().ogrecu_draw_views(hs, 1, C.byref(dslice), mv.ctypes.data_as(capi.c_float_p), mi.ctypes.data_as(capi.c_float_p),
+                                      li.ctypes.data_as(capi.c_float_p)))
+
+    def render_and_composite_sl():
+        render_slice()
+        check(lib().ogrecu_flush(rt.handle))
+        with torch.cuda.stream(T.stream):
+            result[0] = composite_sort_last(ctx, plane, zplane, h, (0.1, 0.2, 0.3, 1.0), 1.0, dst=0)
+
+    def render_slice_flush():
+        render_slice()
+        check(lib().ogrecu_flush(rt.handle))
+    dt_render_sl = T.time(render_slice_flush, iters=5, warm=2)
+    sl_stats = rt.stats()
+    dt_sl = T.time(render_and_composite_sl, iters=10, warm=5)          # the all-to-all connects its peers lazily: warm it up
+
+    def composite_only():
+        with torch.cuda.stream(T.stream):
+            result[0] = composite_sort_last(ctx, plane, zplane, h, (0.1, 0.2, 0.3, 1.0), 1.0, dst=0)
+    dt_comp = T.time(composite_only, iters=10, warm=2)
+    render_slice_flush()
+    with torch.cuda.stream(T.stream):
+        result[0] = composite_sort_last(ctx, plane, zplane, h, (0.1, 0.2, 0.3, 1.0), 1.0, dst=0)
+    T.barrier()
+    ok_sl = None
+    if RANK == 0:
+        ok_sl = bool(np.array_equal(result[0][0].cpu().numpy(), whole))
+    T.barrier()
+    sort_last = {"ms_per_frame_render_only": dt_render_sl * 1e3, "ms_per_frame_with_composite": dt_sl * 1e3, "ms_composite_only": dt_comp * 1e3,
+                 "frames_per_s": 1 / dt_sl,
+                 "Mtri_per_s": ntri / dt_sl / 1e6, "identical_to_single_gpu_frame": ok_sl, "stats_rank0": sl_stats,
+                 "exchange_bytes_per_rank": int(w * h * 7 * (WORLD - 1) / WORLD),
+                 "split": "sort-last: rank r draws triangles [r T/G, (r+1) T/G), all-to-all of strips, per-pixel depth merge "
+                          "(ogrecu_composite_depth_dev), gather to rank 0"}
     return {"config": "c5 one 3840x2160 frame, %d triangles, textured, lit: split-frame over %d GPUs (contiguous strips of tile rows), "
                       "NCCL gather of the strips to rank 0 at readback" % (ntri, WORLD), "n_gpus": WORLD,
             "ms_per_frame_render_only": dt_render * 1e3, "ms_per_frame_with_composite": dt * 1e3, "frames_per_s": 1 / dt,
             "Mtri_per_s": ntri / dt / 1e6, "composite_bytes": int(w * h * 3 * (WORLD - 1) / WORLD),
-            "identical_to_single_gpu_frame": ok, "stats_rank0_strip": strip_stats, "interleaved": interleaved}
+            "identical_to_single_gpu_frame": ok, "stats_rank0_strip": strip_stats, "interleaved": interleaved, "sort_last": sort_last}
 
 
 def main():

@@ -1,5 +1,11 @@
-timeout 900 python -m pytest tests/test_skin_tile_gpu.py tests/test_golden_gpu.py tests/test_full_size_gpu.py -x -q 2>&1 | tail -3
-python bench.py --no-cpu-baseline --steps 100 2>/dev/null | python -c "
-import json,sys
-d=json.loads(sys.stdin.read()); x=d['extra']
-print('value %.0f e2e %.0f states %.0f roof %.3f other %.3f'%(d['value'], d['e2e']['value'], d['e2e']['states_value'], d['roofline']['frac'], x['roofline_other_form']['frac']), ['%.1f'%(1e3*v) for v in x['fused_ms_per_submesh']], ['%.1f'%(1e3*v) for v in x['skin_ms_per_submesh']])"
+for n in 8 4; do
+python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2954$n tools/bench_configs.py --config c5 > gpurun_out/c5_sl_n$n.out 2> gpurun_out/c5_sl_n$n.err; echo rc=$?
+grep '^{' gpurun_out/c5_sl_n$n.out > gpurun_out/configs_c5_n${n}_r01n.jsonl
+python - <<P
+import json
+d=json.loads(open('gpurun_out/configs_c5_n${n}_r01n.jsonl').read())
+print($n,'strips', round(d['ms_per_frame_render_only'],3), round(d['ms_per_frame_with_composite'],3), d['identical_to_single_gpu_frame'])
+print($n,'bands ', round(d['interleaved']['ms_per_frame_render_only'],3), round(d['interleaved']['ms_per_frame_with_composite'],3), d['interleaved']['identical_to_single_gpu_frame'])
+print($n,"sortlast", round(d["sort_last"]["ms_per_frame_render_only"],3), round(d["sort_last"]["ms_per_frame_with_composite"],3), round(d["sort_last"]["ms_composite_only"],3), d['sort_last']['identical_to_single_gpu_frame'])
+P
+done
