@@ -470,7 +470,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", default="c1,c3,c4,c5")
     ap.add_argument("--views", type=int, default=1024)
-    ap.add_argument("--chunk", type=int, default=16, help="views per ogrecu_draw_views pass")
+    ap.add_argument("--chunk", type=int, default=32, help="views per ogrecu_draw_views pass")
     ap.add_argument("--c3-tris", type=int, default=2000000)
     ap.add_argument("--c4-tris", type=int, default=1000000)
     ap.add_argument("--c5-tris", type=int, default=20000000)

@@ -1,11 +1,7 @@
-for n in 8 4; do
-python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2954$n tools/bench_configs.py --config c5 > gpurun_out/c5_sl_n$n.out 2> gpurun_out/c5_sl_n$n.err; echo rc=$?
-grep '^{' gpurun_out/c5_sl_n$n.out > gpurun_out/configs_c5_n${n}_r01n.jsonl
-python - <<P
-import json
-d=json.loads(open('gpurun_out/configs_c5_n${n}_r01n.jsonl').read())
-print($n,'strips', round(d['ms_per_frame_render_only'],3), round(d['ms_per_frame_with_composite'],3), d['identical_to_single_gpu_frame'])
-print($n,'bands ', round(d['interleaved']['ms_per_frame_render_only'],3), round(d['interleaved']['ms_per_frame_with_composite'],3), d['interleaved']['identical_to_single_gpu_frame'])
-print($n,"sortlast", round(d["sort_last"]["ms_per_frame_render_only"],3), round(d["sort_last"]["ms_per_frame_with_composite"],3), round(d["sort_last"]["ms_composite_only"],3), d['sort_last']['identical_to_single_gpu_frame'])
-P
-done
+for c in 8 16 32 64; do python tools/bench_configs.py --config c4 --views 256 --chunk $c | python -c "
+import sys,json
+d=json.loads(sys.stdin.read()); print('chunk $c', round(d['views_per_s_device']), round(d['ms_per_view_device'],4))"; done
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 100 --warmup 3 2>/dev/null | grep '^{' | python -c "
+import sys,json
+d=json.loads(sys.stdin.read()); print('N=2 value', round(d['value']), 'e2e', round(d['e2e']['value']), 'states', round(d['e2e']['states_value']))"
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 3 --warmup 1 2>/dev/null | grep '^{' | cut -c1-160
