@@ -313,6 +313,17 @@ OGRECU_API int ogrecu_pose_blend_instanced_dev(ogrecu_ctx* ctx, const float* wei
                                                uint32_t dst_stride_bytes, uint32_t num_instances,
                                                size_t dst_instance_stride_bytes);
 
+/* The two normal passes around the pose blends of a frame (Entity::_updateAnimation, OgreEntity.cpp:823-864), for
+ * num_instances buffers at once: reset = the zeroing of initialisePoseVertexData (OgreEntity.cpp:1180-1204) when the poses
+ * carry normals; finalise = Entity::finalisePoseNormals (OgreEntity.cpp:1207-1261): where the accumulated normal is shorter
+ * than 1 the base-mesh normal (shared by all instances) fills in with weight 1 - length, then Vector3::normalise.
+ * Pointers name the normal of vertex 0. */
+OGRECU_API int ogrecu_pose_normals_reset_dev(ogrecu_ctx* ctx, float* dst_norm_dev, uint32_t num_vertices, uint32_t dst_stride_bytes,
+                                             uint32_t num_instances, size_t dst_instance_stride_bytes);
+OGRECU_API int ogrecu_pose_normals_finalise_dev(ogrecu_ctx* ctx, float* dst_norm_dev, const float* base_norm_dev,
+                                                uint32_t num_vertices, uint32_t dst_stride_bytes, uint32_t base_stride_bytes,
+                                                uint32_t num_instances, size_t dst_instance_stride_bytes);
+
 /* ------------------------------------------ silhouette / shadow-volume indices ------ */
 /* ShadowCaster::generateShadowVolume (OgreMain/src/OgreShadowCaster.cpp:191-515) as an order-preserving stream
  * compaction on the device.  The edge list of a mesh (EdgeData, OgreEdgeListBuilder.h:50-160) is uploaded once:

@@ -109,6 +109,8 @@ SIGNATURES = {
     "ogrecu_pose_blend_dev": (C.c_int, [C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]),
     "ogrecu_pose_blend_instanced_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32,
                                                   C.c_size_t]),
+    "ogrecu_pose_normals_reset_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_size_t]),
+    "ogrecu_pose_normals_finalise_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_size_t]),
     "ogrecu_edges_create": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, c_void_pp]),
     "ogrecu_edges_destroy": (C.c_int, [C.c_void_p]),
     "ogrecu_shadow_use_mcguire": (C.c_int, [C.c_uint32, C.c_void_p, C.c_void_p]),

@@ -454,6 +454,28 @@ __global__ void pose_blend_kernel(const float* __restrict__ weights, float weigh
     p[2] = fadd(p[2], fmul(oz, w));
 }
 
+// Entity::finalisePoseNormals (OgreEntity.cpp:1207-1261) for many instances: where the accumulated pose normal is shorter
+// than 1 (- 1e-4) the base mesh normal fills in with weight 1 - length, then Vector3::normalise.  `zero_first` instead
+// performs initialisePoseVertexData's reset of the normals (:1180-1204) so that a frame needs no separate memset.
+__global__ void pose_normals_kernel(uint8_t* __restrict__ dst_norm, const uint8_t* __restrict__ src_norm, uint32_t n, uint32_t dst_stride,
+                                    uint32_t src_stride, size_t dst_inst_stride, int zero_first)
+{
+    const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n) return;
+    float* d = reinterpret_cast<float*>(dst_norm + (size_t)blockIdx.y * dst_inst_stride + (size_t)v * dst_stride);
+    if (zero_first) { d[0] = 0.0f; d[1] = 0.0f; d[2] = 0.0f; return; }
+    const float* s = reinterpret_cast<const float*>(src_norm + (size_t)v * src_stride);
+    float x = d[0], y = d[1], z = d[2];
+    const float len = fsqrt(fadd(fadd(fadd(0.0f, fmul(x, x)), fmul(y, y)), fmul(z, z)));
+    if (fadd(len, 1e-4f) < 1.0f) {
+        const float bw = fsub(1.0f, len);
+        x = fadd(x, fmul(__ldg(s), bw)); y = fadd(y, fmul(__ldg(s + 1), bw)); z = fadd(z, fmul(__ldg(s + 2), bw));
+    }
+    const float l2 = fsqrt(fadd(fadd(fadd(0.0f, fmul(x, x)), fmul(y, y)), fmul(z, z)));
+    if (l2 > 0.0f) { const float inv = fdiv(1.0f, l2); x = fmul(x, inv); y = fmul(y, inv); z = fmul(z, inv); }
+    d[0] = x; d[1] = y; d[2] = z;
+}
+
 inline bool aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
 
 int validate_skin_job(const ogrecu_skin_job& j)
@@ -726,6 +748,35 @@ int ogrecu_pose_blend_instanced_dev(ogrecu_ctx* ctx, const float* weights_dev, c
     OGRECU_CUDA(cudaGetLastError());
     count_launch(ctx);
     return OGRECU_OK;
+}
+
+static int pose_normals_launch(ogrecu_ctx* ctx, float* dst, const float* src, uint32_t n, uint32_t dst_stride, uint32_t src_stride, uint32_t ninst,
+                               size_t inst_stride, int zero_first)
+{
+    OGRECU_REQUIRE(ctx, "ctx is NULL");
+    if (n == 0 || ninst == 0) return OGRECU_OK;
+    OGRECU_REQUIRE(dst && (zero_first || src), "NULL stream pointer");
+    OGRECU_REQUIRE((((uintptr_t)dst | (uintptr_t)src | dst_stride | src_stride | inst_stride) & 3) == 0, "streams must be 4-byte aligned");
+    OGRECU_REQUIRE(ninst <= 65535, "at most 65535 instances per call");
+    OGRECU_CUDA(cudaSetDevice(ctx->device));
+    pose_normals_kernel<<<dim3(div_up(n, 256), ninst), 256, 0, ctx->stream>>>((uint8_t*)dst, (const uint8_t*)src, n, dst_stride, src_stride, inst_stride,
+                                                                             zero_first);
+    OGRECU_CUDA(cudaGetLastError());
+    count_launch(ctx);
+    return OGRECU_OK;
+}
+
+int ogrecu_pose_normals_reset_dev(ogrecu_ctx* ctx, float* dst_norm_dev, uint32_t num_vertices, uint32_t dst_stride_bytes, uint32_t num_instances,
+                                  size_t dst_instance_stride_bytes)
+{
+    return pose_normals_launch(ctx, dst_norm_dev, nullptr, num_vertices, dst_stride_bytes, 0, num_instances, dst_instance_stride_bytes, 1);
+}
+
+int ogrecu_pose_normals_finalise_dev(ogrecu_ctx* ctx, float* dst_norm_dev, const float* base_norm_dev, uint32_t num_vertices,
+                                     uint32_t dst_stride_bytes, uint32_t base_stride_bytes, uint32_t num_instances, size_t dst_instance_stride_bytes)
+{
+    return pose_normals_launch(ctx, dst_norm_dev, base_norm_dev, num_vertices, dst_stride_bytes, base_stride_bytes, num_instances,
+                               dst_instance_stride_bytes, 0);
 }
 
 int ogrecu_pose_blend_dev(ogrecu_ctx* ctx, float weight, const uint32_t* vertex_index_dev, const float* offsets_dev, uint32_t num_entries,

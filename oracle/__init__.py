@@ -102,6 +102,8 @@ def lib():
         l.oracle_tiny_draw.restype = C.c_uint64
         l.oracle_pose_blend.argtypes = [c_f, vp, vp, C.c_uint32, vp, C.c_uint32]
         l.oracle_pose_blend.restype = None
+        l.oracle_finalise_pose_normals.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32]
+        l.oracle_finalise_pose_normals.restype = None
         l.oracle_shadow_use_mcguire.argtypes = [C.c_uint32, vp, vp]
         l.oracle_shadow_volume.argtypes = [C.c_uint32, vp, vp, vp, vp, C.c_int, C.c_int, C.c_uint32, C.c_int, vp, C.c_uint32, vp, vp]
         l.oracle_shadow_volume.restype = C.c_long

@@ -765,3 +765,20 @@ void oracle_pose_blend(float weight, const uint32_t* idx, const float* off3, uin
         p[2] = p[2] + (off3[3 * i + 2] * weight);
     }
 }
+
+void oracle_finalise_pose_normals(float* dst_norm, const float* src_norm, uint32_t n, uint32_t dst_stride_floats, uint32_t src_stride_floats)
+{
+    for (uint32_t v = 0; v < n; ++v) {
+        float* d = dst_norm + (size_t)v * dst_stride_floats;
+        const float* s = src_norm + (size_t)v * src_stride_floats;
+        float x = d[0], y = d[1], z = d[2];
+        float len = sqrtf(((0.0f + x * x) + y * y) + z * z);          /* Vector3::length */
+        if (len + 1e-4f < 1.0f) {
+            float bw = 1.0f - len;
+            x += s[0] * bw; y += s[1] * bw; z += s[2] * bw;
+        }
+        float l2 = sqrtf(((0.0f + x * x) + y * y) + z * z);           /* Vector3::normalise */
+        if (l2 > 0.0f) { float inv = 1.0f / l2; x *= inv; y *= inv; z *= inv; }
+        d[0] = x; d[1] = y; d[2] = z;
+    }
+}

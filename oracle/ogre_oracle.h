@@ -164,6 +164,9 @@ long oracle_shadow_volume(uint32_t num_groups, const uint32_t* groups, const uin
  * entry dst[idx] += offset * weight, as `*pdst = *pdst + (off * weight)`; nothing at all when weight == 0.
  * `dst` points at the element's first float of vertex 0, stride in floats. */
 void oracle_pose_blend(float weight, const uint32_t* idx, const float* off3, uint32_t n, float* dst, uint32_t stride_floats);
+/* Entity::finalisePoseNormals, OgreMain/src/OgreEntity.cpp:1207-1261: len = |n|; if (len + 1e-4f < 1) n += base * (1 - len);
+ * n.normalise().  dst_norm / src_norm point at the normal of vertex 0 (accumulated pose normals / base mesh normals). */
+void oracle_finalise_pose_normals(float* dst_norm, const float* src_norm, uint32_t n, uint32_t dst_stride_floats, uint32_t src_stride_floats);
 
 #ifdef __cplusplus
 }

@@ -89,6 +89,7 @@ def lib():
         l.ref_bench_palettes.argtypes = [C.c_uint32, vp, sz, vp]
         l.ref_bench_palettes.restype = C.c_double
         l.ref_pose_blend.argtypes = [c_f, C.c_uint32, vp, vp, C.c_uint32, vp, vp, vp, C.c_uint32, C.c_uint32, C.c_int]
+        l.ref_pose_entity.argtypes = [C.c_uint32, vp, C.c_uint32, vp, vp, vp, vp, vp, C.c_int, vp]
         l.ref_shadow_open.argtypes = [C.c_char_p, vp, vp, vp]
         l.ref_shadow_edges.argtypes = [vp, vp, vp]
         l.ref_shadow_edges.restype = None

@@ -798,6 +798,66 @@ API int ref_pose_blend(float weight, uint32_t n_off, const uint32_t* off_idx, co
     } catch (std::exception& ex) { fprintf(stderr, "ref_pose_blend: %s\n", ex.what()); return 1; }
 }
 
+// The whole pose-animation path of an Entity on a hand-built mesh (one sub-mesh, position + normal in one buffer):
+// Entity::_updateAnimation -> initialisePoseVertexData (copy, normals zeroed when the poses carry normals,
+// OgreEntity.cpp:1164-1205) -> Animation::apply -> VertexAnimationTrack::applyPoseToVertexData ->
+// Mesh::softwareVertexPoseBlend per referenced pose (OgreAnimationTrack.cpp:925-944) -> Entity::finalisePoseNormals
+// (OgreEntity.cpp:1207-1261).  pose p owns entries [pose_off[p], pose_off[p+1]) of idx / off3 / nrm3.
+API int ref_pose_entity(uint32_t nverts, const float* posnorm6, uint32_t nposes, const uint32_t* pose_off, const uint32_t* idx, const float* off3,
+                        const float* nrm3, const float* influence, int with_normals, float* out6)
+{
+    try {
+        if (!g_scene.sm) { int rc = ref_scene_open("ogrehead.mesh", 64, 64, 100.0f); if (rc) return rc; }
+        static int serial = 0;
+        const String name = "pose_probe_" + StringConverter::toString(serial++);
+        MeshPtr m = MeshManager::getSingleton().createManual(name, ResourceGroupManager::DEFAULT_RESOURCE_GROUP_NAME);
+        SubMesh* sub = m->createSubMesh();
+        sub->useSharedVertices = false;
+        sub->vertexData = OGRE_NEW VertexData();
+        sub->vertexData->vertexCount = nverts;
+        sub->vertexData->vertexDeclaration->addElement(0, 0, VET_FLOAT3, VES_POSITION);
+        sub->vertexData->vertexDeclaration->addElement(0, 12, VET_FLOAT3, VES_NORMAL);
+        auto vb = HardwareBufferManager::getSingleton().createVertexBuffer(24, nverts, HBU_CPU_TO_GPU);
+        vb->writeData(0, (size_t)nverts * 24, posnorm6, true);
+        sub->vertexData->vertexBufferBinding->setBinding(0, vb);
+        const uint16_t tri[3] = {0, (uint16_t)(nverts > 1 ? 1 : 0), (uint16_t)(nverts > 2 ? 2 : 0)};
+        sub->indexData->indexBuffer = HardwareBufferManager::getSingleton().createIndexBuffer(HardwareIndexBuffer::IT_16BIT, 3, HBU_CPU_TO_GPU);
+        sub->indexData->indexBuffer->writeData(0, 6, tri, true);
+        sub->indexData->indexCount = 3;
+        m->_setBounds(AxisAlignedBox(-100, -100, -100, 100, 100, 100));
+        m->_setBoundingSphereRadius(200);
+        for (uint32_t p = 0; p < nposes; ++p) {
+            Pose* pose = m->createPose(1, "pose" + StringConverter::toString(p));      // target 1 = sub-mesh 0
+            for (uint32_t k = pose_off[p]; k < pose_off[p + 1]; ++k) {
+                const Vector3f o(off3[3 * k], off3[3 * k + 1], off3[3 * k + 2]);
+                if (with_normals) pose->addVertex(idx[k], o, Vector3f(nrm3[3 * k], nrm3[3 * k + 1], nrm3[3 * k + 2]));
+                else pose->addVertex(idx[k], o);
+            }
+        }
+        Animation* anim = m->createAnimation("manual", 0);
+        VertexAnimationTrack* track = anim->createVertexTrack(1, VAT_POSE);
+        VertexPoseKeyFrame* kf = track->createVertexPoseKeyFrame(0);
+        for (uint32_t p = 0; p < nposes; ++p) kf->addPoseReference((ushort)p, influence[p]);
+        m->load();
+        Entity* e = g_scene.sm->createEntity(m);
+        g_scene.sm->getRootSceneNode()->createChildSceneNode()->attachObject(e);
+        AnimationState* as = e->getAnimationState("manual");
+        as->setEnabled(true);
+        as->setTimePosition(0);
+        e->addSoftwareAnimationRequest(with_normals != 0);
+        g_host->root->renderOneFrame();          // advance the frame number: animation is evaluated once per frame
+        e->_updateAnimation();
+        VertexData* vd = e->getSubEntity(0)->_getSoftwareVertexAnimVertexData();
+        auto ob = vd->vertexBufferBinding->getBuffer(vd->vertexDeclaration->findElementBySemantic(VES_POSITION)->getSource());
+        if (ob->getVertexSize() != 24) { fprintf(stderr, "ref_pose_entity: unexpected vertex size %zu\n", ob->getVertexSize()); return 3; }
+        ob->readData(0, (size_t)nverts * 24, out6);
+        // The probe entity and mesh are deliberately kept alive: OGRE pools the temporary blend buffers by the ADDRESS of
+        // their source buffer, and a freed probe buffer's address is reused by the next probe of another size.
+        e->setVisible(false);
+        return 0;
+    } catch (std::exception& ex) { fprintf(stderr, "ref_pose_entity: %s\n", ex.what()); return 1; }
+}
+
 /* ==================================================================== timing ==== */
 
 // `reps` calls of the real SSE softwareVertexSkinning over `ninst` instances (each with its own

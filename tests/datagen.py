@@ -333,3 +333,40 @@ def pose_case(seed, nverts=4000, frac=0.3, with_normals=True):
     nrm_idx = np.sort(rng.choice(nverts, kn, replace=False)).astype(np.uint32) if kn else np.zeros(0, np.uint32)
     nrm = rng.uniform(-1, 1, size=(kn, 3)).astype(np.float32)
     return buf, off_idx, off, nrm_idx, nrm
+
+
+def pose_entity_case(seed, nv, nposes):
+    """Inputs of a whole pose-animated frame: base mesh pos+normal [nv,6], poses (flattened maps with a prefix table),
+    offsets and (sub-unit-length) normals per entry, influences per pose (one of them 0)."""
+    rng = np.random.default_rng(seed)
+    base = rng.uniform(-5, 5, size=(nv, 6)).astype(np.float32)
+    nn = rng.normal(size=(nv, 3))
+    base[:, 3:] = (nn / np.linalg.norm(nn, axis=1, keepdims=True)).astype(np.float32)
+    offs, idx, off, nrm = [0], [], [], []
+    for p in range(nposes):
+        k = max(1, int(nv * rng.uniform(0.05, 0.6)))
+        idx.append(np.sort(rng.choice(nv, k, replace=False)).astype(np.uint32))
+        off.append(rng.uniform(-1, 1, size=(k, 3)).astype(np.float32))
+        n3 = rng.normal(size=(k, 3)); n3 /= np.linalg.norm(n3, axis=1, keepdims=True); n3 *= rng.uniform(0.2, 1.0, size=(k, 1))
+        nrm.append(n3.astype(np.float32))
+        offs.append(offs[-1] + k)
+    infl = rng.uniform(0.1, 1.0, nposes).astype(np.float32)
+    if nposes > 2:
+        infl[1] = 0.0
+    return base, np.array(offs, np.uint32), np.concatenate(idx), np.concatenate(off), np.concatenate(nrm), infl
+
+
+def pose_entity_oracle(oracle, base, offs, idx, off, nrm, infl, with_normals):
+    """initialisePoseVertexData -> softwareVertexPoseBlend per pose -> finalisePoseNormals with the CPU oracle."""
+    o = base.copy()
+    if with_normals:
+        o[:, 3:] = 0
+    for p in range(len(infl)):
+        a, b = int(offs[p]), int(offs[p + 1])
+        ii, oo, n3 = np.ascontiguousarray(idx[a:b]), np.ascontiguousarray(off[a:b]), np.ascontiguousarray(nrm[a:b])
+        oracle.lib().oracle_pose_blend(float(infl[p]), ii.ctypes.data, oo.ctypes.data, b - a, o.ctypes.data, 6)
+        if with_normals:
+            oracle.lib().oracle_pose_blend(float(infl[p]), ii.ctypes.data, n3.ctypes.data, b - a, o.ctypes.data + 12, 6)
+    if with_normals:
+        oracle.lib().oracle_finalise_pose_normals(o.ctypes.data + 12, base.ctypes.data + 12, len(base), 6, 6)
+    return o

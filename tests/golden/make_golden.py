@@ -153,8 +153,18 @@ def save_pose_blend(name):
             assert l.ref_pose_blend(w, len(oi), oi.ctypes.data, off.ctypes.data, len(ni), ni.ctypes.data, nrm.ctypes.data, r.ctypes.data, nv,
                                     buf.shape[1], normals) == 0
             out["c%d_w%d" % (k, j)] = r
+    # whole pose-animated frames of a real Entity (initialisePoseVertexData -> blends -> finalisePoseNormals)
+    from datagen import pose_entity_case
+    frames = [(1, 500, 3, 1), (2, 500, 3, 0), (3, 37, 1, 1), (4, 2000, 5, 1)]
+    out["frames"] = np.array(frames, np.int64)
+    for k, (seed, nv, nposes, normals) in enumerate(frames):
+        base, offs, idx, off, nrm, infl = pose_entity_case(seed, nv, nposes)
+        res = np.zeros((nv, 6), np.float32)
+        assert l.ref_pose_entity(nv, base.ctypes.data, nposes, offs.ctypes.data, idx.ctypes.data, off.ctypes.data, nrm.ctypes.data,
+                                 infl.ctypes.data, normals, res.ctypes.data) == 0
+        out["f%d" % k] = res
     np.savez_compressed(os.path.join(HERE, name), **out)
-    print(name, len(cases), "cases")
+    print(name, len(cases), "cases", len(frames), "entity frames")
 
 
 def save_optutil(name):

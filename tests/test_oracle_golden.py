@@ -165,3 +165,14 @@ def test_oracle_reproduces_ogres_own_pose_blend():
             if normals:
                 oracle.lib().oracle_pose_blend(w, ni.ctypes.data, nrm.ctypes.data, len(ni), o.ctypes.data + 12, buf.shape[1])
             assert np.array_equal(bits(o), bits(z["c%d_w%d" % (k, j)])), (k, w)
+
+
+def test_oracle_reproduces_ogres_own_pose_animated_entities():
+    """Whole pose-animated frames dumped from a real Entity (Entity::_updateAnimation: initialisePoseVertexData, the pose
+    blends of the key frame in order, finalisePoseNormals) vs the restatements chained."""
+    from datagen import pose_entity_case, pose_entity_oracle
+    z = np.load(os.path.join(GOLDEN, "pose_blend.npz"))
+    for k, (seed, nv, nposes, normals) in enumerate(z["frames"]):
+        base, offs, idx, off, nrm, infl = pose_entity_case(int(seed), int(nv), int(nposes))
+        got = pose_entity_oracle(oracle, base, offs, idx, off, nrm, infl, bool(normals))
+        assert np.array_equal(bits(got), bits(z["f%d" % k])), k

@@ -120,3 +120,16 @@ def test_oracle_pose_blend_equals_real_mesh_pose_blend():
             if normals:
                 oracle.lib().oracle_pose_blend(w, ni.ctypes.data, nrm.ctypes.data, len(ni), o.ctypes.data + 12, fpv)
             assert np.array_equal(bits(r), bits(o)), (seed, w)
+
+
+@pytest.mark.parametrize("seed,nv,nposes,normals", [(1, 500, 3, True), (2, 500, 3, False), (3, 37, 1, True), (4, 2000, 5, True)])
+def test_oracle_pose_frame_equals_real_entity(seed, nv, nposes, normals):
+    """The whole pose-animation path of a real Entity on a hand-built mesh (initialisePoseVertexData -> pose blends in
+    key-frame order -> finalisePoseNormals, through Entity::_updateAnimation) vs the restatements chained: identical."""
+    from datagen import pose_entity_case, pose_entity_oracle
+    base, offs, idx, off, nrm, infl = pose_entity_case(seed, nv, nposes)
+    out = np.zeros((nv, 6), np.float32)
+    rc = ref.lib().ref_pose_entity(nv, base.ctypes.data, nposes, offs.ctypes.data, idx.ctypes.data, off.ctypes.data, nrm.ctypes.data,
+                                   infl.ctypes.data, int(normals), out.ctypes.data)
+    assert rc == 0
+    assert np.array_equal(bits(out), bits(pose_entity_oracle(oracle, base, offs, idx, off, nrm, infl, normals)))

@@ -60,3 +60,34 @@ def test_two_poses_in_sequence_and_instances(gpu_ctx):
             oracle.lib().oracle_pose_blend(float(w), oi.ctypes.data, off.ctypes.data, len(oi), ref.ctypes.data, 6)
             oracle.lib().oracle_pose_blend(float(w), ni.ctypes.data, nrm.ctypes.data, len(ni), ref.ctypes.data + 12, 6)
         assert np.array_equal(bits(got[i]), bits(ref)), i
+
+
+@pytest.mark.parametrize("seed,nv,nposes", [(1, 500, 3), (4, 20000, 5), (3, 37, 1)])
+def test_whole_pose_frame_many_instances(gpu_ctx, seed, nv, nposes):
+    """A frame of pose animation for many instances on the device: copy of the base mesh, normals reset
+    (ogrecu_pose_normals_reset_dev), one instanced blend per pose and element with per-instance influences, then
+    ogrecu_pose_normals_finalise_dev — against the oracle chain (which equals the real Entity, tests/test_oracle_vs_ref.py)."""
+    from datagen import pose_entity_case, pose_entity_oracle
+    from ogre_b200 import check, lib
+    ctx = gpu_ctx
+    ninst = 9
+    base, offs, idx, off, nrm, infl = pose_entity_case(seed, nv, nposes)
+    rng = np.random.default_rng(seed + 100)
+    inf_i = (infl[None, :] * rng.uniform(0.3, 1.0, size=(ninst, nposes))).astype(np.float32)
+    inf_i[0] = infl
+    inf_i[2, 0] = 0.0
+    d = ctx.to_device(np.stack([base] * ninst))
+    dbase, didx, doff, dnrm = ctx.to_device(base), ctx.to_device(idx), ctx.to_device(off), ctx.to_device(nrm)
+    dinf = ctx.to_device(np.ascontiguousarray(inf_i.T))                 # [pose][instance]
+    L = lib()
+    check(L.ogrecu_pose_normals_reset_dev(ctx.handle, d.ptr + 12, nv, 24, ninst, nv * 24))
+    for p in range(nposes):
+        a, b = int(offs[p]), int(offs[p + 1])
+        w = dinf.ptr + p * ninst * 4
+        check(L.ogrecu_pose_blend_instanced_dev(ctx.handle, w, didx.ptr + a * 4, doff.ptr + a * 12, b - a, d.ptr, 24, ninst, nv * 24))
+        check(L.ogrecu_pose_blend_instanced_dev(ctx.handle, w, didx.ptr + a * 4, dnrm.ptr + a * 12, b - a, d.ptr + 12, 24, ninst, nv * 24))
+    check(L.ogrecu_pose_normals_finalise_dev(ctx.handle, d.ptr + 12, dbase.ptr + 12, nv, 24, 24, ninst, nv * 24))
+    got = d.download(np.float32).reshape(ninst, nv, 6)
+    for i in range(ninst):
+        ref = pose_entity_oracle(oracle, base, offs, idx, off, nrm, inf_i[i], True)
+        assert np.array_equal(bits(got[i]), bits(ref)), i
