@@ -268,7 +268,8 @@ __device__ __forceinline__ void cta_draw_cache(const SegParams& P, uint32_t g0, 
 // (A spin-free "reduce, scan the block table, then write" compaction: the single-pass chained scan
 //  measured 30 % of its time waiting in the look-back, profiles/r01d notes.  Measured and rejected in r01k: issuing
 //  the index loads of all four rounds before the first vertex gather — setup_write goes from 64 to 80 registers,
-//  one CTA less per SM, C5 2.16 -> 2.25 ms.)
+//  one CTA less per SM, C5 2.16 -> 2.25 ms; staging the CTA's 12 KB of indices through shared memory with one coalesced
+//  copy — same registers, C5 2.15 -> 2.30 ms, C4 8.8 -> 8.4 k views/s.  The index round trip is not what bounds these kernels.)
 __global__ void __launch_bounds__(SB_THREADS) setup_count_kernel(SegParams P)
 {
     __shared__ uint32_t s_lo, s_wp[8], s_wt[8];

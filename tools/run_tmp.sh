@@ -1,7 +1,5 @@
-for c in 8 16 32 64; do python tools/bench_configs.py --config c4 --views 256 --chunk $c | python -c "
+timeout 900 python -m pytest tests/test_raster_gpu.py tests/test_raster_paths_gpu.py tests/test_golden_gpu.py tests/test_full_size_gpu.py -x -q 2>&1 | tail -3
+python tools/bench_configs.py --config c1,c4,c5 --views 256 | python -c "
 import sys,json
-d=json.loads(sys.stdin.read()); print('chunk $c', round(d['views_per_s_device']), round(d['ms_per_view_device'],4))"; done
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 100 --warmup 3 2>/dev/null | grep '^{' | python -c "
-import sys,json
-d=json.loads(sys.stdin.read()); print('N=2 value', round(d['value']), 'e2e', round(d['e2e']['value']), 'states', round(d['e2e']['states_value']))"
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 3 --warmup 1 2>/dev/null | grep '^{' | cut -c1-160
+for l in sys.stdin:
+    d=json.loads(l); print(d['config'][:30], {k:round(v,4) for k,v in d.items() if isinstance(v,float) and ('ms_per' in k or 'views_per_s_device' in k)})"
