@@ -213,7 +213,7 @@ def workload_config(ninst, nverts, sample=False):
 def run_ours(args):
     import torch
     import ogre_b200
-    from ogre_b200 import SkinJob, check, lib
+    from ogre_b200 import AnimJob, SkinJob, check, lib
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -281,9 +281,20 @@ def run_ours(args):
             morph(e, s)
             skin(e, s)
 
+    def anim_jobs(which):
+        arr = (AnimJob * len(dsub))()
+        for k, (e, s) in enumerate(zip(dsub, subs)):
+            arr[k].skin = e[which] if not isinstance(e[which], list) else e[which][0]
+            arr[k].key2 = e["key2"].data_ptr()
+            arr[k].morph_out, arr[k].morph_instance_stride_bytes = None, 0
+            arr[k].dst_instance_stride_bytes = s["nverts"] * 24
+        return arr
+    frame_jobs = anim_jobs("job_fused")
+
     def step_fused():
-        for e, s in zip(dsub, subs):
-            fused(e, s)
+        # one call per frame: the fused morph+skin of all seven sub-meshes (ogrecu_anim_instanced_multi_dev overlaps the
+        # independent launches internally)
+        check(L.ogrecu_anim_instanced_multi_dev(ctx.handle, frame_jobs, len(dsub), d_t.data_ptr(), ninst, nb * 16))
 
     step = step_fused if args.form == "fused" else step_separate
 
@@ -348,15 +359,21 @@ def run_ours(args):
     done = [torch.cuda.Event(), torch.cuda.Event()]
     last = dsub[1]
 
+    set_jobs = []
+    for b in (0, 1):
+        arr = anim_jobs("job_fused")
+        for k, e in enumerate(dsub):
+            arr[k].skin = e["jobs_fused"][b]
+        set_jobs.append(arr)
+
     def step_set(b):
+        if args.form == "fused":
+            check(L.ogrecu_anim_instanced_multi_dev(ctx.handle, set_jobs[b], len(dsub), t_sets[b].data_ptr(), ninst, nb * 16))
+            return
         for e, s in zip(dsub, subs):
-            if args.form == "fused":
-                check(L.ogrecu_anim_instanced_dev(ctx.handle, C.byref(e["jobs_fused"][b]), e["key2"].data_ptr(), t_sets[b].data_ptr(),
-                                                  None, 0, ninst, nb * 16, s["nverts"] * 24))
-            else:
-                check(L.ogrecu_morph_instanced_dev(ctx.handle, t_sets[b].data_ptr(), e["key1"].data_ptr(), e["key2"].data_ptr(),
-                                                   e["tmp"].data_ptr(), 24, 24, 24, s["nverts"], 1, ninst, s["nverts"] * 24))
-                check(L.ogrecu_skin_instanced_dev(ctx.handle, C.byref(e["jobs"][b]), ninst, nb * 16, s["nverts"] * 24, s["nverts"] * 24))
+            check(L.ogrecu_morph_instanced_dev(ctx.handle, t_sets[b].data_ptr(), e["key1"].data_ptr(), e["key2"].data_ptr(),
+                                               e["tmp"].data_ptr(), 24, 24, 24, s["nverts"], 1, ninst, s["nverts"] * 24))
+            check(L.ogrecu_skin_instanced_dev(ctx.handle, C.byref(e["jobs"][b]), ninst, nb * 16, s["nverts"] * 24, s["nverts"] * 24))
 
     e2e_k = [0]
 

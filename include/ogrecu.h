@@ -232,6 +232,20 @@ OGRECU_API int ogrecu_anim_instanced_dev(ogrecu_ctx* ctx, const ogrecu_skin_job*
  * host pointers, pointer palette of Affine3 (`blend_matrices[i]` -> 16 floats).  Pointers
  * that lie inside a mapped ogrecu_buf shadow are resolved to the device copy; anything
  * else is staged through pinned memory.  Synchronous. */
+/* One animation frame of an instanced mesh: the fused morph+skin of EACH of its sub-meshes (what Entity::updateAnimation
+ * does sub-entity by sub-entity, OgreEntity.cpp:823-864) in one call.  All jobs share t_dev, num_instances and the
+ * palette stride (one skeleton instance per entity).  The independent launches are overlapped internally (largest first
+ * over two side streams, forked from and joined into the context's stream), so the call is ordered like one launch. */
+typedef struct ogrecu_anim_job {
+    ogrecu_skin_job skin;                 /* as for ogrecu_anim_instanced_dev: src_pos/src_norm = keyframe 1 */
+    const float* key2;                    /* keyframe 2, same dense layout */
+    float* morph_out;                     /* optional: the morphed intermediate per instance, NULL = not materialised */
+    size_t morph_instance_stride_bytes;
+    size_t dst_instance_stride_bytes;
+} ogrecu_anim_job;
+OGRECU_API int ogrecu_anim_instanced_multi_dev(ogrecu_ctx* ctx, const ogrecu_anim_job* jobs, uint32_t num_jobs, const float* t_dev,
+                                               uint32_t num_instances, size_t palette_stride_floats);
+
 OGRECU_API int ogrecu_software_vertex_skinning_host(
     ogrecu_ctx* ctx,
     const float* src_pos, float* dst_pos, const float* src_norm, float* dst_norm,

@@ -13,9 +13,9 @@ import ctypes as C
 import numpy as np
 
 from . import capi
-from .capi import AnimationDesc, DrawDesc, OgrecuError, RasterStats, SkeletonDesc, SkinJob, check, lib
+from .capi import AnimJob, AnimationDesc, DrawDesc, OgrecuError, RasterStats, SkeletonDesc, SkinJob, check, lib
 
-__all__ = ["Context", "DeviceBuffer", "OptimisedUtil", "Skeleton", "EdgeList", "Texture", "RenderTarget", "DrawDesc", "SkinJob",
+__all__ = ["Context", "DeviceBuffer", "OptimisedUtil", "Skeleton", "EdgeList", "Texture", "RenderTarget", "DrawDesc", "SkinJob", "AnimJob",
            "OgrecuError", "addr", "pinned_empty"]
 
 MAP_READ, MAP_WRITE, MAP_DISCARD = 1, 2, 4

@@ -36,6 +36,12 @@ class SkinJob(C.Structure):
     ]
 
 
+class AnimJob(C.Structure):
+    """ogrecu_anim_job (include/ogrecu.h)"""
+    _fields_ = [("skin", SkinJob), ("key2", C.c_void_p), ("morph_out", C.c_void_p), ("morph_instance_stride_bytes", C.c_size_t),
+                ("dst_instance_stride_bytes", C.c_size_t)]
+
+
 class DrawDesc(C.Structure):
     """ogrecu_draw_desc (include/ogrecu.h)"""
     _fields_ = [
@@ -99,6 +105,7 @@ SIGNATURES = {
     "ogrecu_buf_mark_device_dirty": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t]),
     "ogrecu_buf_resolve": (C.c_int, [C.c_void_p, C.c_void_p, c_void_pp, C.POINTER(C.c_size_t)]),
     "ogrecu_skin_dev": (C.c_int, [C.c_void_p, C.POINTER(SkinJob), C.c_uint32]),
+    "ogrecu_anim_instanced_multi_dev": (C.c_int, [C.c_void_p, C.POINTER(AnimJob), C.c_uint32, C.c_void_p, C.c_uint32, C.c_size_t]),
     "ogrecu_skel_create": (C.c_int, [C.c_void_p, C.POINTER(SkeletonDesc), c_void_pp]),
     "ogrecu_skel_destroy": (C.c_int, [C.c_void_p]),
     "ogrecu_skel_add_animation": (C.c_int, [C.c_void_p, C.POINTER(AnimationDesc), C.POINTER(C.c_uint32)]),

@@ -126,6 +126,11 @@ int ogrecu_shutdown(ogrecu_ctx* ctx)
     for (Scratch* s : {&ctx->jobs, &ctx->stage_in, &ctx->stage_out})
         if (s->ptr) cudaFree(s->ptr);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    for (int k = 0; k < 2; ++k) {
+        if (ctx->side_stream[k]) { cudaStreamSynchronize(ctx->side_stream[k]); cudaStreamDestroy(ctx->side_stream[k]); }
+        if (ctx->side_join[k]) cudaEventDestroy(ctx->side_join[k]);
+    }
+    if (ctx->side_fork) cudaEventDestroy(ctx->side_fork);
     cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return OGRECU_OK;
