@@ -20,8 +20,8 @@ done | tee gpurun_out/sweep_$TAG.txt
 ncu --metrics gpu__time_duration.sum --clock-control none -s 21 -c 42 --csv --log-file gpurun_out/launches_$TAG.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline > /dev/null 2>&1; echo "ncu list rc=$?"
 # full capture of the dominant kernel: 9th skin_tile launch = second step, sub-mesh 1 (1888 verts x 10000, 4 weights)
-ncu --set full --clock-control none --import-source on -k regex:skin_ -s 8 -c 1 -o gpurun_out/prof_fused_$TAG -f \
+ncu --set full --clock-control none --import-source on -k regex:skin_ -s 7 -c 1 -o gpurun_out/prof_fused_$TAG -f \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline > /dev/null 2>&1; echo "ncu full fused rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:skin_ -s 8 -c 1 -o gpurun_out/prof_skin_$TAG -f \
+ncu --set full --clock-control none --import-source on -k regex:skin_ -s 7 -c 1 -o gpurun_out/prof_skin_$TAG -f \
     python bench.py --form separate --steps 2 --warmup 1 --no-cpu-baseline > /dev/null 2>&1; echo "ncu full separate rc=$?"
 ls -la gpurun_out | tail -14
