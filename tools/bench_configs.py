@@ -268,7 +268,9 @@ def c3(ctx, T, args):
     return out
 
 
-def raster_views(ctx, T, desc, rts, mvps, mvits, lights, chunk):
+def raster_views(ctx, T, desc, rts, mvps, mvits, lights, chunk, descs=None):
+    """`descs`: optional per-chunk draw descriptors (chunk k uses descs[k % len(descs)]) for targets that live in more than
+    one context (two contexts per GPU: their pipeline passes run on different streams and overlap)."""
     L = lib()
     n = len(rts)
     handles = (C.c_void_p * n)(*[r.handle for r in rts])
@@ -276,10 +278,11 @@ def raster_views(ctx, T, desc, rts, mvps, mvits, lights, chunk):
     def run():
         for r in rts:
             r.clear(colour=(0.1, 0.2, 0.3, 1.0), depth=1.0)
-        for s in range(0, n, chunk):
+        for k, s in enumerate(range(0, n, chunk)):
             e = min(n, s + chunk)
             hs = (C.c_void_p * (e - s))(*handles[s:e])
-            check(L.ogrecu_draw_views(hs, e - s, C.byref(desc), mvps[s:e].ctypes.data_as(capi.c_float_p),
+            d = descs[k % len(descs)] if descs else desc
+            check(L.ogrecu_draw_views(hs, e - s, C.byref(d), mvps[s:e].ctypes.data_as(capi.c_float_p),
                                       mvits[s:e].ctypes.data_as(capi.c_float_p), lights[s:e].ctypes.data_as(capi.c_float_p)))
     return run
 
@@ -297,8 +300,35 @@ def c4(ctx, T, args):
         mine = view_indices(total_views, RANK, WORLD)
         mvps, mvits, lights = (np.ascontiguousarray(a[mine]) for a in (mvps, mvits, lights))
     nviews = len(mvps)
-    rts = [ogre_b200.RenderTarget(ctx, w, h) for _ in range(nviews)]
-    run = raster_views(ctx, T, desc, rts, mvps, mvits, lights, args.chunk)
+    descs = None
+    if args.contexts > 1:
+        # application-level overlap: the targets of chunk k live in context k % contexts (own stream, own pipeline scratch);
+        # geometry is shared (raw device pointers), the texture is uploaded once per context
+        import torch
+        ctxs, descs = [ctx], [desc]
+        for _ in range(args.contexts - 1):
+            c2 = ogre_b200.Context(LOCAL)
+            st2 = torch.cuda.Stream()
+            c2.set_stream(st2.cuda_stream)
+            tex2 = ogre_b200.Texture(c2, checker_texture(1024))
+            d2 = DrawDesc.from_buffer_copy(desc)
+            d2.texture = tex2.handle
+            keep = keep + (c2, st2, tex2)
+            ctxs.append(c2); descs.append(d2)
+        rts = [ogre_b200.RenderTarget(ctxs[(k // args.chunk) % len(ctxs)], w, h) for k in range(nviews)]
+        run_inner = raster_views(ctx, T, desc, rts, mvps, mvits, lights, args.chunk, descs)
+        side_streams = [x for x in keep if isinstance(x, torch.cuda.Stream)]
+
+        def run():
+            ev = torch.cuda.Event(); ev.record(T.stream)
+            for st in side_streams:
+                st.wait_event(ev)
+            run_inner()
+            for st in side_streams:
+                T.stream.wait_stream(st)
+    else:
+        rts = [ogre_b200.RenderTarget(ctx, w, h) for _ in range(nviews)]
+        run = raster_views(ctx, T, desc, rts, mvps, mvits, lights, args.chunk)
     dt = T.time(run, iters=2, warm=1)
     stats = rts[0].stats()
     host = ogre_b200.pinned_empty((nviews, h, w, 3))     # one pinned read-back buffer for all views
@@ -471,6 +501,7 @@ def main():
     ap.add_argument("--config", default="c1,c3,c4,c5")
     ap.add_argument("--views", type=int, default=1024)
     ap.add_argument("--chunk", type=int, default=32, help="views per ogrecu_draw_views pass")
+    ap.add_argument("--contexts", type=int, default=1, help="c4: contexts (streams) per GPU whose pipeline passes overlap")
     ap.add_argument("--c3-tris", type=int, default=2000000)
     ap.add_argument("--c4-tris", type=int, default=1000000)
     ap.add_argument("--c5-tris", type=int, default=20000000)

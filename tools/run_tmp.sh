@@ -1,7 +1,3 @@
-timeout 900 python -m pytest tests/test_skin_tile_gpu.py tests/test_full_size_gpu.py -x -q -k "multi or full or fused" 2>&1 | tail -3
-python bench.py --no-cpu-baseline --steps 200 2>gpurun_out/b.err | python -c "
-import json,sys
-d=json.loads(sys.stdin.read()); print('value %.0f ms %.4f launches %d e2e %.0f states %.0f roof %.3f'%(d['value'], d['ms_per_step'], d['gpu_launches'], d['e2e']['value'], d['e2e']['states_value'], d['roofline']['frac']))"; tail -3 gpurun_out/b.err
-python bench.py --no-cpu-baseline --steps 100 --form separate 2>/dev/null | python -c "
-import json,sys
-d=json.loads(sys.stdin.read()); print('separate value %.0f e2e %.0f'%(d['value'], d['e2e']['value']))"
+for c in 1 2 3; do python tools/bench_configs.py --config c4 --views 256 --contexts $c 2>gpurun_out/c4ctx_$c.err | python -c "
+import sys,json
+d=json.loads(sys.stdin.read()); print('contexts $c', round(d['views_per_s_device']), round(d['ms_per_view_device'],4))"; tail -2 gpurun_out/c4ctx_$c.err; done
