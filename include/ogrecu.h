@@ -463,6 +463,12 @@ OGRECU_API int ogrecu_composite_depth_dev(ogrecu_ctx* ctx, uint8_t* dst_rgb, flo
  * Colour is RGB8 (3 bytes/pixel); depth is float32. */
 OGRECU_API int ogrecu_rt_read_colour(ogrecu_rt* rt, uint32_t left, uint32_t top, uint32_t right, uint32_t bottom,
                                      uint8_t* dst_host, size_t dst_pitch_bytes);
+/* The same readback converted on the device to a 32-bit, 8-bits-per-channel destination format: every pixel becomes the
+ * native-endian word r << r_shift | g << g_shift | b << b_shift | fill (fill = 0xFF in the alpha or X byte) — the bytes PixelUtil::bulkPixelConversion produces from PF_BYTE_RGB on the CPU in the reference
+ * (PF_A8R8G8B8: shifts 16, 8, 0, fill 0xFF000000). */
+OGRECU_API int ogrecu_rt_read_colour_packed32(ogrecu_rt* rt, uint32_t left, uint32_t top, uint32_t right, uint32_t bottom,
+                                              void* dst_host, size_t dst_pitch_bytes, uint32_t r_shift, uint32_t g_shift,
+                                              uint32_t b_shift, uint32_t fill);
 OGRECU_API int ogrecu_rt_read_depth(ogrecu_rt* rt, uint32_t left, uint32_t top, uint32_t right, uint32_t bottom,
                                     float* dst_host, size_t dst_pitch_bytes);
 /* upload into the planes (render-to-texture sources, tests) */

@@ -328,6 +328,15 @@ class RenderTarget:
         check(lib().ogrecu_rt_read_colour(self.handle, l, t, r, b, out.ctypes.data, (r - l) * 3))
         return out
 
+    def read_colour_packed32(self, r_shift, g_shift, b_shift, fill, box=None, out=None):
+        """copyContentsToMemory into a 32-bit 8-bit-per-channel format, converted on the device (one uint32 per pixel)."""
+        l, t, r, b = box if box else (0, 0, self.width, self.height)
+        if out is None:
+            out = np.empty((b - t, r - l), dtype=np.uint32)
+        assert out.dtype == np.uint32 and out.shape == (b - t, r - l) and out.flags.c_contiguous
+        check(lib().ogrecu_rt_read_colour_packed32(self.handle, l, t, r, b, out.ctypes.data, (r - l) * 4, r_shift, g_shift, b_shift, fill))
+        return out
+
     def read_depth(self, box=None, out=None):
         l, t, r, b = box if box else (0, 0, self.width, self.height)
         if out is None:

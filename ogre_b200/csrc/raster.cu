@@ -1629,6 +1629,51 @@ int ogrecu_rt_read_colour(ogrecu_rt* rt, uint32_t l, uint32_t t, uint32_t r, uin
     return read_plane(rt, rt->colour, 3, l, t, r, b, dst, pitch);
 }
 
+// RGB8 sub-box -> one packed 32-bit word per pixel: r << r_shift | g << g_shift | b << b_shift | fill.  What
+// PixelUtil::bulkPixelConversion does on the CPU in TinyWindow::copyContentsToMemory (OgreTinyWindow.cpp:79) for the
+// 32-bit 8-bits-per-channel destination formats (OgrePixelConversions.h:333-351 and the generic unpack/pack path, which
+// is the identity on 8-bit channels), done before the copy so that the host receives the final bytes.
+__global__ void pack32_kernel(const uint8_t* __restrict__ rgb, uint32_t plane_w, uint32_t l, uint32_t t, uint32_t bw, uint32_t bh,
+                              uint32_t* __restrict__ out, uint32_t rs, uint32_t gs, uint32_t bs, uint32_t fill)
+{
+    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= bw || y >= bh) return;
+    const uint8_t* p = rgb + ((size_t)(t + y) * plane_w + l + x) * 3;
+    out[(size_t)y * bw + x] = ((uint32_t)p[0] << rs) | ((uint32_t)p[1] << gs) | ((uint32_t)p[2] << bs) | fill;
+}
+
+int ogrecu_rt_read_colour_packed32(ogrecu_rt* rt, uint32_t l, uint32_t t, uint32_t r, uint32_t b, void* dst, size_t pitch, uint32_t r_shift,
+                                   uint32_t g_shift, uint32_t b_shift, uint32_t fill)
+{
+    OGRECU_REQUIRE(rt, "rt is NULL");
+    OGRECU_REQUIRE(r <= rt->w && b <= rt->h && l <= r && t <= b, "Invalid box");
+    OGRECU_REQUIRE(r_shift <= 24 && g_shift <= 24 && b_shift <= 24, "channel shifts are 0..24");
+    ogrecu_ctx* ctx = rt->ctx;
+    OGRECU_CHECK(ogrecu_flush(rt));
+    const uint32_t bw = r - l, bh = b - t;
+    if (!bw || !bh) return OGRECU_OK;
+    const size_t row = (size_t)bw * 4;
+    OGRECU_REQUIRE(dst && pitch >= row, "bad destination");
+    OGRECU_CHECK(scratch_reserve(ctx, ctx->stage_out, row * bh));
+    pack32_kernel<<<dim3(div_up(bw, 256), bh), 256, 0, ctx->stream>>>(rt->colour, rt->w, l, t, bw, bh, (uint32_t*)ctx->stage_out.ptr, r_shift, g_shift,
+                                                                       b_shift, fill);
+    OGRECU_CUDA(cudaGetLastError());
+    count_launch(ctx);
+    cudaPointerAttributes pa;
+    if (cudaPointerGetAttributes(&pa, dst) == cudaSuccess && pa.type == cudaMemoryTypeHost) {       // pinned destination: direct DMA
+        OGRECU_CUDA(cudaMemcpy2DAsync(dst, pitch, ctx->stage_out.ptr, row, row, bh, cudaMemcpyDeviceToHost, ctx->stream));
+        OGRECU_CUDA(cudaStreamSynchronize(ctx->stream));
+        return OGRECU_OK;
+    }
+    (void)cudaGetLastError();
+    OGRECU_CHECK(pinned_reserve(ctx, row * bh));
+    OGRECU_CUDA(cudaMemcpyAsync(ctx->pinned, ctx->stage_out.ptr, row * bh, cudaMemcpyDeviceToHost, ctx->stream));
+    OGRECU_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (pitch == row) memcpy(dst, ctx->pinned, row * bh);
+    else for (size_t y = 0; y < bh; ++y) memcpy((uint8_t*)dst + y * pitch, (uint8_t*)ctx->pinned + y * row, row);
+    return OGRECU_OK;
+}
+
 int ogrecu_rt_read_depth(ogrecu_rt* rt, uint32_t l, uint32_t t, uint32_t r, uint32_t b, float* dst, size_t pitch)
 {
     OGRECU_REQUIRE(rt, "rt is NULL");

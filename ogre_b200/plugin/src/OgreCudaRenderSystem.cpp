@@ -365,6 +365,28 @@ void CudaRenderSystem::readColour(ogrecu_rt* rt, const Box& src, const PixelBox&
         OGRECU_THROW_IF(ogrecu_rt_read_colour(rt, src.left, src.top, src.right, src.bottom, dst.data, w * 3));
         return;
     }
+    // 32-bit destinations with 8 bits per colour channel (PF_BYTE_RGBA / PF_BYTE_BGRA / PF_A8R8G8B8 / PF_X8R8G8B8 / ...): converted
+    // on the device, the host receives the final bytes (the reference converts on the CPU, OgreTinyWindow.cpp:79)
+    {
+        int depths[4];
+        unsigned char shifts[4];
+        uint64 masks[4];
+        PixelUtil::getBitDepths(dst.format, depths);
+        PixelUtil::getBitShifts(dst.format, shifts);
+        PixelUtil::getBitMasks(dst.format, masks);
+        const unsigned flags = PixelUtil::getFlags(dst.format);
+        if (PixelUtil::getNumElemBytes(dst.format) == 4 && (flags & PFF_NATIVEENDIAN) && !(flags & (PFF_FLOAT | PFF_INTEGER | PFF_COMPRESSED | PFF_LUMINANCE | PFF_DEPTH)) &&
+            depths[0] == 8 && depths[1] == 8 && depths[2] == 8 && (depths[3] == 8 || depths[3] == 0) && dst.getDepth() == 1)
+        {
+            // alpha: unpackColour gives 1.0 for a source without alpha; the reference's converters also set the X byte of the
+            // X8 formats (checked against the real PixelUtil in tests/test_plugin_gpu.py)
+            const uint32 fill = ~(uint32)(masks[0] | masks[1] | masks[2]);
+            uint8* top = dst.getTopLeftFrontPixelPtr();
+            OGRECU_THROW_IF(ogrecu_rt_read_colour_packed32(rt, src.left, src.top, src.right, src.bottom, top, dst.rowPitch * 4, shifts[0], shifts[1],
+                                                           shifts[2], fill));
+            return;
+        }
+    }
     std::vector<uint8> tmp(w * h * 3);
     OGRECU_THROW_IF(ogrecu_rt_read_colour(rt, src.left, src.top, src.right, src.bottom, tmp.data(), w * 3));
     PixelBox box(w, h, 1, PF_BYTE_RGB, tmp.data());

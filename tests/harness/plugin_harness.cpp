@@ -141,6 +141,40 @@ API int ph_read_colour(uint8_t* dst, int fmt)
     CATCH(1)
 }
 
+// Window read-back in an arbitrary OGRE pixel format through the plugin (device-side conversion for the 32-bit 8-bit-per-
+// channel formats, host PixelUtil otherwise) next to the reference's way: PF_BYTE_RGB read-back converted by the real
+// PixelUtil::bulkPixelConversion.  Returns the number of differing bytes (-1 on error); a sub-box with a padded
+// destination pitch is read too.
+API long ph_read_colour_format_check(const char* format_name)
+{
+    TRY
+    const PixelFormat pf = PixelUtil::getFormatFromName(format_name, true);
+    if (pf == PF_UNKNOWN) { g_err = "unknown pixel format"; return -1; }
+    const size_t bpp = PixelUtil::getNumElemBytes(pf);
+    const uint32_t w = g->w, h = g->h;
+    std::vector<uint8_t> rgb((size_t)w * h * 3), want((size_t)w * h * bpp), got((size_t)w * h * bpp, 0xEE);
+    PixelBox prgb(w, h, 1, PF_BYTE_RGB, rgb.data());
+    g->win->copyContentsToMemory(Box(0, 0, w, h), prgb, RenderTarget::FB_AUTO);
+    PixelBox pwant(w, h, 1, pf, want.data());
+    PixelUtil::bulkPixelConversion(prgb, pwant);
+    PixelBox pgot(w, h, 1, pf, got.data());
+    g->win->copyContentsToMemory(Box(0, 0, w, h), pgot, RenderTarget::FB_AUTO);
+    long bad = 0;
+    for (size_t i = 0; i < want.size(); ++i) bad += want[i] != got[i];
+    // sub-box into a destination with a row pitch wider than the box
+    const uint32_t l = 3, t = 5, r = w - 7, b = h - 2, bw = r - l, bh = b - t, pitch = bw + 9;
+    std::vector<uint8_t> sub((size_t)pitch * bh * bpp, 0xEE);
+    PixelBox psub(bw, bh, 1, pf, sub.data());
+    psub.rowPitch = pitch; psub.slicePitch = (size_t)pitch * bh;
+    g->win->copyContentsToMemory(Box(l, t, r, b), psub, RenderTarget::FB_AUTO);
+    for (uint32_t y = 0; y < bh; ++y) {
+        for (size_t k = 0; k < (size_t)bw * bpp; ++k) bad += sub[(size_t)y * pitch * bpp + k] != want[((size_t)(t + y) * w + l) * bpp + k];
+        for (size_t k = (size_t)bw * bpp; k < (size_t)pitch * bpp; ++k) bad += sub[(size_t)y * pitch * bpp + k] != 0xEE;      // padding untouched
+    }
+    return bad;
+    CATCH(-1)
+}
+
 API int ph_read_colour_box(uint32_t l, uint32_t t, uint32_t r, uint32_t b, uint8_t* dst)
 {
     TRY

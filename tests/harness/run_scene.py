@@ -33,6 +33,7 @@ def main():
     ap.add_argument("--quad", action="store_true")
     ap.add_argument("--skel", default="")
     ap.add_argument("--time", type=int, default=0)
+    ap.add_argument("--formats", default="", help="comma-separated Ogre::PixelFormat names: read-back in that format vs host PixelUtil")
     ap.add_argument("--shadow", type=int, default=0, help="N shadow-volume cases: real generateShadowVolume vs CudaShadowVolume")
     ap.add_argument("--palettes", type=int, default=0, help="bone palettes at N time positions: engine vs CudaSkeletonPalettes")
     a = ap.parse_args()
@@ -111,6 +112,11 @@ def main():
     rgba = np.zeros((h, w, 4), np.uint8)
     ok(L.ph_read_colour(rgba.ctypes.data, 1), "ph_read_colour rgba")
     out["colour_rgba"] = rgba
+    if a.formats:
+        L.ph_read_colour_format_check.restype = C.c_long
+        L.ph_read_colour_format_check.argtypes = [C.c_char_p]
+        out["format_names"] = np.array(a.formats.split(","))
+        out["format_mismatches"] = np.array([L.ph_read_colour_format_check(v.encode()) for v in a.formats.split(",")])
     box = np.zeros((h // 2 - 3, w // 2 - 5, 3), np.uint8)
     ok(L.ph_read_colour_box(5, 3, w // 2, h // 2, box.ctypes.data), "ph_read_colour_box")
     out["colour_box"] = box

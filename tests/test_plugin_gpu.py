@@ -120,3 +120,15 @@ def test_shadow_volume_through_the_plugin_equals_the_engines(tmp_path, mesh):
     z = run_scene(tmp_path, "cuda", "--mesh", mesh, "--size", "64x64", "--cam-z", "100", "--shadow", "24")
     assert int(z["shadow_cases"]) == 24 and int(z["shadow_indices_emitted"]) > 100
     assert len(z["shadow_mismatches"]) == 0, z["shadow_mismatches"]
+
+
+def test_readback_formats_equal_host_pixel_conversion(tmp_path):
+    """RenderWindow::copyContentsToMemory into other destination formats (SURVEY §8f rank 4): the 32-bit 8-bit-per-channel
+    formats are converted on the device (ogrecu_rt_read_colour_packed32), the rest by PixelUtil on the host as in the
+    reference — either way the bytes equal the real PixelUtil::bulkPixelConversion of the PF_BYTE_RGB read-back, for the
+    whole window and for a sub-box with a padded destination pitch."""
+    names = ["PF_A8R8G8B8", "PF_A8B8G8R8", "PF_B8G8R8A8", "PF_R8G8B8A8", "PF_X8R8G8B8", "PF_X8B8G8R8", "PF_R8G8B8", "PF_B8G8R8",
+             "PF_R5G6B5", "PF_L8", "PF_FLOAT32_RGB", "PF_A2R10G10B10"]
+    z = run_scene(tmp_path, "cuda", "--mesh", "ogrehead.mesh", "--size", "320x180", "--formats", ",".join(names))
+    assert list(z["format_names"]) == names
+    assert list(z["format_mismatches"]) == [0] * len(names), dict(zip(names, z["format_mismatches"]))

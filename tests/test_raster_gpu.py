@@ -224,3 +224,22 @@ def test_sort_last_composite_equals_whole_frame(gpu_ctx, world):
     assert (only_first.read_colour() != wc).any()
     for rt in parts + [whole, only_first]:
         rt.destroy()
+
+
+def test_readback_packed32_equals_host_shuffle(gpu_ctx):
+    # ogrecu_rt_read_colour_packed32: RGB8 plane -> r << rs | g << gs | b << bs | fill per pixel, whole target and sub-box
+    import ogre_b200
+    from rasterlib import GpuScene
+    w, h = 250, 130
+    cases = make_scene(31, w, h, ndraws=4, ntri=200)
+    scene = GpuScene(gpu_ctx, cases)
+    rt = ogre_b200.RenderTarget(gpu_ctx, w, h)
+    scene.render(rt, (0.1, 0.2, 0.3, 1.0), 1.0)
+    rgb = rt.read_colour().astype(np.uint32)
+    for rs, gs, bs, fill in [(16, 8, 0, 0xFF000000), (0, 8, 16, 0xFF000000), (24, 16, 8, 0xFF), (8, 16, 24, 0xFF)]:
+        want = (rgb[..., 0] << rs) | (rgb[..., 1] << gs) | (rgb[..., 2] << bs) | fill
+        assert np.array_equal(rt.read_colour_packed32(rs, gs, bs, fill), want)
+        assert np.array_equal(rt.read_colour_packed32(rs, gs, bs, fill, box=(7, 3, 201, 99)), want[3:99, 7:201])
+    pinned = ogre_b200.pinned_empty((h, w), np.uint32)
+    assert np.array_equal(rt.read_colour_packed32(16, 8, 0, 0xFF000000, out=pinned), (rgb[..., 0] << 16) | (rgb[..., 1] << 8) | rgb[..., 2] | 0xFF000000)
+    scene.free(); rt.destroy()

@@ -152,9 +152,24 @@ def c1(ctx, T, args):
         frame(); rt.read_colour(out=host)
     dt_rb = (time.perf_counter() - t0) / 20
     assert np.array_equal(host, colour)
+    # the same frame read back as 32-bit BGRA (PF_A8R8G8B8): converted on the device vs RGB read-back + host shuffle
+    host32 = ogre_b200.pinned_empty((h, w), np.uint32)
+    frame(); rt.read_colour_packed32(16, 8, 0, 0xFF000000, out=host32)
+    t0 = time.perf_counter()
+    for _ in range(20):
+        frame(); rt.read_colour_packed32(16, 8, 0, 0xFF000000, out=host32)
+    dt_rb32 = (time.perf_counter() - t0) / 20
+    t0 = time.perf_counter()
+    for _ in range(5):
+        frame(); rt.read_colour(out=host)
+        conv = (host[..., 0].astype(np.uint32) << 16) | (host[..., 1].astype(np.uint32) << 8) | host[..., 2] | 0xFF000000
+    dt_rb32_host = (time.perf_counter() - t0) / 5
+    assert np.array_equal(conv, host32)
     out = {"config": "c1 ogrehead 1280x720 (4336 tris, 4 draws) replayed through the C ABI", "ms_per_frame_device": dt * 1e3,
            "frames_per_s_device": 1 / dt, "ms_per_frame_with_readback": dt_rb * 1e3, "frames_per_s_with_readback": 1 / dt_rb,
-           "Mtri_per_s_device": 4336 / dt / 1e6, "image_identical_to_tiny": True}
+           "Mtri_per_s_device": 4336 / dt / 1e6, "image_identical_to_tiny": True,
+           "ms_per_frame_with_bgra_readback_device_conversion": dt_rb32 * 1e3,
+           "ms_per_frame_with_bgra_readback_host_conversion_numpy": dt_rb32_host * 1e3}
     if args.cpu:
         from oracle import ref
         if ref.available():

@@ -1,5 +1,4 @@
-for n in 8 4; do
-python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2951$n bench.py --gpus $n --steps 200 --warmup 3 2>/dev/null | grep '^{' > gpurun_out/bench_n${n}_r01o.json; python -c "
-import json
-d=json.load(open('gpurun_out/bench_n${n}_r01o.json')); print('N=$n value', round(d['value']), 'e2e', round(d['e2e']['value']), 'states', round(d['e2e']['states_value']), d['ms_per_step'])"
-done
+timeout 600 python -m pytest tests/test_raster_gpu.py -x -q -k "packed32" 2>&1 | tail -3
+python tools/bench_configs.py --config c1 | python -c "
+import sys,json
+d=json.loads(sys.stdin.read()); print({k:round(v,4) for k,v in d.items() if isinstance(v,float)})"
