@@ -76,13 +76,15 @@ def triangle_range(num_triangles, rank, world):
     return instance_range(num_triangles, rank, world)
 
 
-def composite_sort_last(ctx, colour, depth, height, clear_rgba, clear_depth, dst=0, group=None, want_depth=False):
+def composite_sort_last(ctx, colour, depth, height, clear_rgba, clear_depth, dst=0, group=None, want_depth=False, merge=None):
     """Sort-last composite (ogrecu_composite_depth_dev): every rank passes its full-size planes (torch CUDA tensors
     colour [H, W, 3] uint8, depth [H, W] float32) holding ITS slice of the triangles.  One all-to-all per plane sends
     rows [q R, (q+1) R) of every rank to rank q (R = ceil(H / G) pixel rows), which merges the G versions of its rows in
     rank order with one kernel (smallest depth, later rank on ties); the merged rows are then gathered to `dst`.
     Returns (colour, depth or None) of the whole frame on `dst`, None elsewhere.  The path's one real exchange step:
-    (G-1)/G of 7 bytes per pixel per rank over NVLink.  When G divides H the planes are sent in place (no packing)."""
+    (G-1)/G of 7 bytes per pixel per rank over NVLink.  When G divides H the planes are sent in place (no packing).
+    `merge(recv_c, recv_z)` replaces the device merge in the CPU (gloo) tests of the exchange layout: it must fold
+    recv_*[1:] into recv_*[0] in place."""
     import ctypes as C
     import torch
     import torch.distributed as dist
@@ -102,6 +104,9 @@ def composite_sort_last(ctx, colour, depth, height, clear_rgba, clear_depth, dst
     dist.all_to_all_single(recv_c, send_c, group=group)
     dist.all_to_all_single(recv_z, send_z, group=group)
     n = rows * w
+    if merge is not None:
+        merge(recv_c, recv_z)
+        return _gather_rows(recv_c[0], recv_z[0], rows, world, rank, height, w, dst, group, want_depth)
     clear = (C.c_float * 4)(*[float(v) for v in clear_rgba])
     same_stream = int(lib().ogrecu_get_stream(ctx.handle) or 0) == int(torch.cuda.current_stream().cuda_stream)
     if not same_stream:
@@ -112,12 +117,19 @@ def composite_sort_last(ctx, colour, depth, height, clear_rgba, clear_depth, dst
     if not same_stream:
         ctx.sync()
 
+    return _gather_rows(recv_c[0], recv_z[0], rows, world, rank, height, w, dst, group, want_depth)
+
+
+def _gather_rows(part_c, part_z, rows, world, rank, height, w, dst, group, want_depth):
+    import torch
+    import torch.distributed as dist
+
     def gather_rows(part, shape, dtype):
         full = torch.empty((world * rows,) + shape, dtype=dtype, device=part.device) if rank == dst else None
         dist.gather(part.contiguous(), [full[r * rows:(r + 1) * rows] for r in range(world)] if rank == dst else None, dst=dst, group=group)
         return full[:height] if rank == dst else None
-    frame_c = gather_rows(recv_c[0], (w, 3), torch.uint8)
-    frame_z = gather_rows(recv_z[0], (w,), torch.float32) if want_depth else None
+    frame_c = gather_rows(part_c, (w, 3), torch.uint8)
+    frame_z = gather_rows(part_z, (w,), torch.float32) if want_depth else None
     if rank != dst:
         return None
     return frame_c, frame_z

@@ -91,6 +91,31 @@ def _worker(rank, world, port, w, h, out_dir):
             assert np.array_equal(frame.numpy(), full)
         else:
             assert frame is None
+        # ---- sort-last: each rank holds a full-size colour + depth frame of ITS triangle slice; rows are exchanged
+        # (all-to-all), merged per pixel in rank order and gathered.  The device merge kernel is replaced by its numpy
+        # statement here: smallest depth wins, the later rank on ties, untouched (cleared) pixels never win.
+        rngp = np.random.default_rng(100 + rank)
+        hz, wz = 50, 24                                   # 50 rows over 2 ranks: 25 each (in place); 3 ranks would pad
+        zr = np.where(rngp.random((hz, wz)) < 0.6, rngp.choice([0.25, 0.5, 0.75], size=(hz, wz)), 1.0).astype(np.float32)
+        cr = np.where((zr < 1.0)[..., None], np.uint8(10 + rank), np.array([25, 51, 76], np.uint8)).astype(np.uint8)
+
+        def merge(rc, rz):
+            for r in range(1, world):
+                take = (rz[r] <= rz[0]) & ~((rz[r] == 1.0) & (rc[r] == torch.tensor([25, 51, 76], dtype=torch.uint8)).all(-1))
+                rz[0][take] = rz[r][take]
+                rc[0][take] = rc[r][take]
+        res = shard.composite_sort_last(None, torch.from_numpy(cr), torch.from_numpy(zr), hz, (0.1, 0.2, 0.3, 1.0), 1.0, dst=0, want_depth=True,
+                                        merge=merge)
+        all_z = [torch.zeros(hz, wz) for _ in range(world)]; all_c = [torch.zeros(hz, wz, 3, dtype=torch.uint8) for _ in range(world)]
+        dist.all_gather(all_z, torch.from_numpy(zr)); dist.all_gather(all_c, torch.from_numpy(cr))
+        if rank == 0:
+            ez, ec = all_z[0].clone(), all_c[0].clone()
+            for r in range(1, world):
+                take = (all_z[r] <= ez) & (all_z[r] < 1.0)
+                ez[take] = all_z[r][take]; ec[take] = all_c[r][take]
+            assert torch.equal(res[1], ez) and torch.equal(res[0], ec)
+        else:
+            assert res is None
         # ---- instance sharding: each rank skins its own instances; no collective, only the timing max
         n, ninst = 300, 11
         rng = np.random.default_rng(5)
