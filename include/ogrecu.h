@@ -84,6 +84,8 @@ OGRECU_API uint64_t ogrecu_launch_count(const ogrecu_ctx* ctx);
  *                equivalent to Tiny's in-order loop, else in-order), 1 = always in-order
  *   "raster_xf"  1 = transform every vertex once per flush when the draw gives vertex_count (default),
  *                0 = once per index like Tiny; identical results
+ *   "skel_mode"  0 = bone-palette kernel in use (16 instances of one bone per half-warp), 1 = first version (a lane per
+ *                bone); identical results
  * Unknown names return OGRECU_ERR_INVALID. */
 OGRECU_API int ogrecu_set_config_option(ogrecu_ctx* ctx, const char* name, int value);
 

@@ -86,6 +86,7 @@ struct ogrecu_ctx {
     //   OGRECU_RASTER_MODE 0 auto (visibility path where it is equivalent) | 1 always the in-order path
     //   OGRECU_RASTER_XF   1 (default) transform each vertex once per flush when the draw gives a vertex count | 0 per index
     int skin_mode, skin_ipc, raster_mode, raster_xf;
+    int skel_mode = 0;          // 0: lanes = instances (skel_palette_kernel2) | 1: first version, a lane per bone (A/B)
     // side streams for independent launches of one call (ogrecu_anim_instanced_multi_dev): created on first use
     cudaStream_t side_stream[2] = {nullptr, nullptr};
     cudaEvent_t side_fork = nullptr, side_join[2] = {nullptr, nullptr};

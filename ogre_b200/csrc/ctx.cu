@@ -168,6 +168,7 @@ int ogrecu_set_config_option(ogrecu_ctx* ctx, const char* name, int value)
     if (!strcmp(name, "skin_mode")) { OGRECU_REQUIRE(value >= 0 && value <= 4, "skin_mode is 0..4"); ctx->skin_mode = value; return OGRECU_OK; }
     if (!strcmp(name, "raster_xf")) { OGRECU_REQUIRE(value >= 0 && value <= 1, "raster_xf is 0..1"); ctx->raster_xf = value; return OGRECU_OK; }
     if (!strcmp(name, "raster_mode")) { OGRECU_REQUIRE(value >= 0 && value <= 1, "raster_mode is 0..1"); ctx->raster_mode = value; return OGRECU_OK; }
+    if (!strcmp(name, "skel_mode")) { OGRECU_REQUIRE(value >= 0 && value <= 1, "skel_mode is 0..1"); ctx->skel_mode = value; return OGRECU_OK; }
     if (!strcmp(name, "skin_ipc")) { OGRECU_REQUIRE(value >= 0 && value <= 4096, "skin_ipc is 0..4096"); ctx->skin_ipc = value; return OGRECU_OK; }
     set_error("ogrecu_set_config_option: unknown option '%s'", name);
     return OGRECU_ERR_INVALID;

@@ -104,6 +104,8 @@ struct SkelDev {
     const float* bind;              // [num_bones][10]
     const float* bind_inverse;      // [num_bones][10]
     const AnimDev* anims;           // [num_anims]
+    const int16_t* ppos;            // [num_bones] position (in `order`) of the parent of the bone at position p, -1 = root
+    const uint16_t* level_start;    // [num_levels + 1] first position of each tree level in `order`
 };
 
 // blockDim = (bones rounded up to a warp, instances per CTA)
@@ -215,6 +217,146 @@ __global__ void __launch_bounds__(512) skel_palette_kernel(const SkelDev S, uint
     o[3] = make_float4(0.0f, 0.0f, 0.0f, 1.0f);
 }
 
+
+// ---- the kernel in use: 16 instances x 16 bone slots per CTA.  A half-warp holds 16 INSTANCES of one bone, so the track
+// lookups are uniform per half-warp, the tree walk needs no per-lane level test, and one bone's transforms of the 16
+// instances sit side by side in shared memory.  Bones are taken in tree-level order (`order`); slot s handles the
+// positions s, s + 16, ...  (First version above — a lane per bone — ran every level's derivation step with mostly idle
+// lanes: 55 us for 10 000 x 69; kept for A/B through "skel_mode".)
+constexpr int SK_INST = 16;                 // instances per CTA
+constexpr int SK_SLOTS = 16;                // bone slots per CTA
+constexpr int SK_XF = 10 * SK_INST + 16;    // floats per bone in shared memory (+16: the two half-warps hit different banks)
+
+struct StatePre { int32_t anim; float tp; uint32_t gi; float w; };
+
+__global__ void __launch_bounds__(SK_INST * SK_SLOTS) skel_palette_kernel2(const SkelDev S, uint32_t num_instances, uint32_t num_states,
+                                                                           const int32_t* __restrict__ anim, const float* __restrict__ time,
+                                                                           const float* __restrict__ weight, float* __restrict__ out,
+                                                                           size_t stride_floats)
+{
+    extern __shared__ float s_xf[];                                  // [num_bones][SK_XF]
+    StatePre* s_st = reinterpret_cast<StatePre*>(s_xf + (size_t)S.num_bones * SK_XF);     // [SK_INST][num_states]
+    const uint32_t ix = threadIdx.x, slot = threadIdx.y;
+    const uint32_t inst = blockIdx.x * SK_INST + ix;
+    const bool live = inst < num_instances;
+
+    // ---- phase 0: per (instance, state): wrapped time, global key index, effective weight — once, not once per bone
+    for (uint32_t s = slot; s < num_states; s += SK_SLOTS) {
+        StatePre P{-1, 0.f, 0u, 0.f};
+        if (live) {
+            const int32_t* ia = anim + (size_t)inst * num_states;
+            const float* iw = weight + (size_t)inst * num_states;
+            const int32_t a = ia[s];
+            if (a >= 0 && (uint32_t)a < S.num_anims) {
+                float factor = 1.0f;
+                if (S.blend_mode == 0) {                              // ANIMBLEND_AVERAGE: rebalance when the weights sum above 1
+                    float total = 0.0f;
+                    for (uint32_t q = 0; q < num_states; ++q)
+                        if (ia[q] >= 0) total += iw[q];
+                    if (total > 1.0f) factor = 1.0f / total;
+                }
+                const AnimDev A = S.anims[a];
+                float tp = time[(size_t)inst * num_states + s];
+                if (tp > A.length && A.length > 0.0f) tp = fmodf(tp, A.length);
+                uint32_t lo = 0, hi = A.num_times - 1;                // Animation::_getTimeIndex: lower_bound over [begin, end - 1)
+                while (lo < hi) {
+                    const uint32_t mid = (lo + hi) >> 1;
+                    if (A.times[mid] < tp) lo = mid + 1; else hi = mid;
+                }
+                P = StatePre{a, tp, lo, iw[s] * factor};
+            }
+        }
+        s_st[ix * num_states + s] = P;
+    }
+    __syncthreads();
+
+    // ---- phase 1: local transforms (binding pose, then every enabled state in slot order)
+    for (uint32_t p = slot; p < S.num_bones; p += SK_SLOTS) {
+        const uint32_t b = S.order[p];
+        Xform L = load_xform(S.bind + 10 * b);
+        if (live) {
+            for (uint32_t s = 0; s < num_states; ++s) {
+                const StatePre P = s_st[ix * num_states + s];
+                if (P.anim < 0) continue;
+                const AnimDev A = S.anims[P.anim];
+                const float w = P.w;
+                const int32_t trk = A.bone_track[b];
+                if (trk < 0 || !w) continue;
+                const uint32_t k0 = A.key_offset[trk], nk = A.key_offset[trk + 1] - k0;
+                if (nk == 0) continue;
+                const float tp = P.tp;
+                uint32_t i = A.index_map[(size_t)trk * A.num_times + P.gi];       // AnimationTrack::getKeyFramesAtTime
+                const float4* K = A.keys + 3 * (size_t)k0;
+                const uint32_t i2 = i;
+                const float4 k2a = K[3 * i2];
+                const float t2 = k2a.x;
+                if (i != 0 && tp < t2) --i;
+                const float4 k1a = K[3 * i], k1b = K[3 * i + 1], k1c = K[3 * i + 2];
+                const float t1 = k1a.x;
+                const float f = (t1 == t2) ? 0.0f : (tp - t1) / (t2 - t1);
+                const bool shortest = A.shortest[trk] != 0;
+                Vec3 tr{k1a.y, k1a.z, k1a.w}, sc{k1c.x, k1c.y, k1c.z};
+                Quat ro{k1b.x, k1b.y, k1b.z, k1b.w};
+                if (f != 0.0f) {                                                   // getInterpolatedKeyFrame (IM_LINEAR, RIM_LINEAR)
+                    const float4 k2b = K[3 * i2 + 1], k2c = K[3 * i2 + 2];
+                    ro = q_nlerp(f, ro, Quat{k2b.x, k2b.y, k2b.z, k2b.w}, shortest);
+                    tr = Vec3{k1a.y + f * (k2a.y - k1a.y), k1a.z + f * (k2a.z - k1a.z), k1a.w + f * (k2a.w - k1a.w)};
+                    sc = Vec3{k1c.x + f * (k2c.x - k1c.x), k1c.y + f * (k2c.y - k1c.y), k1c.z + f * (k2c.z - k1c.z)};
+                }
+                const float scl = 1.0f;                                            // applyToNode, no linked skeleton
+                L.p.x += tr.x * w * scl; L.p.y += tr.y * w * scl; L.p.z += tr.z * w * scl;
+                const Quat rot = q_nlerp(w, Quat{1.0f, 0.0f, 0.0f, 0.0f}, ro, shortest);
+                L.q = q_unit(q_mul(L.q, rot));
+                if ((sc.x != 1.0f || sc.y != 1.0f || sc.z != 1.0f) && w != 1.0f)
+                    sc = Vec3{1.0f + w * (sc.x - 1.0f), 1.0f + w * (sc.y - 1.0f), 1.0f + w * (sc.z - 1.0f)};
+                L.s.x *= sc.x; L.s.y *= sc.y; L.s.z *= sc.z;
+            }
+        }
+        float* o = s_xf + (size_t)p * SK_XF + ix;
+        o[0] = L.p.x; o[SK_INST] = L.p.y; o[2 * SK_INST] = L.p.z; o[3 * SK_INST] = L.q.w; o[4 * SK_INST] = L.q.x; o[5 * SK_INST] = L.q.y;
+        o[6 * SK_INST] = L.q.z; o[7 * SK_INST] = L.s.x; o[8 * SK_INST] = L.s.y; o[9 * SK_INST] = L.s.z;
+    }
+    __syncthreads();
+
+    auto load_s = [&](uint32_t p) {
+        const float* o = s_xf + (size_t)p * SK_XF + ix;
+        return Xform{Vec3{o[0], o[SK_INST], o[2 * SK_INST]}, Quat{o[3 * SK_INST], o[4 * SK_INST], o[5 * SK_INST], o[6 * SK_INST]},
+                     Vec3{o[7 * SK_INST], o[8 * SK_INST], o[9 * SK_INST]}};
+    };
+    // ---- phase 2: derived transforms in place, one tree level per round (level 0: derived = local)
+    for (uint32_t l = 1; l < S.num_levels; ++l) {
+        const uint32_t a = S.level_start[l], e = S.level_start[l + 1];
+        for (uint32_t p = a + slot; p < e; p += SK_SLOTS) {
+            const uint32_t b = S.order[p];
+            const Xform D = derive(load_s((uint32_t)S.ppos[p]), load_s(p), S.inherit[2 * b] != 0, S.inherit[2 * b + 1] != 0);
+            float* o = s_xf + (size_t)p * SK_XF + ix;
+            o[0] = D.p.x; o[SK_INST] = D.p.y; o[2 * SK_INST] = D.p.z; o[3 * SK_INST] = D.q.w; o[4 * SK_INST] = D.q.x; o[5 * SK_INST] = D.q.y;
+            o[6 * SK_INST] = D.q.z; o[7 * SK_INST] = D.s.x; o[8 * SK_INST] = D.s.y; o[9 * SK_INST] = D.s.z;
+        }
+        __syncthreads();
+    }
+    if (!live) return;
+    // ---- phase 3: Bone::_getOffsetTransform + makeTransform, 64 contiguous bytes per (instance, bone)
+    for (uint32_t p = slot; p < S.num_bones; p += SK_SLOTS) {
+        const uint32_t b = S.order[p];
+        const Xform D = load_s(p);
+        const Xform I = load_xform(S.bind_inverse + 10 * b);
+        const Vec3 ls{D.s.x * I.s.x, D.s.y * I.s.y, D.s.z * I.s.z};
+        const Quat lr = q_mul(D.q, I.q);
+        const Vec3 rp = q_rotate(lr, Vec3{ls.x * I.p.x, ls.y * I.p.y, ls.z * I.p.z});
+        const Vec3 lt{D.p.x + rp.x, D.p.y + rp.y, D.p.z + rp.z};
+        const float tx = lr.x + lr.x, ty = lr.y + lr.y, tz = lr.z + lr.z;
+        const float twx = tx * lr.w, twy = ty * lr.w, twz = tz * lr.w;
+        const float txx = tx * lr.x, txy = ty * lr.x, txz = tz * lr.x;
+        const float tyy = ty * lr.y, tyz = tz * lr.y, tzz = tz * lr.z;
+        float4* o = reinterpret_cast<float4*>(out + (size_t)inst * stride_floats + 16 * (size_t)b);
+        o[0] = make_float4(ls.x * (1.0f - (tyy + tzz)), ls.y * (txy - twz), ls.z * (txz + twy), lt.x);
+        o[1] = make_float4(ls.x * (txy + twz), ls.y * (1.0f - (txx + tzz)), ls.z * (tyz - twx), lt.y);
+        o[2] = make_float4(ls.x * (txz - twy), ls.y * (tyz + twx), ls.z * (1.0f - (txx + tyy)), lt.z);
+        o[3] = make_float4(0.0f, 0.0f, 0.0f, 1.0f);
+    }
+}
+
 }  // namespace ogrecu
 
 // ---------------------------------------------------------------------------------------------- host side
@@ -226,6 +368,7 @@ struct ogrecu_skel {
     std::vector<float> bind_inverse;
     // device copies of the bone table
     int32_t* d_parent; uint8_t* d_level; uint16_t* d_order; uint8_t* d_inherit; float* d_bind; float* d_bind_inverse;
+    int16_t* d_ppos; uint16_t* d_level_start;
     // animations: host mirror of the device records + the device table
     std::vector<AnimDev> anims;
     std::vector<void*> owned;               // device blocks of the animations
@@ -306,6 +449,16 @@ int ogrecu_skel_create(ogrecu_ctx* ctx, const ogrecu_skeleton_desc* d, ogrecu_sk
     for (uint32_t b = 0; b < n; ++b) order[b] = (uint16_t)b;
     std::stable_sort(order.begin(), order.end(), [&](uint16_t x, uint16_t y) { return level[x] < level[y]; });
     if (!rc) rc = upload(ctx, order.data(), n, &s->d_order);
+    std::vector<int16_t> ppos(n, -1);
+    std::vector<uint16_t> pos_of(n), level_start(levels + 1, (uint16_t)n);
+    for (uint32_t p = 0; p < n; ++p) pos_of[order[p]] = (uint16_t)p;
+    for (uint32_t p = 0; p < n; ++p) {
+        if (d->parent[order[p]] >= 0) ppos[p] = (int16_t)pos_of[d->parent[order[p]]];
+        const uint8_t l = level[order[p]];
+        if (p < level_start[l]) level_start[l] = (uint16_t)p;
+    }
+    if (!rc) rc = upload(ctx, ppos.data(), n, &s->d_ppos);
+    if (!rc) rc = upload(ctx, level_start.data(), level_start.size(), &s->d_level_start);
     if (!rc) rc = upload(ctx, inherit.data(), 2 * (size_t)n, &s->d_inherit);
     if (!rc) rc = upload(ctx, d->bind, 10 * (size_t)n, &s->d_bind);
     if (!rc) rc = upload(ctx, inv.data(), inv.size(), &s->d_bind_inverse);
@@ -319,7 +472,7 @@ int ogrecu_skel_destroy(ogrecu_skel* s)
     if (!s) return OGRECU_OK;
     cudaSetDevice(s->ctx->device);
     cudaStreamSynchronize(s->ctx->stream);
-    for (void* p : {(void*)s->d_parent, (void*)s->d_level, (void*)s->d_order, (void*)s->d_inherit, (void*)s->d_bind, (void*)s->d_bind_inverse, (void*)s->d_anims})
+    for (void* p : {(void*)s->d_parent, (void*)s->d_level, (void*)s->d_order, (void*)s->d_ppos, (void*)s->d_level_start, (void*)s->d_inherit, (void*)s->d_bind, (void*)s->d_bind_inverse, (void*)s->d_anims})
         if (p) cudaFree(p);
     for (void* p : s->owned) cudaFree(p);
     delete s;
@@ -430,7 +583,20 @@ int ogrecu_skel_palettes_dev(ogrecu_skel* s, uint32_t num_instances, uint32_t nu
     SkelDev S{};
     S.num_bones = s->num_bones; S.blend_mode = s->blend_mode; S.num_levels = s->num_levels; S.num_anims = (uint32_t)s->anims.size();
     S.parent = s->d_parent; S.level = s->d_level; S.order = s->d_order; S.inherit = s->d_inherit; S.bind = s->d_bind; S.bind_inverse = s->d_bind_inverse;
-    S.anims = s->d_anims;
+    S.anims = s->d_anims; S.ppos = s->d_ppos; S.level_start = s->d_level_start;
+    if (ctx->skel_mode == 0) {
+        const size_t smem2 = (size_t)s->num_bones * SK_XF * sizeof(float) + (size_t)SK_INST * std::max(num_states, 1u) * sizeof(StatePre);
+        static size_t granted[64] = {0};
+        if (smem2 > 48 * 1024 && smem2 > granted[ctx->device & 63]) {
+            OGRECU_CUDA(cudaFuncSetAttribute(skel_palette_kernel2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            granted[ctx->device & 63] = smem2;
+        }
+        skel_palette_kernel2<<<div_up(num_instances, SK_INST), dim3(SK_INST, SK_SLOTS), smem2, ctx->stream>>>(S, num_instances, num_states, anim_dev, time_dev,
+                                                                                                         weight_dev, palettes_dev, stride_floats);
+        OGRECU_CUDA(cudaGetLastError());
+        count_launch(ctx);
+        return OGRECU_OK;
+    }
     const uint32_t bx = (s->num_bones + 31) & ~31u;
     const uint32_t by = std::max(1u, 256u / bx);
     dim3 block(bx, by), grid(div_up(num_instances, by));

@@ -22,8 +22,11 @@ def ctx():
     c.close()
 
 
+@pytest.mark.parametrize("skel_mode", [0, 1])
 @pytest.mark.parametrize("name", ["sinbad_skeleton.npz", "jaiqua_skeleton.npz"])
-def test_golden_poses_bit_exact(ctx, name):
+def test_golden_poses_bit_exact(ctx, name, skel_mode):
+    # skel_mode 0: the kernel in use (a half-warp = 16 instances of one bone); 1: the first version (a lane per bone)
+    ctx.set_config_option("skel_mode", skel_mode)
     d, poses = load_skeleton(name)
     sk = ogre_b200.Skeleton(ctx, d)
     # Bone::setBindingPose restated on the host side of the library
@@ -34,6 +37,7 @@ def test_golden_poses_bit_exact(ctx, name):
         got = sk.palettes(poses["anim"][sel], poses["time"][sel], poses["weight"][sel])      # disabled slots are -1
         assert np.array_equal(bits(got), bits(poses["palette"][sel])), (name, mode)
     sk.destroy()
+    ctx.set_config_option("skel_mode", 0)
 
 
 @pytest.mark.parametrize("name", ["sinbad_skeleton.npz", "jaiqua_skeleton.npz"])
