@@ -92,6 +92,7 @@ struct AnimDev {
     const uint8_t* shortest;        // [num_tracks]
     const uint16_t* index_map;      // [num_tracks][num_times] AnimationTrack::_buildKeyFrameIndexMap
     const float4* keys;             // [num_keys][3]: (time, tx, ty, tz) (rw, rx, ry, rz) (sx, sy, sz, -)
+    const uint4* bone_rec;          // [num_bones] (first key, key count, track, shortest-path flag) of the bone's track; count 0 = none
 };
 
 struct SkelDev {
@@ -224,7 +225,7 @@ __global__ void __launch_bounds__(512) skel_palette_kernel(const SkelDev S, uint
 // positions s, s + 16, ...  (First version above — a lane per bone — ran every level's derivation step with mostly idle
 // lanes: 55 us for 10 000 x 69; kept for A/B through "skel_mode".)
 constexpr int SK_INST = 16;                 // instances per CTA
-constexpr int SK_SLOTS = 16;                // bone slots per CTA
+constexpr int SK_SLOTS = 16;                // bone slots per CTA (32: 52.9 us instead of 49.8)
 constexpr int SK_XF = 10 * SK_INST + 16;    // floats per bone in shared memory (+16: the two half-warps hit different banks)
 
 struct StatePre { int32_t anim; float tp; uint32_t gi; float w; };
@@ -280,25 +281,26 @@ __global__ void __launch_bounds__(SK_INST * SK_SLOTS) skel_palette_kernel2(const
                 if (P.anim < 0) continue;
                 const AnimDev A = S.anims[P.anim];
                 const float w = P.w;
-                const int32_t trk = A.bone_track[b];
-                if (trk < 0 || !w) continue;
-                const uint32_t k0 = A.key_offset[trk], nk = A.key_offset[trk + 1] - k0;
+                if (!w) continue;
+                const uint4 R = __ldg(A.bone_rec + b);                             // one load: key range, track, shortest-path flag
+                const uint32_t k0 = R.x, nk = R.y, trk = R.z;
                 if (nk == 0) continue;
                 const float tp = P.tp;
-                uint32_t i = A.index_map[(size_t)trk * A.num_times + P.gi];       // AnimationTrack::getKeyFramesAtTime
+                const uint32_t i2 = A.index_map[(size_t)trk * A.num_times + P.gi]; // AnimationTrack::getKeyFramesAtTime
                 const float4* K = A.keys + 3 * (size_t)k0;
-                const uint32_t i2 = i;
-                const float4 k2a = K[3 * i2];
+                // both candidate keys at once (k1 is k2 or the key before it): no load depends on the time comparison
+                const uint32_t ip = i2 ? i2 - 1 : 0;
+                const float4 k2a = K[3 * i2], k2b = K[3 * i2 + 1], k2c = K[3 * i2 + 2];
+                const float4 kpa = K[3 * ip], kpb = K[3 * ip + 1], kpc = K[3 * ip + 2];
                 const float t2 = k2a.x;
-                if (i != 0 && tp < t2) --i;
-                const float4 k1a = K[3 * i], k1b = K[3 * i + 1], k1c = K[3 * i + 2];
+                const bool back = i2 != 0 && tp < t2;
+                const float4 k1a = back ? kpa : k2a, k1b = back ? kpb : k2b, k1c = back ? kpc : k2c;
                 const float t1 = k1a.x;
                 const float f = (t1 == t2) ? 0.0f : (tp - t1) / (t2 - t1);
-                const bool shortest = A.shortest[trk] != 0;
+                const bool shortest = R.w != 0;
                 Vec3 tr{k1a.y, k1a.z, k1a.w}, sc{k1c.x, k1c.y, k1c.z};
                 Quat ro{k1b.x, k1b.y, k1b.z, k1b.w};
                 if (f != 0.0f) {                                                   // getInterpolatedKeyFrame (IM_LINEAR, RIM_LINEAR)
-                    const float4 k2b = K[3 * i2 + 1], k2c = K[3 * i2 + 2];
                     ro = q_nlerp(f, ro, Quat{k2b.x, k2b.y, k2b.z, k2b.w}, shortest);
                     tr = Vec3{k1a.y + f * (k2a.y - k1a.y), k1a.z + f * (k2a.z - k1a.z), k1a.w + f * (k2a.w - k1a.w)};
                     sc = Vec3{k1c.x + f * (k2c.x - k1c.x), k1c.y + f * (k2c.y - k1c.y), k1c.z + f * (k2c.z - k1c.z)};
@@ -546,6 +548,11 @@ int ogrecu_skel_add_animation(ogrecu_skel* s, const ogrecu_animation_desc* d, ui
     OGRECU_CUDA(cudaSetDevice(ctx->device));
     AnimDev A{};
     A.length = d->length; A.num_times = ntimes;
+    std::vector<uint4> bone_rec(nb, make_uint4(0, 0, 0, 0));
+    for (uint32_t t = 0; t < nt; ++t)
+        bone_rec[d->track_bone[t]] = make_uint4(key_offset[t], key_offset[t + 1] - key_offset[t], t, shortest[t] ? 1u : 0u);
+    uint4* d_br;
+    OGRECU_CHECK(upload(ctx, bone_rec.data(), bone_rec.size(), &d_br)); s->owned.push_back(d_br);
     float* d_times; int32_t* d_bt; uint32_t* d_ko; uint8_t* d_sh; uint16_t* d_im; float4* d_keys;
     OGRECU_CHECK(upload(ctx, times.data(), times.size(), &d_times)); s->owned.push_back(d_times);
     OGRECU_CHECK(upload(ctx, bone_track.data(), bone_track.size(), &d_bt)); s->owned.push_back(d_bt);
@@ -553,6 +560,7 @@ int ogrecu_skel_add_animation(ogrecu_skel* s, const ogrecu_animation_desc* d, ui
     OGRECU_CHECK(upload(ctx, shortest.data(), shortest.size(), &d_sh)); s->owned.push_back(d_sh);
     OGRECU_CHECK(upload(ctx, index_map.data(), index_map.size(), &d_im)); s->owned.push_back(d_im);
     OGRECU_CHECK(upload(ctx, keys.data(), keys.size(), &d_keys)); s->owned.push_back(d_keys);
+    A.bone_rec = d_br;
     A.times = d_times; A.bone_track = d_bt; A.key_offset = d_ko; A.shortest = d_sh; A.index_map = d_im; A.keys = d_keys;
     s->anims.push_back(A);
     // the device table of records: regrown geometrically, rewritten whole (animations are added at load time)
