@@ -33,14 +33,16 @@ def test_struct_layouts_match_the_header(tmp_path):
     src = tmp_path / "layout.c"
     src.write_text(
         '#include <stdio.h>\n#include <stddef.h>\n#include "ogrecu.h"\n'
-        'int main(void){printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(ogrecu_skin_job), sizeof(ogrecu_draw_desc),'
+        'int main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(ogrecu_skin_job), sizeof(ogrecu_draw_desc),'
         ' sizeof(ogrecu_raster_stats), offsetof(ogrecu_draw_desc, texture), offsetof(ogrecu_draw_desc, mvp),'
-        ' offsetof(ogrecu_draw_desc, ambient), offsetof(ogrecu_skin_job, num_vertices));return 0;}\n')
+        ' offsetof(ogrecu_draw_desc, ambient), offsetof(ogrecu_skin_job, num_vertices), sizeof(ogrecu_anim_job),'
+        ' offsetof(ogrecu_anim_job, dst_instance_stride_bytes), sizeof(ogrecu_skeleton_desc), sizeof(ogrecu_animation_desc));return 0;}\n')
     exe = tmp_path / "layout"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     got = [int(v) for v in subprocess.check_output([str(exe)]).split()]
     assert got == [C.sizeof(capi.SkinJob), C.sizeof(capi.DrawDesc), C.sizeof(capi.RasterStats), capi.DrawDesc.texture.offset,
-                   capi.DrawDesc.mvp.offset, capi.DrawDesc.ambient.offset, capi.SkinJob.num_vertices.offset]
+                   capi.DrawDesc.mvp.offset, capi.DrawDesc.ambient.offset, capi.SkinJob.num_vertices.offset, C.sizeof(capi.AnimJob),
+                   capi.AnimJob.dst_instance_stride_bytes.offset, C.sizeof(capi.SkeletonDesc), C.sizeof(capi.AnimationDesc)]
 
 
 def test_no_device_is_a_loud_failure_not_a_fallback():
@@ -65,3 +67,13 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 src = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "import oracle" not in src and "ogre_oracle" not in src and "libref_driver" not in src, f
+
+
+def test_header_is_plain_c(tmp_path):
+    # the drop-in boundary is a C ABI: include/ogrecu.h must compile as C99 (and as C++11) with nothing but itself
+    import subprocess
+    src = tmp_path / "h.c"
+    src.write_text('#include "ogrecu.h"\nint main(void){return (int)sizeof(ogrecu_anim_job) * 0;}\n')
+    inc = os.path.join(ROOT, "include")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", inc, "-c", str(src), "-o", str(tmp_path / "h.o")])
+    subprocess.check_call(["g++", "-std=c++11", "-Wall", "-Werror", "-I", inc, "-x", "c++", "-c", str(src), "-o", str(tmp_path / "h2.o")])
