@@ -471,6 +471,14 @@ OGRECU_API int ogrecu_rt_read_colour(ogrecu_rt* rt, uint32_t left, uint32_t top,
 OGRECU_API int ogrecu_rt_read_colour_packed32(ogrecu_rt* rt, uint32_t left, uint32_t top, uint32_t right, uint32_t bottom,
                                               void* dst_host, size_t dst_pitch_bytes, uint32_t r_shift, uint32_t g_shift,
                                               uint32_t b_shift, uint32_t fill);
+/* Scaled read-back: the sub-box resampled to dst_width x dst_height with Image::scale(FILTER_BILINEAR)'s byte arithmetic
+ * (LinearResampler_Byte, OgreMain/src/OgreImageResampler.h:283-339) on the device — what TinyHardwarePixelBuffer::blitToMemory
+ * does on the CPU when the sizes differ (RenderSystems/Tiny/src/OgreTinyHardwarePixelBuffer.cpp:43-47, the read-back of a
+ * RenderTexture, OgreMain/src/OgreRenderTexture.cpp:50-56).  dst_px_bytes = 3: RGB8 rows; 4: packed words as
+ * ogrecu_rt_read_colour_packed32 (Image::scale's temp buffer + bulkPixelConversion tail, OgreImage.cpp:453-457). */
+OGRECU_API int ogrecu_rt_read_colour_scaled(ogrecu_rt* rt, uint32_t left, uint32_t top, uint32_t right, uint32_t bottom, uint32_t dst_width,
+                                            uint32_t dst_height, void* dst_host, size_t dst_pitch_bytes, uint32_t dst_px_bytes,
+                                            uint32_t r_shift, uint32_t g_shift, uint32_t b_shift, uint32_t fill);
 OGRECU_API int ogrecu_rt_read_depth(ogrecu_rt* rt, uint32_t left, uint32_t top, uint32_t right, uint32_t bottom,
                                     float* dst_host, size_t dst_pitch_bytes);
 /* upload into the planes (render-to-texture sources, tests) */

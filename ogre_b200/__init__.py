@@ -337,6 +337,19 @@ class RenderTarget:
         check(lib().ogrecu_rt_read_colour_packed32(self.handle, l, t, r, b, out.ctypes.data, (r - l) * 4, r_shift, g_shift, b_shift, fill))
         return out
 
+    def read_colour_scaled(self, dst_w, dst_h, box=None, packed=None, pad=0):
+        """blitToMemory into a destination of another size: Image::scale(FILTER_BILINEAR)'s byte arithmetic on the device.
+        packed = (r_shift, g_shift, b_shift, fill) returns uint32 words, else RGB8; rows are `pad` pixels wider than dst_w
+        (the padding keeps 0xEE)."""
+        l, t, r, b = box if box else (0, 0, self.width, self.height)
+        if packed is None:
+            out = np.full((dst_h, dst_w + pad, 3), 0xEE, dtype=np.uint8)
+            check(lib().ogrecu_rt_read_colour_scaled(self.handle, l, t, r, b, dst_w, dst_h, out.ctypes.data, (dst_w + pad) * 3, 3, 0, 0, 0, 0))
+        else:
+            out = np.full((dst_h, dst_w + pad), 0xEEEEEEEE, dtype=np.uint32)
+            check(lib().ogrecu_rt_read_colour_scaled(self.handle, l, t, r, b, dst_w, dst_h, out.ctypes.data, (dst_w + pad) * 4, 4, *packed))
+        return out
+
     def read_depth(self, box=None, out=None):
         l, t, r, b = box if box else (0, 0, self.width, self.height)
         if out is None:

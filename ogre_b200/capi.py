@@ -168,6 +168,8 @@ SIGNATURES = {
     "ogrecu_rt_read_colour": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t]),
     "ogrecu_rt_read_colour_packed32": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t, C.c_uint32,
                                                  C.c_uint32, C.c_uint32, C.c_uint32]),
+    "ogrecu_rt_read_colour_scaled": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p,
+                                               C.c_size_t, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]),
     "ogrecu_rt_read_depth": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t]),
     "ogrecu_rt_write_colour": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "ogrecu_rt_write_depth": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),

@@ -1629,6 +1629,25 @@ int ogrecu_rt_read_colour(ogrecu_rt* rt, uint32_t l, uint32_t t, uint32_t r, uin
     return read_plane(rt, rt->colour, 3, l, t, r, b, dst, pitch);
 }
 
+// rows of `row` bytes, tightly packed in ctx->stage_out, -> host rows `pitch` bytes apart; waits for the copy.  A destination
+// in pinned host memory takes the DMA directly, anything else is staged through the context's pinned block.
+static int stage_out_to_host(ogrecu_ctx* ctx, void* dst, size_t pitch, size_t row, size_t rows)
+{
+    cudaPointerAttributes pa;
+    if (cudaPointerGetAttributes(&pa, dst) == cudaSuccess && pa.type == cudaMemoryTypeHost) {
+        OGRECU_CUDA(cudaMemcpy2DAsync(dst, pitch, ctx->stage_out.ptr, row, row, rows, cudaMemcpyDeviceToHost, ctx->stream));
+        OGRECU_CUDA(cudaStreamSynchronize(ctx->stream));
+        return OGRECU_OK;
+    }
+    (void)cudaGetLastError();
+    OGRECU_CHECK(pinned_reserve(ctx, row * rows));
+    OGRECU_CUDA(cudaMemcpyAsync(ctx->pinned, ctx->stage_out.ptr, row * rows, cudaMemcpyDeviceToHost, ctx->stream));
+    OGRECU_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (pitch == row) memcpy(dst, ctx->pinned, row * rows);
+    else for (size_t y = 0; y < rows; ++y) memcpy((uint8_t*)dst + y * pitch, (uint8_t*)ctx->pinned + y * row, row);
+    return OGRECU_OK;
+}
+
 // RGB8 sub-box -> one packed 32-bit word per pixel: r << r_shift | g << g_shift | b << b_shift | fill.  What
 // PixelUtil::bulkPixelConversion does on the CPU in TinyWindow::copyContentsToMemory (OgreTinyWindow.cpp:79) for the
 // 32-bit 8-bits-per-channel destination formats (OgrePixelConversions.h:333-351 and the generic unpack/pack path, which
@@ -1659,19 +1678,71 @@ int ogrecu_rt_read_colour_packed32(ogrecu_rt* rt, uint32_t l, uint32_t t, uint32
                                                                        b_shift, fill);
     OGRECU_CUDA(cudaGetLastError());
     count_launch(ctx);
-    cudaPointerAttributes pa;
-    if (cudaPointerGetAttributes(&pa, dst) == cudaSuccess && pa.type == cudaMemoryTypeHost) {       // pinned destination: direct DMA
-        OGRECU_CUDA(cudaMemcpy2DAsync(dst, pitch, ctx->stage_out.ptr, row, row, bh, cudaMemcpyDeviceToHost, ctx->stream));
-        OGRECU_CUDA(cudaStreamSynchronize(ctx->stream));
-        return OGRECU_OK;
+    return stage_out_to_host(ctx, dst, pitch, row, bh);
+}
+
+// Image::scale(FILTER_BILINEAR) of an RGB8 sub-box = LinearResampler_Byte<3>::scale (OgreMain/src/OgreImage.cpp:389-458,
+// OgreMain/src/OgreImageResampler.h:283-339), one thread per destination pixel: the reference walks the source position
+// incrementally in 16.48 fixed point (sx_48 += stepx), which is x * stepx modulo 2^64 — evaluated directly here.  The blend is
+// the reference's unsigned 8.24 arithmetic, so the bytes are identical.  out_px = 3: RGB8 rows; 4: the scaled pixel packed as
+// pack32_kernel does (the temp-buffer + bulkPixelConversion tail of Image::scale when the formats differ, OgreImage.cpp:453-457).
+__device__ __forceinline__ void scale_axis(uint64_t pos_48, uint32_t extent, uint32_t& s1, uint32_t& s2, uint32_t& frac)
+{
+    uint32_t temp = (uint32_t)(pos_48 >> 36);
+    temp = (temp > 0x800u) ? temp - 0x800u : 0u;
+    frac = temp & 0xFFFu;
+    s1 = temp >> 12;
+    s2 = min(s1 + 1u, extent - 1u);
+}
+
+__global__ void __launch_bounds__(256) scale_rgb8_kernel(const uint8_t* __restrict__ rgb, uint32_t plane_w, uint32_t l, uint32_t t, uint32_t sw,
+                                                         uint32_t sh, uint8_t* __restrict__ out, uint32_t dw, uint32_t dh, uint64_t stepx,
+                                                         uint64_t stepy, uint32_t out_px, uint32_t rs, uint32_t gs, uint32_t bs, uint32_t fill)
+{
+    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= dw || y >= dh) return;
+    uint32_t sx1, sx2, sxf, sy1, sy2, syf;
+    scale_axis((stepx >> 1) - 1 + (uint64_t)x * stepx, sw, sx1, sx2, sxf);
+    scale_axis((stepy >> 1) - 1 + (uint64_t)y * stepy, sh, sy1, sy2, syf);
+    const uint8_t* r1 = rgb + ((size_t)(t + sy1) * plane_w + l) * 3;
+    const uint8_t* r2 = rgb + ((size_t)(t + sy2) * plane_w + l) * 3;
+    const uint32_t sxfsyf = sxf * syf;
+    const uint32_t w11 = 0x1000000u - (sxf << 12) - (syf << 12) + sxfsyf, w21 = (sxf << 12) - sxfsyf, w12 = (syf << 12) - sxfsyf;
+    uint32_t c[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const uint32_t accum = r1[sx1 * 3 + k] * w11 + r1[sx2 * 3 + k] * w21 + r2[sx1 * 3 + k] * w12 + r2[sx2 * 3 + k] * sxfsyf;
+        c[k] = (accum + 0x800000u) >> 24;
     }
-    (void)cudaGetLastError();
-    OGRECU_CHECK(pinned_reserve(ctx, row * bh));
-    OGRECU_CUDA(cudaMemcpyAsync(ctx->pinned, ctx->stage_out.ptr, row * bh, cudaMemcpyDeviceToHost, ctx->stream));
-    OGRECU_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (pitch == row) memcpy(dst, ctx->pinned, row * bh);
-    else for (size_t y = 0; y < bh; ++y) memcpy((uint8_t*)dst + y * pitch, (uint8_t*)ctx->pinned + y * row, row);
-    return OGRECU_OK;
+    if (out_px == 4) reinterpret_cast<uint32_t*>(out)[(size_t)y * dw + x] = (c[0] << rs) | (c[1] << gs) | (c[2] << bs) | fill;
+    else {
+        uint8_t* o = out + ((size_t)y * dw + x) * 3;
+        o[0] = (uint8_t)c[0]; o[1] = (uint8_t)c[1]; o[2] = (uint8_t)c[2];
+    }
+}
+
+int ogrecu_rt_read_colour_scaled(ogrecu_rt* rt, uint32_t l, uint32_t t, uint32_t r, uint32_t b, uint32_t dst_w, uint32_t dst_h, void* dst,
+                                 size_t pitch, uint32_t dst_px_bytes, uint32_t r_shift, uint32_t g_shift, uint32_t b_shift, uint32_t fill)
+{
+    OGRECU_REQUIRE(rt, "rt is NULL");
+    OGRECU_REQUIRE(r <= rt->w && b <= rt->h && l <= r && t <= b, "Invalid box");
+    OGRECU_REQUIRE(dst_px_bytes == 3 || dst_px_bytes == 4, "destination pixels are 3 (RGB8) or 4 (packed) bytes");
+    OGRECU_REQUIRE(dst_px_bytes == 3 || (r_shift <= 24 && g_shift <= 24 && b_shift <= 24), "channel shifts are 0..24");
+    ogrecu_ctx* ctx = rt->ctx;
+    OGRECU_CHECK(ogrecu_flush(rt));
+    const uint32_t sw = r - l, sh = b - t;
+    if (!dst_w || !dst_h) return OGRECU_OK;
+    OGRECU_REQUIRE(sw && sh, "empty source box");
+    OGRECU_REQUIRE(sw < 65536u && sh < 65536u && dst_h < 65536u, "boxes are limited to 65535 pixels per side");
+    const size_t row = (size_t)dst_w * dst_px_bytes;
+    OGRECU_REQUIRE(dst && pitch >= row, "bad destination");
+    OGRECU_CHECK(scratch_reserve(ctx, ctx->stage_out, row * dst_h));
+    const uint64_t stepx = ((uint64_t)sw << 48) / dst_w, stepy = ((uint64_t)sh << 48) / dst_h;      // OgreImageResampler.h:299-300
+    scale_rgb8_kernel<<<dim3(div_up(dst_w, 256), dst_h), 256, 0, ctx->stream>>>(rt->colour, rt->w, l, t, sw, sh, (uint8_t*)ctx->stage_out.ptr, dst_w,
+                                                                                 dst_h, stepx, stepy, dst_px_bytes, r_shift, g_shift, b_shift, fill);
+    OGRECU_CUDA(cudaGetLastError());
+    count_launch(ctx);
+    return stage_out_to_host(ctx, dst, pitch, row, dst_h);
 }
 
 int ogrecu_rt_read_depth(ogrecu_rt* rt, uint32_t l, uint32_t t, uint32_t r, uint32_t b, float* dst, size_t pitch)

@@ -51,6 +51,8 @@ public:
     static void flushPendingDraws();
     /// flush + read a colour box into an arbitrary-format PixelBox (readback path of windows and RTTs)
     static void readColour(ogrecu_rt* rt, const Box& src, const PixelBox& dst);
+    /// read-back into a destination of another size: Image::scale(FILTER_BILINEAR) on the device (ogrecu_rt_read_colour_scaled)
+    static void readColourScaled(ogrecu_rt* rt, const Box& src, const PixelBox& dst);
 
     Real getMinimumDepthInputValue(void) override { return -1.0f; }   // Range [-1.0f, 1.0f], as Tiny
     Real getMaximumDepthInputValue(void) override { return 1.0f; }

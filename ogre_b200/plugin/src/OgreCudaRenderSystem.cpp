@@ -392,4 +392,46 @@ void CudaRenderSystem::readColour(ogrecu_rt* rt, const Box& src, const PixelBox&
     PixelBox box(w, h, 1, PF_BYTE_RGB, tmp.data());
     PixelUtil::bulkPixelConversion(box, dst);   // format conversion as TinyWindow::copyContentsToMemory (OgreTinyWindow.cpp:79)
 }
+
+// true + shifts/fill when `format` is a native-endian 32-bit format with 8 bits per colour channel (what pack32 can write)
+static bool packed32Layout(PixelFormat format, unsigned char shifts[4], uint32& fill)
+{
+    int depths[4];
+    uint64 masks[4];
+    PixelUtil::getBitDepths(format, depths);
+    PixelUtil::getBitShifts(format, shifts);
+    PixelUtil::getBitMasks(format, masks);
+    const unsigned flags = PixelUtil::getFlags(format);
+    fill = ~(uint32)(masks[0] | masks[1] | masks[2]);
+    return PixelUtil::getNumElemBytes(format) == 4 && (flags & PFF_NATIVEENDIAN) &&
+           !(flags & (PFF_FLOAT | PFF_INTEGER | PFF_COMPRESSED | PFF_LUMINANCE | PFF_DEPTH)) && depths[0] == 8 && depths[1] == 8 &&
+           depths[2] == 8 && (depths[3] == 8 || depths[3] == 0);
+}
+
+void CudaRenderSystem::readColourScaled(ogrecu_rt* rt, const Box& src, const PixelBox& dst)
+{
+    flushPendingDraws();
+    const uint32 dw = dst.getWidth(), dh = dst.getHeight();
+    if (!dw || !dh || !src.getWidth() || !src.getHeight()) return;
+    uint8* top = dst.getTopLeftFrontPixelPtr();
+    unsigned char shifts[4];
+    uint32 fill;
+    if (dst.format == PF_BYTE_RGB && dst.getDepth() == 1)
+    {
+        OGRECU_THROW_IF(ogrecu_rt_read_colour_scaled(rt, src.left, src.top, src.right, src.bottom, dw, dh, top, dst.rowPitch * 3, 3, 0, 0, 0, 0));
+        return;
+    }
+    if (dst.getDepth() == 1 && packed32Layout(dst.format, shifts, fill))
+    {
+        OGRECU_THROW_IF(ogrecu_rt_read_colour_scaled(rt, src.left, src.top, src.right, src.bottom, dw, dh, top, dst.rowPitch * 4, 4, shifts[0],
+                                                     shifts[1], shifts[2], fill));
+        return;
+    }
+    // any other destination format: scaled on the device in the source format, converted by PixelUtil on the host — the
+    // temp-buffer tail of Image::scale (OgreImage.cpp:436-457)
+    std::vector<uint8> tmp((size_t)dw * dh * 3);
+    OGRECU_THROW_IF(ogrecu_rt_read_colour_scaled(rt, src.left, src.top, src.right, src.bottom, dw, dh, tmp.data(), (size_t)dw * 3, 3, 0, 0, 0, 0));
+    PixelBox box(dw, dh, 1, PF_BYTE_RGB, tmp.data());
+    PixelUtil::bulkPixelConversion(box, dst);
+}
 } // namespace Ogre

@@ -134,6 +134,12 @@ void CudaHardwarePixelBuffer::blitToMemory(const Box& srcBox, const PixelBox& ds
             CudaRenderSystem::readColour(mParent->getTarget(), srcBox, dst);
             return;
         }
+        if (srcBox.getDepth() == 1 && dst.getDepth() == 1)
+        {
+            // scaled read-back: the resampling runs on the device, only the destination's pixels cross the bus
+            CudaRenderSystem::readColourScaled(mParent->getTarget(), srcBox, dst);
+            return;
+        }
         PixelBox whole = mBuffer;
         CudaRenderSystem::readColour(mParent->getTarget(), Box(0, 0, mWidth, mHeight), whole);
     }

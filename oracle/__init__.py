@@ -104,6 +104,8 @@ def lib():
         l.oracle_pose_blend.restype = None
         l.oracle_finalise_pose_normals.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32]
         l.oracle_finalise_pose_normals.restype = None
+        l.oracle_scale_bilinear_bytes.argtypes = [vp, C.c_uint32, C.c_uint32, sz, C.c_uint32, vp, C.c_uint32, C.c_uint32, sz]
+        l.oracle_scale_bilinear_bytes.restype = None
         l.oracle_shadow_use_mcguire.argtypes = [C.c_uint32, vp, vp]
         l.oracle_shadow_volume.argtypes = [C.c_uint32, vp, vp, vp, vp, C.c_int, C.c_int, C.c_uint32, C.c_int, vp, C.c_uint32, vp, vp]
         l.oracle_shadow_volume.restype = C.c_long
@@ -151,3 +153,14 @@ def shadow_volume(ed, facings, light4, bounds6, flags, separate_light_cap, buffe
                                    int(light4[3] == 0), mc, flags, int(separate_light_cap), out.ctypes.data, buffer_indices,
                                    C.addressof(used), ranges.ctypes.data)
     return out, ranges, used.value, n, mc
+
+
+def scale_bilinear(src, dst_w, dst_h, box=None, dst_pad=0):
+    """LinearResampler_Byte on a (h, w, channels) uint8 image (or its sub-box (l, t, r, b)) -> (dst_h, dst_w + dst_pad, channels);
+    padding pixels keep 0xEE."""
+    src = np.ascontiguousarray(src, np.uint8)
+    h, w, c = src.shape
+    l, t, r, b = box or (0, 0, w, h)
+    out = np.full((dst_h, dst_w + dst_pad, c), 0xEE, np.uint8)
+    lib().oracle_scale_bilinear_bytes(src.ctypes.data + (t * w + l) * c, r - l, b - t, w, c, out.ctypes.data, dst_w, dst_h, dst_w + dst_pad)
+    return out

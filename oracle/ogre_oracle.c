@@ -782,3 +782,45 @@ void oracle_finalise_pose_normals(float* dst_norm, const float* src_norm, uint32
         d[0] = x; d[1] = y; d[2] = z;
     }
 }
+
+/* ====================================================================================================
+ * Scaled read-back: Image::scale(FILTER_BILINEAR) on byte formats
+ * ==================================================================================================== */
+
+/* OgreImageResampler.h:297-311,316-322: position -> (first sample, 12-bit weight of the second sample) */
+static void scale_axis(uint64_t pos_48, uint32_t extent, uint32_t* s1, uint32_t* s2, uint32_t* frac)
+{
+    uint32_t temp = (uint32_t)(pos_48 >> 36);
+    temp = (temp > 0x800u) ? temp - 0x800u : 0u;
+    *frac = temp & 0xFFFu;
+    *s1 = temp >> 12;
+    *s2 = (*s1 + 1u < extent - 1u) ? *s1 + 1u : extent - 1u;        /* std::min(s1 + 1, extent - 1) */
+}
+
+void oracle_scale_bilinear_bytes(const uint8_t* src, uint32_t src_w, uint32_t src_h, size_t src_pitch_px, uint32_t channels,
+                                 uint8_t* dst, uint32_t dst_w, uint32_t dst_h, size_t dst_pitch_px)
+{
+    if (!dst_w || !dst_h || !src_w || !src_h) return;
+    const uint64_t stepx = ((uint64_t)src_w << 48) / dst_w;           /* :299-300 */
+    const uint64_t stepy = ((uint64_t)src_h << 48) / dst_h;
+    uint64_t sy_48 = (stepy >> 1) - 1;                                /* :302 */
+    for (uint32_t y = 0; y < dst_h; ++y, sy_48 += stepy) {
+        uint32_t sy1, sy2, syf;
+        scale_axis(sy_48, src_h, &sy1, &sy2, &syf);
+        const size_t syoff1 = (size_t)sy1 * src_pitch_px, syoff2 = (size_t)sy2 * src_pitch_px;
+        uint8_t* pdst = dst + (size_t)y * dst_pitch_px * channels;
+        uint64_t sx_48 = (stepx >> 1) - 1;                            /* :316 */
+        for (uint32_t x = 0; x < dst_w; ++x, sx_48 += stepx) {
+            uint32_t sx1, sx2, sxf;
+            scale_axis(sx_48, src_w, &sx1, &sx2, &sxf);
+            const uint32_t sxfsyf = sxf * syf;                        /* :324 */
+            for (uint32_t k = 0; k < channels; ++k) {                 /* :325-334, unsigned 32-bit arithmetic */
+                uint32_t accum = src[(sx1 + syoff1) * channels + k] * (0x1000000u - (sxf << 12) - (syf << 12) + sxfsyf) +
+                                 src[(sx2 + syoff1) * channels + k] * ((sxf << 12) - sxfsyf) +
+                                 src[(sx1 + syoff2) * channels + k] * ((syf << 12) - sxfsyf) +
+                                 src[(sx2 + syoff2) * channels + k] * sxfsyf;
+                *pdst++ = (uint8_t)((accum + 0x800000u) >> 24);
+            }
+        }
+    }
+}

@@ -168,6 +168,14 @@ void oracle_pose_blend(float weight, const uint32_t* idx, const float* off3, uin
  * n.normalise().  dst_norm / src_norm point at the normal of vertex 0 (accumulated pose normals / base mesh normals). */
 void oracle_finalise_pose_normals(float* dst_norm, const float* src_norm, uint32_t n, uint32_t dst_stride_floats, uint32_t src_stride_floats);
 
+/* ---- Scaled read-back ---- */
+/* Image::scale(FILTER_BILINEAR) for the byte formats = LinearResampler_Byte<channels>::scale,
+ * OgreMain/src/OgreImage.cpp:389-458 + OgreMain/src/OgreImageResampler.h:283-339 (2D): 16.48 fixed-point source steps,
+ * the half-pixel shift and 12-bit blend weights taken from bits 36..63, 8.24 accumulation, +0x800000 rounding.
+ * Pitches are in PIXELS (PixelBox::rowPitch).  src points at the top-left pixel of the source box. */
+void oracle_scale_bilinear_bytes(const uint8_t* src, uint32_t src_w, uint32_t src_h, size_t src_pitch_px, uint32_t channels,
+                                 uint8_t* dst, uint32_t dst_w, uint32_t dst_h, size_t dst_pitch_px);
+
 #ifdef __cplusplus
 }
 #endif

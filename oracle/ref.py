@@ -97,6 +97,9 @@ def lib():
         l.ref_shadow_volume.restype = C.c_long
         l.ref_shadow_indices.restype = vp
         l.ref_shadow_ranges.restype = vp
+        l.ref_image_scale.argtypes = [vp, C.c_uint32, C.c_uint32, sz, C.c_char_p, vp, C.c_uint32, C.c_uint32, sz, C.c_char_p]
+        l.ref_pixel_format_bytes.argtypes = [C.c_char_p]
+        l.ref_pixel_format_bytes.restype = sz
         l.ref_set_media_dir(MEDIA.encode())
         _lib = l
     return _lib
@@ -244,3 +247,19 @@ def shadow_volume(ed, light4, bounds6, flags, separate_light_cap, buffer_indices
     idx = np.ctypeslib.as_array(C.cast(l.ref_shadow_indices(), C.POINTER(C.c_uint16)), shape=(buffer_indices,)).copy()
     rng = np.ctypeslib.as_array(C.cast(l.ref_shadow_ranges(), C.POINTER(C.c_uint32)), shape=(len(ed["groups"]), 4)).copy()
     return idx, rng, used.value, facings
+
+
+def image_scale(src, dst_w, dst_h, src_fmt="PF_BYTE_RGB", dst_fmt=None, box=None, dst_pad=0):
+    """The real Image::scale(FILTER_BILINEAR) of `src` ((h, w, bytes) uint8, or its sub-box (l, t, r, b)) to dst_w x dst_h in
+    `dst_fmt` (default: the source format); the destination rows are `dst_pad` pixels wider than dst_w (padding keeps 0xEE)."""
+    dst_fmt = dst_fmt or src_fmt
+    src = np.ascontiguousarray(src, np.uint8)
+    h, w, c = src.shape
+    assert c == lib().ref_pixel_format_bytes(src_fmt.encode())
+    l, t, r, b = box or (0, 0, w, h)
+    dc = lib().ref_pixel_format_bytes(dst_fmt.encode())
+    out = np.full((dst_h, dst_w + dst_pad, dc), 0xEE, np.uint8)
+    rc = lib().ref_image_scale(src.ctypes.data + (t * w + l) * c, r - l, b - t, w, src_fmt.encode(), out.ctypes.data, dst_w, dst_h,
+                               dst_w + dst_pad, dst_fmt.encode())
+    assert rc == 0
+    return out

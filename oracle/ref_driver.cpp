@@ -932,6 +932,30 @@ API double ref_bench_morph(float t, const float* a, const float* b, float* d, si
     return best;
 }
 
+/* -------- the real Image::scale / PixelUtil::bulkPixelConversion on caller memory (no Root needed) -------- */
+
+// Image::scale(src box of a `src_plane_w`-pixel-wide plane in format `src_fmt_name`, dst, FILTER_BILINEAR), the call
+// TinyHardwarePixelBuffer::blitToMemory makes when the sizes differ (OgreTinyHardwarePixelBuffer.cpp:43-47).
+// Pitches in pixels.  Returns 0, or 1 for an unknown format name.
+API int ref_image_scale(const uint8_t* src, uint32_t sw, uint32_t sh, size_t src_pitch_px, const char* src_fmt_name, uint8_t* dst,
+                        uint32_t dw, uint32_t dh, size_t dst_pitch_px, const char* dst_fmt_name)
+{
+    const PixelFormat sf = PixelUtil::getFormatFromName(src_fmt_name, true), df = PixelUtil::getFormatFromName(dst_fmt_name, true);
+    if (sf == PF_UNKNOWN || df == PF_UNKNOWN) return 1;
+    PixelBox ps(sw, sh, 1, sf, const_cast<uint8_t*>(src));
+    ps.rowPitch = src_pitch_px; ps.slicePitch = src_pitch_px * sh;
+    PixelBox pd(dw, dh, 1, df, dst);
+    pd.rowPitch = dst_pitch_px; pd.slicePitch = dst_pitch_px * dh;
+    Image::scale(ps, pd, Image::FILTER_BILINEAR);
+    return 0;
+}
+
+API size_t ref_pixel_format_bytes(const char* fmt_name)
+{
+    const PixelFormat f = PixelUtil::getFormatFromName(fmt_name, true);
+    return f == PF_UNKNOWN ? 0 : PixelUtil::getNumElemBytes(f);
+}
+
 API void ref_shutdown(void)
 {
     if (g_host) { g_captured.clear(); g_tex_copies.clear(); g_host->root.reset(); delete g_host; g_host = nullptr; }

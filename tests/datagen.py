@@ -370,3 +370,33 @@ def pose_entity_oracle(oracle, base, offs, idx, off, nrm, infl, with_normals):
     if with_normals:
         oracle.lib().oracle_finalise_pose_normals(o.ctypes.data + 12, base.ctypes.data + 12, len(base), 6, 6)
     return o
+
+
+# ---- scaled read-back (Image::scale FILTER_BILINEAR on byte images) ----
+SCALE_CASES = [  # (seed, src h, src w, box or None, dst w, dst h)
+    (0, 36, 64, None, 32, 18), (1, 36, 64, None, 129, 75), (2, 36, 64, (3, 5, 57, 34), 97, 33), (3, 20, 20, (10, 10, 11, 11), 8, 8),
+    (4, 36, 64, None, 1, 1), (5, 1, 64, None, 64, 3), (6, 48, 1, None, 5, 48), (7, 50, 70, None, 70, 49), (8, 50, 70, None, 69, 50),
+    (9, 7, 9, None, 200, 150), (10, 120, 160, None, 7, 5), (11, 33, 65, (1, 0, 65, 33), 64, 32),
+]
+
+
+def scale_image(seed, h, w, channels=3):
+    """Seeded source image: smooth gradients plus noise, so both interpolation and rounding are exercised."""
+    rng = np.random.default_rng(1000 + seed)
+    y, x = np.mgrid[0:h, 0:w]
+    img = np.stack([(x * 255 // max(1, w - 1)), (y * 255 // max(1, h - 1)), ((x + y) * 7) % 256][:channels] +
+                   [np.full((h, w), 255)] * max(0, channels - 3), axis=-1).astype(np.int64)
+    img = (img + rng.integers(-40, 41, img.shape)).clip(0, 255)
+    img[rng.random((h, w)) < 0.1] = rng.integers(0, 256, channels)
+    return img.astype(np.uint8)
+
+
+# destination formats of the 32-bit 8-bit-per-channel family: name -> (r_shift, g_shift, b_shift, fill) as PixelUtil lays them
+# out on a little-endian host (OgrePixelFormatDescriptions.h)
+PACKED32 = {"PF_A8R8G8B8": (16, 8, 0, 0xFF000000), "PF_A8B8G8R8": (0, 8, 16, 0xFF000000), "PF_B8G8R8A8": (8, 16, 24, 0x000000FF),
+            "PF_R8G8B8A8": (24, 16, 8, 0x000000FF), "PF_X8R8G8B8": (16, 8, 0, 0xFF000000), "PF_X8B8G8R8": (0, 8, 16, 0xFF000000)}
+
+
+def pack32(rgb, r_shift, g_shift, b_shift, fill):
+    c = rgb.astype(np.uint32)
+    return (c[..., 0] << r_shift) | (c[..., 1] << g_shift) | (c[..., 2] << b_shift) | np.uint32(fill)

@@ -19,6 +19,8 @@ container only; the GPU box and the CPU test suite just read the .npz files.
   jaiqua_shadow.npz      the meshes' edge lists (Mesh::buildEdgeList) + 14 shadow-volume cases each (lights, bounds,
   sinbad_shadow.npz      flag combinations, shared-buffer offsets incl. a wrap): light facings from the real EdgeData and the
                          index buffer contents / ShadowRenderable ranges the real ShadowCaster::generateShadowVolume wrote
+  image_scale.npz        outputs of the real Image::scale(FILTER_BILINEAR) on seeded RGB8 images (datagen.SCALE_CASES: up- and
+                         down-scaling, sub-boxes, 1-pixel extents), same format and into PF_A8R8G8B8 / PF_BYTE_RGBA
   optutil_golden.npz     outputs of the real OptimisedUtilSSE / OptimisedUtilGeneral on small
                          seeded inputs (all six functions, edge-case counts and alignments)
 """
@@ -167,6 +169,18 @@ def save_pose_blend(name):
     print(name, len(cases), "cases", len(frames), "entity frames")
 
 
+def save_image_scale(name):
+    from datagen import SCALE_CASES, scale_image
+    out = {}
+    for k, (seed, h, w, box, dw, dh) in enumerate(SCALE_CASES):
+        src = scale_image(seed, h, w)
+        out["c%d_rgb" % k] = ref.image_scale(src, dw, dh, "PF_BYTE_RGB", box=box, dst_pad=k % 3)
+        for fmt in ("PF_A8R8G8B8", "PF_BYTE_RGBA"):
+            out["c%d_%s" % (k, fmt)] = ref.image_scale(src, dw, dh, "PF_BYTE_RGB", fmt, box=box)
+    np.savez_compressed(os.path.join(HERE, name), **out)
+    print(name, len(out), "arrays")
+
+
 def save_optutil(name):
     l = ref.lib()
     rng = np.random.default_rng(2024)
@@ -231,7 +245,11 @@ def save_optutil(name):
 if __name__ == "__main__":
     if not ref.available():
         sys.exit("oracle/_ref is not built: run oracle/build_ref.py and oracle/build_driver.sh first")
+    if sys.argv[1:] == ["image_scale"]:
+        save_image_scale("image_scale.npz")
+        sys.exit(0)
     save_optutil("optutil_golden.npz")
+    save_image_scale("image_scale.npz")
     save_scene("ogrehead_320x180.npz", "ogrehead.mesh", 320, 180)
     save_scene("ogrehead_1280x720.npz", "ogrehead.mesh", 1280, 720)
     save_skeleton("sinbad_skin.npz", "Sinbad.mesh")

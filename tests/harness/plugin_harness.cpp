@@ -214,6 +214,34 @@ API int ph_render_to_texture(uint8_t* dst_rgb)
     CATCH(1)
 }
 
+// Scaled read-back of the render texture (RenderTexture::copyContentsToMemory into a PixelBox of another size ->
+// HardwarePixelBuffer::blitToMemory -> scaling): through the plugin (resampled on the device) next to the reference's way —
+// the unscaled PF_BYTE_RGB read-back resampled by the real Image::scale(FILTER_BILINEAR).  Source box (l,t,r,b), destination
+// dw x dh in `format_name`, destination rows `pad` pixels wider than dw.  Returns differing bytes (-1 on error).
+API long ph_rtt_scaled_check(uint32_t l, uint32_t t, uint32_t r, uint32_t b, uint32_t dw, uint32_t dh, uint32_t pad, const char* format_name)
+{
+    TRY
+    if (!g->rtt) { g_err = "no rtt"; return -1; }
+    const PixelFormat pf = PixelUtil::getFormatFromName(format_name, true);
+    if (pf == PF_UNKNOWN) { g_err = "unknown pixel format"; return -1; }
+    const size_t bpp = PixelUtil::getNumElemBytes(pf);
+    RenderTexture* rt = g->rtt->getBuffer()->getRenderTarget();
+    const uint32_t w = g->w, h = g->h, pitch = dw + pad;
+    std::vector<uint8_t> rgb((size_t)w * h * 3), want((size_t)pitch * dh * bpp, 0xEE), got((size_t)pitch * dh * bpp, 0xEE);
+    PixelBox prgb(w, h, 1, PF_BYTE_RGB, rgb.data());
+    rt->copyContentsToMemory(Box(0, 0, w, h), prgb, RenderTarget::FB_AUTO);
+    PixelBox pwant(dw, dh, 1, pf, want.data());
+    pwant.rowPitch = pitch; pwant.slicePitch = (size_t)pitch * dh;
+    Image::scale(prgb.getSubVolume(Box(l, t, r, b)), pwant, Image::FILTER_BILINEAR);
+    PixelBox pgot(dw, dh, 1, pf, got.data());
+    pgot.rowPitch = pitch; pgot.slicePitch = (size_t)pitch * dh;
+    rt->copyContentsToMemory(Box(l, t, r, b), pgot, RenderTarget::FB_AUTO);
+    long bad = 0;
+    for (size_t i = 0; i < want.size(); ++i) bad += want[i] != got[i];
+    return bad;
+    CATCH(-1)
+}
+
 // Show the render texture on a full-window quad (textured, unlit) and render the window: exercises
 // sampling a TU_RENDERTARGET texture.
 API int ph_show_rtt_on_quad(void)

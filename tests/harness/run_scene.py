@@ -34,6 +34,7 @@ def main():
     ap.add_argument("--skel", default="")
     ap.add_argument("--time", type=int, default=0)
     ap.add_argument("--formats", default="", help="comma-separated Ogre::PixelFormat names: read-back in that format vs host PixelUtil")
+    ap.add_argument("--scaled", action="store_true", help="with --rtt: scaled read-backs of the render texture vs the real Image::scale")
     ap.add_argument("--shadow", type=int, default=0, help="N shadow-volume cases: real generateShadowVolume vs CudaShadowVolume")
     ap.add_argument("--palettes", type=int, default=0, help="bone palettes at N time positions: engine vs CudaSkeletonPalettes")
     a = ap.parse_args()
@@ -132,6 +133,16 @@ def main():
         rtt = np.zeros((h, w, 3), np.uint8)
         ok(L.ph_render_to_texture(rtt.ctypes.data), "ph_render_to_texture")
         out["rtt"] = rtt
+        if a.scaled:
+            L.ph_rtt_scaled_check.restype = C.c_long
+            L.ph_rtt_scaled_check.argtypes = [C.c_uint32] * 7 + [C.c_char_p]
+            cases = []
+            for fmt in ("PF_BYTE_RGB", "PF_A8R8G8B8", "PF_BYTE_RGBA", "PF_X8B8G8R8", "PF_R5G6B5", "PF_L8", "PF_FLOAT32_RGB"):
+                for (l, t, r, b, dw, dh, pad) in ((0, 0, w, h, w // 2, h // 2, 0), (0, 0, w, h, w * 2 + 1, h + 7, 5), (3, 5, w - 7, h - 2, 97, 33, 2),
+                                                  (10, 10, 11, 11, 8, 8, 0), (0, 0, w, h, 1, 1, 0), (0, 0, w, 1, w, 3, 1)):
+                    cases.append((fmt, l, t, r, b, dw, dh, pad, L.ph_rtt_scaled_check(l, t, r, b, dw, dh, pad, fmt.encode())))
+            out["scaled_cases"] = np.array([c[0] + " %d,%d,%d,%d->%dx%d+%d" % c[1:8] for c in cases])
+            out["scaled_mismatches"] = np.array([c[8] for c in cases])
         if a.quad:
             ok(L.ph_show_rtt_on_quad(), "ph_show_rtt_on_quad")
             q = np.zeros((h, w, 3), np.uint8)

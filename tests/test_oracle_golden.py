@@ -176,3 +176,18 @@ def test_oracle_reproduces_ogres_own_pose_animated_entities():
         base, offs, idx, off, nrm, infl = pose_entity_case(int(seed), int(nv), int(nposes))
         got = pose_entity_oracle(oracle, base, offs, idx, off, nrm, infl, bool(normals))
         assert np.array_equal(bits(got), bits(z["f%d" % k])), k
+
+
+def test_oracle_reproduces_ogres_own_image_scale():
+    """Image::scale(FILTER_BILINEAR) on byte images (the scaled blitToMemory read-back, SURVEY §8f rank 4): outputs of the real
+    method on seeded images — same format (with padded destination rows) and into two 32-bit formats (scale, then the
+    bulkPixelConversion tail restated as shifts)."""
+    from datagen import SCALE_CASES, PACKED32, pack32, scale_image
+    z = np.load(os.path.join(GOLDEN, "image_scale.npz"))
+    for k, (seed, h, w, box, dw, dh) in enumerate(SCALE_CASES):
+        src = scale_image(seed, h, w)
+        got = oracle.scale_bilinear(src, dw, dh, box=box, dst_pad=k % 3)
+        assert np.array_equal(got, z["c%d_rgb" % k]), k
+        tight = oracle.scale_bilinear(src, dw, dh, box=box)
+        assert np.array_equal(pack32(tight, *PACKED32["PF_A8R8G8B8"]), z["c%d_PF_A8R8G8B8" % k].view(np.uint32)[..., 0]), k
+        assert np.array_equal(pack32(tight, *PACKED32["PF_A8B8G8R8"]), z["c%d_PF_BYTE_RGBA" % k].view(np.uint32)[..., 0]), k

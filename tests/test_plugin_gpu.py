@@ -132,3 +132,13 @@ def test_readback_formats_equal_host_pixel_conversion(tmp_path):
     z = run_scene(tmp_path, "cuda", "--mesh", "ogrehead.mesh", "--size", "320x180", "--formats", ",".join(names))
     assert list(z["format_names"]) == names
     assert list(z["format_mismatches"]) == [0] * len(names), dict(zip(names, z["format_mismatches"]))
+
+
+def test_scaled_render_texture_readback_equals_image_scale(tmp_path):
+    """RenderTexture::copyContentsToMemory into a PixelBox of another size (-> blitToMemory -> Image::scale in the reference,
+    OgreTinyHardwarePixelBuffer.cpp:43-47): resampled on the device by the plugin, bytes equal the real Image::scale of the
+    unscaled read-back — 7 destination formats x 6 boxes (down, up, sub-box, 1x1 source, 1x1 destination, one-row source)."""
+    z = run_scene(tmp_path, "cuda", "--mesh", "ogrehead.mesh", "--size", "320x180", "--rtt", "--scaled")
+    assert len(z["scaled_cases"]) == 42
+    bad = {str(c): int(m) for c, m in zip(z["scaled_cases"], z["scaled_mismatches"]) if m != 0}
+    assert not bad, bad

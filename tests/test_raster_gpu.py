@@ -243,3 +243,41 @@ def test_readback_packed32_equals_host_shuffle(gpu_ctx):
     pinned = ogre_b200.pinned_empty((h, w), np.uint32)
     assert np.array_equal(rt.read_colour_packed32(16, 8, 0, 0xFF000000, out=pinned), (rgb[..., 0] << 16) | (rgb[..., 1] << 8) | rgb[..., 2] | 0xFF000000)
     scene.free(); rt.destroy()
+
+
+def test_scaled_readback_equals_image_scale(gpu_ctx):
+    """ogrecu_rt_read_colour_scaled: the blitToMemory read-back into a destination of another size,
+    resampled on the device, vs the restated Image::scale(FILTER_BILINEAR) and vs the real one's outputs in
+    tests/golden/image_scale.npz — RGB8 with padded rows, and packed 32-bit destinations."""
+    import os
+    import ogre_b200
+    import oracle
+    from datagen import PACKED32, SCALE_CASES, pack32, scale_image
+    from goldenlib import GOLDEN
+    z = np.load(os.path.join(GOLDEN, "image_scale.npz"))
+    for k, (seed, h, w, box, dw, dh) in enumerate(SCALE_CASES):
+        src = scale_image(seed, h, w)
+        rt = ogre_b200.RenderTarget(gpu_ctx, w, h)
+        rt.write_colour(src)
+        got = rt.read_colour_scaled(dw, dh, box=box, pad=k % 3)
+        assert np.array_equal(got, oracle.scale_bilinear(src, dw, dh, box=box, dst_pad=k % 3)), k
+        assert np.array_equal(got, z["c%d_rgb" % k]), k
+        for name in ("PF_A8R8G8B8", "PF_A8B8G8R8"):
+            words = rt.read_colour_scaled(dw, dh, box=box, packed=PACKED32[name], pad=2)
+            assert np.array_equal(words[:, :dw], pack32(oracle.scale_bilinear(src, dw, dh, box=box), *PACKED32[name])), (k, name)
+            assert (words[:, dw:] == 0xEEEEEEEE).all()
+        assert np.array_equal(rt.read_colour_scaled(dw, dh, box=box, packed=PACKED32["PF_A8R8G8B8"]).view(np.uint8).reshape(dh, dw, 4),
+                              z["c%d_PF_A8R8G8B8" % k]), k
+        rt.destroy()
+    # a rendered frame, full size: 1280x720 -> 640x360 and -> 1920x1080
+    from rasterlib import GpuScene
+    w, h = 1280, 720
+    scene = GpuScene(gpu_ctx, make_scene(77, w, h, ndraws=4, ntri=300))
+    rt = ogre_b200.RenderTarget(gpu_ctx, w, h)
+    scene.render(rt, (0.1, 0.2, 0.3, 1.0), 1.0)
+    rgb = rt.read_colour()
+    for dw, dh in ((640, 360), (1920, 1080), (333, 719)):
+        assert np.array_equal(rt.read_colour_scaled(dw, dh), oracle.scale_bilinear(rgb, dw, dh)), (dw, dh)
+    with pytest.raises(ogre_b200.OgrecuError):
+        rt.read_colour_scaled(10, 10, box=(0, 0, w + 1, h))
+    scene.free(); rt.destroy()
