@@ -47,10 +47,11 @@ def test_harness_with_the_real_tiny_plugin_reproduces_the_golden_image(tmp_path)
     out = str(tmp_path / "tiny.npz")
     # The REFERENCE plugin is retried: TinyRenderSystem never initialises DefaultShader::image / mDepthTest / mBlendAdd
     # (ctor, OgreTinyRenderSystem.cpp:27-46) and was seen to die in sample2D on some runs — the oracle's own undefined
-    # behaviour, not the harness under validation.
+    # behaviour, not the harness under validation.  glibc's MALLOC_PERTURB_=255 zero-fills fresh allocations, so those members
+    # read as NULL / false instead of heap garbage.
     for attempt in range(4):
         r = subprocess.run([sys.executable, os.path.join(HERE, "harness", "run_scene.py"), "--plugin", "tiny", "--size", "320x180",
-                            "--out", out], capture_output=True, text=True, timeout=300)
+                            "--out", out], capture_output=True, text=True, timeout=300, env=dict(os.environ, MALLOC_PERTURB_="255"))
         if r.returncode == 0:
             break
     assert r.returncode == 0, r.stdout + r.stderr

@@ -31,9 +31,12 @@ def run_scene(tmp_path, plugin, *args):
     out = os.path.join(str(tmp_path), "%s_%d.npz" % (plugin, len(os.listdir(str(tmp_path)))))
     # The CUDA plugin gets exactly one attempt.  The REFERENCE plugin is retried: TinyRenderSystem never
     # initialises DefaultShader::image / mDepthTest / mBlendAdd (ctor, OgreTinyRenderSystem.cpp:27-46) and was
-    # seen to die with SIGFPE in sample2D on some hosts; that is the oracle's own undefined behaviour.
+    # seen to die with SIGFPE in sample2D on some hosts; that is the oracle's own undefined behaviour.  Its runs therefore get
+    # glibc's MALLOC_PERTURB_=255 (fresh allocations are zero-filled), which makes those members read as NULL / false.
+    env = dict(os.environ, MALLOC_PERTURB_="255") if plugin != "cuda" else None
     for attempt in range(1 if plugin == "cuda" else 3):
-        r = subprocess.run([sys.executable, RUN, "--plugin", plugin, "--out", out] + list(args), capture_output=True, text=True, timeout=600)
+        r = subprocess.run([sys.executable, RUN, "--plugin", plugin, "--out", out] + list(args), capture_output=True, text=True, timeout=600,
+                           env=env)
         if r.returncode == 0:
             return np.load(out)
     if plugin == "cuda":
