@@ -38,7 +38,7 @@ extern "C" {
 #define OGRECU_API
 #endif
 
-#define OGRECU_ABI_VERSION 3
+#define OGRECU_ABI_VERSION 4
 
 typedef enum ogrecu_status {
     OGRECU_OK = 0,
@@ -427,6 +427,46 @@ typedef struct ogrecu_draw_desc {
 
 /* Record a draw on `rt` (cheap; nothing runs yet).  Draws and clears keep submission order. */
 OGRECU_API int ogrecu_draw(ogrecu_rt* rt, const ogrecu_draw_desc* desc);
+/* ---- "Beyond Tiny" render state (opt-in) ----
+ * State TinyRenderSystem's setters ignore (OgreTinyRenderSystem.cpp:208-297: depth function, culling mode, scissor,
+ * alpha rejection, vertex colours).  A field is honoured only when its OGRECU_EXT_* bit is set; with enable == 0 (or through
+ * plain ogrecu_draw) the draw is Tiny's, bit for bit.  Definitions (the reference has no behaviour of its own here):
+ *   depth_func   replaces Tiny's fixed `frag_depth > zbuf` rejection (tinyrenderer.h:79) while OGRECU_DRAW_DEPTH_TEST is set;
+ *                CMPF_LESS_EQUAL is that rule (kept in Tiny's form, under which a NaN depth passes);
+ *   cull_mode    CULL_CLOCKWISE = Tiny's rule, `cross(p2-p0, p2-p1) > 0` is culled (tinyrenderer.h:37-39); CULL_ANTICLOCKWISE =
+ *                `< 0`; CULL_NONE.  Applies to strips too, whose odd triangles count with the opposite sign (Tiny never culls
+ *                strips, OgreTinyRenderSystem.cpp:410);
+ *   scissor      fragments outside [left,right) x [top,bottom) are dropped; clears still cover the whole target (as Tiny's);
+ *   alpha        the fragment survives iff cmp(alpha, ref) on the texel's alpha byte (255 without a texture), after Tiny's own
+ *                `alpha == 0` discard (OgreTinyRenderSystem.cpp:318);
+ *   colours      c_j = byte * (1/255) per vertex, interpolated as uv is ((c0*b0 + c1*b1) + c2*b2) and multiplied into rgb
+ *                after the texture and before lighting.
+ * A depth function other than CMPF_LESS_EQUAL or an alpha test other than CMPF_ALWAYS_PASS sends the tiles the draw touches
+ * down the in-order raster path. */
+enum {   /* Ogre::CompareFunction, OgreMain/include/OgreCommon.h:61-71 */
+    OGRECU_CMPF_ALWAYS_FAIL = 0, OGRECU_CMPF_ALWAYS_PASS = 1, OGRECU_CMPF_LESS = 2, OGRECU_CMPF_LESS_EQUAL = 3, OGRECU_CMPF_EQUAL = 4,
+    OGRECU_CMPF_NOT_EQUAL = 5, OGRECU_CMPF_GREATER_EQUAL = 6, OGRECU_CMPF_GREATER = 7
+};
+enum { OGRECU_CULL_NONE = 1, OGRECU_CULL_CLOCKWISE = 2, OGRECU_CULL_ANTICLOCKWISE = 3 };   /* Ogre::CullingMode, OgreCommon.h:164-172 */
+enum {
+    OGRECU_EXT_DEPTH_FUNC = 1,      /* RenderSystem::_setDepthBufferParams depthFunction (OgreRenderSystem.h:709)     */
+    OGRECU_EXT_CULL_MODE = 2,       /* RenderSystem::_setCullingMode (:692); CULL_CLOCKWISE is Tiny's built-in rule   */
+    OGRECU_EXT_SCISSOR = 4,         /* RenderSystem::setScissorTest (:916)                                            */
+    OGRECU_EXT_ALPHA_REJECT = 8,    /* RenderSystem::_setAlphaRejectSettings (:643), on the texel's alpha byte        */
+    OGRECU_EXT_VERTEX_COLOUR = 16   /* VES_DIFFUSE stream, VET_UBYTE4_NORM (bytes r,g,b,a), modulates rgb             */
+};
+typedef struct ogrecu_draw_state {
+    uint32_t enable;            /* OGRECU_EXT_* bits                                  */
+    uint32_t depth_func;        /* OGRECU_CMPF_*                                      */
+    uint32_t cull_mode;         /* OGRECU_CULL_*                                      */
+    uint32_t alpha_func;        /* OGRECU_CMPF_*                                      */
+    uint32_t alpha_ref;         /* 0..255                                             */
+    uint32_t scissor[4];        /* left, top, right, bottom (exclusive), pixels       */
+    uint32_t colour_stride;     /* bytes between vertices of `colours`                */
+    const void* colours;        /* DEVICE pointer, offset like the other streams      */
+} ogrecu_draw_state;
+/* ogrecu_draw with the extra state; state == NULL is ogrecu_draw. */
+OGRECU_API int ogrecu_draw_with_state(ogrecu_rt* rt, const ogrecu_draw_desc* desc, const ogrecu_draw_state* state);
 /* Run everything recorded on `rt`: vertex transform + triangle setup, order-preserving
  * tile binning, per-tile raster/shade/blend, coalesced flush to the colour/depth planes.
  * Asynchronous on the stream (_endFrame / readback / buffer lock are the sync points). */

@@ -13,9 +13,9 @@ import ctypes as C
 import numpy as np
 
 from . import capi
-from .capi import AnimJob, AnimationDesc, DrawDesc, OgrecuError, RasterStats, SkeletonDesc, SkinJob, check, lib
+from .capi import AnimJob, AnimationDesc, DrawDesc, DrawState, OgrecuError, RasterStats, SkeletonDesc, SkinJob, check, lib
 
-__all__ = ["Context", "DeviceBuffer", "OptimisedUtil", "Skeleton", "EdgeList", "Texture", "RenderTarget", "DrawDesc", "SkinJob", "AnimJob",
+__all__ = ["Context", "DeviceBuffer", "OptimisedUtil", "Skeleton", "EdgeList", "Texture", "RenderTarget", "DrawDesc", "DrawState", "SkinJob", "AnimJob",
            "OgrecuError", "addr", "pinned_empty"]
 
 MAP_READ, MAP_WRITE, MAP_DISCARD = 1, 2, 4
@@ -23,6 +23,10 @@ CLEAR_COLOUR, CLEAR_DEPTH = 1, 2
 PRIM_TRIANGLE_LIST, PRIM_TRIANGLE_STRIP = 4, 5
 INDEX_NONE, INDEX_U16, INDEX_U32 = 0, 2, 4
 DRAW_DEPTH_TEST, DRAW_DEPTH_WRITE, DRAW_BLEND_ADD, DRAW_LIGHTING = 1, 2, 4, 8
+# opt-in "beyond Tiny" state (ogrecu_draw_state): Ogre::CompareFunction / Ogre::CullingMode values
+EXT_DEPTH_FUNC, EXT_CULL_MODE, EXT_SCISSOR, EXT_ALPHA_REJECT, EXT_VERTEX_COLOUR = 1, 2, 4, 8, 16
+CMPF_ALWAYS_FAIL, CMPF_ALWAYS_PASS, CMPF_LESS, CMPF_LESS_EQUAL, CMPF_EQUAL, CMPF_NOT_EQUAL, CMPF_GREATER_EQUAL, CMPF_GREATER = range(8)
+CULL_NONE, CULL_CLOCKWISE, CULL_ANTICLOCKWISE = 1, 2, 3
 
 
 class _Pinned:
@@ -307,8 +311,11 @@ class RenderTarget:
         c = (C.c_float * 4)(*[float(v) for v in colour])
         check(lib().ogrecu_rt_clear(self.handle, buffers, c, float(depth)))
 
-    def draw(self, desc):
-        check(lib().ogrecu_draw(self.handle, C.byref(desc)))
+    def draw(self, desc, state=None):
+        if state is None:
+            check(lib().ogrecu_draw(self.handle, C.byref(desc)))
+        else:
+            check(lib().ogrecu_draw_with_state(self.handle, C.byref(desc), C.byref(state)))
 
     def flush(self):
         check(lib().ogrecu_flush(self.handle))

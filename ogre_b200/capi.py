@@ -56,6 +56,12 @@ class DrawDesc(C.Structure):
     ]
 
 
+class DrawState(C.Structure):
+    """ogrecu_draw_state (include/ogrecu.h): the opt-in "beyond Tiny" render state"""
+    _fields_ = [("enable", C.c_uint32), ("depth_func", C.c_uint32), ("cull_mode", C.c_uint32), ("alpha_func", C.c_uint32),
+                ("alpha_ref", C.c_uint32), ("scissor", C.c_uint32 * 4), ("colour_stride", C.c_uint32), ("colours", C.c_void_p)]
+
+
 class SkeletonDesc(C.Structure):
     """ogrecu_skeleton_desc (include/ogrecu.h)"""
     _fields_ = [("num_bones", C.c_uint32), ("blend_mode", C.c_uint32), ("parent", C.c_void_p), ("bind", C.c_void_p),
@@ -159,6 +165,7 @@ SIGNATURES = {
     "ogrecu_rt_size": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "ogrecu_rt_clear": (C.c_int, [C.c_void_p, C.c_uint, c_float_p, C.c_float]),
     "ogrecu_draw": (C.c_int, [C.c_void_p, C.POINTER(DrawDesc)]),
+    "ogrecu_draw_with_state": (C.c_int, [C.c_void_p, C.POINTER(DrawDesc), C.POINTER(DrawState)]),
     "ogrecu_flush": (C.c_int, [C.c_void_p]),
     "ogrecu_draw_views": (C.c_int, [C.POINTER(C.c_void_p), C.c_uint32, C.POINTER(DrawDesc), c_float_p, c_float_p, c_float_p]),
     "ogrecu_rt_set_strip": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),

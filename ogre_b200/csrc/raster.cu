@@ -49,6 +49,34 @@ __device__ __forceinline__ int x86_f2i(float f)
 }
 
 // Per-draw state on the device (one TinyRenderSystem::_render call)
+// Ogre::CompareFunction (OgreCommon.h:61-71).  CMPF_LESS_EQUAL keeps Tiny's own form !(new > old) (tinyrenderer.h:79).
+__device__ __forceinline__ bool cmp_depth(uint32_t func, float a, float b)
+{
+    switch (func) {
+    case OGRECU_CMPF_ALWAYS_FAIL: return false;
+    case OGRECU_CMPF_ALWAYS_PASS: return true;
+    case OGRECU_CMPF_LESS: return a < b;
+    case OGRECU_CMPF_LESS_EQUAL: return !(a > b);
+    case OGRECU_CMPF_EQUAL: return a == b;
+    case OGRECU_CMPF_NOT_EQUAL: return a != b;
+    case OGRECU_CMPF_GREATER_EQUAL: return a >= b;
+    default: return a > b;
+    }
+}
+__device__ __forceinline__ bool cmp_alpha(uint32_t func, uint32_t a, uint32_t b)
+{
+    switch (func) {
+    case OGRECU_CMPF_ALWAYS_FAIL: return false;
+    case OGRECU_CMPF_ALWAYS_PASS: return true;
+    case OGRECU_CMPF_LESS: return a < b;
+    case OGRECU_CMPF_LESS_EQUAL: return a <= b;
+    case OGRECU_CMPF_EQUAL: return a == b;
+    case OGRECU_CMPF_NOT_EQUAL: return a != b;
+    case OGRECU_CMPF_GREATER_EQUAL: return a >= b;
+    default: return a > b;
+    }
+}
+
 struct DrawDev {
     const uint8_t* pos; const uint8_t* uv; const uint8_t* nrm; const void* idx;
     const uint8_t* tex;
@@ -56,7 +84,12 @@ struct DrawDev {
     uint32_t is_strip, flags, target, tri_base;
     uint32_t tri_count, tex_w, tex_h, tex_zero_alpha;
     const float4* xf;         // optional: pre-transformed vertices (X, Y, Z, 1/w) of this draw, [vertex_count]
-    uint32_t vertex_count, vert_base, pad0, pad1;
+    uint32_t vertex_count, vert_base;
+    // "beyond Tiny" state (ogrecu_draw_state), all zero for a plain Tiny draw:
+    //   ext = enable bits | depth_func << 8 | cull_mode << 12 | alpha_func << 16 | alpha_ref << 24
+    uint32_t ext, col_stride;
+    const uint8_t* col;        // VES_DIFFUSE bytes r,g,b,a
+    uint32_t sc_x, sc_y;       // scissor: left | (right - 1) << 16, top | (bottom - 1) << 16 (inclusive pixel bounds)
     float mvp[16], texm[16], vp[16];
     float mvit[9];
     float light[3];
@@ -203,9 +236,14 @@ __device__ __forceinline__ void setup_triangle(const SegParams& P, uint32_t g, u
         // non-finite screen coordinates: the reference writes out of bounds (undefined) -> drop
         ok = ok && isfinite(sv.x) && isfinite(sv.y) && isfinite(sv.z) && isfinite(sv.w);
     }
-    if (ok && !D.is_strip) {                                                   // cull: tinyrenderer.h:37-39,55
+    const uint32_t ext = D.ext;
+    // Tiny: lists are culled by its fixed rule (= CULL_CLOCKWISE), strips never (.cpp:410); beyond Tiny: the draw's culling mode
+    const uint32_t cull = (ext & OGRECU_EXT_CULL_MODE) ? ((ext >> 12) & 0xfu) : (D.is_strip ? (uint32_t)OGRECU_CULL_NONE : (uint32_t)OGRECU_CULL_CLOCKWISE);
+    if (ok && cull != OGRECU_CULL_NONE) {                                      // cull: tinyrenderer.h:37-39,55
         float ax = fsub(T.X[2], T.X[0]), ay = fsub(T.Y[2], T.Y[0]), bx = fsub(T.X[2], T.X[1]), by = fsub(T.Y[2], T.Y[1]);
-        if (fsub(fmul(ax, by), fmul(ay, bx)) > 0.0f) ok = false;
+        float cr = fsub(fmul(ax, by), fmul(ay, bx));
+        if ((ext & OGRECU_EXT_CULL_MODE) && D.is_strip && (t & 1u)) cr = -cr;  // a strip's odd triangles wind the other way
+        if (cull == OGRECU_CULL_CLOCKWISE ? cr > 0.0f : cr < 0.0f) ok = false;
     }
     if (ok) {
         float mnx = FLT_MAX, mny = FLT_MAX, mxx = -FLT_MAX, mxy = -FLT_MAX;
@@ -221,6 +259,10 @@ __device__ __forceinline__ void setup_triangle(const SegParams& P, uint32_t g, u
         if (!(mnx < 2147483648.0f) || !(mny < 2147483648.0f) || !(mxx > -2147483648.0f) || !(mxy > -2147483648.0f)) ok = false;
         else {
             T.x0 = (int)mnx; T.x1 = (int)mxx; T.y0 = (int)mny; T.y1 = (int)mxy;    // :68-69 truncation toward zero
+            if (ext & OGRECU_EXT_SCISSOR) {                                        // beyond Tiny: the bbox is the pixel loop
+                T.x0 = max(T.x0, (int)(D.sc_x & 0xffffu)); T.x1 = min(T.x1, (int)(D.sc_x >> 16));
+                T.y0 = max(T.y0, (int)(D.sc_y & 0xffffu)); T.y1 = min(T.y1, (int)(D.sc_y >> 16));
+            }
             if (T.x0 > T.x1 || T.y0 > T.y1) ok = false;
         }
     }
@@ -242,7 +284,10 @@ __device__ __forceinline__ void setup_triangle(const SegParams& P, uint32_t g, u
         const uint32_t fl = D.flags;
         T.ordered = (fl & (OGRECU_DRAW_DEPTH_TEST | OGRECU_DRAW_DEPTH_WRITE | OGRECU_DRAW_BLEND_ADD)) !=
                         (OGRECU_DRAW_DEPTH_TEST | OGRECU_DRAW_DEPTH_WRITE) ||
-                    (D.tex != nullptr && D.tex_zero_alpha != 0);
+                    (D.tex != nullptr && D.tex_zero_alpha != 0) ||
+                    // beyond Tiny: another depth function or an alpha test make the outcome order dependent
+                    ((ext & OGRECU_EXT_DEPTH_FUNC) && ((ext >> 8) & 0xfu) != OGRECU_CMPF_LESS_EQUAL) ||
+                    ((ext & OGRECU_EXT_ALPHA_REJECT) && ((ext >> 16) & 0xfu) != OGRECU_CMPF_ALWAYS_PASS);
     }
 }
 
@@ -600,6 +645,28 @@ __device__ __forceinline__ uint32_t shade_pack(float r, float g, float b)
     return out;
 }
 
+// The fragment-stage part of the "beyond Tiny" state (ogrecu_draw_state, include/ogrecu.h): alpha rejection on the texel's
+// alpha byte, then the interpolated vertex colour multiplied into rgb.  Deliberately NOT inlined: the Tiny path keeps its
+// register budget (64 per thread, 4 CTAs per SM).
+__device__ __noinline__ bool shade_beyond_tiny(const DrawDev* D, uint32_t ext, uint32_t tri, uint32_t alpha, float bc0, float bc1, float bc2,
+                                               float& cr, float& cg, float& cb)
+{
+    if ((ext & OGRECU_EXT_ALPHA_REJECT) && !cmp_alpha((ext >> 16) & 0xfu, alpha, ext >> 24)) return false;
+    if (ext & OGRECU_EXT_VERTEX_COLOUR) {
+        const float inv255 = 1.0f / 255.0f;
+        float vc[3][3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const uchar4 c = __ldg(reinterpret_cast<const uchar4*>(D->col + vertex_index(*D, tri, j) * D->col_stride));
+            vc[j][0] = fmul((float)c.x, inv255); vc[j][1] = fmul((float)c.y, inv255); vc[j][2] = fmul((float)c.z, inv255);
+        }
+        cr = fmul(cr, fadd(fadd(fmul(vc[0][0], bc0), fmul(vc[1][0], bc1)), fmul(vc[2][0], bc2)));
+        cg = fmul(cg, fadd(fadd(fmul(vc[0][1], bc0), fmul(vc[1][1], bc1)), fmul(vc[2][1], bc2)));
+        cb = fmul(cb, fadd(fadd(fmul(vc[0][2], bc0), fmul(vc[1][2], bc1)), fmul(vc[2][2], bc2)));
+    }
+    return true;
+}
+
 // DefaultShader::fragment + the blend / pack tail of triangle() for one fragment
 // (OgreTinyRenderSystem.cpp:310-333, tinyrenderer.h:82-93).  Returns false when the fragment is discarded.
 // The varyings DefaultShader::vertex produced (var_uv = (Tex*(u,v,0,1)).xy, var_normal = MVIT.linear()*n,
@@ -612,6 +679,8 @@ __device__ __forceinline__ bool shade_fragment(const DrawDev* D, uint32_t flags,
     float cr = 1.0f, cg = 1.0f, cb = 1.0f;   // default ColourValue: white (tinyrenderer.h:82)
     const uint8_t* tex = D->tex;
     const bool lit = (flags & OGRECU_DRAW_LIGHTING) != 0;
+    const uint32_t ext = __ldg(&D->ext);
+    uint32_t alpha = 255u;
     size_t vi[3];
     if (tex || lit) {
 #pragma unroll
@@ -639,7 +708,10 @@ __device__ __forceinline__ bool shade_fragment(const DrawDev* D, uint32_t flags,
         uchar4 t4 = __ldg(reinterpret_cast<const uchar4*>(tex) + (size_t)iy * tw_ + ix);
         if (t4.w < 1) return false;                                            // .cpp:318
         cr = fmul((float)t4.x, inv255); cg = fmul((float)t4.y, inv255); cb = fmul((float)t4.z, inv255);
+        alpha = t4.w;
     }
+    if (ext & (OGRECU_EXT_ALPHA_REJECT | OGRECU_EXT_VERTEX_COLOUR))            // beyond Tiny, out of line: Tiny draws pay one test
+        if (!shade_beyond_tiny(D, ext, tri, alpha, bc0, bc1, bc2, cr, cg, cb)) return false;
     if (lit) {
         float nn[3][3];
 #pragma unroll
@@ -730,7 +802,7 @@ constexpr int VIS_SMALL_MAX = 12;   // bbox pixels a single thread walks; larger
 //    makes the outcome order dependent: the tile then falls back to
 //  * the in-order path: one pixel per thread, triangles replayed in submission order.
 template <bool VEC>
-__global__ void __launch_bounds__(RT_THREADS) raster_kernel(RasterParams P)
+__global__ void __launch_bounds__(RT_THREADS, 4) raster_kernel(RasterParams P)
 {
     __shared__ float4 s_hot[CHUNK][5];
     __shared__ __align__(16) uint8_t s_rgb[TILE][TILE * 3];
@@ -941,7 +1013,11 @@ __global__ void __launch_bounds__(RT_THREADS) raster_kernel(RasterParams P)
                     const uint32_t flags = __ldg(&D->flags);
                     if (in_box) {
                         pass = eval_fragment(hf, Px, Py, bc0, bc1, bc2, fd);
-                        if (pass && (flags & OGRECU_DRAW_DEPTH_TEST) && fd > zbuf) pass = false;   // :79
+                        if (pass && (flags & OGRECU_DRAW_DEPTH_TEST)) {
+                            const uint32_t ext = __ldg(&D->ext);
+                            if (ext & OGRECU_EXT_DEPTH_FUNC) pass = cmp_depth((ext >> 8) & 0xfu, fd, zbuf);
+                            else if (fd > zbuf) pass = false;                                      // :79
+                        }
                     }
                     if (!__any_sync(0xffffffffu, pass)) continue;
                     if (pass && shade_fragment(D, flags, hw[18], bc0, bc1, bc2, rgb))
@@ -1068,6 +1144,7 @@ __global__ void clear_depth_kernel(float* __restrict__ depth, size_t n, float v)
 struct Cmd {
     int kind;                  // 0 = draw, 1 = clear
     ogrecu_draw_desc draw;
+    ogrecu_draw_state state;   // enable == 0: a plain Tiny draw
     unsigned clear_buffers;
     float clear_colour[4];
     float clear_depth;
@@ -1119,7 +1196,7 @@ uint32_t tri_count_of(const ogrecu_draw_desc& d)
     return d.draw_count / 3;   // the reference reads past the end when drawCount%3 != 0 (UB); we stop
 }
 
-struct Item { const ogrecu_draw_desc* desc; uint32_t target; const float* mvp; const float* mvit; const float* light; };
+struct Item { const ogrecu_draw_desc* desc; uint32_t target; const float* mvp; const float* mvit; const float* light; const ogrecu_draw_state* state; };
 
 // Run the pipeline for `items` (draws in submission order) over `targets` (same size).
 int run_segment(ogrecu_ctx* ctx, ogrecu_rt* const* targets, uint32_t ntargets, const std::vector<Item>& items)
@@ -1162,6 +1239,18 @@ int run_segment(ogrecu_ctx* ctx, ogrecu_rt* const* targets, uint32_t ntargets, c
         for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) o.mvit[3 * r + c] = mv[4 * r + c];   // Matrix4::linear()
         memcpy(o.light, items[k].light ? items[k].light : d.light_dir, 12);
         memcpy(o.ambient, d.ambient, 16);
+        if (const ogrecu_draw_state* st = items[k].state) if (st->enable) {
+            o.ext = (st->enable & 0x1fu) | (st->depth_func & 0xfu) << 8 | (st->cull_mode & 0xfu) << 12 | (st->alpha_func & 0xfu) << 16 |
+                    (st->alpha_ref & 0xffu) << 24;
+            if (st->enable & OGRECU_EXT_SCISSOR) {
+                // an empty rectangle becomes left > right: every bbox is rejected
+                const uint32_t l = std::min(st->scissor[0], 0xfffeu), tp = std::min(st->scissor[1], 0xfffeu);
+                const uint32_t r = std::min(st->scissor[2], W), b = std::min(st->scissor[3], H);
+                if (r <= l || b <= tp) { o.sc_x = 1u; o.sc_y = 1u; }               // left 1, right 0
+                else { o.sc_x = l | (r - 1) << 16; o.sc_y = tp | (b - 1) << 16; }
+            }
+            if (st->enable & OGRECU_EXT_VERTEX_COLOUR) { o.col = (const uint8_t*)st->colours; o.col_stride = st->colour_stride; }
+        }
     }
     OGRECU_REQUIRE(ntris64 < 0x7fffff00ull, "too many triangles in one flush");
     OGRECU_REQUIRE(nverts64 < 0x7fffff00ull, "too many vertices in one flush");
@@ -1306,7 +1395,7 @@ int rt_flush_cmds(ogrecu_rt* rt)
     ogrecu_rt* one[1] = {rt};
     for (size_t i = 0; i < rt->cmds.size(); ++i) {
         Cmd& c = rt->cmds[i];
-        if (c.kind == 0) { seg.push_back({&c.draw, 0, nullptr, nullptr, nullptr}); continue; }
+        if (c.kind == 0) { seg.push_back({&c.draw, 0, nullptr, nullptr, nullptr, &c.state}); continue; }
         OGRECU_CHECK(run_segment(ctx, one, 1, seg));
         seg.clear();
         const size_t npx = (size_t)rt->w * rt->h;
@@ -1500,9 +1589,20 @@ int ogrecu_rt_clear(ogrecu_rt* rt, unsigned buffers, const float colour_rgba[4],
     return OGRECU_OK;
 }
 
-int ogrecu_draw(ogrecu_rt* rt, const ogrecu_draw_desc* d)
+int ogrecu_draw(ogrecu_rt* rt, const ogrecu_draw_desc* d) { return ogrecu_draw_with_state(rt, d, nullptr); }
+
+int ogrecu_draw_with_state(ogrecu_rt* rt, const ogrecu_draw_desc* d, const ogrecu_draw_state* st)
 {
     OGRECU_REQUIRE(rt && d, "NULL argument");
+    if (st && st->enable) {
+        OGRECU_REQUIRE((st->enable & ~0x1fu) == 0, "unknown OGRECU_EXT_* bit");
+        OGRECU_REQUIRE(!(st->enable & OGRECU_EXT_DEPTH_FUNC) || st->depth_func <= OGRECU_CMPF_GREATER, "bad depth function");
+        OGRECU_REQUIRE(!(st->enable & OGRECU_EXT_ALPHA_REJECT) || (st->alpha_func <= OGRECU_CMPF_GREATER && st->alpha_ref <= 255), "bad alpha rejection");
+        OGRECU_REQUIRE(!(st->enable & OGRECU_EXT_CULL_MODE) || (st->cull_mode >= OGRECU_CULL_NONE && st->cull_mode <= OGRECU_CULL_ANTICLOCKWISE),
+                       "bad culling mode");
+        OGRECU_REQUIRE(!(st->enable & OGRECU_EXT_VERTEX_COLOUR) || (st->colours && ((st->colour_stride | (uintptr_t)st->colours) & 3) == 0),
+                       "vertex colours: NULL or not 4-byte aligned");
+    }
     if (d->prim_type != OGRECU_PRIM_TRIANGLE_LIST && d->prim_type != OGRECU_PRIM_TRIANGLE_STRIP) {
         // TinyRenderSystem::_render silently ignores other operation types (.cpp:354-357)
         return OGRECU_OK;
@@ -1518,6 +1618,7 @@ int ogrecu_draw(ogrecu_rt* rt, const ogrecu_draw_desc* d)
     memset(&c, 0, sizeof c);
     c.kind = 0;
     c.draw = *d;
+    if (st) c.state = *st;
     rt->cmds.push_back(c);
     return OGRECU_OK;
 }
@@ -1548,7 +1649,7 @@ int ogrecu_draw_views(ogrecu_rt* const* rts, uint32_t n_views, const ogrecu_draw
     std::vector<Item> items(n_views);
     for (uint32_t v = 0; v < n_views; ++v)
         items[v] = {desc, v, per_view_mvp + 16 * v, per_view_mvit ? per_view_mvit + 16 * v : nullptr,
-                    per_view_light_dir ? per_view_light_dir + 3 * v : nullptr};
+                    per_view_light_dir ? per_view_light_dir + 3 * v : nullptr, nullptr};
     return run_segment(ctx, rts, n_views, items);
 }
 

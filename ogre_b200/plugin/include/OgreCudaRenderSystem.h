@@ -33,6 +33,15 @@ class CudaRenderSystem : public RenderSystem
 
     bool mDepthTest, mDepthWrite, mBlendAdd;
 
+    // Opt-in "beyond Tiny" mode (config option "Beyond Tiny" = "Yes"): state that Tiny's setters drop
+    // (OgreTinyRenderSystem.cpp:208-297) is kept and sent with every draw as an ogrecu_draw_state.  Off by default: the
+    // render system is then Tiny's twin.
+    bool mBeyondTiny;
+    CompareFunction mDepthFunc, mAlphaFunc;
+    unsigned char mAlphaRef;
+    bool mScissorOn;
+    Rect mScissor;
+
     HardwareBufferManager* mHardwareBufferManager;
     bool mInitialised;
     std::vector<ogrecu_rt*> mDirtyTargets;   // targets with recorded, unflushed work
@@ -75,7 +84,8 @@ public:
     void setLightingEnabled(bool enabled) override { mDoLighting = enabled; }
     void _setViewport(Viewport* vp) override;
     void _endFrame(void) override;
-    void _setCullingMode(CullingMode mode) override { mCullingMode = mode; }
+    void _setCullingMode(CullingMode mode) override { mCullingMode = mode; }   // used in "Beyond Tiny" mode only
+    bool getBeyondTiny() const { return mBeyondTiny; }
     void _setDepthBufferParams(bool depthTest = true, bool depthWrite = true,
                                CompareFunction depthFunction = CMPF_LESS_EQUAL) override;
     void _setDepthBias(float, float) override {}
@@ -84,13 +94,13 @@ public:
     void setStencilState(const StencilState&) override {}
     void applyFixedFunctionParams(const GpuProgramParametersPtr& params, uint16 variabilityMask) override;
     void _render(const RenderOperation& op) override;
-    void setScissorTest(bool, const Rect& = Rect()) override {}
+    void setScissorTest(bool enabled, const Rect& rect = Rect()) override { mScissorOn = enabled; mScissor = rect; }
     void clearFrameBuffer(unsigned int buffers, const ColourValue& colour = ColourValue::Black, float depth = 1.0f,
                           unsigned short stencil = 0) override;
     HardwareOcclusionQuery* createHardwareOcclusionQuery(void) override { return NULL; }
     void _setRenderTarget(RenderTarget* target) override;
     void bindGpuProgramParameters(GpuProgramType, const GpuProgramParametersPtr&, uint16) override {}
-    void _setAlphaRejectSettings(CompareFunction, unsigned char, bool) override {}
+    void _setAlphaRejectSettings(CompareFunction func, unsigned char value, bool) override { mAlphaFunc = func; mAlphaRef = value; }
     void beginProfileEvent(const String&) override {}
     void endProfileEvent(void) override {}
     void markProfileEvent(const String&) override {}

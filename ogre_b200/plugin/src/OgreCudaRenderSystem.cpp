@@ -16,7 +16,8 @@ CudaRenderSystem* CudaRenderSystem::msInstance = 0;
 
 CudaRenderSystem::CudaRenderSystem()
     : mCtx(0), mDeviceIndex(0), mActiveTarget(0), mActiveTargetTexture(0), mDoLighting(false), mTexture(0), mDepthTest(true),
-      mDepthWrite(true), mBlendAdd(false), mHardwareBufferManager(0), mInitialised(false)
+      mDepthWrite(true), mBlendAdd(false), mBeyondTiny(false), mDepthFunc(CMPF_LESS_EQUAL), mAlphaFunc(CMPF_ALWAYS_PASS), mAlphaRef(0),
+      mScissorOn(false), mHardwareBufferManager(0), mInitialised(false)
 {
     LogManager::getSingleton().logMessage(getName() + " created.");
     msInstance = this;
@@ -70,6 +71,12 @@ void CudaRenderSystem::initConfigOptions()
     ogrecu_device_count(&n);
     for (int i = 0; i < n; ++i) dev.possibleValues.push_back(StringConverter::toString(i));
     mOptions[dev.name] = dev;
+    ConfigOption beyond;
+    beyond.name = "Beyond Tiny";      // honour depth function, culling mode, scissor, alpha rejection and vertex colours
+    beyond.currentValue = mBeyondTiny ? "Yes" : "No";
+    beyond.possibleValues = {"No", "Yes"};
+    beyond.immutable = false;
+    mOptions[beyond.name] = beyond;
 }
 
 void CudaRenderSystem::setConfigOption(const String& name, const String& value)
@@ -81,6 +88,7 @@ void CudaRenderSystem::setConfigOption(const String& name, const String& value)
         OgreAssert(!mCtx, "the device cannot change once the context exists");
         mDeviceIndex = StringConverter::parseInt(value);
     }
+    if (name == "Beyond Tiny") mBeyondTiny = StringConverter::parseBool(value);
 }
 
 const String& CudaRenderSystem::getName(void) const
@@ -218,10 +226,11 @@ void CudaRenderSystem::_endFrame(void)
     flushPendingDraws();
 }
 
-void CudaRenderSystem::_setDepthBufferParams(bool depthTest, bool depthWrite, CompareFunction)
+void CudaRenderSystem::_setDepthBufferParams(bool depthTest, bool depthWrite, CompareFunction depthFunction)
 {
     mDepthTest = depthTest;
     mDepthWrite = depthWrite;
+    mDepthFunc = depthFunction;   // Tiny drops it (OgreTinyRenderSystem.cpp:270-274); sent only in "Beyond Tiny" mode
 }
 
 void CudaRenderSystem::setColourBlendState(const ColourBlendState& state) { mBlendAdd = state.destFactor == SBF_ONE; }
@@ -315,9 +324,39 @@ void CudaRenderSystem::_render(const RenderOperation& op)
     memcpy(d.light_dir, mUniformLightDir.ptr(), 12);
     memcpy(d.ambient, mUniformAmbient.ptr(), 16);
 
+    ogrecu_draw_state st;
+    memset(&st, 0, sizeof st);
+    if (mBeyondTiny)
+    {
+        // the Ogre enums ARE the C ABI's values (include/ogrecu.h)
+        st.enable = OGRECU_EXT_DEPTH_FUNC | OGRECU_EXT_CULL_MODE;
+        st.depth_func = mDepthFunc;
+        CullingMode cull = mCullingMode;
+        if (mInvertVertexWinding && cull != CULL_NONE) cull = cull == CULL_CLOCKWISE ? CULL_ANTICLOCKWISE : CULL_CLOCKWISE;
+        st.cull_mode = cull;
+        if (mAlphaFunc != CMPF_ALWAYS_PASS)
+        {
+            st.enable |= OGRECU_EXT_ALPHA_REJECT;
+            st.alpha_func = mAlphaFunc; st.alpha_ref = mAlphaRef;
+        }
+        if (mScissorOn)
+        {
+            st.enable |= OGRECU_EXT_SCISSOR;
+            st.scissor[0] = std::max<int32>(0, mScissor.left); st.scissor[1] = std::max<int32>(0, mScissor.top);
+            st.scissor[2] = std::max<int32>(0, mScissor.right); st.scissor[3] = std::max<int32>(0, mScissor.bottom);
+        }
+        auto diffuse = op.vertexData->vertexDeclaration->findElementBySemantic(VES_DIFFUSE);
+        if (diffuse && diffuse->getType() == VET_UBYTE4_NORM)
+        {
+            Stream col = deviceStream(op, VES_DIFFUSE);
+            st.enable |= OGRECU_EXT_VERTEX_COLOUR;
+            st.colours = col.ptr; st.colour_stride = col.stride;
+        }
+    }
+
     do
     {
-        OGRECU_THROW_IF(ogrecu_draw(mActiveTarget, &d));
+        OGRECU_THROW_IF(ogrecu_draw_with_state(mActiveTarget, &d, mBeyondTiny ? &st : NULL));
     } while (updatePassIterationRenderState());
     noteRecorded(mActiveTarget);
     if (mActiveTargetTexture) mActiveTargetTexture->markTargetRendered();

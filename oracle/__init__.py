@@ -35,6 +35,12 @@ class OracleDraw(C.Structure):
     ]
 
 
+class OracleDrawState(C.Structure):
+    """oracle_draw_state (oracle/ogre_oracle.h): the opt-in "beyond Tiny" render state"""
+    _fields_ = [("enable", C.c_uint32), ("depth_func", C.c_uint32), ("cull_mode", C.c_uint32), ("alpha_func", C.c_uint32),
+                ("alpha_ref", C.c_uint32), ("scissor", C.c_uint32 * 4), ("colour_stride", C.c_uint32), ("colours", vp)]
+
+
 class OracleSkeleton(C.Structure):
     """oracle_skeleton (oracle/ogre_oracle.h)"""
     _fields_ = [("num_bones", C.c_uint32), ("blend_mode", C.c_uint32), ("parent", vp), ("bind", vp), ("inherit", vp)]
@@ -100,6 +106,8 @@ def lib():
         l.oracle_tiny_clear.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_uint, vp, c_f]
         l.oracle_tiny_draw.argtypes = [C.POINTER(OracleDraw), vp, vp, C.c_uint32, C.c_uint32]
         l.oracle_tiny_draw.restype = C.c_uint64
+        l.oracle_tiny_draw_state.argtypes = [C.POINTER(OracleDraw), C.POINTER(OracleDrawState), vp, vp, C.c_uint32, C.c_uint32]
+        l.oracle_tiny_draw_state.restype = C.c_uint64
         l.oracle_pose_blend.argtypes = [c_f, vp, vp, C.c_uint32, vp, C.c_uint32]
         l.oracle_pose_blend.restype = None
         l.oracle_finalise_pose_normals.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32]

@@ -287,11 +287,43 @@ typedef struct tri_setup {
     float iw[3], z[3];
     float uv[3][2];
     float n[3][3];
+    float vc[3][3];   /* vertex colours (beyond-Tiny state only) */
     int x0, x1, y0, y1;
 } tri_setup;
 
-static uint64_t raster_triangle(const oracle_draw* d, const tri_setup* t, uint8_t* colour, float* depth, uint32_t W)
+/* Ogre::CompareFunction (OgreMain/include/OgreCommon.h:61-71) on depths; CMPF_LESS_EQUAL keeps Tiny's own form
+ * `!(new > old)` (tinyrenderer.h:79), under which a NaN passes */
+static int cmp_depth(uint32_t func, float a, float b)
 {
+    switch (func) {
+    case 0: return 0;
+    case 1: return 1;
+    case 2: return a < b;
+    case 3: return !(a > b);
+    case 4: return a == b;
+    case 5: return a != b;
+    case 6: return a >= b;
+    default: return a > b;
+    }
+}
+
+static int cmp_alpha(uint32_t func, uint32_t a, uint32_t b)
+{
+    switch (func) {
+    case 0: return 0;
+    case 1: return 1;
+    case 2: return a < b;
+    case 3: return a <= b;
+    case 4: return a == b;
+    case 5: return a != b;
+    case 6: return a >= b;
+    default: return a > b;
+    }
+}
+
+static uint64_t raster_triangle(const oracle_draw* d, const oracle_draw_state* st, const tri_setup* t, uint8_t* colour, float* depth, uint32_t W)
+{
+    const uint32_t en = st ? st->enable : 0u;
     uint64_t written = 0;
     const float inv255 = 1.0f / 255.0f;
     for (int x = t->x0; x <= t->x1; ++x) {
@@ -309,7 +341,11 @@ static uint64_t raster_triangle(const oracle_draw* d, const tri_setup* t, uint8_
             if (bs0 < 0 || bs1 < 0 || bs2 < 0) continue;         /* tinyrenderer.h:74 */
             if (fd < 0.0) continue;                              /* :76 */
             size_t p = (size_t)y * W + (size_t)x;
-            if (d->depth_test && fd > depth[p]) continue;        /* :79 */
+            if (d->depth_test) {
+                if (en & ORACLE_EXT_DEPTH_FUNC) { if (!cmp_depth(st->depth_func, fd, depth[p])) continue; }
+                else if (fd > depth[p]) continue;                /* :79 */
+            }
+            uint32_t alpha = 255;                                /* no texture: white, alpha 1 */
 
             float col[4] = {1.0f, 1.0f, 1.0f, 1.0f};             /* default ColourValue: white */
             if (d->tex_rgba) {                                   /* DefaultShader::fragment .cpp:312-322 */
@@ -323,7 +359,11 @@ static uint64_t raster_triangle(const oracle_draw* d, const tri_setup* t, uint8_
                 const uint8_t* tx = d->tex_rgba + ((size_t)iy * d->tex_w + (size_t)ix) * 4;
                 if (tx[3] < 1) continue;                         /* alpha discard .cpp:318 */
                 for (int k = 0; k < 4; ++k) col[k] = (float)tx[k] * inv255;
+                alpha = tx[3];
             }
+            if ((en & ORACLE_EXT_ALPHA_REJECT) && !cmp_alpha(st->alpha_func, alpha, st->alpha_ref)) continue;
+            if (en & ORACLE_EXT_VERTEX_COLOUR)                   /* interpolated like uv, modulates rgb */
+                for (int k = 0; k < 3; ++k) col[k] *= (t->vc[0][k] * bc0 + t->vc[1][k] * bc1) + t->vc[2][k] * bc2;
             if (d->lighting) {                                   /* .cpp:324-330 */
                 float n[3];
                 for (int k = 0; k < 3; ++k) n[k] = (t->n[0][k] * bc0 + t->n[1][k] * bc1) + t->n[2][k] * bc2;
@@ -348,12 +388,21 @@ static uint64_t raster_triangle(const oracle_draw* d, const tri_setup* t, uint8_
 
 uint64_t oracle_tiny_draw(const oracle_draw* d, uint8_t* colour, float* depth, uint32_t W, uint32_t H)
 {
+    return oracle_tiny_draw_state(d, NULL, colour, depth, W, H);
+}
+
+uint64_t oracle_tiny_draw_state(const oracle_draw* d, const oracle_draw_state* st, uint8_t* colour, float* depth, uint32_t W, uint32_t H)
+{
     uint64_t written = 0;
-    const int do_cull = !d->is_strip;
+    const uint32_t en = st ? st->enable : 0u;
+    /* Tiny: lists are culled by its fixed rule, strips never (.cpp:410); CULL_CLOCKWISE is that rule */
+    const uint32_t cull = (en & ORACLE_EXT_CULL_MODE) ? st->cull_mode : (d->is_strip ? 1u : 2u);
+    size_t tri = 0;
     /* OgreTinyRenderSystem.cpp:396-411 */
     for (size_t i = 0; i < d->draw_count; i += 3) {
         if (i && d->is_strip) i -= 2;
         if (i + 3 > d->draw_count) break;   /* the reference reads past the end here (UB); we stop */
+        const size_t tri_index = tri++;
         tri_setup t;
         float X[3], Y[3];
         int finite = 1;
@@ -377,6 +426,10 @@ uint64_t oracle_tiny_draw(const oracle_draw* d, uint8_t* colour, float* depth, u
                 for (int r = 0; r < 3; ++r)                       /* Matrix3 * Vector3, OgreMatrix3.h:321-327 */
                     t.n[j][r] = (d->mvit[4 * r + 0] * n[0] + d->mvit[4 * r + 1] * n[1]) + d->mvit[4 * r + 2] * n[2];
             } else { t.n[j][0] = t.n[j][1] = t.n[j][2] = 0; }
+            if (en & ORACLE_EXT_VERTEX_COLOUR) {                  /* VET_UBYTE4_NORM bytes r,g,b,a -> ColourValue(const uchar*) */
+                const uint8_t* c = st->colours + (size_t)st->colour_stride * idx;
+                for (int r = 0; r < 3; ++r) t.vc[j][r] = (float)c[r] * (1.0f / 255.0f);
+            }
             mat4_mul_vec4(d->viewport, clip, q);                  /* tinyrenderer.h:45 */
             float w = q[3];
             float fi = 1.0f / w;                                  /* pts[i] /= w, OgreVector.h:563-570 */
@@ -386,9 +439,12 @@ uint64_t oracle_tiny_draw(const oracle_draw* d, uint8_t* colour, float* depth, u
         }
         if (!finite) continue;   /* reference behaviour undefined here (see header) */
 
-        if (do_cull) {                                            /* tinyrenderer.h:37-39,55 */
+        if (cull != 1u) {                                         /* tinyrenderer.h:37-39,55 */
             float ax = X[2] - X[0], ay = Y[2] - Y[0], bx = X[2] - X[1], by = Y[2] - Y[1];
-            if (ax * by - ay * bx > 0) continue;
+            float cr = ax * by - ay * bx;
+            /* beyond Tiny: a strip's odd triangles have the opposite winding */
+            if ((en & ORACLE_EXT_CULL_MODE) && d->is_strip && (tri_index & 1u)) cr = -cr;
+            if (cull == 2u ? cr > 0 : cr < 0) continue;
         }
         float mnx = FLT_MAX, mny = FLT_MAX, mxx = -FLT_MAX, mxy = -FLT_MAX;
         float cx = (float)(W - 1u), cy = (float)(H - 1u);
@@ -402,6 +458,12 @@ uint64_t oracle_tiny_draw(const oracle_draw* d, uint8_t* colour, float* depth, u
         if (!(mnx < 2147483648.0f) || !(mny < 2147483648.0f) || !(mxx > -2147483648.0f) || !(mxy > -2147483648.0f))
             continue;
         t.x0 = (int)mnx; t.x1 = (int)mxx; t.y0 = (int)mny; t.y1 = (int)mxy;
+        if (en & ORACLE_EXT_SCISSOR) {                            /* pixels outside [left,right) x [top,bottom) are not touched */
+            if ((int64_t)st->scissor[0] > t.x0) t.x0 = (int)st->scissor[0];
+            if ((int64_t)st->scissor[1] > t.y0) t.y0 = (int)st->scissor[1];
+            if ((int64_t)st->scissor[2] - 1 < t.x1) t.x1 = (int)st->scissor[2] - 1;
+            if ((int64_t)st->scissor[3] - 1 < t.y1) t.y1 = (int)st->scissor[3] - 1;
+        }
         if (t.x0 > t.x1 || t.y0 > t.y1) continue;
 
         /* Matrix3::Inverse of ABC, OgreMatrix3.cpp:155-202 (products with the 1-row are exact) */
@@ -413,7 +475,7 @@ uint64_t oracle_tiny_draw(const oracle_draw* d, uint8_t* colour, float* depth, u
             float g = 1.0f / det;
             for (int k = 0; k < 9; ++k) t.c[k] *= g;
         }
-        written += raster_triangle(d, &t, colour, depth, W);
+        written += raster_triangle(d, st, &t, colour, depth, W);
     }
     return written;
 }

@@ -94,6 +94,36 @@ void oracle_tiny_clear(uint8_t* colour_rgb, float* depth, uint32_t w, uint32_t h
  * behaviour there is undefined: out-of-bounds writes).  Returns fragments written. */
 uint64_t oracle_tiny_draw(const oracle_draw* d, uint8_t* colour_rgb, float* depth, uint32_t w, uint32_t h);
 
+/* "Beyond Tiny" render state: state Tiny's setters ignore (OgreTinyRenderSystem.cpp:208-297),
+ * honoured only when its ORACLE_EXT_* bit is set.  NOT a restatement of reference behaviour — the reference has none for
+ * these — but the definition the CUDA path (ogrecu_draw_with_state) is tested against; with enable == 0 the function IS
+ * oracle_tiny_draw.  Semantics:
+ *   depth_func     Ogre::CompareFunction (OgreCommon.h:61-71) replacing Tiny's fixed `frag_depth > zbuf` rejection
+ *                  (tinyrenderer.h:79) while depth_test is on; CMPF_LESS_EQUAL is that rule;
+ *   cull_mode      Ogre::CullingMode (OgreCommon.h:164-172): CULL_CLOCKWISE = Tiny's rule `cross(p2-p0, p2-p1) > 0` is culled
+ *                  (tinyrenderer.h:37-39), CULL_ANTICLOCKWISE = `< 0`, CULL_NONE; applies to strips too, whose odd triangles
+ *                  count with the opposite sign (Tiny never culls strips, .cpp:410);
+ *   scissor        left, top, right, bottom (exclusive): fragments outside are dropped (RenderSystem::setScissorTest);
+ *   alpha_func/ref RenderSystem::_setAlphaRejectSettings: the fragment survives iff cmp(alpha, ref) on the texel's alpha byte
+ *                  (255 without a texture), after Tiny's own `alpha == 0` discard (.cpp:318);
+ *   colours        VES_DIFFUSE as VET_UBYTE4_NORM (bytes r,g,b,a): c_j = byte * (1/255), interpolated as uv is
+ *                  ((c0*b0 + c1*b1) + c2*b2), multiplied into rgb after the texture and before lighting. */
+#define ORACLE_EXT_DEPTH_FUNC 1u
+#define ORACLE_EXT_CULL_MODE 2u
+#define ORACLE_EXT_SCISSOR 4u
+#define ORACLE_EXT_ALPHA_REJECT 8u
+#define ORACLE_EXT_VERTEX_COLOUR 16u
+typedef struct oracle_draw_state {
+    uint32_t enable;
+    uint32_t depth_func;
+    uint32_t cull_mode;
+    uint32_t alpha_func, alpha_ref;
+    uint32_t scissor[4];
+    uint32_t colour_stride;
+    const uint8_t* colours;
+} oracle_draw_state;
+uint64_t oracle_tiny_draw_state(const oracle_draw* d, const oracle_draw_state* st, uint8_t* colour_rgb, float* depth, uint32_t w, uint32_t h);
+
 
 /* ---- Skeleton bone-palette production ---- */
 

@@ -176,7 +176,13 @@ class DrawCase:
     def __init__(self, verts, indices=None, index_type=4, strip=False, texture=None, lighting=True,
                  depth_test=True, depth_write=True, blend_add=False, mvp=None, mvit=None, tex_matrix=None,
                  viewport=None, light_dir=(0.3, 0.5, 0.8), ambient=(0.2, 0.25, 0.3, 1.0),
-                 has_uv=True, has_normals=True):
+                 has_uv=True, has_normals=True, state=None):
+        # state: the opt-in "beyond Tiny" render state, a dict with any of depth_func, cull_mode (Ogre enum values),
+        # scissor (l, t, r, b), alpha (func, ref), colours ((n, 4) uint8 r,g,b,a per vertex)
+        self.state = dict(state) if state else None
+        if self.state and "colours" in self.state:
+            self.state["colours"] = np.ascontiguousarray(self.state["colours"], dtype=np.uint8)
+            assert self.state["colours"].shape == (len(verts), 4)
         self.verts = np.ascontiguousarray(verts, dtype=np.float32)      # [n, 8]
         if indices is None:
             self.index_type, self.indices = 0, None
@@ -213,6 +219,28 @@ class DrawCase:
         d.mvit[:] = self.mvit.reshape(16); d.viewport[:] = self.viewport.reshape(16)
         d.light_dir[:] = self.light_dir; d.ambient[:] = self.ambient
         return d
+
+    def fill_state(self, st, colours_ptr):
+        """Fill an OracleDrawState / ogre_b200.DrawState (same fields) from self.state; colours_ptr = address of the colours."""
+        s = self.state
+        st.enable = 0
+        if "depth_func" in s:
+            st.enable |= 1; st.depth_func = int(s["depth_func"])
+        if "cull_mode" in s:
+            st.enable |= 2; st.cull_mode = int(s["cull_mode"])
+        if "scissor" in s:
+            st.enable |= 4; st.scissor[:] = [int(v) for v in s["scissor"]]
+        if "alpha" in s:
+            st.enable |= 8; st.alpha_func, st.alpha_ref = int(s["alpha"][0]), int(s["alpha"][1])
+        if "colours" in s:
+            st.enable |= 16; st.colours, st.colour_stride = colours_ptr, 4
+        return st
+
+    def oracle_state(self):
+        import oracle
+        if not self.state:
+            return None
+        return self.fill_state(oracle.OracleDrawState(), self.state["colours"].ctypes.data if "colours" in self.state else None)
 
 
 def random_soup(rng, ntri, spread=3.0, size=1.0, strip=False, indexed=True):
@@ -400,3 +428,31 @@ PACKED32 = {"PF_A8R8G8B8": (16, 8, 0, 0xFF000000), "PF_A8B8G8R8": (0, 8, 16, 0xF
 def pack32(rgb, r_shift, g_shift, b_shift, fill):
     c = rgb.astype(np.uint32)
     return (c[..., 0] << r_shift) | (c[..., 1] << g_shift) | (c[..., 2] << b_shift) | np.uint32(fill)
+
+
+# ---- opt-in "beyond Tiny" render state ----
+def random_state(rng, nverts, w, h, what=("depth_func", "cull_mode", "scissor", "alpha", "colours")):
+    """A random ogrecu_draw_state / oracle_draw_state dict (see DrawCase) using the fields named in `what`."""
+    s = {}
+    if "depth_func" in what:
+        s["depth_func"] = int(rng.integers(0, 8))
+    if "cull_mode" in what:
+        s["cull_mode"] = int(rng.integers(1, 4))
+    if "scissor" in what:
+        l, r = sorted(int(v) for v in rng.integers(0, w + 1, 2)); t, b = sorted(int(v) for v in rng.integers(0, h + 1, 2))
+        s["scissor"] = (l, t, r, b)
+    if "alpha" in what:
+        s["alpha"] = (int(rng.integers(0, 8)), int(rng.integers(0, 256)))
+    if "colours" in what:
+        s["colours"] = rng.integers(0, 256, (nverts, 4), dtype=np.uint8)
+    return s
+
+
+def with_states(cases, seed, w, h, what=None):
+    """The same draws, each with a random beyond-Tiny state made of a random subset of the fields (or of `what`)."""
+    rng = np.random.default_rng(seed)
+    names = ("depth_func", "cull_mode", "scissor", "alpha", "colours")
+    for c in cases:
+        pick = what if what is not None else [n for n in names if rng.random() < 0.5]
+        c.state = random_state(rng, len(c.verts), w, h, pick) or None
+    return cases

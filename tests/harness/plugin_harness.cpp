@@ -74,6 +74,7 @@ API int ph_open(const char* plugin_so, const char* rs_name_part, const char* stb
         if (r->getName().find(rs_name_part) != String::npos) rs = r;
     if (!rs) { g_err = "render system not found"; return 2; }
     g->root->setRenderSystem(rs);
+    if (getenv("PH_BEYOND_TINY")) rs->setConfigOption("Beyond Tiny", "Yes");   // CUDA plugin only: opt-in state Tiny ignores
     g->root->initialise(false);
     g->win = g->root->createRenderWindow("harness", w, h, false);
     g->w = w; g->h = h;
@@ -116,6 +117,22 @@ API int ph_scene_open(const char* mesh, float cam_z)
     Entity* e = sm->createEntity(mesh);
     sm->getRootSceneNode()->createChildSceneNode()->attachObject(e);
     g->ent = e;
+    return 0;
+    CATCH(1)
+}
+
+// Pass state of every sub-entity's material (shared materials: test scene only): culling mode (Ogre::CullingMode, 0 = keep),
+// depth function (Ogre::CompareFunction, -1 = keep), alpha rejection (function -1 = keep).  Tiny ignores all of it.
+API int ph_set_pass_state(int cull_mode, int depth_func, int alpha_func, int alpha_ref)
+{
+    TRY
+    if (!g->ent) { g_err = "no entity"; return 2; }
+    for (SubEntity* se : g->ent->getSubEntities()) {
+        Pass* p = se->getMaterial()->getTechnique(0)->getPass(0);
+        if (cull_mode) p->setCullingMode((CullingMode)cull_mode);
+        if (depth_func >= 0) p->setDepthFunction((CompareFunction)depth_func);
+        if (alpha_func >= 0) p->setAlphaRejectSettings((CompareFunction)alpha_func, (unsigned char)alpha_ref);
+    }
     return 0;
     CATCH(1)
 }

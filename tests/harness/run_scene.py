@@ -34,6 +34,8 @@ def main():
     ap.add_argument("--skel", default="")
     ap.add_argument("--time", type=int, default=0)
     ap.add_argument("--formats", default="", help="comma-separated Ogre::PixelFormat names: read-back in that format vs host PixelUtil")
+    ap.add_argument("--pass-state", default="", help="cull,depthfunc,alphafunc,alpharef for every sub-entity's pass (0/-1/-1/0 = keep); "
+                                                     "honoured by the CUDA plugin only when PH_BEYOND_TINY is set in the environment")
     ap.add_argument("--scaled", action="store_true", help="with --rtt: scaled read-backs of the render texture vs the real Image::scale")
     ap.add_argument("--shadow", type=int, default=0, help="N shadow-volume cases: real generateShadowVolume vs CudaShadowVolume")
     ap.add_argument("--palettes", type=int, default=0, help="bone palettes at N time positions: engine vs CudaSkeletonPalettes")
@@ -106,6 +108,8 @@ def main():
             if k == 0:
                 out["shadow_indices_emitted"] = np.array(int((eng != 0xCDCD).sum()))
         out["shadow_cases"], out["shadow_mismatches"] = np.array(a.shadow), np.array(bad, np.int64)
+    if a.pass_state:
+        ok(L.ph_set_pass_state(*[int(v) for v in a.pass_state.split(",")]), "ph_set_pass_state")
     ok(L.ph_render(), "ph_render")
     colour = np.zeros((h, w, 3), np.uint8)
     ok(L.ph_read_colour(colour.ctypes.data, 0), "ph_read_colour")

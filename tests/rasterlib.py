@@ -17,7 +17,11 @@ def render_oracle(cases, w, h, clear=(0.1, 0.2, 0.3, 1.0), depth=1.0, init=None)
     frags = 0
     for case in cases:
         d = case.oracle_desc()
-        frags += lib.oracle_tiny_draw(C.byref(d), colour.ctypes.data, zbuf.ctypes.data, w, h)
+        st = case.oracle_state()
+        if st is None:
+            frags += lib.oracle_tiny_draw(C.byref(d), colour.ctypes.data, zbuf.ctypes.data, w, h)
+        else:
+            frags += lib.oracle_tiny_draw_state(C.byref(d), C.byref(st), colour.ctypes.data, zbuf.ctypes.data, w, h)
     return colour, zbuf, frags
 
 
@@ -27,7 +31,7 @@ class GpuScene:
     def __init__(self, ctx, cases):
         import ogre_b200
         self.ctx, self.cases = ctx, cases
-        self.keep, self.descs, self.textures = [], [], {}
+        self.keep, self.descs, self.states, self.textures = [], [], [], {}
         for case in cases:
             vb = ctx.to_device(case.verts)
             ib = ctx.to_device(case.indices) if case.indices is not None else None
@@ -51,12 +55,18 @@ class GpuScene:
             d.mvit[:] = case.mvit.reshape(16); d.viewport[:] = case.viewport.reshape(16)
             d.light_dir[:] = case.light_dir; d.ambient[:] = case.ambient
             self.descs.append(d)
+            st = None
+            if case.state:
+                cb = ctx.to_device(case.state["colours"]) if "colours" in case.state else None
+                self.keep.append(cb)
+                st = case.fill_state(ogre_b200.DrawState(), cb.ptr if cb is not None else None)
+            self.states.append(st)
 
     def render(self, rt, clear=(0.1, 0.2, 0.3, 1.0), depth=1.0):
         if clear is not None:
             rt.clear(colour=clear, depth=depth)
-        for d in self.descs:
-            rt.draw(d)
+        for d, st in zip(self.descs, self.states):
+            rt.draw(d, st)
         rt.flush()
 
     def free(self):

@@ -23,7 +23,7 @@ def test_header_symbols_are_all_exported_and_bound():
         assert hasattr(lib, n), "libogrecu.so does not export %s" % n
         assert n in capi.SIGNATURES, "ogre_b200/capi.py does not bind %s" % n
     assert sorted(capi.SIGNATURES) == names
-    assert lib.ogrecu_abi_version() == 3
+    assert lib.ogrecu_abi_version() == 4
 
 
 def test_struct_layouts_match_the_header(tmp_path):
@@ -33,16 +33,18 @@ def test_struct_layouts_match_the_header(tmp_path):
     src = tmp_path / "layout.c"
     src.write_text(
         '#include <stdio.h>\n#include <stddef.h>\n#include "ogrecu.h"\n'
-        'int main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(ogrecu_skin_job), sizeof(ogrecu_draw_desc),'
+        'int main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(ogrecu_skin_job), sizeof(ogrecu_draw_desc),'
         ' sizeof(ogrecu_raster_stats), offsetof(ogrecu_draw_desc, texture), offsetof(ogrecu_draw_desc, mvp),'
         ' offsetof(ogrecu_draw_desc, ambient), offsetof(ogrecu_skin_job, num_vertices), sizeof(ogrecu_anim_job),'
-        ' offsetof(ogrecu_anim_job, dst_instance_stride_bytes), sizeof(ogrecu_skeleton_desc), sizeof(ogrecu_animation_desc));return 0;}\n')
+        ' offsetof(ogrecu_anim_job, dst_instance_stride_bytes), sizeof(ogrecu_skeleton_desc), sizeof(ogrecu_animation_desc),'
+        ' sizeof(ogrecu_draw_state), offsetof(ogrecu_draw_state, scissor), offsetof(ogrecu_draw_state, colours));return 0;}\n')
     exe = tmp_path / "layout"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     got = [int(v) for v in subprocess.check_output([str(exe)]).split()]
     assert got == [C.sizeof(capi.SkinJob), C.sizeof(capi.DrawDesc), C.sizeof(capi.RasterStats), capi.DrawDesc.texture.offset,
                    capi.DrawDesc.mvp.offset, capi.DrawDesc.ambient.offset, capi.SkinJob.num_vertices.offset, C.sizeof(capi.AnimJob),
-                   capi.AnimJob.dst_instance_stride_bytes.offset, C.sizeof(capi.SkeletonDesc), C.sizeof(capi.AnimationDesc)]
+                   capi.AnimJob.dst_instance_stride_bytes.offset, C.sizeof(capi.SkeletonDesc), C.sizeof(capi.AnimationDesc),
+                   C.sizeof(capi.DrawState), capi.DrawState.scissor.offset, capi.DrawState.colours.offset]
 
 
 def test_no_device_is_a_loud_failure_not_a_fallback():

@@ -25,7 +25,7 @@ NEED = [os.path.join(ROOT, "ogre_b200", "plugin", "RenderSystem_CUDA.so"), os.pa
         os.path.join(ROOT, "oracle", "_ref", "lib", "libOgreMain.so")]
 
 
-def run_scene(tmp_path, plugin, *args):
+def run_scene(tmp_path, plugin, *args, beyond_tiny=False):
     for f in NEED:
         assert os.path.exists(f), "%s missing: run __graft_entry__.build() where the reference tree is present" % f
     out = os.path.join(str(tmp_path), "%s_%d.npz" % (plugin, len(os.listdir(str(tmp_path)))))
@@ -33,7 +33,7 @@ def run_scene(tmp_path, plugin, *args):
     # initialises DefaultShader::image / mDepthTest / mBlendAdd (ctor, OgreTinyRenderSystem.cpp:27-46) and was
     # seen to die with SIGFPE in sample2D on some hosts; that is the oracle's own undefined behaviour.  Its runs therefore get
     # glibc's MALLOC_PERTURB_=255 (fresh allocations are zero-filled), which makes those members read as NULL / false.
-    env = dict(os.environ, MALLOC_PERTURB_="255") if plugin != "cuda" else None
+    env = dict(os.environ, MALLOC_PERTURB_="255") if plugin != "cuda" else (dict(os.environ, PH_BEYOND_TINY="1") if beyond_tiny else None)
     for attempt in range(1 if plugin == "cuda" else 3):
         r = subprocess.run([sys.executable, RUN, "--plugin", plugin, "--out", out] + list(args), capture_output=True, text=True, timeout=600,
                            env=env)
@@ -145,3 +145,30 @@ def test_scaled_render_texture_readback_equals_image_scale(tmp_path):
     assert len(z["scaled_cases"]) == 42
     bad = {str(c): int(m) for c, m in zip(z["scaled_cases"], z["scaled_mismatches"]) if m != 0}
     assert not bad, bad
+
+
+def test_beyond_tiny_mode_through_the_plugin(tmp_path):
+    """Config option "Beyond Tiny" = Yes: the plugin forwards the pass state Tiny drops.  With OGRE's default
+    pass state (CULL_CLOCKWISE, CMPF_LESS_EQUAL, no alpha rejection) the frame is still Tiny's; culling the other side or not at
+    all, another depth function, or an alpha test change it the way the state says; and with the option off the same pass state
+    is ignored exactly as Tiny ignores it."""
+    args = ["--mesh", "ogrehead.mesh", "--size", "320x180"]
+    tiny = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ogrehead_320x180.npz"))["colour"]
+    bg = np.array([25, 51, 76], np.uint8)
+    covered = lambda img: (img != bg).any(axis=2)
+    default = run_scene(tmp_path, "cuda", *args, beyond_tiny=True)["colour"]
+    assert np.array_equal(default, tiny)
+    ignored = run_scene(tmp_path, "cuda", *args, "--pass-state", "3,7,2,255")["colour"]        # option off: Tiny's twin
+    assert np.array_equal(ignored, tiny)
+    acw = run_scene(tmp_path, "cuda", *args, "--pass-state", "3,-1,-1,0", beyond_tiny=True)["colour"]
+    none = run_scene(tmp_path, "cuda", *args, "--pass-state", "1,-1,-1,0", beyond_tiny=True)["colour"]
+    assert (acw != tiny).any() and covered(acw).sum() > 1000
+    # a closed mesh: the back faces cover the same silhouette; without culling the depth test lets the front faces win
+    assert np.array_equal(covered(none), covered(tiny) | covered(acw))
+    assert (none != tiny).mean() < 0.02
+    nothing = run_scene(tmp_path, "cuda", *args, "--pass-state", "0,0,-1,0", beyond_tiny=True)["colour"]    # CMPF_ALWAYS_FAIL
+    assert not covered(nothing).any()
+    greater = run_scene(tmp_path, "cuda", *args, "--pass-state", "0,7,-1,0", beyond_tiny=True)["colour"]    # CMPF_GREATER vs depth 1: nothing passes
+    assert not covered(greater).any()
+    rejected = run_scene(tmp_path, "cuda", *args, "--pass-state", "0,-1,2,255", beyond_tiny=True)["colour"]  # alpha < 255: opaque texels fail
+    assert covered(rejected).sum() < covered(tiny).sum()
