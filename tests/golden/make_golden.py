@@ -21,6 +21,8 @@ container only; the GPU box and the CPU test suite just read the .npz files.
                          index buffer contents / ShadowRenderable ranges the real ShadowCaster::generateShadowVolume wrote
   image_scale.npz        outputs of the real Image::scale(FILTER_BILINEAR) on seeded RGB8 images (datagen.SCALE_CASES: up- and
                          down-scaling, sub-boxes, 1-pixel extents), same format and into PF_A8R8G8B8 / PF_BYTE_RGBA
+  skel_frames.npz        the frames the real Tiny plugin renders of the software-skinned Sinbad / jaiqua entities (poses at t = 0.3 s
+                         and 1.7 s, 256x256, through tests/harness/run_scene.py on the build host)
   optutil_golden.npz     outputs of the real OptimisedUtilSSE / OptimisedUtilGeneral on small
                          seeded inputs (all six functions, edge-case counts and alignments)
 """
@@ -181,6 +183,21 @@ def save_image_scale(name):
     print(name, len(out), "arrays")
 
 
+def save_skel_frames(name):
+    import subprocess
+    import tempfile
+    out = {}
+    for mesh in ("Sinbad.mesh", "jaiqua.mesh"):
+        with tempfile.TemporaryDirectory() as tmp:
+            f = os.path.join(tmp, "t.npz")
+            subprocess.check_call([sys.executable, os.path.join(ROOT, "tests", "harness", "run_scene.py"), "--plugin", "tiny", "--mesh", mesh,
+                                   "--size", "256x256", "--cam-z", "30", "--skel", "0.3,1.7", "--out", f],
+                                  env=dict(os.environ, MALLOC_PERTURB_="255"))
+            out[mesh] = np.load(f)["colour"]
+    np.savez_compressed(os.path.join(HERE, name), **out)
+    print(name, len(out), "arrays")
+
+
 def save_optutil(name):
     l = ref.lib()
     rng = np.random.default_rng(2024)
@@ -248,8 +265,12 @@ if __name__ == "__main__":
     if sys.argv[1:] == ["image_scale"]:
         save_image_scale("image_scale.npz")
         sys.exit(0)
+    if sys.argv[1:] == ["skel_frames"]:
+        save_skel_frames("skel_frames.npz")
+        sys.exit(0)
     save_optutil("optutil_golden.npz")
     save_image_scale("image_scale.npz")
+    save_skel_frames("skel_frames.npz")
     save_scene("ogrehead_320x180.npz", "ogrehead.mesh", 320, 180)
     save_scene("ogrehead_1280x720.npz", "ogrehead.mesh", 1280, 720)
     save_skeleton("sinbad_skin.npz", "Sinbad.mesh")

@@ -87,9 +87,16 @@ def test_entity_software_skinning_through_cuda_optimised_util(tmp_path, mesh, fi
             assert np.abs(got[:, 3:] - ref[:, 3:]).max() <= 4e-4
     # the skinned buffers feed _render without leaving the device: the frame equals Tiny's frame up to
     # the SSE rsqrt noise in the normals (lighting), positions/coverage identical
-    t = run_scene(tmp_path, "tiny", "--mesh", mesh, "--size", "256x256", "--cam-z", "30", "--skel", times)
-    diff = np.abs(c["colour"].astype(int) - t["colour"].astype(int))
+    # (a) against the frame the real Tiny plugin rendered on the build host (tests/golden/skel_frames.npz): every pixel
+    golden = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "skel_frames.npz"))[mesh]
+    diff = np.abs(c["colour"].astype(int) - golden.astype(int))
     assert diff.max() <= 1, diff.max()
+    # (b) against the real Tiny plugin run live on this host.  The reference's own frame was seen to depend on the host at
+    # isolated pixels (one pixel of the Sinbad frame on one GPU box, with bit-identical skinned vertices and this plugin's
+    # frame equal to (a) everywhere: profiles/r01q_notes.md), so a handful of outliers are tolerated here and only here.
+    t = run_scene(tmp_path, "tiny", "--mesh", mesh, "--size", "256x256", "--cam-z", "30", "--skel", times)
+    diff = np.abs(c["colour"].astype(int) - t["colour"].astype(int)).max(axis=2)
+    assert (diff > 1).sum() <= 4, (int((diff > 1).sum()), int(diff.max()))
     assert list(c["stats"]) == list(t["stats"])
 
 

@@ -165,7 +165,23 @@ def c1(ctx, T, args):
         conv = (host[..., 0].astype(np.uint32) << 16) | (host[..., 1].astype(np.uint32) << 8) | host[..., 2] | 0xFF000000
     dt_rb32_host = (time.perf_counter() - t0) / 5
     assert np.array_equal(conv, host32)
+    # the frame read back at half size (RenderTexture::copyContentsToMemory into a 640x360 box -> Image::scale): resampled on the
+    # device (ogrecu_rt_read_colour_scaled) vs full read-back + the restated Image::scale on one host core (C, -O2)
+    import oracle
+    half = rt.read_colour_scaled(w // 2, h // 2)
+    t0 = time.perf_counter()
+    for _ in range(20):
+        frame(); half = rt.read_colour_scaled(w // 2, h // 2)
+    dt_half = (time.perf_counter() - t0) / 20
+    t0 = time.perf_counter()
+    for _ in range(5):
+        frame(); rt.read_colour(out=host)
+        half_host = oracle.scale_bilinear(host, w // 2, h // 2)
+    dt_half_host = (time.perf_counter() - t0) / 5
+    assert np.array_equal(half, half_host)
     out = {"config": "c1 ogrehead 1280x720 (4336 tris, 4 draws) replayed through the C ABI", "ms_per_frame_device": dt * 1e3,
+           "ms_per_frame_with_half_size_readback_device_scale": dt_half * 1e3,
+           "ms_per_frame_with_half_size_readback_host_scale_1core": dt_half_host * 1e3,
            "frames_per_s_device": 1 / dt, "ms_per_frame_with_readback": dt_rb * 1e3, "frames_per_s_with_readback": 1 / dt_rb,
            "Mtri_per_s_device": 4336 / dt / 1e6, "image_identical_to_tiny": True,
            "ms_per_frame_with_bgra_readback_device_conversion": dt_rb32 * 1e3,
