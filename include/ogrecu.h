@@ -86,6 +86,9 @@ OGRECU_API uint64_t ogrecu_launch_count(const ogrecu_ctx* ctx);
  *                0 = once per index like Tiny; identical results
  *   "skel_mode"  0 = bone-palette kernel in use (16 instances of one bone per half-warp), 1 = first version (a lane per
  *                bone); identical results
+ *   "optutil_sync" 0 (default) = an OptimisedUtil *_host call whose outputs all resolve to ogrecu_buf shadows returns without
+ *                waiting for the device (the next map / read-back / flush of those buffers is the sync point; small host
+ *                inputs such as the bone palette travel through a ring of pinned slots), 1 = every call waits; identical results
  * Unknown names return OGRECU_ERR_INVALID. */
 OGRECU_API int ogrecu_set_config_option(ogrecu_ctx* ctx, const char* name, int value);
 

@@ -15,7 +15,7 @@ import numpy as np
 from . import capi
 from .capi import AnimJob, AnimationDesc, DrawDesc, DrawState, OgrecuError, RasterStats, SkeletonDesc, SkinJob, check, lib
 
-__all__ = ["Context", "DeviceBuffer", "OptimisedUtil", "Skeleton", "EdgeList", "Texture", "RenderTarget", "DrawDesc", "DrawState", "SkinJob", "AnimJob",
+__all__ = ["Context", "DeviceBuffer", "OptimisedUtil", "Skeleton", "EdgeList", "Texture", "RenderTarget", "HardwareBuffer", "DrawDesc", "DrawState", "SkinJob", "AnimJob",
            "OgrecuError", "addr", "pinned_empty"]
 
 MAP_READ, MAP_WRITE, MAP_DISCARD = 1, 2, 4
@@ -135,6 +135,50 @@ class Context:
 def _light4(light):
     a = np.ascontiguousarray(light, dtype=np.float32).reshape(-1)
     return a, a.ctypes.data_as(capi.c_float_p)
+
+
+MAP_READ, MAP_WRITE, MAP_DISCARD = 1, 2, 4
+
+
+class HardwareBuffer:
+    """ogrecu_buf — the HardwareBuffer delegate's storage (OgreMain/include/OgreHardwareBuffer.h:181-186,279-330): a device
+    block with a pinned host shadow.  lock() returns the shadow as a numpy byte view (valid for the buffer's life); OptimisedUtil
+    calls made with addresses inside it run on the device copy."""
+
+    def __init__(self, ctx, nbytes):
+        self.ctx, self.nbytes = ctx, int(nbytes)
+        h = C.c_void_p()
+        check(lib().ogrecu_buf_create(ctx.handle, self.nbytes, C.byref(h)))
+        self.handle = h.value
+
+    def lock(self, mode=MAP_READ | MAP_WRITE, offset=0, length=None):
+        length = self.nbytes - offset if length is None else length
+        p = C.c_void_p()
+        check(lib().ogrecu_buf_map(self.handle, offset, length, mode, C.byref(p)))
+        return np.ctypeslib.as_array(C.cast(p.value, C.POINTER(C.c_uint8)), shape=(length,))
+
+    def unlock(self):
+        check(lib().ogrecu_buf_unmap(self.handle))
+
+    def write(self, array, offset=0):
+        a = np.ascontiguousarray(array).view(np.uint8).reshape(-1)
+        self.lock(MAP_WRITE, offset, a.size)[:] = a
+        self.unlock()
+
+    def read(self, offset=0, length=None):
+        out = self.lock(MAP_READ, offset, length).copy()
+        self.unlock()
+        return out
+
+    def shadow_address(self):
+        a = self.lock(MAP_READ, 0, 0 if self.nbytes == 0 else 1).ctypes.data
+        self.unlock()
+        return a
+
+    def destroy(self):
+        if self.handle:
+            check(lib().ogrecu_buf_destroy(self.handle))
+            self.handle = None
 
 
 class OptimisedUtil:

@@ -86,6 +86,16 @@ struct ogrecu_ctx {
     //   OGRECU_RASTER_MODE 0 auto (visibility path where it is equivalent) | 1 always the in-order path
     //   OGRECU_RASTER_XF   1 (default) transform each vertex once per flush when the draw gives a vertex count | 0 per index
     int skin_mode, skin_ipc, raster_mode, raster_xf;
+    // OptimisedUtil host entry points whose results all land in resolved device buffers do not wait for the device
+    // (config option "optutil_sync" = 0, the default): the next lock / read-back / flush of those buffers is the sync point.
+    // Their small host inputs (bone palettes) go through a ring of pinned slots, each guarded by an event.
+    int optutil_sync = 0;
+    static constexpr int RING_SLOTS = 8;
+    static constexpr size_t RING_SLOT_BYTES = 64 * 1024;
+    uint8_t* ring = nullptr;
+    cudaEvent_t ring_ev[RING_SLOTS] = {};
+    bool ring_used[RING_SLOTS] = {};
+    int ring_next = 0;
     int skel_mode = 0;          // 0: lanes = instances (skel_palette_kernel2) | 1: first version, a lane per bone (A/B)
     // side streams for independent launches of one call (ogrecu_anim_instanced_multi_dev): created on first use
     cudaStream_t side_stream[2] = {nullptr, nullptr};

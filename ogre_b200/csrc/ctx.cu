@@ -126,6 +126,8 @@ int ogrecu_shutdown(ogrecu_ctx* ctx)
     for (Scratch* s : {&ctx->jobs, &ctx->stage_in, &ctx->stage_out})
         if (s->ptr) cudaFree(s->ptr);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->ring) cudaFreeHost(ctx->ring);
+    for (cudaEvent_t e : ctx->ring_ev) if (e) cudaEventDestroy(e);
     for (int k = 0; k < 2; ++k) {
         if (ctx->side_stream[k]) { cudaStreamSynchronize(ctx->side_stream[k]); cudaStreamDestroy(ctx->side_stream[k]); }
         if (ctx->side_join[k]) cudaEventDestroy(ctx->side_join[k]);
@@ -169,6 +171,7 @@ int ogrecu_set_config_option(ogrecu_ctx* ctx, const char* name, int value)
     if (!strcmp(name, "raster_xf")) { OGRECU_REQUIRE(value >= 0 && value <= 1, "raster_xf is 0..1"); ctx->raster_xf = value; return OGRECU_OK; }
     if (!strcmp(name, "raster_mode")) { OGRECU_REQUIRE(value >= 0 && value <= 1, "raster_mode is 0..1"); ctx->raster_mode = value; return OGRECU_OK; }
     if (!strcmp(name, "skel_mode")) { OGRECU_REQUIRE(value >= 0 && value <= 1, "skel_mode is 0..1"); ctx->skel_mode = value; return OGRECU_OK; }
+    if (!strcmp(name, "optutil_sync")) { OGRECU_REQUIRE(value >= 0 && value <= 1, "optutil_sync is 0..1"); ctx->optutil_sync = value; return OGRECU_OK; }
     if (!strcmp(name, "skin_ipc")) { OGRECU_REQUIRE(value >= 0 && value <= 4096, "skin_ipc is 0..4096"); ctx->skin_ipc = value; return OGRECU_OK; }
     set_error("ogrecu_set_config_option: unknown option '%s'", name);
     return OGRECU_ERR_INVALID;

@@ -55,11 +55,29 @@ public:
             } else { r.dev_off = out_total; out_total += up(r.len); }
         }
         in_bytes = in_total; out_bytes = out_total;
+        if (in_total + out_total == 0) return OGRECU_OK;          // everything already lives on the device: nothing to stage
         OGRECU_CHECK(scratch_reserve(ctx, ctx->stage_in, in_total + out_total + ALIGN));
+        uint8_t* dev = (uint8_t*)ctx->stage_in.ptr;
+        if (out_total == 0 && !ctx->optutil_sync && in_total <= ogrecu_ctx::RING_SLOT_BYTES) {
+            // deferred completion: the inputs go through the next slot of the pinned ring; only that slot's previous copy is
+            // waited for, never the stream
+            if (!ctx->ring) OGRECU_CUDA(cudaHostAlloc((void**)&ctx->ring, ogrecu_ctx::RING_SLOTS * ogrecu_ctx::RING_SLOT_BYTES, cudaHostAllocDefault));
+            const int slot = ctx->ring_next;
+            ctx->ring_next = (slot + 1) % ogrecu_ctx::RING_SLOTS;
+            if (!ctx->ring_ev[slot]) OGRECU_CUDA(cudaEventCreateWithFlags(&ctx->ring_ev[slot], cudaEventDisableTiming));
+            if (ctx->ring_used[slot]) OGRECU_CUDA(cudaEventSynchronize(ctx->ring_ev[slot]));
+            uint8_t* pin = ctx->ring + (size_t)slot * ogrecu_ctx::RING_SLOT_BYTES;
+            for (auto& r : ins)
+                if (!r.resolved) { memcpy(pin + r.dev_off, r.host, r.len); r.dev = dev + r.dev_off; }
+            OGRECU_CUDA(cudaMemcpyAsync(dev, pin, in_total, cudaMemcpyHostToDevice, ctx->stream));
+            OGRECU_CUDA(cudaEventRecord(ctx->ring_ev[slot], ctx->stream));
+            ctx->ring_used[slot] = true;
+            deferred = true;
+            return OGRECU_OK;
+        }
         OGRECU_CHECK(pinned_reserve(ctx, in_total + out_total + ALIGN));
         OGRECU_CUDA(cudaStreamSynchronize(ctx->stream));   // pinned block free for reuse
         uint8_t* pin = (uint8_t*)ctx->pinned;
-        uint8_t* dev = (uint8_t*)ctx->stage_in.ptr;
         for (auto& r : ins)
             if (!r.resolved) { memcpy(pin + r.dev_off, r.host, r.len); r.dev = dev + r.dev_off; }
         bool preload_any = false;
@@ -86,10 +104,11 @@ public:
                 if (r.piece == r.stride || r.count <= 1) memcpy(r.host, s, r.count ? (r.count - 1) * r.stride + r.piece : 0);
                 else for (size_t i = 0; i < r.count; ++i) memcpy(r.host + i * r.stride, s + i * r.stride, r.piece);
             }
-        } else {
-            // results live in resolved device buffers; OGRE semantics are synchronous
-            OGRECU_CUDA(cudaStreamSynchronize(ctx->stream));
+        } else if (ctx->optutil_sync) {
+            OGRECU_CUDA(cudaStreamSynchronize(ctx->stream));      // "optutil_sync" = 1: every call waits
         }
+        // else: the results live in resolved device buffers, marked device-dirty: ogrecu_buf_map downloads them after a stream
+        // sync when the host next locks them, and draws / later OptimisedUtil calls consume them in stream order
         return OGRECU_OK;
     }
 
@@ -98,6 +117,7 @@ private:
     std::vector<InReq> ins;
     std::vector<OutReq> outs;
     size_t in_bytes = 0, out_bytes = 0;
+    bool deferred = false;
 };
 
 }  // namespace
