@@ -84,6 +84,7 @@ struct ogrecu_ctx {
     //                     3 single-instance tile kernel even for >= 2 instances (skin_tile.cu instead of skin_pair.cu)
     //   OGRECU_SKIN_IPC   instances per CTA of the tile kernel (0 = auto)
     //   OGRECU_RASTER_MODE 0 auto (visibility path where it is equivalent) | 1 always the in-order path
+    //   OGRECU_OPTUTIL_SYNC 1 = every OptimisedUtil host call waits for the device (default 0: deferred, see optutil_sync)
     //   OGRECU_RASTER_XF   1 (default) transform each vertex once per flush when the draw gives a vertex count | 0 per index
     int skin_mode, skin_ipc, raster_mode, raster_xf;
     // OptimisedUtil host entry points whose results all land in resolved device buffers do not wait for the device

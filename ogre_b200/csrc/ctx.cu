@@ -110,6 +110,8 @@ int ogrecu_init(int device, ogrecu_ctx** out_ctx)
     ctx->raster_mode = ev ? atoi(ev) : 0;
     ev = getenv("OGRECU_RASTER_XF");
     ctx->raster_xf = ev ? atoi(ev) : 1;
+    ev = getenv("OGRECU_OPTUTIL_SYNC");
+    ctx->optutil_sync = ev ? (atoi(ev) != 0) : 0;
     e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete ctx; return cuda_fail(e, "cudaStreamCreate", __FILE__, __LINE__); }
     ctx->stream = ctx->own_stream;

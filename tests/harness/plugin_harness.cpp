@@ -460,6 +460,28 @@ API double ph_frame_time(int frames)
     return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() / frames;
 }
 
+// Seconds per frame of the skeletally animated entity: every frame advances the first animation state by dt, so
+// Entity::_updateAnimation re-skins every sub-mesh through OptimisedUtil before the scene is rendered.
+API double ph_anim_frame_time(int frames, float dt)
+{
+    Entity* e = g->ent;
+    if (!e || !e->hasSkeleton()) return -1.0;
+    AnimationState* st = nullptr;
+    for (auto& kv : e->getAllAnimationStates()->getAnimationStates()) {
+        kv.second->setEnabled(st == nullptr);
+        if (!st) { st = kv.second; st->setLoop(true); }
+    }
+    e->addSoftwareAnimationRequest(true);
+    uint8_t px[3];
+    PixelBox box(1, 1, 1, PF_BYTE_RGB, px);
+    for (int i = 0; i < 3; ++i) { st->addTime(dt); g->root->renderOneFrame(); }
+    g->win->copyContentsToMemory(Box(0, 0, 1, 1), box, RenderTarget::FB_AUTO);
+    auto t0 = std::chrono::steady_clock::now();
+    for (int i = 0; i < frames; ++i) { st->addTime(dt); g->root->renderOneFrame(); }
+    g->win->copyContentsToMemory(Box(0, 0, 1, 1), box, RenderTarget::FB_AUTO);      // includes the device work
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() / frames;
+}
+
 API void ph_close(void)
 {
     if (!g) return;

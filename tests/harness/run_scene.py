@@ -33,6 +33,7 @@ def main():
     ap.add_argument("--quad", action="store_true")
     ap.add_argument("--skel", default="")
     ap.add_argument("--time", type=int, default=0)
+    ap.add_argument("--anim-time", type=int, default=0, help="N frames of the animated entity (re-skinned every frame): seconds per frame")
     ap.add_argument("--formats", default="", help="comma-separated Ogre::PixelFormat names: read-back in that format vs host PixelUtil")
     ap.add_argument("--pass-state", default="", help="cull,depthfunc,alphafunc,alpharef for every sub-entity's pass (0/-1/-1/0 = keep); "
                                                      "honoured by the CUDA plugin only when PH_BEYOND_TINY is set in the environment")
@@ -154,6 +155,11 @@ def main():
             out["quad"] = q
     if a.time:
         out["frame_seconds"] = np.array(L.ph_frame_time(a.time))
+    if a.anim_time:
+        L.ph_anim_frame_time.restype = C.c_double
+        L.ph_anim_frame_time.argtypes = [C.c_int, C.c_float]
+        out["anim_frame_seconds"] = np.array(L.ph_anim_frame_time(a.anim_time, 0.013))
+        print("anim_frame_ms %.4f" % (float(out["anim_frame_seconds"]) * 1e3))
     np.savez_compressed(a.out, **out)
     L.ph_close()
     print("ok", a.plugin, str(out["render_system"]), "tris", out["stats"][0], "batches", out["stats"][1])
