@@ -64,6 +64,18 @@ void CudaHardwareBuffer::copyData(HardwareBuffer& srcBuffer, size_t srcOffset, s
                                   bool discardWholeBuffer)
 {
     // srcBuffer is the other buffer's delegate (HardwareBuffer::copyData, OgreHardwareBuffer.h:326-336)
+    if (auto other = dynamic_cast<CudaHardwareBuffer*>(&srcBuffer))
+    {
+        // both live on the device, whose copy is the current one in stream order (uploads are enqueued at unlock): copy there,
+        // the destination's shadow is refreshed when the host next locks it
+        if (!length) return;
+        OgreAssert(srcOffset + length <= other->getSizeInBytes() && dstOffset + length <= mSizeInBytes, "copy out of range");
+        CudaRenderSystem::flushPendingDraws();
+        OGRECU_THROW_IF(ogrecu_memcpy_d2d(CudaRenderSystem::getInstance()->getContext(), const_cast<void*>(getDevicePtr(dstOffset)),
+                                          other->getDevicePtr(srcOffset), length));
+        OGRECU_THROW_IF(ogrecu_buf_mark_device_dirty(mBuf, dstOffset, length));
+        return;
+    }
     const void* src = srcBuffer.lock(srcOffset, length, HBL_READ_ONLY);
     writeData(dstOffset, length, src, discardWholeBuffer);
     srcBuffer.unlock();

@@ -11,6 +11,7 @@
 #include <OgreRenderTexture.h>
 #include "OgreCudaSkeletonPalettes.h"
 #include "OgreCudaShadowVolume.h"
+#include "OgreCudaPoseAnimation.h"
 #include <OgreShadowCaster.h>
 #include <OgreEdgeListBuilder.h>
 
@@ -257,6 +258,70 @@ API long ph_rtt_scaled_check(uint32_t l, uint32_t t, uint32_t r, uint32_t b, uin
     for (size_t i = 0; i < want.size(); ++i) bad += want[i] != got[i];
     return bad;
     CATCH(-1)
+}
+
+/* -------- pose animation: a hand-built pose-animated Entity (as oracle/ref_driver.cpp ref_pose_entity) evaluated twice -------- */
+// `engine`: OGRE's own Entity::_updateAnimation on buffers of the render system under test (host arithmetic through our
+// lock / unlock); `device`: CudaPoseAnimation (plugin class over ogrecu_pose_*) on a clone of the same vertex data.
+// out6 arrays: nverts x (pos, normal).  CUDA plugin only.
+API int ph_pose_entity(uint32_t nverts, const float* posnorm6, uint32_t nposes, const uint32_t* pose_off, const uint32_t* idx, const float* off3,
+                       const float* nrm3, const float* influence, int with_normals, float* engine6, float* device6)
+{
+    TRY
+    static int serial = 0;
+    const String name = "ph_pose_" + StringConverter::toString(serial++);
+    MeshPtr m = MeshManager::getSingleton().createManual(name, ResourceGroupManager::DEFAULT_RESOURCE_GROUP_NAME);
+    SubMesh* sub = m->createSubMesh();
+    sub->useSharedVertices = false;
+    sub->vertexData = OGRE_NEW VertexData();
+    sub->vertexData->vertexCount = nverts;
+    sub->vertexData->vertexDeclaration->addElement(0, 0, VET_FLOAT3, VES_POSITION);
+    sub->vertexData->vertexDeclaration->addElement(0, 12, VET_FLOAT3, VES_NORMAL);
+    auto vb = HardwareBufferManager::getSingleton().createVertexBuffer(24, nverts, HBU_CPU_TO_GPU);
+    vb->writeData(0, (size_t)nverts * 24, posnorm6, true);
+    sub->vertexData->vertexBufferBinding->setBinding(0, vb);
+    const uint16_t tri[3] = {0, (uint16_t)(nverts > 1 ? 1 : 0), (uint16_t)(nverts > 2 ? 2 : 0)};
+    sub->indexData->indexBuffer = HardwareBufferManager::getSingleton().createIndexBuffer(HardwareIndexBuffer::IT_16BIT, 3, HBU_CPU_TO_GPU);
+    sub->indexData->indexBuffer->writeData(0, 6, tri, true);
+    sub->indexData->indexCount = 3;
+    m->_setBounds(AxisAlignedBox(-100, -100, -100, 100, 100, 100));
+    m->_setBoundingSphereRadius(200);
+    for (uint32_t p = 0; p < nposes; ++p) {
+        Pose* pose = m->createPose(1, "pose" + StringConverter::toString(p));
+        for (uint32_t k = pose_off[p]; k < pose_off[p + 1]; ++k) {
+            const Vector3f o(off3[3 * k], off3[3 * k + 1], off3[3 * k + 2]);
+            if (with_normals) pose->addVertex(idx[k], o, Vector3f(nrm3[3 * k], nrm3[3 * k + 1], nrm3[3 * k + 2]));
+            else pose->addVertex(idx[k], o);
+        }
+    }
+    Animation* anim = m->createAnimation("manual", 0);
+    VertexAnimationTrack* track = anim->createVertexTrack(1, VAT_POSE);
+    VertexPoseKeyFrame* kf = track->createVertexPoseKeyFrame(0);
+    for (uint32_t p = 0; p < nposes; ++p) kf->addPoseReference((ushort)p, influence[p]);
+    m->load();
+    Entity* e = g->sm->createEntity(m);
+    g->sm->getRootSceneNode()->createChildSceneNode()->attachObject(e);
+    AnimationState* as = e->getAnimationState("manual");
+    as->setEnabled(true);
+    as->setTimePosition(0);
+    e->addSoftwareAnimationRequest(with_normals != 0);
+    g->root->renderOneFrame();
+    e->_updateAnimation();
+    VertexData* vd = e->getSubEntity(0)->_getSoftwareVertexAnimVertexData();
+    auto ob = vd->vertexBufferBinding->getBuffer(vd->vertexDeclaration->findElementBySemantic(VES_POSITION)->getSource());
+    if (ob->getVertexSize() != 24) { g_err = "unexpected vertex size"; return 3; }
+    ob->readData(0, (size_t)nverts * 24, engine6);
+    // the same frame on the device, into a clone made the way Entity makes its own (Entity::cloneVertexDataRemoveBlendInfo)
+    CudaPoseAnimation dev(m.get());
+    std::unique_ptr<VertexData> clone(sub->vertexData->clone(true));
+    dev.initialise(sub->vertexData, clone.get(), with_normals != 0);
+    dev.applyKeyFrames(kf, kf, 0.0f, as->getWeight(), clone.get());
+    if (with_normals) dev.finalise(sub->vertexData, clone.get());
+    auto cb = clone->vertexBufferBinding->getBuffer(0);
+    cb->readData(0, (size_t)nverts * 24, device6);
+    e->setVisible(false);
+    return 0;
+    CATCH(1)
 }
 
 // Show the render texture on a full-window quad (textured, unlit) and render the window: exercises

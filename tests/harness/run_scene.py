@@ -37,6 +37,8 @@ def main():
     ap.add_argument("--formats", default="", help="comma-separated Ogre::PixelFormat names: read-back in that format vs host PixelUtil")
     ap.add_argument("--pass-state", default="", help="cull,depthfunc,alphafunc,alpharef for every sub-entity's pass (0/-1/-1/0 = keep); "
                                                      "honoured by the CUDA plugin only when PH_BEYOND_TINY is set in the environment")
+    ap.add_argument("--pose-frames", action="store_true", help="CUDA plugin: the pose-animated frames of tests/golden/pose_blend.npz "
+                                                               "through the engine on our buffers and through CudaPoseAnimation")
     ap.add_argument("--scaled", action="store_true", help="with --rtt: scaled read-backs of the render texture vs the real Image::scale")
     ap.add_argument("--shadow", type=int, default=0, help="N shadow-volume cases: real generateShadowVolume vs CudaShadowVolume")
     ap.add_argument("--palettes", type=int, default=0, help="bone palettes at N time positions: engine vs CudaSkeletonPalettes")
@@ -109,6 +111,17 @@ def main():
             if k == 0:
                 out["shadow_indices_emitted"] = np.array(int((eng != 0xCDCD).sum()))
         out["shadow_cases"], out["shadow_mismatches"] = np.array(a.shadow), np.array(bad, np.int64)
+    if a.pose_frames:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from datagen import pose_entity_case
+        frames = np.load(os.path.join(ROOT, "tests", "golden", "pose_blend.npz"))["frames"]
+        L.ph_pose_entity.argtypes = [C.c_uint32, C.c_void_p, C.c_uint32] + [C.c_void_p] * 5 + [C.c_int, C.c_void_p, C.c_void_p]
+        for k, (seed, nv, nposes, normals) in enumerate(frames):
+            base, offs, idx, off, nrm, infl = pose_entity_case(int(seed), int(nv), int(nposes))
+            eng = np.zeros((int(nv), 6), np.float32); dev = np.zeros_like(eng)
+            ok(L.ph_pose_entity(int(nv), base.ctypes.data, int(nposes), offs.ctypes.data, idx.ctypes.data, off.ctypes.data, nrm.ctypes.data,
+                                infl.ctypes.data, int(normals), eng.ctypes.data, dev.ctypes.data), "ph_pose_entity")
+            out["pose_engine_%d" % k], out["pose_device_%d" % k] = eng, dev
     if a.pass_state:
         ok(L.ph_set_pass_state(*[int(v) for v in a.pass_state.split(",")]), "ph_set_pass_state")
     ok(L.ph_render(), "ph_render")

@@ -179,3 +179,16 @@ def test_beyond_tiny_mode_through_the_plugin(tmp_path):
     assert not covered(greater).any()
     rejected = run_scene(tmp_path, "cuda", *args, "--pass-state", "0,-1,2,255", beyond_tiny=True)["colour"]  # alpha < 255: opaque texels fail
     assert covered(rejected).sum() < covered(tiny).sum()
+
+
+def test_pose_animation_through_the_plugin(tmp_path):
+    """SURVEY §8f rank 3 at the plugin level: whole pose-animated frames of a real Entity.  (a) OGRE's own
+    Entity::_updateAnimation running on the CUDA render system's buffers (host arithmetic through our lock / unlock / copyData,
+    the latter device to device) and (b) CudaPoseAnimation (plugin class over ogrecu_pose_*) on a clone of the vertex data —
+    both bit-identical to the frames the reference build produced (tests/golden/pose_blend.npz)."""
+    z = run_scene(tmp_path, "cuda", "--mesh", "ogrehead.mesh", "--size", "64x64", "--pose-frames")
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pose_blend.npz"))
+    assert len(g["frames"]) >= 4
+    for k in range(len(g["frames"])):
+        assert np.array_equal(bits(z["pose_engine_%d" % k]), bits(g["f%d" % k])), k
+        assert np.array_equal(bits(z["pose_device_%d" % k]), bits(g["f%d" % k])), k
