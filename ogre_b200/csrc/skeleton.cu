@@ -226,11 +226,17 @@ __global__ void __launch_bounds__(512) skel_palette_kernel(const SkelDev S, uint
 // lanes: 55 us for 10 000 x 69; kept for A/B through "skel_mode".)
 constexpr int SK_INST = 16;                 // instances per CTA
 constexpr int SK_SLOTS = 16;                // bone slots per CTA (32: 52.9 us instead of 49.8)
-constexpr int SK_XF = 10 * SK_INST + 16;    // floats per bone in shared memory (+16: the two half-warps hit different banks)
+constexpr int SK_XF = 10 * SK_INST;         // floats per bone in shared memory: [component][instance], the component index of
+                                            // odd tree positions XOR 1 (sk_at) so that a warp's two half-warps — positions p and
+                                            // p + 1 — hit different bank halves.  (A 16-float pad per bone did the same with 48.6 KB
+                                            // per CTA for Sinbad's 69 bones: four CTAs per SM = 592 slots for the 625 CTAs of
+                                            // 10 000 instances, i.e. a second wave of 33 CTAs doubled the 50 us launch.  44.4 KB
+                                            // admit five: one wave.)
+__device__ __forceinline__ uint32_t sk_at(uint32_t p, uint32_t c) { return p * SK_XF + ((c * SK_INST) ^ ((p & 1u) * SK_INST)); }
 
 struct StatePre { int32_t anim; float tp; uint32_t gi; float w; };
 
-__global__ void __launch_bounds__(SK_INST * SK_SLOTS) skel_palette_kernel2(const SkelDev S, uint32_t num_instances, uint32_t num_states,
+__global__ void __launch_bounds__(SK_INST * SK_SLOTS, 5) skel_palette_kernel2(const SkelDev S, uint32_t num_instances, uint32_t num_states,
                                                                            const int32_t* __restrict__ anim, const float* __restrict__ time,
                                                                            const float* __restrict__ weight, float* __restrict__ out,
                                                                            size_t stride_floats)
@@ -240,6 +246,18 @@ __global__ void __launch_bounds__(SK_INST * SK_SLOTS) skel_palette_kernel2(const
     const uint32_t ix = threadIdx.x, slot = threadIdx.y;
     const uint32_t inst = blockIdx.x * SK_INST + ix;
     const bool live = inst < num_instances;
+
+    auto store_s = [&](uint32_t p, const Xform& X) {
+        float* o = s_xf + ix;
+        o[sk_at(p, 0)] = X.p.x; o[sk_at(p, 1)] = X.p.y; o[sk_at(p, 2)] = X.p.z; o[sk_at(p, 3)] = X.q.w; o[sk_at(p, 4)] = X.q.x;
+        o[sk_at(p, 5)] = X.q.y; o[sk_at(p, 6)] = X.q.z; o[sk_at(p, 7)] = X.s.x; o[sk_at(p, 8)] = X.s.y; o[sk_at(p, 9)] = X.s.z;
+    };
+    auto load_s = [&](uint32_t p) {
+        const float* o = s_xf + ix;
+        return Xform{Vec3{o[sk_at(p, 0)], o[sk_at(p, 1)], o[sk_at(p, 2)]},
+                     Quat{o[sk_at(p, 3)], o[sk_at(p, 4)], o[sk_at(p, 5)], o[sk_at(p, 6)]},
+                     Vec3{o[sk_at(p, 7)], o[sk_at(p, 8)], o[sk_at(p, 9)]}};
+    };
 
     // ---- phase 0: per (instance, state): wrapped time, global key index, effective weight — once, not once per bone
     for (uint32_t s = slot; s < num_states; s += SK_SLOTS) {
@@ -314,26 +332,17 @@ __global__ void __launch_bounds__(SK_INST * SK_SLOTS) skel_palette_kernel2(const
                 L.s.x *= sc.x; L.s.y *= sc.y; L.s.z *= sc.z;
             }
         }
-        float* o = s_xf + (size_t)p * SK_XF + ix;
-        o[0] = L.p.x; o[SK_INST] = L.p.y; o[2 * SK_INST] = L.p.z; o[3 * SK_INST] = L.q.w; o[4 * SK_INST] = L.q.x; o[5 * SK_INST] = L.q.y;
-        o[6 * SK_INST] = L.q.z; o[7 * SK_INST] = L.s.x; o[8 * SK_INST] = L.s.y; o[9 * SK_INST] = L.s.z;
+        store_s(p, L);
     }
     __syncthreads();
 
-    auto load_s = [&](uint32_t p) {
-        const float* o = s_xf + (size_t)p * SK_XF + ix;
-        return Xform{Vec3{o[0], o[SK_INST], o[2 * SK_INST]}, Quat{o[3 * SK_INST], o[4 * SK_INST], o[5 * SK_INST], o[6 * SK_INST]},
-                     Vec3{o[7 * SK_INST], o[8 * SK_INST], o[9 * SK_INST]}};
-    };
     // ---- phase 2: derived transforms in place, one tree level per round (level 0: derived = local)
     for (uint32_t l = 1; l < S.num_levels; ++l) {
         const uint32_t a = S.level_start[l], e = S.level_start[l + 1];
         for (uint32_t p = a + slot; p < e; p += SK_SLOTS) {
             const uint32_t b = S.order[p];
             const Xform D = derive(load_s((uint32_t)S.ppos[p]), load_s(p), S.inherit[2 * b] != 0, S.inherit[2 * b + 1] != 0);
-            float* o = s_xf + (size_t)p * SK_XF + ix;
-            o[0] = D.p.x; o[SK_INST] = D.p.y; o[2 * SK_INST] = D.p.z; o[3 * SK_INST] = D.q.w; o[4 * SK_INST] = D.q.x; o[5 * SK_INST] = D.q.y;
-            o[6 * SK_INST] = D.q.z; o[7 * SK_INST] = D.s.x; o[8 * SK_INST] = D.s.y; o[9 * SK_INST] = D.s.z;
+            store_s(p, D);
         }
         __syncthreads();
     }
