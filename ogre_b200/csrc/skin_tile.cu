@@ -300,6 +300,18 @@ int launch_skin_tile(ogrecu_ctx* ctx, SkinTileParams P, uint32_t nw, bool norm, 
     P.tma_store = (force != 1 && al(P.dst, P.dst_inst_stride, 16)) ? 1u : 0u;
     P.load_unit = (vs == 24 && al(P.src, P.src_inst_stride, 8)) ? 8u : 4u;
     P.store_unit = (vs == 24 && al(P.dst, P.dst_inst_stride, 8)) ? 8u : 4u;
+    // one instance, one long stream: persistent CTAs with a resident palette (skin_stream.cu), the tail below 256 vertices here
+    if (force == 0 && skin_stream_eligible(P, nw, fused)) {
+        uint32_t done = 0;
+        OGRECU_CHECK(launch_skin_stream(ctx, P, nw, norm, &done));
+        if (done == P.num_vertices) return OGRECU_OK;
+        SkinTileParams T = P;
+        T.src += (size_t)done * vs; T.dst += (size_t)done * vs;
+        T.blend_index += (size_t)done * P.blend_index_stride;
+        T.blend_weight = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(P.blend_weight) + (size_t)done * P.blend_weight_stride);
+        T.num_vertices = P.num_vertices - done;
+        return launch_skin_tile(ctx, T, nw, norm, fused);
+    }
     // many instances of a pos+normal mesh with one source: instances across the lanes (skin_wide.cu)
     if (force == 4 && skin_wide_eligible(P, norm, fused)) return launch_skin_wide(ctx, P, nw, fused);
     // two or more instances: the pair kernel (skin_pair.cu, packed f32x2, two instances per pass)

@@ -318,3 +318,85 @@ def test_multi_job_frame_equals_single_calls(gpu_ctx):
     check(lib().ogrecu_memcpy_h2d(ctx.handle, da0.ptr, marker.ctypes.data, 16))
     ctx.sync()
     assert (da0.download(np.uint8, 16) == 0x7f).all(), "a side-stream launch finished after work queued behind the call"
+
+
+STREAM_CASES = [
+    # n,       nw, nb, norm   (one instance; n >= 2048 and aligned bases take skin_stream_kernel in skin_mode 0)
+    (2048, 4, 64, True),          # exactly eight tiles, no tail
+    (2049, 4, 64, True),          # one-vertex tail on the tile kernel
+    (4099, 3, 55, True),
+    (5000, 2, 18, True),
+    (2303, 1, 7, True),
+    (70000, 4, 256, True),        # maximum palette (> 48 KB of shared memory)
+    (9001, 4, 30, False),         # positions only
+    (3000, 2, 9, False),
+    (256 * 2500 + 77, 4, 64, True),   # more tiles than resident CTAs: every CTA walks several tiles, the 3-stage ring wraps
+    (256 * 1900, 1, 64, False),
+]
+
+
+@pytest.mark.parametrize("case", STREAM_CASES, ids=lambda c: "n%d_w%d_b%d_%s" % (c[0], c[1], c[2], "pn" if c[3] else "p"))
+def test_single_stream_kernel(gpu_ctx, case):
+    """ogre_b200/csrc/skin_stream.cu: one softwareVertexSkinning call over a long stream (persistent CTAs, resident palette,
+    TMA pipeline over tiles) vs the oracle, bit patterns; and the same call forced onto the tile kernel (skin_mode 3) and the
+    one-thread-per-vertex kernel (skin_mode 2) gives the same bytes, guard bytes around the destination untouched."""
+    from ogre_b200 import check, lib
+    n, nw, nb, norm = case
+    ctx = gpu_ctx
+    vs = 24 if norm else 12
+    rng = np.random.default_rng(n + 7 * nw)
+    src, blend, pals, bone_map = make_inputs(rng, n, nw, nb, 1, norm, True)
+    dsrc = ctx.to_device(src.reshape(-1).view(np.uint8))
+    dbl, dpal, dmap = ctx.to_device(blend), ctx.to_device(pals), ctx.to_device(bone_map)
+    ref = oracle_skin(src[0], blend, np.ascontiguousarray(pals[0][bone_map]), nw, n, norm)
+    results = {}
+    for mode in (0, 3, 2):
+        ddst = ctx.alloc(n * vs + 128)
+        ddst.upload(np.full(n * vs + 128, 0xCD, np.uint8))
+        j = gpu_job(ctx, dsrc.ptr, ddst.ptr + 64, dbl, dpal, dmap, n, nw, nb, norm)
+        ctx.set_config_option("skin_mode", mode)
+        try:
+            check(lib().ogrecu_skin_instanced_dev(ctx.handle, C.byref(j), 1, 0, 0, 0))
+            ctx.sync()
+        finally:
+            ctx.set_config_option("skin_mode", 0)
+        raw = ddst.download(np.uint8)
+        assert (raw[:64] == 0xCD).all() and (raw[64 + n * vs:] == 0xCD).all(), (case, mode, "wrote outside the destination")
+        results[mode] = raw[64:64 + n * vs].copy()
+        ddst.free()
+    got = results[0].view(np.float32).reshape(n, vs // 4)
+    assert np.array_equal(bits(got), bits(ref)), case
+    assert np.array_equal(results[0], results[3]) and np.array_equal(results[0], results[2]), case
+    for b in (dsrc, dbl, dpal, dmap):
+        b.free()
+
+
+def test_single_stream_kernel_special_values(gpu_ctx):
+    # signed zeros, denormals, huge and non-finite values through the stream kernel = the tile kernel, byte for byte
+    from ogre_b200 import check, lib
+    ctx = gpu_ctx
+    n, nw, nb = 4096, 4, 16
+    rng = np.random.default_rng(3)
+    src, blend, pals, bone_map = make_inputs(rng, n, nw, nb, 1, True, True)
+    special = np.array([0.0, -0.0, 1e-42, -1e-42, 3e38, -3e38, np.inf, -np.inf, np.nan, 1.0], np.float32)
+    src.reshape(-1)[::5] = special[rng.integers(0, len(special), src.reshape(-1)[::5].size)]
+    pals.reshape(-1)[::7] = special[rng.integers(0, len(special), pals.reshape(-1)[::7].size)]
+    w = blend[:, 4:].view(np.float32)
+    w[::3, 0] = 0.0; w[1::9, 1] = -0.0
+    dsrc, dbl, dpal, dmap = ctx.to_device(src.reshape(-1).view(np.uint8)), ctx.to_device(blend), ctx.to_device(pals), ctx.to_device(bone_map)
+    out = {}
+    for mode in (0, 3):
+        ddst = ctx.alloc(n * 24)
+        j = gpu_job(ctx, dsrc.ptr, ddst.ptr, dbl, dpal, dmap, n, nw, nb, True)
+        ctx.set_config_option("skin_mode", mode)
+        try:
+            check(lib().ogrecu_skin_instanced_dev(ctx.handle, C.byref(j), 1, 0, 0, 0))
+            ctx.sync()
+        finally:
+            ctx.set_config_option("skin_mode", 0)
+        out[mode] = ddst.download(np.uint8)[:n * 24].view(np.uint32).copy()
+        ddst.free()
+    # NaN payloads may differ between code paths only if the arithmetic differs; it is the same code, so compare raw bits
+    assert np.array_equal(out[0], out[3])
+    for b in (dsrc, dbl, dpal, dmap):
+        b.free()
