@@ -8,13 +8,13 @@
 //
 // Why a separate kernel: skin_tile_kernel pipelines over the INSTANCES of a tile.  With one instance a CTA loaded its blend
 // indices (LDG), gathered the whole palette (3 KB for 64 bones, per 17 KB tile), fetched one source tile, computed, stored and
-// exited — a serial latency chain per CTA hidden only by the four to seven CTAs an SM holds: 0.385 of HBM peak
-// (profiles/r01q_microbench.txt).  Here
+// exited — a serial latency chain per CTA hidden only by the four to seven CTAs an SM holds: 0.385 of HBM peak for four
+// weights, 0.44 for one or two (profiles/r01q_microbench.txt).  Here
 //   * a CTA gathers the palette ONCE and then walks tiles blockIdx.x, + gridDim.x, ... (grid = resident CTAs);
 //   * the source tile and the tile's blend stream (UBYTE4 indices + n float weights interleaved, OGRE's layout,
 //     OgreMesh.cpp:775-800) are both contiguous in memory, so each arrives by ONE cp.async.bulk with mbarrier completion,
-//     issued two tiles ahead; the blend values are read from shared memory (stride 4 + 4n bytes = an odd number of
-//     words: conflict free) instead of by scattered LDG;
+//     issued two tiles ahead; the blend values are read from shared memory (OGRE's stride of 4 + 4n bytes is an odd number of
+//     words for n = 2 and 4: conflict free) instead of by scattered LDG;
 //   * results leave through a double-buffered shared tile by one bulk store per tile, as in skin_tile_kernel.
 // The tail (num_vertices % 256) and anything that does not meet the layout / alignment conditions stay on skin_tile_kernel.
 #include "common.cuh"
@@ -26,7 +26,9 @@ using namespace ogrecu;
 namespace ogrecu {
 
 constexpr int SS_THREADS = 256;
-constexpr int SS_STAGES = 3;
+#ifndef SS_DEFAULT_STAGES
+#define SS_DEFAULT_STAGES 3
+#endif
 
 struct SkinStreamParams {
     const uint8_t* src;        // VS bytes per vertex, 16-byte aligned
@@ -35,6 +37,8 @@ struct SkinStreamParams {
     const float* palette;      // Affine3, 16 floats each, 16-byte aligned
     const uint16_t* bone_map;  // optional
     uint32_t num_matrices, num_tiles;
+    uint32_t blend_stride;     // bytes per vertex of the blend stream (>= 4 + 4 * NW, multiple of 4)
+    uint32_t copy_shift;       // log2 of the palette copies in shared memory (3: one per 16-byte bank group, see s_pal)
 };
 
 __device__ __forceinline__ uint32_t ss_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -47,21 +51,44 @@ __device__ __forceinline__ void ss_mbar_wait(uint32_t bar, uint32_t parity)
     } while (!ok);
 }
 
-template <int NW, bool NORM>
+// skin_math.cuh's collapse_matrix with the rows of matrix m at pal[(3 * m + r) << shift]: same operations, same order
+// (NW == 1 ignores the weight, NW == 2 is lerp(M0, M1, w1), NW >= 3 is w0 * M0 then accumulate; OgreOptimisedUtilSSE.cpp:278-368)
+template <int NW>
+__device__ __forceinline__ void collapse_rows(const float4* __restrict__ pal, const uint32_t shift, const uint32_t idx4, const float* w,
+                                              float4& r0, float4& r1, float4& r2)
+{
+    const uint32_t one = 1u << shift;
+    const float4* m0 = pal + ((3u * (idx4 & 0xffu)) << shift);
+    if (NW == 1) {
+        r0 = m0[0]; r1 = m0[one]; r2 = m0[2 * one];
+    } else if (NW == 2) {
+        const float4* m1 = pal + ((3u * ((idx4 >> 8) & 0xffu)) << shift);
+        r0 = lerp4(m0[0], m1[0], w[1]); r1 = lerp4(m0[one], m1[one], w[1]); r2 = lerp4(m0[2 * one], m1[2 * one], w[1]);
+    } else {
+        r0 = mul4(m0[0], w[0]); r1 = mul4(m0[one], w[0]); r2 = mul4(m0[2 * one], w[0]);
+#pragma unroll
+        for (int b = 1; b < NW; ++b) {
+            const float4* mb = pal + ((3u * ((idx4 >> (8 * b)) & 0xffu)) << shift);
+            r0 = madd4(mb[0], w[b], r0); r1 = madd4(mb[one], w[b], r1); r2 = madd4(mb[2 * one], w[b], r2);
+        }
+    }
+}
+
+template <int NW, bool NORM, int SS_STAGES>
 __global__ void __launch_bounds__(SS_THREADS, 3) skin_stream_kernel(const __grid_constant__ SkinStreamParams P)
 {
     constexpr int VS = NORM ? 24 : 12;              // bytes per vertex
-    constexpr int BS = 4 + 4 * NW;                  // bytes per vertex of the blend stream
     constexpr int TILE_BYTES = SS_THREADS * VS;
-    constexpr int BLEND_BYTES = SS_THREADS * BS;
+    const uint32_t BS = P.blend_stride;             // bytes per vertex of the blend stream
+    const uint32_t BLEND_BYTES = SS_THREADS * BS;
 
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t npal = P.num_matrices * 3;                                   // float4 rows
     uint8_t* s_dst = smem;                                                      // [2][TILE_BYTES]
     uint8_t* s_src = s_dst + 2 * TILE_BYTES;                                    // [STAGES][TILE_BYTES]
     uint8_t* s_bl = s_src + SS_STAGES * TILE_BYTES;                             // [STAGES][BLEND_BYTES]
-    float4* s_pal = reinterpret_cast<float4*>(s_bl + SS_STAGES * BLEND_BYTES);  // [npal]
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_pal + npal);                // [STAGES]
+    float4* s_pal = reinterpret_cast<float4*>(s_bl + SS_STAGES * BLEND_BYTES);  // [npal][copies]
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_pal + ((size_t)npal << P.copy_shift));   // [STAGES]
 
     const uint32_t tid = threadIdx.x;
     if (tid == 0) {
@@ -71,13 +98,21 @@ __global__ void __launch_bounds__(SS_THREADS, 3) skin_stream_kernel(const __grid
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    // the palette, once per CTA: rows 0..2 of every matrix, through bone_map (Mesh::prepareMatricesForVertexBlend, OgreMesh.cpp:1782-1790)
+    // The palette, once per CTA: rows 0..2 of every matrix, through bone_map (Mesh::prepareMatricesForVertexBlend,
+    // OgreMesh.cpp:1782-1790), in 2^copy_shift interleaved COPIES: row p of copy q sits at float4 slot (p << copy_shift) + q, and
+    // lane l reads copy l mod copies.  With eight copies every lane of a quarter-warp owns one 16-byte bank group, so an
+    // LDS.128 of 32 unrelated bone rows takes its minimum of four wavefronts whatever the indices are — with one copy and the
+    // uniformly random indices of the SURVEY §8d stream it took about ten: 0.591 of HBM peak with one copy, 0.604 / 0.670 / 0.967
+    // with two / four / eight (profiles/r01q_microbench.txt).
+    const uint32_t cs = P.copy_shift, ncopy = 1u << cs;
     for (uint32_t p = tid; p < npal; p += SS_THREADS) {
         const uint32_t m = p / 3, r = p - m * 3;
         const uint32_t sm = P.bone_map ? (uint32_t)__ldg(P.bone_map + m) : m;
-        s_pal[p] = __ldg(reinterpret_cast<const float4*>(P.palette + (size_t)sm * 16 + r * 4));
+        const float4 row = __ldg(reinterpret_cast<const float4*>(P.palette + (size_t)sm * 16 + r * 4));
+        for (uint32_t q = 0; q < ncopy; ++q) s_pal[(p << cs) + q] = row;
     }
     __syncthreads();                                                            // barriers initialised, palette visible
+    const float4* my_pal = s_pal + (tid & (ncopy - 1u));
 
     const uint32_t first = blockIdx.x, step = gridDim.x;
     const uint32_t ntiles = P.num_tiles;
@@ -119,7 +154,7 @@ __global__ void __launch_bounds__(SS_THREADS, 3) skin_stream_kernel(const __grid
             x = f[0]; y = f[1]; z = f[2];
         }
         float4 r0, r1, r2;
-        collapse_matrix<NW>(s_pal, idx4, w, r0, r1, r2);
+        collapse_rows<NW>(my_pal, cs, idx4, w, r0, r1, r2);
         float o[NORM ? 6 : 3];
         xform_pos(r0, r1, r2, x, y, z, o[0], o[1], o[2]);
         if (NORM) xform_norm(r0, r1, r2, nx, ny, nz, o[3], o[4], o[5]);
@@ -144,16 +179,17 @@ __global__ void __launch_bounds__(SS_THREADS, 3) skin_stream_kernel(const __grid
     if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory must outlive the reads
 }
 
-static size_t skin_stream_smem(uint32_t nw, bool norm, uint32_t num_matrices)
+static size_t skin_stream_smem(uint32_t blend_stride, bool norm, uint32_t num_matrices, uint32_t copy_shift, int stages)
 {
-    const size_t tile = (size_t)SS_THREADS * (norm ? 24 : 12), blend = (size_t)SS_THREADS * (4 + 4 * nw);
-    return 2 * tile + SS_STAGES * (tile + blend) + (size_t)num_matrices * 48 + SS_STAGES * 8;
+    const size_t tile = (size_t)SS_THREADS * (norm ? 24 : 12), blend = (size_t)SS_THREADS * blend_stride;
+    return 2 * tile + stages * (tile + blend) + (((size_t)num_matrices * 48) << copy_shift) + stages * 8;
 }
 
-template <int NW, bool NORM>
-static int launch_stream_one(ogrecu_ctx* ctx, const SkinStreamParams& P, size_t smem)
+template <int NW, bool NORM, int STAGES>
+static int launch_stream_st(ogrecu_ctx* ctx, const SkinStreamParams& P, bool norm)
 {
-    auto kern = skin_stream_kernel<NW, NORM>;
+    const size_t smem = skin_stream_smem(P.blend_stride, norm, P.num_matrices, P.copy_shift, STAGES);
+    auto kern = skin_stream_kernel<NW, NORM, STAGES>;
     if (smem > 48 * 1024) OGRECU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     OGRECU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SS_THREADS, smem));
@@ -165,12 +201,22 @@ static int launch_stream_one(ogrecu_ctx* ctx, const SkinStreamParams& P, size_t 
     return OGRECU_OK;
 }
 
+template <int NW, bool NORM>
+static int launch_stream_one(ogrecu_ctx* ctx, const SkinStreamParams& P, bool norm)
+{
+    static const int stages = getenv("OGRECU_STREAM_STAGES") ? atoi(getenv("OGRECU_STREAM_STAGES")) : SS_DEFAULT_STAGES;   // A/B
+    if (stages == 2) return launch_stream_st<NW, NORM, 2>(ctx, P, norm);
+    if (stages == 4) return launch_stream_st<NW, NORM, 4>(ctx, P, norm);
+    return launch_stream_st<NW, NORM, 3>(ctx, P, norm);
+}
+
 // One instance, dense layout, interleaved blend stream, everything 16-byte aligned, at least 8 full tiles.
 bool skin_stream_eligible(const SkinTileParams& P, uint32_t nw, bool fused)
 {
     if (fused || P.num_instances != 1 || P.num_vertices < 8u * SS_THREADS || P.num_matrices > 256) return false;
     if (reinterpret_cast<const uint8_t*>(P.blend_weight) != P.blend_index + 4) return false;
-    if (P.blend_weight_stride != 4 + 4 * nw || P.blend_index_stride != 4 + 4 * nw) return false;
+    if (P.blend_weight_stride != P.blend_index_stride || P.blend_index_stride < 4 + 4 * nw || (P.blend_index_stride & 3u) ||
+        P.blend_index_stride > 64) return false;
     return (((uintptr_t)P.src | (uintptr_t)P.dst | (uintptr_t)P.blend_index | (uintptr_t)P.palette) & 15u) == 0;
 }
 
@@ -180,17 +226,22 @@ int launch_skin_stream(ogrecu_ctx* ctx, const SkinTileParams& T, uint32_t nw, bo
     SkinStreamParams P;
     P.src = T.src; P.blend = T.blend_index; P.dst = T.dst; P.palette = T.palette; P.bone_map = T.bone_map;
     P.num_matrices = T.num_matrices; P.num_tiles = T.num_vertices / SS_THREADS;
+    P.blend_stride = T.blend_index_stride;
+    // palette copies: eight (one per bank group) while they fit in 24 KB, then four, two, one
+    static const int forced = getenv("OGRECU_STREAM_COPIES") ? atoi(getenv("OGRECU_STREAM_COPIES")) : -1;   // A/B: log2 of the copies
+    P.copy_shift = T.num_matrices <= 64 ? 3u : T.num_matrices <= 128 ? 2u : 1u;
+    if (nw <= 2 && P.copy_shift > 2) P.copy_shift = 2;   // few row loads per vertex: four copies and one more CTA per SM measured best
+    if (forced >= 0 && forced <= 3) P.copy_shift = (uint32_t)forced;
     *done = P.num_tiles * SS_THREADS;
-    const size_t smem = skin_stream_smem(nw, norm, T.num_matrices);
     switch (nw * 2 + (norm ? 1 : 0)) {
-    case 2: return launch_stream_one<1, false>(ctx, P, smem);
-    case 3: return launch_stream_one<1, true>(ctx, P, smem);
-    case 4: return launch_stream_one<2, false>(ctx, P, smem);
-    case 5: return launch_stream_one<2, true>(ctx, P, smem);
-    case 6: return launch_stream_one<3, false>(ctx, P, smem);
-    case 7: return launch_stream_one<3, true>(ctx, P, smem);
-    case 8: return launch_stream_one<4, false>(ctx, P, smem);
-    default: return launch_stream_one<4, true>(ctx, P, smem);
+    case 2: return launch_stream_one<1, false>(ctx, P, norm);
+    case 3: return launch_stream_one<1, true>(ctx, P, norm);
+    case 4: return launch_stream_one<2, false>(ctx, P, norm);
+    case 5: return launch_stream_one<2, true>(ctx, P, norm);
+    case 6: return launch_stream_one<3, false>(ctx, P, norm);
+    case 7: return launch_stream_one<3, true>(ctx, P, norm);
+    case 8: return launch_stream_one<4, false>(ctx, P, norm);
+    default: return launch_stream_one<4, true>(ctx, P, norm);
     }
 }
 

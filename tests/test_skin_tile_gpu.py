@@ -400,3 +400,28 @@ def test_single_stream_kernel_special_values(gpu_ctx):
     assert np.array_equal(out[0], out[3])
     for b in (dsrc, dbl, dpal, dmap):
         b.free()
+
+
+@pytest.mark.parametrize("nw_used", [1, 2, 3])
+def test_single_stream_kernel_wider_blend_stride(gpu_ctx, nw_used):
+    # a blend stream laid out for four weights (stride 20) skinned with fewer weights per vertex: the stream kernel takes
+    # any stride that is a multiple of 4 bytes
+    from ogre_b200 import check, lib
+    ctx = gpu_ctx
+    n, nb = 256 * 700 + 31, 40
+    rng = np.random.default_rng(50 + nw_used)
+    src, blend, pals, bone_map = make_inputs(rng, n, 4, nb, 1, True, True)
+    dsrc, dbl, dpal, dmap = ctx.to_device(src.reshape(-1).view(np.uint8)), ctx.to_device(blend), ctx.to_device(pals), ctx.to_device(bone_map)
+    ddst = ctx.alloc(n * 24)
+    j = gpu_job(ctx, dsrc.ptr, ddst.ptr, dbl, dpal, dmap, n, 4, nb, True)
+    j.num_weights = nw_used                      # strides stay 20
+    check(lib().ogrecu_skin_instanced_dev(ctx.handle, C.byref(j), 1, 0, 0, 0))
+    ctx.sync()
+    got = ddst.download(np.uint8)[:n * 24].view(np.float32).reshape(n, 6)
+    ref = np.zeros((n, 6), np.float32)
+    s = np.ascontiguousarray(src[0])
+    oracle.skin("sse", s.ctypes.data, ref.ctypes.data, s.ctypes.data + 12, ref.ctypes.data + 12, blend.ctypes.data + 4, blend.ctypes.data,
+                np.ascontiguousarray(pals[0][bone_map]), (24, 24, 24, 24, 20, 20), nw_used, n)
+    assert np.array_equal(bits(got), bits(ref))
+    for b in (dsrc, dbl, dpal, dmap, ddst):
+        b.free()
