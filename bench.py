@@ -19,7 +19,8 @@ Lines printed (rank 0, one JSON line):
              palettes + morph weights from pinned host memory and reads one instance's skinned
              vertices back (the skinned buffers themselves stay in HBM for _render)
   roofline   dominant kernel of the timed step (the 4-weight body sub-mesh launch) vs measured HBM peak;
-             extra.roofline_other_form carries the same for the other --form
+             extra.roofline_other_form carries the same for the other --form; extra.roofline_stream_case is SURVEY §8d's
+             synthetic roofline stream (one call, 2^24 distinct vertices, 68 B per vertex) measured the same way
   cpu_baseline  the unmodified reference (real OptimisedUtilSSE via oracle/_ref) on the host cores
 """
 import argparse
@@ -526,6 +527,48 @@ def run_ours(args):
         extra["morph_only_Mvert_per_s"] = ninst * nverts / (tot["morph"] * 1e-3) / 1e6
         pal_step = ninst * sum(len(s["bone_map"]) for s in subs) * 48
         bytes_step = ninst * nverts * (24 if args.form == "fused" else 72) + pal_step
+        # ---- SURVEY §8d "synthetic stream (roofline case)": ONE softwareVertexSkinning call over 2^24 distinct vertices, 64
+        # bones, 4 weights, uniformly random bone indices (mt19937-style: no locality), pos+normal stride 24, blend stride 20:
+        # 24 + 20 + 24 = 68 algorithmic bytes per vertex.  Outside the timed regions; the kernel is skin_stream_kernel.
+        try:
+            with torch.cuda.stream(stream):
+                sn, snb = 1 << 24, 64
+                g = torch.Generator(device=dev).manual_seed(1234)
+                s_src = torch.empty(sn, 6, device=dev).uniform_(-10, 10, generator=g)
+                s_w = torch.rand(sn, 4, device=dev, generator=g) + 0.05
+                s_w = s_w / s_w.sum(1, keepdim=True)
+                s_blend = torch.empty(sn, 20, device=dev, dtype=torch.uint8)
+                s_blend[:, :4] = torch.randint(0, snb, (sn, 4), device=dev, dtype=torch.uint8, generator=g)
+                s_blend[:, 4:] = s_w.contiguous().view(torch.uint8).reshape(sn, 16)
+                s_pal = torch.eye(4, device=dev).repeat(snb, 1, 1) + 0.01 * torch.randn(snb, 4, 4, device=dev, generator=g)
+                s_pal[:, 3, :] = torch.tensor([0, 0, 0, 1.0], device=dev)
+                s_pal = s_pal.contiguous()
+                s_dst = torch.empty(sn, 6, device=dev)
+            sj = SkinJob()
+            sj.src_pos, sj.src_norm = s_src.data_ptr(), s_src.data_ptr() + 12
+            sj.dst_pos, sj.dst_norm = s_dst.data_ptr(), s_dst.data_ptr() + 12
+            sj.blend_weight, sj.blend_index = s_blend.data_ptr() + 4, s_blend.data_ptr()
+            sj.palette, sj.bone_map = s_pal.data_ptr(), None
+            sj.src_pos_stride = sj.dst_pos_stride = sj.src_norm_stride = sj.dst_norm_stride = 24
+            sj.blend_weight_stride = sj.blend_index_stride = 20
+            sj.num_weights, sj.num_matrices, sj.num_vertices = 4, snb, sn
+            stream.synchronize()
+            for _ in range(3):
+                check(L.ogrecu_skin_instanced_dev(ctx.handle, C.byref(sj), 1, 0, 0, 0))
+            sev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(10)]
+            for a, b in sev:
+                a.record(stream)
+                check(L.ogrecu_skin_instanced_dev(ctx.handle, C.byref(sj), 1, 0, 0, 0))
+                b.record(stream)
+            stream.synchronize()
+            sdur = float(np.median([a.elapsed_time(b) for a, b in sev])) * 1e-3
+            extra["roofline_stream_case"] = {
+                "bound": "hbm", "kernel": "skin_stream_kernel<4,normals> (one call, 2^24 distinct vertices, 64 bones, random bone indices)",
+                "achieved": sn * 68 / sdur / 1e9, "peak": peak, "unit": "GB/s", "frac": sn * 68 / sdur / 1e9 / peak, "launch_ms": sdur * 1e3,
+                "algorithmic_bytes_per_launch": sn * 68, "Mvert_per_s": sn / sdur / 1e6}
+            del s_src, s_w, s_blend, s_pal, s_dst
+        except Exception as ex:      # never lose the contract line over the side measurement
+            extra["roofline_stream_case"] = {"error": repr(ex)}
         extra["step_compulsory_GBps"] = bytes_step / (ms / args.steps * 1e-3) / 1e9
         extra["step_frac_of_hbm_peak"] = extra["step_compulsory_GBps"] / peak
 
