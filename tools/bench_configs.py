@@ -527,6 +527,66 @@ def c5_split(ctx, T, args, rt, run, ntri, nidx, nverts):
             "identical_to_single_gpu_frame": ok, "stats_rank0_strip": strip_stats, "interleaved": interleaved, "sort_last": sort_last}
 
 
+def c2j(ctx, T, args):
+    """config 2, second mesh: jaiqua (1 sub-mesh, 2 460 vertices, 38 bones of which 23 used, 2 weights) x 10 000 animated
+    instances, the real mesh streams and poses of tests/golden/jaiqua_skin.npz; same step as bench.py's (morph + skin, fused
+    and separate).  bench.py itself stays on Sinbad (the workload its contract line names)."""
+    import torch
+    import bench
+    from ogre_b200 import SkinJob
+    bench.FIXTURE = os.path.join(ROOT, "tests", "golden", "jaiqua_skin.npz")
+    subs, palettes = bench.load_sinbad()
+    assert len(subs) == 1
+    s = subs[0]
+    n, ninst, nb = s["nverts"], 10000, palettes.shape[1]
+    pal_h, t_h = bench.instance_inputs(ninst, palettes, RANK)
+    dev = torch.device("cuda", LOCAL)
+    L = lib()
+    with torch.cuda.stream(T.stream):
+        d_pal, d_t = torch.from_numpy(pal_h).to(dev), torch.from_numpy(t_h).to(dev)
+        key1, key2 = torch.from_numpy(s["key1"]).to(dev), torch.from_numpy(s["key2"]).to(dev)
+        blend = torch.from_numpy(s["blend"]).to(dev)
+        bmap = torch.from_numpy(s["bone_map"].view(np.int16)).to(dev)
+        tmp, dst = torch.empty(ninst, n, 6, device=dev), torch.empty(ninst, n, 6, device=dev)
+    j = SkinJob()
+    j.src_pos, j.src_norm = tmp.data_ptr(), tmp.data_ptr() + 12
+    j.dst_pos, j.dst_norm = dst.data_ptr(), dst.data_ptr() + 12
+    j.blend_weight, j.blend_index = blend.data_ptr() + 4, blend.data_ptr()
+    j.palette, j.bone_map = d_pal.data_ptr(), bmap.data_ptr()
+    j.src_pos_stride = j.dst_pos_stride = j.src_norm_stride = j.dst_norm_stride = 24
+    j.blend_weight_stride = j.blend_index_stride = s["blend_stride"]
+    j.num_weights, j.num_matrices, j.num_vertices = s["nw"], len(s["bone_map"]), n
+    jf = SkinJob.from_buffer_copy(j)
+    jf.src_pos, jf.src_norm = key1.data_ptr(), key1.data_ptr() + 12
+    T.stream.synchronize()
+
+    def morph():
+        check(L.ogrecu_morph_instanced_dev(ctx.handle, d_t.data_ptr(), key1.data_ptr(), key2.data_ptr(), tmp.data_ptr(), 24, 24, 24, n, 1,
+                                           ninst, n * 24))
+
+    def skin():
+        check(L.ogrecu_skin_instanced_dev(ctx.handle, C.byref(j), ninst, nb * 16, n * 24, n * 24))
+
+    def fused():
+        check(L.ogrecu_anim_instanced_dev(ctx.handle, C.byref(jf), key2.data_ptr(), d_t.data_ptr(), None, 0, ninst, nb * 16, n * 24))
+
+    def separate():
+        morph(); skin()
+    dt_f, dt_s, dt_skin = T.time(fused, iters=50), T.time(separate, iters=50), T.time(skin, iters=50)
+    # parity spot check: instance 4711 of the fused step against the separate one (bit patterns)
+    fused(); T.stream.synchronize(); a = dst[4711].cpu().numpy().copy()
+    separate(); T.stream.synchronize(); b = dst[4711].cpu().numpy()
+    tot = ninst * n * WORLD
+    pal_bytes = ninst * len(s["bone_map"]) * 48
+    return {"config": "c2 (jaiqua) skeletal skinning: 1 sub-mesh, %d vertices, %d bones (%d used), %d weights x %d instances per GPU; "
+                      "morph + skin" % (n, nb, len(s["bone_map"]), s["nw"], ninst), "n_gpus": WORLD,
+            "fused_ms": dt_f * 1e3, "fused_Mvert_per_s": tot / dt_f / 1e6, "separate_ms": dt_s * 1e3, "separate_Mvert_per_s": tot / dt_s / 1e6,
+            "skin_only_ms": dt_skin * 1e3, "skin_only_Mvert_per_s": tot / dt_skin / 1e6,
+            "fused_frac_of_hbm_peak": (ninst * n * 24 + pal_bytes) / dt_f / 1e9 / PEAK,
+            "skin_only_frac_of_hbm_peak": (ninst * n * 48 + pal_bytes) / dt_skin / 1e9 / PEAK,
+            "fused_equals_separate_bits": bool(np.array_equal(a.view(np.uint32), b.view(np.uint32)))}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", default="c1,c3,c4,c5")
@@ -550,7 +610,7 @@ def main():
     lines = []
     for name in args.config.split(","):
         t0 = time.time()
-        res = {"c1": c1, "c3": c3, "c4": c4, "c5": c5}[name](ctx, T, args)
+        res = {"c1": c1, "c2j": c2j, "c3": c3, "c4": c4, "c5": c5}[name](ctx, T, args)
         res["wall_s"] = time.time() - t0
         if RANK == 0:
             print(json.dumps(res), flush=True)
