@@ -565,6 +565,7 @@ def run_ours(args):
             extra["roofline_stream_case"] = {
                 "bound": "hbm", "kernel": "skin_stream_kernel<4,normals> (one call, 2^24 distinct vertices, 64 bones, random bone indices)",
                 "achieved": sn * 68 / sdur / 1e9, "peak": peak, "unit": "GB/s", "frac": sn * 68 / sdur / 1e9 / peak, "launch_ms": sdur * 1e3,
+                "traffic": traf.get("skin_stream_nw4_2p24_bytes"),
                 "algorithmic_bytes_per_launch": sn * 68, "Mvert_per_s": sn / sdur / 1e6}
             del s_src, s_w, s_blend, s_pal, s_dst
         except Exception as ex:      # never lose the contract line over the side measurement
