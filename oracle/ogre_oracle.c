@@ -572,8 +572,8 @@ static void derive_all(const oracle_skeleton* sk, const xform* local, xform* der
 void oracle_skeleton_bind_inverse(const oracle_skeleton* sk, float* out10)
 {
     uint32_t n = sk->num_bones;
-    xform* local = (xform*)malloc(sizeof(xform) * (n ? n : 1));
-    xform* derived = (xform*)malloc(sizeof(xform) * (n ? n : 1));
+    xform* local = (xform*)calloc(n ? n : 1, sizeof(xform));
+    xform* derived = (xform*)calloc(n ? n : 1, sizeof(xform));
     for (uint32_t b = 0; b < n; ++b) local[b] = load10(sk->bind + 10 * b);
     derive_all(sk, local, derived);
     for (uint32_t b = 0; b < n; ++b) {
