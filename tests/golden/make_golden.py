@@ -22,7 +22,8 @@ container only; the GPU box and the CPU test suite just read the .npz files.
   image_scale.npz        outputs of the real Image::scale(FILTER_BILINEAR) on seeded RGB8 images (datagen.SCALE_CASES: up- and
                          down-scaling, sub-boxes, 1-pixel extents), same format and into PF_A8R8G8B8 / PF_BYTE_RGBA
   skel_frames.npz        the frames the real Tiny plugin renders of the software-skinned Sinbad / jaiqua entities (poses at t = 0.3 s
-                         and 1.7 s, 256x256, through tests/harness/run_scene.py on the build host)
+                         and 1.7 s, 256x256) and of ogrehead at 400x300 from z = 90, through tests/harness/run_scene.py on the
+                         build host
   optutil_golden.npz     outputs of the real OptimisedUtilSSE / OptimisedUtilGeneral on small
                          seeded inputs (all six functions, edge-case counts and alignments)
 """
@@ -194,6 +195,12 @@ def save_skel_frames(name):
                                    "--size", "256x256", "--cam-z", "30", "--skel", "0.3,1.7", "--out", f],
                                   env=dict(os.environ, MALLOC_PERTURB_="255"))
             out[mesh] = np.load(f)["colour"]
+    # the side-by-side scene of tests/test_plugin_gpu.py: ogrehead, 400x300, camera at z = 90
+    with tempfile.TemporaryDirectory() as tmp:
+        f = os.path.join(tmp, "t.npz")
+        subprocess.check_call([sys.executable, os.path.join(ROOT, "tests", "harness", "run_scene.py"), "--plugin", "tiny", "--mesh", "ogrehead.mesh",
+                               "--size", "400x300", "--cam-z", "90", "--out", f], env=dict(os.environ, MALLOC_PERTURB_="255"))
+        out["ogrehead_400x300_z90"] = np.load(f)["colour"]
     np.savez_compressed(os.path.join(HERE, name), **out)
     print(name, len(out), "arrays")
 

@@ -66,7 +66,10 @@ def test_side_by_side_with_the_real_tiny_plugin(tmp_path):
     c = run_scene(tmp_path, "cuda", *args)
     t = run_scene(tmp_path, "tiny", *args)
     assert "Tiny" in str(t["render_system"]) and int(t["optimised_util_replaced"]) == 0
-    assert np.array_equal(c["colour"], t["colour"])
+    # strict against the frame the real Tiny plugin rendered on the build host; against the live reference a handful of outlier
+    # pixels are tolerated (its frame was seen to depend on the host at an isolated pixel, profiles/r01q_notes.md)
+    assert np.array_equal(c["colour"], np.load(os.path.join(GOLDEN, "skel_frames.npz"))["ogrehead_400x300_z90"])
+    assert int((c["colour"] != t["colour"]).any(axis=2).sum()) <= 4
     assert list(c["stats"]) == list(t["stats"])
 
 
