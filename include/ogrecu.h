@@ -101,6 +101,7 @@ OGRECU_API int ogrecu_memcpy_h2d(ogrecu_ctx* ctx, void* dev, const void* host, s
 OGRECU_API int ogrecu_memcpy_d2h(ogrecu_ctx* ctx, void* host, const void* dev, size_t bytes);   /* waits for the copy */
 /* enqueue only (host must be pinned); the data is there after ogrecu_sync or an event the caller records on the stream */
 OGRECU_API int ogrecu_memcpy_d2h_async(ogrecu_ctx* ctx, void* host, const void* dev, size_t bytes);
+/* device to device on the launch stream (HardwareBuffer::copyData between two of our buffers, OgreHardwareBuffer.h:326-336) */
 OGRECU_API int ogrecu_memcpy_d2d(ogrecu_ctx* ctx, void* dst, const void* src, size_t bytes);
 /* host -> device on a stream of the CALLER's (a copy stream), not the context's launch stream: lets a renderer upload
  * frame k+1's inputs (bone palettes, weights) while frame k's kernels run.  Ordering against the launch stream is the
@@ -165,7 +166,8 @@ OGRECU_API int ogrecu_skel_add_animation(ogrecu_skel* skel, const ogrecu_animati
 OGRECU_API int ogrecu_skel_set_blend_mode(ogrecu_skel* skel, uint32_t blend_mode);
 /* the binding-pose inverses in use (computed or given), [num_bones][10], to a HOST array */
 OGRECU_API int ogrecu_skel_get_bind_inverse(ogrecu_skel* skel, float* out10_host);
-/* num_instances skeleton instances, each with `num_states` animation-state slots applied in slot order:
+/* Skeleton::setAnimationState + Skeleton::_getBoneMatrices (OgreMain/src/OgreSkeleton.cpp:162-217,402-424) for
+ * num_instances skeleton instances, each with `num_states` animation-state slots applied in slot order:
  * anim_dev[i*num_states + s] = animation index (< 0: slot disabled), time_dev = AnimationState::getTimePosition,
  * weight_dev = AnimationState::getWeight (all DEVICE arrays).  Writes num_bones Affine3 per instance to
  * palettes_dev + i*palette_stride_floats (16-byte aligned, stride a multiple of 4 floats) — the layout
@@ -476,13 +478,15 @@ OGRECU_API int ogrecu_draw_with_state(ogrecu_rt* rt, const ogrecu_draw_desc* des
 OGRECU_API int ogrecu_flush(ogrecu_rt* rt);
 
 /* Batched offscreen views (config 4): the same draw list (everything but mvp/mvit/light)
- * rendered into n_views targets of identical size in one pipeline pass.
+ * rendered into n_views targets of identical size in one pipeline pass — n_views x TinyRenderSystem::_render
+ * (OgreTinyRenderSystem.cpp:349-414) with the per-camera uniforms of applyFixedFunctionParams (:49-82).
  * per_view_mvp / per_view_mvit: n_views*16 floats (HOST); per_view_light_dir: n_views*3. */
 OGRECU_API int ogrecu_draw_views(ogrecu_rt* const* rts, uint32_t n_views, const ogrecu_draw_desc* desc,
                                  const float* per_view_mvp, const float* per_view_mvit,
                                  const float* per_view_light_dir);
 
-/* Split-frame (config 5): restrict rasterisation on this context to screen tile rows
+/* Split-frame (config 5; no counterpart in the reference, whose triangle() walks the whole bounding box,
+ * tinyrenderer.h:67-69): restrict rasterisation on this context to screen tile rows
  * [y0, y1) (multiples of the tile height); planes outside are left untouched.  The owner
  * of a strip is the only writer, so the composite is a disjoint gather. */
 OGRECU_API int ogrecu_rt_set_strip(ogrecu_rt* rt, uint32_t y0, uint32_t y1);
@@ -493,7 +497,8 @@ OGRECU_API int ogrecu_rt_set_bands(ogrecu_rt* rt, uint32_t band_rows, uint32_t p
 
 /* Sort-last split of one frame (config 5, the scalable form): rank r draws the r-th slice of the TRIANGLES (in submission
  * order) into its own full-size target, and the targets are merged per pixel: smallest depth wins, the later rank on ties,
- * pixels a rank did not touch (still the cleared colour AND depth) never win.  That is Tiny's result whenever every
+ * pixels a rank did not touch (still the cleared colour AND depth) never win (the per-pixel outcome of Tiny's in-order
+ * `frag_depth > zbuf` rule, tinyrenderer.h:79, when the submission order is the rank order).  That is Tiny's result whenever every
  * triangle is opaque, depth-tested and depth-writing (ogrecu_raster_stats.tiles_ordered == 0 on every rank); blended or
  * depth-write-off content must use the screen-space split (ogrecu_rt_set_strip / _set_bands).  The call merges
  * num_sources source planes (RGB8 + f32 depth, num_pixels each, source s at src + s*src_stride_pixels pixels), which must
