@@ -506,6 +506,161 @@ static quat q_normalise(quat q)
     return r;
 }
 
+/* Quaternion::Slerp, OgreQuaternion.cpp:373-413 (RIM_SPHERICAL): msEpsilon = 1e-03f (:42); Math::Sqrt / ATan2 / Sin are the
+ * float overloads of libm (sqrtf, atan2f, sinf, OgreMath.h), so the result is bit-identical to the engine's only where both
+ * run on the same libm — which is how it is pinned (tests/test_oracle_vs_ref.py, same process) */
+static quat q_slerp(float t, quat p, quat q, int shortest)
+{
+    float c = p.w * q.w + p.x * q.x + p.y * q.y + p.z * q.z;         /* Quaternion::Dot */
+    quat r;
+    if (c < 0.0f && shortest) { c = -c; r.w = -q.w; r.x = -q.x; r.y = -q.y; r.z = -q.z; }
+    else r = q;
+    if (fabsf(c) < 1 - 1e-03f) {
+        float sn = sqrtf(1 - c * c);
+        float angle = atan2f(sn, c);
+        float inv = 1.0f / sn;
+        float c0 = sinf((1.0f - t) * angle) * inv;
+        float c1 = sinf(t * angle) * inv;
+        quat o = {c0 * p.w + c1 * r.w, c0 * p.x + c1 * r.x, c0 * p.y + c1 * r.y, c0 * p.z + c1 * r.z};
+        return o;
+    } else {
+        float u = 1.0f - t;
+        quat o = {u * p.w + t * r.w, u * p.x + t * r.x, u * p.y + t * r.y, u * p.z + t * r.z};
+        return q_normalise(o);
+    }
+}
+
+/* ---- IM_SPLINE: SimpleSpline (positions, scales) and RotationalSpline over all key frames of a track ---- */
+
+/* Quaternion::Log, OgreQuaternion.cpp:325-357 */
+static quat q_log(quat q)
+{
+    quat r = {0.0f, q.x, q.y, q.z};
+    if (fabsf(q.w) < 1.0) {
+        float nv = sqrtf(q.x * q.x + q.y * q.y + q.z * q.z);
+        float angle = atan2f(nv, q.w);
+        float sn = sinf(angle);
+        if (fabsf(sn) >= 1e-03f) {
+            float c = angle / sn;
+            r.x = c * q.x; r.y = c * q.y; r.z = c * q.z;
+        }
+    }
+    return r;
+}
+
+/* Quaternion::Exp, OgreQuaternion.cpp:295-323 */
+static quat q_exp(quat q)
+{
+    float angle = sqrtf(q.x * q.x + q.y * q.y + q.z * q.z);
+    float sn = sinf(angle);
+    float ew = expf(q.w);
+    quat r;
+    r.w = ew * cosf(angle);
+    if (fabsf(angle) >= 1e-03f) {
+        float c = ew * (sn / angle);
+        r.x = c * q.x; r.y = c * q.y; r.z = c * q.z;
+    } else {
+        r.x = ew * q.x; r.y = ew * q.y; r.z = ew * q.z;
+    }
+    return r;
+}
+
+/* Quaternion::Inverse, OgreQuaternion.cpp:274-287 */
+static quat q_inverse(quat q)
+{
+    float n = q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z;
+    quat r = {0.0f, 0.0f, 0.0f, 0.0f};
+    if (n > 0.0) { float inv = 1.0f / n; r.w = q.w * inv; r.x = -q.x * inv; r.y = -q.y * inv; r.z = -q.z * inv; }
+    return r;
+}
+
+static quat q_slerp(float t, quat p, quat q, int shortest);
+
+/* Quaternion::Squad, OgreQuaternion.cpp:449-457 */
+static quat q_squad(float t, quat p, quat a, quat b, quat q, int shortest)
+{
+    float st = 2.0f * t * (1.0f - t);
+    quat sp = q_slerp(t, p, q, shortest);
+    quat sq = q_slerp(t, a, b, 0);
+    return q_slerp(st, sp, sq, 0);
+}
+
+/* RotationalSpline::recalcTangents, OgreRotationSpline.cpp (keys: 11 floats per key, rotation wxyz at [4..7]) */
+static void rot_spline_tangents(const float* K, uint32_t n, quat* tan)
+{
+    if (n < 2) return;
+#define KQ(i) ((quat){K[11 * (size_t)(i) + 4], K[11 * (size_t)(i) + 5], K[11 * (size_t)(i) + 6], K[11 * (size_t)(i) + 7]})
+    const quat first = KQ(0), last = KQ(n - 1);
+    const int closed = first.x == last.x && first.y == last.y && first.z == last.z && first.w == last.w;
+    for (uint32_t i = 0; i < n; ++i) {
+        const quat p = KQ(i);
+        const quat invp = q_inverse(p);
+        quat part1, part2;
+        if (i == 0) {
+            part1 = q_log(q_mul(invp, KQ(i + 1)));
+            part2 = closed ? q_log(q_mul(invp, KQ(n - 2))) : q_log(q_mul(invp, p));
+        } else if (i == n - 1) {
+            part1 = closed ? q_log(q_mul(invp, KQ(1))) : q_log(q_mul(invp, p));
+            part2 = q_log(q_mul(invp, KQ(i - 1)));
+        } else {
+            part1 = q_log(q_mul(invp, KQ(i + 1)));
+            part2 = q_log(q_mul(invp, KQ(i - 1)));
+        }
+        const float m = -0.25f;
+        quat pre = {m * (part1.w + part2.w), m * (part1.x + part2.x), m * (part1.y + part2.y), m * (part1.z + part2.z)};
+        tan[i] = q_mul(p, q_exp(pre));
+    }
+#undef KQ
+}
+
+/* SimpleSpline::recalcTangents, OgreSimpleSpline.cpp:156-207, for the 3 floats at K[11 i + off] */
+static void simple_spline_tangents(const float* K, uint32_t n, int off, vec3* tan)
+{
+    if (n < 2) return;
+#define KP(i, c) K[11 * (size_t)(i) + off + (c)]
+    const int closed = KP(0, 0) == KP(n - 1, 0) && KP(0, 1) == KP(n - 1, 1) && KP(0, 2) == KP(n - 1, 2);
+    for (uint32_t i = 0; i < n; ++i) {
+        uint32_t a, b;                                  /* tangent = 0.5 * (P[a] - P[b]) */
+        if (i == 0) { a = 1; b = closed ? n - 2 : 0; }
+        else if (i == n - 1) { if (closed) { tan[i] = tan[0]; continue; } a = i; b = i - 1; }
+        else { a = i + 1; b = i - 1; }
+        tan[i].x = 0.5f * (KP(a, 0) - KP(b, 0)); tan[i].y = 0.5f * (KP(a, 1) - KP(b, 1)); tan[i].z = 0.5f * (KP(a, 2) - KP(b, 2));
+    }
+#undef KP
+}
+
+/* SimpleSpline::interpolate(fromIndex, t), OgreSimpleSpline.cpp:87-154: powers * hCoeffs * pt with Vector4 * Matrix4
+ * (OgreMatrix4.h:588-596), every product and sum of the reference kept, zeros included */
+static vec3 simple_spline_interpolate(const float* K, uint32_t n, int off, const vec3* tan, uint32_t from, float t)
+{
+    const float* p1 = K + 11 * (size_t)from + off;
+    vec3 r = {p1[0], p1[1], p1[2]};
+    if (from + 1 == n || t == 0.0f) return r;
+    const float* p2 = K + 11 * (size_t)(from + 1) + off;
+    if (t == 1.0f) { r.x = p2[0]; r.y = p2[1]; r.z = p2[2]; return r; }
+    const float t2 = t * t, t3 = t2 * t;
+    const float v0 = t3 * 2.0f + t2 * -3.0f + t * 0.0f + 1.0f * 1.0f;
+    const float v1 = t3 * -2.0f + t2 * 3.0f + t * 0.0f + 1.0f * 0.0f;
+    const float v2 = t3 * 1.0f + t2 * -2.0f + t * 1.0f + 1.0f * 0.0f;
+    const float v3 = t3 * 1.0f + t2 * -1.0f + t * 0.0f + 1.0f * 0.0f;
+    const vec3 a = tan[from], b = tan[from + 1];
+    r.x = v0 * p1[0] + v1 * p2[0] + v2 * a.x + v3 * b.x;
+    r.y = v0 * p1[1] + v1 * p2[1] + v2 * a.y + v3 * b.y;
+    r.z = v0 * p1[2] + v1 * p2[2] + v2 * a.z + v3 * b.z;
+    return r;
+}
+
+/* RotationalSpline::interpolate(fromIndex, t, useShortestPath) */
+static quat rot_spline_interpolate(const float* K, uint32_t n, const quat* tan, uint32_t from, float t, int shortest)
+{
+    const float* k = K + 11 * (size_t)from;
+    quat p = {k[4], k[5], k[6], k[7]};
+    if (from + 1 == n || t == 0.0f) return p;
+    quat q = {k[15], k[16], k[17], k[18]};
+    if (t == 1.0f) return q;
+    return q_squad(t, p, tan[from], tan[from + 1], q, shortest);
+}
+
 /* Quaternion::nlerp, OgreQuaternion.cpp:534-549 */
 static quat q_nlerp(float t, quat p, quat q, int shortest)
 {
@@ -614,7 +769,9 @@ int oracle_skeleton_palette(const oracle_skeleton* sk, const float* bind_inverse
     }
     for (uint32_t s = 0; s < nstates && !rc; ++s) {
         const oracle_animation* A = &anims[anim[s]];
-        if (A->interpolation != 0 || A->rotation_interpolation != 0) { rc = 1; break; }
+        if (A->interpolation > 1 || A->rotation_interpolation > 1) { rc = 1; break; }
+        const int spline = A->interpolation == 1;
+        const int spherical = A->rotation_interpolation == 1;
         float w = weight[s] * weight_factor;
         const float scl = 1.0f;                                  /* linked-skeleton scale: none */
         uint32_t nkeys = A->key_offset[A->num_tracks];
@@ -645,13 +802,25 @@ int oracle_skeleton_palette(const oracle_skeleton* sk, const float* bind_inverse
             const float* k1 = K + 11 * i;
             float t1 = k1[0];
             float f = (t1 == t2) ? 0.0f : (tp - t1) / (t2 - t1);
-            /* getInterpolatedKeyFrame (IM_LINEAR, RIM_LINEAR) */
+            /* getInterpolatedKeyFrame (IM_LINEAR with RIM_LINEAR or RIM_SPHERICAL; IM_SPLINE) */
             vec3 tr, sc; quat ro;
             if (f == 0.0f) {
                 tr.x = k1[1]; tr.y = k1[2]; tr.z = k1[3]; ro.w = k1[4]; ro.x = k1[5]; ro.y = k1[6]; ro.z = k1[7]; sc.x = k1[8]; sc.y = k1[9]; sc.z = k1[10];
+            } else if (spline) {
+                /* buildInterpolationSplines (OgreAnimationTrack.cpp:515-549) + the three interpolate calls (:438-450) */
+                quat* rt = (quat*)calloc(nk, sizeof(quat));
+                vec3* pt = (vec3*)calloc(nk, sizeof(vec3));
+                vec3* st = (vec3*)calloc(nk, sizeof(vec3));
+                rot_spline_tangents(K, nk, rt);
+                simple_spline_tangents(K, nk, 1, pt);
+                simple_spline_tangents(K, nk, 8, st);
+                ro = rot_spline_interpolate(K, nk, rt, i, f, A->track_shortest[t]);
+                tr = simple_spline_interpolate(K, nk, 1, pt, i, f);
+                sc = simple_spline_interpolate(K, nk, 8, st, i, f);
+                free(rt); free(pt); free(st);
             } else {
                 quat a = {k1[4], k1[5], k1[6], k1[7]}, b = {k2[4], k2[5], k2[6], k2[7]};
-                ro = q_nlerp(f, a, b, A->track_shortest[t]);
+                ro = spherical ? q_slerp(f, a, b, A->track_shortest[t]) : q_nlerp(f, a, b, A->track_shortest[t]);
                 tr.x = k1[1] + f * (k2[1] - k1[1]); tr.y = k1[2] + f * (k2[2] - k1[2]); tr.z = k1[3] + f * (k2[3] - k1[3]);
                 sc.x = k1[8] + f * (k2[8] - k1[8]); sc.y = k1[9] + f * (k2[9] - k1[9]); sc.z = k1[10] + f * (k2[10] - k1[10]);
             }
@@ -659,7 +828,7 @@ int oracle_skeleton_palette(const oracle_skeleton* sk, const float* bind_inverse
             xform* B = &local[A->track_bone[t]];
             B->p.x += tr.x * w * scl; B->p.y += tr.y * w * scl; B->p.z += tr.z * w * scl;
             quat ident = {1.0f, 0.0f, 0.0f, 0.0f};
-            quat rot = q_nlerp(w, ident, ro, A->track_shortest[t]);
+            quat rot = spherical ? q_slerp(w, ident, ro, A->track_shortest[t]) : q_nlerp(w, ident, ro, A->track_shortest[t]);
             B->q = q_normalise(q_mul(B->q, rot));                 /* Node::rotate, TS_LOCAL */
             if (sc.x != 1.0f || sc.y != 1.0f || sc.z != 1.0f) {
                 if (scl != 1.0f) { sc.x = 1.0f + scl * (sc.x - 1.0f); sc.y = 1.0f + scl * (sc.y - 1.0f); sc.z = 1.0f + scl * (sc.z - 1.0f); }

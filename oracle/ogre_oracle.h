@@ -141,8 +141,9 @@ typedef struct oracle_skeleton {
  * track t owns keys[key_offset[t] .. key_offset[t+1]) sorted by time. */
 typedef struct oracle_animation {
     float length;
-    uint32_t interpolation;             /* 0 = IM_LINEAR (1 = IM_SPLINE: not restated, returns an error) */
-    uint32_t rotation_interpolation;    /* 0 = RIM_LINEAR (1 = RIM_SPHERICAL: not restated) */
+    uint32_t interpolation;             /* 0 = IM_LINEAR, 1 = IM_SPLINE (SimpleSpline / RotationalSpline through libm, as RIM_SPHERICAL) */
+    uint32_t rotation_interpolation;    /* 0 = RIM_LINEAR, 1 = RIM_SPHERICAL (Quaternion::Slerp through libm: bit-identical to the engine
+                                         * only on the same libm; the device path refuses it) */
     uint32_t num_tracks;
     const int32_t* track_bone;          /* [num_tracks] */
     const uint8_t* track_shortest;      /* [num_tracks] NodeAnimationTrack::getUseShortestRotationPath */

@@ -85,6 +85,7 @@ def lib():
         l.ref_skel_anim_info.argtypes = [C.c_uint32, vp, vp, vp, vp, vp, C.c_char_p]
         l.ref_skel_anim_data.argtypes = [C.c_uint32, vp, vp, vp, vp]
         l.ref_skel_anim_data.restype = None
+        l.ref_skel_set_interpolation.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32]
         l.ref_skel_pose_states.argtypes = [C.c_uint32, vp, vp, vp, vp]
         l.ref_bench_palettes.argtypes = [C.c_uint32, vp, sz, vp]
         l.ref_bench_palettes.restype = C.c_double

@@ -586,6 +586,17 @@ API int ref_skel_anim_info(uint32_t a, float* length, uint32_t* interp, uint32_t
     return 0;
 }
 
+// Animation::setInterpolationMode / setRotationInterpolationMode on the real animation (0 = IM_LINEAR / RIM_LINEAR,
+// 1 = IM_SPLINE / RIM_SPHERICAL, OgreAnimation.h:68-84)
+API int ref_skel_set_interpolation(uint32_t a, uint32_t interp, uint32_t rot_interp)
+{
+    Animation* an = skel_anim(a);
+    if (!an) return 1;
+    an->setInterpolationMode((Animation::InterpolationMode)interp);
+    an->setRotationInterpolationMode((Animation::RotationInterpolationMode)rot_interp);
+    return 0;
+}
+
 // track_bone[ntracks], track_shortest[ntracks], key_offset[ntracks + 1], keys[nkeys][11] = time, translate xyz, rotation wxyz, scale xyz
 API void ref_skel_anim_data(uint32_t a, int32_t* track_bone, uint8_t* track_shortest, uint32_t* key_offset, float* keys)
 {

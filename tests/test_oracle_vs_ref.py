@@ -153,3 +153,39 @@ def test_oracle_image_scale_equals_real_image_scale():
     for name, layout in PACKED32.items():
         want = ref.image_scale(src, 120, 31, "PF_BYTE_RGB", name).view(np.uint32)[..., 0]
         assert np.array_equal(pack32(oracle.scale_bilinear(src, 120, 31), *layout), want), name
+
+
+@pytest.mark.parametrize("im,rim", [(0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("mesh", ["Sinbad.mesh", "jaiqua.mesh"])
+def test_oracle_spline_and_spherical_interpolation_equal_real_skeleton_instance(mesh, im, rim):
+    """RIM_SPHERICAL (Quaternion::Slerp in key interpolation and in the weight application, OgreAnimationTrack.cpp:417-421,
+    495-498) and IM_SPLINE (SimpleSpline / RotationalSpline over all keys of a track, :438-450,515-549): every animation of the
+    real skeleton switched to the mode, 200 random multi-state poses, the restatement bit-identical (same libm in one
+    process).  The device path refuses these modes (tests/test_skeleton_gpu.py) — libm's transcendentals have no
+    bit-identical device counterpart."""
+    d = ref.skeleton_def(mesh)
+    try:
+        for a in range(len(d["anims"])):
+            assert ref.lib().ref_skel_set_interpolation(a, im, rim) == 0
+        ds = ref.skeleton_def()
+        assert all(a["rotation_interpolation"] == rim and a["interpolation"] == im for a in ds["anims"])
+        sk = oracle.Skeleton(ds)
+        lin = oracle.Skeleton(d)
+        rng = np.random.default_rng(23)
+        differs = 0
+        for trial in range(200):
+            ns = int(rng.integers(1, 4))
+            an = rng.choice(len(ds["anims"]), ns, replace=False)
+            tm = [rng.uniform(0, ds["anims"][a]["length"]) for a in an]
+            w = rng.uniform(0.0, 1.0, ns) if trial % 3 else np.ones(ns)
+            mode = trial % 2
+            ref.lib().ref_skel_set_blend_mode(mode)
+            r = ref.skeleton_pose_states(ds["num_bones"], an, tm, w)
+            o = sk.palette(an, tm, w, bind_inverse=ds["bind_inverse"], blend_mode=mode)
+            assert np.array_equal(bits(r), bits(o)), (mesh, trial)
+            differs += int(not np.array_equal(bits(o), bits(lin.palette(an, tm, w, bind_inverse=d["bind_inverse"], blend_mode=mode))))
+        assert differs > 100          # the mode really is a different interpolation
+    finally:
+        for a in range(len(d["anims"])):
+            ref.lib().ref_skel_set_interpolation(a, d["anims"][a]["interpolation"], d["anims"][a]["rotation_interpolation"])
+        ref.lib().ref_skel_set_blend_mode(d["blend_mode"])
