@@ -38,7 +38,7 @@ extern "C" {
 #define OGRECU_API
 #endif
 
-#define OGRECU_ABI_VERSION 4
+#define OGRECU_ABI_VERSION 5
 
 typedef enum ogrecu_status {
     OGRECU_OK = 0,
@@ -252,6 +252,28 @@ typedef struct ogrecu_anim_job {
 } ogrecu_anim_job;
 OGRECU_API int ogrecu_anim_instanced_multi_dev(ogrecu_ctx* ctx, const ogrecu_anim_job* jobs, uint32_t num_jobs, const float* t_dev,
                                                uint32_t num_instances, size_t palette_stride_floats);
+
+/* Skin plan: what the instance-pair-per-lane kernel (csrc/skin_lane.cu) precomputes ONCE per sub-mesh from its static
+ * blend stream — the mesh cut into chunks of <= 128 vertices that reference <= 16 palette entries, and per vertex the
+ * slots to take (zero weights and unit first weights are skipped where that is bitwise exact, see the kernel header).
+ * `job` supplies blend_index / blend_weight (+ strides), bone_map, num_weights, num_matrices and num_vertices (DEVICE
+ * pointers; read back synchronously by the call — the plan does not reference them afterwards).  The blend stream is
+ * the VES_BLEND_INDICES / VES_BLEND_WEIGHTS buffer Mesh::softwareVertexBlend locks (OgreMain/src/OgreMesh.cpp:1823-1850)
+ * and the map is SubMesh::blendIndexToBoneIndexMap (:1782-1790); rebuild the plan when either changes.
+ * OGRECU_ERR_UNSUPPORTED: the mesh has no bone locality (four consecutive vertices reference more than 16 palette entries
+ * together with the vertex before them) — pass plans[k] = NULL for it and the tile kernels take the job. */
+typedef struct ogrecu_skin_plan ogrecu_skin_plan;
+OGRECU_API int ogrecu_skin_plan_create(ogrecu_ctx* ctx, const ogrecu_skin_job* job, ogrecu_skin_plan** out);
+OGRECU_API int ogrecu_skin_plan_destroy(ogrecu_skin_plan* plan);
+OGRECU_API int ogrecu_skin_plan_info(const ogrecu_skin_plan* plan, uint32_t* num_chunks);
+/* One animation frame of an instanced mesh, all sub-meshes in ONE launch (Entity::updateAnimation walks the sub-entities,
+ * OgreMain/src/OgreEntity.cpp:823-864): the ogrecu_anim_instanced_multi_dev contract, plus plans[k] for jobs[k].
+ * t_dev != NULL: fused morph + skin (every jobs[k].key2 set); t_dev == NULL: skinning of the shared bind pose in
+ * skin.src_pos (every key2 NULL).  Jobs whose layout the lane kernel does not take (positions only, a destination that is
+ * not 16-byte aligned, morph_out requested, plans[k] NULL) run through the tile kernels of ogrecu_anim_instanced_dev /
+ * ogrecu_skin_instanced_dev; results are bit-identical either way. */
+OGRECU_API int ogrecu_anim_frame_dev(ogrecu_ctx* ctx, const ogrecu_anim_job* jobs, ogrecu_skin_plan* const* plans, uint32_t num_jobs,
+                                     const float* t_dev, uint32_t num_instances, size_t palette_stride_floats);
 
 OGRECU_API int ogrecu_software_vertex_skinning_host(
     ogrecu_ctx* ctx,

@@ -112,6 +112,10 @@ SIGNATURES = {
     "ogrecu_buf_resolve": (C.c_int, [C.c_void_p, C.c_void_p, c_void_pp, C.POINTER(C.c_size_t)]),
     "ogrecu_skin_dev": (C.c_int, [C.c_void_p, C.POINTER(SkinJob), C.c_uint32]),
     "ogrecu_anim_instanced_multi_dev": (C.c_int, [C.c_void_p, C.POINTER(AnimJob), C.c_uint32, C.c_void_p, C.c_uint32, C.c_size_t]),
+    "ogrecu_skin_plan_create": (C.c_int, [C.c_void_p, C.POINTER(SkinJob), c_void_pp]),
+    "ogrecu_skin_plan_destroy": (C.c_int, [C.c_void_p]),
+    "ogrecu_skin_plan_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint32)]),
+    "ogrecu_anim_frame_dev": (C.c_int, [C.c_void_p, C.POINTER(AnimJob), C.POINTER(C.c_void_p), C.c_uint32, C.c_void_p, C.c_uint32, C.c_size_t]),
     "ogrecu_skel_create": (C.c_int, [C.c_void_p, C.POINTER(SkeletonDesc), c_void_pp]),
     "ogrecu_skel_destroy": (C.c_int, [C.c_void_p]),
     "ogrecu_skel_add_animation": (C.c_int, [C.c_void_p, C.POINTER(AnimationDesc), C.POINTER(C.c_uint32)]),

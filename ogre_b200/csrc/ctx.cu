@@ -169,7 +169,7 @@ int ogrecu_sync(ogrecu_ctx* ctx)
 int ogrecu_set_config_option(ogrecu_ctx* ctx, const char* name, int value)
 {
     OGRECU_REQUIRE(ctx && name, "NULL argument");
-    if (!strcmp(name, "skin_mode")) { OGRECU_REQUIRE(value >= 0 && value <= 4, "skin_mode is 0..4"); ctx->skin_mode = value; return OGRECU_OK; }
+    if (!strcmp(name, "skin_mode")) { OGRECU_REQUIRE(value >= 0 && value <= 3, "skin_mode is 0..3"); ctx->skin_mode = value; return OGRECU_OK; }
     if (!strcmp(name, "raster_xf")) { OGRECU_REQUIRE(value >= 0 && value <= 1, "raster_xf is 0..1"); ctx->raster_xf = value; return OGRECU_OK; }
     if (!strcmp(name, "raster_mode")) { OGRECU_REQUIRE(value >= 0 && value <= 1, "raster_mode is 0..1"); ctx->raster_mode = value; return OGRECU_OK; }
     if (!strcmp(name, "skel_mode")) { OGRECU_REQUIRE(value >= 0 && value <= 1, "skel_mode is 0..1"); ctx->skel_mode = value; return OGRECU_OK; }

@@ -295,7 +295,7 @@ int launch_skin_tile(ogrecu_ctx* ctx, SkinTileParams P, uint32_t nw, bool norm, 
     const uint32_t vs = norm ? 24 : 12;
     const uint32_t tiles = div_up(P.num_vertices, ST_THREADS);
     auto al = [](const void* p, size_t stride, size_t a) { return (((uintptr_t)p | stride) & (a - 1)) == 0; };
-    const int force = ctx->skin_mode;   // 0 auto, 1 never TMA (cooperative copies), 3 single-instance tile kernel, 4 wide kernel; for A/B measurements
+    const int force = ctx->skin_mode;   // 0 auto, 1 never TMA (cooperative copies), 3 single-instance tile kernel; for A/B measurements
     P.tma_load = (!fused && force != 1 && al(P.src, P.src_inst_stride, 16)) ? 1u : 0u;
     P.tma_store = (force != 1 && al(P.dst, P.dst_inst_stride, 16)) ? 1u : 0u;
     P.load_unit = (vs == 24 && al(P.src, P.src_inst_stride, 8)) ? 8u : 4u;
@@ -312,8 +312,6 @@ int launch_skin_tile(ogrecu_ctx* ctx, SkinTileParams P, uint32_t nw, bool norm, 
         T.num_vertices = P.num_vertices - done;
         return launch_skin_tile(ctx, T, nw, norm, fused);
     }
-    // many instances of a pos+normal mesh with one source: instances across the lanes (skin_wide.cu)
-    if (force == 4 && skin_wide_eligible(P, norm, fused)) return launch_skin_wide(ctx, P, nw, fused);
     // two or more instances: the pair kernel (skin_pair.cu, packed f32x2, two instances per pass)
     if (P.num_instances >= 2 && force != 3) return launch_skin_pair(ctx, P, nw, norm, fused);
     // instances per CTA: amortise the tile's blend stream while keeping >= ~4 waves of CTAs

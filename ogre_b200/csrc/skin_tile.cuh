@@ -27,10 +27,6 @@ int launch_skin_tile(ogrecu_ctx* ctx, SkinTileParams P, uint32_t num_weights, bo
 // skin_pair.cu: same parameters (alignment fields already derived), two instances per pass.
 int launch_skin_pair(ogrecu_ctx* ctx, SkinTileParams P, uint32_t num_weights, bool with_normals, bool fused_morph);
 
-// skin_wide.cu: instances across the lanes (pos+normal, one source for all instances); alignment fields already derived.
-bool skin_wide_eligible(const SkinTileParams& P, bool with_normals, bool fused_morph);
-int launch_skin_wide(ogrecu_ctx* ctx, SkinTileParams P, uint32_t num_weights, bool fused_morph);
-
 // skin_stream.cu: one instance, one long stream (persistent CTAs, resident palette, TMA pipeline over tiles).  Covers the full
 // 256-vertex tiles and reports how many vertices that was; the caller skins the tail with the tile kernel.
 bool skin_stream_eligible(const SkinTileParams& P, uint32_t num_weights, bool fused_morph);

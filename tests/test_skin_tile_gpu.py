@@ -198,81 +198,6 @@ def test_special_values_through_packed_arithmetic(gpu_ctx, nw, mode):
         b.free()
 
 
-WIDE_CASES = [
-    # n,   nw, nb, ninst, fused, dst_off, zero_frac, special
-    (1888, 4, 55, 70, True, 0, 0.5, False),     # Sinbad's body shape, ragged last instance group (70 = 2 x 32 + 6)
-    (1533, 4, 18, 129, True, 0, 0.7, False),    # odd vertex count: tail group through the word path
-    (583, 3, 6, 64, True, 0, 0.6, False),
-    (302, 1, 2, 96, True, 0, 0.0, False),
-    (77, 2, 7, 65, True, 0, 0.5, False),        # lerp form with w1 == 0
-    (1001, 4, 30, 64, False, 0, 0.5, False),    # shared bind pose, no morph
-    (640, 4, 40, 66, True, 8, 0.5, False),      # destination not 16-byte aligned: word path everywhere
-    (512, 4, 24, 64, True, 0, 0.5, True),       # -0, denormals and non-finite entries in the palettes, zero / tiny first weights
-    (512, 3, 24, 64, True, 0, 0.5, True),
-    (512, 2, 24, 64, True, 0, 0.5, True),
-]
-
-
-@pytest.mark.parametrize("case", WIDE_CASES, ids=lambda c: "n%d_w%d_b%d_i%d_%s_o%d_z%d%s" % (
-    c[0], c[1], c[2], c[3], "F" if c[4] else "S", c[5], int(c[6] * 100), "_special" if c[7] else ""))
-def test_wide_kernel_instances_across_lanes(gpu_ctx, case):
-    """skin_wide.cu (skin_mode 4): a lane per instance, zero-weight slots skipped warp-uniformly where that is a bitwise
-    no-op.  Compared with the oracle (SSE formulation, which multiplies zero weights through) as bit patterns; NaN
-    positions must coincide (payloads are not part of the contract)."""
-    from ogre_b200 import check, lib
-    n, nw, nb, ninst, fused, do, zero_frac, special = case
-    ctx = gpu_ctx
-    rng = np.random.default_rng(n * 7 + nw + ninst)
-    keys, blend, pals, bone_map = make_inputs(rng, n, nw, nb, ninst, True, True)
-    key1, key2 = np.ascontiguousarray(keys[0]), np.ascontiguousarray(keys[1])
-    # zero weights the way real meshes have them: trailing slots are exactly +0, the rest renormalised
-    w = blend[:, 4:].view(np.float32).reshape(n, nw).copy()
-    if nw > 1:
-        keep = 1 + (rng.random((n, 1)) > zero_frac) * rng.integers(0, nw, size=(n, 1))
-        w[np.arange(nw)[None, :] >= keep] = 0.0
-        w = (w / w.sum(axis=1, keepdims=True)).astype(np.float32)
-        w[np.arange(nw)[None, :] >= keep] = 0.0
-        interior = rng.random(n) < 0.05                   # a zero in the middle, a non-zero after it
-        if nw >= 3:
-            w[interior, 1] = 0.0; w[interior, 2] = np.float32(0.25)
-    if special:
-        sp = np.array([0.0, -0.0, -1e-45, 1e-45, -3e-39, 1.1754944e-38, 3e38, -3.2e38, np.inf, -np.inf, np.nan, 1.0, -1.0], np.float32)
-        pm = rng.random(pals.shape) < 0.02
-        pals[pm] = sp[rng.integers(0, len(sp), size=int(pm.sum()))]
-        wz = rng.random(n) < 0.1
-        w[wz, 0] = np.array([0.0, -0.0, 1e-30, 1e-7], np.float32)[rng.integers(0, 4, size=int(wz.sum()))]
-    blend[:, 4:] = w.view(np.uint8).reshape(n, 4 * nw)
-    t = rng.uniform(0, 1, size=ninst).astype(np.float32)
-    dk1, dk2, dt = ctx.to_device(key1), ctx.to_device(key2), ctx.to_device(t)
-    dbl, dpal, dmap = ctx.to_device(blend), ctx.to_device(pals), ctx.to_device(bone_map)
-    ddst = ctx.alloc(ninst * n * 24 + 64)
-    ddst.upload(np.full(ninst * n * 24 + 64, 0xCD, np.uint8))
-    j = gpu_job(ctx, dk1.ptr, ddst.ptr + do, dbl, dpal, dmap, n, nw, nb, True)
-    ctx.set_config_option("skin_mode", 4)
-    try:
-        if fused:
-            check(lib().ogrecu_anim_instanced_dev(ctx.handle, C.byref(j), dk2.ptr, dt.ptr, None, 0, ninst, (nb + 2) * 16, n * 24))
-        else:
-            check(lib().ogrecu_skin_instanced_dev(ctx.handle, C.byref(j), ninst, (nb + 2) * 16, 0, n * 24))
-        ctx.sync()
-    finally:
-        ctx.set_config_option("skin_mode", 0)
-    raw = ddst.download(np.uint8)
-    assert (raw[:do] == 0xCD).all() and (raw[do + ninst * n * 24:] == 0xCD).all(), "wrote outside the destination"
-    got = raw[do:do + ninst * n * 24].view(np.float32).reshape(ninst, n, 6)
-    for i in range(ninst):
-        src = key1
-        if fused:
-            src = np.zeros((n, 6), np.float32)
-            oracle.lib().oracle_morph(float(t[i]), key1.ctypes.data, key2.ctypes.data, src.ctypes.data, 24, 24, 24, n, 1)
-        ref = oracle_skin(src, blend, np.ascontiguousarray(pals[i][bone_map]), nw, n, True)
-        ok = ~np.isnan(ref)
-        assert np.array_equal(np.isnan(got[i]), np.isnan(ref)), (case, i)
-        assert np.array_equal(bits(got[i])[ok], bits(ref)[ok]), (case, i)
-    for b in (dk1, dk2, dt, dbl, dpal, dmap, ddst):
-        b.free()
-
-
 def test_multi_job_frame_equals_single_calls(gpu_ctx):
     """ogrecu_anim_instanced_multi_dev (all sub-meshes of a frame in one call, launches overlapped over side streams and
     joined back into the context's stream) == one ogrecu_anim_instanced_dev per sub-mesh, bit for bit, incl. the optional
