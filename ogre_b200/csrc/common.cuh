@@ -74,6 +74,8 @@ struct ogrecu_ctx {
     ogrecu::Scratch jobs;       // skin job descriptors
     ogrecu::Scratch stage_in;   // host-path staging (device side)
     ogrecu::Scratch stage_out;
+    ogrecu::Scratch lane_counter;   // work-unit counter of skin_lane_kernel
+    ogrecu::Scratch lane_ipal;      // the frame's palettes repacked for skin_lane_kernel
     void* pinned;               // pinned staging (host side)
     size_t pinned_cap;
     // shadow registry: shadow base address -> buffer

@@ -125,7 +125,7 @@ int ogrecu_shutdown(ogrecu_ctx* ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     while (!ctx->targets.empty()) rt_release(ctx->targets.back());
-    for (Scratch* s : {&ctx->jobs, &ctx->stage_in, &ctx->stage_out})
+    for (Scratch* s : {&ctx->jobs, &ctx->stage_in, &ctx->stage_out, &ctx->lane_counter, &ctx->lane_ipal})
         if (s->ptr) cudaFree(s->ptr);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->ring) cudaFreeHost(ctx->ring);

@@ -64,20 +64,49 @@ __device__ __forceinline__ void ln_tma_store_2d(const CUtensorMap* map, uint32_t
                  ::"l"(map), "r"(src_smem), "r"(x), "r"(y) : "memory");
 }
 
-// sqrt then 1/x of both halves, correctly rounded (== __fsqrt_rn / __frcp_rn); the packed fast sequences when the whole
-// warp is in their range (always, for unit-scale normals), the library ones otherwise
-__device__ __forceinline__ void ln_sqrt_rcp(u64 l2, u64 nz, u64& len, u64& inv)
+// sqrt(x) and 1/sqrt(x) of both halves, correctly rounded each (== __frcp_rn(__fsqrt_rn(x))), for the two vertices of a
+// pair at once: the packed Newton sequences of exact_math.cuh when the whole warp is in their range (always, for
+// unit-scale normals), written with the negated intermediates (-h, -d, -x: round-to-nearest is sign-symmetric, so every
+// step has the bits of the original) so that no sign flips are spent; the library functions otherwise.  The two
+// independent chains interleave in the pipeline.
+__device__ __forceinline__ void ln_sqrt_rcp2(const u64 x0, const u64 x1, const u64 nz, u64& len0, u64& inv0, u64& len1, u64& inv1)
 {
-    float a, b;
-    ln_upk(l2, a, b);
-    const bool fast = em_fast_range(__float_as_uint(a)) && em_fast_range(__float_as_uint(b));
+    float a0, b0, a1, b1;
+    ln_upk(x0, a0, b0); ln_upk(x1, a1, b1);
+    const bool fast = em_fast_range(__float_as_uint(a0)) && em_fast_range(__float_as_uint(b0)) &&
+                      em_fast_range(__float_as_uint(a1)) && em_fast_range(__float_as_uint(b1));
     if (__all_sync(0xffffffffu, fast)) {
-        len = em_sqrt_fast2(l2, nz);
-        inv = em_rcp_fast2(len);
+        const u64 half = 0x3f0000003f000000ull, nhalf = 0xbf000000bf000000ull, one = 0x3f8000003f800000ull, zero = 0ull;
+        float y0a, y0b, y1a, y1b;
+        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y0a) : "f"(a0));
+        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y0b) : "f"(b0));
+        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y1a) : "f"(a1));
+        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y1b) : "f"(b1));
+        const u64 y0 = ln_pk(y0a, y0b), y1 = ln_pk(y1a, y1b);
+        const u64 nx0 = ln_sub(zero, x0), nx1 = ln_sub(zero, x1);
+        u64 g0 = em_pfma(x0, y0, nz), g1 = em_pfma(x1, y1, nz);
+        u64 h0 = em_pfma(nhalf, y0, nz), h1 = em_pfma(nhalf, y1, nz);           // -h
+        const u64 r0 = em_pfma(h0, g0, half), r1 = em_pfma(h1, g1, half);
+        g0 = em_pfma(g0, r0, g0); g1 = em_pfma(g1, r1, g1);
+        h0 = em_pfma(h0, r0, h0); h1 = em_pfma(h1, r1, h1);
+        const u64 d0 = em_pfma(g0, g0, nx0), d1 = em_pfma(g1, g1, nx1);         // -(x - g*g)
+        len0 = em_pfma(d0, h0, g0); len1 = em_pfma(d1, h1, g1);
+        float l0a, l0b, l1a, l1b, z0a, z0b, z1a, z1b;
+        ln_upk(len0, l0a, l0b); ln_upk(len1, l1a, l1b);
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(z0a) : "f"(l0a));
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(z0b) : "f"(l0b));
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(z1a) : "f"(l1a));
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(z1b) : "f"(l1b));
+        u64 z0 = ln_pk(z0a, z0b), z1 = ln_pk(z1a, z1b);
+        const u64 nl0 = ln_sub(zero, len0), nl1 = ln_sub(zero, len1);
+        u64 e0 = em_pfma(nl0, z0, one), e1 = em_pfma(nl1, z1, one);
+        z0 = em_pfma(z0, e0, z0); z1 = em_pfma(z1, e1, z1);
+        e0 = em_pfma(nl0, z0, one); e1 = em_pfma(nl1, z1, one);
+        inv0 = em_pfma(z0, e0, z0); inv1 = em_pfma(z1, e1, z1);
     } else {
-        const float la = __fsqrt_rn(a), lb = __fsqrt_rn(b);
-        len = ln_pk(la, lb);
-        inv = ln_pk(__frcp_rn(la), __frcp_rn(lb));
+        const float s0a = __fsqrt_rn(a0), s0b = __fsqrt_rn(b0), s1a = __fsqrt_rn(a1), s1b = __fsqrt_rn(b1);
+        len0 = ln_pk(s0a, s0b); len1 = ln_pk(s1a, s1b);
+        inv0 = ln_pk(__frcp_rn(s0a), __frcp_rn(s0b)); inv1 = ln_pk(__frcp_rn(s1a), __frcp_rn(s1b));
     }
 }
 
@@ -85,333 +114,469 @@ __device__ __forceinline__ void ln_sqrt_rcp(u64 l2, u64 nz, u64& len, u64& inv)
 // one TMA box of 32 rows (48-byte rows run the TMA unit at a quarter of the HBM rate, 96-byte rows at all of it:
 // tools/ubench/store_pattern.cu).  A box must start on a 16-byte boundary: quads of the even instances start at
 // vertices 4q; the odd instances start 8 mod 16 when the instance stride is 8 mod 16 (an odd vertex count), their quads
-// then start at vertices 4q - 1 (phi = 1).  Vertices no whole in-range quad covers (the first three of a phi = 1 row, the
+// then start at vertices 4q - 1 (SHIFT).  Vertices no whole in-range quad covers (the first three of a shifted row, the
 // last n mod 4) are stored directly, 24 bytes per lane.
 struct LaneHalf {
     uint8_t* buf;                   // this warp's staging rows of the half: [32][96 B]
     const CUtensorMap* map;
     uint8_t* dst;                   // this lane's instance of the half (NULL = past the last instance)
-    int32_t v0, v1;                 // chunk-local vertices this warp stores for the half
-    int32_t phi, xoff;              // quad phase; word offset of vertex 0 in the map's rows
+    int32_t xoff;                   // word offset of vertex 0 in the map's rows
 };
 
-template <bool HI>
-__device__ __forceinline__ void ln_emit(const LaneHalf& H, const int32_t v, const int32_t gv, const int32_t nverts, const int32_t row0,
-                                        const uint32_t lane, const u64 (&Oprev)[6], const u64 (&O)[6])
+// vertex pair (ga, ga + 1) of one half: f = the 12 floats.  qs = first vertex of the pair's quad, second = the pair is
+// the quad's second one.
+__device__ __forceinline__ void ln_emit_pair(const LaneHalf& H, const int32_t ga, const int32_t qs, const bool second, const int32_t nverts,
+                                             const int32_t row0, const uint32_t lane, const float (&f)[12])
 {
-    if (v < H.v0 || v >= H.v1) return;
-    const int32_t j = (gv + H.phi) & 3, qs = gv - j;
     if (qs >= 0 && qs + 4 <= nverts) {
-        if (j & 1) {
-            if (j == 1) {                           // the buffer's previous box has been read (issued a quad ago)
-                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                __syncwarp();
-            }
-            float f[12];
-#pragma unroll
-            for (int k = 0; k < 6; ++k) {
-                float lo, hi;
-                ln_upk(Oprev[k], lo, hi); f[k] = HI ? hi : lo;
-                ln_upk(O[k], lo, hi); f[6 + k] = HI ? hi : lo;
-            }
-            float4* r = reinterpret_cast<float4*>(H.buf + lane * 96u + (uint32_t)(j >> 1) * 48u);
-            r[0] = make_float4(f[0], f[1], f[2], f[3]); r[1] = make_float4(f[4], f[5], f[6], f[7]); r[2] = make_float4(f[8], f[9], f[10], f[11]);
-            if (j == 3) {
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // my STS visible to the async proxy
-                __syncwarp();
-#ifndef LN_NO_STORE   // (timing experiments only: the arithmetic without the output stage)
-                if (lane == 0) {
-                    ln_tma_store_2d(H.map, ln_smem_u32(H.buf), qs * 6 + H.xoff, row0);
-                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                }
-#endif
-            }
+        if (!second) {                              // the buffer's previous box has been read (issued a quad ago)
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncwarp();
         }
-    } else if (H.dst) {
-        float2* d = reinterpret_cast<float2*>(H.dst + (size_t)gv * 24);
-        float f[6];
-#pragma unroll
-        for (int k = 0; k < 6; ++k) { float lo, hi; ln_upk(O[k], lo, hi); f[k] = HI ? hi : lo; }
-        d[0] = make_float2(f[0], f[1]); d[1] = make_float2(f[2], f[3]); d[2] = make_float2(f[4], f[5]);
+        float4* r = reinterpret_cast<float4*>(H.buf + lane * 96u + (second ? 48u : 0u));
+        r[0] = make_float4(f[0], f[1], f[2], f[3]); r[1] = make_float4(f[4], f[5], f[6], f[7]); r[2] = make_float4(f[8], f[9], f[10], f[11]);
+        if (second) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // my STS visible to the async proxy
+            __syncwarp();
+#ifndef LN_NO_STORE   // (timing experiments only: the arithmetic without the output stage)
+            if (lane == 0) {
+                ln_tma_store_2d(H.map, ln_smem_u32(H.buf), qs * 6 + H.xoff, row0);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+#endif
+        }
+    } else if (H.dst) {                             // head / tail of the row: 24 bytes per vertex, directly
+        if (ga >= 0 && ga < nverts) {
+            float2* d = reinterpret_cast<float2*>(H.dst + (size_t)ga * 24);
+            d[0] = make_float2(f[0], f[1]); d[1] = make_float2(f[2], f[3]); d[2] = make_float2(f[4], f[5]);
+        }
+        if (ga + 1 >= 0 && ga + 1 < nverts) {
+            float2* d = reinterpret_cast<float2*>(H.dst + (size_t)(ga + 1) * 24);
+            d[0] = make_float2(f[6], f[7]); d[1] = make_float2(f[8], f[9]); d[2] = make_float2(f[10], f[11]);
+        }
     }
 }
 
 struct LaneWalk {
     const uint8_t* s_pal_lane;      // palette base + lane * 16
     const uint4* s_rec;             // [1 + chunk vertices][2]; entry 0 = the vertex before the chunk
-    const float4* s_key;            // [1 + chunk vertices][3 (k1 6, k2 - k1 6) or, without morph, 1.5 -> 2 (k1 6, pad)]
+    const float4* s_key;            // [1 + chunk vertices][3 (k1 6, k2 - k1 6) or, without morph, 2 (k1 6, pad)]
     LaneHalf A, B;
-    int32_t v_begin, nverts;
-    int32_t vfirst, vend;           // chunk-local vertex range walked (vfirst may be -1: the vertex before the chunk)
+    int32_t v_begin, nverts, nv_chunk;
+    int32_t p0, p1;                 // chunk-local vertex pairs of this warp
     int32_t row0;
     uint32_t lane;
+    bool last_run;                  // this warp walks the mesh's last vertices
 };
 
-// The chunk walk of one warp: vertices vfirst..vend-1 in order, every value as the (A, B) pair of the lane's two instances.
-template <int NW, bool MORPH>
+// The chunk walk of one warp: vertex pairs p0..p1-1 in order, every value as the (A, B) pair of the lane's two instances.
+// SHIFT: the odd instances' pairs are (2p - 1, 2p); their half of vertex 2p - 1 is carried from the previous iteration, and
+// the walk starts one iteration early to have it (computing only that vertex).
+template <int NW, bool MORPH, bool SHIFT>
 __device__ __forceinline__ void lane_walk(const LaneWalk& K, const u64 T, const u64 NZ)
 {
-    u64 E[12], Oprev[6];
+    u64 E[12];
 #pragma unroll
     for (int k = 0; k < 12; ++k) E[k] = 0;
+    float carry[6];
 #pragma unroll
-    for (int k = 0; k < 6; ++k) Oprev[k] = 0;
+    for (int k = 0; k < 6; ++k) carry[k] = 0.f;
     uint32_t cur = 0xffffffffu;                       // slot offset whose matrix E is a plain copy of, or none
     const uint32_t lane = K.lane;
+    const bool lead = SHIFT && (K.p0 > 0 || K.v_begin > 0);       // one iteration early, for vertex 2*p0 - 1 alone
 #pragma unroll 1
-    for (int32_t v = K.vfirst; v < K.vend; ++v) {
-        const int32_t gv = K.v_begin + v;                               // mesh vertex (>= 0: chunk 0 never walks its -1)
-        u64 O[6];
-        const uint32_t vl = (uint32_t)(v + 1);
-        const uint4 r0 = K.s_rec[vl * 2u];
-        const float4* ky = K.s_key + vl * (MORPH ? 3u : 2u);
-        u64 V[6];
-        {
+    for (int32_t p = K.p0 - (lead ? 1 : 0); p < K.p1; ++p) {
+        const bool lead_it = SHIFT && p < K.p0;
+        u64 V[2][6], O[2][6], L2[2];
+        // ---- both vertices: keyframes -> animated source
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const uint32_t vl = (uint32_t)(max(min(2 * p + u, K.nv_chunk - 1), -1) + 1);   // past the odd last vertex: repeat it (never stored)
+            const float4* ky = K.s_key + vl * (MORPH ? 3u : 2u);
             const float4 a = ky[0], b = ky[1];
-            V[0] = ln_pk(a.x, a.x); V[1] = ln_pk(a.y, a.y); V[2] = ln_pk(a.z, a.z);     // warp-uniform scalars: ptxas folds the
-            V[3] = ln_pk(a.w, a.w); V[4] = ln_pk(b.x, b.x); V[5] = ln_pk(b.y, b.y);     // duplication into .F32 broadcast operands
+            V[u][0] = ln_pk(a.x, a.x); V[u][1] = ln_pk(a.y, a.y); V[u][2] = ln_pk(a.z, a.z);     // warp-uniform scalars: ptxas folds the
+            V[u][3] = ln_pk(a.w, a.w); V[u][4] = ln_pk(b.x, b.x); V[u][5] = ln_pk(b.y, b.y);     // duplication into .F32 broadcast operands
             if (MORPH) {
                 // dst = a + t*(b-a) (OgreOptimisedUtilGeneral.cpp:249-256); (b - a) is instance-invariant
                 const float4 c = ky[2];
-                V[0] = ln_add(V[0], ln_mul(T, ln_pk(b.z, b.z), NZ)); V[1] = ln_add(V[1], ln_mul(T, ln_pk(b.w, b.w), NZ));
-                V[2] = ln_add(V[2], ln_mul(T, ln_pk(c.x, c.x), NZ)); V[3] = ln_add(V[3], ln_mul(T, ln_pk(c.y, c.y), NZ));
-                V[4] = ln_add(V[4], ln_mul(T, ln_pk(c.z, c.z), NZ)); V[5] = ln_add(V[5], ln_mul(T, ln_pk(c.w, c.w), NZ));
-                // Vector3::normalise (OgreVector.h:494-508): scale by 1/len only when len > 0
-                const u64 l2 = ln_add(ln_add(ln_mul(V[3], V[3], NZ), ln_mul(V[4], V[4], NZ)), ln_mul(V[5], V[5], NZ));
-                u64 len, inv;
-                ln_sqrt_rcp(l2, NZ, len, inv);
+                V[u][0] = ln_add(V[u][0], ln_mul(T, ln_pk(b.z, b.z), NZ)); V[u][1] = ln_add(V[u][1], ln_mul(T, ln_pk(b.w, b.w), NZ));
+                V[u][2] = ln_add(V[u][2], ln_mul(T, ln_pk(c.x, c.x), NZ)); V[u][3] = ln_add(V[u][3], ln_mul(T, ln_pk(c.y, c.y), NZ));
+                V[u][4] = ln_add(V[u][4], ln_mul(T, ln_pk(c.z, c.z), NZ)); V[u][5] = ln_add(V[u][5], ln_mul(T, ln_pk(c.w, c.w), NZ));
+                L2[u] = ln_add(ln_add(ln_mul(V[u][3], V[u][3], NZ), ln_mul(V[u][4], V[u][4], NZ)), ln_mul(V[u][5], V[u][5], NZ));
+            }
+        }
+        if (MORPH) {
+            // Vector3::normalise (OgreVector.h:494-508): scale by 1/len only when len > 0
+            u64 len[2], inv[2];
+            ln_sqrt_rcp2(L2[0], L2[1], NZ, len[0], inv[0], len[1], inv[1]);
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
                 float la, lb, ia, ib;
-                ln_upk(len, la, lb); ln_upk(inv, ia, ib);
+                ln_upk(len[u], la, lb); ln_upk(inv[u], ia, ib);
                 const u64 I = ln_pk(la > 0.0f ? ia : 1.0f, lb > 0.0f ? ib : 1.0f);     // x * 1.0f == x
-                V[3] = ln_mul(V[3], I, NZ); V[4] = ln_mul(V[4], I, NZ); V[5] = ln_mul(V[5], I, NZ);
+                V[u][3] = ln_mul(V[u][3], I, NZ); V[u][4] = ln_mul(V[u][4], I, NZ); V[u][5] = ln_mul(V[u][5], I, NZ);
             }
         }
-        // ---- collapse: E[4*r + c] = (M_A[r][c], M_B[r][c]); control flow is warp-uniform (plan flags).
-        // One load site for slot 0 (E keeps its registers across the paths); a single-matrix vertex whose matrix E
-        // already holds loads nothing.
-        const uint32_t fl = r0.x & 15u, off0 = r0.x & ~15u;
-        const bool single = NW == 1 || (NW == 2 ? !(fl & 2u) : fl == 1u);
-        if (!(single && off0 == cur)) {
-            const ulonglong2* m0 = reinterpret_cast<const ulonglong2*>(K.s_pal_lane + off0);
+        // ---- per vertex: collapse the weighted matrix, transform
 #pragma unroll
-            for (int k = 0; k < 6; ++k) { const ulonglong2 q = m0[k * 32]; E[2 * k] = q.x; E[2 * k + 1] = q.y; }
-        }
-        cur = single ? off0 : 0xffffffffu;
-        if (NW >= 2 && !single) {
-            const float4 w = *reinterpret_cast<const float4*>(&K.s_rec[vl * 2u + 1u]);
-            if (NW == 2) {
-                const ulonglong2* m1 = reinterpret_cast<const ulonglong2*>(K.s_pal_lane + r0.y);
-                const u64 W1 = ln_pk(w.y, w.y);
+        for (int u = 0; u < 2; ++u) {
+            if (u == 0 && lead_it) continue;                            // the early iteration wants vertex 2p + 1 only
+            const uint32_t vl = (uint32_t)(max(min(2 * p + u, K.nv_chunk - 1), -1) + 1);
+            const uint4 r0 = K.s_rec[vl * 2u];
+            // E[4*r + c] = (M_A[r][c], M_B[r][c]); control flow is warp-uniform (plan flags).  One load site for slot 0 (E keeps
+            // its registers across the paths); a single-matrix vertex whose matrix E already holds loads nothing.
+            const uint32_t fl = r0.x & 15u, off0 = r0.x & ~15u;
+            const bool single = NW == 1 || (NW == 2 ? !(fl & 2u) : fl == 1u);
+            if (!(single && off0 == cur)) {
+                const ulonglong2* m0 = reinterpret_cast<const ulonglong2*>(K.s_pal_lane + off0);
 #pragma unroll
-                for (int k = 0; k < 6; ++k) {                           // lerp(M0, M1, w1) = (M1 - M0) * w1 + M0
-                    const ulonglong2 b = m1[k * 32];
-                    E[2 * k] = ln_add(ln_mul(ln_sub(b.x, E[2 * k]), W1, NZ), E[2 * k]);
-                    E[2 * k + 1] = ln_add(ln_mul(ln_sub(b.y, E[2 * k + 1]), W1, NZ), E[2 * k + 1]);
-                }
-            } else {
-                if (!(fl & 1u)) {                                       // w0 == 1.0f: 1 * x == x, nothing to do
-                    const u64 W0 = ln_pk(w.x, w.x);
+                for (int k = 0; k < 6; ++k) { const ulonglong2 q = m0[k * 32]; E[2 * k] = q.x; E[2 * k + 1] = q.y; }
+            }
+            cur = single ? off0 : 0xffffffffu;
+            if (NW >= 2 && !single) {
+                const float4 w = *reinterpret_cast<const float4*>(&K.s_rec[vl * 2u + 1u]);
+                if (NW == 2) {
+                    const ulonglong2* m1 = reinterpret_cast<const ulonglong2*>(K.s_pal_lane + r0.y);
+                    const u64 W1 = ln_pk(w.y, w.y);
 #pragma unroll
-                    for (int k = 0; k < 12; ++k) E[k] = ln_mul(E[k], W0, NZ);
-                }
-                if (fl & 2u) {
-                    const ulonglong2* mb = reinterpret_cast<const ulonglong2*>(K.s_pal_lane + r0.y);
-                    const u64 Wb = ln_pk(w.y, w.y);
-#pragma unroll
-                    for (int k = 0; k < 6; ++k) {
-                        const ulonglong2 q = mb[k * 32];
-                        E[2 * k] = ln_add(ln_mul(q.x, Wb, NZ), E[2 * k]);
-                        E[2 * k + 1] = ln_add(ln_mul(q.y, Wb, NZ), E[2 * k + 1]);
+                    for (int k = 0; k < 6; ++k) {                       // lerp(M0, M1, w1) = (M1 - M0) * w1 + M0
+                        const ulonglong2 b = m1[k * 32];
+                        E[2 * k] = ln_add(ln_mul(ln_sub(b.x, E[2 * k]), W1, NZ), E[2 * k]);
+                        E[2 * k + 1] = ln_add(ln_mul(ln_sub(b.y, E[2 * k + 1]), W1, NZ), E[2 * k + 1]);
                     }
-                }
-                if (fl & 4u) {
-                    const ulonglong2* mb = reinterpret_cast<const ulonglong2*>(K.s_pal_lane + r0.z);
-                    const u64 Wb = ln_pk(w.z, w.z);
+                } else {
+                    if (!(fl & 1u)) {                                   // w0 == 1.0f: 1 * x == x, nothing to do
+                        const u64 W0 = ln_pk(w.x, w.x);
 #pragma unroll
-                    for (int k = 0; k < 6; ++k) {
-                        const ulonglong2 q = mb[k * 32];
-                        E[2 * k] = ln_add(ln_mul(q.x, Wb, NZ), E[2 * k]);
-                        E[2 * k + 1] = ln_add(ln_mul(q.y, Wb, NZ), E[2 * k + 1]);
+                        for (int k = 0; k < 12; ++k) E[k] = ln_mul(E[k], W0, NZ);
                     }
-                }
-                if (NW == 4 && (fl & 8u)) {
-                    const ulonglong2* mb = reinterpret_cast<const ulonglong2*>(K.s_pal_lane + r0.w);
-                    const u64 Wb = ln_pk(w.w, w.w);
+                    if (fl & 2u) {
+                        const ulonglong2* mb = reinterpret_cast<const ulonglong2*>(K.s_pal_lane + r0.y);
+                        const u64 Wb = ln_pk(w.y, w.y);
 #pragma unroll
-                    for (int k = 0; k < 6; ++k) {
-                        const ulonglong2 q = mb[k * 32];
-                        E[2 * k] = ln_add(ln_mul(q.x, Wb, NZ), E[2 * k]);
-                        E[2 * k + 1] = ln_add(ln_mul(q.y, Wb, NZ), E[2 * k + 1]);
+                        for (int k = 0; k < 6; ++k) {
+                            const ulonglong2 q = mb[k * 32];
+                            E[2 * k] = ln_add(ln_mul(q.x, Wb, NZ), E[2 * k]);
+                            E[2 * k + 1] = ln_add(ln_mul(q.y, Wb, NZ), E[2 * k + 1]);
+                        }
+                    }
+                    if (fl & 4u) {
+                        const ulonglong2* mb = reinterpret_cast<const ulonglong2*>(K.s_pal_lane + r0.z);
+                        const u64 Wb = ln_pk(w.z, w.z);
+#pragma unroll
+                        for (int k = 0; k < 6; ++k) {
+                            const ulonglong2 q = mb[k * 32];
+                            E[2 * k] = ln_add(ln_mul(q.x, Wb, NZ), E[2 * k]);
+                            E[2 * k + 1] = ln_add(ln_mul(q.y, Wb, NZ), E[2 * k + 1]);
+                        }
+                    }
+                    if (NW == 4 && (fl & 8u)) {
+                        const ulonglong2* mb = reinterpret_cast<const ulonglong2*>(K.s_pal_lane + r0.w);
+                        const u64 Wb = ln_pk(w.w, w.w);
+#pragma unroll
+                        for (int k = 0; k < 6; ++k) {
+                            const ulonglong2 q = mb[k * 32];
+                            E[2 * k] = ln_add(ln_mul(q.x, Wb, NZ), E[2 * k]);
+                            E[2 * k + 1] = ln_add(ln_mul(q.y, Wb, NZ), E[2 * k + 1]);
+                        }
                     }
                 }
             }
+            // position: (r.x*x + r.y*y) + (r.z*z + r.w)   (__MM_DOT4x3_PS, OgreSIMDHelper.h:204-217)
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+                O[u][r] = ln_add(ln_add(ln_mul(E[4 * r], V[u][0], NZ), ln_mul(E[4 * r + 1], V[u][1], NZ)), ln_add(ln_mul(E[4 * r + 2], V[u][2], NZ), E[4 * r + 3]));
+            // normal: (r.x*x + r.y*y) + r.z*z (OgreSIMDHelper.h:220-227); its exact 1/sqrt(len2) for both vertices below
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+                O[u][3 + r] = ln_add(ln_add(ln_mul(E[4 * r], V[u][3], NZ), ln_mul(E[4 * r + 1], V[u][4], NZ)), ln_mul(E[4 * r + 2], V[u][5], NZ));
+            L2[u] = ln_add(ln_add(ln_mul(O[u][3], O[u][3], NZ), ln_mul(O[u][4], O[u][4], NZ)), ln_mul(O[u][5], O[u][5], NZ));
         }
-        // ---- position: (r.x*x + r.y*y) + (r.z*z + r.w)   (__MM_DOT4x3_PS, OgreSIMDHelper.h:204-217)
+        if (SHIFT && lead_it) L2[0] = L2[1];                            // keep the unused half in range
+        {
+            u64 len[2], R[2];
+            ln_sqrt_rcp2(L2[0], L2[1], NZ, len[0], R[0], len[1], R[1]);
 #pragma unroll
-        for (int r = 0; r < 3; ++r)
-            O[r] = ln_add(ln_add(ln_mul(E[4 * r], V[0], NZ), ln_mul(E[4 * r + 1], V[1], NZ)), ln_add(ln_mul(E[4 * r + 2], V[2], NZ), E[4 * r + 3]));
-        // ---- normal: (r.x*x + r.y*y) + r.z*z (OgreSIMDHelper.h:220-227), then exact 1/sqrt(len2)
-        u64 N[3];
-#pragma unroll
-        for (int r = 0; r < 3; ++r)
-            N[r] = ln_add(ln_add(ln_mul(E[4 * r], V[3], NZ), ln_mul(E[4 * r + 1], V[4], NZ)), ln_mul(E[4 * r + 2], V[5], NZ));
-        const u64 l2 = ln_add(ln_add(ln_mul(N[0], N[0], NZ), ln_mul(N[1], N[1], NZ)), ln_mul(N[2], N[2], NZ));
-        u64 len, R;
-        ln_sqrt_rcp(l2, NZ, len, R);
-        O[3] = ln_mul(N[0], R, NZ); O[4] = ln_mul(N[1], R, NZ); O[5] = ln_mul(N[2], R, NZ);
+            for (int u = 0; u < 2; ++u) { O[u][3] = ln_mul(O[u][3], R[u], NZ); O[u][4] = ln_mul(O[u][4], R[u], NZ); O[u][5] = ln_mul(O[u][5], R[u], NZ); }
+        }
         // ---- output
-        ln_emit<false>(K.A, v, gv, K.nverts, K.row0, lane, Oprev, O);
-        ln_emit<true>(K.B, v, gv, K.nverts, K.row0, lane, Oprev, O);
+        const int32_t ga = K.v_begin + 2 * p;                           // mesh vertex of the pair's first
+        float fa[12], fb[12];
 #pragma unroll
-        for (int k = 0; k < 6; ++k) Oprev[k] = O[k];
+        for (int k = 0; k < 6; ++k) { ln_upk(O[0][k], fa[k], fb[k]); ln_upk(O[1][k], fa[6 + k], fb[6 + k]); }
+        if (!lead_it) {
+            const bool second = (ga & 2) != 0;
+            ln_emit_pair(K.A, ga, ga & ~3, second, K.nverts, K.row0, lane, fa);
+            if (!SHIFT) ln_emit_pair(K.B, ga, ga & ~3, second, K.nverts, K.row0, lane, fb);
+            else {
+                float g[12];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) { g[k] = carry[k]; g[6 + k] = fb[k]; }
+                ln_emit_pair(K.B, ga - 1, (ga & ~3) - 1, second, K.nverts, K.row0, lane, g);
+            }
+        }
+        if (SHIFT) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) carry[k] = fb[6 + k];
+        }
     }
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // shared memory must outlive the reads
-    __syncwarp();
+    // shifted rows, even vertex count: the mesh's last vertex (odd) of the odd instances has no partner
+    if (SHIFT && K.last_run && !(K.nverts & 1) && K.B.dst) {
+        float2* d = reinterpret_cast<float2*>(K.B.dst + (size_t)(K.nverts - 1) * 24);
+        d[0] = make_float2(carry[0], carry[1]); d[1] = make_float2(carry[2], carry[3]); d[2] = make_float2(carry[4], carry[5]);
+    }
 }
 
+__device__ __forceinline__ void ln_mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void ln_mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void ln_mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+
+__device__ __forceinline__ void ln_mbar_wait_relaxed(uint32_t bar, uint32_t parity)      // off the critical path: back off between polls
+{
+    uint32_t ok;
+    for (;;) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) break;
+        __nanosleep(32);
+    }
+}
+
+// Palettes -> the pair layout the lane kernel keeps in shared memory, once per frame: for every group of 64 instances and
+// every palette matrix, 3 KB = [6 chunks][32 lanes] x 16 bytes (A.e, B.e, A.e+1, B.e+1) with A, B = the lane's two instances,
+// so that the lane kernel's producer fetches a chunk's matrices with one bulk copy each and nobody transposes per unit.
+// Also the two exactness hazards per (group, matrix): bit 0 = some instance holds a -0 or a negative denormal (a zero
+// weight may not be skipped when that is the slot-0 matrix), bit 1 = something is not finite or >= 2^127.
+// One warp per (group, matrix); lane = instance pair.
+__global__ void __launch_bounds__(256) palette_repack_kernel(const float* __restrict__ palette, size_t pal_stride_floats, uint32_t ninst, uint32_t nmat,
+                                                              uint32_t groups, uint8_t* __restrict__ ipal, uint32_t* __restrict__ iflags)
+{
+    const uint32_t w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31u;
+    if (w >= groups * nmat) return;
+    const uint32_t g = w / nmat, m = w - g * nmat;
+    const uint32_t ia = min(g * 64u + 2u * lane, ninst - 1u), ib = min(g * 64u + 2u * lane + 1u, ninst - 1u);     // lanes past the end repeat the last instance
+    const float4* pa = reinterpret_cast<const float4*>(palette + (size_t)ia * pal_stride_floats + m * 16u);
+    const float4* pb = reinterpret_cast<const float4*>(palette + (size_t)ib * pal_stride_floats + m * 16u);
+    float4 A[3], B[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) { A[r] = __ldg(pa + r); B[r] = __ldg(pb + r); }
+    bool dz = false, hg = false;
+    float4* d = reinterpret_cast<float4*>(ipal + (size_t)w * LN_SLOT_BYTES) + lane;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const uint32_t u[8] = {__float_as_uint(A[r].x), __float_as_uint(A[r].y), __float_as_uint(A[r].z), __float_as_uint(A[r].w),
+                               __float_as_uint(B[r].x), __float_as_uint(B[r].y), __float_as_uint(B[r].z), __float_as_uint(B[r].w)};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { dz |= ln_neg_zero_or_denormal(u[k]); hg |= ln_huge(u[k]); }
+        d[(2 * r) * 32] = make_float4(A[r].x, B[r].x, A[r].y, B[r].y);
+        d[(2 * r + 1) * 32] = make_float4(A[r].z, B[r].z, A[r].w, B[r].w);
+    }
+    const uint32_t f = (__any_sync(0xffffffffu, dz) ? 1u : 0u) | (__any_sync(0xffffffffu, hg) ? 2u : 0u);
+    if (lane == 0) iflags[w] = f;
+}
+
+// what the producer leaves in a unit buffer besides palettes, records and keyframes
+struct LaneUnitMeta { uint32_t done, job, v_begin, nquads, i0, pad[3]; };     // 32 bytes, followed by the 32 lanes' (tA, tB)
+
+// One persistent CTA per SM: 16 consumer warps walk work units (one vertex chunk x one group of 64 instances), one PRODUCER
+// warp prepares the next unit while they do: it takes the unit from a global counter, gathers the 64 instances' palettes
+// (the chunk's bones only) into the [slot][chunk][lane] pair layout, tests them for the two exactness hazards, and copies
+// the chunk's plan records (with the zero-skip flags withdrawn where a hazard was found) and keyframes.  Two unit buffers,
+// full / empty mbarriers: no CTA barrier after start-up, the consumers never wait for global memory.
 template <bool MORPH>
-__global__ void __launch_bounds__(LN_THREADS, 2) skin_lane_kernel(const __grid_constant__ LaneParams P, const u64 NZ)
+__global__ void __launch_bounds__(LN_THREADS, 1) skin_lane_kernel(const __grid_constant__ LaneParams P, const u64 NZ)
 {
     constexpr int KEY_BYTES = MORPH ? 48 : 32;
+    constexpr uint32_t RAW_BYTES = ((LN_CHUNK_VERTS + 1) * 4 + 15) & ~15;
+    constexpr uint32_t UNIT_BYTES = LN_MAXB * LN_SLOT_BYTES + (LN_CHUNK_VERTS + 1) * LN_REC_BYTES + (LN_CHUNK_VERTS + 1) * KEY_BYTES + RAW_BYTES + 32 + 256;
     extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t* s_stage = smem;                                                       // [warps][A, B][32 x 96 B], 128-byte aligned boxes
-    uint8_t* s_pal = s_stage + LN_WARPS * 2 * LN_BOX_BYTES;                        // [LN_MAXB][6][32] x 16 B
-    uint4* s_rec = reinterpret_cast<uint4*>(s_pal + LN_MAXB * LN_SLOT_BYTES);      // [LN_CHUNK_VERTS + 1][2]
-    float4* s_key = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(s_rec) + (LN_CHUNK_VERTS + 1) * LN_REC_BYTES);
-    uint32_t* s_dirty = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(s_key) + (LN_CHUNK_VERTS + 1) * KEY_BYTES);   // [LN_MAXB + 1]
+    uint8_t* s_stage = smem;                                                       // [consumer warps][A, B][32 x 96 B], 128-byte aligned boxes
+    uint8_t* s_unit = s_stage + LN_WARPS * 2 * LN_BOX_BYTES;                       // [2] x {palette, records, keys, meta}
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_unit + 2 * UNIT_BYTES);        // full[2], empty[2]
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
-    // ---- which (job, chunk, instance group) this CTA is
-    uint32_t j = 0;
+    if (tid == 0) {
+        ln_mbar_init(ln_smem_u32(&s_bar[0]), 2); ln_mbar_init(ln_smem_u32(&s_bar[1]), 2);       // full: the producer's expect_tx arrive + its final arrive
+        ln_mbar_init(ln_smem_u32(&s_bar[2]), LN_WARPS); ln_mbar_init(ln_smem_u32(&s_bar[3]), LN_WARPS);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (wid == LN_WARPS) {
+        // ================================================================ producer warp
+        uint32_t held0 = 0xffffffffu, held1 = 0xffffffffu;                  // which chunk's records / keys each buffer holds
+        uint32_t next_unit = 0;
+        if (lane == 0) next_unit = atomicAdd(P.counter, 1u);
+        for (uint32_t it = 0;; ++it) {
+            const uint32_t b = it & 1u;
+            uint8_t* U = s_unit + b * UNIT_BYTES;
+            uint8_t* u_pal = U;
+            uint4* u_rec = reinterpret_cast<uint4*>(U + LN_MAXB * LN_SLOT_BYTES);
+            uint8_t* u_key = reinterpret_cast<uint8_t*>(u_rec) + (LN_CHUNK_VERTS + 1) * LN_REC_BYTES;
+            uint32_t* u_raw = reinterpret_cast<uint32_t*>(u_key + (LN_CHUNK_VERTS + 1) * KEY_BYTES);
+            LaneUnitMeta* u_meta = reinterpret_cast<LaneUnitMeta*>(reinterpret_cast<uint8_t*>(u_raw) + RAW_BYTES);
+            const uint32_t full = ln_smem_u32(&s_bar[b]);
+            // ---- everything that does not touch the buffer first: the unit, its chunk, its hazard flags
+            const uint32_t unit = __shfl_sync(0xffffffffu, next_unit, 0);
+            const bool done = unit >= P.total_units;
+            uint32_t j = 0, c = 0, g = 0;
+            uint4 ch = make_uint4(0, 0, 0, 0);
+            uint32_t gm_mine = 0, fl_mine = 0;
+            float2 t_mine = make_float2(0.f, 0.f);
+            if (!done) {
 #pragma unroll 1
-    while (j + 1 < P.njobs && blockIdx.x >= P.job[j + 1].first_item) ++j;
-    const LaneJob& J = P.job[j];
-    const uint32_t local = blockIdx.x - J.first_item;
-    const uint32_t c = local / P.groups, g = local - c * P.groups;
-    const uint4* chrec = J.chunks + (size_t)c * 3;         // {v_begin, nquads, nslots, -}, 16 x u16 palette matrix of each slot
-    const uint4 ch = __ldg(chrec);
-    const uint32_t v_begin = ch.x, nquads = ch.y, nslots = ch.z;
-    const uint32_t nv_chunk = min(4u * nquads, J.nverts - v_begin);
-    const uint32_t i0 = g * 64u;
+                while (j + 1 < P.njobs && unit >= P.job[j + 1].first_item) ++j;
+                const uint32_t local = unit - P.job[j].first_item;
+                c = local / P.groups; g = local - c * P.groups;
+                const uint4* chrec = P.job[j].chunks + (size_t)c * 3;      // {v_begin, nquads, nslots, -}, 16 x u16 palette matrix of each slot
+                ch = __ldg(chrec);
+                if (lane < LN_MAXB) gm_mine = (uint32_t)__ldg(reinterpret_cast<const uint16_t*>(chrec + 1) + lane);
+                if (lane < ch.z) fl_mine = __ldg(P.iflags + (size_t)g * P.nmat + gm_mine);
+                next_unit = 0;
+                if (lane == 0) next_unit = atomicAdd(P.counter, 1u);       // the next unit's number travels while this one is prepared
+                if (MORPH) {                                               // the instances' morph weights, as (A, B) per lane
+                    const uint32_t ia = min(g * 64u + 2u * lane, P.ninst - 1u), ib = min(g * 64u + 2u * lane + 1u, P.ninst - 1u);
+                    t_mine = make_float2(__ldg(P.t + ia), __ldg(P.t + ib));
+                }
+            }
+            if (it >= 2) ln_mbar_wait_relaxed(ln_smem_u32(&s_bar[2 + b]), ((it >> 1) - 1u) & 1u);      // the consumers are done with this buffer
+            if (done) {
+                if (lane == 0) { u_meta->done = 1; ln_mbar_arrive(full); ln_mbar_arrive(full); }
+                break;
+            }
+            const LaneJob& J = P.job[j];
+            const uint32_t v_begin = ch.x, nquads = ch.y, nslots = ch.z;
+            const uint32_t nv_chunk = min(4u * nquads, J.nverts - v_begin);
+            const uint32_t i0 = g * 64u;
+            // ---- palettes: one 3 KB bulk copy per slot from the repacked palettes (already in the [chunk][lane] pair layout),
+            // completion counted on the buffer's full barrier
+            if (lane == 0) {
+                asm volatile("mbarrier.arrive.expect_tx.release.cta.shared::cta.b64 _, [%0], %1;" ::"r"(full), "r"(nslots * (uint32_t)LN_SLOT_BYTES) : "memory");
+            }
+            __syncwarp();
+            if (lane < nslots) {
+                const uint8_t* src = P.ipal + ((size_t)g * P.nmat + gm_mine) * LN_SLOT_BYTES;
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(ln_smem_u32(u_pal + lane * LN_SLOT_BYTES)), "l"(src), "r"((uint32_t)LN_SLOT_BYTES), "r"(full) : "memory");
+            }
+            // ---- plan records and keyframes of the chunk (entry 0: the vertex before it); units arrive chunk-major, so the
+            // buffer usually holds them already.  The flag word is kept raw on the side: it is re-derived per unit below.
+            const uint32_t chunk_id = (j << 24) | c;
+            if ((b ? held1 : held0) != chunk_id) {
+                if (b) held1 = chunk_id; else held0 = chunk_id;
+                for (uint32_t e = lane; e <= nv_chunk; e += 32u) {
+                    if (e == 0 && v_begin == 0) continue;
+                    const uint32_t gv = v_begin + e - 1u;
+                    const uint4* r = e == 0 ? J.pre_recs + (size_t)c * 2 : J.recs + (size_t)gv * 2;
+                    const uint4 rec0 = __ldg(r), rec1 = __ldg(r + 1);
+                    const float2* a = reinterpret_cast<const float2*>(J.key1 + (size_t)gv * 24);
+                    const float2 a0 = __ldg(a), a1 = __ldg(a + 1), a2 = __ldg(a + 2);
+                    float* ky = reinterpret_cast<float*>(u_key + e * KEY_BYTES);
+                    ky[0] = a0.x; ky[1] = a0.y; ky[2] = a1.x; ky[3] = a1.y; ky[4] = a2.x; ky[5] = a2.y;
+                    if (MORPH) {
+                        const float2* k2 = reinterpret_cast<const float2*>(J.key2 + (size_t)gv * 24);
+                        const float2 b0 = __ldg(k2), b1 = __ldg(k2 + 1), b2 = __ldg(k2 + 2);
+                        ky[6] = fsub(b0.x, a0.x); ky[7] = fsub(b0.y, a0.y); ky[8] = fsub(b1.x, a1.x);        // (b - a) is instance-invariant
+                        ky[9] = fsub(b1.y, a1.y); ky[10] = fsub(b2.x, a2.x); ky[11] = fsub(b2.y, a2.y);
+                    }
+                    u_rec[e * 2u] = rec0; u_rec[e * 2u + 1u] = rec1;
+                    u_raw[e] = rec0.x;
+                }
+                __syncwarp();
+            }
+            if (MORPH) reinterpret_cast<float2*>(u_meta + 1)[lane] = t_mine;
+            // a vertex whose slot-0 matrix holds a -0 in some instance, or any vertex when something is not finite, takes every slot
+            {
+                const uint32_t dirty_mask = __ballot_sync(0xffffffffu, (fl_mine & 1u) != 0u);
+                const uint32_t huge_any = __any_sync(0xffffffffu, (fl_mine & 2u) != 0u) ? 1u : 0u;
+                const uint32_t fullmask = J.nw >= 3 ? (J.nw == 3 ? 6u : 14u) : 2u;
+                for (uint32_t e = lane; e <= nv_chunk; e += 32u) {
+                    const uint32_t x = u_raw[e];
+                    const uint32_t slot0 = (x & ~15u) / LN_SLOT_BYTES;
+                    reinterpret_cast<uint32_t*>(&u_rec[e * 2u])[0] = (huge_any | ((dirty_mask >> slot0) & 1u)) ? ((x & ~15u) | fullmask) : x;
+                }
+            }
+            if (lane == 0) { u_meta->done = 0; u_meta->job = j; u_meta->v_begin = v_begin; u_meta->nquads = nquads; u_meta->i0 = i0; }
+            __syncwarp();
+            if (lane == 0) ln_mbar_arrive(full);                            // release: everything above is visible to who acquires
+        }
+        return;
+    }
 
-    // ---- palettes of the 64 instances, the chunk's bones only -> [slot][chunk][lane] (A.e, B.e, A.e+1, B.e+1).
-    // Task e = (slot, instance pair, row): three threads read one matrix's 48 bytes.  All loads of a thread first.
-    constexpr int PG = (LN_MAXB * 96 + LN_THREADS - 1) / LN_THREADS;
-    float4 PA[PG], PB[PG];
-    {
-        const uint16_t* slots = reinterpret_cast<const uint16_t*>(chrec + 1);
-#pragma unroll
-        for (int k = 0; k < PG; ++k) {
-            const uint32_t e = tid + LN_THREADS * k;
-            if (e < nslots * 96u) {
-                const uint32_t s = e / 96u, q = e - s * 96u, l = q / 3u, r = q - l * 3u;
-                const uint32_t gm = (uint32_t)__ldg(slots + s);
-                const uint32_t ia = min(i0 + 2u * l, P.ninst - 1u), ib = min(i0 + 2u * l + 1u, P.ninst - 1u);     // lanes past the end repeat the last instance
-                PA[k] = __ldg(reinterpret_cast<const float4*>(P.palette + (size_t)ia * P.pal_stride_floats + gm * 16u + r * 4u));
-                PB[k] = __ldg(reinterpret_cast<const float4*>(P.palette + (size_t)ib * P.pal_stride_floats + gm * 16u + r * 4u));
+    // ==================================================================== consumer warps
+    uint8_t* my_stage = s_stage + wid * (2 * LN_BOX_BYTES);
+    for (uint32_t it = 0;; ++it) {
+        const uint32_t b = it & 1u;
+        const uint8_t* U = s_unit + b * UNIT_BYTES;
+        const uint4* u_rec = reinterpret_cast<const uint4*>(U + LN_MAXB * LN_SLOT_BYTES);
+        const uint8_t* u_key = reinterpret_cast<const uint8_t*>(u_rec) + (LN_CHUNK_VERTS + 1) * LN_REC_BYTES;
+        const LaneUnitMeta* u_meta = reinterpret_cast<const LaneUnitMeta*>(u_key + (LN_CHUNK_VERTS + 1) * KEY_BYTES + RAW_BYTES);
+        ln_mbar_wait(ln_smem_u32(&s_bar[b]), (it >> 1) & 1u);
+        if (u_meta->done) break;
+        const LaneJob& J = P.job[u_meta->job];
+        const uint32_t v_begin = u_meta->v_begin, nquads = u_meta->nquads, i0 = u_meta->i0;
+        const uint32_t nv_chunk = min(4u * nquads, J.nverts - v_begin);
+        // contiguous runs of quads per warp (consecutive vertices share bones: the matrix stays in registers).  (Handing the
+        // quads out on demand through a shared-memory ticket evens the warps out but loses more in per-hand-out overhead:
+        // 0.504 -> 0.527 ms on the bench step.)
+        const uint32_t per = (nquads + LN_WARPS - 1u) / LN_WARPS;
+        const uint32_t q0 = min(wid * per, nquads), q1 = min(q0 + per, nquads);
+        if (q0 < q1) {
+            u64 T = 0;
+            if (MORPH) T = reinterpret_cast<const u64*>(u_meta + 1)[lane];
+            const uint32_t r1 = min(4u * q1, nv_chunk);
+            LaneWalk K;
+            K.s_pal_lane = U + lane * 16u;
+            K.s_rec = u_rec; K.s_key = reinterpret_cast<const float4*>(u_key);
+            K.A.buf = my_stage;
+            K.B.buf = my_stage + LN_BOX_BYTES;
+            K.A.map = &J.mapA; K.B.map = &J.mapB;
+            K.A.dst = i0 + 2u * lane < P.ninst ? J.dst + (size_t)(i0 + 2u * lane) * J.dst_stride : nullptr;
+            K.B.dst = i0 + 2u * lane + 1u < P.ninst ? J.dst + (size_t)(i0 + 2u * lane + 1u) * J.dst_stride : nullptr;
+            K.A.xoff = 0;
+            K.B.xoff = 2 * (int32_t)J.shift;               // shifted: map B starts 8 bytes before the odd instance
+            K.v_begin = (int32_t)v_begin; K.nverts = (int32_t)J.nverts; K.nv_chunk = (int32_t)nv_chunk;
+            K.p0 = (int32_t)(2u * q0); K.p1 = (int32_t)((r1 + 1u) >> 1);
+            K.last_run = v_begin + r1 == J.nverts;
+            K.row0 = (int32_t)(i0 >> 1);
+            K.lane = lane;
+            if (J.shift) {
+                switch (J.nw) {
+                case 1: lane_walk<1, MORPH, true>(K, T, NZ); break;
+                case 2: lane_walk<2, MORPH, true>(K, T, NZ); break;
+                case 3: lane_walk<3, MORPH, true>(K, T, NZ); break;
+                default: lane_walk<4, MORPH, true>(K, T, NZ); break;
+                }
+            } else {
+                switch (J.nw) {
+                case 1: lane_walk<1, MORPH, false>(K, T, NZ); break;
+                case 2: lane_walk<2, MORPH, false>(K, T, NZ); break;
+                case 3: lane_walk<3, MORPH, false>(K, T, NZ); break;
+                default: lane_walk<4, MORPH, false>(K, T, NZ); break;
+                }
             }
         }
+        __syncwarp();
+        if (lane == 0) ln_mbar_arrive(ln_smem_u32(&s_bar[2 + b]));           // this warp no longer reads the unit buffer
     }
-    if (tid <= LN_MAXB) s_dirty[tid] = 0;
-    // raw plan record and keyframes of my vertex (thread 0: the vertex before the chunk, thread 1 + i: chunk vertex i)
-    uint4 rec0 = make_uint4(0, 0, 0, 0), rec1 = rec0;
-    float k1[6], k2[6];
-#pragma unroll
-    for (int k = 0; k < 6; ++k) { k1[k] = 0.f; k2[k] = 0.f; }
-    const bool has_v = tid == 0 ? v_begin > 0 : tid <= nv_chunk;
-    if (has_v) {
-        const uint32_t gv = v_begin + tid - 1u;
-        const uint4* r = tid == 0 ? J.pre_recs + (size_t)c * 2 : J.recs + (size_t)gv * 2;
-        rec0 = __ldg(r); rec1 = __ldg(r + 1);
-        const float* a = reinterpret_cast<const float*>(J.key1 + (size_t)gv * 24);
-#pragma unroll
-        for (int k = 0; k < 6; ++k) k1[k] = __ldg(a + k);
-        if (MORPH) {
-            const float* b = reinterpret_cast<const float*>(J.key2 + (size_t)gv * 24);
-#pragma unroll
-            for (int k = 0; k < 6; ++k) k2[k] = __ldg(b + k);
-        }
-    }
-    __syncthreads();                                       // s_dirty cleared
-    {
-#pragma unroll
-        for (int k = 0; k < PG; ++k) {
-            const uint32_t e = tid + LN_THREADS * k;
-            if (e < nslots * 96u) {
-                const uint32_t s = e / 96u, q = e - s * 96u, l = q / 3u, r = q - l * 3u;
-                const float4 A = PA[k], B = PB[k];
-                const uint32_t u0 = __float_as_uint(A.x), u1 = __float_as_uint(A.y), u2 = __float_as_uint(A.z), u3 = __float_as_uint(A.w);
-                const uint32_t u4 = __float_as_uint(B.x), u5 = __float_as_uint(B.y), u6 = __float_as_uint(B.z), u7 = __float_as_uint(B.w);
-                if (ln_neg_zero_or_denormal(u0) || ln_neg_zero_or_denormal(u1) || ln_neg_zero_or_denormal(u2) || ln_neg_zero_or_denormal(u3) ||
-                    ln_neg_zero_or_denormal(u4) || ln_neg_zero_or_denormal(u5) || ln_neg_zero_or_denormal(u6) || ln_neg_zero_or_denormal(u7)) s_dirty[s] = 1;
-                if (ln_huge(u0) || ln_huge(u1) || ln_huge(u2) || ln_huge(u3) || ln_huge(u4) || ln_huge(u5) || ln_huge(u6) || ln_huge(u7)) s_dirty[LN_MAXB] = 1;
-                float4* d = reinterpret_cast<float4*>(s_pal + s * LN_SLOT_BYTES + (2u * r) * 512u + l * 16u);
-                d[0] = make_float4(A.x, B.x, A.y, B.y);
-                d[32] = make_float4(A.z, B.z, A.w, B.w);
-            }
-        }
-    }
-    __syncthreads();                                       // palettes and exactness flags complete
-    if (has_v) {
-        // a vertex whose slot-0 matrix holds a -0 in some instance, or any vertex when something is not finite, takes every slot
-        const uint32_t slot0 = (rec0.x & ~15u) / LN_SLOT_BYTES;
-        if (s_dirty[LN_MAXB] | s_dirty[slot0]) rec0.x = (rec0.x & ~15u) | (J.nw >= 3 ? (J.nw == 3 ? 6u : 14u) : 2u);
-        s_rec[tid * 2u] = rec0; s_rec[tid * 2u + 1u] = rec1;
-        float* ky = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(s_key) + tid * KEY_BYTES);
-#pragma unroll
-        for (int k = 0; k < 6; ++k) ky[k] = k1[k];
-        if (MORPH) {
-#pragma unroll
-            for (int k = 0; k < 6; ++k) ky[6 + k] = fsub(k2[k], k1[k]);
-        }
-    }
-    __syncthreads();                                       // the last CTA barrier: from here on the warps run independently
-
-    u64 T = 0;
-    if (MORPH) {
-        const uint32_t ia = min(i0 + 2u * lane, P.ninst - 1u), ib = min(i0 + 2u * lane + 1u, P.ninst - 1u);
-        T = ln_pk(__ldg(P.t + ia), __ldg(P.t + ib));
-    }
-    // contiguous runs of quads per warp (consecutive vertices share bones: the matrix stays in registers)
-    const uint32_t per = (nquads + LN_WARPS - 1u) / LN_WARPS;
-    const uint32_t q0 = min(wid * per, nquads), q1 = min(q0 + per, nquads);
-    if (q0 >= q1) return;
-    const int32_t r0 = (int32_t)(4u * q0), r1 = (int32_t)min(4u * q1, nv_chunk);
-    const bool last_run = v_begin + (uint32_t)r1 == J.nverts;
-    const int32_t shift = (int32_t)J.shift;
-    LaneWalk K;
-    K.s_pal_lane = s_pal + lane * 16u;
-    K.s_rec = s_rec; K.s_key = s_key;
-    K.A.buf = s_stage + wid * (2 * LN_BOX_BYTES);
-    K.B.buf = K.A.buf + LN_BOX_BYTES;
-    K.A.map = &J.mapA; K.B.map = &J.mapB;
-    K.A.dst = i0 + 2u * lane < P.ninst ? J.dst + (size_t)(i0 + 2u * lane) * J.dst_stride : nullptr;
-    K.B.dst = i0 + 2u * lane + 1u < P.ninst ? J.dst + (size_t)(i0 + 2u * lane + 1u) * J.dst_stride : nullptr;
-    K.A.phi = 0; K.A.xoff = 0;
-    K.B.phi = shift; K.B.xoff = 2 * shift;                 // shifted: map B starts 8 bytes before the odd instance
-    K.A.v0 = r0; K.A.v1 = r1;
-    // the shifted half stores the quads that START in this run: vertices r0-1 .. r1-2, and the mesh's last run its last vertex too
-    K.B.v0 = (v_begin == 0 && r0 == 0) ? 0 : r0 - shift;
-    K.B.v1 = last_run ? r1 : r1 - shift;
-    K.v_begin = (int32_t)v_begin; K.nverts = (int32_t)J.nverts;
-    K.vfirst = K.B.v0 < r0 ? K.B.v0 : r0;
-    K.vend = r1;
-    K.row0 = (int32_t)(i0 >> 1);
-    K.lane = lane;
-    switch (J.nw) {
-    case 1: lane_walk<1, MORPH>(K, T, NZ); break;
-    case 2: lane_walk<2, MORPH>(K, T, NZ); break;
-    case 3: lane_walk<3, MORPH>(K, T, NZ); break;
-    default: lane_walk<4, MORPH>(K, T, NZ); break;
-    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // shared memory must outlive the TMA reads
+    __syncwarp();
 }
 
 // ------------------------------------------------------------------------------------------------ host side
 
 static size_t lane_smem(bool morph)
 {
-    return (size_t)LN_WARPS * 2 * LN_BOX_BYTES + (size_t)LN_MAXB * LN_SLOT_BYTES + (size_t)(LN_CHUNK_VERTS + 1) * LN_REC_BYTES +
-           (size_t)(LN_CHUNK_VERTS + 1) * (morph ? 48 : 32) + (LN_MAXB + 1) * 4 + 16;
+    const size_t unit = (size_t)LN_MAXB * LN_SLOT_BYTES + (size_t)(LN_CHUNK_VERTS + 1) * LN_REC_BYTES + (size_t)(LN_CHUNK_VERTS + 1) * (morph ? 48 : 32) +
+                        (((LN_CHUNK_VERTS + 1) * 4 + 15) & ~15) + 32 + 256;
+    return (size_t)LN_WARPS * 2 * LN_BOX_BYTES + 2 * unit + 4 * 8;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -459,8 +624,21 @@ bool skin_lane_eligible(const ogrecu_skin_plan* plan, const ogrecu_anim_job& J, 
     return plan->num_vertices == j.num_vertices && plan->num_weights == j.num_weights && plan->num_matrices == j.num_matrices;
 }
 
+int repack_palettes(ogrecu_ctx* ctx, const float* palette, size_t palette_stride_floats, uint32_t num_instances, uint32_t nmat)
+{
+    const uint32_t groups = div_up(num_instances, 64);
+    OGRECU_REQUIRE((size_t)nmat * 16 <= palette_stride_floats, "palette stride smaller than the matrices the plans reference");
+    const size_t ipal_bytes = (size_t)groups * nmat * LN_SLOT_BYTES, iflag_bytes = (size_t)groups * nmat * 4;
+    OGRECU_CHECK(scratch_reserve(ctx, ctx->lane_ipal, ipal_bytes + iflag_bytes));
+    palette_repack_kernel<<<div_up((size_t)groups * nmat, 8), 256, 0, ctx->stream>>>(palette, palette_stride_floats, num_instances, nmat, groups,
+                                                                                 (uint8_t*)ctx->lane_ipal.ptr, (uint32_t*)((uint8_t*)ctx->lane_ipal.ptr + ipal_bytes));
+    OGRECU_CUDA(cudaGetLastError());
+    count_launch(ctx);
+    return OGRECU_OK;
+}
+
 int launch_skin_lane(ogrecu_ctx* ctx, const ogrecu_anim_job* jobs, ogrecu_skin_plan* const* plans, uint32_t num_jobs, const float* t_dev,
-                     uint32_t num_instances, size_t palette_stride_floats, bool morph)
+                     uint32_t num_instances, size_t palette_stride_floats, bool morph, uint32_t nmat)
 {
     OGRECU_REQUIRE(num_jobs >= 1 && num_jobs <= LN_MAX_JOBS, "1..8 jobs per lane launch");
     LaneParams P;
@@ -506,8 +684,17 @@ int launch_skin_lane(ogrecu_ctx* ctx, const ogrecu_anim_job* jobs, ogrecu_skin_p
         else OGRECU_CUDA(cudaFuncSetAttribute(skin_lane_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         granted[morph][ctx->device & 63] = true;
     }
-    if (morph) skin_lane_kernel<true><<<(unsigned)items, LN_THREADS, smem, ctx->stream>>>(P, 0x8000000080000000ull);
-    else skin_lane_kernel<false><<<(unsigned)items, LN_THREADS, smem, ctx->stream>>>(P, 0x8000000080000000ull);
+    // the frame's palettes in the pair layout (repack_palettes, once per frame), then the unit counter of the persistent CTAs
+    P.ipal = (const uint8_t*)ctx->lane_ipal.ptr;
+    P.iflags = (const uint32_t*)((uint8_t*)ctx->lane_ipal.ptr + (size_t)P.groups * nmat * LN_SLOT_BYTES);
+    P.nmat = nmat;
+    OGRECU_CHECK(scratch_reserve(ctx, ctx->lane_counter, 256));
+    OGRECU_CUDA(cudaMemsetAsync(ctx->lane_counter.ptr, 0, 4, ctx->stream));
+    P.counter = (uint32_t*)ctx->lane_counter.ptr;
+    P.total_units = (uint32_t)items;
+    const unsigned grid = (unsigned)std::min<uint64_t>(items, (uint64_t)ctx->sm_count);
+    if (morph) skin_lane_kernel<true><<<grid, LN_THREADS, smem, ctx->stream>>>(P, 0x8000000080000000ull);
+    else skin_lane_kernel<false><<<grid, LN_THREADS, smem, ctx->stream>>>(P, 0x8000000080000000ull);
     OGRECU_CUDA(cudaGetLastError());
     count_launch(ctx);
     return OGRECU_OK;
@@ -592,6 +779,8 @@ int build_skin_plan(ogrecu_ctx* ctx, const uint8_t* blend_index, size_t index_st
         chunks.push_back(c);
     }
     plan->num_chunks = (uint32_t)chunks.size();
+    plan->max_matrix = 0;
+    for (const Chunk& c : chunks) for (uint32_t q = 0; q < c.nslots; ++q) plan->max_matrix = std::max<uint32_t>(plan->max_matrix, c.bones[q]);
     const size_t rb = recs.size() * 4, cb = chunks.size() * sizeof(Chunk), pb = pre_recs.size() * 4;
     OGRECU_CUDA(cudaMalloc(&plan->d_recs, std::max<size_t>(rb, 16)));
     OGRECU_CUDA(cudaMalloc(&plan->d_chunks, std::max<size_t>(cb, 16)));
@@ -670,6 +859,7 @@ int ogrecu_anim_frame_dev(ogrecu_ctx* ctx, const ogrecu_anim_job* jobs, ogrecu_s
     const bool morph = t_dev != nullptr;
     // jobs the lane kernel takes go into launches of up to LN_MAX_JOBS, largest first; the rest take the tile kernels
     std::vector<uint32_t> lane, other;
+    uint32_t lane_nmat = 0;
     for (uint32_t k = 0; k < num_jobs; ++k) {
         OGRECU_REQUIRE(morph ? jobs[k].key2 != nullptr : jobs[k].key2 == nullptr, "key2 and t_dev go together (both or neither)");
         if (jobs[k].skin.num_vertices == 0) continue;
@@ -680,12 +870,18 @@ int ogrecu_anim_frame_dev(ogrecu_ctx* ctx, const ogrecu_anim_job* jobs, ogrecu_s
     std::stable_sort(lane.begin(), lane.end(), [&](uint32_t a, uint32_t b) {
         return (uint64_t)jobs[a].skin.num_vertices * jobs[a].skin.num_weights > (uint64_t)jobs[b].skin.num_vertices * jobs[b].skin.num_weights;
     });
+    if (!lane.empty()) {
+        uint32_t nmat = 0;
+        for (uint32_t k : lane) nmat = std::max(nmat, plans[k]->max_matrix + 1);
+        OGRECU_CHECK(repack_palettes(ctx, jobs[lane[0]].skin.palette, palette_stride_floats, num_instances, nmat));
+        lane_nmat = nmat;
+    }
     for (size_t at = 0; at < lane.size(); at += LN_MAX_JOBS) {
         const uint32_t cnt = (uint32_t)std::min<size_t>(LN_MAX_JOBS, lane.size() - at);
         ogrecu_anim_job jj[LN_MAX_JOBS];
         ogrecu_skin_plan* pp[LN_MAX_JOBS];
         for (uint32_t k = 0; k < cnt; ++k) { jj[k] = jobs[lane[at + k]]; pp[k] = plans[lane[at + k]]; }
-        OGRECU_CHECK(launch_skin_lane(ctx, jj, pp, cnt, t_dev, num_instances, palette_stride_floats, morph));
+        OGRECU_CHECK(launch_skin_lane(ctx, jj, pp, cnt, t_dev, num_instances, palette_stride_floats, morph, lane_nmat));
     }
     for (uint32_t k : other) {
         const ogrecu_anim_job& J = jobs[k];

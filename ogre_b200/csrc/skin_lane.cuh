@@ -9,10 +9,13 @@
 
 namespace ogrecu {
 
-constexpr int LN_WARPS = 8;
-constexpr int LN_THREADS = LN_WARPS * 32;
+constexpr int LN_WARPS = 15;                  // consumer warps; one more warp produces their inputs (16 warps: 128 registers each)
+constexpr int LN_THREADS = (LN_WARPS + 1) * 32;
 constexpr int LN_MAXB = LN_MAXB_N;            // palette entries resident per chunk (a chunk whose first quad plus the vertex before it needs more cannot be planned)
-constexpr int LN_CHUNK_QUADS = 32;            // vertex quads per chunk at most (one vertex per thread in the prologue)
+#ifndef LN_CHUNK_QUADS_N
+#define LN_CHUNK_QUADS_N 30
+#endif
+constexpr int LN_CHUNK_QUADS = LN_CHUNK_QUADS_N;            // vertex quads per chunk at most (one vertex per thread in the prologue)
 constexpr int LN_CHUNK_VERTS = 4 * LN_CHUNK_QUADS;
 constexpr int LN_SLOT_BYTES = 3072;           // 64 instances x 48 bytes
 constexpr int LN_BOX_BYTES = 32 * 96;         // one TMA box: 32 instance rows x 4 vertices
@@ -37,7 +40,11 @@ struct LaneParams {
     const float* palette;            // instance-0 palette (Affine3, 16 floats each)
     const float* t;                  // morph weight per instance (MORPH)
     size_t pal_stride_floats;
-    uint32_t njobs, ninst, groups, pad;
+    uint32_t* counter;               // work-unit counter (zeroed before the launch)
+    const uint8_t* ipal;             // repacked palettes [group][matrix][3072 B]
+    const uint32_t* iflags;          // hazard flags [group][matrix]
+    uint32_t nmat, pad;
+    uint32_t njobs, ninst, groups, total_units;
 };
 
 }  // namespace ogrecu
@@ -46,7 +53,7 @@ struct ogrecu_skin_plan {
     ogrecu_ctx* ctx;
     // what the plan was built from (a job must match to use it)
     uint32_t num_vertices, num_weights, num_matrices;
-    uint32_t num_chunks;
+    uint32_t num_chunks, max_matrix;
     void* d_recs;
     void* d_pre_recs;
     void* d_chunks;
@@ -58,7 +65,9 @@ int build_skin_plan(ogrecu_ctx* ctx, const uint8_t* blend_index, size_t index_st
                     const uint16_t* bone_map, uint32_t nw, uint32_t num_matrices, uint32_t nverts, ogrecu_skin_plan* plan);
 bool skin_lane_eligible(const ogrecu_skin_plan* plan, const ogrecu_anim_job& J, uint32_t num_instances, size_t palette_stride_floats);
 // jobs all eligible; morph = keyframe pairs + t_dev, else the shared bind pose of skin.src_pos
+// the frame's palettes -> pair layout + hazard flags in ctx->lane_ipal (matrices 0 .. nmat-1 of every instance)
+int repack_palettes(ogrecu_ctx* ctx, const float* palette, size_t palette_stride_floats, uint32_t num_instances, uint32_t nmat);
 int launch_skin_lane(ogrecu_ctx* ctx, const ogrecu_anim_job* jobs, ogrecu_skin_plan* const* plans, uint32_t num_jobs, const float* t_dev,
-                     uint32_t num_instances, size_t palette_stride_floats, bool morph);
+                     uint32_t num_instances, size_t palette_stride_floats, bool morph, uint32_t nmat);
 
 }  // namespace ogrecu

@@ -126,7 +126,7 @@ def test_lane_kernel_equals_oracle(gpu_ctx, case):
     finally:
         check(lib().ogrecu_skin_plan_destroy(plan))
     if loc and do == 0 and ninst >= 2:
-        assert ctx.launch_count - launches0 == 1, "the lane kernel is one launch"
+        assert ctx.launch_count - launches0 == 2, "palette repack + the lane kernel"
     raw = ddst.download(np.uint8)
     assert (raw[:do] == 0xCD).all() and (raw[do + total:] == 0xCD).all(), "wrote outside the destination"
     rows = raw[do:do + total].reshape(ninst, stride)
@@ -176,7 +176,7 @@ def test_lane_frame_of_many_sub_meshes_equals_tile_kernels(gpu_ctx):
         outs.append((da, db, jb, dk2, n))
     launches0 = ctx.launch_count
     check(lib().ogrecu_anim_frame_dev(ctx.handle, arr, plans, len(shapes), dt.ptr, ninst, nb * 16))
-    assert ctx.launch_count - launches0 == 2, "ten eligible jobs are two lane launches"
+    assert ctx.launch_count - launches0 == 3, "one palette repack, ten eligible jobs in two lane launches"
     for da, db, jb, dk2, n in outs:
         check(lib().ogrecu_anim_instanced_dev(ctx.handle, C.byref(jb), dk2.ptr, dt.ptr, None, 0, ninst, nb * 16, n * 24))
     ctx.sync()
