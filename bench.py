@@ -2,26 +2,32 @@
 """bench.py — headline benchmark of the OGRE software-rendering hot path on B200.
 
 Contract (driver):  python bench.py --gpus N --steps K --warmup W [--impl reference]
-  N>1 is launched under torch.distributed.run (one rank per GPU, NCCL for barrier/max only —
-  the path shards by instance with NO data-path collective, so scaling is "weak").
+  N>1 is launched under torch.distributed.run (one rank per GPU, NCCL for barrier/max and the split-frame gather only —
+  instances and views shard with NO data-path collective, so scaling is "weak").
 
-Workload (BASELINE.json configs[1]): Sinbad (7 sub-meshes, 5 534 vertices, 69 bones, 1/4/3/1/1/3/4
-weights per vertex; the real mesh streams and 32 real animation poses from tests/golden/sinbad_skin.npz)
-x 10 000 animated instances per GPU.  One STEP = one frame of vertex animation for every instance,
-in the order Entity::updateAnimation runs it (OgreMain/src/OgreEntity.cpp:747-911):
-  softwareVertexMorph   two shared keyframes -> the instance's animated source (pos+normal, stride 24)
+Workload of the contract line (BASELINE.json configs[1]): Sinbad (7 sub-meshes, 5 534 vertices, 69 bones, 1/4/3/1/1/3/4
+weights per vertex; the real mesh streams from tests/golden/sinbad_skin.npz, the real skeleton and its "Dance" animation
+from tests/golden/sinbad_skeleton.npz) x 10 000 animated instances per GPU.  One STEP = one frame of vertex animation for
+every instance, in the order Entity::updateAnimation runs it (OgreMain/src/OgreEntity.cpp:747-911):
+  softwareVertexMorph    two shared keyframes -> the instance's animated source (pos+normal, stride 24)
   softwareVertexSkinning instance source + instance bone palette -> instance output (pos+normal)
+as ONE call, ogrecu_anim_frame_dev (palette repack + the instance-pair-per-lane kernel, csrc/skin_lane.cu).
 metric = skinned vertices per second (Mvert/s), whole job.
 
-Lines printed (rank 0, one JSON line):
-  value      device-timed (CUDA events on the launch stream), inputs resident in HBM
-  e2e        same step through the C ABI with HOST inputs: every step uploads all instance bone
-             palettes + morph weights from pinned host memory and reads one instance's skinned
-             vertices back (the skinned buffers themselves stay in HBM for _render)
-  roofline   dominant kernel of the timed step (the 4-weight body sub-mesh launch) vs measured HBM peak;
-             extra.roofline_other_form carries the same for the other --form; extra.roofline_stream_case is SURVEY §8d's
-             synthetic roofline stream (one call, 2^24 distinct vertices, 68 B per vertex) measured the same way
-  cpu_baseline  the unmodified reference (real OptimisedUtilSSE via oracle/_ref) on the host cores
+One JSON line (rank 0):
+  value      device-timed (CUDA events on the launch stream), palettes and keyframes resident in HBM
+  e2e        the same metric through the whole pipeline an OGRE application runs per frame, host inputs to host result:
+             H2D each instance's ANIMATION STATE (12 B) and morph weight from pinned memory -> bone palettes on the device
+             (ogrecu_skel_palettes_dev = SkeletonInstance::setAnimationState + _getBoneMatrices) -> morph + skin of every
+             instance (the skinned buffers stay in HBM) -> the _render that consumes them (all instances drawn into a
+             1920x1080 target by the rasteriser) -> D2H of the rendered frame.  The reference arm pays no render.
+  roofline   the dominant kernel of the timed step (skin_lane_kernel: one launch covers all seven sub-meshes), timed alone
+             with CUDA events, against the measured HBM peak
+  cpu_baseline  the unmodified reference (oracle/_ref: real SkeletonInstance + OptimisedUtilSSE) on the host cores
+  extra.render  BASELINE's render configs, same run: c1 (ogrehead 1280x720), c4 (1024 offscreen 640x480 views of a
+             1 M-triangle scene, view i -> GPU i mod G), c5 (one 3840x2160 frame of 20 M triangles; split-frame strips +
+             NCCL gather under torchrun) with frames/s, Mtri/s, roofline, the real Tiny as cpu_baseline and an e2e with
+             the full colour read-back.
 """
 import argparse
 import ctypes as C
@@ -31,14 +37,18 @@ import subprocess
 import sys
 import threading
 import time
+import types
 
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
 
 FIXTURE = os.path.join(ROOT, "tests", "golden", "sinbad_skin.npz")
 FALLBACK_HBM_GBS = 6650.0     # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+FRAME_W, FRAME_H = 1920, 1080  # the e2e step's render target
 
 
 def load_sinbad():
@@ -74,6 +84,14 @@ def instance_inputs(ninst, palettes, rank):
     pal += off
     t = ((np.arange(ninst) * 0.01) % 1.0).astype(np.float32)
     return np.ascontiguousarray(pal), t
+
+
+def instance_states(ninst, rank, dance_len):
+    """Per-instance animation state: animation 0 ("Dance"), time position, weight 1."""
+    anim = np.zeros(ninst, np.int32)
+    tpos = np.mod((np.arange(ninst) * 0.01 + rank).astype(np.float32), np.float32(dance_len)).astype(np.float32)
+    weight = np.ones(ninst, np.float32)
+    return anim, tpos, weight
 
 
 class Clocks:
@@ -125,13 +143,26 @@ def hbm_peak():
         return FALLBACK_HBM_GBS, "fallback"
 
 
+def workload_config(ninst, nverts, gpus=1):
+    """The `config` object: the same for both arms (the reference arm runs the same instances on the host cores)."""
+    return {"workload": "config[1] skeletal skinning: Sinbad (7 sub-meshes, %d vertices, 69 bones, 1/4/3/1/1/3/4 weights) x %d animated "
+                        "instances per GPU; step = softwareVertexMorph (2 shared keyframes -> instance source) + softwareVertexSkinning "
+                        "(pos+normal shared-packed, per-instance palette)" % (nverts, ninst),
+            "instances_per_gpu": ninst, "vertices_per_instance": nverts,
+            "form": "fused", "parallelism": "instances sharded per GPU, no collective (dp%d)" % gpus,
+            "l2": "every step writes 1.33 GB of skinned vertices per GPU (>> 126 MB L2): outputs larger than L2, no flush needed"}
+
+
 # ------------------------------------------------------------------------------ reference arm
 
-def reference_step_fn(subs, palettes, ninst, threads):
-    """Returns (fn, kind, cores): fn() runs one morph+skin pass over `ninst` instances on the CPU with
-    the unmodified reference (oracle/_ref) — or the oracle port when that is absent — and returns seconds."""
+def reference_step_fn(subs, palettes, ninst, threads, rank=0):
+    """Returns (fn, kind, cores): fn() runs one frame of `ninst` instances on the CPU with the unmodified reference
+    (oracle/_ref) — SkeletonInstance::setAnimationState + _getBoneMatrices per instance (one thread: OGRE evaluates
+    entities on the render thread and SkeletonInstance is not thread-safe), then softwareVertexMorph +
+    softwareVertexSkinning of every sub-mesh over `threads` host threads — and returns (seconds, seconds in the palettes).
+    Falls back to the oracle port (C restatement, palettes from the fixture poses) where oracle/_ref is absent."""
     from oracle import ref
-    pal, t = instance_inputs(ninst, palettes, 0)
+    pal, t = instance_inputs(ninst, palettes, rank)
     nb = pal.shape[1]
     bufs = []
     for s in subs:
@@ -139,16 +170,24 @@ def reference_step_fn(subs, palettes, ninst, threads):
         bufs.append((np.zeros((ninst, n, 6), np.float32), np.zeros((ninst, n, 6), np.float32)))
     if ref.available():
         l = ref.lib()
+        have_skel = l.ref_skel_open(b"Sinbad.mesh", 64, 64) == 0 and l.ref_skel_num_bones() == nb
+        _, tpos, _ = instance_states(ninst, rank, 1e9)
+        live = np.zeros((ninst, nb, 16), np.float32)
 
         def fn():
-            tot = 0.0
+            tp = 0.0
+            src_pal = pal
+            if have_skel:
+                tp = l.ref_bench_palettes(0, tpos.ctypes.data, ninst, live.ctypes.data)
+                src_pal = live
+            tot = tp
             for s, (tmp, dst) in zip(subs, bufs):
                 bl = s["blend"].ctypes.data
                 tot += l.ref_bench_anim_sub(s["key1"].ctypes.data, s["key2"].ctypes.data, t.ctypes.data, bl + 4, bl,
-                                            s["blend_stride"], s["blend_stride"], s["nw"], s["nverts"], pal.ctypes.data, nb * 16,
+                                            s["blend_stride"], s["blend_stride"], s["nw"], s["nverts"], src_pal.ctypes.data, nb * 16,
                                             s["bone_map"].ctypes.data, len(s["bone_map"]), ninst, tmp.ctypes.data, dst.ctypes.data,
                                             threads, 1)
-            return tot
+            return tot, tp
         return fn, "reference", threads
     # oracle port (C restatement), threaded over instances from Python (ctypes drops the GIL)
     import oracle
@@ -171,7 +210,7 @@ def reference_step_fn(subs, palettes, ninst, threads):
     def fn():
         t0 = time.perf_counter()
         list(pool.map(work, range(threads)))
-        return time.perf_counter() - t0
+        return time.perf_counter() - t0, 0.0
     return fn, "port", threads
 
 
@@ -182,31 +221,34 @@ def run_reference(args):
     subs, palettes = load_sinbad()
     nverts = sum(s["nverts"] for s in subs)
     threads = os.cpu_count() or 1
-    ninst = args.ref_instances
+    ninst = args.instances
     fn, kind, cores = reference_step_fn(subs, palettes, ninst, threads)
-    for _ in range(args.warmup):
+    for _ in range(min(args.warmup, 2)):
         fn()
-    times = [fn() for _ in range(args.steps)]
-    total = sum(times)
-    value = ninst * nverts * args.steps / total / 1e6
+    steps = args.steps
+    times = []
+    t_budget = time.time() + args.ref_seconds
+    for k in range(steps):
+        times.append(fn())
+        if time.time() > t_budget and k + 1 >= 3:          # bounded: the whole run ends within a few minutes
+            break
+    done = len(times)
+    total = sum(x[0] for x in times)
+    tpal = sum(x[1] for x in times)
+    value = ninst * nverts * done / total / 1e6
     line = {
         "impl": "reference", "metric": "skinned_Mvert_per_s", "value": value, "unit": "Mvert/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": total / args.steps * 1e3, "higher_is_better": True,
+        "steps": done, "warmup": min(args.warmup, 2), "ms_per_step": total / done * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(ninst, nverts, sample=True),
+        "config": workload_config(ninst, nverts, args.gpus),
         "cpu_baseline": {"value": value, "unit": "Mvert/s", "cores": cores, "kind": kind,
-                         "sample": "%d of 10000 instances per step (%d vertices), morph+skin, real OptimisedUtilSSE" % (ninst, ninst * nverts)},
+                         "sample": "all %d instances per step (%d vertices): SkeletonInstance::setAnimationState + _getBoneMatrices per "
+                                   "instance on 1 thread (%.1f ms per step), softwareVertexMorph + softwareVertexSkinning through the "
+                                   "real OptimisedUtilSSE on %d threads (%.1f ms per step)" % (
+                                       ninst, ninst * nverts, tpal / done * 1e3, cores, (total - tpal) / done * 1e3)},
         "e2e": {"value": value, "unit": "Mvert/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
-
-
-def workload_config(ninst, nverts, sample=False):
-    return {"workload": "config[1] skeletal skinning: Sinbad (7 sub-meshes, %d vertices, 69 bones, 1/4/3/1/1/3/4 weights) x %d animated "
-                        "instances%s; step = softwareVertexMorph (2 shared keyframes -> instance source) + softwareVertexSkinning "
-                        "(pos+normal shared-packed, per-instance palette)" % (nverts, ninst, " (bounded CPU sample of the 10000)" if sample else " per GPU"),
-            "instances_per_gpu": ninst, "vertices_per_instance": nverts,
-            "l2": "working set per step 2.7 GB per GPU (instance source + output) >> 126 MB L2: inputs larger than L2, no flush needed"}
 
 
 # ------------------------------------------------------------------------------------ our arm
@@ -214,7 +256,9 @@ def workload_config(ninst, nverts, sample=False):
 def run_ours(args):
     import torch
     import ogre_b200
-    from ogre_b200 import AnimJob, SkinJob, check, lib
+    from ogre_b200 import AnimJob, DrawDesc, SkinJob, Skeleton, check, lib
+    from datagen import look_at, perspective, viewport_matrix
+    from goldenlib import load_skeleton
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -237,67 +281,51 @@ def run_ours(args):
     stream = torch.cuda.Stream(device=dev)
     ctx.set_stream(stream.cuda_stream)
     ctx.set_config_option("skin_mode", args.skin_mode)
-    ctx.set_config_option("skin_ipc", args.skin_ipc)
     L = lib()
 
+    # ---- static data: mesh streams, keyframes, one skin plan per sub-mesh (built once from the static blend stream)
     with torch.cuda.stream(stream):
-        d_pal = torch.from_numpy(pal_h).to(dev)
-        d_t = torch.from_numpy(t_h).to(dev)
+        pal_sets = [torch.from_numpy(pal_h).to(dev), torch.from_numpy(pal_h).to(dev)]
+        t_sets = [torch.from_numpy(t_h).to(dev), torch.from_numpy(t_h).to(dev)]
         dsub = []
         for s in subs:
             n = s["nverts"]
             e = {"key1": torch.from_numpy(s["key1"]).to(dev), "key2": torch.from_numpy(s["key2"]).to(dev),
                  "blend": torch.from_numpy(s["blend"]).to(dev), "map": torch.from_numpy(s["bone_map"].view(np.int16)).to(dev),
-                 "tmp": torch.empty(ninst, n, 6, device=dev), "dst": torch.empty(ninst, n, 6, device=dev)}
-            j = SkinJob()
-            j.src_pos, j.src_norm = e["tmp"].data_ptr(), e["tmp"].data_ptr() + 12
-            j.dst_pos, j.dst_norm = e["dst"].data_ptr(), e["dst"].data_ptr() + 12
-            j.blend_weight, j.blend_index = e["blend"].data_ptr() + 4, e["blend"].data_ptr()
-            j.palette, j.bone_map = d_pal.data_ptr(), e["map"].data_ptr()
-            j.src_pos_stride = j.dst_pos_stride = j.src_norm_stride = j.dst_norm_stride = 24
-            j.blend_weight_stride = j.blend_index_stride = s["blend_stride"]
-            j.num_weights, j.num_matrices, j.num_vertices = s["nw"], len(s["bone_map"]), n
-            e["job"] = j
-            jf = SkinJob.from_buffer_copy(j)
-            jf.src_pos, jf.src_norm = e["key1"].data_ptr(), e["key1"].data_ptr() + 12
-            e["job_fused"] = jf
+                 "dst": torch.empty(ninst, n, 6, device=dev)}
             dsub.append(e)
     stream.synchronize()
 
-    def morph(e, s):
-        check(L.ogrecu_morph_instanced_dev(ctx.handle, d_t.data_ptr(), e["key1"].data_ptr(), e["key2"].data_ptr(), e["tmp"].data_ptr(),
-                                           24, 24, 24, s["nverts"], 1, ninst, s["nverts"] * 24))
-
-    def skin(e, s):
-        check(L.ogrecu_skin_instanced_dev(ctx.handle, C.byref(e["job"]), ninst, nb * 16, s["nverts"] * 24, s["nverts"] * 24))
-
-    def fused(e, s):
-        # one pass per sub-mesh: source_i = morph(key1, key2, t[i]) in registers -> skin -> dst_i; no intermediate in HBM
-        j = e["job_fused"]
-        check(L.ogrecu_anim_instanced_dev(ctx.handle, C.byref(j), e["key2"].data_ptr(), d_t.data_ptr(), None, 0, ninst, nb * 16,
-                                          s["nverts"] * 24))
-
-    def step_separate():
-        for e, s in zip(dsub, subs):
-            morph(e, s)
-            skin(e, s)
-
-    def anim_jobs(which):
+    def frame_jobs(b):
         arr = (AnimJob * len(dsub))()
         for k, (e, s) in enumerate(zip(dsub, subs)):
-            arr[k].skin = e[which] if not isinstance(e[which], list) else e[which][0]
+            j = SkinJob()
+            j.src_pos, j.src_norm = e["key1"].data_ptr(), e["key1"].data_ptr() + 12
+            j.dst_pos, j.dst_norm = e["dst"].data_ptr(), e["dst"].data_ptr() + 12
+            j.blend_weight, j.blend_index = e["blend"].data_ptr() + 4, e["blend"].data_ptr()
+            j.palette, j.bone_map = pal_sets[b].data_ptr(), e["map"].data_ptr()
+            j.src_pos_stride = j.dst_pos_stride = j.src_norm_stride = j.dst_norm_stride = 24
+            j.blend_weight_stride = j.blend_index_stride = s["blend_stride"]
+            j.num_weights, j.num_matrices, j.num_vertices = s["nw"], len(s["bone_map"]), s["nverts"]
+            arr[k].skin = j
             arr[k].key2 = e["key2"].data_ptr()
             arr[k].morph_out, arr[k].morph_instance_stride_bytes = None, 0
             arr[k].dst_instance_stride_bytes = s["nverts"] * 24
         return arr
-    frame_jobs = anim_jobs("job_fused")
+    jobs = [frame_jobs(0), frame_jobs(1)]
+    plans = (C.c_void_p * len(dsub))()
+    if args.skin_mode == 0:
+        for k in range(len(dsub)):
+            p = C.c_void_p()
+            check(L.ogrecu_skin_plan_create(ctx.handle, C.byref(jobs[0][k].skin), C.byref(p)))
+            plans[k] = p
 
-    def step_fused():
-        # one call per frame: the fused morph+skin of all seven sub-meshes (ogrecu_anim_instanced_multi_dev overlaps the
-        # independent launches internally)
-        check(L.ogrecu_anim_instanced_multi_dev(ctx.handle, frame_jobs, len(dsub), d_t.data_ptr(), ninst, nb * 16))
+    def anim(b):
+        # one call per frame: morph + skin of all seven sub-meshes of every instance
+        check(L.ogrecu_anim_frame_dev(ctx.handle, jobs[b], plans, len(dsub), t_sets[b].data_ptr(), ninst, nb * 16))
 
-    step = step_fused if args.form == "fused" else step_separate
+    def step():
+        anim(0)
 
     def barrier():
         if dist is not None:
@@ -331,247 +359,199 @@ def run_ours(args):
     launches = ctx.launch_count - launches0
     value = world * ninst * nverts * args.steps / (ms * 1e-3) / 1e6
 
-    # ---- end to end: host palettes + weights in, one instance's skinned vertices out, every step.
-    # Two frames in flight, as a renderer submits them: step k's inputs are uploaded on a copy stream into palette set
-    # k&1 while step k-1's kernels run; step k's result is copied to pinned host memory behind its kernels and is
-    # waited for before step k+2's inputs may overwrite the same set.  Every step still moves all of its inputs H2D
-    # and its result D2H inside the timed region.  The strictly serial form (upload -> kernels -> read-back, one
-    # stream) is timed as well and reported as e2e.serial_value.
-    hp, ht = C.c_void_p(), C.c_void_p()
-    check(L.ogrecu_host_alloc(pal_h.nbytes, C.byref(hp)))
-    check(L.ogrecu_host_alloc(t_h.nbytes, C.byref(ht)))
-    out_bytes = subs[1]["nverts"] * 24                # body sub-mesh (1 888 vertices, 4 weights) of the last instance
-    houts = [C.c_void_p(), C.c_void_p()]
-    for h in houts:
-        check(L.ogrecu_host_alloc(out_bytes, C.byref(h)))
-    C.memmove(hp.value, pal_h.ctypes.data, pal_h.nbytes)
-    C.memmove(ht.value, t_h.ctypes.data, t_h.nbytes)
+    # ---- end to end: host animation states in, rendered frame out, every step.
+    # Two frames in flight, as a renderer submits them: step k's states are uploaded on a copy stream into set k&1 and its
+    # palettes produced right behind them (second context on that stream) while step k-1's kernels run; step k's frame is
+    # copied to pinned host memory behind its render and is waited for before step k+2 may reuse the set.
+    skel_def, _ = load_skeleton("sinbad_skeleton.npz")
+    assert skel_def["num_bones"] == nb
     cstream = torch.cuda.Stream(device=dev)
+    ctx_c = ogre_b200.Context(local)
+    ctx_c.set_stream(cstream.cuda_stream)
+    skel = Skeleton(ctx_c, skel_def)
+    anim_h, tpos_h, w_h = instance_states(ninst, rank, skel_def["anims"][0]["length"])
+    st_n = 3 * ninst * 4
+    hs, ht = C.c_void_p(), C.c_void_p()
+    check(L.ogrecu_host_alloc(st_n, C.byref(hs)))
+    check(L.ogrecu_host_alloc(t_h.nbytes, C.byref(ht)))
+    st_h = np.ctypeslib.as_array(C.cast(hs.value, C.POINTER(C.c_uint8)), shape=(st_n,))
+    st_h[:ninst * 4].view(np.int32)[:] = anim_h
+    st_h[ninst * 4:2 * ninst * 4].view(np.float32)[:] = tpos_h
+    st_h[2 * ninst * 4:].view(np.float32)[:] = w_h
+    C.memmove(ht.value, t_h.ctypes.data, t_h.nbytes)
+    frame_bytes = FRAME_W * FRAME_H * 3
+    hframes = [ogre_b200.pinned_empty((FRAME_H, FRAME_W, 3)) for _ in range(2)]
     with torch.cuda.stream(stream):
-        pal_sets = [d_pal, torch.empty_like(d_pal)]
-        t_sets = [d_t, torch.empty_like(d_t)]
-    for e in dsub:
-        e["jobs_fused"], e["jobs"] = [e["job_fused"]], [e["job"]]
-        for name in ("jobs_fused", "jobs"):
-            j2 = SkinJob.from_buffer_copy(e[name][0])
-            j2.palette = pal_sets[1].data_ptr()
-            e[name].append(j2)
+        st_sets = [torch.empty(st_n, dtype=torch.uint8, device=dev) for _ in range(2)]
+    rts = [ogre_b200.RenderTarget(ctx, FRAME_W, FRAME_H) for _ in range(2)]
+    rt_ptr = []
+    for r in rts:
+        p = C.c_void_p()
+        check(L.ogrecu_rt_colour_device_ptr(r.handle, C.byref(p)))
+        rt_ptr.append(p.value)
+    # the consuming _render: every sub-mesh's [instances x vertices] output buffer drawn as one non-indexed triangle list
+    # (Tiny's drawCount = vertexCount path, OgreTinyRenderSystem.cpp:387-403), lit, depth-tested; the crowd stands on a
+    # 300 x 300 grid and fills most of the frame, seen from above
+    proj = perspective(45, FRAME_W / FRAME_H, 5.0, 3000.0)
+    proj[1, :] *= -1          # OgreMain flips the projection for targets with requiresTextureFlipping (Tiny windows)
+    view = look_at(np.array([148.5, 340.0, 330.0]), (148.5, 0.0, 135.0))
+    mvp = (proj @ view).astype(np.float32)
+    mvit = np.ascontiguousarray(np.linalg.inv(view).T.astype(np.float32))
+    ldir = view[:3, :3] @ np.array([0.4, 0.8, 0.3]); ldir = (ldir / np.linalg.norm(ldir)).astype(np.float32)
+    draws = []
+    tris_per_frame = 0
+    for e, s in zip(dsub, subs):
+        d = DrawDesc()
+        nv = (ninst * s["nverts"]) // 3 * 3
+        d.positions, d.pos_stride = e["dst"].data_ptr(), 24
+        d.normals, d.normal_stride = e["dst"].data_ptr() + 12, 24
+        d.indices, d.index_type, d.draw_count, d.vertex_count = None, 0, nv, nv
+        d.prim_type = ogre_b200.PRIM_TRIANGLE_LIST
+        d.flags = ogre_b200.DRAW_DEPTH_TEST | ogre_b200.DRAW_DEPTH_WRITE | ogre_b200.DRAW_LIGHTING
+        d.mvp[:] = mvp.reshape(16); d.mvit[:] = mvit.reshape(16)
+        d.tex_matrix[:] = np.eye(4, dtype=np.float32).reshape(16)
+        d.viewport[:] = viewport_matrix(FRAME_W, FRAME_H).reshape(16)
+        d.light_dir[:] = ldir
+        d.ambient[:] = (0.25, 0.25, 0.3, 1.0)
+        draws.append(d)
+        tris_per_frame += nv // 3
+
+    def render(b):
+        rts[b].clear(colour=(0.1, 0.2, 0.3, 1.0), depth=1.0)
+        for d in draws:
+            rts[b].draw(d)
+        rts[b].flush()
+
     uploaded = [torch.cuda.Event(), torch.cuda.Event()]
     done = [torch.cuda.Event(), torch.cuda.Event()]
-    last = dsub[1]
-
-    set_jobs = []
-    for b in (0, 1):
-        arr = anim_jobs("job_fused")
-        for k, e in enumerate(dsub):
-            arr[k].skin = e["jobs_fused"][b]
-        set_jobs.append(arr)
-
-    def step_set(b):
-        if args.form == "fused":
-            check(L.ogrecu_anim_instanced_multi_dev(ctx.handle, set_jobs[b], len(dsub), t_sets[b].data_ptr(), ninst, nb * 16))
-            return
-        for e, s in zip(dsub, subs):
-            check(L.ogrecu_morph_instanced_dev(ctx.handle, t_sets[b].data_ptr(), e["key1"].data_ptr(), e["key2"].data_ptr(),
-                                               e["tmp"].data_ptr(), 24, 24, 24, s["nverts"], 1, ninst, s["nverts"] * 24))
-            check(L.ogrecu_skin_instanced_dev(ctx.handle, C.byref(e["jobs"][b]), ninst, nb * 16, s["nverts"] * 24, s["nverts"] * 24))
-
     e2e_k = [0]
+
+    # every entity's parent-node transform: the crowd stands on a 100 x 100 grid, 3 units apart (static, resident)
+    world_h = np.tile(np.eye(4, dtype=np.float32).reshape(1, 16), (ninst, 1))
+    world_h[:, 3] = (np.arange(ninst) % 100) * 3.0
+    world_h[:, 11] = (np.arange(ninst) // 100) * 3.0
+    with torch.cuda.stream(cstream):
+        d_world = torch.from_numpy(world_h).to(dev)
+    cstream.synchronize()
+
+    def produce_palettes(b):
+        # SkeletonInstance::setAnimationState + _getBoneMatrices, then Entity::cacheBoneMatrices' concatenation with the
+        # entity's world transform (OgreEntity.cpp:1307-1330), for every instance; on the copy stream (ctx_c)
+        p = st_sets[b].data_ptr()
+        skel.palettes_dev(ninst, 1, p, p + ninst * 4, p + 2 * ninst * 4, pal_sets[b].data_ptr(), nb * 16)
+        check(L.ogrecu_concat_affine_instanced_dev(ctx_c.handle, d_world.data_ptr(), pal_sets[b].data_ptr(), pal_sets[b].data_ptr(), nb, ninst,
+                                                   nb * 16))
 
     def step_e2e():
         k = e2e_k[0]; e2e_k[0] += 1
         b = k & 1
         # copy stream; set b was last read by step k-2, already waited for below.  (ogrecu_set_stream would drain the
         # launch stream — it is a synchronisation point — so the upload names its stream explicitly.)
-        check(L.ogrecu_memcpy_h2d_on(ctx.handle, cstream.cuda_stream, pal_sets[b].data_ptr(), hp.value, pal_h.nbytes))
-        check(L.ogrecu_memcpy_h2d_on(ctx.handle, cstream.cuda_stream, t_sets[b].data_ptr(), ht.value, t_h.nbytes))
-        uploaded[b].record(cstream)
-        stream.wait_event(uploaded[b])
-        step_set(b)
-        check(L.ogrecu_memcpy_d2h_async(ctx.handle, houts[b].value, last["dst"].data_ptr() + (ninst - 1) * out_bytes, out_bytes))
-        done[b].record(stream)
-        if k > 0:
-            done[b ^ 1].synchronize()                    # the previous step's result is on the host now
-
-    def step_e2e_serial():
-        check(L.ogrecu_memcpy_h2d(ctx.handle, d_pal.data_ptr(), hp.value, pal_h.nbytes))
-        check(L.ogrecu_memcpy_h2d(ctx.handle, d_t.data_ptr(), ht.value, t_h.nbytes))
-        step()
-        # device -> pinned host, synchronous: the step's result is on the host when this returns
-        check(L.ogrecu_memcpy_d2h(ctx.handle, houts[0].value, last["dst"].data_ptr() + (ninst - 1) * out_bytes, out_bytes))
-
-    # ---- end to end with the bone palettes PRODUCED ON THE DEVICE: the host supplies only each
-    # instance's animation state (animation index, time position, weight: 12 B) and morph weight; ogrecu_skel_palettes_dev
-    # does SkeletonInstance::setAnimationState + _getBoneMatrices for all instances, the skinning kernels read the result.
-    from ogre_b200 import Skeleton
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    from goldenlib import load_skeleton
-    skel_def, _ = load_skeleton("sinbad_skeleton.npz")
-    assert skel_def["num_bones"] == nb
-    # the skeleton lives in a second context whose stream is the copy stream: the palettes of step k+1 are produced right
-    # behind their state upload while the launch stream still runs step k's skinning (the palette kernel is latency-bound
-    # and overlaps almost for free)
-    ctx_c = ogre_b200.Context(local)
-    ctx_c.set_stream(cstream.cuda_stream)
-    skel = Skeleton(ctx_c, skel_def)
-    st_n = 3 * ninst * 4
-    hs = C.c_void_p()
-    check(L.ogrecu_host_alloc(st_n, C.byref(hs)))
-    st_h = np.ctypeslib.as_array(C.cast(hs.value, C.POINTER(C.c_uint8)), shape=(st_n,))
-    dance_len = np.float32(skel_def["anims"][0]["length"])
-    st_h[:ninst * 4].view(np.int32)[:] = 0                                                   # animation 0 ("Dance")
-    st_h[ninst * 4:2 * ninst * 4].view(np.float32)[:] = np.mod((np.arange(ninst) * 0.01 + rank).astype(np.float32), dance_len)
-    st_h[2 * ninst * 4:].view(np.float32)[:] = 1.0
-    with torch.cuda.stream(stream):
-        st_sets = [torch.empty(st_n, dtype=torch.uint8, device=dev) for _ in range(2)]
-
-    def produce_palettes(b):
-        p = st_sets[b].data_ptr()
-        skel.palettes_dev(ninst, 1, p, p + ninst * 4, p + 2 * ninst * 4, pal_sets[b].data_ptr(), nb * 16)
-
-    st_k = [0]
-
-    def step_states():
-        k = st_k[0]; st_k[0] += 1
-        b = k & 1
         check(L.ogrecu_memcpy_h2d_on(ctx.handle, cstream.cuda_stream, st_sets[b].data_ptr(), hs.value, st_n))
         check(L.ogrecu_memcpy_h2d_on(ctx.handle, cstream.cuda_stream, t_sets[b].data_ptr(), ht.value, t_h.nbytes))
         produce_palettes(b)                               # on the copy stream (ctx_c), behind the upload
         uploaded[b].record(cstream)
         stream.wait_event(uploaded[b])
-        step_set(b)
-        check(L.ogrecu_memcpy_d2h_async(ctx.handle, houts[b].value, last["dst"].data_ptr() + (ninst - 1) * out_bytes, out_bytes))
+        anim(b)
+        render(b)
+        check(L.ogrecu_memcpy_d2h_async(ctx.handle, hframes[b].ctypes.data, rt_ptr[b], frame_bytes))
+        done[b].record(stream)
+        if k > 0:
+            done[b ^ 1].synchronize()                    # the previous step's frame is on the host now
+
+    def step_e2e_skin_only():
+        # the same without the consuming render: one instance's skinned body sub-mesh read back as the result
+        k = e2e_k[0]; e2e_k[0] += 1
+        b = k & 1
+        check(L.ogrecu_memcpy_h2d_on(ctx.handle, cstream.cuda_stream, st_sets[b].data_ptr(), hs.value, st_n))
+        check(L.ogrecu_memcpy_h2d_on(ctx.handle, cstream.cuda_stream, t_sets[b].data_ptr(), ht.value, t_h.nbytes))
+        produce_palettes(b)
+        uploaded[b].record(cstream)
+        stream.wait_event(uploaded[b])
+        anim(b)
+        check(L.ogrecu_memcpy_d2h_async(ctx.handle, hframes[b].ctypes.data, dsub[1]["dst"].data_ptr() + (ninst - 1) * subs[1]["nverts"] * 24,
+                                        subs[1]["nverts"] * 24))
         done[b].record(stream)
         if k > 0:
             done[b ^ 1].synchronize()
 
+    e2e_steps = max(3, min(args.steps, args.e2e_steps))
     for _ in range(3):
-        step_e2e_serial()
-    ms_e2e_serial = timed(step_e2e_serial, args.steps)
-    for _ in range(4):
-        step_states()
+        step_e2e()
     torch.cuda.synchronize()
     launches1 = ctx.launch_count + ctx_c.launch_count
-    ms_states = timed(step_states, args.steps)
-    launches_states = ctx.launch_count + ctx_c.launch_count - launches1
-    states_value = world * ninst * nverts * args.steps / (ms_states * 1e-3) / 1e6
+    ms_e2e = timed(step_e2e, e2e_steps)
+    launches_e2e = (ctx.launch_count + ctx_c.launch_count - launches1) / e2e_steps
+    e2e_value = world * ninst * nverts * e2e_steps / (ms_e2e * 1e-3) / 1e6
+    torch.cuda.synchronize()
+    covered = float((hframes[(e2e_k[0] - 1) & 1] != np.array([25, 51, 76], np.uint8)).any(axis=2).mean())
+    for _ in range(3):
+        step_e2e_skin_only()
+    torch.cuda.synchronize()
+    ms_skin_only = timed(step_e2e_skin_only, args.steps)
+    skin_only_value = world * ninst * nverts * args.steps / (ms_skin_only * 1e-3) / 1e6
+    clk = clocks.stop() if rank == 0 else None      # sampled across the timed regions (device-resident and e2e)
+    # the two stages of the e2e step alone (device, events): palettes, render
     torch.cuda.synchronize()
     pa, pb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     pa.record(cstream)
-    for _ in range(50):
+    for _ in range(20):
         produce_palettes(0)
     pb.record(cstream)
     cstream.synchronize()
-    ms_pal = pa.elapsed_time(pb) / 50
-    # restore the host-palette inputs in both sets for the timing below (the palette kernel overwrote them)
+    ms_pal = pa.elapsed_time(pb) / 20
+    render(0); torch.cuda.synchronize()
+    ra, rb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ra.record(stream)
+    for _ in range(5):
+        render(0)
+    rb.record(stream)
+    stream.synchronize()
+    ms_render = ra.elapsed_time(rb) / 5
+    # restore the fixture palettes for the measurements below (the palette kernel overwrote the sets)
     for b in (0, 1):
-        check(L.ogrecu_memcpy_h2d(ctx.handle, pal_sets[b].data_ptr(), hp.value, pal_h.nbytes))
-    ctx.sync()
-    for _ in range(4):
-        step_e2e()
-    torch.cuda.synchronize()
-    ms_e2e = timed(step_e2e, args.steps)
-    e2e_value = world * ninst * nverts * args.steps / (ms_e2e * 1e-3) / 1e6
-    e2e_serial_value = world * ninst * nverts * args.steps / (ms_e2e_serial * 1e-3) / 1e6
-    clk = clocks.stop() if rank == 0 else None      # sampled across the timed regions (device-resident and e2e)
+        with torch.cuda.stream(stream):
+            pal_sets[b].copy_(torch.from_numpy(pal_h))
+    stream.synchronize()
 
-    # ---- per-kernel durations (outside the timed regions) for the roofline line
-    kern = {}
-    if rank == 0:
-        evs = []
-        for rep in range(5):
-            for k, (e, s) in enumerate(zip(dsub, subs)):
-                for name, f in (("morph", morph), ("skin", skin), ("fused", fused)):
-                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    a.record(stream); f(e, s); b.record(stream)
-                    evs.append((name, k, a, b))
-        stream.synchronize()
-        for name, k, a, b in evs:
-            kern.setdefault((name, k), []).append(a.elapsed_time(b))
+    # ---- roofline: the dominant kernel alone (the call minus its palette repack launch; palettes unchanged between calls)
     peak, peak_kind = hbm_peak()
-    roof = None
-    extra = {}
+    roof, extra = None, {}
     if rank == 0:
-        k = 1                                           # dominant launch: 4-weight body sub-mesh
-        s = subs[k]
-        nv = s["nverts"]
-        shared_once = nv * s["blend_stride"]            # blend stream: read by every instance, L2-resident, counted once
-        pal_bytes = ninst * len(s["bone_map"]) * 48     # palette rows actually referenced (3 of 4 rows, mapped bones)
-        # algorithmic (compulsory DRAM) bytes per launch
-        alg_sep = ninst * nv * 48 + pal_bytes + shared_once          # skin alone: 24 B/vertex source read + 24 B/vertex written
-        alg_fused = ninst * nv * 24 + pal_bytes + shared_once + nv * 48 + ninst * 4   # fused: only the result is written; keys once
+        step(); stream.synchronize()
+        ctx.set_config_option("lane_reuse_repack", 1)
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(20)]
+        for a, b in evs:
+            a.record(stream); step(); b.record(stream)
+        stream.synchronize()
+        ctx.set_config_option("lane_reuse_repack", 0)
+        dur = float(np.median([a.elapsed_time(b) for a, b in evs])) * 1e-3
+        used = sorted(set(int(x) for s in subs for x in s["bone_map"]))
+        static = sum(s["nverts"] * (48 + s["blend_stride"]) for s in subs)
+        alg = ninst * nverts * 24 + ninst * len(used) * 48 + static + ninst * 4
         try:
             traf = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
         except Exception:
             traf = {}
-
-        def roofline(name, label, alg, key):
-            dur = float(np.mean(kern[(name, k)][1:])) * 1e-3
-            return {"bound": "hbm", "kernel": label % (nv, ninst), "achieved": alg / dur / 1e9, "peak": peak,
-                    "peak_source": (peak_kind + " (MEASURED_PEAKS.json hbm_gbs)") if peak_kind == "measured" else "fallback",
-                    "unit": "GB/s", "frac": alg / dur / 1e9 / peak, "traffic": traf.get(key), "launch_ms": dur * 1e3,
-                    "algorithmic_bytes_per_launch": alg}
-        roof_fused = roofline("fused", "skin_pair_kernel<4,normals,fused morph> (sub-mesh 1: %d verts x %d instances, 4 weights)",
-                              alg_fused, "skin_pair_fused_sub1_bytes")
-        roof_sep = roofline("skin", "skin_pair_kernel<4,normals> (sub-mesh 1: %d verts x %d instances, 4 weights)", alg_sep,
-                            "skin_pair_sub1_bytes")
-        roof = roof_fused if args.form == "fused" else roof_sep
-        extra["roofline_other_form"] = roof_sep if args.form == "fused" else roof_fused
-        tot = {n: sum(np.mean(kern[(n, i)][1:]) for i in range(len(subs))) for n in ("skin", "morph", "fused")}
-        extra["kernel_ms_per_step"] = tot
-        extra["fused_ms_per_submesh"] = [float(np.mean(kern[("fused", i)][1:])) for i in range(len(subs))]
-        extra["skin_ms_per_submesh"] = [float(np.mean(kern[("skin", i)][1:])) for i in range(len(subs))]
-        extra["fused_Mvert_per_s"] = ninst * nverts / (tot["fused"] * 1e-3) / 1e6
-        extra["separate_Mvert_per_s"] = ninst * nverts / ((tot["skin"] + tot["morph"]) * 1e-3) / 1e6
-        extra["skin_only_Mvert_per_s"] = ninst * nverts / (tot["skin"] * 1e-3) / 1e6
-        extra["morph_only_Mvert_per_s"] = ninst * nverts / (tot["morph"] * 1e-3) / 1e6
-        pal_step = ninst * sum(len(s["bone_map"]) for s in subs) * 48
-        bytes_step = ninst * nverts * (24 if args.form == "fused" else 72) + pal_step
-        # ---- SURVEY §8d "synthetic stream (roofline case)": ONE softwareVertexSkinning call over 2^24 distinct vertices, 64
-        # bones, 4 weights, uniformly random bone indices (mt19937-style: no locality), pos+normal stride 24, blend stride 20:
-        # 24 + 20 + 24 = 68 algorithmic bytes per vertex.  Outside the timed regions; the kernel is skin_stream_kernel.
-        try:
-            with torch.cuda.stream(stream):
-                sn, snb = 1 << 24, 64
-                g = torch.Generator(device=dev).manual_seed(1234)
-                s_src = torch.empty(sn, 6, device=dev).uniform_(-10, 10, generator=g)
-                s_w = torch.rand(sn, 4, device=dev, generator=g) + 0.05
-                s_w = s_w / s_w.sum(1, keepdim=True)
-                s_blend = torch.empty(sn, 20, device=dev, dtype=torch.uint8)
-                s_blend[:, :4] = torch.randint(0, snb, (sn, 4), device=dev, dtype=torch.uint8, generator=g)
-                s_blend[:, 4:] = s_w.contiguous().view(torch.uint8).reshape(sn, 16)
-                s_pal = torch.eye(4, device=dev).repeat(snb, 1, 1) + 0.01 * torch.randn(snb, 4, 4, device=dev, generator=g)
-                s_pal[:, 3, :] = torch.tensor([0, 0, 0, 1.0], device=dev)
-                s_pal = s_pal.contiguous()
-                s_dst = torch.empty(sn, 6, device=dev)
-            sj = SkinJob()
-            sj.src_pos, sj.src_norm = s_src.data_ptr(), s_src.data_ptr() + 12
-            sj.dst_pos, sj.dst_norm = s_dst.data_ptr(), s_dst.data_ptr() + 12
-            sj.blend_weight, sj.blend_index = s_blend.data_ptr() + 4, s_blend.data_ptr()
-            sj.palette, sj.bone_map = s_pal.data_ptr(), None
-            sj.src_pos_stride = sj.dst_pos_stride = sj.src_norm_stride = sj.dst_norm_stride = 24
-            sj.blend_weight_stride = sj.blend_index_stride = 20
-            sj.num_weights, sj.num_matrices, sj.num_vertices = 4, snb, sn
-            stream.synchronize()
-            for _ in range(3):
-                check(L.ogrecu_skin_instanced_dev(ctx.handle, C.byref(sj), 1, 0, 0, 0))
-            sev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(10)]
-            for a, b in sev:
-                a.record(stream)
-                check(L.ogrecu_skin_instanced_dev(ctx.handle, C.byref(sj), 1, 0, 0, 0))
-                b.record(stream)
-            stream.synchronize()
-            sdur = float(np.median([a.elapsed_time(b) for a, b in sev])) * 1e-3
-            extra["roofline_stream_case"] = {
-                "bound": "hbm", "kernel": "skin_stream_kernel<4,normals> (one call, 2^24 distinct vertices, 64 bones, random bone indices)",
-                "achieved": sn * 68 / sdur / 1e9, "peak": peak, "unit": "GB/s", "frac": sn * 68 / sdur / 1e9 / peak, "launch_ms": sdur * 1e3,
-                "traffic": traf.get("skin_stream_nw4_2p24_bytes"),
-                "algorithmic_bytes_per_launch": sn * 68, "Mvert_per_s": sn / sdur / 1e6}
-            del s_src, s_w, s_blend, s_pal, s_dst
-        except Exception as ex:      # never lose the contract line over the side measurement
-            extra["roofline_stream_case"] = {"error": repr(ex)}
-        extra["step_compulsory_GBps"] = bytes_step / (ms / args.steps * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": "skin_lane_kernel<morph> (one launch: 7 sub-meshes x %d instances, %d vertices each)" % (ninst, nverts),
+                "achieved": alg / dur / 1e9, "peak": peak,
+                "peak_source": (peak_kind + " (MEASURED_PEAKS.json hbm_gbs)") if peak_kind == "measured" else "fallback",
+                "unit": "GB/s", "frac": alg / dur / 1e9 / peak, "traffic": traf.get("skin_lane_frame_bytes"), "launch_ms": dur * 1e3,
+                "algorithmic_bytes_per_launch": alg,
+                "algorithmic_bytes": "24 B written per vertex-instance + 48 B per (instance, referenced bone) of palette + the mesh "
+                                     "streams once"}
+        step_bytes = alg + ninst * len(used) * 64          # + the repack's read of the palettes
+        extra["step_compulsory_GBps"] = step_bytes / (ms / args.steps * 1e-3) / 1e9
         extra["step_frac_of_hbm_peak"] = extra["step_compulsory_GBps"] / peak
+        extra["e2e_stages_ms"] = {"palettes_10000x69": ms_pal, "morph_skin_frame_call": ms / args.steps, "render_of_all_instances": ms_render,
+                                  "frame_d2h_bytes": frame_bytes}
+        extra["e2e_render"] = {"triangles_per_frame": int(tris_per_frame), "target": "%dx%d" % (FRAME_W, FRAME_H), "covered_fraction": covered,
+                               "Mtri_per_s": tris_per_frame / (ms_render * 1e-3) / 1e6}
+
+    # ---- BASELINE's render configs (c1, c4, c5) in the same run
+    render_cfg = None
+    if not args.no_render:
+        render_cfg = run_render_configs(args, local, rank, world, peak)
 
     # ---- CPU baseline on a bounded sample (rank 0, N=1 only)
     cpu = None
@@ -580,42 +560,112 @@ def run_ours(args):
         sample = args.ref_instances
         fn, kind, cores = reference_step_fn(subs, palettes, sample, threads)
         fn()
-        best, t_end, reps = 1e30, time.time() + args.cpu_seconds, 0
+        best, best_pal, t_end, reps = 1e30, 0.0, time.time() + args.cpu_seconds, 0
         while time.time() < t_end or reps < 3:
-            best = min(best, fn()); reps += 1
+            tt, tp = fn(); reps += 1
+            if tt < best:
+                best, best_pal = tt, tp
         cpu = {"value": sample * nverts / best / 1e6, "unit": "Mvert/s", "cores": cores, "kind": kind,
-               "sample": "%d of the %d instances (%d vertices), morph+skin through the real OptimisedUtilSSE, best of %d passes" % (
-                   sample, ninst, sample * nverts, reps)}
+               "sample": "%d of the %d instances (%d vertices): real SkeletonInstance palettes on 1 thread (%.1f ms) + morph + skin "
+                         "through the real OptimisedUtilSSE on %d threads (%.1f ms), best of %d passes" % (
+                             sample, ninst, sample * nverts, best_pal * 1e3, cores, (best - best_pal) * 1e3, reps),
+               "morph_skin_only_value": sample * nverts / max(best - best_pal, 1e-9) / 1e6}
 
     if rank == 0:
+        if render_cfg is not None:
+            extra["render"] = render_cfg
         line = {
             "metric": "skinned_Mvert_per_s", "value": value, "unit": "Mvert/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict(workload_config(ninst, nverts), form=args.form, parallelism="instances sharded per GPU, no collective (dp%d)" % world),
+            "config": workload_config(ninst, nverts, world),
             "clocks": clk, "gpu_launches": int(launches),
-            "e2e": {"value": e2e_value, "unit": "Mvert/s", "h2d_bytes_per_step": int(pal_h.nbytes + t_h.nbytes),
-                    "d2h_bytes_per_step": int(out_bytes), "ms_per_step": ms_e2e / args.steps,
-                    "serial_value": e2e_serial_value, "serial_ms_per_step": ms_e2e_serial / args.steps,
-                    "states_value": states_value, "states_ms_per_step": ms_states / args.steps,
-                    "states_h2d_bytes_per_step": int(st_n + t_h.nbytes), "states_gpu_launches": int(launches_states),
-                    "states_note": "same step with the bone palettes produced on the device (ogrecu_skel_palettes_dev, %.1f us per "
-                                   "launch for %d instances x %d bones): the host uploads each instance's animation state (12 B) and "
-                                   "morph weight instead of its %d-byte palette" % (ms_pal * 1e3, ninst, nb, nb * 64),
-                    "note": "two frames in flight (upload of step k+1 on a copy stream overlaps the kernels of step k); serial_value = "
-                            "upload -> kernels -> read-back on one stream; skinned vertex buffers stay in HBM for _render, one instance "
-                            "is read back per step as the result"},
+            "e2e": {"value": e2e_value, "unit": "Mvert/s", "h2d_bytes_per_step": int(st_n + t_h.nbytes),
+                    "d2h_bytes_per_step": int(frame_bytes), "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps,
+                    "gpu_launches_per_step": launches_e2e,
+                    "skin_only_value": skin_only_value, "skin_only_ms_per_step": ms_skin_only / args.steps,
+                    "note": "host animation states (12 B per instance) + morph weights in -> bone palettes on the device -> morph + skin "
+                            "of every instance (buffers stay in HBM) -> the consuming _render of all instances (%d triangles into a "
+                            "%dx%d target) -> the frame read back to pinned host memory; two frames in flight.  skin_only_value = the "
+                            "same without the render (one instance's vertices read back)" % (tris_per_frame, FRAME_W, FRAME_H)},
             "roofline": roof, "cpu_baseline": cpu, "extra": extra,
         }
         print(json.dumps(line))
+    for k in range(len(dsub)):
+        if plans[k]:
+            L.ogrecu_skin_plan_destroy(plans[k])
+    for r in rts:
+        r.destroy()
     ctx.set_stream(None)
     skel.destroy()
     ctx_c.set_stream(None)
     ctx_c.close()
-    for h in [hp, ht, hs] + houts:
+    for h in (hs, ht):
         L.ogrecu_host_free(h)
     if dist is not None:
         dist.destroy_process_group()
+
+
+def run_render_configs(args, local, rank, world, peak):
+    """BASELINE.json's render configs through tools/bench_configs.py (same process, own context and stream): c1 ogrehead
+    1280x720, c4 batched offscreen views (view i -> GPU i mod G, no collective), c5 one 4K frame of 20 M triangles
+    (whole frame on one GPU; under torchrun contiguous strips per rank + NCCL gather, interleaved bands, sort-last)."""
+    import ogre_b200
+    import bench_configs as bc
+    ctx = ogre_b200.Context(local)
+    T = bc.Timer(ctx)
+    a = types.SimpleNamespace(cpu=(rank == 0 and world == 1 and not args.no_cpu_baseline), views=args.views, chunk=32, contexts=1,
+                              c3_tris=2000000, c4_tris=1000000, c5_tris=args.c5_tris)
+    out = {}
+    # ---- c1
+    r = bc.c1(ctx, T, a)
+    c1_bytes = 1280 * 720 * 3 + 70000                       # SURVEY §8d: 2.76 MB colour write + 0.07 MB geometry
+    out["c1"] = {"config": r["config"], "frames_per_s": r["frames_per_s_device"], "Mtri_per_s": r["Mtri_per_s_device"],
+                 "ms_per_frame": r["ms_per_frame_device"], "image_identical_to_tiny": r["image_identical_to_tiny"],
+                 "roofline": {"bound": "hbm", "achieved": c1_bytes / (r["ms_per_frame_device"] * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                              "frac": c1_bytes / (r["ms_per_frame_device"] * 1e-3) / 1e9 / peak, "traffic": None,
+                              "note": "latency-bound: 4 draws, 4 336 triangles"},
+                 "e2e": {"value": r["frames_per_s_with_readback"], "unit": "frames/s", "d2h_bytes_per_step": 1280 * 720 * 3,
+                         "ms_per_frame": r["ms_per_frame_with_readback"]},
+                 "cpu_baseline": ({"value": 1e3 / r["cpu_tiny_ms_per_frame"], "unit": "frames/s", "cores": 1, "kind": "reference",
+                                   "sample": r.get("cpu", "")} if "cpu_tiny_ms_per_frame" in r else None)}
+    # ---- c4
+    r = bc.c4(ctx, T, a)
+    view_bytes = 12e6 + 16e6 + 640 * 480 * 7
+    out["c4"] = {"config": r["config"], "n_gpus": world, "views_per_s": r["views_per_s_device"], "Mtri_per_s": r["Mtri_per_s_device"],
+                 "ms_per_view": r["ms_per_view_device"], "sharding": r["sharding"], "covered_fraction": r["covered_fraction"],
+                 "roofline": {"bound": "hbm", "achieved": r["compulsory_GBps_per_gpu"], "peak": peak, "unit": "GB/s",
+                              "frac": r["compulsory_GBps_per_gpu"] / peak, "traffic": None,
+                              "algorithmic_bytes_per_view": int(view_bytes)},
+                 "e2e": {"value": r["views_per_s_with_readback"], "unit": "views/s", "d2h_bytes_per_step": int(r["views_per_gpu"] * 640 * 480 * 3)},
+                 "cpu_baseline": ({"value": 1.0 / r["cpu_s_per_view_1_thread"], "unit": "views/s", "cores": 1, "kind": r["cpu_kind"],
+                                   "sample": "1 of the %d views through TinyRenderSystem::_render" % args.views,
+                                   "gpu_view_identical": r["identical_to_cpu"]} if "cpu_s_per_view_1_thread" in r else None)}
+    # ---- c5
+    r = bc.c5(ctx, T, a)
+    if world == 1:
+        out["c5"] = {"config": r["config"], "n_gpus": 1, "frames_per_s": r["frames_per_s_device"], "Mtri_per_s": r["Mtri_per_s_device"],
+                     "ms_per_frame": r["ms_per_frame_device"], "covered_fraction": r["covered_fraction"],
+                     "roofline": {"bound": "hbm", "achieved": r["compulsory_GBps"], "peak": peak, "unit": "GB/s", "frac": r["compulsory_GBps"] / peak,
+                                  "traffic": None},
+                     "e2e": {"value": 1e3 / r["ms_per_frame_with_readback"], "unit": "frames/s", "d2h_bytes_per_step": 3840 * 2160 * 3,
+                             "ms_per_frame": r["ms_per_frame_with_readback"]},
+                     "cpu_baseline": ({"value": 1.0 / r["cpu_s_per_frame_1_thread"], "unit": "frames/s", "cores": 1, "kind": r["cpu_kind"],
+                                       "sample": "the whole frame through TinyRenderSystem::_render", "gpu_frame_identical": r["identical_to_cpu"]}
+                                      if "cpu_s_per_frame_1_thread" in r else None)}
+    else:
+        best = min((r["ms_per_frame_with_composite"], "strips"), (r["interleaved"]["ms_per_frame_with_composite"], "interleaved bands"),
+                   (r["sort_last"]["ms_per_frame_with_composite"], "sort-last"))
+        out["c5"] = {"config": r["config"], "n_gpus": world, "frames_per_s": 1e3 / best[0], "Mtri_per_s": args.c5_tris / best[0] / 1e3,
+                     "ms_per_frame": best[0], "split": best[1],
+                     "strips": {k: r[k] for k in ("ms_per_frame_render_only", "ms_per_frame_with_composite", "identical_to_single_gpu_frame")},
+                     "interleaved_bands": {k: r["interleaved"][k] for k in ("ms_per_frame_render_only", "ms_per_frame_with_composite",
+                                                                            "identical_to_single_gpu_frame")},
+                     "sort_last": {k: r["sort_last"][k] for k in ("ms_per_frame_render_only", "ms_per_frame_with_composite", "ms_composite_only",
+                                                                  "identical_to_single_gpu_frame")}}
+    ctx.set_stream(None)
+    ctx.close()
+    return out
 
 
 def main():
@@ -624,14 +674,16 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--form", default="fused", choices=["fused", "separate"],
-                    help="fused: one morph+skin pass per sub-mesh (default); separate: softwareVertexMorph then softwareVertexSkinning")
-    ap.add_argument("--skin-mode", type=int, default=0, help="kernel selection for A/B runs (ogrecu_set_config_option)")
-    ap.add_argument("--skin-ipc", type=int, default=0, help="instances per CTA of the tiled kernel, 0 = auto")
+    ap.add_argument("--skin-mode", type=int, default=0, help="0 = lane kernel from plans (default); 1-3 = the tile kernels (A/B runs)")
     ap.add_argument("--instances", type=int, default=10000)
-    ap.add_argument("--ref-instances", type=int, default=1000, help="bounded CPU sample of the instances")
-    ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--ref-instances", type=int, default=1000, help="bounded CPU sample of the instances for cpu_baseline")
+    ap.add_argument("--cpu-seconds", type=float, default=8.0)
+    ap.add_argument("--ref-seconds", type=float, default=150.0, help="--impl reference: stop after this many seconds (>= 3 steps)")
+    ap.add_argument("--e2e-steps", type=int, default=40, help="steps of the end-to-end measurement (each renders every instance)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-render", action="store_true", help="skip extra.render (c1, c4, c5)")
+    ap.add_argument("--views", type=int, default=1024)
+    ap.add_argument("--c5-tris", type=int, default=20000000)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

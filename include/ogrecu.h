@@ -80,6 +80,8 @@ OGRECU_API uint64_t ogrecu_launch_count(const ogrecu_ctx* ctx);
  *   "skin_mode"  0 = auto (tiled stream kernel with TMA where alignment allows), 1 = tiled kernel
  *                with cooperative LDG/STG only, 2 = one-thread-per-vertex kernel
  *   "skin_ipc"   instances per CTA of the tiled kernel, 0 = auto
+ *   "lane_reuse_repack" 1 = ogrecu_anim_frame_dev skips its palette repack launch and reads the previous call's (valid only while
+ *                the palettes are unchanged: lets a benchmark time the lane kernel alone), 0 = default
  *   "raster_mode" 0 = auto (per tile: order-independent visibility resolve where it is provably
  *                equivalent to Tiny's in-order loop, else in-order), 1 = always in-order
  *   "raster_xf"  1 = transform every vertex once per flush when the draw gives vertex_count (default),
@@ -306,6 +308,12 @@ OGRECU_API int ogrecu_software_vertex_morph_host(ogrecu_ctx* ctx, float t, const
  * in the reference). */
 OGRECU_API int ogrecu_concat_affine_dev(ogrecu_ctx* ctx, const float* base_host16, const float* src, float* dst,
                                         size_t num_matrices);
+/* The same for many entities in one launch: what Entity::cacheBoneMatrices (OgreMain/src/OgreEntity.cpp:1307-1330) does per
+ * entity with its parent node's full transform.  bases_dev[i] = instance i's base matrix (16 floats, row major, DEVICE);
+ * instance i's n matrices are at src + i*instance_stride_floats (dst likewise; dst may alias src).  Bit-identical to n calls
+ * of ogrecu_concat_affine_dev. */
+OGRECU_API int ogrecu_concat_affine_instanced_dev(ogrecu_ctx* ctx, const float* bases_dev, const float* src, float* dst, uint32_t n,
+                                                  uint32_t num_instances, size_t instance_stride_floats);
 OGRECU_API int ogrecu_concatenate_affine_matrices_host(ogrecu_ctx* ctx, const float* base16, const float* src,
                                                        float* dst, size_t num_matrices);
 

@@ -148,6 +148,7 @@ SIGNATURES = {
     "ogrecu_software_vertex_morph_host": (C.c_int, [C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
                                                     C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int]),
     "ogrecu_concat_affine_dev": (C.c_int, [C.c_void_p, c_float_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "ogrecu_concat_affine_instanced_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_size_t]),
     "ogrecu_concatenate_affine_matrices_host": (C.c_int, [C.c_void_p, c_float_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "ogrecu_face_normals_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "ogrecu_calculate_face_normals_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t]),

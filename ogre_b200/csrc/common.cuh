@@ -76,6 +76,7 @@ struct ogrecu_ctx {
     ogrecu::Scratch stage_out;
     ogrecu::Scratch lane_counter;   // work-unit counter of skin_lane_kernel
     ogrecu::Scratch lane_ipal;      // the frame's palettes repacked for skin_lane_kernel
+    int lane_reuse_repack = 0;      // measurement switch: ogrecu_anim_frame_dev keeps the previous call's repacked palettes
     void* pinned;               // pinned staging (host side)
     size_t pinned_cap;
     // shadow registry: shadow base address -> buffer

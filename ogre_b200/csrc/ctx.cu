@@ -174,6 +174,7 @@ int ogrecu_set_config_option(ogrecu_ctx* ctx, const char* name, int value)
     if (!strcmp(name, "raster_mode")) { OGRECU_REQUIRE(value >= 0 && value <= 1, "raster_mode is 0..1"); ctx->raster_mode = value; return OGRECU_OK; }
     if (!strcmp(name, "skel_mode")) { OGRECU_REQUIRE(value >= 0 && value <= 1, "skel_mode is 0..1"); ctx->skel_mode = value; return OGRECU_OK; }
     if (!strcmp(name, "optutil_sync")) { OGRECU_REQUIRE(value >= 0 && value <= 1, "optutil_sync is 0..1"); ctx->optutil_sync = value; return OGRECU_OK; }
+    if (!strcmp(name, "lane_reuse_repack")) { OGRECU_REQUIRE(value >= 0 && value <= 1, "lane_reuse_repack is 0..1"); ctx->lane_reuse_repack = value; return OGRECU_OK; }
     if (!strcmp(name, "skin_ipc")) { OGRECU_REQUIRE(value >= 0 && value <= 4096, "skin_ipc is 0..4096"); ctx->skin_ipc = value; return OGRECU_OK; }
     set_error("ogrecu_set_config_option: unknown option '%s'", name);
     return OGRECU_ERR_INVALID;

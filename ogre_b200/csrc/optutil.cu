@@ -292,6 +292,33 @@ __global__ void concat_affine_kernel(const __grid_constant__ Mat4 base, const fl
     dst[mi * 4 + 3] = make_float4(0.f, 0.f, 0.f, 1.f);
 }
 
+// The same for many entities at once — Entity::cacheBoneMatrices (OgreMain/src/OgreEntity.cpp:1307-1330) concatenates every
+// entity's parent-node transform with its bone matrices into mBoneWorldMatrices: instance i uses bases[i] (16 floats, row
+// major) on its n matrices at src + i * stride.  One thread per (instance, matrix); same operation order as above.
+__global__ void concat_affine_instanced_kernel(const float4* __restrict__ bases, const float4* src, float4* dst, uint32_t n, uint32_t ninst,
+                                               size_t stride_f4)
+{
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)n * ninst) return;
+    const uint32_t inst = (uint32_t)(t / n), mi = (uint32_t)(t - (size_t)inst * n);
+    const float4* b = bases + (size_t)inst * 4;
+    const float4 B[4] = {__ldg(b), __ldg(b + 1), __ldg(b + 2), __ldg(b + 3)};
+    const float4* sp = src + (size_t)inst * stride_f4 + (size_t)mi * 4;
+    float4* dp = dst + (size_t)inst * stride_f4 + (size_t)mi * 4;
+    const float4 s0 = sp[0], s1 = sp[1], s2 = sp[2];
+    float4 o[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const float b0 = B[r].x, b1 = B[r].y, b2 = B[r].z, b3 = B[r].w;
+        o[r].x = fadd(fadd(fmul(b0, s0.x), fmul(b1, s1.x)), fadd(fmul(b2, s2.x), fmul(b0, B[3].x)));
+        o[r].y = fadd(fadd(fmul(b0, s0.y), fmul(b1, s1.y)), fadd(fmul(b2, s2.y), fmul(b1, B[3].y)));
+        o[r].z = fadd(fadd(fmul(b0, s0.z), fmul(b1, s1.z)), fadd(fmul(b2, s2.z), fmul(b2, B[3].z)));
+        o[r].w = fadd(fadd(fmul(b0, s0.w), fmul(b1, s1.w)), fadd(fmul(b2, s2.w), fmul(b3, B[3].w)));
+    }
+    dp[0] = o[0]; dp[1] = o[1]; dp[2] = o[2];
+    dp[3] = make_float4(0.f, 0.f, 0.f, 1.f);
+}
+
 /* ------------------------------------------------------------- face normals (K9) --- */
 
 // n = (v1-v0)x(v2-v0), w = -(n.v0); EdgeData::Triangle is 32 bytes with vertIndex[3] at byte 8
@@ -739,6 +766,21 @@ int ogrecu_concat_affine_dev(ogrecu_ctx* ctx, const float* base_host16, const fl
     Mat4 base;
     memcpy(base.m, base_host16, sizeof base.m);
     concat_affine_kernel<<<div_up(n, 64), 64, 0, ctx->stream>>>(base, (const float4*)src, (float4*)dst, n);
+    OGRECU_CUDA(cudaGetLastError());
+    count_launch(ctx);
+    return OGRECU_OK;
+}
+
+int ogrecu_concat_affine_instanced_dev(ogrecu_ctx* ctx, const float* bases_dev, const float* src, float* dst, uint32_t n, uint32_t num_instances,
+                                       size_t instance_stride_floats)
+{
+    OGRECU_REQUIRE(ctx, "ctx is NULL");
+    if (n == 0 || num_instances == 0) return OGRECU_OK;
+    OGRECU_REQUIRE(bases_dev && src && dst && aligned16(bases_dev) && aligned16(src) && aligned16(dst), "matrices must be non-NULL and 16-byte aligned");
+    OGRECU_REQUIRE((instance_stride_floats & 3) == 0 && instance_stride_floats >= (size_t)n * 16, "instance stride must hold n matrices and keep 16-byte alignment");
+    OGRECU_CUDA(cudaSetDevice(ctx->device));
+    concat_affine_instanced_kernel<<<div_up((size_t)n * num_instances, 128), 128, 0, ctx->stream>>>((const float4*)bases_dev, (const float4*)src,
+                                                                                                (float4*)dst, n, num_instances, instance_stride_floats / 4);
     OGRECU_CUDA(cudaGetLastError());
     count_launch(ctx);
     return OGRECU_OK;

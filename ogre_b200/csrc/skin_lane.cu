@@ -873,7 +873,8 @@ int ogrecu_anim_frame_dev(ogrecu_ctx* ctx, const ogrecu_anim_job* jobs, ogrecu_s
     if (!lane.empty()) {
         uint32_t nmat = 0;
         for (uint32_t k : lane) nmat = std::max(nmat, plans[k]->max_matrix + 1);
-        OGRECU_CHECK(repack_palettes(ctx, jobs[lane[0]].skin.palette, palette_stride_floats, num_instances, nmat));
+        if (!(ctx->lane_reuse_repack && ctx->lane_ipal.ptr))
+            OGRECU_CHECK(repack_palettes(ctx, jobs[lane[0]].skin.palette, palette_stride_floats, num_instances, nmat));
         lane_nmat = nmat;
     }
     for (size_t at = 0; at < lane.size(); at += LN_MAX_JOBS) {

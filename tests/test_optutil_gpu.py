@@ -152,6 +152,30 @@ def test_concat_affine(gpu_ctx):
         assert np.abs(got - gen).max() <= 1e-5 * max(1.0, np.abs(gen).max())
 
 
+def test_concat_affine_instanced_equals_the_oracle_per_instance(gpu_ctx):
+    """ogrecu_concat_affine_instanced_dev (Entity::cacheBoneMatrices for many entities in one launch) == the SSE restatement
+    called once per instance with that instance's base matrix; in place, padded instance stride."""
+    import ctypes as C
+    from ogre_b200 import addr, check, lib
+    ctx = gpu_ctx
+    rng = np.random.default_rng(14)
+    for ninst, n, pad in ((1, 69, 0), (37, 69, 2), (300, 5, 0)):
+        bases = rigid_matrices(rng, ninst)
+        bases[:, 3] += rng.uniform(-300, 300, size=ninst).astype(np.float32)
+        src = np.stack([np.concatenate([rigid_matrices(rng, n), np.full((pad, 16), 7.0, np.float32)]) for _ in range(ninst)])
+        ref = src.copy()
+        for i in range(ninst):
+            out = np.zeros((n, 16), np.float32)
+            oracle.lib().oracle_concat_affine_sse(addr(np.ascontiguousarray(bases[i])), addr(np.ascontiguousarray(src[i, :n])), addr(out), n)
+            ref[i, :n] = out
+        db, dm = ctx.to_device(bases), ctx.to_device(src)
+        check(lib().ogrecu_concat_affine_instanced_dev(ctx.handle, db.ptr, dm.ptr, dm.ptr, n, ninst, (n + pad) * 16))
+        ctx.sync()
+        got = dm.download(np.float32).reshape(ninst, n + pad, 16)
+        assert np.array_equal(bits(got), bits(ref))
+        db.free(); dm.free()
+
+
 def test_face_normals_light_facing_extrude(gpu_ctx):
     import ogre_b200
     from ogre_b200 import addr

@@ -318,6 +318,22 @@ def raster_views(ctx, T, desc, rts, mvps, mvits, lights, chunk, descs=None):
     return run
 
 
+def cpu_view(case, w, h, gpu_image, unit):
+    """One frame of `case` on one host core: through the unmodified TinyRenderSystem::_render (oracle/_ref) when it is there,
+    else the oracle port; also says whether the GPU image equals it."""
+    from oracle import ref
+    t0 = time.perf_counter()
+    if ref.available():
+        rc = ref.tiny_render([case], w, h)[0]
+        kind = "reference"
+    else:
+        from rasterlib import render_oracle
+        rc = render_oracle([case], w, h)[0]
+        kind = "port"
+    dt = time.perf_counter() - t0
+    return {"cpu_s_per_%s_1_thread" % unit: dt, "cpu_kind": kind, "identical_to_cpu": bool(np.array_equal(rc, gpu_image))}
+
+
 def c4(ctx, T, args):
     w, h = 640, 480
     n = int(round((args.c4_tris / 2) ** 0.5))
@@ -383,14 +399,10 @@ def c4(ctx, T, args):
            "views_per_s_with_readback": total_views / dt_rb, "covered_fraction": covered, "stats_view0": stats,
            "compulsory_GBps_per_gpu": nviews * (len(idx) * 4 + len(verts) * 32 + w * h * 7) / dt / 1e9}
     if args.cpu:
-        from rasterlib import render_oracle
         case = DrawCase(verts, idx, index_type=4, texture=checker_texture(1024), mvp=mvps[0], mvit=mvits[0], viewport=viewport_matrix(w, h),
                         light_dir=(1, 0, 0), ambient=(0.2, 0.2, 0.25, 1.0))
         case.light_dir = lights[0]
-        t0 = time.perf_counter()
-        rc, rz, _ = render_oracle([case], w, h)
-        out["cpu_oracle_port_s_per_view_1_thread"] = time.perf_counter() - t0
-        out["view0_identical_to_cpu"] = bool(np.array_equal(rc, imgs[0]))
+        out.update(cpu_view(case, w, h, imgs[0], "view"))
     for r in rts:
         r.destroy()
     return out
@@ -422,6 +434,11 @@ def c5(ctx, T, args):
            "ms_per_frame_with_readback": dt_rb * 1e3, "stats": stats,
            "compulsory_GBps": (len(idx) * 4 + len(verts) * 32 + w * h * 7) / dt / 1e9,
            "covered_fraction": float((img != np.array([25, 51, 76], np.uint8)).any(axis=2).mean())}
+    if args.cpu:
+        case = DrawCase(verts, idx, index_type=4, texture=checker_texture(1024), mvp=mvps[0], mvit=mvits[0], viewport=viewport_matrix(w, h),
+                        light_dir=(1, 0, 0), ambient=(0.2, 0.2, 0.25, 1.0))
+        case.light_dir = lights[0]
+        out.update(cpu_view(case, w, h, img, "frame"))
     rt.destroy()
     return out
 
