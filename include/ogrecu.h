@@ -54,6 +54,14 @@ typedef struct ogrecu_buf ogrecu_buf;   /* HardwareBuffer: device storage + pinn
 typedef struct ogrecu_tex ogrecu_tex;   /* RGBA8 texture, 0 mips (TinyTexture)            */
 typedef struct ogrecu_rt  ogrecu_rt;    /* render target: RGB8 colour + f32 depth planes  */
 
+/* THREADING CONTRACT.  A context serves ONE thread at a time: OGRE issues every RenderSystem / OptimisedUtil call from the
+ * render thread (Root::renderOneFrame), and so must any other caller — the launch stream, the scratch arenas, the pinned
+ * staging block and ring, and the recorded command lists of the targets are not synchronised.  The one exception is the
+ * buffer registry: ogrecu_buf_create / ogrecu_buf_destroy / ogrecu_buf_resolve take an internal lock, because OGRE creates
+ * and destroys hardware buffers from resource-loading threads (HardwareBufferManager's mutex-protected sets,
+ * OgreMain/src/OgreHardwareBufferManager.cpp).  Mapping, unmapping and using a buffer stay render-thread operations.
+ * Different contexts (devices) may be driven from different threads. */
+
 /* ------------------------------------------------------------------ context -------- */
 
 OGRECU_API int ogrecu_abi_version(void);

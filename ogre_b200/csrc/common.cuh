@@ -81,6 +81,7 @@ struct ogrecu_ctx {
     size_t pinned_cap;
     // shadow registry: shadow base address -> buffer
     std::map<uintptr_t, ogrecu_buf*> shadows;
+    std::mutex shadows_mutex;       // buffers may be created / destroyed from resource threads (see the threading contract in ogrecu.h)
     std::vector<ogrecu_rt*> targets;
     // development switches read once from the environment (A/B measurements, never a fallback):
     //   OGRECU_SKIN_MODE  0 auto | 1 tile kernels without TMA (cooperative copies) | 2 one-thread-per-vertex kernel |

@@ -275,7 +275,7 @@ int ogrecu_buf_create(ogrecu_ctx* ctx, size_t bytes, ogrecu_buf** out)
     if (e != cudaSuccess) { cudaFree(b->dev); delete b; return cuda_fail(e, "cudaHostAlloc(shadow)", __FILE__, __LINE__); }
     e = cudaEventCreateWithFlags(&b->upload_ev, cudaEventDisableTiming);
     if (e != cudaSuccess) { cudaFree(b->dev); cudaFreeHost(b->shadow); delete b; return cuda_fail(e, "cudaEventCreate", __FILE__, __LINE__); }
-    ctx->shadows[(uintptr_t)b->shadow] = b;
+    { std::lock_guard<std::mutex> g(ctx->shadows_mutex); ctx->shadows[(uintptr_t)b->shadow] = b; }
     *out = b;
     return OGRECU_OK;
 }
@@ -286,7 +286,7 @@ int ogrecu_buf_destroy(ogrecu_buf* b)
     ogrecu_ctx* ctx = b->ctx;
     OGRECU_CUDA(cudaSetDevice(ctx->device));
     OGRECU_CUDA(cudaStreamSynchronize(ctx->stream));
-    ctx->shadows.erase((uintptr_t)b->shadow);
+    { std::lock_guard<std::mutex> g(ctx->shadows_mutex); ctx->shadows.erase((uintptr_t)b->shadow); }
     cudaFree(b->dev);
     cudaFreeHost(b->shadow);
     cudaEventDestroy(b->upload_ev);
@@ -383,6 +383,7 @@ int ogrecu_buf_resolve(ogrecu_ctx* ctx, const void* host_ptr, ogrecu_buf** out_b
     *out_buf = nullptr;
     *out_offset = 0;
     uintptr_t p = (uintptr_t)host_ptr;
+    std::lock_guard<std::mutex> g(ctx->shadows_mutex);
     auto it = ctx->shadows.upper_bound(p);
     if (it == ctx->shadows.begin()) return OGRECU_OK;
     --it;

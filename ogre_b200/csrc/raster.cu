@@ -1393,8 +1393,13 @@ int rt_flush_cmds(ogrecu_rt* rt)
     OGRECU_CUDA(cudaSetDevice(ctx->device));
     std::vector<Item> seg;
     ogrecu_rt* one[1] = {rt};
-    for (size_t i = 0; i < rt->cmds.size(); ++i) {
-        Cmd& c = rt->cmds[i];
+    // The list is consumed on EVERY exit path: a flush that fails half way (out of memory, too many pairs, a CUDA error)
+    // reports once and leaves nothing behind to be replayed — segments that already ran must not run again (additive
+    // blending would apply twice) and the failing draw must not fail on every later lock / read-back.
+    std::vector<Cmd> cmds;
+    cmds.swap(rt->cmds);
+    for (size_t i = 0; i < cmds.size(); ++i) {
+        Cmd& c = cmds[i];
         if (c.kind == 0) { seg.push_back({&c.draw, 0, nullptr, nullptr, nullptr, &c.state}); continue; }
         OGRECU_CHECK(run_segment(ctx, one, 1, seg));
         seg.clear();
@@ -1421,9 +1426,7 @@ int rt_flush_cmds(ogrecu_rt* rt)
             count_launch(ctx);
         }
     }
-    int rc = run_segment(ctx, one, 1, seg);
-    rt->cmds.clear();
-    return rc;
+    return run_segment(ctx, one, 1, seg);
 }
 
 }  // namespace

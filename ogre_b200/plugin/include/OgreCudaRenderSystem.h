@@ -58,6 +58,9 @@ public:
     static CudaRenderSystem* getInstance() { return msInstance; }
     /// run everything recorded on any target (called before buffers/textures that draws may reference change)
     static void flushPendingDraws();
+    /// a target is about to be destroyed: run what is recorded on it, then drop every reference the render system keeps to it
+    /// (the dirty list, the active target); `replacement` takes over as the active target when `rt` was active (window resize)
+    static void forgetTarget(ogrecu_rt* rt, ogrecu_rt* replacement = 0);
     /// flush + read a colour box into an arbitrary-format PixelBox (readback path of windows and RTTs)
     static void readColour(ogrecu_rt* rt, const Box& src, const PixelBox& dst);
     /// read-back into a destination of another size: Image::scale(FILTER_BILINEAR) on the device (ogrecu_rt_read_colour_scaled)

@@ -95,19 +95,28 @@ void CudaPoseAnimation::applyPose(ushort poseIndex, VertexData* dest, float infl
     OgreAssert(poseIndex < mPoses.size(), "pose index out of range");
     if (influence == 0.0f) return;            // Mesh::softwareVertexPoseBlend: "Do nothing if no weight" (OgreMesh.cpp:1952-1954)
     const DevicePose& d = mPoses[poseIndex];
-    Element p = element(dest, VES_POSITION);
+    // Addressing as Mesh::softwareVertexPoseBlend has it (OgreMesh.cpp:1958-2005): the position buffer is locked whole and
+    // vertex i's position sits at pBase + i * vertexSize — neither the position element's offset nor vertexStart enter;
+    // normals are blended only when they live in the SAME buffer as the positions (:1964), at pBase + normal offset.
+    const VertexElement* posElem = dest->vertexDeclaration->findElementBySemantic(VES_POSITION);
+    const VertexElement* normElem = dest->vertexDeclaration->findElementBySemantic(VES_NORMAL);
+    OgreAssert(posElem, "no position element");
+    auto buf = dest->vertexBufferBinding->getBuffer(posElem->getSource());
+    CudaHardwareBuffer* hb = dynamic_cast<CudaHardwareBuffer*>(buf->_getImpl<HardwareBuffer>());
+    OgreAssert(hb, "vertex buffer was not created by CudaHardwareBufferManager");
+    const uint32 stride = (uint32)buf->getVertexSize();
     if (d.numOffsets)
     {
         OGRECU_THROW_IF(ogrecu_pose_blend_dev(mCtx, influence, (const uint32_t*)d.offsetIndex, (const float*)d.offsets, d.numOffsets,
-                                              devicePtr(p), p.stride));
-        OGRECU_THROW_IF(ogrecu_buf_mark_device_dirty(p.buf->getHandle(), p.offset, p.bytes));
+                                              (float*)const_cast<void*>(hb->getDevicePtr(0)), stride));
+        OGRECU_THROW_IF(ogrecu_buf_mark_device_dirty(hb->getHandle(), 0, buf->getSizeInBytes()));
     }
-    Element n = element(dest, VES_NORMAL);
-    if (d.numNormals && n.buf)               // normals only when the pose has them and the target has them (:1981-1985)
+    const bool normals = normElem && d.numNormals && posElem->getSource() == normElem->getSource();
+    if (normals)
     {
         OGRECU_THROW_IF(ogrecu_pose_blend_dev(mCtx, influence, (const uint32_t*)d.normalIndex, (const float*)d.normals, d.numNormals,
-                                              devicePtr(n), n.stride));
-        OGRECU_THROW_IF(ogrecu_buf_mark_device_dirty(n.buf->getHandle(), n.offset, n.bytes));
+                                              (float*)const_cast<void*>(hb->getDevicePtr(normElem->getOffset())), stride));
+        OGRECU_THROW_IF(ogrecu_buf_mark_device_dirty(hb->getHandle(), 0, buf->getSizeInBytes()));
     }
 }
 

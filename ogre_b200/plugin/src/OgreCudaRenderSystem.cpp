@@ -219,6 +219,23 @@ void CudaRenderSystem::flushPendingDraws()
     for (ogrecu_rt* rt : targets) OGRECU_THROW_IF(ogrecu_flush(rt));
 }
 
+void CudaRenderSystem::forgetTarget(ogrecu_rt* rt, ogrecu_rt* replacement)
+{
+    CudaRenderSystem* rs = msInstance;
+    if (!rs || !rt) return;
+    auto it = std::find(rs->mDirtyTargets.begin(), rs->mDirtyTargets.end(), rt);
+    if (it != rs->mDirtyTargets.end())
+    {
+        rs->mDirtyTargets.erase(it);
+        ogrecu_flush(rt);   // recorded clears / draws still run (their results die with the target); never throws from a destructor path
+    }
+    if (rs->mActiveTarget == rt)
+    {
+        rs->mActiveTarget = replacement;
+        if (!replacement) rs->mActiveTargetTexture = 0;
+    }
+}
+
 void CudaRenderSystem::_endFrame(void)
 {
     // launch the frame's recorded work now; it runs asynchronously while OgreMain goes on

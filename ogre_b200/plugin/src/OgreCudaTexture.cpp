@@ -43,7 +43,7 @@ void CudaTexture::freeInternalResourcesImpl(void)
     CudaRenderSystem::flushPendingDraws();   // recorded draws may sample this texture
     mSurfaceList.clear();                    // destroys the RenderTextures before their ogrecu_rt
     if (mDevice) { ogrecu_tex_destroy(mDevice); mDevice = 0; }
-    if (mTarget) { ogrecu_rt_destroy(mTarget); mTarget = 0; }
+    if (mTarget) { CudaRenderSystem::forgetTarget(mTarget); ogrecu_rt_destroy(mTarget); mTarget = 0; }
 }
 
 ogrecu_tex* CudaTexture::getDeviceTexture()

@@ -22,6 +22,9 @@ void CudaWindow::destroy(void)
 {
     if (mTarget)
     {
+        // a clear or draw may be recorded on the target and not flushed yet (manual Viewport::clear, an exception mid-frame):
+        // the render system must not keep a pointer to it
+        CudaRenderSystem::forgetTarget(mTarget);
         ogrecu_rt_destroy(mTarget);
         mTarget = 0;
     }
@@ -29,8 +32,14 @@ void CudaWindow::destroy(void)
 
 void CudaWindow::resize(uint width, uint height)
 {
-    destroy();
-    OGRECU_THROW_IF(ogrecu_rt_create(mCtx, width, height, &mTarget));   // zero-filled like Image::create
+    ogrecu_rt* fresh = 0;
+    OGRECU_THROW_IF(ogrecu_rt_create(mCtx, width, height, &fresh));   // zero-filled like Image::create
+    if (mTarget)
+    {
+        CudaRenderSystem::forgetTarget(mTarget, fresh);                // an active window keeps rendering, into the new target
+        ogrecu_rt_destroy(mTarget);
+    }
+    mTarget = fresh;
     RenderWindow::resize(width, height);
 }
 
