@@ -88,6 +88,13 @@ OGRECU_API uint64_t ogrecu_launch_count(const ogrecu_ctx* ctx);
  *   "skin_mode"  0 = auto (tiled stream kernel with TMA where alignment allows), 1 = tiled kernel
  *                with cooperative LDG/STG only, 2 = one-thread-per-vertex kernel
  *   "skin_ipc"   instances per CTA of the tiled kernel, 0 = auto
+ *   "optutil_batch" 1 = ogrecu_software_vertex_skinning_host calls whose operands all live in ogrecu_bufs are QUEUED (descriptor +
+ *                a copy of the palette) and run as one batched launch at the next point that needs their results: the flush of
+ *                a target, a map of one of their buffers, any other OptimisedUtil host call, a memcpy, ogrecu_sync,
+ *                ogrecu_optutil_flush.  What Entity::updateAnimation issues for a crowd (7 calls per Sinbad entity,
+ *                OgreMain/src/OgreEntity.cpp:747-911) becomes one launch per frame; results are bit-identical.  0 = default:
+ *                every call launches at once.  Callers that mix deferred host calls with *_dev entry points on raw device
+ *                pointers call ogrecu_optutil_flush in between.
  *   "lane_reuse_repack" 1 = ogrecu_anim_frame_dev skips its palette repack launch and reads the previous call's (valid only while
  *                the palettes are unchanged: lets a benchmark time the lane kernel alone), 0 = default
  *   "raster_mode" 0 = auto (per tile: order-independent visibility resolve where it is provably
@@ -293,6 +300,11 @@ OGRECU_API int ogrecu_software_vertex_skinning_host(
     size_t src_pos_stride, size_t dst_pos_stride, size_t src_norm_stride, size_t dst_norm_stride,
     size_t blend_weight_stride, size_t blend_index_stride,
     size_t num_weights_per_vertex, size_t num_vertices);
+
+/* Run the OptimisedUtil jobs queued under "optutil_batch" now (no-op when nothing is queued); stats: batched launches so far
+ * and jobs they carried (queued ones included). */
+OGRECU_API int ogrecu_optutil_flush(ogrecu_ctx* ctx);
+OGRECU_API int ogrecu_optutil_batch_stats(ogrecu_ctx* ctx, uint64_t* flushes, uint64_t* jobs);
 
 /* softwareVertexMorph (OgreOptimisedUtil.h:125-131): dst = a + t*(b-a); with
  * morph_normals the interleaved normal is lerped then normalised (General formulation,

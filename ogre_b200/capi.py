@@ -143,6 +143,8 @@ SIGNATURES = {
         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
         C.POINTER(C.c_void_p), C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t,
         C.c_size_t, C.c_size_t]),
+    "ogrecu_optutil_flush": (C.c_int, [C.c_void_p]),
+    "ogrecu_optutil_batch_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "ogrecu_morph_dev": (C.c_int, [C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
                                    C.c_size_t, C.c_size_t, C.c_size_t, C.c_int]),
     "ogrecu_software_vertex_morph_host": (C.c_int, [C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -55,6 +55,13 @@ struct ogrecu_buf {
     // rewritten by the host before it completes)
     cudaEvent_t upload_ev;
     bool upload_pending;
+    // hazard tracking of deferred work (see "optutil_batch"): the value of the context's epoch at the time the buffer was
+    // referenced; a flush bumps the epoch, which clears every mark at once
+    uint64_t batch_r = 0, batch_w = 0;      // read / written by a queued OptimisedUtil job
+    uint64_t draw_ref = 0;                  // referenced by a recorded, unflushed draw
+    // highest blend index of a (range, stride, weights, vertices) of this buffer, kept until the host next writes it
+    struct MaxIdx { size_t off, stride, nw, n; unsigned max_idx; };
+    std::vector<MaxIdx> maxidx_cache;
 };
 
 struct ogrecu_tex {
@@ -102,6 +109,21 @@ struct ogrecu_ctx {
     bool ring_used[RING_SLOTS] = {};
     int ring_next = 0;
     int skel_mode = 0;          // 0: lanes = instances (skel_palette_kernel2) | 1: first version, a lane per bone (A/B)
+    // deferred, batched OptimisedUtil ("optutil_batch" = 1): softwareVertexSkinning host calls whose operands all live in
+    // ogrecu_bufs are queued (descriptor + a copy of the palette) and run as ONE batched launch at the next point that needs
+    // their results (a draw flush, a map of one of their buffers, any other entry point that may read them, ogrecu_sync)
+    int optutil_batch = 0;
+    uint64_t batch_epoch = 1, draw_epoch = 1;
+    std::vector<ogrecu_skin_job> batch_jobs;
+    std::vector<float> batch_pal;
+    uint8_t* batch_pin[2] = {nullptr, nullptr};
+    size_t batch_pin_cap[2] = {0, 0};
+    cudaEvent_t batch_ev[2] = {nullptr, nullptr};
+    bool batch_ev_used[2] = {false, false};
+    int batch_slot = 0;
+    ogrecu::Scratch batch_dev;
+    uint64_t batch_flushes = 0, batch_jobs_run = 0;
+    std::map<uintptr_t, ogrecu_buf*> dev_registry;      // device base address -> buffer (guarded by shadows_mutex)
     // side streams for independent launches of one call (ogrecu_anim_instanced_multi_dev): created on first use
     cudaStream_t side_stream[2] = {nullptr, nullptr};
     cudaEvent_t side_fork = nullptr, side_join[2] = {nullptr, nullptr};
@@ -113,4 +135,10 @@ int pinned_reserve(ogrecu_ctx* ctx, size_t bytes);
 inline void count_launch(ogrecu_ctx* ctx, unsigned n = 1) { ctx->launches += n; }
 inline unsigned div_up(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
 int rt_release(ogrecu_rt* rt);
+// deferred work (optutil_host.cu / raster.cu)
+int flush_skin_batch(ogrecu_ctx* ctx);                       // run the queued OptimisedUtil jobs now (no-op when empty)
+int flush_all_targets(ogrecu_ctx* ctx);                      // run every target's recorded draws (the queued jobs first)
+ogrecu_buf* buf_of_device_ptr(ogrecu_ctx* ctx, const void* dev_ptr);
+int launch_skin_batched(ogrecu_ctx* ctx, const ogrecu_skin_job* djobs, const uint32_t* dprefix, uint32_t n, unsigned blocks);
+int validate_skin_job_public(const ogrecu_skin_job& j);
 }  // namespace ogrecu

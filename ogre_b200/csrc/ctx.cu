@@ -125,9 +125,10 @@ int ogrecu_shutdown(ogrecu_ctx* ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     while (!ctx->targets.empty()) rt_release(ctx->targets.back());
-    for (Scratch* s : {&ctx->jobs, &ctx->stage_in, &ctx->stage_out, &ctx->lane_counter, &ctx->lane_ipal})
+    for (Scratch* s : {&ctx->jobs, &ctx->stage_in, &ctx->stage_out, &ctx->lane_counter, &ctx->lane_ipal, &ctx->batch_dev})
         if (s->ptr) cudaFree(s->ptr);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    for (int k = 0; k < 2; ++k) { if (ctx->batch_pin[k]) cudaFreeHost(ctx->batch_pin[k]); if (ctx->batch_ev[k]) cudaEventDestroy(ctx->batch_ev[k]); }
     if (ctx->ring) cudaFreeHost(ctx->ring);
     for (cudaEvent_t e : ctx->ring_ev) if (e) cudaEventDestroy(e);
     for (int k = 0; k < 2; ++k) {
@@ -162,6 +163,7 @@ int ogrecu_sync(ogrecu_ctx* ctx)
 {
     OGRECU_REQUIRE(ctx, "ctx is NULL");
     OGRECU_CUDA(cudaSetDevice(ctx->device));
+    OGRECU_CHECK(flush_skin_batch(ctx));
     OGRECU_CUDA(cudaStreamSynchronize(ctx->stream));
     return OGRECU_OK;
 }
@@ -174,6 +176,12 @@ int ogrecu_set_config_option(ogrecu_ctx* ctx, const char* name, int value)
     if (!strcmp(name, "raster_mode")) { OGRECU_REQUIRE(value >= 0 && value <= 1, "raster_mode is 0..1"); ctx->raster_mode = value; return OGRECU_OK; }
     if (!strcmp(name, "skel_mode")) { OGRECU_REQUIRE(value >= 0 && value <= 1, "skel_mode is 0..1"); ctx->skel_mode = value; return OGRECU_OK; }
     if (!strcmp(name, "optutil_sync")) { OGRECU_REQUIRE(value >= 0 && value <= 1, "optutil_sync is 0..1"); ctx->optutil_sync = value; return OGRECU_OK; }
+    if (!strcmp(name, "optutil_batch")) {
+        OGRECU_REQUIRE(value >= 0 && value <= 1, "optutil_batch is 0..1");
+        if (!value) OGRECU_CHECK(flush_skin_batch(ctx));
+        ctx->optutil_batch = value;
+        return OGRECU_OK;
+    }
     if (!strcmp(name, "lane_reuse_repack")) { OGRECU_REQUIRE(value >= 0 && value <= 1, "lane_reuse_repack is 0..1"); ctx->lane_reuse_repack = value; return OGRECU_OK; }
     if (!strcmp(name, "skin_ipc")) { OGRECU_REQUIRE(value >= 0 && value <= 4096, "skin_ipc is 0..4096"); ctx->skin_ipc = value; return OGRECU_OK; }
     set_error("ogrecu_set_config_option: unknown option '%s'", name);
@@ -219,6 +227,7 @@ int ogrecu_memcpy_h2d(ogrecu_ctx* ctx, void* dev, const void* host, size_t bytes
 {
     OGRECU_REQUIRE(ctx && (bytes == 0 || (dev && host)), "NULL argument");
     if (!bytes) return OGRECU_OK;
+    OGRECU_CHECK(flush_skin_batch(ctx));          // queued OptimisedUtil jobs come first (program order)
     OGRECU_CUDA(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
     return OGRECU_OK;
 }
@@ -235,6 +244,7 @@ int ogrecu_memcpy_d2h(ogrecu_ctx* ctx, void* host, const void* dev, size_t bytes
 {
     OGRECU_REQUIRE(ctx && (bytes == 0 || (dev && host)), "NULL argument");
     if (!bytes) return OGRECU_OK;
+    OGRECU_CHECK(flush_skin_batch(ctx));          // queued OptimisedUtil jobs come first (program order)
     OGRECU_CUDA(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     OGRECU_CUDA(cudaStreamSynchronize(ctx->stream));
     return OGRECU_OK;
@@ -244,6 +254,7 @@ int ogrecu_memcpy_d2h_async(ogrecu_ctx* ctx, void* host, const void* dev, size_t
 {
     OGRECU_REQUIRE(ctx && (bytes == 0 || (dev && host)), "NULL argument");
     if (!bytes) return OGRECU_OK;
+    OGRECU_CHECK(flush_skin_batch(ctx));          // queued OptimisedUtil jobs come first (program order)
     OGRECU_CUDA(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     return OGRECU_OK;
 }
@@ -252,6 +263,7 @@ int ogrecu_memcpy_d2d(ogrecu_ctx* ctx, void* dst, const void* src, size_t bytes)
 {
     OGRECU_REQUIRE(ctx && (bytes == 0 || (dst && src)), "NULL argument");
     if (!bytes) return OGRECU_OK;
+    OGRECU_CHECK(flush_skin_batch(ctx));          // queued OptimisedUtil jobs come first (program order)
     OGRECU_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
     return OGRECU_OK;
 }
@@ -275,7 +287,7 @@ int ogrecu_buf_create(ogrecu_ctx* ctx, size_t bytes, ogrecu_buf** out)
     if (e != cudaSuccess) { cudaFree(b->dev); delete b; return cuda_fail(e, "cudaHostAlloc(shadow)", __FILE__, __LINE__); }
     e = cudaEventCreateWithFlags(&b->upload_ev, cudaEventDisableTiming);
     if (e != cudaSuccess) { cudaFree(b->dev); cudaFreeHost(b->shadow); delete b; return cuda_fail(e, "cudaEventCreate", __FILE__, __LINE__); }
-    { std::lock_guard<std::mutex> g(ctx->shadows_mutex); ctx->shadows[(uintptr_t)b->shadow] = b; }
+    { std::lock_guard<std::mutex> g(ctx->shadows_mutex); ctx->shadows[(uintptr_t)b->shadow] = b; ctx->dev_registry[(uintptr_t)b->dev] = b; }
     *out = b;
     return OGRECU_OK;
 }
@@ -285,8 +297,10 @@ int ogrecu_buf_destroy(ogrecu_buf* b)
     if (!b) return OGRECU_OK;
     ogrecu_ctx* ctx = b->ctx;
     OGRECU_CUDA(cudaSetDevice(ctx->device));
+    if (b->draw_ref == ctx->draw_epoch) flush_all_targets(ctx);          // recorded draws still read it
+    if (b->batch_r == ctx->batch_epoch || b->batch_w == ctx->batch_epoch) flush_skin_batch(ctx);
     OGRECU_CUDA(cudaStreamSynchronize(ctx->stream));
-    { std::lock_guard<std::mutex> g(ctx->shadows_mutex); ctx->shadows.erase((uintptr_t)b->shadow); }
+    { std::lock_guard<std::mutex> g(ctx->shadows_mutex); ctx->shadows.erase((uintptr_t)b->shadow); ctx->dev_registry.erase((uintptr_t)b->dev); }
     cudaFree(b->dev);
     cudaFreeHost(b->shadow);
     cudaEventDestroy(b->upload_ev);
@@ -321,6 +335,15 @@ int ogrecu_buf_map(ogrecu_buf* b, size_t offset, size_t length, int mode, void**
     OGRECU_REQUIRE(!b->mapped, "buffer is already mapped");          // HardwareBuffer::lock asserts the same
     OGRECU_REQUIRE(offset <= b->size && length <= b->size - offset, "range out of bounds");
     ogrecu_ctx* ctx = b->ctx;
+    // deferred work that the program order puts before this map: a host write must not reach a buffer that recorded draws or
+    // queued jobs still read (or that a queued job would overwrite afterwards); a host read needs what queued jobs write
+    if (mode & (OGRECU_MAP_WRITE | OGRECU_MAP_DISCARD)) {
+        if (b->draw_ref == ctx->draw_epoch) OGRECU_CHECK(flush_all_targets(ctx));
+        if (b->batch_r == ctx->batch_epoch || b->batch_w == ctx->batch_epoch) OGRECU_CHECK(flush_skin_batch(ctx));
+        b->maxidx_cache.clear();
+    } else if (b->batch_w == ctx->batch_epoch) {
+        OGRECU_CHECK(flush_skin_batch(ctx));
+    }
     if (b->upload_pending) {   // a previous unmap's upload still reads the shadow
         OGRECU_CUDA(cudaEventSynchronize(b->upload_ev));
         b->upload_pending = false;
@@ -376,6 +399,24 @@ int ogrecu_buf_unmap(ogrecu_buf* b)
     }
     return OGRECU_OK;
 }
+
+}  // extern "C"
+
+namespace ogrecu {
+ogrecu_buf* buf_of_device_ptr(ogrecu_ctx* ctx, const void* dev_ptr)
+{
+    if (!dev_ptr) return nullptr;
+    const uintptr_t p = (uintptr_t)dev_ptr;
+    std::lock_guard<std::mutex> g(ctx->shadows_mutex);
+    auto it = ctx->dev_registry.upper_bound(p);
+    if (it == ctx->dev_registry.begin()) return nullptr;
+    --it;
+    ogrecu_buf* b = it->second;
+    return (p < it->first + (b->size ? b->size : 1)) ? b : nullptr;
+}
+}  // namespace ogrecu
+
+extern "C" {
 
 int ogrecu_buf_resolve(ogrecu_ctx* ctx, const void* host_ptr, ogrecu_buf** out_buf, size_t* out_offset)
 {

@@ -525,6 +525,17 @@ int validate_skin_job(const ogrecu_skin_job& j)
 
 }  // namespace
 
+namespace ogrecu {
+int launch_skin_batched(ogrecu_ctx* ctx, const ogrecu_skin_job* djobs, const uint32_t* dprefix, uint32_t n, unsigned blocks)
+{
+    skin_batched_kernel<<<blocks, SKIN_THREADS, 0, ctx->stream>>>(djobs, dprefix, n);
+    OGRECU_CUDA(cudaGetLastError());
+    count_launch(ctx);
+    return OGRECU_OK;
+}
+int validate_skin_job_public(const ogrecu_skin_job& j) { return validate_skin_job(j); }
+}  // namespace ogrecu
+
 extern "C" {
 
 int ogrecu_skin_dev(ogrecu_ctx* ctx, const ogrecu_skin_job* jobs, uint32_t n)

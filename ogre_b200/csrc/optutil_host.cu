@@ -120,9 +120,107 @@ private:
     bool deferred = false;
 };
 
+// [host, host + len) inside one ogrecu_buf's shadow -> the buffer and the device address, else NULL
+static ogrecu_buf* resolve_range(ogrecu_ctx* ctx, const void* host, size_t len, const uint8_t** dev)
+{
+    ogrecu_buf* b = nullptr; size_t off = 0;
+    if (ogrecu_buf_resolve(ctx, host, &b, &off) != OGRECU_OK || !b || off + len > b->size) return nullptr;
+    *dev = (const uint8_t*)b->dev + off;
+    return b;
+}
+
+// highest blend index of the stream, remembered per buffer until the host next writes it (ogrecu_buf_map clears the cache)
+static unsigned max_blend_index(ogrecu_buf* b, const uint8_t* blend_index, size_t stride, size_t nw, size_t n)
+{
+    const size_t off = b ? (size_t)(blend_index - b->shadow) : 0;
+    if (b)
+        for (const auto& c : b->maxidx_cache)
+            if (c.off == off && c.stride == stride && c.nw == nw && c.n == n) return c.max_idx;
+    unsigned max_idx = 0;
+    for (size_t v = 0; v < n; ++v) {
+        const uint8_t* bi = blend_index + v * stride;
+        for (size_t k = 0; k < nw; ++k) max_idx = std::max<unsigned>(max_idx, bi[k]);
+    }
+    if (b) {
+        if (b->maxidx_cache.size() >= 16) b->maxidx_cache.clear();
+        b->maxidx_cache.push_back({off, stride, nw, n, max_idx});
+    }
+    return max_idx;
+}
+
 }  // namespace
 
+namespace ogrecu {
+
+// Run the queued softwareVertexSkinning jobs: descriptors, block prefix and palettes travel in ONE copy from a pinned
+// arena (two arenas alternate, each guarded by an event: no stream synchronisation), one batched launch skins them all.
+int flush_skin_batch(ogrecu_ctx* ctx)
+{
+    const uint32_t n = (uint32_t)ctx->batch_jobs.size();
+    if (n == 0) return OGRECU_OK;
+    OGRECU_CUDA(cudaSetDevice(ctx->device));
+    const size_t jobs_bytes = up((size_t)n * sizeof(ogrecu_skin_job)), prefix_bytes = up(((size_t)n + 1) * 4);
+    const size_t pal_bytes = ctx->batch_pal.size() * 4, total = jobs_bytes + prefix_bytes + pal_bytes;
+    const int s = ctx->batch_slot;
+    ctx->batch_slot ^= 1;
+    if (ctx->batch_ev_used[s]) OGRECU_CUDA(cudaEventSynchronize(ctx->batch_ev[s]));          // this arena's last copy has been read
+    if (ctx->batch_pin_cap[s] < total) {
+        if (ctx->batch_pin[s]) cudaFreeHost(ctx->batch_pin[s]);
+        ctx->batch_pin[s] = nullptr; ctx->batch_pin_cap[s] = 0;
+        const size_t cap = std::max(total * 2, (size_t)1 << 20);
+        if (cudaHostAlloc((void**)&ctx->batch_pin[s], cap, cudaHostAllocDefault) != cudaSuccess) {
+            (void)cudaGetLastError(); ctx->batch_jobs.clear(); ctx->batch_pal.clear(); ++ctx->batch_epoch;
+            set_error("pinned allocation of %zu bytes failed", cap); return OGRECU_ERR_OOM;
+        }
+        ctx->batch_pin_cap[s] = cap;
+    }
+    if (!ctx->batch_ev[s]) OGRECU_CUDA(cudaEventCreateWithFlags(&ctx->batch_ev[s], cudaEventDisableTiming));
+    int rc = scratch_reserve(ctx, ctx->batch_dev, total);
+    uint64_t blocks = 0;
+    if (rc == OGRECU_OK) {
+        uint8_t* pin = ctx->batch_pin[s];
+        uint8_t* dev = (uint8_t*)ctx->batch_dev.ptr;
+        ogrecu_skin_job* hj = (ogrecu_skin_job*)pin;
+        uint32_t* prefix = (uint32_t*)(pin + jobs_bytes);
+        const float* dpal = (const float*)(dev + jobs_bytes + prefix_bytes);
+        for (uint32_t k = 0; k < n; ++k) {
+            hj[k] = ctx->batch_jobs[k];
+            hj[k].palette = dpal + (size_t)(uintptr_t)ctx->batch_jobs[k].palette;            // queued as an offset in floats
+            prefix[k] = (uint32_t)blocks;
+            blocks += div_up(hj[k].num_vertices, 256);
+        }
+        prefix[n] = (uint32_t)blocks;
+        memcpy(pin + jobs_bytes + prefix_bytes, ctx->batch_pal.data(), pal_bytes);
+        cudaError_t e = cudaMemcpyAsync(dev, pin, total, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaEventRecord(ctx->batch_ev[s], ctx->stream);
+        if (e != cudaSuccess) rc = cuda_fail(e, "batch upload", __FILE__, __LINE__);
+        else {
+            ctx->batch_ev_used[s] = true;
+            if (blocks) rc = launch_skin_batched(ctx, (const ogrecu_skin_job*)dev, (const uint32_t*)(dev + jobs_bytes), n, (unsigned)blocks);
+        }
+    }
+    ctx->batch_flushes++; ctx->batch_jobs_run += n;
+    ctx->batch_jobs.clear(); ctx->batch_pal.clear();
+    ++ctx->batch_epoch;                                           // every buffer's batch_r / batch_w mark is stale now
+    return rc;
+}
+
+}  // namespace ogrecu
+
 extern "C" {
+
+int ogrecu_optutil_flush(ogrecu_ctx* ctx)
+{
+    OGRECU_REQUIRE(ctx, "ctx is NULL");
+    return flush_skin_batch(ctx);
+}
+
+int ogrecu_optutil_batch_stats(ogrecu_ctx* ctx, uint64_t* flushes, uint64_t* jobs)
+{
+    OGRECU_REQUIRE(ctx && flushes && jobs, "NULL argument");
+    *flushes = ctx->batch_flushes; *jobs = ctx->batch_jobs_run + ctx->batch_jobs.size();
+    return OGRECU_OK;
+}
 
 int ogrecu_software_vertex_skinning_host(ogrecu_ctx* ctx, const float* src_pos, float* dst_pos, const float* src_norm,
                                          float* dst_norm, const float* blend_weight, const uint8_t* blend_index,
@@ -137,14 +235,55 @@ int ogrecu_software_vertex_skinning_host(ogrecu_ctx* ctx, const float* src_pos, 
     OGRECU_REQUIRE(!src_norm || dst_norm, "src_norm without dst_norm");
     OGRECU_REQUIRE(n <= 0xffffffffull, "too many vertices");
     OGRECU_CUDA(cudaSetDevice(ctx->device));
-
-    // highest palette slot referenced (the reference takes a bare pointer palette)
-    unsigned max_idx = 0;
-    for (size_t v = 0; v < n; ++v) {
-        const uint8_t* bi = blend_index + v * blend_index_stride;
-        for (size_t b = 0; b < nw; ++b) max_idx = std::max<unsigned>(max_idx, bi[b]);
+    const size_t q_sp_len = (n - 1) * src_pos_stride + 12, q_sn_len = src_norm ? (n - 1) * src_norm_stride + 12 : 0;
+    const size_t q_w_len = (n - 1) * blend_weight_stride + 4 * nw, q_i_len = (n - 1) * blend_index_stride + nw;
+    const size_t q_dp_len = (n - 1) * dst_pos_stride + 12, q_dn_len = src_norm ? (n - 1) * dst_norm_stride + 12 : 0;
+    const uint8_t* d_bi = nullptr;
+    ogrecu_buf* b_bi = resolve_range(ctx, blend_index, q_i_len, &d_bi);
+    // highest palette slot referenced (the reference takes a bare pointer palette); scanned once per blend buffer
+    const unsigned nmat = max_blend_index(b_bi, blend_index, blend_index_stride, nw, n) + 1;
+    if (ctx->optutil_batch && !ctx->optutil_sync && b_bi) {
+        // ---- deferred: every operand lives in an ogrecu_buf -> queue the job, copy the palette, return
+        const uint8_t *d_sp = nullptr, *d_sn = nullptr, *d_w = nullptr, *d_dp = nullptr, *d_dn = nullptr;
+        ogrecu_buf* b_sp = resolve_range(ctx, src_pos, q_sp_len, &d_sp);
+        ogrecu_buf* b_sn = src_norm ? resolve_range(ctx, src_norm, q_sn_len, &d_sn) : b_sp;
+        ogrecu_buf* b_w = resolve_range(ctx, blend_weight, q_w_len, &d_w);
+        ogrecu_buf* b_dp = resolve_range(ctx, dst_pos, q_dp_len, &d_dp);
+        ogrecu_buf* b_dn = src_norm ? resolve_range(ctx, dst_norm, q_dn_len, &d_dn) : b_dp;
+        if (b_sp && b_sn && b_w && b_dp && b_dn) {
+            ogrecu_skin_job j;
+            memset(&j, 0, sizeof j);
+            j.src_pos = (const float*)d_sp; j.src_norm = (const float*)d_sn;
+            j.dst_pos = (float*)d_dp; j.dst_norm = src_norm ? (float*)d_dn : nullptr;
+            j.blend_weight = (const float*)d_w; j.blend_index = d_bi;
+            j.src_pos_stride = (uint32_t)src_pos_stride; j.dst_pos_stride = (uint32_t)dst_pos_stride;
+            j.src_norm_stride = (uint32_t)src_norm_stride; j.dst_norm_stride = (uint32_t)dst_norm_stride;
+            j.blend_weight_stride = (uint32_t)blend_weight_stride; j.blend_index_stride = (uint32_t)blend_index_stride;
+            j.num_weights = (uint32_t)nw; j.num_matrices = nmat; j.num_vertices = (uint32_t)n;
+            j.palette = (const float*)(uintptr_t)64;                  // placeholder that passes the alignment check
+            OGRECU_CHECK(validate_skin_job_public(j));
+            // the jobs of one batch run concurrently in one launch, recorded draws run after the batch: whatever the program
+            // order makes depend on an earlier queued job or an unflushed draw goes first
+            if (b_dp->draw_ref == ctx->draw_epoch || b_dn->draw_ref == ctx->draw_epoch) OGRECU_CHECK(flush_all_targets(ctx));
+            const uint64_t ep = ctx->batch_epoch;
+            if (b_sp->batch_w == ep || b_sn->batch_w == ep || b_w->batch_w == ep || b_bi->batch_w == ep || b_dp->batch_w == ep ||
+                b_dp->batch_r == ep || b_dn->batch_w == ep || b_dn->batch_r == ep)
+                OGRECU_CHECK(flush_skin_batch(ctx));
+            const uint64_t now = ctx->batch_epoch;
+            b_sp->batch_r = b_sn->batch_r = b_w->batch_r = b_bi->batch_r = now;
+            b_dp->batch_w = b_dn->batch_w = now;
+            OGRECU_CHECK(ogrecu_buf_mark_device_dirty(b_dp, (size_t)(d_dp - (const uint8_t*)b_dp->dev), q_dp_len));
+            if (src_norm) OGRECU_CHECK(ogrecu_buf_mark_device_dirty(b_dn, (size_t)(d_dn - (const uint8_t*)b_dn->dev), q_dn_len));
+            const size_t pal_off = ctx->batch_pal.size();            // multiple of 16 floats: keeps 16-byte alignment
+            ctx->batch_pal.resize(pal_off + (size_t)nmat * 16);
+            for (unsigned m = 0; m < nmat; ++m) memcpy(&ctx->batch_pal[pal_off + (size_t)m * 16], blend_matrices[m], 64);
+            j.palette = (const float*)(uintptr_t)pal_off;            // an offset in floats until the flush
+            ctx->batch_jobs.push_back(j);
+            if (ctx->batch_jobs.size() >= 65536) OGRECU_CHECK(flush_skin_batch(ctx));
+            return OGRECU_OK;
+        }
     }
-    const unsigned nmat = max_idx + 1;
+    OGRECU_CHECK(flush_skin_batch(ctx));          // immediate path: queued jobs come first (program order)
     std::vector<float> palette((size_t)nmat * 16);
     for (unsigned m = 0; m < nmat; ++m) memcpy(&palette[(size_t)m * 16], blend_matrices[m], 64);
 
@@ -224,6 +363,7 @@ int ogrecu_software_vertex_morph_host(ogrecu_ctx* ctx, float t, const float* src
     const size_t vs = morph_normals ? 24 : 12;
     OGRECU_REQUIRE(stride1 >= vs && stride2 >= vs && dst_stride >= vs, "stride smaller than the vertex");
     OGRECU_CUDA(cudaSetDevice(ctx->device));
+    OGRECU_CHECK(flush_skin_batch(ctx));          // may read what a queued job writes
     Stager st(ctx);
     size_t k1 = st.add_in(src1, (n - 1) * stride1 + vs);
     size_t k2 = st.add_in(src2, (n - 1) * stride2 + vs);
@@ -240,6 +380,7 @@ int ogrecu_concatenate_affine_matrices_host(ogrecu_ctx* ctx, const float* base16
     if (n == 0) return OGRECU_OK;
     OGRECU_REQUIRE(src && dst, "NULL pointer");
     OGRECU_CUDA(cudaSetDevice(ctx->device));
+    OGRECU_CHECK(flush_skin_batch(ctx));          // may read what a queued job writes
     Stager st(ctx);
     size_t ks = st.add_in(src, n * 64);
     size_t kd = st.add_out(dst, n * 64, 64, 64, n);
@@ -255,6 +396,7 @@ int ogrecu_calculate_face_normals_host(ogrecu_ctx* ctx, const float* positions, 
     if (n == 0) return OGRECU_OK;
     OGRECU_REQUIRE(positions && triangles && face_normals, "NULL pointer");
     OGRECU_CUDA(cudaSetDevice(ctx->device));
+    OGRECU_CHECK(flush_skin_batch(ctx));          // may read what a queued job writes
     if (num_vertices == 0) {   // the reference signature carries no vertex count: derive it
         const uint8_t* t = (const uint8_t*)triangles;
         uint32_t mx = 0;
@@ -280,6 +422,7 @@ int ogrecu_calculate_light_facing_host(ogrecu_ctx* ctx, const float* light4, con
     if (n == 0) return OGRECU_OK;
     OGRECU_REQUIRE(face_normals && facings, "NULL pointer");
     OGRECU_CUDA(cudaSetDevice(ctx->device));
+    OGRECU_CHECK(flush_skin_batch(ctx));          // may read what a queued job writes
     Stager st(ctx);
     size_t kn = st.add_in(face_normals, n * 16);
     size_t kd = st.add_out(facings, n, 1, 1, n);
@@ -294,6 +437,7 @@ int ogrecu_extrude_vertices_host(ogrecu_ctx* ctx, const float* light4, float dis
     if (n == 0) return OGRECU_OK;
     OGRECU_REQUIRE(src && dst, "NULL pointer");
     OGRECU_CUDA(cudaSetDevice(ctx->device));
+    OGRECU_CHECK(flush_skin_batch(ctx));          // may read what a queued job writes
     Stager st(ctx);
     size_t ks = st.add_in(src, n * 12);
     size_t kd = st.add_out(dst, n * 12, 12, 12, n);

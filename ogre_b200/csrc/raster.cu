@@ -1391,6 +1391,7 @@ int rt_flush_cmds(ogrecu_rt* rt)
 {
     ogrecu_ctx* ctx = rt->ctx;
     OGRECU_CUDA(cudaSetDevice(ctx->device));
+    OGRECU_CHECK(flush_skin_batch(ctx));     // queued OptimisedUtil jobs produce what the draws read
     std::vector<Item> seg;
     ogrecu_rt* one[1] = {rt};
     // The list is consumed on EVERY exit path: a flush that fails half way (out of memory, too many pairs, a CUDA error)
@@ -1432,6 +1433,16 @@ int rt_flush_cmds(ogrecu_rt* rt)
 }  // namespace
 
 namespace ogrecu {
+
+int flush_all_targets(ogrecu_ctx* ctx)
+{
+    int rc = OGRECU_OK;
+    std::vector<ogrecu_rt*> targets(ctx->targets);
+    for (ogrecu_rt* t : targets)
+        if (!t->cmds.empty()) { const int r = rt_flush_cmds(t); if (rc == OGRECU_OK) rc = r; }
+    ++ctx->draw_epoch;                     // no recorded draw is left: every buffer's draw_ref mark is stale now
+    return rc;
+}
 int rt_release(ogrecu_rt* rt)
 {
     if (!rt) return OGRECU_OK;
@@ -1623,6 +1634,11 @@ int ogrecu_draw_with_state(ogrecu_rt* rt, const ogrecu_draw_desc* d, const ogrec
     c.draw = *d;
     if (st) c.state = *st;
     rt->cmds.push_back(c);
+    // the buffers the draw will read when it is flushed: a host write to one of them (or a deferred OptimisedUtil job that
+    // overwrites one) must run the recorded draws first (ogrecu_buf_map, ogrecu_software_vertex_skinning_host)
+    const void* refs[5] = {d->positions, d->uvs, d->normals, d->indices, (st && (st->enable & OGRECU_EXT_VERTEX_COLOUR)) ? st->colours : nullptr};
+    for (const void* r : refs)
+        if (ogrecu_buf* b = buf_of_device_ptr(rt->ctx, r)) b->draw_ref = rt->ctx->draw_epoch;
     return OGRECU_OK;
 }
 
@@ -1647,6 +1663,7 @@ int ogrecu_draw_views(ogrecu_rt* const* rts, uint32_t n_views, const ogrecu_draw
         OGRECU_CHECK(ogrecu_flush(rts[v]));   // earlier clears / draws on each target come first
     }
     OGRECU_CUDA(cudaSetDevice(ctx->device));
+    OGRECU_CHECK(flush_skin_batch(ctx));      // queued OptimisedUtil jobs may produce what this draw reads
     if (desc->prim_type != OGRECU_PRIM_TRIANGLE_LIST && desc->prim_type != OGRECU_PRIM_TRIANGLE_STRIP) return OGRECU_OK;
     OGRECU_REQUIRE(desc->positions, "VES_POSITION required");
     std::vector<Item> items(n_views);

@@ -14,7 +14,7 @@ class _OgreCudaExport CudaOptimisedUtil : public OptimisedUtil
 {
     static OptimisedUtil* msPrevious;
     static CudaOptimisedUtil msInstance;
-    ogrecu_ctx* ctx() const;
+    ogrecu_ctx* ctx(bool flush = true) const;
 
 public:
     /// make this the process-wide implementation; remembers the one it replaces

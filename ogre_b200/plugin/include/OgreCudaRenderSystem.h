@@ -40,6 +40,7 @@ class CudaRenderSystem : public RenderSystem
     CompareFunction mDepthFunc, mAlphaFunc;
     unsigned char mAlphaRef;
     bool mScissorOn;
+    bool mBatchOptimisedUtil = true;   // config option "OptimisedUtil Batching"
     Rect mScissor;
 
     HardwareBufferManager* mHardwareBufferManager;

@@ -35,10 +35,9 @@ static int mapMode(HardwareBuffer::LockOptions options)
 
 void* CudaHardwareBuffer::lockImpl(size_t offset, size_t length, LockOptions options)
 {
-    // Draws are only recorded by _render; anything that may change a buffer they reference
-    // has to run them first (lock / readback / _endFrame are the flush points).
-    if (options != HBL_READ_ONLY)
-        CudaRenderSystem::flushPendingDraws();
+    // Draws are only recorded by _render and softwareVertexSkinning calls may be queued; a lock that would let the host change
+    // a buffer they reference (or read one they produce) runs them first.  libogrecu tracks which buffers recorded draws and
+    // queued jobs touch (ogrecu_buf_map), so locking entity B's buffers does not flush entity A's draws.
     void* p = 0;
     OGRECU_THROW_IF(ogrecu_buf_map(mBuf, offset, length, mapMode(options), &p));
     return p;

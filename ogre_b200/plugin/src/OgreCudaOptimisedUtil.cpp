@@ -25,12 +25,13 @@ void CudaOptimisedUtil::uninstall()
     if (msImplementation == &msInstance) msImplementation = msPrevious;
 }
 
-ogrecu_ctx* CudaOptimisedUtil::ctx() const
+ogrecu_ctx* CudaOptimisedUtil::ctx(bool flush) const
 {
     CudaRenderSystem* rs = CudaRenderSystem::getInstance();
     OgreAssert(rs, "CUDA render system is not installed");
-    // results land in buffers that recorded draws may read: run those first
-    CudaRenderSystem::flushPendingDraws();
+    // results land in buffers that recorded draws may read: run those first.  (softwareVertexSkinning does not ask for it:
+    // libogrecu checks its destination against the recorded draws itself and queues the call, see "optutil_batch".)
+    if (flush) CudaRenderSystem::flushPendingDraws();
     return rs->getContext();
 }
 
@@ -44,7 +45,7 @@ void CudaOptimisedUtil::softwareVertexSkinning(const float* srcPosPtr, float* de
                                                size_t numWeightsPerVertex, size_t numVertices)
 {
     OGRECU_THROW_IF(ogrecu_software_vertex_skinning_host(
-        ctx(), srcPosPtr, destPosPtr, srcNormPtr, destNormPtr, blendWeightPtr, blendIndexPtr,
+        ctx(false), srcPosPtr, destPosPtr, srcNormPtr, destNormPtr, blendWeightPtr, blendIndexPtr,
         reinterpret_cast<const float* const*>(blendMatrices), srcPosStride, destPosStride, srcNormStride, destNormStride,
         blendWeightStride, blendIndexStride, numWeightsPerVertex, numVertices));
 }

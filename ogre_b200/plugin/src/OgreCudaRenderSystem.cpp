@@ -54,8 +54,10 @@ ogrecu_ctx* CudaRenderSystem::getContext()
     if (!mCtx)
     {
         OGRECU_THROW_IF(ogrecu_init(mDeviceIndex, &mCtx));
+        OGRECU_THROW_IF(ogrecu_set_config_option(mCtx, "optutil_batch", mBatchOptimisedUtil ? 1 : 0));
         LogManager::getSingleton().logMessage("CUDA RenderSystem: libogrecu context on device " +
-                                              StringConverter::toString(mDeviceIndex));
+                                              StringConverter::toString(mDeviceIndex) +
+                                              (mBatchOptimisedUtil ? ", OptimisedUtil calls batched per frame" : ""));
     }
     return mCtx;
 }
@@ -77,6 +79,12 @@ void CudaRenderSystem::initConfigOptions()
     beyond.possibleValues = {"No", "Yes"};
     beyond.immutable = false;
     mOptions[beyond.name] = beyond;
+    ConfigOption batch;
+    batch.name = "OptimisedUtil Batching";   // queue softwareVertexSkinning calls, one batched launch per frame (ogrecu "optutil_batch")
+    batch.currentValue = mBatchOptimisedUtil ? "Yes" : "No";
+    batch.possibleValues = {"No", "Yes"};
+    batch.immutable = false;
+    mOptions[batch.name] = batch;
 }
 
 void CudaRenderSystem::setConfigOption(const String& name, const String& value)
@@ -89,6 +97,11 @@ void CudaRenderSystem::setConfigOption(const String& name, const String& value)
         mDeviceIndex = StringConverter::parseInt(value);
     }
     if (name == "Beyond Tiny") mBeyondTiny = StringConverter::parseBool(value);
+    if (name == "OptimisedUtil Batching")
+    {
+        mBatchOptimisedUtil = StringConverter::parseBool(value);
+        if (mCtx) OGRECU_THROW_IF(ogrecu_set_config_option(mCtx, "optutil_batch", mBatchOptimisedUtil ? 1 : 0));
+    }
 }
 
 const String& CudaRenderSystem::getName(void) const
@@ -213,7 +226,9 @@ void CudaRenderSystem::noteRecorded(ogrecu_rt* rt)
 void CudaRenderSystem::flushPendingDraws()
 {
     CudaRenderSystem* rs = msInstance;
-    if (!rs || rs->mDirtyTargets.empty()) return;
+    if (!rs) return;
+    if (rs->mCtx) OGRECU_THROW_IF(ogrecu_optutil_flush(rs->mCtx));   // queued OptimisedUtil jobs: callers are about to use raw device data
+    if (rs->mDirtyTargets.empty()) return;
     std::vector<ogrecu_rt*> targets;
     targets.swap(rs->mDirtyTargets);
     for (ogrecu_rt* rt : targets) OGRECU_THROW_IF(ogrecu_flush(rt));

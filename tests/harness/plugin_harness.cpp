@@ -15,7 +15,9 @@
 #include <OgreShadowCaster.h>
 #include <OgreEdgeListBuilder.h>
 
+#include <xmmintrin.h>
 #include <chrono>
+#include <cmath>
 #include <csignal>
 #include <execinfo.h>
 #include <unistd.h>
@@ -546,6 +548,129 @@ API double ph_anim_frame_time(int frames, float dt)
     g->win->copyContentsToMemory(Box(0, 0, 1, 1), box, RenderTarget::FB_AUTO);      // includes the device work
     return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() / frames;
 }
+
+// A crowd: `count` entities of one skeletally animated mesh on a square grid (`spacing` apart), every one with its own
+// animation state (time offset i * 0.037 s), seen from above and behind.  The scene BASELINE config 2 describes, through the
+// engine: Root::renderOneFrame -> SceneManager -> Entity::_updateAnimation (skeleton on the CPU, OptimisedUtil per sub-entity)
+// -> _render per sub-entity.
+static std::vector<Entity*> g_crowd;
+static std::vector<AnimationState*> g_crowd_states;
+
+API int ph_crowd_open(const char* mesh, uint32_t count, float spacing)
+{
+    TRY
+    if (ph_scene_open(mesh, 100.0f) != 0) return 1;
+    g_crowd.clear(); g_crowd_states.clear();
+    SceneManager* sm = g->sm;
+    const uint32_t side = (uint32_t)std::ceil(std::sqrt((double)count));
+    const float half = 0.5f * spacing * (side - 1);
+    g->ent->getParentSceneNode()->setPosition(-half, 0, -half);
+    g_crowd.push_back(g->ent);
+    for (uint32_t i = 1; i < count; ++i) {
+        Entity* e = sm->createEntity(mesh);
+        SceneNode* n = sm->getRootSceneNode()->createChildSceneNode();
+        n->setPosition(spacing * (i % side) - half, 0, spacing * (i / side) - half);
+        n->attachObject(e);
+        g_crowd.push_back(e);
+    }
+    for (size_t i = 0; i < g_crowd.size(); ++i) {
+        Entity* e = g_crowd[i];
+        if (!e->hasSkeleton()) return 2;
+        AnimationState* st = nullptr;
+        for (auto& kv : e->getAllAnimationStates()->getAnimationStates()) {
+            kv.second->setEnabled(st == nullptr);
+            if (!st) { st = kv.second; st->setLoop(true); }
+        }
+        st->setTimePosition(0.037f * (float)i);
+        e->addSoftwareAnimationRequest(true);
+        // pinned submission order (see ph_pin_submission_order): sub-entity k of every entity in priority group 100 + (n-1-k)
+        const size_t nsub = e->getNumSubEntities();
+        for (size_t k = 0; k < nsub; ++k) e->getSubEntity(k)->setRenderQueueGroupAndPriority(RENDER_QUEUE_MAIN, (ushort)(100 + nsub - 1 - k));
+        g_crowd_states.push_back(st);
+    }
+    SceneNode* cn = g->cam->getParentSceneNode();
+    const float d = std::max(60.0f, 1.6f * half + 40.0f);
+    cn->setPosition(0, 0.8f * d, d);
+    cn->lookAt(Vector3(0, 0, 0), Node::TS_WORLD);
+    g->cam->setFarClipDistance(0);      // infinite
+    return 0;
+    CATCH(3)
+}
+
+API size_t ph_crowd_vertices(void)
+{
+    size_t n = 0;
+    for (Entity* e : g_crowd)
+        for (size_t k = 0; k < e->getNumSubEntities(); ++k) {
+            const SubMesh* sm = e->getSubEntity(k)->getSubMesh();
+            n += sm->useSharedVertices ? 0 : sm->vertexData->vertexCount;
+        }
+    if (!g_crowd.empty() && g_crowd[0]->getMesh()->sharedVertexData) n += g_crowd.size() * g_crowd[0]->getMesh()->sharedVertexData->vertexCount;
+    return n;
+}
+
+// seconds per frame of the crowd: every entity's animation advances by dt, so every frame re-evaluates every skeleton and
+// re-skins every sub-mesh; ends with a 1-pixel read-back so that the device work is inside the clock
+API double ph_crowd_frame_time(int frames, float dt)
+{
+    if (g_crowd.empty()) return -1.0;
+    uint8_t px[3];
+    PixelBox box(1, 1, 1, PF_BYTE_RGB, px);
+    for (int i = 0; i < 2; ++i) {
+        for (AnimationState* st : g_crowd_states) st->addTime(dt);
+        g->root->renderOneFrame();
+    }
+    g->win->copyContentsToMemory(Box(0, 0, 1, 1), box, RenderTarget::FB_AUTO);
+    auto t0 = std::chrono::steady_clock::now();
+    for (int i = 0; i < frames; ++i) {
+        for (AnimationState* st : g_crowd_states) st->addTime(dt);
+        g->root->renderOneFrame();
+    }
+    g->win->copyContentsToMemory(Box(0, 0, 1, 1), box, RenderTarget::FB_AUTO);
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() / frames;
+}
+
+// one more crowd frame at a fixed pose (every state set to offset + t), then the whole frame as RGB
+API int ph_crowd_render_at(float t, uint8_t* dst_rgb)
+{
+    TRY
+    for (size_t i = 0; i < g_crowd_states.size(); ++i) g_crowd_states[i]->setTimePosition(0.037f * (float)i + t);
+    g->root->renderOneFrame();
+    PixelBox box(g->win->getWidth(), g->win->getHeight(), 1, PF_BYTE_RGB, dst_rgb);
+    g->win->copyContentsToMemory(Box(0, 0, g->win->getWidth(), g->win->getHeight()), box, RenderTarget::FB_AUTO);
+    return 0;
+    CATCH(1)
+}
+
+// CUDA plugin only: its "OptimisedUtil Batching" option at run time
+API int ph_set_rs_option(const char* name, const char* value)
+{
+    TRY
+    g->root->getRenderSystem()->setConfigOption(name, value);
+    return 0;
+    CATCH(1)
+}
+
+// Submission order of the entity's sub-entities.  OGRE's render queue groups renderables by Pass and orders the groups by
+// pass hash, then by Pass* ADDRESS (QueuedRenderableCollection::PassGroupLess, OgreMain/src/OgreRenderQueueSortingGrouping.cpp):
+// passes whose hashes tie are drawn in an order that depends on the heap layout of the run.  Tiny (and this plugin) let a later
+// fragment of EQUAL depth win, so a pixel where two sub-meshes coincide depends on that order.  Distinct priorities pin it:
+// mode 0 = sub-entity i gets priority 100 + i (ascending), 1 = descending.
+API int ph_pin_submission_order(int mode)
+{
+    TRY
+    if (!g->ent) return 1;
+    const size_t n = g->ent->getNumSubEntities();
+    for (size_t i = 0; i < n; ++i)
+        g->ent->getSubEntity(i)->setRenderQueueGroupAndPriority(RENDER_QUEUE_MAIN, (ushort)(100 + (mode ? n - 1 - i : i)));
+    return 0;
+    CATCH(2)
+}
+
+// The SSE control/status register of this thread: rounding mode, flush-to-zero (bit 15) and denormals-are-zero (bit 6).
+// Libraries loaded into the host process may change it; the reference's arithmetic depends on it (tools/tiny_host_check.py).
+API unsigned ph_get_mxcsr(void) { return _mm_getcsr(); }
+API void ph_set_mxcsr(unsigned v) { _mm_setcsr(v); }
 
 API void ph_close(void)
 {

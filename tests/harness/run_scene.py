@@ -33,6 +33,7 @@ def main():
     ap.add_argument("--quad", action="store_true")
     ap.add_argument("--skel", default="")
     ap.add_argument("--time", type=int, default=0)
+    ap.add_argument("--order", type=int, default=-1, help="pin the sub-entities' submission order: 0 ascending, 1 descending (-1: OGRE's)")
     ap.add_argument("--anim-time", type=int, default=0, help="N frames of the animated entity (re-skinned every frame): seconds per frame")
     ap.add_argument("--formats", default="", help="comma-separated Ogre::PixelFormat names: read-back in that format vs host PixelUtil")
     ap.add_argument("--pass-state", default="", help="cull,depthfunc,alphafunc,alpharef for every sub-entity's pass (0/-1/-1/0 = keep); "
@@ -67,10 +68,18 @@ def main():
         if rc:
             raise SystemExit("%s failed (%d): %s" % (what, rc, L.ph_error().decode()))
 
+    L.ph_get_mxcsr.restype = C.c_uint
+    L.ph_set_mxcsr.argtypes = [C.c_uint]
+    mxcsr_in = L.ph_get_mxcsr()
+    if os.environ.get("PH_MXCSR"):                    # diagnostic: force the SSE control register (0x1f80 = IEEE default)
+        L.ph_set_mxcsr(int(os.environ["PH_MXCSR"], 0))
     ok(L.ph_open(so.encode(), name.encode(), os.path.join(REFLIB, "Codec_STBI.so").encode(), MEDIA.encode(), w, h), "ph_open")
-    out = {"render_system": np.array(L.ph_render_system_name().decode()),
+    out = {"mxcsr_at_start": np.array(mxcsr_in), "mxcsr_after_open": np.array(L.ph_get_mxcsr()),
+           "render_system": np.array(L.ph_render_system_name().decode()),
            "optimised_util_replaced": np.array(L.ph_optimised_util_replaced())}
     ok(L.ph_scene_open(a.mesh.encode(), a.cam_z), "ph_scene_open")
+    if a.order >= 0:
+        ok(L.ph_pin_submission_order(a.order), "ph_pin_submission_order")
     if a.skel:
         for k, t in enumerate(float(v) for v in a.skel.split(",")):
             ok(L.ph_skel_pose(t), "ph_skel_pose")

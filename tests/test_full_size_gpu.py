@@ -8,6 +8,9 @@ takes minutes to hours at these sizes) plus oracle spot checks on random samples
             20 000 random face normals equal the oracle.
   config 5  3840x2160, 5 M triangles (bounded for test time; the bench uses 20 M): four contiguous strips and eight
             interleaved bands compose to exactly the whole frame rendered at once (colour and depth).
+  configs 4, 5 at FULL size against the CPU: two views of the 1 M-triangle scene at 640x480 and the 20 M-triangle 3840x2160
+            frame equal the unmodified TinyRenderSystem::_render (oracle/_ref; about 5 s of CPU for the 4K frame) — colour
+            exact, depth bit-exact.
 """
 import ctypes as C
 import os
@@ -172,3 +175,51 @@ def test_config5_split_frames_compose_at_4k(gpu_ctx):
         comp_c[rows] = c[rows]; comp_z[rows] = z[rows]
     assert np.array_equal(comp_c, whole_c) and np.array_equal(bits(comp_z), bits(whole_z))
     rt.destroy()
+
+
+def _cpu_frame(case, w, h):
+    """colour, depth of one DrawCase on the CPU: the unmodified TinyRenderSystem::_render (oracle/_ref) where it is built,
+    else the oracle's C restatement (pinned against it by tests/test_oracle_vs_ref.py)"""
+    from oracle import ref
+    if ref.available():
+        c, z = ref.tiny_render([case], w, h)[:2]
+        return c, z, "reference"
+    from rasterlib import render_oracle
+    c, z, _ = render_oracle([case], w, h)
+    return c, z, "port"
+
+
+@pytest.mark.parametrize("name,ntri,w,h,view", [("config4 view", 1000000, 640, 480, 0), ("config4 view", 1000000, 640, 480, 517),
+                                                ("config5 frame", 20000000, 3840, 2160, 0)],
+                         ids=["c4_view0", "c4_view517", "c5_frame"])
+def test_full_size_raster_configs_equal_the_cpu_reference(gpu_ctx, name, ntri, w, h, view):
+    """BASELINE configs 4 and 5 at their full sizes (1 M triangles at 640x480; 20 M triangles at 3840x2160, the scenes
+    bench.py renders) against the CPU: colour exact, depth bit-exact."""
+    import ogre_b200
+    from ogre_b200 import capi, check, lib
+    from datagen import DrawCase, viewport_matrix
+    from rasterlib import assert_images_equal
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import bench_configs as bc
+    ctx = gpu_ctx
+    n = int(round((ntri / 2) ** 0.5))
+    verts, idx = bc.terrain(n)
+    tex = bc.checker_texture(1024)
+    mvps, mvits, lights = bc.camera_ring(1024 if view else 1, w, h)
+    mvp, mvit, light = (np.ascontiguousarray(a[view:view + 1]) for a in (mvps, mvits, lights))
+    desc, keep = bc.upload_scene(ctx, verts, idx, tex, w, h)
+    rt = ogre_b200.RenderTarget(ctx, w, h)
+    rt.clear(colour=(0.1, 0.2, 0.3, 1.0), depth=1.0)
+    handles = (C.c_void_p * 1)(rt.handle)
+    check(lib().ogrecu_draw_views(handles, 1, C.byref(desc), mvp.ctypes.data_as(capi.c_float_p), mvit.ctypes.data_as(capi.c_float_p),
+                                  light.ctypes.data_as(capi.c_float_p)))
+    got_c, got_z = rt.read_colour(), rt.read_depth()
+    rt.destroy()
+    for k in keep[:2]:
+        k.free()
+    case = DrawCase(verts, idx, index_type=4, texture=tex, mvp=mvp[0], mvit=mvit[0], viewport=viewport_matrix(w, h), light_dir=(1, 0, 0),
+                    ambient=(0.2, 0.2, 0.25, 1.0))
+    case.light_dir = light[0]
+    ref_c, ref_z, kind = _cpu_frame(case, w, h)
+    assert (ref_z != 1.0).mean() > 0.2, "the scene must cover the frame"
+    assert_images_equal(got_c, got_z, ref_c, ref_z, "%s vs the CPU %s" % (name, kind))
