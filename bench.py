@@ -389,23 +389,32 @@ def run_ours(args):
         p = C.c_void_p()
         check(L.ogrecu_rt_colour_device_ptr(r.handle, C.byref(p)))
         rt_ptr.append(p.value)
-    # the consuming _render: every sub-mesh's [instances x vertices] output buffer drawn as one non-indexed triangle list
-    # (Tiny's drawCount = vertexCount path, OgreTinyRenderSystem.cpp:387-403), lit, depth-tested; the crowd stands on a
-    # 300 x 300 grid and fills most of the frame, seen from above
+    # the consuming _render: one instanced, indexed draw per sub-mesh over its [instances x vertices] output buffer (what
+    # TinyRenderSystem::_render is handed per sub-entity, OgreTinyRenderSystem.cpp:349-414, for every entity at once), lit,
+    # depth-tested; the crowd stands on a 300 x 300 grid and fills most of the frame, seen from above
     proj = perspective(45, FRAME_W / FRAME_H, 5.0, 3000.0)
     proj[1, :] *= -1          # OgreMain flips the projection for targets with requiresTextureFlipping (Tiny windows)
     view = look_at(np.array([148.5, 340.0, 330.0]), (148.5, 0.0, 135.0))
     mvp = (proj @ view).astype(np.float32)
     mvit = np.ascontiguousarray(np.linalg.inv(view).T.astype(np.float32))
     ldir = view[:3, :3] @ np.array([0.4, 0.8, 0.3]); ldir = (ldir / np.linalg.norm(ldir)).astype(np.float32)
-    draws = []
+    # Sinbad's real triangle lists (the edge-list fixture keeps every sub-mesh's index triples in mesh order)
+    shadow = np.load(os.path.join(ROOT, "tests", "golden", "sinbad_shadow.npz"))
+    draws, keep_idx = [], []
     tris_per_frame = 0
-    for e, s in zip(dsub, subs):
+    for k, (e, s) in enumerate(zip(dsub, subs)):
+        g = shadow["groups"][k]
+        assert int(g[4]) == s["nverts"]
+        tri = np.ascontiguousarray(shadow["tris"][int(g[2]):int(g[2]) + int(g[3])].astype(np.uint32).reshape(-1))
+        with torch.cuda.stream(stream):
+            d_idx = torch.from_numpy(tri.view(np.int32)).to(dev)
+        keep_idx.append(d_idx)
         d = DrawDesc()
-        nv = (ninst * s["nverts"]) // 3 * 3
         d.positions, d.pos_stride = e["dst"].data_ptr(), 24
         d.normals, d.normal_stride = e["dst"].data_ptr() + 12, 24
-        d.indices, d.index_type, d.draw_count, d.vertex_count = None, 0, nv, nv
+        d.indices, d.index_type, d.draw_count = d_idx.data_ptr(), 4, len(tri)
+        d.vertex_count = ninst * s["nverts"]
+        d.instance_count, d.instance_vertex_count = ninst, s["nverts"]        # every instance: the same indices, its own vertices
         d.prim_type = ogre_b200.PRIM_TRIANGLE_LIST
         d.flags = ogre_b200.DRAW_DEPTH_TEST | ogre_b200.DRAW_DEPTH_WRITE | ogre_b200.DRAW_LIGHTING
         d.mvp[:] = mvp.reshape(16); d.mvit[:] = mvit.reshape(16)
@@ -414,7 +423,8 @@ def run_ours(args):
         d.light_dir[:] = ldir
         d.ambient[:] = (0.25, 0.25, 0.3, 1.0)
         draws.append(d)
-        tris_per_frame += nv // 3
+        tris_per_frame += ninst * (len(tri) // 3)
+    stream.synchronize()
 
     def render(b):
         rts[b].clear(colour=(0.1, 0.2, 0.3, 1.0), depth=1.0)
@@ -501,6 +511,7 @@ def run_ours(args):
     cstream.synchronize()
     ms_pal = pa.elapsed_time(pb) / 20
     render(0); torch.cuda.synchronize()
+    render_stats = rts[0].stats()
     ra, rb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ra.record(stream)
     for _ in range(5):
@@ -546,7 +557,7 @@ def run_ours(args):
         extra["e2e_stages_ms"] = {"palettes_10000x69": ms_pal, "morph_skin_frame_call": ms / args.steps, "render_of_all_instances": ms_render,
                                   "frame_d2h_bytes": frame_bytes}
         extra["e2e_render"] = {"triangles_per_frame": int(tris_per_frame), "target": "%dx%d" % (FRAME_W, FRAME_H), "covered_fraction": covered,
-                               "Mtri_per_s": tris_per_frame / (ms_render * 1e-3) / 1e6}
+                               "Mtri_per_s": tris_per_frame / (ms_render * 1e-3) / 1e6, "stats": render_stats}
 
     # ---- BASELINE's render configs (c1, c4, c5) in the same run
     render_cfg = None

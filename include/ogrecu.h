@@ -478,6 +478,13 @@ typedef struct ogrecu_draw_desc {
     float viewport[16];         /* mVP from _setViewport (.cpp:230-262)                   */
     float light_dir[3];         /* uniform_lightDir                                       */
     float ambient[4];           /* uniform_ambientCol                                     */
+    /* Instancing (triangle lists only; 0 = a plain draw).  RenderOperation::numberOfInstances
+     * (OgreMain/include/OgreRenderOperation.h:133) is ignored by Tiny (.cpp:349-414); here instance i draws the same
+     * draw_count indices with i * instance_vertex_count added to every vertex index (non-indexed: to the running vertex
+     * number) — the vertex streams hold instance_count copies of the mesh back to back, as ogrecu_anim_frame_dev writes
+     * them.  Equal to instance_count separate draws in instance order.  vertex_count then counts ALL instances. */
+    uint32_t instance_count;
+    uint32_t instance_vertex_count;
 } ogrecu_draw_desc;
 
 /* Record a draw on `rt` (cheap; nothing runs yet).  Draws and clears keep submission order. */

@@ -53,6 +53,7 @@ class DrawDesc(C.Structure):
         ("texture", C.c_void_p),
         ("mvp", C.c_float * 16), ("tex_matrix", C.c_float * 16), ("mvit", C.c_float * 16),
         ("viewport", C.c_float * 16), ("light_dir", C.c_float * 3), ("ambient", C.c_float * 4),
+        ("instance_count", C.c_uint32), ("instance_vertex_count", C.c_uint32),
     ]
 
 

@@ -90,6 +90,7 @@ struct DrawDev {
     uint32_t ext, col_stride;
     const uint8_t* col;        // VES_DIFFUSE bytes r,g,b,a
     uint32_t sc_x, sc_y;       // scissor: left | (right - 1) << 16, top | (bottom - 1) << 16 (inclusive pixel bounds)
+    uint32_t inst_tris, inst_verts;   // instanced list: triangles per instance (0 = plain draw), vertex index step per instance
     float mvp[16], texm[16], vp[16];
     float mvit[9];
     float light[3];
@@ -177,10 +178,16 @@ __global__ void __launch_bounds__(256) vertex_xf_kernel(XfParams P)
 // OgreTinyRenderSystem.cpp:396-403); 16-bit indices are read unsigned (the reference reads int16: UB >= 32768)
 __device__ __forceinline__ size_t vertex_index(const DrawDev& D, uint32_t t, int j)
 {
+    size_t base = 0;
+    if (D.inst_tris) {                                   // instanced list: the same indices, shifted per instance
+        const uint32_t inst = t / D.inst_tris;
+        t -= inst * D.inst_tris;
+        base = (size_t)inst * D.inst_verts;
+    }
     const size_t k = (D.is_strip ? (size_t)t : (size_t)t * 3) + j;
-    if (D.index_type == 2) return __ldg((const uint16_t*)D.idx + k);
-    if (D.index_type == 4) return __ldg((const uint32_t*)D.idx + k);
-    return k;
+    if (D.index_type == 2) return base + __ldg((const uint16_t*)D.idx + k);
+    if (D.index_type == 4) return base + __ldg((const uint32_t*)D.idx + k);
+    return base + k;
 }
 
 constexpr int SB_THREADS = 256;
@@ -1193,7 +1200,9 @@ int exclusive_scan_u32(ogrecu_ctx* ctx, Scratch& sums, uint32_t* data, size_t n,
 uint32_t tri_count_of(const ogrecu_draw_desc& d)
 {
     if (d.prim_type == OGRECU_PRIM_TRIANGLE_STRIP) return d.draw_count >= 3 ? d.draw_count - 2 : 0;
-    return d.draw_count / 3;   // the reference reads past the end when drawCount%3 != 0 (UB); we stop
+    const uint64_t per = d.draw_count / 3;   // the reference reads past the end when drawCount%3 != 0 (UB); we stop
+    const uint64_t all = per * (d.instance_count ? d.instance_count : 1);
+    return all > 0xffffffffull ? 0xffffffffu : (uint32_t)all;
 }
 
 struct Item { const ogrecu_draw_desc* desc; uint32_t target; const float* mvp; const float* mvit; const float* light; const ogrecu_draw_state* state; };
@@ -1224,6 +1233,8 @@ int run_segment(ogrecu_ctx* ctx, ogrecu_rt* const* targets, uint32_t ntargets, c
         o.target = items[k].target;
         o.tri_base = (uint32_t)ntris64;
         o.tri_count = tri_count_of(d);
+        o.inst_tris = d.instance_count ? d.draw_count / 3 : 0;
+        o.inst_verts = d.instance_vertex_count;
         ntris64 += o.tri_count;
         // vertex pre-transform when the caller bounded the vertex range and it is not mostly unused
         o.vert_base = (uint32_t)nverts64;
@@ -1627,6 +1638,8 @@ int ogrecu_draw_with_state(ogrecu_rt* rt, const ogrecu_draw_desc* d, const ogrec
     OGRECU_REQUIRE(((d->pos_stride | d->uv_stride | d->normal_stride | (uintptr_t)d->positions | (uintptr_t)d->uvs | (uintptr_t)d->normals) & 3) == 0,
                    "vertex streams must be 4-byte aligned");
     OGRECU_REQUIRE(!d->texture || d->texture->ctx == rt->ctx, "texture belongs to another context");
+    OGRECU_REQUIRE(!d->instance_count || d->prim_type == OGRECU_PRIM_TRIANGLE_LIST, "instanced draws are triangle lists");
+    OGRECU_REQUIRE((uint64_t)(d->draw_count / 3) * (d->instance_count ? d->instance_count : 1) < 0xffffffffull, "too many triangles in one draw");
     if (tri_count_of(*d) == 0) return OGRECU_OK;
     Cmd c;
     memset(&c, 0, sizeof c);
