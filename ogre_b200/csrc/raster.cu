@@ -123,6 +123,7 @@ struct SegParams {
     uint64_t* pairs;          // (tile key << 32 | compact triangle index), submission order
     uint64_t pair_capacity;
     uint32_t* block_agg;      // [nblocks][2]: pairs, survivors of each 1024-triangle CTA
+    uint8_t* alive;           // [ntris]: 0 = the count pass dropped the triangle (culled, off screen, no covered pixel), else 1
     unsigned long long* bases;// [nblocks][2]: their exclusive scans
     uint32_t* ctl;            // [2] total pairs  [3] total survivors
     uint32_t width, height;
@@ -199,6 +200,12 @@ __device__ __forceinline__ bool owns_row(const SegParams& P, uint32_t ty)
     return P.band_period <= 1 || (ty / P.band_tiles) % P.band_period == P.band_phase;
 }
 
+#ifndef SETUP_COVER_MAX
+#define SETUP_COVER_MAX 6        // triangles whose bounding box holds at most this many pixels are tested for coverage at set-up
+#endif
+__device__ __forceinline__ void expand_xy(float X0, float X1, float X2, float Y0, float Y1, float Y2, float hf[20]);
+__device__ __forceinline__ bool eval_fragment(const float* hf, float Px, float Py, float& bc0, float& bc1, float& bc2, float& fd);
+
 struct TriSetup {
     float X[3], Y[3], Z[3], IW[3];
     int x0, x1, y0, y1;
@@ -209,6 +216,7 @@ struct TriSetup {
 // Everything Tiny does per triangle before its pixel loop (OgreTinyRenderSystem.cpp:396-410,
 // tinyrenderer.h:45-69): fetch / transform the three vertices, cull, bounding box, plus the number of
 // 16x16 tiles of this strip the box touches.  Pure function of (g, draw table): both passes below call it.
+template <bool COVER>
 __device__ __forceinline__ void setup_triangle(const SegParams& P, uint32_t g, uint32_t lo0, uint32_t lo0_end, const float* s_mat, TriSetup& T)
 {
     T.ntiles = 0; T.ordered = false; T.x0 = 0; T.x1 = -1; T.y0 = 0; T.y1 = -1;
@@ -273,6 +281,28 @@ __device__ __forceinline__ void setup_triangle(const SegParams& P, uint32_t g, u
             if (T.x0 > T.x1 || T.y0 > T.y1) ok = false;
         }
     }
+#if SETUP_COVER_MAX > 0
+    // Early coverage cull.  In scenes of sub-pixel triangles (config 5: 0.4 pixels per triangle, the crowd of config 2: 40
+    // bounding boxes per pixel) most triangles contain no pixel CENTRE at all: Tiny walks their bounding box and rejects
+    // every pixel (tinyrenderer.h:70-76).  For a box of a few pixels that walk is done here, with the very operations the
+    // raster kernel would use (expand_xy + eval_fragment): a triangle none of whose pixels passes the inside / depth >= 0
+    // tests can produce no fragment whatever the target holds, so it gets no record, no (tile, triangle) pair, no sort key and
+    // no visit by the tile's CTA.  A NaN anywhere passes the tests as it does in Tiny (comparisons with NaN are false) and
+    // keeps the triangle.
+    if (COVER && ok && (T.x1 - T.x0 + 1) * (T.y1 - T.y0 + 1) <= SETUP_COVER_MAX) {
+        float hf[20];
+        expand_xy(T.X[0], T.X[1], T.X[2], T.Y[0], T.Y[1], T.Y[2], hf);
+        hf[9] = T.IW[0]; hf[10] = T.IW[1]; hf[11] = T.IW[2];
+        hf[12] = T.Z[0]; hf[13] = T.Z[1]; hf[14] = T.Z[2];
+        bool any = false;
+        for (int py = T.y0; py <= T.y1; ++py)
+            for (int px = T.x0; px <= T.x1; ++px) {
+                float b0, b1, b2, fd;
+                any = any || eval_fragment(hf, (float)px, (float)py, b0, b1, b2, fd);
+            }
+        ok = any;
+    }
+#endif
     if (ok) {
         int tx0 = T.x0 >> TILE_SHIFT, tx1 = T.x1 >> TILE_SHIFT;
         int ty0 = max(T.y0 >> TILE_SHIFT, (int)P.strip_ty0), ty1 = min(T.y1 >> TILE_SHIFT, (int)P.strip_ty1 - 1);
@@ -336,8 +366,9 @@ __global__ void __launch_bounds__(SB_THREADS) setup_count_kernel(SegParams P)
         const uint32_t g = g0 + (uint32_t)k * SB_THREADS + tid;
         if (g < P.ntris) {
             TriSetup T;
-            setup_triangle(P, g, lo0, lo0_end, s_mat, T);
+            setup_triangle<true>(P, g, lo0, lo0_end, s_mat, T);
             np += T.ntiles; nt += T.ntiles ? 1u : 0u;
+            P.alive[g] = T.ntiles ? 1 : 0;                 // the write pass skips the dead without touching their vertices
         }
     }
 #pragma unroll
@@ -400,7 +431,7 @@ __global__ void __launch_bounds__(SB_THREADS) setup_write_kernel(SegParams P)
         const uint32_t g = g0 + (uint32_t)k * SB_THREADS + tid;
         TriSetup T;
         T.ntiles = 0;
-        if (g < P.ntris) setup_triangle(P, g, lo0, lo0_end, s_mat, T);
+        if (g < P.ntris && __ldg(&P.alive[g])) setup_triangle<false>(P, g, lo0, lo0_end, s_mat, T);   // survivors only, coverage already decided
         const uint32_t surv = T.ntiles ? 1u : 0u;
         uint32_t ip = T.ntiles, it = surv;
 #pragma unroll
@@ -758,10 +789,10 @@ __device__ __forceinline__ RecRaw load_rec(const TriRec* r)
     return RecRaw{__ldg(rp), __ldg(rp + 1), __ldg(rp + 2), __ldg(rp + 3)};
 }
 
-__device__ __forceinline__ void expand_raw(const RecRaw& R, float hf[20])
+// hf[0..8] = Matrix3::Inverse of [[X0,X1,X2],[Y0,Y1,Y2],[1,1,1]] (the one definition: set-up's coverage cull and the raster
+// kernel's pixel loops must agree bit for bit)
+__device__ __forceinline__ void expand_xy(float X0, float X1, float X2, float Y0, float Y1, float Y2, float hf[20])
 {
-    const float4 a = R.a, b = R.b, c = R.c, d = R.d;
-    const float X0 = a.x, X1 = a.y, X2 = a.z, Y0 = a.w, Y1 = b.x, Y2 = b.y;
     hf[0] = fsub(Y1, Y2); hf[1] = fsub(X2, X1); hf[2] = fsub(fmul(X1, Y2), fmul(X2, Y1));
     hf[3] = fsub(Y2, Y0); hf[4] = fsub(X0, X2); hf[5] = fsub(fmul(X2, Y0), fmul(X0, Y2));
     hf[6] = fsub(Y0, Y1); hf[7] = fsub(X1, X0); hf[8] = fsub(fmul(X0, Y1), fmul(X1, Y0));
@@ -771,6 +802,12 @@ __device__ __forceinline__ void expand_raw(const RecRaw& R, float hf[20])
 #pragma unroll
         for (int k = 0; k < 9; ++k) hf[k] = fmul(hf[k], gi);
     }
+}
+
+__device__ __forceinline__ void expand_raw(const RecRaw& R, float hf[20])
+{
+    const float4 a = R.a, b = R.b, c = R.c, d = R.d;
+    expand_xy(a.x, a.y, a.z, a.w, b.x, b.y, hf);
     hf[9] = b.z; hf[10] = b.w; hf[11] = c.x;
     hf[12] = c.y; hf[13] = c.z; hf[14] = c.w;
     hf[15] = d.x; hf[16] = d.y; hf[17] = d.z; hf[18] = d.w; hf[19] = 0.f;
@@ -1174,7 +1211,7 @@ namespace {
 
 // per-context raster scratch (grown on demand, reused across flushes)
 struct RasterScratch {
-    Scratch draws, targets, rec, cnt, sums, pairs_a, pairs_b, tile_count, hist, counters, xf;
+    Scratch draws, targets, rec, cnt, sums, pairs_a, pairs_b, tile_count, hist, counters, xf, alive;
 };
 std::map<ogrecu_ctx*, RasterScratch>& scratch_map()
 {
@@ -1281,7 +1318,7 @@ int run_segment(ogrecu_ctx* ctx, ogrecu_rt* const* targets, uint32_t ntargets, c
         for (DrawDev& o : dd) if (o.vertex_count) o.xf = (const float4*)S.xf.ptr + o.vert_base;
     }
     const uint32_t nblocks = div_up(ntris, SB_BLOCK);
-    OGRECU_CHECK(scratch_reserve(ctx, S.rec, (size_t)ntris * sizeof(TriRec)));
+    OGRECU_CHECK(scratch_reserve(ctx, S.alive, (size_t)ntris));
     // control block: block aggregates [nblocks][2] u32 | bases [nblocks][2] u64 | ctl[4] | tile flags [nkeys] (flags zeroed per pass)
     const size_t agg_bytes = ((size_t)nblocks * 8 + 15) & ~(size_t)15, base_bytes = (size_t)nblocks * 16;
     const size_t ctl_bytes = agg_bytes + base_bytes + 16 + (size_t)nkeys * 4;
@@ -1300,7 +1337,8 @@ int run_segment(ogrecu_ctx* ctx, ogrecu_rt* const* targets, uint32_t ntargets, c
 
     SegParams P;
     P.draws = (const DrawDev*)S.draws.ptr; P.ndraws = (uint32_t)dd.size(); P.ntris = ntris;
-    P.rec = (TriRec*)S.rec.ptr;
+    P.rec = nullptr;                 // sized after the count pass (survivors only)
+    P.alive = (uint8_t*)S.alive.ptr;
     P.block_agg = (uint32_t*)S.cnt.ptr;
     P.bases = (unsigned long long*)((uint8_t*)S.cnt.ptr + agg_bytes);
     P.ctl = (uint32_t*)((uint8_t*)S.cnt.ptr + agg_bytes + base_bytes);
@@ -1338,6 +1376,8 @@ int run_segment(ogrecu_ctx* ctx, ogrecu_rt* const* targets, uint32_t ntargets, c
     if (npairs == 0) return OGRECU_OK;
 
     // ---- K1c: compact records + (tile, triangle) pairs in submission order
+    OGRECU_CHECK(scratch_reserve(ctx, S.rec, (size_t)(nsurv + SB_THREADS) * sizeof(TriRec)));    // a round's copy-out runs in whole rows
+    P.rec = (TriRec*)S.rec.ptr;
     OGRECU_CHECK(scratch_reserve(ctx, S.pairs_a, npairs * sizeof(uint64_t)));
     OGRECU_CHECK(scratch_reserve(ctx, S.pairs_b, npairs * sizeof(uint64_t)));
     P.pairs = (uint64_t*)S.pairs_a.ptr;
