@@ -405,14 +405,14 @@ def run_ours(args):
     for k, (e, s) in enumerate(zip(dsub, subs)):
         g = shadow["groups"][k]
         assert int(g[4]) == s["nverts"]
-        tri = np.ascontiguousarray(shadow["tris"][int(g[2]):int(g[2]) + int(g[3])].astype(np.uint32).reshape(-1))
+        tri = np.ascontiguousarray(shadow["tris"][int(g[2]):int(g[2]) + int(g[3])].astype(np.uint16).reshape(-1))   # IT_16BIT, as Sinbad.mesh has them
         with torch.cuda.stream(stream):
-            d_idx = torch.from_numpy(tri.view(np.int32)).to(dev)
+            d_idx = torch.from_numpy(tri.view(np.int16)).to(dev)
         keep_idx.append(d_idx)
         d = DrawDesc()
         d.positions, d.pos_stride = e["dst"].data_ptr(), 24
         d.normals, d.normal_stride = e["dst"].data_ptr() + 12, 24
-        d.indices, d.index_type, d.draw_count = d_idx.data_ptr(), 4, len(tri)
+        d.indices, d.index_type, d.draw_count = d_idx.data_ptr(), 2, len(tri)
         d.vertex_count = ninst * s["nverts"]
         d.instance_count, d.instance_vertex_count = ninst, s["nverts"]        # every instance: the same indices, its own vertices
         d.prim_type = ogre_b200.PRIM_TRIANGLE_LIST

@@ -123,7 +123,7 @@ struct SegParams {
     uint64_t* pairs;          // (tile key << 32 | compact triangle index), submission order
     uint64_t pair_capacity;
     uint32_t* block_agg;      // [nblocks][2]: pairs, survivors of each 1024-triangle CTA
-    uint8_t* alive;           // [ntris]: 0 = the count pass dropped the triangle (culled, off screen, no covered pixel), else 1
+    uint8_t* alive;           // [ntris]: tiles the triangle touches per the count pass (0 = dropped: culled, off screen, no covered pixel; 255 = 255 or more)
     unsigned long long* bases;// [nblocks][2]: their exclusive scans
     uint32_t* ctl;            // [2] total pairs  [3] total survivors
     uint32_t width, height;
@@ -205,6 +205,7 @@ __device__ __forceinline__ bool owns_row(const SegParams& P, uint32_t ty)
 #endif
 __device__ __forceinline__ void expand_xy(float X0, float X1, float X2, float Y0, float Y1, float Y2, float hf[20]);
 __device__ __forceinline__ bool eval_fragment(const float* hf, float Px, float Py, float& bc0, float& bc1, float& bc2, float& fd);
+__device__ __forceinline__ bool covers_pixel(const float* hf, float Px, float Py);
 
 struct TriSetup {
     float X[3], Y[3], Z[3], IW[3];
@@ -296,10 +297,7 @@ __device__ __forceinline__ void setup_triangle(const SegParams& P, uint32_t g, u
         hf[12] = T.Z[0]; hf[13] = T.Z[1]; hf[14] = T.Z[2];
         bool any = false;
         for (int py = T.y0; py <= T.y1; ++py)
-            for (int px = T.x0; px <= T.x1; ++px) {
-                float b0, b1, b2, fd;
-                any = any || eval_fragment(hf, (float)px, (float)py, b0, b1, b2, fd);
-            }
+            for (int px = T.x0; px <= T.x1; ++px) any = any || covers_pixel(hf, (float)px, (float)py);
         ok = any;
     }
 #endif
@@ -368,7 +366,7 @@ __global__ void __launch_bounds__(SB_THREADS) setup_count_kernel(SegParams P)
             TriSetup T;
             setup_triangle<true>(P, g, lo0, lo0_end, s_mat, T);
             np += T.ntiles; nt += T.ntiles ? 1u : 0u;
-            P.alive[g] = T.ntiles ? 1 : 0;                 // the write pass skips the dead without touching their vertices
+            P.alive[g] = (uint8_t)min(T.ntiles, 255u);     // tiles of the triangle (0 = dropped; 255 = that many or more)
         }
     }
 #pragma unroll
@@ -414,68 +412,93 @@ __global__ void __launch_bounds__(1024) setup_scan_kernel(uint32_t* block_agg, u
     }
 }
 
-// K1c: the same per-triangle work again, now with the CTA's global bases known: compact records and
-// pairs are written in submission order, records through shared memory as one contiguous run per round.
+// K1c: with the CTA's global bases known, compact records and pairs are written in submission order.  The count pass left
+// every triangle's tile count, so the prefix sums over the CTA's 1024 triangles need no vertex data (one barrier), and only
+// the SURVIVORS are set up again — densely: survivor number i of the CTA is handled by thread i mod 256, whatever lane first
+// saw it.  (In a scene of sub-pixel triangles one in sixteen survives: four barrier-separated rounds of a mostly idle CTA
+// were latency bound at four CTAs per SM.)
 __global__ void __launch_bounds__(SB_THREADS) setup_write_kernel(SegParams P)
 {
-    __shared__ uint32_t s_lo, s_wp[8], s_wt[8];
+    __shared__ uint32_t s_lo, s_wp[SB_ROUNDS][8], s_wt[SB_ROUNDS][8];
     __shared__ float s_mat[32];
     __shared__ float4 s_rec[SB_THREADS][4];
+    __shared__ uint2 s_list[SB_BLOCK];            // (triangle, exclusive pair offset in the CTA) of the CTA's survivors, in order
     const unsigned tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint32_t g0 = blockIdx.x * (uint32_t)SB_BLOCK;
     uint32_t lo0, lo0_end;
     cta_draw_cache(P, g0, &s_lo, s_mat, lo0, lo0_end);
-    unsigned long long base_p = P.bases[2 * blockIdx.x], base_t = P.bases[2 * blockIdx.x + 1];
+    const unsigned long long base_p = P.bases[2 * blockIdx.x], base_t = P.bases[2 * blockIdx.x + 1];
 
+    uint32_t nt[SB_ROUNDS], ip[SB_ROUNDS], it[SB_ROUNDS];
+#pragma unroll
     for (int k = 0; k < SB_ROUNDS; ++k) {
         const uint32_t g = g0 + (uint32_t)k * SB_THREADS + tid;
-        TriSetup T;
-        T.ntiles = 0;
-        if (g < P.ntris && __ldg(&P.alive[g])) setup_triangle<false>(P, g, lo0, lo0_end, s_mat, T);   // survivors only, coverage already decided
-        const uint32_t surv = T.ntiles ? 1u : 0u;
-        uint32_t ip = T.ntiles, it = surv;
+        nt[k] = g < P.ntris ? (uint32_t)__ldg(&P.alive[g]) : 0u;
+    }
+#pragma unroll
+    for (int k = 0; k < SB_ROUNDS; ++k) {
+        if (nt[k] == 255u) {                           // a large triangle: its exact tile count
+            TriSetup T;
+            setup_triangle<false>(P, g0 + (uint32_t)k * SB_THREADS + tid, lo0, lo0_end, s_mat, T);
+            nt[k] = T.ntiles;
+        }
+        ip[k] = nt[k]; it[k] = nt[k] ? 1u : 0u;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            uint32_t a = __shfl_up_sync(0xffffffffu, ip, o), c = __shfl_up_sync(0xffffffffu, it, o);
-            if (lane >= (unsigned)o) { ip += a; it += c; }
+            uint32_t a = __shfl_up_sync(0xffffffffu, ip[k], o), c = __shfl_up_sync(0xffffffffu, it[k], o);
+            if (lane >= (unsigned)o) { ip[k] += a; it[k] += c; }
         }
-        __syncthreads();                       // previous round's s_rec / s_wp consumed
-        if (lane == 31) { s_wp[wid] = ip; s_wt[wid] = it; }
-        __syncthreads();
+        if (lane == 31) { s_wp[k][wid] = ip[k]; s_wt[k][wid] = it[k]; }
+    }
+    __syncthreads();
+    uint32_t run_p = 0, run_t = 0;                     // pairs / survivors of the earlier rounds
+#pragma unroll
+    for (int k = 0; k < SB_ROUNDS; ++k) {
         uint32_t wbp = 0, wbt = 0, tp = 0, tt = 0;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) { if (w < (int)wid) { wbp += s_wp[w]; wbt += s_wt[w]; } tp += s_wp[w]; tt += s_wt[w]; }
-        const uint32_t ep = wbp + ip - T.ntiles, et = wbt + it - surv;   // exclusive inside the round
-        if (surv) {
-            s_rec[et][0] = make_float4(T.X[0], T.X[1], T.X[2], T.Y[0]);
-            s_rec[et][1] = make_float4(T.Y[1], T.Y[2], T.IW[0], T.IW[1]);
-            s_rec[et][2] = make_float4(T.IW[2], T.Z[0], T.Z[1], T.Z[2]);
-            s_rec[et][3] = make_float4(__uint_as_float((uint32_t)T.x0 | ((uint32_t)T.x1 << 16)), __uint_as_float((uint32_t)T.y0 | ((uint32_t)T.y1 << 16)),
-                                       __uint_as_float(T.draw), __uint_as_float(T.tri));
-        }
-        __syncthreads();
-        {
-            float4* dst = reinterpret_cast<float4*>(P.rec + base_t);
-            const float4* src = &s_rec[0][0];
-            for (uint32_t q = tid; q < tt * 4u; q += SB_THREADS) dst[q] = src[q];
-        }
-        if (T.ntiles && base_p + tp <= P.pair_capacity) {
-            const uint32_t target = __ldg(&P.draws[T.draw].target);
-            const int tx0 = T.x0 >> TILE_SHIFT, tx1 = T.x1 >> TILE_SHIFT;
-            const int ty0 = max(T.y0 >> TILE_SHIFT, (int)P.strip_ty0), ty1 = min(T.y1 >> TILE_SHIFT, (int)P.strip_ty1 - 1);
-            const uint32_t tbase = target * P.tiles_x * P.tiles_y;
-            const uint32_t ci = (uint32_t)(base_t + et);
-            uint64_t* out = P.pairs + base_p + ep;
-            for (int ty = ty0; ty <= ty1; ++ty) {
-                if (!owns_row(P, (uint32_t)ty)) continue;
-                for (int tx = tx0; tx <= tx1; ++tx) {
-                    const uint32_t key = tbase + (uint32_t)ty * P.tiles_x + (uint32_t)tx;
-                    *out++ = ((uint64_t)key << 32) | ci;
-                    if (T.ordered) atomicOr(&P.tile_flags[key], 1u);
+        for (int w = 0; w < 8; ++w) { if (w < (int)wid) { wbp += s_wp[k][w]; wbt += s_wt[k][w]; } tp += s_wp[k][w]; tt += s_wt[k][w]; }
+        if (nt[k]) s_list[run_t + wbt + it[k] - 1u] = make_uint2(g0 + (uint32_t)k * SB_THREADS + tid, run_p + wbp + ip[k] - nt[k]);
+        run_p += tp; run_t += tt;
+    }
+    __syncthreads();
+    const uint32_t tot_t = run_t, tot_p = run_p;
+    const bool room = base_p + tot_p <= P.pair_capacity;
+    // ---- survivors in passes of 256: thread i sets up survivor c0 + i
+    for (uint32_t c0 = 0; c0 < tot_t; c0 += SB_THREADS) {
+        const uint32_t n = min((uint32_t)SB_THREADS, tot_t - c0);
+        if (tid < n) {
+            const uint2 me = s_list[c0 + tid];
+            TriSetup T;
+            setup_triangle<false>(P, me.x, lo0, lo0_end, s_mat, T);
+            s_rec[tid][0] = make_float4(T.X[0], T.X[1], T.X[2], T.Y[0]);
+            s_rec[tid][1] = make_float4(T.Y[1], T.Y[2], T.IW[0], T.IW[1]);
+            s_rec[tid][2] = make_float4(T.IW[2], T.Z[0], T.Z[1], T.Z[2]);
+            s_rec[tid][3] = make_float4(__uint_as_float((uint32_t)T.x0 | ((uint32_t)T.x1 << 16)), __uint_as_float((uint32_t)T.y0 | ((uint32_t)T.y1 << 16)),
+                                        __uint_as_float(T.draw), __uint_as_float(T.tri));
+            if (room) {
+                const uint32_t target = __ldg(&P.draws[T.draw].target);
+                const int tx0 = T.x0 >> TILE_SHIFT, tx1 = T.x1 >> TILE_SHIFT;
+                const int ty0 = max(T.y0 >> TILE_SHIFT, (int)P.strip_ty0), ty1 = min(T.y1 >> TILE_SHIFT, (int)P.strip_ty1 - 1);
+                const uint32_t tbase = target * P.tiles_x * P.tiles_y;
+                const uint32_t ci = (uint32_t)(base_t + c0 + tid);
+                uint64_t* out = P.pairs + base_p + me.y;
+                for (int ty = ty0; ty <= ty1; ++ty) {
+                    if (!owns_row(P, (uint32_t)ty)) continue;
+                    for (int tx = tx0; tx <= tx1; ++tx) {
+                        const uint32_t key = tbase + (uint32_t)ty * P.tiles_x + (uint32_t)tx;
+                        *out++ = ((uint64_t)key << 32) | ci;
+                        if (T.ordered) atomicOr(&P.tile_flags[key], 1u);
+                    }
                 }
             }
         }
-        base_p += tp; base_t += tt;
+        __syncthreads();
+        {
+            float4* dst = reinterpret_cast<float4*>(P.rec + base_t + c0);
+            const float4* src = &s_rec[0][0];
+            for (uint32_t q = tid; q < n * 4u; q += SB_THREADS) dst[q] = src[q];
+        }
+        if (c0 + SB_THREADS < tot_t) __syncthreads();      // s_rec is rewritten by the next pass
     }
 }
 
@@ -828,6 +851,21 @@ __device__ __forceinline__ bool eval_fragment(const float* hf, float Px, float P
     bc0 = fmul(f, bc0); bc1 = fmul(f, bc1); bc2 = fmul(f, bc2);
     fd = fadd(fadd(fadd(0.0f, fmul(hf[12], bc0)), fmul(hf[13], bc1)), fmul(hf[14], bc2));   // :73
     return !(bs0 < 0.f || bs1 < 0.f || bs2 < 0.f) && !(fd < 0.0f);             // :74,:76
+}
+
+// eval_fragment's verdict alone, the three edge functions first: most pixels of a sub-pixel triangle's box fail them and never
+// reach the perspective division (same operations in the same order where they are evaluated)
+__device__ __forceinline__ bool covers_pixel(const float* hf, float Px, float Py)
+{
+    const float bs0 = fadd(fadd(fmul(hf[0], Px), fmul(hf[1], Py)), hf[2]);
+    const float bs1 = fadd(fadd(fmul(hf[3], Px), fmul(hf[4], Py)), hf[5]);
+    const float bs2 = fadd(fadd(fmul(hf[6], Px), fmul(hf[7], Py)), hf[8]);
+    if (bs0 < 0.f || bs1 < 0.f || bs2 < 0.f) return false;
+    float bc0 = fmul(bs0, hf[9]), bc1 = fmul(bs1, hf[10]), bc2 = fmul(bs2, hf[11]);
+    const float f = fdiv(1.0f, fadd(fadd(bc0, bc1), bc2));
+    bc0 = fmul(f, bc0); bc1 = fmul(f, bc1); bc2 = fmul(f, bc2);
+    const float fd = fadd(fadd(fadd(0.0f, fmul(hf[12], bc0)), fmul(hf[13], bc1)), fmul(hf[14], bc2));
+    return !(fd < 0.0f);
 }
 
 #ifndef RASTER_PREFETCH
