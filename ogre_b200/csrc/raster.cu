@@ -91,6 +91,7 @@ struct DrawDev {
     const uint8_t* col;        // VES_DIFFUSE bytes r,g,b,a
     uint32_t sc_x, sc_y;       // scissor: left | (right - 1) << 16, top | (bottom - 1) << 16 (inclusive pixel bounds)
     uint32_t inst_tris, inst_verts;   // instanced list: triangles per instance (0 = plain draw), vertex index step per instance
+    uint32_t inst_magic, pad_;        // min(floor(2^32 / inst_tris), 2^32 - 1): triangle -> instance without a hardware divide
     float mvp[16], texm[16], vp[16];
     float mvit[9];
     float light[3];
@@ -172,7 +173,20 @@ __global__ void __launch_bounds__(256) vertex_xf_kernel(XfParams P)
     const DrawDev& D = P.draws[lo];
     const uint32_t vi = v - D.vert_base;
     const float* p = (const float*)(D.pos + (size_t)vi * D.pos_stride);
-    P.out[v] = transform_vertex(D.mvp, D.vp, __ldg(p), __ldg(p + 1), __ldg(p + 2));
+    float4 sv = transform_vertex(D.mvp, D.vp, __ldg(p), __ldg(p + 1), __ldg(p + 2));
+    // a vertex with any non-finite screen coordinate drops its triangles (setup_triangle): mark it in X, the one field they test
+    if (!(isfinite(sv.y) && isfinite(sv.z) && isfinite(sv.w))) sv.x = __int_as_float(0x7fc00000);
+    P.out[v] = sv;
+}
+
+// triangle t of an instanced list -> (instance, triangle inside the instance).  q = umulhi(t, floor(2^32 / n)) is the quotient or
+// one less (the estimate is low by t * frac(2^32 / n) / 2^32 < 1), so one correction step makes it exact.
+__device__ __forceinline__ uint32_t instance_of(uint32_t& t, uint32_t inst_tris, uint32_t inst_magic)
+{
+    uint32_t q = __umulhi(t, inst_magic), r = t - q * inst_tris;
+    if (r >= inst_tris) { ++q; r -= inst_tris; }
+    t = r;
+    return q;
 }
 
 // index of vertex j of triangle t (list: 3t+j, strip: t+j — sliding window without winding flip,
@@ -180,15 +194,45 @@ __global__ void __launch_bounds__(256) vertex_xf_kernel(XfParams P)
 __device__ __forceinline__ size_t vertex_index(const DrawDev& D, uint32_t t, int j)
 {
     size_t base = 0;
-    if (D.inst_tris) {                                   // instanced list: the same indices, shifted per instance
-        const uint32_t inst = t / D.inst_tris;
-        t -= inst * D.inst_tris;
-        base = (size_t)inst * D.inst_verts;
-    }
+    if (D.inst_tris) base = (size_t)instance_of(t, D.inst_tris, D.inst_magic) * D.inst_verts;   // instanced list: the same indices, shifted per instance
     const size_t k = (D.is_strip ? (size_t)t : (size_t)t * 3) + j;
     if (D.index_type == 2) return base + __ldg((const uint16_t*)D.idx + k);
     if (D.index_type == 4) return base + __ldg((const uint32_t*)D.idx + k);
     return base + k;
+}
+
+// The draw fields every triangle's set-up reads, fetched ONCE per triangle through the read-only path (the compiler re-read them
+// from the draw table around every branch when they were plain loads: 330 of the count pass's 575 instructions per triangle-warp,
+// three hardware divides among them; profiles/r02_notes.md).
+struct DrawHot {
+    const float4* xf; const void* idx; const uint8_t* pos;
+    uint32_t nxf, pos_stride, index_type, is_strip, ext, tri_base, inst_tris, inst_verts, inst_magic;
+};
+__device__ __forceinline__ DrawHot load_hot(const DrawDev* D)
+{
+    DrawHot H;
+    H.xf = (const float4*)__ldg((const unsigned long long*)&D->xf);
+    H.idx = (const void*)__ldg((const unsigned long long*)&D->idx);
+    H.pos = (const uint8_t*)__ldg((const unsigned long long*)&D->pos);
+    H.nxf = __ldg(&D->vertex_count); H.pos_stride = __ldg(&D->pos_stride); H.index_type = __ldg(&D->index_type);
+    H.is_strip = __ldg(&D->is_strip); H.ext = __ldg(&D->ext); H.tri_base = __ldg(&D->tri_base);
+    const uint2 in = __ldg((const uint2*)&D->inst_tris);
+    H.inst_tris = in.x; H.inst_verts = in.y; H.inst_magic = __ldg(&D->inst_magic);
+    return H;
+}
+// the three vertex indices of triangle t of the draw
+__device__ __forceinline__ void triangle_vertices(const DrawHot& H, uint32_t t, size_t vi[3])
+{
+    size_t base = 0;
+    if (H.inst_tris) base = (size_t)instance_of(t, H.inst_tris, H.inst_magic) * H.inst_verts;
+    const size_t k = H.is_strip ? (size_t)t : (size_t)t * 3;
+    if (H.index_type == 2) {
+        const uint16_t* ix = (const uint16_t*)H.idx + k;
+        vi[0] = base + __ldg(ix); vi[1] = base + __ldg(ix + 1); vi[2] = base + __ldg(ix + 2);
+    } else if (H.index_type == 4) {
+        const uint32_t* ix = (const uint32_t*)H.idx + k;
+        vi[0] = base + __ldg(ix); vi[1] = base + __ldg(ix + 1); vi[2] = base + __ldg(ix + 2);
+    } else { vi[0] = base + k; vi[1] = base + k + 1; vi[2] = base + k + 2; }
 }
 
 constexpr int SB_THREADS = 256;
@@ -232,45 +276,44 @@ __device__ __forceinline__ void setup_triangle(const SegParams& P, uint32_t g, u
         }
     }
     const DrawDev& D = P.draws[lo];
+    const DrawHot H = load_hot(&D);
     const float* Mmvp = same ? s_mat : D.mvp;
     const float* Mvp = same ? s_mat + 16 : D.vp;
-    const uint32_t t = g - D.tri_base;
+    const uint32_t t = g - H.tri_base;
     T.draw = lo; T.tri = t;
     bool ok = true;
-    const float4* xf = D.xf;
-    const uint32_t nxf = D.vertex_count;
+    size_t vi[3];
+    triangle_vertices(H, t, vi);
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
-        const size_t vi = vertex_index(D, t, j);
         float4 sv;
-        if (xf && vi < nxf) sv = __ldg(xf + vi);                               // transformed once per vertex (vertex_xf_kernel)
-        else {
-            const float* p = (const float*)(D.pos + vi * D.pos_stride);
+        // non-finite screen coordinates: the reference writes out of bounds (undefined) -> drop
+        if (H.xf && vi[j] < H.nxf) {                                           // transformed once per vertex (vertex_xf_kernel), which
+            sv = __ldg(H.xf + vi[j]);                                          // folds the four tests into X
+            ok = ok && isfinite(sv.x);
+        } else {
+            const float* p = (const float*)(H.pos + vi[j] * H.pos_stride);
             sv = transform_vertex(Mmvp, Mvp, __ldg(p), __ldg(p + 1), __ldg(p + 2));
+            ok = ok && isfinite(sv.x) && isfinite(sv.y) && isfinite(sv.z) && isfinite(sv.w);
         }
         T.X[j] = sv.x; T.Y[j] = sv.y; T.Z[j] = sv.z; T.IW[j] = sv.w;
-        // non-finite screen coordinates: the reference writes out of bounds (undefined) -> drop
-        ok = ok && isfinite(sv.x) && isfinite(sv.y) && isfinite(sv.z) && isfinite(sv.w);
     }
-    const uint32_t ext = D.ext;
+    const uint32_t ext = H.ext;
     // Tiny: lists are culled by its fixed rule (= CULL_CLOCKWISE), strips never (.cpp:410); beyond Tiny: the draw's culling mode
-    const uint32_t cull = (ext & OGRECU_EXT_CULL_MODE) ? ((ext >> 12) & 0xfu) : (D.is_strip ? (uint32_t)OGRECU_CULL_NONE : (uint32_t)OGRECU_CULL_CLOCKWISE);
+    const uint32_t cull = (ext & OGRECU_EXT_CULL_MODE) ? ((ext >> 12) & 0xfu) : (H.is_strip ? (uint32_t)OGRECU_CULL_NONE : (uint32_t)OGRECU_CULL_CLOCKWISE);
     if (ok && cull != OGRECU_CULL_NONE) {                                      // cull: tinyrenderer.h:37-39,55
         float ax = fsub(T.X[2], T.X[0]), ay = fsub(T.Y[2], T.Y[0]), bx = fsub(T.X[2], T.X[1]), by = fsub(T.Y[2], T.Y[1]);
         float cr = fsub(fmul(ax, by), fmul(ay, bx));
-        if ((ext & OGRECU_EXT_CULL_MODE) && D.is_strip && (t & 1u)) cr = -cr;  // a strip's odd triangles wind the other way
+        if ((ext & OGRECU_EXT_CULL_MODE) && H.is_strip && (t & 1u)) cr = -cr;  // a strip's odd triangles wind the other way
         if (cull == OGRECU_CULL_CLOCKWISE ? cr > 0.0f : cr < 0.0f) ok = false;
     }
     if (ok) {
-        float mnx = FLT_MAX, mny = FLT_MAX, mxx = -FLT_MAX, mxy = -FLT_MAX;
+        // tinyrenderer.h:58-65 clamps as it goes: mn = max(0, min(mn, X[j])), mx = min(c, max(mx, X[j])) from +-FLT_MAX.  For the
+        // finite coordinates that reach this point min / max are lattice operations, so that fold equals max(0, min(X0, X1, X2)) and
+        // min(c, max(X0, X1, X2)) (it may give -0 where the fold gives +0: both truncate to pixel 0).
         const float cx = (float)(P.width - 1u), cy = (float)(P.height - 1u);
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {                                          // tinyrenderer.h:58-65
-            mnx = std_max(0.f, std_min(mnx, T.X[j]));
-            mxx = std_min(cx, std_max(mxx, T.X[j]));
-            mny = std_max(0.f, std_min(mny, T.Y[j]));
-            mxy = std_min(cy, std_max(mxy, T.Y[j]));
-        }
+        const float mnx = fmaxf(0.f, fminf(fminf(T.X[0], T.X[1]), T.X[2])), mxx = fminf(cx, fmaxf(fmaxf(T.X[0], T.X[1]), T.X[2]));
+        const float mny = fmaxf(0.f, fminf(fminf(T.Y[0], T.Y[1]), T.Y[2])), mxy = fminf(cy, fmaxf(fmaxf(T.Y[0], T.Y[1]), T.Y[2]));
         // beyond +-2^31 the reference's (int) loop bounds are undefined -> drop
         if (!(mnx < 2147483648.0f) || !(mny < 2147483648.0f) || !(mxx > -2147483648.0f) || !(mxy > -2147483648.0f)) ok = false;
         else {
@@ -296,8 +339,12 @@ __device__ __forceinline__ void setup_triangle(const SegParams& P, uint32_t g, u
         hf[9] = T.IW[0]; hf[10] = T.IW[1]; hf[11] = T.IW[2];
         hf[12] = T.Z[0]; hf[13] = T.Z[1]; hf[14] = T.Z[2];
         bool any = false;
-        for (int py = T.y0; py <= T.y1; ++py)
-            for (int px = T.x0; px <= T.x1; ++px) any = any || covers_pixel(hf, (float)px, (float)py);
+        int px = T.x0, py = T.y0;
+#pragma unroll 1
+        for (int n = (T.x1 - T.x0 + 1) * (T.y1 - T.y0 + 1); n > 0 && !any; --n) {       // one flat loop over the box's few pixels
+            any = covers_pixel(hf, (float)px, (float)py);
+            if (++px > T.x1) { px = T.x0; ++py; }
+        }
         ok = any;
     }
 #endif
@@ -381,17 +428,24 @@ __global__ void __launch_bounds__(SB_THREADS) setup_count_kernel(SegParams P)
     }
 }
 
-// K1b: exclusive scan of the block table in place (one CTA; 64-bit running sums), totals -> ctl[2..3]
-__global__ void __launch_bounds__(1024) setup_scan_kernel(uint32_t* block_agg, uint32_t nblocks, uint32_t* ctl, unsigned long long* bases)
+// K1b: exclusive scan of the block table (one CTA, eight table entries per thread and round; 64-bit running sums), totals -> ctl[2..3]
+constexpr int SS_ITEMS = 8;
+__global__ void __launch_bounds__(1024) setup_scan_kernel(const uint32_t* __restrict__ block_agg, uint32_t nblocks, uint32_t* ctl, unsigned long long* bases)
 {
     __shared__ unsigned long long s_wp[32], s_wt[32], s_carry[2];
     const unsigned tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (tid == 0) { s_carry[0] = 0; s_carry[1] = 0; }
     __syncthreads();
-    for (uint32_t b0 = 0; b0 < nblocks; b0 += 1024) {
-        const uint32_t b = b0 + tid;
-        unsigned long long vp = b < nblocks ? block_agg[2 * b] : 0, vt = b < nblocks ? block_agg[2 * b + 1] : 0;
-        unsigned long long ip = vp, it = vt;
+    for (uint32_t b0 = 0; b0 < nblocks; b0 += 1024 * SS_ITEMS) {
+        const uint32_t b = b0 + tid * SS_ITEMS;
+        uint32_t vp[SS_ITEMS], vt[SS_ITEMS];
+        unsigned long long sp = 0, st = 0;
+#pragma unroll
+        for (int i = 0; i < SS_ITEMS; ++i) {
+            const uint2 v = b + i < nblocks ? __ldg(reinterpret_cast<const uint2*>(block_agg) + b + i) : make_uint2(0u, 0u);
+            vp[i] = v.x; vt[i] = v.y; sp += v.x; st += v.y;
+        }
+        unsigned long long ip = sp, it = st;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             unsigned long long a = __shfl_up_sync(0xffffffffu, ip, o), c = __shfl_up_sync(0xffffffffu, it, o);
@@ -401,7 +455,12 @@ __global__ void __launch_bounds__(1024) setup_scan_kernel(uint32_t* block_agg, u
         __syncthreads();
         unsigned long long wbp = 0, wbt = 0, tp = 0, tt = 0;
         for (int w = 0; w < 32; ++w) { if (w < (int)wid) { wbp += s_wp[w]; wbt += s_wt[w]; } tp += s_wp[w]; tt += s_wt[w]; }
-        if (b < nblocks) { bases[2 * b] = s_carry[0] + wbp + ip - vp; bases[2 * b + 1] = s_carry[1] + wbt + it - vt; }
+        unsigned long long rp = s_carry[0] + wbp + ip - sp, rt = s_carry[1] + wbt + it - st;
+#pragma unroll
+        for (int i = 0; i < SS_ITEMS; ++i) {
+            if (b + i < nblocks) { bases[2 * (size_t)(b + i)] = rp; bases[2 * (size_t)(b + i) + 1] = rt; }
+            rp += vp[i]; rt += vt[i];
+        }
         __syncthreads();
         if (tid == 0) { s_carry[0] += tp; s_carry[1] += tt; }
         __syncthreads();
@@ -1310,6 +1369,7 @@ int run_segment(ogrecu_ctx* ctx, ogrecu_rt* const* targets, uint32_t ntargets, c
         o.tri_count = tri_count_of(d);
         o.inst_tris = d.instance_count ? d.draw_count / 3 : 0;
         o.inst_verts = d.instance_vertex_count;
+        o.inst_magic = o.inst_tris ? (uint32_t)std::min<uint64_t>((1ull << 32) / o.inst_tris, 0xffffffffull) : 0;
         ntris64 += o.tri_count;
         // vertex pre-transform when the caller bounded the vertex range and it is not mostly unused
         o.vert_base = (uint32_t)nverts64;
