@@ -284,19 +284,27 @@ __device__ __forceinline__ void setup_triangle(const SegParams& P, uint32_t g, u
     bool ok = true;
     size_t vi[3];
     triangle_vertices(H, t, vi);
+    // non-finite screen coordinates: the reference writes out of bounds (undefined) -> drop
+    if (H.xf && vi[0] < H.nxf && vi[1] < H.nxf && vi[2] < H.nxf) {
+        // transformed once per vertex (vertex_xf_kernel, which folds the four finite tests into X).  The three gathers are issued
+        // back to back: behind a branch per vertex they made a chain of three L2 round trips (28 % of the count pass's stall samples).
+        const float4 s0 = __ldg(H.xf + vi[0]), s1 = __ldg(H.xf + vi[1]), s2 = __ldg(H.xf + vi[2]);
+        T.X[0] = s0.x; T.Y[0] = s0.y; T.Z[0] = s0.z; T.IW[0] = s0.w;
+        T.X[1] = s1.x; T.Y[1] = s1.y; T.Z[1] = s1.z; T.IW[1] = s1.w;
+        T.X[2] = s2.x; T.Y[2] = s2.y; T.Z[2] = s2.z; T.IW[2] = s2.w;
+        ok = isfinite(s0.x) & isfinite(s1.x) & isfinite(s2.x);
+    } else {
 #pragma unroll
-    for (int j = 0; j < 3; ++j) {
-        float4 sv;
-        // non-finite screen coordinates: the reference writes out of bounds (undefined) -> drop
-        if (H.xf && vi[j] < H.nxf) {                                           // transformed once per vertex (vertex_xf_kernel), which
-            sv = __ldg(H.xf + vi[j]);                                          // folds the four tests into X
-            ok = ok && isfinite(sv.x);
-        } else {
-            const float* p = (const float*)(H.pos + vi[j] * H.pos_stride);
-            sv = transform_vertex(Mmvp, Mvp, __ldg(p), __ldg(p + 1), __ldg(p + 2));
+        for (int j = 0; j < 3; ++j) {
+            float4 sv;
+            if (H.xf && vi[j] < H.nxf) sv = __ldg(H.xf + vi[j]);
+            else {
+                const float* p = (const float*)(H.pos + vi[j] * H.pos_stride);
+                sv = transform_vertex(Mmvp, Mvp, __ldg(p), __ldg(p + 1), __ldg(p + 2));
+            }
             ok = ok && isfinite(sv.x) && isfinite(sv.y) && isfinite(sv.z) && isfinite(sv.w);
+            T.X[j] = sv.x; T.Y[j] = sv.y; T.Z[j] = sv.z; T.IW[j] = sv.w;
         }
-        T.X[j] = sv.x; T.Y[j] = sv.y; T.Z[j] = sv.z; T.IW[j] = sv.w;
     }
     const uint32_t ext = H.ext;
     // Tiny: lists are culled by its fixed rule (= CULL_CLOCKWISE), strips never (.cpp:410); beyond Tiny: the draw's culling mode
@@ -428,46 +436,56 @@ __global__ void __launch_bounds__(SB_THREADS) setup_count_kernel(SegParams P)
     }
 }
 
-// K1b: exclusive scan of the block table (one CTA, eight table entries per thread and round; 64-bit running sums), totals -> ctl[2..3]
+// K1b: exclusive scan of the block table (64-bit running sums), totals -> ctl[2..3].  One CTA per 8192 table entries; each first
+// sums every entry before its own (a coalesced read of at most the whole table out of L2: the table has one entry per 1024
+// triangles, so this stays far below the count pass even when a thousand CTAs repeat it), then scans its own.  No CTA waits for
+// another.
 constexpr int SS_ITEMS = 8;
+constexpr int SS_CHUNK = 1024 * SS_ITEMS;
 __global__ void __launch_bounds__(1024) setup_scan_kernel(const uint32_t* __restrict__ block_agg, uint32_t nblocks, uint32_t* ctl, unsigned long long* bases)
 {
-    __shared__ unsigned long long s_wp[32], s_wt[32], s_carry[2];
+    __shared__ unsigned long long s_wp[32], s_wt[32];
     const unsigned tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (tid == 0) { s_carry[0] = 0; s_carry[1] = 0; }
+    const uint32_t b0 = blockIdx.x * (uint32_t)SS_CHUNK;
+    const uint2* agg = reinterpret_cast<const uint2*>(block_agg);
+    // ---- carry: everything before this chunk
+    unsigned long long cp = 0, ct = 0;
+    for (uint32_t i = tid; i < b0; i += 1024) { const uint2 v = __ldg(agg + i); cp += v.x; ct += v.y; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { cp += __shfl_xor_sync(0xffffffffu, cp, o); ct += __shfl_xor_sync(0xffffffffu, ct, o); }
+    if (lane == 0) { s_wp[wid] = cp; s_wt[wid] = ct; }
     __syncthreads();
-    for (uint32_t b0 = 0; b0 < nblocks; b0 += 1024 * SS_ITEMS) {
-        const uint32_t b = b0 + tid * SS_ITEMS;
-        uint32_t vp[SS_ITEMS], vt[SS_ITEMS];
-        unsigned long long sp = 0, st = 0;
+    cp = 0; ct = 0;
+    for (int w = 0; w < 32; ++w) { cp += s_wp[w]; ct += s_wt[w]; }
+    __syncthreads();
+    // ---- this chunk
+    const uint32_t b = b0 + tid * SS_ITEMS;
+    uint32_t vp[SS_ITEMS], vt[SS_ITEMS];
+    unsigned long long sp = 0, st = 0;
 #pragma unroll
-        for (int i = 0; i < SS_ITEMS; ++i) {
-            const uint2 v = b + i < nblocks ? __ldg(reinterpret_cast<const uint2*>(block_agg) + b + i) : make_uint2(0u, 0u);
-            vp[i] = v.x; vt[i] = v.y; sp += v.x; st += v.y;
-        }
-        unsigned long long ip = sp, it = st;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            unsigned long long a = __shfl_up_sync(0xffffffffu, ip, o), c = __shfl_up_sync(0xffffffffu, it, o);
-            if (lane >= (unsigned)o) { ip += a; it += c; }
-        }
-        if (lane == 31) { s_wp[wid] = ip; s_wt[wid] = it; }
-        __syncthreads();
-        unsigned long long wbp = 0, wbt = 0, tp = 0, tt = 0;
-        for (int w = 0; w < 32; ++w) { if (w < (int)wid) { wbp += s_wp[w]; wbt += s_wt[w]; } tp += s_wp[w]; tt += s_wt[w]; }
-        unsigned long long rp = s_carry[0] + wbp + ip - sp, rt = s_carry[1] + wbt + it - st;
-#pragma unroll
-        for (int i = 0; i < SS_ITEMS; ++i) {
-            if (b + i < nblocks) { bases[2 * (size_t)(b + i)] = rp; bases[2 * (size_t)(b + i) + 1] = rt; }
-            rp += vp[i]; rt += vt[i];
-        }
-        __syncthreads();
-        if (tid == 0) { s_carry[0] += tp; s_carry[1] += tt; }
-        __syncthreads();
+    for (int i = 0; i < SS_ITEMS; ++i) {
+        const uint2 v = b + i < nblocks ? __ldg(agg + b + i) : make_uint2(0u, 0u);
+        vp[i] = v.x; vt[i] = v.y; sp += v.x; st += v.y;
     }
-    if (tid == 0) {
-        ctl[2] = (uint32_t)min(s_carry[0], 0xffffffffull);
-        ctl[3] = (uint32_t)min(s_carry[1], 0xffffffffull);
+    unsigned long long ip = sp, it = st;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned long long a = __shfl_up_sync(0xffffffffu, ip, o), c = __shfl_up_sync(0xffffffffu, it, o);
+        if (lane >= (unsigned)o) { ip += a; it += c; }
+    }
+    if (lane == 31) { s_wp[wid] = ip; s_wt[wid] = it; }
+    __syncthreads();
+    unsigned long long wbp = 0, wbt = 0, tp = 0, tt = 0;
+    for (int w = 0; w < 32; ++w) { if (w < (int)wid) { wbp += s_wp[w]; wbt += s_wt[w]; } tp += s_wp[w]; tt += s_wt[w]; }
+    unsigned long long rp = cp + wbp + ip - sp, rt = ct + wbt + it - st;
+#pragma unroll
+    for (int i = 0; i < SS_ITEMS; ++i) {
+        if (b + i < nblocks) { bases[2 * (size_t)(b + i)] = rp; bases[2 * (size_t)(b + i) + 1] = rt; }
+        rp += vp[i]; rt += vt[i];
+    }
+    if (tid == 0 && blockIdx.x == gridDim.x - 1) {
+        ctl[2] = (uint32_t)min(cp + tp, 0xffffffffull);
+        ctl[3] = (uint32_t)min(ct + tt, 0xffffffffull);
     }
 }
 
@@ -1457,7 +1475,7 @@ int run_segment(ogrecu_ctx* ctx, ogrecu_rt* const* targets, uint32_t ntargets, c
     // ---- K1a/K1b: count survivors and pairs per CTA, scan the CTA table
     OGRECU_CUDA(cudaMemsetAsync(P.ctl, 0, 16 + (size_t)nkeys * 4, ctx->stream));
     setup_count_kernel<<<nblocks, SB_THREADS, 0, ctx->stream>>>(P);
-    setup_scan_kernel<<<1, 1024, 0, ctx->stream>>>(P.block_agg, nblocks, P.ctl, P.bases);
+    setup_scan_kernel<<<div_up(nblocks, (uint32_t)SS_CHUNK), 1024, 0, ctx->stream>>>(P.block_agg, nblocks, P.ctl, P.bases);
     OGRECU_CUDA(cudaGetLastError());
     count_launch(ctx, 2);
     OGRECU_CUDA(cudaMemcpyAsync(ctl_host, P.ctl, 16, cudaMemcpyDeviceToHost, ctx->stream));
