@@ -170,7 +170,8 @@ def reference_step_fn(subs, palettes, ninst, threads, rank=0):
         bufs.append((np.zeros((ninst, n, 6), np.float32), np.zeros((ninst, n, 6), np.float32)))
     if ref.available():
         l = ref.lib()
-        have_skel = l.ref_skel_open(b"Sinbad.mesh", 64, 64) == 0 and l.ref_skel_num_bones() == nb
+        # (ref_skel_num_bones counts the palette of the last evaluated pose: evaluate one)
+        have_skel = l.ref_skel_open(b"Sinbad.mesh", 64, 64) == 0 and l.ref_skel_pose(0.0) == 0 and l.ref_skel_num_bones() == nb
         _, tpos, _ = instance_states(ninst, rank, 1e9)
         live = np.zeros((ninst, nb, 16), np.float32)
 
@@ -564,6 +565,10 @@ def run_ours(args):
     if not args.no_render:
         render_cfg = run_render_configs(args, local, rank, world, peak)
 
+    # ---- the drop-in plugin end to end: a crowd of Entity objects through Root::renderOneFrame (rank 0, N=1: one Root per process)
+    if rank == 0 and world == 1 and not args.no_plugin:
+        extra["plugin_e2e"] = run_plugin_e2e(args)
+
     # ---- CPU baseline on a bounded sample (rank 0, N=1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -615,6 +620,46 @@ def run_ours(args):
         L.ogrecu_host_free(h)
     if dist is not None:
         dist.destroy_process_group()
+
+
+def run_plugin_e2e(args):
+    """extra.plugin_e2e: `--plugin-entities` animated Sinbad Entity objects in a stock OGRE scene, every one re-skinned each frame by
+    Entity::_updateAnimation -> Mesh::softwareVertexBlend -> OptimisedUtil (OgreEntity.cpp:747-911, OgreMesh.cpp:1792-1897) and
+    drawn by Root::renderOneFrame, through RenderSystem_CUDA.so (OptimisedUtil calls queued and flushed as one launch; and unqueued)
+    and through the unmodified RenderSystem_Tiny.so + OptimisedUtilSSE (the CPU baseline) in the same harness.  One process each."""
+    import subprocess
+    script = os.path.join(ROOT, "tests", "harness", "run_crowd.py")
+    if not os.path.exists(os.path.join(ROOT, "tests", "harness", "libplugin_harness.so")):
+        return {"unavailable": "tests/harness/libplugin_harness.so is not built (needs oracle/_ref: the reference's own OgreMain)"}
+    out = {"scene": "%d Sinbad entities, %s target, Root::renderOneFrame per frame (animation advanced every frame)" % (
+        args.plugin_entities, args.plugin_size)}
+    runs = [("cuda_batched", ["--plugin", "cuda", "--batch", "1", "--frames", "10"]),
+            ("cuda_unbatched", ["--plugin", "cuda", "--batch", "0", "--frames", "3"]),
+            ("tiny_sse_cpu", ["--plugin", "tiny", "--frames", "2"])]
+    frames = {}
+    for name, argv in runs:
+        npz = "/tmp/ogrecu_plugin_e2e_%s_%d.npz" % (name, os.getpid())
+        try:
+            r = subprocess.run([sys.executable, script, "--count", str(args.plugin_entities), "--size", args.plugin_size, "--out", npz] + argv,
+                               capture_output=True, text=True, timeout=240)
+            d = json.loads(r.stdout.strip().splitlines()[-1])
+            out[name] = {"ms_per_frame": d["s_per_frame"] * 1e3, "Mvert_per_s": d["Mvert_per_s"], "vertices_per_frame": d["vertices_per_frame"],
+                         "triangles": d["triangles"], "batches": d["batches"]}
+            frames[name] = np.load(npz)["frame"]
+        except Exception as e:                                   # noqa: BLE001 - reported, not fatal to the bench line
+            out[name] = {"error": "%s: %s" % (type(e).__name__, str(e)[:200])}
+        finally:
+            if os.path.exists(npz):
+                os.remove(npz)
+    if "cuda_batched" in frames and "cuda_unbatched" in frames:
+        out["batched_frame_identical_to_unbatched"] = bool(np.array_equal(frames["cuda_batched"], frames["cuda_unbatched"]))
+    if "cuda_batched" in frames and "tiny_sse_cpu" in frames:
+        a, b = frames["cuda_batched"].astype(np.int16), frames["tiny_sse_cpu"].astype(np.int16)
+        diff = np.abs(a - b).max(axis=2)
+        out["vs_tiny_frame"] = {"pixels_differing": int((diff > 0).sum()), "max_abs_diff": int(diff.max()),
+                                "note": "Tiny skins with OptimisedUtilSSE whose normals use rsqrtps (approximate): a lit pixel may "
+                                        "differ by one 8-bit step; positions / coverage are bit-identical (tests/test_plugin_gpu.py)"}
+    return out
 
 
 def run_render_configs(args, local, rank, world, peak):
@@ -693,6 +738,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=40, help="steps of the end-to-end measurement (each renders every instance)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-render", action="store_true", help="skip extra.render (c1, c4, c5)")
+    ap.add_argument("--no-plugin", action="store_true", help="skip extra.plugin_e2e (the Entity crowd through Root::renderOneFrame)")
+    ap.add_argument("--plugin-entities", type=int, default=1000)
+    ap.add_argument("--plugin-size", default="1280x720")
     ap.add_argument("--views", type=int, default=1024)
     ap.add_argument("--c5-tris", type=int, default=20000000)
     args = ap.parse_args()

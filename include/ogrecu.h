@@ -109,6 +109,14 @@ OGRECU_API uint64_t ogrecu_launch_count(const ogrecu_ctx* ctx);
  * Unknown names return OGRECU_ERR_INVALID. */
 OGRECU_API int ogrecu_set_config_option(ogrecu_ctx* ctx, const char* name, int value);
 
+/* Profiler ranges (RenderSystem::beginProfileEvent / endProfileEvent / markProfileEvent,
+ * OgreMain/include/OgreRenderSystem.h:1104-1115; the GL render systems map them to KHR_debug groups): NVTX ranges and markers on
+ * the calling thread, visible in Nsight Systems / Compute around the launches they bracket.  The library also opens its own
+ * ranges around a target's flush and the batched OptimisedUtil flush.  No-ops when no tool is attached. */
+OGRECU_API int ogrecu_profile_begin(ogrecu_ctx* ctx, const char* name);
+OGRECU_API int ogrecu_profile_end(ogrecu_ctx* ctx);
+OGRECU_API int ogrecu_profile_mark(ogrecu_ctx* ctx, const char* name);
+
 /* raw device / pinned memory for callers that keep data resident */
 OGRECU_API int ogrecu_malloc(ogrecu_ctx* ctx, size_t bytes, void** dev_ptr);
 OGRECU_API int ogrecu_free(ogrecu_ctx* ctx, void* dev_ptr);

@@ -94,6 +94,9 @@ SIGNATURES = {
     "ogrecu_get_stream": (C.c_void_p, [C.c_void_p]),
     "ogrecu_sync": (C.c_int, [C.c_void_p]),
     "ogrecu_launch_count": (C.c_uint64, [C.c_void_p]),
+    "ogrecu_profile_begin": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "ogrecu_profile_end": (C.c_int, [C.c_void_p]),
+    "ogrecu_profile_mark": (C.c_int, [C.c_void_p, C.c_char_p]),
     "ogrecu_malloc": (C.c_int, [C.c_void_p, C.c_size_t, c_void_pp]),
     "ogrecu_free": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ogrecu_host_alloc": (C.c_int, [C.c_size_t, c_void_pp]),

@@ -1,6 +1,7 @@
 // common.cuh — shared internals of libogrecu.so (not part of the public C ABI).
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <stdint.h>
 #include <stddef.h>
 #include <mutex>
@@ -83,6 +84,7 @@ struct ogrecu_ctx {
     ogrecu::Scratch stage_out;
     ogrecu::Scratch lane_counter;   // work-unit counter of skin_lane_kernel
     ogrecu::Scratch lane_ipal;      // the frame's palettes repacked for skin_lane_kernel
+    int profile_depth = 0;          // open ogrecu_profile_begin ranges
     int lane_reuse_repack = 0;      // measurement switch: ogrecu_anim_frame_dev keeps the previous call's repacked palettes
     void* pinned;               // pinned staging (host side)
     size_t pinned_cap;
@@ -133,6 +135,9 @@ namespace ogrecu {
 int scratch_reserve(ogrecu_ctx* ctx, Scratch& s, size_t bytes);
 int pinned_reserve(ogrecu_ctx* ctx, size_t bytes);
 inline void count_launch(ogrecu_ctx* ctx, unsigned n = 1) { ctx->launches += n; }
+// NVTX range over a scope (the library's own flushes)
+struct ProfileScope { explicit ProfileScope(const char* n) { nvtxRangePushA(n); } ~ProfileScope() { nvtxRangePop(); } };
+
 inline unsigned div_up(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
 int rt_release(ogrecu_rt* rt);
 // deferred work (optutil_host.cu / raster.cu)

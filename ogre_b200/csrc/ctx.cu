@@ -67,6 +67,28 @@ extern "C" {
 int ogrecu_abi_version(void) { return OGRECU_ABI_VERSION; }
 const char* ogrecu_last_error_string(void) { return g_err; }
 
+int ogrecu_profile_begin(ogrecu_ctx* ctx, const char* name)
+{
+    OGRECU_REQUIRE(ctx && name, "NULL argument");
+    nvtxRangePushA(name);
+    ++ctx->profile_depth;
+    return OGRECU_OK;
+}
+int ogrecu_profile_end(ogrecu_ctx* ctx)
+{
+    OGRECU_REQUIRE(ctx, "ctx is NULL");
+    OGRECU_REQUIRE(ctx->profile_depth > 0, "ogrecu_profile_end without a matching begin");
+    nvtxRangePop();
+    --ctx->profile_depth;
+    return OGRECU_OK;
+}
+int ogrecu_profile_mark(ogrecu_ctx* ctx, const char* name)
+{
+    OGRECU_REQUIRE(ctx && name, "NULL argument");
+    nvtxMarkA(name);
+    return OGRECU_OK;
+}
+
 int ogrecu_device_count(int* count)
 {
     OGRECU_REQUIRE(count, "count is NULL");

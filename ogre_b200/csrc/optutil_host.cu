@@ -158,6 +158,7 @@ int flush_skin_batch(ogrecu_ctx* ctx)
 {
     const uint32_t n = (uint32_t)ctx->batch_jobs.size();
     if (n == 0) return OGRECU_OK;
+    ProfileScope range("ogrecu: batched OptimisedUtil flush");
     OGRECU_CUDA(cudaSetDevice(ctx->device));
     const size_t jobs_bytes = up((size_t)n * sizeof(ogrecu_skin_job)), prefix_bytes = up(((size_t)n + 1) * 4);
     const size_t pal_bytes = ctx->batch_pal.size() * 4, total = jobs_bytes + prefix_bytes + pal_bytes;

@@ -1557,6 +1557,8 @@ int run_segment(ogrecu_ctx* ctx, ogrecu_rt* const* targets, uint32_t ntargets, c
 int rt_flush_cmds(ogrecu_rt* rt)
 {
     ogrecu_ctx* ctx = rt->ctx;
+    if (rt->cmds.empty() && ctx->batch_jobs.empty()) return OGRECU_OK;
+    ProfileScope range("ogrecu: target flush");
     OGRECU_CUDA(cudaSetDevice(ctx->device));
     OGRECU_CHECK(flush_skin_batch(ctx));     // queued OptimisedUtil jobs produce what the draws read
     std::vector<Item> seg;

@@ -105,9 +105,10 @@ public:
     void _setRenderTarget(RenderTarget* target) override;
     void bindGpuProgramParameters(GpuProgramType, const GpuProgramParametersPtr&, uint16) override {}
     void _setAlphaRejectSettings(CompareFunction func, unsigned char value, bool) override { mAlphaFunc = func; mAlphaRef = value; }
-    void beginProfileEvent(const String&) override {}
-    void endProfileEvent(void) override {}
-    void markProfileEvent(const String&) override {}
+    // NVTX ranges / markers around whatever the application brackets (OgreRenderSystem.h:1104-1115)
+    void beginProfileEvent(const String& eventName) override { if (mCtx) ogrecu_profile_begin(mCtx, eventName.c_str()); }
+    void endProfileEvent(void) override { if (mCtx) ogrecu_profile_end(mCtx); }
+    void markProfileEvent(const String& event) override { if (mCtx) ogrecu_profile_mark(mCtx, event.c_str()); }
 };
 } // namespace Ogre
 #endif

@@ -112,3 +112,17 @@ def test_partial_write_lock_after_a_pending_device_write_keeps_both(gpu_ctx):
     want[240:264] = 0xAB
     assert np.array_equal(r.dst.read(), want)
     r.free()
+
+
+def test_profile_events_nest_and_reject_an_unmatched_end(gpu_ctx):
+    """RenderSystem::beginProfileEvent / endProfileEvent / markProfileEvent (OgreRenderSystem.h:1104-1115) -> NVTX ranges: no tool
+    attached here, so only the bookkeeping is visible — nesting works and an end without a begin is an error, not a crash."""
+    from ogre_b200 import lib
+    L, h = lib(), gpu_ctx.handle
+    assert L.ogrecu_profile_begin(h, b"frame") == 0
+    assert L.ogrecu_profile_begin(h, b"shadow pass") == 0
+    assert L.ogrecu_profile_mark(h, b"marker") == 0
+    assert L.ogrecu_profile_end(h) == 0
+    assert L.ogrecu_profile_end(h) == 0
+    assert L.ogrecu_profile_end(h) != 0
+    assert b"without a matching begin" in L.ogrecu_last_error_string()
