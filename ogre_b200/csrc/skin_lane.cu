@@ -526,8 +526,11 @@ __global__ void __launch_bounds__(LN_THREADS, 1) skin_lane_kernel(const __grid_c
         // contiguous runs of quads per warp (consecutive vertices share bones: the matrix stays in registers).  (Handing the
         // quads out on demand through a shared-memory ticket evens the warps out but loses more in per-hand-out overhead:
         // 0.504 -> 0.527 ms on the bench step.)
+        // (the run a warp takes rotates from unit to unit: a chunk with fewer runs than warps leaves a different warp idle every time,
+        // and the idle one is already a unit ahead when its turn comes)
         const uint32_t per = (nquads + LN_WARPS - 1u) / LN_WARPS;
-        const uint32_t q0 = min(wid * per, nquads), q1 = min(q0 + per, nquads);
+        const uint32_t run = (wid + it * 4u) % LN_WARPS;
+        const uint32_t q0 = min(run * per, nquads), q1 = min(q0 + per, nquads);
         if (q0 < q1) {
             u64 T = 0;
             if (MORPH) T = reinterpret_cast<const u64*>(u_meta + 1)[lane];
@@ -718,7 +721,10 @@ int build_skin_plan(ogrecu_ctx* ctx, const uint8_t* blend_index, size_t index_st
                 return OGRECU_ERR_INVALID;
             }
     uint32_t v = 0;
+    uint32_t quad_limit = LN_CHUNK_QUADS;
     while (v < nverts) {
+        const uint32_t v_chunk = v;
+        bool cut_by_bones = false;
         Chunk c;
         memset(&c, 0, sizeof c);
         c.v_begin = v;
@@ -753,7 +759,7 @@ int build_skin_plan(ogrecu_ctx* ctx, const uint8_t* blend_index, size_t index_st
             const uint8_t* bi = blend_index + (size_t)(v - 1) * index_stride;
             for (uint32_t b = 0; b < nw; ++b) add_bone(bi[b]);
         }
-        while (c.nquads < LN_CHUNK_QUADS && v < nverts) {
+        while (c.nquads < quad_limit && v < nverts) {
             uint32_t add[16], nadd = 0;                 // bones the next quad brings in
             for (uint32_t u = v; u < v + 4 && u < nverts; ++u) {
                 const uint8_t* bi = blend_index + (size_t)u * index_stride;
@@ -766,6 +772,7 @@ int build_skin_plan(ogrecu_ctx* ctx, const uint8_t* blend_index, size_t index_st
             }
             if (nlocal + nadd > LN_MAXB) {
                 if (c.nquads == 0) { set_error("skin plan: one vertex quad references more than %d palette entries", LN_MAXB); return OGRECU_ERR_UNSUPPORTED; }
+                cut_by_bones = true;
                 break;
             }
             for (uint32_t q = 0; q < nadd; ++q) add_bone(add[q]);
@@ -773,6 +780,14 @@ int build_skin_plan(ogrecu_ctx* ctx, const uint8_t* blend_index, size_t index_st
             v = std::min(v + 4, nverts);
             c.nquads++;
         }
+        // The consumer warps split a chunk's quads evenly (LN_WARPS runs): a chunk the palette limit cut at, say, 22 quads would leave
+        // 8 of 15 warps with half the work of the others.  Cut it at the multiple of LN_WARPS below instead and start over there.
+        if (cut_by_bones && c.nquads > LN_WARPS && c.nquads % LN_WARPS != 0) {
+            quad_limit = c.nquads / LN_WARPS * LN_WARPS;
+            v = v_chunk;
+            continue;
+        }
+        quad_limit = LN_CHUNK_QUADS;
         c.nslots = nlocal;
         pre_recs.resize(pre_recs.size() + 8, 0);
         if (c.v_begin > 0) make_rec(c.v_begin - 1, &pre_recs[pre_recs.size() - 8]);

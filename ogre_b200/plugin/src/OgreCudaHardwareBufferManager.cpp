@@ -1,3 +1,4 @@
+#include "OgreCudaHostTiming.h"
 #include "OgreCudaHardwareBufferManager.h"
 #include "OgreCudaRenderSystem.h"
 #include "OgreDefaultHardwareBufferManager.h"
@@ -38,12 +39,17 @@ void* CudaHardwareBuffer::lockImpl(size_t offset, size_t length, LockOptions opt
     // Draws are only recorded by _render and softwareVertexSkinning calls may be queued; a lock that would let the host change
     // a buffer they reference (or read one they produce) runs them first.  libogrecu tracks which buffers recorded draws and
     // queued jobs touch (ogrecu_buf_map), so locking entity B's buffers does not flush entity A's draws.
+    OGRECU_TIME(HT_LOCK);
     void* p = 0;
     OGRECU_THROW_IF(ogrecu_buf_map(mBuf, offset, length, mapMode(options), &p));
     return p;
 }
 
-void CudaHardwareBuffer::unlockImpl(void) { OGRECU_THROW_IF(ogrecu_buf_unmap(mBuf)); }
+void CudaHardwareBuffer::unlockImpl(void)
+{
+    OGRECU_TIME(HT_UNLOCK);
+    OGRECU_THROW_IF(ogrecu_buf_unmap(mBuf));
+}
 
 void CudaHardwareBuffer::readData(size_t offset, size_t length, void* pDest)
 {

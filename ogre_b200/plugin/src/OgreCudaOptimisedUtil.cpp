@@ -1,3 +1,4 @@
+#include "OgreCudaHostTiming.h"
 #include "OgreCudaOptimisedUtil.h"
 #include "OgreCudaRenderSystem.h"
 #include "OgreEdgeListBuilder.h"
@@ -44,6 +45,7 @@ void CudaOptimisedUtil::softwareVertexSkinning(const float* srcPosPtr, float* de
                                                size_t destNormStride, size_t blendWeightStride, size_t blendIndexStride,
                                                size_t numWeightsPerVertex, size_t numVertices)
 {
+    OGRECU_TIME(HT_SKIN);
     OGRECU_THROW_IF(ogrecu_software_vertex_skinning_host(
         ctx(false), srcPosPtr, destPosPtr, srcNormPtr, destNormPtr, blendWeightPtr, blendIndexPtr,
         reinterpret_cast<const float* const*>(blendMatrices), srcPosStride, destPosStride, srcNormStride, destNormStride,
@@ -54,6 +56,7 @@ void CudaOptimisedUtil::softwareVertexMorph(float t, const float* srcPos1, const
                                             size_t pos1VSize, size_t pos2VSize, size_t dstVSize, size_t numVertices,
                                             bool morphNormals)
 {
+    OGRECU_TIME(HT_OTHER_UTIL);
     OGRECU_THROW_IF(ogrecu_software_vertex_morph_host(ctx(), t, srcPos1, srcPos2, dstPos, pos1VSize, pos2VSize, dstVSize,
                                                       numVertices, morphNormals ? 1 : 0));
 }

@@ -1,3 +1,4 @@
+#include "OgreCudaHostTiming.h"
 #include "OgreCudaRenderSystem.h"
 
 #include "OgreCudaDepthBuffer.h"
@@ -227,6 +228,7 @@ void CudaRenderSystem::flushPendingDraws()
 {
     CudaRenderSystem* rs = msInstance;
     if (!rs) return;
+    OGRECU_TIME(HT_FLUSH);
     if (rs->mCtx) OGRECU_THROW_IF(ogrecu_optutil_flush(rs->mCtx));   // queued OptimisedUtil jobs: callers are about to use raw device data
     if (rs->mDirtyTargets.empty()) return;
     std::vector<ogrecu_rt*> targets;
@@ -253,6 +255,7 @@ void CudaRenderSystem::forgetTarget(ogrecu_rt* rt, ogrecu_rt* replacement)
 
 void CudaRenderSystem::_endFrame(void)
 {
+    OGRECU_TIME(HT_END_FRAME);
     // launch the frame's recorded work now; it runs asynchronously while OgreMain goes on
     // (Root::_fireFrameRenderingQueued, OgreRoot.cpp:1156, is the designed overlap window)
     flushPendingDraws();
@@ -314,6 +317,7 @@ Stream deviceStream(const RenderOperation& op, VertexElementSemantic sem)
 
 void CudaRenderSystem::_render(const RenderOperation& op)
 {
+    OGRECU_TIME(HT_RENDER);
     RenderSystem::_render(op);   // face / batch / vertex statistics (OgreMain/src/OgreRenderSystem.cpp:622)
 
     bool isStrip = op.operationType == RenderOperation::OT_TRIANGLE_STRIP;
@@ -506,3 +510,15 @@ void CudaRenderSystem::readColourScaled(ogrecu_rt* rt, const Box& src, const Pix
     PixelUtil::bulkPixelConversion(box, dst);
 }
 } // namespace Ogre
+
+#ifdef OGRECU_HOST_TIMING
+namespace Ogre { uint64_t HostTimer::acc[HT_COUNT] = {}; uint64_t HostTimer::calls[HT_COUNT] = {}; }
+// ticks and calls per bucket since the last read (buckets: render, skin, other OptimisedUtil, lock, unlock, flush, endFrame)
+extern "C" __attribute__((visibility("default"))) void ogrecu_plugin_host_timing(uint64_t* acc, uint64_t* calls)
+{
+    for (int i = 0; i < Ogre::HT_COUNT; ++i) {
+        acc[i] = Ogre::HostTimer::acc[i]; calls[i] = Ogre::HostTimer::calls[i];
+        Ogre::HostTimer::acc[i] = 0; Ogre::HostTimer::calls[i] = 0;
+    }
+}
+#endif
