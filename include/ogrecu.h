@@ -38,7 +38,7 @@ extern "C" {
 #define OGRECU_API
 #endif
 
-#define OGRECU_ABI_VERSION 5
+#define OGRECU_ABI_VERSION 6
 
 typedef enum ogrecu_status {
     OGRECU_OK = 0,
@@ -75,6 +75,25 @@ OGRECU_API int ogrecu_init(int device, ogrecu_ctx** out_ctx);
 OGRECU_API int ogrecu_shutdown(ogrecu_ctx* ctx);
 OGRECU_API int ogrecu_device(const ogrecu_ctx* ctx, int* device);
 
+/* DEVICE GROUP: one context that drives `num_devices` GPUs of this node from one process (what a C++ OGRE application that
+ * loads the plugin has: RenderSystem config options "Devices" / "Split Frame", OgreMain/src/OgreRenderSystem.cpp:834 is the hook).
+ * devices[0] is the ROOT: buffers, textures, every OptimisedUtil / skeleton / shadow entry point and the host-facing copies run
+ * there, exactly as on a single-device context.  The other devices are PEERS that only run raster passes:
+ *   - ogrecu_buf / ogrecu_tex objects get a replica on every peer; a replica is brought up to date by a peer copy over NVLink
+ *     (only the byte range that changed on the root since the last time) when a draw that runs on that peer references it;
+ *     device pointers that are not inside an ogrecu_buf are read in place through peer access;
+ *   - a render target lives on one device (ogrecu_rt_create_placed, placement = index into `devices`): its draws, clears and
+ *     read-backs run on that device, so independent targets (the batched offscreen views of BASELINE config 4,
+ *     ogrecu_draw_views) spread over the group without any exchange;
+ *   - or it is SPLIT (placement = OGRECU_PLACE_SPLIT): the planes live on the root, the frame's tile rows are dealt out in
+ *     interleaved bands ("split_band_tiles" tile rows each, band b -> device b mod num_devices), every device runs the per-triangle
+ *     set-up for its own bands and rasterises them STRAIGHT INTO THE ROOT'S PLANES through peer stores — there is no composite
+ *     pass and no exchange step; the root's stream continues when all devices have finished (BASELINE config 5).
+ * Results are identical to a single-device context's.  Requires peer access between all members (OGRECU_ERR_UNSUPPORTED
+ * otherwise).  All members are shut down with the root.  The threading contract is that of a single context. */
+OGRECU_API int ogrecu_init_devices(int num_devices, const int* devices, ogrecu_ctx** out_ctx);
+OGRECU_API int ogrecu_num_devices(const ogrecu_ctx* ctx, int* num_devices);
+
 /* Launch on an externally owned cudaStream_t (e.g. the bench's timing stream).  Passing
  * NULL restores the context's own stream. */
 OGRECU_API int ogrecu_set_stream(ogrecu_ctx* ctx, void* cuda_stream);
@@ -97,6 +116,7 @@ OGRECU_API uint64_t ogrecu_launch_count(const ogrecu_ctx* ctx);
  *                pointers call ogrecu_optutil_flush in between.
  *   "lane_reuse_repack" 1 = ogrecu_anim_frame_dev skips its palette repack launch and reads the previous call's (valid only while
  *                the palettes are unchanged: lets a benchmark time the lane kernel alone), 0 = default
+ *   "split_band_tiles" tile rows (16 pixels each) per interleaved band of the split targets created afterwards (default 4)
  *   "raster_mode" 0 = auto (per tile: order-independent visibility resolve where it is provably
  *                equivalent to Tiny's in-order loop, else in-order), 1 = always in-order
  *   "raster_xf"  1 = transform every vertex once per flush when the draw gives vertex_count (default),
@@ -445,6 +465,10 @@ OGRECU_API int ogrecu_tex_copy_from_rt(ogrecu_tex* tex, ogrecu_rt* rt);
 /* Render target = TinyWindow colour Image (PF_BYTE_RGB, tightly packed,
  * OgreTinyWindow.cpp:38-42) + TinyDepthBuffer Image (PF_FLOAT32_R, OgreTinyDepthBuffer.h:20). */
 OGRECU_API int ogrecu_rt_create(ogrecu_ctx* ctx, uint32_t width, uint32_t height, ogrecu_rt** out);
+/* ... on device `placement` of the context's device group (0 = the root = what ogrecu_rt_create does), or split over all of its
+ * devices (see ogrecu_init_devices).  On a single-device context OGRECU_PLACE_SPLIT and 0 both give an ordinary target. */
+#define OGRECU_PLACE_SPLIT (-1)
+OGRECU_API int ogrecu_rt_create_placed(ogrecu_ctx* ctx, uint32_t width, uint32_t height, int placement, ogrecu_rt** out);
 OGRECU_API int ogrecu_rt_destroy(ogrecu_rt* rt);
 OGRECU_API int ogrecu_rt_size(const ogrecu_rt* rt, uint32_t* width, uint32_t* height);
 

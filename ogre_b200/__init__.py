@@ -94,11 +94,20 @@ class DeviceBuffer:
 class Context:
     """One CUDA device (ogrecu_ctx).  Raises OgrecuError when no device is usable."""
 
-    def __init__(self, device=0):
+    def __init__(self, device=0, devices=None):
+        """device: one CUDA device; devices=[d0, d1, ...]: a device group driven from this process (ogrecu_init_devices: d0 is the
+        root, the others take raster passes of placed / split targets)."""
         h = C.c_void_p()
-        check(lib().ogrecu_init(int(device), C.byref(h)))
+        if devices is not None:
+            devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+            check(lib().ogrecu_init_devices(len(devices), devs, C.byref(h)))
+            self.device = int(devices[0])
+            self.num_devices = len(devices)
+        else:
+            check(lib().ogrecu_init(int(device), C.byref(h)))
+            self.device = int(device)
+            self.num_devices = 1
         self.handle = h.value
-        self.device = int(device)
 
     def close(self):
         if self.handle:
@@ -169,6 +178,13 @@ class HardwareBuffer:
         out = self.lock(MAP_READ, offset, length).copy()
         self.unlock()
         return out
+
+    @property
+    def device_ptr(self):
+        """address of the device copy (draw descriptions, *_dev entry points)"""
+        p = C.c_void_p()
+        check(lib().ogrecu_buf_device_ptr(self.handle, C.byref(p)))
+        return p.value
 
     def shadow_address(self):
         a = self.lock(MAP_READ, 0, 0 if self.nbytes == 0 else 1).ctypes.data
@@ -337,13 +353,20 @@ class Texture:
             self.handle = None
 
 
+PLACE_SPLIT = -1
+
+
 class RenderTarget:
     """RGB8 colour + f32 depth planes (TinyWindow + TinyDepthBuffer)."""
 
-    def __init__(self, ctx, width, height):
+    def __init__(self, ctx, width, height, placement=None):
+        """placement (device groups): None / 0 = on the root, k = on device k of the group, PLACE_SPLIT = split over all devices"""
         self.ctx, self.width, self.height = ctx, int(width), int(height)
         h = C.c_void_p()
-        check(lib().ogrecu_rt_create(ctx.handle, self.width, self.height, C.byref(h)))
+        if placement is None:
+            check(lib().ogrecu_rt_create(ctx.handle, self.width, self.height, C.byref(h)))
+        else:
+            check(lib().ogrecu_rt_create_placed(ctx.handle, self.width, self.height, int(placement), C.byref(h)))
         self.handle = h.value
 
     def destroy(self):

@@ -89,6 +89,9 @@ SIGNATURES = {
     "ogrecu_device_count": (C.c_int, [C.POINTER(C.c_int)]),
     "ogrecu_init": (C.c_int, [C.c_int, c_void_pp]),
     "ogrecu_shutdown": (C.c_int, [C.c_void_p]),
+    "ogrecu_init_devices": (C.c_int, [C.c_int, C.POINTER(C.c_int), c_void_pp]),
+    "ogrecu_num_devices": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
+    "ogrecu_rt_create_placed": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, c_void_pp]),
     "ogrecu_device": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
     "ogrecu_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ogrecu_get_stream": (C.c_void_p, [C.c_void_p]),

@@ -41,10 +41,16 @@ struct Scratch {
 
 }  // namespace ogrecu
 
+constexpr int OGRECU_MAX_PEERS = 7;      // a device group is at most 8 devices: the root and seven peers
+
 struct ogrecu_buf {
     ogrecu_ctx* ctx;
     size_t size;
     void* dev;          // device storage
+    // device group (ogrecu_init_devices): one replica per peer device, brought up to date over NVLink when a draw that runs on
+    // that peer references the buffer.  [peer_lo, peer_hi) = bytes of the root copy the replica has not seen yet.
+    void* peer_dev[OGRECU_MAX_PEERS];
+    size_t peer_lo[OGRECU_MAX_PEERS], peer_hi[OGRECU_MAX_PEERS];
     uint8_t* shadow;    // pinned host shadow (allocated lazily on first map)
     bool mapped;
     int map_mode;
@@ -70,10 +76,19 @@ struct ogrecu_tex {
     uint32_t w, h;
     uint8_t* dev;       // RGBA8, tightly packed
     int has_zero_alpha; // any texel with alpha == 0 (enables the discard test)
+    uint8_t* peer_dev[OGRECU_MAX_PEERS];     // device group: replicas, whole-texture refresh when stale
+    bool peer_stale[OGRECU_MAX_PEERS];
 };
 
 struct ogrecu_ctx {
     int device;
+    // device group (ogrecu_init_devices): the root context owns the buffers, textures, OptimisedUtil work and the host-facing
+    // API; each peer is a full context of its own device (stream, scratch arenas) that only ever runs raster passes
+    ogrecu_ctx* root = nullptr;             // peers: the group's root; the root and single-device contexts: NULL
+    std::vector<ogrecu_ctx*> peers;         // root: the other devices, peers[k - 1] = device index k of the group
+    int dev_index = 0;                      // position in the group (0 = root)
+    cudaEvent_t group_ev = nullptr;         // "this context's stream got here": cross-device ordering
+    int split_band_tiles = 4;               // split targets: tile rows per interleaved band
     cudaStream_t own_stream;
     cudaStream_t stream;        // current launch stream (own or external)
     uint64_t launches;
@@ -132,14 +147,28 @@ struct ogrecu_ctx {
 };
 
 namespace ogrecu {
+inline ogrecu_ctx* root_of(ogrecu_ctx* ctx) { return ctx->root ? ctx->root : ctx; }
+// `other`'s stream continues only after everything `ctx`'s stream has been given so far
+int stream_wait(ogrecu_ctx* other, ogrecu_ctx* ctx);
+// the address `p` of the root's memory as device `peer` should read it: inside an ogrecu_buf -> the peer's replica, refreshed on
+// the peer's stream if stale (call stream_wait(peer, root) first); anything else -> unchanged (peer access over NVLink)
+int replica_ptr(ogrecu_ctx* peer, const void* p, const void** out);
+int replica_tex(ogrecu_ctx* peer, ogrecu_tex* t, const uint8_t** out);
 int scratch_reserve(ogrecu_ctx* ctx, Scratch& s, size_t bytes);
 int pinned_reserve(ogrecu_ctx* ctx, size_t bytes);
 inline void count_launch(ogrecu_ctx* ctx, unsigned n = 1) { ctx->launches += n; }
+// the current device for a scope (targets placed on a peer of a device group are served on that peer); restored on exit
+struct DeviceScope {
+    int prev = -1;
+    explicit DeviceScope(int d) { int cur = -1; cudaGetDevice(&cur); if (cur != d) { prev = cur; cudaSetDevice(d); } }
+    ~DeviceScope() { if (prev >= 0) cudaSetDevice(prev); }
+};
 // NVTX range over a scope (the library's own flushes)
 struct ProfileScope { explicit ProfileScope(const char* n) { nvtxRangePushA(n); } ~ProfileScope() { nvtxRangePop(); } };
 
 inline unsigned div_up(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
 int rt_release(ogrecu_rt* rt);
+void free_raster_scratch(ogrecu_ctx* ctx);                   // the context's raster arenas (no-op when it has none)
 // deferred work (optutil_host.cu / raster.cu)
 int flush_skin_batch(ogrecu_ctx* ctx);                       // run the queued OptimisedUtil jobs now (no-op when empty)
 int flush_all_targets(ogrecu_ctx* ctx);                      // run every target's recorded draws (the queued jobs first)

@@ -62,6 +62,61 @@ int pinned_reserve(ogrecu_ctx* ctx, size_t bytes)
 
 using namespace ogrecu;
 
+
+// bytes [lo, hi) of the root copy changed: every peer replica has to fetch them before its next use
+static void replicas_stale(ogrecu_buf* b, size_t lo, size_t hi)
+{
+    const size_t n = b->ctx->peers.size();
+    for (size_t k = 0; k < n; ++k) {
+        if (b->peer_lo[k] >= b->peer_hi[k]) { b->peer_lo[k] = lo; b->peer_hi[k] = hi; }
+        else { b->peer_lo[k] = std::min(b->peer_lo[k], lo); b->peer_hi[k] = std::max(b->peer_hi[k], hi); }
+    }
+}
+
+namespace ogrecu {
+int stream_wait(ogrecu_ctx* other, ogrecu_ctx* ctx)
+{
+    OGRECU_CUDA(cudaSetDevice(ctx->device));
+    OGRECU_CUDA(cudaEventRecord(ctx->group_ev, ctx->stream));
+    OGRECU_CUDA(cudaSetDevice(other->device));
+    OGRECU_CUDA(cudaStreamWaitEvent(other->stream, ctx->group_ev, 0));
+    return OGRECU_OK;
+}
+
+int replica_ptr(ogrecu_ctx* peer, const void* p, const void** out)
+{
+    *out = p;
+    ogrecu_ctx* root = peer->root;
+    if (!root || !p) return OGRECU_OK;
+    ogrecu_buf* b = buf_of_device_ptr(root, p);
+    if (!b) return OGRECU_OK;                                   // not one of our buffers: the peer reads the root's memory directly
+    const int k = peer->dev_index - 1;
+    if (b->peer_lo[k] < b->peer_hi[k]) {
+        OGRECU_CUDA(cudaSetDevice(peer->device));
+        OGRECU_CUDA(cudaMemcpyPeerAsync((uint8_t*)b->peer_dev[k] + b->peer_lo[k], peer->device, (const uint8_t*)b->dev + b->peer_lo[k], root->device,
+                                        b->peer_hi[k] - b->peer_lo[k], peer->stream));
+        b->peer_lo[k] = b->peer_hi[k] = 0;
+    }
+    *out = (const uint8_t*)b->peer_dev[k] + ((const uint8_t*)p - (const uint8_t*)b->dev);
+    return OGRECU_OK;
+}
+
+int replica_tex(ogrecu_ctx* peer, ogrecu_tex* t, const uint8_t** out)
+{
+    *out = t ? t->dev : nullptr;
+    if (!t || !peer->root) return OGRECU_OK;
+    const int k = peer->dev_index - 1;
+    if (!t->peer_dev[k]) return OGRECU_OK;                      // created before the group existed: read it over NVLink
+    if (t->peer_stale[k]) {
+        OGRECU_CUDA(cudaSetDevice(peer->device));
+        OGRECU_CUDA(cudaMemcpyPeerAsync(t->peer_dev[k], peer->device, t->dev, peer->root->device, (size_t)t->w * t->h * 4, peer->stream));
+        t->peer_stale[k] = false;
+    }
+    *out = t->peer_dev[k];
+    return OGRECU_OK;
+}
+}  // namespace ogrecu
+
 extern "C" {
 
 int ogrecu_abi_version(void) { return OGRECU_ABI_VERSION; }
@@ -141,12 +196,71 @@ int ogrecu_init(int device, ogrecu_ctx** out_ctx)
     return OGRECU_OK;
 }
 
+int ogrecu_init_devices(int num_devices, const int* devices, ogrecu_ctx** out_ctx)
+{
+    OGRECU_REQUIRE(out_ctx && devices, "NULL argument");
+    *out_ctx = nullptr;
+    OGRECU_REQUIRE(num_devices >= 1 && num_devices <= OGRECU_MAX_PEERS + 1, "1..8 devices per group");
+    for (int a = 0; a < num_devices; ++a)
+        for (int b = 0; b < a; ++b) OGRECU_REQUIRE(devices[a] != devices[b], "a device appears twice in the group");
+    std::vector<ogrecu_ctx*> all;
+    auto undo = [&]() { for (ogrecu_ctx* c : all) { c->root = nullptr; c->peers.clear(); ogrecu_shutdown(c); } };
+    for (int k = 0; k < num_devices; ++k) {
+        ogrecu_ctx* c = nullptr;
+        const int rc = ogrecu_init(devices[k], &c);
+        if (rc != OGRECU_OK) { undo(); return rc; }
+        c->dev_index = k;
+        all.push_back(c);
+    }
+    // every device reads and writes every other's memory directly (NVLink / NVSwitch): the split targets' planes live on the root
+    // and the peers rasterise into them, replicas are refreshed by peer copies, raw device pointers stay valid group-wide
+    for (int a = 0; a < num_devices; ++a)
+        for (int b = 0; b < num_devices; ++b) {
+            if (a == b) continue;
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, devices[a], devices[b]);
+            if (!can) {
+                set_error("ogrecu_init_devices: device %d cannot access device %d's memory (no peer access)", devices[a], devices[b]);
+                undo();
+                return OGRECU_ERR_UNSUPPORTED;
+            }
+            cudaSetDevice(devices[a]);
+            const cudaError_t e = cudaDeviceEnablePeerAccess(devices[b], 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { undo(); return cuda_fail(e, "cudaDeviceEnablePeerAccess", __FILE__, __LINE__); }
+            cudaGetLastError();
+        }
+    for (int k = 0; k < num_devices; ++k) {
+        cudaSetDevice(devices[k]);
+        const cudaError_t e = cudaEventCreateWithFlags(&all[k]->group_ev, cudaEventDisableTiming);
+        if (e != cudaSuccess) { undo(); return cuda_fail(e, "cudaEventCreate", __FILE__, __LINE__); }
+        if (k) { all[k]->root = all[0]; all[0]->peers.push_back(all[k]); }
+    }
+    cudaSetDevice(devices[0]);
+    *out_ctx = all[0];
+    return OGRECU_OK;
+}
+
+int ogrecu_num_devices(const ogrecu_ctx* ctx, int* num_devices)
+{
+    OGRECU_REQUIRE(ctx && num_devices, "NULL argument");
+    *num_devices = 1 + (int)root_of(const_cast<ogrecu_ctx*>(ctx))->peers.size();
+    return OGRECU_OK;
+}
+
 int ogrecu_shutdown(ogrecu_ctx* ctx)
 {
     if (!ctx) return OGRECU_OK;
+    if (ctx->root) { set_error("ogrecu_shutdown: shut the group's root context down, not a peer"); return OGRECU_ERR_INVALID; }
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    while (!ctx->targets.empty()) rt_release(ctx->targets.back());
+    while (!ctx->targets.empty()) rt_release(ctx->targets.back());      // split targets first: their aliases name the peers
+    {
+        std::vector<ogrecu_ctx*> peers;
+        peers.swap(ctx->peers);
+        for (ogrecu_ctx* p : peers) { p->root = nullptr; ogrecu_shutdown(p); }
+    }
+    cudaSetDevice(ctx->device);
+    free_raster_scratch(ctx);
     for (Scratch* s : {&ctx->jobs, &ctx->stage_in, &ctx->stage_out, &ctx->lane_counter, &ctx->lane_ipal, &ctx->batch_dev})
         if (s->ptr) cudaFree(s->ptr);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
@@ -158,6 +272,7 @@ int ogrecu_shutdown(ogrecu_ctx* ctx)
         if (ctx->side_join[k]) cudaEventDestroy(ctx->side_join[k]);
     }
     if (ctx->side_fork) cudaEventDestroy(ctx->side_fork);
+    if (ctx->group_ev) cudaEventDestroy(ctx->group_ev);
     cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return OGRECU_OK;
@@ -185,7 +300,12 @@ int ogrecu_sync(ogrecu_ctx* ctx)
 {
     OGRECU_REQUIRE(ctx, "ctx is NULL");
     OGRECU_CUDA(cudaSetDevice(ctx->device));
-    OGRECU_CHECK(flush_skin_batch(ctx));
+    OGRECU_CHECK(flush_skin_batch(root_of(ctx)));
+    for (ogrecu_ctx* p : ctx->peers) {
+        OGRECU_CUDA(cudaSetDevice(p->device));
+        OGRECU_CUDA(cudaStreamSynchronize(p->stream));
+    }
+    OGRECU_CUDA(cudaSetDevice(ctx->device));
     OGRECU_CUDA(cudaStreamSynchronize(ctx->stream));
     return OGRECU_OK;
 }
@@ -205,6 +325,7 @@ int ogrecu_set_config_option(ogrecu_ctx* ctx, const char* name, int value)
         return OGRECU_OK;
     }
     if (!strcmp(name, "lane_reuse_repack")) { OGRECU_REQUIRE(value >= 0 && value <= 1, "lane_reuse_repack is 0..1"); ctx->lane_reuse_repack = value; return OGRECU_OK; }
+    if (!strcmp(name, "split_band_tiles")) { OGRECU_REQUIRE(value >= 1 && value <= 1024, "split_band_tiles is 1..1024"); ctx->split_band_tiles = value; return OGRECU_OK; }
     if (!strcmp(name, "skin_ipc")) { OGRECU_REQUIRE(value >= 0 && value <= 4096, "skin_ipc is 0..4096"); ctx->skin_ipc = value; return OGRECU_OK; }
     set_error("ogrecu_set_config_option: unknown option '%s'", name);
     return OGRECU_ERR_INVALID;
@@ -309,6 +430,17 @@ int ogrecu_buf_create(ogrecu_ctx* ctx, size_t bytes, ogrecu_buf** out)
     if (e != cudaSuccess) { cudaFree(b->dev); delete b; return cuda_fail(e, "cudaHostAlloc(shadow)", __FILE__, __LINE__); }
     e = cudaEventCreateWithFlags(&b->upload_ev, cudaEventDisableTiming);
     if (e != cudaSuccess) { cudaFree(b->dev); cudaFreeHost(b->shadow); delete b; return cuda_fail(e, "cudaEventCreate", __FILE__, __LINE__); }
+    for (size_t k = 0; k < ctx->peers.size(); ++k) {             // device group: a replica on every peer, filled on first use
+        cudaSetDevice(ctx->peers[k]->device);
+        e = cudaMalloc(&b->peer_dev[k], bytes ? bytes : 1);
+        if (e != cudaSuccess) {
+            for (size_t q = 0; q < k; ++q) { cudaSetDevice(ctx->peers[q]->device); cudaFree(b->peer_dev[q]); }
+            cudaSetDevice(ctx->device);
+            cudaFree(b->dev); cudaFreeHost(b->shadow); cudaEventDestroy(b->upload_ev); delete b;
+            return cuda_fail(e, "cudaMalloc(buffer replica)", __FILE__, __LINE__);
+        }
+    }
+    if (!ctx->peers.empty()) cudaSetDevice(ctx->device);
     { std::lock_guard<std::mutex> g(ctx->shadows_mutex); ctx->shadows[(uintptr_t)b->shadow] = b; ctx->dev_registry[(uintptr_t)b->dev] = b; }
     *out = b;
     return OGRECU_OK;
@@ -322,6 +454,12 @@ int ogrecu_buf_destroy(ogrecu_buf* b)
     if (b->draw_ref == ctx->draw_epoch) flush_all_targets(ctx);          // recorded draws still read it
     if (b->batch_r == ctx->batch_epoch || b->batch_w == ctx->batch_epoch) flush_skin_batch(ctx);
     OGRECU_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (size_t k = 0; k < ctx->peers.size(); ++k) {
+        cudaSetDevice(ctx->peers[k]->device);
+        cudaStreamSynchronize(ctx->peers[k]->stream);
+        cudaFree(b->peer_dev[k]);
+    }
+    if (!ctx->peers.empty()) cudaSetDevice(ctx->device);
     { std::lock_guard<std::mutex> g(ctx->shadows_mutex); ctx->shadows.erase((uintptr_t)b->shadow); ctx->dev_registry.erase((uintptr_t)b->dev); }
     cudaFree(b->dev);
     cudaFreeHost(b->shadow);
@@ -343,6 +481,7 @@ int ogrecu_buf_mark_device_dirty(ogrecu_buf* b, size_t offset, size_t length)
 {
     OGRECU_REQUIRE(b && offset <= b->size && length <= b->size - offset, "range out of bounds");
     if (!length) return OGRECU_OK;
+    replicas_stale(b, offset, offset + length);
     if (!b->dev_dirty) { b->dev_dirty = true; b->dev_dirty_lo = offset; b->dev_dirty_hi = offset + length; }
     else {
         if (offset < b->dev_dirty_lo) b->dev_dirty_lo = offset;
@@ -412,6 +551,7 @@ int ogrecu_buf_unmap(ogrecu_buf* b)
         for (auto& pc : piece)
             if (pc[1] > pc[0]) {
                 OGRECU_CUDA(cudaMemcpyAsync((uint8_t*)b->dev + pc[0], b->shadow + pc[0], pc[1] - pc[0], cudaMemcpyHostToDevice, ctx->stream));
+                replicas_stale(b, pc[0], pc[1]);
                 any = true;
             }
         if (any) {

@@ -1316,6 +1316,10 @@ struct ogrecu_rt {
     float* depth;
     uint32_t strip_y0, strip_y1;     // pixel rows rasterised here (multiples of TILE, or h)
     uint32_t band_tiles = 1, band_phase = 0, band_period = 1;   // interleaved bands of tile rows (period 1 = every band)
+    // device group: a SPLIT target's planes live on the root; aliases[k - 1] describes the same planes to peer k, which rasterises
+    // the bands it owns straight into them over NVLink (no composite pass).  A PLACED target lives wholly on one peer (ctx = that peer).
+    bool split = false;
+    std::vector<ogrecu_rt*> aliases;
     std::vector<Cmd> cmds;
     ogrecu_raster_stats stats;
     int stats_slot;          // index of this target in the last segment's counter table
@@ -1360,9 +1364,25 @@ uint32_t tri_count_of(const ogrecu_draw_desc& d)
 struct Item { const ogrecu_draw_desc* desc; uint32_t target; const float* mvp; const float* mvit; const float* light; const ogrecu_draw_state* state; };
 
 // Run the pipeline for `items` (draws in submission order) over `targets` (same size).
-int run_segment(ogrecu_ctx* ctx, ogrecu_rt* const* targets, uint32_t ntargets, const std::vector<Item>& items)
+// One pipeline pass over `items` on `ctx`, in two host phases so that the devices of a group overlap: segment_begin enqueues
+// everything up to the count pass and the read-back of its two totals, segment_finish waits for them, sizes the record and
+// pair arrays and enqueues the rest.
+struct SegRun {
+    ogrecu_ctx* ctx = nullptr;
+    std::vector<ogrecu_rt*> targets;
+    SegParams P;
+    uint32_t* ctl_host = nullptr;
+    uint32_t nblocks = 0, nkeys = 0;
+    bool live = false;          // segment_finish has work to do
+};
+
+int segment_begin(ogrecu_ctx* ctx, ogrecu_rt* const* targets, uint32_t ntargets, const std::vector<Item>& items, SegRun& run)
 {
+    run.live = false;
+    run.ctx = ctx;
+    run.targets.assign(targets, targets + ntargets);
     if (items.empty()) return OGRECU_OK;
+    OGRECU_CUDA(cudaSetDevice(ctx->device));
     RasterScratch& S = scratch_map()[ctx];
     ogrecu_rt* rt0 = targets[0];
     const uint32_t W = rt0->w, H = rt0->h;
@@ -1395,7 +1415,10 @@ int run_segment(ogrecu_ctx* ctx, ogrecu_rt* const* targets, uint32_t ntargets, c
             o.vertex_count = d.vertex_count;
             nverts64 += d.vertex_count;
         }
-        if (d.texture) { o.tex = d.texture->dev; o.tex_w = d.texture->w; o.tex_h = d.texture->h; o.tex_zero_alpha = d.texture->has_zero_alpha; }
+        if (d.texture) {
+            OGRECU_CHECK(replica_tex(ctx, const_cast<ogrecu_tex*>(d.texture), &o.tex));                 // a peer of a device group samples its own replica
+            o.tex_w = d.texture->w; o.tex_h = d.texture->h; o.tex_zero_alpha = d.texture->has_zero_alpha;
+        }
         memcpy(o.mvp, items[k].mvp ? items[k].mvp : d.mvp, 64);
         memcpy(o.texm, d.tex_matrix, 64);
         memcpy(o.vp, d.viewport, 64);
@@ -1479,6 +1502,25 @@ int run_segment(ogrecu_ctx* ctx, ogrecu_rt* const* targets, uint32_t ntargets, c
     OGRECU_CUDA(cudaGetLastError());
     count_launch(ctx, 2);
     OGRECU_CUDA(cudaMemcpyAsync(ctl_host, P.ctl, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    run.P = P; run.ctl_host = ctl_host; run.nblocks = nblocks; run.nkeys = nkeys;
+    run.live = true;
+    return OGRECU_OK;
+}
+
+int segment_finish(SegRun& run)
+{
+    if (!run.live) return OGRECU_OK;
+    run.live = false;
+    ogrecu_ctx* ctx = run.ctx;
+    ogrecu_rt* const* targets = run.targets.data();
+    const uint32_t ntargets = (uint32_t)run.targets.size();
+    ogrecu_rt* rt0 = targets[0];
+    SegParams& P = run.P;
+    uint32_t* ctl_host = run.ctl_host;
+    const uint32_t nblocks = run.nblocks, nkeys = run.nkeys, ntris = P.ntris;
+    const uint32_t W = P.width, H = P.height, tiles_x = P.tiles_x, tiles_y = P.tiles_y, strip_ty0 = P.strip_ty0, strip_ty1 = P.strip_ty1;
+    OGRECU_CUDA(cudaSetDevice(ctx->device));
+    RasterScratch& S = scratch_map()[ctx];
     OGRECU_CUDA(cudaStreamSynchronize(ctx->stream));
     const uint64_t npairs = ctl_host[2], nsurv = ctl_host[3];
     OGRECU_REQUIRE(npairs < 0xffffffffull, "too many (triangle, tile) pairs in one flush");
@@ -1554,25 +1596,104 @@ int run_segment(ogrecu_ctx* ctx, ogrecu_rt* const* targets, uint32_t ntargets, c
     return OGRECU_OK;
 }
 
+int run_segment(ogrecu_ctx* ctx, ogrecu_rt* const* targets, uint32_t ntargets, const std::vector<Item>& items)
+{
+    SegRun run;
+    OGRECU_CHECK(segment_begin(ctx, targets, ntargets, items, run));
+    return segment_finish(run);
+}
+
+// The draw descriptions of a segment as device `dev` reads them: pointers into ogrecu_bufs become the peer's replicas (refreshed
+// on its stream when stale), textures are replaced inside segment_begin, anything else is read in place over NVLink.
+struct PeerSeg {
+    std::vector<ogrecu_draw_desc> descs;
+    std::vector<ogrecu_draw_state> states;
+    std::vector<Item> items;
+};
+int translate_segment(ogrecu_ctx* dev, const std::vector<Item>& seg, PeerSeg& out)
+{
+    out.descs.resize(seg.size()); out.states.resize(seg.size()); out.items = seg;
+    for (size_t i = 0; i < seg.size(); ++i) {
+        ogrecu_draw_desc& d = out.descs[i];
+        d = *seg[i].desc;
+        OGRECU_CHECK(replica_ptr(dev, d.positions, &d.positions));
+        OGRECU_CHECK(replica_ptr(dev, d.uvs, &d.uvs));
+        OGRECU_CHECK(replica_ptr(dev, d.normals, &d.normals));
+        OGRECU_CHECK(replica_ptr(dev, d.indices, &d.indices));
+        out.items[i].desc = &d;
+        if (seg[i].state) {
+            out.states[i] = *seg[i].state;
+            if (out.states[i].enable & OGRECU_EXT_VERTEX_COLOUR) OGRECU_CHECK(replica_ptr(dev, out.states[i].colours, &out.states[i].colours));
+            out.items[i].state = &out.states[i];
+        }
+    }
+    return OGRECU_OK;
+}
+
+// One segment of one target on every device that takes part in it: the target's own context, or — for a split target — the
+// root and all peers, each on the bands it owns.  Both host phases run device by device, so the devices' passes overlap.
+int run_segment_group(ogrecu_rt* rt, const std::vector<Item>& seg)
+{
+    if (seg.empty()) return OGRECU_OK;
+    ogrecu_ctx* ctx = rt->ctx;
+    if (!rt->split && !ctx->root) { ogrecu_rt* one[1] = {rt}; return run_segment(ctx, one, 1, seg); }
+    std::vector<ogrecu_rt*> parts;
+    parts.push_back(rt);
+    for (ogrecu_rt* a : rt->aliases) parts.push_back(a);
+    std::vector<SegRun> runs(parts.size());
+    std::vector<PeerSeg> tr(parts.size());
+    int rc = OGRECU_OK;
+    for (size_t k = 0; k < parts.size() && rc == OGRECU_OK; ++k) {
+        ogrecu_ctx* dev = parts[k]->ctx;
+        ogrecu_rt* one[1] = {parts[k]};
+        if (dev->root) {
+            rc = translate_segment(dev, seg, tr[k]);
+            if (rc == OGRECU_OK) rc = segment_begin(dev, one, 1, tr[k].items, runs[k]);
+        } else rc = segment_begin(dev, one, 1, seg, runs[k]);
+    }
+    for (size_t k = 0; k < parts.size(); ++k) {                 // every begun pass is finished (or at least waited for) on every path
+        const int r = rc == OGRECU_OK ? segment_finish(runs[k]) : (cudaSetDevice(parts[k]->ctx->device), cudaStreamSynchronize(parts[k]->ctx->stream), OGRECU_OK);
+        if (rc == OGRECU_OK) rc = r;
+    }
+    if (rt->split) {                                            // the statistics of a split target: the sum over its devices
+        for (ogrecu_rt* a : rt->aliases) { rt->stats.triangles_binned += a->stats.triangles_binned; rt->stats.tile_pairs += a->stats.tile_pairs; }
+    }
+    return rc;
+}
+
 int rt_flush_cmds(ogrecu_rt* rt)
 {
-    ogrecu_ctx* ctx = rt->ctx;
-    if (rt->cmds.empty() && ctx->batch_jobs.empty()) return OGRECU_OK;
+    ogrecu_ctx* ctx = rt->ctx;                       // where the planes are cleared / read: the root, or the peer a target was placed on
+    ogrecu_ctx* root = root_of(ctx);
+    if (rt->cmds.empty() && root->batch_jobs.empty()) return OGRECU_OK;
     ProfileScope range("ogrecu: target flush");
+    OGRECU_CUDA(cudaSetDevice(root->device));
+    OGRECU_CHECK(flush_skin_batch(root));     // queued OptimisedUtil jobs produce what the draws read
+    if (rt->cmds.empty()) return OGRECU_OK;
+    // device group: the peers that take part start after everything the root's stream holds so far (uploads, OptimisedUtil results)
+    std::vector<ogrecu_ctx*> others;
+    if (ctx->root) others.push_back(ctx);
+    for (ogrecu_rt* a : rt->aliases) others.push_back(a->ctx);
+    for (ogrecu_ctx* o : others) OGRECU_CHECK(stream_wait(o, root));
     OGRECU_CUDA(cudaSetDevice(ctx->device));
-    OGRECU_CHECK(flush_skin_batch(ctx));     // queued OptimisedUtil jobs produce what the draws read
     std::vector<Item> seg;
-    ogrecu_rt* one[1] = {rt};
     // The list is consumed on EVERY exit path: a flush that fails half way (out of memory, too many pairs, a CUDA error)
     // reports once and leaves nothing behind to be replayed — segments that already ran must not run again (additive
     // blending would apply twice) and the failing draw must not fail on every later lock / read-back.
     std::vector<Cmd> cmds;
     cmds.swap(rt->cmds);
-    for (size_t i = 0; i < cmds.size(); ++i) {
+    int rc = OGRECU_OK;
+    for (size_t i = 0; i < cmds.size() && rc == OGRECU_OK; ++i) {
         Cmd& c = cmds[i];
         if (c.kind == 0) { seg.push_back({&c.draw, 0, nullptr, nullptr, nullptr, &c.state}); continue; }
-        OGRECU_CHECK(run_segment(ctx, one, 1, seg));
+        rc = run_segment_group(rt, seg);
+        if (rc != OGRECU_OK) break;
+        const bool had_draws = !seg.empty();
         seg.clear();
+        // a clear runs where the planes live; on a split target it is ordered after the peers' earlier passes and before their later ones
+        if (rt->split && had_draws) for (ogrecu_rt* a : rt->aliases) if ((rc = stream_wait(ctx, a->ctx)) != OGRECU_OK) break;
+        if (rc != OGRECU_OK) break;
+        OGRECU_CUDA(cudaSetDevice(ctx->device));
         const size_t npx = (size_t)rt->w * rt->h;
         if (c.clear_buffers & OGRECU_CLEAR_COLOUR) {
             const float* col = c.clear_colour;
@@ -1595,8 +1716,14 @@ int rt_flush_cmds(ogrecu_rt* rt)
             OGRECU_CUDA(cudaGetLastError());
             count_launch(ctx);
         }
+        if (rt->split) for (ogrecu_rt* a : rt->aliases) if ((rc = stream_wait(a->ctx, ctx)) != OGRECU_OK) break;
     }
-    return run_segment(ctx, one, 1, seg);
+    if (rc == OGRECU_OK) rc = run_segment_group(rt, seg);
+    // the root goes on (read-back, the next frame's uploads and OptimisedUtil calls into the buffers the peers copied from) only after
+    // the peers are through; a placed target's own stream already orders its read-back
+    for (ogrecu_ctx* o : others) { const int r = stream_wait(root, o); if (rc == OGRECU_OK) rc = r; }
+    cudaSetDevice(root->device);
+    return rc;
 }
 
 }  // namespace
@@ -1606,31 +1733,41 @@ namespace ogrecu {
 int flush_all_targets(ogrecu_ctx* ctx)
 {
     int rc = OGRECU_OK;
+    ctx = root_of(ctx);
     std::vector<ogrecu_rt*> targets(ctx->targets);
+    for (ogrecu_ctx* p : ctx->peers) targets.insert(targets.end(), p->targets.begin(), p->targets.end());     // targets placed on peers
     for (ogrecu_rt* t : targets)
         if (!t->cmds.empty()) { const int r = rt_flush_cmds(t); if (rc == OGRECU_OK) rc = r; }
     ++ctx->draw_epoch;                     // no recorded draw is left: every buffer's draw_ref mark is stale now
     return rc;
 }
+void free_raster_scratch(ogrecu_ctx* ctx)
+{
+    auto sm = scratch_map().find(ctx);
+    if (sm == scratch_map().end()) return;
+    cudaSetDevice(ctx->device);
+    RasterScratch& S = sm->second;
+    for (Scratch* s : {&S.draws, &S.targets, &S.rec, &S.cnt, &S.sums, &S.pairs_a, &S.pairs_b, &S.tile_count, &S.hist, &S.counters, &S.xf, &S.alive})
+        if (s->ptr) cudaFree(s->ptr);
+    scratch_map().erase(sm);
+}
 int rt_release(ogrecu_rt* rt)
 {
     if (!rt) return OGRECU_OK;
     ogrecu_ctx* ctx = rt->ctx;
+    for (ogrecu_rt* a : rt->aliases) {                 // the peers' views of a split target's planes
+        cudaSetDevice(a->ctx->device);
+        cudaStreamSynchronize(a->ctx->stream);
+        delete a;
+    }
+    rt->aliases.clear();
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     cudaFree(rt->colour);
     cudaFree(rt->depth);
     auto it = std::find(ctx->targets.begin(), ctx->targets.end(), rt);
     if (it != ctx->targets.end()) ctx->targets.erase(it);
-    if (ctx->targets.empty()) {
-        auto sm = scratch_map().find(ctx);
-        if (sm != scratch_map().end()) {
-            RasterScratch& S = sm->second;
-            for (Scratch* s : {&S.draws, &S.targets, &S.rec, &S.cnt, &S.sums, &S.pairs_a, &S.pairs_b, &S.tile_count, &S.hist, &S.counters, &S.xf})
-                if (s->ptr) cudaFree(s->ptr);
-            scratch_map().erase(sm);
-        }
-    }
+    if (ctx->targets.empty() && ctx->root == nullptr && ctx->peers.empty()) free_raster_scratch(ctx);      // (a group keeps its arenas until shutdown)
     delete rt;
     return OGRECU_OK;
 }
@@ -1647,11 +1784,23 @@ int ogrecu_tex_create(ogrecu_ctx* ctx, uint32_t w, uint32_t h, ogrecu_tex** out)
     *out = nullptr;
     OGRECU_CUDA(cudaSetDevice(ctx->device));
     ogrecu_tex* t = new ogrecu_tex();
+    memset(t, 0, sizeof *t);
     t->ctx = ctx; t->w = w; t->h = h; t->has_zero_alpha = 0; t->dev = nullptr;
     cudaError_t e = cudaMalloc((void**)&t->dev, (size_t)w * h * 4);
     if (e != cudaSuccess) { delete t; return cuda_fail(e, "cudaMalloc(texture)", __FILE__, __LINE__); }
     e = cudaMemsetAsync(t->dev, 0xff, (size_t)w * h * 4, ctx->stream);
     if (e != cudaSuccess) { cudaFree(t->dev); delete t; return cuda_fail(e, "cudaMemset(texture)", __FILE__, __LINE__); }
+    for (size_t k = 0; k < ctx->peers.size(); ++k) {              // device group: a replica per peer, refreshed when a draw there samples it
+        cudaSetDevice(ctx->peers[k]->device);
+        e = cudaMalloc((void**)&t->peer_dev[k], (size_t)w * h * 4);
+        if (e != cudaSuccess) {
+            for (size_t q = 0; q < k; ++q) { cudaSetDevice(ctx->peers[q]->device); cudaFree(t->peer_dev[q]); }
+            cudaSetDevice(ctx->device); cudaFree(t->dev); delete t;
+            return cuda_fail(e, "cudaMalloc(texture replica)", __FILE__, __LINE__);
+        }
+        t->peer_stale[k] = true;
+    }
+    if (!ctx->peers.empty()) cudaSetDevice(ctx->device);
     *out = t;
     return OGRECU_OK;
 }
@@ -1661,6 +1810,9 @@ int ogrecu_tex_destroy(ogrecu_tex* t)
     if (!t) return OGRECU_OK;
     OGRECU_CUDA(cudaSetDevice(t->ctx->device));
     OGRECU_CUDA(cudaStreamSynchronize(t->ctx->stream));
+    for (size_t k = 0; k < t->ctx->peers.size(); ++k)
+        if (t->peer_dev[k]) { cudaSetDevice(t->ctx->peers[k]->device); cudaStreamSynchronize(t->ctx->peers[k]->stream); cudaFree(t->peer_dev[k]); }
+    cudaSetDevice(t->ctx->device);
     cudaFree(t->dev);
     delete t;
     return OGRECU_OK;
@@ -1683,6 +1835,7 @@ int ogrecu_tex_upload(ogrecu_tex* t, const uint8_t* rgba, size_t pitch)
     }
     t->has_zero_alpha = zero_alpha;
     OGRECU_CUDA(cudaMemcpyAsync(t->dev, ctx->pinned, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    for (size_t k = 0; k < ctx->peers.size(); ++k) t->peer_stale[k] = true;
     return OGRECU_OK;
 }
 
@@ -1703,15 +1856,18 @@ int ogrecu_tex_download(ogrecu_tex* t, uint8_t* rgba, size_t pitch)
 int ogrecu_tex_copy_from_rt(ogrecu_tex* t, ogrecu_rt* rt)
 {
     OGRECU_REQUIRE(t && rt, "NULL argument");
-    OGRECU_REQUIRE(t->ctx == rt->ctx, "texture and target belong to different contexts");
+    OGRECU_REQUIRE(t->ctx == root_of(rt->ctx), "texture and target belong to different contexts");
     OGRECU_REQUIRE(t->w == rt->w && t->h == rt->h, "texture and target sizes differ");
     OGRECU_CHECK(ogrecu_flush(rt));
-    ogrecu_ctx* ctx = t->ctx;
+    ogrecu_ctx* ctx = rt->ctx;                         // where the planes live (a peer for a placed target: it writes the root's texels over NVLink)
+    if (ctx != t->ctx) OGRECU_CHECK(stream_wait(ctx, t->ctx));
     OGRECU_CUDA(cudaSetDevice(ctx->device));
     const size_t npx = (size_t)t->w * t->h;
     rgb_to_rgba_kernel<<<div_up(div_up(npx, 4), 256), 256, 0, ctx->stream>>>(rt->colour, t->dev, npx);
     OGRECU_CUDA(cudaGetLastError());
     count_launch(ctx);
+    if (ctx != t->ctx) { OGRECU_CHECK(stream_wait(t->ctx, ctx)); OGRECU_CUDA(cudaSetDevice(t->ctx->device)); }
+    for (size_t k = 0; k < t->ctx->peers.size(); ++k) t->peer_stale[k] = true;
     t->has_zero_alpha = 0;
     return OGRECU_OK;
 }
@@ -1725,26 +1881,51 @@ int ogrecu_tex_device_ptr(ogrecu_tex* t, void** dev_ptr)
 
 /* ---- render targets ---- */
 
-int ogrecu_rt_create(ogrecu_ctx* ctx, uint32_t w, uint32_t h, ogrecu_rt** out)
+int ogrecu_rt_create_placed(ogrecu_ctx* ctx, uint32_t w, uint32_t h, int placement, ogrecu_rt** out)
 {
     OGRECU_REQUIRE(ctx && out, "NULL argument");
     OGRECU_REQUIRE(w >= 1 && h >= 1 && w <= 32768 && h <= 32768, "render target size out of range");
     *out = nullptr;
-    OGRECU_CUDA(cudaSetDevice(ctx->device));
+    ogrecu_ctx* root = root_of(ctx);
+    const int ndev = 1 + (int)root->peers.size();
+    OGRECU_REQUIRE(placement == OGRECU_PLACE_SPLIT || (placement >= 0 && placement < ndev), "placement: a device index of the group or OGRECU_PLACE_SPLIT");
+    ogrecu_ctx* home = placement > 0 ? root->peers[placement - 1] : root;       // where the planes live
+    OGRECU_CUDA(cudaSetDevice(home->device));
     ogrecu_rt* rt = new ogrecu_rt();
-    rt->ctx = ctx; rt->w = w; rt->h = h; rt->colour = nullptr; rt->depth = nullptr;
+    rt->ctx = home; rt->w = w; rt->h = h; rt->colour = nullptr; rt->depth = nullptr;
     rt->strip_y0 = 0; rt->strip_y1 = h;
     memset(&rt->stats, 0, sizeof rt->stats);
     rt->stats_slot = 0; rt->stats_pending = false;
     const size_t npx = (size_t)w * h;
     cudaError_t e = cudaMalloc((void**)&rt->colour, npx * 3 + 16);
     if (e == cudaSuccess) e = cudaMalloc((void**)&rt->depth, npx * 4 + 16);
-    if (e == cudaSuccess) e = cudaMemsetAsync(rt->colour, 0, npx * 3 + 16, ctx->stream);    // Image::create zero-fills
-    if (e == cudaSuccess) e = cudaMemsetAsync(rt->depth, 0, npx * 4 + 16, ctx->stream);
-    if (e != cudaSuccess) { cudaFree(rt->colour); cudaFree(rt->depth); delete rt; return cuda_fail(e, "render target allocation", __FILE__, __LINE__); }
-    ctx->targets.push_back(rt);
+    if (e == cudaSuccess) e = cudaMemsetAsync(rt->colour, 0, npx * 3 + 16, home->stream);    // Image::create zero-fills
+    if (e == cudaSuccess) e = cudaMemsetAsync(rt->depth, 0, npx * 4 + 16, home->stream);
+    if (e != cudaSuccess) { cudaFree(rt->colour); cudaFree(rt->depth); delete rt; cudaSetDevice(root->device); return cuda_fail(e, "render target allocation", __FILE__, __LINE__); }
+    if (placement == OGRECU_PLACE_SPLIT && ndev > 1) {
+        // interleaved bands of tile rows, band b -> device b mod ndev; the peers see the root's planes through alias targets
+        rt->split = true;
+        rt->band_tiles = (uint32_t)root->split_band_tiles; rt->band_phase = 0; rt->band_period = (uint32_t)ndev;
+        for (int k = 1; k < ndev; ++k) {
+            ogrecu_rt* a = new ogrecu_rt();
+            a->ctx = root->peers[k - 1]; a->w = w; a->h = h; a->colour = rt->colour; a->depth = rt->depth;
+            a->strip_y0 = 0; a->strip_y1 = h;
+            a->band_tiles = rt->band_tiles; a->band_phase = (uint32_t)k; a->band_period = (uint32_t)ndev;
+            memset(&a->stats, 0, sizeof a->stats);
+            a->stats_slot = 0; a->stats_pending = false;
+            rt->aliases.push_back(a);
+        }
+    }
+    home->targets.push_back(rt);
+    if (home != root) OGRECU_CUDA(cudaSetDevice(root->device));
     *out = rt;
     return OGRECU_OK;
+}
+
+int ogrecu_rt_create(ogrecu_ctx* ctx, uint32_t w, uint32_t h, ogrecu_rt** out)
+{
+    OGRECU_REQUIRE(ctx, "NULL argument");
+    return ogrecu_rt_create_placed(ctx, w, h, ctx->dev_index, out);
 }
 
 int ogrecu_rt_destroy(ogrecu_rt* rt) { return rt_release(rt); }
@@ -1795,7 +1976,7 @@ int ogrecu_draw_with_state(ogrecu_rt* rt, const ogrecu_draw_desc* d, const ogrec
     OGRECU_REQUIRE(d->index_type == OGRECU_INDEX_NONE || d->indices, "indices are NULL");
     OGRECU_REQUIRE(((d->pos_stride | d->uv_stride | d->normal_stride | (uintptr_t)d->positions | (uintptr_t)d->uvs | (uintptr_t)d->normals) & 3) == 0,
                    "vertex streams must be 4-byte aligned");
-    OGRECU_REQUIRE(!d->texture || d->texture->ctx == rt->ctx, "texture belongs to another context");
+    OGRECU_REQUIRE(!d->texture || d->texture->ctx == root_of(rt->ctx), "texture belongs to another context");
     OGRECU_REQUIRE(!d->instance_count || d->prim_type == OGRECU_PRIM_TRIANGLE_LIST, "instanced draws are triangle lists");
     OGRECU_REQUIRE((uint64_t)(d->draw_count / 3) * (d->instance_count ? d->instance_count : 1) < 0xffffffffull, "too many triangles in one draw");
     if (tri_count_of(*d) == 0) return OGRECU_OK;
@@ -1808,8 +1989,9 @@ int ogrecu_draw_with_state(ogrecu_rt* rt, const ogrecu_draw_desc* d, const ogrec
     // the buffers the draw will read when it is flushed: a host write to one of them (or a deferred OptimisedUtil job that
     // overwrites one) must run the recorded draws first (ogrecu_buf_map, ogrecu_software_vertex_skinning_host)
     const void* refs[5] = {d->positions, d->uvs, d->normals, d->indices, (st && (st->enable & OGRECU_EXT_VERTEX_COLOUR)) ? st->colours : nullptr};
+    ogrecu_ctx* root = root_of(rt->ctx);
     for (const void* r : refs)
-        if (ogrecu_buf* b = buf_of_device_ptr(rt->ctx, r)) b->draw_ref = rt->ctx->draw_epoch;
+        if (ogrecu_buf* b = buf_of_device_ptr(root, r)) b->draw_ref = root->draw_epoch;
     return OGRECU_OK;
 }
 
@@ -1825,29 +2007,64 @@ int ogrecu_draw_views(ogrecu_rt* const* rts, uint32_t n_views, const ogrecu_draw
 {
     OGRECU_REQUIRE(rts && desc && per_view_mvp, "NULL argument");
     if (n_views == 0) return OGRECU_OK;
-    ogrecu_ctx* ctx = rts[0]->ctx;
+    OGRECU_REQUIRE(rts[0], "NULL target");
+    ogrecu_ctx* root = root_of(rts[0]->ctx);
     for (uint32_t v = 0; v < n_views; ++v) {
-        OGRECU_REQUIRE(rts[v] && rts[v]->ctx == ctx, "targets must share one context");
+        OGRECU_REQUIRE(rts[v] && root_of(rts[v]->ctx) == root, "targets must share one context (or one device group)");
+        OGRECU_REQUIRE(!rts[v]->split, "batched views go to whole targets: place them on the group's devices instead of splitting them");
         OGRECU_REQUIRE(rts[v]->w == rts[0]->w && rts[v]->h == rts[0]->h, "targets must have identical size");
         OGRECU_REQUIRE(rts[v]->strip_y0 == rts[0]->strip_y0 && rts[v]->strip_y1 == rts[0]->strip_y1 && rts[v]->band_period == rts[0]->band_period &&
                        rts[v]->band_phase == rts[0]->band_phase && rts[v]->band_tiles == rts[0]->band_tiles, "targets must share the strip");
         OGRECU_CHECK(ogrecu_flush(rts[v]));   // earlier clears / draws on each target come first
     }
-    OGRECU_CUDA(cudaSetDevice(ctx->device));
-    OGRECU_CHECK(flush_skin_batch(ctx));      // queued OptimisedUtil jobs may produce what this draw reads
+    OGRECU_CUDA(cudaSetDevice(root->device));
+    OGRECU_CHECK(flush_skin_batch(root));      // queued OptimisedUtil jobs may produce what this draw reads
     if (desc->prim_type != OGRECU_PRIM_TRIANGLE_LIST && desc->prim_type != OGRECU_PRIM_TRIANGLE_STRIP) return OGRECU_OK;
     OGRECU_REQUIRE(desc->positions, "VES_POSITION required");
-    std::vector<Item> items(n_views);
+    // One pipeline pass per device over the views whose targets live there (a single context: one pass over all of them).  The
+    // geometry is replicated, so the passes share nothing; both host phases go device by device and the passes overlap.
+    std::vector<ogrecu_ctx*> owners;
     for (uint32_t v = 0; v < n_views; ++v)
-        items[v] = {desc, v, per_view_mvp + 16 * v, per_view_mvit ? per_view_mvit + 16 * v : nullptr,
-                    per_view_light_dir ? per_view_light_dir + 3 * v : nullptr, nullptr};
-    return run_segment(ctx, rts, n_views, items);
+        if (std::find(owners.begin(), owners.end(), rts[v]->ctx) == owners.end()) owners.push_back(rts[v]->ctx);
+    const size_t G = owners.size();
+    std::vector<std::vector<ogrecu_rt*>> targets(G);
+    std::vector<std::vector<Item>> items(G);
+    std::vector<PeerSeg> tr(G);
+    std::vector<SegRun> runs(G);
+    int rc = OGRECU_OK;
+    for (size_t g = 0; g < G && rc == OGRECU_OK; ++g) {
+        ogrecu_ctx* dev = owners[g];
+        const ogrecu_draw_desc* d = desc;
+        if (dev->root) {
+            rc = stream_wait(dev, root);
+            std::vector<Item> one(1, Item{desc, 0, nullptr, nullptr, nullptr, nullptr});
+            if (rc == OGRECU_OK) rc = translate_segment(dev, one, tr[g]);
+            if (rc != OGRECU_OK) break;
+            d = &tr[g].descs[0];
+        }
+        for (uint32_t v = 0; v < n_views; ++v) {
+            if (rts[v]->ctx != dev) continue;
+            items[g].push_back({d, (uint32_t)targets[g].size(), per_view_mvp + 16 * v, per_view_mvit ? per_view_mvit + 16 * v : nullptr,
+                                per_view_light_dir ? per_view_light_dir + 3 * v : nullptr, nullptr});
+            targets[g].push_back(rts[v]);
+        }
+        rc = segment_begin(dev, targets[g].data(), (uint32_t)targets[g].size(), items[g], runs[g]);
+    }
+    for (size_t g = 0; g < G; ++g) {
+        const int r = rc == OGRECU_OK ? segment_finish(runs[g]) : (cudaSetDevice(owners[g]->device), cudaStreamSynchronize(owners[g]->stream), OGRECU_OK);
+        if (rc == OGRECU_OK) rc = r;
+    }
+    for (size_t g = 0; g < G; ++g)
+        if (owners[g]->root) { const int r = stream_wait(root, owners[g]); if (rc == OGRECU_OK) rc = r; }
+    cudaSetDevice(root->device);
+    return rc;
 }
 
 int ogrecu_rt_set_strip(ogrecu_rt* rt, uint32_t y0, uint32_t y1)
 {
     OGRECU_REQUIRE(rt, "rt is NULL");
     OGRECU_REQUIRE(y0 % TILE == 0 && (y1 % TILE == 0 || y1 >= rt->h) && y0 <= y1, "strip rows must be multiples of the tile height");
+    OGRECU_REQUIRE(!rt->split, "a split target's rows are assigned by the device group");
     OGRECU_CHECK(ogrecu_flush(rt));
     rt->strip_y0 = std::min(y0, rt->h);
     rt->strip_y1 = std::min(y1, rt->h);
@@ -1880,6 +2097,7 @@ int ogrecu_rt_set_bands(ogrecu_rt* rt, uint32_t band_rows, uint32_t phase, uint3
     OGRECU_REQUIRE(rt, "rt is NULL");
     OGRECU_REQUIRE(band_rows >= TILE && band_rows % TILE == 0, "band height must be a positive multiple of the tile height");
     OGRECU_REQUIRE(period >= 1 && phase < period, "phase must be below period");
+    OGRECU_REQUIRE(!rt->split, "a split target's rows are assigned by the device group");
     OGRECU_CHECK(ogrecu_flush(rt));
     rt->strip_y0 = 0; rt->strip_y1 = rt->h;
     rt->band_tiles = band_rows / TILE; rt->band_phase = phase; rt->band_period = period;
@@ -1893,6 +2111,7 @@ static int read_plane(ogrecu_rt* rt, const uint8_t* plane, size_t px_bytes, uint
     OGRECU_REQUIRE(r <= rt->w && b <= rt->h && l <= r && t <= b, "Invalid box");
     ogrecu_ctx* ctx = rt->ctx;
     OGRECU_CHECK(ogrecu_flush(rt));
+    DeviceScope on_device(rt->ctx->device);
     const size_t row = (size_t)(r - l) * px_bytes, rows = b - t;
     if (!row || !rows) return OGRECU_OK;
     OGRECU_REQUIRE(dst && pitch >= row, "bad destination");
@@ -1961,6 +2180,7 @@ int ogrecu_rt_read_colour_packed32(ogrecu_rt* rt, uint32_t l, uint32_t t, uint32
     OGRECU_REQUIRE(r_shift <= 24 && g_shift <= 24 && b_shift <= 24, "channel shifts are 0..24");
     ogrecu_ctx* ctx = rt->ctx;
     OGRECU_CHECK(ogrecu_flush(rt));
+    DeviceScope on_device(rt->ctx->device);
     const uint32_t bw = r - l, bh = b - t;
     if (!bw || !bh) return OGRECU_OK;
     const size_t row = (size_t)bw * 4;
@@ -2022,6 +2242,7 @@ int ogrecu_rt_read_colour_scaled(ogrecu_rt* rt, uint32_t l, uint32_t t, uint32_t
     OGRECU_REQUIRE(dst_px_bytes == 3 || (r_shift <= 24 && g_shift <= 24 && b_shift <= 24), "channel shifts are 0..24");
     ogrecu_ctx* ctx = rt->ctx;
     OGRECU_CHECK(ogrecu_flush(rt));
+    DeviceScope on_device(rt->ctx->device);
     const uint32_t sw = r - l, sh = b - t;
     if (!dst_w || !dst_h) return OGRECU_OK;
     OGRECU_REQUIRE(sw && sh, "empty source box");
@@ -2047,6 +2268,7 @@ static int write_plane(ogrecu_rt* rt, uint8_t* plane, size_t px_bytes, const uin
 {
     ogrecu_ctx* ctx = rt->ctx;
     OGRECU_CHECK(ogrecu_flush(rt));
+    DeviceScope on_device(rt->ctx->device);
     const size_t row = (size_t)rt->w * px_bytes;
     OGRECU_REQUIRE(src && pitch >= row, "bad source");
     OGRECU_CHECK(pinned_reserve(ctx, row * rt->h));
@@ -2089,7 +2311,7 @@ int ogrecu_rt_last_stats(ogrecu_rt* rt, ogrecu_raster_stats* out)
         auto sm = scratch_map().find(rt->ctx);
         if (sm != scratch_map().end() && sm->second.counters.ptr) {
             uint32_t c[2] = {0, 0};
-            OGRECU_CUDA(cudaSetDevice(rt->ctx->device));
+            DeviceScope on_device(rt->ctx->device);
             OGRECU_CUDA(cudaMemcpyAsync(c, (uint32_t*)sm->second.counters.ptr + 2 * rt->stats_slot, sizeof c, cudaMemcpyDeviceToHost, rt->ctx->stream));
             OGRECU_CUDA(cudaStreamSynchronize(rt->ctx->stream));
             rt->stats.tiles_visibility = c[0];

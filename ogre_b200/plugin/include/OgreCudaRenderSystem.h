@@ -41,6 +41,11 @@ class CudaRenderSystem : public RenderSystem
     unsigned char mAlphaRef;
     bool mScissorOn;
     bool mBatchOptimisedUtil = true;   // config option "OptimisedUtil Batching"
+    // config options "Devices" (a device group driven by this process: "0,1,2,3", "All"; empty = the one "Device") and "Split Frame"
+    // (windows are split over the group's devices in interleaved bands; render textures are placed round-robin either way)
+    std::vector<int> mDevices;
+    bool mSplitFrame = true;
+    int mNextPlacement = 0;
     Rect mScissor;
 
     HardwareBufferManager* mHardwareBufferManager;
@@ -106,6 +111,10 @@ public:
     void bindGpuProgramParameters(GpuProgramType, const GpuProgramParametersPtr&, uint16) override {}
     void _setAlphaRejectSettings(CompareFunction func, unsigned char value, bool) override { mAlphaFunc = func; mAlphaRef = value; }
     // NVTX ranges / markers around whatever the application brackets (OgreRenderSystem.h:1104-1115)
+    // where the next target goes on the device group: windows are split ("Split Frame") or live on the root, render textures
+    // take the devices in turn (the batched offscreen views of BASELINE config 4 then run side by side)
+    int placementForWindow() const;
+    int placementForRenderTexture();
     void beginProfileEvent(const String& eventName) override { if (mCtx) ogrecu_profile_begin(mCtx, eventName.c_str()); }
     void endProfileEvent(void) override { if (mCtx) ogrecu_profile_end(mCtx); }
     void markProfileEvent(const String& event) override { if (mCtx) ogrecu_profile_mark(mCtx, event.c_str()); }

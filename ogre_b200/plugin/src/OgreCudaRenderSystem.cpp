@@ -54,10 +54,22 @@ ogrecu_ctx* CudaRenderSystem::getContext()
 {
     if (!mCtx)
     {
-        OGRECU_THROW_IF(ogrecu_init(mDeviceIndex, &mCtx));
+        String where;
+        if (mDevices.size() > 1)
+        {
+            OGRECU_THROW_IF(ogrecu_init_devices((int)mDevices.size(), mDevices.data(), &mCtx));
+            where = "device group";
+            for (int d : mDevices) where += " " + StringConverter::toString(d);
+            where += mSplitFrame ? " (windows split over the group)" : " (windows on the first device)";
+        }
+        else
+        {
+            if (mDevices.size() == 1) mDeviceIndex = mDevices[0];
+            OGRECU_THROW_IF(ogrecu_init(mDeviceIndex, &mCtx));
+            where = "device " + StringConverter::toString(mDeviceIndex);
+        }
         OGRECU_THROW_IF(ogrecu_set_config_option(mCtx, "optutil_batch", mBatchOptimisedUtil ? 1 : 0));
-        LogManager::getSingleton().logMessage("CUDA RenderSystem: libogrecu context on device " +
-                                              StringConverter::toString(mDeviceIndex) +
+        LogManager::getSingleton().logMessage("CUDA RenderSystem: libogrecu context on " + where +
                                               (mBatchOptimisedUtil ? ", OptimisedUtil calls batched per frame" : ""));
     }
     return mCtx;
@@ -74,6 +86,28 @@ void CudaRenderSystem::initConfigOptions()
     ogrecu_device_count(&n);
     for (int i = 0; i < n; ++i) dev.possibleValues.push_back(StringConverter::toString(i));
     mOptions[dev.name] = dev;
+    ConfigOption devs;
+    devs.name = "Devices";           // several GPUs driven by this process (libogrecu device group); empty = only "Device"
+    devs.currentValue = "";
+    devs.immutable = false;
+    devs.possibleValues.push_back("");
+    if (n > 1)
+    {
+        String all;
+        for (int i = 0; i < n; ++i)
+        {
+            all += (i ? "," : "") + StringConverter::toString(i);
+            if (i) devs.possibleValues.push_back(all);
+        }
+        devs.possibleValues.push_back("All");
+    }
+    mOptions[devs.name] = devs;
+    ConfigOption split;
+    split.name = "Split Frame";      // with "Devices": windows are rasterised by all devices in interleaved bands of tile rows
+    split.currentValue = mSplitFrame ? "Yes" : "No";
+    split.possibleValues = {"No", "Yes"};
+    split.immutable = false;
+    mOptions[split.name] = split;
     ConfigOption beyond;
     beyond.name = "Beyond Tiny";      // honour depth function, culling mode, scissor, alpha rejection and vertex colours
     beyond.currentValue = mBeyondTiny ? "Yes" : "No";
@@ -97,12 +131,36 @@ void CudaRenderSystem::setConfigOption(const String& name, const String& value)
         OgreAssert(!mCtx, "the device cannot change once the context exists");
         mDeviceIndex = StringConverter::parseInt(value);
     }
+    if (name == "Devices")
+    {
+        OgreAssert(!mCtx, "the devices cannot change once the context exists");
+        mDevices.clear();
+        if (value == "All" || value == "all")
+        {
+            int n = 0;
+            ogrecu_device_count(&n);
+            for (int i = 0; i < n; ++i) mDevices.push_back(i);
+        }
+        else
+            for (const String& tok : StringUtil::split(value, ", ")) mDevices.push_back(StringConverter::parseInt(tok));
+    }
+    if (name == "Split Frame") mSplitFrame = StringConverter::parseBool(value);
     if (name == "Beyond Tiny") mBeyondTiny = StringConverter::parseBool(value);
     if (name == "OptimisedUtil Batching")
     {
         mBatchOptimisedUtil = StringConverter::parseBool(value);
         if (mCtx) OGRECU_THROW_IF(ogrecu_set_config_option(mCtx, "optutil_batch", mBatchOptimisedUtil ? 1 : 0));
     }
+}
+
+int CudaRenderSystem::placementForWindow() const { return (mDevices.size() > 1 && mSplitFrame) ? OGRECU_PLACE_SPLIT : 0; }
+
+int CudaRenderSystem::placementForRenderTexture()
+{
+    if (mDevices.size() <= 1) return 0;
+    const int k = mNextPlacement;
+    mNextPlacement = (mNextPlacement + 1) % (int)mDevices.size();
+    return k;
 }
 
 const String& CudaRenderSystem::getName(void) const

@@ -33,7 +33,7 @@ void CudaTexture::createInternalResourcesImpl(void)
     mNumMipmaps = mNumRequestedMipmaps = 0;   // like Tiny: no mip chain (OgreTinyTexture.cpp:45)
     mBuffer.create(mFormat, mWidth, mHeight, mDepth, getNumFaces(), mNumMipmaps);
     if (mUsage & TU_RENDERTARGET)
-        OGRECU_THROW_IF(ogrecu_rt_create(mCtx, mWidth, mHeight, &mTarget));
+        OGRECU_THROW_IF(ogrecu_rt_create_placed(mCtx, mWidth, mHeight, CudaRenderSystem::getInstance()->placementForRenderTexture(), &mTarget));
     mDirty = true;
     createSurfaceList();
 }

@@ -33,7 +33,7 @@ void CudaWindow::destroy(void)
 void CudaWindow::resize(uint width, uint height)
 {
     ogrecu_rt* fresh = 0;
-    OGRECU_THROW_IF(ogrecu_rt_create(mCtx, width, height, &fresh));   // zero-filled like Image::create
+    OGRECU_THROW_IF(ogrecu_rt_create_placed(mCtx, width, height, CudaRenderSystem::getInstance()->placementForWindow(), &fresh));   // zero-filled like Image::create
     if (mTarget)
     {
         CudaRenderSystem::forgetTarget(mTarget, fresh);                // an active window keeps rendering, into the new target

@@ -78,6 +78,8 @@ API int ph_open(const char* plugin_so, const char* rs_name_part, const char* stb
     if (!rs) { g_err = "render system not found"; return 2; }
     g->root->setRenderSystem(rs);
     if (getenv("PH_BEYOND_TINY")) rs->setConfigOption("Beyond Tiny", "Yes");   // CUDA plugin only: opt-in state Tiny ignores
+    if (const char* devs = getenv("PH_DEVICES")) rs->setConfigOption("Devices", devs);          // CUDA plugin only: a device group, e.g. "0,1" or "All"
+    if (const char* split = getenv("PH_SPLIT_FRAME")) rs->setConfigOption("Split Frame", split);
     g->root->initialise(false);
     g->win = g->root->createRenderWindow("harness", w, h, false);
     g->w = w; g->h = h;

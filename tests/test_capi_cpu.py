@@ -23,7 +23,7 @@ def test_header_symbols_are_all_exported_and_bound():
         assert hasattr(lib, n), "libogrecu.so does not export %s" % n
         assert n in capi.SIGNATURES, "ogre_b200/capi.py does not bind %s" % n
     assert sorted(capi.SIGNATURES) == names
-    assert lib.ogrecu_abi_version() == 5
+    assert lib.ogrecu_abi_version() == 6
 
 
 def test_struct_layouts_match_the_header(tmp_path):

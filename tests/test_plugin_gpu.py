@@ -25,7 +25,7 @@ NEED = [os.path.join(ROOT, "ogre_b200", "plugin", "RenderSystem_CUDA.so"), os.pa
         os.path.join(ROOT, "oracle", "_ref", "lib", "libOgreMain.so")]
 
 
-def run_scene(tmp_path, plugin, *args, beyond_tiny=False):
+def run_scene(tmp_path, plugin, *args, beyond_tiny=False, devices=None, split=None):
     for f in NEED:
         assert os.path.exists(f), "%s missing: run __graft_entry__.build() where the reference tree is present" % f
     out = os.path.join(str(tmp_path), "%s_%d.npz" % (plugin, len(os.listdir(str(tmp_path)))))
@@ -39,6 +39,10 @@ def run_scene(tmp_path, plugin, *args, beyond_tiny=False):
     #    equal depth win, and one pixel of the Sinbad frame ((138,109) at 256x256) lies where two sub-meshes coincide.  The
     #    callers below pass --order 1 (distinct render-queue priorities, descending) to both plugins.
     env = dict(os.environ, MALLOC_PERTURB_="255") if plugin != "cuda" else (dict(os.environ, PH_BEYOND_TINY="1") if beyond_tiny else None)
+    if devices is not None:                                   # the plugin's "Devices" / "Split Frame" options (a libogrecu device group)
+        env = dict(env or os.environ, PH_DEVICES=devices)
+        if split is not None:
+            env["PH_SPLIT_FRAME"] = split
     r = subprocess.run([sys.executable, RUN, "--plugin", plugin, "--out", out] + list(args), capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout + r.stderr
     return np.load(out)
@@ -59,6 +63,32 @@ def test_ogrehead_through_root_matches_tiny_golden(tmp_path, size, fixture):
     assert np.array_equal(c["colour_box"], g["colour"][3:h // 2, 5:w // 2])
     # a real RenderTexture (Tiny has none): same camera, same size -> the same image
     assert np.array_equal(c["rtt"], g["colour"])
+
+
+def gpu_count():
+    import ctypes as C
+    import ogre_b200
+    n = C.c_int(0)
+    ogre_b200.lib().ogrecu_device_count(C.byref(n))
+    return n.value
+
+
+@pytest.mark.parametrize("split", ["Yes", "No"])
+def test_device_group_through_the_plugin_options(tmp_path, split):
+    """config options "Devices" = All, "Split Frame": the window is rasterised by every GPU of the box (split) or by the first one,
+    the render texture lives on a peer either way; the frame, the statistics and the skinned entity equal the single-device run"""
+    if gpu_count() < 2:
+        pytest.skip("needs two GPUs")
+    g = np.load(os.path.join(GOLDEN, "ogrehead_1280x720.npz"))
+    c = run_scene(tmp_path, "cuda", "--mesh", "ogrehead.mesh", "--size", "1280x720", "--rtt", devices="All", split=split)
+    assert list(c["stats"]) == [4336, 4]
+    assert np.array_equal(c["colour"], g["colour"]) and np.array_equal(bits(c["depth"]), bits(g["depth"]))
+    assert np.array_equal(c["rtt"], g["colour"])
+    one = run_scene(tmp_path, "cuda", "--mesh", "Sinbad.mesh", "--size", "256x256", "--skel", "0.3,1.7", "--order", "1")
+    many = run_scene(tmp_path, "cuda", "--mesh", "Sinbad.mesh", "--size", "256x256", "--skel", "0.3,1.7", "--order", "1", devices="All", split=split)
+    for k in one.files:
+        if k.startswith("frame") or k.startswith("skinned") or k in ("colour", "depth"):
+            assert np.array_equal(one[k], many[k]), k
 
 
 def test_side_by_side_with_the_real_tiny_plugin(tmp_path):
