@@ -89,6 +89,7 @@ struct ogrecu_ctx {
     int dev_index = 0;                      // position in the group (0 = root)
     cudaEvent_t group_ev = nullptr;         // "this context's stream got here": cross-device ordering
     int split_band_tiles = 4;               // split targets: tile rows per interleaved band
+    int split_mode = 0;                     // split targets: 0 = sort-last where the content allows, else bands | 1 = always bands
     cudaStream_t own_stream;
     cudaStream_t stream;        // current launch stream (own or external)
     uint64_t launches;

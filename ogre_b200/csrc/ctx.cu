@@ -325,6 +325,7 @@ int ogrecu_set_config_option(ogrecu_ctx* ctx, const char* name, int value)
         return OGRECU_OK;
     }
     if (!strcmp(name, "lane_reuse_repack")) { OGRECU_REQUIRE(value >= 0 && value <= 1, "lane_reuse_repack is 0..1"); ctx->lane_reuse_repack = value; return OGRECU_OK; }
+    if (!strcmp(name, "split_mode")) { OGRECU_REQUIRE(value >= 0 && value <= 1, "split_mode is 0..1"); ctx->split_mode = value; return OGRECU_OK; }
     if (!strcmp(name, "split_band_tiles")) { OGRECU_REQUIRE(value >= 1 && value <= 1024, "split_band_tiles is 1..1024"); ctx->split_band_tiles = value; return OGRECU_OK; }
     if (!strcmp(name, "skin_ipc")) { OGRECU_REQUIRE(value >= 0 && value <= 4096, "skin_ipc is 0..4096"); ctx->skin_ipc = value; return OGRECU_OK; }
     set_error("ogrecu_set_config_option: unknown option '%s'", name);

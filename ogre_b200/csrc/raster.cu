@@ -19,6 +19,7 @@
 // Every float op is an explicit __f*_rn intrinsic in the reference's association (SURVEY
 // Appendix A): no FMA contraction, IEEE division.
 #include "common.cuh"
+#include <limits>
 
 #include <algorithm>
 #include <cfloat>
@@ -1288,6 +1289,31 @@ __global__ void composite_depth_kernel(uint8_t* __restrict__ dst_rgb, float* __r
     }
 }
 
+
+// Sort-last merge of a split target (device group): the root rendered its slice of the triangles into the real planes, peer j
+// rendered slice j into private planes that started with depth +INF.  Folding the peers in slice order with Tiny's own test —
+// a fragment is rejected when depth > zbuf (tinyrenderer.h:77) — gives what the in-order loop over all slices leaves behind for
+// opaque, depth-tested, depth-writing content: the smallest depth, the latest submission among equals.  Every device merges its
+// own share of the pixels, reading the peers' planes and writing the root's through peer access.
+struct MergeSrc { const uint8_t* rgb[OGRECU_MAX_PEERS]; const float* z[OGRECU_MAX_PEERS]; int n; };
+__global__ void __launch_bounds__(256) merge_sort_last_kernel(uint8_t* __restrict__ root_rgb, float* __restrict__ root_z, MergeSrc S, size_t p0, size_t p1)
+{
+    const size_t p = p0 + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= p1) return;
+    float z = root_z[p];
+    int best = -1;
+    for (int j = 0; j < S.n; ++j) {
+        const float zj = S.z[j][p];
+        if (__float_as_uint(zj) != 0x7f800000u && !(zj > z)) { z = zj; best = j; }
+    }
+    if (best >= 0) {
+        root_z[p] = z;
+        const uint8_t* c = S.rgb[best] + p * 3;
+        uint8_t* d = root_rgb + p * 3;
+        d[0] = c[0]; d[1] = c[1]; d[2] = c[2];
+    }
+}
+
 __global__ void clear_depth_kernel(float* __restrict__ depth, size_t n, float v)
 {
     size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
@@ -1320,6 +1346,8 @@ struct ogrecu_rt {
     // the bands it owns straight into them over NVLink (no composite pass).  A PLACED target lives wholly on one peer (ctx = that peer).
     bool split = false;
     std::vector<ogrecu_rt*> aliases;
+    uint8_t* sl_colour = nullptr;      // aliases: this peer's private planes for the sort-last form of a split segment
+    float* sl_depth = nullptr;
     std::vector<Cmd> cmds;
     ogrecu_raster_stats stats;
     int stats_slot;          // index of this target in the last segment's counter table
@@ -1630,6 +1658,136 @@ int translate_segment(ogrecu_ctx* dev, const std::vector<Item>& seg, PeerSeg& ou
     return OGRECU_OK;
 }
 
+
+// ---- sort-last form of a split segment (see merge_sort_last_kernel)
+bool sort_last_eligible(ogrecu_ctx* root, const std::vector<Item>& seg)
+{
+    if (root->split_mode != 0) return false;
+    uint64_t tris = 0;
+    for (const Item& it : seg) {
+        const ogrecu_draw_desc& d = *it.desc;
+        if (d.prim_type != OGRECU_PRIM_TRIANGLE_LIST || d.instance_count) return false;
+        if ((d.flags & (OGRECU_DRAW_DEPTH_TEST | OGRECU_DRAW_DEPTH_WRITE | OGRECU_DRAW_BLEND_ADD)) != (OGRECU_DRAW_DEPTH_TEST | OGRECU_DRAW_DEPTH_WRITE)) return false;
+        if (d.texture && d.texture->has_zero_alpha) return false;
+        if (const ogrecu_draw_state* st = it.state) {
+            if ((st->enable & OGRECU_EXT_DEPTH_FUNC) && st->depth_func != OGRECU_CMPF_LESS_EQUAL) return false;
+            if ((st->enable & OGRECU_EXT_ALPHA_REJECT) && st->alpha_func != OGRECU_CMPF_ALWAYS_PASS) return false;
+            if ((st->enable & OGRECU_EXT_VERTEX_COLOUR) && d.index_type == OGRECU_INDEX_NONE) return false;     // (its colour stream would have to be sliced too)
+        }
+        tris += d.draw_count / 3;
+    }
+    return tris >= 262144;            // below that the private planes' clear and the merge cost more than the split saves
+}
+
+int run_segment_sort_last(ogrecu_rt* rt, const std::vector<Item>& seg)
+{
+    ogrecu_ctx* root = rt->ctx;
+    const size_t G = 1 + rt->aliases.size();
+    const size_t npx = (size_t)rt->w * rt->h;
+    const float inf = std::numeric_limits<float>::infinity();
+    std::vector<ogrecu_rt> tmp(G);                   // whole-frame views of the planes each device draws into
+    std::vector<std::vector<ogrecu_draw_desc>> descs(G);
+    std::vector<std::vector<Item>> items(G);
+    std::vector<PeerSeg> tr(G);
+    std::vector<SegRun> runs(G);
+    int rc = OGRECU_OK;
+    for (size_t k = 0; k < G && rc == OGRECU_OK; ++k) {
+        ogrecu_rt* part = k ? rt->aliases[k - 1] : rt;
+        ogrecu_ctx* dev = part->ctx;
+        OGRECU_CUDA(cudaSetDevice(dev->device));
+        tmp[k].ctx = dev; tmp[k].w = rt->w; tmp[k].h = rt->h; tmp[k].strip_y0 = 0; tmp[k].strip_y1 = rt->h;
+        tmp[k].colour = rt->colour; tmp[k].depth = rt->depth;
+        memset(&tmp[k].stats, 0, sizeof tmp[k].stats); tmp[k].stats_slot = 0; tmp[k].stats_pending = false;
+        if (k) {
+            if (!part->sl_colour) {
+                cudaError_t e = cudaMalloc((void**)&part->sl_colour, npx * 3 + 16);
+                if (e == cudaSuccess) e = cudaMalloc((void**)&part->sl_depth, npx * 4 + 16);
+                if (e != cudaSuccess) { cudaFree(part->sl_colour); part->sl_colour = nullptr; rc = cuda_fail(e, "sort-last planes", __FILE__, __LINE__); break; }
+            }
+            tmp[k].colour = part->sl_colour; tmp[k].depth = part->sl_depth;
+            clear_depth_kernel<<<div_up(div_up(npx, 4), 256), 256, 0, dev->stream>>>(part->sl_depth, npx, inf);
+            count_launch(dev);
+        }
+        // slice k of every draw's triangles
+        descs[k].reserve(seg.size());
+        for (const Item& it : seg) {
+            ogrecu_draw_desc d = *it.desc;
+            const uint64_t nt = d.draw_count / 3, lo = nt * k / G, hi = nt * (k + 1) / G;
+            if (hi == lo) continue;
+            if (d.index_type == OGRECU_INDEX_NONE) {
+                d.positions = (const uint8_t*)d.positions + lo * 3 * d.pos_stride;
+                if (d.uvs) d.uvs = (const uint8_t*)d.uvs + lo * 3 * d.uv_stride;
+                if (d.normals) d.normals = (const uint8_t*)d.normals + lo * 3 * d.normal_stride;
+                if (d.vertex_count) d.vertex_count = (uint32_t)((hi - lo) * 3);
+            } else d.indices = (const uint8_t*)d.indices + lo * 3 * d.index_type;
+            d.draw_count = (uint32_t)((hi - lo) * 3);
+            descs[k].push_back(d);
+            Item ni = it;
+            ni.desc = &descs[k].back();
+            items[k].push_back(ni);
+        }
+        ogrecu_rt* one[1] = {&tmp[k]};
+        if (dev->root) {
+            rc = translate_segment(dev, items[k], tr[k]);
+            if (rc == OGRECU_OK) rc = segment_begin(dev, one, 1, tr[k].items, runs[k]);
+        } else rc = segment_begin(dev, one, 1, items[k], runs[k]);
+    }
+    for (size_t k = 0; k < G; ++k) {
+        ogrecu_ctx* dev = k ? rt->aliases[k - 1]->ctx : root;
+        const int r = rc == OGRECU_OK ? segment_finish(runs[k]) : (cudaSetDevice(dev->device), cudaStreamSynchronize(dev->stream), OGRECU_OK);
+        if (rc == OGRECU_OK) rc = r;
+    }
+    if (rc != OGRECU_OK) return rc;
+    rt->stats = tmp[0].stats;
+    for (size_t k = 1; k < G; ++k) {
+        rt->stats.triangles_in += tmp[k].stats.triangles_in; rt->stats.triangles_binned += tmp[k].stats.triangles_binned;
+        rt->stats.tile_pairs += tmp[k].stats.tile_pairs;
+    }
+    rt->stats_pending = false;
+    // every device has to see every slice finished before it merges its share of the pixels
+    for (size_t k = 0; k < G; ++k) {
+        ogrecu_ctx* dev = k ? rt->aliases[k - 1]->ctx : root;
+        OGRECU_CUDA(cudaSetDevice(dev->device));
+        OGRECU_CUDA(cudaEventRecord(dev->group_ev, dev->stream));
+    }
+    MergeSrc S;
+    memset(&S, 0, sizeof S);
+    S.n = (int)G - 1;
+    for (size_t j = 1; j < G; ++j) { S.rgb[j - 1] = rt->aliases[j - 1]->sl_colour; S.z[j - 1] = rt->aliases[j - 1]->sl_depth; }
+    for (size_t k = 0; k < G; ++k) {
+        ogrecu_ctx* dev = k ? rt->aliases[k - 1]->ctx : root;
+        OGRECU_CUDA(cudaSetDevice(dev->device));
+        for (size_t j = 0; j < G; ++j) {
+            if (j == k) continue;
+            ogrecu_ctx* other = j ? rt->aliases[j - 1]->ctx : root;
+            OGRECU_CUDA(cudaStreamWaitEvent(dev->stream, other->group_ev, 0));
+        }
+        const size_t p0 = npx * k / G, p1 = npx * (k + 1) / G;
+        if (p1 > p0) {
+            merge_sort_last_kernel<<<div_up(p1 - p0, 256), 256, 0, dev->stream>>>(rt->colour, rt->depth, S, p0, p1);
+            OGRECU_CUDA(cudaGetLastError());
+            count_launch(dev);
+        }
+    }
+    // the next pass on any device (a later segment, the private planes' next clear) comes after every merge
+    for (size_t k = 0; k < G; ++k) {
+        ogrecu_ctx* dev = k ? rt->aliases[k - 1]->ctx : root;
+        OGRECU_CUDA(cudaSetDevice(dev->device));
+        OGRECU_CUDA(cudaEventRecord(dev->group_ev, dev->stream));
+    }
+    for (size_t k = 0; k < G; ++k) {
+        ogrecu_ctx* dev = k ? rt->aliases[k - 1]->ctx : root;
+        OGRECU_CUDA(cudaSetDevice(dev->device));
+        for (size_t j = 0; j < G; ++j) {
+            if (j == k) continue;
+            ogrecu_ctx* other = j ? rt->aliases[j - 1]->ctx : root;
+            OGRECU_CUDA(cudaStreamWaitEvent(dev->stream, other->group_ev, 0));
+        }
+    }
+    OGRECU_CUDA(cudaSetDevice(root->device));
+    return OGRECU_OK;
+}
+
 // One segment of one target on every device that takes part in it: the target's own context, or — for a split target — the
 // root and all peers, each on the bands it owns.  Both host phases run device by device, so the devices' passes overlap.
 int run_segment_group(ogrecu_rt* rt, const std::vector<Item>& seg)
@@ -1637,6 +1795,7 @@ int run_segment_group(ogrecu_rt* rt, const std::vector<Item>& seg)
     if (seg.empty()) return OGRECU_OK;
     ogrecu_ctx* ctx = rt->ctx;
     if (!rt->split && !ctx->root) { ogrecu_rt* one[1] = {rt}; return run_segment(ctx, one, 1, seg); }
+    if (rt->split && sort_last_eligible(ctx, seg)) return run_segment_sort_last(rt, seg);
     std::vector<ogrecu_rt*> parts;
     parts.push_back(rt);
     for (ogrecu_rt* a : rt->aliases) parts.push_back(a);
@@ -1661,7 +1820,9 @@ int run_segment_group(ogrecu_rt* rt, const std::vector<Item>& seg)
     return rc;
 }
 
-int rt_flush_cmds(ogrecu_rt* rt)
+// `handshake` = false: the caller has already ordered the target's device after the root's stream and will order the root after it
+// (ogrecu_draw_views does that once per device for all of its targets instead of once per target)
+int rt_flush_cmds(ogrecu_rt* rt, bool handshake = true)
 {
     ogrecu_ctx* ctx = rt->ctx;                       // where the planes are cleared / read: the root, or the peer a target was placed on
     ogrecu_ctx* root = root_of(ctx);
@@ -1672,7 +1833,7 @@ int rt_flush_cmds(ogrecu_rt* rt)
     if (rt->cmds.empty()) return OGRECU_OK;
     // device group: the peers that take part start after everything the root's stream holds so far (uploads, OptimisedUtil results)
     std::vector<ogrecu_ctx*> others;
-    if (ctx->root) others.push_back(ctx);
+    if (ctx->root && handshake) others.push_back(ctx);
     for (ogrecu_rt* a : rt->aliases) others.push_back(a->ctx);
     for (ogrecu_ctx* o : others) OGRECU_CHECK(stream_wait(o, root));
     OGRECU_CUDA(cudaSetDevice(ctx->device));
@@ -1758,6 +1919,8 @@ int rt_release(ogrecu_rt* rt)
     for (ogrecu_rt* a : rt->aliases) {                 // the peers' views of a split target's planes
         cudaSetDevice(a->ctx->device);
         cudaStreamSynchronize(a->ctx->stream);
+        cudaFree(a->sl_colour);
+        cudaFree(a->sl_depth);
         delete a;
     }
     rt->aliases.clear();
@@ -2015,18 +2178,24 @@ int ogrecu_draw_views(ogrecu_rt* const* rts, uint32_t n_views, const ogrecu_draw
         OGRECU_REQUIRE(rts[v]->w == rts[0]->w && rts[v]->h == rts[0]->h, "targets must have identical size");
         OGRECU_REQUIRE(rts[v]->strip_y0 == rts[0]->strip_y0 && rts[v]->strip_y1 == rts[0]->strip_y1 && rts[v]->band_period == rts[0]->band_period &&
                        rts[v]->band_phase == rts[0]->band_phase && rts[v]->band_tiles == rts[0]->band_tiles, "targets must share the strip");
-        OGRECU_CHECK(ogrecu_flush(rts[v]));   // earlier clears / draws on each target come first
     }
     OGRECU_CUDA(cudaSetDevice(root->device));
     OGRECU_CHECK(flush_skin_batch(root));      // queued OptimisedUtil jobs may produce what this draw reads
-    if (desc->prim_type != OGRECU_PRIM_TRIANGLE_LIST && desc->prim_type != OGRECU_PRIM_TRIANGLE_STRIP) return OGRECU_OK;
-    OGRECU_REQUIRE(desc->positions, "VES_POSITION required");
     // One pipeline pass per device over the views whose targets live there (a single context: one pass over all of them).  The
     // geometry is replicated, so the passes share nothing; both host phases go device by device and the passes overlap.
     std::vector<ogrecu_ctx*> owners;
     for (uint32_t v = 0; v < n_views; ++v)
         if (std::find(owners.begin(), owners.end(), rts[v]->ctx) == owners.end()) owners.push_back(rts[v]->ctx);
     const size_t G = owners.size();
+    // the peers start after everything the root's stream holds so far — ordered once per device, not once per target
+    for (ogrecu_ctx* dev : owners) if (dev->root) OGRECU_CHECK(stream_wait(dev, root));
+    for (uint32_t v = 0; v < n_views; ++v)
+        if (!rts[v]->cmds.empty()) OGRECU_CHECK(rt_flush_cmds(rts[v], false));     // earlier clears / draws on each target come first
+    if (desc->prim_type != OGRECU_PRIM_TRIANGLE_LIST && desc->prim_type != OGRECU_PRIM_TRIANGLE_STRIP) {
+        for (ogrecu_ctx* dev : owners) if (dev->root) OGRECU_CHECK(stream_wait(root, dev));
+        return OGRECU_OK;
+    }
+    OGRECU_REQUIRE(desc->positions, "VES_POSITION required");
     std::vector<std::vector<ogrecu_rt*>> targets(G);
     std::vector<std::vector<Item>> items(G);
     std::vector<PeerSeg> tr(G);
@@ -2036,9 +2205,8 @@ int ogrecu_draw_views(ogrecu_rt* const* rts, uint32_t n_views, const ogrecu_draw
         ogrecu_ctx* dev = owners[g];
         const ogrecu_draw_desc* d = desc;
         if (dev->root) {
-            rc = stream_wait(dev, root);
             std::vector<Item> one(1, Item{desc, 0, nullptr, nullptr, nullptr, nullptr});
-            if (rc == OGRECU_OK) rc = translate_segment(dev, one, tr[g]);
+            rc = translate_segment(dev, one, tr[g]);
             if (rc != OGRECU_OK) break;
             d = &tr[g].descs[0];
         }

@@ -275,3 +275,49 @@ def test_render_texture_on_a_peer_can_be_sampled_by_a_split_target(group):
     qs.render(dst)
     assert_images_equal(dst.read_colour(), dst.read_depth(), qc, qz, "split target sampling a peer's render texture")
     qs.free(); scene.free(); tex.destroy(); dst.destroy(); src_rt.destroy()
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_split_target_sort_last_form_equals_the_oracle(group, mode):
+    """a split target with a big opaque, depth-tested draw: "split_mode" 0 takes the sort-last form (every device draws its slice
+    of the TRIANGLES into private planes, merged through peer memory), 1 keeps the bands; both equal the oracle, including
+    pixels where coplanar duplicates of different slices tie in depth (the later slice wins), pixels nothing touches, prior
+    content of the target (a second frame drawn over the first without a clear), and a blended draw that follows (bands)"""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import bench_configs as bc
+    w, h = 640, 480
+    verts, idx = bc.terrain(380)
+    tri = idx.reshape(-1, 3)
+    dup = tri[1000:4000].copy()
+    extra = verts[dup.reshape(-1)].copy()
+    extra[:, 6:8] += 0.37
+    verts2 = np.concatenate([verts, extra]).astype(np.float32)
+    idx2 = np.concatenate([idx, len(verts) + np.arange(len(extra), dtype=np.uint32)]).astype(np.uint32)
+    assert len(idx2) // 3 >= 262144
+    mvps, mvits, lights = bc.camera_ring(3, w, h)
+    tex = bc.checker_texture(256)
+    big = [DrawCase(verts2, idx2, index_type=4, texture=tex, mvp=mvps[k], mvit=mvits[k], viewport=viewport_matrix(w, h), ambient=(0.2, 0.2, 0.25, 1.0))
+           for k in range(2)]
+    for k in range(2):
+        big[k].light_dir = lights[k]
+    small = make_scene(3, w, h, ndraws=3, ntri=300)          # blended / depth-write-off draws among them
+    group.set_config_option("split_mode", mode)
+    try:
+        rt = ogre_b200.RenderTarget(group, w, h, placement=ogre_b200.PLACE_SPLIT)
+        scene = GpuScene(group, big + small)
+        # frame: clear, big draw (view 0); then WITHOUT a clear the big draw from view 1 over it, then the small mixed draws
+        rt.clear(colour=(0.1, 0.2, 0.3, 1.0), depth=1.0)
+        rt.draw(scene.descs[0]); rt.flush()
+        rc, rz, _ = render_oracle(big[:1], w, h)
+        assert_images_equal(rt.read_colour(), rt.read_depth(), rc, rz, "sort-last form, first frame (mode %d)" % mode)
+        rt.draw(scene.descs[1])
+        for d, st in list(zip(scene.descs, scene.states))[2:]:
+            rt.draw(d, st)
+        rt.flush()
+        rc, rz, _ = render_oracle(big[1:] + small, w, h, clear=None, init=(rc, rz))
+        assert_images_equal(rt.read_colour(), rt.read_depth(), rc, rz, "sort-last form over prior content + bands after it (mode %d)" % mode)
+        scene.free(); rt.destroy()
+    finally:
+        group.set_config_option("split_mode", 0)
