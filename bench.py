@@ -565,6 +565,14 @@ def run_ours(args):
     if not args.no_render:
         render_cfg = run_render_configs(args, local, rank, world, peak)
 
+    # ---- the same render configs through the C ABI's device group: ONE process (rank 0's) drives all N GPUs, the other ranks idle
+    if world > 1 and not args.no_render:
+        group_cfg = run_device_group(args, rank, world, dist)
+        if rank == 0 and render_cfg is not None and group_cfg:
+            for key in ("c4", "c5"):
+                if key in render_cfg and key in group_cfg:
+                    render_cfg[key]["capi_device_group"] = group_cfg[key]
+
     # ---- the drop-in plugin end to end: a crowd of Entity objects through Root::renderOneFrame (rank 0, N=1: one Root per process)
     if rank == 0 and world == 1 and not args.no_plugin:
         extra["plugin_e2e"] = run_plugin_e2e(args)
@@ -620,6 +628,35 @@ def run_ours(args):
         L.ogrecu_host_free(h)
     if dist is not None:
         dist.destroy_process_group()
+
+
+def run_device_group(args, rank, world, dist):
+    """extra.render.{c4,c5}.capi_device_group (N > 1): tools/bench_group.py in a process of its own started by rank 0 — ogrecu_init_devices
+    over the N GPUs of the node, config 4's views on targets placed round-robin, config 5's frame on a split target, every frame
+    checked against a single-device context.  The other ranks wait on a host-side (gloo) barrier, their GPUs idle."""
+    import subprocess
+    out = {}
+    try:
+        gloo = dist.new_group(backend="gloo")
+    except Exception:                                            # noqa: BLE001
+        gloo = None
+    if rank == 0:
+        try:
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_group.py"), "--devices", ",".join(str(d) for d in range(world)),
+                                "--views", str(args.views), "--c5-tris", str(args.c5_tris)], capture_output=True, text=True, timeout=420)
+            for ln in r.stdout.strip().splitlines():
+                if ln.startswith("{"):
+                    d = json.loads(ln)
+                    out["c4" if d["config"].startswith("c4") else "c5"] = d
+            if not out:
+                out = {"c4": {"error": (r.stderr or r.stdout)[-300:]}}
+        except Exception as e:                                   # noqa: BLE001 - reported, not fatal to the bench line
+            out = {"c4": {"error": "%s: %s" % (type(e).__name__, str(e)[:200])}}
+    if gloo is not None:
+        dist.barrier(group=gloo)
+    else:
+        dist.barrier()
+    return out
 
 
 def run_plugin_e2e(args):

@@ -103,8 +103,9 @@ def c5(devices, tris, band_tiles):
     tex = bc.checker_texture(1024)
     mvps, mvits, lights = bc.camera_ring(1, w, h)
     out = {"config": "c5 one 3840x2160 frame, %d triangles, textured, lit: C-ABI device group of %d GPUs in one process, split target "
-                     "(interleaved bands of %d tile rows, band b -> device b mod G, every device rasterises into the root's planes over "
-                     "NVLink: no composite pass)" % (ntri, len(devices), band_tiles), "n_gpus": len(devices), "triangles": ntri}
+                     "(this opaque, depth-tested content takes the sort-last form: every device draws its slice of the triangles into private "
+                     "planes, each device merges its share of the pixels into the root's planes through peer memory; other content: "
+                     "interleaved bands of %d tile rows rasterised straight into the root's planes)" % (ntri, len(devices), band_tiles), "n_gpus": len(devices), "triangles": ntri}
     frames = {}
     for name, devs in (("single", devices[:1]), ("group", devices)):
         ctx = ogre_b200.Context(devices=devs) if len(devs) > 1 else ogre_b200.Context(devs[0])
