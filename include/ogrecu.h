@@ -449,6 +449,20 @@ OGRECU_API int ogrecu_shadow_volume_dev(ogrecu_edges* edges, const char* facings
                                         uint32_t buffer_indices, uint32_t* used_inout, uint32_t* ranges4_host,
                                         uint32_t* emitted);
 
+/* The same for up to 8 lights in ONE submission without a host round trip (BASELINE config 3: face normals -> light facing
+ * -> extrusion -> silhouettes of 8 lights back to back on the stream).  Light l reads facings_dev + l * facing_stride_bytes
+ * (ogrecu_light_facing_multi_dev's layout), has its own directional / use_mcguire / flags, and writes the region
+ * [l * region_indices, (l + 1) * region_indices) of indices_dev; a device pass between the count and scatter kernels does what
+ * the host does in the single-light call (CTA bases, group totals, McGuire fan apex, section offsets).  ranges4_host
+ * [light][group][4] (index values are absolute positions in indices_dev) and result2_host [light][2] = {indices emitted — or
+ * needed, when status is 1 —, status: 0 ok, 1 did not fit the region: nothing written} are copied asynchronously: valid after
+ * ogrecu_sync (pass pinned memory, ogrecu_host_alloc, for the copies to be asynchronous).  Index bytes per light equal the
+ * single-light call's. */
+OGRECU_API int ogrecu_shadow_volumes_multi_dev(ogrecu_edges* edges, uint32_t num_lights, const char* facings_dev, size_t facing_stride_bytes,
+                                               const int* directional, const int* use_mcguire, const uint32_t* flags,
+                                               int separate_light_cap, uint32_t index_type, void* indices_dev, uint32_t region_indices,
+                                               uint32_t* ranges4_host, uint32_t* result2_host);
+
 /* ------------------------------------------------------------------ rasteriser ----- */
 /* TinyTexture / TinyHardwarePixelBuffer (RenderSystems/Tiny/src/OgreTinyTexture.cpp:30-57):
  * always RGBA8, tightly packed, 0 mips. */

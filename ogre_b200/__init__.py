@@ -328,6 +328,18 @@ class EdgeList:
                                              C.byref(emitted)))
         return ranges, used.value, emitted.value
 
+    def shadow_volumes_multi(self, facings_ptr, facing_stride, directional, use_mcguire, flags, separate_light_cap, index_type, indices_ptr,
+                             region_indices):
+        """several lights in one submission (ogrecu_shadow_volumes_multi_dev): returns (ranges[L, G, 4], result[L, 2]) after a sync"""
+        n = len(flags)
+        d = (C.c_int * n)(*[int(v) for v in directional]); m = (C.c_int * n)(*[int(v) for v in use_mcguire])
+        f = (C.c_uint32 * n)(*[int(v) for v in flags])
+        ranges = pinned_empty((n, len(self.groups), 4), np.uint32); result = pinned_empty((n, 2), np.uint32)
+        check(lib().ogrecu_shadow_volumes_multi_dev(self.handle, n, facings_ptr, int(facing_stride), d, m, f, int(separate_light_cap), int(index_type),
+                                                    indices_ptr, int(region_indices), ranges.ctypes.data, result.ctypes.data))
+        self.ctx.sync()
+        return ranges.copy(), result.copy()
+
     def destroy(self):
         if self.handle:
             check(lib().ogrecu_edges_destroy(self.handle))

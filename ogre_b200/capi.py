@@ -138,6 +138,8 @@ SIGNATURES = {
     "ogrecu_edges_create": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, c_void_pp]),
     "ogrecu_edges_destroy": (C.c_int, [C.c_void_p]),
     "ogrecu_shadow_use_mcguire": (C.c_int, [C.c_uint32, C.c_void_p, C.c_void_p]),
+    "ogrecu_shadow_volumes_multi_dev": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                                  C.POINTER(C.c_uint32), C.c_int, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]),
     "ogrecu_shadow_volume_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint32, C.c_int, C.c_uint32, C.c_void_p, C.c_uint32,
                                            C.POINTER(C.c_uint32), C.c_void_p, C.POINTER(C.c_uint32)]),
     "ogrecu_skin_instanced_dev": (C.c_int, [C.c_void_p, C.POINTER(SkinJob), C.c_uint32, C.c_size_t, C.c_size_t, C.c_size_t]),

@@ -106,3 +106,61 @@ def test_buffer_too_small_is_an_error(ctx):
     with pytest.raises(ogre_b200.OgrecuError):
         run_gpu(ctx, el, c["facings"], False, 0, 3, False, 2, 100, 0)
     el.destroy()
+
+
+def test_multi_light_call_equals_single_light_calls(ctx):
+    """ogrecu_shadow_volumes_multi_dev: up to 8 lights, one submission, no host round trip — every light's region holds the bytes
+    the single-light call writes, the ranges are the single call's shifted to the region, and a light whose indices do not fit
+    reports so and writes nothing.  Golden edge lists (several groups, McGuire fans) and the large torus."""
+    combos = [(3, 0, False), (7, 1, True), (2, 1, False), (1, 0, True), (0, 0, False), (3, 1, False), (6, 0, True), (5, 1, True)]
+    for name in ("sinbad_shadow.npz", "jaiqua_shadow.npz", "torus"):
+        if name == "torus":
+            ed = torus_edges(120)
+            nt = len(ed["tris"])
+            rng = np.random.default_rng(11)
+            facing_sets = [(rng.random(nt) < p).astype(np.int8) for p in (0.5, 0.1, 0.9, 0.5, 0.0, 1.0, 0.3, 0.7)]
+        else:
+            ed, cases = load_shadow(name)
+            nt = len(ed["tris"])
+            facing_sets = [np.ascontiguousarray(cases[k % len(cases)]["facings"], np.int8) for k in range(8)]
+        el = ogre_b200.EdgeList(ctx, ed)
+        for index_type, sep in ((2, False), (4, True)):
+            dt = np.uint16 if index_type == 2 else np.uint32
+            fill = 0xCDCD if index_type == 2 else 0xCDCDCDCD
+            singles = []
+            for (flags, mc, directional), fac in zip(combos, facing_sets):
+                idx, ranges, used, emitted = run_gpu(ctx, el, fac, directional, mc, flags, sep, index_type, 9 * nt + 64, 0)
+                singles.append((idx[:emitted], ranges, emitted))
+            region = max(e for _, _, e in singles) + 5
+            stride = (nt + 15) // 16 * 16
+            fac_all = np.zeros((8, stride), np.int8)
+            for l, fac in enumerate(facing_sets):
+                fac_all[l, :nt] = fac
+            dfac = ctx.to_device(fac_all)
+            didx = ctx.to_device(np.full(8 * region, fill, dt))
+            ranges, result = el.shadow_volumes_multi(dfac.ptr, stride, [c[2] for c in combos], [c[1] for c in combos], [c[0] for c in combos],
+                                                    sep, index_type, didx.ptr, region)
+            got = didx.download(dt).reshape(8, region)
+            for l, (ref_idx, ref_ranges, emitted) in enumerate(singles):
+                assert tuple(result[l]) == (emitted, 0), (name, l)
+                assert np.array_equal(got[l, :emitted], ref_idx), (name, index_type, l)
+                assert (got[l, emitted:] == fill).all(), "wrote past its indices"
+                shifted = ref_ranges.copy().astype(np.int64)
+                shifted[:, 0] += l * region
+                if sep and (combos[l][0] & 1):
+                    shifted[:, 2] += l * region
+                cols = 4 if (sep and combos[l][0] & 1) else 2
+                assert np.array_equal(ranges[l][:, :cols].astype(np.int64), shifted[:, :cols]), (name, l)
+            # regions too small for the biggest light: that light reports and writes nothing, the others are unaffected
+            small = max(e for _, _, e in singles) - 1
+            didx2 = ctx.to_device(np.full(8 * small, fill, dt))
+            _, result2 = el.shadow_volumes_multi(dfac.ptr, stride, [c[2] for c in combos], [c[1] for c in combos], [c[0] for c in combos],
+                                                 sep, index_type, didx2.ptr, small)
+            got2 = didx2.download(dt).reshape(8, small)
+            for l, (ref_idx, _, emitted) in enumerate(singles):
+                if emitted > small:
+                    assert tuple(result2[l]) == (emitted, 1) and (got2[l] == fill).all(), (name, l)
+                else:
+                    assert tuple(result2[l]) == (emitted, 0) and np.array_equal(got2[l, :emitted], ref_idx), (name, l)
+            dfac.free(); didx.free(); didx2.free()
+        el.destroy()

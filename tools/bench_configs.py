@@ -267,6 +267,22 @@ def c3(ctx, T, args):
         silhouettes()
     ctx.sync()
     t_sil = (time.perf_counter() - t0) / reps           # synchronous API (counts come back to the host): wall clock
+    # the same for the 8 lights in one submission without a host round trip, and the whole frame (normals -> facing -> extrusion ->
+    # silhouettes) back to back on the stream
+    region = 12 * nt
+    dirs, mcs, fls = (C.c_int * 8)(*[0] * 8), (C.c_int * 8)(*[0] * 8), (C.c_uint32 * 8)(*[3] * 8)
+    rng_host = ogre_b200.pinned_empty((8, len(el.groups), 4), np.uint32); res_host = ogre_b200.pinned_empty((8, 2), np.uint32)
+
+    def silhouettes_multi():
+        check(L.ogrecu_shadow_volumes_multi_dev(el.handle, 8, dfac.ptr, nt, dirs, mcs, fls, 0, 4, didx.ptr, region, rng_host.ctypes.data,
+                                                res_host.ctypes.data))
+
+    def frame_with_silhouettes():
+        fn(); facing(); extrude_fused(); silhouettes_multi()
+    t_silm = T.time(silhouettes_multi)
+    t_all_sil = T.time(frame_with_silhouettes)
+    ctx.sync()
+    assert int(res_host[:, 0].sum()) == sil["emitted"] and not res_host[:, 1].any()
     b_fn = nt * 48 + nv * 12
     b_fac = nt * 16 + 8 * nt           # normals read ONCE for the 8 lights (fused), 8 facing bytes written
     b_ext = 8 * nv * 24
@@ -279,7 +295,10 @@ def c3(ctx, T, args):
                                "frac_of_hbm_peak": b_extf / t_extf / 1e9 / PEAK, "note": "one launch, positions read once (frame uses this)"},
            "shadow_volume_indices_8": {"ms": t_sil * 1e3, "edges": int(len(el.groups) and el.groups[0][1]), "indices_emitted": int(sil["emitted"]),
                                        "Medge_per_s": 8 * int(el.groups[0][1]) / t_sil / 1e6,
-                                       "note": "generateShadowVolume for 8 lights, dark + light caps, 32-bit indices; synchronous calls, wall clock"}}
+                                       "note": "generateShadowVolume for 8 lights, dark + light caps, 32-bit indices; synchronous calls, wall clock"},
+           "shadow_volume_indices_8_one_submission": {"ms": t_silm * 1e3, "Medge_per_s": 8 * int(el.groups[0][1]) / t_silm / 1e6,
+                                                      "note": "ogrecu_shadow_volumes_multi_dev: 3 launches for the 8 lights, no host round trip; device time"},
+           "ms_per_frame_with_silhouettes": t_all_sil * 1e3}
     if args.cpu:
         from oracle import ref
         if ref.available():
