@@ -4,7 +4,10 @@
 #include <nvtx3/nvToolsExt.h>
 #include <stdint.h>
 #include <stddef.h>
+#include <condition_variable>
+#include <functional>
 #include <mutex>
+#include <thread>
 #include <map>
 #include <string>
 #include <vector>
@@ -89,6 +92,7 @@ struct ogrecu_ctx {
     int dev_index = 0;                      // position in the group (0 = root)
     cudaEvent_t group_ev = nullptr;         // "this context's stream got here": cross-device ordering
     int split_band_tiles = 4;               // split targets: tile rows per interleaved band
+    struct GroupPool* pool = nullptr;       // root: one host thread per peer, so that the devices' passes are submitted side by side
     int split_mode = 0;                     // split targets: 0 = sort-last where the content allows, else bands | 1 = always bands
     cudaStream_t own_stream;
     cudaStream_t stream;        // current launch stream (own or external)
@@ -149,6 +153,11 @@ struct ogrecu_ctx {
 
 namespace ogrecu {
 inline ogrecu_ctx* root_of(ogrecu_ctx* ctx) { return ctx->root ? ctx->root : ctx; }
+// fn(0) on the calling thread, fn(1) .. fn(n-1) on the group's worker threads, all at once; the first failure's status (and its
+// error text) is returned.  Each fn(k) must touch only task k's state and set its own device.  Serial when there is no pool.
+int group_parallel(ogrecu_ctx* root, size_t n, const std::function<int(size_t)>& fn);
+void group_pool_create(ogrecu_ctx* root);
+void group_pool_destroy(ogrecu_ctx* root);
 // `other`'s stream continues only after everything `ctx`'s stream has been given so far
 int stream_wait(ogrecu_ctx* other, ogrecu_ctx* ctx);
 // the address `p` of the root's memory as device `peer` should read it: inside an ogrecu_buf -> the peer's replica, refreshed on

@@ -117,6 +117,87 @@ int replica_tex(ogrecu_ctx* peer, ogrecu_tex* t, const uint8_t** out)
 }
 }  // namespace ogrecu
 
+
+/* ---- host threads of a device group: submitting the devices' passes one after the other from one thread costs ~60 us per device
+ * (table building, a few dozen CUDA calls) and staggers them; with a worker per peer the passes start together ---- */
+struct GroupPool {
+    struct W {
+        std::thread th;
+        std::mutex m;
+        std::condition_variable cv;
+        const std::function<int(size_t)>* fn = nullptr;
+        size_t arg = 0;
+        int rc = OGRECU_OK;
+        bool stop = false;
+        char err[512] = "";
+    };
+    std::vector<W*> ws;
+};
+
+namespace ogrecu {
+static void pool_worker(GroupPool::W* w)
+{
+    std::unique_lock<std::mutex> lk(w->m);
+    for (;;) {
+        w->cv.wait(lk, [&] { return w->fn != nullptr || w->stop; });
+        if (w->stop) return;
+        const std::function<int(size_t)>* fn = w->fn;
+        lk.unlock();
+        const int rc = (*fn)(w->arg);
+        lk.lock();
+        w->rc = rc;
+        if (rc != OGRECU_OK) { strncpy(w->err, g_err, sizeof w->err - 1); w->err[sizeof w->err - 1] = 0; }
+        w->fn = nullptr;
+        w->cv.notify_all();
+    }
+}
+
+void group_pool_create(ogrecu_ctx* root)
+{
+    if (root->pool || root->peers.empty()) return;
+    root->pool = new GroupPool();
+    for (size_t k = 0; k < root->peers.size(); ++k) {
+        GroupPool::W* w = new GroupPool::W();
+        w->th = std::thread(pool_worker, w);
+        root->pool->ws.push_back(w);
+    }
+}
+
+void group_pool_destroy(ogrecu_ctx* root)
+{
+    if (!root->pool) return;
+    for (GroupPool::W* w : root->pool->ws) {
+        { std::lock_guard<std::mutex> g(w->m); w->stop = true; }
+        w->cv.notify_all();
+        w->th.join();
+        delete w;
+    }
+    delete root->pool;
+    root->pool = nullptr;
+}
+
+int group_parallel(ogrecu_ctx* root, size_t n, const std::function<int(size_t)>& fn)
+{
+    if (n == 0) return OGRECU_OK;
+    GroupPool* P = root->pool;
+    const size_t nw = P ? std::min(P->ws.size(), n - 1) : 0;
+    for (size_t i = 0; i < nw; ++i) {
+        GroupPool::W* w = P->ws[i];
+        { std::lock_guard<std::mutex> g(w->m); w->arg = i + 1; w->rc = OGRECU_OK; w->fn = &fn; }
+        w->cv.notify_all();
+    }
+    int rc = fn(0);
+    for (size_t k = nw + 1; k < n; ++k) { const int r = fn(k); if (rc == OGRECU_OK) rc = r; }      // more tasks than workers: the rest here
+    for (size_t i = 0; i < nw; ++i) {
+        GroupPool::W* w = P->ws[i];
+        std::unique_lock<std::mutex> lk(w->m);
+        w->cv.wait(lk, [&] { return w->fn == nullptr; });
+        if (rc == OGRECU_OK && w->rc != OGRECU_OK) { rc = w->rc; set_error("%s", w->err); }
+    }
+    return rc;
+}
+}  // namespace ogrecu
+
 extern "C" {
 
 int ogrecu_abi_version(void) { return OGRECU_ABI_VERSION; }
@@ -236,6 +317,7 @@ int ogrecu_init_devices(int num_devices, const int* devices, ogrecu_ctx** out_ct
         if (k) { all[k]->root = all[0]; all[0]->peers.push_back(all[k]); }
     }
     cudaSetDevice(devices[0]);
+    group_pool_create(all[0]);
     *out_ctx = all[0];
     return OGRECU_OK;
 }
@@ -253,6 +335,7 @@ int ogrecu_shutdown(ogrecu_ctx* ctx)
     if (ctx->root) { set_error("ogrecu_shutdown: shut the group's root context down, not a peer"); return OGRECU_ERR_INVALID; }
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    group_pool_destroy(ctx);
     while (!ctx->targets.empty()) rt_release(ctx->targets.back());      // split targets first: their aliases name the peers
     {
         std::vector<ogrecu_ctx*> peers;

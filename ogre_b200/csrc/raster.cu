@@ -1365,6 +1365,13 @@ std::map<ogrecu_ctx*, RasterScratch>& scratch_map()
     static std::map<ogrecu_ctx*, RasterScratch> m;
     return m;
 }
+// a context's arenas; the map itself is shared by the host threads of a device group (std::map nodes do not move)
+RasterScratch& scratch_of(ogrecu_ctx* ctx)
+{
+    static std::mutex mu;
+    std::lock_guard<std::mutex> g(mu);
+    return scratch_map()[ctx];
+}
 
 int exclusive_scan_u32(ogrecu_ctx* ctx, Scratch& sums, uint32_t* data, size_t n, uint64_t** total_dev)
 {
@@ -1411,7 +1418,7 @@ int segment_begin(ogrecu_ctx* ctx, ogrecu_rt* const* targets, uint32_t ntargets,
     run.targets.assign(targets, targets + ntargets);
     if (items.empty()) return OGRECU_OK;
     OGRECU_CUDA(cudaSetDevice(ctx->device));
-    RasterScratch& S = scratch_map()[ctx];
+    RasterScratch& S = scratch_of(ctx);
     ogrecu_rt* rt0 = targets[0];
     const uint32_t W = rt0->w, H = rt0->h;
     const uint32_t tiles_x = div_up(W, TILE), tiles_y = div_up(H, TILE);
@@ -1548,7 +1555,7 @@ int segment_finish(SegRun& run)
     const uint32_t nblocks = run.nblocks, nkeys = run.nkeys, ntris = P.ntris;
     const uint32_t W = P.width, H = P.height, tiles_x = P.tiles_x, tiles_y = P.tiles_y, strip_ty0 = P.strip_ty0, strip_ty1 = P.strip_ty1;
     OGRECU_CUDA(cudaSetDevice(ctx->device));
-    RasterScratch& S = scratch_map()[ctx];
+    RasterScratch& S = scratch_of(ctx);
     OGRECU_CUDA(cudaStreamSynchronize(ctx->stream));
     const uint64_t npairs = ctl_host[2], nsurv = ctl_host[3];
     OGRECU_REQUIRE(npairs < 0xffffffffull, "too many (triangle, tile) pairs in one flush");
@@ -1690,8 +1697,7 @@ int run_segment_sort_last(ogrecu_rt* rt, const std::vector<Item>& seg)
     std::vector<std::vector<Item>> items(G);
     std::vector<PeerSeg> tr(G);
     std::vector<SegRun> runs(G);
-    int rc = OGRECU_OK;
-    for (size_t k = 0; k < G && rc == OGRECU_OK; ++k) {
+    int rc = group_parallel(root, G, [&](size_t k) -> int {
         ogrecu_rt* part = k ? rt->aliases[k - 1] : rt;
         ogrecu_ctx* dev = part->ctx;
         OGRECU_CUDA(cudaSetDevice(dev->device));
@@ -1702,7 +1708,7 @@ int run_segment_sort_last(ogrecu_rt* rt, const std::vector<Item>& seg)
             if (!part->sl_colour) {
                 cudaError_t e = cudaMalloc((void**)&part->sl_colour, npx * 3 + 16);
                 if (e == cudaSuccess) e = cudaMalloc((void**)&part->sl_depth, npx * 4 + 16);
-                if (e != cudaSuccess) { cudaFree(part->sl_colour); part->sl_colour = nullptr; rc = cuda_fail(e, "sort-last planes", __FILE__, __LINE__); break; }
+                if (e != cudaSuccess) { cudaFree(part->sl_colour); part->sl_colour = nullptr; return cuda_fail(e, "sort-last planes", __FILE__, __LINE__); }
             }
             tmp[k].colour = part->sl_colour; tmp[k].depth = part->sl_depth;
             clear_depth_kernel<<<div_up(div_up(npx, 4), 256), 256, 0, dev->stream>>>(part->sl_depth, npx, inf);
@@ -1728,15 +1734,22 @@ int run_segment_sort_last(ogrecu_rt* rt, const std::vector<Item>& seg)
         }
         ogrecu_rt* one[1] = {&tmp[k]};
         if (dev->root) {
-            rc = translate_segment(dev, items[k], tr[k]);
-            if (rc == OGRECU_OK) rc = segment_begin(dev, one, 1, tr[k].items, runs[k]);
-        } else rc = segment_begin(dev, one, 1, items[k], runs[k]);
+            OGRECU_CHECK(translate_segment(dev, items[k], tr[k]));
+            return segment_begin(dev, one, 1, tr[k].items, runs[k]);
+        }
+        return segment_begin(dev, one, 1, items[k], runs[k]);
+    });
+    {
+        const int rc_begin = rc;
+        const int rc2 = group_parallel(root, G, [&](size_t k) -> int {
+            ogrecu_ctx* dev = k ? rt->aliases[k - 1]->ctx : root;
+            if (rc_begin == OGRECU_OK) return segment_finish(runs[k]);
+            cudaSetDevice(dev->device); cudaStreamSynchronize(dev->stream);
+            return OGRECU_OK;
+        });
+        if (rc == OGRECU_OK) rc = rc2;
     }
-    for (size_t k = 0; k < G; ++k) {
-        ogrecu_ctx* dev = k ? rt->aliases[k - 1]->ctx : root;
-        const int r = rc == OGRECU_OK ? segment_finish(runs[k]) : (cudaSetDevice(dev->device), cudaStreamSynchronize(dev->stream), OGRECU_OK);
-        if (rc == OGRECU_OK) rc = r;
-    }
+    cudaSetDevice(root->device);
     if (rc != OGRECU_OK) return rc;
     rt->stats = tmp[0].stats;
     for (size_t k = 1; k < G; ++k) {
@@ -1801,19 +1814,25 @@ int run_segment_group(ogrecu_rt* rt, const std::vector<Item>& seg)
     for (ogrecu_rt* a : rt->aliases) parts.push_back(a);
     std::vector<SegRun> runs(parts.size());
     std::vector<PeerSeg> tr(parts.size());
-    int rc = OGRECU_OK;
-    for (size_t k = 0; k < parts.size() && rc == OGRECU_OK; ++k) {
+    ogrecu_ctx* root = root_of(ctx);
+    // both host phases run on one thread per device (group_parallel), so the devices' passes are submitted side by side
+    int rc = group_parallel(root, parts.size(), [&](size_t k) -> int {
         ogrecu_ctx* dev = parts[k]->ctx;
         ogrecu_rt* one[1] = {parts[k]};
         if (dev->root) {
-            rc = translate_segment(dev, seg, tr[k]);
-            if (rc == OGRECU_OK) rc = segment_begin(dev, one, 1, tr[k].items, runs[k]);
-        } else rc = segment_begin(dev, one, 1, seg, runs[k]);
-    }
-    for (size_t k = 0; k < parts.size(); ++k) {                 // every begun pass is finished (or at least waited for) on every path
-        const int r = rc == OGRECU_OK ? segment_finish(runs[k]) : (cudaSetDevice(parts[k]->ctx->device), cudaStreamSynchronize(parts[k]->ctx->stream), OGRECU_OK);
-        if (rc == OGRECU_OK) rc = r;
-    }
+            OGRECU_CHECK(translate_segment(dev, seg, tr[k]));
+            return segment_begin(dev, one, 1, tr[k].items, runs[k]);
+        }
+        return segment_begin(dev, one, 1, seg, runs[k]);
+    });
+    const int rc_begin = rc;
+    const int rc2 = group_parallel(root, parts.size(), [&](size_t k) -> int {      // every begun pass is finished (or at least waited for) on every path
+        if (rc_begin == OGRECU_OK) return segment_finish(runs[k]);
+        cudaSetDevice(parts[k]->ctx->device); cudaStreamSynchronize(parts[k]->ctx->stream);
+        return OGRECU_OK;
+    });
+    if (rc == OGRECU_OK) rc = rc2;
+    cudaSetDevice(ctx->device);
     if (rt->split) {                                            // the statistics of a split target: the sum over its devices
         for (ogrecu_rt* a : rt->aliases) { rt->stats.triangles_binned += a->stats.triangles_binned; rt->stats.tile_pairs += a->stats.tile_pairs; }
     }
@@ -2200,14 +2219,12 @@ int ogrecu_draw_views(ogrecu_rt* const* rts, uint32_t n_views, const ogrecu_draw
     std::vector<std::vector<Item>> items(G);
     std::vector<PeerSeg> tr(G);
     std::vector<SegRun> runs(G);
-    int rc = OGRECU_OK;
-    for (size_t g = 0; g < G && rc == OGRECU_OK; ++g) {
+    int rc = group_parallel(root, G, [&](size_t g) -> int {
         ogrecu_ctx* dev = owners[g];
         const ogrecu_draw_desc* d = desc;
         if (dev->root) {
             std::vector<Item> one(1, Item{desc, 0, nullptr, nullptr, nullptr, nullptr});
-            rc = translate_segment(dev, one, tr[g]);
-            if (rc != OGRECU_OK) break;
+            OGRECU_CHECK(translate_segment(dev, one, tr[g]));
             d = &tr[g].descs[0];
         }
         for (uint32_t v = 0; v < n_views; ++v) {
@@ -2216,11 +2233,16 @@ int ogrecu_draw_views(ogrecu_rt* const* rts, uint32_t n_views, const ogrecu_draw
                                 per_view_light_dir ? per_view_light_dir + 3 * v : nullptr, nullptr});
             targets[g].push_back(rts[v]);
         }
-        rc = segment_begin(dev, targets[g].data(), (uint32_t)targets[g].size(), items[g], runs[g]);
-    }
-    for (size_t g = 0; g < G; ++g) {
-        const int r = rc == OGRECU_OK ? segment_finish(runs[g]) : (cudaSetDevice(owners[g]->device), cudaStreamSynchronize(owners[g]->stream), OGRECU_OK);
-        if (rc == OGRECU_OK) rc = r;
+        return segment_begin(dev, targets[g].data(), (uint32_t)targets[g].size(), items[g], runs[g]);
+    });
+    {
+        const int rc_begin = rc;
+        const int rc2 = group_parallel(root, G, [&](size_t g) -> int {
+            if (rc_begin == OGRECU_OK) return segment_finish(runs[g]);
+            cudaSetDevice(owners[g]->device); cudaStreamSynchronize(owners[g]->stream);
+            return OGRECU_OK;
+        });
+        if (rc == OGRECU_OK) rc = rc2;
     }
     for (size_t g = 0; g < G; ++g)
         if (owners[g]->root) { const int r = stream_wait(root, owners[g]); if (rc == OGRECU_OK) rc = r; }
