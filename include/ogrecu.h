@@ -179,8 +179,11 @@ OGRECU_API int ogrecu_buf_resolve(ogrecu_ctx* ctx, const void* host_ptr, ogrecu_
  * Animation::apply OgreAnimation.cpp:326-342, NodeAnimationTrack::applyToNode OgreAnimationTrack.cpp:473-512,
  * Node::updateFromParentImpl OgreNode.cpp:202-256, Bone::_getOffsetTransform OgreBone.cpp:88-105).  With it a
  * frame uploads the animation STATES of the instances (a few bytes each) instead of 64 B x bones palettes.
- * Results are bit-identical to the engine's (tests/test_skeleton_gpu.py).  Not covered (the call fails with
- * OGRECU_ERR_UNSUPPORTED): IM_SPLINE, RIM_SPHERICAL, blend masks, manually controlled bones. */
+ * Results are bit-identical to the engine's for IM_LINEAR / RIM_LINEAR animations (tests/test_skeleton_gpu.py).  IM_SPLINE and
+ * RIM_SPHERICAL (OgreAnimationTrack.cpp:417-450, Quaternion::Slerp / Squad, SimpleSpline / RotationalSpline) are evaluated too:
+ * spline tangents are made once on the host at ogrecu_skel_add_animation, translations and scales stay exact, rotations go through
+ * the device's sinf / atan2f and agree with the engine within 2e-5 of a matrix's largest element (the stated tolerance of
+ * those modes).  Not covered: blend masks, manually controlled bones. */
 typedef struct ogrecu_skel ogrecu_skel;
 
 typedef struct ogrecu_skeleton_desc {
@@ -195,8 +198,8 @@ typedef struct ogrecu_skeleton_desc {
 
 typedef struct ogrecu_animation_desc {
     float length;                       /* Animation::getLength                                                     */
-    uint32_t interpolation;             /* 0 = IM_LINEAR                                                            */
-    uint32_t rotation_interpolation;    /* 0 = RIM_LINEAR                                                           */
+    uint32_t interpolation;             /* 0 = IM_LINEAR, 1 = IM_SPLINE (OgreAnimation.h:70-76)                     */
+    uint32_t rotation_interpolation;    /* 0 = RIM_LINEAR, 1 = RIM_SPHERICAL (OgreAnimation.h:79-90)                */
     uint32_t num_tracks;                /* node tracks, at most one per bone                                        */
     const int32_t*  track_bone;         /* [num_tracks] bone handle                                                 */
     const uint8_t*  track_shortest;     /* [num_tracks] getUseShortestRotationPath                                  */

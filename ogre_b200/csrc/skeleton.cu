@@ -59,6 +59,45 @@ HD Quat q_nlerp(float t, const Quat& p, const Quat& q, bool shortest)
     return q_unit(r);
 }
 
+// Quaternion::Slerp, OgreQuaternion.cpp:373-413 (msEpsilon = 1e-03f).  sqrtf is correctly rounded on both sides; atan2f and sinf
+// are libm's on the host and CUDA's (<= 2 ulp) on the device: RIM_SPHERICAL / IM_SPLINE rotations carry a TOLERANCE, not the
+// bit-identity of the linear modes (tests/test_skeleton_gpu.py states it).
+HD Quat q_slerp(float t, const Quat& p, const Quat& q, bool shortest)
+{
+    float c = p.w * q.w + p.x * q.x + p.y * q.y + p.z * q.z;
+    Quat r = q;
+    if (c < 0.0f && shortest) { c = -c; r = Quat{-q.w, -q.x, -q.y, -q.z}; }
+    if (fabsf(c) < 1 - 1e-03f) {
+        const float sn = sqrtf(1 - c * c);
+        const float angle = atan2f(sn, c);
+        const float inv = 1.0f / sn;
+        const float c0 = sinf((1.0f - t) * angle) * inv;
+        const float c1 = sinf(t * angle) * inv;
+        return Quat{c0 * p.w + c1 * r.w, c0 * p.x + c1 * r.x, c0 * p.y + c1 * r.y, c0 * p.z + c1 * r.z};
+    }
+    const float u = 1.0f - t;
+    return q_unit(Quat{u * p.w + t * r.w, u * p.x + t * r.x, u * p.y + t * r.y, u * p.z + t * r.z});
+}
+
+// Quaternion::Squad, OgreQuaternion.cpp:449-457
+HD Quat q_squad(float t, const Quat& p, const Quat& a, const Quat& b, const Quat& q, bool shortest)
+{
+    const float st = 2.0f * t * (1.0f - t);
+    return q_slerp(st, q_slerp(t, p, q, shortest), q_slerp(t, a, b, false), false);
+}
+
+// SimpleSpline::interpolate(fromIndex, t), OgreSimpleSpline.cpp:87-154: powers * hCoeffs * pt with Vector4 * Matrix4
+// (OgreMatrix4.h:588-596), every product and sum of the reference kept, zeros included — pure arithmetic, bit-exact
+HD Vec3 hermite(float t, const Vec3& p1, const Vec3& p2, const Vec3& a, const Vec3& b)
+{
+    const float t2 = t * t, t3 = t2 * t;
+    const float v0 = t3 * 2.0f + t2 * -3.0f + t * 0.0f + 1.0f * 1.0f;
+    const float v1 = t3 * -2.0f + t2 * 3.0f + t * 0.0f + 1.0f * 0.0f;
+    const float v2 = t3 * 1.0f + t2 * -2.0f + t * 1.0f + 1.0f * 0.0f;
+    const float v3 = t3 * 1.0f + t2 * -1.0f + t * 0.0f + 1.0f * 0.0f;
+    return Vec3{v0 * p1.x + v1 * p2.x + v2 * a.x + v3 * b.x, v0 * p1.y + v1 * p2.y + v2 * a.y + v3 * b.y, v0 * p1.z + v1 * p2.z + v2 * a.z + v3 * b.z};
+}
+
 HD Vec3 q_rotate(const Quat& q, const Vec3& v)      // Quaternion * Vector3 ("nVidia SDK implementation")
 {
     Vec3 uv{q.y * v.z - q.z * v.y, q.z * v.x - q.x * v.z, q.x * v.y - q.y * v.x};
@@ -93,6 +132,8 @@ struct AnimDev {
     const uint16_t* index_map;      // [num_tracks][num_times] AnimationTrack::_buildKeyFrameIndexMap
     const float4* keys;             // [num_keys][3]: (time, tx, ty, tz) (rw, rx, ry, rz) (sx, sy, sz, -)
     const uint4* bone_rec;          // [num_bones] (first key, key count, track, shortest-path flag) of the bone's track; count 0 = none
+    uint32_t mode;                  // bit 0: IM_SPLINE, bit 1: RIM_SPHERICAL (OgreAnimation.h:70-90)
+    const float4* tangents;         // IM_SPLINE: [num_keys][3] spline tangents of (translate, -) (rotation wxyz) (scale, -), made on the host
 };
 
 struct SkelDev {
@@ -234,8 +275,36 @@ constexpr int SK_XF = 10 * SK_INST;         // floats per bone in shared memory:
                                             // admit five: one wave.)
 __device__ __forceinline__ uint32_t sk_at(uint32_t p, uint32_t c) { return p * SK_XF + ((c * SK_INST) ^ ((p & 1u) * SK_INST)); }
 
+// getInterpolatedKeyFrame for IM_SPLINE (OgreAnimationTrack.cpp:438-450: the three splines' interpolate(fromIndex, t); a track's
+// tangents are precomputed at ogrecu_skel_add_animation) and for IM_LINEAR with RIM_SPHERICAL (:417-432).  `key` = absolute index of
+// the first key of the pair, whose successor is the second (f != 0 implies the step back of getKeyFramesAtTime).  Out of line:
+// the linear path keeps its registers.
+__device__ __noinline__ void interpolate_nonlinear(const AnimDev& A, uint32_t key, float f, bool shortest, Vec3& tr, Quat& ro, Vec3& sc)
+{
+    const float4* K = A.keys + 3 * (size_t)key;
+    const float4 a0 = K[0], a1 = K[1], a2 = K[2], b0 = K[3], b1 = K[4], b2 = K[5];
+    const Quat qa{a1.x, a1.y, a1.z, a1.w}, qb{b1.x, b1.y, b1.z, b1.w};
+    if (A.mode & 1u) {
+        // (interpolate() returns the second point itself at t == 1; f < 1 here: tp < t2)
+        const float4* T = A.tangents + 3 * (size_t)key;
+        const float4 ta0 = T[0], ta1 = T[1], ta2 = T[2], tb0 = T[3], tb1 = T[4], tb2 = T[5];
+        tr = hermite(f, Vec3{a0.y, a0.z, a0.w}, Vec3{b0.y, b0.z, b0.w}, Vec3{ta0.x, ta0.y, ta0.z}, Vec3{tb0.x, tb0.y, tb0.z});
+        sc = hermite(f, Vec3{a2.x, a2.y, a2.z}, Vec3{b2.x, b2.y, b2.z}, Vec3{ta2.x, ta2.y, ta2.z}, Vec3{tb2.x, tb2.y, tb2.z});
+        ro = q_squad(f, qa, Quat{ta1.x, ta1.y, ta1.z, ta1.w}, Quat{tb1.x, tb1.y, tb1.z, tb1.w}, qb, shortest);
+    } else {
+        ro = q_slerp(f, qa, qb, shortest);
+        tr = Vec3{a0.y + f * (b0.y - a0.y), a0.z + f * (b0.z - a0.z), a0.w + f * (b0.w - a0.w)};
+        sc = Vec3{a2.x + f * (b2.x - a2.x), a2.y + f * (b2.y - a2.y), a2.z + f * (b2.z - a2.z)};
+    }
+}
+
+__device__ __noinline__ Quat slerp_out_of_line(float t, const Quat& p, const Quat& q, bool shortest) { return q_slerp(t, p, q, shortest); }
+
 struct StatePre { int32_t anim; float tp; uint32_t gi; float w; };
 
+// NONLINEAR = some animation of the skeleton is IM_SPLINE / RIM_SPHERICAL; the all-linear instantiation has no trace of that path
+// (with the out-of-line call in it the linear launch went from 64 to 81 us: stack frame, one CTA less in flight)
+template <bool NONLINEAR>
 __global__ void __launch_bounds__(SK_INST * SK_SLOTS, 5) skel_palette_kernel2(const SkelDev S, uint32_t num_instances, uint32_t num_states,
                                                                            const int32_t* __restrict__ anim, const float* __restrict__ time,
                                                                            const float* __restrict__ weight, float* __restrict__ out,
@@ -318,14 +387,17 @@ __global__ void __launch_bounds__(SK_INST * SK_SLOTS, 5) skel_palette_kernel2(co
                 const bool shortest = R.w != 0;
                 Vec3 tr{k1a.y, k1a.z, k1a.w}, sc{k1c.x, k1c.y, k1c.z};
                 Quat ro{k1b.x, k1b.y, k1b.z, k1b.w};
-                if (f != 0.0f) {                                                   // getInterpolatedKeyFrame (IM_LINEAR, RIM_LINEAR)
-                    ro = q_nlerp(f, ro, Quat{k2b.x, k2b.y, k2b.z, k2b.w}, shortest);
-                    tr = Vec3{k1a.y + f * (k2a.y - k1a.y), k1a.z + f * (k2a.z - k1a.z), k1a.w + f * (k2a.w - k1a.w)};
-                    sc = Vec3{k1c.x + f * (k2c.x - k1c.x), k1c.y + f * (k2c.y - k1c.y), k1c.z + f * (k2c.z - k1c.z)};
+                if (f != 0.0f) {                                                   // getInterpolatedKeyFrame
+                    if (!NONLINEAR || A.mode == 0) {                               // IM_LINEAR, RIM_LINEAR
+                        ro = q_nlerp(f, ro, Quat{k2b.x, k2b.y, k2b.z, k2b.w}, shortest);
+                        tr = Vec3{k1a.y + f * (k2a.y - k1a.y), k1a.z + f * (k2a.z - k1a.z), k1a.w + f * (k2a.w - k1a.w)};
+                        sc = Vec3{k1c.x + f * (k2c.x - k1c.x), k1c.y + f * (k2c.y - k1c.y), k1c.z + f * (k2c.z - k1c.z)};
+                    } else interpolate_nonlinear(A, k0 + (back ? ip : i2), f, shortest, tr, ro, sc);
                 }
                 const float scl = 1.0f;                                            // applyToNode, no linked skeleton
                 L.p.x += tr.x * w * scl; L.p.y += tr.y * w * scl; L.p.z += tr.z * w * scl;
-                const Quat rot = q_nlerp(w, Quat{1.0f, 0.0f, 0.0f, 0.0f}, ro, shortest);
+                const Quat ident{1.0f, 0.0f, 0.0f, 0.0f};
+                const Quat rot = (NONLINEAR && (A.mode & 2u)) ? slerp_out_of_line(w, ident, ro, shortest) : q_nlerp(w, ident, ro, shortest);
                 L.q = q_unit(q_mul(L.q, rot));
                 if ((sc.x != 1.0f || sc.y != 1.0f || sc.z != 1.0f) && w != 1.0f)
                     sc = Vec3{1.0f + w * (sc.x - 1.0f), 1.0f + w * (sc.y - 1.0f), 1.0f + w * (sc.z - 1.0f)};
@@ -507,11 +579,7 @@ int ogrecu_skel_get_bind_inverse(ogrecu_skel* s, float* out)
 int ogrecu_skel_add_animation(ogrecu_skel* s, const ogrecu_animation_desc* d, uint32_t* out_index)
 {
     OGRECU_REQUIRE(s && d, "NULL argument");
-    if (d->interpolation != 0 || d->rotation_interpolation != 0) {
-        set_error("ogrecu_skel_add_animation: only IM_LINEAR / RIM_LINEAR animations are supported (got %u / %u)", d->interpolation,
-                  d->rotation_interpolation);
-        return OGRECU_ERR_UNSUPPORTED;
-    }
+    OGRECU_REQUIRE(d->interpolation <= 1 && d->rotation_interpolation <= 1, "interpolation is IM_LINEAR (0) or IM_SPLINE (1), rotation RIM_LINEAR (0) or RIM_SPHERICAL (1)");
     OGRECU_REQUIRE(d->num_tracks == 0 || (d->track_bone && d->key_offset && d->keys), "track tables are required");
     const uint32_t nt = d->num_tracks, nb = s->num_bones;
     const uint32_t nkeys = nt ? d->key_offset[nt] : 0;
@@ -569,6 +637,82 @@ int ogrecu_skel_add_animation(ogrecu_skel* s, const ogrecu_animation_desc* d, ui
     OGRECU_CHECK(upload(ctx, shortest.data(), shortest.size(), &d_sh)); s->owned.push_back(d_sh);
     OGRECU_CHECK(upload(ctx, index_map.data(), index_map.size(), &d_im)); s->owned.push_back(d_im);
     OGRECU_CHECK(upload(ctx, keys.data(), keys.size(), &d_keys)); s->owned.push_back(d_keys);
+    A.mode = (d->interpolation ? 1u : 0u) | (d->rotation_interpolation ? 2u : 0u);
+    A.tangents = nullptr;
+    if (d->interpolation) {
+        // NodeAnimationTrack::buildInterpolationSplines (OgreAnimationTrack.cpp:515-549): SimpleSpline::recalcTangents
+        // (OgreSimpleSpline.cpp:156-207) for translate and scale, RotationalSpline::recalcTangents (OgreRotationSpline.cpp) with
+        // Quaternion::Log / Exp / Inverse (OgreQuaternion.cpp:274-357) for the rotations — once per track, on the host, in the
+        // reference's operation order (the float overloads of libm, as OgreMath.h uses them)
+        std::vector<float4> tan(3 * (size_t)std::max(nkeys, 1u), make_float4(0.f, 0.f, 0.f, 0.f));
+        auto KQ = [&](uint32_t k) { const float* f = d->keys + 11 * (size_t)k; return Quat{f[4], f[5], f[6], f[7]}; };
+        auto q_log = [](const Quat& q) {
+            Quat r{0.0f, q.x, q.y, q.z};
+            if (fabsf(q.w) < 1.0) {
+                const float nv = sqrtf(q.x * q.x + q.y * q.y + q.z * q.z);
+                const float angle = atan2f(nv, q.w);
+                const float sn = sinf(angle);
+                if (fabsf(sn) >= 1e-03f) { const float c = angle / sn; r.x = c * q.x; r.y = c * q.y; r.z = c * q.z; }
+            }
+            return r;
+        };
+        auto q_exp = [](const Quat& q) {
+            const float angle = sqrtf(q.x * q.x + q.y * q.y + q.z * q.z);
+            const float sn = sinf(angle);
+            const float ew = expf(q.w);
+            Quat r;
+            r.w = ew * cosf(angle);
+            if (fabsf(angle) >= 1e-03f) { const float c = ew * (sn / angle); r.x = c * q.x; r.y = c * q.y; r.z = c * q.z; }
+            else { r.x = ew * q.x; r.y = ew * q.y; r.z = ew * q.z; }
+            return r;
+        };
+        auto q_inverse = [](const Quat& q) {
+            const float n = q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z;
+            Quat r{0.0f, 0.0f, 0.0f, 0.0f};
+            if (n > 0.0) { const float inv = 1.0f / n; r = Quat{q.w * inv, -q.x * inv, -q.y * inv, -q.z * inv}; }
+            return r;
+        };
+        for (uint32_t t = 0; t < nt; ++t) {
+            const uint32_t k0 = d->key_offset[t], n = d->key_offset[t + 1] - k0;
+            if (n < 2) continue;
+            for (int which = 0; which < 2; ++which) {                  // translate (floats 1..3) and scale (8..10)
+                const int off = which ? 8 : 1;
+                auto P = [&](uint32_t i, int c) { return d->keys[11 * (size_t)(k0 + i) + off + c]; };
+                const bool closed = P(0, 0) == P(n - 1, 0) && P(0, 1) == P(n - 1, 1) && P(0, 2) == P(n - 1, 2);
+                for (uint32_t i = 0; i < n; ++i) {
+                    uint32_t a, b;
+                    float4& out = tan[3 * (size_t)(k0 + i) + (which ? 2 : 0)];
+                    if (i == 0) { a = 1; b = closed ? n - 2 : 0; }
+                    else if (i == n - 1) { if (closed) { out = tan[3 * (size_t)k0 + (which ? 2 : 0)]; continue; } a = i; b = i - 1; }
+                    else { a = i + 1; b = i - 1; }
+                    out = make_float4(0.5f * (P(a, 0) - P(b, 0)), 0.5f * (P(a, 1) - P(b, 1)), 0.5f * (P(a, 2) - P(b, 2)), 0.f);
+                }
+            }
+            const Quat first = KQ(k0), last = KQ(k0 + n - 1);
+            const bool closed = first.x == last.x && first.y == last.y && first.z == last.z && first.w == last.w;
+            for (uint32_t i = 0; i < n; ++i) {
+                const Quat pq = KQ(k0 + i), invp = q_inverse(pq);
+                Quat part1, part2;
+                if (i == 0) {
+                    part1 = q_log(q_mul(invp, KQ(k0 + 1)));
+                    part2 = closed ? q_log(q_mul(invp, KQ(k0 + n - 2))) : q_log(q_mul(invp, pq));
+                } else if (i == n - 1) {
+                    part1 = closed ? q_log(q_mul(invp, KQ(k0 + 1))) : q_log(q_mul(invp, pq));
+                    part2 = q_log(q_mul(invp, KQ(k0 + i - 1)));
+                } else {
+                    part1 = q_log(q_mul(invp, KQ(k0 + i + 1)));
+                    part2 = q_log(q_mul(invp, KQ(k0 + i - 1)));
+                }
+                const float m = -0.25f;
+                const Quat pre{m * (part1.w + part2.w), m * (part1.x + part2.x), m * (part1.y + part2.y), m * (part1.z + part2.z)};
+                const Quat tq = q_mul(pq, q_exp(pre));
+                tan[3 * (size_t)(k0 + i) + 1] = make_float4(tq.w, tq.x, tq.y, tq.z);
+            }
+        }
+        float4* d_tan;
+        OGRECU_CHECK(upload(ctx, tan.data(), tan.size(), &d_tan)); s->owned.push_back(d_tan);
+        A.tangents = d_tan;
+    }
     A.bone_rec = d_br;
     A.times = d_times; A.bone_track = d_bt; A.key_offset = d_ko; A.shortest = d_sh; A.index_map = d_im; A.keys = d_keys;
     s->anims.push_back(A);
@@ -601,15 +745,21 @@ int ogrecu_skel_palettes_dev(ogrecu_skel* s, uint32_t num_instances, uint32_t nu
     S.num_bones = s->num_bones; S.blend_mode = s->blend_mode; S.num_levels = s->num_levels; S.num_anims = (uint32_t)s->anims.size();
     S.parent = s->d_parent; S.level = s->d_level; S.order = s->d_order; S.inherit = s->d_inherit; S.bind = s->d_bind; S.bind_inverse = s->d_bind_inverse;
     S.anims = s->d_anims; S.ppos = s->d_ppos; S.level_start = s->d_level_start;
+    for (const AnimDev& a : s->anims)
+        OGRECU_REQUIRE(a.mode == 0 || ctx->skel_mode == 0, "IM_SPLINE / RIM_SPHERICAL animations need the default palette kernel (skel_mode 0)");
     if (ctx->skel_mode == 0) {
         const size_t smem2 = (size_t)s->num_bones * SK_XF * sizeof(float) + (size_t)SK_INST * std::max(num_states, 1u) * sizeof(StatePre);
-        static size_t granted[64] = {0};
-        if (smem2 > 48 * 1024 && smem2 > granted[ctx->device & 63]) {
-            OGRECU_CUDA(cudaFuncSetAttribute(skel_palette_kernel2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-            granted[ctx->device & 63] = smem2;
+        bool nonlinear = false;
+        for (const AnimDev& a : s->anims) nonlinear |= a.mode != 0;
+        static size_t granted[2][64] = {};
+        if (smem2 > 48 * 1024 && smem2 > granted[nonlinear][ctx->device & 63]) {
+            if (nonlinear) OGRECU_CUDA(cudaFuncSetAttribute(skel_palette_kernel2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            else OGRECU_CUDA(cudaFuncSetAttribute(skel_palette_kernel2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            granted[nonlinear][ctx->device & 63] = smem2;
         }
-        skel_palette_kernel2<<<div_up(num_instances, SK_INST), dim3(SK_INST, SK_SLOTS), smem2, ctx->stream>>>(S, num_instances, num_states, anim_dev, time_dev,
-                                                                                                         weight_dev, palettes_dev, stride_floats);
+        const dim3 grid2(div_up(num_instances, SK_INST)), block2(SK_INST, SK_SLOTS);
+        if (nonlinear) skel_palette_kernel2<true><<<grid2, block2, smem2, ctx->stream>>>(S, num_instances, num_states, anim_dev, time_dev, weight_dev, palettes_dev, stride_floats);
+        else skel_palette_kernel2<false><<<grid2, block2, smem2, ctx->stream>>>(S, num_instances, num_states, anim_dev, time_dev, weight_dev, palettes_dev, stride_floats);
         OGRECU_CUDA(cudaGetLastError());
         count_launch(ctx);
         return OGRECU_OK;

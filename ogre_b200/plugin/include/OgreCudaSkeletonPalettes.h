@@ -19,8 +19,9 @@ namespace Ogre
 class _OgreCudaExport CudaSkeletonPalettes
 {
 public:
-    /// uploads the skeleton; throws ERR_RENDERINGAPI_ERROR for what the device path does not cover
-    /// (IM_SPLINE / RIM_SPHERICAL animations) — there is no CPU path to fall back to
+    /// uploads the skeleton with all its animations (IM_LINEAR / RIM_LINEAR: bit-identical palettes; IM_SPLINE / RIM_SPHERICAL:
+    /// within 2e-5 of a matrix's largest element, the device's sinf / atan2f stand in for libm's); throws ERR_RENDERINGAPI_ERROR
+    /// for what the device path does not cover — there is no CPU path to fall back to
     explicit CudaSkeletonPalettes(const Skeleton* skeleton);
     ~CudaSkeletonPalettes();
 
