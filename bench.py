@@ -710,6 +710,10 @@ def run_render_configs(args, local, rank, world, peak):
     a = types.SimpleNamespace(cpu=(rank == 0 and world == 1 and not args.no_cpu_baseline), views=args.views, chunk=32, contexts=1,
                               c3_tris=2000000, c4_tris=1000000, c5_tris=args.c5_tris)
     out = {}
+    try:
+        traf = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+    except Exception:
+        traf = {}
     # ---- c1
     r = bc.c1(ctx, T, a)
     c1_bytes = 1280 * 720 * 3 + 70000                       # 2.76 MB colour write + 0.07 MB geometry
@@ -740,7 +744,10 @@ def run_render_configs(args, local, rank, world, peak):
         out["c5"] = {"config": r["config"], "n_gpus": 1, "frames_per_s": r["frames_per_s_device"], "Mtri_per_s": r["Mtri_per_s_device"],
                      "ms_per_frame": r["ms_per_frame_device"], "covered_fraction": r["covered_fraction"],
                      "roofline": {"bound": "hbm", "achieved": r["compulsory_GBps"], "peak": peak, "unit": "GB/s", "frac": r["compulsory_GBps"] / peak,
-                                  "traffic": None},
+                                  "traffic": traf.get("c5_frame_bytes"),
+                                  "note": "whole frame (all kernels of the pipeline pass): algorithmic = indices + vertices + planes once; traffic = "
+                                          "ncu DRAM bytes of one frame (profiles/r02e_traffic_c5.csv); the pass is bound by per-triangle "
+                                          "instruction issue and per-tile latency, not by bytes"},
                      "e2e": {"value": 1e3 / r["ms_per_frame_with_readback"], "unit": "frames/s", "d2h_bytes_per_step": 3840 * 2160 * 3,
                              "ms_per_frame": r["ms_per_frame_with_readback"]},
                      "cpu_baseline": ({"value": 1.0 / r["cpu_s_per_frame_1_thread"], "unit": "frames/s", "cores": 1, "kind": r["cpu_kind"],

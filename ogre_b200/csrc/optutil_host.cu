@@ -398,7 +398,13 @@ int ogrecu_calculate_face_normals_host(ogrecu_ctx* ctx, const float* positions, 
     OGRECU_REQUIRE(positions && triangles && face_normals, "NULL pointer");
     OGRECU_CUDA(cudaSetDevice(ctx->device));
     OGRECU_CHECK(flush_skin_batch(ctx));          // may read what a queued job writes
-    if (num_vertices == 0) {   // the reference signature carries no vertex count: derive it
+    if (num_vertices == 0) {   // the reference signature carries no vertex count
+        ogrecu_buf* pb = nullptr;
+        size_t poff = 0;
+        OGRECU_CHECK(ogrecu_buf_resolve(ctx, positions, &pb, &poff));
+        if (pb) num_vertices = (pb->size - poff) / 12;          // resident positions are used in place: nothing to size, nothing to scan
+    }
+    if (num_vertices == 0) {   // positions in plain host memory have to be staged: their extent is the highest index referenced
         const uint8_t* t = (const uint8_t*)triangles;
         uint32_t mx = 0;
         for (size_t i = 0; i < n; ++i) {

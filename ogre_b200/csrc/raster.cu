@@ -673,15 +673,20 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(const uint32_t
 /* ------------------------------------------------------------- tile boundaries ------ */
 // tile_start[k] = first position of key k in the SORTED pair array (== position of the next larger key
 // for empty tiles), tile_start[nkeys] = npairs.  Every entry is written exactly once: no memset, no atomics.
+// tile_start[k] = first sorted pair whose key is >= k (k = nkeys: the end), by binary search: one thread per tile, no serial fill of
+// the runs of empty tiles (a thread per PAIR that fills the gap before its key spent 52 us of a config-5 frame in the one
+// thread that owned the empty tail)
 __global__ void __launch_bounds__(256) tile_bounds_kernel(const uint64_t* __restrict__ pairs, uint32_t npairs, uint32_t nkeys,
                                                           uint32_t* __restrict__ tile_start)
 {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= npairs) return;
-    const uint32_t key = (uint32_t)(pairs[i] >> 32);
-    const uint32_t first = i ? (uint32_t)(pairs[i - 1] >> 32) + 1u : 0u;
-    for (uint32_t k = first; k <= key; ++k) tile_start[k] = i;       // empty when key == previous key
-    if (i == npairs - 1) for (uint32_t k = key + 1; k <= nkeys; ++k) tile_start[k] = npairs;
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k > nkeys) return;
+    uint32_t lo = 0, hi = npairs;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if ((uint32_t)(__ldg(pairs + mid) >> 32) < k) lo = mid + 1; else hi = mid;
+    }
+    tile_start[k] = lo;
 }
 
 /* ------------------------------------------------------ stable LSD radix sort ------- */
@@ -1599,7 +1604,7 @@ int segment_finish(SegRun& run)
         std::swap(pa, pb);
     }
     uint32_t* tile_start = (uint32_t*)S.tile_count.ptr;
-    tile_bounds_kernel<<<div_up(npairs, 256), 256, 0, ctx->stream>>>(pa, (uint32_t)npairs, nkeys, tile_start);
+    tile_bounds_kernel<<<div_up((size_t)nkeys + 1, 256), 256, 0, ctx->stream>>>(pa, (uint32_t)npairs, nkeys, tile_start);
     OGRECU_CUDA(cudaGetLastError());
     count_launch(ctx);
 
