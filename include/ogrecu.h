@@ -183,7 +183,7 @@ OGRECU_API int ogrecu_buf_resolve(ogrecu_ctx* ctx, const void* host_ptr, ogrecu_
  * RIM_SPHERICAL (OgreAnimationTrack.cpp:417-450, Quaternion::Slerp / Squad, SimpleSpline / RotationalSpline) are evaluated too:
  * spline tangents are made once on the host at ogrecu_skel_add_animation, translations and scales stay exact, rotations go through
  * the device's sinf / atan2f and agree with the engine within 2e-5 of a matrix's largest element (the stated tolerance of
- * those modes).  Not covered: blend masks, manually controlled bones. */
+ * those modes).  Blend masks and manually controlled bones: ogrecu_skel_palettes_ex_dev. */
 typedef struct ogrecu_skel ogrecu_skel;
 
 typedef struct ogrecu_skeleton_desc {
@@ -223,6 +223,27 @@ OGRECU_API int ogrecu_skel_get_bind_inverse(ogrecu_skel* skel, float* out10_host
 OGRECU_API int ogrecu_skel_palettes_dev(ogrecu_skel* skel, uint32_t num_instances, uint32_t num_states,
                                         const int32_t* anim_dev, const float* time_dev, const float* weight_dev,
                                         float* palettes_dev, size_t palette_stride_floats);
+
+/* ... with what an AnimationStateSet / SkeletonInstance can carry besides (time, weight):
+ *   - AnimationState blend masks (OgreAnimationState.h createBlendMask / setBlendMaskEntry; Animation::apply with a mask,
+ *     OgreAnimation.cpp:344-357: a track's weight becomes mask[bone handle] * weight): mask_dev[(i * mask_instance_stride_floats) +
+ *     s * num_bones + b] for instance i, state slot s, bone b; stride 0 = one set shared by all instances; a state without a mask
+ *     has ones;
+ *   - manually controlled bones (Bone::setManuallyControlled, OgreBone.cpp:82-86): Skeleton::reset leaves them alone
+ *     (OgreSkeleton.cpp:233-240), so they start from the local transform they hold — manual_dev[(i * num_manual + k) * 10 ..] =
+ *     position xyz, orientation wxyz (as the bone holds it: Node::setOrientation normalises), scale xyz of bone manual_bones[k]
+ *     (HOST array of handles) in instance i — and tracks that name them still apply on top, as in the reference.
+ * Bit-identical to the engine like the plain call (tests/test_skeleton_gpu.py).  opt == NULL: the plain call. */
+typedef struct ogrecu_palette_options {
+    const float*    mask_dev;
+    size_t          mask_instance_stride_floats;
+    uint32_t        num_manual;
+    const uint32_t* manual_bones;
+    const float*    manual_dev;
+} ogrecu_palette_options;
+OGRECU_API int ogrecu_skel_palettes_ex_dev(ogrecu_skel* skel, uint32_t num_instances, uint32_t num_states,
+                                           const int32_t* anim_dev, const float* time_dev, const float* weight_dev,
+                                           const ogrecu_palette_options* opt, float* palettes_dev, size_t palette_stride_floats);
 
 /* -------------------------------------------------------------- OptimisedUtil ------ */
 /* Ogre::OptimisedUtil, OgreMain/include/OgreOptimisedUtil.h:99-206; arithmetic replays

@@ -282,16 +282,33 @@ class Skeleton:
         check(lib().ogrecu_skel_palettes_dev(self.handle, int(num_instances), int(num_states), anim_ptr, time_ptr, weight_ptr,
                                              out_ptr, int(stride_floats or self.num_bones * 16)))
 
-    def palettes(self, anim, time, weight):
-        """Host convenience (tests): anim/time/weight [num_instances, num_states] -> palettes [num_instances, num_bones, 16]."""
+    def palettes(self, anim, time, weight, mask=None, manual_bones=None, manual=None):
+        """Host convenience (tests): anim/time/weight [num_instances, num_states] -> palettes [num_instances, num_bones, 16].
+        mask: blend masks [num_instances, num_states, num_bones] or [num_states, num_bones] (shared); manual_bones: handles of the
+        manually controlled bones, manual: their local transforms [num_instances, k, 10] (ogrecu_skel_palettes_ex_dev)."""
         anim = np.ascontiguousarray(anim, np.int32); time = np.ascontiguousarray(time, np.float32)
         weight = np.ascontiguousarray(weight, np.float32)
         ni, ns = anim.shape
         da, dt, dw = self.ctx.to_device(anim), self.ctx.to_device(time), self.ctx.to_device(weight)
         out = self.ctx.alloc(ni * self.num_bones * 64)
-        self.palettes_dev(ni, ns, da.ptr, dt.ptr, dw.ptr, out.ptr)
+        keep = [da, dt, dw, out]
+        if mask is None and manual_bones is None:
+            self.palettes_dev(ni, ns, da.ptr, dt.ptr, dw.ptr, out.ptr)
+        else:
+            from .capi import PaletteOptions
+            opt = PaletteOptions()
+            if mask is not None:
+                m = np.ascontiguousarray(mask, np.float32)
+                dm = self.ctx.to_device(m); keep.append(dm)
+                opt.mask_dev = dm.ptr
+                opt.mask_instance_stride_floats = ns * self.num_bones if m.ndim == 3 else 0
+            if manual_bones is not None and len(manual_bones):
+                hb = (C.c_uint32 * len(manual_bones))(*[int(v) for v in manual_bones])
+                dx = self.ctx.to_device(np.ascontiguousarray(manual, np.float32)); keep.append(dx)
+                opt.num_manual = len(manual_bones); opt.manual_bones = hb; opt.manual_dev = dx.ptr
+            check(lib().ogrecu_skel_palettes_ex_dev(self.handle, ni, ns, da.ptr, dt.ptr, dw.ptr, C.byref(opt), out.ptr, self.num_bones * 16))
         res = out.download(np.float32).reshape(ni, self.num_bones, 16)
-        for b in (da, dt, dw, out):
+        for b in keep:
             b.free()
         return res
 

@@ -69,6 +69,12 @@ class SkeletonDesc(C.Structure):
                 ("inherit", C.c_void_p), ("bind_inverse", C.c_void_p)]
 
 
+class PaletteOptions(C.Structure):
+    """ogrecu_palette_options"""
+    _fields_ = [("mask_dev", C.c_void_p), ("mask_instance_stride_floats", C.c_size_t), ("num_manual", C.c_uint32),
+                ("manual_bones", C.POINTER(C.c_uint32)), ("manual_dev", C.c_void_p)]
+
+
 class AnimationDesc(C.Structure):
     """ogrecu_animation_desc (include/ogrecu.h)"""
     _fields_ = [("length", C.c_float), ("interpolation", C.c_uint32), ("rotation_interpolation", C.c_uint32),
@@ -130,6 +136,8 @@ SIGNATURES = {
     "ogrecu_skel_get_bind_inverse": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ogrecu_skel_palettes_dev": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                            C.c_size_t]),
+    "ogrecu_skel_palettes_ex_dev": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(PaletteOptions),
+                                              C.c_void_p, C.c_size_t]),
     "ogrecu_pose_blend_dev": (C.c_int, [C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]),
     "ogrecu_pose_blend_instanced_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32,
                                                   C.c_size_t]),

@@ -304,11 +304,19 @@ struct StatePre { int32_t anim; float tp; uint32_t gi; float w; };
 
 // NONLINEAR = some animation of the skeleton is IM_SPLINE / RIM_SPHERICAL; the all-linear instantiation has no trace of that path
 // (with the out-of-line call in it the linear launch went from 64 to 81 us: stack frame, one CTA less in flight)
-template <bool NONLINEAR>
+// EXTRA = the call carries AnimationState blend masks and / or manually controlled bones (ogrecu_palette_options)
+struct PalExtra {
+    const float* mask;              // [instance][state][bone] (instance stride mask_stride floats, 0 = shared), NULL = none
+    size_t mask_stride;
+    const int16_t* manual_slot;     // [bone] row of the instance's manual transforms, -1 = animated from the binding pose; NULL = none
+    const float* manual;            // [instance][num_manual][10]
+    uint32_t num_manual;
+};
+template <bool NONLINEAR, bool EXTRA>
 __global__ void __launch_bounds__(SK_INST * SK_SLOTS, 5) skel_palette_kernel2(const SkelDev S, uint32_t num_instances, uint32_t num_states,
                                                                            const int32_t* __restrict__ anim, const float* __restrict__ time,
                                                                            const float* __restrict__ weight, float* __restrict__ out,
-                                                                           size_t stride_floats)
+                                                                           size_t stride_floats, const PalExtra X)
 {
     extern __shared__ float s_xf[];                                  // [num_bones][SK_XF]
     StatePre* s_st = reinterpret_cast<StatePre*>(s_xf + (size_t)S.num_bones * SK_XF);     // [SK_INST][num_states]
@@ -362,12 +370,17 @@ __global__ void __launch_bounds__(SK_INST * SK_SLOTS, 5) skel_palette_kernel2(co
     for (uint32_t p = slot; p < S.num_bones; p += SK_SLOTS) {
         const uint32_t b = S.order[p];
         Xform L = load_xform(S.bind + 10 * b);
+        if (EXTRA && live && X.manual_slot) {                  // Skeleton::reset leaves a manually controlled bone with what it holds
+            const int ms = X.manual_slot[b];
+            if (ms >= 0) L = load_xform(X.manual + ((size_t)inst * X.num_manual + (uint32_t)ms) * 10);
+        }
         if (live) {
             for (uint32_t s = 0; s < num_states; ++s) {
                 const StatePre P = s_st[ix * num_states + s];
                 if (P.anim < 0) continue;
                 const AnimDev A = S.anims[P.anim];
-                const float w = P.w;
+                float w = P.w;
+                if (EXTRA && X.mask) w = X.mask[(size_t)inst * X.mask_stride + (size_t)s * S.num_bones + b] * w;     // (*blendMask)[handle] * weight
                 if (!w) continue;
                 const uint4 R = __ldg(A.bone_rec + b);                             // one load: key range, track, shortest-path flag
                 const uint32_t k0 = R.x, nk = R.y, trk = R.z;
@@ -456,6 +469,8 @@ struct ogrecu_skel {
     std::vector<AnimDev> anims;
     std::vector<void*> owned;               // device blocks of the animations
     AnimDev* d_anims; size_t d_anims_cap;
+    int16_t* d_manual_slot = nullptr;       // [num_bones] of the last call with manually controlled bones
+    std::vector<int16_t> manual_slot_host;
 };
 
 namespace {
@@ -733,8 +748,41 @@ int ogrecu_skel_add_animation(ogrecu_skel* s, const ogrecu_animation_desc* d, ui
 int ogrecu_skel_palettes_dev(ogrecu_skel* s, uint32_t num_instances, uint32_t num_states, const int32_t* anim_dev,
                              const float* time_dev, const float* weight_dev, float* palettes_dev, size_t stride_floats)
 {
+    return ogrecu_skel_palettes_ex_dev(s, num_instances, num_states, anim_dev, time_dev, weight_dev, nullptr, palettes_dev, stride_floats);
+}
+
+int ogrecu_skel_palettes_ex_dev(ogrecu_skel* s, uint32_t num_instances, uint32_t num_states, const int32_t* anim_dev, const float* time_dev,
+                                const float* weight_dev, const ogrecu_palette_options* opt, float* palettes_dev, size_t stride_floats)
+{
     OGRECU_REQUIRE(s && palettes_dev, "NULL argument");
     if (!num_instances) return OGRECU_OK;
+    PalExtra X{};
+    if (opt) {
+        if (opt->mask_dev) {
+            OGRECU_REQUIRE(opt->mask_instance_stride_floats == 0 || opt->mask_instance_stride_floats >= (size_t)num_states * s->num_bones,
+                           "blend-mask instance stride smaller than states x bones");
+            X.mask = opt->mask_dev; X.mask_stride = opt->mask_instance_stride_floats;
+        }
+        if (opt->num_manual) {
+            OGRECU_REQUIRE(opt->manual_bones && opt->manual_dev, "manual bones need their handles and their local transforms");
+            OGRECU_REQUIRE(s->ctx->skel_mode == 0, "manual bones need the default palette kernel (skel_mode 0)");
+            std::vector<int16_t> slot(s->num_bones, -1);
+            for (uint32_t k = 0; k < opt->num_manual; ++k) {
+                OGRECU_REQUIRE(opt->manual_bones[k] < s->num_bones, "manual bone handle outside the skeleton");
+                OGRECU_REQUIRE(slot[opt->manual_bones[k]] < 0, "a manual bone is listed twice");
+                slot[opt->manual_bones[k]] = (int16_t)k;
+            }
+            OGRECU_CUDA(cudaSetDevice(s->ctx->device));
+            if (slot != s->manual_slot_host) {                          // the list rarely changes: uploaded when it does
+                if (!s->d_manual_slot) { OGRECU_CUDA(cudaMalloc((void**)&s->d_manual_slot, (size_t)s->num_bones * 2)); s->owned.push_back(s->d_manual_slot); }
+                OGRECU_CUDA(cudaStreamSynchronize(s->ctx->stream));
+                s->manual_slot_host = slot;
+                OGRECU_CUDA(cudaMemcpyAsync(s->d_manual_slot, s->manual_slot_host.data(), (size_t)s->num_bones * 2, cudaMemcpyHostToDevice, s->ctx->stream));
+            }
+            X.manual_slot = s->d_manual_slot; X.manual = opt->manual_dev; X.num_manual = opt->num_manual;
+        }
+        OGRECU_REQUIRE(!X.mask || s->ctx->skel_mode == 0, "blend masks need the default palette kernel (skel_mode 0)");
+    }
     OGRECU_REQUIRE(num_states == 0 || (anim_dev && time_dev && weight_dev), "state arrays are required");
     OGRECU_REQUIRE(num_states <= 64, "at most 64 animation-state slots per instance");
     OGRECU_REQUIRE(stride_floats >= 16 * (size_t)s->num_bones && (stride_floats & 3) == 0, "palette stride too small or not a multiple of 4 floats");
@@ -751,15 +799,19 @@ int ogrecu_skel_palettes_dev(ogrecu_skel* s, uint32_t num_instances, uint32_t nu
         const size_t smem2 = (size_t)s->num_bones * SK_XF * sizeof(float) + (size_t)SK_INST * std::max(num_states, 1u) * sizeof(StatePre);
         bool nonlinear = false;
         for (const AnimDev& a : s->anims) nonlinear |= a.mode != 0;
-        static size_t granted[2][64] = {};
-        if (smem2 > 48 * 1024 && smem2 > granted[nonlinear][ctx->device & 63]) {
-            if (nonlinear) OGRECU_CUDA(cudaFuncSetAttribute(skel_palette_kernel2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-            else OGRECU_CUDA(cudaFuncSetAttribute(skel_palette_kernel2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-            granted[nonlinear][ctx->device & 63] = smem2;
+        const bool extra = X.mask != nullptr || X.manual_slot != nullptr;
+        const void* fn = nonlinear ? (extra ? (const void*)skel_palette_kernel2<true, true> : (const void*)skel_palette_kernel2<true, false>)
+                                   : (extra ? (const void*)skel_palette_kernel2<false, true> : (const void*)skel_palette_kernel2<false, false>);
+        static size_t granted[4][64] = {};
+        const int which = (nonlinear ? 2 : 0) + (extra ? 1 : 0);
+        if (smem2 > 48 * 1024 && smem2 > granted[which][ctx->device & 63]) {
+            OGRECU_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            granted[which][ctx->device & 63] = smem2;
         }
         const dim3 grid2(div_up(num_instances, SK_INST)), block2(SK_INST, SK_SLOTS);
-        if (nonlinear) skel_palette_kernel2<true><<<grid2, block2, smem2, ctx->stream>>>(S, num_instances, num_states, anim_dev, time_dev, weight_dev, palettes_dev, stride_floats);
-        else skel_palette_kernel2<false><<<grid2, block2, smem2, ctx->stream>>>(S, num_instances, num_states, anim_dev, time_dev, weight_dev, palettes_dev, stride_floats);
+        void* args[] = {(void*)&S, (void*)&num_instances, (void*)&num_states, (void*)&anim_dev, (void*)&time_dev, (void*)&weight_dev,
+                        (void*)&palettes_dev, (void*)&stride_floats, (void*)&X};
+        OGRECU_CUDA(cudaLaunchKernel(fn, grid2, block2, args, smem2, ctx->stream));
         OGRECU_CUDA(cudaGetLastError());
         count_launch(ctx);
         return OGRECU_OK;

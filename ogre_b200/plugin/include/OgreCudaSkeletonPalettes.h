@@ -29,7 +29,8 @@ public:
 
     /// `count` state sets (one per entity instance) -> count * getNumBones() matrices in `dst` (host memory):
     /// for each set what skeletonInstance->setAnimationState(*set); skeletonInstance->_getBoneMatrices(dst) gives.
-    /// Enabled states are applied in the set's enabled order.  Blend masks and manual bones are not supported.
+    /// Enabled states are applied in the set's enabled order, with their blend masks.  Manually controlled bones are a
+    /// property of a SkeletonInstance, which this call does not see: ogrecu_skel_palettes_ex_dev takes them.
     void getBoneMatrices(const AnimationStateSet* const* sets, size_t count, Affine3* dst);
 
     /// same, leaving the palettes in device memory for the skinning kernels (ogrecu_skin_instanced_dev /
@@ -47,6 +48,8 @@ private:
     void* mStates; size_t mStatesCap;
     void* mPalettes; size_t mPalettesCap;
     std::vector<uint8> mHostStates;
+    std::vector<float> mHostMasks;           // blend masks of the last call, [count][slots][bones]
+    void* mMasks = 0; size_t mMasksCap = 0;
 };
 } // namespace Ogre
 #endif

@@ -82,6 +82,7 @@ CudaSkeletonPalettes::CudaSkeletonPalettes(const Skeleton* sk)
 CudaSkeletonPalettes::~CudaSkeletonPalettes()
 {
     if (mStates) ogrecu_free(mCtx, mStates);
+    if (mMasks) ogrecu_free(mCtx, mMasks);
     if (mPalettes) ogrecu_free(mCtx, mPalettes);
     ogrecu_skel_destroy(mSkel);
 }
@@ -96,13 +97,23 @@ void CudaSkeletonPalettes::run(const AnimationStateSet* const* sets, size_t coun
     int32* anim = reinterpret_cast<int32*>(mHostStates.data());
     float* time = reinterpret_cast<float*>(mHostStates.data() + n * 4);
     float* weight = reinterpret_cast<float*>(mHostStates.data() + n * 8);
+    // AnimationState blend masks (Animation::apply with a mask, OgreAnimation.cpp:344-357): [count][slots][bones], ones where a
+    // state has none; only built when some state carries one
+    bool anyMask = false;
+    for (size_t i = 0; i < count && !anyMask; ++i)
+        for (const AnimationState* st : sets[i]->getEnabledAnimationStates()) anyMask |= st->hasBlendMask();
+    if (anyMask) mHostMasks.assign(n * mNumBones, 1.0f);
     for (size_t i = 0; i < count; ++i)
     {
         size_t s = 0;
         for (const AnimationState* st : sets[i]->getEnabledAnimationStates())
         {
-            if (st->hasBlendMask())
-                OGRE_EXCEPT(Exception::ERR_NOT_IMPLEMENTED, "blend masks are not supported by the device palette path");
+            if (anyMask && st->hasBlendMask())
+            {
+                const AnimationState::BoneBlendMask* m = st->getBlendMask();
+                OgreAssert(m->size() >= mNumBones, "blend mask smaller than the skeleton");
+                memcpy(&mHostMasks[(i * slots + s) * mNumBones], m->data(), mNumBones * sizeof(float));
+            }
             auto it = mAnimIndex.find(st->getAnimationName());
             // "tolerate state entries for animations we're not aware of" (OgreSkeleton.cpp:203)
             anim[i * slots + s] = it == mAnimIndex.end() ? -1 : it->second;
@@ -129,9 +140,25 @@ void CudaSkeletonPalettes::run(const AnimationStateSet* const* sets, size_t coun
     }
     OGRECU_THROW_IF(ogrecu_memcpy_h2d(mCtx, mStates, mHostStates.data(), mHostStates.size()));
     uint8* base = static_cast<uint8*>(mStates);
-    OGRECU_THROW_IF(ogrecu_skel_palettes_dev(mSkel, (uint32)count, (uint32)slots, reinterpret_cast<const int32_t*>(base),
-                                             reinterpret_cast<const float*>(base + n * 4), reinterpret_cast<const float*>(base + n * 8),
-                                             static_cast<float*>(mPalettes), (size_t)mNumBones * 16));
+    ogrecu_palette_options opt;
+    memset(&opt, 0, sizeof opt);
+    if (anyMask)
+    {
+        const size_t maskBytes = mHostMasks.size() * sizeof(float);
+        if (maskBytes > mMasksCap)
+        {
+            if (mMasks) OGRECU_THROW_IF(ogrecu_free(mCtx, mMasks));
+            mMasks = 0;
+            mMasksCap = maskBytes * 2;
+            OGRECU_THROW_IF(ogrecu_malloc(mCtx, mMasksCap, &mMasks));
+        }
+        OGRECU_THROW_IF(ogrecu_memcpy_h2d(mCtx, mMasks, mHostMasks.data(), maskBytes));
+        opt.mask_dev = static_cast<const float*>(mMasks);
+        opt.mask_instance_stride_floats = slots * mNumBones;
+    }
+    OGRECU_THROW_IF(ogrecu_skel_palettes_ex_dev(mSkel, (uint32)count, (uint32)slots, reinterpret_cast<const int32_t*>(base),
+                                                reinterpret_cast<const float*>(base + n * 4), reinterpret_cast<const float*>(base + n * 8),
+                                                anyMask ? &opt : NULL, static_cast<float*>(mPalettes), (size_t)mNumBones * 16));
 }
 
 void CudaSkeletonPalettes::getBoneMatrices(const AnimationStateSet* const* sets, size_t count, Affine3* dst)

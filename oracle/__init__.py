@@ -70,14 +70,19 @@ class Skeleton:
         self.bind_inverse = np.zeros((d["num_bones"], 10), np.float32)
         lib().oracle_skeleton_bind_inverse(C.byref(self.sk), self.bind_inverse.ctypes.data)
 
-    def palette(self, anim, time, weight, bind_inverse=None, blend_mode=None):
+    def palette(self, anim, time, weight, bind_inverse=None, blend_mode=None, mask=None, manual_slot=None, manual=None):
+        """mask: [states, bones] blend masks; manual_slot [bones] (row of `manual` or -1), manual [k, 10] local transforms"""
         self.sk.blend_mode = self.d["blend_mode"] if blend_mode is None else int(blend_mode)
         anim = np.ascontiguousarray(anim, np.int32); time = np.ascontiguousarray(time, np.float32)
         weight = np.ascontiguousarray(weight, np.float32)
         bi = self.bind_inverse if bind_inverse is None else np.ascontiguousarray(bind_inverse, np.float32)
         out = np.zeros((self.d["num_bones"], 16), np.float32)
-        rc = lib().oracle_skeleton_palette(C.byref(self.sk), bi.ctypes.data, self.anims, len(anim), anim.ctypes.data,
-                                           time.ctypes.data, weight.ctypes.data, out.ctypes.data)
+        mk = None if mask is None else np.ascontiguousarray(mask, np.float32)
+        ms = None if manual_slot is None else np.ascontiguousarray(manual_slot, np.int32)
+        mx = None if manual is None else np.ascontiguousarray(manual, np.float32)
+        rc = lib().oracle_skeleton_palette_ex(C.byref(self.sk), bi.ctypes.data, self.anims, len(anim), anim.ctypes.data,
+                                              time.ctypes.data, weight.ctypes.data, None if mk is None else mk.ctypes.data,
+                                              None if ms is None else ms.ctypes.data, None if mx is None else mx.ctypes.data, out.ctypes.data)
         if rc:
             raise ValueError("interpolation mode not restated by the oracle")
         return out
@@ -120,6 +125,7 @@ def lib():
         l.oracle_skeleton_bind_inverse.argtypes = [C.POINTER(OracleSkeleton), vp]
         l.oracle_skeleton_bind_inverse.restype = None
         l.oracle_skeleton_palette.argtypes = [C.POINTER(OracleSkeleton), vp, C.POINTER(OracleAnimation), C.c_uint32, vp, vp, vp, vp]
+        l.oracle_skeleton_palette_ex.argtypes = [C.POINTER(OracleSkeleton), vp, C.POINTER(OracleAnimation), C.c_uint32, vp, vp, vp, vp, vp, vp, vp]
         for n in ("oracle_skin_general", "oracle_skin_sse", "oracle_morph", "oracle_concat_affine_sse",
                   "oracle_concat_affine_general", "oracle_face_normals", "oracle_light_facing_sse",
                   "oracle_light_facing_general", "oracle_extrude", "oracle_tiny_clear"):

@@ -750,15 +750,21 @@ static int cmp_float(const void* a, const void* b)
     return (x > y) - (x < y);
 }
 
-int oracle_skeleton_palette(const oracle_skeleton* sk, const float* bind_inverse10, const oracle_animation* anims,
-                            uint32_t nstates, const int32_t* anim, const float* time, const float* weight, float* out16)
+/* mask: AnimationState blend masks, [nstates][num_bones] (state s scales its weight per bone: Animation::apply with a blend mask,
+ * OgreAnimation.cpp:344-357), NULL = none.  manual_slot: [num_bones], >= 0 for a manually controlled bone = row of manual10 that
+ * holds the local transform the bone has when setAnimationState runs (Skeleton::reset leaves such bones alone,
+ * OgreSkeleton.cpp:233-240; tracks still apply on top of it), NULL = no manual bones. */
+int oracle_skeleton_palette_ex(const oracle_skeleton* sk, const float* bind_inverse10, const oracle_animation* anims,
+                               uint32_t nstates, const int32_t* anim, const float* time, const float* weight, const float* mask,
+                               const int32_t* manual_slot, const float* manual10, float* out16)
 {
     uint32_t n = sk->num_bones;
     xform* local = (xform*)malloc(sizeof(xform) * (n ? n : 1));
     xform* derived = (xform*)malloc(sizeof(xform) * (n ? n : 1));
     int rc = 0;
-    /* Skeleton::reset -> Node::resetToInitialState */
-    for (uint32_t b = 0; b < n; ++b) local[b] = load10(sk->bind + 10 * b);
+    /* Skeleton::reset -> Node::resetToInitialState (manually controlled bones keep what they hold) */
+    for (uint32_t b = 0; b < n; ++b)
+        local[b] = (manual_slot && manual_slot[b] >= 0) ? load10(manual10 + 10 * (size_t)manual_slot[b]) : load10(sk->bind + 10 * b);
 
     /* ANIMBLEND_AVERAGE: rebalance when the enabled weights sum to more than 1 (OgreSkeleton.cpp:174-195) */
     float weight_factor = 1.0f;
@@ -772,7 +778,7 @@ int oracle_skeleton_palette(const oracle_skeleton* sk, const float* bind_inverse
         if (A->interpolation > 1 || A->rotation_interpolation > 1) { rc = 1; break; }
         const int spline = A->interpolation == 1;
         const int spherical = A->rotation_interpolation == 1;
-        float w = weight[s] * weight_factor;
+        const float w_state = weight[s] * weight_factor;
         const float scl = 1.0f;                                  /* linked-skeleton scale: none */
         uint32_t nkeys = A->key_offset[A->num_tracks];
         /* Animation::buildKeyFrameTimeList: the sorted set of all key times */
@@ -788,6 +794,8 @@ int oracle_skeleton_palette(const oracle_skeleton* sk, const float* bind_inverse
         if (nt) { while (gi + 1 < nt && times[gi] < tp) ++gi; }   /* lower_bound over [begin, end-1) */
         for (uint32_t t = 0; t < A->num_tracks; ++t) {
             uint32_t k0 = A->key_offset[t], nk = A->key_offset[t + 1] - k0;
+            /* (*blendMask)[b->getHandle()] * weight, OgreAnimation.cpp:355 */
+            const float w = mask ? mask[(size_t)s * n + (uint32_t)A->track_bone[t]] * w_state : w_state;
             if (nk == 0 || !w) continue;
             const float* K = A->keys + 11 * (size_t)k0;
             /* AnimationTrack::_buildKeyFrameIndexMap, entry gi only: the first local key whose time is >= times[gi]
@@ -863,6 +871,12 @@ int oracle_skeleton_palette(const oracle_skeleton* sk, const float* bind_inverse
     }
     free(local); free(derived);
     return rc;
+}
+
+int oracle_skeleton_palette(const oracle_skeleton* sk, const float* bind_inverse10, const oracle_animation* anims,
+                            uint32_t nstates, const int32_t* anim, const float* time, const float* weight, float* out16)
+{
+    return oracle_skeleton_palette_ex(sk, bind_inverse10, anims, nstates, anim, time, weight, NULL, NULL, NULL, out16);
 }
 
 

@@ -168,6 +168,11 @@ void oracle_skeleton_bind_inverse(const oracle_skeleton* sk, float* out10);
  * that is not restated. */
 int oracle_skeleton_palette(const oracle_skeleton* sk, const float* bind_inverse10, const oracle_animation* anims,
                             uint32_t nstates, const int32_t* anim, const float* time, const float* weight, float* out16);
+/* ... with AnimationState blend masks ([nstates][num_bones], NULL = none) and manually controlled bones (manual_slot [num_bones]:
+ * row of manual10 holding the bone's local transform, -1 = animated normally; NULL = none) */
+int oracle_skeleton_palette_ex(const oracle_skeleton* sk, const float* bind_inverse10, const oracle_animation* anims,
+                               uint32_t nstates, const int32_t* anim, const float* time, const float* weight, const float* mask,
+                               const int32_t* manual_slot, const float* manual10, float* out16);
 
 /* ---- Silhouette extraction / shadow-volume index generation ---- */
 

@@ -87,6 +87,7 @@ def lib():
         l.ref_skel_anim_data.restype = None
         l.ref_skel_set_interpolation.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32]
         l.ref_skel_pose_states.argtypes = [C.c_uint32, vp, vp, vp, vp]
+        l.ref_skel_pose_states_ex.argtypes = [C.c_uint32, vp, vp, vp, vp, C.c_uint32, vp, vp, vp]
         l.ref_bench_palettes.argtypes = [C.c_uint32, vp, sz, vp]
         l.ref_bench_palettes.restype = C.c_double
         l.ref_pose_blend.argtypes = [c_f, C.c_uint32, vp, vp, C.c_uint32, vp, vp, vp, C.c_uint32, C.c_uint32, C.c_int]
@@ -220,6 +221,20 @@ def skeleton_pose_states(num_bones, anim, time, weight):
     weight = np.ascontiguousarray(weight, np.float32)
     out = np.zeros((num_bones, 16), np.float32)
     rc = lib().ref_skel_pose_states(len(anim), anim.ctypes.data, time.ctypes.data, weight.ctypes.data, out.ctypes.data)
+    assert rc == 0, rc
+    return out
+
+
+def skeleton_pose_states_ex(num_bones, anim, time, weight, mask=None, manual_handles=(), manual=None):
+    """... with AnimationState blend masks ([states, bones]) and manually controlled bones (handles + [k, 10] local transforms)."""
+    anim = np.ascontiguousarray(anim, np.uint32); time = np.ascontiguousarray(time, np.float32)
+    weight = np.ascontiguousarray(weight, np.float32)
+    mk = None if mask is None else np.ascontiguousarray(mask, np.float32)
+    mh = np.ascontiguousarray(manual_handles, np.uint32)
+    mx = np.ascontiguousarray(manual if manual is not None else np.zeros((0, 10)), np.float32)
+    out = np.zeros((num_bones, 16), np.float32)
+    rc = lib().ref_skel_pose_states_ex(len(anim), anim.ctypes.data, time.ctypes.data, weight.ctypes.data, None if mk is None else mk.ctypes.data,
+                                       len(mh), mh.ctypes.data, mx.ctypes.data, out.ctypes.data)
     assert rc == 0, rc
     return out
 

@@ -643,6 +643,52 @@ API int ref_skel_pose_states(uint32_t n, const uint32_t* anim, const float* time
     } catch (std::exception& ex) { fprintf(stderr, "ref_skel_pose_states: %s\n", ex.what()); return 1; }
 }
 
+// ... with AnimationState blend masks (mask: [n][numBones], NULL = none; AnimationState::createBlendMask / setBlendMaskData) and
+// manually controlled bones (manual_handles[k]: Bone::setManuallyControlled(true) + position / orientation / scale from
+// manual10[k]; Skeleton::reset leaves such bones alone, OgreSkeleton.cpp:233-240).  Everything is restored afterwards.
+API int ref_skel_pose_states_ex(uint32_t n, const uint32_t* anim, const float* time, const float* weight, const float* mask,
+                                uint32_t nmanual, const uint32_t* manual_handles, const float* manual10, float* bones_out)
+{
+    try {
+        Entity* e = g_skel_ent;
+        SkeletonInstance* sk = e->getSkeleton();
+        const size_t nb = sk->getNumBones();
+        AnimationStateSet* set = e->getAllAnimationStates();
+        for (auto& kv : set->getAnimationStates()) { kv.second->setEnabled(false); if (kv.second->hasBlendMask()) kv.second->destroyBlendMask(); }
+        std::vector<AnimationState*> used;
+        for (uint32_t i = 0; i < n; ++i) {
+            Animation* an = skel_anim(anim[i]);
+            if (!an) return 2;
+            AnimationState* st = set->getAnimationState(an->getName());
+            st->setLoop(false);
+            st->setEnabled(true);
+            st->setTimePosition(time[i]);
+            st->setWeight(weight[i]);
+            if (mask) { st->createBlendMask(nb, 1.0f); st->_setBlendMaskData(mask + (size_t)i * nb); }
+            used.push_back(st);
+        }
+        for (uint32_t k = 0; k < nmanual; ++k) {
+            Bone* b = sk->getBone((unsigned short)manual_handles[k]);
+            const float* x = manual10 + 10 * (size_t)k;
+            b->setManuallyControlled(true);
+            b->setPosition(Vector3(x[0], x[1], x[2]));
+            b->setOrientation(Quaternion(x[3], x[4], x[5], x[6]));
+            b->setScale(Vector3(x[7], x[8], x[9]));
+        }
+        sk->setAnimationState(*set);
+        std::vector<Affine3> m(nb);
+        sk->_getBoneMatrices(m.data());
+        memcpy(bones_out, m.data(), m.size() * 64);
+        for (uint32_t k = 0; k < nmanual; ++k) {
+            Bone* b = sk->getBone((unsigned short)manual_handles[k]);
+            b->setManuallyControlled(false);
+            b->reset();
+        }
+        for (AnimationState* st : used) if (st->hasBlendMask()) st->destroyBlendMask();
+        return 0;
+    } catch (std::exception& ex) { fprintf(stderr, "ref_skel_pose_states_ex: %s\n", ex.what()); return 1; }
+}
+
 // CPU timing of the same: `ninst` palette evaluations (one enabled state each, time[i]); seconds for one pass, 1 thread
 // (SkeletonInstance is not thread-safe and OGRE evaluates entities serially on the render thread).
 API double ref_bench_palettes(uint32_t anim, const float* time, size_t ninst, float* bones_out)

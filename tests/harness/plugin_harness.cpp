@@ -417,11 +417,25 @@ API int ph_skel_palettes(uint32_t n, const float* times, float* engine, float* d
     first->setLoop(true); first->setEnabled(true); first->setWeight(1.0f);
     std::vector<std::unique_ptr<AnimationStateSet>> copies;
     std::vector<const AnimationStateSet*> ptrs;
+    std::vector<float> mask(nb);
     for (uint32_t i = 0; i < n; ++i) {
         first->setTimePosition(times[i]);
+        // every other pose with a blend mask on the state (Animation::apply with a mask, OgreAnimation.cpp:344-357)
+        const bool masked = (i & 1u) != 0;
+        if (masked) {
+            for (size_t b = 0; b < nb; ++b) mask[b] = float((b * 7 + i) % 5) * 0.25f;
+            first->createBlendMask(nb, 1.0f);
+            for (size_t b = 0; b < nb; ++b) first->setBlendMaskEntry(b, mask[b]);
+        }
         sk->setAnimationState(*set);
         sk->_getBoneMatrices(reinterpret_cast<Affine3*>(engine) + i * nb);
         copies.emplace_back(new AnimationStateSet(*set));
+        if (masked) {                                            // (the copy constructor of AnimationState drops the mask)
+            AnimationState* c = copies.back()->getAnimationState(first->getAnimationName());
+            c->createBlendMask(nb, 1.0f);
+            for (size_t b = 0; b < nb; ++b) c->setBlendMaskEntry(b, mask[b]);
+            first->destroyBlendMask();
+        }
         ptrs.push_back(copies.back().get());
     }
     CudaSkeletonPalettes pal(sk);

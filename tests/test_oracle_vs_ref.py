@@ -191,6 +191,68 @@ def test_oracle_spline_and_spherical_interpolation_equal_real_skeleton_instance(
         ref.lib().ref_skel_set_blend_mode(d["blend_mode"])
 
 
+def random_manual_bones(rng, d, k):
+    """k manually controlled bones with local transforms near their binding pose"""
+    handles = rng.choice(d["num_bones"], k, replace=False).astype(np.uint32)
+    x = np.array(d["bind"], np.float32).reshape(-1, 10)[handles].copy()
+    x[:, 0:3] += rng.uniform(-0.5, 0.5, (k, 3)).astype(np.float32)
+    q = x[:, 3:7].astype(np.float64) + rng.uniform(-0.3, 0.3, (k, 4))
+    x[:, 3:7] = (q / np.linalg.norm(q, axis=1, keepdims=True)).astype(np.float32)
+    x[:, 7:10] *= rng.uniform(0.8, 1.25, (k, 3)).astype(np.float32)
+    slot = np.full(d["num_bones"], -1, np.int32)
+    slot[handles] = np.arange(k, dtype=np.int32)
+    return handles, x, slot
+
+
+def held_by_the_bone(x):
+    """what a Bone holds after setPosition / setOrientation / setScale: Node::setOrientation normalises the quaternion
+    (OgreNode.cpp: mOrientation = q; mOrientation.normalise()), in float32 as Quaternion::normalise does: (1.0f / len) * q"""
+    x = np.array(x, np.float32).copy()
+    if len(x):
+        q = x[:, 3:7]
+        n2 = ((q[:, 0] * q[:, 0] + q[:, 1] * q[:, 1]) + q[:, 2] * q[:, 2]) + q[:, 3] * q[:, 3]
+        s = np.float32(1.0) / np.sqrt(n2, dtype=np.float32)
+        x[:, 3:7] = s[:, None] * q
+    return x
+
+
+@pytest.mark.parametrize("mesh", ["Sinbad.mesh", "jaiqua.mesh"])
+def test_oracle_blend_masks_and_manual_bones_equal_real_skeleton_instance(mesh):
+    """AnimationState blend masks (Animation::apply with a mask, OgreAnimation.cpp:344-357: mask[bone] * weight per track) and
+    manually controlled bones (Skeleton::reset leaves them alone, OgreSkeleton.cpp:233-240; their tracks apply on top of what they
+    hold): 150 random multi-state poses against the real SkeletonInstance, masks with zeros and ones among the values, 0-4 manual
+    bones per pose — bit-identical."""
+    d = ref.skeleton_def(mesh)
+    sk = oracle.Skeleton(d)
+    rng = np.random.default_rng(41)
+    nb = d["num_bones"]
+    plain_differs = 0
+    for trial in range(150):
+        ns = int(rng.integers(1, 4))
+        an = rng.choice(len(d["anims"]), ns, replace=False)
+        tm = [rng.uniform(0, d["anims"][a]["length"]) for a in an]
+        w = rng.uniform(0.0, 1.0, ns) if trial % 3 else np.ones(ns)
+        mode = trial % 2
+        mask = None
+        if trial % 4 != 3:
+            mask = rng.uniform(0, 1, (ns, nb)).astype(np.float32)
+            mask[rng.uniform(size=(ns, nb)) < 0.2] = 0.0
+            mask[rng.uniform(size=(ns, nb)) < 0.2] = 1.0
+        k = int(rng.integers(0, 5))
+        handles, xf, slot = random_manual_bones(rng, d, k)
+        ref.lib().ref_skel_set_blend_mode(mode)
+        r = ref.skeleton_pose_states_ex(nb, an, tm, w, mask, handles, xf)
+        o = sk.palette(an, tm, w, bind_inverse=d["bind_inverse"], blend_mode=mode, mask=mask, manual_slot=slot if k else None,
+                       manual=held_by_the_bone(xf) if k else None)
+        assert np.array_equal(bits(r), bits(o)), (mesh, trial)
+        plain_differs += int(not np.array_equal(bits(o), bits(sk.palette(an, tm, w, bind_inverse=d["bind_inverse"], blend_mode=mode))))
+        # the engine is left as it was: the next plain pose is the plain pose
+        if trial % 25 == 0:
+            assert np.array_equal(bits(ref.skeleton_pose_states(nb, an, tm, w)), bits(sk.palette(an, tm, w, bind_inverse=d["bind_inverse"], blend_mode=mode)))
+    assert plain_differs > 100
+    ref.lib().ref_skel_set_blend_mode(d["blend_mode"])
+
+
 def test_oracle_streams_fuzz_against_real_optimised_util():
     """Live fuzz of the remaining OptimisedUtil restatements against the real implementations (which = 0 SSE, 1 General in
     oracle/ref_driver.cpp): random counts incl. 1-17 and counts = 0..3 mod 4, random values incl. signed zeros and large

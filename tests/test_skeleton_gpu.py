@@ -157,6 +157,57 @@ def test_spline_translation_and_scale_are_exact(ctx):
     sk.destroy()
 
 
+@pytest.mark.parametrize("name", ["sinbad_skeleton.npz", "jaiqua_skeleton.npz"])
+@pytest.mark.parametrize("shared_mask", [False, True])
+def test_blend_masks_and_manual_bones_bit_exact(ctx, name, shared_mask):
+    """ogrecu_skel_palettes_ex_dev: per-state blend masks (per instance, or one set shared by all) and manually controlled bones with
+    per-instance local transforms — the oracle for these is pinned bit for bit against the real SkeletonInstance
+    (tests/test_oracle_vs_ref.py::test_oracle_blend_masks_and_manual_bones_equal_real_skeleton_instance); the device equals it."""
+    d, _ = load_skeleton(name)
+    sk = ogre_b200.Skeleton(ctx, d, use_given_bind_inverse=True)
+    osk = oracle.Skeleton(d)
+    rng = np.random.default_rng(77)
+    ni, ns, nb = 403, 3, d["num_bones"]
+    na = len(d["anims"])
+    anim = rng.integers(-1, na, size=(ni, ns)).astype(np.int32)
+    for i in range(ni):
+        seen = set()
+        for s in range(ns):
+            if anim[i, s] in seen:
+                anim[i, s] = -1
+            seen.add(int(anim[i, s]))
+    length = np.array([a["length"] for a in d["anims"]] + [0.0], np.float32)
+    time = (rng.uniform(0, 1.2, size=(ni, ns)) * length[anim]).astype(np.float32)
+    weight = rng.uniform(0, 1, size=(ni, ns)).astype(np.float32)
+    weight[rng.uniform(size=(ni, ns)) < 0.2] = 1.0
+    mask = rng.uniform(0, 1, size=((ns, nb) if shared_mask else (ni, ns, nb))).astype(np.float32)
+    mask[rng.uniform(size=mask.shape) < 0.2] = 0.0
+    mask[rng.uniform(size=mask.shape) < 0.2] = 1.0
+    k = 4
+    handles = rng.choice(nb, k, replace=False).astype(np.uint32)
+    bind = np.array(d["bind"], np.float32).reshape(-1, 10)
+    manual = np.repeat(bind[handles][None], ni, axis=0).copy()
+    manual[:, :, 0:3] += rng.uniform(-0.5, 0.5, (ni, k, 3)).astype(np.float32)
+    q = manual[:, :, 3:7].astype(np.float64) + rng.uniform(-0.3, 0.3, (ni, k, 4))
+    manual[:, :, 3:7] = (q / np.linalg.norm(q, axis=2, keepdims=True)).astype(np.float32)
+    manual[:, :, 7:10] *= rng.uniform(0.8, 1.25, (ni, k, 3)).astype(np.float32)
+    slot = np.full(nb, -1, np.int32); slot[handles] = np.arange(k, dtype=np.int32)
+    for mode in (0, 1):
+        sk.set_blend_mode(mode)
+        got = sk.palettes(anim, time, weight, mask=mask, manual_bones=handles, manual=manual)
+        only_mask = sk.palettes(anim, time, weight, mask=mask)
+        for i in range(0, ni, 5):
+            on = anim[i] >= 0
+            # the oracle takes the masks of the ENABLED states in order (disabled slots are skipped on both sides)
+            mi = (mask if shared_mask else mask[i])[on]
+            want = osk.palette(anim[i][on], time[i][on], weight[i][on], bind_inverse=d["bind_inverse"], blend_mode=mode, mask=mi,
+                               manual_slot=slot, manual=manual[i])
+            assert np.array_equal(bits(got[i]), bits(want)), (name, mode, i)
+            want = osk.palette(anim[i][on], time[i][on], weight[i][on], bind_inverse=d["bind_inverse"], blend_mode=mode, mask=mi)
+            assert np.array_equal(bits(only_mask[i]), bits(want)), (name, mode, i, "mask only")
+    sk.destroy()
+
+
 def test_bad_modes_and_the_first_kernel_fail_loudly(ctx):
     d, _ = load_skeleton("jaiqua_skeleton.npz")
     sk = ogre_b200.Skeleton(ctx, dict(d, anims=[]))
