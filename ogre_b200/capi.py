@@ -190,6 +190,7 @@ SIGNATURES = {
     "ogrecu_rt_clear": (C.c_int, [C.c_void_p, C.c_uint, c_float_p, C.c_float]),
     "ogrecu_draw": (C.c_int, [C.c_void_p, C.POINTER(DrawDesc)]),
     "ogrecu_draw_with_state": (C.c_int, [C.c_void_p, C.POINTER(DrawDesc), C.POINTER(DrawState)]),
+    "ogrecu_draw_refs": (C.c_int, [C.c_void_p, C.POINTER(DrawDesc), C.c_void_p, C.POINTER(C.c_void_p), C.c_uint32]),
     "ogrecu_flush": (C.c_int, [C.c_void_p]),
     "ogrecu_draw_views": (C.c_int, [C.POINTER(C.c_void_p), C.c_uint32, C.POINTER(DrawDesc), c_float_p, c_float_p, c_float_p]),
     "ogrecu_rt_set_strip": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),

@@ -137,7 +137,8 @@ struct ogrecu_ctx {
     int optutil_batch = 0;
     uint64_t batch_epoch = 1, draw_epoch = 1;
     std::vector<ogrecu_skin_job> batch_jobs;
-    std::vector<float> batch_pal;
+    float* batch_palpin[2] = {nullptr, nullptr};     // pinned, per arena: the queued jobs' palettes are gathered straight into it
+    size_t batch_pal_cap[2] = {0, 0}, batch_pal_floats = 0;
     uint8_t* batch_pin[2] = {nullptr, nullptr};
     size_t batch_pin_cap[2] = {0, 0};
     cudaEvent_t batch_ev[2] = {nullptr, nullptr};

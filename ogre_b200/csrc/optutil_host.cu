@@ -129,6 +129,15 @@ static ogrecu_buf* resolve_range(ogrecu_ctx* ctx, const void* host, size_t len, 
     return b;
 }
 
+// the same when the range probably lies in a buffer already found (normals beside positions, weights beside indices): one
+// comparison instead of a locked map look-up
+static ogrecu_buf* resolve_near(ogrecu_ctx* ctx, ogrecu_buf* hint, const void* host, size_t len, const uint8_t** dev)
+{
+    const uint8_t* p = (const uint8_t*)host;
+    if (hint && p >= hint->shadow && p + len <= hint->shadow + hint->size) { *dev = (const uint8_t*)hint->dev + (p - hint->shadow); return hint; }
+    return resolve_range(ctx, host, len, dev);
+}
+
 // highest blend index of the stream, remembered per buffer until the host next writes it (ogrecu_buf_map clears the cache)
 static unsigned max_blend_index(ogrecu_buf* b, const uint8_t* blend_index, size_t stride, size_t nw, size_t n)
 {
@@ -161,16 +170,16 @@ int flush_skin_batch(ogrecu_ctx* ctx)
     ProfileScope range("ogrecu: batched OptimisedUtil flush");
     OGRECU_CUDA(cudaSetDevice(ctx->device));
     const size_t jobs_bytes = up((size_t)n * sizeof(ogrecu_skin_job)), prefix_bytes = up(((size_t)n + 1) * 4);
-    const size_t pal_bytes = ctx->batch_pal.size() * 4, total = jobs_bytes + prefix_bytes + pal_bytes;
+    const size_t pal_bytes = ctx->batch_pal_floats * 4, head = jobs_bytes + prefix_bytes, total = head + pal_bytes;
     const int s = ctx->batch_slot;
     ctx->batch_slot ^= 1;
-    if (ctx->batch_ev_used[s]) OGRECU_CUDA(cudaEventSynchronize(ctx->batch_ev[s]));          // this arena's last copy has been read
-    if (ctx->batch_pin_cap[s] < total) {
+    // (the arena's previous upload was waited for when the batch's first job was queued: its palettes already sit in batch_palpin[s])
+    if (ctx->batch_pin_cap[s] < head) {
         if (ctx->batch_pin[s]) cudaFreeHost(ctx->batch_pin[s]);
         ctx->batch_pin[s] = nullptr; ctx->batch_pin_cap[s] = 0;
-        const size_t cap = std::max(total * 2, (size_t)1 << 20);
+        const size_t cap = std::max(head * 2, (size_t)1 << 16);
         if (cudaHostAlloc((void**)&ctx->batch_pin[s], cap, cudaHostAllocDefault) != cudaSuccess) {
-            (void)cudaGetLastError(); ctx->batch_jobs.clear(); ctx->batch_pal.clear(); ++ctx->batch_epoch;
+            (void)cudaGetLastError(); ctx->batch_jobs.clear(); ctx->batch_pal_floats = 0; ++ctx->batch_epoch;
             set_error("pinned allocation of %zu bytes failed", cap); return OGRECU_ERR_OOM;
         }
         ctx->batch_pin_cap[s] = cap;
@@ -183,7 +192,7 @@ int flush_skin_batch(ogrecu_ctx* ctx)
         uint8_t* dev = (uint8_t*)ctx->batch_dev.ptr;
         ogrecu_skin_job* hj = (ogrecu_skin_job*)pin;
         uint32_t* prefix = (uint32_t*)(pin + jobs_bytes);
-        const float* dpal = (const float*)(dev + jobs_bytes + prefix_bytes);
+        const float* dpal = (const float*)(dev + head);
         for (uint32_t k = 0; k < n; ++k) {
             hj[k] = ctx->batch_jobs[k];
             hj[k].palette = dpal + (size_t)(uintptr_t)ctx->batch_jobs[k].palette;            // queued as an offset in floats
@@ -191,8 +200,8 @@ int flush_skin_batch(ogrecu_ctx* ctx)
             blocks += div_up(hj[k].num_vertices, 256);
         }
         prefix[n] = (uint32_t)blocks;
-        memcpy(pin + jobs_bytes + prefix_bytes, ctx->batch_pal.data(), pal_bytes);
-        cudaError_t e = cudaMemcpyAsync(dev, pin, total, cudaMemcpyHostToDevice, ctx->stream);
+        cudaError_t e = cudaMemcpyAsync(dev, pin, head, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess && pal_bytes) e = cudaMemcpyAsync(dev + head, ctx->batch_palpin[s], pal_bytes, cudaMemcpyHostToDevice, ctx->stream);
         if (e == cudaSuccess) e = cudaEventRecord(ctx->batch_ev[s], ctx->stream);
         if (e != cudaSuccess) rc = cuda_fail(e, "batch upload", __FILE__, __LINE__);
         else {
@@ -201,7 +210,7 @@ int flush_skin_batch(ogrecu_ctx* ctx)
         }
     }
     ctx->batch_flushes++; ctx->batch_jobs_run += n;
-    ctx->batch_jobs.clear(); ctx->batch_pal.clear();
+    ctx->batch_jobs.clear(); ctx->batch_pal_floats = 0;
     ++ctx->batch_epoch;                                           // every buffer's batch_r / batch_w mark is stale now
     return rc;
 }
@@ -247,10 +256,10 @@ int ogrecu_software_vertex_skinning_host(ogrecu_ctx* ctx, const float* src_pos, 
         // ---- deferred: every operand lives in an ogrecu_buf -> queue the job, copy the palette, return
         const uint8_t *d_sp = nullptr, *d_sn = nullptr, *d_w = nullptr, *d_dp = nullptr, *d_dn = nullptr;
         ogrecu_buf* b_sp = resolve_range(ctx, src_pos, q_sp_len, &d_sp);
-        ogrecu_buf* b_sn = src_norm ? resolve_range(ctx, src_norm, q_sn_len, &d_sn) : b_sp;
-        ogrecu_buf* b_w = resolve_range(ctx, blend_weight, q_w_len, &d_w);
+        ogrecu_buf* b_sn = src_norm ? resolve_near(ctx, b_sp, src_norm, q_sn_len, &d_sn) : b_sp;
+        ogrecu_buf* b_w = resolve_near(ctx, b_bi, blend_weight, q_w_len, &d_w);
         ogrecu_buf* b_dp = resolve_range(ctx, dst_pos, q_dp_len, &d_dp);
-        ogrecu_buf* b_dn = src_norm ? resolve_range(ctx, dst_norm, q_dn_len, &d_dn) : b_dp;
+        ogrecu_buf* b_dn = src_norm ? resolve_near(ctx, b_dp, dst_norm, q_dn_len, &d_dn) : b_dp;
         if (b_sp && b_sn && b_w && b_dp && b_dn) {
             ogrecu_skin_job j;
             memset(&j, 0, sizeof j);
@@ -275,9 +284,26 @@ int ogrecu_software_vertex_skinning_host(ogrecu_ctx* ctx, const float* src_pos, 
             b_dp->batch_w = b_dn->batch_w = now;
             OGRECU_CHECK(ogrecu_buf_mark_device_dirty(b_dp, (size_t)(d_dp - (const uint8_t*)b_dp->dev), q_dp_len));
             if (src_norm) OGRECU_CHECK(ogrecu_buf_mark_device_dirty(b_dn, (size_t)(d_dn - (const uint8_t*)b_dn->dev), q_dn_len));
-            const size_t pal_off = ctx->batch_pal.size();            // multiple of 16 floats: keeps 16-byte alignment
-            ctx->batch_pal.resize(pal_off + (size_t)nmat * 16);
-            for (unsigned m = 0; m < nmat; ++m) memcpy(&ctx->batch_pal[pal_off + (size_t)m * 16], blend_matrices[m], 64);
+            // the palette is gathered straight into the pinned block the flush uploads from (a vector + one more copy of all the
+            // frame's palettes at the flush cost 1.5 ms per 7 000 jobs)
+            const int slot = ctx->batch_slot;
+            if (ctx->batch_jobs.empty() && ctx->batch_ev_used[slot]) OGRECU_CUDA(cudaEventSynchronize(ctx->batch_ev[slot]));   // its last upload has been read
+            const size_t pal_off = ctx->batch_pal_floats;            // multiple of 16 floats: keeps 16-byte alignment
+            if (pal_off + (size_t)nmat * 16 > ctx->batch_pal_cap[slot]) {
+                const size_t cap = std::max<size_t>(2 * (pal_off + (size_t)nmat * 16), (size_t)1 << 18);
+                float* fresh = nullptr;
+                if (cudaHostAlloc((void**)&fresh, cap * 4, cudaHostAllocDefault) != cudaSuccess) {
+                    (void)cudaGetLastError();
+                    set_error("pinned allocation of %zu bytes failed", cap * 4);
+                    return OGRECU_ERR_OOM;
+                }
+                if (pal_off) memcpy(fresh, ctx->batch_palpin[slot], pal_off * 4);
+                if (ctx->batch_palpin[slot]) cudaFreeHost(ctx->batch_palpin[slot]);
+                ctx->batch_palpin[slot] = fresh; ctx->batch_pal_cap[slot] = cap;
+            }
+            float* pal_dst = ctx->batch_palpin[slot] + pal_off;
+            for (unsigned m = 0; m < nmat; ++m) memcpy(pal_dst + (size_t)m * 16, blend_matrices[m], 64);
+            ctx->batch_pal_floats = pal_off + (size_t)nmat * 16;
             j.palette = (const float*)(uintptr_t)pal_off;            // an offset in floats until the flush
             ctx->batch_jobs.push_back(j);
             if (ctx->batch_jobs.size() >= 65536) OGRECU_CHECK(flush_skin_batch(ctx));

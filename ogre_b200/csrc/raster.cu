@@ -2142,7 +2142,18 @@ int ogrecu_rt_clear(ogrecu_rt* rt, unsigned buffers, const float colour_rgba[4],
 
 int ogrecu_draw(ogrecu_rt* rt, const ogrecu_draw_desc* d) { return ogrecu_draw_with_state(rt, d, nullptr); }
 
-int ogrecu_draw_with_state(ogrecu_rt* rt, const ogrecu_draw_desc* d, const ogrecu_draw_state* st)
+static int record_draw(ogrecu_rt* rt, const ogrecu_draw_desc* d, const ogrecu_draw_state* st, const ogrecu_buf* const* refs, uint32_t num_refs);
+
+int ogrecu_draw_with_state(ogrecu_rt* rt, const ogrecu_draw_desc* d, const ogrecu_draw_state* st) { return record_draw(rt, d, st, nullptr, 0); }
+
+int ogrecu_draw_refs(ogrecu_rt* rt, const ogrecu_draw_desc* d, const ogrecu_draw_state* st, const ogrecu_buf* const* refs, uint32_t num_refs)
+{
+    OGRECU_REQUIRE(refs || num_refs == 0, "refs is NULL");
+    return record_draw(rt, d, st, refs ? refs : (const ogrecu_buf* const*)&refs, num_refs);
+}
+
+// refs == NULL: the buffers the draw reads are looked up from its device pointers; otherwise the caller names them
+static int record_draw(ogrecu_rt* rt, const ogrecu_draw_desc* d, const ogrecu_draw_state* st, const ogrecu_buf* const* refs, uint32_t num_refs)
 {
     OGRECU_REQUIRE(rt && d, "NULL argument");
     if (st && st->enable) {
@@ -2175,9 +2186,14 @@ int ogrecu_draw_with_state(ogrecu_rt* rt, const ogrecu_draw_desc* d, const ogrec
     rt->cmds.push_back(c);
     // the buffers the draw will read when it is flushed: a host write to one of them (or a deferred OptimisedUtil job that
     // overwrites one) must run the recorded draws first (ogrecu_buf_map, ogrecu_software_vertex_skinning_host)
-    const void* refs[5] = {d->positions, d->uvs, d->normals, d->indices, (st && (st->enable & OGRECU_EXT_VERTEX_COLOUR)) ? st->colours : nullptr};
     ogrecu_ctx* root = root_of(rt->ctx);
-    for (const void* r : refs)
+    if (refs) {
+        for (uint32_t k = 0; k < num_refs; ++k)
+            if (refs[k]) { OGRECU_REQUIRE(refs[k]->ctx == root, "a referenced buffer belongs to another context"); const_cast<ogrecu_buf*>(refs[k])->draw_ref = root->draw_epoch; }
+        return OGRECU_OK;
+    }
+    const void* ptrs[5] = {d->positions, d->uvs, d->normals, d->indices, (st && (st->enable & OGRECU_EXT_VERTEX_COLOUR)) ? st->colours : nullptr};
+    for (const void* r : ptrs)
         if (ogrecu_buf* b = buf_of_device_ptr(root, r)) b->draw_ref = root->draw_epoch;
     return OGRECU_OK;
 }

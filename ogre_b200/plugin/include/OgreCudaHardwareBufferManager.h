@@ -17,6 +17,7 @@ namespace Ogre
 class CudaHardwareBuffer : public HardwareBuffer
 {
     ogrecu_buf* mBuf;
+    const uint8* mDevice;        // device address of byte 0 (fixed for the buffer's life)
     void* lockImpl(size_t offset, size_t length, LockOptions options) override;
     void unlockImpl(void) override;
 
@@ -31,7 +32,7 @@ public:
 
     ogrecu_buf* getHandle() const { return mBuf; }
     /// device address of byte `offset`
-    const void* getDevicePtr(size_t offset = 0) const;
+    const void* getDevicePtr(size_t offset = 0) const { return mDevice + offset; }
 };
 
 class CudaHardwareBufferManager : public HardwareBufferManager

@@ -6,10 +6,13 @@
 namespace Ogre
 {
 CudaHardwareBuffer::CudaHardwareBuffer(ogrecu_ctx* ctx, size_t sizeInBytes, Usage usage)
-    : HardwareBuffer(usage, false), mBuf(0)   // the pinned shadow lives inside ogrecu_buf, not in OgreMain
+    : HardwareBuffer(usage, false), mBuf(0), mDevice(0)   // the pinned shadow lives inside ogrecu_buf, not in OgreMain
 {
     mSizeInBytes = sizeInBytes;
     OGRECU_THROW_IF(ogrecu_buf_create(ctx, sizeInBytes, &mBuf));
+    void* d = 0;
+    OGRECU_THROW_IF(ogrecu_buf_device_ptr(mBuf, &d));
+    mDevice = static_cast<const uint8*>(d);
 }
 
 CudaHardwareBuffer::~CudaHardwareBuffer()
@@ -84,13 +87,6 @@ void CudaHardwareBuffer::copyData(HardwareBuffer& srcBuffer, size_t srcOffset, s
     const void* src = srcBuffer.lock(srcOffset, length, HBL_READ_ONLY);
     writeData(dstOffset, length, src, discardWholeBuffer);
     srcBuffer.unlock();
-}
-
-const void* CudaHardwareBuffer::getDevicePtr(size_t offset) const
-{
-    void* d = 0;
-    OGRECU_THROW_IF(ogrecu_buf_device_ptr(mBuf, &d));
-    return static_cast<const uint8*>(d) + offset;
 }
 
 HardwareVertexBufferSharedPtr CudaHardwareBufferManager::createVertexBuffer(size_t vertexSize, size_t numVerts,

@@ -355,20 +355,21 @@ struct Stream
 {
     const void* ptr;
     uint32 stride;
+    ogrecu_buf* buf;
 };
 
-// device address of the first element of `sem`, the way TinyRenderSystem's getData() computes the
+// device address of the first element of a vertex element, the way TinyRenderSystem's getData() computes the
 // host address (OgreTinyRenderSystem.cpp:335-347): base + elemOffset + vertexStart*stride
-Stream deviceStream(const RenderOperation& op, VertexElementSemantic sem)
+Stream deviceStream(const RenderOperation& op, const VertexElement* element)
 {
-    Stream s = {0, 0};
-    auto element = op.vertexData->vertexDeclaration->findElementBySemantic(sem);
+    Stream s = {0, 0, 0};
     if (!element) return s;
     s.stride = (uint32)op.vertexData->vertexDeclaration->getVertexSize(element->getSource());
     auto buf = op.vertexData->vertexBufferBinding->getBuffer(element->getSource());
     auto impl = dynamic_cast<CudaHardwareBuffer*>(buf->_getImpl<HardwareBuffer>());
     OgreAssert(impl, "vertex buffer was not created by CudaHardwareBufferManager");
     s.ptr = impl->getDevicePtr(element->getOffset() + op.vertexData->vertexStart * s.stride);
+    s.buf = impl->getHandle();
     return s;
 }
 } // namespace
@@ -383,10 +384,25 @@ void CudaRenderSystem::_render(const RenderOperation& op)
         return;
     if (!mActiveTarget) return;
 
-    Stream pos = deviceStream(op, VES_POSITION);
+    // one walk over the declaration (findElementBySemantic walks it once per semantic; this runs once per sub-entity and frame)
+    const VertexElement *ePos = 0, *eUv = 0, *eNrm = 0, *eCol = 0;
+    for (const VertexElement& el : op.vertexData->vertexDeclaration->getElements())
+    {
+        if (el.getIndex() != 0) continue;                     // findElementBySemantic(sem, 0): the first element of index 0
+        switch (el.getSemantic())
+        {
+        case VES_POSITION: if (!ePos) ePos = &el; break;
+        case VES_TEXTURE_COORDINATES: if (!eUv) eUv = &el; break;
+        case VES_NORMAL: if (!eNrm) eNrm = &el; break;
+        case VES_DIFFUSE: if (!eCol) eCol = &el; break;
+        default: break;
+        }
+    }
+    Stream pos = deviceStream(op, ePos);
     OgreAssert(pos.ptr, "VES_POSITION required");
-    Stream uv = deviceStream(op, VES_TEXTURE_COORDINATES);
-    Stream nrm = deviceStream(op, VES_NORMAL);
+    Stream uv = deviceStream(op, eUv);
+    Stream nrm = deviceStream(op, eNrm);
+    const ogrecu_buf* refs[5] = {pos.buf, uv.buf, nrm.buf, 0, 0};
 
     mDoLighting &= bool(nrm.ptr);   // sticky, as in Tiny (OgreTinyRenderSystem.cpp:369)
 
@@ -406,6 +422,7 @@ void CudaRenderSystem::_render(const RenderOperation& op)
         d.index_type = ib->getIndexSize() == 2 ? OGRECU_INDEX_U16 : OGRECU_INDEX_U32;
         d.indices = impl->getDevicePtr(op.indexData->indexStart * ib->getIndexSize());
         d.draw_count = (uint32_t)op.indexData->indexCount;
+        refs[3] = impl->getHandle();
     }
     d.prim_type = isStrip ? OGRECU_PRIM_TRIANGLE_STRIP : OGRECU_PRIM_TRIANGLE_LIST;
     d.flags = (mDepthTest ? OGRECU_DRAW_DEPTH_TEST : 0) | (mDepthWrite ? OGRECU_DRAW_DEPTH_WRITE : 0) |
@@ -439,10 +456,10 @@ void CudaRenderSystem::_render(const RenderOperation& op)
             st.scissor[0] = std::max<int32>(0, mScissor.left); st.scissor[1] = std::max<int32>(0, mScissor.top);
             st.scissor[2] = std::max<int32>(0, mScissor.right); st.scissor[3] = std::max<int32>(0, mScissor.bottom);
         }
-        auto diffuse = op.vertexData->vertexDeclaration->findElementBySemantic(VES_DIFFUSE);
-        if (diffuse && diffuse->getType() == VET_UBYTE4_NORM)
+        if (eCol && eCol->getType() == VET_UBYTE4_NORM)
         {
-            Stream col = deviceStream(op, VES_DIFFUSE);
+            Stream col = deviceStream(op, eCol);
+            refs[4] = col.buf;
             st.enable |= OGRECU_EXT_VERTEX_COLOUR;
             st.colours = col.ptr; st.colour_stride = col.stride;
         }
@@ -450,7 +467,7 @@ void CudaRenderSystem::_render(const RenderOperation& op)
 
     do
     {
-        OGRECU_THROW_IF(ogrecu_draw_with_state(mActiveTarget, &d, mBeyondTiny ? &st : NULL));
+        OGRECU_THROW_IF(ogrecu_draw_refs(mActiveTarget, &d, mBeyondTiny ? &st : NULL, refs, 5));
     } while (updatePassIterationRenderState());
     noteRecorded(mActiveTarget);
     if (mActiveTargetTexture) mActiveTargetTexture->markTargetRendered();
