@@ -262,6 +262,16 @@ struct TriSetup {
 // Everything Tiny does per triangle before its pixel loop (OgreTinyRenderSystem.cpp:396-410,
 // tinyrenderer.h:45-69): fetch / transform the three vertices, cull, bounding box, plus the number of
 // 16x16 tiles of this strip the box touches.  Pure function of (g, draw table): both passes below call it.
+// a vertex of a draw that gave no vertex count (or an index past it): transformed here, per index, like Tiny.  Out of line and by
+// value: the pre-transformed path (every draw OGRE submits) carries none of its address set-up and keeps its registers.
+__device__ __noinline__ float4 fetch_untransformed(const DrawDev* D, const uint8_t* pos, uint32_t pos_stride, size_t vi, const float* s_mat)
+{
+    const float* Mmvp = s_mat ? s_mat : D->mvp;
+    const float* Mvp = s_mat ? s_mat + 16 : D->vp;
+    const float* p = (const float*)(pos + vi * pos_stride);
+    return transform_vertex(Mmvp, Mvp, __ldg(p), __ldg(p + 1), __ldg(p + 2));
+}
+
 template <bool COVER>
 __device__ __forceinline__ void setup_triangle(const SegParams& P, uint32_t g, uint32_t lo0, uint32_t lo0_end, const float* s_mat, TriSetup& T)
 {
@@ -278,8 +288,6 @@ __device__ __forceinline__ void setup_triangle(const SegParams& P, uint32_t g, u
     }
     const DrawDev& D = P.draws[lo];
     const DrawHot H = load_hot(&D);
-    const float* Mmvp = same ? s_mat : D.mvp;
-    const float* Mvp = same ? s_mat + 16 : D.vp;
     const uint32_t t = g - H.tri_base;
     T.draw = lo; T.tri = t;
     bool ok = true;
@@ -297,12 +305,7 @@ __device__ __forceinline__ void setup_triangle(const SegParams& P, uint32_t g, u
     } else {
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
-            float4 sv;
-            if (H.xf && vi[j] < H.nxf) sv = __ldg(H.xf + vi[j]);
-            else {
-                const float* p = (const float*)(H.pos + vi[j] * H.pos_stride);
-                sv = transform_vertex(Mmvp, Mvp, __ldg(p), __ldg(p + 1), __ldg(p + 2));
-            }
+            const float4 sv = (H.xf && vi[j] < H.nxf) ? __ldg(H.xf + vi[j]) : fetch_untransformed(&D, H.pos, H.pos_stride, vi[j], same ? s_mat : nullptr);
             ok = ok && isfinite(sv.x) && isfinite(sv.y) && isfinite(sv.z) && isfinite(sv.w);
             T.X[j] = sv.x; T.Y[j] = sv.y; T.Z[j] = sv.z; T.IW[j] = sv.w;
         }
