@@ -398,24 +398,28 @@ __global__ void __launch_bounds__(LN_THREADS, 1) skin_lane_kernel(const __grid_c
     constexpr uint32_t UNIT_BYTES = LN_MAXB * LN_SLOT_BYTES + (LN_CHUNK_VERTS + 1) * LN_REC_BYTES + (LN_CHUNK_VERTS + 1) * KEY_BYTES + RAW_BYTES + 32 + 256;
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* s_stage = smem;                                                       // [consumer warps][A, B][32 x 96 B], 128-byte aligned boxes
-    uint8_t* s_unit = s_stage + LN_WARPS * 2 * LN_BOX_BYTES;                       // [2] x {palette, records, keys, meta}
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_unit + 2 * UNIT_BYTES);        // full[2], empty[2]
+    uint8_t* s_unit = s_stage + LN_WARPS * 2 * LN_BOX_BYTES;                       // [LN_NBUF] x {palette, records, keys, meta}
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_unit + LN_NBUF * UNIT_BYTES);  // full[LN_NBUF], empty[LN_NBUF]
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
     if (tid == 0) {
-        ln_mbar_init(ln_smem_u32(&s_bar[0]), 2); ln_mbar_init(ln_smem_u32(&s_bar[1]), 2);       // full: the producer's expect_tx arrive + its final arrive
-        ln_mbar_init(ln_smem_u32(&s_bar[2]), LN_WARPS); ln_mbar_init(ln_smem_u32(&s_bar[3]), LN_WARPS);
+        for (int k = 0; k < LN_NBUF; ++k) {
+            ln_mbar_init(ln_smem_u32(&s_bar[k]), 2);                       // full: the producer's expect_tx arrive + its final arrive
+            ln_mbar_init(ln_smem_u32(&s_bar[LN_NBUF + k]), LN_WARPS);      // empty: every consumer warp
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
     if (wid == LN_WARPS) {
         // ================================================================ producer warp
-        uint32_t held0 = 0xffffffffu, held1 = 0xffffffffu;                  // which chunk's records / keys each buffer holds
+        uint32_t held[LN_NBUF];                                             // which chunk's records / keys each buffer holds
+#pragma unroll
+        for (int k = 0; k < LN_NBUF; ++k) held[k] = 0xffffffffu;
         uint32_t next_unit = 0;
         if (lane == 0) next_unit = atomicAdd(P.counter, 1u);
         for (uint32_t it = 0;; ++it) {
-            const uint32_t b = it & 1u;
+            const uint32_t b = it % LN_NBUF, use = it / LN_NBUF;           // buffer, and how many times it has been used before
             uint8_t* U = s_unit + b * UNIT_BYTES;
             uint8_t* u_pal = U;
             uint4* u_rec = reinterpret_cast<uint4*>(U + LN_MAXB * LN_SLOT_BYTES);
@@ -446,7 +450,7 @@ __global__ void __launch_bounds__(LN_THREADS, 1) skin_lane_kernel(const __grid_c
                     t_mine = make_float2(__ldg(P.t + ia), __ldg(P.t + ib));
                 }
             }
-            if (it >= 2) ln_mbar_wait_relaxed(ln_smem_u32(&s_bar[2 + b]), ((it >> 1) - 1u) & 1u);      // the consumers are done with this buffer
+            if (use) ln_mbar_wait_relaxed(ln_smem_u32(&s_bar[LN_NBUF + b]), (use - 1u) & 1u);            // the consumers are done with this buffer
             if (done) {
                 if (lane == 0) { u_meta->done = 1; ln_mbar_arrive(full); ln_mbar_arrive(full); }
                 break;
@@ -469,8 +473,10 @@ __global__ void __launch_bounds__(LN_THREADS, 1) skin_lane_kernel(const __grid_c
             // ---- plan records and keyframes of the chunk (entry 0: the vertex before it); units arrive chunk-major, so the
             // buffer usually holds them already.  The flag word is kept raw on the side: it is re-derived per unit below.
             const uint32_t chunk_id = (j << 24) | c;
-            if ((b ? held1 : held0) != chunk_id) {
-                if (b) held1 = chunk_id; else held0 = chunk_id;
+            bool have = false;
+#pragma unroll
+            for (int k = 0; k < LN_NBUF; ++k) if ((uint32_t)k == b) { have = held[k] == chunk_id; held[k] = chunk_id; }
+            if (!have) {
                 for (uint32_t e = lane; e <= nv_chunk; e += 32u) {
                     if (e == 0 && v_begin == 0) continue;
                     const uint32_t gv = v_begin + e - 1u;
@@ -513,12 +519,12 @@ __global__ void __launch_bounds__(LN_THREADS, 1) skin_lane_kernel(const __grid_c
     // ==================================================================== consumer warps
     uint8_t* my_stage = s_stage + wid * (2 * LN_BOX_BYTES);
     for (uint32_t it = 0;; ++it) {
-        const uint32_t b = it & 1u;
+        const uint32_t b = it % LN_NBUF;
         const uint8_t* U = s_unit + b * UNIT_BYTES;
         const uint4* u_rec = reinterpret_cast<const uint4*>(U + LN_MAXB * LN_SLOT_BYTES);
         const uint8_t* u_key = reinterpret_cast<const uint8_t*>(u_rec) + (LN_CHUNK_VERTS + 1) * LN_REC_BYTES;
         const LaneUnitMeta* u_meta = reinterpret_cast<const LaneUnitMeta*>(u_key + (LN_CHUNK_VERTS + 1) * KEY_BYTES + RAW_BYTES);
-        ln_mbar_wait(ln_smem_u32(&s_bar[b]), (it >> 1) & 1u);
+        ln_mbar_wait(ln_smem_u32(&s_bar[b]), (it / LN_NBUF) & 1u);
         if (u_meta->done) break;
         const LaneJob& J = P.job[u_meta->job];
         const uint32_t v_begin = u_meta->v_begin, nquads = u_meta->nquads, i0 = u_meta->i0;
@@ -567,7 +573,7 @@ __global__ void __launch_bounds__(LN_THREADS, 1) skin_lane_kernel(const __grid_c
             }
         }
         __syncwarp();
-        if (lane == 0) ln_mbar_arrive(ln_smem_u32(&s_bar[2 + b]));           // this warp no longer reads the unit buffer
+        if (lane == 0) ln_mbar_arrive(ln_smem_u32(&s_bar[LN_NBUF + b]));     // this warp no longer reads the unit buffer
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // shared memory must outlive the TMA reads
     __syncwarp();
@@ -579,7 +585,7 @@ static size_t lane_smem(bool morph)
 {
     const size_t unit = (size_t)LN_MAXB * LN_SLOT_BYTES + (size_t)(LN_CHUNK_VERTS + 1) * LN_REC_BYTES + (size_t)(LN_CHUNK_VERTS + 1) * (morph ? 48 : 32) +
                         (((LN_CHUNK_VERTS + 1) * 4 + 15) & ~15) + 32 + 256;
-    return (size_t)LN_WARPS * 2 * LN_BOX_BYTES + 2 * unit + 4 * 8;
+    return (size_t)LN_WARPS * 2 * LN_BOX_BYTES + LN_NBUF * unit + 2 * LN_NBUF * 8;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,

@@ -9,7 +9,14 @@
 
 namespace ogrecu {
 
-constexpr int LN_WARPS = 15;                  // consumer warps; one more warp produces their inputs (16 warps: 128 registers each)
+#ifndef LN_WARPS_N
+#define LN_WARPS_N 15
+#endif
+#ifndef LN_NBUF_N
+#define LN_NBUF_N 2
+#endif
+constexpr int LN_WARPS = LN_WARPS_N;          // consumer warps; one more warp produces their inputs (16 warps: 128 registers each)
+constexpr int LN_NBUF = LN_NBUF_N;            // unit buffers: the producer runs this many units ahead of the slowest consumer warp
 constexpr int LN_THREADS = (LN_WARPS + 1) * 32;
 constexpr int LN_MAXB = LN_MAXB_N;            // palette entries resident per chunk (a chunk whose first quad plus the vertex before it needs more cannot be planned)
 #ifndef LN_CHUNK_QUADS_N
@@ -21,7 +28,7 @@ constexpr int LN_SLOT_BYTES = 3072;           // 64 instances x 48 bytes
 constexpr int LN_BOX_BYTES = 32 * 96;         // one TMA box: 32 instance rows x 4 vertices
 constexpr int LN_REC_BYTES = 32;              // plan record per vertex: 4 slot offsets (+ flags in the low bits of the first) and 4 weights
 constexpr int LN_MAX_JOBS = 8;
-static_assert(LN_MAXB >= 16 && LN_MAXB * LN_SLOT_BYTES < 65536 * 16, "palette window");
+static_assert(LN_MAXB >= 4 && LN_MAXB <= 16 && LN_MAXB * LN_SLOT_BYTES < 65536 * 16, "palette window");
 
 struct LaneJob {
     CUtensorMap mapA, mapB;          // destination as [instance pair][words]: even instances / odd instances
