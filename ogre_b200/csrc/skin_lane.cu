@@ -338,6 +338,24 @@ __device__ __forceinline__ void ln_mbar_wait(uint32_t bar, uint32_t parity)
     } while (!ok);
 }
 
+#ifndef LN_CONSUMER_SLEEP
+#define LN_CONSUMER_SLEEP 0
+#endif
+__device__ __forceinline__ void ln_mbar_wait_consumer(uint32_t bar, uint32_t parity)
+{
+#if LN_CONSUMER_SLEEP > 0
+    uint32_t ok;
+    for (;;) {          // 15 warps polling in a tight loop take issue slots from the one warp they are waiting for
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) break;
+        __nanosleep(LN_CONSUMER_SLEEP);
+    }
+#else
+    ln_mbar_wait(bar, parity);
+#endif
+}
+
 __device__ __forceinline__ void ln_mbar_wait_relaxed(uint32_t bar, uint32_t parity)      // off the critical path: back off between polls
 {
     uint32_t ok;
@@ -390,6 +408,16 @@ struct LaneUnitMeta { uint32_t done, job, v_begin, nquads, i0, pad[3]; };     //
 // (the chunk's bones only) into the [slot][chunk][lane] pair layout, tests them for the two exactness hazards, and copies
 // the chunk's plan records (with the zero-skip flags withdrawn where a hazard was found) and keyframes.  Two unit buffers,
 // full / empty mbarriers: no CTA barrier after start-up, the consumers never wait for global memory.
+// Development only (-DLN_PROFILE, tools/build_variant.sh): cycles CTA 0 spends in the phases of its producer warp and of consumer
+// warp 0, accumulated behind the unit counter and read by ogrecu_debug_lane_profile.
+#ifdef LN_PROFILE
+#define LN_PROF_DECL long long prof_t0 = clock64(); const bool prof_on = blockIdx.x == 0 && (threadIdx.x & 31) == 0
+#define LN_PROF(slot) do { if (prof_on) { const long long t1 = clock64(); atomicAdd(reinterpret_cast<unsigned long long*>(P.counter) + 8 + (slot), (unsigned long long)(t1 - prof_t0)); prof_t0 = t1; } } while (0)
+#else
+#define LN_PROF_DECL
+#define LN_PROF(slot)
+#endif
+
 template <bool MORPH>
 __global__ void __launch_bounds__(LN_THREADS, 1) skin_lane_kernel(const __grid_constant__ LaneParams P, const u64 NZ)
 {
@@ -416,8 +444,14 @@ __global__ void __launch_bounds__(LN_THREADS, 1) skin_lane_kernel(const __grid_c
         uint32_t held[LN_NBUF];                                             // which chunk's records / keys each buffer holds
 #pragma unroll
         for (int k = 0; k < LN_NBUF; ++k) held[k] = 0xffffffffu;
-        uint32_t next_unit = 0;
-        if (lane == 0) next_unit = atomicAdd(P.counter, 1u);
+        // Units are taken from the global counter in PAIRS of consecutive numbers: units are numbered chunk-major, so a pair shares
+        // its chunk, and the second unit copies the chunk's records and keyframes — 121 entries of ten loads each, the producer's
+        // longest job — from the first unit's buffer instead of fetching them again.  (Taken one by one, the 157 groups of a chunk
+        // went to 148 different SMs and every unit refilled them from global memory.  Batches of 4 / 8 / 16 / 32 units: 0.468 /
+        // 0.482 / 0.518 / 0.672 ms against 0.463 — the tail of the launch grows with the batch; profiles/r02_notes.md.)
+        uint32_t batch_next = 0, cur = 0, cur_end = 0;
+        if (lane == 0) batch_next = atomicAdd(P.counter, (uint32_t)LN_UNIT_BATCH);
+        LN_PROF_DECL;
         for (uint32_t it = 0;; ++it) {
             const uint32_t b = it % LN_NBUF, use = it / LN_NBUF;           // buffer, and how many times it has been used before
             uint8_t* U = s_unit + b * UNIT_BYTES;
@@ -428,8 +462,16 @@ __global__ void __launch_bounds__(LN_THREADS, 1) skin_lane_kernel(const __grid_c
             LaneUnitMeta* u_meta = reinterpret_cast<LaneUnitMeta*>(reinterpret_cast<uint8_t*>(u_raw) + RAW_BYTES);
             const uint32_t full = ln_smem_u32(&s_bar[b]);
             // ---- everything that does not touch the buffer first: the unit, its chunk, its hazard flags
-            const uint32_t unit = __shfl_sync(0xffffffffu, next_unit, 0);
+            bool new_batch = false;
+            if (cur == cur_end) {
+                cur = __shfl_sync(0xffffffffu, batch_next, 0);
+                cur_end = min(cur + (uint32_t)LN_UNIT_BATCH, P.total_units);
+                if (cur_end < cur) cur_end = cur;                       // past the end: `done` below
+                new_batch = true;
+            }
+            const uint32_t unit = cur;
             const bool done = unit >= P.total_units;
+            if (!done) ++cur;
             uint32_t j = 0, c = 0, g = 0;
             uint4 ch = make_uint4(0, 0, 0, 0);
             uint32_t gm_mine = 0, fl_mine = 0;
@@ -443,14 +485,18 @@ __global__ void __launch_bounds__(LN_THREADS, 1) skin_lane_kernel(const __grid_c
                 ch = __ldg(chrec);
                 if (lane < LN_MAXB) gm_mine = (uint32_t)__ldg(reinterpret_cast<const uint16_t*>(chrec + 1) + lane);
                 if (lane < ch.z) fl_mine = __ldg(P.iflags + (size_t)g * P.nmat + gm_mine);
-                next_unit = 0;
-                if (lane == 0) next_unit = atomicAdd(P.counter, 1u);       // the next unit's number travels while this one is prepared
+                if (new_batch) {
+                    batch_next = 0;
+                    if (lane == 0) batch_next = atomicAdd(P.counter, (uint32_t)LN_UNIT_BATCH);      // the next batch's number travels while this one is worked on
+                }
                 if (MORPH) {                                               // the instances' morph weights, as (A, B) per lane
                     const uint32_t ia = min(g * 64u + 2u * lane, P.ninst - 1u), ib = min(g * 64u + 2u * lane + 1u, P.ninst - 1u);
                     t_mine = make_float2(__ldg(P.t + ia), __ldg(P.t + ib));
                 }
             }
+            LN_PROF(0);                                                    // prep: unit, chunk record, flags, weights
             if (use) ln_mbar_wait_relaxed(ln_smem_u32(&s_bar[LN_NBUF + b]), (use - 1u) & 1u);            // the consumers are done with this buffer
+            LN_PROF(1);                                                    // waiting for the buffer
             if (done) {
                 if (lane == 0) { u_meta->done = 1; ln_mbar_arrive(full); ln_mbar_arrive(full); }
                 break;
@@ -472,31 +518,66 @@ __global__ void __launch_bounds__(LN_THREADS, 1) skin_lane_kernel(const __grid_c
             }
             // ---- plan records and keyframes of the chunk (entry 0: the vertex before it); units arrive chunk-major, so the
             // buffer usually holds them already.  The flag word is kept raw on the side: it is re-derived per unit below.
+            LN_PROF(2);                                                    // issuing the palette copies
             const uint32_t chunk_id = (j << 24) | c;
             bool have = false;
+            int other = -1;                                                 // another buffer that holds this chunk's records
 #pragma unroll
-            for (int k = 0; k < LN_NBUF; ++k) if ((uint32_t)k == b) { have = held[k] == chunk_id; held[k] = chunk_id; }
-            if (!have) {
-                for (uint32_t e = lane; e <= nv_chunk; e += 32u) {
-                    if (e == 0 && v_begin == 0) continue;
+            for (int k = 0; k < LN_NBUF; ++k) {
+                if ((uint32_t)k == b) { have = held[k] == chunk_id; held[k] = chunk_id; }
+                else if (held[k] == chunk_id) other = k;
+            }
+            if (!have && other >= 0) {
+                // the consumers may be reading that buffer: so does this copy, nobody writes it.  (Its flag words were patched for
+                // another group of instances; they are re-derived from the raw copy below.)
+                const uint32_t n16 = ((nv_chunk + 1u) * (LN_REC_BYTES + KEY_BYTES)) / 16u, r16 = ((nv_chunk + 1u) * 4u + 15u) / 16u;
+                const uint8_t* O = s_unit + (uint32_t)other * UNIT_BYTES;
+                const uint4* o_rec = reinterpret_cast<const uint4*>(O + LN_MAXB * LN_SLOT_BYTES);
+                const uint4* o_key = reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(o_rec) + (LN_CHUNK_VERTS + 1) * LN_REC_BYTES);
+                const uint4* o_raw = reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(o_key) + (LN_CHUNK_VERTS + 1) * KEY_BYTES);
+                const uint32_t nrec16 = (nv_chunk + 1u) * (LN_REC_BYTES / 16u);
+                for (uint32_t q = lane; q < n16; q += 32u) {
+                    if (q < nrec16) u_rec[q] = o_rec[q];
+                    else reinterpret_cast<uint4*>(u_key)[q - nrec16] = o_key[q - nrec16];
+                }
+                for (uint32_t q = lane; q < r16; q += 32u) reinterpret_cast<uint4*>(u_raw)[q] = o_raw[q];
+                __syncwarp();
+            } else if (!have) {
+                // from global memory: all of the lane's loads first (up to four entries of ten loads), then the stores — in one loop
+                // the shared-memory stores kept the iterations' loads apart and the fill cost four L2 round trips
+                constexpr int NIT = (LN_CHUNK_VERTS + 1 + 31) / 32;
+                uint4 rr0[NIT], rr1[NIT];
+                float2 ka[NIT][3], kb[NIT][3];
+#pragma unroll
+                for (int q = 0; q < NIT; ++q) {
+                    const uint32_t e = lane + 32u * (uint32_t)q;
+                    if (e > nv_chunk || (e == 0 && v_begin == 0)) continue;
                     const uint32_t gv = v_begin + e - 1u;
                     const uint4* r = e == 0 ? J.pre_recs + (size_t)c * 2 : J.recs + (size_t)gv * 2;
-                    const uint4 rec0 = __ldg(r), rec1 = __ldg(r + 1);
+                    rr0[q] = __ldg(r); rr1[q] = __ldg(r + 1);
                     const float2* a = reinterpret_cast<const float2*>(J.key1 + (size_t)gv * 24);
-                    const float2 a0 = __ldg(a), a1 = __ldg(a + 1), a2 = __ldg(a + 2);
-                    float* ky = reinterpret_cast<float*>(u_key + e * KEY_BYTES);
-                    ky[0] = a0.x; ky[1] = a0.y; ky[2] = a1.x; ky[3] = a1.y; ky[4] = a2.x; ky[5] = a2.y;
+                    ka[q][0] = __ldg(a); ka[q][1] = __ldg(a + 1); ka[q][2] = __ldg(a + 2);
                     if (MORPH) {
                         const float2* k2 = reinterpret_cast<const float2*>(J.key2 + (size_t)gv * 24);
-                        const float2 b0 = __ldg(k2), b1 = __ldg(k2 + 1), b2 = __ldg(k2 + 2);
-                        ky[6] = fsub(b0.x, a0.x); ky[7] = fsub(b0.y, a0.y); ky[8] = fsub(b1.x, a1.x);        // (b - a) is instance-invariant
-                        ky[9] = fsub(b1.y, a1.y); ky[10] = fsub(b2.x, a2.x); ky[11] = fsub(b2.y, a2.y);
+                        kb[q][0] = __ldg(k2); kb[q][1] = __ldg(k2 + 1); kb[q][2] = __ldg(k2 + 2);
                     }
-                    u_rec[e * 2u] = rec0; u_rec[e * 2u + 1u] = rec1;
-                    u_raw[e] = rec0.x;
+                }
+#pragma unroll
+                for (int q = 0; q < NIT; ++q) {
+                    const uint32_t e = lane + 32u * (uint32_t)q;
+                    if (e > nv_chunk || (e == 0 && v_begin == 0)) continue;
+                    float* ky = reinterpret_cast<float*>(u_key + e * KEY_BYTES);
+                    ky[0] = ka[q][0].x; ky[1] = ka[q][0].y; ky[2] = ka[q][1].x; ky[3] = ka[q][1].y; ky[4] = ka[q][2].x; ky[5] = ka[q][2].y;
+                    if (MORPH) {                                            // (b - a) is instance-invariant
+                        ky[6] = fsub(kb[q][0].x, ka[q][0].x); ky[7] = fsub(kb[q][0].y, ka[q][0].y); ky[8] = fsub(kb[q][1].x, ka[q][1].x);
+                        ky[9] = fsub(kb[q][1].y, ka[q][1].y); ky[10] = fsub(kb[q][2].x, ka[q][2].x); ky[11] = fsub(kb[q][2].y, ka[q][2].y);
+                    }
+                    u_rec[e * 2u] = rr0[q]; u_rec[e * 2u + 1u] = rr1[q];
+                    u_raw[e] = rr0[q].x;
                 }
                 __syncwarp();
             }
+            LN_PROF(3);                                                    // records / keys
             if (MORPH) reinterpret_cast<float2*>(u_meta + 1)[lane] = t_mine;
             // a vertex whose slot-0 matrix holds a -0 in some instance, or any vertex when something is not finite, takes every slot
             {
@@ -512,19 +593,25 @@ __global__ void __launch_bounds__(LN_THREADS, 1) skin_lane_kernel(const __grid_c
             if (lane == 0) { u_meta->done = 0; u_meta->job = j; u_meta->v_begin = v_begin; u_meta->nquads = nquads; u_meta->i0 = i0; }
             __syncwarp();
             if (lane == 0) ln_mbar_arrive(full);                            // release: everything above is visible to who acquires
+            LN_PROF(4);                                                    // flag patch, meta, arrive
         }
         return;
     }
 
     // ==================================================================== consumer warps
     uint8_t* my_stage = s_stage + wid * (2 * LN_BOX_BYTES);
+#ifdef LN_PROFILE
+    long long prof_t0 = clock64(); const bool prof_on = blockIdx.x == 0 && tid == 0;
+#endif
     for (uint32_t it = 0;; ++it) {
         const uint32_t b = it % LN_NBUF;
         const uint8_t* U = s_unit + b * UNIT_BYTES;
         const uint4* u_rec = reinterpret_cast<const uint4*>(U + LN_MAXB * LN_SLOT_BYTES);
         const uint8_t* u_key = reinterpret_cast<const uint8_t*>(u_rec) + (LN_CHUNK_VERTS + 1) * LN_REC_BYTES;
         const LaneUnitMeta* u_meta = reinterpret_cast<const LaneUnitMeta*>(u_key + (LN_CHUNK_VERTS + 1) * KEY_BYTES + RAW_BYTES);
-        ln_mbar_wait(ln_smem_u32(&s_bar[b]), (it / LN_NBUF) & 1u);
+        LN_PROF(5);                                                        // consumer: arrive + loop overhead
+        ln_mbar_wait_consumer(ln_smem_u32(&s_bar[b]), (it / LN_NBUF) & 1u);
+        LN_PROF(6);                                                        // consumer: waiting for the unit
         if (u_meta->done) break;
         const LaneJob& J = P.job[u_meta->job];
         const uint32_t v_begin = u_meta->v_begin, nquads = u_meta->nquads, i0 = u_meta->i0;
@@ -573,6 +660,7 @@ __global__ void __launch_bounds__(LN_THREADS, 1) skin_lane_kernel(const __grid_c
             }
         }
         __syncwarp();
+        LN_PROF(7);                                                        // consumer: walking its run
         if (lane == 0) ln_mbar_arrive(ln_smem_u32(&s_bar[LN_NBUF + b]));     // this warp no longer reads the unit buffer
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // shared memory must outlive the TMA reads
@@ -698,7 +786,11 @@ int launch_skin_lane(ogrecu_ctx* ctx, const ogrecu_anim_job* jobs, ogrecu_skin_p
     P.iflags = (const uint32_t*)((uint8_t*)ctx->lane_ipal.ptr + (size_t)P.groups * nmat * LN_SLOT_BYTES);
     P.nmat = nmat;
     OGRECU_CHECK(scratch_reserve(ctx, ctx->lane_counter, 256));
+#ifdef LN_PROFILE
+    OGRECU_CUDA(cudaMemsetAsync(ctx->lane_counter.ptr, 0, 256, ctx->stream));
+#else
     OGRECU_CUDA(cudaMemsetAsync(ctx->lane_counter.ptr, 0, 4, ctx->stream));
+#endif
     P.counter = (uint32_t*)ctx->lane_counter.ptr;
     P.total_units = (uint32_t)items;
     const unsigned grid = (unsigned)std::min<uint64_t>(items, (uint64_t)ctx->sm_count);
@@ -915,5 +1007,16 @@ int ogrecu_anim_frame_dev(ogrecu_ctx* ctx, const ogrecu_anim_job* jobs, ogrecu_s
     }
     return OGRECU_OK;
 }
+
+#ifdef LN_PROFILE
+// development builds only: the phase cycle counts of the last lane launch (see LN_PROF)
+__attribute__((visibility("default"))) int ogrecu_debug_lane_profile(ogrecu_ctx* ctx, unsigned long long* out16)
+{
+    OGRECU_CUDA(cudaSetDevice(ctx->device));
+    OGRECU_CUDA(cudaStreamSynchronize(ctx->stream));
+    OGRECU_CUDA(cudaMemcpy(out16, (const uint8_t*)ctx->lane_counter.ptr + 64, 128, cudaMemcpyDeviceToHost));
+    return OGRECU_OK;
+}
+#endif
 
 }  // extern "C"

@@ -16,6 +16,10 @@ namespace ogrecu {
 #define LN_NBUF_N 2
 #endif
 constexpr int LN_WARPS = LN_WARPS_N;          // consumer warps; one more warp produces their inputs (16 warps: 128 registers each)
+#ifndef LN_UNIT_BATCH_N
+#define LN_UNIT_BATCH_N 2
+#endif
+constexpr int LN_UNIT_BATCH = LN_UNIT_BATCH_N;   // consecutive work units a CTA takes from the global counter at a time
 constexpr int LN_NBUF = LN_NBUF_N;            // unit buffers: the producer runs this many units ahead of the slowest consumer warp
 constexpr int LN_THREADS = (LN_WARPS + 1) * 32;
 constexpr int LN_MAXB = LN_MAXB_N;            // palette entries resident per chunk (a chunk whose first quad plus the vertex before it needs more cannot be planned)

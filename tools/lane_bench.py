@@ -97,10 +97,20 @@ def main():
     bad = [i for i, e in enumerate(ds) if not torch.equal(e["a"].view(torch.int32), e["b"].view(torch.int32))]
     nverts = sum(s["nverts"] for s in subs)
     ms_old, ms_new = timed(old, args.steps), timed(new, args.steps)
+    prof = None
+    if hasattr(C.CDLL(os.environ.get("OGRECU_LIB", "")) if os.environ.get("OGRECU_LIB") else object(), "ogrecu_debug_lane_profile"):
+        # a -DLN_PROFILE build: cycles of CTA 0's producer phases and consumer warp 0 over ONE launch
+        D = C.CDLL(os.environ["OGRECU_LIB"])
+        new(); 
+        out = (C.c_uint64 * 16)()
+        D.ogrecu_debug_lane_profile(C.c_void_p(ctx.handle), out)
+        names = ["producer prep", "producer waits for buffer", "producer issues copies", "producer records/keys", "producer patch+arrive",
+                 "consumer loop", "consumer waits for unit", "consumer walks"]
+        prof = {n: round(out[k] / 1965.0, 1) for k, n in enumerate(names)}          # microseconds at 1.965 GHz
     out = {"tag": args.tag, "lib": os.environ.get("OGRECU_LIB", "default"), "instances": ninst, "identical": same, "differing_sub_meshes": bad,
            "chunks": chunks, "ms_old": round(ms_old, 4), "ms_new": round(ms_new, 4),
            "gvert_old": round(ninst * nverts / ms_old / 1e6, 1), "gvert_new": round(ninst * nverts / ms_new / 1e6, 1),
-           "frac_new": round(ninst * nverts * 24 / (ms_new * 1e-3) / 6537e9, 3)}
+           "frac_new": round(ninst * nverts * 24 / (ms_new * 1e-3) / 6537e9, 3), "phase_us_cta0": prof}
     if args.per_sub:
         per = []
         for i in range(len(ds)):
