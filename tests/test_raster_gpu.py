@@ -329,3 +329,87 @@ def test_instanced_draw_equals_expanded_indices(gpu_ctx, index_type, blend):
     scene.render(rt)
     assert_images_equal(rt.read_colour(), rt.read_depth(), rc, rz, "instanced draw, per-index transform")
     scene.free(); rt.destroy()
+
+
+def test_draw_views_clear_batching_keeps_per_target_clears(gpu_ctx):
+    """ogrecu_draw_views runs the targets' pending clears as one launch when they all hold the same single clear; targets cleared to
+    DIFFERENT values, a target with a depth-only clear, and a target with an earlier draw recorded take the per-target path — every
+    view still equals the oracle on its own initial contents"""
+    import ctypes as C
+    import ogre_b200
+    from ogre_b200 import capi, check, lib
+    from datagen import DrawCase, look_at, perspective, random_soup, viewport_matrix
+    from rasterlib import GpuScene
+    ctx = gpu_ctx
+    w, h = 160, 96
+    rng = np.random.default_rng(5)
+    verts, idx = random_soup(rng, 800, size=0.5)
+    proj = perspective(50, w / h, 0.5, 100.0)
+    nviews = 5
+    mvps, mvits, lights = [], [], []
+    for k in range(nviews):
+        view = look_at(rng.uniform(-2, 2, 3) + np.array([0, 0, 9.0]), rng.uniform(-1, 1, 3))
+        mvps.append((proj @ view).astype(np.float32)); mvits.append(np.ascontiguousarray(np.linalg.inv(view).T, dtype=np.float32))
+        l = rng.normal(size=3); lights.append((l / np.linalg.norm(l)).astype(np.float32))
+    cases = []
+    for k in range(nviews):
+        c = DrawCase(verts, idx, index_type=4, mvp=mvps[k], mvit=mvits[k], viewport=viewport_matrix(w, h), ambient=(0.2, 0.2, 0.25, 1.0), has_uv=False)
+        c.light_dir = lights[k]
+        cases.append(c)
+    mv, mi, li = [np.ascontiguousarray(np.stack(a)) for a in (mvps, mvits, lights)]
+    scene = GpuScene(ctx, [cases[0]])
+    fp = capi.c_float_p
+    for variant in ("same", "different colours", "one depth-only", "one with a draw before"):
+        rts = [ogre_b200.RenderTarget(ctx, w, h) for _ in range(nviews)]
+        refs = []
+        for k, r in enumerate(rts):
+            colour = (0.1, 0.2, 0.3, 1.0) if variant != "different colours" else (0.1 * k, 0.2, 0.3, 1.0)
+            if variant == "one depth-only" and k == 2:
+                r.clear(colour=(0.5, 0.5, 0.5, 1.0), depth=1.0); r.flush()
+                r.clear(buffers=ogre_b200.CLEAR_DEPTH, depth=0.97)
+                refs.append(render_oracle([cases[k]], w, h, clear=None, init=(np.full((h, w, 3), 128, np.uint8), np.full((h, w), 0.97, np.float32))))
+            elif variant == "one with a draw before" and k == 1:
+                r.clear(colour=colour, depth=1.0)
+                r.draw(scene.descs[0])
+                refs.append(render_oracle([cases[0], cases[k]], w, h, clear=colour))
+            else:
+                r.clear(colour=colour, depth=1.0)
+                refs.append(render_oracle([cases[k]], w, h, clear=colour))
+        hs = (C.c_void_p * nviews)(*[r.handle for r in rts])
+        check(lib().ogrecu_draw_views(hs, nviews, C.byref(scene.descs[0]), mv.ctypes.data_as(fp), mi.ctypes.data_as(fp), li.ctypes.data_as(fp)))
+        for k, r in enumerate(rts):
+            assert_images_equal(r.read_colour(), r.read_depth(), refs[k][0], refs[k][1], "%s, view %d" % (variant, k))
+            r.destroy()
+    scene.free()
+
+
+def test_named_buffers_are_tracked_like_looked_up_ones(gpu_ctx):
+    """ogrecu_draw_refs: the caller names the ogrecu_bufs a draw reads; a host write to one of them before the flush must still run the
+    recorded draw first (the same hazard rule as for pointers the library looks up itself)"""
+    import ctypes as C
+    import ogre_b200
+    from ogre_b200 import check, lib
+    ctx = gpu_ctx
+    w, h = 128, 96
+    cases = make_scene(8, w, h, ndraws=1, ntri=300)
+    case = cases[0]
+    case.texture = None
+    rc, rz, _ = render_oracle([case], w, h)
+    vb = ogre_b200.HardwareBuffer(ctx, case.verts.nbytes); vb.write(case.verts)
+    ib = ogre_b200.HardwareBuffer(ctx, case.indices.nbytes); ib.write(case.indices)
+    d = ogre_b200.DrawDesc()
+    d.positions, d.pos_stride = vb.device_ptr, 32
+    d.normals, d.normal_stride = (vb.device_ptr + 12, 32) if case.has_normals else (None, 0)
+    d.indices, d.index_type, d.draw_count, d.vertex_count = ib.device_ptr, case.index_type, case.draw_count, len(case.verts)
+    d.prim_type = ogre_b200.PRIM_TRIANGLE_LIST
+    d.flags = ((ogre_b200.DRAW_DEPTH_TEST if case.depth_test else 0) | (ogre_b200.DRAW_DEPTH_WRITE if case.depth_write else 0) |
+               (ogre_b200.DRAW_BLEND_ADD if case.blend_add else 0) | (ogre_b200.DRAW_LIGHTING if case.lighting else 0))
+    d.mvp[:] = case.mvp.reshape(16); d.tex_matrix[:] = case.tex_matrix.reshape(16); d.mvit[:] = case.mvit.reshape(16)
+    d.viewport[:] = case.viewport.reshape(16); d.light_dir[:] = case.light_dir; d.ambient[:] = case.ambient
+    rt = ogre_b200.RenderTarget(ctx, w, h)
+    rt.clear(colour=(0.1, 0.2, 0.3, 1.0), depth=1.0)
+    refs = (C.c_void_p * 2)(vb.handle, ib.handle)
+    check(lib().ogrecu_draw_refs(rt.handle, C.byref(d), None, refs, 2))
+    vb.write(np.zeros_like(case.verts))                  # recorded, not flushed: the write has to wait for the draw
+    assert_images_equal(rt.read_colour(), rt.read_depth(), rc, rz, "draw recorded with named buffers, vertices overwritten afterwards")
+    rt.destroy(); vb.destroy(); ib.destroy()
