@@ -108,6 +108,13 @@ struct ogrecu_ctx {
     int lane_reuse_repack = 0;      // measurement switch: ogrecu_anim_frame_dev keeps the previous call's repacked palettes
     void* pinned;               // pinned staging (host side)
     size_t pinned_cap;
+    // the raster passes' draw / target tables: two pinned blocks used in turn, each guarded by an event, so that recording a pass
+    // does not have to wait for the stream (the single block needed a cudaStreamSynchronize before every pass)
+    uint8_t* tab_pin[2] = {nullptr, nullptr};
+    size_t tab_cap[2] = {0, 0};
+    cudaEvent_t tab_ev[2] = {nullptr, nullptr};
+    bool tab_used[2] = {false, false};
+    int tab_slot = 0;
     // shadow registry: shadow base address -> buffer
     std::map<uintptr_t, ogrecu_buf*> shadows;
     std::mutex shadows_mutex;       // buffers may be created / destroyed from resource threads (see the threading contract in ogrecu.h)

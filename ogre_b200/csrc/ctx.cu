@@ -347,6 +347,7 @@ int ogrecu_shutdown(ogrecu_ctx* ctx)
     for (Scratch* s : {&ctx->jobs, &ctx->stage_in, &ctx->stage_out, &ctx->lane_counter, &ctx->lane_ipal, &ctx->batch_dev})
         if (s->ptr) cudaFree(s->ptr);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    for (int k = 0; k < 2; ++k) { if (ctx->tab_pin[k]) cudaFreeHost(ctx->tab_pin[k]); if (ctx->tab_ev[k]) cudaEventDestroy(ctx->tab_ev[k]); }
     for (int k = 0; k < 2; ++k) {
         if (ctx->batch_pin[k]) cudaFreeHost(ctx->batch_pin[k]);
         if (ctx->batch_palpin[k]) cudaFreeHost(ctx->batch_palpin[k]);

@@ -1456,6 +1456,7 @@ struct SegRun {
     SegParams P;
     uint32_t* ctl_host = nullptr;
     uint32_t nblocks = 0, nkeys = 0;
+    int tab_slot = 0;           // pinned table block of this pass (its event is recorded once the totals have been copied back)
     bool live = false;          // segment_finish has work to do
 };
 
@@ -1548,14 +1549,24 @@ int segment_begin(ogrecu_ctx* ctx, ogrecu_rt* const* targets, uint32_t ntargets,
     OGRECU_CHECK(scratch_reserve(ctx, S.tile_count, ((size_t)nkeys + 1) * sizeof(uint32_t)));
     // tables go through the pinned block (stream-ordered, no pageable-copy stall)
     size_t tab_bytes = dd.size() * sizeof(DrawDev) + td.size() * sizeof(TargetDev) + 16;
-    OGRECU_CHECK(pinned_reserve(ctx, tab_bytes));
-    OGRECU_CUDA(cudaStreamSynchronize(ctx->stream));
-    memcpy(ctx->pinned, dd.data(), dd.size() * sizeof(DrawDev));
-    memcpy((uint8_t*)ctx->pinned + dd.size() * sizeof(DrawDev), td.data(), td.size() * sizeof(TargetDev));
-    OGRECU_CUDA(cudaMemcpyAsync(S.draws.ptr, ctx->pinned, dd.size() * sizeof(DrawDev), cudaMemcpyHostToDevice, ctx->stream));
-    OGRECU_CUDA(cudaMemcpyAsync(S.targets.ptr, (uint8_t*)ctx->pinned + dd.size() * sizeof(DrawDev), td.size() * sizeof(TargetDev),
-                                cudaMemcpyHostToDevice, ctx->stream));
-    uint32_t* ctl_host = (uint32_t*)((uint8_t*)ctx->pinned + dd.size() * sizeof(DrawDev) + td.size() * sizeof(TargetDev));
+    const int slot = ctx->tab_slot;
+    ctx->tab_slot ^= 1;
+    if (ctx->tab_used[slot]) OGRECU_CUDA(cudaEventSynchronize(ctx->tab_ev[slot]));      // the pass before last has read its tables (long ago)
+    if (ctx->tab_cap[slot] < tab_bytes) {
+        if (ctx->tab_pin[slot]) cudaFreeHost(ctx->tab_pin[slot]);
+        ctx->tab_pin[slot] = nullptr; ctx->tab_cap[slot] = 0;
+        const size_t cap = std::max<size_t>(2 * tab_bytes, (size_t)1 << 16);
+        OGRECU_CUDA(cudaHostAlloc((void**)&ctx->tab_pin[slot], cap, cudaHostAllocDefault));
+        ctx->tab_cap[slot] = cap;
+    }
+    if (!ctx->tab_ev[slot]) OGRECU_CUDA(cudaEventCreateWithFlags(&ctx->tab_ev[slot], cudaEventDisableTiming));
+    uint8_t* tab = ctx->tab_pin[slot];
+    memcpy(tab, dd.data(), dd.size() * sizeof(DrawDev));
+    memcpy(tab + dd.size() * sizeof(DrawDev), td.data(), td.size() * sizeof(TargetDev));
+    OGRECU_CUDA(cudaMemcpyAsync(S.draws.ptr, tab, dd.size() * sizeof(DrawDev), cudaMemcpyHostToDevice, ctx->stream));
+    OGRECU_CUDA(cudaMemcpyAsync(S.targets.ptr, tab + dd.size() * sizeof(DrawDev), td.size() * sizeof(TargetDev), cudaMemcpyHostToDevice, ctx->stream));
+    uint32_t* ctl_host = (uint32_t*)(tab + dd.size() * sizeof(DrawDev) + td.size() * sizeof(TargetDev));
+    run.tab_slot = slot;
 
     SegParams P;
     P.draws = (const DrawDev*)S.draws.ptr; P.ndraws = (uint32_t)dd.size(); P.ntris = ntris;
@@ -1585,6 +1596,8 @@ int segment_begin(ogrecu_ctx* ctx, ogrecu_rt* const* targets, uint32_t ntargets,
     OGRECU_CUDA(cudaGetLastError());
     count_launch(ctx, 2);
     OGRECU_CUDA(cudaMemcpyAsync(ctl_host, P.ctl, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    OGRECU_CUDA(cudaEventRecord(ctx->tab_ev[run.tab_slot], ctx->stream));
+    ctx->tab_used[run.tab_slot] = true;
     run.P = P; run.ctl_host = ctl_host; run.nblocks = nblocks; run.nkeys = nkeys;
     run.live = true;
     return OGRECU_OK;
