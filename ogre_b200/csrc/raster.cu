@@ -510,36 +510,46 @@ __global__ void __launch_bounds__(SB_THREADS) setup_write_kernel(SegParams P)
     cta_draw_cache(P, g0, &s_lo, s_mat, lo0, lo0_end);
     const unsigned long long base_p = P.bases[2 * blockIdx.x], base_t = P.bases[2 * blockIdx.x + 1];
 
-    uint32_t nt[SB_ROUNDS], ip[SB_ROUNDS], it[SB_ROUNDS];
+    // thread t owns the four consecutive triangles g0 + 4t .. 4t+3 (one 32-bit load of their tile-count bytes), so the prefix sums
+    // over the CTA's 1024 triangles are ONE warp scan of two values and one pass over the eight warp totals (four scans when every
+    // round of 256 was scanned by itself)
+    static_assert(SB_ROUNDS == 4, "four tile-count bytes per thread");
+    const uint32_t gt = g0 + 4u * tid;
+    uint32_t nt[4] = {0u, 0u, 0u, 0u};
+    if (gt + 3u < P.ntris) {
+        const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(P.alive + gt));          // g0 is a multiple of 1024, the plane is 256-byte aligned
+        nt[0] = w & 0xffu; nt[1] = (w >> 8) & 0xffu; nt[2] = (w >> 16) & 0xffu; nt[3] = w >> 24;
+    } else {
 #pragma unroll
-    for (int k = 0; k < SB_ROUNDS; ++k) {
-        const uint32_t g = g0 + (uint32_t)k * SB_THREADS + tid;
-        nt[k] = g < P.ntris ? (uint32_t)__ldg(&P.alive[g]) : 0u;
+        for (int k = 0; k < 4; ++k) nt[k] = gt + (uint32_t)k < P.ntris ? (uint32_t)__ldg(&P.alive[gt + k]) : 0u;
     }
+    uint32_t sum_p = 0, sum_t = 0;
 #pragma unroll
-    for (int k = 0; k < SB_ROUNDS; ++k) {
+    for (int k = 0; k < 4; ++k) {
         if (nt[k] == 255u) {                           // a large triangle: its exact tile count
             TriSetup T;
-            setup_triangle<false>(P, g0 + (uint32_t)k * SB_THREADS + tid, lo0, lo0_end, s_mat, T);
+            setup_triangle<false>(P, gt + (uint32_t)k, lo0, lo0_end, s_mat, T);
             nt[k] = T.ntiles;
         }
-        ip[k] = nt[k]; it[k] = nt[k] ? 1u : 0u;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t a = __shfl_up_sync(0xffffffffu, ip[k], o), c = __shfl_up_sync(0xffffffffu, it[k], o);
-            if (lane >= (unsigned)o) { ip[k] += a; it[k] += c; }
-        }
-        if (lane == 31) { s_wp[k][wid] = ip[k]; s_wt[k][wid] = it[k]; }
+        sum_p += nt[k]; sum_t += nt[k] ? 1u : 0u;
     }
+    uint32_t ip = sum_p, it = sum_t;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t a = __shfl_up_sync(0xffffffffu, ip, o), c = __shfl_up_sync(0xffffffffu, it, o);
+        if (lane >= (unsigned)o) { ip += a; it += c; }
+    }
+    if (lane == 31) { s_wp[0][wid] = ip; s_wt[0][wid] = it; }
     __syncthreads();
-    uint32_t run_p = 0, run_t = 0;                     // pairs / survivors of the earlier rounds
+    uint32_t run_p = 0, run_t = 0;
+    {
+        uint32_t wbp = 0, wbt = 0;
 #pragma unroll
-    for (int k = 0; k < SB_ROUNDS; ++k) {
-        uint32_t wbp = 0, wbt = 0, tp = 0, tt = 0;
+        for (int w = 0; w < 8; ++w) { if (w < (int)wid) { wbp += s_wp[0][w]; wbt += s_wt[0][w]; } run_p += s_wp[0][w]; run_t += s_wt[0][w]; }
+        uint32_t off_p = wbp + ip - sum_p, off_t = wbt + it - sum_t;          // exclusive prefixes of this thread's first triangle
 #pragma unroll
-        for (int w = 0; w < 8; ++w) { if (w < (int)wid) { wbp += s_wp[k][w]; wbt += s_wt[k][w]; } tp += s_wp[k][w]; tt += s_wt[k][w]; }
-        if (nt[k]) s_list[run_t + wbt + it[k] - 1u] = make_uint2(g0 + (uint32_t)k * SB_THREADS + tid, run_p + wbp + ip[k] - nt[k]);
-        run_p += tp; run_t += tt;
+        for (int k = 0; k < 4; ++k)
+            if (nt[k]) { s_list[off_t] = make_uint2(gt + (uint32_t)k, off_p); off_p += nt[k]; ++off_t; }
     }
     __syncthreads();
     const uint32_t tot_t = run_t, tot_p = run_p;
