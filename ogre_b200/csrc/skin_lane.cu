@@ -110,70 +110,121 @@ __device__ __forceinline__ void ln_sqrt_rcp2(const u64 x0, const u64 x1, const u
     }
 }
 
-// One half (even or odd instances) of the output stage.  A quad = 4 consecutive vertices = one 96-byte row per instance =
-// one TMA box of 32 rows (48-byte rows run the TMA unit at a quarter of the HBM rate, 96-byte rows at all of it:
-// tools/ubench/store_pattern.cu).  A box must start on a 16-byte boundary: quads of the even instances start at
-// vertices 4q; the odd instances start 8 mod 16 when the instance stride is 8 mod 16 (an odd vertex count), their quads
-// then start at vertices 4q - 1 (SHIFT).  Vertices no whole in-range quad covers (the first three of a shifted row, the
-// last n mod 4) are stored directly, 24 bytes per lane.
-struct LaneHalf {
-    uint8_t* buf;                   // this warp's staging rows of the half: [32][96 B]
-    const CUtensorMap* map;
-    uint8_t* dst;                   // this lane's instance of the half (NULL = past the last instance)
-    int32_t xoff;                   // word offset of vertex 0 in the map's rows
+// shared memory through 32-bit shared-window addresses: no generic -> shared conversion and no 64-bit pointer in the walk's
+// registers.  volatile: a unit buffer is refilled between units, the loads may not be merged across the barrier waits.
+__device__ __forceinline__ float4 ln_lds_f4(const uint32_t a)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint4 ln_lds_u4(const uint32_t a)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void ln_sts_f4(const uint32_t a, const float x, const float y, const float z, const float w)
+{
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+// the six LDS.128 of one palette matrix of the lane's instance pair ([chunk][lane] layout: 512 bytes between chunks)
+__device__ __forceinline__ void ln_lds6(const uint32_t a, u64 (&q)[12])
+{
+    asm volatile("ld.shared.v2.b64 {%0, %1}, [%12];\n\t"
+                 "ld.shared.v2.b64 {%2, %3}, [%12 + 512];\n\t"
+                 "ld.shared.v2.b64 {%4, %5}, [%12 + 1024];\n\t"
+                 "ld.shared.v2.b64 {%6, %7}, [%12 + 1536];\n\t"
+                 "ld.shared.v2.b64 {%8, %9}, [%12 + 2048];\n\t"
+                 "ld.shared.v2.b64 {%10, %11}, [%12 + 2560];"
+                 : "=l"(q[0]), "=l"(q[1]), "=l"(q[2]), "=l"(q[3]), "=l"(q[4]), "=l"(q[5]), "=l"(q[6]), "=l"(q[7]), "=l"(q[8]), "=l"(q[9]), "=l"(q[10]), "=l"(q[11])
+                 : "r"(a));
+}
+// e = RN(RN(m * w) + e), the sum back into e's own registers
+__device__ __forceinline__ void ln_acc(u64& e, const u64 m, const u64 w, const u64 nz)
+{
+    asm("{\n\t.reg .b64 t;\n\tfma.rn.f32x2 t, %1, %2, %3;\n\tadd.rn.f32x2 %0, t, %0;\n\t}" : "+l"(e) : "l"(m), "l"(w), "l"(nz));
+}
+// one weighted matrix added to the collapsed one
+__device__ __forceinline__ void ln_add_slot(u64 (&E)[12], const uint32_t a, const u64 W, const u64 NZ)
+{
+    u64 q[12];
+    ln_lds6(a, q);
+#pragma unroll
+    for (int k = 0; k < 12; ++k) ln_acc(E[k], q[k], W, NZ);
+}
+
+// The output stage.  A quad = 4 consecutive vertices = one 96-byte row per instance = one TMA box of 32 rows (48-byte rows run
+// the TMA unit at a quarter of the HBM rate, 96-byte rows at all of it: tools/ubench/store_pattern.cu).  A box must start on
+// a 16-byte boundary: quads of the even instances (half 0) start at vertices 4q; the odd instances (half 1) start 8 mod 16
+// when the instance stride is 8 mod 16 (an odd vertex count), their quads then start at vertices 4q - 1 (SHIFT).  Vertices no
+// whole in-range quad covers (the first three of a shifted row, the last n mod 4) are stored directly, 24 bytes per lane.
+struct LaneWalk {
+    uint32_t pal_lane;              // shared address of the palette window + lane * 16
+    uint32_t rec;                   // [1 + chunk vertices][2 x 16 B]; entry 0 = the vertex before the chunk
+    uint32_t key;                   // [1 + chunk vertices][48 B (k1 6, k2 - k1 6) or, without morph, 32 B (k1 6, pad)]
+    uint32_t stage;                 // this warp's staging rows: half 0 [32][96 B], half 1 behind it
+    uint32_t job;                   // index into LaneParams::job
+    int32_t v_begin, nverts, nv_chunk;
+    int32_t p0, p1;                 // chunk-local vertex pairs of this warp
+    int32_t row0;                   // first instance pair of the group
+    uint32_t lane;
+    bool last_run;                  // this warp walks the mesh's last vertices
 };
 
-// vertex pair (ga, ga + 1) of one half: f = the 12 floats.  qs = first vertex of the pair's quad, second = the pair is
-// the quad's second one.
-__device__ __forceinline__ void ln_emit_pair(const LaneHalf& H, const int32_t ga, const int32_t qs, const bool second, const int32_t nverts,
-                                             const int32_t row0, const uint32_t lane, const float (&f)[12])
+// this lane's instance of a half, or NULL past the last instance (head / tail stores only: kept out of the walk's registers)
+__device__ __forceinline__ uint8_t* ln_lane_dst(const LaneParams& P, const LaneWalk& K, const uint32_t half)
 {
-    if (qs >= 0 && qs + 4 <= nverts) {
+    const uint32_t inst = 2u * (uint32_t)K.row0 + 2u * K.lane + half;
+    const LaneJob& J = P.job[K.job];
+    return inst < P.ninst ? J.dst + (size_t)inst * J.dst_stride : nullptr;
+}
+
+// vertex pair (ga, ga + 1) of one half: f = the 12 floats.  qs = first vertex of the pair's quad, second = the pair is
+// the quad's second one.  xoff = word offset of vertex 0 in the half's tensor-map rows.
+template <int HALF>
+__device__ __forceinline__ void ln_emit_pair(const LaneParams& P, const LaneWalk& K, const int32_t ga, const int32_t qs, const bool second,
+                                             const int32_t xoff, const float (&f)[12])
+{
+    const uint32_t buf = K.stage + (HALF ? (uint32_t)LN_BOX_BYTES : 0u);
+    if (qs >= 0 && qs + 4 <= K.nverts) {
         if (!second) {                              // the buffer's previous box has been read (issued a quad ago)
-            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            if (K.lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             __syncwarp();
         }
-        float4* r = reinterpret_cast<float4*>(H.buf + lane * 96u + (second ? 48u : 0u));
-        r[0] = make_float4(f[0], f[1], f[2], f[3]); r[1] = make_float4(f[4], f[5], f[6], f[7]); r[2] = make_float4(f[8], f[9], f[10], f[11]);
+        const uint32_t r = buf + K.lane * 96u + (second ? 48u : 0u);
+        ln_sts_f4(r, f[0], f[1], f[2], f[3]); ln_sts_f4(r + 16u, f[4], f[5], f[6], f[7]); ln_sts_f4(r + 32u, f[8], f[9], f[10], f[11]);
         if (second) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // my STS visible to the async proxy
             __syncwarp();
 #ifndef LN_NO_STORE   // (timing experiments only: the arithmetic without the output stage)
-            if (lane == 0) {
-                ln_tma_store_2d(H.map, ln_smem_u32(H.buf), qs * 6 + H.xoff, row0);
+            if (K.lane == 0) {
+                const LaneJob& J = P.job[K.job];
+                ln_tma_store_2d(HALF ? &J.mapB : &J.mapA, buf, qs * 6 + xoff, K.row0);
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
 #endif
         }
-    } else if (H.dst) {                             // head / tail of the row: 24 bytes per vertex, directly
-        if (ga >= 0 && ga < nverts) {
-            float2* d = reinterpret_cast<float2*>(H.dst + (size_t)ga * 24);
-            d[0] = make_float2(f[0], f[1]); d[1] = make_float2(f[2], f[3]); d[2] = make_float2(f[4], f[5]);
-        }
-        if (ga + 1 >= 0 && ga + 1 < nverts) {
-            float2* d = reinterpret_cast<float2*>(H.dst + (size_t)(ga + 1) * 24);
-            d[0] = make_float2(f[6], f[7]); d[1] = make_float2(f[8], f[9]); d[2] = make_float2(f[10], f[11]);
+    } else {                                        // head / tail of the row: 24 bytes per vertex, directly
+        uint8_t* dst = ln_lane_dst(P, K, HALF);
+        if (dst) {
+            if (ga >= 0 && ga < K.nverts) {
+                float2* d = reinterpret_cast<float2*>(dst + (size_t)ga * 24);
+                d[0] = make_float2(f[0], f[1]); d[1] = make_float2(f[2], f[3]); d[2] = make_float2(f[4], f[5]);
+            }
+            if (ga + 1 >= 0 && ga + 1 < K.nverts) {
+                float2* d = reinterpret_cast<float2*>(dst + (size_t)(ga + 1) * 24);
+                d[0] = make_float2(f[6], f[7]); d[1] = make_float2(f[8], f[9]); d[2] = make_float2(f[10], f[11]);
+            }
         }
     }
 }
-
-struct LaneWalk {
-    const uint8_t* s_pal_lane;      // palette base + lane * 16
-    const uint4* s_rec;             // [1 + chunk vertices][2]; entry 0 = the vertex before the chunk
-    const float4* s_key;            // [1 + chunk vertices][3 (k1 6, k2 - k1 6) or, without morph, 2 (k1 6, pad)]
-    LaneHalf A, B;
-    int32_t v_begin, nverts, nv_chunk;
-    int32_t p0, p1;                 // chunk-local vertex pairs of this warp
-    int32_t row0;
-    uint32_t lane;
-    bool last_run;                  // this warp walks the mesh's last vertices
-};
 
 // The chunk walk of one warp: vertex pairs p0..p1-1 in order, every value as the (A, B) pair of the lane's two instances.
 // SHIFT: the odd instances' pairs are (2p - 1, 2p); their half of vertex 2p - 1 is carried from the previous iteration, and
 // the walk starts one iteration early to have it (computing only that vertex).
 template <int NW, bool MORPH, bool SHIFT>
-__device__ __forceinline__ void lane_walk(const LaneWalk& K, const u64 T, const u64 NZ)
+__device__ __forceinline__ void lane_walk(const LaneParams& P, const LaneWalk& K, const u64 T, const u64 NZ)
 {
     u64 E[12];
 #pragma unroll
@@ -182,7 +233,6 @@ __device__ __forceinline__ void lane_walk(const LaneWalk& K, const u64 T, const 
 #pragma unroll
     for (int k = 0; k < 6; ++k) carry[k] = 0.f;
     uint32_t cur = 0xffffffffu;                       // slot offset whose matrix E is a plain copy of, or none
-    const uint32_t lane = K.lane;
     const bool lead = SHIFT && (K.p0 > 0 || K.v_begin > 0);       // one iteration early, for vertex 2*p0 - 1 alone
 #pragma unroll 1
     for (int32_t p = K.p0 - (lead ? 1 : 0); p < K.p1; ++p) {
@@ -192,13 +242,13 @@ __device__ __forceinline__ void lane_walk(const LaneWalk& K, const u64 T, const 
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
             const uint32_t vl = (uint32_t)(max(min(2 * p + u, K.nv_chunk - 1), -1) + 1);   // past the odd last vertex: repeat it (never stored)
-            const float4* ky = K.s_key + vl * (MORPH ? 3u : 2u);
-            const float4 a = ky[0], b = ky[1];
+            const uint32_t ky = K.key + vl * (MORPH ? 48u : 32u);
+            const float4 a = ln_lds_f4(ky), b = ln_lds_f4(ky + 16u);
             V[u][0] = ln_pk(a.x, a.x); V[u][1] = ln_pk(a.y, a.y); V[u][2] = ln_pk(a.z, a.z);     // warp-uniform scalars: ptxas folds the
             V[u][3] = ln_pk(a.w, a.w); V[u][4] = ln_pk(b.x, b.x); V[u][5] = ln_pk(b.y, b.y);     // duplication into .F32 broadcast operands
             if (MORPH) {
                 // dst = a + t*(b-a) (OgreOptimisedUtilGeneral.cpp:249-256); (b - a) is instance-invariant
-                const float4 c = ky[2];
+                const float4 c = ln_lds_f4(ky + 32u);
                 V[u][0] = ln_add(V[u][0], ln_mul(T, ln_pk(b.z, b.z), NZ)); V[u][1] = ln_add(V[u][1], ln_mul(T, ln_pk(b.w, b.w), NZ));
                 V[u][2] = ln_add(V[u][2], ln_mul(T, ln_pk(c.x, c.x), NZ)); V[u][3] = ln_add(V[u][3], ln_mul(T, ln_pk(c.y, c.y), NZ));
                 V[u][4] = ln_add(V[u][4], ln_mul(T, ln_pk(c.z, c.z), NZ)); V[u][5] = ln_add(V[u][5], ln_mul(T, ln_pk(c.w, c.w), NZ));
@@ -222,64 +272,34 @@ __device__ __forceinline__ void lane_walk(const LaneWalk& K, const u64 T, const 
         for (int u = 0; u < 2; ++u) {
             if (u == 0 && lead_it) continue;                            // the early iteration wants vertex 2p + 1 only
             const uint32_t vl = (uint32_t)(max(min(2 * p + u, K.nv_chunk - 1), -1) + 1);
-            const uint4 r0 = K.s_rec[vl * 2u];
+            const uint4 r0 = ln_lds_u4(K.rec + vl * 32u);
             // E[4*r + c] = (M_A[r][c], M_B[r][c]); control flow is warp-uniform (plan flags).  One load site for slot 0 (E keeps
             // its registers across the paths); a single-matrix vertex whose matrix E already holds loads nothing.
             const uint32_t fl = r0.x & 15u, off0 = r0.x & ~15u;
             const bool single = NW == 1 || (NW == 2 ? !(fl & 2u) : fl == 1u);
-            if (!(single && off0 == cur)) {
-                const ulonglong2* m0 = reinterpret_cast<const ulonglong2*>(K.s_pal_lane + off0);
-#pragma unroll
-                for (int k = 0; k < 6; ++k) { const ulonglong2 q = m0[k * 32]; E[2 * k] = q.x; E[2 * k + 1] = q.y; }
-            }
+#ifdef LN_NO_ECACHE
+            ln_lds6(K.pal_lane + off0, E);
+#else
+            if (!(single && off0 == cur)) ln_lds6(K.pal_lane + off0, E);
             cur = single ? off0 : 0xffffffffu;
+#endif
             if (NW >= 2 && !single) {
-                const float4 w = *reinterpret_cast<const float4*>(&K.s_rec[vl * 2u + 1u]);
+                const float4 w = ln_lds_f4(K.rec + vl * 32u + 16u);
                 if (NW == 2) {
-                    const ulonglong2* m1 = reinterpret_cast<const ulonglong2*>(K.s_pal_lane + r0.y);
+                    u64 q[12];
+                    ln_lds6(K.pal_lane + r0.y, q);
                     const u64 W1 = ln_pk(w.y, w.y);
 #pragma unroll
-                    for (int k = 0; k < 6; ++k) {                       // lerp(M0, M1, w1) = (M1 - M0) * w1 + M0
-                        const ulonglong2 b = m1[k * 32];
-                        E[2 * k] = ln_add(ln_mul(ln_sub(b.x, E[2 * k]), W1, NZ), E[2 * k]);
-                        E[2 * k + 1] = ln_add(ln_mul(ln_sub(b.y, E[2 * k + 1]), W1, NZ), E[2 * k + 1]);
-                    }
+                    for (int k = 0; k < 12; ++k) E[k] = ln_add(ln_mul(ln_sub(q[k], E[k]), W1, NZ), E[k]);     // lerp(M0, M1, w1) = (M1 - M0) * w1 + M0
                 } else {
                     if (!(fl & 1u)) {                                   // w0 == 1.0f: 1 * x == x, nothing to do
                         const u64 W0 = ln_pk(w.x, w.x);
 #pragma unroll
                         for (int k = 0; k < 12; ++k) E[k] = ln_mul(E[k], W0, NZ);
                     }
-                    if (fl & 2u) {
-                        const ulonglong2* mb = reinterpret_cast<const ulonglong2*>(K.s_pal_lane + r0.y);
-                        const u64 Wb = ln_pk(w.y, w.y);
-#pragma unroll
-                        for (int k = 0; k < 6; ++k) {
-                            const ulonglong2 q = mb[k * 32];
-                            E[2 * k] = ln_add(ln_mul(q.x, Wb, NZ), E[2 * k]);
-                            E[2 * k + 1] = ln_add(ln_mul(q.y, Wb, NZ), E[2 * k + 1]);
-                        }
-                    }
-                    if (fl & 4u) {
-                        const ulonglong2* mb = reinterpret_cast<const ulonglong2*>(K.s_pal_lane + r0.z);
-                        const u64 Wb = ln_pk(w.z, w.z);
-#pragma unroll
-                        for (int k = 0; k < 6; ++k) {
-                            const ulonglong2 q = mb[k * 32];
-                            E[2 * k] = ln_add(ln_mul(q.x, Wb, NZ), E[2 * k]);
-                            E[2 * k + 1] = ln_add(ln_mul(q.y, Wb, NZ), E[2 * k + 1]);
-                        }
-                    }
-                    if (NW == 4 && (fl & 8u)) {
-                        const ulonglong2* mb = reinterpret_cast<const ulonglong2*>(K.s_pal_lane + r0.w);
-                        const u64 Wb = ln_pk(w.w, w.w);
-#pragma unroll
-                        for (int k = 0; k < 6; ++k) {
-                            const ulonglong2 q = mb[k * 32];
-                            E[2 * k] = ln_add(ln_mul(q.x, Wb, NZ), E[2 * k]);
-                            E[2 * k + 1] = ln_add(ln_mul(q.y, Wb, NZ), E[2 * k + 1]);
-                        }
-                    }
+                    if (fl & 2u) ln_add_slot(E, K.pal_lane + r0.y, ln_pk(w.y, w.y), NZ);
+                    if (fl & 4u) ln_add_slot(E, K.pal_lane + r0.z, ln_pk(w.z, w.z), NZ);
+                    if (NW == 4 && (fl & 8u)) ln_add_slot(E, K.pal_lane + r0.w, ln_pk(w.w, w.w), NZ);
                 }
             }
             // position: (r.x*x + r.y*y) + (r.z*z + r.w)   (__MM_DOT4x3_PS, OgreSIMDHelper.h:204-217)
@@ -306,13 +326,13 @@ __device__ __forceinline__ void lane_walk(const LaneWalk& K, const u64 T, const 
         for (int k = 0; k < 6; ++k) { ln_upk(O[0][k], fa[k], fb[k]); ln_upk(O[1][k], fa[6 + k], fb[6 + k]); }
         if (!lead_it) {
             const bool second = (ga & 2) != 0;
-            ln_emit_pair(K.A, ga, ga & ~3, second, K.nverts, K.row0, lane, fa);
-            if (!SHIFT) ln_emit_pair(K.B, ga, ga & ~3, second, K.nverts, K.row0, lane, fb);
+            ln_emit_pair<0>(P, K, ga, ga & ~3, second, 0, fa);
+            if (!SHIFT) ln_emit_pair<1>(P, K, ga, ga & ~3, second, 0, fb);
             else {
                 float g[12];
 #pragma unroll
                 for (int k = 0; k < 6; ++k) { g[k] = carry[k]; g[6 + k] = fb[k]; }
-                ln_emit_pair(K.B, ga - 1, (ga & ~3) - 1, second, K.nverts, K.row0, lane, g);
+                ln_emit_pair<1>(P, K, ga - 1, (ga & ~3) - 1, second, 2, g);       // shifted: map B starts 8 bytes before the odd instance
             }
         }
         if (SHIFT) {
@@ -321,9 +341,12 @@ __device__ __forceinline__ void lane_walk(const LaneWalk& K, const u64 T, const 
         }
     }
     // shifted rows, even vertex count: the mesh's last vertex (odd) of the odd instances has no partner
-    if (SHIFT && K.last_run && !(K.nverts & 1) && K.B.dst) {
-        float2* d = reinterpret_cast<float2*>(K.B.dst + (size_t)(K.nverts - 1) * 24);
-        d[0] = make_float2(carry[0], carry[1]); d[1] = make_float2(carry[2], carry[3]); d[2] = make_float2(carry[4], carry[5]);
+    if (SHIFT && K.last_run && !(K.nverts & 1)) {
+        uint8_t* dst = ln_lane_dst(P, K, 1);
+        if (dst) {
+            float2* d = reinterpret_cast<float2*>(dst + (size_t)(K.nverts - 1) * 24);
+            d[0] = make_float2(carry[0], carry[1]); d[1] = make_float2(carry[2], carry[3]); d[2] = make_float2(carry[4], carry[5]);
+        }
     }
 }
 
@@ -629,15 +652,10 @@ __global__ void __launch_bounds__(LN_THREADS, 1) skin_lane_kernel(const __grid_c
             if (MORPH) T = reinterpret_cast<const u64*>(u_meta + 1)[lane];
             const uint32_t r1 = min(4u * q1, nv_chunk);
             LaneWalk K;
-            K.s_pal_lane = U + lane * 16u;
-            K.s_rec = u_rec; K.s_key = reinterpret_cast<const float4*>(u_key);
-            K.A.buf = my_stage;
-            K.B.buf = my_stage + LN_BOX_BYTES;
-            K.A.map = &J.mapA; K.B.map = &J.mapB;
-            K.A.dst = i0 + 2u * lane < P.ninst ? J.dst + (size_t)(i0 + 2u * lane) * J.dst_stride : nullptr;
-            K.B.dst = i0 + 2u * lane + 1u < P.ninst ? J.dst + (size_t)(i0 + 2u * lane + 1u) * J.dst_stride : nullptr;
-            K.A.xoff = 0;
-            K.B.xoff = 2 * (int32_t)J.shift;               // shifted: map B starts 8 bytes before the odd instance
+            K.pal_lane = ln_smem_u32(U) + lane * 16u;
+            K.rec = ln_smem_u32(u_rec); K.key = ln_smem_u32(u_key);
+            K.stage = ln_smem_u32(my_stage);
+            K.job = u_meta->job;
             K.v_begin = (int32_t)v_begin; K.nverts = (int32_t)J.nverts; K.nv_chunk = (int32_t)nv_chunk;
             K.p0 = (int32_t)(2u * q0); K.p1 = (int32_t)((r1 + 1u) >> 1);
             K.last_run = v_begin + r1 == J.nverts;
@@ -645,17 +663,17 @@ __global__ void __launch_bounds__(LN_THREADS, 1) skin_lane_kernel(const __grid_c
             K.lane = lane;
             if (J.shift) {
                 switch (J.nw) {
-                case 1: lane_walk<1, MORPH, true>(K, T, NZ); break;
-                case 2: lane_walk<2, MORPH, true>(K, T, NZ); break;
-                case 3: lane_walk<3, MORPH, true>(K, T, NZ); break;
-                default: lane_walk<4, MORPH, true>(K, T, NZ); break;
+                case 1: lane_walk<1, MORPH, true>(P, K, T, NZ); break;
+                case 2: lane_walk<2, MORPH, true>(P, K, T, NZ); break;
+                case 3: lane_walk<3, MORPH, true>(P, K, T, NZ); break;
+                default: lane_walk<4, MORPH, true>(P, K, T, NZ); break;
                 }
             } else {
                 switch (J.nw) {
-                case 1: lane_walk<1, MORPH, false>(K, T, NZ); break;
-                case 2: lane_walk<2, MORPH, false>(K, T, NZ); break;
-                case 3: lane_walk<3, MORPH, false>(K, T, NZ); break;
-                default: lane_walk<4, MORPH, false>(K, T, NZ); break;
+                case 1: lane_walk<1, MORPH, false>(P, K, T, NZ); break;
+                case 2: lane_walk<2, MORPH, false>(P, K, T, NZ); break;
+                case 3: lane_walk<3, MORPH, false>(P, K, T, NZ); break;
+                default: lane_walk<4, MORPH, false>(P, K, T, NZ); break;
                 }
             }
         }
