@@ -64,6 +64,14 @@ __device__ __forceinline__ void ln_tma_store_2d(const CUtensorMap* map, uint32_t
                  ::"l"(map), "r"(src_smem), "r"(x), "r"(y) : "memory");
 }
 
+// (sqrt(x), 1 / sqrt(x)) by the library's correctly rounded functions: lengths outside the packed Newton sequences' range.  Out of
+// line: inlined, its eight conditional slow-path calls sat in the middle of the walk's loop and of its register allocation.
+__device__ __noinline__ float2 ln_sqrt_rcp_slow(const float x)
+{
+    const float s = __fsqrt_rn(x);
+    return make_float2(s, __frcp_rn(s));
+}
+
 // sqrt(x) and 1/sqrt(x) of both halves, correctly rounded each (== __frcp_rn(__fsqrt_rn(x))), for the two vertices of a
 // pair at once: the packed Newton sequences of exact_math.cuh when the whole warp is in their range (always, for
 // unit-scale normals), written with the negated intermediates (-h, -d, -x: round-to-nearest is sign-symmetric, so every
@@ -104,9 +112,9 @@ __device__ __forceinline__ void ln_sqrt_rcp2(const u64 x0, const u64 x1, const u
         e0 = em_pfma(nl0, z0, one); e1 = em_pfma(nl1, z1, one);
         inv0 = em_pfma(z0, e0, z0); inv1 = em_pfma(z1, e1, z1);
     } else {
-        const float s0a = __fsqrt_rn(a0), s0b = __fsqrt_rn(b0), s1a = __fsqrt_rn(a1), s1b = __fsqrt_rn(b1);
-        len0 = ln_pk(s0a, s0b); len1 = ln_pk(s1a, s1b);
-        inv0 = ln_pk(__frcp_rn(s0a), __frcp_rn(s0b)); inv1 = ln_pk(__frcp_rn(s1a), __frcp_rn(s1b));
+        const float2 r0 = ln_sqrt_rcp_slow(a0), r1 = ln_sqrt_rcp_slow(b0), r2 = ln_sqrt_rcp_slow(a1), r3 = ln_sqrt_rcp_slow(b1);
+        len0 = ln_pk(r0.x, r1.x); len1 = ln_pk(r2.x, r3.x);
+        inv0 = ln_pk(r0.y, r1.y); inv1 = ln_pk(r2.y, r3.y);
     }
 }
 
@@ -237,7 +245,8 @@ __device__ __forceinline__ void lane_walk(const LaneParams& P, const LaneWalk& K
 #pragma unroll 1
     for (int32_t p = K.p0 - (lead ? 1 : 0); p < K.p1; ++p) {
         const bool lead_it = SHIFT && p < K.p0;
-        u64 V[2][6], O[2][6], L2[2];
+        u64 V[2][6], N[2][3], L2[2];
+        float fa[12], fb[12];                                            // the two vertices' results of the even / odd instance
         // ---- both vertices: keyframes -> animated source
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
@@ -277,12 +286,12 @@ __device__ __forceinline__ void lane_walk(const LaneParams& P, const LaneWalk& K
             // its registers across the paths); a single-matrix vertex whose matrix E already holds loads nothing.
             const uint32_t fl = r0.x & 15u, off0 = r0.x & ~15u;
             const bool single = NW == 1 || (NW == 2 ? !(fl & 2u) : fl == 1u);
-#ifdef LN_NO_ECACHE
-            ln_lds6(K.pal_lane + off0, E);
-#else
-            if (!(single && off0 == cur)) ln_lds6(K.pal_lane + off0, E);
-            cur = single ? off0 : 0xffffffffu;
-#endif
+            // (kept across vertices only by single-weight meshes, whose consecutive vertices mostly share the bone: with more weights
+            // one vertex in eight found its matrix there, and E stayed live through the keyframe stage for it)
+            if (NW == 1) {
+                if (off0 != cur) ln_lds6(K.pal_lane + off0, E);
+                cur = off0;
+            } else ln_lds6(K.pal_lane + off0, E);
             if (NW >= 2 && !single) {
                 const float4 w = ln_lds_f4(K.rec + vl * 32u + 16u);
                 if (NW == 2) {
@@ -302,28 +311,39 @@ __device__ __forceinline__ void lane_walk(const LaneParams& P, const LaneWalk& K
                     if (NW == 4 && (fl & 8u)) ln_add_slot(E, K.pal_lane + r0.w, ln_pk(w.w, w.w), NZ);
                 }
             }
-            // position: (r.x*x + r.y*y) + (r.z*z + r.w)   (__MM_DOT4x3_PS, OgreSIMDHelper.h:204-217)
+            // position: (r.x*x + r.y*y) + (r.z*z + r.w)   (__MM_DOT4x3_PS, OgreSIMDHelper.h:204-217).  The last addition per instance:
+            // its results land in the order the staging rows want them instead of as (A, B) pairs that need re-sorting.
 #pragma unroll
-            for (int r = 0; r < 3; ++r)
-                O[u][r] = ln_add(ln_add(ln_mul(E[4 * r], V[u][0], NZ), ln_mul(E[4 * r + 1], V[u][1], NZ)), ln_add(ln_mul(E[4 * r + 2], V[u][2], NZ), E[4 * r + 3]));
+            for (int r = 0; r < 3; ++r) {
+                const u64 s0 = ln_add(ln_mul(E[4 * r], V[u][0], NZ), ln_mul(E[4 * r + 1], V[u][1], NZ)), s1 = ln_add(ln_mul(E[4 * r + 2], V[u][2], NZ), E[4 * r + 3]);
+                float s0a, s0b, s1a, s1b;
+                ln_upk(s0, s0a, s0b); ln_upk(s1, s1a, s1b);
+                fa[6 * u + r] = __fadd_rn(s0a, s1a); fb[6 * u + r] = __fadd_rn(s0b, s1b);
+            }
             // normal: (r.x*x + r.y*y) + r.z*z (OgreSIMDHelper.h:220-227); its exact 1/sqrt(len2) for both vertices below
 #pragma unroll
             for (int r = 0; r < 3; ++r)
-                O[u][3 + r] = ln_add(ln_add(ln_mul(E[4 * r], V[u][3], NZ), ln_mul(E[4 * r + 1], V[u][4], NZ)), ln_mul(E[4 * r + 2], V[u][5], NZ));
-            L2[u] = ln_add(ln_add(ln_mul(O[u][3], O[u][3], NZ), ln_mul(O[u][4], O[u][4], NZ)), ln_mul(O[u][5], O[u][5], NZ));
+                N[u][r] = ln_add(ln_add(ln_mul(E[4 * r], V[u][3], NZ), ln_mul(E[4 * r + 1], V[u][4], NZ)), ln_mul(E[4 * r + 2], V[u][5], NZ));
+            L2[u] = ln_add(ln_add(ln_mul(N[u][0], N[u][0], NZ), ln_mul(N[u][1], N[u][1], NZ)), ln_mul(N[u][2], N[u][2], NZ));
         }
         if (SHIFT && lead_it) L2[0] = L2[1];                            // keep the unused half in range
         {
             u64 len[2], R[2];
             ln_sqrt_rcp2(L2[0], L2[1], NZ, len[0], R[0], len[1], R[1]);
 #pragma unroll
-            for (int u = 0; u < 2; ++u) { O[u][3] = ln_mul(O[u][3], R[u], NZ); O[u][4] = ln_mul(O[u][4], R[u], NZ); O[u][5] = ln_mul(O[u][5], R[u], NZ); }
+            for (int u = 0; u < 2; ++u) {
+                float ra, rb;
+                ln_upk(R[u], ra, rb);
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    float na, nb;
+                    ln_upk(N[u][r], na, nb);
+                    fa[6 * u + 3 + r] = __fmul_rn(na, ra); fb[6 * u + 3 + r] = __fmul_rn(nb, rb);
+                }
+            }
         }
         // ---- output
         const int32_t ga = K.v_begin + 2 * p;                           // mesh vertex of the pair's first
-        float fa[12], fb[12];
-#pragma unroll
-        for (int k = 0; k < 6; ++k) { ln_upk(O[0][k], fa[k], fb[k]); ln_upk(O[1][k], fa[6 + k], fb[6 + k]); }
         if (!lead_it) {
             const bool second = (ga & 2) != 0;
             ln_emit_pair<0>(P, K, ga, ga & ~3, second, 0, fa);
