@@ -164,58 +164,62 @@ __device__ __forceinline__ void ln_add_slot(u64 (&E)[12], const uint32_t a, cons
 
 // The output stage.  A quad = 4 consecutive vertices = one 96-byte row per instance = one TMA box of 32 rows (48-byte rows run
 // the TMA unit at a quarter of the HBM rate, 96-byte rows at all of it: tools/ubench/store_pattern.cu).  A box must start on
-// a 16-byte boundary: quads of the even instances (half 0) start at vertices 4q; the odd instances (half 1) start 8 mod 16
-// when the instance stride is 8 mod 16 (an odd vertex count), their quads then start at vertices 4q - 1 (SHIFT).  Vertices no
-// whole in-range quad covers (the first three of a shifted row, the last n mod 4) are stored directly, 24 bytes per lane.
+// a 16-byte boundary.  Even instances start on one; odd instances start 8 mod 16 when the instance stride is 8 mod 16 (an odd
+// vertex count), their quads then start at vertices 4q - 1 (PHASE 1).  A warp's 64 instances are all even or all odd (a group
+// = the even or the odd half of 128 consecutive instances; lane l holds instances 2l and 2l + 64 of that half as its pair), so
+// the whole warp walks the same quads: vertices [4q - PHASE, 4q - PHASE + 4).  Vertices no whole in-range quad covers (the
+// first three of a shifted row, the last ones of the mesh) are stored directly, 24 bytes per lane.
 struct LaneWalk {
     uint32_t pal_lane;              // shared address of the palette window + lane * 16
     uint32_t rec;                   // [1 + chunk vertices][2 x 16 B]; entry 0 = the vertex before the chunk
     uint32_t key;                   // [1 + chunk vertices][48 B (k1 6, k2 - k1 6) or, without morph, 32 B (k1 6, pad)]
-    uint32_t stage;                 // this warp's staging rows: half 0 [32][96 B], half 1 behind it
+    uint32_t stage_lane;            // this warp's staging rows ([2 halves][32][96 B]) + lane * 96
     uint32_t job;                   // index into LaneParams::job
+    uint32_t odd;                   // the group holds the odd instances of its 128
     int32_t v_begin, nverts, nv_chunk;
-    int32_t p0, p1;                 // chunk-local vertex pairs of this warp
-    int32_t row0;                   // first instance pair of the group
+    int32_t p0, p1;                 // chunk-local vertex pairs of this warp: vertices (2p - PHASE, 2p - PHASE + 1)
+    int32_t row0;                   // the group's first row in the tensor map of its parity (= first instance / 2)
     uint32_t lane;
-    bool last_run;                  // this warp walks the mesh's last vertices
 };
 
-// this lane's instance of a half, or NULL past the last instance (head / tail stores only: kept out of the walk's registers)
-__device__ __forceinline__ uint8_t* ln_lane_dst(const LaneParams& P, const LaneWalk& K, const uint32_t half)
-{
-    const uint32_t inst = 2u * (uint32_t)K.row0 + 2u * K.lane + half;
-    const LaneJob& J = P.job[K.job];
-    return inst < P.ninst ? J.dst + (size_t)inst * J.dst_stride : nullptr;
-}
-
-// vertex pair (ga, ga + 1) of one half: f = the 12 floats.  qs = first vertex of the pair's quad, second = the pair is
-// the quad's second one.  xoff = word offset of vertex 0 in the half's tensor-map rows.
-template <int HALF>
+// vertex pair (ga, ga + 1) of both halves: fa / fb = the 12 floats of the lane's first / second instance.  qs = first vertex of
+// the pair's quad, second = the pair is the quad's second one.
+template <int PHASE>
 __device__ __forceinline__ void ln_emit_pair(const LaneParams& P, const LaneWalk& K, const int32_t ga, const int32_t qs, const bool second,
-                                             const int32_t xoff, const float (&f)[12])
+                                             const float (&fa)[12], const float (&fb)[12])
 {
-    const uint32_t buf = K.stage + (HALF ? (uint32_t)LN_BOX_BYTES : 0u);
     if (qs >= 0 && qs + 4 <= K.nverts) {
-        if (!second) {                              // the buffer's previous box has been read (issued a quad ago)
+        if (!second) {                              // the buffers' previous boxes have been read (issued a quad ago)
             if (K.lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             __syncwarp();
         }
-        const uint32_t r = buf + K.lane * 96u + (second ? 48u : 0u);
-        ln_sts_f4(r, f[0], f[1], f[2], f[3]); ln_sts_f4(r + 16u, f[4], f[5], f[6], f[7]); ln_sts_f4(r + 32u, f[8], f[9], f[10], f[11]);
+        const uint32_t r = K.stage_lane + (second ? 48u : 0u);
+        ln_sts_f4(r, fa[0], fa[1], fa[2], fa[3]); ln_sts_f4(r + 16u, fa[4], fa[5], fa[6], fa[7]); ln_sts_f4(r + 32u, fa[8], fa[9], fa[10], fa[11]);
+        ln_sts_f4(r + LN_BOX_BYTES, fb[0], fb[1], fb[2], fb[3]); ln_sts_f4(r + LN_BOX_BYTES + 16u, fb[4], fb[5], fb[6], fb[7]);
+        ln_sts_f4(r + LN_BOX_BYTES + 32u, fb[8], fb[9], fb[10], fb[11]);
         if (second) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // my STS visible to the async proxy
             __syncwarp();
 #ifndef LN_NO_STORE   // (timing experiments only: the arithmetic without the output stage)
             if (K.lane == 0) {
                 const LaneJob& J = P.job[K.job];
-                ln_tma_store_2d(HALF ? &J.mapB : &J.mapA, buf, qs * 6 + xoff, K.row0);
+                const CUtensorMap* map = K.odd ? &J.mapB : &J.mapA;
+                const int32_t x = qs * 6 + 2 * PHASE;                           // shifted: map B starts 8 bytes before the odd instance
+                ln_tma_store_2d(map, K.stage_lane, x, K.row0);
+                ln_tma_store_2d(map, K.stage_lane + LN_BOX_BYTES, x, K.row0 + 32);
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
 #endif
         }
     } else {                                        // head / tail of the row: 24 bytes per vertex, directly
-        uint8_t* dst = ln_lane_dst(P, K, HALF);
-        if (dst) {
+        const LaneJob& J = P.job[K.job];
+        const uint32_t ia = 2u * (uint32_t)K.row0 + K.odd + 2u * K.lane, ib = ia + 64u;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const uint32_t inst = h ? ib : ia;
+            if (inst >= P.ninst) continue;
+            uint8_t* dst = J.dst + (size_t)inst * J.dst_stride;
+            const float (&f)[12] = h ? fb : fa;
             if (ga >= 0 && ga < K.nverts) {
                 float2* d = reinterpret_cast<float2*>(dst + (size_t)ga * 24);
                 d[0] = make_float2(f[0], f[1]); d[1] = make_float2(f[2], f[3]); d[2] = make_float2(f[4], f[5]);
@@ -229,28 +233,21 @@ __device__ __forceinline__ void ln_emit_pair(const LaneParams& P, const LaneWalk
 }
 
 // The chunk walk of one warp: vertex pairs p0..p1-1 in order, every value as the (A, B) pair of the lane's two instances.
-// SHIFT: the odd instances' pairs are (2p - 1, 2p); their half of vertex 2p - 1 is carried from the previous iteration, and
-// the walk starts one iteration early to have it (computing only that vertex).
-template <int NW, bool MORPH, bool SHIFT>
+template <int NW, bool MORPH, int PHASE>
 __device__ __forceinline__ void lane_walk(const LaneParams& P, const LaneWalk& K, const u64 T, const u64 NZ)
 {
     u64 E[12];
 #pragma unroll
     for (int k = 0; k < 12; ++k) E[k] = 0;
-    float carry[6];
-#pragma unroll
-    for (int k = 0; k < 6; ++k) carry[k] = 0.f;
     uint32_t cur = 0xffffffffu;                       // slot offset whose matrix E is a plain copy of, or none
-    const bool lead = SHIFT && (K.p0 > 0 || K.v_begin > 0);       // one iteration early, for vertex 2*p0 - 1 alone
 #pragma unroll 1
-    for (int32_t p = K.p0 - (lead ? 1 : 0); p < K.p1; ++p) {
-        const bool lead_it = SHIFT && p < K.p0;
+    for (int32_t p = K.p0; p < K.p1; ++p) {
         u64 V[2][6], N[2][3], L2[2];
-        float fa[12], fb[12];                                            // the two vertices' results of the even / odd instance
+        float fa[12], fb[12];                                            // the two vertices' results of the lane's first / second instance
         // ---- both vertices: keyframes -> animated source
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
-            const uint32_t vl = (uint32_t)(max(min(2 * p + u, K.nv_chunk - 1), -1) + 1);   // past the odd last vertex: repeat it (never stored)
+            const uint32_t vl = (uint32_t)min(2 * p + u + 1 - PHASE, K.nv_chunk);     // entry of the vertex; past the last one: repeat it (never stored)
             const uint32_t ky = K.key + vl * (MORPH ? 48u : 32u);
             const float4 a = ln_lds_f4(ky), b = ln_lds_f4(ky + 16u);
             V[u][0] = ln_pk(a.x, a.x); V[u][1] = ln_pk(a.y, a.y); V[u][2] = ln_pk(a.z, a.z);     // warp-uniform scalars: ptxas folds the
@@ -279,11 +276,9 @@ __device__ __forceinline__ void lane_walk(const LaneParams& P, const LaneWalk& K
         // ---- per vertex: collapse the weighted matrix, transform
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
-            if (u == 0 && lead_it) continue;                            // the early iteration wants vertex 2p + 1 only
-            const uint32_t vl = (uint32_t)(max(min(2 * p + u, K.nv_chunk - 1), -1) + 1);
+            const uint32_t vl = (uint32_t)min(2 * p + u + 1 - PHASE, K.nv_chunk);
             const uint4 r0 = ln_lds_u4(K.rec + vl * 32u);
-            // E[4*r + c] = (M_A[r][c], M_B[r][c]); control flow is warp-uniform (plan flags).  One load site for slot 0 (E keeps
-            // its registers across the paths); a single-matrix vertex whose matrix E already holds loads nothing.
+            // E[4*r + c] = (M_A[r][c], M_B[r][c]); control flow is warp-uniform (plan flags)
             const uint32_t fl = r0.x & 15u, off0 = r0.x & ~15u;
             const bool single = NW == 1 || (NW == 2 ? !(fl & 2u) : fl == 1u);
             // (kept across vertices only by single-weight meshes, whose consecutive vertices mostly share the bone: with more weights
@@ -326,7 +321,6 @@ __device__ __forceinline__ void lane_walk(const LaneParams& P, const LaneWalk& K
                 N[u][r] = ln_add(ln_add(ln_mul(E[4 * r], V[u][3], NZ), ln_mul(E[4 * r + 1], V[u][4], NZ)), ln_mul(E[4 * r + 2], V[u][5], NZ));
             L2[u] = ln_add(ln_add(ln_mul(N[u][0], N[u][0], NZ), ln_mul(N[u][1], N[u][1], NZ)), ln_mul(N[u][2], N[u][2], NZ));
         }
-        if (SHIFT && lead_it) L2[0] = L2[1];                            // keep the unused half in range
         {
             u64 len[2], R[2];
             ln_sqrt_rcp2(L2[0], L2[1], NZ, len[0], R[0], len[1], R[1]);
@@ -343,30 +337,8 @@ __device__ __forceinline__ void lane_walk(const LaneParams& P, const LaneWalk& K
             }
         }
         // ---- output
-        const int32_t ga = K.v_begin + 2 * p;                           // mesh vertex of the pair's first
-        if (!lead_it) {
-            const bool second = (ga & 2) != 0;
-            ln_emit_pair<0>(P, K, ga, ga & ~3, second, 0, fa);
-            if (!SHIFT) ln_emit_pair<1>(P, K, ga, ga & ~3, second, 0, fb);
-            else {
-                float g[12];
-#pragma unroll
-                for (int k = 0; k < 6; ++k) { g[k] = carry[k]; g[6 + k] = fb[k]; }
-                ln_emit_pair<1>(P, K, ga - 1, (ga & ~3) - 1, second, 2, g);       // shifted: map B starts 8 bytes before the odd instance
-            }
-        }
-        if (SHIFT) {
-#pragma unroll
-            for (int k = 0; k < 6; ++k) carry[k] = fb[6 + k];
-        }
-    }
-    // shifted rows, even vertex count: the mesh's last vertex (odd) of the odd instances has no partner
-    if (SHIFT && K.last_run && !(K.nverts & 1)) {
-        uint8_t* dst = ln_lane_dst(P, K, 1);
-        if (dst) {
-            float2* d = reinterpret_cast<float2*>(dst + (size_t)(K.nverts - 1) * 24);
-            d[0] = make_float2(carry[0], carry[1]); d[1] = make_float2(carry[2], carry[3]); d[2] = make_float2(carry[4], carry[5]);
-        }
+        const int32_t ga = K.v_begin + 2 * p - PHASE;                   // mesh vertex of the pair's first
+        ln_emit_pair<PHASE>(P, K, ga, K.v_begin + 4 * (p >> 1) - PHASE, (p & 1) != 0, fa, fb);
     }
 }
 
@@ -415,14 +387,15 @@ __device__ __forceinline__ void ln_mbar_wait_relaxed(uint32_t bar, uint32_t pari
 // so that the lane kernel's producer fetches a chunk's matrices with one bulk copy each and nobody transposes per unit.
 // Also the two exactness hazards per (group, matrix): bit 0 = some instance holds a -0 or a negative denormal (a zero
 // weight may not be skipped when that is the slot-0 matrix), bit 1 = something is not finite or >= 2^127.
-// One warp per (group, matrix); lane = instance pair.
+// One warp per (group, matrix); lane = instance pair (2l and 2l + 64 of the group's even or odd half of 128 instances).
 __global__ void __launch_bounds__(256) palette_repack_kernel(const float* __restrict__ palette, size_t pal_stride_floats, uint32_t ninst, uint32_t nmat,
                                                               uint32_t groups, uint8_t* __restrict__ ipal, uint32_t* __restrict__ iflags)
 {
     const uint32_t w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31u;
     if (w >= groups * nmat) return;
     const uint32_t g = w / nmat, m = w - g * nmat;
-    const uint32_t ia = min(g * 64u + 2u * lane, ninst - 1u), ib = min(g * 64u + 2u * lane + 1u, ninst - 1u);     // lanes past the end repeat the last instance
+    const uint32_t i0 = (g >> 1) * 128u + (g & 1u) + 2u * lane;                                 // group = even or odd instances of 128
+    const uint32_t ia = min(i0, ninst - 1u), ib = min(i0 + 64u, ninst - 1u);                    // past the end: repeat the last instance
     const float4* pa = reinterpret_cast<const float4*>(palette + (size_t)ia * pal_stride_floats + m * 16u);
     const float4* pb = reinterpret_cast<const float4*>(palette + (size_t)ib * pal_stride_floats + m * 16u);
     float4 A[3], B[3];
@@ -444,7 +417,7 @@ __global__ void __launch_bounds__(256) palette_repack_kernel(const float* __rest
 }
 
 // what the producer leaves in a unit buffer besides palettes, records and keyframes
-struct LaneUnitMeta { uint32_t done, job, v_begin, nquads, i0, pad[3]; };     // 32 bytes, followed by the 32 lanes' (tA, tB)
+struct LaneUnitMeta { uint32_t done, job, v_begin, nquads, group, pad[3]; };     // 32 bytes, followed by the 32 lanes' (tA, tB)
 
 // One persistent CTA per SM: 16 consumer warps walk work units (one vertex chunk x one group of 64 instances), one PRODUCER
 // warp prepares the next unit while they do: it takes the unit from a global counter, gathers the 64 instances' palettes
@@ -533,7 +506,8 @@ __global__ void __launch_bounds__(LN_THREADS, 1) skin_lane_kernel(const __grid_c
                     if (lane == 0) batch_next = atomicAdd(P.counter, (uint32_t)LN_UNIT_BATCH);      // the next batch's number travels while this one is worked on
                 }
                 if (MORPH) {                                               // the instances' morph weights, as (A, B) per lane
-                    const uint32_t ia = min(g * 64u + 2u * lane, P.ninst - 1u), ib = min(g * 64u + 2u * lane + 1u, P.ninst - 1u);
+                    const uint32_t i0 = (g >> 1) * 128u + (g & 1u) + 2u * lane;
+                    const uint32_t ia = min(i0, P.ninst - 1u), ib = min(i0 + 64u, P.ninst - 1u);
                     t_mine = make_float2(__ldg(P.t + ia), __ldg(P.t + ib));
                 }
             }
@@ -547,7 +521,6 @@ __global__ void __launch_bounds__(LN_THREADS, 1) skin_lane_kernel(const __grid_c
             const LaneJob& J = P.job[j];
             const uint32_t v_begin = ch.x, nquads = ch.y, nslots = ch.z;
             const uint32_t nv_chunk = min(4u * nquads, J.nverts - v_begin);
-            const uint32_t i0 = g * 64u;
             // ---- palettes: one 3 KB bulk copy per slot from the repacked palettes (already in the [chunk][lane] pair layout),
             // completion counted on the buffer's full barrier
             if (lane == 0) {
@@ -594,9 +567,10 @@ __global__ void __launch_bounds__(LN_THREADS, 1) skin_lane_kernel(const __grid_c
 #pragma unroll
                 for (int q = 0; q < NIT; ++q) {
                     const uint32_t e = lane + 32u * (uint32_t)q;
-                    if (e > nv_chunk || (e == 0 && v_begin == 0)) continue;
-                    const uint32_t gv = v_begin + e - 1u;
-                    const uint4* r = e == 0 ? J.pre_recs + (size_t)c * 2 : J.recs + (size_t)gv * 2;
+                    if (e > nv_chunk) continue;
+                    const bool head = e == 0 && v_begin == 0;               // no vertex before the mesh: the shifted walk computes entry 0 all the same
+                    const uint32_t gv = head ? 0u : v_begin + e - 1u;       // (and stores nothing for it), so it gets vertex 0's record
+                    const uint4* r = head ? J.recs : e == 0 ? J.pre_recs + (size_t)c * 2 : J.recs + (size_t)gv * 2;
                     rr0[q] = __ldg(r); rr1[q] = __ldg(r + 1);
                     const float2* a = reinterpret_cast<const float2*>(J.key1 + (size_t)gv * 24);
                     ka[q][0] = __ldg(a); ka[q][1] = __ldg(a + 1); ka[q][2] = __ldg(a + 2);
@@ -608,7 +582,7 @@ __global__ void __launch_bounds__(LN_THREADS, 1) skin_lane_kernel(const __grid_c
 #pragma unroll
                 for (int q = 0; q < NIT; ++q) {
                     const uint32_t e = lane + 32u * (uint32_t)q;
-                    if (e > nv_chunk || (e == 0 && v_begin == 0)) continue;
+                    if (e > nv_chunk) continue;
                     float* ky = reinterpret_cast<float*>(u_key + e * KEY_BYTES);
                     ky[0] = ka[q][0].x; ky[1] = ka[q][0].y; ky[2] = ka[q][1].x; ky[3] = ka[q][1].y; ky[4] = ka[q][2].x; ky[5] = ka[q][2].y;
                     if (MORPH) {                                            // (b - a) is instance-invariant
@@ -633,7 +607,7 @@ __global__ void __launch_bounds__(LN_THREADS, 1) skin_lane_kernel(const __grid_c
                     reinterpret_cast<uint32_t*>(&u_rec[e * 2u])[0] = (huge_any | ((dirty_mask >> slot0) & 1u)) ? ((x & ~15u) | fullmask) : x;
                 }
             }
-            if (lane == 0) { u_meta->done = 0; u_meta->job = j; u_meta->v_begin = v_begin; u_meta->nquads = nquads; u_meta->i0 = i0; }
+            if (lane == 0) { u_meta->done = 0; u_meta->job = j; u_meta->v_begin = v_begin; u_meta->nquads = nquads; u_meta->group = g; }
             __syncwarp();
             if (lane == 0) ln_mbar_arrive(full);                            // release: everything above is visible to who acquires
             LN_PROF(4);                                                    // flag patch, meta, arrive
@@ -657,7 +631,7 @@ __global__ void __launch_bounds__(LN_THREADS, 1) skin_lane_kernel(const __grid_c
         LN_PROF(6);                                                        // consumer: waiting for the unit
         if (u_meta->done) break;
         const LaneJob& J = P.job[u_meta->job];
-        const uint32_t v_begin = u_meta->v_begin, nquads = u_meta->nquads, i0 = u_meta->i0;
+        const uint32_t v_begin = u_meta->v_begin, nquads = u_meta->nquads, group = u_meta->group;
         const uint32_t nv_chunk = min(4u * nquads, J.nverts - v_begin);
         // contiguous runs of quads per warp (consecutive vertices share bones: the matrix stays in registers).  (Handing the
         // quads out on demand through a shared-memory ticket evens the warps out but loses more in per-hand-out overhead:
@@ -670,30 +644,34 @@ __global__ void __launch_bounds__(LN_THREADS, 1) skin_lane_kernel(const __grid_c
         if (q0 < q1) {
             u64 T = 0;
             if (MORPH) T = reinterpret_cast<const u64*>(u_meta + 1)[lane];
-            const uint32_t r1 = min(4u * q1, nv_chunk);
+            // the odd instances of a mesh whose instance stride is 8 mod 16 walk quads that start one vertex early (PHASE 1): chunk
+            // vertices [4 q0 - 1, 4 q1 - 1) — the chunk's last vertex is the next chunk's entry 0 —, up to the end in the mesh's last run
+            const uint32_t odd = group & 1u, phase = J.shift & odd;
+            const bool mesh_end = q1 == nquads && v_begin + nv_chunk == J.nverts;
+            const uint32_t v_end = mesh_end ? nv_chunk : 4u * q1 - phase;
             LaneWalk K;
             K.pal_lane = ln_smem_u32(U) + lane * 16u;
             K.rec = ln_smem_u32(u_rec); K.key = ln_smem_u32(u_key);
-            K.stage = ln_smem_u32(my_stage);
+            K.stage_lane = ln_smem_u32(my_stage) + lane * 96u;
             K.job = u_meta->job;
+            K.odd = odd;
             K.v_begin = (int32_t)v_begin; K.nverts = (int32_t)J.nverts; K.nv_chunk = (int32_t)nv_chunk;
-            K.p0 = (int32_t)(2u * q0); K.p1 = (int32_t)((r1 + 1u) >> 1);
-            K.last_run = v_begin + r1 == J.nverts;
-            K.row0 = (int32_t)(i0 >> 1);
+            K.p0 = (int32_t)(2u * q0); K.p1 = (int32_t)((v_end + phase + 1u) >> 1);
+            K.row0 = (int32_t)((group >> 1) * 64u);
             K.lane = lane;
-            if (J.shift) {
+            if (phase) {
                 switch (J.nw) {
-                case 1: lane_walk<1, MORPH, true>(P, K, T, NZ); break;
-                case 2: lane_walk<2, MORPH, true>(P, K, T, NZ); break;
-                case 3: lane_walk<3, MORPH, true>(P, K, T, NZ); break;
-                default: lane_walk<4, MORPH, true>(P, K, T, NZ); break;
+                case 1: lane_walk<1, MORPH, 1>(P, K, T, NZ); break;
+                case 2: lane_walk<2, MORPH, 1>(P, K, T, NZ); break;
+                case 3: lane_walk<3, MORPH, 1>(P, K, T, NZ); break;
+                default: lane_walk<4, MORPH, 1>(P, K, T, NZ); break;
                 }
             } else {
                 switch (J.nw) {
-                case 1: lane_walk<1, MORPH, false>(P, K, T, NZ); break;
-                case 2: lane_walk<2, MORPH, false>(P, K, T, NZ); break;
-                case 3: lane_walk<3, MORPH, false>(P, K, T, NZ); break;
-                default: lane_walk<4, MORPH, false>(P, K, T, NZ); break;
+                case 1: lane_walk<1, MORPH, 0>(P, K, T, NZ); break;
+                case 2: lane_walk<2, MORPH, 0>(P, K, T, NZ); break;
+                case 3: lane_walk<3, MORPH, 0>(P, K, T, NZ); break;
+                default: lane_walk<4, MORPH, 0>(P, K, T, NZ); break;
                 }
             }
         }
@@ -761,7 +739,7 @@ bool skin_lane_eligible(const ogrecu_skin_plan* plan, const ogrecu_anim_job& J, 
 
 int repack_palettes(ogrecu_ctx* ctx, const float* palette, size_t palette_stride_floats, uint32_t num_instances, uint32_t nmat)
 {
-    const uint32_t groups = div_up(num_instances, 64);
+    const uint32_t groups = 2 * div_up(num_instances, 128);          // the even and the odd instances of every 128
     OGRECU_REQUIRE((size_t)nmat * 16 <= palette_stride_floats, "palette stride smaller than the matrices the plans reference");
     const size_t ipal_bytes = (size_t)groups * nmat * LN_SLOT_BYTES, iflag_bytes = (size_t)groups * nmat * 4;
     OGRECU_CHECK(scratch_reserve(ctx, ctx->lane_ipal, ipal_bytes + iflag_bytes));
@@ -780,7 +758,7 @@ int launch_skin_lane(ogrecu_ctx* ctx, const ogrecu_anim_job* jobs, ogrecu_skin_p
     memset(&P, 0, sizeof P);
     P.njobs = num_jobs;
     P.ninst = num_instances;
-    P.groups = div_up(num_instances, 64);
+    P.groups = 2 * div_up(num_instances, 128);
     P.palette = jobs[0].skin.palette;
     P.pal_stride_floats = palette_stride_floats;
     P.t = t_dev;
@@ -793,7 +771,7 @@ int launch_skin_lane(ogrecu_ctx* ctx, const ogrecu_anim_job* jobs, ogrecu_skin_p
         const uint64_t S = J.dst_instance_stride_bytes;
         const uint64_t words = (uint64_t)J.skin.num_vertices * 6;
         // odd instances: 16-byte aligned when S is a multiple of 16; otherwise (S = 8 mod 16) their map starts 8 bytes early
-        // and the kernel pairs their vertices (2p-1, 2p) so that every box still starts on a 16-byte boundary
+        // and their groups walk quads of vertices 4q-1 .. 4q+2 so that every box still starts on a 16-byte boundary
         const uint32_t shift = (S & 8) ? 1u : 0u;
         OGRECU_CHECK(make_map(&L.mapA, J.skin.dst_pos, words, (num_instances + 1) / 2, 2 * S));
         OGRECU_CHECK(make_map(&L.mapB, (uint8_t*)J.skin.dst_pos + S - 8 * shift, words + 2 * shift, num_instances / 2, 2 * S));
