@@ -788,10 +788,19 @@ def main():
     ap.add_argument("--views", type=int, default=1024)
     ap.add_argument("--c5-tris", type=int, default=20000000)
     args = ap.parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+    # stdout carries the ONE JSON line and nothing else: what libraries write to file descriptor 1 on their own (NCCL's version
+    # banner under torchrun) goes to stderr; print() keeps the real stdout
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real_stdout
+    try:
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_ours(args)
+    finally:
+        real_stdout.flush()
 
 
 if __name__ == "__main__":
