@@ -11,6 +11,7 @@
 #include <vector>
 #include "skin_math.cuh"
 #include "skin_tile.cuh"
+#include "exact_math.cuh"
 
 #include <cstring>
 
@@ -382,6 +383,42 @@ __device__ __forceinline__ void extrude_dir(float dx, float dy, float dz, float 
     ox = fmul(dx, dist); oy = fmul(dy, dist); oz = fmul(dz, dist);
 }
 
+// The four vertices of a thread extruded away from a point light.  sqrt and 1 / len by the branch-free exact sequences of
+// exact_math.cuh when all four squared lengths are in their range (every vertex that is neither on the light nor 2^20 units
+// from it), the four chains interleaved; __fsqrt_rn / __fdiv_rn otherwise.  Same bits either way: both are the correctly
+// rounded sqrt and reciprocal (tools/ubench/exact_rsq.cu) — the two library calls were two thirds of the kernel's instructions.
+__device__ __forceinline__ void extrude_point4(const float (&s)[12], int cnt, float lx, float ly, float lz, float dist, float (&o)[12])
+{
+    float dx[4], dy[4], dz[4], l2[4];
+    bool fast = true;
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+        dx[v] = fsub(s[3 * v], lx); dy[v] = fsub(s[3 * v + 1], ly); dz[v] = fsub(s[3 * v + 2], lz);
+        l2[v] = fadd(fadd(fadd(0.0f, fmul(dx[v], dx[v])), fmul(dy[v], dy[v])), fmul(dz[v], dz[v]));
+        if (v < cnt) fast = fast && em_fast_range(__float_as_uint(l2[v]));
+    }
+    if (fast) {
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            if (v < cnt) {
+                const float inv = em_rcp_fast(em_sqrt_fast(l2[v]));            // len > 0 in the fast range
+                o[3 * v] = fadd(s[3 * v], fmul(fmul(dx[v], inv), dist));
+                o[3 * v + 1] = fadd(s[3 * v + 1], fmul(fmul(dy[v], inv), dist));
+                o[3 * v + 2] = fadd(s[3 * v + 2], fmul(fmul(dz[v], inv), dist));
+            }
+        }
+    } else {
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            if (v < cnt) {
+                float ex, ey, ez;
+                extrude_dir(dx[v], dy[v], dz[v], dist, ex, ey, ez);
+                o[3 * v] = fadd(s[3 * v], ex); o[3 * v + 1] = fadd(s[3 * v + 1], ey); o[3 * v + 2] = fadd(s[3 * v + 2], ez);
+            }
+        }
+    }
+}
+
 // packed xyz; each thread handles 4 vertices = 12 floats (three float4 when aligned)
 template <bool POINT, bool ALIGNED>
 __global__ void extrude_kernel(float lx, float ly, float lz, float dist, const float* __restrict__ src, float* __restrict__ dst, size_t n)
@@ -398,14 +435,13 @@ __global__ void extrude_kernel(float lx, float ly, float lz, float dist, const f
     } else {
         for (int k = 0; k < cnt * 3; ++k) s[k] = src[v0 * 3 + k];
     }
-    float ex, ey, ez;
-    if (!POINT) extrude_dir(-lx, -ly, -lz, dist, ex, ey, ez);
+    if (POINT) extrude_point4(s, cnt, lx, ly, lz, dist, o);
+    else {
+        float ex, ey, ez;
+        extrude_dir(-lx, -ly, -lz, dist, ex, ey, ez);
 #pragma unroll
-    for (int v = 0; v < 4; ++v) {
-        if (v < cnt) {
-            if (POINT) extrude_dir(fsub(s[3 * v], lx), fsub(s[3 * v + 1], ly), fsub(s[3 * v + 2], lz), dist, ex, ey, ez);
-            o[3 * v] = fadd(s[3 * v], ex); o[3 * v + 1] = fadd(s[3 * v + 1], ey); o[3 * v + 2] = fadd(s[3 * v + 2], ez);
-        }
+        for (int v = 0; v < 4; ++v)
+            if (v < cnt) { o[3 * v] = fadd(s[3 * v], ex); o[3 * v + 1] = fadd(s[3 * v + 1], ey); o[3 * v + 2] = fadd(s[3 * v + 2], ez); }
     }
     if (ALIGNED && cnt == 4) {
         float4* q = reinterpret_cast<float4*>(dst + v0 * 3);
@@ -443,14 +479,13 @@ __global__ void extrude_multi_kernel(const __grid_constant__ Lights L, uint32_t 
         const uint32_t li = blockIdx.y;
         const float lx = L.l[li][0], ly = L.l[li][1], lz = L.l[li][2];
         const bool point = !(L.l[li][3] == 0.0f);
-        float ex = 0.f, ey = 0.f, ez = 0.f;
-        if (!point) extrude_dir(-lx, -ly, -lz, dist, ex, ey, ez);
+        if (point) extrude_point4(s, cnt, lx, ly, lz, dist, o);
+        else {
+            float ex, ey, ez;
+            extrude_dir(-lx, -ly, -lz, dist, ex, ey, ez);
 #pragma unroll
-        for (int v = 0; v < 4; ++v) {
-            if (v < cnt) {
-                if (point) extrude_dir(fsub(s[3 * v], lx), fsub(s[3 * v + 1], ly), fsub(s[3 * v + 2], lz), dist, ex, ey, ez);
-                o[3 * v] = fadd(s[3 * v], ex); o[3 * v + 1] = fadd(s[3 * v + 1], ey); o[3 * v + 2] = fadd(s[3 * v + 2], ez);
-            }
+            for (int v = 0; v < 4; ++v)
+                if (v < cnt) { o[3 * v] = fadd(s[3 * v], ex); o[3 * v + 1] = fadd(s[3 * v + 1], ey); o[3 * v + 2] = fadd(s[3 * v + 2], ez); }
         }
         float* d = dst + li * dst_light_stride + v0 * 3;
         if (vec) {
