@@ -216,6 +216,47 @@ def test_extrude_same_buffer_tail(gpu_ctx):
         assert np.array_equal(bits(got), bits(ref))
 
 
+def test_extrude_lengths_outside_the_fast_range(gpu_ctx):
+    """The extrusion takes its exact branch-free sqrt / reciprocal sequences only when the four squared lengths of a thread are
+    in their range; a vertex on the light (length 0: Vector3::normalise leaves it alone), denormal, huge (squared length
+    overflows) distances take the library path.  Mixed inside and across the groups of four, bit for bit against
+    the oracle, single-light and multi-light entry points."""
+    import ogre_b200
+    from ogre_b200 import addr, capi, check, lib
+    ctx = gpu_ctx
+    ou = ogre_b200.OptimisedUtil(ctx)
+    rng = np.random.default_rng(11)
+    light = np.array([1.5, -2.0, 0.25, 1.0], np.float32)
+    nv = 4099
+    pos = rng.uniform(-10, 10, size=(nv, 3)).astype(np.float32)
+    special = [light[:3],                                   # on the light: length 0
+               light[:3] + np.float32(1e-30),                # denormal squared length
+               light[:3] + np.array([1e-21, 0, 0], np.float32),
+               np.array([3e19, 1e19, -2e19], np.float32),    # squared length overflows to inf
+               np.array([1e25, 0, 0], np.float32),
+               light[:3] + np.array([2.0 ** -20, 0, 0], np.float32),   # the ends of the fast range
+               light[:3] + np.array([2.0 ** 19.9, 0, 0], np.float32)]
+    where = rng.choice(nv, size=6 * len(special), replace=False)
+    for i, w in enumerate(where):
+        pos[w] = special[i % len(special)]
+    pos[0:4] = special[0:4]                                  # a whole group of four off the fast path
+    ref = np.zeros((nv, 3), np.float32); got = np.ones((nv, 3), np.float32)
+    with np.errstate(all="ignore"):
+        oracle.lib().oracle_extrude(addr(light), 250.0, addr(pos), addr(ref), nv)
+    ou.extrudeVertices(light, 250.0, addr(pos), addr(got), nv)
+    assert np.array_equal(bits(got), bits(ref))
+    lights = np.stack([light, np.array([-4.0, 9.0, 2.0, 1.0], np.float32), np.array([0.3, -0.9, 0.1, 0.0], np.float32)])
+    dpos, dout = ctx.to_device(pos), ctx.alloc(3 * 3 * nv * 4)
+    check(lib().ogrecu_extrude_multi_dev(ctx.handle, lights.ctypes.data_as(capi.c_float_p), 3, 250.0, dpos.ptr, dout.ptr, 3 * nv, nv))
+    gm = dout.download(np.float32).reshape(3, nv, 3)
+    for k in range(3):
+        r = np.zeros((nv, 3), np.float32)
+        l = np.ascontiguousarray(lights[k])
+        oracle.lib().oracle_extrude(addr(l), 250.0, addr(pos), addr(r), nv)
+        assert np.array_equal(bits(gm[k]), bits(r)), k
+    dpos.free(); dout.free()
+
+
 def test_extrude_multi_light_equals_per_light(gpu_ctx):
     """ogrecu_extrude_multi_dev: 1..8 lights in one launch (positions read once), per light bit-identical to the oracle;
     point and directional lights mixed, aligned and unaligned strides, ragged vertex counts."""
