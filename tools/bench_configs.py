@@ -608,7 +608,21 @@ def c2j(ctx, T, args):
 
     def separate():
         morph(); skin()
+    # the same step through the lane kernel (round 2: plan + ogrecu_anim_frame_dev, what bench.py times for Sinbad)
+    from ogre_b200 import AnimJob
+    aj = (AnimJob * 1)()
+    aj[0].skin = jf
+    aj[0].key2 = key2.data_ptr()
+    aj[0].dst_instance_stride_bytes = n * 24
+    plan = C.c_void_p()
+    check(L.ogrecu_skin_plan_create(ctx.handle, C.byref(aj[0].skin), C.byref(plan)))
+    plans = (C.c_void_p * 1)(plan)
+
+    def lane():
+        check(L.ogrecu_anim_frame_dev(ctx.handle, aj, plans, 1, d_t.data_ptr(), ninst, nb * 16))
     dt_f, dt_s, dt_skin = T.time(fused, iters=50), T.time(separate, iters=50), T.time(skin, iters=50)
+    dt_lane = T.time(lane, iters=50)
+    lane(); T.stream.synchronize(); lane_bits = dst[4711].cpu().numpy().copy()
     # parity spot check: instance 4711 of the fused step against the separate one (bit patterns)
     fused(); T.stream.synchronize(); a = dst[4711].cpu().numpy().copy()
     separate(); T.stream.synchronize(); b = dst[4711].cpu().numpy()
@@ -618,6 +632,8 @@ def c2j(ctx, T, args):
                       "morph + skin" % (n, nb, len(s["bone_map"]), s["nw"], ninst), "n_gpus": WORLD,
             "fused_ms": dt_f * 1e3, "fused_Mvert_per_s": tot / dt_f / 1e6, "separate_ms": dt_s * 1e3, "separate_Mvert_per_s": tot / dt_s / 1e6,
             "skin_only_ms": dt_skin * 1e3, "skin_only_Mvert_per_s": tot / dt_skin / 1e6,
+            "lane_ms": dt_lane * 1e3, "lane_Mvert_per_s": tot / dt_lane / 1e6, "lane_frac_of_hbm_peak": (ninst * n * 24 + pal_bytes) / dt_lane / 1e9 / PEAK,
+            "lane_equals_separate_bits": bool(np.array_equal(lane_bits.view(np.uint32), b.view(np.uint32))),
             "fused_frac_of_hbm_peak": (ninst * n * 24 + pal_bytes) / dt_f / 1e9 / PEAK,
             "skin_only_frac_of_hbm_peak": (ninst * n * 48 + pal_bytes) / dt_skin / 1e9 / PEAK,
             "fused_equals_separate_bits": bool(np.array_equal(a.view(np.uint32), b.view(np.uint32)))}
