@@ -967,6 +967,9 @@ __device__ __forceinline__ bool covers_pixel(const float* hf, float Px, float Py
 #ifndef RASTER_PREFETCH
 #define RASTER_PREFETCH 1       // 0: none, 1: pairs one chunk ahead (C5 2.21 -> 2.15 ms), 2: also records one chunk ahead (80 registers: 2.18 ms)
 #endif
+#ifndef RT_MIN_CTAS
+#define RT_MIN_CTAS 5           // tile CTAs per SM the register allocation is bounded for (48 registers, 40 bytes spilled: C4 -1.7 %, C5 -1.8 % against 4; 6: 40 registers, 188 bytes, no further gain)
+#endif
 constexpr int VIS_SMALL_MAX = 12;   // bbox pixels a single thread walks; larger triangles go to a warp
 
 // One CTA per 16x16 tile.  Two ways to resolve the tile's triangle list, same result:
@@ -980,7 +983,7 @@ constexpr int VIS_SMALL_MAX = 12;   // bbox pixels a single thread walks; larger
 //    makes the outcome order dependent: the tile then falls back to
 //  * the in-order path: one pixel per thread, triangles replayed in submission order.
 template <bool VEC>
-__global__ void __launch_bounds__(RT_THREADS, 4) raster_kernel(RasterParams P)
+__global__ void __launch_bounds__(RT_THREADS, RT_MIN_CTAS) raster_kernel(RasterParams P)
 {
     __shared__ float4 s_hot[CHUNK][5];
     __shared__ __align__(16) uint8_t s_rgb[TILE][TILE * 3];
