@@ -236,6 +236,15 @@ __device__ __forceinline__ void triangle_vertices(const DrawHot& H, uint32_t t, 
     } else { vi[0] = base + k; vi[1] = base + k + 1; vi[2] = base + k + 2; }
 }
 
+// CTAs per SM the set-up passes' registers are bounded for.  Both passes wait on gathers (indices -> transformed vertices) more than they
+// compute; six CTAs (40 registers, 64 / ~100 bytes spilled) against the four the unbounded 64 registers gave: C4 0.0560 -> 0.0539 ms
+// per view, C5 1.132 -> 1.079 ms, the crowd frame's render 2.69 -> 2.56 ms (profiles/r02i_setup_min_ctas.txt; 5 / 5: 0.0548, 1.103, 2.60).
+#ifndef SC_MIN_CTAS
+#define SC_MIN_CTAS 6
+#endif
+#ifndef SW_MIN_CTAS
+#define SW_MIN_CTAS 6
+#endif
 constexpr int SB_THREADS = 256;
 constexpr int SB_ROUNDS = 4;                         // 256-triangle rounds per CTA
 constexpr int SB_BLOCK = SB_THREADS * SB_ROUNDS;     // triangles per CTA = per entry of the block-aggregate table
@@ -409,7 +418,7 @@ __device__ __forceinline__ void cta_draw_cache(const SegParams& P, uint32_t g0, 
 //  the index loads of all four rounds before the first vertex gather — setup_write goes from 64 to 80 registers,
 //  one CTA less per SM, C5 2.16 -> 2.25 ms; staging the CTA's 12 KB of indices through shared memory with one coalesced
 //  copy — same registers, C5 2.15 -> 2.30 ms, C4 8.8 -> 8.4 k views/s.  The index round trip is not what bounds these kernels.)
-__global__ void __launch_bounds__(SB_THREADS) setup_count_kernel(SegParams P)
+__global__ void __launch_bounds__(SB_THREADS, SC_MIN_CTAS) setup_count_kernel(SegParams P)
 {
     __shared__ uint32_t s_lo, s_wp[8], s_wt[8];
     __shared__ float s_mat[32];
@@ -498,7 +507,7 @@ __global__ void __launch_bounds__(1024) setup_scan_kernel(const uint32_t* __rest
 // the SURVIVORS are set up again — densely: survivor number i of the CTA is handled by thread i mod 256, whatever lane first
 // saw it.  (In a scene of sub-pixel triangles one in sixteen survives: four barrier-separated rounds of a mostly idle CTA
 // were latency bound at four CTAs per SM.)
-__global__ void __launch_bounds__(SB_THREADS) setup_write_kernel(SegParams P)
+__global__ void __launch_bounds__(SB_THREADS, SW_MIN_CTAS) setup_write_kernel(SegParams P)
 {
     __shared__ uint32_t s_lo, s_wp[SB_ROUNDS][8], s_wt[SB_ROUNDS][8];
     __shared__ float s_mat[32];
